@@ -1,0 +1,169 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE.  ctypes access to the plain-C restatement (oracle/nbabfs_oracle.c).
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this; the product never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "restatement"])
+
+
+def _lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(_HERE, "liboracle_nbabfs.so")
+    if not os.path.exists(path):
+        build()
+    lib = C.CDLL(path)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+    lib.orc_create.restype = vp
+    lib.orc_create.argtypes = [C.c_int, dp, ip, C.c_int, ip, dp, dp, C.c_int, ip, dp, dp, C.c_int, ip, C.c_int, ip, C.c_int, dp, dp]
+    lib.orc_destroy.argtypes = [vp]
+    lib.orc_set_options.argtypes = [vp] + [C.c_double] * 6 + [C.c_int, C.c_int]
+    lib.orc_energy.restype = C.c_int
+    lib.orc_energy.argtypes = [vp, dp, dp, C.c_int, dp, dp, dp, dp]
+    for f in ("orc_num_primary_pairs", "orc_num_image_pairs", "orc_num_14_pairs"):
+        getattr(lib, f).restype = C.c_long
+        getattr(lib, f).argtypes = [vp]
+    lib.orc_num_images.restype = C.c_int
+    lib.orc_num_images.argtypes = [vp]
+    lib.orc_get_primary_pairs.argtypes = [vp, ip]
+    lib.orc_get_image_info.argtypes = [vp, C.c_int, ip, dp]
+    lib.orc_get_image_pairs.argtypes = [vp, C.c_int, ip]
+    lib.orc_get_image_coordinates.argtypes = [vp, C.c_int, dp]
+    lib.orc_make_factors.argtypes = [C.c_double] * 3 + [dp]
+    lib.orc_make_M.argtypes = [dp, dp, dp]
+    lib.orc_pair.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
+    _LIB = lib
+    return lib
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class OracleNB:
+    """Same interface as oracle/refnb.py:RefNB, backed by the restatement."""
+
+    def __init__(self, system, **options):
+        self.lib = _lib()
+        s = self.sys = system
+        self.n = s["n"]
+        q = np.ascontiguousarray(s["charges"], np.float64)
+        lt = np.ascontiguousarray(s["ljtypes"], np.int32)
+        ex = np.ascontiguousarray(s["exclusions"], np.int32).reshape(-1)
+        p14 = np.ascontiguousarray(s["pairs14"], np.int32).reshape(-1)
+        rot = np.ascontiguousarray(s["rot"], np.float64).reshape(-1)
+        trn = np.ascontiguousarray(s["trans"], np.float64).reshape(-1)
+        ntrans = 0 if s["box"] is None else len(s["trans"])
+        self.h = self.lib.orc_create(self.n, _d(q), _i(lt), s["ntypes"], _i(s["tableindex"]), _d(s["tableA"]), _d(s["tableB"]),
+                                     s["ntypes"], _i(s["tableindex14"]), _d(s["tableA14"]), _d(s["tableB14"]),
+                                     len(ex) // 2, _i(ex) if len(ex) else None, len(p14) // 2, _i(p14) if len(p14) else None,
+                                     ntrans, _d(rot) if ntrans else None, _d(trn) if ntrans else None)
+        self.opts = dict(dampingCutoff=0.5, innerCutoff=8.0, outerCutoff=12.0, listCutoff=13.5, dielectric=1.0,
+                         electrostaticScale14=s.get("electrostaticScale14", 1.0), checkForInverses=True, imageExpandFactor=0)
+        self.set_options(**options)
+
+    def set_options(self, **kw):
+        for k in kw:
+            if k not in self.opts:
+                raise ValueError("unknown option " + k)
+        self.opts.update(kw)
+        o = self.opts
+        self.lib.orc_set_options(self.h, o["dampingCutoff"], o["innerCutoff"], o["outerCutoff"], o["listCutoff"],
+                                 o["dielectric"], o["electrostaticScale14"], int(o["checkForInverses"]), int(o["imageExpandFactor"]))
+
+    def energy(self, xyz=None, box=None, force_new=False, gradients=True):
+        xyz = np.ascontiguousarray(self.sys["xyz"] if xyz is None else xyz, np.float64)
+        box = self.sys["box"] if box is None else box
+        boxa = None if box is None else np.ascontiguousarray(box, np.float64)
+        e = np.zeros(6)
+        g = np.zeros((self.n, 3)) if gradients else None
+        dm = np.zeros((3, 3)) if gradients else None
+        tm = np.zeros(2)
+        upd = self.lib.orc_energy(self.h, _d(xyz), _d(boxa), int(force_new), _d(e), _d(g), _d(dm), _d(tm))
+        return dict(energies=e, grad=g, dEdM=dm, updated=bool(upd), t_update=tm[0], t_energy=tm[1])
+
+    def counts(self):
+        return dict(primary=self.lib.orc_num_primary_pairs(self.h), images=self.lib.orc_num_images(self.h),
+                    image_pairs=self.lib.orc_num_image_pairs(self.h), pairs14=self.lib.orc_num_14_pairs(self.h))
+
+    def primary_pairs(self):
+        n = self.lib.orc_num_primary_pairs(self.h)
+        p = np.zeros((n, 2), np.int32)
+        if n:
+            self.lib.orc_get_primary_pairs(self.h, _i(p))
+        return p
+
+    def images(self, coordinates=False):
+        out = []
+        for k in range(self.lib.orc_num_images(self.h)):
+            info = np.zeros(6, np.int32)
+            sc = np.zeros(1)
+            self.lib.orc_get_image_info(self.h, k, _i(info), _d(sc))
+            p = np.zeros((info[4], 2), np.int32)
+            if info[4]:
+                self.lib.orc_get_image_pairs(self.h, k, _i(p))
+            d = dict(t=int(info[0]), a=int(info[1]), b=int(info[2]), c=int(info[3]), scale=float(sc[0]), pairs=p)
+            if coordinates:
+                xyz = np.zeros((self.n, 3))
+                self.lib.orc_get_image_coordinates(self.h, k, _d(xyz))
+                d["xyz"] = xyz
+            out.append(d)
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.orc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_factors(damp, inner, outer):
+    out = np.zeros(21)
+    _lib().orc_make_factors(damp, inner, outer, _d(out))
+    return out
+
+
+def make_M(box6):
+    b = np.ascontiguousarray(box6, np.float64)
+    m = np.zeros((3, 3))
+    im = np.zeros((3, 3))
+    _lib().orc_make_M(_d(b), _d(m), _d(im))
+    return m, im
+
+
+def pair(factors, r2, qij, Aij, Bij):
+    f = np.ascontiguousarray(factors, np.float64)
+    e = np.zeros(2)
+    dF = C.c_double(0.0)
+    _lib().orc_pair(_d(f), r2, qij, Aij, Bij, _d(e), C.byref(dF))
+    return e[0], e[1], dF.value
+
+
+def canonical_primary(pairs):
+    """unordered pair set -> sorted array of (max, min) encoded as int64 keys"""
+    p = np.asarray(pairs, np.int64).reshape(-1, 2)
+    hi, lo = np.maximum(p[:, 0], p[:, 1]), np.minimum(p[:, 0], p[:, 1])
+    return np.sort(hi * (1 << 32) + lo)
+
+
+def canonical_cross(pairs):
+    p = np.asarray(pairs, np.int64).reshape(-1, 2)
+    return np.sort(p[:, 0] * (1 << 32) + p[:, 1])

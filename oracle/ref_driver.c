@@ -1,0 +1,289 @@
+/* oracle/ref_driver.c -- TEST INFRASTRUCTURE (never linked into the product library).
+ *
+ * Drives the UNMODIFIED reference C implementation (headers/sources used where they lie under
+ * /root/reference) through the same sequence the Cython layer uses:
+ *   NBModelABFS.SetUp  : pMolecule-1.9.0/extensions/pyrex/pMolecule.NBModelABFS.pyx:181-273
+ *   NBModelABFS.Energy : pMolecule-1.9.0/extensions/pyrex/pMolecule.NBModelABFS.pyx:108-122
+ * Default generator options: pMolecule.NBModelABFS.pyx:59-71 ; cellSize = factor*cutoff as in
+ * pCore-1.9.0/extensions/pyrex/pCore.PairListGenerator.pyx:104.
+ * Identity container construction: pCore.Transformation3Container.pyx:159-168.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#ifdef USEOPENMP
+#include <omp.h>
+#endif
+
+#include "NBModelABFS.h"
+#include "NBModelABFSState.h"
+#include "PairwiseInteraction.h"
+#include "PairListGenerator.h"
+#include "LJParameterContainer.h"
+#include "MMAtomContainer.h"
+#include "SymmetryParameters.h"
+#include "SymmetryParameterGradients.h"
+#include "Transformation3Container.h"
+#include "ImageList.h"
+#include "ref_driver.h"
+
+struct RefNB {
+    int n, ntrans;
+    MMAtomContainer            *mm;
+    LJParameterContainer       *lj, *lj14;
+    PairList                   *excl, *i14;
+    Transformation3Container   *tc;
+    SymmetryParameters         *sp;
+    SymmetryParameterGradients *spg;
+    NBModelABFS                *nb;
+    PairListGenerator          *gen;
+    PairwiseInteractionABFS    *pw;
+    NBModelABFSState           *st;
+    Coordinates3               *x, *g;
+};
+
+static double now_s(void)
+{
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double) ts.tv_sec + 1.0e-9 * (double) ts.tv_nsec;
+}
+
+static LJParameterContainer *make_lj(int nt, const int *tableindex, const double *tA, const double *tB)
+{
+    LJParameterContainer *lj = LJParameterContainer_Allocate(nt);
+    int i, m = (nt * (nt + 1)) / 2;
+    for (i = 0; i < nt * nt; i++) lj->tableindex[i] = tableindex[i];
+    for (i = 0; i < m; i++) { lj->tableA[i] = tA[i]; lj->tableB[i] = tB[i]; }
+    return lj;
+}
+
+RefNB *refnb_create(int n, const double *charges, const int *ljtypes,
+                    int ntypes, const int *tableindex, const double *tableA, const double *tableB,
+                    int ntypes14, const int *tableindex14, const double *tableA14, const double *tableB14,
+                    int nexcl, const int *exclPairs, int n14, const int *pairs14,
+                    int ntrans, const double *rot, const double *trans)
+{
+    int i, t, r, c;
+    RefNB *h = (RefNB *) calloc(1, sizeof(RefNB));
+    if (h == NULL) return NULL;
+    h->n = n; h->ntrans = ntrans;
+    h->mm = MMAtomContainer_Allocate(n);
+    for (i = 0; i < n; i++) {
+        h->mm->data[i].QACTIVE  = True;
+        h->mm->data[i].atomtype = ljtypes[i];
+        h->mm->data[i].ljtype   = ljtypes[i];
+        h->mm->data[i].charge   = charges[i];
+    }
+    h->lj = make_lj(ntypes, tableindex, tableA, tableB);
+    if (tableindex14 != NULL) h->lj14 = make_lj(ntypes14, tableindex14, tableA14, tableB14);
+    else                      h->lj14 = make_lj(ntypes, tableindex, tableA, tableB);
+    if (nexcl > 0) {
+        int *tmp = (int *) malloc(sizeof(int) * 2 * (size_t) nexcl);
+        memcpy(tmp, exclPairs, sizeof(int) * 2 * (size_t) nexcl);
+        h->excl = PairList_FromIntegerPairArray(True, nexcl, tmp);
+        free(tmp);
+    }
+    if (n14 > 0) {
+        int *tmp = (int *) malloc(sizeof(int) * 2 * (size_t) n14);
+        memcpy(tmp, pairs14, sizeof(int) * 2 * (size_t) n14);
+        h->i14 = PairList_FromIntegerPairArray(True, n14, tmp);
+        free(tmp);
+    }
+    if (ntrans > 0) {
+        h->tc = Transformation3Container_Allocate(ntrans);
+        h->tc->QOWNER = True;
+        for (t = 0; t < ntrans; t++) {
+            Transformation3 *T = Transformation3_Allocate();
+            for (r = 0; r < 3; r++) {
+                for (c = 0; c < 3; c++) Matrix33_Item(T->rotation, r, c) = rot[9 * t + 3 * r + c];
+                Vector3_Item(T->translation, r) = trans[3 * t + r];
+            }
+            h->tc->items[t] = T;
+        }
+        Transformation3Container_FindIdentity(h->tc);
+        Transformation3Container_FindInverses(h->tc);
+        h->sp  = SymmetryParameters_Allocate();
+        h->spg = SymmetryParameterGradients_Allocate();
+    }
+    h->nb  = NBModelABFS_Allocate();
+    h->gen = PairListGenerator_Allocate();
+    h->pw  = PairwiseInteractionABFS_Allocate();
+    h->x   = Coordinates3_Allocate(n);
+    h->g   = Coordinates3_Allocate(n);
+    refnb_set_options(h, 0.5, 8.0, 12.0, 13.5, 1.0, 1.0, 1, 0, 0.5, 0, 1, 0);
+    h->st = NBModelABFSState_SetUp(h->mm, NULL, NULL, h->excl, h->i14, h->lj, h->lj14, NULL, NULL, NULL, h->tc, h->nb->qcmmCoupling);
+    if (h->st == NULL) { refnb_destroy(h); return NULL; }
+    return h;
+}
+
+void refnb_destroy(RefNB *h)
+{
+    if (h == NULL) return;
+    NBModelABFSState_Deallocate(&(h->st));
+    Coordinates3_Deallocate(&(h->x));
+    Coordinates3_Deallocate(&(h->g));
+    PairwiseInteractionABFS_Deallocate(&(h->pw));
+    PairListGenerator_Deallocate(&(h->gen));
+    NBModelABFS_Deallocate(&(h->nb));
+    if (h->spg != NULL) SymmetryParameterGradients_Deallocate(&(h->spg));
+    if (h->sp  != NULL) SymmetryParameters_Deallocate(&(h->sp));
+    if (h->tc  != NULL) Transformation3Container_Deallocate(&(h->tc));
+    PairList_Deallocate(&(h->i14));
+    PairList_Deallocate(&(h->excl));
+    LJParameterContainer_Deallocate(&(h->lj14));
+    LJParameterContainer_Deallocate(&(h->lj));
+    MMAtomContainer_Deallocate(&(h->mm));
+    free(h);
+}
+
+void refnb_set_options(RefNB *h, double damp, double inner, double outer, double list,
+                       double dielectric, double elecScale14, int checkForInverses, int imageExpandFactor,
+                       double cellSizeFactor, int method, int useGridByCell, int sortIndices)
+{
+    h->nb->dampingCutoff        = damp;
+    h->nb->innerCutoff          = inner;
+    h->nb->outerCutoff          = outer;
+    h->nb->listCutoff           = list;
+    h->nb->dielectric           = dielectric;
+    h->nb->electrostaticScale14 = elecScale14;
+    h->nb->checkForInverses     = checkForInverses ? True : False;
+    h->nb->imageExpandFactor    = imageExpandFactor;
+    h->pw->dampingCutoff = damp; h->pw->innerCutoff = inner; h->pw->outerCutoff = outer;
+    h->gen->cutoff               = list;
+    h->gen->cutoffCellSizeFactor = cellSizeFactor;
+    h->gen->cellSize             = cellSizeFactor * list;
+    h->gen->minimumCellExtent    = 2;
+    h->gen->minimumPoints        = 500;
+    h->gen->sortIndices          = sortIndices ? True : False;
+    h->gen->useGridByCell        = useGridByCell ? True : False;
+    if (method == 1) h->gen->minimumPoints = 2000000000;              /* never use the grid */
+    if (method == 2) { h->gen->minimumPoints = 0; h->gen->minimumCellExtent = 0; }
+}
+
+int refnb_energy(RefNB *h, const double *xyz, const double *box, int forceNew,
+                 double *energies, double *grad, double *dEdM, double *timings)
+{
+    int i, updated;
+    Status status = Status_Continue;
+    double t0, t1, t2;
+    for (i = 0; i < h->n; i++) {
+        Coordinates3_Item(h->x, i, 0) = xyz[3 * i];
+        Coordinates3_Item(h->x, i, 1) = xyz[3 * i + 1];
+        Coordinates3_Item(h->x, i, 2) = xyz[3 * i + 2];
+    }
+    Coordinates3_Set(h->g, 0.0);
+    if (h->ntrans > 0) {
+        SymmetryParameters_SetCrystalParameters(h->sp, box[0], box[1], box[2], box[3], box[4], box[5]);
+        Matrix33_Set(h->spg->dEdM, 0.0);
+    }
+    if (forceNew) h->st->isNew = True;
+    NBModelABFSState_Initialize(h->st, h->x, h->sp, (grad != NULL) ? h->g : NULL, (grad != NULL) ? h->spg : NULL);
+    t0 = now_s();
+    updated = (int) NBModelABFS_Update(h->nb, h->gen, h->st, &status);
+    t1 = now_s();
+    if (status != Status_Continue) return -1;
+    NBModelABFS_MMMMEnergy(h->nb, h->pw, h->st);
+    t2 = now_s();
+    if (timings != NULL) { timings[0] = t1 - t0; timings[1] = t2 - t1; }
+    energies[0] = h->st->emmel;   energies[1] = h->st->emmlj;
+    energies[2] = h->st->emmel14; energies[3] = h->st->emmlj14;
+    energies[4] = h->st->eimmmel; energies[5] = h->st->eimmmlj;
+    if (grad != NULL) {
+        for (i = 0; i < h->n; i++) {
+            grad[3 * i]     += Coordinates3_Item(h->g, i, 0);
+            grad[3 * i + 1] += Coordinates3_Item(h->g, i, 1);
+            grad[3 * i + 2] += Coordinates3_Item(h->g, i, 2);
+        }
+        if ((dEdM != NULL) && (h->spg != NULL)) {
+            int r, c;
+            for (r = 0; r < 3; r++) for (c = 0; c < 3; c++) dEdM[3 * r + c] += Matrix33_Item(h->spg->dEdM, r, c);
+        }
+    }
+    return updated;
+}
+
+long refnb_num_primary_pairs(RefNB *h) { return (h->st->nbmmmm == NULL) ? 0 : (long) h->st->nbmmmm->npairs; }
+long refnb_num_14_pairs(RefNB *h)      { return (h->st->nbmmmm14 == NULL) ? 0 : (long) h->st->nbmmmm14->npairs; }
+int  refnb_num_images(RefNB *h)        { return (h->st->inbmmmm == NULL) ? 0 : ImageList_NumberOfImages(h->st->inbmmmm); }
+long refnb_num_image_pairs(RefNB *h)   { return (h->st->inbmmmm == NULL) ? 0 : (long) ImageList_NumberOfPairs(h->st->inbmmmm); }
+int  refnb_uses_grid(RefNB *h)         { return (int) h->st->useGridSearch; }
+int  refnb_num_threads(void)
+{
+#ifdef USEOPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+static void dump_pairs(PairList *pl, int *pairs)
+{
+    int r, k; long m = 0;
+    if (pl == NULL) return;
+    PairList_MakeRecords(pl);
+    for (r = 0; r < pl->numberOfRecords; r++) {
+        IndexedSelection *rec = pl->records[r];
+        for (k = 0; k < rec->nindices; k++) { pairs[2 * m] = rec->index; pairs[2 * m + 1] = rec->indices[k]; m++; }
+    }
+}
+
+void refnb_get_primary_pairs(RefNB *h, int *pairs) { dump_pairs(h->st->nbmmmm, pairs); }
+
+void refnb_get_image_info(RefNB *h, int k, int *info, double *scale)
+{
+    ImageList *il = h->st->inbmmmm;
+    Image *im; int t;
+    ImageList_MakeRecords(il);
+    im = il->records[k];
+    info[0] = -1;
+    for (t = 0; t < h->tc->nitems; t++) if (h->tc->items[t] == im->transformation3) info[0] = t;
+    info[1] = im->a; info[2] = im->b; info[3] = im->c;
+    info[4] = (im->pairlist == NULL) ? 0 : im->pairlist->npairs;
+    info[5] = 0;
+    scale[0] = im->scale;
+}
+
+void refnb_get_image_pairs(RefNB *h, int k, int *pairs)
+{
+    ImageList *il = h->st->inbmmmm;
+    ImageList_MakeRecords(il);
+    dump_pairs(il->records[k]->pairlist, pairs);
+}
+
+void refnb_make_factors(double damp, double inner, double outer, double *out)
+{
+    PairwiseInteractionABFS *pw = PairwiseInteractionABFS_Allocate();
+    PairwiseInteractionABFSFactors f;
+    pw->dampingCutoff = damp; pw->innerCutoff = inner; pw->outerCutoff = outer;
+    PairwiseInteractionABFS_MakeFactors(pw, &f);
+    out[0] = f.r2Damp; out[1] = f.r2On; out[2] = f.r2Off;
+    out[3] = f.a; out[4] = f.b; out[5] = f.c; out[6] = f.d;
+    out[7] = f.qShift1; out[8] = f.qShift2; out[9] = f.qF0; out[10] = f.qAlpha;
+    out[11] = f.aF6; out[12] = f.aK12; out[13] = f.aShift12; out[14] = f.aF0; out[15] = f.aAlpha;
+    out[16] = f.bF3; out[17] = f.bK6; out[18] = f.bShift6; out[19] = f.bF0; out[20] = f.bAlpha;
+    PairwiseInteractionABFS_Deallocate(&pw);
+}
+
+void refnb_lj_table(int ntypes, const double *eps, const double *sigma, int amber,
+                    int *tableindex, double *tableA, double *tableB)
+{
+    LJParameterContainer *lj = LJParameterContainer_Allocate(ntypes);
+    int i, m = (ntypes * (ntypes + 1)) / 2;
+    for (i = 0; i < ntypes; i++) { lj->epsilon[i] = eps[i]; lj->sigma[i] = sigma[i]; }
+    if (amber) LJParameterContainer_MakeTableAMBER(lj); else LJParameterContainer_MakeTableOPLS(lj);
+    for (i = 0; i < ntypes * ntypes; i++) tableindex[i] = lj->tableindex[i];
+    for (i = 0; i < m; i++) { tableA[i] = lj->tableA[i]; tableB[i] = lj->tableB[i]; }
+    LJParameterContainer_Deallocate(&lj);
+}
+
+void refnb_make_M(const double *box, double *M9, double *invM9)
+{
+    SymmetryParameters *sp = SymmetryParameters_Allocate();
+    int r, c;
+    SymmetryParameters_SetCrystalParameters(sp, box[0], box[1], box[2], box[3], box[4], box[5]);
+    for (r = 0; r < 3; r++) for (c = 0; c < 3; c++) {
+        M9[3 * r + c]    = Matrix33_Item(sp->M, r, c);
+        invM9[3 * r + c] = Matrix33_Item(sp->inverseM, r, c);
+    }
+    SymmetryParameters_Deallocate(&sp);
+}

@@ -1,0 +1,174 @@
+"""oracle/refnb.py -- TEST INFRASTRUCTURE.  ctypes access to the compiled, unmodified reference
+(oracle/_ref/libref_nbabfs*.so, built by oracle/Makefile from /root/reference) through the flat driver
+oracle/ref_driver.c.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+ENERGY_LABELS = ("MM/MM Elect.", "MM/MM LJ", "MM/MM 1-4 Elect.", "MM/MM 1-4 LJ", "MM/MM Image Elect.", "MM/MM Image LJ")
+
+
+def available(omp=False):
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_nbabfs_omp.so" if omp else "libref_nbabfs.so"))
+
+
+def _lib(omp=False):
+    key = bool(omp)
+    if key in _LIBS:
+        return _LIBS[key]
+    path = os.path.join(_HERE, "_ref", "libref_nbabfs_omp.so" if omp else "libref_nbabfs.so")
+    lib = C.CDLL(path)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+    lib.refnb_create.restype = vp
+    lib.refnb_create.argtypes = [C.c_int, dp, ip, C.c_int, ip, dp, dp, C.c_int, ip, dp, dp,
+                                 C.c_int, ip, C.c_int, ip, C.c_int, dp, dp]
+    lib.refnb_destroy.argtypes = [vp]
+    lib.refnb_set_options.argtypes = [vp] + [C.c_double] * 6 + [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
+    lib.refnb_energy.restype = C.c_int
+    lib.refnb_energy.argtypes = [vp, dp, dp, C.c_int, dp, dp, dp, dp]
+    lib.refnb_num_primary_pairs.restype = C.c_long
+    lib.refnb_num_primary_pairs.argtypes = [vp]
+    lib.refnb_num_image_pairs.restype = C.c_long
+    lib.refnb_num_image_pairs.argtypes = [vp]
+    lib.refnb_num_14_pairs.restype = C.c_long
+    lib.refnb_num_14_pairs.argtypes = [vp]
+    lib.refnb_num_images.restype = C.c_int
+    lib.refnb_num_images.argtypes = [vp]
+    lib.refnb_uses_grid.restype = C.c_int
+    lib.refnb_uses_grid.argtypes = [vp]
+    lib.refnb_num_threads.restype = C.c_int
+    lib.refnb_get_primary_pairs.argtypes = [vp, ip]
+    lib.refnb_get_image_info.argtypes = [vp, C.c_int, ip, dp]
+    lib.refnb_get_image_pairs.argtypes = [vp, C.c_int, ip]
+    lib.refnb_make_factors.argtypes = [C.c_double] * 3 + [dp]
+    lib.refnb_lj_table.argtypes = [C.c_int, dp, dp, C.c_int, ip, dp, dp]
+    lib.refnb_make_M.argtypes = [dp, dp, dp]
+    _LIBS[key] = lib
+    return lib
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class RefNB:
+    """The reference NBModelABFS + state for one system dict (see pdynamo-mirror_b200/workloads.py)."""
+
+    def __init__(self, system, omp=False, **options):
+        self.lib = _lib(omp)
+        s = self.sys = system
+        self.n = s["n"]
+        q = np.ascontiguousarray(s["charges"], np.float64)
+        lt = np.ascontiguousarray(s["ljtypes"], np.int32)
+        ex = np.ascontiguousarray(s["exclusions"], np.int32).reshape(-1)
+        p14 = np.ascontiguousarray(s["pairs14"], np.int32).reshape(-1)
+        rot = np.ascontiguousarray(s["rot"], np.float64).reshape(-1)
+        trn = np.ascontiguousarray(s["trans"], np.float64).reshape(-1)
+        ntrans = 0 if s["box"] is None else len(s["trans"])
+        self.h = self.lib.refnb_create(self.n, _d(q), _i(lt), s["ntypes"], _i(s["tableindex"]), _d(s["tableA"]), _d(s["tableB"]),
+                                       s["ntypes"], _i(s["tableindex14"]), _d(s["tableA14"]), _d(s["tableB14"]),
+                                       len(ex) // 2, _i(ex) if len(ex) else None, len(p14) // 2, _i(p14) if len(p14) else None,
+                                       ntrans, _d(rot) if ntrans else None, _d(trn) if ntrans else None)
+        if not self.h:
+            raise RuntimeError("refnb_create failed")
+        self.opts = dict(dampingCutoff=0.5, innerCutoff=8.0, outerCutoff=12.0, listCutoff=13.5, dielectric=1.0,
+                         electrostaticScale14=s.get("electrostaticScale14", 1.0), checkForInverses=True,
+                         imageExpandFactor=0, cutoffCellSizeFactor=0.5, method=0, useGridByCell=True, sortIndices=False)
+        self.set_options(**options)
+
+    def set_options(self, **kw):
+        for k in kw:
+            if k not in self.opts:
+                raise ValueError("unknown option " + k)
+        self.opts.update(kw)
+        o = self.opts
+        self.lib.refnb_set_options(self.h, o["dampingCutoff"], o["innerCutoff"], o["outerCutoff"], o["listCutoff"],
+                                   o["dielectric"], o["electrostaticScale14"], int(o["checkForInverses"]),
+                                   int(o["imageExpandFactor"]), o["cutoffCellSizeFactor"], int(o["method"]),
+                                   int(o["useGridByCell"]), int(o["sortIndices"]))
+
+    def energy(self, xyz=None, box=None, force_new=False, gradients=True):
+        """Returns dict(energies[6], grad[n,3], dEdM[3,3], updated, t_update, t_energy)."""
+        xyz = np.ascontiguousarray(self.sys["xyz"] if xyz is None else xyz, np.float64)
+        box = self.sys["box"] if box is None else box
+        boxa = None if box is None else np.ascontiguousarray(box, np.float64)
+        e = np.zeros(6)
+        g = np.zeros((self.n, 3)) if gradients else None
+        dm = np.zeros((3, 3)) if gradients else None
+        tm = np.zeros(2)
+        upd = self.lib.refnb_energy(self.h, _d(xyz), _d(boxa), int(force_new), _d(e), _d(g), _d(dm), _d(tm))
+        if upd < 0:
+            raise RuntimeError("reference NBModelABFS_Update failed")
+        return dict(energies=e, grad=g, dEdM=dm, updated=bool(upd), t_update=tm[0], t_energy=tm[1])
+
+    def counts(self):
+        return dict(primary=self.lib.refnb_num_primary_pairs(self.h), images=self.lib.refnb_num_images(self.h),
+                    image_pairs=self.lib.refnb_num_image_pairs(self.h), pairs14=self.lib.refnb_num_14_pairs(self.h),
+                    grid=bool(self.lib.refnb_uses_grid(self.h)))
+
+    def primary_pairs(self):
+        n = self.lib.refnb_num_primary_pairs(self.h)
+        p = np.zeros((n, 2), np.int32)
+        if n:
+            self.lib.refnb_get_primary_pairs(self.h, _i(p))
+        return p
+
+    def images(self):
+        """list of dict(t,a,b,c,scale,pairs[np,2])"""
+        out = []
+        for k in range(self.lib.refnb_num_images(self.h)):
+            info = np.zeros(6, np.int32)
+            sc = np.zeros(1)
+            self.lib.refnb_get_image_info(self.h, k, _i(info), _d(sc))
+            p = np.zeros((info[4], 2), np.int32)
+            if info[4]:
+                self.lib.refnb_get_image_pairs(self.h, k, _i(p))
+            out.append(dict(t=int(info[0]), a=int(info[1]), b=int(info[2]), c=int(info[3]), scale=float(sc[0]), pairs=p))
+        return out
+
+    def num_threads(self):
+        return self.lib.refnb_num_threads()
+
+    def close(self):
+        if self.h:
+            self.lib.refnb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_factors(damp, inner, outer):
+    out = np.zeros(21)
+    _lib().refnb_make_factors(damp, inner, outer, _d(out))
+    return out
+
+
+def lj_table(eps, sigma, style):
+    eps = np.ascontiguousarray(eps, np.float64)
+    sigma = np.ascontiguousarray(sigma, np.float64)
+    nt = len(eps)
+    ti = np.zeros(nt * nt, np.int32)
+    ta = np.zeros(nt * (nt + 1) // 2)
+    tb = np.zeros(nt * (nt + 1) // 2)
+    _lib().refnb_lj_table(nt, _d(eps), _d(sigma), 1 if style == "amber" else 0, _i(ti), _d(ta), _d(tb))
+    return ti, ta, tb
+
+
+def make_M(box6):
+    b = np.ascontiguousarray(box6, np.float64)
+    m = np.zeros((3, 3))
+    im = np.zeros((3, 3))
+    _lib().refnb_make_M(_d(b), _d(m), _d(im))
+    return m, im

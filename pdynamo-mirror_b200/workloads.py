@@ -1,0 +1,285 @@
+"""Synthetic MM systems for the NBModelABFS hot path.
+
+Everything here is plain numpy and deterministic (64-bit LCG, no numpy RNG state) so that the same
+arrays are produced in this container, on the GPU box, for the CUDA path, the oracle and the compiled
+reference.  A system is a dict of flat arrays -- the same data the reference keeps in MMAtomContainer
+(pMolecule-1.9.0/extensions/cinclude/MMAtomContainer.h:24-35), LJParameterContainer
+(pMolecule-1.9.0/extensions/cinclude/LJParameterContainer.h) and the exclusion / 1-4 PairLists
+(pMolecule-1.9.0/pMolecule/MMModel.py builds them from connectivity).
+
+Units follow pDynamo: Angstrom, kJ/mol, elementary charges.
+"""
+import numpy as np
+
+KCAL = 4.184
+
+# TIP3P (parameters/forceFields/opls/bookSmallExamples/atomTypes.yaml:13,18, lennardJonesParameters.yaml:23,28)
+TIP3P_QO, TIP3P_QH = -0.834, 0.417
+TIP3P_EPS_O = 0.1521 * KCAL
+TIP3P_SIG_O = 3.15061
+TIP3P_ROH = 0.9572
+TIP3P_HOH = 104.52
+
+
+# ----------------------------------------------------------------------------------------------------
+# LJ tables: restatement of LJParameterContainer_MakeTable
+# (pMolecule-1.9.0/extensions/csource/LJParameterContainer.c:184-210)
+# ----------------------------------------------------------------------------------------------------
+def make_lj_table(eps, sigma, style="opls"):
+    """Return (tableindex[nt*nt] int32, tableA[nt(nt+1)/2], tableB[...]).
+
+    style "opls" : geometric sigma, A = 4 e s^12, B = 4 e s^6          (MakeTableOPLS)
+    style "amber": arithmetic sigma (= r_min), A = e s^12, B = 2 e s^6 (MakeTableAMBER)
+    """
+    eps = np.asarray(eps, dtype=np.float64)
+    sigma = np.asarray(sigma, dtype=np.float64)
+    nt = len(eps)
+    tindex = np.zeros(nt * nt, dtype=np.int32)
+    tA = np.zeros(nt * (nt + 1) // 2)
+    tB = np.zeros(nt * (nt + 1) // 2)
+    n = 0
+    for i in range(nt):
+        for j in range(i + 1):
+            eij = np.sqrt(eps[i] * eps[j])
+            if style == "opls":
+                sij = np.sqrt(sigma[i] * sigma[j])
+            else:
+                sij = 0.5 * (sigma[i] + sigma[j])
+            sij6 = sij ** 6
+            sij12 = sij6 * sij6
+            if style == "opls":
+                eij = eij * 4.0
+            else:
+                sij6 = sij6 * 2.0
+            tA[n] = eij * sij12
+            tB[n] = eij * sij6
+            tindex[j + i * nt] = n
+            tindex[i + j * nt] = n
+            n += 1
+    return tindex, tA, tB
+
+
+# ----------------------------------------------------------------------------------------------------
+# deterministic uniform stream: s = s*6364136223846793005 + 1442695040888963407 ; u = (s>>11)/2^53
+# vectorised through the closed form s_k = a^k s_0 + c (a^{k-1} + ... + 1)  (mod 2^64)
+# ----------------------------------------------------------------------------------------------------
+_LCG_A = np.uint64(6364136223846793005)
+_LCG_C = np.uint64(1442695040888963407)
+
+
+def lcg_uniform(seed, count):
+    with np.errstate(over="ignore"):
+        a = np.full(count, _LCG_A, dtype=np.uint64)
+        ak = np.cumprod(a)                                   # a^1 .. a^count (mod 2^64)
+        geo = np.concatenate(([np.uint64(1)], ak[:-1]))      # a^0 .. a^(count-1)
+        sk = ak * np.uint64(seed) + _LCG_C * np.cumsum(geo)  # s_1 .. s_count
+    return (sk >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
+def _water_geometry(o, u):
+    """o[nw,3] oxygen positions, u[nw,6] uniforms (3 jitter already applied by caller, 3 orientation)."""
+    nw = o.shape[0]
+    ct = 1.0 - 2.0 * u[:, 3]
+    st = np.sqrt(np.maximum(0.0, 1.0 - ct * ct))
+    ph = 2.0 * np.pi * u[:, 4]
+    psi = 2.0 * np.pi * u[:, 5]
+    b = np.stack([st * np.cos(ph), st * np.sin(ph), ct], axis=1)          # bisector
+    ref = np.where(np.abs(b[:, 2:3]) < 0.9, np.array([[0.0, 0.0, 1.0]]), np.array([[1.0, 0.0, 0.0]]))
+    e1 = np.cross(b, ref)
+    e1 /= np.linalg.norm(e1, axis=1, keepdims=True)
+    e2 = np.cross(b, e1)
+    p = e1 * np.cos(psi)[:, None] + e2 * np.sin(psi)[:, None]             # in-plane normal to bisector
+    half = np.deg2rad(TIP3P_HOH) / 2.0
+    h1 = o + TIP3P_ROH * (np.cos(half) * b + np.sin(half) * p)
+    h2 = o + TIP3P_ROH * (np.cos(half) * b - np.sin(half) * p)
+    xyz = np.empty((nw, 3, 3))
+    xyz[:, 0], xyz[:, 1], xyz[:, 2] = o, h1, h2
+    return xyz.reshape(3 * nw, 3)
+
+
+def water_lattice(ncell, a, seed=12345, jitter=0.2, keep=None):
+    """ncell^3 TIP3P waters on a cubic lattice in a box of side a.  Returns (xyz[3nw,3], nw).
+    keep: optional boolean mask over the ncell^3 lattice sites (uniforms are drawn for all sites so that
+    the positions of the kept waters do not depend on the mask)."""
+    nw = ncell ** 3
+    sp = a / ncell
+    u = lcg_uniform(seed, 6 * nw).reshape(nw, 6)
+    g = np.arange(ncell)
+    ix, iy, iz = np.meshgrid(g, g, g, indexing="ij")
+    site = np.stack([ix.ravel(), iy.ravel(), iz.ravel()], axis=1).astype(np.float64)
+    o = (site + 0.5) * sp + (2.0 * u[:, :3] - 1.0) * jitter
+    if keep is not None:
+        o, u = o[keep], u[keep]
+    return _water_geometry(o, u), o.shape[0]
+
+
+def _water_topology(nw, first=0):
+    o = first + 3 * np.arange(nw, dtype=np.int32)
+    excl = np.concatenate([np.stack([o + 1, o], 1), np.stack([o + 2, o], 1), np.stack([o + 2, o + 1], 1)])
+    return excl.astype(np.int32)
+
+
+def _finish(xyz, charges, ljtypes, eps, sigma, style, excl, pairs14, a, name, eps14=None, sigma14=None, scale14=1.0):
+    tindex, tA, tB = make_lj_table(eps, sigma, style)
+    sysd = dict(name=name, n=int(xyz.shape[0]),
+                xyz=np.ascontiguousarray(xyz, dtype=np.float64),
+                charges=np.ascontiguousarray(charges, dtype=np.float64),
+                ljtypes=np.ascontiguousarray(ljtypes, dtype=np.int32),
+                ntypes=int(len(eps)), tableindex=tindex, tableA=tA, tableB=tB,
+                exclusions=np.ascontiguousarray(excl, dtype=np.int32).reshape(-1, 2),
+                pairs14=np.ascontiguousarray(pairs14, dtype=np.int32).reshape(-1, 2),
+                electrostaticScale14=float(scale14))
+    if eps14 is None:
+        eps14, sigma14 = eps, sigma
+    t14 = make_lj_table(eps14, sigma14, style)
+    sysd.update(tableindex14=t14[0], tableA14=t14[1], tableB14=t14[2])
+    if a is None:
+        sysd.update(box=None, rot=np.zeros((0, 3, 3)), trans=np.zeros((0, 3)))
+    else:
+        box = np.array([a, a, a, 90.0, 90.0, 90.0]) if np.isscalar(a) else np.asarray(a, dtype=np.float64)
+        sysd.update(box=box, rot=np.eye(3)[None].copy(), trans=np.zeros((1, 3)))      # P1: identity only
+    return sysd
+
+
+def water_box(ncell=6, a=None, seed=12345, jitter=0.2, name=None):
+    """Config 1 / 5 family: ncell^3 TIP3P waters, OPLS (geometric) LJ table, P1 cubic box.
+    ncell=6 -> W216 (648 atoms, a=18.63); ncell=20 -> 24 000 atoms (a=62.1); ncell=70 -> M1 (1 029 000 atoms)."""
+    if a is None:
+        a = 3.105 * ncell
+    xyz, nw = water_lattice(ncell, a, seed, jitter)
+    charges = np.tile([TIP3P_QO, TIP3P_QH, TIP3P_QH], nw)
+    ljtypes = np.tile([0, 1, 1], nw)
+    return _finish(xyz, charges, ljtypes, [TIP3P_EPS_O, 0.0], [TIP3P_SIG_O, 0.0], "opls",
+                   _water_topology(nw), np.zeros((0, 2), np.int32), a, name or "water%d" % nw, scale14=0.5)
+
+
+def _chain_topology(first, n):
+    i = first + np.arange(n, dtype=np.int32)
+    e12 = np.stack([i[1:], i[:-1]], 1)
+    e13 = np.stack([i[2:], i[:-2]], 1)
+    e14 = np.stack([i[3:], i[:-3]], 1)
+    return np.concatenate([e12, e13, e14]), e14
+
+
+def _snake_in_sphere(center, radius, spacing, count):
+    """Boustrophedon path over cubic lattice sites inside a sphere: consecutive atoms are lattice neighbours
+    inside a row; rows and planes are traversed back and forth."""
+    m = int(np.ceil(radius / spacing))
+    pts = []
+    fy = 1
+    for kx in range(-m, m + 1):
+        ys = range(-m, m + 1) if fy > 0 else range(m, -m - 1, -1)
+        fz = 1
+        for ky in ys:
+            zs = range(-m, m + 1) if fz > 0 else range(m, -m - 1, -1)
+            row = [(kx, ky, kz) for kz in zs if (kx * kx + ky * ky + kz * kz) * spacing * spacing <= radius * radius]
+            if row:
+                pts.extend(row)
+                fz = -fz
+        fy = -fy
+    pts = np.array(pts, dtype=np.float64) * spacing + center
+    if pts.shape[0] < count:
+        raise ValueError("sphere too small for chain: %d < %d" % (pts.shape[0], count))
+    return pts[:count]
+
+
+def jac_like(natoms=23558, nchain=2489, ncell=20, a=62.23, seed=12345, ntypes=35):
+    """Config 3 stand-in for DHFR/JAC (benchmarks/data/dhfr/systemData.yaml:3-5: 23 558 atoms, a = 62.23):
+    a TIP3P lattice with a central sphere of waters replaced by an nchain-atom heteropolymer with
+    ntypes-2 extra LJ types, 1-2/1-3/1-4 exclusions, a 1-4 list with its own LJ table and CHARMM/AMBER
+    (arithmetic r_min) combination, net charge -11 like DHFR."""
+    nwat = (natoms - nchain) // 3
+    if 3 * nwat + nchain != natoms:
+        raise ValueError("natoms - nchain must be a multiple of 3")
+    sp = a / ncell
+    g = (np.arange(ncell) + 0.5) * sp
+    ix, iy, iz = np.meshgrid(g, g, g, indexing="ij")
+    d2 = (ix.ravel() - a / 2) ** 2 + (iy.ravel() - a / 2) ** 2 + (iz.ravel() - a / 2) ** 2
+    order = np.argsort(d2, kind="stable")
+    keep = np.ones(ncell ** 3, dtype=bool)
+    nremove = ncell ** 3 - nwat
+    keep[order[:nremove]] = False
+    rcav = np.sqrt(d2[order[nremove - 1]])
+    wxyz, nw = water_lattice(ncell, a, seed, 0.2, keep)
+    assert nw == nwat
+    spacing = 1.9
+    cxyz = _snake_in_sphere(np.array([a / 2, a / 2, a / 2]), rcav - 1.6, spacing, nchain)
+    u = lcg_uniform(seed + 77, 5 * nchain + 4 * ntypes).reshape(-1)
+    cxyz = cxyz + (2.0 * u[:3 * nchain].reshape(nchain, 3) - 1.0) * 0.12
+    ctype = 2 + np.minimum((u[3 * nchain:4 * nchain] * (ntypes - 2)).astype(np.int32), ntypes - 3)
+    cq = (2.0 * u[4 * nchain:5 * nchain] - 1.0) * 0.55
+    cq += (-11.0 - cq.sum()) / nchain
+    ut = u[5 * nchain:].reshape(ntypes, 4)
+    eps = np.empty(ntypes)
+    rmin = np.empty(ntypes)
+    eps[0], rmin[0] = TIP3P_EPS_O, TIP3P_SIG_O * 2.0 ** (1.0 / 6.0)      # CHARMM TIP3P
+    eps[1], rmin[1] = 0.046 * KCAL, 2 * 0.2245
+    eps[2:] = (0.02 + 0.18 * ut[2:, 0]) * KCAL
+    rmin[2:] = 2.0 * (0.70 + 0.45 * ut[2:, 1])
+    eps14 = eps.copy()
+    rmin14 = rmin.copy()
+    eps14[2:] *= 0.5 + 0.5 * ut[2:, 2]
+    rmin14[2:] *= 0.9 + 0.1 * ut[2:, 3]
+    xyz = np.concatenate([cxyz, wxyz])
+    charges = np.concatenate([cq, np.tile([TIP3P_QO, TIP3P_QH, TIP3P_QH], nwat)])
+    ljtypes = np.concatenate([ctype, np.tile([0, 1, 1], nwat)])
+    cexcl, c14 = _chain_topology(0, nchain)
+    excl = np.concatenate([cexcl, _water_topology(nwat, nchain)])
+    return _finish(xyz, charges, ljtypes, eps, rmin, "amber", excl, c14, a, "jac%d" % natoms,
+                   eps14=eps14, sigma14=rmin14, scale14=1.0)
+
+
+def solvated_solute(solute_xyz, solute_q, solute_types, solute_eps, solute_rmin, bonds, ncell=9, a=27.945,
+                    seed=12345, exclude_radius=2.8, name="bala_water"):
+    """Config 2: a small solute (e.g. blocked alanine dipeptide) centred in an ncell^3 TIP3P box with
+    overlapping waters removed, CHARMM-style (arithmetic) LJ, bonded 1-2/1-3 exclusions and a 1-4 list."""
+    solute_xyz = np.asarray(solute_xyz, dtype=np.float64)
+    ns = solute_xyz.shape[0]
+    solute_xyz = solute_xyz - solute_xyz.mean(0) + a / 2
+    sp = a / ncell
+    wfull, nwfull = water_lattice(ncell, a, seed, 0.2)
+    o = wfull[0::3]
+    d = np.sqrt(((o[:, None, :] - solute_xyz[None, :, :]) ** 2).sum(-1)).min(1)
+    keep = d > exclude_radius
+    wxyz, nw = water_lattice(ncell, a, seed, 0.2, keep)
+    # bonded graph distances on the solute
+    adj = [set() for _ in range(ns)]
+    for i, j in bonds:
+        adj[i].add(j)
+        adj[j].add(i)
+    excl, p14 = set(), set()
+    for i in range(ns):
+        d1 = adj[i]
+        d2 = set().union(*[adj[j] for j in d1]) - d1 - {i} if d1 else set()
+        d3 = (set().union(*[adj[j] for j in d2]) if d2 else set()) - d2 - d1 - {i}
+        for j in d1 | d2 | d3:
+            excl.add((max(i, j), min(i, j)))
+        for j in d3:
+            p14.add((max(i, j), min(i, j)))
+    excl = np.array(sorted(excl), dtype=np.int32).reshape(-1, 2)
+    p14 = np.array(sorted(p14), dtype=np.int32).reshape(-1, 2)
+    nst = len(solute_eps)
+    eps = np.concatenate([[TIP3P_EPS_O, 0.046 * KCAL], np.asarray(solute_eps, dtype=np.float64)])
+    rmin = np.concatenate([[TIP3P_SIG_O * 2.0 ** (1.0 / 6.0), 2 * 0.2245], np.asarray(solute_rmin, dtype=np.float64)])
+    xyz = np.concatenate([solute_xyz, wxyz])
+    charges = np.concatenate([np.asarray(solute_q, dtype=np.float64), np.tile([TIP3P_QO, TIP3P_QH, TIP3P_QH], nw)])
+    ljtypes = np.concatenate([2 + np.asarray(solute_types, dtype=np.int32), np.tile([0, 1, 1], nw)])
+    excl = np.concatenate([excl, _water_topology(nw, ns)])
+    return _finish(xyz, charges, ljtypes, eps, rmin, "amber", excl, p14, a, name, scale14=1.0)
+
+
+def perturbed(system, amplitude, seed=999):
+    """Copy of a system with every coordinate displaced uniformly in [-amplitude, amplitude] (for update-heuristic tests)."""
+    s = dict(system)
+    u = lcg_uniform(seed, 3 * system["n"]).reshape(-1, 3)
+    s["xyz"] = system["xyz"] + (2.0 * u - 1.0) * amplitude
+    return s
+
+
+WORKLOADS = {
+    "w216": lambda: water_box(6, name="w216"),
+    "w1728": lambda: water_box(12, name="w1728"),
+    "jac": lambda: jac_like(),
+    "water24k": lambda: water_box(20, name="water24k"),
+    "m1": lambda: water_box(70, name="m1"),
+}
