@@ -1,0 +1,128 @@
+/* include/nbabfs_b200.h -- C-ABI of libnbabfs_b200.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for ONE hot path of pDynamo 1.9.0: the NBModelABFS MM/MM non-bonded term
+ * (force-switched Coulomb + Lennard-Jones energy and gradients), the cutoff pair lists it is evaluated
+ * over (PairListGenerator) and the explicit periodic images (ImageList / SymmetryParameters).
+ *
+ * Plain pointers and sizes only; no torch / CUDA types in the signatures.  Every entry point names the
+ * reference interface it replaces (paths relative to the pDynamo tree; pM = pMolecule-1.9.0/extensions,
+ * pC = pCore-1.9.0/extensions).  INTEGRATION.md shows the Cython binding a pDynamo maintainer would add.
+ *
+ * Conventions kept from the reference boundary:
+ *   - Status out-parameter, written only on failure; NBB200_STATUS_CONTINUE (=16, pC/cinclude/Status.h:37)
+ *     means OK; NULL return = allocation / device failure.  CUDA errors never abort: they map to a status.
+ *   - all functions are NULL tolerant;
+ *   - coordinates and gradients are N x 3 row-major fp64 (Coordinates3, pC/cinclude/Coordinates3.h:26),
+ *     gradients and dE/dM are ACCUMULATED into the caller's arrays (System.Energy adds bonded terms first);
+ *   - synchronous at return of NBModelABFS_B200_MMMMEnergy (energies are read immediately by the caller,
+ *     pM/pyrex/pMolecule.NBModelABFS.pyx:119-121).
+ */
+#ifndef NBABFS_B200_H
+#define NBABFS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* pC/cinclude/Status.h:21-70 (values used at this boundary) */
+#define NBB200_STATUS_NORMAL            0
+#define NBB200_STATUS_LOGIC_ERROR      10
+#define NBB200_STATUS_CONTINUE         16
+#define NBB200_STATUS_INVALID_ARGUMENT 22
+#define NBB200_STATUS_OUT_OF_MEMORY    41
+
+/* Opaque device-resident state: replaces NBModelABFSState (pM/cinclude/NBModelABFSState.h:33-124) together
+ * with the option blocks of NBModelABFS (pM/cinclude/NBModelABFS.h) and PairwiseInteractionABFS
+ * (pM/cinclude/PairwiseInteraction.h:24-37) it is evaluated with. */
+typedef struct NBB200State NBB200State;
+
+/* Energy slots, in the order of NBModelABFSState.GetEnergies (pM/pyrex/pMolecule.NBModelABFSState.pyx:41-59). */
+enum { NBB200_EMMEL = 0, NBB200_EMMLJ = 1, NBB200_EMMEL14 = 2, NBB200_EMMLJ14 = 3, NBB200_EIMMMEL = 4, NBB200_EIMMMLJ = 5 };
+
+/* ---- library ------------------------------------------------------------------------------------- */
+int         nbb200_device_count(void);               /* number of visible CUDA devices (0 without a GPU/driver) */
+const char *nbb200_last_error(void);                 /* text of the last failure on this thread */
+const char *nbb200_version(void);
+
+/* ---- state ----------------------------------------------------------------------------------------
+ * replaces NBModelABFSState_SetUp (pM/csource/NBModelABFSState.c:316-420) for a pure-MM system:
+ *   charges[n], ljtypes[n]            <- MMAtomContainer.data[i].{charge,ljtype} (pM/cinclude/MMAtomContainer.h:24-35)
+ *   tableindex[nt*nt], tableA/B[...]  <- LJParameterContainer (pM/cinclude/LJParameterContainer.h), normal and 1-4
+ *   exclPairs[2*nexcl], pairs14[2*n14]<- exclusions / interactions14 PairLists as index pairs
+ *   rot[9*ntrans], trans[3*ntrans]    <- Transformation3Container items (fractional); ntrans = 0: no symmetry
+ * device: CUDA ordinal.  Inputs are copied (the reference aliases them, NBModelABFSState.c:384-395). */
+NBB200State *NBModelABFSState_B200_SetUp(int device, int n, const double *charges, const int *ljtypes,
+                                         int ntypes, const int *tableindex, const double *tableA, const double *tableB,
+                                         int ntypes14, const int *tableindex14, const double *tableA14, const double *tableB14,
+                                         int nexcl, const int *exclPairs, int n14, const int *pairs14,
+                                         int ntrans, const double *rot, const double *trans, int *status);
+/* replaces NBModelABFSState_Deallocate (pM/csource/NBModelABFSState.c:137-188) */
+void NBModelABFSState_B200_Deallocate(NBB200State **state);
+
+/* replaces the option fields set by NBModelABFS.SetOptions (pM/pyrex/pMolecule.NBModelABFS.pyx:140-179):
+ * NBModelABFS.{dampingCutoff,innerCutoff,outerCutoff,listCutoff,dielectric,electrostaticScale14,
+ * checkForInverses,imageExpandFactor} and the three cutoffs of PairwiseInteractionABFS. */
+void NBModelABFS_B200_SetOptions(NBB200State *state, double dampingCutoff, double innerCutoff, double outerCutoff,
+                                 double listCutoff, double dielectric, double electrostaticScale14,
+                                 int checkForInverses, int imageExpandFactor);
+
+/* replaces NBModelABFSState_Initialize (pM/csource/NBModelABFSState.c:231-273) + NBModelABFS_Update
+ * (pM/csource/NBModelABFS.c:508-623): takes this call's coordinates (host, xyz[3n]) and lattice
+ * box6 = {a,b,c,alpha,beta,gamma} (ignored when ntrans = 0), decides with the reference's heuristics
+ * (CheckForUpdate :691-746, CheckForImageUpdate :635-684) whether the lists must be rebuilt and rebuilds
+ * them on the device.  forceNew != 0 sets state->isNew first.  Returns 1 if lists were rebuilt, else 0. */
+int NBModelABFS_B200_Update(NBB200State *state, const double *xyz, const double *box6, int forceNew, int *status);
+/* same, coordinates already resident on the device (d_xyz: device pointer, fp64 [3n]) */
+int NBModelABFS_B200_UpdateDevice(NBB200State *state, const double *d_xyz, const double *box6, int forceNew, int *status);
+
+/* replaces NBModelABFS_MMMMEnergy (pM/csource/NBModelABFS.c:228-301): energies[6] (slots above) are set;
+ * grad[3n] (host, nullable) and dEdM[9] (nullable) are accumulated into. */
+void NBModelABFS_B200_MMMMEnergy(NBB200State *state, double *energies, double *grad, double *dEdM, int *status);
+/* same, gradients accumulated into a device array d_grad[3n] (nullable) */
+void NBModelABFS_B200_MMMMEnergyDevice(NBB200State *state, double *energies, double *d_grad, double *dEdM, int *status);
+
+/* ---- list inspection: what PairList / ImageList hold in the reference ------------------------------
+ * statistics of NBModelABFSState (pM/cinclude/NBModelABFSState.h:38-71) */
+long NBModelABFSState_B200_NumberOfPairs(NBB200State *state, int image /* -1: primary list nbmmmm; k >= 0: image k */);
+int  NBModelABFSState_B200_NumberOfImages(NBB200State *state);
+long NBModelABFSState_B200_NumberOfImagePairs(NBB200State *state);
+long NBModelABFSState_B200_NumberOf14Pairs(NBB200State *state);
+/* Image record (pM/cinclude/ImageList.h:19-28): info = {t, a, b, c, npairs, 0}, scale */
+void NBModelABFSState_B200_GetImageInfo(NBB200State *state, int image, int *info, double *scale);
+/* explicit (i, j) pairs of one list, expanded from the tile masks on the device:
+ * replaces PairList_ToIntegerPairArray (pC/csource/PairList.c:253).  pairs[2*npairs] host; returns npairs. */
+long NBModelABFSState_B200_GetPairs(NBB200State *state, int image, int *pairs, int *status);
+
+/* ---- stand-alone generators -----------------------------------------------------------------------
+ * replace PairListGenerator_SelfPairListFromCoordinates3 (pC/csource/PairListGenerator.c:530-553) and
+ * PairListGenerator_CrossPairListFromDoubleCoordinates3 (:414-446) for the no-radii / no-selection case:
+ * all pairs with (dx*dx + dy*dy) + dz*dz <= cutoff*cutoff in fp64, minus exclusions for the self list.
+ * On return *pairs is a malloc'ed int[2*npairs] (free with nbb200_free); returns npairs or -1. */
+long PairListGenerator_B200_SelfPairListFromCoordinates3(int device, int n, const double *xyz, double cutoff,
+                                                         int nexcl, const int *exclPairs, int **pairs, int *status);
+long PairListGenerator_B200_CrossPairListFromDoubleCoordinates3(int device, int n1, const double *xyz1, int n2, const double *xyz2,
+                                                                double cutoff, int **pairs, int *status);
+void nbb200_free(void *p);
+
+/* PairwiseInteractionABFS_MakeFactors (pM/csource/PairwiseInteraction.c:89-141): host helper, out[21] */
+void PairwiseInteractionABFS_B200_MakeFactors(double dampingCutoff, double innerCutoff, double outerCutoff, double *out21);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------------
+ * Use the caller's CUDA stream (e.g. torch's current stream) so that the caller's events bracket the work. */
+void nbb200_set_stream(NBB200State *state, void *cudaStream);
+/* Device time of the phases of the LAST Update / MMMMEnergy pair, from CUDA events on the state's stream (ms):
+ * out[0] list rebuild (all kernels), out[1] tile-pair force kernel, out[2] 1-4 kernel, out[3] displacement check,
+ * out[4] explicit pair expansion (last GetPairs), out[5..7] reserved.  Enabled by nbb200_enable_timing(state, 1). */
+void nbb200_enable_timing(NBB200State *state, int on);
+void nbb200_get_timings(NBB200State *state, double *out8);
+/* counters of the current lists: out[0] tiles, out[1] work items, out[2] i-blocks, out[3] extended (halo) atoms,
+ * out[4] list pairs (popcount of all masks), out[5] kernel launches since SetUp, out[6] tile capacity per block, out[7] images */
+void nbb200_get_counters(NBB200State *state, long *out8);
+/* spatial decomposition over ranks (section 8e): this state evaluates only the i-blocks b with b % nranks == rank
+ * in units of contiguous chunks; energies/gradients are then partial sums to be reduced by the caller (NCCL). */
+void nbb200_set_partition(NBB200State *state, int rank, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,69 @@
+"""ctypes binding of libnbabfs_b200.so (include/nbabfs_b200.h).  There is no CPU fallback: if the CUDA
+library is missing or no device is visible, loading / SetUp fails loudly."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnbabfs_b200.so")
+STATUS_CONTINUE = 16
+_LIB = None
+
+dp, ip, vp, lp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_long)
+
+SIGNATURES = {
+    "nbb200_device_count": (C.c_int, []),
+    "nbb200_last_error": (C.c_char_p, []),
+    "nbb200_version": (C.c_char_p, []),
+    "NBModelABFSState_B200_SetUp": (vp, [C.c_int, C.c_int, dp, ip, C.c_int, ip, dp, dp, C.c_int, ip, dp, dp,
+                                        C.c_int, ip, C.c_int, ip, C.c_int, dp, dp, ip]),
+    "NBModelABFSState_B200_Deallocate": (None, [C.POINTER(vp)]),
+    "NBModelABFS_B200_SetOptions": (None, [vp] + [C.c_double] * 6 + [C.c_int, C.c_int]),
+    "NBModelABFS_B200_Update": (C.c_int, [vp, dp, dp, C.c_int, ip]),
+    "NBModelABFS_B200_UpdateDevice": (C.c_int, [vp, vp, dp, C.c_int, ip]),
+    "NBModelABFS_B200_MMMMEnergy": (None, [vp, dp, dp, dp, ip]),
+    "NBModelABFS_B200_MMMMEnergyDevice": (None, [vp, dp, vp, dp, ip]),
+    "NBModelABFSState_B200_NumberOfPairs": (C.c_long, [vp, C.c_int]),
+    "NBModelABFSState_B200_NumberOfImages": (C.c_int, [vp]),
+    "NBModelABFSState_B200_NumberOfImagePairs": (C.c_long, [vp]),
+    "NBModelABFSState_B200_NumberOf14Pairs": (C.c_long, [vp]),
+    "NBModelABFSState_B200_GetImageInfo": (None, [vp, C.c_int, ip, dp]),
+    "NBModelABFSState_B200_GetPairs": (C.c_long, [vp, C.c_int, ip, ip]),
+    "PairListGenerator_B200_SelfPairListFromCoordinates3": (C.c_long, [C.c_int, C.c_int, dp, C.c_double, C.c_int, ip, C.POINTER(ip), ip]),
+    "PairListGenerator_B200_CrossPairListFromDoubleCoordinates3": (C.c_long, [C.c_int, C.c_int, dp, C.c_int, dp, C.c_double, C.POINTER(ip), ip]),
+    "nbb200_free": (None, [vp]),
+    "PairwiseInteractionABFS_B200_MakeFactors": (None, [C.c_double] * 3 + [dp]),
+    "nbb200_set_stream": (None, [vp, vp]),
+    "nbb200_enable_timing": (None, [vp, C.c_int]),
+    "nbb200_get_timings": (None, [vp, dp]),
+    "nbb200_get_counters": (None, [vp, lp]),
+    "nbb200_set_partition": (None, [vp, C.c_int, C.c_int]),
+}
+
+
+class CLibraryError(RuntimeError):
+    """Raised where the reference raises pCore.CLibraryError (pCore-1.9.0/pCore/CoreObjects.py:12)."""
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise CLibraryError("libnbabfs_b200.so is not built (run python pdynamo-mirror_b200/build.py); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        _LIB = L
+    return _LIB
+
+
+def last_error():
+    return lib().nbb200_last_error().decode()
+
+
+def d_(a):
+    return None if a is None else a.ctypes.data_as(dp)
+
+
+def i_(a):
+    return None if a is None else a.ctypes.data_as(ip)

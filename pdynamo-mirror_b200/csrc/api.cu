@@ -1,0 +1,482 @@
+// api.cu -- the C-ABI of libnbabfs_b200.so (see include/nbabfs_b200.h for the contract and the reference
+// interfaces each entry point replaces).  Host-side control flow mirrors NBModelABFS_Update
+// (pMolecule-1.9.0/extensions/csource/NBModelABFS.c:508-623) and NBModelABFS_MMMMEnergy (:228-301).
+#include "../../include/nbabfs_b200.h"
+#include "nbb200_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+namespace nbb200 {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+bool cuda_ok(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return true;
+    g_error = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return false;
+}
+
+static void set_status(int *status, int value) { if (status != nullptr) *status = value; }
+
+static void destroy(State *s)
+{
+    if (s == nullptr) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    s->q32.release(); s->q64.release(); s->ljtype.release(); s->ljAB.release(); s->ljAB14.release();
+    s->exclPtr.release(); s->exclCol.release(); s->pairs14.release();
+    s->x.release(); s->xref.release(); s->grad.release();
+    s->imageOps.release(); s->imageBoxes.release(); s->baseOpsDev.release(); s->visitDisp.release(); s->visitInfo.release(); s->bboxDev.release();
+    s->eX.release(); s->eAtom.release(); s->eSet.release(); s->eKey.release(); s->eSortBuf.release();
+    s->cellStart.release(); s->cellFill.release(); s->scanTmp.release(); s->order.release();
+    s->sX.release(); s->sAtom.release(); s->invPerm.release(); s->blockBox.release();
+    s->tileJ.release(); s->tileMask.release(); s->items.release(); s->setPairs.release(); s->accum.release();
+    s->pairBuf.release(); s->pairCursor.release();
+    if (s->counters) cudaFree(s->counters);
+    if (s->hx) cudaFreeHost(s->hx);
+    if (s->hgrad) cudaFreeHost(s->hgrad);
+    if (s->hsmall) cudaFreeHost(s->hsmall);
+    if (s->haveEvents) for (auto &e : s->ev) cudaEventDestroy(e);
+    if (s->ownStream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+constexpr size_t kSmallDoubles = 1 << 16;
+
+static State *create(int device, int n, const double *charges, const int *ljtypes,
+                     int ntypes, const int *tableindex, const double *tableA, const double *tableB,
+                     int ntypes14, const int *tableindex14, const double *tableA14, const double *tableB14,
+                     int nexcl, const int *exclPairs, int n14, const int *pairs14, int ntrans, const double *rot, const double *trans, int *status)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); set_error("no CUDA device available: libnbabfs_b200 has no CPU fallback"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return nullptr; }
+    if (n <= 0 || charges == nullptr || ljtypes == nullptr || ntypes <= 0 || tableindex == nullptr || tableA == nullptr || tableB == nullptr ||
+        device < 0 || device >= ndev || (nexcl > 0 && exclPairs == nullptr) || (n14 > 0 && pairs14 == nullptr) || (ntrans > 0 && (rot == nullptr || trans == nullptr))) {
+        set_error("invalid argument to NBModelABFSState_B200_SetUp"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr;
+    }
+    for (int i = 0; i < n; i++) if (ljtypes[i] < 0 || ljtypes[i] >= ntypes) { set_error("ljtype out of range"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr; }
+    for (int k = 0; k < 2 * nexcl; k++) if (exclPairs[k] < 0 || exclPairs[k] >= n) { set_error("exclusion index out of range"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr; }
+    for (int k = 0; k < 2 * n14; k++) if (pairs14[k] < 0 || pairs14[k] >= n) { set_error("1-4 index out of range"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr; }
+    State *s = new (std::nothrow) State();
+    if (s == nullptr) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return nullptr; }
+    s->device = device;
+    bool ok = cuda_ok(cudaSetDevice(device), "cudaSetDevice");
+    ok = ok && cuda_ok(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    s->ownStream = true;
+    s->n = n; s->ntypes = ntypes; s->nexcl = nexcl; s->n14 = n14;
+    if (tableindex14 == nullptr) { ntypes14 = ntypes; tableindex14 = tableindex; tableA14 = tableA; tableB14 = tableB; }
+    s->ntypes14 = ntypes14;
+    // topology -> device
+    std::vector<float> q32(n);
+    for (int i = 0; i < n; i++) q32[i] = (float) charges[i];
+    std::vector<float2> ab((size_t) ntypes * ntypes);
+    for (int i = 0; i < ntypes * ntypes; i++) { ab[i].x = (float) tableA[tableindex[i]]; ab[i].y = (float) tableB[tableindex[i]]; }
+    std::vector<double2> ab14((size_t) ntypes14 * ntypes14);
+    for (int i = 0; i < ntypes14 * ntypes14; i++) { ab14[i].x = tableA14[tableindex14[i]]; ab14[i].y = tableB14[tableindex14[i]]; }
+    // symmetric exclusion CSR (SelfPairList_MakeConnections, pCore-1.9.0/extensions/csource/PairList.c:458-526)
+    std::vector<int> ptr((size_t) n + 1, 0), col;
+    for (int k = 0; k < nexcl; k++) { const int i = exclPairs[2 * k], j = exclPairs[2 * k + 1]; if (i != j) { ptr[i + 1]++; ptr[j + 1]++; } }
+    for (int i = 0; i < n; i++) ptr[i + 1] += ptr[i];
+    col.resize((size_t) std::max(1, ptr[n]));
+    {
+        std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+        for (int k = 0; k < nexcl; k++) { const int i = exclPairs[2 * k], j = exclPairs[2 * k + 1]; if (i != j) { col[cur[i]++] = j; col[cur[j]++] = i; } }
+    }
+    std::vector<int2> p14((size_t) std::max(1, n14));
+    for (int k = 0; k < n14; k++) { p14[k].x = pairs14[2 * k]; p14[k].y = pairs14[2 * k + 1]; }
+    ok = ok && s->q32.ensure(n) && s->q64.ensure(n) && s->ljtype.ensure(n) && s->ljAB.ensure(ab.size()) && s->ljAB14.ensure(ab14.size()) &&
+         s->exclPtr.ensure(ptr.size()) && s->exclCol.ensure(col.size()) && s->pairs14.ensure(p14.size()) &&
+         s->x.ensure(3 * (size_t) n) && s->xref.ensure(3 * (size_t) n) && s->grad.ensure(3 * (size_t) n);
+    ok = ok && cuda_ok(cudaMalloc((void **) &s->counters, sizeof(DeviceCounters)), "cudaMalloc counters");
+    ok = ok && cuda_ok(cudaMallocHost((void **) &s->hx, sizeof(double) * 3 * (size_t) n), "cudaMallocHost");
+    ok = ok && cuda_ok(cudaMallocHost((void **) &s->hgrad, sizeof(double) * 3 * (size_t) n), "cudaMallocHost");
+    ok = ok && cuda_ok(cudaMallocHost((void **) &s->hsmall, sizeof(double) * kSmallDoubles), "cudaMallocHost");
+    if (ok) {
+        ok = cuda_ok(cudaMemcpy(s->q32.p, q32.data(), sizeof(float) * n, cudaMemcpyHostToDevice), "H2D") &&
+             cuda_ok(cudaMemcpy(s->q64.p, charges, sizeof(double) * n, cudaMemcpyHostToDevice), "H2D") &&
+             cuda_ok(cudaMemcpy(s->ljtype.p, ljtypes, sizeof(int) * n, cudaMemcpyHostToDevice), "H2D") &&
+             cuda_ok(cudaMemcpy(s->ljAB.p, ab.data(), sizeof(float2) * ab.size(), cudaMemcpyHostToDevice), "H2D") &&
+             cuda_ok(cudaMemcpy(s->ljAB14.p, ab14.data(), sizeof(double2) * ab14.size(), cudaMemcpyHostToDevice), "H2D") &&
+             cuda_ok(cudaMemcpy(s->exclPtr.p, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice), "H2D") &&
+             cuda_ok(cudaMemcpy(s->exclCol.p, col.data(), sizeof(int) * col.size(), cudaMemcpyHostToDevice), "H2D") &&
+             cuda_ok(cudaMemcpy(s->pairs14.p, p14.data(), sizeof(int2) * p14.size(), cudaMemcpyHostToDevice), "H2D") &&
+             cuda_ok(cudaMemset(s->counters, 0, sizeof(DeviceCounters)), "memset");
+    }
+    if (ok) {
+        for (auto &e : s->ev) ok = ok && cuda_ok(cudaEventCreate(&e), "cudaEventCreate");
+        s->haveEvents = ok;
+    }
+    if (!ok) { destroy(s); set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return nullptr; }
+    if (ntrans > 0) s->trans.set(ntrans, rot, trans);
+    make_abfs_factors(s->damp, s->inner, s->outer, s->factors);
+    init_force_kernel_attributes();
+    return s;
+}
+
+static void fetch_pair_counts(State &s)
+{
+    if (s.pairCountsValid) return;
+    std::vector<unsigned long long> cnt((size_t) s.nsets, 0ULL);
+    if (s.setPairs.p != nullptr && s.nsets > 0) {
+        cudaMemcpyAsync(cnt.data(), s.setPairs.p, sizeof(unsigned long long) * s.nsets, cudaMemcpyDeviceToHost, s.stream);
+        cudaStreamSynchronize(s.stream);
+    }
+    s.primaryPairs = (long) cnt[0];
+    s.imagePairs.assign(s.nsets - 1, 0);
+    for (int k = 1; k < s.nsets; k++) s.imagePairs[k - 1] = (long) cnt[k];
+    s.pairCountsValid = true;
+}
+
+// candidate images with at least one pair, in plan order = the reference's ImageList order
+static std::vector<int> live_images(State &s)
+{
+    fetch_pair_counts(s);
+    std::vector<int> live;
+    for (size_t k = 0; k < s.imagePairs.size(); k++) if (s.imagePairs[k] > 0) live.push_back((int) k);
+    return live;
+}
+
+static int update_common(State &s, const double *box6, int forceNew, int *status)
+{
+    s.numberOfCalls += 1;
+    if (s.trans.n > 0) {
+        if (box6 == nullptr) { set_error("box6 is required when transformations are present"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return 0; }
+        s.lattice.set_crystal(box6);
+    }
+    if (forceNew) s.isNew = true;
+    bool doUpdate = s.isNew;
+    doUpdate = doUpdate || (s.list != s.stListCutoff) || (s.outer != s.stOuterCutoff);
+    if (doUpdate) { s.stListCutoff = s.list; s.stOuterCutoff = s.outer; }
+    double maxDisp = 0.0;
+    if (s.timing) { s.timings[0] = 0.0; s.timings[3] = 0.0; }
+    bool checked = false;
+    if (!doUpdate) {
+        const double buffac = 0.5 * (s.list - s.stOuterCutoff);
+        double maxr2 = 0.0; int exceeded = 0;
+        if (!displacement_check(s, buffac * buffac, &maxr2, &exceeded)) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
+        checked = true;
+        doUpdate = exceeded != 0;
+        maxDisp = std::sqrt(maxr2);
+    }
+    if (!doUpdate && s.trans.n > 0 && s.haveRefLattice) {
+        fetch_pair_counts(s);
+        // NOTE: the reference rebuilds only the image lists here; this implementation rebuilds all lists at the
+        // current coordinates (a valid list either way; documented in DESIGN.md).
+        doUpdate = check_for_image_update(s.trans, s.lattice, s.refLattice, s.plan.images, s.imagePairs, s.list, s.stOuterCutoff, maxDisp);
+    }
+    if (doUpdate) {
+        if (s.timing) cudaEventRecord(s.ev[0], s.stream);
+        if (!cuda_ok(cudaMemcpyAsync(s.xref.p, s.xcur, sizeof(double) * 3 * (size_t) s.n, cudaMemcpyDeviceToDevice, s.stream), "xref copy") || !build_lists(s)) {
+            set_status(status, NBB200_STATUS_OUT_OF_MEMORY);
+            s.isNew = true;
+            return 0;
+        }
+        if (s.timing) cudaEventRecord(s.ev[1], s.stream);
+        s.refLattice = s.lattice; s.haveRefLattice = true;
+        s.numberOfUpdates += 1;
+    }
+    if (s.timing) {
+        cudaStreamSynchronize(s.stream);
+        float ms = 0.f;
+        if (doUpdate) { cudaEventElapsedTime(&ms, s.ev[0], s.ev[1]); s.timings[0] = ms; }
+        if (checked) { cudaEventElapsedTime(&ms, s.ev[6], s.ev[7]); s.timings[3] = ms; }
+    }
+    s.isNew = false;
+    return doUpdate ? 1 : 0;
+}
+
+static bool energy_common(State &s, double *energies, double *d_grad, double *dEdM)
+{
+    // energy-time image operations: Orthogonalize(S, t + (a,b,c)) with the CURRENT lattice (NBModelABFS.c:1246-1256)
+    std::vector<ImageOpDev> ops((size_t) s.nsets);
+    std::memset(ops.data(), 0, sizeof(ImageOpDev) * ops.size());
+    ops[0].R[0] = ops[0].R[4] = ops[0].R[8] = 1.0; ops[0].scale = 1.0; ops[0].pureTranslation = 1;
+    for (int k = 1; k < s.nsets; k++) {
+        const CandidateImage &im = s.plan.images[k - 1];
+        const double xt[3] = {s.trans.trans[3 * im.t] + (double) im.a, s.trans.trans[3 * im.t + 1] + (double) im.b, s.trans.trans[3 * im.t + 2] + (double) im.c};
+        const RealSpaceOp op = orthogonalize(s.trans.rot[im.t], xt, s.lattice);
+        std::memcpy(ops[k].R, op.R.v, sizeof(double) * 9);
+        std::memcpy(ops[k].tv, op.tv, sizeof(double) * 3);
+        ops[k].scale = im.scale; ops[k].pureTranslation = op.pureTranslation ? 1 : 0;
+    }
+    if (!s.imageOps.ensure(ops.size())) return false;
+    NBB_CUDA(cudaMemcpyAsync(s.imageOps.p, ops.data(), sizeof(ImageOpDev) * ops.size(), cudaMemcpyHostToDevice, s.stream));
+    if (!launch_forces(s, d_grad)) return false;
+    const size_t accumCount = (size_t) 16 * (s.nsets + 1);
+    if (accumCount > kSmallDoubles) { set_error("too many images for the result buffer"); return false; }
+    NBB_CUDA(cudaMemcpyAsync(s.hsmall, s.accum.p, sizeof(double) * accumCount, cudaMemcpyDeviceToHost, s.stream));
+    NBB_CUDA(cudaStreamSynchronize(s.stream));
+    const double *acc = s.hsmall;
+    for (int k = 0; k < 6; k++) energies[k] = 0.0;
+    energies[NBB200_EMMEL] = acc[0]; energies[NBB200_EMMLJ] = acc[1];
+    for (int k = 1; k < s.nsets; k++) { energies[NBB200_EIMMMEL] += acc[16 * k]; energies[NBB200_EIMMMLJ] += acc[16 * k + 1]; }
+    energies[NBB200_EMMEL14] = acc[16 * s.nsets]; energies[NBB200_EMMLJ14] = acc[16 * s.nsets + 1];
+    if (dEdM != nullptr && d_grad != nullptr) {
+        for (int k = 1; k < s.nsets; k++) {
+            const CandidateImage &im = s.plan.images[k - 1];
+            const double xt[3] = {s.trans.trans[3 * im.t] + (double) im.a, s.trans.trans[3 * im.t + 1] + (double) im.b, s.trans.trans[3 * im.t + 2] + (double) im.c};
+            image_derivatives(dEdM, s.lattice, s.trans.rot[im.t], xt, acc + 16 * k + 5, acc + 16 * k + 2);
+        }
+    }
+    if (s.timing) {
+        float ms = 0.f;
+        s.timings[1] = s.timings[2] = 0.0;
+        if (s.hostCounters.itemCount > 0) { cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]); s.timings[1] = ms; }
+        if (s.n14 > 0 && s.rank == 0) { cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]); s.timings[2] = ms; }
+    }
+    return true;
+}
+
+}  // namespace nbb200
+
+using namespace nbb200;
+
+extern "C" {
+
+int nbb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+const char *nbb200_last_error(void) { return g_error.c_str(); }
+const char *nbb200_version(void) { return "nbabfs_b200 0.1 (sm_100a)"; }
+
+NBB200State *NBModelABFSState_B200_SetUp(int device, int n, const double *charges, const int *ljtypes,
+                                         int ntypes, const int *tableindex, const double *tableA, const double *tableB,
+                                         int ntypes14, const int *tableindex14, const double *tableA14, const double *tableB14,
+                                         int nexcl, const int *exclPairs, int n14, const int *pairs14,
+                                         int ntrans, const double *rot, const double *trans, int *status)
+{
+    return reinterpret_cast<NBB200State *>(create(device, n, charges, ljtypes, ntypes, tableindex, tableA, tableB, ntypes14, tableindex14, tableA14, tableB14,
+                                                  nexcl, exclPairs, n14, pairs14, ntrans, rot, trans, status));
+}
+
+void NBModelABFSState_B200_Deallocate(NBB200State **state)
+{
+    if (state == nullptr || *state == nullptr) return;
+    destroy(reinterpret_cast<State *>(*state));
+    *state = nullptr;
+}
+
+void NBModelABFS_B200_SetOptions(NBB200State *state, double dampingCutoff, double innerCutoff, double outerCutoff, double listCutoff,
+                                 double dielectric, double electrostaticScale14, int checkForInverses, int imageExpandFactor)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    s.damp = dampingCutoff; s.inner = innerCutoff; s.outer = outerCutoff; s.list = listCutoff;
+    s.dielectric = dielectric; s.scale14 = electrostaticScale14;
+    if ((s.checkForInverses != (checkForInverses != 0)) || s.expandFactor != imageExpandFactor) s.isNew = true;
+    s.checkForInverses = checkForInverses != 0; s.expandFactor = imageExpandFactor;
+    make_abfs_factors(s.damp, s.inner, s.outer, s.factors);
+}
+
+int NBModelABFS_B200_Update(NBB200State *state, const double *xyz, const double *box6, int forceNew, int *status)
+{
+    if (state == nullptr || xyz == nullptr) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    std::memcpy(s.hx, xyz, sizeof(double) * 3 * (size_t) s.n);
+    if (!cuda_ok(cudaMemcpyAsync(s.x.p, s.hx, sizeof(double) * 3 * (size_t) s.n, cudaMemcpyHostToDevice, s.stream), "H2D coordinates")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
+    s.xcur = s.x.p;
+    return update_common(s, box6, forceNew, status);
+}
+
+int NBModelABFS_B200_UpdateDevice(NBB200State *state, const double *d_xyz, const double *box6, int forceNew, int *status)
+{
+    if (state == nullptr || d_xyz == nullptr) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    s.xcur = d_xyz;
+    return update_common(s, box6, forceNew, status);
+}
+
+void NBModelABFS_B200_MMMMEnergy(NBB200State *state, double *energies, double *grad, double *dEdM, int *status)
+{
+    if (state == nullptr || energies == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (s.xcur == nullptr) { set_error("MMMMEnergy called before Update"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+    double *dg = nullptr;
+    if (grad != nullptr) {
+        dg = s.grad.p;
+        if (!cuda_ok(cudaMemsetAsync(dg, 0, sizeof(double) * 3 * (size_t) s.n, s.stream), "memset grad")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+    }
+    bool ok = energy_common(s, energies, dg, dEdM);
+    if (ok && grad != nullptr) {
+        ok = cuda_ok(cudaMemcpyAsync(s.hgrad, dg, sizeof(double) * 3 * (size_t) s.n, cudaMemcpyDeviceToHost, s.stream), "D2H grad") &&
+             cuda_ok(cudaStreamSynchronize(s.stream), "sync");
+        if (ok) { const size_t m = 3 * (size_t) s.n; for (size_t i = 0; i < m; i++) grad[i] += s.hgrad[i]; }
+    }
+    if (!ok) set_status(status, NBB200_STATUS_LOGIC_ERROR);
+}
+
+void NBModelABFS_B200_MMMMEnergyDevice(NBB200State *state, double *energies, double *d_grad, double *dEdM, int *status)
+{
+    if (state == nullptr || energies == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (s.xcur == nullptr) { set_error("MMMMEnergy called before Update"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+    if (!energy_common(s, energies, d_grad, dEdM)) set_status(status, NBB200_STATUS_LOGIC_ERROR);
+}
+
+long NBModelABFSState_B200_NumberOfPairs(NBB200State *state, int image)
+{
+    if (state == nullptr) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (image < 0) { fetch_pair_counts(s); return s.primaryPairs; }
+    const std::vector<int> live = live_images(s);
+    if (image >= (int) live.size()) return 0;
+    return s.imagePairs[live[image]];
+}
+
+int NBModelABFSState_B200_NumberOfImages(NBB200State *state)
+{
+    if (state == nullptr) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    return (int) live_images(s).size();
+}
+
+long NBModelABFSState_B200_NumberOfImagePairs(NBB200State *state)
+{
+    if (state == nullptr) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    fetch_pair_counts(s);
+    long t = 0;
+    for (long v : s.imagePairs) t += v;
+    return t;
+}
+
+long NBModelABFSState_B200_NumberOf14Pairs(NBB200State *state)
+{
+    return (state == nullptr) ? 0 : (long) reinterpret_cast<State *>(state)->n14;
+}
+
+void NBModelABFSState_B200_GetImageInfo(NBB200State *state, int image, int *info, double *scale)
+{
+    if (state == nullptr || info == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    const std::vector<int> live = live_images(s);
+    if (image < 0 || image >= (int) live.size()) return;
+    const CandidateImage &im = s.plan.images[live[image]];
+    info[0] = im.t; info[1] = im.a; info[2] = im.b; info[3] = im.c; info[4] = (int) s.imagePairs[live[image]]; info[5] = 0;
+    if (scale != nullptr) *scale = im.scale;
+}
+
+long NBModelABFSState_B200_GetPairs(NBB200State *state, int image, int *pairs, int *status)
+{
+    if (state == nullptr) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (!expand_pairs(s)) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return -1; }
+    int set = 0;
+    if (image >= 0) {
+        const std::vector<int> live = live_images(s);
+        if (image >= (int) live.size()) return 0;
+        set = 1 + live[image];
+    }
+    const unsigned long long lo = s.pairOffsets[set], hi = s.pairOffsets[set + 1];
+    if (pairs != nullptr && hi > lo) {
+        if (!cuda_ok(cudaMemcpy(pairs, s.pairBuf.p + 2 * lo, sizeof(int) * 2 * (hi - lo), cudaMemcpyDeviceToHost), "D2H pairs")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return -1; }
+    }
+    return (long) (hi - lo);
+}
+
+static long standalone(int device, int n1, const double *xyz1, int n2, const double *xyz2, double cutoff, int nexcl, const int *excl, int **pairs, int *status)
+{
+    if (pairs == nullptr || xyz1 == nullptr || n1 <= 0 || cutoff <= 0.0) { set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return -1; }
+    *pairs = nullptr;
+    std::vector<double> q((size_t) n1, 0.0);
+    std::vector<int> lt((size_t) n1, 0);
+    const int ti[1] = {0};
+    const double ta[1] = {0.0};
+    State *s = create(device, n1, q.data(), lt.data(), 1, ti, ta, ta, 1, ti, ta, ta, nexcl, excl, 0, nullptr, 0, nullptr, nullptr, status);
+    if (s == nullptr) return -1;
+    long result = -1;
+    DevBuf<double> x2;
+    bool ok = true;
+    s->list = cutoff;
+    ok = cuda_ok(cudaMemcpy(s->x.p, xyz1, sizeof(double) * 3 * (size_t) n1, cudaMemcpyHostToDevice), "H2D");
+    s->xcur = s->x.p;
+    if (ok && xyz2 != nullptr) {
+        ok = n2 > 0 && x2.ensure(3 * (size_t) n2) && cuda_ok(cudaMemcpy(x2.p, xyz2, sizeof(double) * 3 * (size_t) n2, cudaMemcpyHostToDevice), "H2D");
+    }
+    ok = ok && build_lists_standalone(*s, xyz2 != nullptr ? x2.p : nullptr, n2) && expand_pairs(*s);
+    if (ok) {
+        const int set = (xyz2 != nullptr) ? 1 : 0;
+        const unsigned long long lo = s->pairOffsets[set], hi = s->pairOffsets[set + 1];
+        int *out = (int *) std::malloc(sizeof(int) * 2 * (size_t) std::max<unsigned long long>(1ULL, hi - lo));
+        if (out != nullptr && (hi == lo || cuda_ok(cudaMemcpy(out, s->pairBuf.p + 2 * lo, sizeof(int) * 2 * (hi - lo), cudaMemcpyDeviceToHost), "D2H pairs"))) {
+            *pairs = out; result = (long) (hi - lo);
+        } else { std::free(out); set_status(status, NBB200_STATUS_OUT_OF_MEMORY); }
+    } else set_status(status, NBB200_STATUS_OUT_OF_MEMORY);
+    x2.release();
+    destroy(s);
+    return result;
+}
+
+long PairListGenerator_B200_SelfPairListFromCoordinates3(int device, int n, const double *xyz, double cutoff, int nexcl, const int *exclPairs, int **pairs, int *status)
+{
+    return standalone(device, n, xyz, 0, nullptr, cutoff, nexcl, exclPairs, pairs, status);
+}
+
+long PairListGenerator_B200_CrossPairListFromDoubleCoordinates3(int device, int n1, const double *xyz1, int n2, const double *xyz2, double cutoff, int **pairs, int *status)
+{
+    if (xyz2 == nullptr) { set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return -1; }
+    return standalone(device, n1, xyz1, n2, xyz2, cutoff, 0, nullptr, pairs, status);
+}
+
+void nbb200_free(void *p) { std::free(p); }
+
+void PairwiseInteractionABFS_B200_MakeFactors(double dampingCutoff, double innerCutoff, double outerCutoff, double *out21)
+{
+    if (out21 != nullptr) make_abfs_factors(dampingCutoff, innerCutoff, outerCutoff, out21);
+}
+
+void nbb200_set_stream(NBB200State *state, void *cudaStream)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (s.ownStream && s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    s.stream = reinterpret_cast<cudaStream_t>(cudaStream);
+    s.ownStream = false;
+}
+
+void nbb200_enable_timing(NBB200State *state, int on) { if (state != nullptr) reinterpret_cast<State *>(state)->timing = on != 0; }
+
+void nbb200_get_timings(NBB200State *state, double *out8)
+{
+    if (state == nullptr || out8 == nullptr) return;
+    std::memcpy(out8, reinterpret_cast<State *>(state)->timings, sizeof(double) * 8);
+}
+
+void nbb200_get_counters(NBB200State *state, long *out8)
+{
+    if (state == nullptr || out8 == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    fetch_pair_counts(s);
+    long pairs = s.primaryPairs;
+    for (long v : s.imagePairs) pairs += v;
+    out8[0] = s.hostCounters.tileTotal; out8[1] = s.hostCounters.itemCount; out8[2] = s.nblocks; out8[3] = s.hostCounters.extCount;
+    out8[4] = pairs; out8[5] = s.launches; out8[6] = s.tileStride; out8[7] = (long) live_images(s).size();
+}
+
+void nbb200_set_partition(NBB200State *state, int rank, int nranks)
+{
+    if (state == nullptr || nranks < 1 || rank < 0 || rank >= nranks) return;
+    State &s = *reinterpret_cast<State *>(state);
+    s.rank = rank; s.nranks = nranks; s.isNew = true;
+}
+
+}  // extern "C"

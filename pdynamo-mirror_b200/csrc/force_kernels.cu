@@ -1,0 +1,310 @@
+// force_kernels.cu -- the MM/MM energy + gradient kernels (sm_100a).
+//
+// Replaces PairwiseInteractionABFS_MMMMEnergy (analytic branch, pM/csource/PairwiseInteraction.c:292-429, loop :374-427,
+// macros pM/cinclude/PairwiseInteraction.h:72-119) as driven by NBModelABFS_MMMMEnergy (pM/csource/NBModelABFS.c:228-301)
+// and MMMMImageEnergy (:1161-1313), including the image gradient rotation (:1295-1298) and the sums needed by
+// SymmetryParameterGradients_ImageDerivatives (pM/csource/SymmetryParameterGradients.c:158-238).
+//
+// k_tile_forces: one warp per work item (= one i-block x up to 8 tiles of one image).  Lane l owns i atom l of the
+// block and, per tile, j slot l.  The 32x32 tile is walked in 32 steps; at step k lane l evaluates (i = l, j = (l+k)%32)
+// and then hands its j data AND its j-force accumulator to lane l-1 (warp shuffles), so both the i and the j force are
+// plain register accumulations (no shared-memory atomics, Newton's third law used once per pair).  Pair math is fp32 in
+// block-local coordinates (fp64 coordinates minus the i-block centre, rounded once), accumulation per tile in fp32,
+// across tiles / into global memory in fp64.
+#include "nbb200_internal.h"
+#include <algorithm>
+#include <cstring>
+
+namespace nbb200 {
+
+struct ForceArgs {
+    const WorkItem *items; int nitems; unsigned int *workCursor;
+    const int *tileJ; const unsigned int *tileMask;
+    const int *sAtom; int n;
+    const double *x;
+    const double *blockBox;
+    const float *q32; const int *ljtype; const float2 *ljAB; int ntypes;
+    const ImageOpDev *ops;
+    AbfsF32 F; float qScale;
+    double *grad; double *accum;
+};
+
+#ifndef NBB_RSQRT_NEWTON
+#define NBB_RSQRT_NEWTON 1
+#endif
+
+// one pair in fp32.  qij, A, B are zero for masked pairs so every output is exactly zero for them.
+__device__ __forceinline__ void abfs_pair(const AbfsF32 &F, float r2, float qij, float A, float B, float &eq, float &elj, float &f2)
+{
+    float s = rsqrtf(r2);
+#if NBB_RSQRT_NEWTON
+    s = fmaf(0.5f * s, fmaf(-r2 * s, s, 1.0f), s);               // one Newton step: MUFU.RSQ is ~1 ulp, energies need better
+#endif
+    const float s2 = s * s;
+    float dFq, dFl;
+    if (r2 > F.r2On) {                                            // switching region
+        const float P = fmaf(-r2, fmaf(fmaf(F.d, r2, F.c), r2, F.b), F.a);
+        const float Q = fmaf(r2, fmaf(fmaf(F.d5, r2, F.c3), r2, F.b), F.a);
+        eq  = qij * fmaf(s, P, F.qShift2);
+        dFq = -0.5f * qij * s * Q * s2;
+        const float s6 = s2 * s2 * s2;
+        const float l1 = s6 - F.aF6, l2 = fmaf(s, s2, -F.bF3);
+        const float Ak = A * F.aK12, Bk = B * F.bK6;
+        elj = Ak * l1 * l1 - Bk * l2 * l2;
+        dFl = -3.0f * s6 * (2.0f * Ak * l1 * s2 - Bk * l2 * (r2 * s));
+    } else if (r2 >= F.r2Damp) {                                  // plain shifted region
+        eq  = qij * (s + F.qShift1);
+        dFq = -0.5f * qij * s * s2;
+        const float s6 = s2 * s2 * s2;
+        elj = A * fmaf(s6, s6, -F.aShift12) - B * (s6 - F.bShift6);
+        dFl = -3.0f * s6 * (2.0f * A * s6 - B) * s2;
+    } else {                                                      // damped core (r < dampingCutoff), practically never taken
+        eq  = qij * fmaf(-F.qAlpha, r2, F.qF0);
+        dFq = -qij * F.qAlpha;
+        elj = A * fmaf(-F.aAlpha, r2, F.aF0) - B * fmaf(-F.bAlpha, r2, F.bF0);
+        dFl = -A * F.aAlpha + B * F.bAlpha;
+    }
+    f2 = 2.0f * (dFq + dFl);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+constexpr int kForceThreads = 256;
+
+__global__ void __launch_bounds__(kForceThreads) k_tile_forces(ForceArgs A)
+{
+    extern __shared__ float2 sLJ[];                               // [ntypes*ntypes] (A, B)
+    for (int i = threadIdx.x; i < A.ntypes * A.ntypes; i += blockDim.x) sLJ[i] = A.ljAB[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const AbfsF32 F = A.F;
+    const int src = (lane + 1) & 31;
+
+    for (;;) {
+        unsigned int it = 0;
+        if (lane == 0) it = atomicAdd(A.workCursor, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= (unsigned int) A.nitems) break;
+        const WorkItem wi = A.items[it];
+        const ImageOpDev *op = A.ops + wi.image;
+        const bool isImage = wi.image > 0;
+        const bool pureT = op->pureTranslation != 0;
+        const double cx = A.blockBox[9 * wi.block + 6], cy = A.blockBox[9 * wi.block + 7], cz = A.blockBox[9 * wi.block + 8];
+
+        // i atom of this lane
+        const int si = wi.block * kTile + lane;
+        const int ai = (si < A.n) ? A.sAtom[si] : -1;
+        float xi = 0.f, yi = 0.f, zi = 0.f, qi = 0.f;
+        int ti = 0;
+        if (ai >= 0) {
+            xi = (float) (A.x[3 * ai] - cx); yi = (float) (A.x[3 * ai + 1] - cy); zi = (float) (A.x[3 * ai + 2] - cz);
+            qi = A.q32[ai] * A.qScale;
+            ti = A.ljtype[ai] * A.ntypes;
+        }
+        double fix = 0.0, fiy = 0.0, fiz = 0.0, eQ = 0.0, eL = 0.0;
+        double G0 = 0.0, G1 = 0.0, G2 = 0.0, W[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) W[k] = 0.0;
+
+        for (int t = 0; t < wi.tileCount; t++) {
+            const size_t T = ((size_t) wi.tileStart + t) * kTile + lane;
+            const int aj = A.tileJ[T];
+            const unsigned int mask = A.tileMask[T];
+            double xj64 = 0.0, yj64 = 0.0, zj64 = 0.0;
+            float xj = 0.f, yj = 0.f, zj = 0.f, qj = 0.f;
+            int tj = 0;
+            if (aj >= 0) {
+                xj64 = A.x[3 * aj]; yj64 = A.x[3 * aj + 1]; zj64 = A.x[3 * aj + 2];
+                double px = xj64, py = yj64, pz = zj64;
+                if (isImage) {
+                    if (pureT) { px += op->tv[0]; py += op->tv[1]; pz += op->tv[2]; }
+                    else {
+                        px = op->R[0] * xj64 + op->R[1] * yj64 + op->R[2] * zj64 + op->tv[0];
+                        py = op->R[3] * xj64 + op->R[4] * yj64 + op->R[5] * zj64 + op->tv[1];
+                        pz = op->R[6] * xj64 + op->R[7] * yj64 + op->R[8] * zj64 + op->tv[2];
+                    }
+                }
+                xj = (float) (px - cx); yj = (float) (py - cy); zj = (float) (pz - cz);
+                qj = A.q32[aj];
+                tj = A.ljtype[aj];
+            }
+            float fxi = 0.f, fyi = 0.f, fzi = 0.f, fxj = 0.f, fyj = 0.f, fzj = 0.f, eq = 0.f, el = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < kTile; k++) {
+                const float dx = xi - xj, dy = yi - yj, dz = zi - zj;
+                float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                const bool on = ((mask >> k) & 1u) && (r2 <= F.r2Off);
+                const float2 ab = sLJ[ti + tj];
+                const float qij = on ? qi * qj : 0.f;
+                const float Aij = on ? ab.x : 0.f, Bij = on ? ab.y : 0.f;
+                r2 = on ? r2 : 1.0f;
+                float e1, e2, f2;
+                abfs_pair(F, r2, qij, Aij, Bij, e1, e2, f2);
+                eq += e1; el += e2;
+                const float gx = f2 * dx, gy = f2 * dy, gz = f2 * dz;
+                fxi += gx; fyi += gy; fzi += gz;
+                fxj -= gx; fyj -= gy; fzj -= gz;
+                // hand the j atom and its accumulator to the neighbouring lane
+                fxj = __shfl_sync(0xffffffffu, fxj, src); fyj = __shfl_sync(0xffffffffu, fyj, src); fzj = __shfl_sync(0xffffffffu, fzj, src);
+                if (k < kTile - 1) {
+                    xj = __shfl_sync(0xffffffffu, xj, src); yj = __shfl_sync(0xffffffffu, yj, src); zj = __shfl_sync(0xffffffffu, zj, src);
+                    qj = __shfl_sync(0xffffffffu, qj, src); tj = __shfl_sync(0xffffffffu, tj, src);
+                }
+            }
+            // after 32 hand-overs the accumulator of j slot `lane` is back in this lane
+            fix += (double) fxi; fiy += (double) fyi; fiz += (double) fzi;
+            eQ += (double) eq; eL += (double) el;
+            if (aj >= 0) {
+                const double sc = op->scale;
+                double gx = sc * (double) fxj, gy = sc * (double) fyj, gz = sc * (double) fzj;       // gradient on the (image) atom
+                if (isImage) {
+                    G0 += gx; G1 += gy; G2 += gz;
+                    if (!pureT) {
+                        W[0] += gx * xj64; W[1] += gx * yj64; W[2] += gx * zj64;
+                        W[3] += gy * xj64; W[4] += gy * yj64; W[5] += gy * zj64;
+                        W[6] += gz * xj64; W[7] += gz * yj64; W[8] += gz * zj64;
+                        const double rx = op->R[0] * gx + op->R[3] * gy + op->R[6] * gz;           // R^T g'
+                        const double ry = op->R[1] * gx + op->R[4] * gy + op->R[7] * gz;
+                        const double rz = op->R[2] * gx + op->R[5] * gy + op->R[8] * gz;
+                        gx = rx; gy = ry; gz = rz;
+                    }
+                }
+                if (A.grad != nullptr) {
+                    atomicAdd(&A.grad[3 * aj], gx); atomicAdd(&A.grad[3 * aj + 1], gy); atomicAdd(&A.grad[3 * aj + 2], gz);
+                }
+            }
+        }
+        const double sc = op->scale;
+        if (ai >= 0 && A.grad != nullptr) {
+            atomicAdd(&A.grad[3 * ai], sc * fix); atomicAdd(&A.grad[3 * ai + 1], sc * fiy); atomicAdd(&A.grad[3 * ai + 2], sc * fiz);
+        }
+        double *acc = A.accum + 16 * wi.image;
+        eQ = warp_sum(eQ) * sc; eL = warp_sum(eL) * sc;
+        if (lane == 0) { atomicAdd(&acc[0], eQ); atomicAdd(&acc[1], eL); }
+        if (isImage) {
+            G0 = warp_sum(G0); G1 = warp_sum(G1); G2 = warp_sum(G2);
+            if (lane == 0) { atomicAdd(&acc[2], G0); atomicAdd(&acc[3], G1); atomicAdd(&acc[4], G2); }
+            if (!pureT) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) { const double w = warp_sum(W[k]); if (lane == 0) atomicAdd(&acc[5 + k], w); }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// 1-4 interactions: explicit pair list, their own LJ table and electrostatic scale, never imaged
+// (NBModelABFS_MMMMEnergy third call, pM/csource/NBModelABFS.c:275-294).  A few thousand pairs: plain fp64.
+// ------------------------------------------------------------------------------------------------------
+struct F64Factors { double v[21]; };
+
+__global__ void k_pairs14(const int2 *__restrict__ pairs, int npairs, const double *__restrict__ x, const double *__restrict__ q, const int *__restrict__ ljtype,
+                          const double2 *__restrict__ ljAB, int ntypes, F64Factors FF, double eScale, double *grad, double *acc)
+{
+    const double *F = FF.v;
+    double eq = 0.0, el = 0.0;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gridDim.x * blockDim.x) {
+        const int i = pairs[p].x, j = pairs[p].y;
+        const double dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 > F[2]) continue;
+        const double qij = eScale * q[i] * q[j];
+        const double2 ab = ljAB[ljtype[i] * ntypes + ljtype[j]];
+        double s = 0.0, s2 = 0.0, dF = 0.0, e1, e2;
+        if (!(r2 < F[0])) { s2 = 1.0 / r2; s = sqrt(s2); }
+        if (r2 > F[1]) {
+            e1 = qij * (s * (F[3] - r2 * (F[4] + r2 * (F[5] + F[6] * r2))) + F[8]);
+            dF += -qij * 0.5 * s * (F[3] + r2 * (F[4] + r2 * (3.0 * F[5] + 5.0 * F[6] * r2))) / r2;
+        } else if (r2 > F[0]) { e1 = qij * (s + F[7]); dF += -qij * 0.5 * s / r2; }
+        else { e1 = qij * (F[9] - F[10] * r2); dF += -qij * F[10]; }
+        const double s6 = s2 * s2 * s2;
+        if (r2 > F[1]) {
+            const double l1 = s6 - F[11], l2 = (s / r2) - F[16];
+            e2 = ab.x * F[12] * l1 * l1 - ab.y * F[17] * l2 * l2;
+            dF += -3.0 * s6 * (2.0 * ab.x * F[12] * l1 / r2 - ab.y * F[17] * l2 / s);
+        } else if (r2 > F[0]) {
+            e2 = ab.x * (s6 * s6 - F[13]) - ab.y * (s6 - F[18]);
+            dF += -3.0 * s6 * (2.0 * ab.x * s6 - ab.y) / r2;
+        } else {
+            e2 = ab.x * (F[14] - F[15] * r2) - ab.y * (F[19] - F[20] * r2);
+            dF += -ab.x * F[15] + ab.y * F[20];
+        }
+        eq += e1; el += e2;
+        if (grad != nullptr) {
+            const double gx = 2.0 * dF * dx, gy = 2.0 * dF * dy, gz = 2.0 * dF * dz;
+            atomicAdd(&grad[3 * i], gx); atomicAdd(&grad[3 * i + 1], gy); atomicAdd(&grad[3 * i + 2], gz);
+            atomicAdd(&grad[3 * j], -gx); atomicAdd(&grad[3 * j + 1], -gy); atomicAdd(&grad[3 * j + 2], -gz);
+        }
+    }
+    eq = warp_sum(eq); el = warp_sum(el);
+    if ((threadIdx.x & 31) == 0 && (eq != 0.0 || el != 0.0)) { atomicAdd(&acc[0], eq); atomicAdd(&acc[1], el); }
+}
+
+static int g_forceBlocksPerSM = 0, g_numSMs = 0;
+
+void init_force_kernel_attributes()
+{
+    cudaFuncSetAttribute(k_tile_forces, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaGetDeviceProperties(&prop, dev);
+    g_numSMs = prop.multiProcessorCount;
+}
+
+bool launch_forces(State &s, double *d_grad)
+{
+    const int nitems = (int) s.hostCounters.itemCount;
+    const size_t accumCount = (size_t) 16 * (s.nsets + 1);
+    if (!s.accum.ensure(accumCount)) return false;
+    NBB_CUDA(cudaMemsetAsync(s.accum.p, 0, sizeof(double) * accumCount, s.stream));
+    NBB_CUDA(cudaMemsetAsync(&s.counters->workCursor, 0, sizeof(unsigned int), s.stream));
+    const double eScale = (1.0 / s.dielectric) * kE2AngstromToKJMol;
+    if (nitems > 0) {
+        ForceArgs A;
+        A.items = s.items.p; A.nitems = nitems; A.workCursor = &s.counters->workCursor;
+        A.tileJ = s.tileJ.p; A.tileMask = s.tileMask.p; A.sAtom = s.sAtom.p; A.n = s.n;
+        A.x = s.xcur; A.blockBox = s.blockBox.p;
+        A.q32 = s.q32.p; A.ljtype = s.ljtype.p; A.ljAB = s.ljAB.p; A.ntypes = s.ntypes;
+        A.ops = s.imageOps.p;
+        const double *f = s.factors;
+        AbfsF32 &F = A.F;
+        F.r2Damp = (float) f[0]; F.r2On = (float) f[1]; F.r2Off = (float) f[2];
+        F.a = (float) f[3]; F.b = (float) f[4]; F.c = (float) f[5]; F.d = (float) f[6]; F.c3 = (float) (3.0 * f[5]); F.d5 = (float) (5.0 * f[6]);
+        F.qShift1 = (float) f[7]; F.qShift2 = (float) f[8]; F.qF0 = (float) f[9]; F.qAlpha = (float) f[10];
+        F.aF6 = (float) f[11]; F.aK12 = (float) f[12]; F.aShift12 = (float) f[13]; F.aF0 = (float) f[14]; F.aAlpha = (float) f[15];
+        F.bF3 = (float) f[16]; F.bK6 = (float) f[17]; F.bShift6 = (float) f[18]; F.bF0 = (float) f[19]; F.bAlpha = (float) f[20];
+        A.qScale = (float) eScale;
+        A.grad = d_grad; A.accum = s.accum.p;
+        const size_t smem = sizeof(float2) * (size_t) s.ntypes * s.ntypes;
+        if (smem > 160 * 1024) { set_error("too many LJ types for the shared-memory table"); return false; }
+        if (g_numSMs == 0) init_force_kernel_attributes();
+        int perSM = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_tile_forces, kForceThreads, smem);
+        if (perSM < 1) perSM = 1;
+        g_forceBlocksPerSM = perSM;
+        const int warpsPerBlock = kForceThreads / 32;
+        const int grid = std::max(1, std::min(g_numSMs * perSM, (nitems + warpsPerBlock - 1) / warpsPerBlock));
+        if (s.timing) cudaEventRecord(s.ev[2], s.stream);
+        k_tile_forces<<<grid, kForceThreads, smem, s.stream>>>(A);
+        if (s.timing) cudaEventRecord(s.ev[3], s.stream);
+        s.launches += 1;
+    }
+    if (s.n14 > 0 && s.rank == 0) {
+        F64Factors FF;
+        std::memcpy(FF.v, s.factors, sizeof(FF.v));
+        const int threads = 128, nblk = std::max(1, std::min(1184, (s.n14 + threads - 1) / threads));
+        if (s.timing) cudaEventRecord(s.ev[4], s.stream);
+        k_pairs14<<<nblk, threads, 0, s.stream>>>(s.pairs14.p, s.n14, s.xcur, s.q64.p, s.ljtype.p, s.ljAB14.p, s.ntypes14, FF,
+                                                    eScale * s.scale14, d_grad, s.accum.p + 16 * s.nsets);
+        if (s.timing) cudaEventRecord(s.ev[5], s.stream);
+        s.launches += 1;
+    }
+    return cuda_ok(cudaGetLastError(), "force kernels");
+}
+
+}  // namespace nbb200

@@ -1,0 +1,779 @@
+// list_build.cu -- device side of the pair-list rebuild (sm_100a).
+//
+// Replaces, for the pure-MM case, what NBModelABFS_Update drives on the CPU in the reference
+// (pM = pMolecule-1.9.0/extensions, pC = pCore-1.9.0/extensions):
+//   GenerateLists -> PairListGenerator_SelfPairListFromCoordinates3        pM/csource/NBModelABFS.c:1050-1108, pC/csource/PairListGenerator.c:530-553,946-1099
+//   GenerateImageLists -> PairListGenerator_CrossPairListFromDoubleCoordinates3   pM/csource/NBModelABFS.c:753-1045, pC/csource/PairListGenerator.c:414-446,703-791
+//   Coordinates3_MakeGridAndOccupancy / RegularGridOccupancy_Fill (counting sort) pC/csource/Coordinates3.c:1164, pC/csource/RegularGridOccupancy.c:77-147
+//   CheckForUpdate                                                         pM/csource/NBModelABFS.c:691-746
+//
+// Output format (B200-first, not the reference's linked lists): atoms are counting-sorted into grid cells,
+// consecutive runs of 32 sorted atoms form i-blocks, and for every i-block the builder emits TILES: 32 j atoms
+// (individually selected: each has at least one list pair with the block) plus a 32x32 bit mask.  Mask bit (i, j)
+// is set iff the reference would put the pair on its list:
+//     (dx*dx + dy*dy) + dz*dz <= listCutoff^2   in fp64 WITHOUT fused multiply-add        (PairListGenerator.c:70-81,131-139)
+//     and, for the primary list, i != j counted once and (i, j) not excluded            (PairListGenerator.c:100-113,1063-1085)
+// with dx = x_i - x'_j and x'_j the image coordinate produced by the reference's own operation sequence
+// (rotate, translate, then the +d / -d displacement walk of GenerateImageLists, :953-958,1003-1009).
+// The explicit (i, j) lists the reference holds are recovered from the masks by expand_pairs() below.
+//
+// This file is compiled with -fmad=false; the distance predicate additionally uses __dmul_rn/__dadd_rn.
+#include "nbb200_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace nbb200 {
+
+// ------------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ref_dist2(double dx, double dy, double dz)
+{
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// x' = R x + tv exactly as Coordinates3_Rotate + Coordinates3_Translate do it (pC/csource/Coordinates3.c:1473-1500,1772-1800)
+__device__ __forceinline__ void ref_transform(const double *op, double x0, double y0, double z0, double &x1, double &y1, double &z1)
+{
+    x1 = __dadd_rn(__dadd_rn(__dmul_rn(op[0], x0), __dmul_rn(op[1], y0)), __dmul_rn(op[2], z0));
+    y1 = __dadd_rn(__dadd_rn(__dmul_rn(op[3], x0), __dmul_rn(op[4], y0)), __dmul_rn(op[5], z0));
+    z1 = __dadd_rn(__dadd_rn(__dmul_rn(op[6], x0), __dmul_rn(op[7], y0)), __dmul_rn(op[8], z0));
+    x1 = __dadd_rn(x1, op[9]); y1 = __dadd_rn(y1, op[10]); z1 = __dadd_rn(z1, op[11]);
+}
+
+__device__ __forceinline__ int cell_coord(double v, double lo, double invh, int dim)
+{
+    int c = (int) floor((v - lo) * invh);
+    return min(dim - 1, max(0, c));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// bounding boxes of the primary coordinates (op 0) and of the coordinates transformed by each base operation
+// (Coordinates3_EnclosingOrthorhombicBox, pC/csource/Coordinates3.c:498-...): partial min/max per CTA, then one CTA.
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_bbox_partial(const double *__restrict__ x, int n, const double *__restrict__ ops, int nops, double *__restrict__ partial)
+{
+    // partial[(blockIdx.x * (nops) + o) * 6 + {min xyz, max xyz}]
+    extern __shared__ double sh[];
+    for (int o = 0; o < nops; o++) {
+        double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            double p[3] = {x[3 * i], x[3 * i + 1], x[3 * i + 2]};
+            if (o > 0) ref_transform(ops + 12 * (o - 1), p[0], p[1], p[2], p[0], p[1], p[2]);
+            for (int d = 0; d < 3; d++) { mn[d] = fmin(mn[d], p[d]); mx[d] = fmax(mx[d], p[d]); }
+        }
+        for (int d = 0; d < 3; d++) {
+            for (int off = 16; off > 0; off >>= 1) {
+                mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], off));
+                mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], off));
+            }
+        }
+        const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        if ((threadIdx.x & 31) == 0) for (int d = 0; d < 3; d++) { sh[w * 6 + d] = mn[d]; sh[w * 6 + 3 + d] = mx[d]; }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            double v = sh[threadIdx.x];
+            for (int k = 1; k < nw; k++) v = (threadIdx.x < 3) ? fmin(v, sh[k * 6 + threadIdx.x]) : fmax(v, sh[k * 6 + threadIdx.x]);
+            partial[((size_t) blockIdx.x * nops + o) * 6 + threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_bbox_final(const double *__restrict__ partial, int nblk, int nops, double *__restrict__ out)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // o*6 + c
+    if (idx >= nops * 6) return;
+    const int c = idx % 6;
+    double v = partial[idx];
+    for (int k = 1; k < nblk; k++) { const double u = partial[(size_t) k * nops * 6 + idx]; v = (c < 3) ? fmin(v, u) : fmax(v, u); }
+    out[idx] = v;
+}
+
+bool device_bbox(State &s, int nops, double *hostMin, double *hostExt)
+{
+    const int threads = 256;
+    int nblk = std::min(512, (s.n + threads * 4 - 1) / (threads * 4));
+    if (nblk < 1) nblk = 1;
+    if (!s.bboxDev.ensure((size_t) (nblk + 1) * nops * 6)) return false;
+    double *partial = s.bboxDev.p + (size_t) nops * 6;
+    k_bbox_partial<<<nblk, threads, (threads / 32) * 6 * sizeof(double), s.stream>>>(s.xcur, s.n, s.baseOpsDev.p, nops, partial);
+    k_bbox_final<<<(nops * 6 + 63) / 64, 64, 0, s.stream>>>(partial, nblk, nops, s.bboxDev.p);
+    s.launches += 2;
+    NBB_CUDA(cudaMemcpyAsync(s.hsmall, s.bboxDev.p, sizeof(double) * nops * 6, cudaMemcpyDeviceToHost, s.stream));
+    NBB_CUDA(cudaStreamSynchronize(s.stream));
+    for (int o = 0; o < nops; o++)
+        for (int d = 0; d < 3; d++) { hostMin[3 * o + d] = s.hsmall[6 * o + d]; hostExt[3 * o + d] = s.hsmall[6 * o + 3 + d] - s.hsmall[6 * o + d]; }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// CheckForUpdate (pM/csource/NBModelABFS.c:691-746): max |x - x_ref|^2 and "any atom beyond buffac".
+// The reference's early exit only matters when an update happens (then the maximum is not used further).
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_displacement(const double *__restrict__ x, const double *__restrict__ xref, int n, double buffacsq, unsigned long long *__restrict__ out)
+{
+    double m = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double dx = x[3 * i] - xref[3 * i], dy = x[3 * i + 1] - xref[3 * i + 1], dz = x[3 * i + 2] - xref[3 * i + 2];
+        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        m = fmax(m, r2);
+    }
+    for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long) __double_as_longlong(m));   // r2 >= 0: bit pattern is monotone
+}
+
+bool displacement_check(State &s, double buffacsq, double *maxr2, int *exceeded)
+{
+    if (!s.bboxDev.ensure(64)) return false;
+    unsigned long long *out = reinterpret_cast<unsigned long long *>(s.bboxDev.p);
+    NBB_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned long long), s.stream));
+    const int threads = 256;
+    const int nblk = std::max(1, std::min(1184, (s.n + threads - 1) / threads));
+    if (s.timing) cudaEventRecord(s.ev[6], s.stream);
+    k_displacement<<<nblk, threads, 0, s.stream>>>(s.xcur, s.xref.p, s.n, buffacsq, out);
+    if (s.timing) cudaEventRecord(s.ev[7], s.stream);
+    s.launches += 1;
+    NBB_CUDA(cudaMemcpyAsync(s.hsmall, out, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    NBB_CUDA(cudaStreamSynchronize(s.stream));
+    *maxr2 = s.hsmall[0];
+    *exceeded = (*maxr2 > buffacsq) ? 1 : 0;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// extended atoms: set 0 = the n primary atoms (entry e = atom index), sets 1.. = image atoms that fall inside
+// the search box (primary bounding box dilated by the cutoff).  Image coordinates follow the reference walk.
+// ------------------------------------------------------------------------------------------------------
+struct ExtendArgs {
+    const double *x; int n;
+    const double *baseOps;             // 12 doubles per transformation
+    const double *visitDisp; const int *visitInfo; int nvisits;     // visitInfo: (t, image) per visit
+    double boxLo[3], boxHi[3];         // search box with a small safety margin
+    BuildGrid grid;
+    double *eX; int *eAtom; int *eSet; int *eKey; unsigned long long *eSort;
+    unsigned int *cellCount; unsigned int extCap; DeviceCounters *counters;
+};
+
+__device__ __forceinline__ void classify(const BuildGrid &g, int set, int atom, double px, double py, double pz, int &key, unsigned long long &sortKey)
+{
+    const int cx = cell_coord(px, g.lo[0], g.invh, g.dim[0]), cy = cell_coord(py, g.lo[1], g.invh, g.dim[1]), cz = cell_coord(pz, g.lo[2], g.invh, g.dim[2]);
+    key = set * g.ncell + (cx * g.dim[1] + cy) * g.dim[2] + cz;
+    // position inside the cell: 8 z slabs, then 4 y rows, then 4 x columns -> runs of sorted atoms are compact boxes
+    const double fx = (px - g.lo[0]) * g.invh - cx, fy = (py - g.lo[1]) * g.invh - cy, fz = (pz - g.lo[2]) * g.invh - cz;
+    const int sx = min(3, max(0, (int) (fx * 4.0))), sy = min(3, max(0, (int) (fy * 4.0))), sz = min(7, max(0, (int) (fz * 8.0)));
+    sortKey = ((unsigned long long) (sz * 16 + sy * 4 + sx) << 32) | (unsigned int) atom;
+}
+
+__global__ void k_extend(ExtendArgs A)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A.n) return;
+    const double x0 = A.x[3 * j], y0 = A.x[3 * j + 1], z0 = A.x[3 * j + 2];
+    int key; unsigned long long sk;
+    classify(A.grid, 0, j, x0, y0, z0, key, sk);
+    A.eX[3 * j] = x0; A.eX[3 * j + 1] = y0; A.eX[3 * j + 2] = z0;
+    A.eAtom[j] = j; A.eSet[j] = 0; A.eKey[j] = key; A.eSort[j] = sk;
+    atomicAdd(&A.cellCount[key], 1u);
+    int tcur = -1;
+    double ux = 0, uy = 0, uz = 0;
+    for (int v = 0; v < A.nvisits; v++) {
+        const int t = A.visitInfo[2 * v], image = A.visitInfo[2 * v + 1];
+        if (t != tcur) { ref_transform(A.baseOps + 12 * t, x0, y0, z0, ux, uy, uz); tcur = t; }
+        const double dx = A.visitDisp[3 * v], dy = A.visitDisp[3 * v + 1], dz = A.visitDisp[3 * v + 2];
+        const double wx = __dadd_rn(ux, dx), wy = __dadd_rn(uy, dy), wz = __dadd_rn(uz, dz);
+        if (image >= 0 && wx >= A.boxLo[0] && wx <= A.boxHi[0] && wy >= A.boxLo[1] && wy <= A.boxHi[1] && wz >= A.boxLo[2] && wz <= A.boxHi[2]) {
+            const unsigned int slot = atomicAdd(&A.counters->extCount, 1u);
+            if (slot < A.extCap) {
+                const size_t e = (size_t) A.n + slot;
+                classify(A.grid, 1 + image, j, wx, wy, wz, key, sk);
+                A.eX[3 * e] = wx; A.eX[3 * e + 1] = wy; A.eX[3 * e + 2] = wz;
+                A.eAtom[e] = j; A.eSet[e] = 1 + image; A.eKey[e] = key; A.eSort[e] = sk;
+                atomicAdd(&A.cellCount[key], 1u);
+            } else atomicOr(&A.counters->overflow, 1u);
+        }
+        ux = __dadd_rn(wx, __dmul_rn(dx, -1.0)); uy = __dadd_rn(wy, __dmul_rn(dy, -1.0)); uz = __dadd_rn(wz, __dmul_rn(dz, -1.0));
+    }
+}
+
+// stand-alone cross list front end: set 1 = a second coordinate array, taken as given (points outside the
+// search box cannot pair with anything and are dropped)
+__global__ void k_extend_cross(const double *__restrict__ x2, int n2, int n1, BuildGrid grid, double3 boxLo, double3 boxHi, double *eX, int *eAtom, int *eSet,
+                               int *eKey, unsigned long long *eSort, unsigned int *cellCount, DeviceCounters *counters)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n2) return;
+    const double px = x2[3 * j], py = x2[3 * j + 1], pz = x2[3 * j + 2];
+    if (!(px >= boxLo.x && px <= boxHi.x && py >= boxLo.y && py <= boxHi.y && pz >= boxLo.z && pz <= boxHi.z)) return;
+    const size_t e = (size_t) n1 + atomicAdd(&counters->extCount, 1u);
+    int key; unsigned long long sk;
+    classify(grid, 1, j, px, py, pz, key, sk);
+    eX[3 * e] = px; eX[3 * e + 1] = py; eX[3 * e + 2] = pz;
+    eAtom[e] = j; eSet[e] = 1; eKey[e] = key; eSort[e] = sk;
+    atomicAdd(&cellCount[key], 1u);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// exclusive scan of the cell counts (counting sort, cf. RegularGridOccupancy_Fill pC/csource/RegularGridOccupancy.c:94-126)
+// ------------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024, kScanPer = 4, kScanChunk = kScanThreads * kScanPer;
+
+__device__ unsigned int block_exclusive_scan(unsigned int v, unsigned int *total)
+{
+    __shared__ unsigned int wsum[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned int inc = v;
+    for (int off = 1; off < 32; off <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += u; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        unsigned int s = (lane < (int) (blockDim.x >> 5)) ? wsum[lane] : 0u, si = s;
+        for (int off = 1; off < 32; off <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, si, off); if (lane >= off) si += u; }
+        wsum[lane] = si - s;
+        if (lane == 31) *total = si;
+    }
+    __syncthreads();
+    const unsigned int r = wsum[w] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void k_scan_chunks(const unsigned int *__restrict__ in, unsigned int *__restrict__ out, unsigned int *__restrict__ sums, int n)
+{
+    __shared__ unsigned int total;
+    const int base = blockIdx.x * kScanChunk + threadIdx.x * kScanPer;
+    unsigned int v[kScanPer], t = 0;
+    for (int k = 0; k < kScanPer; k++) { v[k] = (base + k < n) ? in[base + k] : 0u; t += v[k]; }
+    unsigned int ex = block_exclusive_scan(t, &total);
+    for (int k = 0; k < kScanPer; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void k_scan_sums(unsigned int *sums, int nchunks, unsigned int *grand)
+{
+    __shared__ unsigned int total;
+    unsigned int carry = 0;
+    for (int base = 0; base < nchunks; base += kScanThreads) {
+        const int i = base + threadIdx.x;
+        const unsigned int v = (i < nchunks) ? sums[i] : 0u;
+        const unsigned int ex = block_exclusive_scan(v, &total);
+        if (i < nchunks) sums[i] = ex + carry;
+        __syncthreads();
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand = carry;
+}
+
+__global__ void k_scan_add(unsigned int *out, const unsigned int *__restrict__ sums, int n, const unsigned int *grand)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] += sums[i / kScanChunk];
+    if (i == n) out[n] = *grand;
+}
+
+__global__ void k_scatter(const int *__restrict__ eKey, int ne, const unsigned int *__restrict__ cellStart, unsigned int *cellFill, int *order)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    const int key = eKey[e];
+    order[cellStart[key] + atomicAdd(&cellFill[key], 1u)] = e;
+}
+
+// deterministic order inside each cell: insertion sort by (sub-cell key, atom index)
+__global__ void k_sort_cells(const unsigned int *__restrict__ cellStart, int nkeys, const unsigned long long *__restrict__ eSort, int *order)
+{
+    const int key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= nkeys) return;
+    const int lo = (int) cellStart[key], hi = (int) cellStart[key + 1];
+    if (hi - lo > 4096) return;      // pathological density: keep the (valid, but arbitrary) scatter order
+    for (int i = lo + 1; i < hi; i++) {
+        const int e = order[i];
+        const unsigned long long k = eSort[e];
+        int p = i - 1;
+        while (p >= lo && eSort[order[p]] > k) { order[p + 1] = order[p]; p--; }
+        order[p + 1] = e;
+    }
+}
+
+__global__ void k_gather_sorted(const int *__restrict__ order, int ne, const double *__restrict__ eX, const int *__restrict__ eAtom, const int *__restrict__ eSet,
+                                double *sX, int *sAtom, int *invPerm)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ne) return;
+    const int e = order[p];
+    sX[3 * p] = eX[3 * e]; sX[3 * p + 1] = eX[3 * e + 1]; sX[3 * p + 2] = eX[3 * e + 2];
+    const int a = eAtom[e];
+    sAtom[p] = a;
+    if (eSet[e] == 0) invPerm[a] = p;
+}
+
+// per i-block (32 consecutive sorted primary atoms): min, max, centre
+__global__ void k_block_boxes(const double *__restrict__ sX, int n, int nblocks, double *__restrict__ blockBox)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= nblocks) return;
+    const int s = b * kTile + lane;
+    double mn[3], mx[3];
+    for (int d = 0; d < 3; d++) { const double v = (s < n) ? sX[3 * s + d] : 0.0; mn[d] = (s < n) ? v : 1e300; mx[d] = (s < n) ? v : -1e300; }
+    for (int d = 0; d < 3; d++)
+        for (int off = 16; off > 0; off >>= 1) { mn[d] = fmin(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], off)); mx[d] = fmax(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], off)); }
+    if (lane < 3) { blockBox[9 * b + lane] = mn[lane]; blockBox[9 * b + 3 + lane] = mx[lane]; blockBox[9 * b + 6 + lane] = 0.5 * (mn[lane] + mx[lane]); }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// the tile builder: one CTA per i-block
+// ------------------------------------------------------------------------------------------------------
+struct TileArgs {
+    int n, nblocks, nsets, firstBlock, selfEnabled;
+    double cutoff, cutoff2;
+    BuildGrid grid;
+    const double *sX; const int *sAtom; const int *invPerm;
+    const unsigned int *cellStart;
+    const double *blockBox;
+    const ImageBoxDev *imageBoxes;     // [nsets], slot 0 unused
+    const int *exclPtr; const int *exclCol;
+    int tileStride; int *tileJ; unsigned int *tileMask;
+    WorkItem *items; unsigned int itemCap;
+    unsigned long long *setPairs;
+    DeviceCounters *counters;
+};
+
+constexpr int kMaxRows = 64;
+constexpr int kQueueCap = kBuildThreads + kTile;
+
+__global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
+{
+    __shared__ double sxi[kTile][3];
+    __shared__ double sbox[6];
+    __shared__ int rowStart[kMaxRows];
+    __shared__ int rowPrefix[kMaxRows + 1];
+    __shared__ int qAtom[kQueueCap];
+    __shared__ unsigned int qMask[kQueueCap];
+    __shared__ int warpCnt[kBuildThreads / 32];
+    __shared__ int qCount, emitted;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = A.firstBlock + blockIdx.x;
+    if (tid < kTile) {
+        const int s = b * kTile + tid;
+        for (int d = 0; d < 3; d++) sxi[tid][d] = (s < A.n) ? A.sX[3 * s + d] : 1.0e30;     // padding rows never pass the test
+    }
+    if (tid < 6) sbox[tid] = A.blockBox[9 * b + tid];
+    if (tid == 0) { qCount = 0; emitted = 0; }
+    __syncthreads();
+
+    const BuildGrid g = A.grid;
+    const double reach = A.cutoff + 1.0e-6;
+    int c0[3], c1[3];
+    for (int d = 0; d < 3; d++) {
+        c0[d] = cell_coord(sbox[d] - reach, g.lo[d], g.invh, g.dim[d]);
+        c1[d] = cell_coord(sbox[3 + d] + reach, g.lo[d], g.invh, g.dim[d]);
+    }
+    const int nrowsY = c1[1] - c0[1] + 1, nrowsTotal = (c1[0] - c0[0] + 1) * nrowsY;
+    const double reject2 = A.cutoff2 * (1.0 + 1.0e-12) + 1.0e-9;
+
+    for (int set = 0; set < A.nsets; set++) {
+        if (set == 0 && !A.selfEnabled) continue;
+        if (set > 0) {                                   // whole-image prefilter (uniform for the CTA)
+            const ImageBoxDev ib = A.imageBoxes[set];
+            bool overlap = true;
+            for (int d = 0; d < 3; d++) overlap = overlap && (ib.lo[d] <= sbox[3 + d] + reach) && (ib.hi[d] >= sbox[d] - reach);
+            if (!overlap) continue;
+        }
+        const int imageStart = emitted;                  // all threads read the same value (synchronised below)
+        unsigned long long myPairs = 0;
+        __syncthreads();
+        for (int rowBase = 0; rowBase < nrowsTotal; rowBase += kMaxRows) {
+            const int nrows = min(kMaxRows, nrowsTotal - rowBase);
+            if (tid < nrows) {
+                const int r = rowBase + tid, cx = c0[0] + r / nrowsY, cy = c0[1] + r % nrowsY;
+                const int keyLo = set * g.ncell + (cx * g.dim[1] + cy) * g.dim[2] + c0[2];
+                int start = (int) A.cellStart[keyLo], end = (int) A.cellStart[keyLo + (c1[2] - c0[2]) + 1];
+                if (set == 0) start = max(start, b * kTile);     // primary list: each unordered pair once (own block: triangle below)
+                rowStart[tid] = start;
+                rowPrefix[tid + 1] = max(0, end - start);
+            }
+            __syncthreads();
+            if (tid == 0) { rowPrefix[0] = 0; for (int r = 0; r < nrows; r++) rowPrefix[r + 1] += rowPrefix[r]; }
+            __syncthreads();
+            const int total = rowPrefix[nrows];
+            for (int base = 0; base < total; base += kBuildThreads) {
+                const int c = base + tid;
+                unsigned int colmask = 0;
+                int atom = -1;
+                if (c < total) {
+                    int lo = 0, hi = nrows;                      // last row r with rowPrefix[r] <= c
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rowPrefix[mid] <= c) lo = mid; else hi = mid; }
+                    const int s = rowStart[lo] + (c - rowPrefix[lo]);
+                    const double xj = A.sX[3 * s], yj = A.sX[3 * s + 1], zj = A.sX[3 * s + 2];
+                    // conservative reject against the block box
+                    const double ex = fmax(0.0, fmax(sbox[0] - xj, xj - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - yj, yj - sbox[4])),
+                                 ez = fmax(0.0, fmax(sbox[2] - zj, zj - sbox[5]));
+                    if (ex * ex + ey * ey + ez * ez <= reject2) {
+#pragma unroll 4
+                        for (int i = 0; i < kTile; i++) {
+                            const double r2 = ref_dist2(sxi[i][0] - xj, sxi[i][1] - yj, sxi[i][2] - zj);
+                            colmask |= (r2 <= A.cutoff2) ? (1u << i) : 0u;
+                        }
+                        atom = A.sAtom[s];
+                        if (set == 0 && colmask != 0u) {
+                            if ((s >> 5) == b) colmask &= (1u << (s & 31)) - 1u;      // own block: i < j only, no self pair
+                            for (int k = A.exclPtr[atom]; k < A.exclPtr[atom + 1]; k++) {
+                                const int sp = A.invPerm[A.exclCol[k]];
+                                if ((sp >> 5) == b) colmask &= ~(1u << (sp & 31));
+                            }
+                        }
+                    }
+                }
+                const bool keep = colmask != 0u;
+                myPairs += __popc(colmask);
+                const unsigned int bal = __ballot_sync(0xffffffffu, keep);
+                if (lane == 0) warpCnt[warp] = __popc(bal);
+                __syncthreads();
+                int offset = qCount;
+                for (int w = 0; w < warp; w++) offset += warpCnt[w];
+                if (keep) { const int q = offset + __popc(bal & ((1u << lane) - 1u)); qAtom[q] = atom; qMask[q] = colmask; }
+                __syncthreads();
+                int newCount = qCount;
+                for (int w = 0; w < kBuildThreads / 32; w++) newCount += warpCnt[w];
+                const int ntiles = newCount / kTile;
+                // emit full tiles: warp w writes tiles w, w+4, ...
+                for (int t = warp; t < ntiles; t += kBuildThreads / 32) {
+                    const int slot = emitted + t;
+                    const unsigned int cm = qMask[t * kTile + lane];
+                    unsigned int row = 0;
+                    for (int i = 0; i < kTile; i++) { const unsigned int v = __ballot_sync(0xffffffffu, (cm >> i) & 1u); if (lane == i) row = v; }
+                    if (slot < A.tileStride) {
+                        const size_t T = ((size_t) b * A.tileStride + slot) * kTile + lane;
+                        A.tileJ[T] = qAtom[t * kTile + lane];
+                        A.tileMask[T] = __funnelshift_r(row, row, lane);             // bit k <-> j slot (lane + k) % 32
+                    }
+                }
+                __syncthreads();
+                const int rem = newCount - ntiles * kTile;
+                int ra = 0; unsigned int rm = 0;
+                if (tid < rem) { ra = qAtom[ntiles * kTile + tid]; rm = qMask[ntiles * kTile + tid]; }
+                __syncthreads();
+                if (tid < rem) { qAtom[tid] = ra; qMask[tid] = rm; }
+                if (tid == 0) { qCount = rem; emitted += ntiles; }
+                __syncthreads();
+            }
+        }
+        // flush the partial tile of this set
+        if (qCount > 0) {
+            if (warp == 0) {
+                const int slot = emitted;
+                const unsigned int cm = (lane < qCount) ? qMask[lane] : 0u;
+                unsigned int row = 0;
+                for (int i = 0; i < kTile; i++) { const unsigned int v = __ballot_sync(0xffffffffu, (cm >> i) & 1u); if (lane == i) row = v; }
+                if (slot < A.tileStride) {
+                    const size_t T = ((size_t) b * A.tileStride + slot) * kTile + lane;
+                    A.tileJ[T] = (lane < qCount) ? qAtom[lane] : -1;
+                    A.tileMask[T] = __funnelshift_r(row, row, lane);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) { qCount = 0; emitted += 1; }
+            __syncthreads();
+        }
+        // work items and pair statistics of this set
+        for (int off = 16; off > 0; off >>= 1) myPairs += __shfl_xor_sync(0xffffffffu, myPairs, off);
+        if (lane == 0 && myPairs) atomicAdd(&A.setPairs[set], myPairs);
+        if (tid == 0) {
+            const int last = min(emitted, A.tileStride), ntl = last - imageStart;
+            if (ntl > 0) {
+                const int nitems = (ntl + kItemTiles - 1) / kItemTiles;
+                const unsigned int pos = atomicAdd(&A.counters->itemCount, (unsigned int) nitems);
+                if (pos + nitems <= A.itemCap) {
+                    for (int k = 0; k < nitems; k++) {
+                        WorkItem w;
+                        w.block = b; w.image = set; w.tileStart = b * A.tileStride + imageStart + k * kItemTiles;
+                        w.tileCount = min(kItemTiles, ntl - k * kItemTiles);
+                        A.items[pos + k] = w;
+                    }
+                } else atomicOr(&A.counters->overflow, 4u);
+                atomicAdd(&A.counters->tileTotal, (unsigned int) ntl);
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        atomicMax(&A.counters->maxTilesBlock, (unsigned int) emitted);
+        if (emitted > A.tileStride) atomicOr(&A.counters->overflow, 2u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// explicit pair lists from the masks: one warp per work item; pairs of set k land in [pairOffsets[k], ...)
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_expand_pairs(const WorkItem *__restrict__ items, int nitems, const int *__restrict__ tileJ, const unsigned int *__restrict__ tileMask,
+                               const int *__restrict__ sAtom, int n, unsigned long long *cursor, int *__restrict__ pairs)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int it = w; it < nitems; it += nw) {
+        const WorkItem wi = items[it];
+        const int si = wi.block * kTile + lane;
+        const int ai = (si < n) ? sAtom[si] : -1;
+        for (int t = 0; t < wi.tileCount; t++) {
+            const size_t T = ((size_t) wi.tileStart + t) * kTile;
+            const int aj = tileJ[T + lane];
+            const unsigned int rot = tileMask[T + lane];
+            const unsigned int row = __funnelshift_l(rot, rot, lane);       // undo the rotation: bit s <-> j slot s
+            const int cnt = __popc(row);
+            int inc = cnt;
+            for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += u; }
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            unsigned long long base = 0;
+            if (lane == 0 && total) base = atomicAdd(&cursor[wi.image], (unsigned long long) total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            unsigned long long pos = base + (unsigned long long) (inc - cnt);
+            // divergence-free gather of the j atoms: every lane walks all 32 slots
+            const unsigned int m = row;
+            for (int sidx = 0; sidx < kTile; sidx++) {
+                const int j = __shfl_sync(0xffffffffu, aj, sidx);
+                if ((m >> sidx) & 1u) { pairs[2 * pos] = ai; pairs[2 * pos + 1] = j; pos++; }
+            }
+        }
+    }
+}
+
+bool expand_pairs(State &s)
+{
+    if (s.pairsExpanded) return true;
+    const int nsets = s.nsets;
+    // pair counts per set
+    std::vector<unsigned long long> cnt(nsets);
+    NBB_CUDA(cudaMemcpyAsync(cnt.data(), s.setPairs.p, sizeof(unsigned long long) * nsets, cudaMemcpyDeviceToHost, s.stream));
+    NBB_CUDA(cudaStreamSynchronize(s.stream));
+    s.pairOffsets.assign(nsets + 1, 0);
+    for (int k = 0; k < nsets; k++) s.pairOffsets[k + 1] = s.pairOffsets[k] + cnt[k];
+    const unsigned long long total = s.pairOffsets[nsets];
+    if (!s.pairBuf.ensure((size_t) 2 * total + 2)) return false;
+    if (!s.pairCursor.ensure(nsets)) return false;
+    NBB_CUDA(cudaMemcpyAsync(s.pairCursor.p, s.pairOffsets.data(), sizeof(unsigned long long) * nsets, cudaMemcpyHostToDevice, s.stream));
+    const int nitems = (int) s.hostCounters.itemCount;
+    if (nitems > 0) {
+        if (s.timing) cudaEventRecord(s.ev[8], s.stream);
+        const int threads = 256, nblk = std::max(1, std::min(148 * 8, (nitems + 7) / 8));
+        k_expand_pairs<<<nblk, threads, 0, s.stream>>>(s.items.p, nitems, s.tileJ.p, s.tileMask.p, s.sAtom.p, s.n, s.pairCursor.p, s.pairBuf.p);
+        s.launches += 1;
+        if (s.timing) cudaEventRecord(s.ev[9], s.stream);
+    }
+    NBB_CUDA(cudaStreamSynchronize(s.stream));
+    if (s.timing && nitems > 0) { float ms = 0; cudaEventElapsedTime(&ms, s.ev[8], s.ev[9]); s.timings[4] = ms; }
+    s.pairsExpanded = true;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host orchestration of one rebuild
+// ------------------------------------------------------------------------------------------------------
+static bool exclusive_scan(State &s, unsigned int *counts, unsigned int *out, int n)
+{
+    const int nchunks = (n + kScanChunk - 1) / kScanChunk;
+    if (!s.scanTmp.ensure((size_t) nchunks + 2)) return false;
+    unsigned int *sums = s.scanTmp.p, *grand = s.scanTmp.p + nchunks;
+    k_scan_chunks<<<nchunks, kScanThreads, 0, s.stream>>>(counts, out, sums, n);
+    k_scan_sums<<<1, kScanThreads, 0, s.stream>>>(sums, nchunks, grand);
+    k_scan_add<<<(n + 1 + 255) / 256, 256, 0, s.stream>>>(out, sums, n, grand);
+    s.launches += 3;
+    return true;
+}
+
+static void setup_grid(State &s, const double *lo, const double *hi)
+{
+    BuildGrid &g = s.grid;
+    g.h = 0.5 * s.list;
+    // keep the number of keys bounded for very large / very sparse systems
+    for (;;) {
+        long cells = 1;
+        for (int d = 0; d < 3; d++) { g.dim[d] = std::max(1, (int) std::floor((hi[d] - lo[d]) / g.h) + 1); cells *= g.dim[d]; }
+        if (cells * (long) s.nsets <= 6000000L) break;
+        g.h *= 1.26;
+    }
+    g.invh = 1.0 / g.h;
+    for (int d = 0; d < 3; d++) g.lo[d] = lo[d];
+    g.ncell = g.dim[0] * g.dim[1] * g.dim[2];
+}
+
+// sort the extended atoms, build blocks, tiles and work items.  On entry the extended atoms (eX, eAtom, eSet, eKey,
+// eSort, cell counts in cellFill) are on the device and counters->extCount holds the number of non-primary entries.
+static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound)
+{
+    const int nkeys = s.nsets * s.grid.ncell;
+    const size_t neMax = (size_t) s.n + extUpperBound;
+    if (!s.cellStart.ensure((size_t) nkeys + 2) || !s.order.ensure(neMax) || !s.sX.ensure(3 * neMax) || !s.sAtom.ensure(neMax) || !s.invPerm.ensure((size_t) s.n)) return false;
+    if (!exclusive_scan(s, s.cellFill.p, s.cellStart.p, nkeys)) return false;
+    NBB_CUDA(cudaMemsetAsync(s.cellFill.p, 0, sizeof(unsigned int) * nkeys, s.stream));
+    // number of extended atoms actually appended
+    NBB_CUDA(cudaMemcpyAsync(&s.hostCounters, s.counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, s.stream));
+    NBB_CUDA(cudaStreamSynchronize(s.stream));
+    if (s.hostCounters.overflow & 1u) { set_error("extended atom capacity exceeded"); return false; }
+    const int ne = s.n + (int) s.hostCounters.extCount;
+    k_scatter<<<(ne + 255) / 256, 256, 0, s.stream>>>(s.eKey.p, ne, s.cellStart.p, s.cellFill.p, s.order.p);
+    k_sort_cells<<<(nkeys + 127) / 128, 128, 0, s.stream>>>(s.cellStart.p, nkeys, s.eSortBuf.p, s.order.p);
+    k_gather_sorted<<<(ne + 255) / 256, 256, 0, s.stream>>>(s.order.p, ne, s.eX.p, s.eAtom.p, s.eSet.p, s.sX.p, s.sAtom.p, s.invPerm.p);
+    s.nblocks = (s.n + kTile - 1) / kTile;
+    if (!s.blockBox.ensure((size_t) 9 * s.nblocks)) return false;
+    k_block_boxes<<<(s.nblocks * 32 + 255) / 256, 256, 0, s.stream>>>(s.sX.p, s.n, s.nblocks, s.blockBox.p);
+    s.launches += 4;
+
+    // tiles: fixed-stride region per i-block (HBM is plentiful: 180 GB), retried with a larger stride on overflow
+    const int b0 = (int) (((long) s.nblocks * s.rank) / s.nranks), b1 = (int) (((long) s.nblocks * (s.rank + 1)) / s.nranks);
+    const int myBlocks = b1 - b0;
+    int perSet = (s.n + kTile - 1) / kTile + 1;
+    int stride = s.tileStride > 0 ? s.tileStride : std::min(s.nsets * perSet, 96);
+    for (int attempt = 0; attempt < 6; attempt++) {
+        s.tileStride = stride;
+        const size_t ntl = (size_t) s.nblocks * stride;
+        s.itemCap = (size_t) std::max(1, myBlocks) * ((size_t) stride / kItemTiles + s.nsets + 1);
+        if (!s.tileJ.ensure(ntl * kTile) || !s.tileMask.ensure(ntl * kTile) || !s.items.ensure(s.itemCap) || !s.setPairs.ensure((size_t) s.nsets)) return false;
+        NBB_CUDA(cudaMemsetAsync(s.setPairs.p, 0, sizeof(unsigned long long) * s.nsets, s.stream));
+        NBB_CUDA(cudaMemsetAsync(&s.counters->itemCount, 0, sizeof(unsigned int) * 4, s.stream));   // itemCount, tileTotal, maxTilesBlock, overflow
+        if (myBlocks > 0) {
+            TileArgs A;
+            A.n = s.n; A.nblocks = s.nblocks; A.nsets = s.nsets; A.firstBlock = b0; A.selfEnabled = selfEnabled ? 1 : 0;
+            A.cutoff = s.list; A.cutoff2 = s.list * s.list;
+            A.grid = s.grid;
+            A.sX = s.sX.p; A.sAtom = s.sAtom.p; A.invPerm = s.invPerm.p; A.cellStart = s.cellStart.p; A.blockBox = s.blockBox.p;
+            A.imageBoxes = s.imageBoxes.p; A.exclPtr = s.exclPtr.p; A.exclCol = s.exclCol.p;
+            A.tileStride = stride; A.tileJ = s.tileJ.p; A.tileMask = s.tileMask.p;
+            A.items = s.items.p; A.itemCap = (unsigned int) s.itemCap; A.setPairs = s.setPairs.p; A.counters = s.counters;
+            k_build_tiles<<<myBlocks, kBuildThreads, 0, s.stream>>>(A);
+            s.launches += 1;
+        }
+        NBB_CUDA(cudaMemcpyAsync(&s.hostCounters, s.counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, s.stream));
+        NBB_CUDA(cudaStreamSynchronize(s.stream));
+        if (!cuda_ok(cudaGetLastError(), "k_build_tiles")) return false;
+        if ((s.hostCounters.overflow & 6u) == 0u) return true;
+        stride = std::max(stride * 2, (int) s.hostCounters.maxTilesBlock + 8);
+    }
+    set_error("tile capacity exceeded after retries");
+    return false;
+}
+
+bool build_lists(State &s)
+{
+    const int n = s.n;
+    const int ntr = s.trans.n;
+    // 1. base operations and bounding boxes -> image plan (host logic, symmetry_host.cpp)
+    std::vector<double> ops((size_t) 12 * std::max(1, ntr));
+    std::vector<RealSpaceOp> base(ntr);
+    for (int t = 0; t < ntr; t++) {
+        base[t] = orthogonalize(s.trans.rot[t], &s.trans.trans[3 * t], s.lattice);
+        std::memcpy(&ops[12 * t], base[t].R.v, sizeof(double) * 9);
+        std::memcpy(&ops[12 * t + 9], base[t].tv, sizeof(double) * 3);
+    }
+    if (!s.baseOpsDev.ensure(ops.size())) return false;
+    NBB_CUDA(cudaMemcpyAsync(s.baseOpsDev.p, ops.data(), sizeof(double) * ops.size(), cudaMemcpyHostToDevice, s.stream));
+    std::vector<double> bmin(3 * (1 + ntr)), bext(3 * (1 + ntr));
+    if (!device_bbox(s, 1 + ntr, bmin.data(), bext.data())) return false;
+    if (ntr > 0) plan_images(s.trans, s.lattice, s.list, s.checkForInverses, s.expandFactor, bmin.data(), bext.data(), s.plan);
+    else {
+        s.plan = ImagePlan();
+        for (int d = 0; d < 3; d++) { s.plan.lower[d] = bmin[d] - s.list; s.plan.upper[d] = (bext[d] + bmin[d]) + s.list; }
+    }
+    const int nimg = (int) s.plan.images.size(), nvis = (int) s.plan.visits.size();
+    s.nsets = 1 + nimg;
+    s.imagePairs.assign(nimg, -1); s.primaryPairs = -1; s.pairCountsValid = false; s.pairsExpanded = false;
+
+    // 2. grid over the search box, per-image list-time boxes, visits
+    const double margin = 1.0e-6;
+    double lo[3], hi[3];
+    for (int d = 0; d < 3; d++) { lo[d] = s.plan.lower[d] - margin; hi[d] = s.plan.upper[d] + margin; }
+    setup_grid(s, lo, hi);
+    std::vector<ImageBoxDev> boxes(s.nsets);
+    std::memset(boxes.data(), 0, sizeof(ImageBoxDev) * boxes.size());
+    for (int k = 0; k < nimg; k++) for (int d = 0; d < 3; d++) { boxes[1 + k].lo[d] = s.plan.images[k].lo[d]; boxes[1 + k].hi[d] = s.plan.images[k].hi[d]; }
+    std::vector<double> vdisp((size_t) 3 * std::max(1, nvis));
+    std::vector<int> vinfo((size_t) 2 * std::max(1, nvis));
+    for (int v = 0; v < nvis; v++) {
+        for (int d = 0; d < 3; d++) vdisp[3 * v + d] = s.plan.visits[v].disp[d];
+        vinfo[2 * v] = s.plan.visits[v].t; vinfo[2 * v + 1] = s.plan.visits[v].image;
+    }
+    if (!s.imageBoxes.ensure(boxes.size()) || !s.visitDisp.ensure(vdisp.size()) || !s.visitInfo.ensure(vinfo.size())) return false;
+    NBB_CUDA(cudaMemcpyAsync(s.imageBoxes.p, boxes.data(), sizeof(ImageBoxDev) * boxes.size(), cudaMemcpyHostToDevice, s.stream));
+    NBB_CUDA(cudaMemcpyAsync(s.visitDisp.p, vdisp.data(), sizeof(double) * vdisp.size(), cudaMemcpyHostToDevice, s.stream));
+    NBB_CUDA(cudaMemcpyAsync(s.visitInfo.p, vinfo.data(), sizeof(int) * vinfo.size(), cudaMemcpyHostToDevice, s.stream));
+
+    // 3. extended-atom capacity: image atoms inside the search box.  Upper bound from the box overlap volumes.
+    double need = 0.0;
+    for (int k = 0; k < nimg; k++) {
+        double frac = 1.0;
+        for (int d = 0; d < 3; d++) {
+            const double il = s.plan.images[k].lo[d], iu = s.plan.images[k].hi[d];
+            const double ov = std::min(iu, hi[d]) - std::max(il, lo[d]);
+            const double len = std::max(iu - il, 1.0e-9);
+            frac *= std::min(1.0, std::max(0.0, ov + 2.0) / len);           // +2 A slack for density fluctuations
+        }
+        need += frac * n;
+    }
+    unsigned int extCap = (unsigned int) std::min((double) nimg * n, need * 1.25 + 1024.0);
+    if (n <= 65536) extCap = (unsigned int) ((size_t) nimg * n);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const size_t neMax = (size_t) n + extCap;
+        const int nkeys = s.nsets * s.grid.ncell;
+        if (!s.eX.ensure(3 * neMax) || !s.eAtom.ensure(neMax) || !s.eSet.ensure(neMax) || !s.eKey.ensure(neMax) || !s.eSortBuf.ensure(neMax) ||
+            !s.cellFill.ensure((size_t) nkeys + 2)) return false;
+        NBB_CUDA(cudaMemsetAsync(s.cellFill.p, 0, sizeof(unsigned int) * ((size_t) nkeys + 2), s.stream));
+        NBB_CUDA(cudaMemsetAsync(s.counters, 0, sizeof(DeviceCounters), s.stream));
+        ExtendArgs E;
+        E.x = s.xcur; E.n = n; E.baseOps = s.baseOpsDev.p; E.visitDisp = s.visitDisp.p; E.visitInfo = s.visitInfo.p; E.nvisits = nvis;
+        for (int d = 0; d < 3; d++) { E.boxLo[d] = lo[d]; E.boxHi[d] = hi[d]; }
+        E.grid = s.grid;
+        E.eX = s.eX.p; E.eAtom = s.eAtom.p; E.eSet = s.eSet.p; E.eKey = s.eKey.p; E.eSort = s.eSortBuf.p;
+        E.cellCount = s.cellFill.p; E.extCap = extCap; E.counters = s.counters;
+        k_extend<<<(n + 127) / 128, 128, 0, s.stream>>>(E);
+        s.launches += 1;
+        s.extCap = extCap;
+        if (sort_and_tile(s, true, extCap)) return true;
+        if (!(s.hostCounters.overflow & 1u)) return false;
+        extCap = (unsigned int) ((size_t) nimg * n);                       // exact worst case, retry once
+    }
+    return false;
+}
+
+// stand-alone generators (PairListGenerator_* entry points): sets are given coordinate arrays, no symmetry
+bool build_lists_standalone(State &s, const double *d_x2, int n2)
+{
+    const int n = s.n;
+    std::vector<double> bmin(3), bext(3);
+    if (!s.baseOpsDev.ensure(12)) return false;
+    if (!device_bbox(s, 1, bmin.data(), bext.data())) return false;
+    s.plan = ImagePlan();
+    double lo[3], hi[3];
+    for (int d = 0; d < 3; d++) { lo[d] = bmin[d] - s.list - 1.0e-6; hi[d] = (bext[d] + bmin[d]) + s.list + 1.0e-6; s.plan.lower[d] = lo[d]; s.plan.upper[d] = hi[d]; }
+    s.nsets = d_x2 ? 2 : 1;
+    s.imagePairs.assign(s.nsets - 1, -1); s.primaryPairs = -1; s.pairCountsValid = false; s.pairsExpanded = false;
+    setup_grid(s, lo, hi);
+    std::vector<ImageBoxDev> boxes(s.nsets);
+    for (auto &bx : boxes) for (int d = 0; d < 3; d++) { bx.lo[d] = -1.0e300; bx.hi[d] = 1.0e300; }
+    if (!s.imageBoxes.ensure(boxes.size())) return false;
+    NBB_CUDA(cudaMemcpyAsync(s.imageBoxes.p, boxes.data(), sizeof(ImageBoxDev) * boxes.size(), cudaMemcpyHostToDevice, s.stream));
+    const unsigned int extCap = d_x2 ? (unsigned int) n2 : 0u;
+    const size_t neMax = (size_t) n + extCap;
+    const int nkeys = s.nsets * s.grid.ncell;
+    if (!s.eX.ensure(3 * neMax) || !s.eAtom.ensure(neMax) || !s.eSet.ensure(neMax) || !s.eKey.ensure(neMax) || !s.eSortBuf.ensure(neMax) ||
+        !s.cellFill.ensure((size_t) nkeys + 2) || !s.visitDisp.ensure(3) || !s.visitInfo.ensure(2)) return false;
+    NBB_CUDA(cudaMemsetAsync(s.cellFill.p, 0, sizeof(unsigned int) * ((size_t) nkeys + 2), s.stream));
+    NBB_CUDA(cudaMemsetAsync(s.counters, 0, sizeof(DeviceCounters), s.stream));
+    ExtendArgs E;
+    E.x = s.xcur; E.n = n; E.baseOps = s.baseOpsDev.p; E.visitDisp = s.visitDisp.p; E.visitInfo = s.visitInfo.p; E.nvisits = 0;
+    for (int d = 0; d < 3; d++) { E.boxLo[d] = lo[d]; E.boxHi[d] = hi[d]; }
+    E.grid = s.grid;
+    E.eX = s.eX.p; E.eAtom = s.eAtom.p; E.eSet = s.eSet.p; E.eKey = s.eKey.p; E.eSort = s.eSortBuf.p;
+    E.cellCount = s.cellFill.p; E.extCap = extCap; E.counters = s.counters;
+    k_extend<<<(n + 127) / 128, 128, 0, s.stream>>>(E);
+    s.launches += 1;
+    if (d_x2) {
+        k_extend_cross<<<(n2 + 127) / 128, 128, 0, s.stream>>>(d_x2, n2, n, s.grid, make_double3(lo[0], lo[1], lo[2]), make_double3(hi[0], hi[1], hi[2]), s.eX.p, s.eAtom.p, s.eSet.p, s.eKey.p, s.eSortBuf.p, s.cellFill.p, s.counters);
+        s.launches += 1;
+    }
+    s.extCap = extCap;
+    return sort_and_tile(s, d_x2 == nullptr, extCap);
+}
+
+}  // namespace nbb200

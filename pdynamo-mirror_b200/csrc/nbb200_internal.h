@@ -1,0 +1,174 @@
+// nbb200_internal.h -- internal declarations of libnbabfs_b200.so (not installed; the public ABI is include/nbabfs_b200.h)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "symmetry_host.h"
+
+namespace nbb200 {
+
+constexpr int kTile = 32;            // atoms per i-block and j slots per tile (one warp)
+constexpr int kItemTiles = 8;        // max tiles per work item (i-block state is amortised over them)
+constexpr int kBuildThreads = 128;   // CTA size of the tile builder
+
+void set_error(const std::string &msg);
+bool cuda_ok(cudaError_t e, const char *what);
+#define NBB_CUDA(call) do { if (!::nbb200::cuda_ok((call), #call)) return false; } while (0)
+
+// growable device buffer (never shrinks); plain cudaMalloc: sizes are O(N) or O(tiles), allocated at rebuilds only
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    bool ensure(size_t count)
+    {
+        if (count <= cap) return true;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = count + count / 8 + 64;
+        if (!cuda_ok(cudaMalloc((void **) &p, want * sizeof(T)), "cudaMalloc")) return false;
+        cap = want;
+        return true;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// ABFS constants in fp32 for the tile kernel (derived from the 21 fp64 factors)
+struct AbfsF32 {
+    float r2Damp, r2On, r2Off;
+    float a, b, c, d, c3, d5, qShift1, qShift2, qF0, qAlpha;
+    float aF6, aK12, aShift12, aF0, aAlpha, bF3, bK6, bShift6, bF0, bAlpha;
+};
+
+// per image, energy-time real-space operation x' = R x + tv, scale, flags (device copy, fp64)
+struct ImageOpDev {
+    double R[9];
+    double tv[3];
+    double scale;
+    int pureTranslation;
+    int pad;
+};
+
+// per image, list-time data for the tile builder
+struct ImageBoxDev {
+    double lo[3], hi[3];
+};
+
+struct WorkItem { int block, image, tileStart, tileCount; };
+
+// counters living in device memory (one allocation)
+struct DeviceCounters {
+    unsigned int extCount;       // extended (halo) atoms appended after the n primary ones
+    unsigned int itemCount;      // work items
+    unsigned int tileTotal;      // tiles emitted
+    unsigned int maxTilesBlock;  // largest tile count of any i-block (capacity check)
+    unsigned int overflow;       // bit0: extended capacity, bit1: tile capacity, bit2: item capacity
+    unsigned int workCursor;     // dynamic work distribution of the force kernel
+    unsigned int pad[2];
+};
+
+struct BuildGrid {
+    double lo[3];
+    double h, invh;
+    int dim[3];
+    int ncell;
+};
+
+struct State;
+
+// ---- list_build.cu
+bool build_lists_standalone(State &s, const double *d_x2, int n2);
+bool build_lists(State &s);                              // everything between "coordinates on device" and "tiles + items ready"
+bool expand_pairs(State &s);                             // explicit (i,j) pairs per list from the tile masks
+bool device_bbox(State &s, int nops, double *hostMin, double *hostExt);
+bool displacement_check(State &s, double buffacsq, double *maxr2, int *exceeded);
+
+// ---- force_kernels.cu
+bool launch_forces(State &s, double *d_grad);
+void init_force_kernel_attributes();
+
+struct State {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    bool timing = false;
+    long launches = 0;
+
+    // topology / parameters
+    int n = 0, ntypes = 0, ntypes14 = 0, nexcl = 0, n14 = 0;
+    DevBuf<float> q32;
+    DevBuf<double> q64;
+    DevBuf<int> ljtype;
+    DevBuf<float2> ljAB;            // [nt*nt] (A, B) expanded table, fp32
+    DevBuf<double2> ljAB14;         // [nt14*nt14] fp64 for the 1-4 kernel
+    DevBuf<int> exclPtr, exclCol;   // symmetric CSR
+    DevBuf<int2> pairs14;
+    Transformations trans;
+
+    // options (NBModelABFS / PairwiseInteractionABFS)
+    double damp = 0.5, inner = 8.0, outer = 12.0, list = 13.5, dielectric = 1.0, scale14 = 1.0;
+    bool checkForInverses = true;
+    int expandFactor = 0;
+    double factors[21];
+
+    // reference-state bookkeeping (NBModelABFSState)
+    bool isNew = true;
+    double stListCutoff = 0.0, stOuterCutoff = 0.0;
+    Lattice lattice, refLattice;
+    bool haveRefLattice = false;
+    long numberOfCalls = 0, numberOfUpdates = 0;
+
+    // coordinates
+    DevBuf<double> x, xref, grad;
+    const double *xcur = nullptr;   // coordinates of the current call (s.x.p or a caller-owned device array)
+    double *hx = nullptr, *hgrad = nullptr;      // pinned staging
+    double *hsmall = nullptr;                    // pinned small results
+    size_t hcap = 0;
+
+    // image plan of the current lists
+    ImagePlan plan;
+    std::vector<long> imagePairs;                // per candidate image (list pairs), -1 = not fetched yet
+    long primaryPairs = -1;
+    bool pairCountsValid = false;
+    DevBuf<ImageOpDev> imageOps;                 // [1 + nimages], slot 0 = identity (primary)
+    DevBuf<ImageBoxDev> imageBoxes;
+    DevBuf<double> baseOpsDev;                   // per transformation 12 doubles
+    DevBuf<double> visitDisp;                    // per visit 3 doubles
+    DevBuf<int> visitInfo;                       // per visit: t, image
+    DevBuf<double> bboxDev;                      // reduction output
+
+    // extended atoms and the sort
+    BuildGrid grid;
+    int nsets = 1;                               // 1 + candidate images
+    size_t extCap = 0;
+    DevBuf<double> eX;  DevBuf<int> eAtom; DevBuf<int> eSet; DevBuf<int> eKey; DevBuf<unsigned long long> eSortBuf;
+    DevBuf<unsigned int> cellStart, cellFill, scanTmp;
+    DevBuf<int> order;
+    DevBuf<double> sX; DevBuf<int> sAtom; DevBuf<int> invPerm;
+    int nblocks = 0;
+    DevBuf<double> blockBox;                     // per block: min[3], max[3], center[3]
+    // tiles
+    int tileStride = 0;
+    DevBuf<int> tileJ; DevBuf<unsigned int> tileMask;
+    DevBuf<WorkItem> items; size_t itemCap = 0;
+    DevBuf<unsigned long long> setPairs;         // per set list-pair counts
+    DeviceCounters *counters = nullptr;
+    DeviceCounters hostCounters{};
+    // accumulators of the force kernels: per set 16 doubles {eq, elj, G[3], W[9], pad}; slot nsets = 1-4 terms
+    DevBuf<double> accum;
+    // explicit pairs
+    DevBuf<int> pairBuf; DevBuf<unsigned long long> pairCursor;
+    std::vector<unsigned long long> pairOffsets;
+    bool pairsExpanded = false;
+
+    // partition over ranks
+    int rank = 0, nranks = 1;
+
+    // timing
+    cudaEvent_t ev[12] = {};
+    double timings[8] = {};
+    bool haveEvents = false;
+};
+
+}  // namespace nbb200
