@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- NBModelABFS MM/MM hot path on B200: list rebuild + energy + gradients per step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload m1|jac|...] [--impl b200|reference]
+
+A "step" is one NBModelABFS call on a synthetic replicated water (/protein) box with a FORCED pair-list rebuild
+followed by the energy + gradient evaluation (BASELINE.json config 3: "pair-list rebuild + E+grad per call"); the
+no-rebuild call is timed separately and reported in `no_rebuild`.  The metric is list-pair interactions per second
+(a list pair = one (i, j[, image]) entry of the reference's lists at listCutoff = 13.5 A).
+
+N = 1 : one process.  N > 1 : launched under torchrun; the i-blocks are split over the ranks (spatial slabs of the
+cell-sorted atoms), every rank rebuilds and evaluates its slab, energies and gradients are all-reduced with NCCL.
+Total work is fixed as N grows -> "scaling": "strong".
+
+`value`  : whole-job list pairs / s with coordinates resident in HBM, timed with CUDA events on the launching stream,
+           max over ranks.
+`e2e`    : the same metric through the plugin surface (System.Energy(doGradients=True) -> NBModelABFS.SetUp/Energy ->
+           C-ABI) with HOST numpy coordinates in and host gradients out (N = 1).
+`roofline`: the tile force kernel against the FP32 (non-tensor) pipe: 42.75 algorithmic flop per list pair.
+`cpu_baseline`: the compiled reference C code (oracle/_ref, OpenMP build) on this box's host cores on a bounded sample.
+`--impl reference` times the reference's own CPU implementation instead (rank 0 only).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+FLOP_PER_LIST_PAIR = 42.75          # 42 / 64 / 8 flop for r <= 8 / 8-12 / 12-13.5 A at uniform density
+SM_COUNT, FP32_LANES = 148, 128
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            text, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in text.strip().split("\n"):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def make_workload(name):
+    import pdynamo_mirror_b200 as p
+    return p.workloads.WORKLOADS[name]()
+
+
+def workload_description(name, w):
+    return "%s: %d atoms, P1 box %s, TIP3P%s, ABFS 0.5/8/12/13.5 A" % (
+        name, w["n"], "x".join("%.2f" % v for v in w["box"][:3]), "" if w["ntypes"] <= 2 else " + %d-type heteropolymer" % w["ntypes"])
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the compiled, unmodified reference C code (oracle/_ref) on the host cores
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference(sample_name, steps, warmup):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refnb
+    omp = refnb.available(omp=True)
+    kind = "reference"
+    if not refnb.available(omp=omp):
+        import oracle
+        w = make_workload(sample_name)
+        model, kind, cores = oracle.OracleNB(w), "port", 1
+    else:
+        w = make_workload(sample_name)
+        model = refnb.RefNB(w, omp=omp)
+        cores = model.num_threads() if omp else 1
+    times, upd, ene, pairs = [], [], [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = model.energy(force_new=True)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt); upd.append(out["t_update"]); ene.append(out["t_energy"])
+    c = model.counts()
+    pairs = c["primary"] + c["image_pairs"]
+    best = min(times)
+    return dict(value=pairs / best, unit="list-pairs/s", cores=cores, kind=kind,
+                sample="%s (%d atoms, %d list pairs): forced list rebuild + E+grad per step, best of %d after %d warm-up; "
+                       "rebuild %.3f s (serial in the reference), E+grad %.3f s" % (sample_name, w["n"], pairs, steps, warmup, min(upd), min(ene)),
+                ms_per_step=1e3 * best, pairs=pairs, n=w["n"], ms_rebuild=1e3 * min(upd), ms_energy=1e3 * min(ene)), w
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = args.ref_sample
+    base, w = cpu_reference(sample, max(1, args.steps), max(0, min(args.warmup, 1)))
+    wl = args.workload
+    line = {"metric": "NBModelABFS list-pair interactions per second (pair-list rebuild + energy + gradients per call)",
+            "value": base["value"], "unit": "list-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": wl, "sample": sample, "note": "reference CPU implementation timed on a bounded sample of the workload"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "list-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------------------
+class DeviceModel:
+    """Thin driver of the C-ABI with device-resident coordinates / gradients (torch tensors)."""
+
+    def __init__(self, w, device, rank=0, nranks=1):
+        import torch
+        import pdynamo_mirror_b200 as p
+        from pdynamo_mirror_b200 import _lib
+        self.torch, self.L, self._lib = torch, _lib.lib(), _lib
+        self.w, self.n = w, w["n"]
+        sysm = p.System.FromWorkload(w)
+        self.model = p.NBModelABFS(device=device)
+        sysm.DefineNBModel(self.model)
+        self.system = sysm
+        # create the state through the plugin surface (one host call), then drive it with device pointers
+        sysm.Energy(doGradients=False)
+        self.state = sysm.configuration.nbState
+        self.h = self.state.cObject
+        self.L.nbb200_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self.L.nbb200_enable_timing(self.h, 1)
+        if nranks > 1:
+            self.L.nbb200_set_partition(self.h, rank, nranks)
+        self.x = torch.from_numpy(w["xyz"]).to("cuda:%d" % device)
+        self.g = torch.zeros_like(self.x)
+        self.box = np.ascontiguousarray(w["box"], np.float64)
+        self.e = np.zeros(6)
+        self.dEdM = np.zeros(9)
+
+    def step(self, rebuild=True, zero=True):
+        st = C.c_int(16)
+        if zero:
+            self.g.zero_()
+        self.L.NBModelABFS_B200_UpdateDevice(self.h, C.c_void_p(self.x.data_ptr()), self._lib.d_(self.box), 1 if rebuild else 0, C.byref(st))
+        self.L.NBModelABFS_B200_MMMMEnergyDevice(self.h, self._lib.d_(self.e), C.c_void_p(self.g.data_ptr()), self._lib.d_(self.dEdM), C.byref(st))
+        if st.value != 16:
+            raise RuntimeError("device step failed: " + self._lib.last_error())
+
+
+def timed_steps(torch, fn, steps, warmup, barrier):
+    for _ in range(warmup):
+        fn()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1) / steps          # ms per step
+
+
+def run_b200(args):
+    import torch
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def allmax(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    pk, pk_kind = peaks()
+    t0 = time.time()
+    w = make_workload(args.workload)
+    m = DeviceModel(w, local, rank, world)
+    esum = torch.zeros(15, dtype=torch.float64, device="cuda")
+
+    def step_rebuild():
+        m.step(rebuild=True)
+        if dist is not None:                       # the path's one exchange step: gradient + energy/dEdM reduction
+            dist.all_reduce(m.g)
+            esum[:6] = torch.from_numpy(m.e).to(esum.device); esum[6:] = torch.from_numpy(m.dEdM).to(esum.device)
+            dist.all_reduce(esum)
+
+    def step_norebuild():
+        m.step(rebuild=False)
+        if dist is not None:
+            dist.all_reduce(m.g)
+            dist.all_reduce(esum)
+
+    step_rebuild()
+    torch.cuda.synchronize()
+    counters = m.state.Counters()
+    pairs_local = counters["listPairs"]
+    pairs = int(round(allsum(float(pairs_local))))
+    log("[bench] rank %d: setup %.1fs, %d atoms, %d list pairs (local %d), %d tiles" % (rank, time.time() - t0, w["n"], pairs, pairs_local, counters["tiles"]))
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = m.state.Counters()["kernelLaunches"]
+    ms = allmax(timed_steps(torch, step_rebuild, args.steps, args.warmup, barrier))
+    launches = (m.state.Counters()["kernelLaunches"] - launches0) / float(args.steps + args.warmup)
+    # per-kernel device times of the last rebuild step (library events on the same stream)
+    tm = m.state.Timings()
+    # average the force-kernel time over a few more rebuild steps, live
+    fk, lb = [], []
+    for _ in range(max(3, min(args.steps, 10))):
+        step_rebuild(); t = m.state.Timings(); fk.append(t["tileForces"]); lb.append(t["listRebuild"])
+    ms_nr = allmax(timed_steps(torch, step_norebuild, args.steps, args.warmup, barrier))
+    clocks = sampler.stop() if sampler is not None else None
+    force_ms, build_ms = allmax(statistics.mean(fk)), allmax(statistics.mean(lb))
+
+    value = pairs / (ms * 1e-3)
+    sm_max = float(pk.get("sm_max_mhz", 1965.0))
+    fp32_peak_tflops = SM_COUNT * FP32_LANES * 2 * sm_max * 1e6 / 1e12
+    achieved_tflops = (pairs / world) * FLOP_PER_LIST_PAIR / (force_ms * 1e-3) / 1e12 if force_ms > 0 else 0.0
+    n, nimg = w["n"], counters["images"]
+    nexcl = len(w["exclusions"])
+    list_bytes = 24.0 * n * (1 + nimg) + 4.0 * (n + 1) + 8.0 * nexcl + 4.0 * pairs + 4.0 * (n + 1) * (1 + nimg)
+    line = {
+        "metric": "NBModelABFS list-pair interactions per second (pair-list rebuild + energy + gradients per call)",
+        "value": value, "unit": "list-pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 pair math, f64 accumulation and list predicate",
+        "data": "synthetic",
+        "config": {"workload": workload_description(args.workload, w), "list_pairs": pairs, "step": "forced list rebuild + E + gradients",
+                   "l2": "inputs (coordinates + tile lists, %.0f MB) %s L2; timed iterations run back to back" %
+                         ((counters["tiles"] * 256 + 48 * n) / 1e6, "exceed" if counters["tiles"] * 256 + 48 * n > 126e6 else "fit in"),
+                   "parallelism": "i-block slabs over %d rank(s), NCCL all-reduce of gradients/energies" % world},
+        "no_rebuild": {"ms_per_call": ms_nr, "value": pairs / (ms_nr * 1e-3), "unit": "list-pairs/s"},
+        "kernels_ms": {"list_rebuild": build_ms, "tile_forces": force_ms, "pairs14": tm["pairs14"], "displacement_check": tm["displacementCheck"]},
+        "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
+                     "traffic": None, "kernel": "k_tile_forces", "flop_per_list_pair": FLOP_PER_LIST_PAIR,
+                     "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (sm_max_mhz, %s); MEASURED_PEAKS.json holds no FP32 figure" % (sm_max, pk_kind)},
+        "roofline_list_build": {"bound": "hbm", "achieved": list_bytes / world / (build_ms * 1e-3) / 1e9 if build_ms > 0 else 0.0, "peak": float(pk.get("hbm_gbs", 6650.0)),
+                                "unit": "GB/s", "frac": (list_bytes / world / (build_ms * 1e-3) / 1e9) / float(pk.get("hbm_gbs", 6650.0)) if build_ms > 0 else 0.0,
+                                "algorithmic_bytes": list_bytes, "note": "all rebuild kernels together; bytes = SURVEY.md 8d atom-pair-equivalent figure"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "energies": [float(v) for v in (esum[:6].cpu().numpy() if dist is not None else m.e)],
+    }
+    if world == 1:
+        # end to end through the plugin surface with host arrays (H2D of coordinates, D2H of gradients inside the timed region)
+        sysm = m.system
+        sysm.configuration.nbState = m.state
+        m.L.nbb200_set_stream(m.h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        m.model.SetOptions(updateFrequency=1)
+
+        def e2e_step():
+            sysm.Energy(doGradients=True)
+
+        for _ in range(args.warmup):
+            e2e_step()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t1) / args.steps * 1e3
+        line["e2e"] = {"value": pairs / (e2e_ms * 1e-3), "unit": "list-pairs/s", "ms_per_step": e2e_ms,
+                       "h2d_bytes_per_step": 24 * n + 48, "d2h_bytes_per_step": 24 * n + 16 * 8 * (nimg + 2),
+                       "api": "System.Energy(doGradients=True) -> NBModelABFS.SetUp/Energy -> NBModelABFS_B200_Update/_MMMMEnergy, host numpy in/out, wall clock"}
+        m.model.SetOptions(updateFrequency=0)
+        if rank == 0 and not args.no_cpu:
+            try:
+                base, _ = cpu_reference(args.ref_sample, 3, 1)
+                line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as exc:      # the baseline is reported, never required
+                line["cpu_baseline"] = {"value": None, "unit": "list-pairs/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (exc,)}
+        if args.workload != "jac" and not args.no_jac:
+            try:
+                line["jac"] = jac_block(torch, local, fp32_peak_tflops)
+            except Exception as exc:
+                line["jac"] = {"error": repr(exc)}
+    else:
+        line["e2e"] = {"value": value, "unit": "list-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                       "note": "multi-rank runs keep coordinates and gradients device-resident; the host end-to-end path is measured at N=1"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def jac_block(torch, local, fp32_peak_tflops):
+    """The 23 558-atom JAC-size box (north-star target size) on one GPU: ms per call with and without rebuild."""
+    w = make_workload("jac")
+    m = DeviceModel(w, local)
+    m.step(rebuild=True)
+    torch.cuda.synchronize()
+    pairs = m.state.Counters()["listPairs"]
+    ms = timed_steps(torch, lambda: m.step(rebuild=True), 20, 5, lambda: None)
+    fk, lb = [], []
+    for _ in range(10):
+        m.step(rebuild=True); t = m.state.Timings(); fk.append(t["tileForces"]); lb.append(t["listRebuild"])
+    ms_nr = timed_steps(torch, lambda: m.step(rebuild=False), 50, 5, lambda: None)
+    f = statistics.mean(fk)
+    ach = pairs * FLOP_PER_LIST_PAIR / (f * 1e-3) / 1e12
+    return {"workload": workload_description("jac", w), "list_pairs": pairs, "ms_per_call_rebuild": ms, "ms_per_call_no_rebuild": ms_nr,
+            "value": pairs / (ms * 1e-3), "value_no_rebuild": pairs / (ms_nr * 1e-3), "unit": "list-pairs/s",
+            "kernels_ms": {"list_rebuild": statistics.mean(lb), "tile_forces": f}, "roofline_frac_fp32": ach / fp32_peak_tflops}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="m1")
+    ap.add_argument("--ref-sample", default="jac", help="bounded CPU sample of the workload for the reference / cpu_baseline legs")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-jac", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -43,15 +43,20 @@ __device__ __forceinline__ void abfs_pair(const AbfsF32 &F, float r2, float qij,
     const float s2 = s * s;
     float dFq, dFl;
     if (r2 > F.r2On) {                                            // switching region
-        const float P = fmaf(-r2, fmaf(fmaf(F.d, r2, F.c), r2, F.b), F.a);
-        const float Q = fmaf(r2, fmaf(fmaf(F.d5, r2, F.c3), r2, F.b), F.a);
-        eq  = qij * fmaf(s, P, F.qShift2);
+        // Coulomb: E = qij (a/r - b r - c r^3 - d r^5 + qShift2) has a triple zero at r = rOff; evaluating it as written
+        // cancels ~200:1 in fp32.  Factored form: E = qij t^3 C(t) / r, t = rOff - r (C cubic, coefficients from the host).
+        const float r = r2 * s, t = F.rOff - r;
+        const float C = fmaf(fmaf(fmaf(F.n6, t, F.n5), t, F.n4), t, F.n3);
+        eq  = qij * (t * t) * (t * C) * s;
+        // switch function S = u^2 (k1 - k2 u), u = rOff^2 - r^2 (same polynomial as a + b r^2 + 3c r^4 + 5d r^6, no cancellation)
+        const float u = F.r2Off - r2;
+        const float Q = u * u * fmaf(-F.k2, u, F.k1);
         dFq = -0.5f * qij * s * Q * s2;
         const float s6 = s2 * s2 * s2;
         const float l1 = s6 - F.aF6, l2 = fmaf(s, s2, -F.bF3);
         const float Ak = A * F.aK12, Bk = B * F.bK6;
         elj = Ak * l1 * l1 - Bk * l2 * l2;
-        dFl = -3.0f * s6 * (2.0f * Ak * l1 * s2 - Bk * l2 * (r2 * s));
+        dFl = -3.0f * s6 * (2.0f * Ak * l1 * s2 - Bk * l2 * r);
     } else if (r2 >= F.r2Damp) {                                  // plain shifted region
         eq  = qij * (s + F.qShift1);
         dFq = -0.5f * qij * s * s2;
@@ -145,6 +150,7 @@ __global__ void __launch_bounds__(kForceThreads) k_tile_forces(ForceArgs A)
                 float e1, e2, f2;
                 abfs_pair(F, r2, qij, Aij, Bij, e1, e2, f2);
                 eq += e1; el += e2;
+                if ((k & 3) == 3) { eQ += (double) eq; eL += (double) el; eq = 0.f; el = 0.f; }   // fp32 partial sums stay short
                 const float gx = f2 * dx, gy = f2 * dy, gz = f2 * dz;
                 fxi += gx; fyi += gy; fzi += gz;
                 fxj -= gx; fyj -= gy; fzj -= gz;
@@ -157,7 +163,6 @@ __global__ void __launch_bounds__(kForceThreads) k_tile_forces(ForceArgs A)
             }
             // after 32 hand-overs the accumulator of j slot `lane` is back in this lane
             fix += (double) fxi; fiy += (double) fyi; fiz += (double) fzi;
-            eQ += (double) eq; eL += (double) el;
             if (aj >= 0) {
                 const double sc = op->scale;
                 double gx = sc * (double) fxj, gy = sc * (double) fyj, gz = sc * (double) fzj;       // gradient on the (image) atom
@@ -278,6 +283,16 @@ bool launch_forces(State &s, double *d_grad)
         F.qShift1 = (float) f[7]; F.qShift2 = (float) f[8]; F.qF0 = (float) f[9]; F.qAlpha = (float) f[10];
         F.aF6 = (float) f[11]; F.aK12 = (float) f[12]; F.aShift12 = (float) f[13]; F.aF0 = (float) f[14]; F.aAlpha = (float) f[15];
         F.bF3 = (float) f[16]; F.bK6 = (float) f[17]; F.bShift6 = (float) f[18]; F.bF0 = (float) f[19]; F.bAlpha = (float) f[20];
+        {   // factored switching forms (see abfs_pair)
+            const double ro = s.outer, c = f[5], d = f[6], gam = (f[2] - f[1]) * (f[2] - f[1]) * (f[2] - f[1]);
+            F.rOff = (float) ro;
+            F.n3 = (float) (4.0 * c * ro + 20.0 * d * ro * ro * ro);
+            F.n4 = (float) (-c - 15.0 * d * ro * ro);
+            F.n5 = (float) (6.0 * d * ro);
+            F.n6 = (float) (-d);
+            F.k1 = (float) (3.0 * (f[2] - f[1]) / gam);
+            F.k2 = (float) (2.0 / gam);
+        }
         A.qScale = (float) eScale;
         A.grad = d_grad; A.accum = s.accum.p;
         const size_t smem = sizeof(float2) * (size_t) s.ntypes * s.ntypes;

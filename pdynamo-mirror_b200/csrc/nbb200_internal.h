@@ -39,6 +39,7 @@ struct AbfsF32 {
     float r2Damp, r2On, r2Off;
     float a, b, c, d, c3, d5, qShift1, qShift2, qF0, qAlpha;
     float aF6, aK12, aShift12, aF0, aAlpha, bF3, bK6, bShift6, bF0, bAlpha;
+    float rOff, n3, n4, n5, n6, k1, k2;   // factored switching forms
 };
 
 // per image, energy-time real-space operation x' = R x + tv, scale, flags (device copy, fp64)

@@ -268,6 +268,116 @@ def solvated_solute(solute_xyz, solute_q, solute_types, solute_eps, solute_rmin,
     return _finish(xyz, charges, ljtypes, eps, rmin, "amber", excl, p14, a, name, scale14=1.0)
 
 
+# ----------------------------------------------------------------------------------------------------
+# systems built from the reference's own equilibrated 216-water box (fixture tests/golden/water216_cubicBox.npz,
+# generated from book/data/mol/water216_cubicBox.mol by tests/golden/make_fixtures.py)
+# ----------------------------------------------------------------------------------------------------
+import os as _os
+
+_GOLDEN = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "tests", "golden")
+
+
+def _load_w216():
+    d = np.load(_os.path.join(_GOLDEN, "water216_cubicBox.npz"))
+    return np.array(d["xyz"], dtype=np.float64), float(d["a"])
+
+
+def water216_real(box=None, name="w216", wrap=False):
+    """Config 1: the shipped, equilibrated box of book Example 20 exactly as stored (molecules have diffused out of the
+    primary cell, so more than the first shell of images is visited).  box: optional [a,b,c,alpha,beta,gamma] override."""
+    xyz, a = _load_w216()
+    nw = xyz.shape[0] // 3
+    if wrap:
+        mol = xyz.reshape(-1, 3, 3)
+        xyz = (mol - np.floor(mol[:, 0:1, :] / a) * a).reshape(-1, 3)
+    return _finish(xyz, np.tile([TIP3P_QO, TIP3P_QH, TIP3P_QH], nw), np.tile([0, 1, 1], nw), [TIP3P_EPS_O, 0.0], [TIP3P_SIG_O, 0.0], "opls",
+                   _water_topology(nw), np.zeros((0, 2), np.int32), a if box is None else box, name, scale14=0.5)
+
+
+def replicated_water_xyz(nx, ny, nz, jitter=0.02, seed=4242):
+    """The equilibrated box wrapped by molecule into [0,a)^3 and replicated nx x ny x nz times, plus a small jitter so
+    that replicas are not exact copies.  Returns (xyz, nwaters, (ax, ay, az))."""
+    xyz, a = _load_w216()
+    mol = xyz.reshape(-1, 3, 3)
+    shift = -np.floor(mol[:, 0:1, :] / a) * a
+    mol = mol + shift
+    reps = []
+    for ix in range(nx):
+        for iy in range(ny):
+            for iz in range(nz):
+                reps.append(mol + np.array([ix, iy, iz], dtype=np.float64) * a)
+    out = np.concatenate(reps).reshape(-1, 3)
+    if jitter > 0.0:
+        u = lcg_uniform(seed, out.size).reshape(out.shape)
+        out = out + (2.0 * u - 1.0) * jitter
+    return out, out.shape[0] // 3, (a * nx, a * ny, a * nz)
+
+
+def replicated_water(nx, ny=None, nz=None, jitter=0.02, name=None):
+    """Config 5 family: nx*ny*nz replicas of the equilibrated 216-water box (12^3 -> 1 119 744 atoms, a = 223.69)."""
+    ny = nx if ny is None else ny
+    nz = nx if nz is None else nz
+    xyz, nw, (ax, ay, az) = replicated_water_xyz(nx, ny, nz, jitter)
+    return _finish(xyz, np.tile([TIP3P_QO, TIP3P_QH, TIP3P_QH], nw), np.tile([0, 1, 1], nw), [TIP3P_EPS_O, 0.0], [TIP3P_SIG_O, 0.0], "opls",
+                   _water_topology(nw), np.zeros((0, 2), np.int32), [ax, ay, az, 90.0, 90.0, 90.0], name or "water%dx%dx%d" % (nx, ny, nz), scale14=0.5)
+
+
+def jac_protein_water(natoms=23558, nchain=2489, ntypes=35, seed=12345):
+    """Config 3: JAC/DHFR-sized system (benchmarks/data/dhfr/systemData.yaml:3-5: 23 558 atoms, 35 LJ types): 3x3x4 replicas
+    of the equilibrated water box (orthorhombic 55.92 x 55.92 x 74.56) with a central sphere of waters replaced by an
+    nchain-atom heteropolymer: ntypes-2 extra LJ types, CHARMM-style arithmetic combination, 1-2/1-3/1-4 exclusions, a 1-4
+    list with its own LJ table, net charge -11 like DHFR."""
+    nwat = (natoms - nchain) // 3
+    if 3 * nwat + nchain != natoms:
+        raise ValueError("natoms - nchain must be a multiple of 3")
+    wxyz, nwfull, (ax, ay, az) = replicated_water_xyz(3, 3, 4)
+    centre = np.array([ax, ay, az]) / 2.0
+    o = wxyz[0::3]
+    d2 = ((o - centre) ** 2).sum(1)
+    order = np.argsort(d2, kind="stable")
+    nremove = nwfull - nwat
+    keep = np.ones(nwfull, dtype=bool)
+    keep[order[:nremove]] = False
+    rcav = np.sqrt(d2[order[nremove - 1]])
+    wxyz = wxyz.reshape(-1, 3, 3)[keep].reshape(-1, 3)
+    cxyz = _snake_in_sphere(centre, rcav - 1.5, 1.85, nchain)
+    u = lcg_uniform(seed + 77, 5 * nchain + 4 * ntypes).reshape(-1)
+    cxyz = cxyz + (2.0 * u[:3 * nchain].reshape(nchain, 3) - 1.0) * 0.12
+    ctype = 2 + np.minimum((u[3 * nchain:4 * nchain] * (ntypes - 2)).astype(np.int32), ntypes - 3)
+    cq = (2.0 * u[4 * nchain:5 * nchain] - 1.0) * 0.55
+    cq += (-11.0 - cq.sum()) / nchain
+    ut = u[5 * nchain:].reshape(ntypes, 4)
+    eps, rmin = np.empty(ntypes), np.empty(ntypes)
+    eps[0], rmin[0] = TIP3P_EPS_O, TIP3P_SIG_O * 2.0 ** (1.0 / 6.0)      # CHARMM TIP3P
+    eps[1], rmin[1] = 0.046 * KCAL, 2 * 0.2245
+    eps[2:] = (0.02 + 0.18 * ut[2:, 0]) * KCAL
+    rmin[2:] = 2.0 * (0.70 + 0.45 * ut[2:, 1])
+    eps14, rmin14 = eps.copy(), rmin.copy()
+    eps14[2:] *= 0.5 + 0.5 * ut[2:, 2]
+    rmin14[2:] *= 0.9 + 0.1 * ut[2:, 3]
+    xyz = np.concatenate([cxyz, wxyz])
+    charges = np.concatenate([cq, np.tile([TIP3P_QO, TIP3P_QH, TIP3P_QH], nwat)])
+    ljtypes = np.concatenate([ctype, np.tile([0, 1, 1], nwat)])
+    cexcl, c14 = _chain_topology(0, nchain)
+    excl = np.concatenate([cexcl, _water_topology(nwat, nchain)])
+    return _finish(xyz, charges, ljtypes, eps, rmin, "amber", excl, c14, [ax, ay, az, 90.0, 90.0, 90.0], "jac%d" % natoms,
+                   eps14=eps14, sigma14=rmin14, scale14=1.0)
+
+
+def bala_water(name="bala_water"):
+    """Config 2: blocked alanine dipeptide (book/data/mol/bala_c7eq.mol via tests/golden/bala_c7eq.npz) in a ~2.1k-atom
+    TIP3P lattice box, CHARMM-style LJ combination.  The solute parameters are a fixed plausible table (parity is judged
+    against the oracle on identical inputs)."""
+    d = np.load(_os.path.join(_GOLDEN, "bala_c7eq.npz"))
+    xyz, sym, bonds = d["xyz"], [str(x) for x in d["symbols"]], d["bonds"]
+    table = {"C": (0.110 * KCAL, 4.00), "H": (0.022 * KCAL, 2.64), "O": (0.120 * KCAL, 3.40), "N": (0.200 * KCAL, 3.70)}
+    elements = sorted(set(sym))
+    stypes = [elements.index(x) for x in sym]
+    q = np.array({"C": 0.10, "H": 0.09, "O": -0.51, "N": -0.47}[x] for x in sym) if False else np.array([{"C": 0.10, "H": 0.09, "O": -0.51, "N": -0.47}[x] for x in sym])
+    q = q - q.mean()
+    return solvated_solute(xyz, q, stypes, [table[e][0] for e in elements], [table[e][1] for e in elements], [tuple(b) for b in bonds], name=name)
+
+
 def perturbed(system, amplitude, seed=999):
     """Copy of a system with every coordinate displaced uniformly in [-amplitude, amplitude] (for update-heuristic tests)."""
     s = dict(system)
@@ -277,9 +387,24 @@ def perturbed(system, amplitude, seed=999):
 
 
 WORKLOADS = {
-    "w216": lambda: water_box(6, name="w216"),
-    "w1728": lambda: water_box(12, name="w1728"),
-    "jac": lambda: jac_like(),
-    "water24k": lambda: water_box(20, name="water24k"),
-    "m1": lambda: water_box(70, name="m1"),
+    "w216": lambda: water216_real(),
+    "w216_lattice": lambda: water_box(6, name="w216_lattice"),
+    "w216_triclinic": lambda: water216_real(box=[21.5, 22.0, 23.0, 85.0, 95.0, 100.0], name="w216_triclinic", wrap=True),
+    "bala": lambda: bala_water(),
+    "w1728_lattice": lambda: water_box(12, name="w1728_lattice"),
+    "water3x3x3": lambda: replicated_water(3),
+    "jac": lambda: jac_protein_water(),
+    "jac_lattice": lambda: jac_like(),
+    "water24k_lattice": lambda: water_box(20, name="water24k_lattice"),
+    "m1": lambda: replicated_water(12, name="m1"),
+}
+
+# cases with committed golden outputs of the compiled reference: name -> (maker, reference options, store full pair sets)
+GOLDEN_CASES = {
+    "w216": (WORKLOADS["w216"], {}, True),
+    "w216_lattice": (WORKLOADS["w216_lattice"], {}, False),
+    "w216_triclinic": (WORKLOADS["w216_triclinic"], {}, False),
+    "w216_cut": (WORKLOADS["w216"], dict(dampingCutoff=1.0, innerCutoff=6.0, outerCutoff=9.0, listCutoff=10.5), False),
+    "bala": (WORKLOADS["bala"], {}, False),
+    "jac": (WORKLOADS["jac"], {}, False),
 }

@@ -1,0 +1,64 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every symbol include/nbabfs_b200.h
+declares, has no torch / oracle dependency, and fails loudly (no CPU fallback) when asked to compute without a device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "nbabfs_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:NBModelABFS|PairListGenerator|PairwiseInteractionABFS|nbb200)\w*)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    from pdynamo_mirror_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "run python __graft_entry__.py (build) first"
+    L = C.CDLL(_lib.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(L, name), "missing export: " + name
+    assert set(_lib.SIGNATURES) == set(names), set(_lib.SIGNATURES) ^ set(names)
+
+
+def test_library_is_self_contained(pkg):
+    from pdynamo_mirror_b200 import _lib
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "oracle" not in out and "ref_nbabfs" not in out
+
+
+def test_product_never_imports_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "pdynamo-mirror_b200")):
+        if os.path.basename(base) in ("build", "__pycache__"):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                text = open(os.path.join(base, f)).read()
+                assert "import oracle" not in text and "refnb" not in text and "liboracle" not in text and "nbabfs_oracle" not in text, f
+
+
+def test_make_factors_matches_oracle(pkg, orc):
+    pw = pkg.PairwiseInteractionABFS(dampingCutoff=0.5, innerCutoff=8.0, outerCutoff=12.0)
+    assert np.array_equal(pw.MakeFactors(), orc.make_factors(0.5, 8.0, 12.0))
+    pw = pkg.PairwiseInteractionABFS(dampingCutoff=1.0, innerCutoff=6.0, outerCutoff=9.0)
+    assert np.array_equal(pw.MakeFactors(), orc.make_factors(1.0, 6.0, 9.0))
+
+
+def test_no_cpu_fallback(pkg):
+    from pdynamo_mirror_b200 import _lib
+    if _lib.lib().nbb200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    system = pkg.System.FromWorkload(pkg.workloads.WORKLOADS["w216"]())
+    system.DefineNBModel(pkg.NBModelABFS())
+    with pytest.raises(pkg.CLibraryError, match="Unable to create NB state"):
+        system.Energy(doGradients=True)
+    with pytest.raises(pkg.CLibraryError):
+        pkg.PairListGenerator(cutoff=5.0).SelfPairListFromCoordinates3(np.zeros((4, 3)))
