@@ -365,17 +365,46 @@ def jac_protein_water(natoms=23558, nchain=2489, ntypes=35, seed=12345):
 
 
 def bala_water(name="bala_water"):
-    """Config 2: blocked alanine dipeptide (book/data/mol/bala_c7eq.mol via tests/golden/bala_c7eq.npz) in a ~2.1k-atom
-    TIP3P lattice box, CHARMM-style LJ combination.  The solute parameters are a fixed plausible table (parity is judged
-    against the oracle on identical inputs)."""
+    """Config 2: blocked alanine dipeptide (book/data/mol/bala_c7eq.mol via tests/golden/bala_c7eq.npz) solvated in 2x2x2
+    replicas of the equilibrated water box (a = 37.282; waters whose O lies within 2.8 A of the solute removed; ~5.1k atoms),
+    CHARMM-style LJ combination, bonded 1-2/1-3/1-4 exclusions and a 1-4 list.  The solute parameters are a fixed plausible
+    table (parity is judged against the oracle on identical inputs)."""
     d = np.load(_os.path.join(_GOLDEN, "bala_c7eq.npz"))
-    xyz, sym, bonds = d["xyz"], [str(x) for x in d["symbols"]], d["bonds"]
+    sxyz, sym, bonds = np.array(d["xyz"], dtype=np.float64), [str(x) for x in d["symbols"]], [tuple(int(v) for v in b) for b in d["bonds"]]
     table = {"C": (0.110 * KCAL, 4.00), "H": (0.022 * KCAL, 2.64), "O": (0.120 * KCAL, 3.40), "N": (0.200 * KCAL, 3.70)}
     elements = sorted(set(sym))
-    stypes = [elements.index(x) for x in sym]
-    q = np.array({"C": 0.10, "H": 0.09, "O": -0.51, "N": -0.47}[x] for x in sym) if False else np.array([{"C": 0.10, "H": 0.09, "O": -0.51, "N": -0.47}[x] for x in sym])
+    stypes = np.array([elements.index(x) for x in sym], dtype=np.int32)
+    q = np.array([{"C": 0.10, "H": 0.09, "O": -0.51, "N": -0.47}[x] for x in sym])
     q = q - q.mean()
-    return solvated_solute(xyz, q, stypes, [table[e][0] for e in elements], [table[e][1] for e in elements], [tuple(b) for b in bonds], name=name)
+    wxyz, nwfull, (ax, ay, az) = replicated_water_xyz(2, 2, 2)
+    ns = len(sym)
+    sxyz = sxyz - sxyz.mean(0) + np.array([ax, ay, az]) / 2.0
+    o = wxyz[0::3]
+    dmin = np.sqrt(((o[:, None, :] - sxyz[None, :, :]) ** 2).sum(-1)).min(1)
+    wxyz = wxyz.reshape(-1, 3, 3)[dmin > 2.8].reshape(-1, 3)
+    nw = wxyz.shape[0] // 3
+    adj = [set() for _ in range(ns)]
+    for i, j in bonds:
+        adj[i].add(j)
+        adj[j].add(i)
+    excl, p14 = set(), set()
+    for i in range(ns):
+        d1 = adj[i]
+        d2 = (set().union(*[adj[j] for j in d1]) if d1 else set()) - d1 - {i}
+        d3 = (set().union(*[adj[j] for j in d2]) if d2 else set()) - d2 - d1 - {i}
+        for j in d1 | d2 | d3:
+            excl.add((max(i, j), min(i, j)))
+        for j in d3:
+            p14.add((max(i, j), min(i, j)))
+    excl = np.array(sorted(excl), dtype=np.int32).reshape(-1, 2)
+    p14 = np.array(sorted(p14), dtype=np.int32).reshape(-1, 2)
+    eps = np.concatenate([[TIP3P_EPS_O, 0.046 * KCAL], [table[e][0] for e in elements]])
+    rmin = np.concatenate([[TIP3P_SIG_O * 2.0 ** (1.0 / 6.0), 2 * 0.2245], [table[e][1] for e in elements]])
+    xyz = np.concatenate([sxyz, wxyz])
+    charges = np.concatenate([q, np.tile([TIP3P_QO, TIP3P_QH, TIP3P_QH], nw)])
+    ljtypes = np.concatenate([2 + stypes, np.tile([0, 1, 1], nw)])
+    excl = np.concatenate([excl, _water_topology(nw, ns)])
+    return _finish(xyz, charges, ljtypes, eps, rmin, "amber", excl, p14, [ax, ay, az, 90.0, 90.0, 90.0], name, scale14=1.0)
 
 
 def perturbed(system, amplitude, seed=999):
