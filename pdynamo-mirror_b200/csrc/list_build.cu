@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
                 if (tid == 0) { qCount = rem; emitted += ntiles; }
                 __syncthreads();
             }
+            __syncthreads();        // rowStart / rowPrefix are rewritten by the next batch (needed when total == 0)
         }
         // flush the partial tile of this set
         if (qCount > 0) {
