@@ -29,47 +29,87 @@ struct ForceArgs {
     double *grad; double *accum;
 };
 
-#ifndef NBB_RSQRT_NEWTON
-#define NBB_RSQRT_NEWTON 1
-#endif
-
-// one pair in fp32.  qij, A, B are zero for masked pairs so every output is exactly zero for them.
-__device__ __forceinline__ void abfs_pair(const AbfsF32 &F, float r2, float qij, float A, float B, float &eq, float &elj, float &f2)
+// ------------------------------------------------------------------------------------------------------
+// pair math, fp32, branch free.  The three regions of the reference macros (damped core r < rDamp, plain shifted
+// rDamp <= r <= rOn, switched rOn < r <= rOff) are folded into ONE instruction stream with per-lane selected coefficients,
+// because the lanes of a warp always mix regions (a divergent branch would execute every path anyway):
+//   Coulomb  E = qij (s G + sh)          G = 1, sh = qShift1 (plain) | G = t^3 C(t), sh = 0 (switched; t = rOff - r, C cubic:
+//                                         the reference polynomial a/r - b r - c r^3 - d r^5 + qShift2 has a triple zero at rOff
+//                                         and cancels ~200:1 in fp32 when evaluated as written)
+//            2 dE/d(r^2) = -qij s^3 Q    Q = 1 (plain) | u^2 (k1 - k2 u), u = rOff^2 - r^2 (the switch function, factored)
+//   LJ       E = A pa - B pb             pa = ka (s6 - xa)^2 - wa, pb = kb (s3 - xb)^2 - wb
+//                                         plain: ka = 1, xa = 0, wa = aShift12, kb = 1, xb = 0, wb = bShift6
+//                                         switched: ka = aK12, xa = aF6, wa = 0, kb = bK6, xb = bF3, wb = 0
+//            2 dE/d(r^2) = -6 s^2 (2 A ka (s6 - xa) s6 - B kb (s3 - xb) s3)
+// The damped core (r < dampingCutoff = 0.5 A) never occurs in a physical system; lanes that hit it are patched by a
+// rarely taken slow path that reproduces the reference's damped formulas (including its LJ-B sign quirk).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rsqrt_fast(float x)
 {
-    float s = rsqrtf(r2);
-#if NBB_RSQRT_NEWTON
-    s = fmaf(0.5f * s, fmaf(-r2 * s, s, 1.0f), s);               // one Newton step: MUFU.RSQ is ~1 ulp, energies need better
-#endif
-    const float s2 = s * s;
-    float dFq, dFl;
-    if (r2 > F.r2On) {                                            // switching region
-        // Coulomb: E = qij (a/r - b r - c r^3 - d r^5 + qShift2) has a triple zero at r = rOff; evaluating it as written
-        // cancels ~200:1 in fp32.  Factored form: E = qij t^3 C(t) / r, t = rOff - r (C cubic, coefficients from the host).
-        const float r = r2 * s, t = F.rOff - r;
-        const float C = fmaf(fmaf(fmaf(F.n6, t, F.n5), t, F.n4), t, F.n3);
-        eq  = qij * (t * t) * (t * C) * s;
-        // switch function S = u^2 (k1 - k2 u), u = rOff^2 - r^2 (same polynomial as a + b r^2 + 3c r^4 + 5d r^6, no cancellation)
-        const float u = F.r2Off - r2;
-        const float Q = u * u * fmaf(-F.k2, u, F.k1);
-        dFq = -0.5f * qij * s * Q * s2;
-        const float s6 = s2 * s2 * s2;
-        const float l1 = s6 - F.aF6, l2 = fmaf(s, s2, -F.bF3);
-        const float Ak = A * F.aK12, Bk = B * F.bK6;
-        elj = Ak * l1 * l1 - Bk * l2 * l2;
-        dFl = -3.0f * s6 * (2.0f * Ak * l1 * s2 - Bk * l2 * r);
-    } else if (r2 >= F.r2Damp) {                                  // plain shifted region
-        eq  = qij * (s + F.qShift1);
-        dFq = -0.5f * qij * s * s2;
-        const float s6 = s2 * s2 * s2;
-        elj = A * fmaf(s6, s6, -F.aShift12) - B * (s6 - F.bShift6);
-        dFl = -3.0f * s6 * (2.0f * A * s6 - B) * s2;
-    } else {                                                      // damped core (r < dampingCutoff), practically never taken
-        eq  = qij * fmaf(-F.qAlpha, r2, F.qF0);
-        dFq = -qij * F.qAlpha;
-        elj = A * fmaf(-F.aAlpha, r2, F.aF0) - B * fmaf(-F.bAlpha, r2, F.bF0);
-        dFl = -A * F.aAlpha + B * F.bAlpha;
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct PairOut { float e1, e2, g; };      // elect, LJ, g = -2 dE/d(r^2)  (force on i = g * (xi - xj), gradient = -that)
+
+__device__ __forceinline__ PairOut abfs_pair(const AbfsF32 &F, float r2, float qij, float A, float B)
+{
+    float s = rsqrt_fast(r2);
+    {   // one Newton step: MUFU.RSQ alone (~1e-7 relative) would dominate the energy error budget
+        const float rr = r2 * s;
+        s = fmaf(0.5f * s, fmaf(-rr, s, 1.0f), s);
     }
-    f2 = 2.0f * (dFq + dFl);
+    const float r = r2 * s, s2 = s * s, s3 = s * s2, s6 = s3 * s3;
+    const bool plain = r2 <= F.r2On;
+    // Coulomb
+    const float t = F.rOff - r;
+    const float C = fmaf(fmaf(fmaf(F.n6, t, F.n5), t, F.n4), t, F.n3);
+    const float t3C = (t * t) * (t * C);
+    const float G = plain ? 1.0f : t3C, sh = plain ? F.qShift1 : 0.0f;
+    const float u = F.r2Off - r2;
+    const float Qs = (u * u) * fmaf(-F.k2, u, F.k1);
+    const float Q = plain ? 1.0f : Qs;
+    PairOut o;
+    o.e1 = qij * fmaf(s, G, sh);
+    const float gq = (qij * s3) * Q;
+    // Lennard-Jones
+    const float ka = plain ? 1.0f : F.aK12, xa = plain ? 0.0f : F.aF6, wa = plain ? F.aShift12 : 0.0f;
+    const float kb = plain ? 1.0f : F.bK6,  xb = plain ? 0.0f : F.bF3, wb = plain ? F.bShift6 : 0.0f;
+    const float la = s6 - xa, lb = s3 - xb;
+    const float kla = ka * la, klb = kb * lb;
+    o.e2 = fmaf(A, fmaf(kla, la, -wa), -(B * fmaf(klb, lb, -wb)));
+    const float m = fmaf(2.0f * (A * kla), s6, -((B * klb) * s3));
+    o.g = fmaf(6.0f * s2, m, gq);
+    return o;
+}
+
+// Slow path for tiles that contain a pair inside the damped core, r^2 < r2Damp (reference: PairwiseInteraction.h:72-119,
+// third branches, with s = s2 = 0): returns the CORRECTION (damped minus what abfs_pair produced) for this lane's
+// accumulators c = {fxi, fyi, fzi, fxj, fyj, fzj, eq, el}; the j part is rotated home like in the main loop.
+__device__ __noinline__ void damped_tile_fix(const AbfsF32 &F, unsigned int mask, const float4 *myPosq, const unsigned char *ljRow, const int *myLj,
+                                            float xi, float yi, float zi, float qi, int src, float *c)
+{
+    float fxi = 0.f, fyi = 0.f, fzi = 0.f, fxj = 0.f, fyj = 0.f, fzj = 0.f, eq = 0.f, el = 0.f;
+    for (int k = 0; k < kTile; k++) {
+        const float4 p = myPosq[k];
+        const float2 ab = *reinterpret_cast<const float2 *>(ljRow + myLj[k]);
+        const float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
+        const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        if (((mask >> k) & 1u) && (r2 < F.r2Damp)) {
+            const float qij = qi * p.w;
+            const PairOut o = abfs_pair(F, r2, qij, ab.x, ab.y);
+            const float e1 = qij * fmaf(-F.qAlpha, r2, F.qF0);
+            const float e2 = ab.x * fmaf(-F.aAlpha, r2, F.aF0) - ab.y * fmaf(-F.bAlpha, r2, F.bF0);
+            const float g = -2.0f * (-qij * F.qAlpha - ab.x * F.aAlpha + ab.y * F.bAlpha) - o.g;
+            eq += e1 - o.e1; el += e2 - o.e2;
+            const float gx = g * dx, gy = g * dy, gz = g * dz;
+            fxi -= gx; fyi -= gy; fzi -= gz;
+            fxj += gx; fyj += gy; fzj += gz;
+        }
+        fxj = __shfl_sync(0xffffffffu, fxj, src); fyj = __shfl_sync(0xffffffffu, fyj, src); fzj = __shfl_sync(0xffffffffu, fzj, src);
+    }
+    c[0] = fxi; c[1] = fyi; c[2] = fzi; c[3] = fxj; c[4] = fyj; c[5] = fzj; c[6] = eq; c[7] = el;
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -79,15 +119,28 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 constexpr int kForceThreads = 256;
+constexpr int kForceWarps = kForceThreads / 32;
 
-__global__ void __launch_bounds__(kForceThreads) k_tile_forces(ForceArgs A)
+// per-warp staging of one j tile: entries duplicated (64 slots) so that slot (lane + k) needs no wrap-around arithmetic
+struct __align__(16) JStage {
+    float4 posq[2 * kTile];      // x, y, z (block-local), charge
+    int    ljoff[2 * kTile];     // byte offset of the LJ-table row of the j type
+};
+
+template <bool kRot>
+__global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(ForceArgs A)
 {
-    extern __shared__ float2 sLJ[];                               // [ntypes*ntypes] (A, B)
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    JStage *stage = reinterpret_cast<JStage *>(smemRaw) + (threadIdx.x >> 5);
+    float2 *sLJ = reinterpret_cast<float2 *>(smemRaw + sizeof(JStage) * kForceWarps);      // [ntypes*ntypes] (A, B)
     for (int i = threadIdx.x; i < A.ntypes * A.ntypes; i += blockDim.x) sLJ[i] = A.ljAB[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const AbfsF32 F = A.F;
     const int src = (lane + 1) & 31;
+    const unsigned char *ljBase = reinterpret_cast<const unsigned char *>(sLJ);
+    const float4 *myPosq = stage->posq + lane;
+    const int *myLj = stage->ljoff + lane;
 
     for (;;) {
         unsigned int it = 0;
@@ -97,31 +150,34 @@ __global__ void __launch_bounds__(kForceThreads) k_tile_forces(ForceArgs A)
         const WorkItem wi = A.items[it];
         const ImageOpDev *op = A.ops + wi.image;
         const bool isImage = wi.image > 0;
-        const bool pureT = op->pureTranslation != 0;
+        const bool pureT = kRot ? (op->pureTranslation != 0) : true;
         const double cx = A.blockBox[9 * wi.block + 6], cy = A.blockBox[9 * wi.block + 7], cz = A.blockBox[9 * wi.block + 8];
+        const double sc = op->scale;
 
         // i atom of this lane
         const int si = wi.block * kTile + lane;
         const int ai = (si < A.n) ? A.sAtom[si] : -1;
         float xi = 0.f, yi = 0.f, zi = 0.f, qi = 0.f;
-        int ti = 0;
+        const unsigned char *ljRow = ljBase;
         if (ai >= 0) {
             xi = (float) (A.x[3 * ai] - cx); yi = (float) (A.x[3 * ai + 1] - cy); zi = (float) (A.x[3 * ai + 2] - cz);
             qi = A.q32[ai] * A.qScale;
-            ti = A.ljtype[ai] * A.ntypes;
+            ljRow = ljBase + (size_t) A.ljtype[ai] * A.ntypes * sizeof(float2);
         }
         double fix = 0.0, fiy = 0.0, fiz = 0.0, eQ = 0.0, eL = 0.0;
         double G0 = 0.0, G1 = 0.0, G2 = 0.0, W[9];
+        if (kRot) {
 #pragma unroll
-        for (int k = 0; k < 9; k++) W[k] = 0.0;
+            for (int k = 0; k < 9; k++) W[k] = 0.0;
+        }
 
         for (int t = 0; t < wi.tileCount; t++) {
             const size_t T = ((size_t) wi.tileStart + t) * kTile + lane;
             const int aj = A.tileJ[T];
             const unsigned int mask = A.tileMask[T];
             double xj64 = 0.0, yj64 = 0.0, zj64 = 0.0;
-            float xj = 0.f, yj = 0.f, zj = 0.f, qj = 0.f;
-            int tj = 0;
+            float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+            int lj = 0;
             if (aj >= 0) {
                 xj64 = A.x[3 * aj]; yj64 = A.x[3 * aj + 1]; zj64 = A.x[3 * aj + 2];
                 double px = xj64, py = yj64, pz = zj64;
@@ -133,42 +189,51 @@ __global__ void __launch_bounds__(kForceThreads) k_tile_forces(ForceArgs A)
                         pz = op->R[6] * xj64 + op->R[7] * yj64 + op->R[8] * zj64 + op->tv[2];
                     }
                 }
-                xj = (float) (px - cx); yj = (float) (py - cy); zj = (float) (pz - cz);
-                qj = A.q32[aj];
-                tj = A.ljtype[aj];
+                pj = make_float4((float) (px - cx), (float) (py - cy), (float) (pz - cz), A.q32[aj]);
+                lj = A.ljtype[aj] * (int) sizeof(float2);
             }
+            __syncwarp();                                   // previous tile fully consumed
+            stage->posq[lane] = pj; stage->posq[lane + kTile] = pj;
+            stage->ljoff[lane] = lj; stage->ljoff[lane + kTile] = lj;
+            __syncwarp();
+
             float fxi = 0.f, fyi = 0.f, fzi = 0.f, fxj = 0.f, fyj = 0.f, fzj = 0.f, eq = 0.f, el = 0.f;
+            float r2min = F.r2Off;
+            unsigned int mrev = __brev(mask);               // step k tests the sign bit, then shifts
 #pragma unroll 8
             for (int k = 0; k < kTile; k++) {
-                const float dx = xi - xj, dy = yi - yj, dz = zi - zj;
-                float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                const bool on = ((mask >> k) & 1u) && (r2 <= F.r2Off);
-                const float2 ab = sLJ[ti + tj];
-                const float qij = on ? qi * qj : 0.f;
-                const float Aij = on ? ab.x : 0.f, Bij = on ? ab.y : 0.f;
-                r2 = on ? r2 : 1.0f;
-                float e1, e2, f2;
-                abfs_pair(F, r2, qij, Aij, Bij, e1, e2, f2);
-                eq += e1; el += e2;
+                const float4 p = myPosq[k];                 // j slot (lane + k) % 32
+                const float2 ab = *reinterpret_cast<const float2 *>(ljRow + myLj[k]);
+                const float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
+                const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                const bool on = ((int) mrev < 0) && (r2 <= F.r2Off);
+                mrev <<= 1;
+                // masked pairs are evaluated AT the outer cutoff, where energy and force vanish (to ~1e-16 kJ/mol): one select
+                // on the input instead of three on the outputs, and r2m doubles as the damped-core detector
+                const float r2m = on ? r2 : F.r2Off;
+                r2min = fminf(r2min, r2m);
+                const PairOut o = abfs_pair(F, r2m, qi * p.w, ab.x, ab.y);
+                eq += o.e1; el += o.e2;
                 if ((k & 3) == 3) { eQ += (double) eq; eL += (double) el; eq = 0.f; el = 0.f; }   // fp32 partial sums stay short
-                const float gx = f2 * dx, gy = f2 * dy, gz = f2 * dz;
-                fxi += gx; fyi += gy; fzi += gz;
-                fxj -= gx; fyj -= gy; fzj -= gz;
-                // hand the j atom and its accumulator to the neighbouring lane
+                const float gx = o.g * dx, gy = o.g * dy, gz = o.g * dz;      // force on i; the energy gradient is the negative
+                fxi -= gx; fyi -= gy; fzi -= gz;
+                fxj += gx; fyj += gy; fzj += gz;
+                // hand the j-gradient accumulator to the lane that evaluates this j slot next
                 fxj = __shfl_sync(0xffffffffu, fxj, src); fyj = __shfl_sync(0xffffffffu, fyj, src); fzj = __shfl_sync(0xffffffffu, fzj, src);
-                if (k < kTile - 1) {
-                    xj = __shfl_sync(0xffffffffu, xj, src); yj = __shfl_sync(0xffffffffu, yj, src); zj = __shfl_sync(0xffffffffu, zj, src);
-                    qj = __shfl_sync(0xffffffffu, qj, src); tj = __shfl_sync(0xffffffffu, tj, src);
-                }
+            }
+            if (__any_sync(0xffffffffu, r2min < F.r2Damp)) {   // damped core: practically never; patch the tile with the reference formulas
+                float c[8];
+                damped_tile_fix(F, mask, myPosq, ljRow, myLj, xi, yi, zi, qi, src, c);
+                fxi += c[0]; fyi += c[1]; fzi += c[2]; fxj += c[3]; fyj += c[4]; fzj += c[5];
+                eQ += (double) c[6]; eL += (double) c[7];
             }
             // after 32 hand-overs the accumulator of j slot `lane` is back in this lane
             fix += (double) fxi; fiy += (double) fyi; fiz += (double) fzi;
             if (aj >= 0) {
-                const double sc = op->scale;
                 double gx = sc * (double) fxj, gy = sc * (double) fyj, gz = sc * (double) fzj;       // gradient on the (image) atom
                 if (isImage) {
                     G0 += gx; G1 += gy; G2 += gz;
-                    if (!pureT) {
+                    if (kRot && !pureT) {
                         W[0] += gx * xj64; W[1] += gx * yj64; W[2] += gx * zj64;
                         W[3] += gy * xj64; W[4] += gy * yj64; W[5] += gy * zj64;
                         W[6] += gz * xj64; W[7] += gz * yj64; W[8] += gz * zj64;
@@ -183,7 +248,6 @@ __global__ void __launch_bounds__(kForceThreads) k_tile_forces(ForceArgs A)
                 }
             }
         }
-        const double sc = op->scale;
         if (ai >= 0 && A.grad != nullptr) {
             atomicAdd(&A.grad[3 * ai], sc * fix); atomicAdd(&A.grad[3 * ai + 1], sc * fiy); atomicAdd(&A.grad[3 * ai + 2], sc * fiz);
         }
@@ -193,7 +257,7 @@ __global__ void __launch_bounds__(kForceThreads) k_tile_forces(ForceArgs A)
         if (isImage) {
             G0 = warp_sum(G0); G1 = warp_sum(G1); G2 = warp_sum(G2);
             if (lane == 0) { atomicAdd(&acc[2], G0); atomicAdd(&acc[3], G1); atomicAdd(&acc[4], G2); }
-            if (!pureT) {
+            if (kRot && !pureT) {
 #pragma unroll
                 for (int k = 0; k < 9; k++) { const double w = warp_sum(W[k]); if (lane == 0) atomicAdd(&acc[5 + k], w); }
             }
@@ -253,7 +317,8 @@ static int g_forceBlocksPerSM = 0, g_numSMs = 0;
 
 void init_force_kernel_attributes()
 {
-    cudaFuncSetAttribute(k_tile_forces, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaDeviceProp prop;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -295,17 +360,21 @@ bool launch_forces(State &s, double *d_grad)
         }
         A.qScale = (float) eScale;
         A.grad = d_grad; A.accum = s.accum.p;
-        const size_t smem = sizeof(float2) * (size_t) s.ntypes * s.ntypes;
+        const size_t smem = sizeof(JStage) * kForceWarps + sizeof(float2) * (size_t) s.ntypes * s.ntypes;
         if (smem > 160 * 1024) { set_error("too many LJ types for the shared-memory table"); return false; }
         if (g_numSMs == 0) init_force_kernel_attributes();
+        bool rot = false;                                   // any image with a genuine rotation?
+        for (const RealSpaceOp &b : s.plan.baseOps) rot = rot || !b.pureTranslation;
         int perSM = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_tile_forces, kForceThreads, smem);
+        if (rot) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_tile_forces<true>, kForceThreads, smem);
+        else     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_tile_forces<false>, kForceThreads, smem);
         if (perSM < 1) perSM = 1;
         g_forceBlocksPerSM = perSM;
         const int warpsPerBlock = kForceThreads / 32;
         const int grid = std::max(1, std::min(g_numSMs * perSM, (nitems + warpsPerBlock - 1) / warpsPerBlock));
         if (s.timing) cudaEventRecord(s.ev[2], s.stream);
-        k_tile_forces<<<grid, kForceThreads, smem, s.stream>>>(A);
+        if (rot) k_tile_forces<true><<<grid, kForceThreads, smem, s.stream>>>(A);
+        else     k_tile_forces<false><<<grid, kForceThreads, smem, s.stream>>>(A);
         if (s.timing) cudaEventRecord(s.ev[3], s.stream);
         s.launches += 1;
     }
