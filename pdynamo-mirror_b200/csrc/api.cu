@@ -33,7 +33,7 @@ static void destroy(State *s)
     s->x.release(); s->xref.release(); s->grad.release();
     s->imageOps.release(); s->imageBoxes.release(); s->baseOpsDev.release(); s->visitDisp.release(); s->visitInfo.release(); s->bboxDev.release();
     s->eX.release(); s->eAtom.release(); s->eSet.release(); s->eKey.release(); s->eSortBuf.release();
-    s->cellStart.release(); s->cellFill.release(); s->scanTmp.release(); s->order.release();
+    s->cellStart.release(); s->cellFill.release(); s->scanTmp.release(); s->order.release(); s->order2.release();
     s->sX.release(); s->sAtom.release(); s->invPerm.release(); s->blockBox.release();
     s->tileJ.release(); s->tileMask.release(); s->items.release(); s->setPairs.release(); s->accum.release();
     s->pairBuf.release(); s->pairCursor.release();

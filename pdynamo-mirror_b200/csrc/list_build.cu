@@ -83,12 +83,12 @@ __global__ void k_bbox_partial(const double *__restrict__ x, int n, const double
 
 __global__ void k_bbox_final(const double *__restrict__ partial, int nblk, int nops, double *__restrict__ out)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // o*6 + c
-    if (idx >= nops * 6) return;
-    const int c = idx % 6;
-    double v = partial[idx];
-    for (int k = 1; k < nblk; k++) { const double u = partial[(size_t) k * nops * 6 + idx]; v = (c < 3) ? fmin(v, u) : fmax(v, u); }
-    out[idx] = v;
+    const int idx = blockIdx.x;                                  // o*6 + c, one warp each
+    const int c = idx % 6, lane = threadIdx.x;
+    double v = (c < 3) ? 1e300 : -1e300;
+    for (int k = lane; k < nblk; k += 32) { const double u = partial[(size_t) k * nops * 6 + idx]; v = (c < 3) ? fmin(v, u) : fmax(v, u); }
+    for (int off = 16; off > 0; off >>= 1) { const double u = __shfl_xor_sync(0xffffffffu, v, off); v = (c < 3) ? fmin(v, u) : fmax(v, u); }
+    if (lane == 0) out[idx] = v;
 }
 
 bool device_bbox(State &s, int nops, double *hostMin, double *hostExt)
@@ -99,7 +99,7 @@ bool device_bbox(State &s, int nops, double *hostMin, double *hostExt)
     if (!s.bboxDev.ensure((size_t) (nblk + 1) * nops * 6)) return false;
     double *partial = s.bboxDev.p + (size_t) nops * 6;
     k_bbox_partial<<<nblk, threads, (threads / 32) * 6 * sizeof(double), s.stream>>>(s.xcur, s.n, s.baseOpsDev.p, nops, partial);
-    k_bbox_final<<<(nops * 6 + 63) / 64, 64, 0, s.stream>>>(partial, nblk, nops, s.bboxDev.p);
+    k_bbox_final<<<nops * 6, 32, 0, s.stream>>>(partial, nblk, nops, s.bboxDev.p);
     s.launches += 2;
     NBB_CUDA(cudaMemcpyAsync(s.hsmall, s.bboxDev.p, sizeof(double) * nops * 6, cudaMemcpyDeviceToHost, s.stream));
     NBB_CUDA(cudaStreamSynchronize(s.stream));
@@ -281,19 +281,29 @@ __global__ void k_scatter(const int *__restrict__ eKey, int ne, const unsigned i
     order[cellStart[key] + atomicAdd(&cellFill[key], 1u)] = e;
 }
 
-// deterministic order inside each cell: insertion sort by (sub-cell key, atom index)
-__global__ void k_sort_cells(const unsigned int *__restrict__ cellStart, int nkeys, const unsigned long long *__restrict__ eSort, int *order)
+// deterministic order inside each cell: rank sort by (sub-cell key, atom index), one warp per cell, out of place
+__global__ void k_sort_cells(const unsigned int *__restrict__ cellStart, int nkeys, const unsigned long long *__restrict__ eSort,
+                             const int *__restrict__ order, int *__restrict__ sorted)
 {
-    const int key = blockIdx.x * blockDim.x + threadIdx.x;
+    const int key = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (key >= nkeys) return;
-    const int lo = (int) cellStart[key], hi = (int) cellStart[key + 1];
-    if (hi - lo > 4096) return;      // pathological density: keep the (valid, but arbitrary) scatter order
-    for (int i = lo + 1; i < hi; i++) {
-        const int e = order[i];
-        const unsigned long long k = eSort[e];
-        int p = i - 1;
-        while (p >= lo && eSort[order[p]] > k) { order[p + 1] = order[p]; p--; }
-        order[p + 1] = e;
+    const int lo = (int) cellStart[key], m = (int) cellStart[key + 1] - lo;
+    if (m <= 0) return;
+    if (m > 2048) {                     // pathological density: keep the (valid, but arbitrary) scatter order
+        for (int i = lane; i < m; i += 32) sorted[lo + i] = order[lo + i];
+        return;
+    }
+    for (int base = 0; base < m; base += 32) {
+        const bool mine = base + lane < m;
+        const int e = mine ? order[lo + base + lane] : 0;
+        const unsigned long long k = mine ? eSort[e] : 0ULL;
+        int rank = 0;
+        for (int b2 = 0; b2 < m; b2 += 32) {
+            const unsigned long long ko = (b2 + lane < m) ? eSort[order[lo + b2 + lane]] : ~0ULL;
+            const int cnt = min(32, m - b2);
+            for (int t = 0; t < cnt; t++) rank += (__shfl_sync(0xffffffffu, ko, t) < k) ? 1 : 0;
+        }
+        if (mine) sorted[lo + rank] = e;
     }
 }
 
@@ -341,38 +351,65 @@ struct TileArgs {
 };
 
 constexpr int kMaxRows = 64;
-constexpr int kQueueCap = kBuildThreads + kTile;
+constexpr int kBuildWarps = kBuildThreads / 32;
+
+// transpose 32 column masks (one per lane / j slot) into row masks (one per lane / i atom), pre-rotated for the force kernel
+__device__ __forceinline__ unsigned int rows_from_columns(unsigned int cm, int lane)
+{
+    unsigned int row = 0;
+#pragma unroll
+    for (int i = 0; i < kTile; i++) { const unsigned int v = __ballot_sync(0xffffffffu, (cm >> i) & 1u); if (lane == i) row = v; }
+    return __funnelshift_r(row, row, lane);                  // bit k <-> j slot (lane + k) % 32
+}
 
 __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
 {
-    __shared__ double sxi[kTile][3];
-    __shared__ double sbox[6];
+    __shared__ double sxi[kTile][3];                         // exact coordinates of the block atoms
+    __shared__ float4 sxf[kTile];                            // block-local fp32 copies for the prefilter
+    __shared__ double sbox[9];
     __shared__ int rowStart[kMaxRows];
     __shared__ int rowPrefix[kMaxRows + 1];
-    __shared__ int qAtom[kQueueCap];
-    __shared__ unsigned int qMask[kQueueCap];
-    __shared__ int warpCnt[kBuildThreads / 32];
-    __shared__ int qCount, emitted;
+    __shared__ int qAtom[kBuildWarps][2 * kTile];            // per-warp queues of kept candidates
+    __shared__ unsigned int qMask[kBuildWarps][2 * kTile];
+    __shared__ int qCnt[kBuildWarps];
+    __shared__ int mAtom[kBuildWarps * kTile];               // leftovers of the four warps, merged per set
+    __shared__ unsigned int mMask[kBuildWarps * kTile];
+    __shared__ int emitted;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = A.firstBlock + blockIdx.x;
+    if (tid < 9) sbox[tid] = A.blockBox[9 * b + tid];
+    if (tid == 0) emitted = 0;
+    if (tid < kBuildWarps) qCnt[tid] = 0;
+    __syncthreads();
     if (tid < kTile) {
         const int s = b * kTile + tid;
-        for (int d = 0; d < 3; d++) sxi[tid][d] = (s < A.n) ? A.sX[3 * s + d] : 1.0e30;     // padding rows never pass the test
+        float f[3];
+        for (int d = 0; d < 3; d++) {
+            const double v = (s < A.n) ? A.sX[3 * s + d] : 1.0e30;        // padding rows never pass the test
+            sxi[tid][d] = v;
+            f[d] = (s < A.n) ? (float) (v - sbox[6 + d]) : 1.0e15f;
+        }
+        sxf[tid] = make_float4(f[0], f[1], f[2], 0.f);
     }
-    if (tid < 6) sbox[tid] = A.blockBox[9 * b + tid];
-    if (tid == 0) { qCount = 0; emitted = 0; }
     __syncthreads();
 
     const BuildGrid g = A.grid;
     const double reach = A.cutoff + 1.0e-6;
     int c0[3], c1[3];
+    double maxAbs = 0.0;
     for (int d = 0; d < 3; d++) {
         c0[d] = cell_coord(sbox[d] - reach, g.lo[d], g.invh, g.dim[d]);
         c1[d] = cell_coord(sbox[3 + d] + reach, g.lo[d], g.invh, g.dim[d]);
+        maxAbs = fmax(maxAbs, 0.5 * (sbox[3 + d] - sbox[d]) + reach);
     }
     const int nrowsY = c1[1] - c0[1] + 1, nrowsTotal = (c1[0] - c0[0] + 1) * nrowsY;
     const double reject2 = A.cutoff2 * (1.0 + 1.0e-12) + 1.0e-9;
+    // fp32 prefilter: |r2_fp32 - r2_exact| <= eps for every candidate that survives the box reject (block-local coordinates,
+    // magnitude <= maxAbs); decisions inside the band are taken by the exact fp64 predicate
+    const double delta = 6.0e-7 * maxAbs;
+    const float eps = (float) (2.0 * (3.5 * reach * delta + 3.0e-7 * A.cutoff2));
+    const float c2lo = (float) A.cutoff2 - eps, c2hi = (float) A.cutoff2 + eps;
 
     for (int set = 0; set < A.nsets; set++) {
         if (set == 0 && !A.selfEnabled) continue;
@@ -382,7 +419,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
             for (int d = 0; d < 3; d++) overlap = overlap && (ib.lo[d] <= sbox[3 + d] + reach) && (ib.hi[d] >= sbox[d] - reach);
             if (!overlap) continue;
         }
-        const int imageStart = emitted;                  // all threads read the same value (synchronised below)
+        const int imageStart = emitted;                  // uniform: last written before a barrier
         unsigned long long myPairs = 0;
         __syncthreads();
         for (int rowBase = 0; rowBase < nrowsTotal; rowBase += kMaxRows) {
@@ -399,8 +436,9 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
             if (tid == 0) { rowPrefix[0] = 0; for (int r = 0; r < nrows; r++) rowPrefix[r + 1] += rowPrefix[r]; }
             __syncthreads();
             const int total = rowPrefix[nrows];
-            for (int base = 0; base < total; base += kBuildThreads) {
-                const int c = base + tid;
+            // every warp walks its own chunks of 32 consecutive candidates and keeps a private queue: no CTA barrier in here
+            for (int base = warp * kTile; base < total; base += kBuildThreads) {
+                const int c = base + lane;
                 unsigned int colmask = 0;
                 int atom = -1;
                 if (c < total) {
@@ -412,8 +450,19 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
                     const double ex = fmax(0.0, fmax(sbox[0] - xj, xj - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - yj, yj - sbox[4])),
                                  ez = fmax(0.0, fmax(sbox[2] - zj, zj - sbox[5]));
                     if (ex * ex + ey * ey + ez * ez <= reject2) {
-#pragma unroll 4
+                        const float fx = (float) (xj - sbox[6]), fy = (float) (yj - sbox[7]), fz = (float) (zj - sbox[8]);
+                        unsigned int amb = 0;
+#pragma unroll 8
                         for (int i = 0; i < kTile; i++) {
+                            const float4 p = sxf[i];
+                            const float dx = p.x - fx, dy = p.y - fy, dz = p.z - fz;
+                            const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                            colmask |= (r2 <= c2lo) ? (1u << i) : 0u;
+                            amb |= (r2 > c2lo && r2 < c2hi) ? (1u << i) : 0u;
+                        }
+                        while (amb) {                            // inside the band: the reference predicate decides
+                            const int i = __ffs(amb) - 1;
+                            amb &= amb - 1;
                             const double r2 = ref_dist2(sxi[i][0] - xj, sxi[i][1] - yj, sxi[i][2] - zj);
                             colmask |= (r2 <= A.cutoff2) ? (1u << i) : 0u;
                         }
@@ -430,58 +479,55 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
                 const bool keep = colmask != 0u;
                 myPairs += __popc(colmask);
                 const unsigned int bal = __ballot_sync(0xffffffffu, keep);
-                if (lane == 0) warpCnt[warp] = __popc(bal);
-                __syncthreads();
-                int offset = qCount;
-                for (int w = 0; w < warp; w++) offset += warpCnt[w];
-                if (keep) { const int q = offset + __popc(bal & ((1u << lane) - 1u)); qAtom[q] = atom; qMask[q] = colmask; }
-                __syncthreads();
-                int newCount = qCount;
-                for (int w = 0; w < kBuildThreads / 32; w++) newCount += warpCnt[w];
-                const int ntiles = newCount / kTile;
-                // emit full tiles: warp w writes tiles w, w+4, ...
-                for (int t = warp; t < ntiles; t += kBuildThreads / 32) {
-                    const int slot = emitted + t;
-                    const unsigned int cm = qMask[t * kTile + lane];
-                    unsigned int row = 0;
-                    for (int i = 0; i < kTile; i++) { const unsigned int v = __ballot_sync(0xffffffffu, (cm >> i) & 1u); if (lane == i) row = v; }
+                int cnt = qCnt[warp];
+                if (keep) { const int q = cnt + __popc(bal & ((1u << lane) - 1u)); qAtom[warp][q] = atom; qMask[warp][q] = colmask; }
+                cnt += __popc(bal);
+                __syncwarp();
+                if (cnt >= kTile) {                              // emit one full tile from the front of the queue
+                    int slot = 0;
+                    if (lane == 0) slot = atomicAdd(&emitted, 1);
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    const unsigned int rot = rows_from_columns(qMask[warp][lane], lane);
                     if (slot < A.tileStride) {
                         const size_t T = ((size_t) b * A.tileStride + slot) * kTile + lane;
-                        A.tileJ[T] = qAtom[t * kTile + lane];
-                        A.tileMask[T] = __funnelshift_r(row, row, lane);             // bit k <-> j slot (lane + k) % 32
+                        A.tileJ[T] = qAtom[warp][lane];
+                        A.tileMask[T] = rot;
                     }
+                    const int ra = qAtom[warp][kTile + lane];
+                    const unsigned int rm = qMask[warp][kTile + lane];
+                    __syncwarp();
+                    qAtom[warp][lane] = ra; qMask[warp][lane] = rm;
+                    cnt -= kTile;
                 }
-                __syncthreads();
-                const int rem = newCount - ntiles * kTile;
-                int ra = 0; unsigned int rm = 0;
-                if (tid < rem) { ra = qAtom[ntiles * kTile + tid]; rm = qMask[ntiles * kTile + tid]; }
-                __syncthreads();
-                if (tid < rem) { qAtom[tid] = ra; qMask[tid] = rm; }
-                if (tid == 0) { qCount = rem; emitted += ntiles; }
-                __syncthreads();
+                if (lane == 0) qCnt[warp] = cnt;
+                __syncwarp();
             }
-            __syncthreads();        // rowStart / rowPrefix are rewritten by the next batch (needed when total == 0)
+            __syncthreads();        // rowStart / rowPrefix are rewritten by the next batch
         }
-        // flush the partial tile of this set
-        if (qCount > 0) {
-            if (warp == 0) {
-                const int slot = emitted;
-                const unsigned int cm = (lane < qCount) ? qMask[lane] : 0u;
-                unsigned int row = 0;
-                for (int i = 0; i < kTile; i++) { const unsigned int v = __ballot_sync(0xffffffffu, (cm >> i) & 1u); if (lane == i) row = v; }
-                if (slot < A.tileStride) {
-                    const size_t T = ((size_t) b * A.tileStride + slot) * kTile + lane;
-                    A.tileJ[T] = (lane < qCount) ? qAtom[lane] : -1;
-                    A.tileMask[T] = __funnelshift_r(row, row, lane);
-                }
+        // merge the leftovers of the four warps (< 32 each) and emit them as up to four tiles, the last one padded
+        int off = 0, totalLeft = 0;
+        for (int w = 0; w < kBuildWarps; w++) { if (w < warp) off += qCnt[w]; totalLeft += qCnt[w]; }
+        if (lane < qCnt[warp]) { mAtom[off + lane] = qAtom[warp][lane]; mMask[off + lane] = qMask[warp][lane]; }
+        __syncthreads();
+        const int nLeftTiles = (totalLeft + kTile - 1) / kTile;
+        if (warp < nLeftTiles) {
+            const int q = warp * kTile + lane;
+            const unsigned int cm = (q < totalLeft) ? mMask[q] : 0u;
+            const unsigned int rot = rows_from_columns(cm, lane);
+            const int slot = emitted + warp;
+            if (slot < A.tileStride) {
+                const size_t T = ((size_t) b * A.tileStride + slot) * kTile + lane;
+                A.tileJ[T] = (q < totalLeft) ? mAtom[q] : -1;
+                A.tileMask[T] = rot;
             }
-            __syncthreads();
-            if (tid == 0) { qCount = 0; emitted += 1; }
-            __syncthreads();
         }
+        __syncthreads();
+        if (tid == 0) emitted += nLeftTiles;
+        if (tid < kBuildWarps) qCnt[tid] = 0;
         // work items and pair statistics of this set
-        for (int off = 16; off > 0; off >>= 1) myPairs += __shfl_xor_sync(0xffffffffu, myPairs, off);
+        for (int o = 16; o > 0; o >>= 1) myPairs += __shfl_xor_sync(0xffffffffu, myPairs, o);
         if (lane == 0 && myPairs) atomicAdd(&A.setPairs[set], myPairs);
+        __syncthreads();
         if (tid == 0) {
             const int last = min(emitted, A.tileStride), ntl = last - imageStart;
             if (ntl > 0) {
@@ -606,7 +652,7 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
 {
     const int nkeys = s.nsets * s.grid.ncell;
     const size_t neMax = (size_t) s.n + extUpperBound;
-    if (!s.cellStart.ensure((size_t) nkeys + 2) || !s.order.ensure(neMax) || !s.sX.ensure(3 * neMax) || !s.sAtom.ensure(neMax) || !s.invPerm.ensure((size_t) s.n)) return false;
+    if (!s.cellStart.ensure((size_t) nkeys + 2) || !s.order.ensure(neMax) || !s.order2.ensure(neMax) || !s.sX.ensure(3 * neMax) || !s.sAtom.ensure(neMax) || !s.invPerm.ensure((size_t) s.n)) return false;
     if (!exclusive_scan(s, s.cellFill.p, s.cellStart.p, nkeys)) return false;
     NBB_CUDA(cudaMemsetAsync(s.cellFill.p, 0, sizeof(unsigned int) * nkeys, s.stream));
     // number of extended atoms actually appended
@@ -615,8 +661,8 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     if (s.hostCounters.overflow & 1u) { set_error("extended atom capacity exceeded"); return false; }
     const int ne = s.n + (int) s.hostCounters.extCount;
     k_scatter<<<(ne + 255) / 256, 256, 0, s.stream>>>(s.eKey.p, ne, s.cellStart.p, s.cellFill.p, s.order.p);
-    k_sort_cells<<<(nkeys + 127) / 128, 128, 0, s.stream>>>(s.cellStart.p, nkeys, s.eSortBuf.p, s.order.p);
-    k_gather_sorted<<<(ne + 255) / 256, 256, 0, s.stream>>>(s.order.p, ne, s.eX.p, s.eAtom.p, s.eSet.p, s.sX.p, s.sAtom.p, s.invPerm.p);
+    k_sort_cells<<<(nkeys + 7) / 8, 256, 0, s.stream>>>(s.cellStart.p, nkeys, s.eSortBuf.p, s.order.p, s.order2.p);
+    k_gather_sorted<<<(ne + 255) / 256, 256, 0, s.stream>>>(s.order2.p, ne, s.eX.p, s.eAtom.p, s.eSet.p, s.sX.p, s.sAtom.p, s.invPerm.p);
     s.nblocks = (s.n + kTile - 1) / kTile;
     if (!s.blockBox.ensure((size_t) 9 * s.nblocks)) return false;
     k_block_boxes<<<(s.nblocks * 32 + 255) / 256, 256, 0, s.stream>>>(s.sX.p, s.n, s.nblocks, s.blockBox.p);

@@ -145,7 +145,7 @@ struct State {
     size_t extCap = 0;
     DevBuf<double> eX;  DevBuf<int> eAtom; DevBuf<int> eSet; DevBuf<int> eKey; DevBuf<unsigned long long> eSortBuf;
     DevBuf<unsigned int> cellStart, cellFill, scanTmp;
-    DevBuf<int> order;
+    DevBuf<int> order, order2;
     DevBuf<double> sX; DevBuf<int> sAtom; DevBuf<int> invPerm;
     int nblocks = 0;
     DevBuf<double> blockBox;                     // per block: min[3], max[3], center[3]
