@@ -353,13 +353,18 @@ struct TileArgs {
 constexpr int kMaxRows = 64;
 constexpr int kBuildWarps = kBuildThreads / 32;
 
-// transpose 32 column masks (one per lane / j slot) into row masks (one per lane / i atom), pre-rotated for the force kernel
-__device__ __forceinline__ unsigned int rows_from_columns(unsigned int cm, int lane)
+// transpose 32 column masks (one per lane / j slot, bit i = block atom i) into row masks (one per lane / i atom, bit s = j slot)
+// with the 5-stage block-swap butterfly, then pre-rotate for the force kernel
+__device__ __forceinline__ unsigned int rows_from_columns(unsigned int x, int lane)
 {
-    unsigned int row = 0;
 #pragma unroll
-    for (int i = 0; i < kTile; i++) { const unsigned int v = __ballot_sync(0xffffffffu, (cm >> i) & 1u); if (lane == i) row = v; }
-    return __funnelshift_r(row, row, lane);                  // bit k <-> j slot (lane + k) % 32
+    for (int st = 0; st < 5; st++) {
+        const int sh = 16 >> st;
+        const unsigned int m = (st == 0) ? 0x0000ffffu : (st == 1) ? 0x00ff00ffu : (st == 2) ? 0x0f0f0f0fu : (st == 3) ? 0x33333333u : 0x55555555u;
+        const unsigned int o = __shfl_xor_sync(0xffffffffu, x, sh);
+        x = (lane & sh) ? ((x & ~m) | ((o & ~m) >> sh)) : ((x & m) | ((o & m) << sh));
+    }
+    return __funnelshift_r(x, x, lane);                      // bit k <-> j slot (lane + k) % 32
 }
 
 __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
@@ -408,8 +413,8 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
     // fp32 prefilter: |r2_fp32 - r2_exact| <= eps for every candidate that survives the box reject (block-local coordinates,
     // magnitude <= maxAbs); decisions inside the band are taken by the exact fp64 predicate
     const double delta = 6.0e-7 * maxAbs;
-    const float eps = (float) (2.0 * (3.5 * reach * delta + 3.0e-7 * A.cutoff2));
-    const float c2lo = (float) A.cutoff2 - eps, c2hi = (float) A.cutoff2 + eps;
+    const float eps = (float) (2.0 * (3.5 * reach * delta + 3.0e-7 * A.cutoff2) + 2.0e-5);   // also covers the rounding of cutoff^2 to fp32
+    const float c2f = (float) A.cutoff2;
 
     for (int set = 0; set < A.nsets; set++) {
         if (set == 0 && !A.selfEnabled) continue;
@@ -426,81 +431,90 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
             const int nrows = min(kMaxRows, nrowsTotal - rowBase);
             if (tid < nrows) {
                 const int r = rowBase + tid, cx = c0[0] + r / nrowsY, cy = c0[1] + r % nrowsY;
-                const int keyLo = set * g.ncell + (cx * g.dim[1] + cy) * g.dim[2] + c0[2];
-                int start = (int) A.cellStart[keyLo], end = (int) A.cellStart[keyLo + (c1[2] - c0[2]) + 1];
-                if (set == 0) start = max(start, b * kTile);     // primary list: each unordered pair once (own block: triangle below)
+                // z range of this row: only the part of the column of cells that can be within reach of the block box
+                const double xlo = g.lo[0] + cx * g.h, ylo = g.lo[1] + cy * g.h;
+                const double ex = fmax(0.0, fmax(sbox[0] - (xlo + g.h), xlo - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - (ylo + g.h), ylo - sbox[4]));
+                const double rem = reach * reach - ex * ex - ey * ey;
+                int start = 0, end = 0;
+                if (rem >= 0.0) {
+                    const double dz = sqrt(rem) + 1.0e-6;
+                    const int z0 = cell_coord(sbox[2] - dz, g.lo[2], g.invh, g.dim[2]), z1 = cell_coord(sbox[5] + dz, g.lo[2], g.invh, g.dim[2]);
+                    const int keyLo = set * g.ncell + (cx * g.dim[1] + cy) * g.dim[2] + z0;
+                    start = (int) A.cellStart[keyLo]; end = (int) A.cellStart[keyLo + (z1 - z0) + 1];
+                    if (set == 0) start = max(start, b * kTile);     // primary list: each unordered pair once (own block: triangle below)
+                }
                 rowStart[tid] = start;
-                rowPrefix[tid + 1] = max(0, end - start);
+                rowPrefix[tid] = max(0, end - start);                // (count of the row)
             }
             __syncthreads();
-            if (tid == 0) { rowPrefix[0] = 0; for (int r = 0; r < nrows; r++) rowPrefix[r + 1] += rowPrefix[r]; }
-            __syncthreads();
-            const int total = rowPrefix[nrows];
-            // every warp walks its own chunks of 32 consecutive candidates and keeps a private queue: no CTA barrier in here
-            for (int base = warp * kTile; base < total; base += kBuildThreads) {
-                const int c = base + lane;
-                unsigned int colmask = 0;
-                int atom = -1;
-                if (c < total) {
-                    int lo = 0, hi = nrows;                      // last row r with rowPrefix[r] <= c
-                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (rowPrefix[mid] <= c) lo = mid; else hi = mid; }
-                    const int s = rowStart[lo] + (c - rowPrefix[lo]);
-                    const double xj = A.sX[3 * s], yj = A.sX[3 * s + 1], zj = A.sX[3 * s + 2];
-                    // conservative reject against the block box
-                    const double ex = fmax(0.0, fmax(sbox[0] - xj, xj - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - yj, yj - sbox[4])),
-                                 ez = fmax(0.0, fmax(sbox[2] - zj, zj - sbox[5]));
-                    if (ex * ex + ey * ey + ez * ez <= reject2) {
-                        const float fx = (float) (xj - sbox[6]), fy = (float) (yj - sbox[7]), fz = (float) (zj - sbox[8]);
-                        unsigned int amb = 0;
+            // every warp walks whole rows in chunks of 32 consecutive candidates and keeps a private queue: no CTA barrier in here
+            for (int r = warp; r < nrows; r += kBuildWarps) {
+                const int rs = rowStart[r], rc = rowPrefix[r];
+                for (int base = 0; base < rc; base += kTile) {
+                    const int c = base + lane;
+                    unsigned int colmask = 0;
+                    int atom = -1;
+                    if (c < rc) {
+                        const int s = rs + c;
+                        const double xj = A.sX[3 * s], yj = A.sX[3 * s + 1], zj = A.sX[3 * s + 2];
+                        // conservative reject against the block box
+                        const double ex = fmax(0.0, fmax(sbox[0] - xj, xj - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - yj, yj - sbox[4])),
+                                     ez = fmax(0.0, fmax(sbox[2] - zj, zj - sbox[5]));
+                        if (ex * ex + ey * ey + ez * ez <= reject2) {
+                            const float fx = (float) (xj - sbox[6]), fy = (float) (yj - sbox[7]), fz = (float) (zj - sbox[8]);
+                            float band = 1.0e30f;                    // min over the block atoms of |r2 - cutoff^2|
 #pragma unroll 8
-                        for (int i = 0; i < kTile; i++) {
-                            const float4 p = sxf[i];
-                            const float dx = p.x - fx, dy = p.y - fy, dz = p.z - fz;
-                            const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                            colmask |= (r2 <= c2lo) ? (1u << i) : 0u;
-                            amb |= (r2 > c2lo && r2 < c2hi) ? (1u << i) : 0u;
-                        }
-                        while (amb) {                            // inside the band: the reference predicate decides
-                            const int i = __ffs(amb) - 1;
-                            amb &= amb - 1;
-                            const double r2 = ref_dist2(sxi[i][0] - xj, sxi[i][1] - yj, sxi[i][2] - zj);
-                            colmask |= (r2 <= A.cutoff2) ? (1u << i) : 0u;
-                        }
-                        atom = A.sAtom[s];
-                        if (set == 0 && colmask != 0u) {
-                            if ((s >> 5) == b) colmask &= (1u << (s & 31)) - 1u;      // own block: i < j only, no self pair
-                            for (int k = A.exclPtr[atom]; k < A.exclPtr[atom + 1]; k++) {
-                                const int sp = A.invPerm[A.exclCol[k]];
-                                if ((sp >> 5) == b) colmask &= ~(1u << (sp & 31));
+                            for (int i = 0; i < kTile; i++) {
+                                const float4 p = sxf[i];
+                                const float dx = p.x - fx, dy = p.y - fy, dz = p.z - fz;
+                                const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                                colmask |= (r2 <= c2f) ? (1u << i) : 0u;
+                                band = fminf(band, fabsf(r2 - c2f));
+                            }
+                            if (band <= eps) {                       // some distance is within the fp32 error band: the reference predicate decides
+                                colmask = 0u;
+                                for (int i = 0; i < kTile; i++) {
+                                    const double r2 = ref_dist2(sxi[i][0] - xj, sxi[i][1] - yj, sxi[i][2] - zj);
+                                    colmask |= (r2 <= A.cutoff2) ? (1u << i) : 0u;
+                                }
+                            }
+                            atom = A.sAtom[s];
+                            if (set == 0 && colmask != 0u) {
+                                if ((s >> 5) == b) colmask &= (1u << (s & 31)) - 1u;      // own block: i < j only, no self pair
+                                for (int k = A.exclPtr[atom]; k < A.exclPtr[atom + 1]; k++) {
+                                    const int sp = A.invPerm[A.exclCol[k]];
+                                    if ((sp >> 5) == b) colmask &= ~(1u << (sp & 31));
+                                }
                             }
                         }
                     }
-                }
-                const bool keep = colmask != 0u;
-                myPairs += __popc(colmask);
-                const unsigned int bal = __ballot_sync(0xffffffffu, keep);
-                int cnt = qCnt[warp];
-                if (keep) { const int q = cnt + __popc(bal & ((1u << lane) - 1u)); qAtom[warp][q] = atom; qMask[warp][q] = colmask; }
-                cnt += __popc(bal);
-                __syncwarp();
-                if (cnt >= kTile) {                              // emit one full tile from the front of the queue
-                    int slot = 0;
-                    if (lane == 0) slot = atomicAdd(&emitted, 1);
-                    slot = __shfl_sync(0xffffffffu, slot, 0);
-                    const unsigned int rot = rows_from_columns(qMask[warp][lane], lane);
-                    if (slot < A.tileStride) {
-                        const size_t T = ((size_t) b * A.tileStride + slot) * kTile + lane;
-                        A.tileJ[T] = qAtom[warp][lane];
-                        A.tileMask[T] = rot;
-                    }
-                    const int ra = qAtom[warp][kTile + lane];
-                    const unsigned int rm = qMask[warp][kTile + lane];
+                    const bool keep = colmask != 0u;
+                    myPairs += __popc(colmask);
+                    const unsigned int bal = __ballot_sync(0xffffffffu, keep);
+                    if (bal == 0u) continue;
+                    int cnt = qCnt[warp];
+                    if (keep) { const int q = cnt + __popc(bal & ((1u << lane) - 1u)); qAtom[warp][q] = atom; qMask[warp][q] = colmask; }
+                    cnt += __popc(bal);
                     __syncwarp();
-                    qAtom[warp][lane] = ra; qMask[warp][lane] = rm;
-                    cnt -= kTile;
+                    if (cnt >= kTile) {                              // emit one full tile from the front of the queue
+                        int slot = 0;
+                        if (lane == 0) slot = atomicAdd(&emitted, 1);
+                        slot = __shfl_sync(0xffffffffu, slot, 0);
+                        const unsigned int rot = rows_from_columns(qMask[warp][lane], lane);
+                        if (slot < A.tileStride) {
+                            const size_t T = ((size_t) b * A.tileStride + slot) * kTile + lane;
+                            A.tileJ[T] = qAtom[warp][lane];
+                            A.tileMask[T] = rot;
+                        }
+                        const int ra = qAtom[warp][kTile + lane];
+                        const unsigned int rm = qMask[warp][kTile + lane];
+                        __syncwarp();
+                        qAtom[warp][lane] = ra; qMask[warp][lane] = rm;
+                        cnt -= kTile;
+                    }
+                    if (lane == 0) qCnt[warp] = cnt;
+                    __syncwarp();
                 }
-                if (lane == 0) qCnt[warp] = cnt;
-                __syncwarp();
             }
             __syncthreads();        // rowStart / rowPrefix are rewritten by the next batch
         }
