@@ -137,7 +137,7 @@ def run_reference(args):
         return
     sample = args.ref_sample
     base, w = cpu_reference(sample, max(1, args.steps), max(0, min(args.warmup, 1)))
-    wl = args.workload
+    wl = workload_description(args.workload, make_workload(args.workload))
     line = {"metric": "NBModelABFS list-pair interactions per second (pair-list rebuild + energy + gradients per call)",
             "value": base["value"], "unit": "list-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -213,6 +213,7 @@ def run_b200(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
 
     def barrier():
@@ -239,18 +240,23 @@ def run_b200(args):
     m = DeviceModel(w, local, rank, world)
     esum = torch.zeros(15, dtype=torch.float64, device="cuda")
 
+    small = torch.zeros(15, dtype=torch.float64).pin_memory() if world > 1 else None
+
+    def exchange():                                # the path's one exchange step: gradient + energy/dEdM sum over ranks
+        dist.all_reduce(m.g)
+        small[:6] = torch.from_numpy(m.e); small[6:] = torch.from_numpy(m.dEdM)
+        esum.copy_(small, non_blocking=True)
+        dist.all_reduce(esum)
+
     def step_rebuild():
         m.step(rebuild=True)
-        if dist is not None:                       # the path's one exchange step: gradient + energy/dEdM reduction
-            dist.all_reduce(m.g)
-            esum[:6] = torch.from_numpy(m.e).to(esum.device); esum[6:] = torch.from_numpy(m.dEdM).to(esum.device)
-            dist.all_reduce(esum)
+        if dist is not None:
+            exchange()
 
     def step_norebuild():
         m.step(rebuild=False)
         if dist is not None:
-            dist.all_reduce(m.g)
-            dist.all_reduce(esum)
+            exchange()
 
     step_rebuild()
     torch.cuda.synchronize()
