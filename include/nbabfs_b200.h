@@ -20,6 +20,8 @@
 #ifndef NBABFS_B200_H
 #define NBABFS_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -103,6 +105,12 @@ long PairListGenerator_B200_SelfPairListFromCoordinates3(int device, int n, cons
 long PairListGenerator_B200_CrossPairListFromDoubleCoordinates3(int device, int n1, const double *xyz1, int n2, const double *xyz2,
                                                                 double cutoff, int **pairs, int *status);
 void nbb200_free(void *p);
+
+/* Page-locked host arrays.  Coordinates3 / gradient arrays allocated here (instead of Memory_Allocate_Array_Real,
+ * pC/csource/Memory.c) are transferred by DMA without a staging copy; Update / MMMMEnergy detect them automatically
+ * (cudaPointerGetAttributes) and fall back to an internal pinned staging buffer for ordinary pageable arrays. */
+void *nbb200_host_alloc(size_t bytes);
+void  nbb200_host_free(void *p);
 
 /* PairwiseInteractionABFS_MakeFactors (pM/csource/PairwiseInteraction.c:89-141): host helper, out[21] */
 void PairwiseInteractionABFS_B200_MakeFactors(double dampingCutoff, double innerCutoff, double outerCutoff, double *out21);

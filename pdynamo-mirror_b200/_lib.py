@@ -31,6 +31,8 @@ SIGNATURES = {
     "PairListGenerator_B200_SelfPairListFromCoordinates3": (C.c_long, [C.c_int, C.c_int, dp, C.c_double, C.c_int, ip, C.POINTER(ip), ip]),
     "PairListGenerator_B200_CrossPairListFromDoubleCoordinates3": (C.c_long, [C.c_int, C.c_int, dp, C.c_int, dp, C.c_double, C.POINTER(ip), ip]),
     "nbb200_free": (None, [vp]),
+    "nbb200_host_alloc": (vp, [C.c_size_t]),
+    "nbb200_host_free": (None, [vp]),
     "PairwiseInteractionABFS_B200_MakeFactors": (None, [C.c_double] * 3 + [dp]),
     "nbb200_set_stream": (None, [vp, vp]),
     "nbb200_enable_timing": (None, [vp, C.c_int]),
@@ -67,3 +69,29 @@ def d_(a):
 
 def i_(a):
     return None if a is None else a.ctypes.data_as(ip)
+
+
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            lib().nbb200_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_array(shape, dtype="float64"):
+    """numpy array in page-locked host memory (nbb200_host_alloc): transferred by DMA without a staging copy.
+    Falls back to an ordinary array when no CUDA device is available (there is nothing to transfer to then)."""
+    import numpy as np
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = lib().nbb200_host_alloc(n) if lib().nbb200_device_count() > 0 else None
+    if not ptr:
+        return np.zeros(shape, dtype=dtype)
+    buf = (C.c_char * n).from_address(ptr)
+    buf._owner = _PinnedOwner(ptr)                      # the ctypes buffer is the numpy base: freed with the last view
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    arr[...] = 0
+    return arr

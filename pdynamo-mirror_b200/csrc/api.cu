@@ -23,6 +23,14 @@ bool cuda_ok(cudaError_t e, const char *what)
 
 static void set_status(int *status, int value) { if (status != nullptr) *status = value; }
 
+// true if p is page-locked host memory (cudaMallocHost / cudaHostRegister): DMA needs no staging copy
+static bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 static void destroy(State *s)
 {
     if (s == nullptr) return;
@@ -281,8 +289,9 @@ int NBModelABFS_B200_Update(NBB200State *state, const double *xyz, const double 
     if (state == nullptr || xyz == nullptr) return 0;
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
-    std::memcpy(s.hx, xyz, sizeof(double) * 3 * (size_t) s.n);
-    if (!cuda_ok(cudaMemcpyAsync(s.x.p, s.hx, sizeof(double) * 3 * (size_t) s.n, cudaMemcpyHostToDevice, s.stream), "H2D coordinates")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
+    const double *src = xyz;
+    if (!is_pinned_host(xyz)) { std::memcpy(s.hx, xyz, sizeof(double) * 3 * (size_t) s.n); src = s.hx; }
+    if (!cuda_ok(cudaMemcpyAsync(s.x.p, src, sizeof(double) * 3 * (size_t) s.n, cudaMemcpyHostToDevice, s.stream), "H2D coordinates")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
     s.xcur = s.x.p;
     return update_common(s, box6, forceNew, status);
 }
@@ -303,15 +312,19 @@ void NBModelABFS_B200_MMMMEnergy(NBB200State *state, double *energies, double *g
     cudaSetDevice(s.device);
     if (s.xcur == nullptr) { set_error("MMMMEnergy called before Update"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
     double *dg = nullptr;
+    const bool direct = grad != nullptr && is_pinned_host(grad);       // accumulate on the device, DMA straight into the caller's array
+    const size_t gbytes = sizeof(double) * 3 * (size_t) s.n;
     if (grad != nullptr) {
         dg = s.grad.p;
-        if (!cuda_ok(cudaMemsetAsync(dg, 0, sizeof(double) * 3 * (size_t) s.n, s.stream), "memset grad")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+        const bool ok0 = direct ? cuda_ok(cudaMemcpyAsync(dg, grad, gbytes, cudaMemcpyHostToDevice, s.stream), "H2D grad")
+                                : cuda_ok(cudaMemsetAsync(dg, 0, gbytes, s.stream), "memset grad");
+        if (!ok0) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
     }
     bool ok = energy_common(s, energies, dg, dEdM);
     if (ok && grad != nullptr) {
-        ok = cuda_ok(cudaMemcpyAsync(s.hgrad, dg, sizeof(double) * 3 * (size_t) s.n, cudaMemcpyDeviceToHost, s.stream), "D2H grad") &&
+        ok = cuda_ok(cudaMemcpyAsync(direct ? grad : s.hgrad, dg, gbytes, cudaMemcpyDeviceToHost, s.stream), "D2H grad") &&
              cuda_ok(cudaStreamSynchronize(s.stream), "sync");
-        if (ok) { const size_t m = 3 * (size_t) s.n; for (size_t i = 0; i < m; i++) grad[i] += s.hgrad[i]; }
+        if (ok && !direct) { const size_t m = 3 * (size_t) s.n; for (size_t i = 0; i < m; i++) grad[i] += s.hgrad[i]; }
     }
     if (!ok) set_status(status, NBB200_STATUS_LOGIC_ERROR);
 }
@@ -436,6 +449,15 @@ long PairListGenerator_B200_CrossPairListFromDoubleCoordinates3(int device, int 
 }
 
 void nbb200_free(void *p) { std::free(p); }
+
+void *nbb200_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (!cuda_ok(cudaMallocHost(&p, bytes ? bytes : 1), "cudaMallocHost")) return nullptr;
+    return p;
+}
+
+void nbb200_host_free(void *p) { if (p != nullptr) cudaFreeHost(p); }
 
 void PairwiseInteractionABFS_B200_MakeFactors(double dampingCutoff, double innerCutoff, double outerCutoff, double *out21)
 {

@@ -96,6 +96,7 @@ class System:
         self.energyModel = None
         self.symmetry = None
         self.timings = {"NB Set Up": 0.0, "NB Evaluation": 0.0, "Energy": 0.0}
+        self._gradients = None
 
     @classmethod
     def FromWorkload(cls, w):
@@ -107,7 +108,9 @@ class System:
         em.exclusions = SelfPairList(w["exclusions"]) if len(w["exclusions"]) else None
         em.interactions14 = SelfPairList(w["pairs14"]) if len(w["pairs14"]) else None
         em.electrostaticScale14 = w.get("electrostaticScale14", 1.0)
-        self.coordinates3 = np.array(w["xyz"], dtype=np.float64)
+        from ._lib import pinned_array
+        self.coordinates3 = pinned_array(w["xyz"].shape)        # page-locked: DMA without a staging copy
+        self.coordinates3[...] = w["xyz"]
         if w["box"] is not None:
             b = w["box"]
             self.DefineSymmetry(a=b[0], b=b[1], c=b[2], alpha=b[3], beta=b[4], gamma=b[5],
@@ -146,7 +149,13 @@ class System:
         cfg = self.configuration
         cfg.ClearTemporaryAttributes()
         if doGradients:
-            cfg.SetTemporaryAttribute("gradients3", np.zeros((len(self.energyModel.mmAtoms), 3)))
+            n = len(self.energyModel.mmAtoms)
+            if self._gradients is None or self._gradients.shape[0] != n:
+                from ._lib import pinned_array
+                self._gradients = pinned_array((n, 3))          # reused, page-locked gradient storage (zeroed per call as System.Energy does)
+            else:
+                self._gradients.fill(0.0)
+            cfg.SetTemporaryAttribute("gradients3", self._gradients)
             if self.symmetry is not None:
                 cfg.SetTemporaryAttribute("symmetryParameterGradients", SymmetryParameterGradients())
         em = self.energyModel
