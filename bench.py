@@ -49,6 +49,17 @@ def peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
+def ncu_traffic(workload, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the force kernel per launch, from the committed ncu capture of the
+    same workload (profiles/traffic.json); None when no capture matches."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get("%s@%d" % (workload, world))
+    except Exception:
+        return None
+
+
 class ClockSampler:
     QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -298,7 +309,7 @@ def run_b200(args):
         "no_rebuild": {"ms_per_call": ms_nr, "value": pairs / (ms_nr * 1e-3), "unit": "list-pairs/s"},
         "kernels_ms": {"list_rebuild": build_ms, "tile_forces": force_ms, "pairs14": tm["pairs14"], "displacement_check": tm["displacementCheck"]},
         "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
-                     "traffic": None, "kernel": "k_tile_forces", "flop_per_list_pair": FLOP_PER_LIST_PAIR,
+                     "traffic": ncu_traffic(args.workload, world), "kernel": "k_tile_forces", "flop_per_list_pair": FLOP_PER_LIST_PAIR,
                      "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (sm_max_mhz, %s); MEASURED_PEAKS.json holds no FP32 figure" % (sm_max, pk_kind)},
         "roofline_list_build": {"bound": "hbm", "achieved": list_bytes / world / (build_ms * 1e-3) / 1e9 if build_ms > 0 else 0.0, "peak": float(pk.get("hbm_gbs", 6650.0)),
                                 "unit": "GB/s", "frac": (list_bytes / world / (build_ms * 1e-3) / 1e9) / float(pk.get("hbm_gbs", 6650.0)) if build_ms > 0 else 0.0,
@@ -326,7 +337,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t1) / args.steps * 1e3
         line["e2e"] = {"value": pairs / (e2e_ms * 1e-3), "unit": "list-pairs/s", "ms_per_step": e2e_ms,
-                       "h2d_bytes_per_step": 24 * n + 48, "d2h_bytes_per_step": 24 * n + 16 * 8 * (nimg + 2),
+                       "h2d_bytes_per_step": 2 * 24 * n + 48 + 128 * (nimg + 1), "d2h_bytes_per_step": 24 * n + 16 * 8 * (nimg + 2),
                        "api": "System.Energy(doGradients=True) -> NBModelABFS.SetUp/Energy -> NBModelABFS_B200_Update/_MMMMEnergy, host numpy in/out, wall clock"}
         m.model.SetOptions(updateFrequency=0)
         if rank == 0 and not args.no_cpu:
@@ -351,8 +362,8 @@ def run_b200(args):
 
 
 def jac_block(torch, local, fp32_peak_tflops):
-    """The 23 558-atom JAC-size box (north-star target size) on one GPU: ms per call with and without rebuild."""
-    w = make_workload("jac")
+    """The 23 558-atom DHFR/JAC box (north-star target size; the reference's own benchmark input) on one GPU."""
+    w = make_workload("dhfr")
     m = DeviceModel(w, local)
     m.step(rebuild=True)
     torch.cuda.synchronize()
@@ -364,7 +375,7 @@ def jac_block(torch, local, fp32_peak_tflops):
     ms_nr = timed_steps(torch, lambda: m.step(rebuild=False), 50, 5, lambda: None)
     f = statistics.mean(fk)
     ach = pairs * FLOP_PER_LIST_PAIR / (f * 1e-3) / 1e12
-    return {"workload": workload_description("jac", w), "list_pairs": pairs, "ms_per_call_rebuild": ms, "ms_per_call_no_rebuild": ms_nr,
+    return {"workload": workload_description("dhfr", w) + " (the reference's own JAC benchmark input, benchmarks/data/dhfr)", "list_pairs": pairs, "ms_per_call_rebuild": ms, "ms_per_call_no_rebuild": ms_nr,
             "value": pairs / (ms * 1e-3), "value_no_rebuild": pairs / (ms_nr * 1e-3), "unit": "list-pairs/s",
             "kernels_ms": {"list_rebuild": statistics.mean(lb), "tile_forces": f}, "roofline_frac_fp32": ach / fp32_peak_tflops}
 
@@ -376,7 +387,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="m1")
-    ap.add_argument("--ref-sample", default="jac", help="bounded CPU sample of the workload for the reference / cpu_baseline legs")
+    ap.add_argument("--ref-sample", default="dhfr", help="bounded CPU sample of the workload for the reference / cpu_baseline legs")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-jac", action="store_true")
     args = ap.parse_args()

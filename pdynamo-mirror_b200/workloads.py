@@ -407,6 +407,18 @@ def bala_water(name="bala_water"):
     return _finish(xyz, charges, ljtypes, eps, rmin, "amber", excl, p14, [ax, ay, az, 90.0, 90.0, 90.0], name, scale14=1.0)
 
 
+def dhfr_jac(name="dhfr"):
+    """The reference's own JAC benchmark system (benchmarks/data/dhfr: 23 558 atoms, CHARMM22, cubic a = 62.23), from the
+    fixture tests/golden/dhfr_jac.npz (tests/golden/make_fixtures.py).  Its per-term NB energies are published in
+    benchmarks/log/systemBenchmarks_Serial_1ps.log:397-403 -- a known-answer vector for this path."""
+    d = np.load(_os.path.join(_GOLDEN, "dhfr_jac.npz"))
+    w = _finish(d["xyz"], d["charges"], d["ljtypes"], d["eps"], d["sigma"], "amber", d["exclusions"], d["pairs14"], float(d["a"]), name,
+                eps14=d["eps14"], sigma14=d["sigma14"], scale14=1.0)
+    w["published_energies"] = np.array(d["published_energies"])
+    w["published_counts"] = np.array(d["published_counts"])
+    return w
+
+
 def perturbed(system, amplitude, seed=999):
     """Copy of a system with every coordinate displaced uniformly in [-amplitude, amplitude] (for update-heuristic tests)."""
     s = dict(system)
@@ -423,6 +435,7 @@ WORKLOADS = {
     "w1728_lattice": lambda: water_box(12, name="w1728_lattice"),
     "water3x3x3": lambda: replicated_water(3),
     "jac": lambda: jac_protein_water(),
+    "dhfr": lambda: dhfr_jac(),
     "jac_lattice": lambda: jac_like(),
     "water24k_lattice": lambda: water_box(20, name="water24k_lattice"),
     "m1": lambda: replicated_water(12, name="m1"),

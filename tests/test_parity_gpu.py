@@ -70,6 +70,26 @@ def test_parity_vs_oracle_and_reference_golden(pkg, orc, name):
     assert ("MM/MM 1-4 Elect." in terms) == (len(w["pairs14"]) > 0)
 
 
+def test_published_dhfr_known_answer(pkg, orc):
+    """The reference's own JAC benchmark input: published per-term energies (4 decimals) and list sizes
+    (benchmarks/log/systemBenchmarks_Serial_1ps.log:392-403), plus full parity against the oracle."""
+    w = pkg.workloads.WORKLOADS["dhfr"]()
+    system, st, e, g, dm = gpu_energy(pkg, w)
+    pub = w["published_energies"]
+    assert abs(e.sum() - pub.sum()) <= E_TOL * abs(pub.sum())
+    for k in range(6):
+        assert abs(e[k] - pub[k]) <= E_TOL * abs(pub[k]) + 1.0e-7 * np.abs(pub).sum() + 5.0e-5, (k, e[k], pub[k])
+    primary, image_pairs, nimages, n14 = [int(v) for v in w["published_counts"][:4]]
+    assert (st.NumberOfPairs(), st.NumberOfImagePairs(), st.NumberOfImages(), st.NumberOf14Pairs()) == (primary, image_pairs, nimages, n14)
+    o = orc.OracleNB(w)
+    ref = o.energy(force_new=True)
+    check_numbers("dhfr", e, g, dm, ref["energies"], ref["grad"], ref["dEdM"])
+    assert np.array_equal(orc.canonical_primary(st.Pairs(-1)), orc.canonical_primary(o.primary_pairs()))
+    for x, y in zip(st.Images(), o.images()):
+        assert (x["t"], x["a"], x["b"], x["c"], x["scale"]) == (y["t"], y["a"], y["b"], y["c"], y["scale"])
+        assert np.array_equal(orc.canonical_cross(x["pairs"]), orc.canonical_cross(y["pairs"]))
+
+
 def test_update_heuristic_and_stale_lists(pkg, orc):
     """CheckForUpdate semantics: no rebuild below (list-outer)/2, rebuild above; between rebuilds both sides evaluate
     the SAME stale list at the new coordinates, so the numbers must still agree."""
