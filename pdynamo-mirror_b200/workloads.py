@@ -419,6 +419,49 @@ def dhfr_jac(name="dhfr"):
     return w
 
 
+CRYSTAL_NAMES = ("ALAALA", "ALAMET01", "AQARUF", "BEVXEF01", "GLYALB", "GLYGLY", "GUFQON", "HXACAN19", "IWANID", "LCDMPP10", "WIRYEB", "WABZOO")
+
+
+def _bond_exclusions(n, bonds):
+    adj = [set() for _ in range(n)]
+    for i, j in bonds:
+        adj[int(i)].add(int(j))
+        adj[int(j)].add(int(i))
+    excl, p14 = set(), set()
+    for i in range(n):
+        d1 = adj[i]
+        d2 = (set().union(*[adj[j] for j in d1]) if d1 else set()) - d1 - {i}
+        d3 = (set().union(*[adj[j] for j in d2]) if d2 else set()) - d2 - d1 - {i}
+        for j in d1 | d2 | d3:
+            excl.add((max(i, j), min(i, j)))
+        for j in d3:
+            p14.add((max(i, j), min(i, j)))
+    return (np.array(sorted(excl), dtype=np.int32).reshape(-1, 2), np.array(sorted(p14), dtype=np.int32).reshape(-1, 2))
+
+
+def crystal(name):
+    """One of the 12 molecular crystals of pMolecule-1.9.0/tests/CrystalMMEnergies.py (fixture tests/golden/crystals.npz):
+    genuine space-group operations (rotations, screw axes, inversions), tiny cells (tens to hundreds of images inside the
+    13.5 A list cutoff), monoclinic / hexagonal / rhombohedral / triclinic lattices.  LJ tables are the topology's A/B
+    coefficient tables; 1-4 pairs use half the LJ table and electrostaticScale14 = 0.5 (OPLS convention of the test)."""
+    d = np.load(_os.path.join(_GOLDEN, "crystals.npz"))
+    xyz, q, types, nbi = d[name + "_xyz"], d[name + "_q"], d[name + "_type"], d[name + "_nbindex"]
+    nt = nbi.shape[0]
+    # triangular table in the reference's layout (LJParameterContainer: tableindex[nt*nt] -> n(n+1)/2 entries)
+    tindex = np.zeros(nt * nt, dtype=np.int32)
+    tA, tB, k = np.zeros(nt * (nt + 1) // 2), np.zeros(nt * (nt + 1) // 2), 0
+    for i in range(nt):
+        for j in range(i + 1):
+            tA[k], tB[k] = d[name + "_A"][nbi[i, j]], d[name + "_B"][nbi[i, j]]
+            tindex[j + i * nt] = tindex[i + j * nt] = k
+            k += 1
+    excl, p14 = _bond_exclusions(len(q), d[name + "_bonds"])
+    return dict(name=name, n=int(len(q)), xyz=np.ascontiguousarray(xyz, np.float64), charges=np.ascontiguousarray(q, np.float64),
+                ljtypes=np.ascontiguousarray(types, np.int32), ntypes=int(nt), tableindex=tindex, tableA=tA, tableB=tB,
+                tableindex14=tindex.copy(), tableA14=0.5 * tA, tableB14=0.5 * tB, exclusions=excl, pairs14=p14,
+                electrostaticScale14=0.5, box=np.array(d[name + "_box"]), rot=np.array(d[name + "_rot"]), trans=np.array(d[name + "_trans"]))
+
+
 def perturbed(system, amplitude, seed=999):
     """Copy of a system with every coordinate displaced uniformly in [-amplitude, amplitude] (for update-heuristic tests)."""
     s = dict(system)
@@ -441,6 +484,9 @@ WORKLOADS = {
     "m1": lambda: replicated_water(12, name="m1"),
 }
 
+for _c in CRYSTAL_NAMES:
+    WORKLOADS["crystal_" + _c] = (lambda c=_c: crystal(c))
+
 # cases with committed golden outputs of the compiled reference: name -> (maker, reference options, store full pair sets)
 GOLDEN_CASES = {
     "w216": (WORKLOADS["w216"], {}, True),
@@ -450,3 +496,5 @@ GOLDEN_CASES = {
     "bala": (WORKLOADS["bala"], {}, False),
     "jac": (WORKLOADS["jac"], {}, False),
 }
+for _c in CRYSTAL_NAMES:
+    GOLDEN_CASES["crystal_" + _c] = (WORKLOADS["crystal_" + _c], {}, False)

@@ -164,6 +164,111 @@ def make_dhfr():
           (len(d["charges"]), len(d["exclusions"]), len(d["pairs14"]), len(d["types"]), d["charges"].sum()))
 
 
+# ----------------------------------------------------------------------------------------------------
+# The 12 molecular crystals of pMolecule-1.9.0/tests/CrystalMMEnergies.py (:30-63): AMBER top/crd files from
+# pMolecule-1.9.0/data/molecularCrystals, space-group operations and cell parameters from the test file.  Non-P1 space
+# groups exercise rotations S != I, self-inverse images (scale 0.5), inverse-pair skipping and triclinic cells.
+# Only what the NB path needs is read (charges, LJ coefficient tables, bonds); the published crystal energies include
+# bonded terms and are therefore not usable as NB known answers -- parity on these inputs is against the compiled reference.
+# ----------------------------------------------------------------------------------------------------
+_CRYSTAL_OPS = {"C2": ["(x,y,z)", "(-x,y,-z)"],
+                "I4": ["(x,y,z)", "(-x,-y,z)", "(-y,x,z)", "(y,-x,z)", "(x+1/2,y+1/2,z+1/2)", "(-x+1/2,-y+1/2,z+1/2)", "(-y+1/2,x+1/2,z+1/2)", "(y+1/2,-x+1/2,z+1/2)"],
+                "P1": ["(x,y,z)"],
+                "P21a": ["(x,y,z)", "(-x+1/2,y+1/2,-z)", "(-x,-y,-z)", "(x+1/2,-y+1/2,z)"],
+                "P212121": ["(x,y,z)", "(-x+1/2,-y,z+1/2)", "(-x,y+1/2,-z+1/2)", "(x+1/2,-y+1/2,-z)"],
+                "P61": ["(x,y,z)", "(-y,x-y,z+1/3)", "(-x+y,-x,z+2/3)", "(-x,-y,z+1/2)", "(y,-x+y,z+5/6)", "(x-y,x,z+1/6)"],
+                "P21c": ["(x,y,z)", "(-x,y+1/2,-z+1/2)", "(-x,-y,-z)", "(x,-y+1/2,z+1/2)"],
+                "R3": ["(x,y,z)", "(z,x,y)", "(y,z,x)"]}
+_CRYSTALS = [("ALAALA", "I4", dict(a=17.9850, b=17.9850, c=5.1540)),
+             ("ALAMET01", "P21c", dict(a=13.089, b=5.329, c=15.921, beta=108.57)),
+             ("AQARUF", "P61", dict(a=14.3720, b=14.3720, c=9.8282, gamma=120.0)),
+             ("BEVXEF01", "P212121", dict(a=9.6590, b=9.6720, c=10.7390)),
+             ("GLYALB", "P212121", dict(a=9.6930, b=9.5240, c=7.5370)),
+             ("GLYGLY", "P21a", dict(a=7.812, b=9.566, c=9.410, beta=124.60)),
+             ("GUFQON", "P212121", dict(a=7.2750, b=9.0970, c=10.5070)),
+             ("HXACAN19", "P21a", dict(a=12.8720, b=9.3700, c=7.0850, beta=115.6200)),
+             ("IWANID", "C2", dict(a=23.091, b=5.494, c=17.510, beta=117.88)),
+             ("LCDMPP10", "P1", dict(a=8.067, b=6.082, c=5.155, alpha=131.7, beta=82.4, gamma=106.6)),
+             ("WIRYEB", "P61", dict(a=14.4240, b=14.4240, c=9.9960, gamma=120.0)),
+             ("WABZOO", "R3", dict(a=12.5940, b=12.5940, c=12.5940, alpha=118.03, beta=118.03, gamma=118.03))]
+
+
+def _symop(ostring):
+    """pCore.Transformation3.pyx:127-163 (Transformation3_FromSymmetryOperationString)"""
+    t = ostring.replace(" ", "").strip("()")
+    rot, tr = np.zeros((3, 3)), np.zeros(3)
+    for i, s in enumerate(t.split(",")):
+        ns = [s[0:1]]
+        for j, c in enumerate(s[1:]):
+            if s[j:j + 1].isdigit() and not (c.isdigit() or c == "."):
+                ns.append(".")
+            ns.append(c.lower())
+        if ns[-1].isdigit():
+            ns.append(".")
+        e = "".join(ns)
+        t0 = eval(e, {}, dict(x=0.0, y=0.0, z=0.0))
+        rx = eval(e, {}, dict(x=1.0, y=0.0, z=0.0)) - t0
+        ry = eval(e, {}, dict(x=1.0, y=1.0, z=0.0)) - t0 - rx
+        rz = eval(e, {}, dict(x=1.0, y=1.0, z=1.0)) - t0 - rx - ry
+        tr[i], rot[i] = t0, (rx, ry, rz)
+    return rot, tr
+
+
+def _amber_top(path):
+    flags, cur = {}, None
+    with open(path) as f:
+        for line in f:
+            if line.startswith("%FLAG"):
+                cur = line.split()[1]
+                flags[cur] = []
+            elif line.startswith("%FORMAT") or line.startswith("%VERSION"):
+                fmt = line
+                if cur is not None:
+                    flags[cur].append(("fmt", line.strip()))
+            elif cur is not None:
+                flags[cur].append(("data", line.rstrip("\n")))
+    out = {}
+    for k, items in flags.items():
+        fmt = [v for t, v in items if t == "fmt"][0]
+        width = int(fmt.split("(")[1].rstrip(")").lower().replace("e", "a").replace("i", "a").split("a")[1].split(".")[0])
+        vals = []
+        for t, v in items:
+            if t == "data":
+                vals += [v[i:i + width] for i in range(0, len(v), width) if v[i:i + width].strip()]
+        out[k] = vals
+    return out
+
+
+def make_crystals():
+    base = os.path.join(REF, "pMolecule-1.9.0/data/molecularCrystals")
+    data = {"names": np.array([c[0] for c in _CRYSTALS])}
+    for name, group, cell in _CRYSTALS:
+        top = _amber_top(os.path.join(base, name + ".top"))
+        n = int(top["POINTERS"][0])
+        ntypes = int(top["POINTERS"][1])
+        q = np.array([float(v) for v in top["CHARGE"]]) / 18.2223
+        ati = np.array([int(v) for v in top["ATOM_TYPE_INDEX"]], dtype=np.int32) - 1
+        nbi = np.array([int(v) for v in top["NONBONDED_PARM_INDEX"]], dtype=np.int32).reshape(ntypes, ntypes) - 1
+        acoef = np.array([float(v) for v in top["LENNARD_JONES_ACOEF"]]) * 4.184
+        bcoef = np.array([float(v) for v in top["LENNARD_JONES_BCOEF"]]) * 4.184
+        bonds = [int(v) for v in top.get("BONDS_INC_HYDROGEN", [])] + [int(v) for v in top.get("BONDS_WITHOUT_HYDROGEN", [])]
+        bonds = np.array(bonds, dtype=np.int64).reshape(-1, 3)[:, :2] // 3
+        with open(os.path.join(base, name + ".crd")) as f:
+            lines = f.read().split("\n")
+        vals = [float(l[i:i + 12]) for l in lines[2:] for i in range(0, len(l), 12) if l[i:i + 12].strip()]
+        xyz = np.array(vals[:3 * n]).reshape(n, 3)
+        ops = [_symop(o) for o in _CRYSTAL_OPS[group]]
+        box = [cell["a"], cell["b"], cell["c"], cell.get("alpha", 90.0), cell.get("beta", 90.0), cell.get("gamma", 90.0)]
+        assert len(q) == n and nbi.min() >= 0
+        data[name + "_xyz"], data[name + "_q"], data[name + "_type"] = xyz, q, ati
+        data[name + "_nbindex"], data[name + "_A"], data[name + "_B"] = nbi.astype(np.int32), acoef, bcoef
+        data[name + "_bonds"] = bonds.astype(np.int32)
+        data[name + "_rot"], data[name + "_trans"] = np.array([o[0] for o in ops]), np.array([o[1] for o in ops])
+        data[name + "_box"] = np.array(box)
+        print(name, group, n, "atoms", ntypes, "types", len(bonds), "bonds", len(ops), "operations")
+    np.savez_compressed(os.path.join(HERE, "crystals.npz"), **data)
+
+
 def pair_hash(keys):
     return hashlib.sha256(np.ascontiguousarray(keys, dtype=np.int64).tobytes()).hexdigest()
 
@@ -198,5 +303,6 @@ if __name__ == "__main__":
     if what in ("inputs", "all"):
         make_inputs()
         make_dhfr()
+        make_crystals()
     if what in ("golden", "all"):
         make_golden()
