@@ -13,6 +13,7 @@
 // across tiles / into global memory in fp64.
 #include "nbb200_internal.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace nbb200 {
@@ -266,6 +267,266 @@ __global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(For
 }
 
 // ------------------------------------------------------------------------------------------------------
+// k_tile_forces_x2: the same tile walk with TWO pairs per lane per step, evaluated with Blackwell's packed fp32
+// instructions (fma/mul/add/sub.rn.f32x2 -> FFMA2 / FMUL2 / FADD2).  Measured on B200 (scripts/microbench): FFMA2 issues at
+// half the rate of FFMA for the same flops, i.e. it halves the ISSUE slots of the arithmetic; the scalar kernel is issue
+// bound (84 slots per pair at 78 %), so packing moves the bound to the FMA pipe itself (~52 pipe cycles per pair).
+// Lane l owns i atom l; a tile's 32 j slots are staged as 16 slot pairs (m, m+16); at step k (0..15) lane l evaluates the
+// pair of slots m = (l + k) % 16, m + 16.  Lanes l and l^16 therefore walk the same slots with different i atoms: the j
+// accumulators rotate inside each half warp (3 packed = 6 shuffles per step) and the two halves are added at the end.
+// ------------------------------------------------------------------------------------------------------
+// slow path of the x2 kernel for tiles with a pair inside the damped core (same contract as damped_tile_fix; the j part
+// is returned for slot `lane`, already summed over the two half warps, as a GRADIENT correction with the main loop's sign)
+__device__ __noinline__ void damped_tile_fix_x2(const AbfsF32 &F, unsigned int row, const float4 *myXY, const float4 *myZQ, const unsigned char *ljRow,
+                                               const int2 *myLj, float xi, float yi, float zi, float qi, int lmod, int half, int src, float *c)
+{
+    float fxi = 0.f, fyi = 0.f, fzi = 0.f, eq = 0.f, el = 0.f;
+    float fj[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    for (int k = 0; k < 16; k++) {
+        const float4 pxy = myXY[k], pzq = myZQ[k];
+        const int2 lo2 = myLj[k];
+        const int m = (lmod + k) & 15;
+        for (int h = 0; h < 2; h++) {
+            const float px = h ? pxy.y : pxy.x, py = h ? pxy.w : pxy.z, pz = h ? pzq.y : pzq.x, qj = h ? pzq.w : pzq.z;
+            const float2 ab = *reinterpret_cast<const float2 *>(ljRow + (h ? lo2.y : lo2.x));      // (A, -B)
+            const float dx = xi - px, dy = yi - py, dz = zi - pz;
+            const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            if (((row >> (m + 16 * h)) & 1u) && (r2 < F.r2Damp)) {
+                const float qij = qi * qj, Aij = ab.x, Bij = -ab.y;
+                const PairOut o = abfs_pair(F, r2, qij, Aij, Bij);
+                const float e1 = qij * fmaf(-F.qAlpha, r2, F.qF0);
+                const float e2 = Aij * fmaf(-F.aAlpha, r2, F.aF0) - Bij * fmaf(-F.bAlpha, r2, F.bF0);
+                const float g = -2.0f * (-qij * F.qAlpha - Aij * F.aAlpha + Bij * F.bAlpha) - o.g;
+                eq += e1 - o.e1; el += e2 - o.e2;
+                const float gx = g * dx, gy = g * dy, gz = g * dz;
+                fxi -= gx; fyi -= gy; fzi -= gz;
+                fj[h][0] += gx; fj[h][1] += gy; fj[h][2] += gz;
+            }
+        }
+        for (int h = 0; h < 2; h++) for (int d = 0; d < 3; d++) fj[h][d] = __shfl_sync(0xffffffffu, fj[h][d], src);
+    }
+    for (int h = 0; h < 2; h++) for (int d = 0; d < 3; d++) fj[h][d] += __shfl_xor_sync(0xffffffffu, fj[h][d], 16);
+    c[0] = fxi; c[1] = fyi; c[2] = fzi; c[3] = fj[half][0]; c[4] = fj[half][1]; c[5] = fj[half][2]; c[6] = eq; c[7] = el;
+}
+
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo_of(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi_of(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 sel2(bool pa, bool pb, float ta, float fa) { return pk(pa ? ta : fa, pb ? ta : fa); }
+
+// constants duplicated into both halves (kernel parameter -> constant bank, 64-bit operands)
+struct AbfsX2 {
+    float2 one, mhalf, two, msix;
+    float2 rOff, r2Off, n3, n4, n5, n6, mk1, k2;
+    float r2On, r2Damp, r2OffS, qShift1, aK12, aF6, mShift12, bK6, bF3, mShift6;
+};
+
+struct __align__(16) JStage2 {
+    float4 xy[2 * 16];       // xa, xb, ya, yb   (a = slot m, b = slot m + 16), duplicated for wrap-free indexing
+    float4 zq[2 * 16];       // za, zb, qa, qb
+    int2   lj[2 * 16];       // LJ row byte offsets of the two j types
+};
+
+__device__ __forceinline__ const float2 &c2(const float2 &v) { return v; }
+#define C2(v) (*reinterpret_cast<const f32x2 *>(&(v)))
+
+template <bool kRot>
+__global__ void __launch_bounds__(kForceThreads, 2) k_tile_forces_x2(ForceArgs A, AbfsX2 X)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    JStage2 *stage = reinterpret_cast<JStage2 *>(smemRaw) + (threadIdx.x >> 5);
+    float2 *sLJ = reinterpret_cast<float2 *>(smemRaw + sizeof(JStage2) * kForceWarps);      // [ntypes*ntypes] (A, -B)
+    for (int i = threadIdx.x; i < A.ntypes * A.ntypes; i += blockDim.x) { const float2 ab = A.ljAB[i]; sLJ[i] = make_float2(ab.x, -ab.y); }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, lmod = lane & 15, half = lane >> 4;
+    const AbfsF32 F = A.F;
+    const int src = (lane & 16) | ((lane + 1) & 15);
+    const unsigned char *ljBase = reinterpret_cast<const unsigned char *>(sLJ);
+    const float4 *myXY = stage->xy + lmod;
+    const float4 *myZQ = stage->zq + lmod;
+    const int2 *myLj = stage->lj + lmod;
+
+    for (;;) {
+        unsigned int it = 0;
+        if (lane == 0) it = atomicAdd(A.workCursor, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= (unsigned int) A.nitems) break;
+        const WorkItem wi = A.items[it];
+        const ImageOpDev *op = A.ops + wi.image;
+        const bool isImage = wi.image > 0;
+        const bool pureT = kRot ? (op->pureTranslation != 0) : true;
+        const double cx = A.blockBox[9 * wi.block + 6], cy = A.blockBox[9 * wi.block + 7], cz = A.blockBox[9 * wi.block + 8];
+        const double sc = op->scale;
+
+        const int si = wi.block * kTile + lane;
+        const int ai = (si < A.n) ? A.sAtom[si] : -1;
+        float xi = 0.f, yi = 0.f, zi = 0.f, qi = 0.f;
+        const unsigned char *ljRow = ljBase;
+        if (ai >= 0) {
+            xi = (float) (A.x[3 * ai] - cx); yi = (float) (A.x[3 * ai + 1] - cy); zi = (float) (A.x[3 * ai + 2] - cz);
+            qi = A.q32[ai] * A.qScale;
+            ljRow = ljBase + (size_t) A.ljtype[ai] * A.ntypes * sizeof(float2);
+        }
+        const f32x2 xi2 = pk(xi, xi), yi2 = pk(yi, yi), zi2 = pk(zi, zi), qi2 = pk(qi, qi);
+        double fix = 0.0, fiy = 0.0, fiz = 0.0, eQ = 0.0, eL = 0.0;
+        double G0 = 0.0, G1 = 0.0, G2 = 0.0, W[9];
+        if (kRot) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) W[k] = 0.0;
+        }
+
+        for (int t = 0; t < wi.tileCount; t++) {
+            const size_t T = ((size_t) wi.tileStart + t) * kTile + lane;
+            const int aj = A.tileJ[T];
+            const unsigned int rotmask = A.tileMask[T];
+            double xj64 = 0.0, yj64 = 0.0, zj64 = 0.0;
+            float px32 = 0.f, py32 = 0.f, pz32 = 0.f, qj = 0.f;
+            int lj = 0;
+            if (aj >= 0) {
+                xj64 = A.x[3 * aj]; yj64 = A.x[3 * aj + 1]; zj64 = A.x[3 * aj + 2];
+                double px = xj64, py = yj64, pz = zj64;
+                if (isImage) {
+                    if (pureT) { px += op->tv[0]; py += op->tv[1]; pz += op->tv[2]; }
+                    else {
+                        px = op->R[0] * xj64 + op->R[1] * yj64 + op->R[2] * zj64 + op->tv[0];
+                        py = op->R[3] * xj64 + op->R[4] * yj64 + op->R[5] * zj64 + op->tv[1];
+                        pz = op->R[6] * xj64 + op->R[7] * yj64 + op->R[8] * zj64 + op->tv[2];
+                    }
+                }
+                px32 = (float) (px - cx); py32 = (float) (py - cy); pz32 = (float) (pz - cz);
+                qj = A.q32[aj];
+                lj = A.ljtype[aj] * (int) sizeof(float2);
+            }
+            __syncwarp();                                   // previous tile fully consumed
+            {   // slot `lane` = pair element (lmod, half); scalar stores into the packed pair layout, twice (wrap-free indexing)
+                float *pxy = reinterpret_cast<float *>(stage->xy), *pzq = reinterpret_cast<float *>(stage->zq);
+                int *plj = reinterpret_cast<int *>(stage->lj);
+#pragma unroll
+                for (int d = 0; d < 2; d++) {
+                    const int m = lmod + 16 * d;
+                    pxy[4 * m + half] = px32; pxy[4 * m + 2 + half] = py32;
+                    pzq[4 * m + half] = pz32; pzq[4 * m + 2 + half] = qj;
+                    plj[2 * m + half] = lj;
+                }
+            }
+            __syncwarp();
+            // masks: canonical row (bit s <-> slot s), halves rotated by lmod, bit-reversed so that step k tests the sign bit
+            const unsigned int row = __funnelshift_l(rotmask, rotmask, lane);
+            const unsigned int lowh = row & 0xffffu, highh = row >> 16;
+            unsigned int ma = __brev(((lowh >> lmod) | (lowh << (16 - lmod))) & 0xffffu);
+            unsigned int mb = __brev(((highh >> lmod) | (highh << (16 - lmod))) & 0xffffu);
+
+            f32x2 fxi = 0ULL, fyi = 0ULL, fzi = 0ULL, fxj = 0ULL, fyj = 0ULL, fzj = 0ULL, eq = 0ULL, el = 0ULL;   // fxj.. hold MINUS the j gradient
+            float r2min = F.r2Off;
+#pragma unroll 4
+            for (int k = 0; k < 16; k++) {
+                const float4 pxy = myXY[k], pzq = myZQ[k];
+                const int2 lo2 = myLj[k];
+                const float2 aba = *reinterpret_cast<const float2 *>(ljRow + lo2.x), abb = *reinterpret_cast<const float2 *>(ljRow + lo2.y);
+                const f32x2 dx = sub2(xi2, pk(pxy.x, pxy.y)), dy = sub2(yi2, pk(pxy.z, pxy.w)), dz = sub2(zi2, pk(pzq.x, pzq.y));
+                const f32x2 r2raw = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
+                const float r2a0 = lo_of(r2raw), r2b0 = hi_of(r2raw);
+                const bool ona = ((int) ma < 0) && (r2a0 <= F.r2Off), onb = ((int) mb < 0) && (r2b0 <= F.r2Off);
+                ma <<= 1; mb <<= 1;
+                const float r2a = ona ? r2a0 : F.r2Off, r2b = onb ? r2b0 : F.r2Off;       // masked pairs sit AT the cutoff: zero energy and force
+                r2min = fminf(r2min, fminf(r2a, r2b));
+                const f32x2 r2 = pk(r2a, r2b);
+                f32x2 s = pk(rsqrt_fast(r2a), rsqrt_fast(r2b));
+                {   // Newton: s <- s - 0.5 s (r2 s^2 - 1)
+                    const f32x2 rr = mul2(r2, s);
+                    const f32x2 e = sub2(mul2(rr, s), C2(X.one));
+                    s = fma2(mul2(s, C2(X.mhalf)), e, s);
+                }
+                const f32x2 r = mul2(r2, s), s2 = mul2(s, s), s3 = mul2(s, s2), s6 = mul2(s3, s3);
+                const bool pa = r2a <= F.r2On, pb = r2b <= F.r2On;
+                const f32x2 qij = mul2(qi2, pk(pzq.z, pzq.w));
+                // Coulomb
+                const f32x2 tt = sub2(C2(X.rOff), r);
+                const f32x2 Cc = fma2(fma2(fma2(C2(X.n6), tt, C2(X.n5)), tt, C2(X.n4)), tt, C2(X.n3));
+                const f32x2 t3C = mul2(mul2(tt, tt), mul2(tt, Cc));
+                const f32x2 Gs = pk(pa ? 1.0f : lo_of(t3C), pb ? 1.0f : hi_of(t3C));
+                const f32x2 sh = sel2(pa, pb, F.qShift1, 0.0f);
+                const f32x2 e1 = mul2(qij, fma2(s, Gs, sh));
+                const f32x2 u = sub2(C2(X.r2Off), r2);
+                const f32x2 mQs = mul2(mul2(u, u), fma2(C2(X.k2), u, C2(X.mk1)));                   // -(u^2 (k1 - k2 u))
+                const f32x2 mQ = pk(pa ? -1.0f : lo_of(mQs), pb ? -1.0f : hi_of(mQs));
+                const f32x2 mgq = mul2(mul2(qij, s3), mQ);                                           // -(qij s^3 Q)
+                // Lennard-Jones (table holds (A, -B))
+                const f32x2 ka = sel2(pa, pb, 1.0f, F.aK12), xa = sel2(pa, pb, 0.0f, F.aF6), mwa = sel2(pa, pb, -F.aShift12, 0.0f);
+                const f32x2 kb = sel2(pa, pb, 1.0f, F.bK6),  xb = sel2(pa, pb, 0.0f, F.bF3), mwb = sel2(pa, pb, -F.bShift6, 0.0f);
+                const f32x2 Aij = pk(aba.x, abb.x), mBij = pk(aba.y, abb.y);
+                const f32x2 la = sub2(s6, xa), lb = sub2(s3, xb);
+                const f32x2 kla = mul2(ka, la), klb = mul2(kb, lb);
+                const f32x2 e2 = fma2(Aij, fma2(kla, la, mwa), mul2(mBij, fma2(klb, lb, mwb)));
+                const f32x2 mm = fma2(C2(X.two), mul2(mul2(Aij, kla), s6), mul2(mul2(mBij, klb), s3));
+                const f32x2 mg = fma2(mul2(s2, C2(X.msix)), mm, mgq);                                 // -g
+                eq = add2(eq, e1); el = add2(el, e2);
+                if ((k & 3) == 3) {
+                    eQ += (double) (lo_of(eq) + hi_of(eq)); eL += (double) (lo_of(el) + hi_of(el));
+                    eq = 0ULL; el = 0ULL;
+                }
+                fxi = fma2(mg, dx, fxi); fyi = fma2(mg, dy, fyi); fzi = fma2(mg, dz, fzi);           // fi -= g d
+                fxj = fma2(mg, dx, fxj); fyj = fma2(mg, dy, fyj); fzj = fma2(mg, dz, fzj);           // (-fj) -= g d
+                fxj = __shfl_sync(0xffffffffu, fxj, src); fyj = __shfl_sync(0xffffffffu, fyj, src); fzj = __shfl_sync(0xffffffffu, fzj, src);
+            }
+            // both half warps hold partial (negated) gradients of slots (lmod, lmod+16): add them, lane l keeps slot l
+            float gjx, gjy, gjz;
+            {
+                const f32x2 ox = __shfl_xor_sync(0xffffffffu, fxj, 16), oy = __shfl_xor_sync(0xffffffffu, fyj, 16), oz = __shfl_xor_sync(0xffffffffu, fzj, 16);
+                fxj = add2(fxj, ox); fyj = add2(fyj, oy); fzj = add2(fzj, oz);
+                gjx = -(half ? hi_of(fxj) : lo_of(fxj)); gjy = -(half ? hi_of(fyj) : lo_of(fyj)); gjz = -(half ? hi_of(fzj) : lo_of(fzj));
+            }
+            float cfx = lo_of(fxi) + hi_of(fxi), cfy = lo_of(fyi) + hi_of(fyi), cfz = lo_of(fzi) + hi_of(fzi);
+            if (__any_sync(0xffffffffu, r2min < F.r2Damp)) {   // damped core: practically never; patch the tile with the reference formulas
+                float c[8];
+                damped_tile_fix_x2(F, row, myXY, myZQ, ljRow, myLj, xi, yi, zi, qi, lmod, half, src, c);
+                cfx += c[0]; cfy += c[1]; cfz += c[2]; gjx += c[3]; gjy += c[4]; gjz += c[5];
+                eQ += (double) c[6]; eL += (double) c[7];
+            }
+            fix += (double) cfx; fiy += (double) cfy; fiz += (double) cfz;
+            if (aj >= 0) {
+                double gx = sc * (double) gjx, gy = sc * (double) gjy, gz = sc * (double) gjz;       // gradient on the (image) atom
+                if (isImage) {
+                    G0 += gx; G1 += gy; G2 += gz;
+                    if (kRot && !pureT) {
+                        W[0] += gx * xj64; W[1] += gx * yj64; W[2] += gx * zj64;
+                        W[3] += gy * xj64; W[4] += gy * yj64; W[5] += gy * zj64;
+                        W[6] += gz * xj64; W[7] += gz * yj64; W[8] += gz * zj64;
+                        const double rx = op->R[0] * gx + op->R[3] * gy + op->R[6] * gz;           // R^T g'
+                        const double ry = op->R[1] * gx + op->R[4] * gy + op->R[7] * gz;
+                        const double rz = op->R[2] * gx + op->R[5] * gy + op->R[8] * gz;
+                        gx = rx; gy = ry; gz = rz;
+                    }
+                }
+                if (A.grad != nullptr) {
+                    atomicAdd(&A.grad[3 * aj], gx); atomicAdd(&A.grad[3 * aj + 1], gy); atomicAdd(&A.grad[3 * aj + 2], gz);
+                }
+            }
+        }
+        if (ai >= 0 && A.grad != nullptr) {
+            atomicAdd(&A.grad[3 * ai], sc * fix); atomicAdd(&A.grad[3 * ai + 1], sc * fiy); atomicAdd(&A.grad[3 * ai + 2], sc * fiz);
+        }
+        double *acc = A.accum + 16 * wi.image;
+        eQ = warp_sum(eQ) * sc; eL = warp_sum(eL) * sc;
+        if (lane == 0) { atomicAdd(&acc[0], eQ); atomicAdd(&acc[1], eL); }
+        if (isImage) {
+            G0 = warp_sum(G0); G1 = warp_sum(G1); G2 = warp_sum(G2);
+            if (lane == 0) { atomicAdd(&acc[2], G0); atomicAdd(&acc[3], G1); atomicAdd(&acc[4], G2); }
+            if (kRot && !pureT) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) { const double w = warp_sum(W[k]); if (lane == 0) atomicAdd(&acc[5 + k], w); }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // 1-4 interactions: explicit pair list, their own LJ table and electrostatic scale, never imaged
 // (NBModelABFS_MMMMEnergy third call, pM/csource/NBModelABFS.c:275-294).  A few thousand pairs: plain fp64.
 // ------------------------------------------------------------------------------------------------------
@@ -319,6 +580,8 @@ void init_force_kernel_attributes()
 {
     cudaFuncSetAttribute(k_tile_forces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_tile_forces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces_x2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces_x2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaDeviceProp prop;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -373,8 +636,25 @@ bool launch_forces(State &s, double *d_grad)
         const int warpsPerBlock = kForceThreads / 32;
         const int grid = std::max(1, std::min(g_numSMs * perSM, (nitems + warpsPerBlock - 1) / warpsPerBlock));
         if (s.timing) cudaEventRecord(s.ev[2], s.stream);
-        if (rot) k_tile_forces<true><<<grid, kForceThreads, smem, s.stream>>>(A);
-        else     k_tile_forces<false><<<grid, kForceThreads, smem, s.stream>>>(A);
+        static const bool useX2 = []() { const char *e = std::getenv("NBB200_FORCE_KERNEL"); return !(e != nullptr && std::strcmp(e, "scalar") == 0); }();
+        if (useX2) {
+            AbfsX2 X;
+            auto dup = [](double v) { return make_float2((float) v, (float) v); };
+            X.one = dup(1.0); X.mhalf = dup(-0.5); X.two = dup(2.0); X.msix = dup(-6.0);
+            X.rOff = dup(F.rOff); X.r2Off = dup(F.r2Off); X.n3 = dup(F.n3); X.n4 = dup(F.n4); X.n5 = dup(F.n5); X.n6 = dup(F.n6);
+            X.mk1 = dup(-F.k1); X.k2 = dup(F.k2);
+            X.r2On = F.r2On; X.r2Damp = F.r2Damp; X.r2OffS = F.r2Off; X.qShift1 = F.qShift1; X.aK12 = F.aK12; X.aF6 = F.aF6;
+            X.mShift12 = -F.aShift12; X.bK6 = F.bK6; X.bF3 = F.bF3; X.mShift6 = -F.bShift6;
+            const size_t smem2 = sizeof(JStage2) * kForceWarps + sizeof(float2) * (size_t) s.ntypes * s.ntypes;
+            int perSM2 = 0;
+            if (rot) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM2, k_tile_forces_x2<true>, kForceThreads, smem2);
+            else     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM2, k_tile_forces_x2<false>, kForceThreads, smem2);
+            if (perSM2 < 1) perSM2 = 1;
+            const int grid2 = std::max(1, std::min(g_numSMs * perSM2, (nitems + warpsPerBlock - 1) / warpsPerBlock));
+            if (rot) k_tile_forces_x2<true><<<grid2, kForceThreads, smem2, s.stream>>>(A, X);
+            else     k_tile_forces_x2<false><<<grid2, kForceThreads, smem2, s.stream>>>(A, X);
+        } else if (rot) k_tile_forces<true><<<grid, kForceThreads, smem, s.stream>>>(A);
+        else            k_tile_forces<false><<<grid, kForceThreads, smem, s.stream>>>(A);
         if (s.timing) cudaEventRecord(s.ev[3], s.stream);
         s.launches += 1;
     }
