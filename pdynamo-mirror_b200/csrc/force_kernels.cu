@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(For
             ljRow = ljBase + (size_t) A.ljtype[ai] * A.ntypes * sizeof(float2);
         }
         double fix = 0.0, fiy = 0.0, fiz = 0.0, eQ = 0.0, eL = 0.0;
-        double G0 = 0.0, G1 = 0.0, G2 = 0.0, W[9];
+        double W[9];
         if (kRot) {
 #pragma unroll
             for (int k = 0; k < 9; k++) W[k] = 0.0;
@@ -233,7 +233,6 @@ __global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(For
             if (aj >= 0) {
                 double gx = sc * (double) fxj, gy = sc * (double) fyj, gz = sc * (double) fzj;       // gradient on the (image) atom
                 if (isImage) {
-                    G0 += gx; G1 += gy; G2 += gz;
                     if (kRot && !pureT) {
                         W[0] += gx * xj64; W[1] += gx * yj64; W[2] += gx * zj64;
                         W[3] += gy * xj64; W[4] += gy * yj64; W[5] += gy * zj64;
@@ -256,7 +255,8 @@ __global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(For
         eQ = warp_sum(eQ) * sc; eL = warp_sum(eL) * sc;
         if (lane == 0) { atomicAdd(&acc[0], eQ); atomicAdd(&acc[1], eL); }
         if (isImage) {
-            G0 = warp_sum(G0); G1 = warp_sum(G1); G2 = warp_sum(G2);
+            // sum over the image atoms of their gradient = minus the sum of the i-side gradients of this item (Newton's third law)
+            const double G0 = -warp_sum(fix) * sc, G1 = -warp_sum(fiy) * sc, G2 = -warp_sum(fiz) * sc;
             if (lane == 0) { atomicAdd(&acc[2], G0); atomicAdd(&acc[3], G1); atomicAdd(&acc[4], G2); }
             if (kRot && !pureT) {
 #pragma unroll
@@ -336,8 +336,8 @@ struct __align__(16) JStage2 {
 __device__ __forceinline__ const float2 &c2(const float2 &v) { return v; }
 #define C2(v) (*reinterpret_cast<const f32x2 *>(&(v)))
 
-template <bool kRot>
-__global__ void __launch_bounds__(kForceThreads, 2) k_tile_forces_x2(ForceArgs A, AbfsX2 X)
+template <bool kRot, int kMinBlocks, int kUnroll>
+__global__ void __launch_bounds__(kForceThreads, kMinBlocks) k_tile_forces_x2(ForceArgs A, AbfsX2 X)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     JStage2 *stage = reinterpret_cast<JStage2 *>(smemRaw) + (threadIdx.x >> 5);
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kForceThreads, 2) k_tile_forces_x2(ForceArgs A
         }
         const f32x2 xi2 = pk(xi, xi), yi2 = pk(yi, yi), zi2 = pk(zi, zi), qi2 = pk(qi, qi);
         double fix = 0.0, fiy = 0.0, fiz = 0.0, eQ = 0.0, eL = 0.0;
-        double G0 = 0.0, G1 = 0.0, G2 = 0.0, W[9];
+        double W[9];
         if (kRot) {
 #pragma unroll
             for (int k = 0; k < 9; k++) W[k] = 0.0;
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kForceThreads, 2) k_tile_forces_x2(ForceArgs A
 
             f32x2 fxi = 0ULL, fyi = 0ULL, fzi = 0ULL, fxj = 0ULL, fyj = 0ULL, fzj = 0ULL, eq = 0ULL, el = 0ULL;   // fxj.. hold MINUS the j gradient
             float r2min = F.r2Off;
-#pragma unroll 4
+#pragma unroll kUnroll
             for (int k = 0; k < 16; k++) {
                 const float4 pxy = myXY[k], pzq = myZQ[k];
                 const int2 lo2 = myLj[k];
@@ -493,7 +493,6 @@ __global__ void __launch_bounds__(kForceThreads, 2) k_tile_forces_x2(ForceArgs A
             if (aj >= 0) {
                 double gx = sc * (double) gjx, gy = sc * (double) gjy, gz = sc * (double) gjz;       // gradient on the (image) atom
                 if (isImage) {
-                    G0 += gx; G1 += gy; G2 += gz;
                     if (kRot && !pureT) {
                         W[0] += gx * xj64; W[1] += gx * yj64; W[2] += gx * zj64;
                         W[3] += gy * xj64; W[4] += gy * yj64; W[5] += gy * zj64;
@@ -516,7 +515,8 @@ __global__ void __launch_bounds__(kForceThreads, 2) k_tile_forces_x2(ForceArgs A
         eQ = warp_sum(eQ) * sc; eL = warp_sum(eL) * sc;
         if (lane == 0) { atomicAdd(&acc[0], eQ); atomicAdd(&acc[1], eL); }
         if (isImage) {
-            G0 = warp_sum(G0); G1 = warp_sum(G1); G2 = warp_sum(G2);
+            // sum over the image atoms of their gradient = minus the sum of the i-side gradients of this item (Newton's third law)
+            const double G0 = -warp_sum(fix) * sc, G1 = -warp_sum(fiy) * sc, G2 = -warp_sum(fiz) * sc;
             if (lane == 0) { atomicAdd(&acc[2], G0); atomicAdd(&acc[3], G1); atomicAdd(&acc[4], G2); }
             if (kRot && !pureT) {
 #pragma unroll
@@ -580,8 +580,13 @@ void init_force_kernel_attributes()
 {
     cudaFuncSetAttribute(k_tile_forces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_tile_forces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_tile_forces_x2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_tile_forces_x2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces_x2<false, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces_x2<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces_x2<false, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces_x2<false, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces_x2<false, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces_x2<false, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces_x2<true, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaDeviceProp prop;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -646,13 +651,17 @@ bool launch_forces(State &s, double *d_grad)
             X.r2On = F.r2On; X.r2Damp = F.r2Damp; X.r2OffS = F.r2Off; X.qShift1 = F.qShift1; X.aK12 = F.aK12; X.aF6 = F.aF6;
             X.mShift12 = -F.aShift12; X.bK6 = F.bK6; X.bF3 = F.bF3; X.mShift6 = -F.bShift6;
             const size_t smem2 = sizeof(JStage2) * kForceWarps + sizeof(float2) * (size_t) s.ntypes * s.ntypes;
+            static const int minBlocks = []() { const char *e = std::getenv("NBB200_X2_BLOCKS"); const int v = e ? std::atoi(e) : 3; return (v >= 2 && v <= 4) ? v : 3; }();
+            static const int unroll = []() { const char *e = std::getenv("NBB200_X2_UNROLL"); return e ? std::atoi(e) : 4; }();
+            void (*kern)(ForceArgs, AbfsX2) = rot ? k_tile_forces_x2<true, 2, 4>
+                                                  : (minBlocks == 2 ? (unroll == 2 ? k_tile_forces_x2<false, 2, 2> : k_tile_forces_x2<false, 2, 4>)
+                                                     : minBlocks == 4 ? k_tile_forces_x2<false, 4, 1>
+                                                     : (unroll == 1 ? k_tile_forces_x2<false, 3, 1> : unroll == 2 ? k_tile_forces_x2<false, 3, 2> : k_tile_forces_x2<false, 3, 4>));
             int perSM2 = 0;
-            if (rot) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM2, k_tile_forces_x2<true>, kForceThreads, smem2);
-            else     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM2, k_tile_forces_x2<false>, kForceThreads, smem2);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM2, kern, kForceThreads, smem2);
             if (perSM2 < 1) perSM2 = 1;
             const int grid2 = std::max(1, std::min(g_numSMs * perSM2, (nitems + warpsPerBlock - 1) / warpsPerBlock));
-            if (rot) k_tile_forces_x2<true><<<grid2, kForceThreads, smem2, s.stream>>>(A, X);
-            else     k_tile_forces_x2<false><<<grid2, kForceThreads, smem2, s.stream>>>(A, X);
+            kern<<<grid2, kForceThreads, smem2, s.stream>>>(A, X);
         } else if (rot) k_tile_forces<true><<<grid, kForceThreads, smem, s.stream>>>(A);
         else            k_tile_forces<false><<<grid, kForceThreads, smem, s.stream>>>(A);
         if (s.timing) cudaEventRecord(s.ev[3], s.stream);

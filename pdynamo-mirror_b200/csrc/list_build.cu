@@ -42,6 +42,14 @@ __device__ __forceinline__ void ref_transform(const double *op, double x0, doubl
     x1 = __dadd_rn(x1, op[9]); y1 = __dadd_rn(y1, op[10]); z1 = __dadd_rn(z1, op[11]);
 }
 
+// packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): two distance tests per instruction in the prefilter
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 __device__ __forceinline__ int cell_coord(double v, double lo, double invh, int dim)
 {
     int c = (int) floor((v - lo) * invh);
@@ -370,7 +378,8 @@ __device__ __forceinline__ unsigned int rows_from_columns(unsigned int x, int la
 __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
 {
     __shared__ double sxi[kTile][3];                         // exact coordinates of the block atoms
-    __shared__ float4 sxf[kTile];                            // block-local fp32 copies for the prefilter
+    __shared__ float4 sxy[kTile / 2];                        // block-local fp32 copies for the prefilter, atoms paired (i, i+16):
+    __shared__ float2 szz[kTile / 2];                        //   {x_i, x_i+16, y_i, y_i+16} and {z_i, z_i+16}
     __shared__ double sbox[9];
     __shared__ int rowStart[kMaxRows];
     __shared__ int rowPrefix[kMaxRows + 1];
@@ -395,7 +404,9 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
             sxi[tid][d] = v;
             f[d] = (s < A.n) ? (float) (v - sbox[6 + d]) : 1.0e15f;
         }
-        sxf[tid] = make_float4(f[0], f[1], f[2], 0.f);
+        float *pxy = reinterpret_cast<float *>(sxy), *pzz = reinterpret_cast<float *>(szz);
+        const int m = tid & 15, h = tid >> 4;
+        pxy[4 * m + h] = f[0]; pxy[4 * m + 2 + h] = f[1]; pzz[2 * m + h] = f[2];
     }
     __syncthreads();
 
@@ -463,13 +474,17 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
                         if (ex * ex + ey * ey + ez * ez <= reject2) {
                             const float fx = (float) (xj - sbox[6]), fy = (float) (yj - sbox[7]), fz = (float) (zj - sbox[8]);
                             float band = 1.0e30f;                    // min over the block atoms of |r2 - cutoff^2|
+                            const f32x2 fx2 = pk2(fx, fx), fy2 = pk2(fy, fy), fz2 = pk2(fz, fz);
 #pragma unroll 8
-                            for (int i = 0; i < kTile; i++) {
-                                const float4 p = sxf[i];
-                                const float dx = p.x - fx, dy = p.y - fy, dz = p.z - fz;
-                                const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                                colmask |= (r2 <= c2f) ? (1u << i) : 0u;
-                                band = fminf(band, fabsf(r2 - c2f));
+                            for (int i = 0; i < kTile / 2; i++) {    // block atoms i and i + 16 in one packed evaluation
+                                const float4 pxy = sxy[i];
+                                const float2 pz = szz[i];
+                                const f32x2 dx = sub2(pk2(pxy.x, pxy.y), fx2), dy = sub2(pk2(pxy.z, pxy.w), fy2), dz = sub2(pk2(pz.x, pz.y), fz2);
+                                float r2a, r2b;
+                                unpk2(fma2(dx, dx, fma2(dy, dy, mul2(dz, dz))), r2a, r2b);
+                                colmask |= (r2a <= c2f) ? (1u << i) : 0u;
+                                colmask |= (r2b <= c2f) ? (0x10000u << i) : 0u;
+                                band = fminf(band, fminf(fabsf(r2a - c2f), fabsf(r2b - c2f)));
                             }
                             if (band <= eps) {                       // some distance is within the fp32 error band: the reference predicate decides
                                 colmask = 0u;

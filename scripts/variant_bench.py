@@ -1,0 +1,14 @@
+"""Time the force kernel for the kernel variants selected through environment variables (development aid)."""
+import os, subprocess, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+variants = [dict(NBB200_FORCE_KERNEL="scalar"), dict(NBB200_X2_BLOCKS="2"), dict(NBB200_X2_BLOCKS="3"), dict(NBB200_X2_BLOCKS="4")]
+wl = sys.argv[1] if len(sys.argv) > 1 else "m1"
+for v in variants:
+    env = dict(os.environ); env.update(v)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3", "--no-cpu", "--no-jac", "--workload", wl],
+                         env=env, capture_output=True, text=True)
+    try:
+        d = json.loads(out.stdout.strip().split("\n")[-1])
+        print(v, "tile_forces %.3f ms  rebuild %.3f ms  step %.3f ms" % (d["kernels_ms"]["tile_forces"], d["kernels_ms"]["list_rebuild"], d["ms_per_step"]), flush=True)
+    except Exception as e:
+        print(v, "failed", e, out.stderr[-500:])
