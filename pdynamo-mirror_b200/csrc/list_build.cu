@@ -50,6 +50,18 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
+// Boustrophedon ("snake") cell order: columns (cx, cy) are walked with y reversed on odd cx and z reversed on odd columns, so
+// that consecutive cells in the sorted order are always spatial neighbours.  32-atom i-blocks are runs of the sorted order;
+// without the snake a block that straddles the end of a z column would span the whole box (huge bounding box, thousands of
+// useless candidates in the tile builder, half-empty tiles in the force kernel).
+__device__ __forceinline__ int snake_column(const BuildGrid &g, int cx, int cy) { return cx * g.dim[1] + ((cx & 1) ? g.dim[1] - 1 - cy : cy); }
+__device__ __forceinline__ bool snake_reversed(int column) { return (column & 1) != 0; }
+__device__ __forceinline__ int snake_cell(const BuildGrid &g, int cx, int cy, int cz)
+{
+    const int col = snake_column(g, cx, cy);
+    return col * g.dim[2] + (snake_reversed(col) ? g.dim[2] - 1 - cz : cz);
+}
+
 __device__ __forceinline__ int cell_coord(double v, double lo, double invh, int dim)
 {
     int c = (int) floor((v - lo) * invh);
@@ -167,11 +179,12 @@ struct ExtendArgs {
 __device__ __forceinline__ void classify(const BuildGrid &g, int set, int atom, double px, double py, double pz, int &key, unsigned long long &sortKey)
 {
     const int cx = cell_coord(px, g.lo[0], g.invh, g.dim[0]), cy = cell_coord(py, g.lo[1], g.invh, g.dim[1]), cz = cell_coord(pz, g.lo[2], g.invh, g.dim[2]);
-    key = set * g.ncell + (cx * g.dim[1] + cy) * g.dim[2] + cz;
+    key = set * g.ncell + snake_cell(g, cx, cy, cz);
+    const bool rev = snake_reversed(snake_column(g, cx, cy));
     // position inside the cell: 8 z slabs, then 4 y rows, then 4 x columns -> runs of sorted atoms are compact boxes
     const double fx = (px - g.lo[0]) * g.invh - cx, fy = (py - g.lo[1]) * g.invh - cy, fz = (pz - g.lo[2]) * g.invh - cz;
     const int sx = min(3, max(0, (int) (fx * 4.0))), sy = min(3, max(0, (int) (fy * 4.0))), sz = min(7, max(0, (int) (fz * 8.0)));
-    sortKey = ((unsigned long long) (sz * 16 + sy * 4 + sx) << 32) | (unsigned int) atom;
+    sortKey = ((unsigned long long) ((rev ? 7 - sz : sz) * 16 + sy * 4 + sx) << 32) | (unsigned int) atom;
 }
 
 __global__ void k_extend(ExtendArgs A)
@@ -450,7 +463,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
                 if (rem >= 0.0) {
                     const double dz = sqrt(rem) + 1.0e-6;
                     const int z0 = cell_coord(sbox[2] - dz, g.lo[2], g.invh, g.dim[2]), z1 = cell_coord(sbox[5] + dz, g.lo[2], g.invh, g.dim[2]);
-                    const int keyLo = set * g.ncell + (cx * g.dim[1] + cy) * g.dim[2] + z0;
+                    const int keyLo = set * g.ncell + min(snake_cell(g, cx, cy, z0), snake_cell(g, cx, cy, z1));   // the z run is contiguous either way
                     start = (int) A.cellStart[keyLo]; end = (int) A.cellStart[keyLo + (z1 - z0) + 1];
                     if (set == 0) start = max(start, b * kTile);     // primary list: each unordered pair once (own block: triangle below)
                 }
