@@ -128,12 +128,19 @@ struct __align__(16) JStage {
     int    ljoff[2 * kTile];     // byte offset of the LJ-table row of the j type
 };
 
-template <bool kRot>
-__global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(ForceArgs A)
+// per-warp shared scratch: staged j tile + fp64 accumulators of the work item (kept out of registers: 64 regs -> 4 CTAs/SM)
+struct __align__(16) WarpScratch {
+    JStage j;
+    double acc[5][kTile];        // i-gradient x, y, z and the two energies of the item, one column per lane
+};
+
+template <bool kRot, int kMinBlocks>
+__global__ void __launch_bounds__(kForceThreads, kMinBlocks) k_tile_forces(ForceArgs A)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    JStage *stage = reinterpret_cast<JStage *>(smemRaw) + (threadIdx.x >> 5);
-    float2 *sLJ = reinterpret_cast<float2 *>(smemRaw + sizeof(JStage) * kForceWarps);      // [ntypes*ntypes] (A, B)
+    WarpScratch *ws = reinterpret_cast<WarpScratch *>(smemRaw) + (threadIdx.x >> 5);
+    JStage *stage = &ws->j;
+    float2 *sLJ = reinterpret_cast<float2 *>(smemRaw + sizeof(WarpScratch) * kForceWarps);      // [ntypes*ntypes] (A, B)
     for (int i = threadIdx.x; i < A.ntypes * A.ntypes; i += blockDim.x) sLJ[i] = A.ljAB[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -152,8 +159,7 @@ __global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(For
         const ImageOpDev *op = A.ops + wi.image;
         const bool isImage = wi.image > 0;
         const bool pureT = kRot ? (op->pureTranslation != 0) : true;
-        const double cx = A.blockBox[9 * wi.block + 6], cy = A.blockBox[9 * wi.block + 7], cz = A.blockBox[9 * wi.block + 8];
-        const double sc = op->scale;
+        const double *centre = A.blockBox + 9 * wi.block + 6;
 
         // i atom of this lane
         const int si = wi.block * kTile + lane;
@@ -161,11 +167,12 @@ __global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(For
         float xi = 0.f, yi = 0.f, zi = 0.f, qi = 0.f;
         const unsigned char *ljRow = ljBase;
         if (ai >= 0) {
-            xi = (float) (A.x[3 * ai] - cx); yi = (float) (A.x[3 * ai + 1] - cy); zi = (float) (A.x[3 * ai + 2] - cz);
+            xi = (float) (A.x[3 * ai] - centre[0]); yi = (float) (A.x[3 * ai + 1] - centre[1]); zi = (float) (A.x[3 * ai + 2] - centre[2]);
             qi = A.q32[ai] * A.qScale;
             ljRow = ljBase + (size_t) A.ljtype[ai] * A.ntypes * sizeof(float2);
         }
-        double fix = 0.0, fiy = 0.0, fiz = 0.0, eQ = 0.0, eL = 0.0;
+#pragma unroll
+        for (int c = 0; c < 5; c++) ws->acc[c][lane] = 0.0;
         double W[9];
         if (kRot) {
 #pragma unroll
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(For
                         pz = op->R[6] * xj64 + op->R[7] * yj64 + op->R[8] * zj64 + op->tv[2];
                     }
                 }
-                pj = make_float4((float) (px - cx), (float) (py - cy), (float) (pz - cz), A.q32[aj]);
+                pj = make_float4((float) (px - centre[0]), (float) (py - centre[1]), (float) (pz - centre[2]), A.q32[aj]);
                 lj = A.ljtype[aj] * (int) sizeof(float2);
             }
             __syncwarp();                                   // previous tile fully consumed
@@ -198,6 +205,8 @@ __global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(For
             stage->ljoff[lane] = lj; stage->ljoff[lane + kTile] = lj;
             __syncwarp();
 
+            // per tile everything is fp32: 32 terms per accumulator (the energies' fp32 rounding, ~2e-5 kJ/mol per lane and tile,
+            // averages to < 1e-7 of the total over the ~1e6 lane-tiles of a system); the flush to fp64 happens once per tile
             float fxi = 0.f, fyi = 0.f, fzi = 0.f, fxj = 0.f, fyj = 0.f, fzj = 0.f, eq = 0.f, el = 0.f;
             float r2min = F.r2Off;
             unsigned int mrev = __brev(mask);               // step k tests the sign bit, then shifts
@@ -215,10 +224,8 @@ __global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(For
                 r2min = fminf(r2min, r2m);
                 const PairOut o = abfs_pair(F, r2m, qi * p.w, ab.x, ab.y);
                 eq += o.e1; el += o.e2;
-                if ((k & 3) == 3) { eQ += (double) eq; eL += (double) el; eq = 0.f; el = 0.f; }   // fp32 partial sums stay short
-                const float gx = o.g * dx, gy = o.g * dy, gz = o.g * dz;      // force on i; the energy gradient is the negative
-                fxi -= gx; fyi -= gy; fzi -= gz;
-                fxj += gx; fyj += gy; fzj += gz;
+                fxi = fmaf(-o.g, dx, fxi); fyi = fmaf(-o.g, dy, fyi); fzi = fmaf(-o.g, dz, fzi);      // gradient = -(force on i) = -g d
+                fxj = fmaf(o.g, dx, fxj); fyj = fmaf(o.g, dy, fyj); fzj = fmaf(o.g, dz, fzj);
                 // hand the j-gradient accumulator to the lane that evaluates this j slot next
                 fxj = __shfl_sync(0xffffffffu, fxj, src); fyj = __shfl_sync(0xffffffffu, fyj, src); fzj = __shfl_sync(0xffffffffu, fzj, src);
             }
@@ -226,11 +233,13 @@ __global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(For
                 float c[8];
                 damped_tile_fix(F, mask, myPosq, ljRow, myLj, xi, yi, zi, qi, src, c);
                 fxi += c[0]; fyi += c[1]; fzi += c[2]; fxj += c[3]; fyj += c[4]; fzj += c[5];
-                eQ += (double) c[6]; eL += (double) c[7];
+                eq += c[6]; el += c[7];
             }
             // after 32 hand-overs the accumulator of j slot `lane` is back in this lane
-            fix += (double) fxi; fiy += (double) fyi; fiz += (double) fzi;
+            ws->acc[0][lane] += (double) fxi; ws->acc[1][lane] += (double) fyi; ws->acc[2][lane] += (double) fzi;
+            ws->acc[3][lane] += (double) eq;  ws->acc[4][lane] += (double) el;
             if (aj >= 0) {
+                const double sc = op->scale;
                 double gx = sc * (double) fxj, gy = sc * (double) fyj, gz = sc * (double) fzj;       // gradient on the (image) atom
                 if (isImage) {
                     if (kRot && !pureT) {
@@ -248,11 +257,13 @@ __global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(For
                 }
             }
         }
+        const double sc = op->scale;
+        const double fix = ws->acc[0][lane], fiy = ws->acc[1][lane], fiz = ws->acc[2][lane];
         if (ai >= 0 && A.grad != nullptr) {
             atomicAdd(&A.grad[3 * ai], sc * fix); atomicAdd(&A.grad[3 * ai + 1], sc * fiy); atomicAdd(&A.grad[3 * ai + 2], sc * fiz);
         }
         double *acc = A.accum + 16 * wi.image;
-        eQ = warp_sum(eQ) * sc; eL = warp_sum(eL) * sc;
+        const double eQ = warp_sum(ws->acc[3][lane]) * sc, eL = warp_sum(ws->acc[4][lane]) * sc;
         if (lane == 0) { atomicAdd(&acc[0], eQ); atomicAdd(&acc[1], eL); }
         if (isImage) {
             // sum over the image atoms of their gradient = minus the sum of the i-side gradients of this item (Newton's third law)
@@ -266,15 +277,6 @@ __global__ void __launch_bounds__(kForceThreads, kRot ? 2 : 3) k_tile_forces(For
     }
 }
 
-// ------------------------------------------------------------------------------------------------------
-// k_tile_forces_x2: the same tile walk with TWO pairs per lane per step, evaluated with Blackwell's packed fp32
-// instructions (fma/mul/add/sub.rn.f32x2 -> FFMA2 / FMUL2 / FADD2).  Measured on B200 (scripts/microbench): FFMA2 issues at
-// half the rate of FFMA for the same flops, i.e. it halves the ISSUE slots of the arithmetic; the scalar kernel is issue
-// bound (84 slots per pair at 78 %), so packing moves the bound to the FMA pipe itself (~52 pipe cycles per pair).
-// Lane l owns i atom l; a tile's 32 j slots are staged as 16 slot pairs (m, m+16); at step k (0..15) lane l evaluates the
-// pair of slots m = (l + k) % 16, m + 16.  Lanes l and l^16 therefore walk the same slots with different i atoms: the j
-// accumulators rotate inside each half warp (3 packed = 6 shuffles per step) and the two halves are added at the end.
-// ------------------------------------------------------------------------------------------------------
 // slow path of the x2 kernel for tiles with a pair inside the damped core (same contract as damped_tile_fix; the j part
 // is returned for slot `lane`, already summed over the two half warps, as a GRADIENT correction with the main loop's sign)
 __device__ __noinline__ void damped_tile_fix_x2(const AbfsF32 &F, unsigned int row, const float4 *myXY, const float4 *myZQ, const unsigned char *ljRow,
@@ -578,8 +580,9 @@ static int g_forceBlocksPerSM = 0, g_numSMs = 0;
 
 void init_force_kernel_attributes()
 {
-    cudaFuncSetAttribute(k_tile_forces<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_tile_forces<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(k_tile_forces<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_tile_forces_x2<false, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_tile_forces_x2<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_tile_forces_x2<false, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
@@ -628,14 +631,15 @@ bool launch_forces(State &s, double *d_grad)
         }
         A.qScale = (float) eScale;
         A.grad = d_grad; A.accum = s.accum.p;
-        const size_t smem = sizeof(JStage) * kForceWarps + sizeof(float2) * (size_t) s.ntypes * s.ntypes;
+        const size_t smem = sizeof(WarpScratch) * kForceWarps + sizeof(float2) * (size_t) s.ntypes * s.ntypes;
         if (smem > 160 * 1024) { set_error("too many LJ types for the shared-memory table"); return false; }
         if (g_numSMs == 0) init_force_kernel_attributes();
         bool rot = false;                                   // any image with a genuine rotation?
         for (const RealSpaceOp &b : s.plan.baseOps) rot = rot || !b.pureTranslation;
         int perSM = 0;
-        if (rot) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_tile_forces<true>, kForceThreads, smem);
-        else     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_tile_forces<false>, kForceThreads, smem);
+        static const int scalarBlocks = []() { const char *e = std::getenv("NBB200_SCALAR_BLOCKS"); return (e && std::atoi(e) == 4) ? 4 : 3; }();
+        void (*skern)(ForceArgs) = rot ? k_tile_forces<true, 2> : (scalarBlocks == 4 ? k_tile_forces<false, 4> : k_tile_forces<false, 3>);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, skern, kForceThreads, smem);
         if (perSM < 1) perSM = 1;
         g_forceBlocksPerSM = perSM;
         const int warpsPerBlock = kForceThreads / 32;
@@ -662,8 +666,7 @@ bool launch_forces(State &s, double *d_grad)
             if (perSM2 < 1) perSM2 = 1;
             const int grid2 = std::max(1, std::min(g_numSMs * perSM2, (nitems + warpsPerBlock - 1) / warpsPerBlock));
             kern<<<grid2, kForceThreads, smem2, s.stream>>>(A, X);
-        } else if (rot) k_tile_forces<true><<<grid, kForceThreads, smem, s.stream>>>(A);
-        else            k_tile_forces<false><<<grid, kForceThreads, smem, s.stream>>>(A);
+        } else skern<<<grid, kForceThreads, smem, s.stream>>>(A);
         if (s.timing) cudaEventRecord(s.ev[3], s.stream);
         s.launches += 1;
     }

@@ -1,7 +1,7 @@
 """Time the force kernel for the kernel variants selected through environment variables (development aid)."""
 import os, subprocess, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-variants = [dict(NBB200_FORCE_KERNEL="scalar"), dict(NBB200_X2_BLOCKS="2"), dict(NBB200_X2_BLOCKS="3"), dict(NBB200_X2_BLOCKS="4")]
+variants = [dict(NBB200_FORCE_KERNEL="scalar", NBB200_SCALAR_BLOCKS="3"), dict(NBB200_FORCE_KERNEL="scalar", NBB200_SCALAR_BLOCKS="4"), dict(NBB200_X2_BLOCKS="2")]
 wl = sys.argv[1] if len(sys.argv) > 1 else "m1"
 for v in variants:
     env = dict(os.environ); env.update(v)
