@@ -57,10 +57,12 @@ struct PairOut { float e1, e2, g; };      // elect, LJ, g = -2 dE/d(r^2)  (force
 __device__ __forceinline__ PairOut abfs_pair(const AbfsF32 &F, float r2, float qij, float A, float B)
 {
     float s = rsqrt_fast(r2);
+#ifndef NBB_NO_NEWTON
     {   // one Newton step: MUFU.RSQ alone (~1e-7 relative) would dominate the energy error budget
         const float rr = r2 * s;
         s = fmaf(0.5f * s, fmaf(-rr, s, 1.0f), s);
     }
+#endif
     const float r = r2 * s, s2 = s * s, s3 = s * s2, s6 = s3 * s3;
     const bool plain = r2 <= F.r2On;
     // Coulomb
@@ -179,10 +181,13 @@ __global__ void __launch_bounds__(kForceThreads, kMinBlocks) k_tile_forces(Force
             for (int k = 0; k < 9; k++) W[k] = 0.0;
         }
 
+        size_t T = (size_t) wi.tileStart * kTile + lane;
+        int ajNext = A.tileJ[T];
+        unsigned int maskNext = A.tileMask[T];
         for (int t = 0; t < wi.tileCount; t++) {
-            const size_t T = ((size_t) wi.tileStart + t) * kTile + lane;
-            const int aj = A.tileJ[T];
-            const unsigned int mask = A.tileMask[T];
+            const int aj = ajNext;
+            const unsigned int mask = maskNext;
+            if (t + 1 < wi.tileCount) { T += kTile; ajNext = A.tileJ[T]; maskNext = A.tileMask[T]; }   // descriptor of the next tile: in flight during this one
             double xj64 = 0.0, yj64 = 0.0, zj64 = 0.0;
             float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
             int lj = 0;
@@ -645,7 +650,9 @@ bool launch_forces(State &s, double *d_grad)
         const int warpsPerBlock = kForceThreads / 32;
         const int grid = std::max(1, std::min(g_numSMs * perSM, (nitems + warpsPerBlock - 1) / warpsPerBlock));
         if (s.timing) cudaEventRecord(s.ev[2], s.stream);
-        static const bool useX2 = []() { const char *e = std::getenv("NBB200_FORCE_KERNEL"); return !(e != nullptr && std::strcmp(e, "scalar") == 0); }();
+        // default: the scalar-instruction kernel (24 warps/SM, issue bound at ~84 %); NBB200_FORCE_KERNEL=x2 selects the packed
+        // f32x2 variant (fewer issue slots, but 128 registers -> 16 warps/SM and latency bound: 5 % slower on B200, see profiles/)
+        static const bool useX2 = []() { const char *e = std::getenv("NBB200_FORCE_KERNEL"); return e != nullptr && std::strcmp(e, "x2") == 0; }();
         if (useX2) {
             AbfsX2 X;
             auto dup = [](double v) { return make_float2((float) v, (float) v); };
@@ -655,7 +662,7 @@ bool launch_forces(State &s, double *d_grad)
             X.r2On = F.r2On; X.r2Damp = F.r2Damp; X.r2OffS = F.r2Off; X.qShift1 = F.qShift1; X.aK12 = F.aK12; X.aF6 = F.aF6;
             X.mShift12 = -F.aShift12; X.bK6 = F.bK6; X.bF3 = F.bF3; X.mShift6 = -F.bShift6;
             const size_t smem2 = sizeof(JStage2) * kForceWarps + sizeof(float2) * (size_t) s.ntypes * s.ntypes;
-            static const int minBlocks = []() { const char *e = std::getenv("NBB200_X2_BLOCKS"); const int v = e ? std::atoi(e) : 3; return (v >= 2 && v <= 4) ? v : 3; }();
+            static const int minBlocks = []() { const char *e = std::getenv("NBB200_X2_BLOCKS"); const int v = e ? std::atoi(e) : 2; return (v >= 2 && v <= 4) ? v : 2; }();
             static const int unroll = []() { const char *e = std::getenv("NBB200_X2_UNROLL"); return e ? std::atoi(e) : 4; }();
             void (*kern)(ForceArgs, AbfsX2) = rot ? k_tile_forces_x2<true, 2, 4>
                                                   : (minBlocks == 2 ? (unroll == 2 ? k_tile_forces_x2<false, 2, 2> : k_tile_forces_x2<false, 2, 4>)
