@@ -49,12 +49,14 @@ static void destroy(State *s)
     if (s->hx) cudaFreeHost(s->hx);
     if (s->hgrad) cudaFreeHost(s->hgrad);
     if (s->hsmall) cudaFreeHost(s->hsmall);
+    if (s->hops) cudaFreeHost(s->hops);
     if (s->haveEvents) for (auto &e : s->ev) cudaEventDestroy(e);
     if (s->ownStream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
 
 constexpr size_t kSmallDoubles = 1 << 16;
+constexpr size_t kOpsBytes = 4096 * sizeof(ImageOpDev);
 
 static State *create(int device, int n, const double *charges, const int *ljtypes,
                      int ntypes, const int *tableindex, const double *tableA, const double *tableB,
@@ -104,6 +106,7 @@ static State *create(int device, int n, const double *charges, const int *ljtype
     ok = ok && cuda_ok(cudaMallocHost((void **) &s->hx, sizeof(double) * 3 * (size_t) n), "cudaMallocHost");
     ok = ok && cuda_ok(cudaMallocHost((void **) &s->hgrad, sizeof(double) * 3 * (size_t) n), "cudaMallocHost");
     ok = ok && cuda_ok(cudaMallocHost((void **) &s->hsmall, sizeof(double) * kSmallDoubles), "cudaMallocHost");
+    ok = ok && cuda_ok(cudaMallocHost((void **) &s->hops, kOpsBytes), "cudaMallocHost");
     if (ok) {
         ok = cuda_ok(cudaMemcpy(s->q32.p, q32.data(), sizeof(float) * n, cudaMemcpyHostToDevice), "H2D") &&
              cuda_ok(cudaMemcpy(s->q64.p, charges, sizeof(double) * n, cudaMemcpyHostToDevice), "H2D") &&
@@ -198,33 +201,45 @@ static int update_common(State &s, const double *box6, int forceNew, int *status
     return doUpdate ? 1 : 0;
 }
 
-static bool energy_common(State &s, double *energies, double *d_grad, double *dEdM)
+// enqueue one energy evaluation on the state's stream: image operations (only when the lattice or the lists changed),
+// force kernels, read-back of the accumulators.  No synchronisation here.
+static bool energy_enqueue(State &s, double *d_grad)
 {
     // energy-time image operations: Orthogonalize(S, t + (a,b,c)) with the CURRENT lattice (NBModelABFS.c:1246-1256)
-    std::vector<ImageOpDev> ops((size_t) s.nsets);
-    std::memset(ops.data(), 0, sizeof(ImageOpDev) * ops.size());
-    ops[0].R[0] = ops[0].R[4] = ops[0].R[8] = 1.0; ops[0].scale = 1.0; ops[0].pureTranslation = 1;
-    for (int k = 1; k < s.nsets; k++) {
-        const CandidateImage &im = s.plan.images[k - 1];
-        const double xt[3] = {s.trans.trans[3 * im.t] + (double) im.a, s.trans.trans[3 * im.t + 1] + (double) im.b, s.trans.trans[3 * im.t + 2] + (double) im.c};
-        const RealSpaceOp op = orthogonalize(s.trans.rot[im.t], xt, s.lattice);
-        std::memcpy(ops[k].R, op.R.v, sizeof(double) * 9);
-        std::memcpy(ops[k].tv, op.tv, sizeof(double) * 3);
-        ops[k].scale = im.scale; ops[k].pureTranslation = op.pureTranslation ? 1 : 0;
+    const bool latticeSame = s.opsValid && s.opsGeneration == s.numberOfUpdates && std::memcmp(s.opsLattice.v, s.lattice.M.v, sizeof(double) * 9) == 0;
+    if (!latticeSame) {
+        ImageOpDev *ops = reinterpret_cast<ImageOpDev *>(s.hops);
+        if ((size_t) s.nsets * sizeof(ImageOpDev) > kOpsBytes) { set_error("too many images for the operation buffer"); return false; }
+        std::memset(ops, 0, sizeof(ImageOpDev) * (size_t) s.nsets);
+        ops[0].R[0] = ops[0].R[4] = ops[0].R[8] = 1.0; ops[0].scale = 1.0; ops[0].pureTranslation = 1;
+        for (int k = 1; k < s.nsets; k++) {
+            const CandidateImage &im = s.plan.images[k - 1];
+            const double xt[3] = {s.trans.trans[3 * im.t] + (double) im.a, s.trans.trans[3 * im.t + 1] + (double) im.b, s.trans.trans[3 * im.t + 2] + (double) im.c};
+            const RealSpaceOp op = orthogonalize(s.trans.rot[im.t], xt, s.lattice);
+            std::memcpy(ops[k].R, op.R.v, sizeof(double) * 9);
+            std::memcpy(ops[k].tv, op.tv, sizeof(double) * 3);
+            ops[k].scale = im.scale; ops[k].pureTranslation = op.pureTranslation ? 1 : 0;
+        }
+        if (!s.imageOps.ensure((size_t) s.nsets)) return false;
+        NBB_CUDA(cudaMemcpyAsync(s.imageOps.p, ops, sizeof(ImageOpDev) * (size_t) s.nsets, cudaMemcpyHostToDevice, s.stream));
+        s.opsLattice = s.lattice.M; s.opsGeneration = s.numberOfUpdates; s.opsValid = true;
     }
-    if (!s.imageOps.ensure(ops.size())) return false;
-    NBB_CUDA(cudaMemcpyAsync(s.imageOps.p, ops.data(), sizeof(ImageOpDev) * ops.size(), cudaMemcpyHostToDevice, s.stream));
     if (!launch_forces(s, d_grad)) return false;
     const size_t accumCount = (size_t) 16 * (s.nsets + 1);
     if (accumCount > kSmallDoubles) { set_error("too many images for the result buffer"); return false; }
     NBB_CUDA(cudaMemcpyAsync(s.hsmall, s.accum.p, sizeof(double) * accumCount, cudaMemcpyDeviceToHost, s.stream));
-    NBB_CUDA(cudaStreamSynchronize(s.stream));
+    return true;
+}
+
+// after the stream has been synchronised: energies, dE/dM, timings from the accumulators
+static void energy_finish(State &s, double *energies, bool haveGrad, double *dEdM)
+{
     const double *acc = s.hsmall;
     for (int k = 0; k < 6; k++) energies[k] = 0.0;
     energies[NBB200_EMMEL] = acc[0]; energies[NBB200_EMMLJ] = acc[1];
     for (int k = 1; k < s.nsets; k++) { energies[NBB200_EIMMMEL] += acc[16 * k]; energies[NBB200_EIMMMLJ] += acc[16 * k + 1]; }
     energies[NBB200_EMMEL14] = acc[16 * s.nsets]; energies[NBB200_EMMLJ14] = acc[16 * s.nsets + 1];
-    if (dEdM != nullptr && d_grad != nullptr) {
+    if (dEdM != nullptr && haveGrad) {
         for (int k = 1; k < s.nsets; k++) {
             const CandidateImage &im = s.plan.images[k - 1];
             const double xt[3] = {s.trans.trans[3 * im.t] + (double) im.a, s.trans.trans[3 * im.t + 1] + (double) im.b, s.trans.trans[3 * im.t + 2] + (double) im.c};
@@ -237,7 +252,6 @@ static bool energy_common(State &s, double *energies, double *d_grad, double *dE
         if (s.hostCounters.itemCount > 0) { cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]); s.timings[1] = ms; }
         if (s.n14 > 0 && s.rank == 0) { cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]); s.timings[2] = ms; }
     }
-    return true;
 }
 
 }  // namespace nbb200
@@ -320,11 +334,12 @@ void NBModelABFS_B200_MMMMEnergy(NBB200State *state, double *energies, double *g
                                 : cuda_ok(cudaMemsetAsync(dg, 0, gbytes, s.stream), "memset grad");
         if (!ok0) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
     }
-    bool ok = energy_common(s, energies, dg, dEdM);
-    if (ok && grad != nullptr) {
-        ok = cuda_ok(cudaMemcpyAsync(direct ? grad : s.hgrad, dg, gbytes, cudaMemcpyDeviceToHost, s.stream), "D2H grad") &&
-             cuda_ok(cudaStreamSynchronize(s.stream), "sync");
-        if (ok && !direct) { const size_t m = 3 * (size_t) s.n; for (size_t i = 0; i < m; i++) grad[i] += s.hgrad[i]; }
+    bool ok = energy_enqueue(s, dg);
+    if (ok && grad != nullptr) ok = cuda_ok(cudaMemcpyAsync(direct ? grad : s.hgrad, dg, gbytes, cudaMemcpyDeviceToHost, s.stream), "D2H grad");
+    ok = ok && cuda_ok(cudaStreamSynchronize(s.stream), "sync");          // the one synchronisation of the call
+    if (ok) {
+        energy_finish(s, energies, grad != nullptr, dEdM);
+        if (grad != nullptr && !direct) { const size_t m = 3 * (size_t) s.n; for (size_t i = 0; i < m; i++) grad[i] += s.hgrad[i]; }
     }
     if (!ok) set_status(status, NBB200_STATUS_LOGIC_ERROR);
 }
@@ -335,7 +350,8 @@ void NBModelABFS_B200_MMMMEnergyDevice(NBB200State *state, double *energies, dou
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
     if (s.xcur == nullptr) { set_error("MMMMEnergy called before Update"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
-    if (!energy_common(s, energies, d_grad, dEdM)) set_status(status, NBB200_STATUS_LOGIC_ERROR);
+    if (energy_enqueue(s, d_grad) && cuda_ok(cudaStreamSynchronize(s.stream), "sync")) energy_finish(s, energies, d_grad != nullptr, dEdM);
+    else set_status(status, NBB200_STATUS_LOGIC_ERROR);
 }
 
 long NBModelABFSState_B200_NumberOfPairs(NBB200State *state, int image)

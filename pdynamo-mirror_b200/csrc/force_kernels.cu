@@ -606,13 +606,13 @@ bool launch_forces(State &s, double *d_grad)
 {
     const int nitems = (int) s.hostCounters.itemCount;
     const size_t accumCount = (size_t) 16 * (s.nsets + 1);
-    if (!s.accum.ensure(accumCount)) return false;
-    NBB_CUDA(cudaMemsetAsync(s.accum.p, 0, sizeof(double) * accumCount, s.stream));
-    NBB_CUDA(cudaMemsetAsync(&s.counters->workCursor, 0, sizeof(unsigned int), s.stream));
+    if (!s.accum.ensure(accumCount + 1)) return false;                    // + one slot that holds the work cursor: a single memset
+    NBB_CUDA(cudaMemsetAsync(s.accum.p, 0, sizeof(double) * (accumCount + 1), s.stream));
+    unsigned int *workCursor = reinterpret_cast<unsigned int *>(s.accum.p + accumCount);
     const double eScale = (1.0 / s.dielectric) * kE2AngstromToKJMol;
     if (nitems > 0) {
         ForceArgs A;
-        A.items = s.items.p; A.nitems = nitems; A.workCursor = &s.counters->workCursor;
+        A.items = s.items.p; A.nitems = nitems; A.workCursor = workCursor;
         A.tileJ = s.tileJ.p; A.tileMask = s.tileMask.p; A.sAtom = s.sAtom.p; A.n = s.n;
         A.x = s.xcur; A.blockBox = s.blockBox.p;
         A.q32 = s.q32.p; A.ljtype = s.ljtype.p; A.ljAB = s.ljAB.p; A.ntypes = s.ntypes;

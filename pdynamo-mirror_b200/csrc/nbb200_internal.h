@@ -125,6 +125,8 @@ struct State {
     const double *xcur = nullptr;   // coordinates of the current call (s.x.p or a caller-owned device array)
     double *hx = nullptr, *hgrad = nullptr;      // pinned staging
     double *hsmall = nullptr;                    // pinned small results
+    void *hops = nullptr;                        // pinned staging of the image operations
+    Mat3 opsLattice{}; long opsGeneration = -1; bool opsValid = false;
     size_t hcap = 0;
 
     // image plan of the current lists
