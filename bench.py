@@ -381,41 +381,35 @@ def jac_block(torch, local, fp32_peak_tflops):
             "kernels_ms": {"list_rebuild": statistics.mean(lb), "tile_forces": f}, "roofline_frac_fp32": ach / fp32_peak_tflops}
 
 
-def md_block(torch, local, steps=200):
-    """BASELINE.json config 4 call pattern: velocity-Verlet MD on the 23 558-atom DHFR/JAC box through the plugin surface
-    (System.Energy(doGradients=True), host arrays).  Only the NB forces exist in this repository (bonded terms are out of
-    scope), so this measures the call pattern -- displacement-triggered list updates vs a forced update every 10 steps -- not
-    a physical trajectory.  Integrator: numpy on the host, dt = 1 fs, Maxwell velocities at 300 K (PCG64 seed 491831)."""
+def md_block(torch, local, steps=300):
+    """BASELINE.json config 4 call pattern on the 23 558-atom DHFR/JAC box through the plugin surface
+    (System.Energy(doGradients=True), host arrays in and out, one call per MD step).  Only the NB forces exist in this repository
+    (bonded terms are out of scope) and NB-only dynamics of a bonded system is not stable, so the trajectory is a synthetic
+    random walk with MD-like step lengths (0.03 A rms per coordinate and step: the displacement criterion of the reference,
+    any atom beyond 0.75 A, fires every ~15-30 steps as in its DHFR run, 13.7 calls per update).  Two update policies: the
+    reference's displacement heuristic, and a forced update every 10 steps."""
     import pdynamo_mirror_b200 as p
     w = make_workload("dhfr")
     n = w["n"]
-    first = np.array([str(t)[0] for t in np.load(os.path.join(ROOT, "tests", "golden", "dhfr_jac.npz"))["types"]])
-    mass_by = {"H": 1.008, "C": 12.011, "N": 14.007, "O": 15.999, "S": 32.06}
-    mass = np.array([mass_by.get(first[t], 12.0) for t in w["ljtypes"]])[:, None]
     out = {}
     for label, freq in (("displacement_triggered", 0), ("update_every_10", 10)):
         sysm = p.System.FromWorkload(w)
         sysm.DefineNBModel(p.NBModelABFS(device=local, updateFrequency=freq))
         rng = np.random.Generator(np.random.PCG64(491831))
-        v = rng.standard_normal((n, 3)) * np.sqrt(0.0083144626 * 300.0 / mass)        # A/ps (kT/m in (kJ/mol)/amu = 100 A^2/ps^2 / 100)
-        v *= 10.0
-        dt = 0.001
         sysm.Energy(doGradients=True)
-        a = -100.0 * sysm.configuration.gradients3 / mass
         x = sysm.coordinates3
+        kicks = rng.standard_normal((8, n, 3)) * 0.03          # pre-drawn steps, reused cyclically: no RNG cost in the timed loop
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            x += v * dt + (0.5 * dt * dt) * a
+        for k in range(steps):
+            x += kicks[k & 7]
             sysm.Energy(doGradients=True)
-            a_new = -100.0 * sysm.configuration.gradients3 / mass
-            v += (0.5 * dt) * (a + a_new)
-            a = a_new
         wall = time.perf_counter() - t0
         st = sysm.configuration.nbState
         out[label] = {"steps_per_s": steps / wall, "ms_per_step": 1e3 * wall / steps, "steps": steps, "list_updates": int(st.numberOfUpdates) - 1,
                       "nb_setup_ms_per_step": 1e3 * sysm.timings["NB Set Up"] / (steps + 1), "nb_evaluation_ms_per_step": 1e3 * sysm.timings["NB Evaluation"] / (steps + 1)}
-    out["note"] = "NB forces only (bonded terms out of scope); host numpy velocity Verlet, dt 1 fs, 300 K; the reference needs 0.65 s per step serial / 0.20 s with 8 OpenMP threads on this system (benchmarks/log/systemBenchmarks_*_1ps.log)"
+    out["note"] = ("synthetic random-walk trajectory, NB term only, host arrays every step; for scale: the reference spends 0.587 s (serial) / 0.122 s "
+                   "(8 OpenMP threads) per NB evaluation and 0.68 s per list update on this system (benchmarks/log/systemBenchmarks_*_1ps.log)")
     return out
 
 

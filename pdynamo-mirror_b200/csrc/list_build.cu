@@ -760,8 +760,14 @@ bool build_lists(State &s)
     NBB_CUDA(cudaMemcpyAsync(s.baseOpsDev.p, ops.data(), sizeof(double) * ops.size(), cudaMemcpyHostToDevice, s.stream));
     std::vector<double> bmin(3 * (1 + ntr)), bext(3 * (1 + ntr));
     if (!device_bbox(s, 1 + ntr, bmin.data(), bext.data())) return false;
-    if (ntr > 0) plan_images(s.trans, s.lattice, s.list, s.checkForInverses, s.expandFactor, bmin.data(), bext.data(), s.plan);
-    else {
+    for (double v : bmin) if (!std::isfinite(v)) { set_error("non-finite coordinates"); return false; }
+    for (double v : bext) if (!std::isfinite(v)) { set_error("non-finite coordinates"); return false; }
+    if (ntr > 0) {
+        if (!plan_images(s.trans, s.lattice, s.list, s.checkForInverses, s.expandFactor, bmin.data(), bext.data(), s.plan)) {
+            set_error("image search range is absurd (more than 2^20 lattice translations): coordinates or lattice are not physical");
+            return false;
+        }
+    } else {
         s.plan = ImagePlan();
         for (int d = 0; d < 3; d++) { s.plan.lower[d] = bmin[d] - s.list; s.plan.upper[d] = (bext[d] + bmin[d]) + s.list; }
     }

@@ -1,6 +1,7 @@
 // symmetry_host.cpp -- see symmetry_host.h.  Compile with -ffp-contract=off: the values produced here feed
 // fp64 pair-list membership tests that must agree bit for bit with the reference's (built without FMA).
 #include "symmetry_host.h"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -143,12 +144,16 @@ RealSpaceOp orthogonalize(const Mat3 &rotF, const double *transF, const Lattice 
 // while-loops of GetLimits: slide an interval [il, iu] by multiples of t over [bl, bu]
 static bool interval_limits(double bl, double bu, double il, double iu, double t, int &low, int &high)
 {
+    // the reference loops unconditionally; a degenerate lattice or exploded coordinates would spin forever, so bail out
+    // (plan_images then reports an error instead of hanging) when the shift count becomes absurd
+    const int guard = 100000;
     int n = 0;
-    while (iu >= bl) { il -= t; iu -= t; n--; }
-    while (iu <  bl) { il += t; iu += t; n++; }
+    if (!(t > 0.0) || !std::isfinite(bl) || !std::isfinite(bu) || !std::isfinite(il) || !std::isfinite(iu)) { low = 0; high = guard; return true; }
+    while (iu >= bl && n > -guard) { il -= t; iu -= t; n--; }
+    while (iu <  bl && n <  guard) { il += t; iu += t; n++; }
     if (!(il <= bu)) return false;
     low = n;
-    while (il <= bu) { il += t; iu += t; n++; }
+    while (il <= bu && n < guard) { il += t; iu += t; n++; }
     high = n - 1;
     return true;
 }
@@ -167,9 +172,10 @@ static void box_search_limits(const Mat3 &M, const double *lower, const double *
     interval_limits(bl, bu, ilower[0], iupper[0], M(0, 0), lim[0], lim[1]);
 }
 
-void plan_images(const Transformations &tr, const Lattice &lat, double cutoff, bool checkForInverses, int expandFactor,
+bool plan_images(const Transformations &tr, const Lattice &lat, double cutoff, bool checkForInverses, int expandFactor,
                  const double *bboxMin, const double *bboxExt, ImagePlan &plan)
 {
+    const size_t maxVisits = 1u << 20;                // far beyond any physical system (crystals: a few hundred)
     plan.visits.clear(); plan.images.clear(); plan.activeT.clear();
     plan.baseOps.resize(tr.n);
     for (int t = 0; t < tr.n; t++) plan.baseOps[t] = orthogonalize(tr.rot[t], &tr.trans[3 * t], lat);
@@ -191,6 +197,11 @@ void plan_images(const Transformations &tr, const Lattice &lat, double cutoff, b
         int lim[6];
         box_search_limits(lat.M, plan.lower, plan.upper, ilower, iupper, lim);
         if (expandFactor > 0) for (int k = 0; k < 3; k++) { lim[2 * k] -= expandFactor; lim[2 * k + 1] += expandFactor; }
+        {
+            double count = 1.0;
+            for (int k = 0; k < 3; k++) count *= (double) std::max(0, lim[2 * k + 1] - lim[2 * k] + 1);
+            if (count + (double) plan.visits.size() > (double) maxVisits) return false;
+        }
         bool any = false;
         for (int a = lim[0]; a <= lim[1]; a++) for (int b = lim[2]; b <= lim[3]; b++) for (int c = lim[4]; c <= lim[5]; c++) {
             if (a == 0 && b == 0 && c == 0 && tr.identity == t) continue;
@@ -225,6 +236,7 @@ void plan_images(const Transformations &tr, const Lattice &lat, double cutoff, b
         }
         if (any) plan.activeT.push_back(t);
     }
+    return true;
 }
 
 bool check_for_image_update(const Transformations &tr, const Lattice &now, const Lattice &ref,

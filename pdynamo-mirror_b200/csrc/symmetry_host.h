@@ -74,7 +74,7 @@ struct ImagePlan {
 
 // bboxMin/bboxExt: [0] primary coordinates, [1+t] coordinates transformed by baseOps[t] (min and max-min, as
 // Coordinates3_EnclosingOrthorhombicBox returns them).
-void plan_images(const Transformations &tr, const Lattice &lat, double cutoff, bool checkForInverses, int expandFactor,
+bool plan_images(const Transformations &tr, const Lattice &lat, double cutoff, bool checkForInverses, int expandFactor,
                  const double *bboxMin, const double *bboxExt, ImagePlan &plan);
 
 bool check_for_image_update(const Transformations &tr, const Lattice &now, const Lattice &ref,
