@@ -137,7 +137,7 @@ struct __align__(16) WarpScratch {
 };
 
 template <bool kRot, int kMinBlocks>
-__global__ void __launch_bounds__(kForceThreads, kMinBlocks) k_tile_forces(ForceArgs A)
+__global__ void __launch_bounds__(kForceThreads, kMinBlocks) k_tile_forces(const __grid_constant__ ForceArgs A)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     WarpScratch *ws = reinterpret_cast<WarpScratch *>(smemRaw) + (threadIdx.x >> 5);
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kForceThreads, kMinBlocks) k_tile_forces(Force
     for (int i = threadIdx.x; i < A.ntypes * A.ntypes; i += blockDim.x) sLJ[i] = A.ljAB[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const AbfsF32 F = A.F;
+    const AbfsF32 &F = A.F;
     const int src = (lane + 1) & 31;
     const unsigned char *ljBase = reinterpret_cast<const unsigned char *>(sLJ);
     const float4 *myPosq = stage->posq + lane;
@@ -282,82 +282,94 @@ __global__ void __launch_bounds__(kForceThreads, kMinBlocks) k_tile_forces(Force
     }
 }
 
-// slow path of the x2 kernel for tiles with a pair inside the damped core (same contract as damped_tile_fix; the j part
-// is returned for slot `lane`, already summed over the two half warps, as a GRADIENT correction with the main loop's sign)
-__device__ __noinline__ void damped_tile_fix_x2(const AbfsF32 &F, unsigned int row, const float4 *myXY, const float4 *myZQ, const unsigned char *ljRow,
-                                               const int2 *myLj, float xi, float yi, float zi, float qi, int lmod, int half, int src, float *c)
-{
-    float fxi = 0.f, fyi = 0.f, fzi = 0.f, eq = 0.f, el = 0.f;
-    float fj[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-    for (int k = 0; k < 16; k++) {
-        const float4 pxy = myXY[k], pzq = myZQ[k];
-        const int2 lo2 = myLj[k];
-        const int m = (lmod + k) & 15;
-        for (int h = 0; h < 2; h++) {
-            const float px = h ? pxy.y : pxy.x, py = h ? pxy.w : pxy.z, pz = h ? pzq.y : pzq.x, qj = h ? pzq.w : pzq.z;
-            const float2 ab = *reinterpret_cast<const float2 *>(ljRow + (h ? lo2.y : lo2.x));      // (A, -B)
-            const float dx = xi - px, dy = yi - py, dz = zi - pz;
-            const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-            if (((row >> (m + 16 * h)) & 1u) && (r2 < F.r2Damp)) {
-                const float qij = qi * qj, Aij = ab.x, Bij = -ab.y;
-                const PairOut o = abfs_pair(F, r2, qij, Aij, Bij);
-                const float e1 = qij * fmaf(-F.qAlpha, r2, F.qF0);
-                const float e2 = Aij * fmaf(-F.aAlpha, r2, F.aF0) - Bij * fmaf(-F.bAlpha, r2, F.bF0);
-                const float g = -2.0f * (-qij * F.qAlpha - Aij * F.aAlpha + Bij * F.bAlpha) - o.g;
-                eq += e1 - o.e1; el += e2 - o.e2;
-                const float gx = g * dx, gy = g * dy, gz = g * dz;
-                fxi -= gx; fyi -= gy; fzi -= gz;
-                fj[h][0] += gx; fj[h][1] += gy; fj[h][2] += gz;
-            }
-        }
-        for (int h = 0; h < 2; h++) for (int d = 0; d < 3; d++) fj[h][d] = __shfl_sync(0xffffffffu, fj[h][d], src);
-    }
-    for (int h = 0; h < 2; h++) for (int d = 0; d < 3; d++) fj[h][d] += __shfl_xor_sync(0xffffffffu, fj[h][d], 16);
-    c[0] = fxi; c[1] = fyi; c[2] = fzi; c[3] = fj[half][0]; c[4] = fj[half][1]; c[5] = fj[half][2]; c[6] = eq; c[7] = el;
-}
-
+// ------------------------------------------------------------------------------------------------------
+// k_tile_forces_x2: the same tile walk with Blackwell's packed fp32 instructions (FFMA2 / FMUL2 / FADD2).
+// Lane (half, lmod) owns TWO i atoms of the block, lmod (element a) and lmod + 16 (element b), and every packed instruction
+// works on the pairs (a, j) and (b, j) of ONE j atom, whose data are scalar (broadcast) operands: half the shared-memory
+// traffic per pair of the one-atom-per-lane walk, which is what bounds a packed kernel (the LSU data pipe).  Half warp h walks
+// the 16 j slots 16h .. 16h+15 in 16 steps (lane lmod sees slot 16h + (lmod + k) % 16); the scalar j accumulator travels
+// inside the half warp and is back home (slot = lane) after 16 steps.  Region selection is arithmetic (p = 1 plain,
+// 0 switched; pm = 1 - p) so that it stays in the packed domain: a packed instruction takes one issue slot for two pairs.
+// ------------------------------------------------------------------------------------------------------
 typedef unsigned long long f32x2;
 
 __device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 bc(float v) { return pk(v, v); }
 __device__ __forceinline__ float lo_of(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
 __device__ __forceinline__ float hi_of(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f32x2 sel2(bool pa, bool pb, float ta, float fa) { return pk(pa ? ta : fa, pb ? ta : fa); }
-
-// constants duplicated into both halves (kernel parameter -> constant bank, 64-bit operands)
-struct AbfsX2 {
-    float2 one, mhalf, two, msix;
-    float2 rOff, r2Off, n3, n4, n5, n6, mk1, k2;
-    float r2On, r2Damp, r2OffS, qShift1, aK12, aF6, mShift12, bK6, bF3, mShift6;
-};
 
 struct __align__(16) JStage2 {
-    float4 xy[2 * 16];       // xa, xb, ya, yb   (a = slot m, b = slot m + 16), duplicated for wrap-free indexing
-    float4 zq[2 * 16];       // za, zb, qa, qb
-    int2   lj[2 * 16];       // LJ row byte offsets of the two j types
+    float4 posq[2][2 * 16];  // per half warp: its 16 j slots (x, y, z block-local, charge), duplicated for wrap-free indexing
+    int    ljoff[2][2 * 16]; // byte offset (inside a table row) of the LJ entry of the j type
 };
 
-__device__ __forceinline__ const float2 &c2(const float2 &v) { return v; }
-#define C2(v) (*reinterpret_cast<const f32x2 *>(&(v)))
+struct __align__(16) WarpScratch2 {
+    JStage2 j;
+    double acc[8][kTile];    // i gradient of element a (x, y, z), of element b (x, y, z), the two energies; one column per lane
+};
 
-template <bool kRot, int kMinBlocks, int kUnroll>
-__global__ void __launch_bounds__(kForceThreads, kMinBlocks) k_tile_forces_x2(ForceArgs A, AbfsX2 X)
+// slow path of the x2 kernel for tiles with a pair inside the damped core (same contract as damped_tile_fix):
+// c = {fa.xyz, fb.xyz, fj.xyz, eq, el} corrections with the main loop's signs (fa, fb: i gradients; fj: MINUS the j gradient)
+__device__ __noinline__ void damped_tile_fix_x2(const AbfsF32 &F, unsigned int mm, const float4 *myPosq, const int *myLj, const unsigned char *ljRowA,
+                                               const unsigned char *ljRowB, const float *xi, const float *yi, const float *zi, const float *qi, int src, float *c)
+{
+    float fi[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    float fj[3] = {0.f, 0.f, 0.f}, eq = 0.f, el = 0.f;
+    for (int k = 0; k < 16; k++) {
+        const float4 pj = myPosq[k];
+        const int lo = myLj[k];
+        for (int h = 0; h < 2; h++) {
+            const float4 ab = *reinterpret_cast<const float4 *>((h ? ljRowB : ljRowA) + lo);      // (A, -B, ., .)
+            const float dx = xi[h] - pj.x, dy = yi[h] - pj.y, dz = zi[h] - pj.z;
+            const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            const bool bit = h ? ((mm & 0x8000u) != 0u) : ((int) mm < 0);
+            if (bit && (r2 < F.r2Damp)) {
+                const float qij = qi[h] * pj.w, Aij = ab.x, Bij = -ab.y;
+                const PairOut o = abfs_pair(F, r2, qij, Aij, Bij);
+                const float e1 = qij * fmaf(-F.qAlpha, r2, F.qF0);
+                const float e2 = Aij * fmaf(-F.aAlpha, r2, F.aF0) - Bij * fmaf(-F.bAlpha, r2, F.bF0);
+                const float g = -2.0f * (-qij * F.qAlpha - Aij * F.aAlpha + Bij * F.bAlpha) - o.g;
+                eq += e1 - o.e1; el += e2 - o.e2;
+                const float gx = g * dx, gy = g * dy, gz = g * dz;
+                fi[h][0] -= gx; fi[h][1] -= gy; fi[h][2] -= gz;
+                fj[0] -= gx; fj[1] -= gy; fj[2] -= gz;
+            }
+        }
+        mm <<= 1;
+        for (int d = 0; d < 3; d++) fj[d] = __shfl_sync(0xffffffffu, fj[d], src);
+    }
+    c[0] = fi[0][0]; c[1] = fi[0][1]; c[2] = fi[0][2]; c[3] = fi[1][0]; c[4] = fi[1][1]; c[5] = fi[1][2];
+    c[6] = fj[0]; c[7] = fj[1]; c[8] = fj[2]; c[9] = eq; c[10] = el;
+}
+
+template <bool kRot, int kThreads, int kMinBlocks, int kUnroll>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_tile_forces_x2(const __grid_constant__ ForceArgs A)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    JStage2 *stage = reinterpret_cast<JStage2 *>(smemRaw) + (threadIdx.x >> 5);
-    float2 *sLJ = reinterpret_cast<float2 *>(smemRaw + sizeof(JStage2) * kForceWarps);      // [ntypes*ntypes] (A, -B)
-    for (int i = threadIdx.x; i < A.ntypes * A.ntypes; i += blockDim.x) { const float2 ab = A.ljAB[i]; sLJ[i] = make_float2(ab.x, -ab.y); }
+    constexpr int kWarps = kThreads / 32;
+    WarpScratch2 *ws = reinterpret_cast<WarpScratch2 *>(smemRaw) + (threadIdx.x >> 5);
+    JStage2 *stage = &ws->j;
+    float4 *sLJ = reinterpret_cast<float4 *>(smemRaw + sizeof(WarpScratch2) * kWarps);      // [ntypes*ntypes] (A, -B, -(A aShift12 - B bShift6), 0)
+    const AbfsF32 &F = A.F;
+    for (int i = threadIdx.x; i < A.ntypes * A.ntypes; i += blockDim.x) {
+        const float2 ab = A.ljAB[i];
+        sLJ[i] = make_float4(ab.x, -ab.y, -(ab.x * F.aShift12 - ab.y * F.bShift6), 0.f);
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, lmod = lane & 15, half = lane >> 4;
-    const AbfsF32 F = A.F;
-    const int src = (lane & 16) | ((lane + 1) & 15);
+    // rotation source inside the half warp; bounced through shared memory so that the compiler keeps it in a register
+    // instead of rematerialising it from %tid in every step
+    volatile int *srcSlot = reinterpret_cast<volatile int *>(&ws->acc[0][0]) + lane;
+    *srcSlot = (lane & 16) | ((lane + 1) & 15);
+    const int src = *srcSlot;
+    __syncwarp();
     const unsigned char *ljBase = reinterpret_cast<const unsigned char *>(sLJ);
-    const float4 *myXY = stage->xy + lmod;
-    const float4 *myZQ = stage->zq + lmod;
-    const int2 *myLj = stage->lj + lmod;
+    const float4 *myPosq = stage->posq[half] + lmod;
+    const int *myLj = stage->ljoff[half] + lmod;
 
     for (;;) {
         unsigned int it = 0;
@@ -368,35 +380,50 @@ __global__ void __launch_bounds__(kForceThreads, kMinBlocks) k_tile_forces_x2(Fo
         const ImageOpDev *op = A.ops + wi.image;
         const bool isImage = wi.image > 0;
         const bool pureT = kRot ? (op->pureTranslation != 0) : true;
-        const double cx = A.blockBox[9 * wi.block + 6], cy = A.blockBox[9 * wi.block + 7], cz = A.blockBox[9 * wi.block + 8];
-        const double sc = op->scale;
+        const double *centre = A.blockBox + 9 * wi.block + 6;
 
-        const int si = wi.block * kTile + lane;
-        const int ai = (si < A.n) ? A.sAtom[si] : -1;
-        float xi = 0.f, yi = 0.f, zi = 0.f, qi = 0.f;
-        const unsigned char *ljRow = ljBase;
-        if (ai >= 0) {
-            xi = (float) (A.x[3 * ai] - cx); yi = (float) (A.x[3 * ai + 1] - cy); zi = (float) (A.x[3 * ai + 2] - cz);
-            qi = A.q32[ai] * A.qScale;
-            ljRow = ljBase + (size_t) A.ljtype[ai] * A.ntypes * sizeof(float2);
+        // the two i atoms of this lane: block slots lmod and lmod + 16 (both half warps hold the same two atoms)
+        float xi[2] = {0.f, 0.f}, yi[2] = {0.f, 0.f}, zi[2] = {0.f, 0.f}, qi[2] = {0.f, 0.f};
+        const unsigned char *ljRowA = ljBase, *ljRowB = ljBase;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int si = wi.block * kTile + lmod + 16 * h;
+            const int ai = (si < A.n) ? A.sAtom[si] : -1;
+            if (ai >= 0) {
+                xi[h] = (float) (A.x[3 * ai] - centre[0]); yi[h] = (float) (A.x[3 * ai + 1] - centre[1]); zi[h] = (float) (A.x[3 * ai + 2] - centre[2]);
+                qi[h] = A.q32[ai] * A.qScale;
+                const unsigned char *row = ljBase + (size_t) A.ljtype[ai] * A.ntypes * sizeof(float4);
+                if (h == 0) ljRowA = row; else ljRowB = row;
+            }
         }
-        const f32x2 xi2 = pk(xi, xi), yi2 = pk(yi, yi), zi2 = pk(zi, zi), qi2 = pk(qi, qi);
-        double fix = 0.0, fiy = 0.0, fiz = 0.0, eQ = 0.0, eL = 0.0;
+        const f32x2 xi2 = pk(xi[0], xi[1]), yi2 = pk(yi[0], yi[1]), zi2 = pk(zi[0], zi[1]), nqi2 = pk(-qi[0], -qi[1]);
+#pragma unroll
+        for (int c = 0; c < 8; c++) ws->acc[c][lane] = 0.0;
         double W[9];
         if (kRot) {
 #pragma unroll
             for (int k = 0; k < 9; k++) W[k] = 0.0;
         }
 
+        // two-deep software pipeline over the tiles of the item: the descriptor (j index, mask) of tile t+2 and the gathered
+        // atom data of tile t+1 are in flight while tile t is evaluated
+        size_t T = (size_t) wi.tileStart * kTile + lane;
+        int ajCur = A.tileJ[T];
+        unsigned int maskCur = A.tileMask[T];
+        int ajB = -1;
+        unsigned int maskB = 0u;
+        if (wi.tileCount > 1) { ajB = A.tileJ[T + kTile]; maskB = A.tileMask[T + kTile]; }
+        double gx64 = 0.0, gy64 = 0.0, gz64 = 0.0;
+        float gq = 0.f;
+        int gt = 0;
+        if (ajCur >= 0) { gx64 = A.x[3 * ajCur]; gy64 = A.x[3 * ajCur + 1]; gz64 = A.x[3 * ajCur + 2]; gq = A.q32[ajCur]; gt = A.ljtype[ajCur]; }
         for (int t = 0; t < wi.tileCount; t++) {
-            const size_t T = ((size_t) wi.tileStart + t) * kTile + lane;
-            const int aj = A.tileJ[T];
-            const unsigned int rotmask = A.tileMask[T];
-            double xj64 = 0.0, yj64 = 0.0, zj64 = 0.0;
-            float px32 = 0.f, py32 = 0.f, pz32 = 0.f, qj = 0.f;
+            const int aj = ajCur;
+            const unsigned int rotmask = maskCur;
+            const double xj64 = gx64, yj64 = gy64, zj64 = gz64;
+            float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
             int lj = 0;
             if (aj >= 0) {
-                xj64 = A.x[3 * aj]; yj64 = A.x[3 * aj + 1]; zj64 = A.x[3 * aj + 2];
                 double px = xj64, py = yj64, pz = zj64;
                 if (isImage) {
                     if (pureT) { px += op->tv[0]; py += op->tv[1]; pz += op->tv[2]; }
@@ -406,99 +433,101 @@ __global__ void __launch_bounds__(kForceThreads, kMinBlocks) k_tile_forces_x2(Fo
                         pz = op->R[6] * xj64 + op->R[7] * yj64 + op->R[8] * zj64 + op->tv[2];
                     }
                 }
-                px32 = (float) (px - cx); py32 = (float) (py - cy); pz32 = (float) (pz - cz);
-                qj = A.q32[aj];
-                lj = A.ljtype[aj] * (int) sizeof(float2);
+                pj = make_float4((float) (px - centre[0]), (float) (py - centre[1]), (float) (pz - centre[2]), gq);
+                lj = gt * (int) sizeof(float4);
             }
-            __syncwarp();                                   // previous tile fully consumed
-            {   // slot `lane` = pair element (lmod, half); scalar stores into the packed pair layout, twice (wrap-free indexing)
-                float *pxy = reinterpret_cast<float *>(stage->xy), *pzq = reinterpret_cast<float *>(stage->zq);
-                int *plj = reinterpret_cast<int *>(stage->lj);
-#pragma unroll
-                for (int d = 0; d < 2; d++) {
-                    const int m = lmod + 16 * d;
-                    pxy[4 * m + half] = px32; pxy[4 * m + 2 + half] = py32;
-                    pzq[4 * m + half] = pz32; pzq[4 * m + 2 + half] = qj;
-                    plj[2 * m + half] = lj;
-                }
-            }
-            __syncwarp();
-            // masks: canonical row (bit s <-> slot s), halves rotated by lmod, bit-reversed so that step k tests the sign bit
-            const unsigned int row = __funnelshift_l(rotmask, rotmask, lane);
-            const unsigned int lowh = row & 0xffffu, highh = row >> 16;
-            unsigned int ma = __brev(((lowh >> lmod) | (lowh << (16 - lmod))) & 0xffffu);
-            unsigned int mb = __brev(((highh >> lmod) | (highh << (16 - lmod))) & 0xffffu);
+            // next tile: gather its atoms now, and fetch the descriptor of the tile after it
+            ajCur = ajB; maskCur = maskB;
+            gx64 = 0.0; gy64 = 0.0; gz64 = 0.0; gq = 0.f; gt = 0;
+            if (ajCur >= 0) { gx64 = A.x[3 * ajCur]; gy64 = A.x[3 * ajCur + 1]; gz64 = A.x[3 * ajCur + 2]; gq = A.q32[ajCur]; gt = A.ljtype[ajCur]; }
+            ajB = -1; maskB = 0u;
+            if (t + 2 < wi.tileCount) { ajB = A.tileJ[T + 2 * kTile]; maskB = A.tileMask[T + 2 * kTile]; }
+            T += kTile;
 
-            f32x2 fxi = 0ULL, fyi = 0ULL, fzi = 0ULL, fxj = 0ULL, fyj = 0ULL, fzj = 0ULL, eq = 0ULL, el = 0ULL;   // fxj.. hold MINUS the j gradient
+            __syncwarp();                                   // previous tile fully consumed
+            stage->posq[half][lmod] = pj; stage->posq[half][lmod + 16] = pj;        // j slot = lane
+            stage->ljoff[half][lmod] = lj; stage->ljoff[half][lmod + 16] = lj;
+            __syncwarp();
+            // masks: canonical row of an i atom (bit s <-> slot s) lives in the lane of that atom; fetch the rows of this lane's two
+            // atoms, keep the 16 slots of this half warp, rotate by lmod and bit-reverse both into one word: step k tests
+            // bit 31 (element a) and bit 15 (element b), then shifts left
+            unsigned int mm;
+            {
+                const unsigned int row = __funnelshift_l(rotmask, rotmask, lane);
+                const unsigned int ga = (__shfl_sync(0xffffffffu, row, lmod) >> (16 * half)) & 0xffffu;
+                const unsigned int gb = (__shfl_sync(0xffffffffu, row, lmod + 16) >> (16 * half)) & 0xffffu;
+                const unsigned int ma = ((ga >> lmod) | (ga << (16 - lmod))) & 0xffffu, mb = ((gb >> lmod) | (gb << (16 - lmod))) & 0xffffu;
+                mm = (__brev(ma) & 0xffff0000u) | (__brev(mb) >> 16);
+            }
+            const unsigned int mm0 = mm;
+
+            f32x2 fxi = 0ULL, fyi = 0ULL, fzi = 0ULL, eq = 0ULL, el = 0ULL;   // i gradients of (a, b); eq holds the NEGATED Coulomb energy
+            float fxj = 0.f, fyj = 0.f, fzj = 0.f;                            // MINUS the j gradient
             float r2min = F.r2Off;
 #pragma unroll kUnroll
             for (int k = 0; k < 16; k++) {
-                const float4 pxy = myXY[k], pzq = myZQ[k];
-                const int2 lo2 = myLj[k];
-                const float2 aba = *reinterpret_cast<const float2 *>(ljRow + lo2.x), abb = *reinterpret_cast<const float2 *>(ljRow + lo2.y);
-                const f32x2 dx = sub2(xi2, pk(pxy.x, pxy.y)), dy = sub2(yi2, pk(pxy.z, pxy.w)), dz = sub2(zi2, pk(pzq.x, pzq.y));
+                const float4 p = myPosq[k];
+                const int lo = myLj[k];
+                const unsigned char *ea = ljRowA + lo, *eb = ljRowB + lo;
+                const f32x2 Aij = pk(*reinterpret_cast<const float *>(ea), *reinterpret_cast<const float *>(eb));
+                const f32x2 mBij = pk(*reinterpret_cast<const float *>(ea + 4), *reinterpret_cast<const float *>(eb + 4));
+                const f32x2 mSij = pk(*reinterpret_cast<const float *>(ea + 8), *reinterpret_cast<const float *>(eb + 8));
+                const f32x2 dx = sub2(xi2, bc(p.x)), dy = sub2(yi2, bc(p.y)), dz = sub2(zi2, bc(p.z));
                 const f32x2 r2raw = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
-                const float r2a0 = lo_of(r2raw), r2b0 = hi_of(r2raw);
-                const bool ona = ((int) ma < 0) && (r2a0 <= F.r2Off), onb = ((int) mb < 0) && (r2b0 <= F.r2Off);
-                ma <<= 1; mb <<= 1;
-                const float r2a = ona ? r2a0 : F.r2Off, r2b = onb ? r2b0 : F.r2Off;       // masked pairs sit AT the cutoff: zero energy and force
+                const bool ba = (int) mm < 0, bb = (mm & 0x8000u) != 0u;
+                mm <<= 1;
+                // masked pairs sit AT the outer cutoff: zero energy and force
+                const float r2a = ba ? fminf(lo_of(r2raw), F.r2Off) : F.r2Off, r2b = bb ? fminf(hi_of(r2raw), F.r2Off) : F.r2Off;
                 r2min = fminf(r2min, fminf(r2a, r2b));
                 const f32x2 r2 = pk(r2a, r2b);
                 f32x2 s = pk(rsqrt_fast(r2a), rsqrt_fast(r2b));
-                {   // Newton: s <- s - 0.5 s (r2 s^2 - 1)
-                    const f32x2 rr = mul2(r2, s);
-                    const f32x2 e = sub2(mul2(rr, s), C2(X.one));
-                    s = fma2(mul2(s, C2(X.mhalf)), e, s);
+                {   // Newton: s <- s + (-0.5 s) (r2 s^2 - 1)
+                    const f32x2 e = fma2(mul2(r2, s), s, bc(-1.0f));
+                    s = fma2(mul2(s, bc(-0.5f)), e, s);
                 }
-                const f32x2 r = mul2(r2, s), s2 = mul2(s, s), s3 = mul2(s, s2), s6 = mul2(s3, s3);
-                const bool pa = r2a <= F.r2On, pb = r2b <= F.r2On;
-                const f32x2 qij = mul2(qi2, pk(pzq.z, pzq.w));
-                // Coulomb
-                const f32x2 tt = sub2(C2(X.rOff), r);
-                const f32x2 Cc = fma2(fma2(fma2(C2(X.n6), tt, C2(X.n5)), tt, C2(X.n4)), tt, C2(X.n3));
-                const f32x2 t3C = mul2(mul2(tt, tt), mul2(tt, Cc));
-                const f32x2 Gs = pk(pa ? 1.0f : lo_of(t3C), pb ? 1.0f : hi_of(t3C));
-                const f32x2 sh = sel2(pa, pb, F.qShift1, 0.0f);
-                const f32x2 e1 = mul2(qij, fma2(s, Gs, sh));
-                const f32x2 u = sub2(C2(X.r2Off), r2);
-                const f32x2 mQs = mul2(mul2(u, u), fma2(C2(X.k2), u, C2(X.mk1)));                   // -(u^2 (k1 - k2 u))
-                const f32x2 mQ = pk(pa ? -1.0f : lo_of(mQs), pb ? -1.0f : hi_of(mQs));
-                const f32x2 mgq = mul2(mul2(qij, s3), mQ);                                           // -(qij s^3 Q)
-                // Lennard-Jones (table holds (A, -B))
-                const f32x2 ka = sel2(pa, pb, 1.0f, F.aK12), xa = sel2(pa, pb, 0.0f, F.aF6), mwa = sel2(pa, pb, -F.aShift12, 0.0f);
-                const f32x2 kb = sel2(pa, pb, 1.0f, F.bK6),  xb = sel2(pa, pb, 0.0f, F.bF3), mwb = sel2(pa, pb, -F.bShift6, 0.0f);
-                const f32x2 Aij = pk(aba.x, abb.x), mBij = pk(aba.y, abb.y);
-                const f32x2 la = sub2(s6, xa), lb = sub2(s3, xb);
-                const f32x2 kla = mul2(ka, la), klb = mul2(kb, lb);
-                const f32x2 e2 = fma2(Aij, fma2(kla, la, mwa), mul2(mBij, fma2(klb, lb, mwb)));
-                const f32x2 mm = fma2(C2(X.two), mul2(mul2(Aij, kla), s6), mul2(mul2(mBij, klb), s3));
-                const f32x2 mg = fma2(mul2(s2, C2(X.msix)), mm, mgq);                                 // -g
-                eq = add2(eq, e1); el = add2(el, e2);
-                if ((k & 3) == 3) {
-                    eQ += (double) (lo_of(eq) + hi_of(eq)); eL += (double) (lo_of(el) + hi_of(el));
-                    eq = 0ULL; el = 0ULL;
-                }
-                fxi = fma2(mg, dx, fxi); fyi = fma2(mg, dy, fyi); fzi = fma2(mg, dz, fzi);           // fi -= g d
-                fxj = fma2(mg, dx, fxj); fyj = fma2(mg, dy, fyj); fzj = fma2(mg, dz, fzj);           // (-fj) -= g d
+                const f32x2 s2 = mul2(s, s), s3 = mul2(s, s2), s6 = mul2(s3, s3);
+                const f32x2 p1 = pk(r2a <= F.r2On ? 1.0f : 0.0f, r2b <= F.r2On ? 1.0f : 0.0f);   // 1: plain region, 0: switched
+                const f32x2 pm = sub2(bc(1.0f), p1);
+                const f32x2 nqij = mul2(nqi2, bc(p.w));                                            // -qi qj
+                // Coulomb energy (negated): nqij (s G + p qShift1), G = p + pm t^3 C(t); with tn = r - rOff = -t the signs of the
+                // odd powers live in the coefficients: t^3 C(t) = tn^2 (tn (-n3 + n4 tn - n5 tn^2 + n6 tn^3))
+                const f32x2 tn = fma2(r2, s, bc(-F.rOff));
+                const f32x2 Cn = fma2(fma2(fma2(bc(F.n6), tn, bc(-F.n5)), tn, bc(F.n4)), tn, bc(-F.n3));
+                const f32x2 t3C = mul2(mul2(tn, tn), mul2(tn, Cn));
+                const f32x2 G = fma2(pm, t3C, p1);
+                eq = fma2(nqij, fma2(s, G, mul2(p1, bc(F.qShift1))), eq);
+                // Coulomb force factor (negated): nqij s^3 Q, Q = p + pm u^2 (k1 - k2 u)
+                const f32x2 u = sub2(bc(F.r2Off), r2);
+                const f32x2 Qs = mul2(mul2(u, u), fma2(bc(-F.k2), u, bc(F.k1)));
+                const f32x2 Q = fma2(pm, Qs, p1);
+                const f32x2 mgq = mul2(mul2(nqij, s3), Q);
+                // Lennard-Jones: A ka (s6 - xa)^2 - B kb (s3 - xb)^2 - p (A aShift12 - B bShift6), X = A ka la, Y = -B kb lb
+                const f32x2 la = fma2(pm, bc(-F.aF6), s6), lb = fma2(pm, bc(-F.bF3), s3);
+                const f32x2 Xa = mul2(Aij, mul2(fma2(pm, bc(F.aK12 - 1.0f), bc(1.0f)), la)), Yb = mul2(mBij, mul2(fma2(pm, bc(F.bK6 - 1.0f), bc(1.0f)), lb));
+                el = fma2(Xa, la, el); el = fma2(Yb, lb, el); el = fma2(p1, mSij, el);
+                const f32x2 mmLJ = fma2(bc(2.0f), mul2(Xa, s6), mul2(Yb, s3));
+                const f32x2 mg = fma2(mul2(s2, bc(-6.0f)), mmLJ, mgq);                               // -g
+                fxi = fma2(mg, dx, fxi); fyi = fma2(mg, dy, fyi); fzi = fma2(mg, dz, fzi);
+                fxj = fmaf(lo_of(mg), lo_of(dx), fxj); fyj = fmaf(lo_of(mg), lo_of(dy), fyj); fzj = fmaf(lo_of(mg), lo_of(dz), fzj);
+                fxj = fmaf(hi_of(mg), hi_of(dx), fxj); fyj = fmaf(hi_of(mg), hi_of(dy), fyj); fzj = fmaf(hi_of(mg), hi_of(dz), fzj);
+                // hand the j accumulator to the lane that evaluates this j slot next
                 fxj = __shfl_sync(0xffffffffu, fxj, src); fyj = __shfl_sync(0xffffffffu, fyj, src); fzj = __shfl_sync(0xffffffffu, fzj, src);
             }
-            // both half warps hold partial (negated) gradients of slots (lmod, lmod+16): add them, lane l keeps slot l
-            float gjx, gjy, gjz;
-            {
-                const f32x2 ox = __shfl_xor_sync(0xffffffffu, fxj, 16), oy = __shfl_xor_sync(0xffffffffu, fyj, 16), oz = __shfl_xor_sync(0xffffffffu, fzj, 16);
-                fxj = add2(fxj, ox); fyj = add2(fyj, oy); fzj = add2(fzj, oz);
-                gjx = -(half ? hi_of(fxj) : lo_of(fxj)); gjy = -(half ? hi_of(fyj) : lo_of(fyj)); gjz = -(half ? hi_of(fzj) : lo_of(fzj));
-            }
-            float cfx = lo_of(fxi) + hi_of(fxi), cfy = lo_of(fyi) + hi_of(fyi), cfz = lo_of(fzi) + hi_of(fzi);
+            // after 16 hand-overs inside the half warp the accumulator of j slot `lane` is back in this lane
+            float ca[3] = {lo_of(fxi), lo_of(fyi), lo_of(fzi)}, cb[3] = {hi_of(fxi), hi_of(fyi), hi_of(fzi)};
+            float ceq = -(lo_of(eq) + hi_of(eq)), cel = lo_of(el) + hi_of(el);
             if (__any_sync(0xffffffffu, r2min < F.r2Damp)) {   // damped core: practically never; patch the tile with the reference formulas
-                float c[8];
-                damped_tile_fix_x2(F, row, myXY, myZQ, ljRow, myLj, xi, yi, zi, qi, lmod, half, src, c);
-                cfx += c[0]; cfy += c[1]; cfz += c[2]; gjx += c[3]; gjy += c[4]; gjz += c[5];
-                eQ += (double) c[6]; eL += (double) c[7];
+                float c[11];
+                damped_tile_fix_x2(F, mm0, myPosq, myLj, ljRowA, ljRowB, xi, yi, zi, qi, src, c);
+                ca[0] += c[0]; ca[1] += c[1]; ca[2] += c[2]; cb[0] += c[3]; cb[1] += c[4]; cb[2] += c[5];
+                fxj += c[6]; fyj += c[7]; fzj += c[8]; ceq += c[9]; cel += c[10];
             }
-            fix += (double) cfx; fiy += (double) cfy; fiz += (double) cfz;
+            ws->acc[0][lane] += (double) ca[0]; ws->acc[1][lane] += (double) ca[1]; ws->acc[2][lane] += (double) ca[2];
+            ws->acc[3][lane] += (double) cb[0]; ws->acc[4][lane] += (double) cb[1]; ws->acc[5][lane] += (double) cb[2];
+            ws->acc[6][lane] += (double) ceq;   ws->acc[7][lane] += (double) cel;
             if (aj >= 0) {
-                double gx = sc * (double) gjx, gy = sc * (double) gjy, gz = sc * (double) gjz;       // gradient on the (image) atom
+                const double sc = op->scale;
+                double gx = -sc * (double) fxj, gy = -sc * (double) fyj, gz = -sc * (double) fzj;    // gradient on the (image) atom
                 if (isImage) {
                     if (kRot && !pureT) {
                         W[0] += gx * xj64; W[1] += gx * yj64; W[2] += gx * zj64;
@@ -515,11 +544,26 @@ __global__ void __launch_bounds__(kForceThreads, kMinBlocks) k_tile_forces_x2(Fo
                 }
             }
         }
-        if (ai >= 0 && A.grad != nullptr) {
-            atomicAdd(&A.grad[3 * ai], sc * fix); atomicAdd(&A.grad[3 * ai + 1], sc * fiy); atomicAdd(&A.grad[3 * ai + 2], sc * fiz);
+        // the two half warps hold partial i gradients (their 16 j slots each) of the same two atoms: exchange, and let lane l
+        // finish block atom l (half 0: element a = lmod, half 1: element b = lmod + 16)
+        const double sc = op->scale;
+        double fix, fiy, fiz;
+        {
+            const double ax = ws->acc[0][lane], ay = ws->acc[1][lane], az = ws->acc[2][lane];
+            const double bx = ws->acc[3][lane], by = ws->acc[4][lane], bz = ws->acc[5][lane];
+            const double ox = __shfl_xor_sync(0xffffffffu, half ? ax : bx, 16), oy = __shfl_xor_sync(0xffffffffu, half ? ay : by, 16);
+            const double oz = __shfl_xor_sync(0xffffffffu, half ? az : bz, 16);
+            fix = (half ? bx : ax) + ox; fiy = (half ? by : ay) + oy; fiz = (half ? bz : az) + oz;
+        }
+        {
+            const int si = wi.block * kTile + lane;
+            const int ai = (si < A.n) ? A.sAtom[si] : -1;
+            if (ai >= 0 && A.grad != nullptr) {
+                atomicAdd(&A.grad[3 * ai], sc * fix); atomicAdd(&A.grad[3 * ai + 1], sc * fiy); atomicAdd(&A.grad[3 * ai + 2], sc * fiz);
+            }
         }
         double *acc = A.accum + 16 * wi.image;
-        eQ = warp_sum(eQ) * sc; eL = warp_sum(eL) * sc;
+        const double eQ = warp_sum(ws->acc[6][lane]) * sc, eL = warp_sum(ws->acc[7][lane]) * sc;
         if (lane == 0) { atomicAdd(&acc[0], eQ); atomicAdd(&acc[1], eL); }
         if (isImage) {
             // sum over the image atoms of their gradient = minus the sum of the i-side gradients of this item (Newton's third law)
@@ -530,6 +574,7 @@ __global__ void __launch_bounds__(kForceThreads, kMinBlocks) k_tile_forces_x2(Fo
                 for (int k = 0; k < 9; k++) { const double w = warp_sum(W[k]); if (lane == 0) atomicAdd(&acc[5 + k], w); }
             }
         }
+        __syncwarp();                                       // acc columns are re-zeroed by the next item
     }
 }
 
@@ -583,18 +628,25 @@ __global__ void k_pairs14(const int2 *__restrict__ pairs, int npairs, const doub
 
 static int g_forceBlocksPerSM = 0, g_numSMs = 0;
 
+typedef void (*X2Kernel)(ForceArgs);
+struct X2Variant { const char *name; X2Kernel fn; int threads; };
+static const X2Variant kX2Variants[] = {
+    {"128x4u2", k_tile_forces_x2<false, 128, 4, 2>, 128}, {"128x4u4", k_tile_forces_x2<false, 128, 4, 4>, 128},
+    {"128x5u2", k_tile_forces_x2<false, 128, 5, 2>, 128}, {"128x5u4", k_tile_forces_x2<false, 128, 5, 4>, 128},
+    {"128x6u2", k_tile_forces_x2<false, 128, 6, 2>, 128}, {"128x6u1", k_tile_forces_x2<false, 128, 6, 1>, 128},
+    {"128x5u8", k_tile_forces_x2<false, 128, 5, 8>, 128}, {"128x5u16", k_tile_forces_x2<false, 128, 5, 16>, 128},
+    {"128x4u8", k_tile_forces_x2<false, 128, 4, 8>, 128}, {"128x4u16", k_tile_forces_x2<false, 128, 4, 16>, 128},
+    {"256x2u4", k_tile_forces_x2<false, 256, 2, 4>, 256}, {"128x3u4", k_tile_forces_x2<false, 128, 3, 4>, 128},
+};
+static const X2Variant kX2Rot = {"rot", k_tile_forces_x2<true, 128, 3, 2>, 128};
+
 void init_force_kernel_attributes()
 {
     cudaFuncSetAttribute(k_tile_forces<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_tile_forces<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaFuncSetAttribute(k_tile_forces<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_tile_forces_x2<false, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_tile_forces_x2<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_tile_forces_x2<false, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_tile_forces_x2<false, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_tile_forces_x2<false, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_tile_forces_x2<false, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute(k_tile_forces_x2<true, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    for (const X2Variant &v : kX2Variants) cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(kX2Rot.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     cudaDeviceProp prop;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -654,25 +706,20 @@ bool launch_forces(State &s, double *d_grad)
         // f32x2 variant (fewer issue slots, but 128 registers -> 16 warps/SM and latency bound: 5 % slower on B200, see profiles/)
         static const bool useX2 = []() { const char *e = std::getenv("NBB200_FORCE_KERNEL"); return e != nullptr && std::strcmp(e, "x2") == 0; }();
         if (useX2) {
-            AbfsX2 X;
-            auto dup = [](double v) { return make_float2((float) v, (float) v); };
-            X.one = dup(1.0); X.mhalf = dup(-0.5); X.two = dup(2.0); X.msix = dup(-6.0);
-            X.rOff = dup(F.rOff); X.r2Off = dup(F.r2Off); X.n3 = dup(F.n3); X.n4 = dup(F.n4); X.n5 = dup(F.n5); X.n6 = dup(F.n6);
-            X.mk1 = dup(-F.k1); X.k2 = dup(F.k2);
-            X.r2On = F.r2On; X.r2Damp = F.r2Damp; X.r2OffS = F.r2Off; X.qShift1 = F.qShift1; X.aK12 = F.aK12; X.aF6 = F.aF6;
-            X.mShift12 = -F.aShift12; X.bK6 = F.bK6; X.bF3 = F.bF3; X.mShift6 = -F.bShift6;
-            const size_t smem2 = sizeof(JStage2) * kForceWarps + sizeof(float2) * (size_t) s.ntypes * s.ntypes;
-            static const int minBlocks = []() { const char *e = std::getenv("NBB200_X2_BLOCKS"); const int v = e ? std::atoi(e) : 2; return (v >= 2 && v <= 4) ? v : 2; }();
-            static const int unroll = []() { const char *e = std::getenv("NBB200_X2_UNROLL"); return e ? std::atoi(e) : 4; }();
-            void (*kern)(ForceArgs, AbfsX2) = rot ? k_tile_forces_x2<true, 2, 4>
-                                                  : (minBlocks == 2 ? (unroll == 2 ? k_tile_forces_x2<false, 2, 2> : k_tile_forces_x2<false, 2, 4>)
-                                                     : minBlocks == 4 ? k_tile_forces_x2<false, 4, 1>
-                                                     : (unroll == 1 ? k_tile_forces_x2<false, 3, 1> : unroll == 2 ? k_tile_forces_x2<false, 3, 2> : k_tile_forces_x2<false, 3, 4>));
+            static const X2Variant *chosen = []() {
+                const char *e = std::getenv("NBB200_X2_VARIANT");
+                for (const X2Variant &v : kX2Variants) if (e != nullptr && std::strcmp(e, v.name) == 0) return &v;
+                return &kX2Variants[0];
+            }();
+            const X2Variant &v = rot ? kX2Rot : *chosen;
+            const int warps2 = v.threads / 32;
+            const size_t smem2 = sizeof(WarpScratch2) * warps2 + sizeof(float4) * (size_t) s.ntypes * s.ntypes;
+            if (smem2 > 160 * 1024) { set_error("too many LJ types for the shared-memory table"); return false; }
             int perSM2 = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM2, kern, kForceThreads, smem2);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM2, v.fn, v.threads, smem2);
             if (perSM2 < 1) perSM2 = 1;
-            const int grid2 = std::max(1, std::min(g_numSMs * perSM2, (nitems + warpsPerBlock - 1) / warpsPerBlock));
-            kern<<<grid2, kForceThreads, smem2, s.stream>>>(A, X);
+            const int grid2 = std::max(1, std::min(g_numSMs * perSM2, (nitems + warps2 - 1) / warps2));
+            v.fn<<<grid2, v.threads, smem2, s.stream>>>(A);
         } else skern<<<grid, kForceThreads, smem, s.stream>>>(A);
         if (s.timing) cudaEventRecord(s.ev[3], s.stream);
         s.launches += 1;

@@ -1,8 +1,9 @@
 """Time the force kernel for the kernel variants selected through environment variables (development aid)."""
 import os, subprocess, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-variants = [dict(NBB200_FORCE_KERNEL="scalar", NBB200_SCALAR_BLOCKS="3"), dict(NBB200_FORCE_KERNEL="scalar", NBB200_SCALAR_BLOCKS="4"), dict(NBB200_X2_BLOCKS="2")]
 wl = sys.argv[1] if len(sys.argv) > 1 else "m1"
+names = sys.argv[2].split(",") if len(sys.argv) > 2 else ["128x4u2", "128x4u4", "128x5u2", "128x5u4", "128x6u2"]
+variants = [dict(NBB200_FORCE_KERNEL="scalar", NBB200_SCALAR_BLOCKS="3")] + [dict(NBB200_FORCE_KERNEL="x2", NBB200_X2_VARIANT=n) for n in names]
 for v in variants:
     env = dict(os.environ); env.update(v)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3", "--no-cpu", "--no-jac", "--workload", wl],
