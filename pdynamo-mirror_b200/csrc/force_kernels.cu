@@ -310,6 +310,7 @@ struct __align__(16) JStage2 {
 struct __align__(16) WarpScratch2 {
     JStage2 j;
     double acc[8][kTile];    // i gradient of element a (x, y, z), of element b (x, y, z), the two energies; one column per lane
+    double off[4];           // per item: image translation minus block centre (x, y, z), image scale
 };
 
 // slow path of the x2 kernel for tiles with a pair inside the damped core (same contract as damped_tile_fix):
@@ -371,16 +372,25 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_tile_forces_x2(const _
     const float4 *myPosq = stage->posq[half] + lmod;
     const int *myLj = stage->ljoff[half] + lmod;
 
+    // work items are claimed one ahead: the cursor atomic and the item record of the NEXT item are in flight during this one
+    unsigned int itNext = 0;
+    if (lane == 0) itNext = atomicAdd(A.workCursor, 1u);
+    itNext = __shfl_sync(0xffffffffu, itNext, 0);
+    WorkItem wiNext = A.items[min(itNext, (unsigned int) (A.nitems - 1))];
     for (;;) {
-        unsigned int it = 0;
-        if (lane == 0) it = atomicAdd(A.workCursor, 1u);
-        it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= (unsigned int) A.nitems) break;
-        const WorkItem wi = A.items[it];
+        if (itNext >= (unsigned int) A.nitems) break;
+        const WorkItem wi = wiNext;
+        if (lane == 0) itNext = atomicAdd(A.workCursor, 1u);
+        itNext = __shfl_sync(0xffffffffu, itNext, 0);
+        wiNext = A.items[min(itNext, (unsigned int) (A.nitems - 1))];
         const ImageOpDev *op = A.ops + wi.image;
         const bool isImage = wi.image > 0;
         const bool pureT = kRot ? (op->pureTranslation != 0) : true;
         const double *centre = A.blockBox + 9 * wi.block + 6;
+        // fp64 offset from absolute (primary) coordinates to block-local ones, translation of the image folded in; shared per warp
+        if (lane < 3) ws->off[lane] = ((isImage && pureT) ? op->tv[lane] : 0.0) - centre[lane];
+        if (lane == 3) ws->off[3] = op->scale;
+        __syncwarp();
 
         // the two i atoms of this lane: block slots lmod and lmod + 16 (both half warps hold the same two atoms)
         float xi[2] = {0.f, 0.f}, yi[2] = {0.f, 0.f}, zi[2] = {0.f, 0.f}, qi[2] = {0.f, 0.f};
@@ -425,15 +435,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_tile_forces_x2(const _
             int lj = 0;
             if (aj >= 0) {
                 double px = xj64, py = yj64, pz = zj64;
-                if (isImage) {
-                    if (pureT) { px += op->tv[0]; py += op->tv[1]; pz += op->tv[2]; }
-                    else {
-                        px = op->R[0] * xj64 + op->R[1] * yj64 + op->R[2] * zj64 + op->tv[0];
-                        py = op->R[3] * xj64 + op->R[4] * yj64 + op->R[5] * zj64 + op->tv[1];
-                        pz = op->R[6] * xj64 + op->R[7] * yj64 + op->R[8] * zj64 + op->tv[2];
-                    }
+                if (kRot && isImage && !pureT) {
+                    px = op->R[0] * xj64 + op->R[1] * yj64 + op->R[2] * zj64 + op->tv[0];
+                    py = op->R[3] * xj64 + op->R[4] * yj64 + op->R[5] * zj64 + op->tv[1];
+                    pz = op->R[6] * xj64 + op->R[7] * yj64 + op->R[8] * zj64 + op->tv[2];
                 }
-                pj = make_float4((float) (px - centre[0]), (float) (py - centre[1]), (float) (pz - centre[2]), gq);
+                pj = make_float4((float) (px + ws->off[0]), (float) (py + ws->off[1]), (float) (pz + ws->off[2]), gq);
                 lj = gt * (int) sizeof(float4);
             }
             // next tile: gather its atoms now, and fetch the descriptor of the tile after it
@@ -489,6 +496,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_tile_forces_x2(const _
                 const f32x2 p1 = pk(r2a <= F.r2On ? 1.0f : 0.0f, r2b <= F.r2On ? 1.0f : 0.0f);   // 1: plain region, 0: switched
                 const f32x2 pm = sub2(bc(1.0f), p1);
                 const f32x2 nqij = mul2(nqi2, bc(p.w));                                            // -qi qj
+                // (per-element selects of the region constants were tried instead of the arithmetic blends: the compiler turns
+                // them into MOV pairs, 52 instead of 43 issue slots per pair, and the kernel is 2 % slower)
                 // Coulomb energy (negated): nqij (s G + p qShift1), G = p + pm t^3 C(t); with tn = r - rOff = -t the signs of the
                 // odd powers live in the coefficients: t^3 C(t) = tn^2 (tn (-n3 + n4 tn - n5 tn^2 + n6 tn^3))
                 const f32x2 tn = fma2(r2, s, bc(-F.rOff));
@@ -526,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_tile_forces_x2(const _
             ws->acc[3][lane] += (double) cb[0]; ws->acc[4][lane] += (double) cb[1]; ws->acc[5][lane] += (double) cb[2];
             ws->acc[6][lane] += (double) ceq;   ws->acc[7][lane] += (double) cel;
             if (aj >= 0) {
-                const double sc = op->scale;
+                const double sc = ws->off[3];
                 double gx = -sc * (double) fxj, gy = -sc * (double) fyj, gz = -sc * (double) fzj;    // gradient on the (image) atom
                 if (isImage) {
                     if (kRot && !pureT) {
@@ -546,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_tile_forces_x2(const _
         }
         // the two half warps hold partial i gradients (their 16 j slots each) of the same two atoms: exchange, and let lane l
         // finish block atom l (half 0: element a = lmod, half 1: element b = lmod + 16)
-        const double sc = op->scale;
+        const double sc = ws->off[3];
         double fix, fiy, fiz;
         {
             const double ax = ws->acc[0][lane], ay = ws->acc[1][lane], az = ws->acc[2][lane];

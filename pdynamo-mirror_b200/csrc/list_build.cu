@@ -357,7 +357,7 @@ __global__ void k_block_boxes(const double *__restrict__ sX, int n, int nblocks,
 // the tile builder: one CTA per i-block
 // ------------------------------------------------------------------------------------------------------
 struct TileArgs {
-    int n, nblocks, nsets, firstBlock, selfEnabled;
+    int n, nblocks, nsets, firstBlock, selfEnabled, itemTiles;
     double cutoff, cutoff2;
     BuildGrid grid;
     const double *sX; const int *sAtom; const int *invPerm;
@@ -573,13 +573,13 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
         if (tid == 0) {
             const int last = min(emitted, A.tileStride), ntl = last - imageStart;
             if (ntl > 0) {
-                const int nitems = (ntl + kItemTiles - 1) / kItemTiles;
+                const int nitems = (ntl + A.itemTiles - 1) / A.itemTiles;
                 const unsigned int pos = atomicAdd(&A.counters->itemCount, (unsigned int) nitems);
                 if (pos + nitems <= A.itemCap) {
                     for (int k = 0; k < nitems; k++) {
                         WorkItem w;
-                        w.block = b; w.image = set; w.tileStart = b * A.tileStride + imageStart + k * kItemTiles;
-                        w.tileCount = min(kItemTiles, ntl - k * kItemTiles);
+                        w.block = b; w.image = set; w.tileStart = b * A.tileStride + imageStart + k * A.itemTiles;
+                        w.tileCount = min(A.itemTiles, ntl - k * A.itemTiles);
                         A.items[pos + k] = w;
                     }
                 } else atomicOr(&A.counters->overflow, 4u);
@@ -715,17 +715,19 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     const int myBlocks = b1 - b0;
     int perSet = (s.n + kTile - 1) / kTile + 1;
     int stride = s.tileStride > 0 ? s.tileStride : std::min(s.nsets * perSet, 96);
+    // tiles per work item: long items amortise the per-item prologue of the force kernel, short ones keep small systems spread over all SMs
+    const int itemTiles = (s.n >= 400000) ? 16 : (s.n >= 60000 ? 8 : 4);
     for (int attempt = 0; attempt < 6; attempt++) {
         s.tileStride = stride;
         const size_t ntl = (size_t) s.nblocks * stride;
-        s.itemCap = (size_t) std::max(1, myBlocks) * ((size_t) stride / kItemTiles + s.nsets + 1);
+        s.itemCap = (size_t) std::max(1, myBlocks) * ((size_t) stride / itemTiles + s.nsets + 1);
         if (!s.tileJ.ensure(ntl * kTile) || !s.tileMask.ensure(ntl * kTile) || !s.items.ensure(s.itemCap) || !s.setPairs.ensure((size_t) s.nsets)) return false;
         NBB_CUDA(cudaMemsetAsync(s.setPairs.p, 0, sizeof(unsigned long long) * s.nsets, s.stream));
         NBB_CUDA(cudaMemsetAsync(&s.counters->itemCount, 0, sizeof(unsigned int) * 4, s.stream));   // itemCount, tileTotal, maxTilesBlock, overflow
         if (myBlocks > 0) {
             TileArgs A;
             A.n = s.n; A.nblocks = s.nblocks; A.nsets = s.nsets; A.firstBlock = b0; A.selfEnabled = selfEnabled ? 1 : 0;
-            A.cutoff = s.list; A.cutoff2 = s.list * s.list;
+            A.cutoff = s.list; A.cutoff2 = s.list * s.list; A.itemTiles = itemTiles;
             A.grid = s.grid;
             A.sX = s.sX.p; A.sAtom = s.sAtom.p; A.invPerm = s.invPerm.p; A.cellStart = s.cellStart.p; A.blockBox = s.blockBox.p;
             A.imageBoxes = s.imageBoxes.p; A.exclPtr = s.exclPtr.p; A.exclCol = s.exclCol.p;
