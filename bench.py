@@ -304,7 +304,7 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": workload_description(args.workload, w), "list_pairs": pairs, "step": "forced list rebuild + E + gradients",
                    "l2": "inputs (coordinates + tile lists, %.0f MB) %s L2; timed iterations run back to back" %
-                         ((counters["tiles"] * 256 + 48 * n) / 1e6, "exceed" if counters["tiles"] * 256 + 48 * n > 126e6 else "fit in"),
+                         ((counters["tiles"] * 128 + 80 * n) / 1e6, "exceed" if counters["tiles"] * 128 + 80 * n > 126e6 else "fit in"),
                    "parallelism": "i-block slabs over %d rank(s), NCCL all-reduce of gradients/energies" % world},
         "no_rebuild": {"ms_per_call": ms_nr, "value": pairs / (ms_nr * 1e-3), "unit": "list-pairs/s"},
         "kernels_ms": {"list_rebuild": build_ms, "tile_forces": force_ms, "pairs14": tm["pairs14"], "displacement_check": tm["displacementCheck"]},

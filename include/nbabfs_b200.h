@@ -124,7 +124,7 @@ void nbb200_set_stream(NBB200State *state, void *cudaStream);
 void nbb200_enable_timing(NBB200State *state, int on);
 void nbb200_get_timings(NBB200State *state, double *out8);
 /* counters of the current lists: out[0] tiles, out[1] work items, out[2] i-blocks, out[3] extended (halo) atoms,
- * out[4] list pairs (popcount of all masks), out[5] kernel launches since SetUp, out[6] tile capacity per block, out[7] images */
+ * out[4] list pairs (popcount of all masks), out[5] kernel launches since SetUp, out[6] tiles per pool chunk (= per work item), out[7] images */
 void nbb200_get_counters(NBB200State *state, long *out8);
 /* spatial decomposition over ranks (section 8e): this state evaluates only the i-blocks b with b % nranks == rank
  * in units of contiguous chunks; energies/gradients are then partial sums to be reduced by the caller (NCCL). */

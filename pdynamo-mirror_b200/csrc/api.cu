@@ -43,7 +43,7 @@ static void destroy(State *s)
     s->eX.release(); s->eAtom.release(); s->eSet.release(); s->eKey.release(); s->eSortBuf.release();
     s->cellStart.release(); s->cellFill.release(); s->scanTmp.release(); s->order.release(); s->order2.release();
     s->sX.release(); s->sAtom.release(); s->invPerm.release(); s->blockBox.release();
-    s->tileJ.release(); s->tileMask.release(); s->items.release(); s->setPairs.release(); s->accum.release();
+    s->tileDesc.release(); s->recA.release(); s->recB.release(); s->gradSorted.release(); s->items.release(); s->setPairs.release(); s->accum.release();
     s->pairBuf.release(); s->pairCursor.release();
     if (s->counters) cudaFree(s->counters);
     if (s->hx) cudaFreeHost(s->hx);
@@ -65,6 +65,7 @@ static State *create(int device, int n, const double *charges, const int *ljtype
 {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); set_error("no CUDA device available: libnbabfs_b200 has no CPU fallback"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return nullptr; }
+    if (n > kMaxAtoms) { set_error("more than 16.7 M atoms per state are not supported (24-bit tile slots)"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr; }
     if (n <= 0 || charges == nullptr || ljtypes == nullptr || ntypes <= 0 || tableindex == nullptr || tableA == nullptr || tableB == nullptr ||
         device < 0 || device >= ndev || (nexcl > 0 && exclPairs == nullptr) || (n14 > 0 && pairs14 == nullptr) || (ntrans > 0 && (rot == nullptr || trans == nullptr))) {
         set_error("invalid argument to NBModelABFSState_B200_SetUp"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr;
@@ -219,6 +220,13 @@ static bool energy_enqueue(State &s, double *d_grad)
             std::memcpy(ops[k].R, op.R.v, sizeof(double) * 9);
             std::memcpy(ops[k].tv, op.tv, sizeof(double) * 3);
             ops[k].scale = im.scale; ops[k].pureTranslation = op.pureTranslation ? 1 : 0;
+            // the same operation in the grid-relative frame of the atom records (force_kernels.cu)
+            for (int r = 0; r < 3; r++) {
+                const double *o = s.grid.lo;
+                ops[k].cr[r] = op.R.v[3 * r] * o[0] + op.R.v[3 * r + 1] * o[1] + op.R.v[3 * r + 2] * o[2] + op.tv[r] - o[r];
+                const double kt = 8.0 * std::nearbyint(op.tv[r] * 0.125);
+                ops[k].kt[r] = (float) kt; ops[k].tl[r] = (float) (op.tv[r] - kt);
+            }
         }
         if (!s.imageOps.ensure((size_t) s.nsets)) return false;
         NBB_CUDA(cudaMemcpyAsync(s.imageOps.p, ops, sizeof(ImageOpDev) * (size_t) s.nsets, cudaMemcpyHostToDevice, s.stream));
@@ -506,8 +514,8 @@ void nbb200_get_counters(NBB200State *state, long *out8)
     fetch_pair_counts(s);
     long pairs = s.primaryPairs;
     for (long v : s.imagePairs) pairs += v;
-    out8[0] = s.hostCounters.tileTotal; out8[1] = s.hostCounters.itemCount; out8[2] = s.nblocks; out8[3] = s.hostCounters.extCount;
-    out8[4] = pairs; out8[5] = s.launches; out8[6] = s.tileStride; out8[7] = (long) live_images(s).size();
+    out8[0] = s.hostCounters.tilesUsed; out8[1] = s.hostCounters.itemCount; out8[2] = s.nblocks; out8[3] = s.hostCounters.extCount;
+    out8[4] = pairs; out8[5] = s.launches; out8[6] = s.chunkTiles; out8[7] = (long) live_images(s).size();
 }
 
 void nbb200_set_partition(NBB200State *state, int rank, int nranks)

@@ -354,10 +354,18 @@ __global__ void k_block_boxes(const double *__restrict__ sX, int n, int nblocks,
 }
 
 // ------------------------------------------------------------------------------------------------------
-// the tile builder: one CTA per i-block
+// the tile builder: one WARP per (sort block of 32 atoms, set); nothing is shared between the warps of a CTA.
+//
+// Stage A walks the cell rows around the block box and rejects candidates against the box; the survivors are compacted
+// into a warp queue, so that stage B -- the 32 distance tests per candidate, fp32 with an exact fp64 decision inside the
+// rounding band -- always runs on full warps.  A candidate's 32-bit column mask is split into the four bytes of the block's
+// four i-clusters (8 atoms each): every cluster gets its own stream of j entries (a cluster only lists the atoms that are
+// within the cutoff of one of ITS 8 atoms: 65 % of the 8 x 32 slots of a tile are list pairs, against 47 % for 32 x 32).
+// Tiles are written into a global pool that is handed out in chunks of `chunkTiles` tiles; a chunk is a work item of the
+// force kernel.
 // ------------------------------------------------------------------------------------------------------
 struct TileArgs {
-    int n, nblocks, nsets, firstBlock, selfEnabled, itemTiles;
+    int n, nblocks, nsets, firstBlock, myBlocks, selfEnabled, chunkTiles, rawJ;
     double cutoff, cutoff2;
     BuildGrid grid;
     const double *sX; const int *sAtom; const int *invPerm;
@@ -365,66 +373,103 @@ struct TileArgs {
     const double *blockBox;
     const ImageBoxDev *imageBoxes;     // [nsets], slot 0 unused
     const int *exclPtr; const int *exclCol;
-    int tileStride; int *tileJ; unsigned int *tileMask;
+    unsigned int *tileDesc; unsigned int tileCap;
     WorkItem *items; unsigned int itemCap;
     unsigned long long *setPairs;
     DeviceCounters *counters;
 };
 
-constexpr int kMaxRows = 64;
 constexpr int kBuildWarps = kBuildThreads / 32;
+constexpr int kSubBlocks = kTile / kCluster;
 
-// transpose 32 column masks (one per lane / j slot, bit i = block atom i) into row masks (one per lane / i atom, bit s = j slot)
-// with the 5-stage block-swap butterfly, then pre-rotate for the force kernel
-__device__ __forceinline__ unsigned int rows_from_columns(unsigned int x, int lane)
+struct __align__(16) BuildWarp {
+    double sxi[kTile][3];                        // exact coordinates of the block atoms
+    float4 sxy[kTile / 2];                       // block-local fp32 copies for the prefilter, atoms paired (i, i+16):
+    float2 szz[kTile / 2];                       //   {x_i, x_i+16, y_i, y_i+16} and {z_i, z_i+16}
+    int rowStart[kTile], rowCount[kTile];
+    int cand[2 * kTile];                         // sorted positions of the candidates that survived the box reject
+    unsigned int sub[kSubBlocks][2 * kTile];     // per i-cluster: j reference | column byte << 24
+};
+
+// per-warp stream state of one i-cluster (warp-uniform values)
+struct SubStream { int count; unsigned int chunkBase; int chunkUsed; };
+
+__device__ __forceinline__ void push_item(const TileArgs &A, int lane, int cluster, int set, const SubStream &st)
 {
-#pragma unroll
-    for (int st = 0; st < 5; st++) {
-        const int sh = 16 >> st;
-        const unsigned int m = (st == 0) ? 0x0000ffffu : (st == 1) ? 0x00ff00ffu : (st == 2) ? 0x0f0f0f0fu : (st == 3) ? 0x33333333u : 0x55555555u;
-        const unsigned int o = __shfl_xor_sync(0xffffffffu, x, sh);
-        x = (lane & sh) ? ((x & ~m) | ((o & ~m) >> sh)) : ((x & m) | ((o & m) << sh));
+    if (lane == 0) {
+        const unsigned int pos = atomicAdd(&A.counters->itemCount, 1u);
+        if (pos < A.itemCap) {
+            WorkItem w;
+            w.block = cluster; w.image = set; w.tileStart = (int) st.chunkBase; w.tileCount = st.chunkUsed;
+            A.items[pos] = w;
+        } else atomicOr(&A.counters->overflow, 4u);
+        atomicAdd(&A.counters->tilesUsed, (unsigned int) st.chunkUsed);
     }
-    return __funnelshift_r(x, x, lane);                      // bit k <-> j slot (lane + k) % 32
+}
+
+// write the first `count` (<= 32) entries of a cluster queue as one tile.  The queue holds COLUMN bytes (bit i = cluster atom i
+// pairs with this j); the force kernel wants, in lane (g, m) = (slot group, cluster atom), the ROW byte whose bit k is the pair
+// (atom m, slot 8 g + (m + k) % 8): an 8 x 8 transpose plus rotation inside each group of 8 lanes.
+__device__ __forceinline__ void emit_tile(const TileArgs &A, int lane, int cluster, int set, const unsigned int *queue, int count, SubStream &st)
+{
+    const unsigned int word = (lane < count) ? queue[lane] : kEmptySlot;
+    const unsigned int byte = word >> 24;
+    const int m = lane & 7;
+    unsigned int row = 0;
+#pragma unroll
+    for (int k = 0; k < kCluster; k++) {
+        const unsigned int bq = __shfl_sync(0xffffffffu, byte, (lane & 24) | ((m + k) & 7));
+        row |= ((bq >> m) & 1u) << k;
+    }
+    if (st.chunkUsed == 0) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(&A.counters->tileTotal, (unsigned int) A.chunkTiles);
+        st.chunkBase = __shfl_sync(0xffffffffu, base, 0);
+    }
+    const bool fits = (unsigned long long) st.chunkBase + (unsigned int) A.chunkTiles <= (unsigned long long) A.tileCap;
+    if (fits) A.tileDesc[((size_t) st.chunkBase + st.chunkUsed) * kTile + lane] = (word & kEmptySlot) | (row << 24);
+    else if (lane == 0) atomicOr(&A.counters->overflow, 2u);
+    st.chunkUsed += 1;
+    if (st.chunkUsed == A.chunkTiles) {
+        if (fits) push_item(A, lane, cluster, set, st);
+        st.chunkUsed = 0;
+    }
 }
 
 __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
 {
-    __shared__ double sxi[kTile][3];                         // exact coordinates of the block atoms
-    __shared__ float4 sxy[kTile / 2];                        // block-local fp32 copies for the prefilter, atoms paired (i, i+16):
-    __shared__ float2 szz[kTile / 2];                        //   {x_i, x_i+16, y_i, y_i+16} and {z_i, z_i+16}
-    __shared__ double sbox[9];
-    __shared__ int rowStart[kMaxRows];
-    __shared__ int rowPrefix[kMaxRows + 1];
-    __shared__ int qAtom[kBuildWarps][2 * kTile];            // per-warp queues of kept candidates
-    __shared__ unsigned int qMask[kBuildWarps][2 * kTile];
-    __shared__ int qCnt[kBuildWarps];
-    __shared__ int mAtom[kBuildWarps * kTile];               // leftovers of the four warps, merged per set
-    __shared__ unsigned int mMask[kBuildWarps * kTile];
-    __shared__ int emitted;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = A.firstBlock + blockIdx.x;
-    if (tid < 9) sbox[tid] = A.blockBox[9 * b + tid];
-    if (tid == 0) emitted = 0;
-    if (tid < kBuildWarps) qCnt[tid] = 0;
-    __syncthreads();
-    if (tid < kTile) {
-        const int s = b * kTile + tid;
+    __shared__ BuildWarp sw[kBuildWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long wg = (long) blockIdx.x * kBuildWarps + warp;
+    if (wg >= (long) A.myBlocks * A.nsets) return;           // whole warps leave: no CTA barrier below
+    const int set = (int) (wg / A.myBlocks), b = A.firstBlock + (int) (wg % A.myBlocks);
+    if (set == 0 && !A.selfEnabled) return;
+    BuildWarp &W = sw[warp];
+    double sbox[9];
+#pragma unroll
+    for (int d = 0; d < 9; d++) sbox[d] = A.blockBox[9 * b + d];
+    const double reach = A.cutoff + 1.0e-6;
+    if (set > 0) {                                           // whole-image prefilter
+        const ImageBoxDev ib = A.imageBoxes[set];
+        bool overlap = true;
+        for (int d = 0; d < 3; d++) overlap = overlap && (ib.lo[d] <= sbox[3 + d] + reach) && (ib.hi[d] >= sbox[d] - reach);
+        if (!overlap) return;
+    }
+    {
+        const int s = b * kTile + lane;
         float f[3];
         for (int d = 0; d < 3; d++) {
-            const double v = (s < A.n) ? A.sX[3 * s + d] : 1.0e30;        // padding rows never pass the test
-            sxi[tid][d] = v;
+            const double v = (s < A.n) ? A.sX[3 * s + d] : 1.0e30;            // padding rows never pass the test
+            W.sxi[lane][d] = v;
             f[d] = (s < A.n) ? (float) (v - sbox[6 + d]) : 1.0e15f;
         }
-        float *pxy = reinterpret_cast<float *>(sxy), *pzz = reinterpret_cast<float *>(szz);
-        const int m = tid & 15, h = tid >> 4;
+        float *pxy = reinterpret_cast<float *>(W.sxy), *pzz = reinterpret_cast<float *>(W.szz);
+        const int m = lane & 15, h = lane >> 4;
         pxy[4 * m + h] = f[0]; pxy[4 * m + 2 + h] = f[1]; pzz[2 * m + h] = f[2];
     }
-    __syncthreads();
+    __syncwarp();
 
     const BuildGrid g = A.grid;
-    const double reach = A.cutoff + 1.0e-6;
     int c0[3], c1[3];
     double maxAbs = 0.0;
     for (int d = 0; d < 3; d++) {
@@ -439,178 +484,150 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
     const double delta = 6.0e-7 * maxAbs;
     const float eps = (float) (2.0 * (3.5 * reach * delta + 3.0e-7 * A.cutoff2) + 2.0e-5);   // also covers the rounding of cutoff^2 to fp32
     const float c2f = (float) A.cutoff2;
+    const unsigned int ltMask = (1u << lane) - 1u;
 
-    for (int set = 0; set < A.nsets; set++) {
-        if (set == 0 && !A.selfEnabled) continue;
-        if (set > 0) {                                   // whole-image prefilter (uniform for the CTA)
-            const ImageBoxDev ib = A.imageBoxes[set];
-            bool overlap = true;
-            for (int d = 0; d < 3; d++) overlap = overlap && (ib.lo[d] <= sbox[3 + d] + reach) && (ib.hi[d] >= sbox[d] - reach);
-            if (!overlap) continue;
-        }
-        const int imageStart = emitted;                  // uniform: last written before a barrier
-        unsigned long long myPairs = 0;
-        __syncthreads();
-        for (int rowBase = 0; rowBase < nrowsTotal; rowBase += kMaxRows) {
-            const int nrows = min(kMaxRows, nrowsTotal - rowBase);
-            if (tid < nrows) {
-                const int r = rowBase + tid, cx = c0[0] + r / nrowsY, cy = c0[1] + r % nrowsY;
-                // z range of this row: only the part of the column of cells that can be within reach of the block box
-                const double xlo = g.lo[0] + cx * g.h, ylo = g.lo[1] + cy * g.h;
-                const double ex = fmax(0.0, fmax(sbox[0] - (xlo + g.h), xlo - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - (ylo + g.h), ylo - sbox[4]));
-                const double rem = reach * reach - ex * ex - ey * ey;
-                int start = 0, end = 0;
-                if (rem >= 0.0) {
-                    const double dz = sqrt(rem) + 1.0e-6;
-                    const int z0 = cell_coord(sbox[2] - dz, g.lo[2], g.invh, g.dim[2]), z1 = cell_coord(sbox[5] + dz, g.lo[2], g.invh, g.dim[2]);
-                    const int keyLo = set * g.ncell + min(snake_cell(g, cx, cy, z0), snake_cell(g, cx, cy, z1));   // the z run is contiguous either way
-                    start = (int) A.cellStart[keyLo]; end = (int) A.cellStart[keyLo + (z1 - z0) + 1];
-                    if (set == 0) start = max(start, b * kTile);     // primary list: each unordered pair once (own block: triangle below)
-                }
-                rowStart[tid] = start;
-                rowPrefix[tid] = max(0, end - start);                // (count of the row)
-            }
-            __syncthreads();
-            // every warp walks whole rows in chunks of 32 consecutive candidates and keeps a private queue: no CTA barrier in here
-            for (int r = warp; r < nrows; r += kBuildWarps) {
-                const int rs = rowStart[r], rc = rowPrefix[r];
-                for (int base = 0; base < rc; base += kTile) {
-                    const int c = base + lane;
-                    unsigned int colmask = 0;
-                    int atom = -1;
-                    if (c < rc) {
-                        const int s = rs + c;
-                        const double xj = A.sX[3 * s], yj = A.sX[3 * s + 1], zj = A.sX[3 * s + 2];
-                        // conservative reject against the block box
-                        const double ex = fmax(0.0, fmax(sbox[0] - xj, xj - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - yj, yj - sbox[4])),
-                                     ez = fmax(0.0, fmax(sbox[2] - zj, zj - sbox[5]));
-                        if (ex * ex + ey * ey + ez * ez <= reject2) {
-                            const float fx = (float) (xj - sbox[6]), fy = (float) (yj - sbox[7]), fz = (float) (zj - sbox[8]);
-                            float band = 1.0e30f;                    // min over the block atoms of |r2 - cutoff^2|
-                            const f32x2 fx2 = pk2(fx, fx), fy2 = pk2(fy, fy), fz2 = pk2(fz, fz);
+    SubStream st[kSubBlocks];
+#pragma unroll
+    for (int q = 0; q < kSubBlocks; q++) { st[q].count = 0; st[q].chunkBase = 0u; st[q].chunkUsed = 0; }
+    int candCnt = 0;
+    unsigned long long myPairs = 0;
+
+    // stage B on the first `count` queued candidates
+    auto stage_b = [&](int count) {
+        unsigned int colmask = 0u, jref = 0u;
+        if (lane < count) {
+            const int s = W.cand[lane];
+            const double xj = A.sX[3 * s], yj = A.sX[3 * s + 1], zj = A.sX[3 * s + 2];
+            const float fx = (float) (xj - sbox[6]), fy = (float) (yj - sbox[7]), fz = (float) (zj - sbox[8]);
+            float band = 1.0e30f;                        // min over the block atoms of |r2 - cutoff^2|
+            const f32x2 fx2 = pk2(fx, fx), fy2 = pk2(fy, fy), fz2 = pk2(fz, fz);
 #pragma unroll 8
-                            for (int i = 0; i < kTile / 2; i++) {    // block atoms i and i + 16 in one packed evaluation
-                                const float4 pxy = sxy[i];
-                                const float2 pz = szz[i];
-                                const f32x2 dx = sub2(pk2(pxy.x, pxy.y), fx2), dy = sub2(pk2(pxy.z, pxy.w), fy2), dz = sub2(pk2(pz.x, pz.y), fz2);
-                                float r2a, r2b;
-                                unpk2(fma2(dx, dx, fma2(dy, dy, mul2(dz, dz))), r2a, r2b);
-                                colmask |= (r2a <= c2f) ? (1u << i) : 0u;
-                                colmask |= (r2b <= c2f) ? (0x10000u << i) : 0u;
-                                band = fminf(band, fminf(fabsf(r2a - c2f), fabsf(r2b - c2f)));
-                            }
-                            if (band <= eps) {                       // some distance is within the fp32 error band: the reference predicate decides
-                                colmask = 0u;
-                                for (int i = 0; i < kTile; i++) {
-                                    const double r2 = ref_dist2(sxi[i][0] - xj, sxi[i][1] - yj, sxi[i][2] - zj);
-                                    colmask |= (r2 <= A.cutoff2) ? (1u << i) : 0u;
-                                }
-                            }
-                            atom = A.sAtom[s];
-                            if (set == 0 && colmask != 0u) {
-                                if ((s >> 5) == b) colmask &= (1u << (s & 31)) - 1u;      // own block: i < j only, no self pair
-                                for (int k = A.exclPtr[atom]; k < A.exclPtr[atom + 1]; k++) {
-                                    const int sp = A.invPerm[A.exclCol[k]];
-                                    if ((sp >> 5) == b) colmask &= ~(1u << (sp & 31));
-                                }
-                            }
-                        }
+            for (int i = 0; i < kTile / 2; i++) {        // block atoms i and i + 16 in one packed evaluation
+                const float4 pxy = W.sxy[i];
+                const float2 pz = W.szz[i];
+                const f32x2 dx = sub2(pk2(pxy.x, pxy.y), fx2), dy = sub2(pk2(pxy.z, pxy.w), fy2), dz = sub2(pk2(pz.x, pz.y), fz2);
+                float r2a, r2b;
+                unpk2(fma2(dx, dx, fma2(dy, dy, mul2(dz, dz))), r2a, r2b);
+                colmask |= (r2a <= c2f) ? (1u << i) : 0u;
+                colmask |= (r2b <= c2f) ? (0x10000u << i) : 0u;
+                band = fminf(band, fminf(fabsf(r2a - c2f), fabsf(r2b - c2f)));
+            }
+            if (band <= eps) {                           // some distance is within the fp32 error band: the reference predicate decides
+                colmask = 0u;
+                for (int i = 0; i < kTile; i++) {
+                    const double r2 = ref_dist2(W.sxi[i][0] - xj, W.sxi[i][1] - yj, W.sxi[i][2] - zj);
+                    colmask |= (r2 <= A.cutoff2) ? (1u << i) : 0u;
+                }
+            }
+            if (colmask != 0u) {
+                const int atom = A.sAtom[s];
+                if (set == 0) {
+                    if ((s >> 5) == b) colmask &= (1u << (s & 31)) - 1u;          // own block: i < j only, no self pair
+                    for (int k = A.exclPtr[atom]; k < A.exclPtr[atom + 1]; k++) {
+                        const int sp = A.invPerm[A.exclCol[k]];
+                        if ((sp >> 5) == b) colmask &= ~(1u << (sp & 31));
                     }
-                    const bool keep = colmask != 0u;
-                    myPairs += __popc(colmask);
-                    const unsigned int bal = __ballot_sync(0xffffffffu, keep);
-                    if (bal == 0u) continue;
-                    int cnt = qCnt[warp];
-                    if (keep) { const int q = cnt + __popc(bal & ((1u << lane) - 1u)); qAtom[warp][q] = atom; qMask[warp][q] = colmask; }
-                    cnt += __popc(bal);
+                    jref = (unsigned int) s;                                      // primary atoms: sorted position = extended position
+                } else jref = A.rawJ ? (unsigned int) atom : (unsigned int) A.invPerm[atom];
+            }
+        }
+        myPairs += __popc(colmask);
+#pragma unroll
+        for (int q = 0; q < kSubBlocks; q++) {
+            const unsigned int byte = (colmask >> (kCluster * q)) & 0xffu;
+            const unsigned int bal = __ballot_sync(0xffffffffu, byte != 0u);
+            if (bal == 0u) continue;
+            if (byte != 0u) W.sub[q][st[q].count + __popc(bal & ltMask)] = jref | (byte << 24);
+            st[q].count += __popc(bal);
+            __syncwarp();
+            if (st[q].count >= kTile) {
+                emit_tile(A, lane, kSubBlocks * b + q, set, W.sub[q], kTile, st[q]);
+                const unsigned int rest = W.sub[q][kTile + lane];
+                __syncwarp();
+                W.sub[q][lane] = rest;
+                st[q].count -= kTile;
+                __syncwarp();
+            }
+        }
+    };
+
+    for (int rowBase = 0; rowBase < nrowsTotal; rowBase += kTile) {
+        const int nrows = min(kTile, nrowsTotal - rowBase);
+        if (lane < nrows) {
+            const int r = rowBase + lane, cx = c0[0] + r / nrowsY, cy = c0[1] + r % nrowsY;
+            // z range of this row: only the part of the column of cells that can be within reach of the block box
+            const double xlo = g.lo[0] + cx * g.h, ylo = g.lo[1] + cy * g.h;
+            const double ex = fmax(0.0, fmax(sbox[0] - (xlo + g.h), xlo - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - (ylo + g.h), ylo - sbox[4]));
+            const double rem = reach * reach - ex * ex - ey * ey;
+            int start = 0, end = 0;
+            if (rem >= 0.0) {
+                const double dz = sqrt(rem) + 1.0e-6;
+                const int z0 = cell_coord(sbox[2] - dz, g.lo[2], g.invh, g.dim[2]), z1 = cell_coord(sbox[5] + dz, g.lo[2], g.invh, g.dim[2]);
+                const int keyLo = set * g.ncell + min(snake_cell(g, cx, cy, z0), snake_cell(g, cx, cy, z1));   // the z run is contiguous either way
+                start = (int) A.cellStart[keyLo]; end = (int) A.cellStart[keyLo + (z1 - z0) + 1];
+                if (set == 0) start = max(start, b * kTile);     // primary list: each unordered pair once (own block: triangle in stage B)
+            }
+            W.rowStart[lane] = start;
+            W.rowCount[lane] = max(0, end - start);
+        }
+        __syncwarp();
+        for (int r = 0; r < nrows; r++) {
+            const int rs = W.rowStart[r], rc = W.rowCount[r];
+            for (int base = 0; base < rc; base += kTile) {
+                const int c = base + lane;
+                bool keep = false;
+                if (c < rc) {
+                    const int s = rs + c;
+                    const double xj = A.sX[3 * s], yj = A.sX[3 * s + 1], zj = A.sX[3 * s + 2];
+                    // conservative reject against the block box
+                    const double ex = fmax(0.0, fmax(sbox[0] - xj, xj - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - yj, yj - sbox[4])),
+                                 ez = fmax(0.0, fmax(sbox[2] - zj, zj - sbox[5]));
+                    keep = ex * ex + ey * ey + ez * ez <= reject2;
+                }
+                const unsigned int bal = __ballot_sync(0xffffffffu, keep);
+                if (bal == 0u) continue;
+                if (keep) W.cand[candCnt + __popc(bal & ltMask)] = rs + c;
+                candCnt += __popc(bal);
+                __syncwarp();
+                if (candCnt >= kTile) {
+                    stage_b(kTile);
+                    const int rest = W.cand[kTile + lane];
                     __syncwarp();
-                    if (cnt >= kTile) {                              // emit one full tile from the front of the queue
-                        int slot = 0;
-                        if (lane == 0) slot = atomicAdd(&emitted, 1);
-                        slot = __shfl_sync(0xffffffffu, slot, 0);
-                        const unsigned int rot = rows_from_columns(qMask[warp][lane], lane);
-                        if (slot < A.tileStride) {
-                            const size_t T = ((size_t) b * A.tileStride + slot) * kTile + lane;
-                            A.tileJ[T] = qAtom[warp][lane];
-                            A.tileMask[T] = rot;
-                        }
-                        const int ra = qAtom[warp][kTile + lane];
-                        const unsigned int rm = qMask[warp][kTile + lane];
-                        __syncwarp();
-                        qAtom[warp][lane] = ra; qMask[warp][lane] = rm;
-                        cnt -= kTile;
-                    }
-                    if (lane == 0) qCnt[warp] = cnt;
+                    W.cand[lane] = rest;
+                    candCnt -= kTile;
                     __syncwarp();
                 }
             }
-            __syncthreads();        // rowStart / rowPrefix are rewritten by the next batch
         }
-        // merge the leftovers of the four warps (< 32 each) and emit them as up to four tiles, the last one padded
-        int off = 0, totalLeft = 0;
-        for (int w = 0; w < kBuildWarps; w++) { if (w < warp) off += qCnt[w]; totalLeft += qCnt[w]; }
-        if (lane < qCnt[warp]) { mAtom[off + lane] = qAtom[warp][lane]; mMask[off + lane] = qMask[warp][lane]; }
-        __syncthreads();
-        const int nLeftTiles = (totalLeft + kTile - 1) / kTile;
-        if (warp < nLeftTiles) {
-            const int q = warp * kTile + lane;
-            const unsigned int cm = (q < totalLeft) ? mMask[q] : 0u;
-            const unsigned int rot = rows_from_columns(cm, lane);
-            const int slot = emitted + warp;
-            if (slot < A.tileStride) {
-                const size_t T = ((size_t) b * A.tileStride + slot) * kTile + lane;
-                A.tileJ[T] = (q < totalLeft) ? mAtom[q] : -1;
-                A.tileMask[T] = rot;
-            }
-        }
-        __syncthreads();
-        if (tid == 0) emitted += nLeftTiles;
-        if (tid < kBuildWarps) qCnt[tid] = 0;
-        // work items and pair statistics of this set
-        for (int o = 16; o > 0; o >>= 1) myPairs += __shfl_xor_sync(0xffffffffu, myPairs, o);
-        if (lane == 0 && myPairs) atomicAdd(&A.setPairs[set], myPairs);
-        __syncthreads();
-        if (tid == 0) {
-            const int last = min(emitted, A.tileStride), ntl = last - imageStart;
-            if (ntl > 0) {
-                const int nitems = (ntl + A.itemTiles - 1) / A.itemTiles;
-                const unsigned int pos = atomicAdd(&A.counters->itemCount, (unsigned int) nitems);
-                if (pos + nitems <= A.itemCap) {
-                    for (int k = 0; k < nitems; k++) {
-                        WorkItem w;
-                        w.block = b; w.image = set; w.tileStart = b * A.tileStride + imageStart + k * A.itemTiles;
-                        w.tileCount = min(A.itemTiles, ntl - k * A.itemTiles);
-                        A.items[pos + k] = w;
-                    }
-                } else atomicOr(&A.counters->overflow, 4u);
-                atomicAdd(&A.counters->tileTotal, (unsigned int) ntl);
-            }
-        }
-        __syncthreads();
+        __syncwarp();                                    // the row tables are rewritten by the next batch
     }
-    if (tid == 0) {
-        atomicMax(&A.counters->maxTilesBlock, (unsigned int) emitted);
-        if (emitted > A.tileStride) atomicOr(&A.counters->overflow, 2u);
+    if (candCnt > 0) stage_b(candCnt);
+#pragma unroll
+    for (int q = 0; q < kSubBlocks; q++) {
+        if (st[q].count > 0) emit_tile(A, lane, kSubBlocks * b + q, set, W.sub[q], st[q].count, st[q]);
+        if (st[q].chunkUsed > 0 && (unsigned long long) st[q].chunkBase + (unsigned int) A.chunkTiles <= (unsigned long long) A.tileCap)
+            push_item(A, lane, kSubBlocks * b + q, set, st[q]);
     }
+    for (int o = 16; o > 0; o >>= 1) myPairs += __shfl_xor_sync(0xffffffffu, myPairs, o);
+    if (lane == 0 && myPairs) atomicAdd(&A.setPairs[set], myPairs);
 }
 
 // ------------------------------------------------------------------------------------------------------
-// explicit pair lists from the masks: one warp per work item; pairs of set k land in [pairOffsets[k], ...)
+// explicit pair lists from the tiles: one warp per work item; pairs of set k land in [pairOffsets[k], ...)
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_expand_pairs(const WorkItem *__restrict__ items, int nitems, const int *__restrict__ tileJ, const unsigned int *__restrict__ tileMask,
-                               const int *__restrict__ sAtom, int n, unsigned long long *cursor, int *__restrict__ pairs)
+__global__ void k_expand_pairs(const WorkItem *__restrict__ items, int nitems, const unsigned int *__restrict__ tileDesc,
+                               const int *__restrict__ sAtom, int n, int rawJ, unsigned long long *cursor, int *__restrict__ pairs)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, m = lane & 7;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (int it = w; it < nitems; it += nw) {
         const WorkItem wi = items[it];
-        const int si = wi.block * kTile + lane;
+        const int si = wi.block * kCluster + m;
         const int ai = (si < n) ? sAtom[si] : -1;
         for (int t = 0; t < wi.tileCount; t++) {
-            const size_t T = ((size_t) wi.tileStart + t) * kTile;
-            const int aj = tileJ[T + lane];
-            const unsigned int rot = tileMask[T + lane];
-            const unsigned int row = __funnelshift_l(rot, rot, lane);       // undo the rotation: bit s <-> j slot s
+            const unsigned int d = tileDesc[((size_t) wi.tileStart + t) * kTile + lane];
+            const unsigned int sj = d & kEmptySlot, row = d >> 24;       // bit k <-> j slot (lane & 24) | ((m + k) & 7)
+            const int aj = (sj == kEmptySlot) ? -1 : ((rawJ && wi.image > 0) ? (int) sj : sAtom[sj]);
             const int cnt = __popc(row);
             int inc = cnt;
             for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += u; }
@@ -619,11 +636,10 @@ __global__ void k_expand_pairs(const WorkItem *__restrict__ items, int nitems, c
             if (lane == 0 && total) base = atomicAdd(&cursor[wi.image], (unsigned long long) total);
             base = __shfl_sync(0xffffffffu, base, 0);
             unsigned long long pos = base + (unsigned long long) (inc - cnt);
-            // divergence-free gather of the j atoms: every lane walks all 32 slots
-            const unsigned int m = row;
-            for (int sidx = 0; sidx < kTile; sidx++) {
-                const int j = __shfl_sync(0xffffffffu, aj, sidx);
-                if ((m >> sidx) & 1u) { pairs[2 * pos] = ai; pairs[2 * pos + 1] = j; pos++; }
+#pragma unroll
+            for (int k = 0; k < kCluster; k++) {
+                const int j = __shfl_sync(0xffffffffu, aj, (lane & 24) | ((m + k) & 7));
+                if ((row >> k) & 1u) { pairs[2 * pos] = ai; pairs[2 * pos + 1] = j; pos++; }
             }
         }
     }
@@ -647,7 +663,7 @@ bool expand_pairs(State &s)
     if (nitems > 0) {
         if (s.timing) cudaEventRecord(s.ev[8], s.stream);
         const int threads = 256, nblk = std::max(1, std::min(148 * 8, (nitems + 7) / 8));
-        k_expand_pairs<<<nblk, threads, 0, s.stream>>>(s.items.p, nitems, s.tileJ.p, s.tileMask.p, s.sAtom.p, s.n, s.pairCursor.p, s.pairBuf.p);
+        k_expand_pairs<<<nblk, threads, 0, s.stream>>>(s.items.p, nitems, s.tileDesc.p, s.sAtom.p, s.n, s.rawJ ? 1 : 0, s.pairCursor.p, s.pairBuf.p);
         s.launches += 1;
         if (s.timing) cudaEventRecord(s.ev[9], s.stream);
     }
@@ -710,37 +726,49 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     k_block_boxes<<<(s.nblocks * 32 + 255) / 256, 256, 0, s.stream>>>(s.sX.p, s.n, s.nblocks, s.blockBox.p);
     s.launches += 4;
 
-    // tiles: fixed-stride region per i-block (HBM is plentiful: 180 GB), retried with a larger stride on overflow
+    // tiles: a global pool handed out in chunks (= work items); sized from the pair density, retried once with the exact need
     const int b0 = (int) (((long) s.nblocks * s.rank) / s.nranks), b1 = (int) (((long) s.nblocks * (s.rank + 1)) / s.nranks);
     const int myBlocks = b1 - b0;
-    int perSet = (s.n + kTile - 1) / kTile + 1;
-    int stride = s.tileStride > 0 ? s.tileStride : std::min(s.nsets * perSet, 96);
-    // tiles per work item: long items amortise the per-item prologue of the force kernel, short ones keep small systems spread over all SMs
-    const int itemTiles = (s.n >= 400000) ? 16 : (s.n >= 60000 ? 8 : 4);
-    for (int attempt = 0; attempt < 6; attempt++) {
-        s.tileStride = stride;
-        const size_t ntl = (size_t) s.nblocks * stride;
-        s.itemCap = (size_t) std::max(1, myBlocks) * ((size_t) stride / itemTiles + s.nsets + 1);
-        if (!s.tileJ.ensure(ntl * kTile) || !s.tileMask.ensure(ntl * kTile) || !s.items.ensure(s.itemCap) || !s.setPairs.ensure((size_t) s.nsets)) return false;
+    // tiles per chunk / work item: long items amortise the per-item prologue of the force kernel, short ones keep small systems spread over all SMs
+    const int chunk = (s.n >= 400000) ? 32 : (s.n >= 60000 ? 16 : 8);
+    if (chunk != s.chunkTiles) { s.chunkTiles = chunk; s.tileCap = 0; }
+    size_t cap = s.tileCap;
+    if (cap == 0) {
+        // expected list pairs from the mean density inside the search box; 8 x 32 tiles are about half full
+        double vol = 1.0;
+        for (int d = 0; d < 3; d++) vol *= std::max(1.0, s.plan.upper[d] - s.plan.lower[d] - 2.0 * s.list);
+        const double density = std::min(0.2, (double) s.n / vol);
+        const double pairsPerAtom = 0.5 * density * (4.0 / 3.0) * 3.14159265358979 * s.list * s.list * s.list + 8.0;
+        const double tiles = pairsPerAtom * ((double) s.n * myBlocks / std::max(1, s.nblocks)) / (kCluster * kTile * 0.5);
+        const double streams = (double) kSubBlocks * myBlocks * std::min(s.nsets, 6);
+        cap = (size_t) (1.2 * tiles + streams * chunk) + 1024;
+    }
+    for (int attempt = 0; attempt < 4; attempt++) {
+        if (cap * kTile >= ((size_t) 1 << 31)) { set_error("tile pool exceeds 2^31 descriptor words"); return false; }
+        s.tileCap = cap;
+        s.itemCap = cap / chunk + 64;
+        if (!s.tileDesc.ensure(cap * kTile) || !s.items.ensure(s.itemCap) || !s.setPairs.ensure((size_t) s.nsets)) return false;
         NBB_CUDA(cudaMemsetAsync(s.setPairs.p, 0, sizeof(unsigned long long) * s.nsets, s.stream));
-        NBB_CUDA(cudaMemsetAsync(&s.counters->itemCount, 0, sizeof(unsigned int) * 4, s.stream));   // itemCount, tileTotal, maxTilesBlock, overflow
+        NBB_CUDA(cudaMemsetAsync(&s.counters->itemCount, 0, sizeof(unsigned int) * 4, s.stream));   // itemCount, tileTotal, tilesUsed, overflow
         if (myBlocks > 0) {
             TileArgs A;
-            A.n = s.n; A.nblocks = s.nblocks; A.nsets = s.nsets; A.firstBlock = b0; A.selfEnabled = selfEnabled ? 1 : 0;
-            A.cutoff = s.list; A.cutoff2 = s.list * s.list; A.itemTiles = itemTiles;
+            A.n = s.n; A.nblocks = s.nblocks; A.nsets = s.nsets; A.firstBlock = b0; A.myBlocks = myBlocks; A.selfEnabled = selfEnabled ? 1 : 0;
+            A.chunkTiles = chunk; A.rawJ = s.rawJ ? 1 : 0;
+            A.cutoff = s.list; A.cutoff2 = s.list * s.list;
             A.grid = s.grid;
             A.sX = s.sX.p; A.sAtom = s.sAtom.p; A.invPerm = s.invPerm.p; A.cellStart = s.cellStart.p; A.blockBox = s.blockBox.p;
             A.imageBoxes = s.imageBoxes.p; A.exclPtr = s.exclPtr.p; A.exclCol = s.exclCol.p;
-            A.tileStride = stride; A.tileJ = s.tileJ.p; A.tileMask = s.tileMask.p;
+            A.tileDesc = s.tileDesc.p; A.tileCap = (unsigned int) cap;
             A.items = s.items.p; A.itemCap = (unsigned int) s.itemCap; A.setPairs = s.setPairs.p; A.counters = s.counters;
-            k_build_tiles<<<myBlocks, kBuildThreads, 0, s.stream>>>(A);
+            const long warps = (long) myBlocks * s.nsets;
+            k_build_tiles<<<(unsigned int) ((warps + kBuildWarps - 1) / kBuildWarps), kBuildThreads, 0, s.stream>>>(A);
             s.launches += 1;
         }
         NBB_CUDA(cudaMemcpyAsync(&s.hostCounters, s.counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, s.stream));
         NBB_CUDA(cudaStreamSynchronize(s.stream));
         if (!cuda_ok(cudaGetLastError(), "k_build_tiles")) return false;
         if ((s.hostCounters.overflow & 6u) == 0u) return true;
-        stride = std::max(stride * 2, (int) s.hostCounters.maxTilesBlock + 8);
+        cap = (size_t) (1.15 * (double) s.hostCounters.tileTotal) + 1024;       // the cursor kept counting: this is the exact need
     }
     set_error("tile capacity exceeded after retries");
     return false;
@@ -775,6 +803,7 @@ bool build_lists(State &s)
     }
     const int nimg = (int) s.plan.images.size(), nvis = (int) s.plan.visits.size();
     s.nsets = 1 + nimg;
+    s.rawJ = false;
     s.imagePairs.assign(nimg, -1); s.primaryPairs = -1; s.pairCountsValid = false; s.pairsExpanded = false;
 
     // 2. grid over the search box, per-image list-time boxes, visits
@@ -844,6 +873,8 @@ bool build_lists_standalone(State &s, const double *d_x2, int n2)
     double lo[3], hi[3];
     for (int d = 0; d < 3; d++) { lo[d] = bmin[d] - s.list - 1.0e-6; hi[d] = (bext[d] + bmin[d]) + s.list + 1.0e-6; s.plan.lower[d] = lo[d]; s.plan.upper[d] = hi[d]; }
     s.nsets = d_x2 ? 2 : 1;
+    s.rawJ = d_x2 != nullptr;
+    if (n2 > kMaxAtoms) { set_error("more than 16.7 M points in the second array"); return false; }
     s.imagePairs.assign(s.nsets - 1, -1); s.primaryPairs = -1; s.pairCountsValid = false; s.pairsExpanded = false;
     setup_grid(s, lo, hi);
     std::vector<ImageBoxDev> boxes(s.nsets);

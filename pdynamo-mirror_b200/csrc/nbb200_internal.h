@@ -9,9 +9,11 @@
 
 namespace nbb200 {
 
-constexpr int kTile = 32;            // atoms per i-block and j slots per tile (one warp)
-constexpr int kItemTiles = 8;        // max tiles per work item (i-block state is amortised over them)
-constexpr int kBuildThreads = 128;   // CTA size of the tile builder
+constexpr int kTile = 32;            // atoms per sort block (one builder warp) and j slots per tile (one force-kernel warp)
+constexpr int kCluster = 8;          // atoms per i-cluster of the force kernel: a tile is 8 i atoms x 32 j slots
+constexpr int kBuildThreads = 128;   // CTA size of the tile builder (four independent warps)
+constexpr unsigned int kEmptySlot = 0x00FFFFFFu;    // j field of an unused tile slot; atoms / sorted positions use 24 bits
+constexpr int kMaxAtoms = 0x00FFFFFF;               // hence at most 16.7 M atoms per state
 
 void set_error(const std::string &msg);
 bool cuda_ok(cudaError_t e, const char *what);
@@ -49,6 +51,9 @@ struct ImageOpDev {
     double scale;
     int pureTranslation;
     int pad;
+    // in the grid-relative frame of the atom records (X = x - origin = K + xl, K a multiple of 8 A):
+    double cr[3];            // rotations: X' = R X + cr, cr = R origin + tv - origin
+    float kt[3], tl[3];      // pure translations: tv = kt + tl, kt a multiple of 8 A (exact in fp32), |tl| <= 4 A
 };
 
 // per image, list-time data for the tile builder
@@ -56,14 +61,14 @@ struct ImageBoxDev {
     double lo[3], hi[3];
 };
 
-struct WorkItem { int block, image, tileStart, tileCount; };
+struct WorkItem { int block, image, tileStart, tileCount; };   // block = i-cluster index (8 sorted atoms); tiles are contiguous
 
 // counters living in device memory (one allocation)
 struct DeviceCounters {
     unsigned int extCount;       // extended (halo) atoms appended after the n primary ones
     unsigned int itemCount;      // work items
-    unsigned int tileTotal;      // tiles emitted
-    unsigned int maxTilesBlock;  // largest tile count of any i-block (capacity check)
+    unsigned int tileTotal;      // tile pool cursor: tiles reserved in chunks (the tail of a stream's last chunk stays unused)
+    unsigned int tilesUsed;      // tiles actually written
     unsigned int overflow;       // bit0: extended capacity, bit1: tile capacity, bit2: item capacity
     unsigned int workCursor;     // dynamic work distribution of the force kernel
     unsigned int pad[2];
@@ -151,10 +156,15 @@ struct State {
     DevBuf<double> sX; DevBuf<int> sAtom; DevBuf<int> invPerm;
     int nblocks = 0;
     DevBuf<double> blockBox;                     // per block: min[3], max[3], center[3]
-    // tiles
-    int tileStride = 0;
-    DevBuf<int> tileJ; DevBuf<unsigned int> tileMask;
+    // tiles: 32 descriptor words each (low 24 bits: sorted position of the j atom, high 8 bits: row mask of the lane)
+    int chunkTiles = 0;                          // tiles per pool chunk = max tiles per work item
+    size_t tileCap = 0;                          // pool capacity in tiles
+    bool rawJ = false;                           // stand-alone cross lists: the j field of sets > 0 is an index into the second array
+    DevBuf<unsigned int> tileDesc;
     DevBuf<WorkItem> items; size_t itemCap = 0;
+    // per energy call: atom records in sorted order (A: xl, yl, zl, q; B: Kx, Ky, Kz, LJ type) and the sorted-order gradient
+    DevBuf<float4> recA, recB;
+    DevBuf<double> gradSorted;
     DevBuf<unsigned long long> setPairs;         // per set list-pair counts
     DeviceCounters *counters = nullptr;
     DeviceCounters hostCounters{};

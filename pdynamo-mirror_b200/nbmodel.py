@@ -180,7 +180,7 @@ class NBModelABFSState:
     def Counters(self):
         out = (C.c_long * 8)()
         _lib.lib().nbb200_get_counters(self.cObject, out)
-        keys = ("tiles", "workItems", "iBlocks", "haloAtoms", "listPairs", "kernelLaunches", "tileStride", "images")
+        keys = ("tiles", "workItems", "iBlocks", "haloAtoms", "listPairs", "kernelLaunches", "chunkTiles", "images")
         return dict(zip(keys, [int(v) for v in out]))
 
     def Timings(self):

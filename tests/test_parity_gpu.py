@@ -277,28 +277,3 @@ def test_full_size_m1_properties(pkg):
     rep = g_b.reshape(1728, 648, 3)
     rms = np.sqrt((g_u ** 2).mean())
     assert np.sqrt(((rep - g_u[None]) ** 2).mean()) <= 2e-5 * rms
-
-
-def test_packed_f32x2_kernel_variant_in_subprocess(pkg):
-    """The alternative tile kernel (FFMA2/FMUL2/FADD2, two pairs per lane per step; NBB200_FORCE_KERNEL=x2) must give the same
-    answers: run the DHFR known-answer and a rotation crystal in a fresh process with the variant selected."""
-    import os
-    import subprocess
-    import sys
-    code = (
-        "import sys, numpy as np\n"
-        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
-        "import pdynamo_mirror_b200 as p, oracle\n"
-        "for name in ('dhfr', 'crystal_GLYGLY', 'w216'):\n"
-        "    w = p.workloads.WORKLOADS[name]()\n"
-        "    s = p.System.FromWorkload(w); s.DefineNBModel(p.NBModelABFS()); s.Energy(doGradients=True)\n"
-        "    ref = oracle.OracleNB(w).energy(force_new=True)\n"
-        "    e, g = s.configuration.nbState.energies, s.configuration.gradients3\n"
-        "    tol = 1e-6 if w['n'] > 100 else 1e-5\n"
-        "    assert abs(e.sum() - ref['energies'].sum()) <= tol * np.abs(ref['energies']).sum(), (name, e, ref['energies'])\n"
-        "    assert np.sqrt(((g - ref['grad']) ** 2).mean()) <= 1e-5 * np.sqrt((ref['grad'] ** 2).mean()), name\n"
-        "    assert np.linalg.norm(s.configuration.symmetryParameterGradients.dEdM - ref['dEdM']) <= 1e-5 * np.linalg.norm(ref['dEdM'])\n"
-        "print('x2 ok')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
-    env = dict(os.environ, NBB200_FORCE_KERNEL="x2")
-    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "x2 ok" in out.stdout, out.stdout + out.stderr
