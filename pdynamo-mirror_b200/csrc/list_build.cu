@@ -394,7 +394,7 @@ struct __align__(16) BuildWarp {
     float4 sxy[kTile / 2];                       // block-local fp32 copies for the prefilter, atoms paired (i, i+16):
     float2 szz[kTile / 2];                       //   {x_i, x_i+16, y_i, y_i+16} and {z_i, z_i+16}
     int rowStart[kTile], rowCount[kTile];
-    int cand[kCandRing];                         // ring of sorted positions of the candidates that survived the box reject
+    float4 cand[kCandRing];                      // ring of the candidates that survived the box reject: block-local fp32 x, y, z and the sorted position
     unsigned int bloom[kBloomWords];             // sorted positions (mod 2048) of the exclusion partners of the block atoms
     unsigned int sub[kSubBlocks][2 * kTile];     // per i-cluster: j reference | column byte << 24
     SubStream st[kSubBlocks];
@@ -500,7 +500,10 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
         maxAbs = fmax(maxAbs, 0.5 * (sbox[3 + d] - sbox[d]) + reach);
     }
     const int nrowsY = c1[1] - c0[1] + 1, nrowsTotal = (c1[0] - c0[0] + 1) * nrowsY;
-    const double reject2 = A.cutoff2 * (1.0 + 1.0e-12) + 1.0e-9;
+    // box reject in fp32: half extents of the block box around its centre; candidates are at most ~maxAbs away when they matter, so the
+    // rounding of the local coordinates (<= 6e-8 * maxAbs each) moves r2 by far less than the margin
+    const float hx = (float) (0.5 * (sbox[3] - sbox[0])), hy = (float) (0.5 * (sbox[4] - sbox[1])), hz = (float) (0.5 * (sbox[5] - sbox[2]));
+    const float reject2f = (float) (A.cutoff2 * (1.0 + 1.0e-5) + 1.0e-3);
     // fp32 prefilter: |r2_fp32 - r2_exact| <= eps for every candidate that survives the box reject (block-local coordinates,
     // magnitude <= maxAbs); decisions inside the band are taken by the exact fp64 predicate
     const double delta = 6.0e-7 * maxAbs;
@@ -509,6 +512,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
     const unsigned int ltMask = (1u << lane) - 1u;
 
     int candHead = 0, candTail = 0;
+    unsigned int counts = 0u;                    // entries waiting in the four cluster queues, one byte each
     unsigned long long myPairs = 0;
     // scan cursor: rows are taken in batches of 32 (row tables in shared memory), each row in units of kScanUnroll chunks
     int rowBase = -kTile, nrows = 0, r = 0, base = 0, rs = 0, rc = 0;
@@ -558,12 +562,15 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
             }
 #pragma unroll
             for (int u = 0; u < kScanUnroll; u++) {
-                const double ex = fmax(0.0, fmax(sbox[0] - xj[u], xj[u] - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - yj[u], yj[u] - sbox[4])),
-                             ez = fmax(0.0, fmax(sbox[2] - zj[u], zj[u] - sbox[5]));
-                const bool keep = ex * ex + ey * ey + ez * ez <= reject2;
-                const unsigned int bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) W.cand[(candTail + __popc(bal & ltMask)) & (kCandRing - 1)] = rs + base + u * kTile + lane;
-                candTail += __popc(bal);
+                if (base + u * kTile < rc) {
+                    // conservative reject against the block box, in block-local fp32 (the threshold carries the rounding margin)
+                    const float fx = (float) (xj[u] - sbox[6]), fy = (float) (yj[u] - sbox[7]), fz = (float) (zj[u] - sbox[8]);
+                    const float ex = fmaxf(0.f, fabsf(fx) - hx), ey = fmaxf(0.f, fabsf(fy) - hy), ez = fmaxf(0.f, fabsf(fz) - hz);
+                    const bool keep = fmaf(ex, ex, fmaf(ey, ey, ez * ez)) <= reject2f;
+                    const unsigned int bal = __ballot_sync(0xffffffffu, keep);
+                    if (keep) W.cand[(candTail + __popc(bal & ltMask)) & (kCandRing - 1)] = make_float4(fx, fy, fz, __int_as_float(rs + base + u * kTile + lane));
+                    candTail += __popc(bal);
+                }
             }
             base += kTile * kScanUnroll;
             __syncwarp();
@@ -575,9 +582,9 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
             flushed = count == 0;
             unsigned int colmask = 0u, jref = 0u;
             if (lane < count) {
-                const int s = W.cand[(candHead + lane) & (kCandRing - 1)];
-                const double xj = A.sX[3 * s], yj = A.sX[3 * s + 1], zj = A.sX[3 * s + 2];
-                const float fx = (float) (xj - sbox[6]), fy = (float) (yj - sbox[7]), fz = (float) (zj - sbox[8]);
+                const float4 cj = W.cand[(candHead + lane) & (kCandRing - 1)];
+                const int s = __float_as_int(cj.w);
+                const float fx = cj.x, fy = cj.y, fz = cj.z;
                 float band = 1.0e30f;                        // min over the block atoms of |r2 - cutoff^2|
                 const f32x2 fx2 = pk2(fx, fx), fy2 = pk2(fy, fy), fz2 = pk2(fz, fz), c22 = pk2(c2f, c2f);
                 unsigned int ca = 0u, cb = 0u;               // sign bits of r2 - cutoff^2, shifted in from the right
@@ -595,6 +602,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
                 colmask = (__brev(ca) >> 16) | (__brev(cb) & 0xffff0000u);     // r2 < cutoff^2 (equality sits inside the band)
                 if (band <= eps) {                           // some distance is within the fp32 error band: the reference predicate decides
                     colmask = 0u;
+                    const double xj = A.sX[3 * s], yj = A.sX[3 * s + 1], zj = A.sX[3 * s + 2];
                     for (int i = 0; i < kTile; i++) {
                         const double r2 = ref_dist2(W.sxi[i][0] - xj, W.sxi[i][1] - yj, W.sxi[i][2] - zj);
                         colmask |= (r2 <= A.cutoff2) ? (1u << i) : 0u;
@@ -619,26 +627,27 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
             }
             candHead += count;
             myPairs += __popc(colmask);
-#pragma unroll 1
+            // push the candidate into the queues of the clusters it pairs with (unrolled, no barrier in between) ...
+#pragma unroll
             for (int q = 0; q < kSubBlocks; q++) {
                 const unsigned int byte = (colmask >> (kCluster * q)) & 0xffu;
                 const unsigned int bal = __ballot_sync(0xffffffffu, byte != 0u);
-                int cnt = W.st[q].count;
+                if (byte != 0u) W.sub[q][((counts >> (8 * q)) & 0xffu) + __popc(bal & ltMask)] = jref | (byte << 24);
+                counts += (unsigned int) __popc(bal) << (8 * q);
+            }
+            __syncwarp();
+            // ... and emit full tiles (at the very end: whatever is left, and close the open chunks)
+#pragma unroll 1
+            for (int q = 0; q < kSubBlocks; q++) {
+                const int cnt = (int) ((counts >> (8 * q)) & 0xffu);
                 const bool flushNow = flushed && (cnt > 0 || W.st[q].chunkUsed > 0);
-                if (bal == 0u && !flushNow) continue;
-                if (byte != 0u) W.sub[q][cnt + __popc(bal & ltMask)] = jref | (byte << 24);
-                cnt += __popc(bal);
+                if (cnt < kTile && !flushNow) continue;
+                const int n = min(cnt, kTile);
+                emit_tile(A, lane, kSubBlocks * b + q, set, W.sub[q], n, &W.st[q]);
+                const unsigned int rest = W.sub[q][kTile + lane];
                 __syncwarp();
-                if (cnt >= kTile || flushNow) {
-                    const int n = min(cnt, kTile);
-                    emit_tile(A, lane, kSubBlocks * b + q, set, W.sub[q], n, &W.st[q]);
-                    const unsigned int rest = W.sub[q][kTile + lane];
-                    __syncwarp();
-                    W.sub[q][lane] = rest;
-                    cnt -= n;
-                }
-                __syncwarp();
-                if (lane == 0) W.st[q].count = cnt;
+                W.sub[q][lane] = rest;
+                counts -= (unsigned int) n << (8 * q);
                 __syncwarp();
             }
         }
