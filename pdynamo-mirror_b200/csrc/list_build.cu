@@ -21,6 +21,7 @@
 #include "nbb200_internal.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace nbb200 {
@@ -779,7 +780,8 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     if (chunk != s.chunkTiles) { s.chunkTiles = chunk; s.tileCap = 0; }
     // small systems: deal the rows of a block to several warps until the GPU is full (each part has its own, padded, j streams)
     int split = 1;
-    while (split < 8 && (long) myBlocks * split * 2 <= 148L * 16) split *= 2;
+    static const long splitTarget = []() { const char *e = std::getenv("NBB200_SPLIT_TARGET"); return (e && std::atol(e) > 0) ? std::atol(e) : 148L * 16; }();
+    while (split < 8 && (long) myBlocks * split * 2 <= splitTarget) split *= 2;
     size_t cap = s.tileCap;
     if (cap == 0) {
         // expected list pairs from the mean density inside the search box; 8 x 32 tiles are about half full
