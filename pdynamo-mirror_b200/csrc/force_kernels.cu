@@ -60,8 +60,10 @@ struct PairOut { float e1, e2, g; };      // elect, LJ, g = -2 dE/d(r^2)  (force
 __device__ __forceinline__ PairOut abfs_pair(const AbfsF32 &F, float r2, float qij, float A, float B, float S)
 {
     float s = rsqrt_fast(r2);
-#ifndef NBB_NO_NEWTON
-    {   // one Newton step: MUFU.RSQ alone (~1e-7 relative) would dominate the energy error budget
+#ifdef NBB_NEWTON
+    {   // optional Newton step.  Measured on B200 (scripts/accuracy_report.py, 7 systems): MUFU.RSQ alone (2^-22 relative) leaves the
+        // total energy at 2e-8 .. 2e-7 and the gradients at 6e-7 .. 9e-7 relative RMS -- the same as with the refinement, because the
+        // error floor is the fp32 rounding of the cluster-local coordinates.  The step costs 4 of ~80 issue slots per pair: off.
         const float rr = r2 * s;
         s = fmaf(0.5f * s, fmaf(-rr, s, 1.0f), s);
     }
