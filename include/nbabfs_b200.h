@@ -130,6 +130,30 @@ void nbb200_get_counters(NBB200State *state, long *out8);
  * in units of contiguous chunks; energies/gradients are then partial sums to be reduced by the caller (NCCL). */
 void nbb200_set_partition(NBB200State *state, int rank, int nranks);
 
+/* ---- several GPUs ------------------------------------------------------------
+ * Every rank sorts all atoms the same way (cell order); rank r owns the contiguous slab of sorted positions
+ * [s0, s1) = the i-blocks nbb200_set_partition gave it, i.e. a spatial slab.  Its lists reference, inside every other
+ * rank's slab, a contiguous range of sorted positions (the halo).  Per call the ranks exchange exactly these ranges:
+ * positions of halo atoms to the ranks that list them, gradient contributions back to the owners
+ * (pdynamo-mirror_b200/parallel.py drives this with NCCL send/recv); energies and dE/dM are all-reduced.
+ * There is no counterpart in the reference (its only parallelism is an OpenMP team, NBModelABFSState.c:401). */
+void nbb200_get_slab(NBB200State *state, long *out4);          /* s0, s1, n, number of i-blocks */
+/* after a rebuild: out[2 r], out[2 r + 1] = [lo, hi) sorted positions this rank's lists reference in rank r's slab (0, 0: none) */
+int  nbb200_touched_ranges(NBB200State *state, long *out);
+/* sorted-order gradient accumulator owned by the caller (device, 3 n doubles): zeroed and filled by ...MMMMEnergySorted */
+void nbb200_set_sorted_gradient_buffer(NBB200State *state, double *d_buf);
+/* max_i |x_i - xref_i|^2 of CheckForUpdate (pM/csource/NBModelABFS.c:691-746) for a collective update decision */
+double nbb200_max_displacement(NBB200State *state, const double *d_xyz, int *status);
+/* NBModelABFS_B200_UpdateDevice with the displacement decision taken by the caller (all ranks must rebuild together) */
+int  NBModelABFS_B200_UpdateDeviceDecided(NBB200State *state, const double *d_xyz, const double *box6, int doUpdate, int *status);
+/* NBModelABFS_B200_MMMMEnergyDevice that leaves the gradient in SORTED order in the sorted-gradient buffer (partial: own i atoms and
+ * the j atoms of the own lists, 1-4 pairs whose first atom is owned) */
+void NBModelABFS_B200_MMMMEnergySorted(NBB200State *state, double *energies, double *dEdM, int *status);
+/* out[k] = x[atom(s0 + k)], x[atom(s0 + k)] = in[k], grad[atom(s)] += sortedGradient[s] for k < count; device arrays, 3 doubles per atom */
+void nbb200_gather_sorted(NBB200State *state, const double *d_x, long s0, long count, double *d_out);
+void nbb200_scatter_sorted(NBB200State *state, const double *d_in, long s0, long count, double *d_x);
+void nbb200_unsort_add(NBB200State *state, long s0, long count, double *d_grad);
+
 #ifdef __cplusplus
 }
 #endif

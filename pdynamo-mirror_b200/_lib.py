@@ -39,6 +39,15 @@ SIGNATURES = {
     "nbb200_get_timings": (None, [vp, dp]),
     "nbb200_get_counters": (None, [vp, lp]),
     "nbb200_set_partition": (None, [vp, C.c_int, C.c_int]),
+    "nbb200_get_slab": (None, [vp, lp]),
+    "nbb200_touched_ranges": (C.c_int, [vp, lp]),
+    "nbb200_set_sorted_gradient_buffer": (None, [vp, vp]),
+    "nbb200_max_displacement": (C.c_double, [vp, vp, ip]),
+    "NBModelABFS_B200_UpdateDeviceDecided": (C.c_int, [vp, vp, dp, C.c_int, ip]),
+    "NBModelABFS_B200_MMMMEnergySorted": (None, [vp, dp, dp, ip]),
+    "nbb200_gather_sorted": (None, [vp, vp, C.c_long, C.c_long, vp]),
+    "nbb200_scatter_sorted": (None, [vp, vp, C.c_long, C.c_long, vp]),
+    "nbb200_unsort_add": (None, [vp, C.c_long, C.c_long, vp]),
 }
 
 

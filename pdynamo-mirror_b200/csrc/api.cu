@@ -153,7 +153,7 @@ static std::vector<int> live_images(State &s)
     return live;
 }
 
-static int update_common(State &s, const double *box6, int forceNew, int *status)
+static int update_common(State &s, const double *box6, int forceNew, int *status, int decided = -1)
 {
     s.numberOfCalls += 1;
     if (s.trans.n > 0) {
@@ -167,7 +167,8 @@ static int update_common(State &s, const double *box6, int forceNew, int *status
     double maxDisp = 0.0;
     if (s.timing) { s.timings[0] = 0.0; s.timings[3] = 0.0; }
     bool checked = false;
-    if (!doUpdate) {
+    if (decided >= 0) doUpdate = doUpdate || decided != 0;       // several ranks: the displacement decision was taken collectively by the caller
+    if (!doUpdate && decided < 0) {
         const double buffac = 0.5 * (s.list - s.stOuterCutoff);
         double maxr2 = 0.0; int exceeded = 0;
         if (!displacement_check(s, buffac * buffac, &maxr2, &exceeded)) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
@@ -204,7 +205,7 @@ static int update_common(State &s, const double *box6, int forceNew, int *status
 
 // enqueue one energy evaluation on the state's stream: image operations (only when the lattice or the lists changed),
 // force kernels, read-back of the accumulators.  No synchronisation here.
-static bool energy_enqueue(State &s, double *d_grad)
+static bool energy_enqueue(State &s, double *d_grad, bool sortedOnly = false)
 {
     // energy-time image operations: Orthogonalize(S, t + (a,b,c)) with the CURRENT lattice (NBModelABFS.c:1246-1256)
     const bool latticeSame = s.opsValid && s.opsGeneration == s.numberOfUpdates && std::memcmp(s.opsLattice.v, s.lattice.M.v, sizeof(double) * 9) == 0;
@@ -232,7 +233,7 @@ static bool energy_enqueue(State &s, double *d_grad)
         NBB_CUDA(cudaMemcpyAsync(s.imageOps.p, ops, sizeof(ImageOpDev) * (size_t) s.nsets, cudaMemcpyHostToDevice, s.stream));
         s.opsLattice = s.lattice.M; s.opsGeneration = s.numberOfUpdates; s.opsValid = true;
     }
-    if (!launch_forces(s, d_grad)) return false;
+    if (!launch_forces(s, d_grad, sortedOnly)) return false;
     const size_t accumCount = (size_t) 16 * (s.nsets + 1);
     if (accumCount > kSmallDoubles) { set_error("too many images for the result buffer"); return false; }
     NBB_CUDA(cudaMemcpyAsync(s.hsmall, s.accum.p, sizeof(double) * accumCount, cudaMemcpyDeviceToHost, s.stream));
@@ -258,7 +259,7 @@ static void energy_finish(State &s, double *energies, bool haveGrad, double *dEd
         float ms = 0.f;
         s.timings[1] = s.timings[2] = 0.0;
         if (s.hostCounters.itemCount > 0) { cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]); s.timings[1] = ms; }
-        if (s.n14 > 0 && s.rank == 0) { cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]); s.timings[2] = ms; }
+        if (s.n14 > 0) { cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]); s.timings[2] = ms; }
     }
 }
 
@@ -516,6 +517,103 @@ void nbb200_get_counters(NBB200State *state, long *out8)
     for (long v : s.imagePairs) pairs += v;
     out8[0] = s.hostCounters.tilesUsed; out8[1] = s.hostCounters.itemCount; out8[2] = s.nblocks; out8[3] = s.hostCounters.extCount;
     out8[4] = pairs; out8[5] = s.launches; out8[6] = s.chunkTiles; out8[7] = (long) live_images(s).size();
+}
+
+/* ---- section 8e: sorted-space slabs and halo ranges ---- */
+void nbb200_get_slab(NBB200State *state, long *out4)
+{
+    if (state == nullptr || out4 == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    out4[0] = s.ownLo; out4[1] = s.ownHi; out4[2] = s.n; out4[3] = s.nblocks;
+}
+
+void nbb200_set_sorted_gradient_buffer(NBB200State *state, double *d_buf)
+{
+    if (state != nullptr) reinterpret_cast<State *>(state)->gsExternal = d_buf;
+}
+
+int nbb200_touched_ranges(NBB200State *state, long *out)
+{
+    if (state == nullptr || out == nullptr) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    return touched_ranges(s, out) ? 1 : 0;
+}
+
+double nbb200_max_displacement(NBB200State *state, const double *d_xyz, int *status)
+{
+    if (state == nullptr || d_xyz == nullptr) return 0.0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (s.isNew) return 0.0;                                   // no reference coordinates yet
+    const double *keep = s.xcur;
+    s.xcur = d_xyz;
+    double maxr2 = 0.0; int exceeded = 0;
+    const bool ok = displacement_check(s, 0.0, &maxr2, &exceeded);
+    s.xcur = keep;
+    if (!ok) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0.0; }
+    return maxr2;
+}
+
+int NBModelABFS_B200_UpdateDeviceDecided(NBB200State *state, const double *d_xyz, const double *box6, int doUpdate, int *status)
+{
+    if (state == nullptr || d_xyz == nullptr) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    s.xcur = d_xyz;
+    return update_common(s, box6, 0, status, doUpdate != 0 ? 1 : 0);
+}
+
+void NBModelABFS_B200_MMMMEnergySorted(NBB200State *state, double *energies, double *dEdM, int *status)
+{
+    if (state == nullptr || energies == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (s.xcur == nullptr) { set_error("MMMMEnergy called before Update"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+    if (energy_enqueue(s, nullptr, true) && cuda_ok(cudaStreamSynchronize(s.stream), "sync")) energy_finish(s, energies, true, dEdM);
+    else set_status(status, NBB200_STATUS_LOGIC_ERROR);
+}
+
+static __global__ void k_gather_sorted_x(const double *__restrict__ x, const int *__restrict__ sAtom, long s0, long count, double *__restrict__ out)
+{
+    const long k = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int a = sAtom[s0 + k];
+    out[3 * k] = x[3 * a]; out[3 * k + 1] = x[3 * a + 1]; out[3 * k + 2] = x[3 * a + 2];
+}
+
+static __global__ void k_scatter_sorted_x(const double *__restrict__ in, const int *__restrict__ sAtom, long s0, long count, double *__restrict__ x)
+{
+    const long k = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int a = sAtom[s0 + k];
+    x[3 * a] = in[3 * k]; x[3 * a + 1] = in[3 * k + 1]; x[3 * a + 2] = in[3 * k + 2];
+}
+
+void nbb200_gather_sorted(NBB200State *state, const double *d_x, long s0, long count, double *d_out)
+{
+    if (state == nullptr || count <= 0) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    k_gather_sorted_x<<<(unsigned int) ((count + 255) / 256), 256, 0, s.stream>>>(d_x, s.sAtom.p, s0, count, d_out);
+    s.launches += 1;
+}
+
+void nbb200_scatter_sorted(NBB200State *state, const double *d_in, long s0, long count, double *d_x)
+{
+    if (state == nullptr || count <= 0) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    k_scatter_sorted_x<<<(unsigned int) ((count + 255) / 256), 256, 0, s.stream>>>(d_in, s.sAtom.p, s0, count, d_x);
+    s.launches += 1;
+}
+
+void nbb200_unsort_add(NBB200State *state, long s0, long count, double *d_grad)
+{
+    if (state == nullptr || count <= 0) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    unsort_gradients(s, s0, s0 + count, d_grad);
 }
 
 void nbb200_set_partition(NBB200State *state, int rank, int nranks)

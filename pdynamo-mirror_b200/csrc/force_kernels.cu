@@ -318,9 +318,9 @@ __global__ void k_pack_records(const double *__restrict__ x, const int *__restri
     recB[s] = make_float4((float) KX, (float) KY, (float) KZ, __int_as_float(ljtype[a]));
 }
 
-__global__ void k_unsort_gradients(const double *__restrict__ gs, const int *__restrict__ sAtom, int n, double *__restrict__ grad)
+__global__ void k_unsort_gradients(const double *__restrict__ gs, const int *__restrict__ sAtom, int s0, int n, double *__restrict__ grad)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int a = sAtom[s];
     grad[3 * a] += gs[3 * s]; grad[3 * a + 1] += gs[3 * s + 1]; grad[3 * a + 2] += gs[3 * s + 2];
@@ -333,12 +333,15 @@ __global__ void k_unsort_gradients(const double *__restrict__ gs, const int *__r
 struct F64Factors { double v[21]; };
 
 __global__ void k_pairs14(const int2 *__restrict__ pairs, int npairs, const double *__restrict__ x, const double *__restrict__ q, const int *__restrict__ ljtype,
-                          const double2 *__restrict__ ljAB, int ntypes, F64Factors FF, double eScale, double *grad, double *acc)
+                          const double2 *__restrict__ ljAB, int ntypes, F64Factors FF, double eScale, const int *__restrict__ invPerm, int ownLo, int ownHi,
+                          double *gradSorted, double *acc)
 {
     const double *F = FF.v;
     double eq = 0.0, el = 0.0;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npairs; p += gridDim.x * blockDim.x) {
         const int i = pairs[p].x, j = pairs[p].y;
+        const int si = invPerm[i], sj = invPerm[j];
+        if (si < ownLo || si >= ownHi) continue;             // several ranks: a pair belongs to the rank that owns its first atom
         const double dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
         const double r2 = dx * dx + dy * dy + dz * dz;
         if (r2 > F[2]) continue;
@@ -364,10 +367,10 @@ __global__ void k_pairs14(const int2 *__restrict__ pairs, int npairs, const doub
             dF += -ab.x * F[15] + ab.y * F[20];
         }
         eq += e1; el += e2;
-        if (grad != nullptr) {
+        if (gradSorted != nullptr) {
             const double gx = 2.0 * dF * dx, gy = 2.0 * dF * dy, gz = 2.0 * dF * dz;
-            atomicAdd(&grad[3 * i], gx); atomicAdd(&grad[3 * i + 1], gy); atomicAdd(&grad[3 * i + 2], gz);
-            atomicAdd(&grad[3 * j], -gx); atomicAdd(&grad[3 * j + 1], -gy); atomicAdd(&grad[3 * j + 2], -gz);
+            atomicAdd(&gradSorted[3 * si], gx); atomicAdd(&gradSorted[3 * si + 1], gy); atomicAdd(&gradSorted[3 * si + 2], gz);
+            atomicAdd(&gradSorted[3 * sj], -gx); atomicAdd(&gradSorted[3 * sj + 1], -gy); atomicAdd(&gradSorted[3 * sj + 2], -gz);
         }
     }
     eq = warp_sum(eq); el = warp_sum(el);
@@ -397,8 +400,25 @@ void init_force_kernel_attributes()
     g_numSMs = prop.multiProcessorCount;
 }
 
-bool launch_forces(State &s, double *d_grad)
+bool unsort_gradients(State &s, long s0, long s1, double *d_grad)
 {
+    if (s1 <= s0 || d_grad == nullptr || s.gs == nullptr) return true;
+    const int threads = 256;
+    k_unsort_gradients<<<(unsigned int) ((s1 - s0 + threads - 1) / threads), threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad);
+    s.launches += 1;
+    return cuda_ok(cudaGetLastError(), "k_unsort_gradients");
+}
+
+// d_grad: atom-order gradient to accumulate into (nullable).  sortedOnly: leave the gradient in sorted order in s.gs (the caller
+// exchanges halo ranges and unsorts its own slab, section 8e); the two are exclusive.
+bool launch_forces(State &s, double *d_grad, bool sortedOnly)
+{
+    const bool wantGrad = d_grad != nullptr || sortedOnly;
+    if (wantGrad) {
+        if (s.gsExternal != nullptr) s.gs = s.gsExternal;
+        else { if (!s.gradSorted.ensure(3 * (size_t) s.n)) return false; s.gs = s.gradSorted.p; }
+        NBB_CUDA(cudaMemsetAsync(s.gs, 0, sizeof(double) * 3 * (size_t) s.n, s.stream));
+    }
     const int nitems = (int) s.hostCounters.itemCount;
     const size_t accumCount = (size_t) 16 * (s.nsets + 1);
     if (!s.accum.ensure(accumCount + 1)) return false;                    // + one slot that holds the work cursor: a single memset
@@ -409,10 +429,6 @@ bool launch_forces(State &s, double *d_grad)
         if (!s.recA.ensure((size_t) s.n) || !s.recB.ensure((size_t) s.n)) return false;
         const int pthreads = 256, pblocks = (s.n + pthreads - 1) / pthreads;
         k_pack_records<<<pblocks, pthreads, 0, s.stream>>>(s.xcur, s.sAtom.p, s.n, s.q32.p, s.ljtype.p, s.grid.lo[0], s.grid.lo[1], s.grid.lo[2], s.recA.p, s.recB.p);
-        if (d_grad != nullptr) {
-            if (!s.gradSorted.ensure(3 * (size_t) s.n)) return false;
-            NBB_CUDA(cudaMemsetAsync(s.gradSorted.p, 0, sizeof(double) * 3 * (size_t) s.n, s.stream));
-        }
         ForceArgs A;
         A.items = s.items.p; A.nitems = nitems; A.workCursor = workCursor;
         A.tileDesc = s.tileDesc.p; A.recA = s.recA.p; A.recB = s.recB.p; A.n = s.n;
@@ -437,7 +453,7 @@ bool launch_forces(State &s, double *d_grad)
             F.k2 = (float) (2.0 / gam);
         }
         A.qScale = (float) eScale;
-        A.gradSorted = (d_grad != nullptr) ? s.gradSorted.p : nullptr; A.accum = s.accum.p;
+        A.gradSorted = wantGrad ? s.gs : nullptr; A.accum = s.accum.p;
         if (g_numSMs == 0) init_force_kernel_attributes();
         bool rot = false;                                   // any image with a genuine rotation?
         for (const RealSpaceOp &b : s.plan.baseOps) rot = rot || !b.pureTranslation;
@@ -458,21 +474,18 @@ bool launch_forces(State &s, double *d_grad)
         v.fn<<<grid, v.threads, smem, s.stream>>>(A);
         if (s.timing) cudaEventRecord(s.ev[3], s.stream);
         s.launches += 2;
-        if (d_grad != nullptr) {
-            k_unsort_gradients<<<pblocks, pthreads, 0, s.stream>>>(s.gradSorted.p, s.sAtom.p, s.n, d_grad);
-            s.launches += 1;
-        }
     }
-    if (s.n14 > 0 && s.rank == 0) {
+    if (s.n14 > 0) {
         F64Factors FF;
         std::memcpy(FF.v, s.factors, sizeof(FF.v));
         const int threads = 128, nblk = std::max(1, std::min(1184, (s.n14 + threads - 1) / threads));
         if (s.timing) cudaEventRecord(s.ev[4], s.stream);
         k_pairs14<<<nblk, threads, 0, s.stream>>>(s.pairs14.p, s.n14, s.xcur, s.q64.p, s.ljtype.p, s.ljAB14.p, s.ntypes14, FF,
-                                                    eScale * s.scale14, d_grad, s.accum.p + 16 * s.nsets);
+                                                    eScale * s.scale14, s.invPerm.p, s.ownLo, s.ownHi, wantGrad ? s.gs : nullptr, s.accum.p + 16 * s.nsets);
         if (s.timing) cudaEventRecord(s.ev[5], s.stream);
         s.launches += 1;
     }
+    if (d_grad != nullptr && !unsort_gradients(s, 0, s.n, d_grad)) return false;
     return cuda_ok(cudaGetLastError(), "force kernels");
 }
 

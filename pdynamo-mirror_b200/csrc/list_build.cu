@@ -691,6 +691,88 @@ __global__ void k_expand_pairs(const WorkItem *__restrict__ items, int nitems, c
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// section 8e: which sorted positions do this rank's lists reference inside every rank's slab?  [min, max + 1) per slab:
+// the halo ranges of the gradient / position exchange (the rank's own slab is always whole)
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_touched_ranges(const WorkItem *__restrict__ items, int nitems, const unsigned int *__restrict__ tileDesc, int nblocks, int nranks, int *tab)
+{
+    extern __shared__ int shTab[];                            // [2 * nranks]
+    for (int k = threadIdx.x; k < 2 * nranks; k += blockDim.x) shTab[k] = (k & 1) ? 0 : 0x7fffffff;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int it = w; it < nitems; it += nw) {
+        const WorkItem wi = items[it];
+        int lo = 0x7fffffff, hi = 0;
+        for (int t = 0; t < wi.tileCount; t++) {
+            const unsigned int sj = tileDesc[((size_t) wi.tileStart + t) * kTile + lane] & kEmptySlot;
+            if (sj != kEmptySlot) { lo = min(lo, (int) sj); hi = max(hi, (int) sj + 1); }
+        }
+        // a work item's j atoms are spatially compact: they fall into very few slabs; walk the slabs between min and max
+        if (hi > lo) {
+            // slab r holds blocks [nblocks r / R, nblocks (r + 1) / R); entries that straddle slabs are clipped per slab
+            const int bLo = lo >> 5, bHi = (hi - 1) >> 5;
+            int r = (int) (((long) bLo * nranks) / nblocks);
+            while (r > 0 && (int) (((long) nblocks * r) / nranks) > bLo) r--;
+            while (r + 1 < nranks && (int) (((long) nblocks * (r + 1)) / nranks) <= bLo) r++;
+            for (; r < nranks; r++) {
+                const int s0 = (int) (((long) nblocks * r) / nranks) * kTile, s1 = (int) (((long) nblocks * (r + 1)) / nranks) * kTile;
+                if (s0 > ((bHi + 1) << 5)) break;
+                const int a = max(lo, s0), b = min(hi, s1);
+                if (b > a) { atomicMin(&shTab[2 * r], a); atomicMax(&shTab[2 * r + 1], b); }
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < 2 * nranks; k += blockDim.x) {
+        if (k & 1) { if (shTab[k] > 0) atomicMax(&tab[k], shTab[k]); }
+        else if (shTab[k] != 0x7fffffff) atomicMin(&tab[k], shTab[k]);
+    }
+}
+
+// 1-4 partners of owned atoms are excluded from the lists, but their gradients travel the same way
+__global__ void k_touched_14(const int2 *__restrict__ pairs, int npairs, const int *__restrict__ invPerm, int ownLo, int ownHi, int nblocks, int nranks, int *tab)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const int si = invPerm[pairs[p].x], sj = invPerm[pairs[p].y];
+    if (si < ownLo || si >= ownHi) return;
+    const int bj = sj >> 5;
+    int r = (int) (((long) bj * nranks) / nblocks);
+    while (r > 0 && (int) (((long) nblocks * r) / nranks) > bj) r--;
+    while (r + 1 < nranks && (int) (((long) nblocks * (r + 1)) / nranks) <= bj) r++;
+    atomicMin(&tab[2 * r], sj); atomicMax(&tab[2 * r + 1], sj + 1);
+}
+
+bool touched_ranges(State &s, long *out)
+{
+    const int R = s.nranks;
+    std::vector<int> init(2 * (size_t) R);
+    for (int r = 0; r < R; r++) { init[2 * r] = 0x7fffffff; init[2 * r + 1] = 0; }
+    if (!s.rangeTab.ensure(2 * (size_t) R)) return false;
+    NBB_CUDA(cudaMemcpyAsync(s.rangeTab.p, init.data(), sizeof(int) * 2 * R, cudaMemcpyHostToDevice, s.stream));
+    const int nitems = (int) s.hostCounters.itemCount;
+    if (nitems > 0) {
+        const int threads = 256, nblk = std::max(1, std::min(148 * 8, (nitems + 7) / 8));
+        k_touched_ranges<<<nblk, threads, sizeof(int) * 2 * R, s.stream>>>(s.items.p, nitems, s.tileDesc.p, s.nblocks, R, s.rangeTab.p);
+        s.launches += 1;
+    }
+    if (s.n14 > 0) {
+        k_touched_14<<<(s.n14 + 255) / 256, 256, 0, s.stream>>>(s.pairs14.p, s.n14, s.invPerm.p, s.ownLo, s.ownHi, s.nblocks, R, s.rangeTab.p);
+        s.launches += 1;
+    }
+    std::vector<int> tab(2 * (size_t) R);
+    NBB_CUDA(cudaMemcpyAsync(tab.data(), s.rangeTab.p, sizeof(int) * 2 * R, cudaMemcpyDeviceToHost, s.stream));
+    NBB_CUDA(cudaStreamSynchronize(s.stream));
+    for (int r = 0; r < R; r++) {
+        long lo = tab[2 * r], hi = tab[2 * r + 1];
+        if (hi <= lo) { lo = 0; hi = 0; }
+        out[2 * r] = lo; out[2 * r + 1] = std::min<long>(hi, s.n);
+    }
+    return true;
+}
+
 bool expand_pairs(State &s)
 {
     if (s.pairsExpanded) return true;
@@ -775,6 +857,7 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     // tiles: a global pool handed out in chunks (= work items); sized from the pair density, retried once with the exact need
     const int b0 = (int) (((long) s.nblocks * s.rank) / s.nranks), b1 = (int) (((long) s.nblocks * (s.rank + 1)) / s.nranks);
     const int myBlocks = b1 - b0;
+    s.ownLo = b0 * kTile; s.ownHi = std::min(s.n, b1 * kTile);
     // tiles per chunk / work item: long items amortise the per-item prologue of the force kernel, short ones keep small systems spread over all SMs
     const int chunk = (s.n >= 400000) ? 32 : (s.n >= 60000 ? 16 : 8);
     if (chunk != s.chunkTiles) { s.chunkTiles = chunk; s.tileCap = 0; }

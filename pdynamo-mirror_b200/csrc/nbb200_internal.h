@@ -89,9 +89,11 @@ bool build_lists(State &s);                              // everything between "
 bool expand_pairs(State &s);                             // explicit (i,j) pairs per list from the tile masks
 bool device_bbox(State &s, int nops, double *hostMin, double *hostExt);
 bool displacement_check(State &s, double buffacsq, double *maxr2, int *exceeded);
+bool touched_ranges(State &s, long *out);                // per rank slab: [lo, hi) of the sorted positions this rank's lists reference
 
 // ---- force_kernels.cu
-bool launch_forces(State &s, double *d_grad);
+bool launch_forces(State &s, double *d_grad, bool sortedOnly);
+bool unsort_gradients(State &s, long s0, long s1, double *d_grad);
 void init_force_kernel_attributes();
 
 struct State {
@@ -165,6 +167,9 @@ struct State {
     // per energy call: atom records in sorted order (A: xl, yl, zl, q; B: Kx, Ky, Kz, LJ type) and the sorted-order gradient
     DevBuf<float4> recA, recB;
     DevBuf<double> gradSorted;
+    double *gs = nullptr, *gsExternal = nullptr;   // sorted-order gradient of the last call: own buffer or one set by the caller (section 8e)
+    int ownLo = 0, ownHi = 0;                    // sorted positions of the i-blocks this rank owns (whole system for one rank)
+    DevBuf<int> rangeTab;                        // touched sorted range per rank slab (min, max+1)
     DevBuf<unsigned long long> setPairs;         // per set list-pair counts
     DeviceCounters *counters = nullptr;
     DeviceCounters hostCounters{};

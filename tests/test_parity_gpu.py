@@ -259,6 +259,66 @@ def test_partitioned_states_sum_to_the_whole(pkg):
     assert np.allclose(es, e, rtol=2e-7, atol=1e-6) and np.allclose(gs, g, rtol=1e-6, atol=1e-4) and np.allclose(dms, dm, rtol=1e-6, atol=1e-3)
 
 
+@pytest.mark.parametrize("name", ["water3x3x3", "dhfr", "crystal_GLYGLY"])
+def test_slab_halo_exchange_emulated_on_one_gpu(pkg, name):
+    """Section 8e on one GPU: three states own complementary slabs; each leaves its partial gradient in sorted order.  Emulating
+    the halo -> owner exchange with the ranges nbb200_touched_ranges reports must reproduce the unpartitioned gradient: the ranges
+    cover every atom a rank contributes to (list j atoms, images, 1-4 partners) and nothing is counted twice."""
+    import ctypes as C
+    import torch
+    from pdynamo_mirror_b200 import _lib
+    from pdynamo_mirror_b200.parallel import slab_range
+    L = _lib.lib()
+    w = pkg.workloads.WORKLOADS[name]()
+    n, R = w["n"], 3
+    system, st, e, g, dm = gpu_energy(pkg, w)
+    x = torch.from_numpy(w["xyz"]).cuda()
+    box = np.ascontiguousarray(w["box"], np.float64)
+    states, gss, tables, es, dms = [], [], [], np.zeros(6), np.zeros(9)
+    for rank in range(R):
+        s2 = pkg.System.FromWorkload(w)
+        s2.DefineNBModel(pkg.NBModelABFS())
+        s2.Energy()
+        h = s2.configuration.nbState.cObject
+        L.nbb200_set_partition(h, rank, R)
+        gs = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+        L.nbb200_set_sorted_gradient_buffer(h, C.c_void_p(gs.data_ptr()))
+        status = C.c_int(16)
+        assert L.NBModelABFS_B200_UpdateDeviceDecided(h, C.c_void_p(x.data_ptr()), _lib.d_(box), 1, C.byref(status)) == 1
+        ee, dd = np.zeros(6), np.zeros(9)
+        L.NBModelABFS_B200_MMMMEnergySorted(h, _lib.d_(ee), _lib.d_(dd), C.byref(status))
+        assert status.value == 16, _lib.last_error()
+        tab = (C.c_long * (2 * R))()
+        assert L.nbb200_touched_ranges(h, tab) == 1
+        states.append(s2); gss.append(gs); tables.append(np.array(tab[:]).reshape(R, 2)); es += ee; dms += dd
+    slab = (C.c_long * 4)()
+    L.nbb200_get_slab(states[0].configuration.nbState.cObject, slab)
+    slabs = [slab_range(int(slab[3]), n, r, R) for r in range(R)]
+    total = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+    for p in range(R):
+        touched = torch.zeros(n, dtype=torch.bool, device="cuda")
+        touched[slabs[p][0]:slabs[p][1]] = True
+        for r in range(R):
+            lo, hi = tables[p][r]
+            if r != p and hi > lo:
+                assert slabs[r][0] <= lo and hi <= slabs[r][1]
+                touched[lo:hi] = True
+        assert float(gss[p][~touched].abs().max()) == 0.0 if bool((~touched).any()) else True     # nothing outside slab + halo ranges
+    for r in range(R):                                    # halo -> owners, then every owner unsorts its slab
+        s0, s1 = slabs[r]
+        for p in range(R):
+            if p != r:
+                lo, hi = tables[p][r]
+                if hi > lo:
+                    gss[r][lo:hi] += gss[p][lo:hi]
+        L.nbb200_unsort_add(states[r].configuration.nbState.cObject, s0, s1 - s0, C.c_void_p(total.data_ptr()))
+    torch.cuda.synchronize()
+    gt = total.cpu().numpy()
+    assert np.allclose(es, e, rtol=2e-7, atol=1e-6)
+    assert np.sqrt(((gt - g) ** 2).mean()) <= 2e-6 * np.sqrt((g ** 2).mean())
+    assert np.allclose(dms.reshape(3, 3), dm, rtol=1e-5, atol=1e-3)
+
+
 def test_full_size_m1_properties(pkg):
     """Config 5 at full size (1 119 744 atoms): the oracle would need minutes, so size-independent properties instead.
     With jitter = 0 the box is an exact 12x12x12 replication of the wrapped 216-water cell, hence
