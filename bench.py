@@ -182,8 +182,6 @@ class DeviceModel:
         self.h = self.state.cObject
         self.L.nbb200_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
         self.L.nbb200_enable_timing(self.h, 1)
-        if nranks > 1:
-            self.L.nbb200_set_partition(self.h, rank, nranks)
         self.x = torch.from_numpy(w["xyz"]).to("cuda:%d" % device)
         self.g = torch.zeros_like(self.x)
         self.box = np.ascontiguousarray(w["box"], np.float64)
@@ -224,7 +222,7 @@ def run_b200(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the one JSON line
+        os.environ.pop("NCCL_DEBUG", None)          # NCCL prints its version banner on stdout at any debug level: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
 
     def barrier():
@@ -249,25 +247,26 @@ def run_b200(args):
     t0 = time.time()
     w = make_workload(args.workload)
     m = DeviceModel(w, local, rank, world)
-    esum = torch.zeros(15, dtype=torch.float64, device="cuda")
-
-    small = torch.zeros(15, dtype=torch.float64).pin_memory() if world > 1 else None
-
-    def exchange():                                # the path's one exchange step: gradient + energy/dEdM sum over ranks
-        dist.all_reduce(m.g)
-        small[:6] = torch.from_numpy(m.e); small[6:] = torch.from_numpy(m.dEdM)
-        esum.copy_(small, non_blocking=True)
-        dist.all_reduce(esum)
+    dn = None
+    if world > 1:
+        # section 8e: spatial slabs in sorted space; per call the ranks exchange halo positions (all slabs when the lists are rebuilt)
+        # and halo gradient contributions point to point, and all-reduce 15 scalars (pdynamo-mirror_b200/parallel.py)
+        from pdynamo_mirror_b200.parallel import DistributedNB
+        dn = DistributedNB(m.state, w["n"], 0.5 * (m.model.listCutoff - m.model.outerCutoff), rank, world, m.x.device)
 
     def step_rebuild():
-        m.step(rebuild=True)
-        if dist is not None:
-            exchange()
+        if dn is None:
+            m.step(rebuild=True)
+        else:
+            m.g.zero_()
+            dn.call(m.x, m.box, m.g, force_rebuild=True)
 
     def step_norebuild():
-        m.step(rebuild=False)
-        if dist is not None:
-            exchange()
+        if dn is None:
+            m.step(rebuild=False)
+        else:
+            m.g.zero_()
+            dn.call(m.x, m.box, m.g)
 
     step_rebuild()
     torch.cuda.synchronize()
@@ -305,7 +304,8 @@ def run_b200(args):
         "config": {"workload": workload_description(args.workload, w), "list_pairs": pairs, "step": "forced list rebuild + E + gradients",
                    "l2": "inputs (coordinates + tile lists, %.0f MB) %s L2; timed iterations run back to back" %
                          ((counters["tiles"] * 128 + 80 * n) / 1e6, "exceed" if counters["tiles"] * 128 + 80 * n > 126e6 else "fit in"),
-                   "parallelism": "i-block slabs over %d rank(s), NCCL all-reduce of gradients/energies" % world},
+                   "parallelism": ("1 GPU" if world == 1 else "%d spatial slabs of the cell-sorted order; per step NCCL send/recv of all slab positions (list rebuild) "
+                                   "or halo positions (no rebuild) and of halo gradient contributions to their owners, all-reduce of 15 scalars" % world)},
         "no_rebuild": {"ms_per_call": ms_nr, "value": pairs / (ms_nr * 1e-3), "unit": "list-pairs/s"},
         "kernels_ms": {"list_rebuild": build_ms, "tile_forces": force_ms, "pairs14": tm["pairs14"], "displacement_check": tm["displacementCheck"]},
         "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
@@ -316,7 +316,7 @@ def run_b200(args):
                                 "algorithmic_bytes": list_bytes, "note": "all rebuild kernels together; bytes = SURVEY.md 8d atom-pair-equivalent figure"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "energies": [float(v) for v in (esum[:6].cpu().numpy() if dist is not None else m.e)],
+        "energies": [float(v) for v in (dn.results()[0] if dn is not None else m.e)],
     }
     if world == 1:
         # end to end through the plugin surface with host arrays (H2D of coordinates, D2H of gradients inside the timed region)
@@ -353,13 +353,40 @@ def run_b200(args):
             except Exception as exc:
                 line["jac"] = {"error": repr(exc)}
     else:
+        line["distributed_check"] = distributed_check(torch, dist, m, dn, w, local)
+        line["halo"] = {"halo_atoms_per_step_no_rebuild": int(dn.exchange.halo_atoms()),
+                        "atoms_owned": int(dn.slabs[rank][1] - dn.slabs[rank][0]), "list_updates": dn.updates}
         line["e2e"] = {"value": value, "unit": "list-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                        "note": "multi-rank runs keep coordinates and gradients device-resident; the host end-to-end path is measured at N=1"}
+    if dn is not None and os.environ.get("NBB200_DIST_PROFILE"):
+        for label, forced in (("rebuild", True), ("no-rebuild", False)):
+            dn.profile = {}
+            for _ in range(10):
+                m.g.zero_(); dn.call(m.x, m.box, m.g, force_rebuild=forced)
+            log("[bench] rank %d %s phases (ms/step, synchronised): %s" % (rank, label, {k: round(100.0 * v, 3) for k, v in dn.profile.items()}))
+            dn.profile = None
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def distributed_check(torch, dist, m, dn, w, local):
+    """N > 1: every rank also evaluates the WHOLE system on its own GPU (one unpartitioned state) and compares the distributed
+    energies (after the all-reduce) and the gradients of the atoms it owns."""
+    ref = DeviceModel(w, local)
+    ref.step(rebuild=True)
+    m.g.zero_()
+    dn.call(m.x, m.box, m.g, force_rebuild=True)
+    torch.cuda.synchronize()
+    e, _ = dn.results()
+    mask = (m.g.abs().sum(1) > 0)                            # the atoms this rank owns (every atom of these systems feels a force)
+    gerr = float(((m.g - ref.g)[mask] ** 2).mean().sqrt() / (ref.g[mask] ** 2).mean().sqrt()) if bool(mask.any()) else 0.0
+    t = torch.tensor([abs(e.sum() - ref.e.sum()) / abs(ref.e.sum()), gerr, float(mask.sum())], dtype=torch.float64, device="cuda")
+    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return {"energy_rel_err": float(tmax[0]), "owned_gradient_rel_rms_err_max": float(tmax[1]), "atoms_with_gradient_all_ranks": int(t[2]), "atoms": int(w["n"])}
 
 
 def jac_block(torch, local, fp32_peak_tflops):

@@ -138,8 +138,12 @@ void nbb200_set_partition(NBB200State *state, int rank, int nranks);
  * (pdynamo-mirror_b200/parallel.py drives this with NCCL send/recv); energies and dE/dM are all-reduced.
  * There is no counterpart in the reference (its only parallelism is an OpenMP team, NBModelABFSState.c:401). */
 void nbb200_get_slab(NBB200State *state, long *out4);          /* s0, s1, n, number of i-blocks */
-/* after a rebuild: out[2 r], out[2 r + 1] = [lo, hi) sorted positions this rank's lists reference in rank r's slab (0, 0: none) */
+/* after a rebuild: out[4 r + 2 h], out[4 r + 2 h + 1] = [lo, hi) sorted positions this rank's lists reference in the lower (h = 0) /
+ * upper (h = 1) half of rank r's slab (0, 0: none).  Two ranges per slab: periodic images reach both ends of a neighbour's slab. */
 int  nbb200_touched_ranges(NBB200State *state, long *out);
+/* the same table written to a DEVICE array d_out[4 nranks] on the state's stream, without host synchronisation (the exchange of the
+ * tables between the ranks then overlaps the energy kernels) */
+int  nbb200_touched_ranges_device(NBB200State *state, long *d_out);
 /* sorted-order gradient accumulator owned by the caller (device, 3 n doubles): zeroed and filled by ...MMMMEnergySorted */
 void nbb200_set_sorted_gradient_buffer(NBB200State *state, double *d_buf);
 /* max_i |x_i - xref_i|^2 of CheckForUpdate (pM/csource/NBModelABFS.c:691-746) for a collective update decision */

@@ -41,6 +41,7 @@ SIGNATURES = {
     "nbb200_set_partition": (None, [vp, C.c_int, C.c_int]),
     "nbb200_get_slab": (None, [vp, lp]),
     "nbb200_touched_ranges": (C.c_int, [vp, lp]),
+    "nbb200_touched_ranges_device": (C.c_int, [vp, vp]),
     "nbb200_set_sorted_gradient_buffer": (None, [vp, vp]),
     "nbb200_max_displacement": (C.c_double, [vp, vp, ip]),
     "NBModelABFS_B200_UpdateDeviceDecided": (C.c_int, [vp, vp, dp, C.c_int, ip]),

@@ -43,7 +43,7 @@ static void destroy(State *s)
     s->eX.release(); s->eAtom.release(); s->eSet.release(); s->eKey.release(); s->eSortBuf.release();
     s->cellStart.release(); s->cellFill.release(); s->scanTmp.release(); s->order.release(); s->order2.release();
     s->sX.release(); s->sAtom.release(); s->invPerm.release(); s->blockBox.release();
-    s->tileDesc.release(); s->recA.release(); s->recB.release(); s->gradSorted.release(); s->items.release(); s->setPairs.release(); s->accum.release();
+    s->tileDesc.release(); s->recA.release(); s->recB.release(); s->gradSorted.release(); s->items.release(); s->rangeTab.release(); s->rangeOut.release(); s->setPairs.release(); s->accum.release();
     s->pairBuf.release(); s->pairCursor.release();
     if (s->counters) cudaFree(s->counters);
     if (s->hx) cudaFreeHost(s->hx);
@@ -538,6 +538,14 @@ int nbb200_touched_ranges(NBB200State *state, long *out)
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
     return touched_ranges(s, out) ? 1 : 0;
+}
+
+int nbb200_touched_ranges_device(NBB200State *state, long *d_out)
+{
+    if (state == nullptr || d_out == nullptr) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    return touched_ranges_async(s, d_out) ? 1 : 0;
 }
 
 double nbb200_max_displacement(NBB200State *state, const double *d_xyz, int *status)

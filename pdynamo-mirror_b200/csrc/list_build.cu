@@ -695,37 +695,48 @@ __global__ void k_expand_pairs(const WorkItem *__restrict__ items, int nitems, c
 // section 8e: which sorted positions do this rank's lists reference inside every rank's slab?  [min, max + 1) per slab:
 // the halo ranges of the gradient / position exchange (the rank's own slab is always whole)
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_touched_ranges(const WorkItem *__restrict__ items, int nitems, const unsigned int *__restrict__ tileDesc, int nblocks, int nranks, int *tab)
+__global__ void k_touched_ranges(const WorkItem *__restrict__ items, int nitems, int chunkTiles, const unsigned int *__restrict__ tileDesc, int nblocks, int nranks, int *tab)
 {
-    extern __shared__ int shTab[];                            // [2 * nranks]
-    for (int k = threadIdx.x; k < 2 * nranks; k += blockDim.x) shTab[k] = (k & 1) ? 0 : 0x7fffffff;
+    extern __shared__ int shTab[];                            // [nranks][2 halves][min, max + 1]
+    for (int k = threadIdx.x; k < 4 * nranks; k += blockDim.x) shTab[k] = (k & 1) ? 0 : 0x7fffffff;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (int it = w; it < nitems; it += nw) {
+    // one THREAD per (work item, tile slot of its chunk): eight independent 128-bit loads per thread keep the memory system busy
+    // (a warp per tile is latency bound here); the whole tile pool is read once
+    const long nslots = (long) nitems * chunkTiles, nth = (long) gridDim.x * blockDim.x;
+    for (long w = (long) blockIdx.x * blockDim.x + threadIdx.x; w < nslots; w += nth) {
+        const int it = (int) (w / chunkTiles), t = (int) (w % chunkTiles);
         const WorkItem wi = items[it];
-        int lo = 0x7fffffff, hi = 0;
-        for (int t = 0; t < wi.tileCount; t++) {
-            const unsigned int sj = tileDesc[((size_t) wi.tileStart + t) * kTile + lane] & kEmptySlot;
-            if (sj != kEmptySlot) { lo = min(lo, (int) sj); hi = max(hi, (int) sj + 1); }
+        if (t >= wi.tileCount) continue;
+        const uint4 *tp = reinterpret_cast<const uint4 *>(tileDesc + ((size_t) wi.tileStart + t) * kTile);
+        uint4 v[kTile / 4];
+#pragma unroll
+        for (int k = 0; k < kTile / 4; k++) v[k] = tp[k];
+        unsigned int lo = kEmptySlot, hi = 0u;
+#pragma unroll
+        for (int k = 0; k < kTile / 4; k++) {
+            const unsigned int e[4] = {v[k].x & kEmptySlot, v[k].y & kEmptySlot, v[k].z & kEmptySlot, v[k].w & kEmptySlot};
+#pragma unroll
+            for (int c = 0; c < 4; c++) { lo = min(lo, e[c]); hi = max(hi, e[c] == kEmptySlot ? 0u : e[c] + 1u); }
         }
-        // a work item's j atoms are spatially compact: they fall into very few slabs; walk the slabs between min and max
-        if (hi > lo) {
-            // slab r holds blocks [nblocks r / R, nblocks (r + 1) / R); entries that straddle slabs are clipped per slab
-            const int bLo = lo >> 5, bHi = (hi - 1) >> 5;
-            int r = (int) (((long) bLo * nranks) / nblocks);
-            while (r > 0 && (int) (((long) nblocks * r) / nranks) > bLo) r--;
-            while (r + 1 < nranks && (int) (((long) nblocks * (r + 1)) / nranks) <= bLo) r++;
-            for (; r < nranks; r++) {
-                const int s0 = (int) (((long) nblocks * r) / nranks) * kTile, s1 = (int) (((long) nblocks * (r + 1)) / nranks) * kTile;
-                if (s0 > ((bHi + 1) << 5)) break;
-                const int a = max(lo, s0), b = min(hi, s1);
-                if (b > a) { atomicMin(&shTab[2 * r], a); atomicMax(&shTab[2 * r + 1], b); }
-            }
+        if (hi <= lo) continue;
+        // a tile's j atoms are spatially compact: they fall into very few slabs; walk the slabs between min and max.
+        // slab r holds blocks [nblocks r / R, nblocks (r + 1) / R); ranges that straddle slabs are clipped per slab
+        const int bLo = (int) (lo >> 5), bHi = (int) ((hi - 1) >> 5);
+        int r = (int) (((long) bLo * nranks) / nblocks);
+        while (r > 0 && (int) (((long) nblocks * r) / nranks) > bLo) r--;
+        while (r + 1 < nranks && (int) (((long) nblocks * (r + 1)) / nranks) <= bLo) r++;
+        for (; r < nranks; r++) {
+            const int s0 = (int) (((long) nblocks * r) / nranks) * kTile, s1 = (int) (((long) nblocks * (r + 1)) / nranks) * kTile;
+            if (s0 > ((bHi + 1) << 5)) break;
+            // two ranges per slab (its lower and upper half): with periodic images a rank reaches both ends of a neighbour's slab
+            const int mid = (s0 + s1) >> 1;
+            const int a0 = max((int) lo, s0), b0 = min((int) hi, mid), a1 = max((int) lo, mid), b1 = min((int) hi, s1);
+            if (b0 > a0) { if (a0 < shTab[4 * r]) atomicMin(&shTab[4 * r], a0); if (b0 > shTab[4 * r + 1]) atomicMax(&shTab[4 * r + 1], b0); }
+            if (b1 > a1) { if (a1 < shTab[4 * r + 2]) atomicMin(&shTab[4 * r + 2], a1); if (b1 > shTab[4 * r + 3]) atomicMax(&shTab[4 * r + 3], b1); }
         }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < 2 * nranks; k += blockDim.x) {
+    for (int k = threadIdx.x; k < 4 * nranks; k += blockDim.x) {
         if (k & 1) { if (shTab[k] > 0) atomicMax(&tab[k], shTab[k]); }
         else if (shTab[k] != 0x7fffffff) atomicMin(&tab[k], shTab[k]);
     }
@@ -742,34 +753,58 @@ __global__ void k_touched_14(const int2 *__restrict__ pairs, int npairs, const i
     int r = (int) (((long) bj * nranks) / nblocks);
     while (r > 0 && (int) (((long) nblocks * r) / nranks) > bj) r--;
     while (r + 1 < nranks && (int) (((long) nblocks * (r + 1)) / nranks) <= bj) r++;
-    atomicMin(&tab[2 * r], sj); atomicMax(&tab[2 * r + 1], sj + 1);
+    const int s0 = (int) (((long) nblocks * r) / nranks) * kTile, s1 = (int) (((long) nblocks * (r + 1)) / nranks) * kTile;
+    const int h = (sj >= ((s0 + s1) >> 1)) ? 1 : 0;
+    atomicMin(&tab[4 * r + 2 * h], sj); atomicMax(&tab[4 * r + 2 * h + 1], sj + 1);
 }
 
-bool touched_ranges(State &s, long *out)
+static __global__ void k_ranges_finish(const int *__restrict__ tab, int count, int n, int ownRank, long *__restrict__ out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;      // one thread per (slab, half)
+    if (k >= count) return;
+    long lo = tab[2 * k], hi = tab[2 * k + 1];
+    if (hi <= lo || (k >> 1) == ownRank) { lo = 0; hi = 0; }  // the own slab is never exchanged
+    out[2 * k] = lo; out[2 * k + 1] = hi < n ? hi : n;
+}
+
+// enqueue the range computation; the table [nranks][2][2] (long) lands in d_out (device) without any host synchronisation
+bool touched_ranges_async(State &s, long *d_out)
 {
     const int R = s.nranks;
-    std::vector<int> init(2 * (size_t) R);
-    for (int r = 0; r < R; r++) { init[2 * r] = 0x7fffffff; init[2 * r + 1] = 0; }
-    if (!s.rangeTab.ensure(2 * (size_t) R)) return false;
-    NBB_CUDA(cudaMemcpyAsync(s.rangeTab.p, init.data(), sizeof(int) * 2 * R, cudaMemcpyHostToDevice, s.stream));
+    std::vector<int> init(4 * (size_t) R);
+    for (int k = 0; k < 2 * R; k++) { init[2 * k] = 0x7fffffff; init[2 * k + 1] = 0; }
+    if (!s.rangeTab.ensure(4 * (size_t) R)) return false;
+    // pinned staging (hsmall is free between an update and the next energy call)
+    int *stage = reinterpret_cast<int *>(s.hsmall);
+    std::memcpy(stage, init.data(), sizeof(int) * 4 * R);
+    NBB_CUDA(cudaMemcpyAsync(s.rangeTab.p, stage, sizeof(int) * 4 * R, cudaMemcpyHostToDevice, s.stream));
     const int nitems = (int) s.hostCounters.itemCount;
     if (nitems > 0) {
-        const int threads = 256, nblk = std::max(1, std::min(148 * 8, (nitems + 7) / 8));
-        k_touched_ranges<<<nblk, threads, sizeof(int) * 2 * R, s.stream>>>(s.items.p, nitems, s.tileDesc.p, s.nblocks, R, s.rangeTab.p);
+        const int threads = 256;
+        const long slots = (long) nitems * s.chunkTiles;
+        const long blocks = std::min<long>(148 * 8, (slots + threads - 1) / threads);
+        k_touched_ranges<<<(unsigned int) blocks, threads, sizeof(int) * 4 * R, s.stream>>>(s.items.p, nitems, s.chunkTiles, s.tileDesc.p, s.nblocks, R, s.rangeTab.p);
         s.launches += 1;
     }
     if (s.n14 > 0) {
         k_touched_14<<<(s.n14 + 255) / 256, 256, 0, s.stream>>>(s.pairs14.p, s.n14, s.invPerm.p, s.ownLo, s.ownHi, s.nblocks, R, s.rangeTab.p);
         s.launches += 1;
     }
-    std::vector<int> tab(2 * (size_t) R);
-    NBB_CUDA(cudaMemcpyAsync(tab.data(), s.rangeTab.p, sizeof(int) * 2 * R, cudaMemcpyDeviceToHost, s.stream));
+    k_ranges_finish<<<(2 * R + 63) / 64, 64, 0, s.stream>>>(s.rangeTab.p, 2 * R, s.n, s.rank, d_out);
+    s.launches += 1;
+    return cuda_ok(cudaGetLastError(), "touched ranges");
+}
+
+bool touched_ranges(State &s, long *out)
+{
+    const int R = s.nranks;
+    if (!s.rangeOut.ensure(4 * (size_t) R)) return false;
+    if (!touched_ranges_async(s, s.rangeOut.p)) return false;
+    std::vector<long> tab(4 * (size_t) R);
+    NBB_CUDA(cudaMemcpyAsync(tab.data(), s.rangeOut.p, sizeof(long) * 4 * R, cudaMemcpyDeviceToHost, s.stream));
     NBB_CUDA(cudaStreamSynchronize(s.stream));
-    for (int r = 0; r < R; r++) {
-        long lo = tab[2 * r], hi = tab[2 * r + 1];
-        if (hi <= lo) { lo = 0; hi = 0; }
-        out[2 * r] = lo; out[2 * r + 1] = std::min<long>(hi, s.n);
-    }
+    for (int k = 0; k < 4 * R; k++) out[k] = tab[k];
+    // (the synchronous variant reports the own slab's ranges as empty, too)
     return true;
 }
 

@@ -89,7 +89,8 @@ bool build_lists(State &s);                              // everything between "
 bool expand_pairs(State &s);                             // explicit (i,j) pairs per list from the tile masks
 bool device_bbox(State &s, int nops, double *hostMin, double *hostExt);
 bool displacement_check(State &s, double buffacsq, double *maxr2, int *exceeded);
-bool touched_ranges(State &s, long *out);                // per rank slab: [lo, hi) of the sorted positions this rank's lists reference
+bool touched_ranges(State &s, long *out);
+bool touched_ranges_async(State &s, long *d_out);      // the same table written to a device array, no host synchronisation                // per rank slab: [lo, hi) of the sorted positions this rank's lists reference
 
 // ---- force_kernels.cu
 bool launch_forces(State &s, double *d_grad, bool sortedOnly);
@@ -169,7 +170,7 @@ struct State {
     DevBuf<double> gradSorted;
     double *gs = nullptr, *gsExternal = nullptr;   // sorted-order gradient of the last call: own buffer or one set by the caller (section 8e)
     int ownLo = 0, ownHi = 0;                    // sorted positions of the i-blocks this rank owns (whole system for one rank)
-    DevBuf<int> rangeTab;                        // touched sorted range per rank slab (min, max+1)
+    DevBuf<int> rangeTab; DevBuf<long> rangeOut;                        // touched sorted range per rank slab (min, max+1)
     DevBuf<unsigned long long> setPairs;         // per set list-pair counts
     DeviceCounters *counters = nullptr;
     DeviceCounters hostCounters{};

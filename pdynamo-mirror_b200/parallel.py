@@ -42,24 +42,44 @@ def reduce_results(energies, dEdM, grad, group=None):
 
 
 class SlabExchange:
-    """The two halo exchanges in sorted space.  table[p, r] = [lo, hi): sorted positions rank p's lists reference inside rank r's
-    slab (lo == hi: none).  Works on any torch device / backend with point-to-point support."""
+    """The two halo exchanges in sorted space.  table[p, r, h] = [lo, hi): sorted positions rank p's lists reference inside the
+    lower (h = 0) / upper (h = 1) half of rank r's slab (lo == hi: none).  Works on any torch device / backend with point-to-point
+    support."""
 
     def __init__(self, rank, world, group=None):
         self.rank, self.world, self.group = rank, world, group
-        self.table = np.zeros((world, world, 2), np.int64)
+        self.table = np.zeros((world, world, 2, 2), np.int64)
         self._recv = {}
 
     def set_ranges(self, mine, device):
-        """mine[r] = [lo, hi) of this rank (nbb200_touched_ranges); gathers everybody's.  The own slab is never exchanged."""
+        """mine[r, h] = [lo, hi) of this rank (nbb200_touched_ranges); gathers everybody's.  The own slab is never exchanged."""
         import torch
         import torch.distributed as dist
-        t = torch.as_tensor(np.asarray(mine, np.int64).reshape(self.world, 2)).to(device)
-        t[self.rank] = 0
-        out = [torch.empty_like(t) for _ in range(self.world)]
-        dist.all_gather(out, t, group=self.group)
-        self.table = torch.stack(out).cpu().numpy()
+        mine = np.asarray(mine, np.int64).reshape(self.world, 2, 2).copy()
+        mine[self.rank] = 0
+        t = torch.from_numpy(mine).to(device)
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=device)
+        if device.type == "cuda":
+            dist.all_gather_into_tensor(out, t, group=self.group)
+        else:                                                # gloo
+            parts = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(parts, t, group=self.group)
+            out = torch.stack(parts)
+        self.table = out.cpu().numpy()
         self._recv = {}
+
+    def ranges(self, p, r):
+        """Non-empty ranges rank p references inside rank r's slab (adjacent halves merge into one message)."""
+        (a0, b0), (a1, b1) = self.table[p, r]
+        out = []
+        if b0 > a0:
+            out.append([int(a0), int(b0)])
+        if b1 > a1:
+            if out and out[-1][1] == a1:
+                out[-1][1] = int(b1)
+            else:
+                out.append([int(a1), int(b1)])
+        return out
 
     def _run(self, ops):
         import torch.distributed as dist
@@ -76,38 +96,38 @@ class SlabExchange:
         for r in range(self.world):
             if r == self.rank:
                 continue
-            lo, hi = self.table[self.rank, r]
-            if hi > lo:
+            for lo, hi in self.ranges(self.rank, r):
                 ops.append(dist.P2POp(dist.isend, gs[lo:hi], r, self.group))
-            lo, hi = self.table[r, self.rank]
-            if hi > lo:
-                key = ("g", r, int(hi - lo))
+            for lo, hi in self.ranges(r, self.rank):
+                key = ("g", r, lo, hi)
                 buf = self._recv.get(key)
                 if buf is None:
-                    buf = self._recv[key] = torch.empty((int(hi - lo), gs.shape[1]), dtype=gs.dtype, device=gs.device)
+                    buf = self._recv[key] = torch.empty((hi - lo, gs.shape[1]), dtype=gs.dtype, device=gs.device)
                 ops.append(dist.P2POp(dist.irecv, buf, r, self.group))
-                adds.append((int(lo), int(hi), buf))
+                adds.append((lo, hi, buf))
         self._run(ops)
         for lo, hi, buf in adds:
             gs[lo:hi] += buf
 
     def owners_to_halo(self, xs):
         """xs[n, 3] sorted-order positions, authoritative inside the own slab: send the sub-ranges the other ranks list, receive
-        the own halo ranges in place."""
+        the own halo ranges in place.  Returns the received ranges."""
         import torch.distributed as dist
-        ops = []
+        ops, got = [], []
         for r in range(self.world):
             if r == self.rank:
                 continue
-            lo, hi = self.table[r, self.rank]
-            if hi > lo:
+            for lo, hi in self.ranges(r, self.rank):
                 ops.append(dist.P2POp(dist.isend, xs[lo:hi], r, self.group))
-            lo, hi = self.table[self.rank, r]
-            if hi > lo:
+            for lo, hi in self.ranges(self.rank, r):
                 ops.append(dist.P2POp(dist.irecv, xs[lo:hi], r, self.group))
+                got.append((lo, hi))
         self._run(ops)
-        return [(int(self.table[self.rank, r, 0]), int(self.table[self.rank, r, 1])) for r in range(self.world)
-                if r != self.rank and self.table[self.rank, r, 1] > self.table[self.rank, r, 0]]
+        return got
+
+    def halo_atoms(self):
+        """Atoms whose positions this rank receives (= whose gradient contributions it sends) per call without a rebuild."""
+        return sum(hi - lo for r in range(self.world) if r != self.rank for lo, hi in self.ranges(self.rank, r))
 
     def allgather_slabs(self, xs, slabs):
         """List rebuild: every rank needs every position.  slabs[r] = [s0, s1) of rank r; received in place."""
@@ -137,12 +157,21 @@ class DistributedNB:
         self.h, self.n, self.rank, self.world, self.group = state.cObject, n, rank, world, group
         self.buffac2 = float(buffer_distance) ** 2            # (listCutoff - outerCutoff) / 2, squared: CheckForUpdate's criterion
         self.L.nbb200_set_partition(self.h, rank, world)
+        if torch.device(device).type == "cuda":              # library kernels and the exchanges are ordered by one stream
+            self.L.nbb200_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
         self.gs = torch.zeros((n, 3), dtype=torch.float64, device=device)
         self.xs = torch.zeros((n, 3), dtype=torch.float64, device=device)
         self.L.nbb200_set_sorted_gradient_buffer(self.h, C.c_void_p(self.gs.data_ptr()))
         self.exchange = SlabExchange(rank, world, group)
         self.flag = torch.zeros(1, dtype=torch.float64, device=device)
         self.small = torch.zeros(15, dtype=torch.float64, device=device)
+        self.small_host = torch.zeros(15, dtype=torch.float64)
+        if torch.device(device).type == "cuda":
+            self.small_host = self.small_host.pin_memory()
+        self.tab_mine = torch.zeros(4 * world, dtype=torch.int64, device=device)
+        self.tab_all = torch.zeros(4 * world * world, dtype=torch.int64, device=device)
+        self.tab_host = torch.zeros(4 * world * world, dtype=torch.int64).pin_memory()
+        self.profile = None                                  # set to a dict to collect wall-clock seconds per phase (synchronising: debugging only)
         self.first, self.box, self.slabs = True, None, None
         self.energies, self.dEdM = np.zeros(6), np.zeros(9)
         self.updates = 0
@@ -153,19 +182,35 @@ class DistributedNB:
         nblocks = int(out[3])
         return [slab_range(nblocks, self.n, r, self.world) for r in range(self.world)]
 
+    def _tick(self, name):
+        if self.profile is not None:
+            import time
+            self.torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.profile[name] = self.profile.get(name, 0.0) + now - self._t
+            self._t = now
+
     def call(self, x, box, g=None, force_rebuild=False):
+        """force_rebuild must be the same on all ranks (it skips the collective decision)."""
         import torch.distributed as dist
         L, st = self.L, C.c_int(16)
+        if self.profile is not None:
+            import time
+            self.torch.cuda.synchronize()
+            self._t = time.perf_counter()
         xp = C.c_void_p(x.data_ptr())
         box = np.ascontiguousarray(box, np.float64)
         rebuild = True
         if not self.first:
             s0, s1 = self.slabs[self.rank]
-            moved = L.nbb200_max_displacement(self.h, xp, C.byref(st)) > self.buffac2
-            changed = self.box is None or not np.array_equal(self.box, box)
-            self.flag[0] = 1.0 if (moved or changed or force_rebuild) else 0.0
-            dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)       # all ranks rebuild together
-            rebuild = bool(self.flag.item() > 0.0)
+            rebuild = bool(force_rebuild)
+            if not rebuild:
+                moved = L.nbb200_max_displacement(self.h, xp, C.byref(st)) > self.buffac2
+                changed = self.box is None or not np.array_equal(self.box, box)
+                self.flag[0] = 1.0 if (moved or changed) else 0.0
+                dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)   # all ranks rebuild together
+                rebuild = bool(self.flag.item() > 0.0)
+            self._tick("decide")
             L.nbb200_gather_sorted(self.h, xp, s0, s1 - s0, C.c_void_p(self.xs[s0:].data_ptr()))
             if rebuild:                                      # every rank needs every position for the sort
                 self.exchange.allgather_slabs(self.xs, self.slabs)
@@ -173,27 +218,38 @@ class DistributedNB:
             else:                                            # positions of the halo atoms only
                 for lo, hi in self.exchange.owners_to_halo(self.xs):
                     L.nbb200_scatter_sorted(self.h, C.c_void_p(self.xs[lo:].data_ptr()), lo, hi - lo, xp)
+            self._tick("positions")
         updated = L.NBModelABFS_B200_UpdateDeviceDecided(self.h, xp, self._lib.d_(box), 1 if rebuild else 0, C.byref(st))
         if st.value != 16:
             raise RuntimeError("distributed update failed: " + self._lib.last_error())
+        self._tick("update")
         if updated:
+            # the halo ranges of the new lists: computed and all-gathered on the device, copied to pinned host memory without a host
+            # synchronisation; they are read after the energy call has synchronised anyway
             self.updates += 1
-            mine = (C.c_long * (2 * self.world))()
-            if not L.nbb200_touched_ranges(self.h, mine):
+            if not L.nbb200_touched_ranges_device(self.h, C.c_void_p(self.tab_mine.data_ptr())):
                 raise RuntimeError("touched ranges failed: " + self._lib.last_error())
-            self.exchange.set_ranges(np.array(mine[:], np.int64), x.device)
+            dist.all_gather_into_tensor(self.tab_all, self.tab_mine, group=self.group)
+            self.tab_host.copy_(self.tab_all, non_blocking=True)
             self.slabs = self._slabs()
         self.first, self.box = False, box.copy()
         L.NBModelABFS_B200_MMMMEnergySorted(self.h, self._lib.d_(self.energies), self._lib.d_(self.dEdM), C.byref(st))
         if st.value != 16:
             raise RuntimeError("distributed energy failed: " + self._lib.last_error())
+        if updated:
+            self.exchange.table = self.tab_host.numpy().reshape(self.world, self.world, 2, 2).copy()
+            self.exchange._recv = {}
+        self._tick("energy")
         self.exchange.halo_to_owners(self.gs)
         if g is not None:
             s0, s1 = self.slabs[self.rank]
             L.nbb200_unsort_add(self.h, s0, s1 - s0, C.c_void_p(g.data_ptr()))
-        self.small[:6] = self.torch.from_numpy(self.energies).to(self.small.device)
-        self.small[6:] = self.torch.from_numpy(self.dEdM).to(self.small.device)
+        self._tick("gradients")
+        self.small_host[:6] = self.torch.from_numpy(self.energies)
+        self.small_host[6:] = self.torch.from_numpy(self.dEdM)
+        self.small.copy_(self.small_host, non_blocking=True)
         dist.all_reduce(self.small, group=self.group)
+        self._tick("scalars")
         return updated
 
     def results(self):

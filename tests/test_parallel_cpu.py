@@ -75,8 +75,11 @@ def _halo_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     n, slabs = 100, [(0, 48), (48, 100)]
     # rank 0 lists atoms 48..69 of slab 1; rank 1 lists atoms 0..9 of slab 0 (periodic wrap)
-    mine = np.zeros((world, 2), np.int64)
-    mine[1 - rank] = (48, 70) if rank == 0 else (0, 10)
+    mine = np.zeros((world, 2, 2), np.int64)               # [slab][lower / upper half] = [lo, hi)
+    if rank == 0:
+        mine[1, 0] = (48, 70)
+    else:
+        mine[0, 0] = (0, 10); mine[0, 1] = (40, 48)          # rank 1 reaches both ends of slab 0 (periodic wrap)
     ex = SlabExchange(rank, world)
     ex.set_ranges(mine, torch.device("cpu"))
     rng = np.random.default_rng(7 + rank)
@@ -107,16 +110,18 @@ def test_halo_exchanges_gloo_world2():
     part = [np.random.default_rng(7 + r).random((100, 3)) for r in range(2)]
     for rank in range(2):
         table, gs, xs, halo, xa = got[rank]
-        assert table[0, 1].tolist() == [48, 70] and table[1, 0].tolist() == [0, 10] and table[0, 0].tolist() == [0, 0]
+        assert table[0, 1, 0].tolist() == [48, 70] and table[1, 0, 0].tolist() == [0, 10] and table[1, 0, 1].tolist() == [40, 48]
+        assert not table[0, 0].any() and not table[1, 1].any()
     # gradients: the owner's slab holds its own partial plus the other rank's halo contribution, nothing else moved
     g0, g1 = got[0][1], got[1][1]
-    exp0 = part[0].copy(); exp0[0:10] += part[1][0:10]
+    exp0 = part[0].copy(); exp0[0:10] += part[1][0:10]; exp0[40:48] += part[1][40:48]
     exp1 = part[1].copy(); exp1[48:70] += part[0][48:70]
     assert np.allclose(g0[:48], exp0[:48]) and np.allclose(g1[48:], exp1[48:])
     # positions: rank 0 received 48..69 from rank 1 (value s + 0.5), rank 1 received 0..9 from rank 0 (value s)
     x0, x1 = got[0][2], got[1][2]
     assert np.allclose(x0[48:70, 0], np.arange(48, 70) + 0.5) and np.all(x0[70:] == -1.0) and got[0][3] == [(48, 70)]
-    assert np.allclose(x1[0:10, 0], np.arange(0, 10)) and np.all(x1[10:48] == -1.0) and got[1][3] == [(0, 10)]
+    assert np.allclose(x1[0:10, 0], np.arange(0, 10)) and np.all(x1[10:40] == -1.0) and np.allclose(x1[40:48, 0], np.arange(40, 48))
+    assert got[1][3] == [(0, 10), (40, 48)]
     # rebuild: everybody has everything
     for rank in range(2):
         xa = got[rank][4]

@@ -288,9 +288,9 @@ def test_slab_halo_exchange_emulated_on_one_gpu(pkg, name):
         ee, dd = np.zeros(6), np.zeros(9)
         L.NBModelABFS_B200_MMMMEnergySorted(h, _lib.d_(ee), _lib.d_(dd), C.byref(status))
         assert status.value == 16, _lib.last_error()
-        tab = (C.c_long * (2 * R))()
+        tab = (C.c_long * (4 * R))()
         assert L.nbb200_touched_ranges(h, tab) == 1
-        states.append(s2); gss.append(gs); tables.append(np.array(tab[:]).reshape(R, 2)); es += ee; dms += dd
+        states.append(s2); gss.append(gs); tables.append(np.array(tab[:]).reshape(R, 2, 2)); es += ee; dms += dd
     slab = (C.c_long * 4)()
     L.nbb200_get_slab(states[0].configuration.nbState.cObject, slab)
     slabs = [slab_range(int(slab[3]), n, r, R) for r in range(R)]
@@ -299,18 +299,18 @@ def test_slab_halo_exchange_emulated_on_one_gpu(pkg, name):
         touched = torch.zeros(n, dtype=torch.bool, device="cuda")
         touched[slabs[p][0]:slabs[p][1]] = True
         for r in range(R):
-            lo, hi = tables[p][r]
-            if r != p and hi > lo:
-                assert slabs[r][0] <= lo and hi <= slabs[r][1]
-                touched[lo:hi] = True
+            for lo, hi in tables[p][r]:
+                if r != p and hi > lo:
+                    assert slabs[r][0] <= lo and hi <= slabs[r][1]
+                    touched[lo:hi] = True
         assert float(gss[p][~touched].abs().max()) == 0.0 if bool((~touched).any()) else True     # nothing outside slab + halo ranges
     for r in range(R):                                    # halo -> owners, then every owner unsorts its slab
         s0, s1 = slabs[r]
         for p in range(R):
             if p != r:
-                lo, hi = tables[p][r]
-                if hi > lo:
-                    gss[r][lo:hi] += gss[p][lo:hi]
+                for lo, hi in tables[p][r]:
+                    if hi > lo:
+                        gss[r][lo:hi] += gss[p][lo:hi]
         L.nbb200_unsort_add(states[r].configuration.nbState.cObject, s0, s1 - s0, C.c_void_p(total.data_ptr()))
     torch.cuda.synchronize()
     gt = total.cpu().numpy()
