@@ -252,7 +252,7 @@ def run_b200(args):
         # section 8e: spatial slabs in sorted space; per call the ranks exchange halo positions (all slabs when the lists are rebuilt)
         # and halo gradient contributions point to point, and all-reduce 15 scalars (pdynamo-mirror_b200/parallel.py)
         from pdynamo_mirror_b200.parallel import DistributedNB
-        dn = DistributedNB(m.state, w["n"], 0.5 * (m.model.listCutoff - m.model.outerCutoff), rank, world, m.x.device)
+        dn = DistributedNB(m.state, w["n"], 0.5 * (m.model.listCutoff - m.model.outerCutoff), rank, world, m.x.device, transport=os.environ.get("NBB200_TRANSPORT"))
 
     def step_rebuild():
         if dn is None:
@@ -354,7 +354,7 @@ def run_b200(args):
                 line["jac"] = {"error": repr(exc)}
     else:
         line["distributed_check"] = distributed_check(torch, dist, m, dn, w, local)
-        line["halo"] = {"halo_atoms_per_step_no_rebuild": int(dn.exchange.halo_atoms()),
+        line["halo"] = {"halo_atoms_per_step_no_rebuild": int(dn.halo_atoms()), "transport": dn.transport,
                         "atoms_owned": int(dn.slabs[rank][1] - dn.slabs[rank][0]), "list_updates": dn.updates}
         line["e2e"] = {"value": value, "unit": "list-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                        "note": "multi-rank runs keep coordinates and gradients device-resident; the host end-to-end path is measured at N=1"}

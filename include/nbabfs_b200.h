@@ -158,6 +158,22 @@ void nbb200_gather_sorted(NBB200State *state, const double *d_x, long s0, long c
 void nbb200_scatter_sorted(NBB200State *state, const double *d_in, long s0, long count, double *d_x);
 void nbb200_unsort_add(NBB200State *state, long s0, long count, double *d_grad);
 
+/* Peer memory (CUDA IPC; one process per GPU of one NVLink / NVSwitch node): the two halo exchanges as plain kernels that read /
+ * write the other ranks' buffers, no library collective on the data path.  Every rank exports its sorted-order gradient accumulator and
+ * sorted positions (2 x 64-byte handles), imports everybody else's, and then per call:
+ *   nbb200_peer_begin           zero the own accumulator, publish the positions of the own slab            (before a collective B1)
+ *   nbb200_peer_pull_positions  x[atom(s)] = positions of rank r for the halo ranges (or whole slabs: rebuild) (after B1)
+ *   ...UpdateDeviceDecided, nbb200_touched_ranges_device + all-gather of the tables (when rebuilt), ...MMMMEnergySorted
+ *   nbb200_peer_push_gradients  atomically add the own halo contributions into their owners' accumulators   (before a collective B2)
+ *   nbb200_unsort_add           own slab -> atom order                                                        (after B2)
+ * B1 / B2 are any stream-ordered collectives the caller needs anyway (the update decision, the all-reduce of the 15 scalars).
+ * d_table: device copy of all ranks' range tables [nranks][nranks][2][2] (long), row p = nbb200_touched_ranges_device of rank p. */
+int  nbb200_peer_export(NBB200State *state, char *handles128);
+int  nbb200_peer_import(NBB200State *state, int rank, const char *handles128);
+void nbb200_peer_begin(NBB200State *state, const double *d_x, long s0, long count);
+void nbb200_peer_pull_positions(NBB200State *state, const long *d_table, const long *slabEdges, int wholeSlabs, double *d_x);
+void nbb200_peer_push_gradients(NBB200State *state, const long *d_table);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,8 @@ static void destroy(State *s)
     s->sX.release(); s->sAtom.release(); s->invPerm.release(); s->blockBox.release();
     s->tileDesc.release(); s->recA.release(); s->recB.release(); s->gradSorted.release(); s->items.release(); s->rangeTab.release(); s->rangeOut.release(); s->setPairs.release(); s->accum.release();
     s->pairBuf.release(); s->pairCursor.release();
+    for (int r = 0; r < State::kMaxPeers; r++) if (s->peerOpened[r]) { cudaIpcCloseMemHandle(s->peerGs[r]); cudaIpcCloseMemHandle(s->peerXs[r]); }
+    s->symGs.release(); s->symXs.release();
     if (s->counters) cudaFree(s->counters);
     if (s->hx) cudaFreeHost(s->hx);
     if (s->hgrad) cudaFreeHost(s->hgrad);
@@ -624,9 +626,113 @@ void nbb200_unsort_add(NBB200State *state, long s0, long count, double *d_grad)
     unsort_gradients(s, s0, s0 + count, d_grad);
 }
 
+/* ---- peer memory: the halo exchanges as plain kernels over NVLink (no NCCL call on the data path) ---- */
+struct PeerPtrs { double *p[State::kMaxPeers]; };
+struct SlabEdges { long s[State::kMaxPeers + 1]; };
+
+// positions: x[atom(s)] = xs_owner[s] for the sorted positions this rank needs from rank r = blockIdx.y >> 1:
+// the whole slab of r (list rebuild: slab edges given) or the halo range (r, h = blockIdx.y & 1) of the device table
+static __global__ void k_peer_pull(PeerPtrs xs, SlabEdges edges, const long *__restrict__ table, int rank, int nranks, int wholeSlabs,
+                                   const int *__restrict__ sAtom, double *__restrict__ x)
+{
+    const int r = blockIdx.y >> 1, h = blockIdx.y & 1;
+    if (r == rank) return;
+    long lo, hi;
+    if (wholeSlabs) { if (h) return; lo = edges.s[r]; hi = edges.s[r + 1]; }
+    else { const long *t = table + (((long) rank * nranks + r) * 2 + h) * 2; lo = t[0]; hi = t[1]; }
+    const double *src = xs.p[r];
+    for (long s = lo + (long) blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += (long) gridDim.x * blockDim.x) {
+        const int a = sAtom[s];
+        x[3 * a] = src[3 * s]; x[3 * a + 1] = src[3 * s + 1]; x[3 * a + 2] = src[3 * s + 2];
+    }
+}
+
+// gradients: gs_owner[s] += gs_mine[s] over this rank's halo ranges inside rank r's slab (atomics resolved in the owner's L2)
+static __global__ void k_peer_push(PeerPtrs gs, const long *__restrict__ table, int rank, int nranks, const double *__restrict__ mine)
+{
+    const int r = blockIdx.y >> 1, h = blockIdx.y & 1;
+    if (r == rank) return;
+    const long *t = table + (((long) rank * nranks + r) * 2 + h) * 2;
+    const long lo = 3 * t[0], hi = 3 * t[1];
+    double *dst = gs.p[r];
+    for (long k = lo + (long) blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += (long) gridDim.x * blockDim.x) {
+        const double v = mine[k];
+        if (v != 0.0) atomicAdd(&dst[k], v);
+    }
+}
+
+int nbb200_peer_export(NBB200State *state, char *handles128)
+{
+    if (state == nullptr || handles128 == nullptr) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (!s.symGs.ensure(3 * (size_t) s.n) || !s.symXs.ensure(3 * (size_t) s.n)) return 0;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hg, hx;
+    if (!cuda_ok(cudaIpcGetMemHandle(&hg, s.symGs.p), "cudaIpcGetMemHandle") || !cuda_ok(cudaIpcGetMemHandle(&hx, s.symXs.p), "cudaIpcGetMemHandle")) return 0;
+    std::memcpy(handles128, &hg, 64); std::memcpy(handles128 + 64, &hx, 64);
+    s.gsExternal = s.symGs.p;
+    return 1;
+}
+
+int nbb200_peer_import(NBB200State *state, int rank, const char *handles128)
+{
+    if (state == nullptr || handles128 == nullptr || rank < 0 || rank >= State::kMaxPeers) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (rank == s.rank) { s.peerGs[rank] = s.symGs.p; s.peerXs[rank] = s.symXs.p; return 1; }
+    cudaIpcMemHandle_t hg, hx;
+    std::memcpy(&hg, handles128, 64); std::memcpy(&hx, handles128 + 64, 64);
+    void *pg = nullptr, *px = nullptr;
+    if (!cuda_ok(cudaIpcOpenMemHandle(&pg, hg, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle") ||
+        !cuda_ok(cudaIpcOpenMemHandle(&px, hx, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return 0;
+    s.peerGs[rank] = (double *) pg; s.peerXs[rank] = (double *) px; s.peerOpened[rank] = true;
+    s.peersReady = true;
+    return 1;
+}
+
+/* start of a call: zero the own gradient accumulator and publish the positions of the own slab (sorted order), all on the stream */
+void nbb200_peer_begin(NBB200State *state, const double *d_x, long s0, long count)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    cudaMemsetAsync(s.symGs.p, 0, sizeof(double) * 3 * (size_t) s.n, s.stream);
+    s.gsZeroed = true;
+    if (count > 0 && d_x != nullptr) {
+        k_gather_sorted_x<<<(unsigned int) ((count + 255) / 256), 256, 0, s.stream>>>(d_x, s.sAtom.p, s0, count, s.symXs.p + 3 * s0);
+        s.launches += 1;
+    }
+}
+
+/* after a collective that orders it behind every rank's nbb200_peer_begin: fetch positions from their owners into d_x (atom order) */
+void nbb200_peer_pull_positions(NBB200State *state, const long *d_table, const long *slabEdges /* host, nranks + 1 */, int wholeSlabs, double *d_x)
+{
+    if (state == nullptr || d_x == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    PeerPtrs P; SlabEdges E;
+    for (int r = 0; r < State::kMaxPeers; r++) P.p[r] = s.peerXs[r];
+    for (int r = 0; r <= State::kMaxPeers; r++) E.s[r] = (slabEdges != nullptr && r <= s.nranks) ? slabEdges[r] : 0;
+    k_peer_pull<<<dim3(wholeSlabs ? 148 : 32, 2 * s.nranks), 256, 0, s.stream>>>(P, E, d_table, s.rank, s.nranks, wholeSlabs, s.sAtom.p, d_x);
+    s.launches += 1;
+}
+
+/* after the energy call: add this rank's halo contributions into their owners' accumulators */
+void nbb200_peer_push_gradients(NBB200State *state, const long *d_table)
+{
+    if (state == nullptr || d_table == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    PeerPtrs P;
+    for (int r = 0; r < State::kMaxPeers; r++) P.p[r] = s.peerGs[r];
+    k_peer_push<<<dim3(32, 2 * s.nranks), 256, 0, s.stream>>>(P, d_table, s.rank, s.nranks, s.symGs.p);
+    s.launches += 1;
+}
+
 void nbb200_set_partition(NBB200State *state, int rank, int nranks)
 {
-    if (state == nullptr || nranks < 1 || rank < 0 || rank >= nranks) return;
+    if (state == nullptr || nranks < 1 || rank < 0 || rank >= nranks || nranks > State::kMaxPeers) return;
     State &s = *reinterpret_cast<State *>(state);
     s.rank = rank; s.nranks = nranks; s.isNew = true;
 }

@@ -417,7 +417,8 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
     if (wantGrad) {
         if (s.gsExternal != nullptr) s.gs = s.gsExternal;
         else { if (!s.gradSorted.ensure(3 * (size_t) s.n)) return false; s.gs = s.gradSorted.p; }
-        NBB_CUDA(cudaMemsetAsync(s.gs, 0, sizeof(double) * 3 * (size_t) s.n, s.stream));
+        if (!s.gsZeroed) NBB_CUDA(cudaMemsetAsync(s.gs, 0, sizeof(double) * 3 * (size_t) s.n, s.stream));
+        s.gsZeroed = false;
     }
     const int nitems = (int) s.hostCounters.itemCount;
     const size_t accumCount = (size_t) 16 * (s.nsets + 1);

@@ -170,7 +170,14 @@ struct State {
     DevBuf<double> gradSorted;
     double *gs = nullptr, *gsExternal = nullptr;   // sorted-order gradient of the last call: own buffer or one set by the caller (section 8e)
     int ownLo = 0, ownHi = 0;                    // sorted positions of the i-blocks this rank owns (whole system for one rank)
-    DevBuf<int> rangeTab; DevBuf<long> rangeOut;                        // touched sorted range per rank slab (min, max+1)
+    DevBuf<int> rangeTab; DevBuf<long> rangeOut;
+    // peer memory (CUDA IPC, one process per GPU of one node): every rank's sorted-order gradient accumulator and sorted positions
+    static constexpr int kMaxPeers = 16;
+    DevBuf<double> symGs, symXs;                 // this rank's buffers (cudaMalloc: exportable)
+    double *peerGs[kMaxPeers] = {}, *peerXs[kMaxPeers] = {};
+    bool peerOpened[kMaxPeers] = {};
+    bool peersReady = false;
+    bool gsZeroed = false;                       // the caller zeroed the sorted gradient for this call already (before the ranks' barrier)                        // touched sorted range per rank slab (min, max+1)
     DevBuf<unsigned long long> setPairs;         // per set list-pair counts
     DeviceCounters *counters = nullptr;
     DeviceCounters hostCounters{};

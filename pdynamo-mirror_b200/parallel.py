@@ -148,29 +148,50 @@ class SlabExchange:
 class DistributedNB:
     """Drives one NBModelABFS state per rank through the slab / halo scheme above.  x[n, 3] and g[n, 3] are device tensors in ATOM
     order on every rank; a rank keeps the positions of its own atoms current (after the first call, which takes a replicated x)
-    and receives the gradient of its own atoms."""
+    and receives the gradient of its own atoms.
 
-    def __init__(self, state, n, buffer_distance, rank, world, device, group=None):
+    transport "peer" (default on GPUs): the ranks map each other's buffers (CUDA IPC over NVLink) and the two halo exchanges are
+    plain kernels of the library -- pull positions from their owners, push gradient contributions into the owners' accumulators
+    with atomics; the only collectives are the ones the call needs anyway (update decision, all-reduce of 15 scalars), and they
+    double as the barriers that order the peer accesses.  transport "p2p": the same exchanges as send/recv messages (SlabExchange)."""
+
+    def __init__(self, state, n, buffer_distance, rank, world, device, group=None, transport=None):
         import torch
+        import torch.distributed as dist
         from . import _lib
         self.torch, self.L, self._lib = torch, _lib.lib(), _lib
         self.h, self.n, self.rank, self.world, self.group = state.cObject, n, rank, world, group
         self.buffac2 = float(buffer_distance) ** 2            # (listCutoff - outerCutoff) / 2, squared: CheckForUpdate's criterion
+        device = torch.device(device)
         self.L.nbb200_set_partition(self.h, rank, world)
-        if torch.device(device).type == "cuda":              # library kernels and the exchanges are ordered by one stream
+        if device.type == "cuda":                            # library kernels and the exchanges are ordered by one stream
             self.L.nbb200_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        self.gs = torch.zeros((n, 3), dtype=torch.float64, device=device)
-        self.xs = torch.zeros((n, 3), dtype=torch.float64, device=device)
-        self.L.nbb200_set_sorted_gradient_buffer(self.h, C.c_void_p(self.gs.data_ptr()))
+        self.transport = transport or ("peer" if device.type == "cuda" else "p2p")
         self.exchange = SlabExchange(rank, world, group)
         self.flag = torch.zeros(1, dtype=torch.float64, device=device)
         self.small = torch.zeros(15, dtype=torch.float64, device=device)
         self.small_host = torch.zeros(15, dtype=torch.float64)
-        if torch.device(device).type == "cuda":
+        if device.type == "cuda":
             self.small_host = self.small_host.pin_memory()
         self.tab_mine = torch.zeros(4 * world, dtype=torch.int64, device=device)
         self.tab_all = torch.zeros(4 * world * world, dtype=torch.int64, device=device)
         self.tab_host = torch.zeros(4 * world * world, dtype=torch.int64).pin_memory()
+        if self.transport == "peer":
+            buf = C.create_string_buffer(128)
+            if not self.L.nbb200_peer_export(self.h, buf):
+                raise RuntimeError("peer export failed: " + _lib.last_error())
+            mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(device)
+            allh = torch.empty(128 * world, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allh, mine, group=group)
+            allh = allh.cpu().numpy().tobytes()
+            for r in range(world):
+                if not self.L.nbb200_peer_import(self.h, r, allh[128 * r:128 * (r + 1)]):
+                    raise RuntimeError("peer import failed: " + _lib.last_error())
+            self.gs = self.xs = None
+        else:
+            self.gs = torch.zeros((n, 3), dtype=torch.float64, device=device)
+            self.xs = torch.zeros((n, 3), dtype=torch.float64, device=device)
+            self.L.nbb200_set_sorted_gradient_buffer(self.h, C.c_void_p(self.gs.data_ptr()))
         self.profile = None                                  # set to a dict to collect wall-clock seconds per phase (synchronising: debugging only)
         self.first, self.box, self.slabs = True, None, None
         self.energies, self.dEdM = np.zeros(6), np.zeros(9)
@@ -190,10 +211,28 @@ class DistributedNB:
             self.profile[name] = self.profile.get(name, 0.0) + now - self._t
             self._t = now
 
+    def halo_atoms(self):
+        self.exchange.table = self.tab_all.cpu().numpy().reshape(self.world, self.world, 2, 2)
+        return self.exchange.halo_atoms()
+
+    def _decide(self, xp, box, force_rebuild, st):
+        """Collective update decision (all ranks rebuild together).  Always one all-reduce: it is also the barrier that orders the
+        peer accesses of this call behind every rank's nbb200_peer_begin.  force_rebuild must be the same on all ranks."""
+        import torch.distributed as dist
+        if force_rebuild:
+            if self.transport == "peer":
+                dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)   # barrier only: stream ordered, no host wait
+            return True
+        moved = self.L.nbb200_max_displacement(self.h, xp, C.byref(st)) > self.buffac2
+        changed = self.box is None or not np.array_equal(self.box, box)
+        self.flag[0] = 1.0 if (moved or changed) else 0.0
+        dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)
+        return bool(self.flag.item() > 0.0)
+
     def call(self, x, box, g=None, force_rebuild=False):
-        """force_rebuild must be the same on all ranks (it skips the collective decision)."""
         import torch.distributed as dist
         L, st = self.L, C.c_int(16)
+        peer = self.transport == "peer"
         if self.profile is not None:
             import time
             self.torch.cuda.synchronize()
@@ -201,54 +240,61 @@ class DistributedNB:
         xp = C.c_void_p(x.data_ptr())
         box = np.ascontiguousarray(box, np.float64)
         rebuild = True
-        if not self.first:
+        if self.first:
+            if peer:                                         # zero the accumulator before anybody can push into it
+                L.nbb200_peer_begin(self.h, None, 0, 0)
+                dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)
+        else:
             s0, s1 = self.slabs[self.rank]
-            rebuild = bool(force_rebuild)
-            if not rebuild:
-                moved = L.nbb200_max_displacement(self.h, xp, C.byref(st)) > self.buffac2
-                changed = self.box is None or not np.array_equal(self.box, box)
-                self.flag[0] = 1.0 if (moved or changed) else 0.0
-                dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)   # all ranks rebuild together
-                rebuild = bool(self.flag.item() > 0.0)
+            if peer:
+                L.nbb200_peer_begin(self.h, xp, s0, s1 - s0)
+            rebuild = self._decide(xp, box, force_rebuild, st)
             self._tick("decide")
-            L.nbb200_gather_sorted(self.h, xp, s0, s1 - s0, C.c_void_p(self.xs[s0:].data_ptr()))
-            if rebuild:                                      # every rank needs every position for the sort
-                self.exchange.allgather_slabs(self.xs, self.slabs)
-                L.nbb200_scatter_sorted(self.h, C.c_void_p(self.xs.data_ptr()), 0, self.n, xp)
-            else:                                            # positions of the halo atoms only
-                for lo, hi in self.exchange.owners_to_halo(self.xs):
-                    L.nbb200_scatter_sorted(self.h, C.c_void_p(self.xs[lo:].data_ptr()), lo, hi - lo, xp)
+            if peer:
+                edges = (C.c_long * (self.world + 1))(*([sl[0] for sl in self.slabs] + [self.n]))
+                L.nbb200_peer_pull_positions(self.h, C.c_void_p(self.tab_all.data_ptr()), edges, 1 if rebuild else 0, xp)
+            else:
+                L.nbb200_gather_sorted(self.h, xp, s0, s1 - s0, C.c_void_p(self.xs[s0:].data_ptr()))
+                if rebuild:                                  # every rank needs every position for the sort
+                    self.exchange.allgather_slabs(self.xs, self.slabs)
+                    L.nbb200_scatter_sorted(self.h, C.c_void_p(self.xs.data_ptr()), 0, self.n, xp)
+                else:                                        # positions of the halo atoms only
+                    for lo, hi in self.exchange.owners_to_halo(self.xs):
+                        L.nbb200_scatter_sorted(self.h, C.c_void_p(self.xs[lo:].data_ptr()), lo, hi - lo, xp)
             self._tick("positions")
         updated = L.NBModelABFS_B200_UpdateDeviceDecided(self.h, xp, self._lib.d_(box), 1 if rebuild else 0, C.byref(st))
         if st.value != 16:
             raise RuntimeError("distributed update failed: " + self._lib.last_error())
         self._tick("update")
         if updated:
-            # the halo ranges of the new lists: computed and all-gathered on the device, copied to pinned host memory without a host
-            # synchronisation; they are read after the energy call has synchronised anyway
+            # the halo ranges of the new lists: computed and all-gathered on the device (stream ordered, no host wait)
             self.updates += 1
             if not L.nbb200_touched_ranges_device(self.h, C.c_void_p(self.tab_mine.data_ptr())):
                 raise RuntimeError("touched ranges failed: " + self._lib.last_error())
             dist.all_gather_into_tensor(self.tab_all, self.tab_mine, group=self.group)
-            self.tab_host.copy_(self.tab_all, non_blocking=True)
+            if not peer:
+                self.tab_host.copy_(self.tab_all, non_blocking=True)
             self.slabs = self._slabs()
         self.first, self.box = False, box.copy()
         L.NBModelABFS_B200_MMMMEnergySorted(self.h, self._lib.d_(self.energies), self._lib.d_(self.dEdM), C.byref(st))
         if st.value != 16:
             raise RuntimeError("distributed energy failed: " + self._lib.last_error())
-        if updated:
-            self.exchange.table = self.tab_host.numpy().reshape(self.world, self.world, 2, 2).copy()
-            self.exchange._recv = {}
         self._tick("energy")
-        self.exchange.halo_to_owners(self.gs)
-        if g is not None:
-            s0, s1 = self.slabs[self.rank]
-            L.nbb200_unsort_add(self.h, s0, s1 - s0, C.c_void_p(g.data_ptr()))
+        s0, s1 = self.slabs[self.rank]
+        if peer:
+            L.nbb200_peer_push_gradients(self.h, C.c_void_p(self.tab_all.data_ptr()))
+        else:
+            if updated:                                      # read after the energy call has synchronised the stream
+                self.exchange.table = self.tab_host.numpy().reshape(self.world, self.world, 2, 2).copy()
+                self.exchange._recv = {}
+            self.exchange.halo_to_owners(self.gs)
         self._tick("gradients")
         self.small_host[:6] = self.torch.from_numpy(self.energies)
         self.small_host[6:] = self.torch.from_numpy(self.dEdM)
         self.small.copy_(self.small_host, non_blocking=True)
-        dist.all_reduce(self.small, group=self.group)
+        dist.all_reduce(self.small, group=self.group)        # also orders the unsort below behind every rank's push
+        if g is not None:
+            L.nbb200_unsort_add(self.h, s0, s1 - s0, C.c_void_p(g.data_ptr()))
         self._tick("scalars")
         return updated
 
