@@ -309,7 +309,7 @@ def run_b200(args):
         "no_rebuild": {"ms_per_call": ms_nr, "value": pairs / (ms_nr * 1e-3), "unit": "list-pairs/s"},
         "kernels_ms": {"list_rebuild": build_ms, "tile_forces": force_ms, "pairs14": tm["pairs14"], "displacement_check": tm["displacementCheck"]},
         "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
-                     "traffic": ncu_traffic(args.workload, world), "kernel": "k_tile_forces", "flop_per_list_pair": FLOP_PER_LIST_PAIR,
+                     "traffic": ncu_traffic(args.workload, world), "kernel": "k_cluster_forces", "flop_per_list_pair": FLOP_PER_LIST_PAIR,
                      "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (sm_max_mhz, %s); MEASURED_PEAKS.json holds no FP32 figure" % (sm_max, pk_kind)},
         "roofline_list_build": {"bound": "hbm", "achieved": list_bytes / world / (build_ms * 1e-3) / 1e9 if build_ms > 0 else 0.0, "peak": float(pk.get("hbm_gbs", 6650.0)),
                                 "unit": "GB/s", "frac": (list_bytes / world / (build_ms * 1e-3) / 1e9) / float(pk.get("hbm_gbs", 6650.0)) if build_ms > 0 else 0.0,
