@@ -80,6 +80,10 @@ int NBModelABFS_B200_UpdateDevice(NBB200State *state, const double *d_xyz, const
 /* replaces NBModelABFS_MMMMEnergy (pM/csource/NBModelABFS.c:228-301): energies[6] (slots above) are set;
  * grad[3n] (host, nullable) and dEdM[9] (nullable) are accumulated into. */
 void NBModelABFS_B200_MMMMEnergy(NBB200State *state, double *energies, double *grad, double *dEdM, int *status);
+/* on != 0: NBModelABFS_B200_MMMMEnergy SETS grad[3n] instead of accumulating into it (dE/dM is still accumulated).  For a caller
+ * that evaluates the NB term first: System.Energy's zero fill of gradients3 (pMolecule-1.9.0/pMolecule/System.py:272-318) and the
+ * upload of the array are then not needed.  Default 0 = the reference's accumulation. */
+void nbb200_set_gradient_overwrite(NBB200State *state, int on);
 /* same, gradients accumulated into a device array d_grad[3n] (nullable) */
 void NBModelABFS_B200_MMMMEnergyDevice(NBB200State *state, double *energies, double *d_grad, double *dEdM, int *status);
 

@@ -39,6 +39,7 @@ SIGNATURES = {
     "nbb200_get_timings": (None, [vp, dp]),
     "nbb200_get_counters": (None, [vp, lp]),
     "nbb200_set_partition": (None, [vp, C.c_int, C.c_int]),
+    "nbb200_set_gradient_overwrite": (None, [vp, C.c_int]),
     "nbb200_get_slab": (None, [vp, lp]),
     "nbb200_touched_ranges": (C.c_int, [vp, lp]),
     "nbb200_touched_ranges_device": (C.c_int, [vp, vp]),

@@ -338,10 +338,11 @@ void NBModelABFS_B200_MMMMEnergy(NBB200State *state, double *energies, double *g
     if (s.xcur == nullptr) { set_error("MMMMEnergy called before Update"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
     double *dg = nullptr;
     const bool direct = grad != nullptr && is_pinned_host(grad);       // accumulate on the device, DMA straight into the caller's array
+    const bool upload = direct && !s.gradOverwrite;                      // overwrite mode: the caller's values are not needed at all
     const size_t gbytes = sizeof(double) * 3 * (size_t) s.n;
     if (grad != nullptr) {
         dg = s.grad.p;
-        const bool ok0 = direct ? cuda_ok(cudaMemcpyAsync(dg, grad, gbytes, cudaMemcpyHostToDevice, s.stream), "H2D grad")
+        const bool ok0 = upload ? cuda_ok(cudaMemcpyAsync(dg, grad, gbytes, cudaMemcpyHostToDevice, s.stream), "H2D grad")
                                 : cuda_ok(cudaMemsetAsync(dg, 0, gbytes, s.stream), "memset grad");
         if (!ok0) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
     }
@@ -350,7 +351,11 @@ void NBModelABFS_B200_MMMMEnergy(NBB200State *state, double *energies, double *g
     ok = ok && cuda_ok(cudaStreamSynchronize(s.stream), "sync");          // the one synchronisation of the call
     if (ok) {
         energy_finish(s, energies, grad != nullptr, dEdM);
-        if (grad != nullptr && !direct) { const size_t m = 3 * (size_t) s.n; for (size_t i = 0; i < m; i++) grad[i] += s.hgrad[i]; }
+        if (grad != nullptr && !direct) {
+            const size_t m = 3 * (size_t) s.n;
+            if (s.gradOverwrite) std::memcpy(grad, s.hgrad, sizeof(double) * m);
+            else for (size_t i = 0; i < m; i++) grad[i] += s.hgrad[i];
+        }
     }
     if (!ok) set_status(status, NBB200_STATUS_LOGIC_ERROR);
 }
@@ -728,6 +733,11 @@ void nbb200_peer_push_gradients(NBB200State *state, const long *d_table)
     for (int r = 0; r < State::kMaxPeers; r++) P.p[r] = s.peerGs[r];
     k_peer_push<<<dim3(32, 2 * s.nranks), 256, 0, s.stream>>>(P, d_table, s.rank, s.nranks, s.symGs.p);
     s.launches += 1;
+}
+
+void nbb200_set_gradient_overwrite(NBB200State *state, int on)
+{
+    if (state != nullptr) reinterpret_cast<State *>(state)->gradOverwrite = on != 0;
 }
 
 void nbb200_set_partition(NBB200State *state, int rank, int nranks)

@@ -177,6 +177,7 @@ struct State {
     double *peerGs[kMaxPeers] = {}, *peerXs[kMaxPeers] = {};
     bool peerOpened[kMaxPeers] = {};
     bool peersReady = false;
+    bool gradOverwrite = false;                  // MMMMEnergy (host arrays) sets the caller's gradient instead of accumulating
     bool gsZeroed = false;                       // the caller zeroed the sorted gradient for this call already (before the ranks' barrier)                        // touched sorted range per rank slab (min, max+1)
     DevBuf<unsigned long long> setPairs;         // per set list-pair counts
     DeviceCounters *counters = nullptr;

@@ -259,8 +259,10 @@ class NBModel:
 class NBModelABFS(NBModel):
     """Atom-based force-switching NB model on the GPU; drop-in for pMolecule.NBModelABFS.
 
-    Extra (non-reference) options, both optional: device (CUDA ordinal, default 0) and updateFrequency
-    (force a list rebuild every k-th call; default 0 = the reference's displacement heuristic only)."""
+    Extra (non-reference) options, all optional: device (CUDA ordinal, default 0), updateFrequency (force a list rebuild every
+    k-th call; default 0 = the reference's displacement heuristic only) and overwriteGradients (default False = the reference's
+    accumulation into configuration.gradients3; True: the NB call SETS the gradients, for callers that evaluate the NB term first
+    and so need neither a zero fill of the host array nor its upload)."""
 
     def _Initialize(self):
         self.generator = None
@@ -274,13 +276,13 @@ class NBModelABFS(NBModel):
         self.checkForInverses, self.dampingCutoff, self._dielectric, self._electrostaticScale14 = True, 0.5, 1.0, 1.0
         self.imageExpandFactor, self._innerCutoff, self._listCutoff, self._outerCutoff = 0, 8.0, 13.5, 12.0
         self.qcmmCoupling, self.useCentering = "RC Coupling", False
-        self.device, self.updateFrequency = 0, 0
+        self.device, self.updateFrequency, self.overwriteGradients = 0, 0, False
 
     def __getstate__(self):
         state = dict(checkForInverses=self.checkForInverses, imageExpandFactor=self.imageExpandFactor, dampingCutoff=self.dampingCutoff,
                      dielectric=self._dielectric, electrostaticScale14=self._electrostaticScale14, innerCutoff=self._innerCutoff,
                      listCutoff=self._listCutoff, outerCutoff=self._outerCutoff, qcmmCoupling=self.qcmmCoupling, useCentering=self.useCentering,
-                     device=self.device, updateFrequency=self.updateFrequency)
+                     device=self.device, updateFrequency=self.updateFrequency, overwriteGradients=self.overwriteGradients)
         if self.generator is not None:
             state["generator"] = self.generator
         if self.mmmmPairwiseInteraction is not None:
@@ -307,7 +309,8 @@ class NBModelABFS(NBModel):
         simple = dict(dampingCutoff="dampingCutoff", dielectric="_dielectric", electrostaticScale14="_electrostaticScale14", generator="generator",
                       imageExpandFactor="imageExpandFactor", innerCutoff="_innerCutoff", listCutoff="_listCutoff", outerCutoff="_outerCutoff",
                       mmmmPairwiseInteraction="mmmmPairwiseInteraction", qcmmPairwiseInteraction="qcmmPairwiseInteraction",
-                      qcqcPairwiseInteraction="qcqcPairwiseInteraction", device="device", updateFrequency="updateFrequency")
+                      qcqcPairwiseInteraction="qcqcPairwiseInteraction", device="device", updateFrequency="updateFrequency",
+                      overwriteGradients="overwriteGradients")
         for key, attr in simple.items():
             if key in kw:
                 setattr(self, attr, kw.pop(key))
@@ -408,6 +411,7 @@ class NBModelABFS(NBModel):
                 raise TypeError("gradients3 must be a C-contiguous float64 array (it is accumulated into in place)")
             dEdM = None if spg is None else spg.dEdM
             status = C.c_int(_lib.STATUS_CONTINUE)
+            _lib.lib().nbb200_set_gradient_overwrite(nbState.cObject, 1 if self.overwriteGradients else 0)
             _lib.lib().NBModelABFS_B200_MMMMEnergy(nbState.cObject, d_(nbState.energies), d_(g), d_(dEdM), C.byref(status))
             if status.value != _lib.STATUS_CONTINUE:
                 raise CLibraryError("NB energy evaluation failed. " + _lib.last_error())

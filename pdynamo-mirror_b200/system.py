@@ -150,10 +150,14 @@ class System:
         cfg.ClearTemporaryAttributes()
         if doGradients:
             n = len(self.energyModel.mmAtoms)
+            # System.Energy zeroes gradients3 and every term accumulates (pMolecule-1.9.0/pMolecule/System.py:272-318).  The NB model
+            # is the only (hence the first) term of this mirror: with overwriteGradients it SETS the array, which fuses the zero fill
+            # into the NB call (no host memset, no upload); the default keeps the reference's fill + accumulate.
+            overwrite = bool(getattr(self.energyModel.nbModel, "overwriteGradients", False))
             if self._gradients is None or self._gradients.shape[0] != n:
                 from ._lib import pinned_array
-                self._gradients = pinned_array((n, 3))          # reused, page-locked gradient storage (zeroed per call as System.Energy does)
-            else:
+                self._gradients = pinned_array((n, 3))          # reused, page-locked gradient storage
+            elif not overwrite:
                 self._gradients.fill(0.0)
             cfg.SetTemporaryAttribute("gradients3", self._gradients)
             if self.symmetry is not None:

@@ -477,6 +477,7 @@ WORKLOADS = {
     "bala": lambda: bala_water(),
     "w1728_lattice": lambda: water_box(12, name="w1728_lattice"),
     "water3x3x3": lambda: replicated_water(3),
+    "water4x4x4": lambda: replicated_water(4),           # 41 472 atoms: the bounded CPU sample of m1 (same generator, same density)
     "jac": lambda: jac_protein_water(),
     "dhfr": lambda: dhfr_jac(),
     "jac_lattice": lambda: jac_like(),

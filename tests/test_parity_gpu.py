@@ -319,6 +319,29 @@ def test_slab_halo_exchange_emulated_on_one_gpu(pkg, name):
     assert np.allclose(dms.reshape(3, 3), dm, rtol=1e-5, atol=1e-3)
 
 
+def test_overwrite_gradients_option(pkg):
+    """overwriteGradients=True: the NB call sets gradients3 (whatever it held) to exactly what the default accumulates onto zeros;
+    pinned and pageable host arrays."""
+    w = pkg.workloads.WORKLOADS["w216"]()
+    system, st, e, g, dm = gpu_energy(pkg, w)
+    for pinned in (True, False):
+        s2 = pkg.System.FromWorkload(w)
+        model = pkg.NBModelABFS(overwriteGradients=True)
+        s2.DefineNBModel(model)
+        s2.Energy(doGradients=True)
+        cfg = s2.configuration
+        assert np.allclose(cfg.gradients3, g, rtol=1e-12, atol=1e-9)
+        garbage = cfg.gradients3 if pinned else np.empty_like(g)
+        garbage[...] = 1.0e6
+        cfg.gradients3 = garbage
+        model.Energy(cfg)
+        assert np.allclose(garbage, g, rtol=1e-12, atol=1e-9)
+        model.SetOptions(overwriteGradients=False)            # and back to accumulation
+        garbage[...] = 1.0
+        model.Energy(cfg)
+        assert np.allclose(garbage, g + 1.0, rtol=1e-12, atol=1e-9)
+
+
 def test_full_size_m1_properties(pkg):
     """Config 5 at full size (1 119 744 atoms): the oracle would need minutes, so size-independent properties instead.
     With jitter = 0 the box is an exact 12x12x12 replication of the wrapped 216-water cell, hence
