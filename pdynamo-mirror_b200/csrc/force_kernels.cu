@@ -161,12 +161,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
     const float4 *myPosq = stage->posq[g] + m;
     const int *myLj = stage->ljoff[g] + m;
 
+    // work items are claimed one ahead: the cursor atomic and the item record of the NEXT item are in flight during this one
+    unsigned int itNext = 0;
+    if (lane == 0) itNext = atomicAdd(A.workCursor, 1u);
+    itNext = __shfl_sync(0xffffffffu, itNext, 0);
+    WorkItem wiNext = A.items[min(itNext, (unsigned int) (A.nitems - 1))];
     for (;;) {
-        unsigned int it = 0;
-        if (lane == 0) it = atomicAdd(A.workCursor, 1u);
-        it = __shfl_sync(0xffffffffu, it, 0);
-        if (it >= (unsigned int) A.nitems) break;
-        const WorkItem wi = A.items[it];
+        if (itNext >= (unsigned int) A.nitems) break;
+        const WorkItem wi = wiNext;
+        if (lane == 0) itNext = atomicAdd(A.workCursor, 1u);
+        itNext = __shfl_sync(0xffffffffu, itNext, 0);
+        wiNext = A.items[min(itNext, (unsigned int) (A.nitems - 1))];
         const ImageOpDev *op = A.ops + wi.image;
         const bool isImage = wi.image > 0;
         const bool pureT = kRot ? (op->pureTranslation != 0) : true;

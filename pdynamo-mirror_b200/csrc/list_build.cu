@@ -894,7 +894,8 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     const int myBlocks = b1 - b0;
     s.ownLo = b0 * kTile; s.ownHi = std::min(s.n, b1 * kTile);
     // tiles per chunk / work item: long items amortise the per-item prologue of the force kernel, short ones keep small systems spread over all SMs
-    const int chunk = (s.n >= 400000) ? 32 : (s.n >= 60000 ? 16 : 8);
+    static const int chunkOverride = []() { const char *e = std::getenv("NBB200_CHUNK"); return e ? std::atoi(e) : 0; }();
+    const int chunk = chunkOverride > 0 ? chunkOverride : ((s.n >= 400000) ? 32 : (s.n >= 60000 ? 16 : 8));
     if (chunk != s.chunkTiles) { s.chunkTiles = chunk; s.tileCap = 0; }
     // small systems: deal the rows of a block to several warps until the GPU is full (each part has its own, padded, j streams)
     int split = 1;
