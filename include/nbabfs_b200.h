@@ -58,6 +58,11 @@ NBB200State *NBModelABFSState_B200_SetUp(int device, int n, const double *charge
                                          int ntypes14, const int *tableindex14, const double *tableA14, const double *tableB14,
                                          int nexcl, const int *exclPairs, int n14, const int *pairs14,
                                          int ntrans, const double *rot, const double *trans, int *status);
+/* the fixedAtoms argument of NBModelABFSState_SetUp (freeSelection = complement, pM/csource/NBModelABFSState.c:345): the lists keep a
+ * pair only if at least one of its atoms is free (orSelection of PairListGenerator_*, pC/csource/PairListGenerator.c:118-139; 1-4 list:
+ * GenerateLists14, pM/csource/NBModelABFS.c:1113-1128) and CheckForUpdate ignores fixed atoms (:723-739).  Call after SetUp, before the
+ * first Update; nfixed = 0 clears.  Marks the state new (lists are rebuilt). */
+void NBModelABFSState_B200_SetFixedAtoms(NBB200State *state, int nfixed, const int *fixed, int *status);
 /* replaces NBModelABFSState_Deallocate (pM/csource/NBModelABFSState.c:137-188) */
 void NBModelABFSState_B200_Deallocate(NBB200State **state);
 

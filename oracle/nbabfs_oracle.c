@@ -37,8 +37,9 @@ struct OrcNB {
     int *tindex, *tindex14;
     double *tA, *tB, *tA14, *tB14;
     int *exclPtr, *exclCol;           /* symmetric CSR of exclusions (pC/csource/PairList.c:458-526) */
-    long n14;
-    int *p14;
+    long n14, n14all;
+    int *p14, *p14all;               /* 1-4 pairs after / before the fixed-atom filter */
+    char *fixed;                      /* NULL or flags: fixed atoms (freeSelection = complement, NBModelABFSState.c:345) */
     double *rot, *trans;
     int *inverses;
     /* options */
@@ -318,8 +319,9 @@ OrcNB *orc_create(int n, const double *charges, const int *ljtypes,
     }
     /* 1-4 list: GenerateLists14 -> SelfPairList_FromSelfPairList with all atoms MM and free = the input list
      * (pM/csource/NBModelABFS.c:1113-1156, pC/csource/PairList.c:342). */
-    h->n14 = n14;
+    h->n14 = h->n14all = n14;
     h->p14 = (int *) dupmem(pairs14, sizeof(int) * 2 * (size_t) n14);
+    h->p14all = (int *) dupmem(pairs14, sizeof(int) * 2 * (size_t) n14);
     h->rot = (double *) dupmem(rot, sizeof(double) * 9 * (size_t) ntrans);
     h->trans = (double *) dupmem(trans, sizeof(double) * 3 * (size_t) ntrans);
     /* Transformation3Container_FindIdentity / _FindInverses pC/csource/Transformation3Container.c:58-72,120-154 */
@@ -357,9 +359,30 @@ void orc_destroy(OrcNB *h)
 {
     if (h == NULL) return;
     free_images(h);
-    free(h->primary); free(h->xref); free(h->inverses); free(h->rot); free(h->trans); free(h->p14);
+    free(h->primary); free(h->xref); free(h->inverses); free(h->rot); free(h->trans); free(h->p14); free(h->p14all); free(h->fixed);
     free(h->exclPtr); free(h->exclCol); free(h->tindex); free(h->tindex14); free(h->tA); free(h->tB); free(h->tA14); free(h->tB14);
     free(h->q); free(h->ljtype); free(h);
+}
+
+/* fixedAtoms of NBModelABFSState_SetUp (pM/csource/NBModelABFSState.c:316-345): lists keep a pair only if one of its atoms is free
+ * (orSelection of the generators; GenerateLists14 -> SelfPairList_FromSelfPairList, NBModelABFS.c:1113-1128, pC/csource/PairList.c:342),
+ * and CheckForUpdate ignores fixed atoms.  nfixed = 0 clears. */
+void orc_set_fixed(OrcNB *h, int nfixed, const int *fixed)
+{
+    long k, m = 0;
+    int i;
+    free(h->fixed); h->fixed = NULL;
+    if (nfixed > 0) {
+        h->fixed = (char *) calloc((size_t) h->n, 1);
+        for (i = 0; i < nfixed; i++) if (fixed[i] >= 0 && fixed[i] < h->n) h->fixed[fixed[i]] = 1;
+    }
+    for (k = 0; k < h->n14all; k++) {
+        const int a = h->p14all[2 * k], b = h->p14all[2 * k + 1];
+        if (h->fixed != NULL && h->fixed[a] && h->fixed[b]) continue;
+        h->p14[2 * m] = a; h->p14[2 * m + 1] = b; m++;
+    }
+    h->n14 = m;
+    h->isNew = 1;
 }
 
 void orc_set_options(OrcNB *h, double damp, double inner, double outer, double list,
@@ -424,6 +447,7 @@ static void pair_search(const OrcNB *h, int n, const double *x1, const double *x
                 int j = items[k];
                 double dx, dy, dz;
                 if (self && (j >= i || flag[j])) continue;
+                if (h->fixed != NULL && h->fixed[i] && h->fixed[j]) continue;   /* orSelection = freeSelection: QORI || QOR[j] (PairListGenerator.c:118-139) */
                 dx = xi - x2[3 * j]; dy = yi - x2[3 * j + 1]; dz = zi - x2[3 * j + 2];
                 if ((dx * dx + dy * dy + dz * dz) <= c2) pb_push(out, i, j);
             }
@@ -592,13 +616,14 @@ static void generate_image_lists(OrcNB *h, const double *x, const double *M, con
 }
 
 /* CheckForUpdate pM/csource/NBModelABFS.c:691-746 (no fixed atoms) */
-static int check_for_update(int n, const double *x, const double *xref, double listCutoff, double outerCutoff, double *maxDisp)
+static int check_for_update(int n, const double *x, const double *xref, const char *fixed, double listCutoff, double outerCutoff, double *maxDisp)
 {
     int i, doUpdate = 0;
     double buffac = 0.5e+00 * (listCutoff - outerCutoff), buffacsq = buffac * buffac, maxr2 = 0.0e+00;
     for (i = 0; i < n; i++) {
         double dx = x[3 * i] - xref[3 * i], dy = x[3 * i + 1] - xref[3 * i + 1], dz = x[3 * i + 2] - xref[3 * i + 2];
         double r2 = dx * dx + dy * dy + dz * dz;
+        if (fixed != NULL && fixed[i]) continue;             /* NBModelABFS.c:723-739 */
         maxr2 = (maxr2 > r2) ? maxr2 : r2;
         if (r2 > buffacsq) { doUpdate = 1; break; }
     }
@@ -663,7 +688,7 @@ int orc_energy(OrcNB *h, const double *x, const double *box, int forceNew,
     doUpdate = h->isNew;
     doUpdate = doUpdate || (h->list != h->stListCutoff) || (h->outer != h->stOuterCutoff);
     if (doUpdate) { h->stListCutoff = h->list; h->stOuterCutoff = h->outer; }
-    doUpdate = doUpdate || check_for_update(n, x, h->xref, h->list, h->stOuterCutoff, &maxDisp);
+    doUpdate = doUpdate || check_for_update(n, x, h->xref, h->fixed, h->list, h->stOuterCutoff, &maxDisp);
     if (doUpdate) {
         PairBuf pb = {0, 0, NULL};
         free(h->primary);

@@ -26,6 +26,7 @@ def _lib():
     lib.orc_create.restype = vp
     lib.orc_create.argtypes = [C.c_int, dp, ip, C.c_int, ip, dp, dp, C.c_int, ip, dp, dp, C.c_int, ip, C.c_int, ip, C.c_int, dp, dp]
     lib.orc_destroy.argtypes = [vp]
+    lib.orc_set_fixed.argtypes = [vp, C.c_int, ip]
     lib.orc_set_options.argtypes = [vp] + [C.c_double] * 6 + [C.c_int, C.c_int]
     lib.orc_energy.restype = C.c_int
     lib.orc_energy.argtypes = [vp, dp, dp, C.c_int, dp, dp, dp, dp]
@@ -74,6 +75,12 @@ class OracleNB:
         self.opts = dict(dampingCutoff=0.5, innerCutoff=8.0, outerCutoff=12.0, listCutoff=13.5, dielectric=1.0,
                          electrostaticScale14=s.get("electrostaticScale14", 1.0), checkForInverses=True, imageExpandFactor=0)
         self.set_options(**options)
+        if s.get("fixed") is not None and len(s["fixed"]) > 0:
+            self.set_fixed(s["fixed"])
+
+    def set_fixed(self, indices):
+        idx = np.ascontiguousarray(indices, np.int32).reshape(-1)
+        self.lib.orc_set_fixed(self.h, len(idx), _i(idx) if len(idx) else None)
 
     def set_options(self, **kw):
         for k in kw:

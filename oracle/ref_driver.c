@@ -25,6 +25,7 @@
 #include "SymmetryParameterGradients.h"
 #include "Transformation3Container.h"
 #include "ImageList.h"
+#include "Selection.h"
 #include "ref_driver.h"
 
 struct RefNB {
@@ -40,6 +41,7 @@ struct RefNB {
     PairwiseInteractionABFS    *pw;
     NBModelABFSState           *st;
     Coordinates3               *x, *g;
+    Selection                  *fixed;
 };
 
 static double now_s(void)
@@ -116,10 +118,27 @@ RefNB *refnb_create(int n, const double *charges, const int *ljtypes,
     return h;
 }
 
+/* fixedAtoms argument of NBModelABFSState_SetUp (pMolecule.NBModelABFS.pyx:181-273 passes system.hardConstraints.fixedAtoms):
+ * the state is created anew with the selection, as SetUp does for a new configuration.  nfixed = 0 clears. */
+int refnb_set_fixed(RefNB *h, int nfixed, const int *fixed)
+{
+    int i;
+    if (h == NULL) return 0;
+    NBModelABFSState_Deallocate(&(h->st));
+    Selection_Deallocate(&(h->fixed));
+    if (nfixed > 0) {
+        h->fixed = Selection_Allocate(nfixed);
+        for (i = 0; i < nfixed; i++) h->fixed->indices[i] = fixed[i];
+    }
+    h->st = NBModelABFSState_SetUp(h->mm, NULL, h->fixed, h->excl, h->i14, h->lj, h->lj14, NULL, NULL, NULL, h->tc, h->nb->qcmmCoupling);
+    return h->st != NULL;
+}
+
 void refnb_destroy(RefNB *h)
 {
     if (h == NULL) return;
     NBModelABFSState_Deallocate(&(h->st));
+    Selection_Deallocate(&(h->fixed));
     Coordinates3_Deallocate(&(h->x));
     Coordinates3_Deallocate(&(h->g));
     PairwiseInteractionABFS_Deallocate(&(h->pw));

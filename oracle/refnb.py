@@ -27,6 +27,8 @@ def _lib(omp=False):
     lib.refnb_create.argtypes = [C.c_int, dp, ip, C.c_int, ip, dp, dp, C.c_int, ip, dp, dp,
                                  C.c_int, ip, C.c_int, ip, C.c_int, dp, dp]
     lib.refnb_destroy.argtypes = [vp]
+    lib.refnb_set_fixed.restype = C.c_int
+    lib.refnb_set_fixed.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
     lib.refnb_set_options.argtypes = [vp] + [C.c_double] * 6 + [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
     lib.refnb_energy.restype = C.c_int
     lib.refnb_energy.argtypes = [vp, dp, dp, C.c_int, dp, dp, dp, dp]
@@ -83,6 +85,14 @@ class RefNB:
                          electrostaticScale14=s.get("electrostaticScale14", 1.0), checkForInverses=True,
                          imageExpandFactor=0, cutoffCellSizeFactor=0.5, method=0, useGridByCell=True, sortIndices=False)
         self.set_options(**options)
+        if s.get("fixed") is not None and len(s["fixed"]) > 0:
+            self.set_fixed(s["fixed"])
+
+    def set_fixed(self, indices):
+        """fixedAtoms of NBModelABFSState_SetUp (the state is created anew, as for a new configuration)."""
+        idx = np.ascontiguousarray(indices, np.int32).reshape(-1)
+        if not self.lib.refnb_set_fixed(self.h, len(idx), _i(idx) if len(idx) else None):
+            raise RuntimeError("refnb_set_fixed failed")
 
     def set_options(self, **kw):
         for k in kw:

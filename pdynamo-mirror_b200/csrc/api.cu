@@ -37,7 +37,7 @@ static void destroy(State *s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     s->q32.release(); s->q64.release(); s->ljtype.release(); s->ljAB.release(); s->ljAB14.release();
-    s->exclPtr.release(); s->exclCol.release(); s->pairs14.release();
+    s->exclPtr.release(); s->exclCol.release(); s->pairs14.release(); s->fixedFlag.release();
     s->x.release(); s->xref.release(); s->grad.release();
     s->imageOps.release(); s->imageBoxes.release(); s->baseOpsDev.release(); s->visitDisp.release(); s->visitInfo.release(); s->bboxDev.release();
     s->eX.release(); s->eAtom.release(); s->eSet.release(); s->eKey.release(); s->eSortBuf.release();
@@ -102,6 +102,7 @@ static State *create(int device, int n, const double *charges, const int *ljtype
     }
     std::vector<int2> p14((size_t) std::max(1, n14));
     for (int k = 0; k < n14; k++) { p14[k].x = pairs14[2 * k]; p14[k].y = pairs14[2 * k + 1]; }
+    s->pairs14All.assign(p14.begin(), p14.begin() + n14);
     ok = ok && s->q32.ensure(n) && s->q64.ensure(n) && s->ljtype.ensure(n) && s->ljAB.ensure(ab.size()) && s->ljAB14.ensure(ab14.size()) &&
          s->exclPtr.ensure(ptr.size()) && s->exclCol.ensure(col.size()) && s->pairs14.ensure(p14.size()) &&
          s->x.ensure(3 * (size_t) n) && s->xref.ensure(3 * (size_t) n) && s->grad.ensure(3 * (size_t) n);
@@ -295,6 +296,29 @@ void NBModelABFSState_B200_Deallocate(NBB200State **state)
     if (state == nullptr || *state == nullptr) return;
     destroy(reinterpret_cast<State *>(*state));
     *state = nullptr;
+}
+
+void NBModelABFSState_B200_SetFixedAtoms(NBB200State *state, int nfixed, const int *fixed, int *status)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (nfixed < 0 || (nfixed > 0 && fixed == nullptr)) { set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return; }
+    std::vector<unsigned char> flag((size_t) s.n, 0);
+    for (int k = 0; k < nfixed; k++) {
+        if (fixed[k] < 0 || fixed[k] >= s.n) { set_error("fixed atom index out of range"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return; }
+        flag[fixed[k]] = 1;
+    }
+    // GenerateLists14 -> SelfPairList_FromSelfPairList(interactions14, mmSelection, freeSelection): at least one free atom
+    std::vector<int2> keep;
+    for (const int2 &p : s.pairs14All) if (nfixed == 0 || !(flag[p.x] && flag[p.y])) keep.push_back(p);
+    bool ok = s.fixedFlag.ensure((size_t) s.n) && s.pairs14.ensure(std::max<size_t>(1, keep.size()));
+    cudaStreamSynchronize(s.stream);
+    ok = ok && cuda_ok(cudaMemcpy(s.fixedFlag.p, flag.data(), (size_t) s.n, cudaMemcpyHostToDevice), "H2D fixed") &&
+         (keep.empty() || cuda_ok(cudaMemcpy(s.pairs14.p, keep.data(), sizeof(int2) * keep.size(), cudaMemcpyHostToDevice), "H2D 1-4"));
+    if (!ok) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return; }
+    s.nfixed = nfixed; s.n14 = (int) keep.size();
+    s.isNew = true;
 }
 
 void NBModelABFS_B200_SetOptions(NBB200State *state, double dampingCutoff, double innerCutoff, double outerCutoff, double listCutoff,

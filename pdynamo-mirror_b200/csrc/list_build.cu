@@ -133,10 +133,12 @@ bool device_bbox(State &s, int nops, double *hostMin, double *hostExt)
 // CheckForUpdate (pM/csource/NBModelABFS.c:691-746): max |x - x_ref|^2 and "any atom beyond buffac".
 // The reference's early exit only matters when an update happens (then the maximum is not used further).
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_displacement(const double *__restrict__ x, const double *__restrict__ xref, int n, double buffacsq, unsigned long long *__restrict__ out)
+__global__ void k_displacement(const double *__restrict__ x, const double *__restrict__ xref, int n, const unsigned char *__restrict__ fixed, double buffacsq,
+                               unsigned long long *__restrict__ out)
 {
     double m = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (fixed != nullptr && fixed[i]) continue;              // NBModelABFS.c:723-739: fixed atoms do not trigger updates
         const double dx = x[3 * i] - xref[3 * i], dy = x[3 * i + 1] - xref[3 * i + 1], dz = x[3 * i + 2] - xref[3 * i + 2];
         const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
         m = fmax(m, r2);
@@ -153,7 +155,7 @@ bool displacement_check(State &s, double buffacsq, double *maxr2, int *exceeded)
     const int threads = 256;
     const int nblk = std::max(1, std::min(1184, (s.n + threads - 1) / threads));
     if (s.timing) cudaEventRecord(s.ev[6], s.stream);
-    k_displacement<<<nblk, threads, 0, s.stream>>>(s.xcur, s.xref.p, s.n, buffacsq, out);
+    k_displacement<<<nblk, threads, 0, s.stream>>>(s.xcur, s.xref.p, s.n, s.nfixed > 0 ? s.fixedFlag.p : nullptr, buffacsq, out);
     if (s.timing) cudaEventRecord(s.ev[7], s.stream);
     s.launches += 1;
     NBB_CUDA(cudaMemcpyAsync(s.hsmall, out, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
@@ -374,6 +376,7 @@ struct TileArgs {
     const double *blockBox;
     const ImageBoxDev *imageBoxes;     // [nsets], slot 0 unused
     const int *exclPtr; const int *exclCol;
+    const unsigned char *fixed;        // nullable: per-atom flags of the fixed atoms
     unsigned int *tileDesc; unsigned int tileCap;
     WorkItem *items; unsigned int itemCap;
     unsigned long long *setPairs;
@@ -492,6 +495,12 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
     }
     __syncwarp();
 
+    // fixed atoms: a pair stays on the lists only if one of its atoms is free (orSelection = freeSelection of the reference generators)
+    unsigned int freeMask = 0xffffffffu;
+    if (A.fixed != nullptr) {
+        const int sb = b * kTile + lane;
+        freeMask = __ballot_sync(0xffffffffu, !(sb < A.n && A.fixed[A.sAtom[sb]]));
+    }
     const BuildGrid g = A.grid;
     int c0[3], c1[3];
     double maxAbs = 0.0;
@@ -609,6 +618,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
                         colmask |= (r2 <= A.cutoff2) ? (1u << i) : 0u;
                     }
                 }
+                if (colmask != 0u && A.fixed != nullptr && A.fixed[A.sAtom[s]]) colmask &= freeMask;   // fixed j: free i atoms only
                 if (colmask != 0u) {
                     if (set == 0) {
                         if ((s >> 5) == b) colmask &= (1u << (s & 31)) - 1u;          // own block: i < j only, no self pair
@@ -928,6 +938,7 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
             A.grid = s.grid;
             A.sX = s.sX.p; A.sAtom = s.sAtom.p; A.invPerm = s.invPerm.p; A.cellStart = s.cellStart.p; A.blockBox = s.blockBox.p;
             A.imageBoxes = s.imageBoxes.p; A.exclPtr = s.exclPtr.p; A.exclCol = s.exclCol.p;
+            A.fixed = s.nfixed > 0 ? s.fixedFlag.p : nullptr;
             A.tileDesc = s.tileDesc.p; A.tileCap = (unsigned int) cap;
             A.items = s.items.p; A.itemCap = (unsigned int) s.itemCap; A.setPairs = s.setPairs.p; A.counters = s.counters;
             const long warps = (long) myBlocks * s.nsets * A.split;

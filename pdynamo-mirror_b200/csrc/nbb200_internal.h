@@ -113,6 +113,9 @@ struct State {
     DevBuf<double2> ljAB14;         // [nt14*nt14] fp64 for the 1-4 kernel
     DevBuf<int> exclPtr, exclCol;   // symmetric CSR
     DevBuf<int2> pairs14;
+    std::vector<int2> pairs14All;                // as given to SetUp; pairs14 / n14 hold the ones with at least one free atom
+    DevBuf<unsigned char> fixedFlag;             // per atom, 1 = fixed (NBModelABFSState_SetUp's fixedAtoms); unused when nfixed == 0
+    int nfixed = 0;
     Transformations trans;
 
     // options (NBModelABFS / PairwiseInteractionABFS)

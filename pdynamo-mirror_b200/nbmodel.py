@@ -351,8 +351,6 @@ class NBModelABFS(NBModel):
             return
         if qcAtoms is not None and len(qcAtoms) > 0:
             raise NotImplementedError("QC atoms: the QC/MM entry points stay on the CPU reference (SURVEY.md 2.2)")
-        if fixedAtoms is not None and len(fixedAtoms) > 0:
-            raise NotImplementedError("fixed atoms are a 'next' row (SURVEY.md 8f.4)")
         L = _lib.lib()
         if not hasattr(configuration, "nbState"):
             transformations = getattr(symmetry, "transformations", None) if symmetry is not None else None
@@ -379,6 +377,11 @@ class NBModelABFS(NBModel):
             nbState.hasSymmetry = ntr > 0
             if (not nbState.cObject) or (status.value != _lib.STATUS_CONTINUE):
                 raise CLibraryError("Unable to create NB state. " + _lib.last_error())
+            if fixedAtoms is not None and len(fixedAtoms) > 0:     # NBModelABFSState_SetUp's fixedAtoms (a Selection in the reference)
+                fx = np.ascontiguousarray(getattr(fixedAtoms, "indices", fixedAtoms), np.int32).reshape(-1)
+                L.NBModelABFSState_B200_SetFixedAtoms(nbState.cObject, len(fx), i_(fx), C.byref(status))
+                if status.value != _lib.STATUS_CONTINUE:
+                    raise CLibraryError("Unable to create NB state. " + _lib.last_error())
             setattr(configuration, "nbState", nbState)
         nbState = configuration.nbState
         self._push_options(nbState)

@@ -96,6 +96,7 @@ class System:
         self.energyModel = None
         self.symmetry = None
         self.timings = {"NB Set Up": 0.0, "NB Evaluation": 0.0, "Energy": 0.0}
+        self.fixedAtoms = None                                 # system.hardConstraints.fixedAtoms of the reference: indices of atoms that do not move
         self._gradients = None
 
     @classmethod
@@ -108,6 +109,8 @@ class System:
         em.exclusions = SelfPairList(w["exclusions"]) if len(w["exclusions"]) else None
         em.interactions14 = SelfPairList(w["pairs14"]) if len(w["pairs14"]) else None
         em.electrostaticScale14 = w.get("electrostaticScale14", 1.0)
+        if w.get("fixed") is not None and len(w["fixed"]) > 0:
+            self.fixedAtoms = np.ascontiguousarray(w["fixed"], np.int32)
         from ._lib import pinned_array
         self.coordinates3 = pinned_array(w["xyz"].shape)        # page-locked: DMA without a staging copy
         self.coordinates3[...] = w["xyz"]
@@ -166,12 +169,14 @@ class System:
         terms = []
         if em.nbModel is not None:
             t1 = time.perf_counter()
-            em.nbModel.SetUp(em.mmAtoms, None, em.ljParameters, em.ljParameters14, None, em.interactions14, em.exclusions, self.symmetry, None, cfg, log=log)
+            em.nbModel.SetUp(em.mmAtoms, None, em.ljParameters, em.ljParameters14, self.fixedAtoms, em.interactions14, em.exclusions, self.symmetry, None, cfg, log=log)
             t2 = time.perf_counter()
             terms.extend(em.nbModel.Energy(cfg))
             t3 = time.perf_counter()
             self.timings["NB Set Up"] += t2 - t1
             self.timings["NB Evaluation"] += t3 - t2
+        if doGradients and self.fixedAtoms is not None and len(self.fixedAtoms) > 0:
+            cfg.gradients3[np.asarray(self.fixedAtoms, np.int64)] = 0.0      # System.Energy: gradients3.SetRowSelection(fixedAtoms, 0.0) (System.py:292,313)
         cfg.SetTemporaryAttribute("energyTerms", terms)
         self.timings["Energy"] += time.perf_counter() - t0
         return sum(v for _, v in terms)

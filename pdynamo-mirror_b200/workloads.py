@@ -470,8 +470,30 @@ def perturbed(system, amplitude, seed=999):
     return s
 
 
+def with_fixed(system, fixed, name):
+    """The same system with a set of fixed atoms (system.hardConstraints.fixedAtoms of the reference)."""
+    out = dict(system)
+    out["fixed"] = np.ascontiguousarray(fixed, np.int32)
+    out["name"] = name
+    return out
+
+
+def _bala_fixed():
+    w = bala_water()
+    n = w["n"]
+    # half of the solute and the oxygens of the solvent: pairs of two fixed atoms leave the lists, mixed pairs stay
+    return with_fixed(w, np.concatenate([np.arange(0, 22, 2), np.arange(22, n, 3)]), "bala_fixed")
+
+
+def _w216_fixed():
+    w = water216_real()
+    return with_fixed(w, np.arange(0, 324), "w216_fixed")          # the first 108 molecules do not move
+
+
 WORKLOADS = {
     "w216": lambda: water216_real(),
+    "bala_fixed": _bala_fixed,
+    "w216_fixed": _w216_fixed,
     "w216_lattice": lambda: water_box(6, name="w216_lattice"),
     "w216_triclinic": lambda: water216_real(box=[21.5, 22.0, 23.0, 85.0, 95.0, 100.0], name="w216_triclinic", wrap=True),
     "bala": lambda: bala_water(),
@@ -496,6 +518,8 @@ GOLDEN_CASES = {
     "w216_cut": (WORKLOADS["w216"], dict(dampingCutoff=1.0, innerCutoff=6.0, outerCutoff=9.0, listCutoff=10.5), False),
     "bala": (WORKLOADS["bala"], {}, False),
     "jac": (WORKLOADS["jac"], {}, False),
+    "bala_fixed": (WORKLOADS["bala_fixed"], {}, False),
+    "w216_fixed": (WORKLOADS["w216_fixed"], {}, False),
 }
 for _c in CRYSTAL_NAMES:
     GOLDEN_CASES["crystal_" + _c] = (WORKLOADS["crystal_" + _c], {}, False)
