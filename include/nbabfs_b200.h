@@ -63,6 +63,12 @@ NBB200State *NBModelABFSState_B200_SetUp(int device, int n, const double *charge
  * GenerateLists14, pM/csource/NBModelABFS.c:1113-1128) and CheckForUpdate ignores fixed atoms (:723-739).  Call after SetUp, before the
  * first Update; nfixed = 0 clears.  Marks the state new (lists are rebuilt). */
 void NBModelABFSState_B200_SetFixedAtoms(NBB200State *state, int nfixed, const int *fixed, int *status);
+/* replaces NBModelABFSState_SetUpCentering (pM/csource/NBModelABFSState.c:425-450; NBModelABFS option useCentering): the isolates
+ * (connected components of the exclusion graph; those with a fixed atom stay) are moved into the primary cell by whole lattice vectors at
+ * every list update and carried along in between (NBModelABFSState_InitializeCoordinates3, :278-311); lists and energies are evaluated on
+ * the centred coordinates.  Call after SetUp / SetFixedAtoms.  Off without exclusions, without transformations or with a single isolate,
+ * as in the reference. */
+void NBModelABFSState_B200_SetUpCentering(NBB200State *state, int useCentering, int *status);
 /* replaces NBModelABFSState_Deallocate (pM/csource/NBModelABFSState.c:137-188) */
 void NBModelABFSState_B200_Deallocate(NBB200State **state);
 

@@ -40,6 +40,9 @@ struct OrcNB {
     long n14, n14all;
     int *p14, *p14all;               /* 1-4 pairs after / before the fixed-atom filter */
     char *fixed;                      /* NULL or flags: fixed atoms (freeSelection = complement, NBModelABFSState.c:345) */
+    int centering, nisolates;         /* useCentering: isolates = connected components of the exclusion graph */
+    int *isoPtr, *isoIdx;
+    double *xc, *isoT;                /* centred coordinates, per-atom isolate translations (NBModelABFSState.c:278-311) */
     double *rot, *trans;
     int *inverses;
     /* options */
@@ -359,7 +362,7 @@ void orc_destroy(OrcNB *h)
 {
     if (h == NULL) return;
     free_images(h);
-    free(h->primary); free(h->xref); free(h->inverses); free(h->rot); free(h->trans); free(h->p14); free(h->p14all); free(h->fixed);
+    free(h->primary); free(h->xref); free(h->inverses); free(h->rot); free(h->trans); free(h->p14); free(h->p14all); free(h->fixed); free(h->isoPtr); free(h->isoIdx); free(h->xc); free(h->isoT);
     free(h->exclPtr); free(h->exclCol); free(h->tindex); free(h->tindex14); free(h->tA); free(h->tB); free(h->tA14); free(h->tB14);
     free(h->q); free(h->ljtype); free(h);
 }
@@ -383,6 +386,61 @@ void orc_set_fixed(OrcNB *h, int nfixed, const int *fixed)
     }
     h->n14 = m;
     h->isNew = 1;
+}
+
+static int cmp_int(const void *a, const void *b) { return (*(const int *) a > *(const int *) b) - (*(const int *) a < *(const int *) b); }
+
+/* NBModelABFSState_SetUpCentering (pM/csource/NBModelABFSState.c:425-450): isolates from the exclusions
+ * (SelfPairList_ToIsolateSelectionContainer, pC/csource/PairList.c:686-770: breadth-first components, indices sorted),
+ * isolates with a fixed atom removed; centring needs exclusions, transformations and more than one isolate. */
+void orc_set_centering(OrcNB *h, int on)
+{
+    int n = h->n, s, i, c, m = 0, niso = 0, *ptr, *idx;
+    char *assigned;
+    free(h->isoPtr); free(h->isoIdx); free(h->xc); free(h->isoT);
+    h->isoPtr = h->isoIdx = NULL; h->xc = h->isoT = NULL; h->centering = 0; h->nisolates = 0; h->isNew = 1;
+    if (!on || h->ntrans <= 0 || h->exclPtr[n] == 0) return;
+    ptr = (int *) malloc(sizeof(int) * ((size_t) n + 1)); idx = (int *) malloc(sizeof(int) * (size_t) n);
+    assigned = (char *) calloc((size_t) n, 1);
+    for (s = 0; s < n; s++) {
+        int start = m, keep = 1;
+        if (assigned[s]) continue;
+        idx[m++] = s; assigned[s] = 1;
+        for (i = start; i < m; i++)
+            for (c = h->exclPtr[idx[i]]; c < h->exclPtr[idx[i] + 1]; c++) { const int j = h->exclCol[c]; if (!assigned[j]) { idx[m++] = j; assigned[j] = 1; } }
+        qsort(idx + start, (size_t) (m - start), sizeof(int), cmp_int);
+        if (h->fixed != NULL) for (i = start; i < m; i++) if (h->fixed[idx[i]]) keep = 0;     /* SelectionContainer_RemoveIsolates */
+        if (keep) ptr[niso++] = start; else m = start;
+    }
+    ptr[niso] = m;
+    free(assigned);
+    if (niso > 1) {
+        h->isoPtr = ptr; h->isoIdx = idx; h->nisolates = niso; h->centering = 1;
+        h->xc = (double *) calloc(3 * (size_t) n, sizeof(double)); h->isoT = (double *) calloc(3 * (size_t) n, sizeof(double));
+    } else { free(ptr); free(idx); }
+}
+
+/* NBModelABFSState_InitializeCoordinates3 (pM/csource/NBModelABFSState.c:278-311) with SymmetryParameters_CenterCoordinates3ByIsolate
+ * (pM/csource/SymmetryParameters.c:82-129), Coordinates3_Center (pC/csource/Coordinates3.c:357-440), _FindCenteringTranslation (:271-290) */
+static const double *centre_coordinates(OrcNB *h, const double *x, const double *M, const double *invM, int doUpdate)
+{
+    int n = h->n, k, i, d;
+    if (!h->centering) return x;
+    if (!doUpdate) { for (i = 0; i < 3 * n; i++) h->xc[i] = x[i] + h->isoT[i]; return h->xc; }
+    memcpy(h->xc, x, sizeof(double) * 3 * (size_t) n);
+    for (k = 0; k < h->nisolates; k++) {
+        double c[3] = {0.0, 0.0, 0.0}, f[3], t[3], na, nb, nc;
+        const int lo = h->isoPtr[k], hi = h->isoPtr[k + 1];
+        const double scale = 1.0e+00 / (double) (hi - lo);
+        for (i = lo; i < hi; i++) for (d = 0; d < 3; d++) c[d] += h->xc[3 * h->isoIdx[i] + d];
+        for (d = 0; d < 3; d++) c[d] *= scale;
+        for (d = 0; d < 3; d++) f[d] = c[0] * invM[3 * d] + c[1] * invM[3 * d + 1] + c[2] * invM[3 * d + 2];
+        na = (double) (-(int) floor(f[0])); nb = (double) (-(int) floor(f[1])); nc = (double) (-(int) floor(f[2]));
+        for (d = 0; d < 3; d++) t[d] = na * M[3 * d] + nb * M[3 * d + 1] + nc * M[3 * d + 2];
+        for (i = lo; i < hi; i++) for (d = 0; d < 3; d++) h->xc[3 * h->isoIdx[i] + d] += t[d];
+    }
+    for (i = 0; i < 3 * n; i++) h->isoT[i] = h->xc[i] + (-1.0e+00) * x[i];
+    return h->xc;
 }
 
 void orc_set_options(OrcNB *h, double damp, double inner, double outer, double list,
@@ -675,9 +733,10 @@ static void image_derivatives(double *dEdM, const double *M, const double *invM,
 }
 
 /* NBModelABFS_Update (pM/csource/NBModelABFS.c:508-623) + NBModelABFS_MMMMEnergy (:228-301) + MMMMImageEnergy (:1161-1313) */
-int orc_energy(OrcNB *h, const double *x, const double *box, int forceNew,
+int orc_energy(OrcNB *h, const double *xin, const double *box, int forceNew,
                double *energies, double *grad, double *dEdM, double *timings)
 {
+    const double *x = xin;                 /* the coordinates the lists and energies see: the input, or the centred copy */
     int n = h->n, doUpdate, k, i;
     double M[9], invM[9], F[21], maxDisp = 0.0e+00, eScale, t0, t1, t2;
     double *ix = NULL, *ig = NULL;
@@ -688,13 +747,14 @@ int orc_energy(OrcNB *h, const double *x, const double *box, int forceNew,
     doUpdate = h->isNew;
     doUpdate = doUpdate || (h->list != h->stListCutoff) || (h->outer != h->stOuterCutoff);
     if (doUpdate) { h->stListCutoff = h->list; h->stOuterCutoff = h->outer; }
-    doUpdate = doUpdate || check_for_update(n, x, h->xref, h->fixed, h->list, h->stOuterCutoff, &maxDisp);
+    doUpdate = doUpdate || check_for_update(n, xin, h->xref, h->fixed, h->list, h->stOuterCutoff, &maxDisp);
+    if (hasSym) x = centre_coordinates(h, xin, M, invM, doUpdate);
     if (doUpdate) {
         PairBuf pb = {0, 0, NULL};
         free(h->primary);
         pair_search(h, n, x, x, h->list, 1, &pb);
         h->primary = pb.p; h->nprimary = pb.n;
-        memcpy(h->xref, x, sizeof(double) * 3 * (size_t) n);
+        memcpy(h->xref, xin, sizeof(double) * 3 * (size_t) n);
     }
     if (hasSym) {
         doUpdate = doUpdate || check_for_image_update(h, M, maxDisp);

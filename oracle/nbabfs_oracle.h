@@ -19,7 +19,8 @@ OrcNB *orc_create(int n, const double *charges, const int *ljtypes,
                   int nexcl, const int *exclPairs, int n14, const int *pairs14,
                   int ntrans, const double *rot, const double *trans);
 void   orc_destroy(OrcNB *h);
-void   orc_set_fixed(OrcNB *h, int nfixed, const int *fixed);   /* NBModelABFSState_SetUp's fixedAtoms; 0 clears */
+void   orc_set_fixed(OrcNB *h, int nfixed, const int *fixed);
+void   orc_set_centering(OrcNB *h, int on);                      /* NBModelABFS.useCentering (call after orc_set_fixed) */   /* NBModelABFSState_SetUp's fixedAtoms; 0 clears */
 void   orc_set_options(OrcNB *h, double damp, double inner, double outer, double list,
                        double dielectric, double elecScale14, int checkForInverses, int imageExpandFactor);
 /* same contract as refnb_energy (oracle/ref_driver.h); timings[2] = list update, energy */

@@ -27,6 +27,7 @@ def _lib():
     lib.orc_create.argtypes = [C.c_int, dp, ip, C.c_int, ip, dp, dp, C.c_int, ip, dp, dp, C.c_int, ip, C.c_int, ip, C.c_int, dp, dp]
     lib.orc_destroy.argtypes = [vp]
     lib.orc_set_fixed.argtypes = [vp, C.c_int, ip]
+    lib.orc_set_centering.argtypes = [vp, C.c_int]
     lib.orc_set_options.argtypes = [vp] + [C.c_double] * 6 + [C.c_int, C.c_int]
     lib.orc_energy.restype = C.c_int
     lib.orc_energy.argtypes = [vp, dp, dp, C.c_int, dp, dp, dp, dp]
@@ -74,9 +75,12 @@ class OracleNB:
                                      ntrans, _d(rot) if ntrans else None, _d(trn) if ntrans else None)
         self.opts = dict(dampingCutoff=0.5, innerCutoff=8.0, outerCutoff=12.0, listCutoff=13.5, dielectric=1.0,
                          electrostaticScale14=s.get("electrostaticScale14", 1.0), checkForInverses=True, imageExpandFactor=0)
+        centering = bool(options.pop("useCentering", False))
         self.set_options(**options)
         if s.get("fixed") is not None and len(s["fixed"]) > 0:
             self.set_fixed(s["fixed"])
+        if centering:
+            self.lib.orc_set_centering(self.h, 1)
 
     def set_fixed(self, indices):
         idx = np.ascontiguousarray(indices, np.int32).reshape(-1)

@@ -42,6 +42,7 @@ struct RefNB {
     NBModelABFSState           *st;
     Coordinates3               *x, *g;
     Selection                  *fixed;
+    int                         centering;
 };
 
 static double now_s(void)
@@ -131,7 +132,24 @@ int refnb_set_fixed(RefNB *h, int nfixed, const int *fixed)
         for (i = 0; i < nfixed; i++) h->fixed->indices[i] = fixed[i];
     }
     h->st = NBModelABFSState_SetUp(h->mm, NULL, h->fixed, h->excl, h->i14, h->lj, h->lj14, NULL, NULL, NULL, h->tc, h->nb->qcmmCoupling);
+    if (h->st != NULL && h->centering) { Status status = Status_Continue; NBModelABFSState_SetUpCentering(h->st, True, &status); }
     return h->st != NULL;
+}
+
+/* NBModelABFS option useCentering: NBModelABFSState_SetUpCentering right after the state is created (pMolecule.NBModelABFS.pyx:245).
+ * The state is created anew, as SetUp does for a new configuration. */
+int refnb_set_centering(RefNB *h, int on)
+{
+    if (h == NULL) return 0;
+    h->centering = on != 0;
+    {
+        int nf = (h->fixed != NULL) ? h->fixed->nindices : 0, ok;
+        int *idx = (nf > 0) ? (int *) malloc(sizeof(int) * (size_t) nf) : NULL, i;
+        for (i = 0; i < nf; i++) idx[i] = h->fixed->indices[i];
+        ok = refnb_set_fixed(h, nf, idx);
+        free(idx);
+        return ok;
+    }
 }
 
 void refnb_destroy(RefNB *h)

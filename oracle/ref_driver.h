@@ -28,6 +28,8 @@ RefNB *refnb_create(int n, const double *charges, const int *ljtypes,
 void   refnb_destroy(RefNB *h);
 /* fixedAtoms of NBModelABFSState_SetUp: re-creates the state with the selection (0 clears); returns 1 on success */
 int    refnb_set_fixed(RefNB *h, int nfixed, const int *fixed);
+/* NBModelABFS.useCentering: NBModelABFSState_SetUpCentering on a newly created state; returns 1 on success */
+int    refnb_set_centering(RefNB *h, int on);
 
 /* NBModelABFS + generator options (pMolecule.NBModelABFS.pyx:59-71,140-179). method: 0 = automatic
  * (DetermineMethod), 1 = force O(N^2) direct (minimumPoints huge), 2 = force grid. useGridByCell as in generator. */

@@ -27,6 +27,8 @@ def _lib(omp=False):
     lib.refnb_create.argtypes = [C.c_int, dp, ip, C.c_int, ip, dp, dp, C.c_int, ip, dp, dp,
                                  C.c_int, ip, C.c_int, ip, C.c_int, dp, dp]
     lib.refnb_destroy.argtypes = [vp]
+    lib.refnb_set_centering.restype = C.c_int
+    lib.refnb_set_centering.argtypes = [vp, C.c_int]
     lib.refnb_set_fixed.restype = C.c_int
     lib.refnb_set_fixed.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
     lib.refnb_set_options.argtypes = [vp] + [C.c_double] * 6 + [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]
@@ -84,9 +86,12 @@ class RefNB:
         self.opts = dict(dampingCutoff=0.5, innerCutoff=8.0, outerCutoff=12.0, listCutoff=13.5, dielectric=1.0,
                          electrostaticScale14=s.get("electrostaticScale14", 1.0), checkForInverses=True,
                          imageExpandFactor=0, cutoffCellSizeFactor=0.5, method=0, useGridByCell=True, sortIndices=False)
+        centering = bool(options.pop("useCentering", False))
         self.set_options(**options)
         if s.get("fixed") is not None and len(s["fixed"]) > 0:
             self.set_fixed(s["fixed"])
+        if centering and not self.lib.refnb_set_centering(self.h, 1):
+            raise RuntimeError("refnb_set_centering failed")
 
     def set_fixed(self, indices):
         """fixedAtoms of NBModelABFSState_SetUp (the state is created anew, as for a new configuration)."""

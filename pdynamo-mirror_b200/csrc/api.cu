@@ -38,6 +38,7 @@ static void destroy(State *s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     s->q32.release(); s->q64.release(); s->ljtype.release(); s->ljAB.release(); s->ljAB14.release();
     s->exclPtr.release(); s->exclCol.release(); s->pairs14.release(); s->fixedFlag.release();
+    s->isoPtr.release(); s->isoIdx.release(); s->xc.release(); s->isoT.release();
     s->x.release(); s->xref.release(); s->grad.release();
     s->imageOps.release(); s->imageBoxes.release(); s->baseOpsDev.release(); s->visitDisp.release(); s->visitInfo.release(); s->bboxDev.release();
     s->eX.release(); s->eAtom.release(); s->eSet.release(); s->eKey.release(); s->eSortBuf.release();
@@ -100,6 +101,7 @@ static State *create(int device, int n, const double *charges, const int *ljtype
         std::vector<int> cur(ptr.begin(), ptr.end() - 1);
         for (int k = 0; k < nexcl; k++) { const int i = exclPairs[2 * k], j = exclPairs[2 * k + 1]; if (i != j) { col[cur[i]++] = j; col[cur[j]++] = i; } }
     }
+    s->hostExclPtr = ptr; s->hostExclCol.assign(col.begin(), col.begin() + ptr[n]);
     std::vector<int2> p14((size_t) std::max(1, n14));
     for (int k = 0; k < n14; k++) { p14[k].x = pairs14[2 * k]; p14[k].y = pairs14[2 * k + 1]; }
     s->pairs14All.assign(p14.begin(), p14.begin() + n14);
@@ -185,9 +187,15 @@ static int update_common(State &s, const double *box6, int forceNew, int *status
         // current coordinates (a valid list either way; documented in DESIGN.md).
         doUpdate = check_for_image_update(s.trans, s.lattice, s.refLattice, s.plan.images, s.imagePairs, s.list, s.stOuterCutoff, maxDisp);
     }
+    const double *xin = s.xcur;
+    if (s.useCentering) {                                    // NBModelABFSState_InitializeCoordinates3: lists and energies see the centred copy
+        if (s.nranks > 1) { set_error("useCentering is not available with a partitioned state"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
+        if (!centre_coordinates(s, xin, doUpdate)) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return 0; }
+        s.xcur = s.xc.p;
+    }
     if (doUpdate) {
         if (s.timing) cudaEventRecord(s.ev[0], s.stream);
-        if (!cuda_ok(cudaMemcpyAsync(s.xref.p, s.xcur, sizeof(double) * 3 * (size_t) s.n, cudaMemcpyDeviceToDevice, s.stream), "xref copy") || !build_lists(s)) {
+        if (!cuda_ok(cudaMemcpyAsync(s.xref.p, xin, sizeof(double) * 3 * (size_t) s.n, cudaMemcpyDeviceToDevice, s.stream), "xref copy") || !build_lists(s)) {
             set_status(status, NBB200_STATUS_OUT_OF_MEMORY);
             s.isNew = true;
             return 0;
@@ -318,7 +326,44 @@ void NBModelABFSState_B200_SetFixedAtoms(NBB200State *state, int nfixed, const i
          (keep.empty() || cuda_ok(cudaMemcpy(s.pairs14.p, keep.data(), sizeof(int2) * keep.size(), cudaMemcpyHostToDevice), "H2D 1-4"));
     if (!ok) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return; }
     s.nfixed = nfixed; s.n14 = (int) keep.size();
+    s.hostFixed = (nfixed > 0) ? flag : std::vector<unsigned char>();
     s.isNew = true;
+}
+
+void NBModelABFSState_B200_SetUpCentering(NBB200State *state, int useCentering, int *status)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    s.useCentering = false; s.nisolates = 0; s.isNew = true;
+    // as the reference: needs exclusions, transformations and the option; silently off otherwise (NBModelABFSState.c:427)
+    if (!useCentering || s.trans.n <= 0 || s.hostExclCol.empty()) return;
+    const int n = s.n;
+    // SelfPairList_ToIsolateSelectionContainer (pC/csource/PairList.c:686-770): breadth-first components in index order, members sorted;
+    // SelectionContainer_RemoveIsolates(fixedAtoms): molecules with a fixed atom do not move
+    std::vector<int> ptr, idx((size_t) n);
+    std::vector<char> assigned((size_t) n, 0);
+    int m = 0;
+    for (int a = 0; a < n; a++) {
+        if (assigned[a]) continue;
+        const int start = m;
+        idx[m++] = a; assigned[a] = 1;
+        for (int i = start; i < m; i++)
+            for (int c = s.hostExclPtr[idx[i]]; c < s.hostExclPtr[idx[i] + 1]; c++) { const int j = s.hostExclCol[c]; if (!assigned[j]) { idx[m++] = j; assigned[j] = 1; } }
+        std::sort(idx.begin() + start, idx.begin() + m);
+        bool keep = true;
+        if (!s.hostFixed.empty()) for (int i = start; i < m; i++) if (s.hostFixed[idx[i]]) keep = false;
+        if (keep) ptr.push_back(start); else m = start;
+    }
+    const int niso = (int) ptr.size();
+    ptr.push_back(m);
+    if (niso <= 1) return;
+    bool ok = s.isoPtr.ensure(ptr.size()) && s.isoIdx.ensure((size_t) std::max(1, m));
+    cudaStreamSynchronize(s.stream);
+    ok = ok && cuda_ok(cudaMemcpy(s.isoPtr.p, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice), "H2D isolates") &&
+         cuda_ok(cudaMemcpy(s.isoIdx.p, idx.data(), sizeof(int) * (size_t) m, cudaMemcpyHostToDevice), "H2D isolates");
+    if (!ok) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return; }
+    s.nisolates = niso; s.useCentering = true;
 }
 
 void NBModelABFS_B200_SetOptions(NBB200State *state, double dampingCutoff, double innerCutoff, double outerCutoff, double listCutoff,

@@ -166,6 +166,67 @@ bool displacement_check(State &s, double buffacsq, double *maxr2, int *exceeded)
 }
 
 // ------------------------------------------------------------------------------------------------------
+// useCentering: NBModelABFSState_InitializeCoordinates3 (pM/csource/NBModelABFSState.c:278-311).  On a list update every isolate
+// (molecule) is translated by whole lattice vectors so that its centre lies in the primary cell
+// (SymmetryParameters_CenterCoordinates3ByIsolate, pM/csource/SymmetryParameters.c:82-129; Coordinates3_Center,
+// pC/csource/Coordinates3.c:357-440; _FindCenteringTranslation :271-290), with the reference's operation order: the lists are
+// built from these coordinates bit for bit.  Between updates the translations of the last update are re-applied.
+// ------------------------------------------------------------------------------------------------------
+struct CentreArgs { double M[9], invM[9]; };
+
+__global__ void k_centre_isolates(const double *__restrict__ xin, int n, const int *__restrict__ isoPtr, const int *__restrict__ isoIdx, int nisolates, CentreArgs C,
+                                  double *__restrict__ xc, double *__restrict__ isoT)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nisolates) return;
+    const int lo = isoPtr[k], hi = isoPtr[k + 1];
+    double c[3] = {0.0, 0.0, 0.0};
+    for (int i = lo; i < hi; i++) {                          // ascending atom index, one running sum per component
+        const int a = isoIdx[i];
+        c[0] = __dadd_rn(c[0], xin[3 * a]); c[1] = __dadd_rn(c[1], xin[3 * a + 1]); c[2] = __dadd_rn(c[2], xin[3 * a + 2]);
+    }
+    const double scale = __ddiv_rn(1.0, (double) (hi - lo));
+    for (int d = 0; d < 3; d++) c[d] = __dmul_rn(c[d], scale);
+    double t[3], nn[3];
+    for (int d = 0; d < 3; d++) {                            // Matrix33_ApplyToVector3(inverseM, centre), then -floor
+        const double f = __dadd_rn(__dadd_rn(__dmul_rn(c[0], C.invM[3 * d]), __dmul_rn(c[1], C.invM[3 * d + 1])), __dmul_rn(c[2], C.invM[3 * d + 2]));
+        nn[d] = (double) (-(int) floor(f));
+    }
+    for (int d = 0; d < 3; d++)                               // SymmetryParameters_Displacement
+        t[d] = __dadd_rn(__dadd_rn(__dmul_rn(nn[0], C.M[3 * d]), __dmul_rn(nn[1], C.M[3 * d + 1])), __dmul_rn(nn[2], C.M[3 * d + 2]));
+    for (int i = lo; i < hi; i++) {
+        const int a = isoIdx[i];
+        for (int d = 0; d < 3; d++) {
+            const double v = __dadd_rn(xin[3 * a + d], t[d]);
+            xc[3 * a + d] = v;
+            isoT[3 * a + d] = __dadd_rn(v, __dmul_rn(-1.0, xin[3 * a + d]));      // isolateTranslations3 = centred - input
+        }
+    }
+}
+
+__global__ void k_apply_translations(const double *__restrict__ xin, const double *__restrict__ isoT, long m, double *__restrict__ xc)
+{
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) xc[i] = __dadd_rn(xin[i], isoT[i]);
+}
+
+bool centre_coordinates(State &s, const double *d_xin, bool doUpdate)
+{
+    const long m = 3 * (long) s.n;
+    if (!s.xc.ensure((size_t) m) || !s.isoT.ensure((size_t) m)) return false;
+    if (doUpdate) {
+        // atoms of removed isolates (fixed atoms) keep their coordinates and a zero translation
+        NBB_CUDA(cudaMemcpyAsync(s.xc.p, d_xin, sizeof(double) * m, cudaMemcpyDeviceToDevice, s.stream));
+        NBB_CUDA(cudaMemsetAsync(s.isoT.p, 0, sizeof(double) * m, s.stream));
+        CentreArgs C;
+        std::memcpy(C.M, s.lattice.M.v, sizeof(C.M)); std::memcpy(C.invM, s.lattice.invM.v, sizeof(C.invM));
+        k_centre_isolates<<<(s.nisolates + 127) / 128, 128, 0, s.stream>>>(d_xin, s.n, s.isoPtr.p, s.isoIdx.p, s.nisolates, C, s.xc.p, s.isoT.p);
+    } else k_apply_translations<<<(unsigned int) ((m + 255) / 256), 256, 0, s.stream>>>(d_xin, s.isoT.p, m, s.xc.p);
+    s.launches += 1;
+    return cuda_ok(cudaGetLastError(), "centring");
+}
+
+// ------------------------------------------------------------------------------------------------------
 // extended atoms: set 0 = the n primary atoms (entry e = atom index), sets 1.. = image atoms that fall inside
 // the search box (primary bounding box dilated by the cutoff).  Image coordinates follow the reference walk.
 // ------------------------------------------------------------------------------------------------------

@@ -89,6 +89,7 @@ bool build_lists(State &s);                              // everything between "
 bool expand_pairs(State &s);                             // explicit (i,j) pairs per list from the tile masks
 bool device_bbox(State &s, int nops, double *hostMin, double *hostExt);
 bool displacement_check(State &s, double buffacsq, double *maxr2, int *exceeded);
+bool centre_coordinates(State &s, const double *d_xin, bool doUpdate);   // useCentering: fills s.xc (and s.isoT on updates)
 bool touched_ranges(State &s, long *out);
 bool touched_ranges_async(State &s, long *d_out);      // the same table written to a device array, no host synchronisation                // per rank slab: [lo, hi) of the sorted positions this rank's lists reference
 
@@ -116,6 +117,13 @@ struct State {
     std::vector<int2> pairs14All;                // as given to SetUp; pairs14 / n14 hold the ones with at least one free atom
     DevBuf<unsigned char> fixedFlag;             // per atom, 1 = fixed (NBModelABFSState_SetUp's fixedAtoms); unused when nfixed == 0
     int nfixed = 0;
+    std::vector<int> hostExclPtr, hostExclCol;   // host copy of the exclusion CSR (isolates for useCentering)
+    std::vector<unsigned char> hostFixed;
+    // useCentering (NBModelABFSState_SetUpCentering): isolates = connected components of the exclusion graph
+    bool useCentering = false;
+    int nisolates = 0;
+    DevBuf<int> isoPtr, isoIdx;
+    DevBuf<double> xc, isoT;                     // centred coordinates, per-atom isolate translations of the last update
     Transformations trans;
 
     // options (NBModelABFS / PairwiseInteractionABFS)

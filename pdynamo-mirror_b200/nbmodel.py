@@ -318,8 +318,6 @@ class NBModelABFS(NBModel):
             self.checkForInverses = bool(kw.pop("checkForInverses"))
         if "useCentering" in kw:
             self.useCentering = bool(kw.pop("useCentering"))
-            if self.useCentering:
-                raise NotImplementedError("useCentering is a 'next' row (SURVEY.md 8f.4); the device path evaluates the input coordinates")
         if "qcmmCoupling" in kw:
             coupling = kw.pop("qcmmCoupling")
             if coupling not in ("MM Coupling", "RC Coupling", "RD Coupling"):
@@ -382,6 +380,10 @@ class NBModelABFS(NBModel):
                 L.NBModelABFSState_B200_SetFixedAtoms(nbState.cObject, len(fx), i_(fx), C.byref(status))
                 if status.value != _lib.STATUS_CONTINUE:
                     raise CLibraryError("Unable to create NB state. " + _lib.last_error())
+            # NBModelABFSState_SetUpCentering ( nbState.cObject, self.cObject.useCentering, &status )  (pMolecule.NBModelABFS.pyx:245)
+            L.NBModelABFSState_B200_SetUpCentering(nbState.cObject, 1 if self.useCentering else 0, C.byref(status))
+            if status.value != _lib.STATUS_CONTINUE:
+                raise CLibraryError("Unable to create NB state. " + _lib.last_error())
             setattr(configuration, "nbState", nbState)
         nbState = configuration.nbState
         self._push_options(nbState)

@@ -520,6 +520,10 @@ GOLDEN_CASES = {
     "jac": (WORKLOADS["jac"], {}, False),
     "bala_fixed": (WORKLOADS["bala_fixed"], {}, False),
     "w216_fixed": (WORKLOADS["w216_fixed"], {}, False),
+    # useCentering: the stored 216-water box has molecules outside the primary cell (42 images without, 13 with centring)
+    "w216_centred": (WORKLOADS["w216"], dict(useCentering=True), False),
+    "w216_triclinic_centred": (WORKLOADS["w216_triclinic"], dict(useCentering=True), False),
+    "w216_fixed_centred": (WORKLOADS["w216_fixed"], dict(useCentering=True), False),
 }
 for _c in CRYSTAL_NAMES:
     GOLDEN_CASES["crystal_" + _c] = (WORKLOADS["crystal_" + _c], {}, False)

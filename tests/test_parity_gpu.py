@@ -42,7 +42,8 @@ def check_numbers(name, e, g, dm, re, rg, rdm):
         assert np.linalg.norm(dm - rdm) <= M_TOL * np.linalg.norm(rdm)
 
 
-@pytest.mark.parametrize("name", ["w216", "w216_lattice", "w216_triclinic", "w216_cut", "bala", "jac", "bala_fixed", "w216_fixed"])
+@pytest.mark.parametrize("name", ["w216", "w216_lattice", "w216_triclinic", "w216_cut", "bala", "jac", "bala_fixed", "w216_fixed", "w216_centred", "w216_triclinic_centred",
+                                  "w216_fixed_centred"])
 def test_parity_vs_oracle_and_reference_golden(pkg, orc, name):
     maker, opts, _ = pkg.workloads.GOLDEN_CASES[name]
     w = maker()
@@ -321,6 +322,30 @@ def test_slab_halo_exchange_emulated_on_one_gpu(pkg, name):
     assert np.allclose(es, e, rtol=2e-7, atol=1e-6)
     assert np.sqrt(((gt - g) ** 2).mean()) <= 2e-6 * np.sqrt((g ** 2).mean())
     assert np.allclose(dms.reshape(3, 3), dm, rtol=1e-5, atol=1e-3)
+
+
+def test_centring_is_carried_between_updates(pkg, orc):
+    """useCentering: on calls without a list update the isolate translations of the last update are re-applied to the new input
+    coordinates (NBModelABFSState_InitializeCoordinates3, doUpdate = False); a larger move triggers an update and a new centring."""
+    w = pkg.workloads.WORKLOADS["w216"]()
+    system = pkg.System.FromWorkload(w)
+    system.DefineNBModel(pkg.NBModelABFS(useCentering=True))
+    o = orc.OracleNB(w, useCentering=True)
+    system.Energy(doGradients=True)
+    o.energy(force_new=True)
+    x = w["xyz"].copy()
+    for step, amp in enumerate((0.01, 0.02, 0.9)):
+        x = x + amp * np.sin(np.arange(x.size).reshape(-1, 3) + step)
+        system.coordinates3[...] = x
+        system.Energy(doGradients=True)
+        ref = o.energy(xyz=x)
+        st = system.configuration.nbState
+        assert (st.numberOfUpdates == 2) == bool(ref["updated"]) == (amp > 0.5)
+        e, g = st.energies, system.configuration.gradients3
+        assert abs(e.sum() - ref["energies"].sum()) <= (1e-6 if amp < 0.5 else 2e-5) * abs(ref["energies"].sum())
+        assert np.sqrt(((g - ref["grad"]) ** 2).mean()) <= 1e-5 * np.sqrt((ref["grad"] ** 2).mean())
+        if ref["updated"]:
+            assert np.array_equal(orc.canonical_primary(st.Pairs(-1)), orc.canonical_primary(o.primary_pairs()))
 
 
 def test_overwrite_gradients_option(pkg):
