@@ -358,50 +358,47 @@ __global__ void k_scan_add(unsigned int *out, const unsigned int *__restrict__ s
     if (i == n) out[n] = *grand;
 }
 
-__global__ void k_scatter(const int *__restrict__ eKey, int ne, const unsigned int *__restrict__ cellStart, unsigned int *cellFill, int *order)
+__global__ void k_scatter(const int *__restrict__ eKey, int n, unsigned int extCap, const DeviceCounters *__restrict__ counters, const unsigned int *__restrict__ cellStart,
+                          unsigned int *cellFill, int *order)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ne = n + (int) min(counters->extCount, extCap);      // read on the device: no host round trip between the kernels of a rebuild
     if (e >= ne) return;
     const int key = eKey[e];
     order[cellStart[key] + atomicAdd(&cellFill[key], 1u)] = e;
 }
 
-// deterministic order inside each cell: rank sort by (sub-cell key, atom index), one warp per cell, out of place
-__global__ void k_sort_cells(const unsigned int *__restrict__ cellStart, int nkeys, const unsigned long long *__restrict__ eSort,
-                             const int *__restrict__ order, int *__restrict__ sorted)
+// deterministic order inside each cell: rank sort by (sub-cell key, atom index), one warp per cell; the sorted arrays (coordinates,
+// atom index, inverse permutation of the primary atoms) are written in the same pass
+__global__ void k_sort_cells(const unsigned int *__restrict__ cellStart, int nkeys, const unsigned long long *__restrict__ eSort, const int *__restrict__ order,
+                             const double *__restrict__ eX, const int *__restrict__ eAtom, const int *__restrict__ eSet,
+                             double *__restrict__ sX, int *__restrict__ sAtom, int *__restrict__ invPerm)
 {
     const int key = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (key >= nkeys) return;
     const int lo = (int) cellStart[key], m = (int) cellStart[key + 1] - lo;
     if (m <= 0) return;
-    if (m > 2048) {                     // pathological density: keep the (valid, but arbitrary) scatter order
-        for (int i = lane; i < m; i += 32) sorted[lo + i] = order[lo + i];
-        return;
-    }
     for (int base = 0; base < m; base += 32) {
         const bool mine = base + lane < m;
         const int e = mine ? order[lo + base + lane] : 0;
-        const unsigned long long k = mine ? eSort[e] : 0ULL;
-        int rank = 0;
-        for (int b2 = 0; b2 < m; b2 += 32) {
-            const unsigned long long ko = (b2 + lane < m) ? eSort[order[lo + b2 + lane]] : ~0ULL;
-            const int cnt = min(32, m - b2);
-            for (int t = 0; t < cnt; t++) rank += (__shfl_sync(0xffffffffu, ko, t) < k) ? 1 : 0;
+        int rank = base + lane;                              // pathological density (> 2048 per cell): keep the (valid, but arbitrary) scatter order
+        if (m <= 2048) {
+            const unsigned long long k = mine ? eSort[e] : 0ULL;
+            rank = 0;
+            for (int b2 = 0; b2 < m; b2 += 32) {
+                const unsigned long long ko = (b2 + lane < m) ? eSort[order[lo + b2 + lane]] : ~0ULL;
+                const int cnt = min(32, m - b2);
+                for (int t = 0; t < cnt; t++) rank += (__shfl_sync(0xffffffffu, ko, t) < k) ? 1 : 0;
+            }
         }
-        if (mine) sorted[lo + rank] = e;
+        if (mine) {
+            const int p = lo + rank;
+            sX[3 * p] = eX[3 * e]; sX[3 * p + 1] = eX[3 * e + 1]; sX[3 * p + 2] = eX[3 * e + 2];
+            const int a = eAtom[e];
+            sAtom[p] = a;
+            if (eSet[e] == 0) invPerm[a] = p;
+        }
     }
-}
-
-__global__ void k_gather_sorted(const int *__restrict__ order, int ne, const double *__restrict__ eX, const int *__restrict__ eAtom, const int *__restrict__ eSet,
-                                double *sX, int *sAtom, int *invPerm)
-{
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= ne) return;
-    const int e = order[p];
-    sX[3 * p] = eX[3 * e]; sX[3 * p + 1] = eX[3 * e + 1]; sX[3 * p + 2] = eX[3 * e + 2];
-    const int a = eAtom[e];
-    sAtom[p] = a;
-    if (eSet[e] == 0) invPerm[a] = p;
 }
 
 // per i-block (32 consecutive sorted primary atoms): min, max, centre
@@ -944,21 +941,17 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
 {
     const int nkeys = s.nsets * s.grid.ncell;
     const size_t neMax = (size_t) s.n + extUpperBound;
-    if (!s.cellStart.ensure((size_t) nkeys + 2) || !s.order.ensure(neMax) || !s.order2.ensure(neMax) || !s.sX.ensure(3 * neMax) || !s.sAtom.ensure(neMax) || !s.invPerm.ensure((size_t) s.n)) return false;
+    if (!s.cellStart.ensure((size_t) nkeys + 2) || !s.order.ensure(neMax) || !s.sX.ensure(3 * neMax) || !s.sAtom.ensure(neMax) || !s.invPerm.ensure((size_t) s.n)) return false;
     if (!exclusive_scan(s, s.cellFill.p, s.cellStart.p, nkeys)) return false;
     NBB_CUDA(cudaMemsetAsync(s.cellFill.p, 0, sizeof(unsigned int) * nkeys, s.stream));
-    // number of extended atoms actually appended
-    NBB_CUDA(cudaMemcpyAsync(&s.hostCounters, s.counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, s.stream));
-    NBB_CUDA(cudaStreamSynchronize(s.stream));
-    if (s.hostCounters.overflow & 1u) { set_error("extended atom capacity exceeded"); return false; }
-    const int ne = s.n + (int) s.hostCounters.extCount;
-    k_scatter<<<(ne + 255) / 256, 256, 0, s.stream>>>(s.eKey.p, ne, s.cellStart.p, s.cellFill.p, s.order.p);
-    k_sort_cells<<<(nkeys + 7) / 8, 256, 0, s.stream>>>(s.cellStart.p, nkeys, s.eSortBuf.p, s.order.p, s.order2.p);
-    k_gather_sorted<<<(ne + 255) / 256, 256, 0, s.stream>>>(s.order2.p, ne, s.eX.p, s.eAtom.p, s.eSet.p, s.sX.p, s.sAtom.p, s.invPerm.p);
+    // the number of extended atoms actually appended stays on the device (no host synchronisation here); an overflow of the extended
+    // capacity is noticed with the counters that come back after the tile builder
+    k_scatter<<<(unsigned int) ((neMax + 255) / 256), 256, 0, s.stream>>>(s.eKey.p, s.n, extUpperBound, s.counters, s.cellStart.p, s.cellFill.p, s.order.p);
+    k_sort_cells<<<(nkeys + 7) / 8, 256, 0, s.stream>>>(s.cellStart.p, nkeys, s.eSortBuf.p, s.order.p, s.eX.p, s.eAtom.p, s.eSet.p, s.sX.p, s.sAtom.p, s.invPerm.p);
     s.nblocks = (s.n + kTile - 1) / kTile;
     if (!s.blockBox.ensure((size_t) 9 * s.nblocks)) return false;
     k_block_boxes<<<(s.nblocks * 32 + 255) / 256, 256, 0, s.stream>>>(s.sX.p, s.n, s.nblocks, s.blockBox.p);
-    s.launches += 4;
+    s.launches += 3;
 
     // tiles: a global pool handed out in chunks (= work items); sized from the pair density, retried once with the exact need
     const int b0 = (int) (((long) s.nblocks * s.rank) / s.nranks), b1 = (int) (((long) s.nblocks * (s.rank + 1)) / s.nranks);
@@ -1009,6 +1002,7 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
         NBB_CUDA(cudaMemcpyAsync(&s.hostCounters, s.counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, s.stream));
         NBB_CUDA(cudaStreamSynchronize(s.stream));
         if (!cuda_ok(cudaGetLastError(), "k_build_tiles")) return false;
+        if (s.hostCounters.overflow & 1u) { set_error("extended atom capacity exceeded"); return false; }      // build_lists retries with the exact bound
         if ((s.hostCounters.overflow & 6u) == 0u) return true;
         cap = (size_t) (1.15 * (double) s.hostCounters.tileTotal) + 1024;       // the cursor kept counting: this is the exact need
     }
