@@ -106,8 +106,8 @@ def make_workload(name):
 
 
 def workload_description(name, w):
-    return "%s: %d atoms, P1 box %s, TIP3P%s, ABFS 0.5/8/12/13.5 A" % (
-        name, w["n"], "x".join("%.2f" % v for v in w["box"][:3]), "" if w["ntypes"] <= 2 else " + %d-type heteropolymer" % w["ntypes"])
+    kind = "two-species ionic fluid" if name.startswith("ionic") else ("TIP3P" + ("" if w["ntypes"] <= 2 else " + %d-type heteropolymer" % w["ntypes"]))
+    return "%s: %d atoms, P1 box %s, %s, ABFS 0.5/8/12/13.5 A" % (name, w["n"], "x".join("%.2f" % v for v in w["box"][:3]), kind)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -361,6 +361,7 @@ def run_b200(args):
             try:
                 line["jac"] = jac_block(torch, local, fp32_peak_tflops)
                 line["md"] = md_block(torch, local)
+                line["md_device"] = md_device_block(torch, local)
             except Exception as exc:
                 line["jac"] = {"error": repr(exc)}
     else:
@@ -448,6 +449,30 @@ def md_block(torch, local, steps=300):
                       "nb_setup_ms_per_step": 1e3 * sysm.timings["NB Set Up"] / (steps + 1), "nb_evaluation_ms_per_step": 1e3 * sysm.timings["NB Evaluation"] / (steps + 1)}
     out["note"] = ("synthetic random-walk trajectory, NB term only, host arrays every step; for scale: the reference spends 0.587 s (serial) / 0.122 s "
                    "(8 OpenMP threads) per NB evaluation and 0.68 s per list update on this system (benchmarks/log/systemBenchmarks_*_1ps.log)")
+    return out
+
+
+def md_device_block(torch, local, steps=1000):
+    """BASELINE.json config 4 as real dynamics: 1000 velocity-Verlet steps (dt = 1 fs, 300 K start) on a JAC-size bond-free ionic fluid
+    (23 520 atoms; the NB term is its whole force field), everything resident on the device (pdynamo-mirror_b200/md.py); per step the
+    host reads 7 scalars.  Two list policies: the reference's displacement heuristic and a forced update every 10 steps."""
+    import pdynamo_mirror_b200 as p
+    w = make_workload("ionic23k")
+    out = {"workload": workload_description("ionic23k", w) + " (LJ + Coulomb fluid, no bonds)"}
+    for label, freq in (("displacement_triggered", 0), ("update_every_10", 10)):
+        sysm = p.System.FromWorkload(w)
+        sysm.DefineNBModel(p.NBModelABFS(device=local))
+        md = p.md.VelocityVerletDynamics(sysm, timeStep=0.001, temperature=300.0, device=local)
+        md.Run(20, updateFrequency=freq)
+        e0, u0 = md.potential + md.kinetic, md.updates
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        traj = md.Run(steps, updateFrequency=freq)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        tot = np.array([a + b for a, b in traj]); kin = np.array([b for _, b in traj])
+        out[label] = {"steps_per_s": steps / wall, "ms_per_step": 1e3 * wall / steps, "steps": steps, "list_updates": md.updates - u0,
+                      "total_energy_drift_over_kinetic": float(np.abs(tot - e0).max() / kin.mean()), "temperature_K": float(2.0 * kin.mean() / (3 * md.n * 8.314472e-3))}
     return out
 
 

@@ -145,6 +145,16 @@ void nbb200_get_counters(NBB200State *state, long *out8);
  * in units of contiguous chunks; energies/gradients are then partial sums to be reduced by the caller (NCCL). */
 void nbb200_set_partition(NBB200State *state, int rank, int nranks);
 
+/* ---- velocity Verlet on the device -----------------------------------------------------
+ * One step of pCore-1.9.0/pCore/VelocityVerletIntegrator.py:60-81 (Iteration) in Cartesian variables, for callers that keep
+ * coordinates, velocities, accelerations and gradients resident on the device between NB calls (device arrays, 3 n doubles; units
+ * A, A/ps, A/ps^2, kJ/mol/A, amu, ps as in pMolecule/SystemGeometryObjectiveFunction.py:18-28):
+ *   first half : x += dt v + dt^2/2 a ; v += dt/2 a
+ *   (energy + gradient call)
+ *   second half: a = -100 g / m ; v += dt/2 a ; *d_ke = kinetic energy in kJ/mol */
+void nbb200_vv_first_half(NBB200State *state, double *d_x, double *d_v, const double *d_a, double dt);
+void nbb200_vv_second_half(NBB200State *state, double *d_v, double *d_a, const double *d_g, const double *d_mass, double dt, double *d_ke);
+
 /* ---- several GPUs ------------------------------------------------------------
  * Every rank sorts all atoms the same way (cell order); rank r owns the contiguous slab of sorted positions
  * [s0, s1) = the i-blocks nbb200_set_partition gave it, i.e. a spatial slab.  Its lists reference, inside every other

@@ -42,6 +42,8 @@ SIGNATURES = {
     "nbb200_get_counters": (None, [vp, lp]),
     "nbb200_set_partition": (None, [vp, C.c_int, C.c_int]),
     "nbb200_set_gradient_overwrite": (None, [vp, C.c_int]),
+    "nbb200_vv_first_half": (None, [vp, vp, vp, vp, C.c_double]),
+    "nbb200_vv_second_half": (None, [vp, vp, vp, vp, vp, C.c_double, vp]),
     "nbb200_get_slab": (None, [vp, lp]),
     "nbb200_touched_ranges": (C.c_int, [vp, lp]),
     "nbb200_touched_ranges_device": (C.c_int, [vp, vp]),

@@ -804,6 +804,53 @@ void nbb200_peer_push_gradients(NBB200State *state, const long *d_table)
     s.launches += 1;
 }
 
+/* ---- velocity Verlet on the device (pCore-1.9.0/pCore/VelocityVerletIntegrator.py:60-81 in Cartesian variables) ---- */
+// first half: x += dt v + dt^2/2 a ; v += dt/2 a
+static __global__ void k_vv_first(double *__restrict__ x, double *__restrict__ v, const double *__restrict__ a, double dt, long m)
+{
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double ai = a[i], vi = v[i];
+    x[i] += dt * vi + 0.5 * dt * dt * ai;
+    v[i] = vi + 0.5 * dt * ai;
+}
+
+// second half: a = -100 g / m (kJ mol^-1 A^-1 amu^-1 -> A ps^-2) ; v += dt/2 a ; kinetic energy 0.5 * 0.01 * sum m v^2 (kJ/mol)
+static __global__ void k_vv_second(double *__restrict__ v, double *__restrict__ a, const double *__restrict__ g, const double *__restrict__ mass, double dt, long m,
+                                   double *__restrict__ ke)
+{
+    double local = 0.0;
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long) gridDim.x * blockDim.x) {
+        const double mi = mass[i / 3], ai = -100.0 * g[i] / mi;
+        const double vi = v[i] + 0.5 * dt * ai;
+        a[i] = ai; v[i] = vi;
+        local += mi * vi * vi;
+    }
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(ke, 0.5 * 0.01 * local);
+}
+
+void nbb200_vv_first_half(NBB200State *state, double *d_x, double *d_v, const double *d_a, double dt)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    const long m = 3 * (long) s.n;
+    k_vv_first<<<(unsigned int) ((m + 255) / 256), 256, 0, s.stream>>>(d_x, d_v, d_a, dt, m);
+    s.launches += 1;
+}
+
+void nbb200_vv_second_half(NBB200State *state, double *d_v, double *d_a, const double *d_g, const double *d_mass, double dt, double *d_ke)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    const long m = 3 * (long) s.n;
+    cudaMemsetAsync(d_ke, 0, sizeof(double), s.stream);
+    k_vv_second<<<(unsigned int) std::min<long>(148 * 8, (m + 255) / 256), 256, 0, s.stream>>>(d_v, d_a, d_g, d_mass, dt, m, d_ke);
+    s.launches += 1;
+}
+
 void nbb200_set_gradient_overwrite(NBB200State *state, int on)
 {
     if (state != nullptr) reinterpret_cast<State *>(state)->gradOverwrite = on != 0;

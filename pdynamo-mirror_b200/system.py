@@ -109,6 +109,7 @@ class System:
         em.exclusions = SelfPairList(w["exclusions"]) if len(w["exclusions"]) else None
         em.interactions14 = SelfPairList(w["pairs14"]) if len(w["pairs14"]) else None
         em.electrostaticScale14 = w.get("electrostaticScale14", 1.0)
+        self.masses = w.get("masses")
         if w.get("fixed") is not None and len(w["fixed"]) > 0:
             self.fixedAtoms = np.ascontiguousarray(w["fixed"], np.int32)
         from ._lib import pinned_array

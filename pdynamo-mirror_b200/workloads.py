@@ -470,6 +470,21 @@ def perturbed(system, amplitude, seed=999):
     return s
 
 
+def ionic_fluid(nx=28, ny=28, nz=30, spacing=3.4, jitter=0.3, seed=777, name=None):
+    """A bond-free Lennard-Jones + Coulomb fluid (alternating charges +-0.4 e on a jittered simple cubic lattice, two LJ types,
+    masses 23 / 35.5 amu): the NB term is the WHOLE force field, so velocity-Verlet dynamics with NBModelABFS alone is physical
+    (BASELINE config 4 needs bonded terms for water / protein boxes, which are out of scope).  28 x 28 x 30 = 23 520 atoms, JAC size."""
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    n = nx * ny * nz
+    u = lcg_uniform(seed, 3 * n).reshape(n, 3)
+    xyz = np.stack([ix.ravel(), iy.ravel(), iz.ravel()], 1).astype(np.float64) * spacing + (2.0 * u - 1.0) * jitter + 0.5 * spacing
+    kind = ((ix + iy + iz) & 1).ravel()
+    out = _finish(xyz, np.where(kind == 0, 0.4, -0.4), kind, [0.4, 0.6], [2.6, 3.4], "opls", np.zeros((0, 2), np.int32), np.zeros((0, 2), np.int32),
+                  [nx * spacing, ny * spacing, nz * spacing, 90.0, 90.0, 90.0], name or "ionic%dx%dx%d" % (nx, ny, nz))
+    out["masses"] = np.where(kind == 0, 23.0, 35.5)
+    return out
+
+
 def with_fixed(system, fixed, name):
     """The same system with a set of fixed atoms (system.hardConstraints.fixedAtoms of the reference)."""
     out = dict(system)
@@ -505,6 +520,8 @@ WORKLOADS = {
     "jac_lattice": lambda: jac_like(),
     "water24k_lattice": lambda: water_box(20, name="water24k_lattice"),
     "m1": lambda: replicated_water(12, name="m1"),
+    "ionic23k": lambda: ionic_fluid(name="ionic23k"),
+    "ionic1k": lambda: ionic_fluid(10, 10, 10, name="ionic1k"),
 }
 
 for _c in CRYSTAL_NAMES:
