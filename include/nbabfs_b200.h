@@ -183,21 +183,30 @@ void nbb200_gather_sorted(NBB200State *state, const double *d_x, long s0, long c
 void nbb200_scatter_sorted(NBB200State *state, const double *d_in, long s0, long count, double *d_x);
 void nbb200_unsort_add(NBB200State *state, long s0, long count, double *d_grad);
 
-/* Peer memory (CUDA IPC; one process per GPU of one NVLink / NVSwitch node): the two halo exchanges as plain kernels that read /
- * write the other ranks' buffers, no library collective on the data path.  Every rank exports its sorted-order gradient accumulator and
- * sorted positions (2 x 64-byte handles), imports everybody else's, and then per call:
- *   nbb200_peer_begin           zero the own accumulator, publish the positions of the own slab            (before a collective B1)
- *   nbb200_peer_pull_positions  x[atom(s)] = positions of rank r for the halo ranges (or whole slabs: rebuild) (after B1)
- *   ...UpdateDeviceDecided, nbb200_touched_ranges_device + all-gather of the tables (when rebuilt), ...MMMMEnergySorted
- *   nbb200_peer_push_gradients  atomically add the own halo contributions into their owners' accumulators   (before a collective B2)
- *   nbb200_unsort_add           own slab -> atom order                                                        (after B2)
- * B1 / B2 are any stream-ordered collectives the caller needs anyway (the update decision, the all-reduce of the 15 scalars).
- * d_table: device copy of all ranks' range tables [nranks][nranks][2][2] (long), row p = nbb200_touched_ranges_device of rank p. */
-int  nbb200_peer_export(NBB200State *state, char *handles128);
-int  nbb200_peer_import(NBB200State *state, int rank, const char *handles128);
+/* Peer memory (CUDA IPC; one process per GPU of one NVLink / NVSwitch node): the halo exchanges AND the synchronisation between the ranks
+ * as plain kernels that read / write the other ranks' buffers -- no library collective in a call.  Every rank exports its sorted-order
+ * gradient accumulator, its sorted positions and a small signal area (3 x 64-byte handles), imports everybody else's, and then per
+ * call (`step` counts the calls, the same on all ranks):
+ *   nbb200_peer_begin           zero the own accumulator, publish the positions of the own slab
+ *   nbb200_peer_signal_begin    write (displacement maximum, step) into every rank's signal area
+ *   nbb200_peer_wait_begin      wait (bounded spin on the own signal area) for all ranks; returns the global displacement maximum
+ *   nbb200_peer_pull_positions  x[atom(s)] = positions of rank r for the own halo ranges (or whole slabs: rebuild)
+ *   ...UpdateDeviceDecided, nbb200_touched_ranges_device (when rebuilt), ...MMMMEnergySorted
+ *   nbb200_peer_push_gradients  atomically add the own halo contributions into their owners' accumulators
+ *   nbb200_peer_signal_end      write (15 scalars, step) into every rank's signal area
+ *   nbb200_peer_wait_end        wait for all ranks (their pushes into the own accumulator are complete); sum of the scalars (read_sums)
+ *   nbb200_unsort_add           own slab -> atom order
+ * d_row: the rank's own range table, device array [nranks][2][2] (long) as written by nbb200_touched_ranges_device. */
+int  nbb200_peer_export(NBB200State *state, char *handles192);
+int  nbb200_peer_import(NBB200State *state, int rank, const char *handles192);
 void nbb200_peer_begin(NBB200State *state, const double *d_x, long s0, long count);
-void nbb200_peer_pull_positions(NBB200State *state, const long *d_table, const long *slabEdges, int wholeSlabs, double *d_x);
-void nbb200_peer_push_gradients(NBB200State *state, const long *d_table);
+void nbb200_peer_signal_begin(NBB200State *state, long step, const double *d_x, int forceRebuild);
+double nbb200_peer_wait_begin(NBB200State *state, long step, int needValue, int *status);   /* needValue = 0: ordering only, no host wait */
+void nbb200_peer_pull_positions(NBB200State *state, const long *d_row, const long *slabEdges, int wholeSlabs, double *d_x);
+void nbb200_peer_push_gradients(NBB200State *state, const long *d_row);
+void nbb200_peer_signal_end(NBB200State *state, long step, const double *scal15);
+void nbb200_peer_wait_end(NBB200State *state, long step);                                   /* on the stream; no host wait */
+void nbb200_peer_read_sums(NBB200State *state, double *sum15, int *status);                 /* synchronises; the sums of the last wait_end */
 
 #ifdef __cplusplus
 }

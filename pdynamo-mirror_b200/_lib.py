@@ -59,6 +59,11 @@ SIGNATURES = {
     "nbb200_peer_begin": (None, [vp, vp, C.c_long, C.c_long]),
     "nbb200_peer_pull_positions": (None, [vp, vp, lp, C.c_int, vp]),
     "nbb200_peer_push_gradients": (None, [vp, vp]),
+    "nbb200_peer_signal_begin": (None, [vp, C.c_long, vp, C.c_int]),
+    "nbb200_peer_wait_begin": (C.c_double, [vp, C.c_long, C.c_int, ip]),
+    "nbb200_peer_signal_end": (None, [vp, C.c_long, dp]),
+    "nbb200_peer_wait_end": (None, [vp, C.c_long]),
+    "nbb200_peer_read_sums": (None, [vp, dp, ip]),
 }
 
 

@@ -46,8 +46,8 @@ static void destroy(State *s)
     s->sX.release(); s->sAtom.release(); s->invPerm.release(); s->blockBox.release();
     s->tileDesc.release(); s->recA.release(); s->recB.release(); s->gradSorted.release(); s->items.release(); s->rangeTab.release(); s->rangeOut.release(); s->setPairs.release(); s->accum.release();
     s->pairBuf.release(); s->pairCursor.release();
-    for (int r = 0; r < State::kMaxPeers; r++) if (s->peerOpened[r]) { cudaIpcCloseMemHandle(s->peerGs[r]); cudaIpcCloseMemHandle(s->peerXs[r]); }
-    s->symGs.release(); s->symXs.release();
+    for (int r = 0; r < State::kMaxPeers; r++) if (s->peerOpened[r]) { cudaIpcCloseMemHandle(s->peerGs[r]); cudaIpcCloseMemHandle(s->peerXs[r]); cudaIpcCloseMemHandle(s->peerSig[r]); }
+    s->symGs.release(); s->symXs.release(); s->symSig.release(); s->sigStage.release();
     if (s->counters) cudaFree(s->counters);
     if (s->hx) cudaFreeHost(s->hx);
     if (s->hgrad) cudaFreeHost(s->hgrad);
@@ -713,7 +713,7 @@ static __global__ void k_peer_pull(PeerPtrs xs, SlabEdges edges, const long *__r
     if (r == rank) return;
     long lo, hi;
     if (wholeSlabs) { if (h) return; lo = edges.s[r]; hi = edges.s[r + 1]; }
-    else { const long *t = table + (((long) rank * nranks + r) * 2 + h) * 2; lo = t[0]; hi = t[1]; }
+    else { const long *t = table + ((long) r * 2 + h) * 2; lo = t[0]; hi = t[1]; }
     const double *src = xs.p[r];
     for (long s = lo + (long) blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += (long) gridDim.x * blockDim.x) {
         const int a = sAtom[s];
@@ -726,7 +726,7 @@ static __global__ void k_peer_push(PeerPtrs gs, const long *__restrict__ table, 
 {
     const int r = blockIdx.y >> 1, h = blockIdx.y & 1;
     if (r == rank) return;
-    const long *t = table + (((long) rank * nranks + r) * 2 + h) * 2;
+    const long *t = table + ((long) r * 2 + h) * 2;
     const long lo = 3 * t[0], hi = 3 * t[1];
     double *dst = gs.p[r];
     for (long k = lo + (long) blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += (long) gridDim.x * blockDim.x) {
@@ -735,34 +735,164 @@ static __global__ void k_peer_push(PeerPtrs gs, const long *__restrict__ table, 
     }
 }
 
-int nbb200_peer_export(NBB200State *state, char *handles128)
+// signal area of one rank (doubles; written by its peers, read by itself)
+constexpr int kSigFlagA = 0;                                   // [kMaxPeers] step of "accumulator zeroed, positions published, displacement written"
+constexpr int kSigDisp = State::kMaxPeers;                     // [kMaxPeers] the peers' displacement maxima (1e300: rebuild requested)
+constexpr int kSigFlagB = 2 * State::kMaxPeers;                // [kMaxPeers] step of "gradients pushed, scalars written"
+constexpr int kSigScal = 3 * State::kMaxPeers;                 // [kMaxPeers][16] the peers' 15 scalars
+constexpr int kSigDoubles = 3 * State::kMaxPeers + 16 * State::kMaxPeers;
+
+int nbb200_peer_export(NBB200State *state, char *handles192)
 {
-    if (state == nullptr || handles128 == nullptr) return 0;
+    if (state == nullptr || handles192 == nullptr) return 0;
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
-    if (!s.symGs.ensure(3 * (size_t) s.n) || !s.symXs.ensure(3 * (size_t) s.n)) return 0;
+    if (!s.symGs.ensure(3 * (size_t) s.n) || !s.symXs.ensure(3 * (size_t) s.n) || !s.symSig.ensure(kSigDoubles) || !s.sigStage.ensure(64)) return 0;
+    cudaMemset(s.symSig.p, 0, sizeof(double) * kSigDoubles);
+    cudaMemset(s.sigStage.p, 0, sizeof(double) * 64);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    cudaIpcMemHandle_t hg, hx;
-    if (!cuda_ok(cudaIpcGetMemHandle(&hg, s.symGs.p), "cudaIpcGetMemHandle") || !cuda_ok(cudaIpcGetMemHandle(&hx, s.symXs.p), "cudaIpcGetMemHandle")) return 0;
-    std::memcpy(handles128, &hg, 64); std::memcpy(handles128 + 64, &hx, 64);
+    cudaIpcMemHandle_t hg, hx, hs;
+    if (!cuda_ok(cudaIpcGetMemHandle(&hg, s.symGs.p), "cudaIpcGetMemHandle") || !cuda_ok(cudaIpcGetMemHandle(&hx, s.symXs.p), "cudaIpcGetMemHandle") ||
+        !cuda_ok(cudaIpcGetMemHandle(&hs, s.symSig.p), "cudaIpcGetMemHandle")) return 0;
+    std::memcpy(handles192, &hg, 64); std::memcpy(handles192 + 64, &hx, 64); std::memcpy(handles192 + 128, &hs, 64);
     s.gsExternal = s.symGs.p;
     return 1;
 }
 
-int nbb200_peer_import(NBB200State *state, int rank, const char *handles128)
+int nbb200_peer_import(NBB200State *state, int rank, const char *handles192)
 {
-    if (state == nullptr || handles128 == nullptr || rank < 0 || rank >= State::kMaxPeers) return 0;
+    if (state == nullptr || handles192 == nullptr || rank < 0 || rank >= State::kMaxPeers) return 0;
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
-    if (rank == s.rank) { s.peerGs[rank] = s.symGs.p; s.peerXs[rank] = s.symXs.p; return 1; }
-    cudaIpcMemHandle_t hg, hx;
-    std::memcpy(&hg, handles128, 64); std::memcpy(&hx, handles128 + 64, 64);
-    void *pg = nullptr, *px = nullptr;
+    if (rank == s.rank) { s.peerGs[rank] = s.symGs.p; s.peerXs[rank] = s.symXs.p; s.peerSig[rank] = s.symSig.p; return 1; }
+    cudaIpcMemHandle_t hg, hx, hs;
+    std::memcpy(&hg, handles192, 64); std::memcpy(&hx, handles192 + 64, 64); std::memcpy(&hs, handles192 + 128, 64);
+    void *pg = nullptr, *px = nullptr, *ps = nullptr;
     if (!cuda_ok(cudaIpcOpenMemHandle(&pg, hg, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle") ||
-        !cuda_ok(cudaIpcOpenMemHandle(&px, hx, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return 0;
-    s.peerGs[rank] = (double *) pg; s.peerXs[rank] = (double *) px; s.peerOpened[rank] = true;
+        !cuda_ok(cudaIpcOpenMemHandle(&px, hx, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle") ||
+        !cuda_ok(cudaIpcOpenMemHandle(&ps, hs, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return 0;
+    s.peerGs[rank] = (double *) pg; s.peerXs[rank] = (double *) px; s.peerSig[rank] = (double *) ps; s.peerOpened[rank] = true;
     s.peersReady = true;
     return 1;
+}
+
+// ---- signalling through peer memory: a rank writes (value, step flag) into every peer's signal area; a waiting kernel spins
+// (bounded) on its own area.  All ranks issue the same sequence of calls, `step` counts them.
+static __global__ void k_signal_a(PeerPtrs sig, int rank, int nranks, double step, const double *__restrict__ localDisp)
+{
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    volatile double *dst = sig.p[r];
+    dst[kSigDisp + rank] = *localDisp;
+    __threadfence_system();
+    dst[kSigFlagA + rank] = step;
+}
+
+static __global__ void k_signal_b(PeerPtrs sig, int rank, int nranks, double step, const double *__restrict__ scal15)
+{
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    volatile double *dst = sig.p[r];
+    for (int k = 0; k < 15; k++) dst[kSigScal + 16 * rank + k] = scal15[k];
+    __threadfence_system();
+    dst[kSigFlagB + rank] = step;
+}
+
+// wait for all ranks' flags (bounded spin: ~2 s, then the timeout flag is raised instead of hanging the GPU), then reduce
+static __global__ void k_wait(double *sigOwn, int flagBase, int nranks, double step, int mode /* 0: max of disp, 1: sum of scalars */, double *out, double *timeout)
+{
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        volatile double *f = sigOwn + flagBase + r;
+        long spins = 0;
+        while (*f < step) { __nanosleep(200); if (++spins > 10000000L) { ok = 0; break; } }
+    }
+    __threadfence_system();
+    __syncthreads();
+    volatile double *v = sigOwn;
+    if (mode == 0) {
+        if (threadIdx.x == 0) { double m = 0.0; for (int k = 0; k < nranks; k++) m = fmax(m, v[kSigDisp + k]); out[0] = m; }
+    } else if (threadIdx.x < 15) {
+        double t = 0.0;
+        for (int k = 0; k < nranks; k++) t += v[kSigScal + 16 * k + threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0 && !ok) *timeout = 1.0;
+}
+
+/* after nbb200_peer_begin: tell every rank that this rank's accumulator is zeroed and its positions are published, together with its
+ * local displacement maximum (forceRebuild != 0: 1e300).  Stream ordered, no host wait. */
+void nbb200_peer_signal_begin(NBB200State *state, long step, const double *d_x, int forceRebuild)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (forceRebuild || s.isNew || d_x == nullptr) {
+        const double big = 1.0e300;
+        cudaMemcpyAsync(s.sigStage.p, &big, sizeof(double), cudaMemcpyHostToDevice, s.stream);      // pageable 8 bytes: staged by the driver
+    } else displacement_enqueue(s, d_x, s.sigStage.p);
+    PeerPtrs P;
+    for (int r = 0; r < State::kMaxPeers; r++) P.p[r] = s.peerSig[r];
+    k_signal_a<<<1, 32, 0, s.stream>>>(P, s.rank, s.nranks, (double) step, s.sigStage.p);
+    s.launches += 1;
+}
+
+/* wait until every rank has signalled `step`; returns the maximum over the ranks of the displacement maxima (one host
+ * synchronisation: the caller decides about the rebuild).  status: logic error on a time-out. */
+double nbb200_peer_wait_begin(NBB200State *state, long step, int needValue, int *status)
+{
+    if (state == nullptr) return 0.0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    k_wait<<<1, 32, 0, s.stream>>>(s.symSig.p, kSigFlagA, s.nranks, (double) step, 0, s.sigStage.p + 17, s.sigStage.p + 33);
+    s.launches += 1;
+    if (!needValue) return 1.0e300;                            // the caller knows the decision (forced rebuild): ordering only, no host wait
+    double out[17] = {0};
+    if (!cuda_ok(cudaMemcpyAsync(s.hsmall + (kSmallDoubles - 192), s.sigStage.p + 17, sizeof(double) * 17, cudaMemcpyDeviceToHost, s.stream), "D2H") ||
+        !cuda_ok(cudaStreamSynchronize(s.stream), "sync")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0.0; }
+    std::memcpy(out, s.hsmall + (kSmallDoubles - 192), sizeof(out));
+    if (out[16] != 0.0) { set_error("time-out waiting for the other ranks (begin)"); set_status(status, NBB200_STATUS_LOGIC_ERROR); }
+    return out[0];
+}
+
+/* after nbb200_peer_push_gradients: hand the 15 scalars (6 energies, dE/dM) to every rank and tell them that this rank's pushes are done */
+void nbb200_peer_signal_end(NBB200State *state, long step, const double *scal15)
+{
+    if (state == nullptr || scal15 == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    double *stage = s.hsmall + (kSmallDoubles - 64);           // pinned; the accumulators of the energy call use the front of hsmall
+    std::memcpy(stage, scal15, sizeof(double) * 15);
+    cudaMemcpyAsync(s.sigStage.p + 1, stage, sizeof(double) * 15, cudaMemcpyHostToDevice, s.stream);
+    PeerPtrs P;
+    for (int r = 0; r < State::kMaxPeers; r++) P.p[r] = s.peerSig[r];
+    k_signal_b<<<1, 32, 0, s.stream>>>(P, s.rank, s.nranks, (double) step, s.sigStage.p + 1);
+    s.launches += 1;
+}
+
+/* wait (on the stream) until every rank has signalled the end of `step`: all pushes into this rank's accumulator are complete and the
+ * scalars are summed; no host wait -- nbb200_peer_read_sums fetches them */
+void nbb200_peer_wait_end(NBB200State *state, long step)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    k_wait<<<1, 32, 0, s.stream>>>(s.symSig.p, kSigFlagB, s.nranks, (double) step, 1, s.sigStage.p + 34, s.sigStage.p + 33);
+    s.launches += 1;
+    cudaMemcpyAsync(s.hsmall + (kSmallDoubles - 128), s.sigStage.p + 33, sizeof(double) * 17, cudaMemcpyDeviceToHost, s.stream);   // [timeout, 15 sums]
+}
+
+void nbb200_peer_read_sums(NBB200State *state, double *sum15, int *status)
+{
+    if (state == nullptr || sum15 == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (!cuda_ok(cudaStreamSynchronize(s.stream), "sync")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+    std::memcpy(sum15, s.hsmall + (kSmallDoubles - 128) + 1, sizeof(double) * 15);
+    if (s.hsmall[kSmallDoubles - 128] != 0.0) { set_error("time-out waiting for the other ranks"); set_status(status, NBB200_STATUS_LOGIC_ERROR); }
 }
 
 /* start of a call: zero the own gradient accumulator and publish the positions of the own slab (sorted order), all on the stream */

@@ -165,6 +165,16 @@ bool displacement_check(State &s, double buffacsq, double *maxr2, int *exceeded)
     return true;
 }
 
+bool displacement_enqueue(State &s, const double *d_x, double *d_out)
+{
+    NBB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), s.stream));
+    const int threads = 256;
+    const int nblk = std::max(1, std::min(1184, (s.n + threads - 1) / threads));
+    k_displacement<<<nblk, threads, 0, s.stream>>>(d_x, s.xref.p, s.n, s.nfixed > 0 ? s.fixedFlag.p : nullptr, 0.0, reinterpret_cast<unsigned long long *>(d_out));
+    s.launches += 1;
+    return cuda_ok(cudaGetLastError(), "k_displacement");
+}
+
 // ------------------------------------------------------------------------------------------------------
 // useCentering: NBModelABFSState_InitializeCoordinates3 (pM/csource/NBModelABFSState.c:278-311).  On a list update every isolate
 // (molecule) is translated by whole lattice vectors so that its centre lies in the primary cell

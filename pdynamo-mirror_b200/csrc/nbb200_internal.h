@@ -89,6 +89,7 @@ bool build_lists(State &s);                              // everything between "
 bool expand_pairs(State &s);                             // explicit (i,j) pairs per list from the tile masks
 bool device_bbox(State &s, int nops, double *hostMin, double *hostExt);
 bool displacement_check(State &s, double buffacsq, double *maxr2, int *exceeded);
+bool displacement_enqueue(State &s, const double *d_x, double *d_out);   // max |x - xref|^2 into a device double, no host synchronisation
 bool centre_coordinates(State &s, const double *d_xin, bool doUpdate);   // useCentering: fills s.xc (and s.isoT on updates)
 bool touched_ranges(State &s, long *out);
 bool touched_ranges_async(State &s, long *d_out);      // the same table written to a device array, no host synchronisation                // per rank slab: [lo, hi) of the sorted positions this rank's lists reference
@@ -185,7 +186,9 @@ struct State {
     // peer memory (CUDA IPC, one process per GPU of one node): every rank's sorted-order gradient accumulator and sorted positions
     static constexpr int kMaxPeers = 16;
     DevBuf<double> symGs, symXs;                 // this rank's buffers (cudaMalloc: exportable)
-    double *peerGs[kMaxPeers] = {}, *peerXs[kMaxPeers] = {};
+    DevBuf<double> symSig;                       // signal area written by the peers: step flags, displacement maxima, the 15 scalars
+    double *peerGs[kMaxPeers] = {}, *peerXs[kMaxPeers] = {}, *peerSig[kMaxPeers] = {};
+    DevBuf<double> sigStage;                     // device staging: [0] local displacement maximum, [1..16] scalars, [17..32] results, [33] timeout flag
     bool peerOpened[kMaxPeers] = {};
     bool peersReady = false;
     bool gradOverwrite = false;                  // MMMMEnergy (host arrays) sets the caller's gradient instead of accumulating

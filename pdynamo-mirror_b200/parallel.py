@@ -150,10 +150,11 @@ class DistributedNB:
     order on every rank; a rank keeps the positions of its own atoms current (after the first call, which takes a replicated x)
     and receives the gradient of its own atoms.
 
-    transport "peer" (default on GPUs): the ranks map each other's buffers (CUDA IPC over NVLink) and the two halo exchanges are
-    plain kernels of the library -- pull positions from their owners, push gradient contributions into the owners' accumulators
-    with atomics; the only collectives are the ones the call needs anyway (update decision, all-reduce of 15 scalars), and they
-    double as the barriers that order the peer accesses.  transport "p2p": the same exchanges as send/recv messages (SlabExchange)."""
+    transport "peer" (default on GPUs): the ranks map each other's buffers (CUDA IPC over NVLink); the two halo exchanges AND the
+    synchronisation are plain kernels of the library -- pull positions from their owners, push gradient contributions into the
+    owners' accumulators with atomics, write (value, step flag) pairs into the peers' signal areas and spin (bounded) on the own one
+    for the update decision and the sum of the 15 scalars.  No library collective inside a call (NCCL only hands the IPC handles
+    round at set-up).  transport "p2p": the same exchanges as NCCL / gloo send/recv messages (SlabExchange) plus two all-reduces."""
 
     def __init__(self, state, n, buffer_distance, rank, world, device, group=None, transport=None):
         import torch
@@ -177,17 +178,19 @@ class DistributedNB:
         self.tab_all = torch.zeros(4 * world * world, dtype=torch.int64, device=device)
         self.tab_host = torch.zeros(4 * world * world, dtype=torch.int64).pin_memory()
         if self.transport == "peer":
-            buf = C.create_string_buffer(128)
+            buf = C.create_string_buffer(192)
             if not self.L.nbb200_peer_export(self.h, buf):
                 raise RuntimeError("peer export failed: " + _lib.last_error())
             mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(device)
-            allh = torch.empty(128 * world, dtype=torch.uint8, device=device)
+            allh = torch.empty(192 * world, dtype=torch.uint8, device=device)
             dist.all_gather_into_tensor(allh, mine, group=group)
             allh = allh.cpu().numpy().tobytes()
             for r in range(world):
-                if not self.L.nbb200_peer_import(self.h, r, allh[128 * r:128 * (r + 1)]):
+                if not self.L.nbb200_peer_import(self.h, r, allh[192 * r:192 * (r + 1)]):
                     raise RuntimeError("peer import failed: " + _lib.last_error())
+            dist.barrier(group=group)                        # every signal area is zeroed and mapped before the first call
             self.gs = self.xs = None
+            self.step, self.sums = 0, np.zeros(15)
         else:
             self.gs = torch.zeros((n, 3), dtype=torch.float64, device=device)
             self.xs = torch.zeros((n, 3), dtype=torch.float64, device=device)
@@ -212,7 +215,10 @@ class DistributedNB:
             self._t = now
 
     def halo_atoms(self):
-        self.exchange.table = self.tab_all.cpu().numpy().reshape(self.world, self.world, 2, 2)
+        if self.transport == "peer":
+            self.exchange.table[self.rank] = self.tab_mine.cpu().numpy().reshape(self.world, 2, 2)
+        else:
+            self.exchange.table = self.tab_all.cpu().numpy().reshape(self.world, self.world, 2, 2)
         return self.exchange.halo_atoms()
 
     def _decide(self, xp, box, force_rebuild, st):
@@ -220,8 +226,6 @@ class DistributedNB:
         peer accesses of this call behind every rank's nbb200_peer_begin.  force_rebuild must be the same on all ranks."""
         import torch.distributed as dist
         if force_rebuild:
-            if self.transport == "peer":
-                dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)   # barrier only: stream ordered, no host wait
             return True
         moved = self.L.nbb200_max_displacement(self.h, xp, C.byref(st)) > self.buffac2
         changed = self.box is None or not np.array_equal(self.box, box)
@@ -240,27 +244,36 @@ class DistributedNB:
         xp = C.c_void_p(x.data_ptr())
         box = np.ascontiguousarray(box, np.float64)
         rebuild = True
-        if self.first:
-            if peer:                                         # zero the accumulator before anybody can push into it
+        changed = self.box is None or not np.array_equal(self.box, box)
+        if peer:
+            # begin: zero the accumulator, publish the own positions, signal; wait for everybody (also the global update decision)
+            self.step += 1
+            if self.first:
                 L.nbb200_peer_begin(self.h, None, 0, 0)
-                dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)
-        else:
-            s0, s1 = self.slabs[self.rank]
-            if peer:
+            else:
+                s0, s1 = self.slabs[self.rank]
                 L.nbb200_peer_begin(self.h, xp, s0, s1 - s0)
+            forced = bool(self.first or force_rebuild or changed)      # known on every rank: the decision needs no host wait
+            L.nbb200_peer_signal_begin(self.h, self.step, xp, 1 if forced else 0)
+            rebuild = L.nbb200_peer_wait_begin(self.h, self.step, 0 if forced else 1, C.byref(st)) > self.buffac2
+            if st.value != 16:
+                raise RuntimeError("distributed begin failed: " + self._lib.last_error())
+            self._tick("decide")
+            if not self.first:
+                edges = (C.c_long * (self.world + 1))(*([sl[0] for sl in self.slabs] + [self.n]))
+                L.nbb200_peer_pull_positions(self.h, C.c_void_p(self.tab_mine.data_ptr()), edges, 1 if rebuild else 0, xp)
+            self._tick("positions")
+        elif not self.first:
+            s0, s1 = self.slabs[self.rank]
             rebuild = self._decide(xp, box, force_rebuild, st)
             self._tick("decide")
-            if peer:
-                edges = (C.c_long * (self.world + 1))(*([sl[0] for sl in self.slabs] + [self.n]))
-                L.nbb200_peer_pull_positions(self.h, C.c_void_p(self.tab_all.data_ptr()), edges, 1 if rebuild else 0, xp)
-            else:
-                L.nbb200_gather_sorted(self.h, xp, s0, s1 - s0, C.c_void_p(self.xs[s0:].data_ptr()))
-                if rebuild:                                  # every rank needs every position for the sort
-                    self.exchange.allgather_slabs(self.xs, self.slabs)
-                    L.nbb200_scatter_sorted(self.h, C.c_void_p(self.xs.data_ptr()), 0, self.n, xp)
-                else:                                        # positions of the halo atoms only
-                    for lo, hi in self.exchange.owners_to_halo(self.xs):
-                        L.nbb200_scatter_sorted(self.h, C.c_void_p(self.xs[lo:].data_ptr()), lo, hi - lo, xp)
+            L.nbb200_gather_sorted(self.h, xp, s0, s1 - s0, C.c_void_p(self.xs[s0:].data_ptr()))
+            if rebuild:                                      # every rank needs every position for the sort
+                self.exchange.allgather_slabs(self.xs, self.slabs)
+                L.nbb200_scatter_sorted(self.h, C.c_void_p(self.xs.data_ptr()), 0, self.n, xp)
+            else:                                            # positions of the halo atoms only
+                for lo, hi in self.exchange.owners_to_halo(self.xs):
+                    L.nbb200_scatter_sorted(self.h, C.c_void_p(self.xs[lo:].data_ptr()), lo, hi - lo, xp)
             self._tick("positions")
         updated = L.NBModelABFS_B200_UpdateDeviceDecided(self.h, xp, self._lib.d_(box), 1 if rebuild else 0, C.byref(st))
         if st.value != 16:
@@ -271,8 +284,8 @@ class DistributedNB:
             self.updates += 1
             if not L.nbb200_touched_ranges_device(self.h, C.c_void_p(self.tab_mine.data_ptr())):
                 raise RuntimeError("touched ranges failed: " + self._lib.last_error())
-            dist.all_gather_into_tensor(self.tab_all, self.tab_mine, group=self.group)
-            if not peer:
+            if not peer:                                     # send/recv messages need the other ranks' tables (sizes on both sides)
+                dist.all_gather_into_tensor(self.tab_all, self.tab_mine, group=self.group)
                 self.tab_host.copy_(self.tab_all, non_blocking=True)
             self.slabs = self._slabs()
         self.first, self.box = False, box.copy()
@@ -282,22 +295,35 @@ class DistributedNB:
         self._tick("energy")
         s0, s1 = self.slabs[self.rank]
         if peer:
-            L.nbb200_peer_push_gradients(self.h, C.c_void_p(self.tab_all.data_ptr()))
-        else:
-            if updated:                                      # read after the energy call has synchronised the stream
-                self.exchange.table = self.tab_host.numpy().reshape(self.world, self.world, 2, 2).copy()
-                self.exchange._recv = {}
-            self.exchange.halo_to_owners(self.gs)
+            L.nbb200_peer_push_gradients(self.h, C.c_void_p(self.tab_mine.data_ptr()))
+            self._tick("gradients")
+            scal = np.concatenate([self.energies, self.dEdM])
+            L.nbb200_peer_signal_end(self.h, self.step, self._lib.d_(scal))
+            L.nbb200_peer_wait_end(self.h, self.step)          # on the stream: all pushes into the own slab are complete, scalars summed
+            if g is not None:
+                L.nbb200_unsort_add(self.h, s0, s1 - s0, C.c_void_p(g.data_ptr()))
+            self._tick("scalars")
+            return updated
+        if updated:                                          # read after the energy call has synchronised the stream
+            self.exchange.table = self.tab_host.numpy().reshape(self.world, self.world, 2, 2).copy()
+            self.exchange._recv = {}
+        self.exchange.halo_to_owners(self.gs)
         self._tick("gradients")
         self.small_host[:6] = self.torch.from_numpy(self.energies)
         self.small_host[6:] = self.torch.from_numpy(self.dEdM)
         self.small.copy_(self.small_host, non_blocking=True)
-        dist.all_reduce(self.small, group=self.group)        # also orders the unsort below behind every rank's push
+        dist.all_reduce(self.small, group=self.group)
         if g is not None:
             L.nbb200_unsort_add(self.h, s0, s1 - s0, C.c_void_p(g.data_ptr()))
         self._tick("scalars")
         return updated
 
     def results(self):
+        if self.transport == "peer":
+            st = C.c_int(16)
+            self.L.nbb200_peer_read_sums(self.h, self._lib.d_(self.sums), C.byref(st))
+            if st.value != 16:
+                raise RuntimeError("distributed end failed: " + self._lib.last_error())
+            return self.sums[:6].copy(), self.sums[6:].reshape(3, 3).copy()
         out = self.small.cpu().numpy()
         return out[:6].copy(), out[6:].reshape(3, 3).copy()
