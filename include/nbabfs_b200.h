@@ -199,6 +199,7 @@ void nbb200_unsort_add(NBB200State *state, long s0, long count, double *d_grad);
  * d_row: the rank's own range table, device array [nranks][2][2] (long) as written by nbb200_touched_ranges_device. */
 int  nbb200_peer_export(NBB200State *state, char *handles192);
 int  nbb200_peer_import(NBB200State *state, int rank, const char *handles192);
+int  nbb200_peer_attach_local(NBB200State *state, int rank, NBB200State *other);   /* same process, same device: rank `rank` is `other` */
 void nbb200_peer_begin(NBB200State *state, const double *d_x, long s0, long count);
 void nbb200_peer_signal_begin(NBB200State *state, long step, const double *d_x, int forceRebuild);
 double nbb200_peer_wait_begin(NBB200State *state, long step, int needValue, int *status);   /* needValue = 0: ordering only, no host wait */

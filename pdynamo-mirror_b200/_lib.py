@@ -56,6 +56,7 @@ SIGNATURES = {
     "nbb200_unsort_add": (None, [vp, C.c_long, C.c_long, vp]),
     "nbb200_peer_export": (C.c_int, [vp, C.c_char_p]),
     "nbb200_peer_import": (C.c_int, [vp, C.c_int, C.c_char_p]),
+    "nbb200_peer_attach_local": (C.c_int, [vp, C.c_int, vp]),
     "nbb200_peer_begin": (None, [vp, vp, C.c_long, C.c_long]),
     "nbb200_peer_pull_positions": (None, [vp, vp, lp, C.c_int, vp]),
     "nbb200_peer_push_gradients": (None, [vp, vp]),

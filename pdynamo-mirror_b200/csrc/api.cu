@@ -776,6 +776,19 @@ int nbb200_peer_import(NBB200State *state, int rank, const char *handles192)
     return 1;
 }
 
+/* same-process variant of nbb200_peer_import (an IPC handle cannot be opened by the process that exported it): rank `rank` is the
+ * state `other` on the same device.  For single-GPU tests of the peer kernels and for callers that run several partitions per process. */
+int nbb200_peer_attach_local(NBB200State *state, int rank, NBB200State *other)
+{
+    if (state == nullptr || other == nullptr || rank < 0 || rank >= State::kMaxPeers) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    State &o = *reinterpret_cast<State *>(other);
+    if (o.symGs.p == nullptr || o.symXs.p == nullptr || o.symSig.p == nullptr) return 0;      // nbb200_peer_export allocates them
+    s.peerGs[rank] = o.symGs.p; s.peerXs[rank] = o.symXs.p; s.peerSig[rank] = o.symSig.p;
+    s.peersReady = true;
+    return 1;
+}
+
 // ---- signalling through peer memory: a rank writes (value, step flag) into every peer's signal area; a waiting kernel spins
 // (bounded) on its own area.  All ranks issue the same sequence of calls, `step` counts them.
 static __global__ void k_signal_a(PeerPtrs sig, int rank, int nranks, double step, const double *__restrict__ localDisp)

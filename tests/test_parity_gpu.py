@@ -324,6 +324,110 @@ def test_slab_halo_exchange_emulated_on_one_gpu(pkg, name):
     assert np.allclose(dms.reshape(3, 3), dm, rtol=1e-5, atol=1e-3)
 
 
+def test_peer_memory_transport_three_partitions_one_gpu(pkg):
+    """The peer-memory transport itself (pull positions, push gradients, signal / bounded-spin-wait kernels) with three partitions
+    in ONE process on one GPU (nbb200_peer_attach_local instead of CUDA IPC): a forced-rebuild call, then a call without rebuild on
+    displaced coordinates where every partition only knows the new positions of its own atoms.  Owners' gradients and the summed
+    scalars must match the unpartitioned state."""
+    import ctypes as C
+    import torch
+    from pdynamo_mirror_b200 import _lib
+    from pdynamo_mirror_b200.parallel import slab_range
+    L = _lib.lib()
+    w = pkg.workloads.WORKLOADS["dhfr"]()
+    n, R = w["n"], 3
+    box = np.ascontiguousarray(w["box"], np.float64)
+    x0 = w["xyz"].copy()
+    x1 = x0 + 0.05 * np.sin(np.arange(x0.size).reshape(-1, 3))          # below the 0.75 A buffer: no rebuild
+    ref = pkg.System.FromWorkload(w); ref.DefineNBModel(pkg.NBModelABFS()); ref.Energy(doGradients=True)
+    e0, g0 = ref.configuration.nbState.energies.copy(), ref.configuration.gradients3.copy()
+    ref.coordinates3[...] = x1; ref.Energy(doGradients=True)
+    assert ref.configuration.nbState.numberOfUpdates == 1
+    e1, g1 = ref.configuration.nbState.energies.copy(), ref.configuration.gradients3.copy()
+
+    systems, hs, xs, rows = [], [], [], []
+    for rank in range(R):
+        s2 = pkg.System.FromWorkload(w); s2.DefineNBModel(pkg.NBModelABFS()); s2.Energy()
+        h = s2.configuration.nbState.cObject
+        L.nbb200_set_partition(h, rank, R)
+        assert L.nbb200_peer_export(h, C.create_string_buffer(192)) == 1
+        systems.append(s2); hs.append(h)
+        xs.append(torch.from_numpy(x0).cuda())
+        rows.append(torch.zeros(4 * R, dtype=torch.int64, device="cuda"))
+    for a in range(R):
+        for b in range(R):
+            assert L.nbb200_peer_attach_local(hs[a], b, hs[b]) == 1
+    status = C.c_int(16)
+    slabs = None
+
+    def one_call(step, forced, xnew):
+        nonlocal slabs
+        total = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+        es = []
+        if slabs is not None:
+            for r in range(R):                               # a rank only knows its own atoms' new positions
+                own = torch.from_numpy(np.ascontiguousarray(sys_atoms[r]))
+                xs[r][own.cuda()] = torch.from_numpy(xnew[sys_atoms[r]]).cuda()
+        torch.cuda.synchronize()                             # torch's stream -> the states' own streams
+        for r in range(R):                                   # phase 1: everybody publishes and signals
+            if slabs is None:
+                L.nbb200_peer_begin(hs[r], None, 0, 0)
+            else:
+                s0, s1 = slabs[r]
+                L.nbb200_peer_begin(hs[r], C.c_void_p(xs[r].data_ptr()), s0, s1 - s0)
+            L.nbb200_peer_signal_begin(hs[r], step, C.c_void_p(xs[r].data_ptr()), 1 if forced else 0)
+        for r in range(R):                                   # phase 2: wait, pull, update, energy, push, signal
+            d = L.nbb200_peer_wait_begin(hs[r], step, 0 if forced else 1, C.byref(status))
+            rebuild = forced or d > 0.75 ** 2
+            assert rebuild == forced
+            if slabs is not None:
+                edges = (C.c_long * (R + 1))(*([sl[0] for sl in slabs] + [n]))
+                L.nbb200_peer_pull_positions(hs[r], C.c_void_p(rows[r].data_ptr()), edges, 1 if rebuild else 0, C.c_void_p(xs[r].data_ptr()))
+            L.NBModelABFS_B200_UpdateDeviceDecided(hs[r], C.c_void_p(xs[r].data_ptr()), _lib.d_(box), 1 if rebuild else 0, C.byref(status))
+            if rebuild:
+                assert L.nbb200_touched_ranges_device(hs[r], C.c_void_p(rows[r].data_ptr())) == 1
+            ee, dd = np.zeros(6), np.zeros(9)
+            L.NBModelABFS_B200_MMMMEnergySorted(hs[r], _lib.d_(ee), _lib.d_(dd), C.byref(status))
+            L.nbb200_peer_push_gradients(hs[r], C.c_void_p(rows[r].data_ptr()))
+            L.nbb200_peer_signal_end(hs[r], step, _lib.d_(np.concatenate([ee, dd])))
+            es.append(ee)
+        assert status.value == 16, _lib.last_error()
+        if forced:
+            slab = (C.c_long * 4)()
+            L.nbb200_get_slab(hs[0], slab)
+            slabs = [slab_range(int(slab[3]), n, r, R) for r in range(R)]
+        sums = []
+        for r in range(R):                                   # phase 3: wait for everybody's pushes, unsort the own slab, read the sums
+            L.nbb200_peer_wait_end(hs[r], step)
+            s0, s1 = slabs[r]
+            L.nbb200_unsort_add(hs[r], s0, s1 - s0, C.c_void_p(total.data_ptr()))
+            out = np.zeros(15)
+            L.nbb200_peer_read_sums(hs[r], _lib.d_(out), C.byref(status))
+            sums.append(out)
+        assert status.value == 16, _lib.last_error()
+        return total.cpu().numpy(), sums
+
+    g, sums = one_call(1, True, x0)
+    # which atoms does each partition own (for the second call)?  the owners' gradient rows are the non-zero rows of the unsort
+    owner_rows = []
+    for r in range(R):
+        t = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        s0, s1 = slabs[r]
+        L.nbb200_unsort_add(hs[r], s0, s1 - s0, C.c_void_p(t.data_ptr()))
+        L.nbb200_peer_read_sums(hs[r], _lib.d_(np.zeros(15)), C.byref(status))          # synchronises the state's stream
+        owner_rows.append(np.nonzero(np.abs(t.cpu().numpy()).sum(1) > 0)[0])
+    sys_atoms = owner_rows
+    assert sum(len(a) for a in sys_atoms) == n
+    for out in sums:
+        assert np.allclose(out[:6], e0, rtol=2e-7, atol=1e-6)
+    assert np.sqrt(((g - g0) ** 2).mean()) <= 2e-6 * np.sqrt((g0 ** 2).mean())
+    g, sums = one_call(2, False, x1)
+    for out in sums:
+        assert np.allclose(out[:6], e1, rtol=2e-7, atol=1e-6)
+    assert np.sqrt(((g - g1) ** 2).mean()) <= 2e-6 * np.sqrt((g1 ** 2).mean())
+
+
 def test_centring_is_carried_between_updates(pkg, orc):
     """useCentering: on calls without a list update the isolate translations of the last update are re-applied to the new input
     coordinates (NBModelABFSState_InitializeCoordinates3, doUpdate = False); a larger move triggers an update and a new centring."""
