@@ -178,17 +178,24 @@ class DistributedNB:
         self.tab_all = torch.zeros(4 * world * world, dtype=torch.int64, device=device)
         self.tab_host = torch.zeros(4 * world * world, dtype=torch.int64).pin_memory()
         if self.transport == "peer":
+            # map everybody's buffers (CUDA IPC).  The outcome is agreed collectively: if any rank cannot export / import (e.g. processes
+            # in different PID namespaces), all ranks fall back to the message transport.
             buf = C.create_string_buffer(192)
-            if not self.L.nbb200_peer_export(self.h, buf):
-                raise RuntimeError("peer export failed: " + _lib.last_error())
+            ok = bool(self.L.nbb200_peer_export(self.h, buf))
             mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(device)
             allh = torch.empty(192 * world, dtype=torch.uint8, device=device)
             dist.all_gather_into_tensor(allh, mine, group=group)
             allh = allh.cpu().numpy().tobytes()
             for r in range(world):
-                if not self.L.nbb200_peer_import(self.h, r, allh[192 * r:192 * (r + 1)]):
-                    raise RuntimeError("peer import failed: " + _lib.last_error())
-            dist.barrier(group=group)                        # every signal area is zeroed and mapped before the first call
+                ok = ok and bool(self.L.nbb200_peer_import(self.h, r, allh[192 * r:192 * (r + 1)]))
+            agreed = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=device)
+            dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=group)   # also: every signal area is zeroed and mapped before the first call
+            if float(agreed.item()) < 1.0:
+                import warnings
+                warnings.warn("peer-memory transport unavailable (%s); using NCCL send/recv" % _lib.last_error())
+                self.transport = "p2p"
+                self.L.nbb200_set_sorted_gradient_buffer(self.h, None)
+        if self.transport == "peer":
             self.gs = self.xs = None
             self.step, self.sums = 0, np.zeros(15)
         else:
@@ -222,8 +229,8 @@ class DistributedNB:
         return self.exchange.halo_atoms()
 
     def _decide(self, xp, box, force_rebuild, st):
-        """Collective update decision (all ranks rebuild together).  Always one all-reduce: it is also the barrier that orders the
-        peer accesses of this call behind every rank's nbb200_peer_begin.  force_rebuild must be the same on all ranks."""
+        """Message transport: collective update decision (all ranks rebuild together) with an all-reduce.  force_rebuild must be the
+        same on all ranks (it skips the collective)."""
         import torch.distributed as dist
         if force_rebuild:
             return True
