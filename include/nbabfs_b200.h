@@ -79,6 +79,19 @@ void NBModelABFS_B200_SetOptions(NBB200State *state, double dampingCutoff, doubl
                                  double listCutoff, double dielectric, double electrostaticScale14,
                                  int checkForInverses, int imageExpandFactor);
 
+/* replaces PairwiseInteractionABFS.SetOptions(useAnalyticForm, splinePointDensity) + MakeSplines for the MM/MM interaction
+ * (pM/pyrex/pMolecule.PairwiseInteraction.pyx:204-239, called from NBModelABFS.CheckPairwiseInteractions, pMolecule.NBModelABFS.pyx:73-82):
+ * useAnalyticForm = 0 selects the cubic-spline branch of PairwiseInteractionABFS_MMMMEnergy (pM/csource/PairwiseInteraction.c:431-531)
+ * for the primary, image and 1-4 terms; the three Delta/Delta tables (PairwiseInteractionABFS_Make{Electrostatic,LennardJonesA,
+ * LennardJonesB}Spline, :148-285, splinePointDensity points per Angstrom, reference default 50) are built from the state's cutoffs
+ * and rebuilt by NBModelABFS_B200_SetOptions.  Default: analytic form (pM/csource/PairwiseInteraction.c:34). */
+void PairwiseInteractionABFS_B200_SetInteractionForm(NBB200State *state, int useAnalyticForm, int splinePointDensity, int *status);
+/* host helper: the table PairwiseInteractionABFS_Make*Spline builds (which = 0 electrostatic in kJ/mol, 1 LJ-A, 2 LJ-B): abscissae
+ * x = r^2, ordinates y and second derivatives h as CubicSpline_MakeFromReal1DArrays leaves them (pC/csource/CubicSpline.c:309-420).
+ * Returns the number of points (pM/cinclude/PairwiseInteraction.h:166-167); with x, y or h NULL only that. */
+int PairwiseInteractionABFS_B200_MakeSpline(int which, double dampingCutoff, double innerCutoff, double outerCutoff, int splinePointDensity,
+                                            double *x, double *y, double *h);
+
 /* replaces NBModelABFSState_Initialize (pM/csource/NBModelABFSState.c:231-273) + NBModelABFS_Update
  * (pM/csource/NBModelABFS.c:508-623): takes this call's coordinates (host, xyz[3n]) and lattice
  * box6 = {a,b,c,alpha,beta,gamma} (ignored when ntrans = 0), decides with the reference's heuristics

@@ -20,6 +20,7 @@
 #define ORC_ECHARGE  1.60217653e-19
 #define ORC_EPS0     8.854187817e-12
 #define ORC_E2A_TO_KJMOL ((1.0e+7 * ORC_AVOGADRO * ORC_ECHARGE * ORC_ECHARGE) / (4.0e+00 * M_PI * ORC_EPS0))
+#define ORC_ANGSTROMS_TO_BOHRS (1.0e-10 / 5.291772083e-11)   /* pC/cinclude/Units.h:21,55-57 */
 #define ORC_DEG2RAD (M_PI / 180.0e+00)
 
 typedef struct {
@@ -48,6 +49,9 @@ struct OrcNB {
     /* options */
     double damp, inner, outer, list, dielectric, scale14;
     int checkForInverses, expandFactor;
+    int useAnalytic, density;         /* PairwiseInteractionABFS.useAnalyticForm / splinePointDensity */
+    int nsp;                          /* spline points */
+    double *spx, *spy[3], *sph[3];    /* shared abscissae x = r^2; ordinates and second derivatives of the electrostatic, LJ-A, LJ-B splines */
     /* state */
     int isNew;
     double stListCutoff, stOuterCutoff;
@@ -253,6 +257,155 @@ void orc_pair(const double *f21, double r2, double qij, double Aij, double Bij, 
     pair_terms(f21, r2, qij, Aij, Bij, &e2[0], &e2[1], dF);
 }
 
+/* ---------------------------------------------------------------------------------------------------
+ * spline form (PairwiseInteractionABFS.useAnalyticForm = False)
+ * ------------------------------------------------------------------------------------------------- */
+/* CubicSpline_MakeFromReal1DArrays with both boundary conditions "first derivative = 0" (pC/csource/CubicSpline.c:309-420): second
+ * derivatives h from the tridiagonal system, solved as LAPACK dgtsv does when no row interchange is needed (the system is diagonally
+ * dominant: |d_i| = (dl + du)/3 against off-diagonals dl/6, du/6) -- forward elimination, back substitution. */
+static void spline_second_derivatives(int n, const double *x, const double *y, double *h)
+{
+    double *dl = (double *) malloc(sizeof(double) * (size_t) n), *d = (double *) malloc(sizeof(double) * (size_t) n), *du = (double *) malloc(sizeof(double) * (size_t) n);
+    double l, u;
+    int i;
+    l = x[1] - x[0];
+    d[0] = l / 3.0e+00; du[0] = l / 6.0e+00; h[0] = (y[1] - y[0]) / l - 0.0e+00;
+    for (i = 1; i < n - 1; i++) {
+        l = x[i] - x[i - 1]; u = x[i + 1] - x[i];
+        dl[i - 1] = l / 6.0e+00; d[i] = (l + u) / 3.0e+00; du[i] = u / 6.0e+00;
+        h[i] = (y[i + 1] - y[i]) / u + (y[i - 1] - y[i]) / l;
+    }
+    u = x[n - 1] - x[n - 2];
+    dl[n - 2] = u / 6.0e+00; d[n - 1] = u / 3.0e+00; h[n - 1] = 0.0e+00 - (y[n - 1] - y[n - 2]) / u;
+    for (i = 0; i < n - 1; i++) {                       /* dgtsv, branch |d_i| >= |dl_i| */
+        double fact = dl[i] / d[i];
+        d[i + 1] = d[i + 1] - fact * du[i];
+        h[i + 1] = h[i + 1] - fact * h[i];
+    }
+    h[n - 1] = h[n - 1] / d[n - 1];
+    if (n > 1) h[n - 2] = (h[n - 2] - du[n - 2] * h[n - 1]) / d[n - 2];
+    for (i = n - 3; i >= 0; i--) h[i] = (h[i] - du[i] * h[i + 1] - 0.0e+00 * h[i + 2]) / d[i];
+    free(dl); free(d); free(du);
+}
+
+/* PairwiseInteractionABFS_Make{Electrostatic,LennardJonesA,LennardJonesB}Spline (pM/csource/PairwiseInteraction.c:148-285):
+ * which = 0 electrostatic in kJ/mol (3: atomic units), 1 LJ-A, 2 LJ-B; abscissae x_i = (i dR)^2, last point (r2Off, 0).
+ * Returns the number of points NumberOfSplinePoints gives (pM/cinclude/PairwiseInteraction.h:166-167); x == NULL: only that. */
+int orc_make_spline(int which, double damp, double inner, double outer, int density, double *x, double *y, double *hh)
+{
+    double F[21], dR, a = (double) density * outer;
+    int n = ((a >= 0) ? (int) (a + 0.5) : (int) (a - 0.5)) + 1, i;
+    if (n < 2) n = 2;
+    if (x == NULL) return n;
+    orc_make_factors(damp, inner, outer, F);
+    dR = outer / (double) (n - 1);
+    for (i = 0; i < n - 1; i++) {
+        double r = dR * (double) i, r2 = r * r, s, s2, s6, f;
+        x[i] = r2;
+        if (r2 < F[R2DAMP]) { s2 = 0.0e+00; s = 0.0e+00; } else { s2 = 1.0e+00 / r2; s = sqrt(s2); }
+        s6 = s2 * s2 * s2;
+        if (which == 0 || which == 3) {
+            if (r2 > F[R2ON])        f = 1.0e+00 * (s * (F[FA] - r2 * (F[FB] + r2 * (F[FC] + F[FD] * r2))) + F[QSHIFT2]);
+            else if (r2 > F[R2DAMP]) f = 1.0e+00 * (s + F[QSHIFT1]);
+            else                     f = 1.0e+00 * (F[QF0] - F[QALPHA] * r2);
+        } else if (which == 1) {
+            if (r2 > F[R2ON])        { double l1 = s6 - F[AF6]; f = 1.0e+00 * F[AK12] * pow(l1, 2); }
+            else if (r2 > F[R2DAMP]) f = 1.0e+00 * (s6 * s6 - F[ASHIFT12]);
+            else                     f = 1.0e+00 * (F[AF0] - F[AALPHA] * r2);
+        } else {
+            if (r2 > F[R2ON])        { double l2 = (s / r2) - F[BF3]; f = -1.0e+00 * F[BK6] * pow(l2, 2); }
+            else if (r2 > F[R2DAMP]) f = -1.0e+00 * (s6 - F[BSHIFT6]);
+            else                     f = -1.0e+00 * (F[BF0] - F[BALPHA] * r2);
+        }
+        y[i] = f;
+    }
+    x[n - 1] = F[R2OFF]; y[n - 1] = 0.0e+00;
+    if (which == 0) for (i = 0; i < n; i++) y[i] *= ORC_E2A_TO_KJMOL;                     /* Real1DArray_Scale = cblas_dscal */
+    if (which == 3) { double sc = 1.0e+00 / ORC_ANGSTROMS_TO_BOHRS; for (i = 0; i < n; i++) y[i] *= sc; }
+    spline_second_derivatives(n, x, y, hh);
+    return n;
+}
+
+/* CubicSpline_EvaluateLUDST + CubicSpline_FastEvaluateFG (pC/csource/CubicSpline.c:138-159, pC/cinclude/CubicSpline.h:30-39) */
+static inline void spline_ludst(int n, const double *x, double x0, int *l, int *u, double *d, double *s, double *t)
+{
+    int l0 = 0, u0 = n - 1, i;
+    while ((u0 - l0) > 1) { i = (u0 + l0) >> 1; if (x[i] > x0) u0 = i; else l0 = i; }
+    *l = l0; *u = u0;
+    *d = (x[u0] - x[l0]);
+    *s = (x0 - x[l0]) / (*d);
+    *t = (x[u0] - x0) / (*d);
+}
+static inline void spline_fg(const double *y, const double *h, int l, int u, double d, double s, double t, double *f, double *g)
+{
+    double hl = h[l] * d / 6.0e+00, hu = h[u] * d / 6.0e+00, yl = y[l], yu = y[u];
+    *f = t * yl + s * yu + d * (t * (t * t - 1.0e+00) * hl + s * (s * s - 1.0e+00) * hu);
+    *g = (yu - yl) / d + (-(3.0e+00 * t * t - 1.0e+00) * hl + (3.0e+00 * s * s - 1.0e+00) * hu);
+}
+void orc_spline_evaluate(int n, const double *x, const double *y, const double *h, double x0, double *f, double *g)
+{
+    int l, u; double d, s, t;
+    spline_ludst(n, x, x0, &l, &u, &d, &s, &t);
+    spline_fg(y, h, l, u, d, s, t, f, g);
+}
+
+static void make_splines(OrcNB *h)
+{
+    int k, n = orc_make_spline(0, h->damp, h->inner, h->outer, h->density, NULL, NULL, NULL);
+    free(h->spx); for (k = 0; k < 3; k++) { free(h->spy[k]); free(h->sph[k]); }
+    h->nsp = n;
+    h->spx = (double *) malloc(sizeof(double) * (size_t) n);
+    for (k = 0; k < 3; k++) {
+        h->spy[k] = (double *) malloc(sizeof(double) * (size_t) n); h->sph[k] = (double *) malloc(sizeof(double) * (size_t) n);
+        orc_make_spline(k, h->damp, h->inner, h->outer, h->density, h->spx, h->spy[k], h->sph[k]);
+    }
+}
+
+/* PairwiseInteractionABFS.SetOptions(useAnalyticForm, splinePointDensity) + MakeSplines; call after orc_set_options */
+void orc_set_interaction_form(OrcNB *h, int useAnalyticForm, int splinePointDensity)
+{
+    h->useAnalytic = useAnalyticForm; h->density = splinePointDensity;
+    make_splines(h);
+}
+
+/* PairwiseInteractionABFS_MMMMEnergy, spline branch: pM/csource/PairwiseInteraction.c:431-531.  Note the charge scale: the
+ * splines carry the kJ/mol unit, so qi = electrostaticScale * q_i (:474). */
+static void mmmm_energy_spline(const OrcNB *h, const int *tindex, const double *tA, const double *tB, int nt,
+                               long npairs, const int *pairs, double electrostaticScale, double ljScale,
+                               const double *crd1, const double *crd2, double *eElect, double *eLJ, double *grd1, double *grd2)
+{
+    double eQQ = 0.0e+00, eL = 0.0e+00, r2Off = h->outer * h->outer;
+    long p;
+    for (p = 0; p < npairs; p++) {
+        int i = pairs[2 * p], j = pairs[2 * p + 1], tij, l, u;
+        double qi = electrostaticScale * h->q[i], qij, Aij, Bij, d, s, t, f, dF, dG;
+        double xij = crd1[3 * i] - crd2[3 * j], yij = crd1[3 * i + 1] - crd2[3 * j + 1], zij = crd1[3 * i + 2] - crd2[3 * j + 2];
+        double r2 = (xij * xij + yij * yij + zij * zij);
+        if (r2 > r2Off) continue;
+        spline_ludst(h->nsp, h->spx, r2, &l, &u, &d, &s, &t);
+        dG = 0.0e+00;
+        qij = qi * h->q[j];
+        spline_fg(h->spy[0], h->sph[0], l, u, d, s, t, &f, &dF);
+        eQQ += (qij * f);
+        dG  += (2.0e+00 * qij * dF);
+        tij = tindex[nt * h->ljtype[i] + h->ljtype[j]];
+        Aij = tA[tij] * ljScale;
+        Bij = tB[tij] * ljScale;
+        spline_fg(h->spy[1], h->sph[1], l, u, d, s, t, &f, &dF);
+        eL += Aij * f;
+        dG += (2.0e+00 * Aij * dF);
+        spline_fg(h->spy[2], h->sph[2], l, u, d, s, t, &f, &dF);
+        eL += Bij * f;
+        dG += (2.0e+00 * Bij * dF);
+        if (grd1 != NULL) {
+            xij *= dG; yij *= dG; zij *= dG;
+            grd1[3 * i] += xij; grd1[3 * i + 1] += yij; grd1[3 * i + 2] += zij;
+            grd2[3 * j] -= xij; grd2[3 * j + 1] -= yij; grd2[3 * j + 2] -= zij;
+        }
+    }
+    *eElect = eQQ; *eLJ = eL;
+}
+
 /* PairwiseInteractionABFS_MMMMEnergy, analytic branch: pM/csource/PairwiseInteraction.c:292-429 (loop :374-427).
  * pairs[(i,j)]: i indexes crd1/grd1, j indexes crd2/grd2. */
 static void mmmm_energy(const OrcNB *h, const double *F, const int *tindex, const double *tA, const double *tB, int nt,
@@ -261,6 +414,7 @@ static void mmmm_energy(const OrcNB *h, const double *F, const int *tindex, cons
 {
     double eScale = electrostaticScale * ORC_E2A_TO_KJMOL, eQQ = 0.0e+00, eL = 0.0e+00;
     long p;
+    if (!h->useAnalytic) { mmmm_energy_spline(h, tindex, tA, tB, nt, npairs, pairs, electrostaticScale, ljScale, crd1, crd2, eElect, eLJ, grd1, grd2); return; }
     for (p = 0; p < npairs; p++) {
         int i = pairs[2 * p], j = pairs[2 * p + 1], tij;
         double qi = eScale * h->q[i], qij, Aij, Bij, eq, el, dF;
@@ -347,6 +501,7 @@ OrcNB *orc_create(int n, const double *charges, const int *ljtypes,
     h->xref = (double *) calloc(3 * (size_t) n, sizeof(double));
     h->isNew = 1;
     h->stListCutoff = h->stOuterCutoff = 0.0;
+    h->useAnalytic = 1; h->density = 50;                        /* pM/csource/PairwiseInteraction.c:34-35 */
     orc_set_options(h, 0.5, 8.0, 12.0, 13.5, 1.0, 1.0, 1, 0);   /* pM/csource/NBModelABFS.c:28-37 */
     return h;
 }
@@ -364,6 +519,7 @@ void orc_destroy(OrcNB *h)
     free_images(h);
     free(h->primary); free(h->xref); free(h->inverses); free(h->rot); free(h->trans); free(h->p14); free(h->p14all); free(h->fixed); free(h->isoPtr); free(h->isoIdx); free(h->xc); free(h->isoT);
     free(h->exclPtr); free(h->exclCol); free(h->tindex); free(h->tindex14); free(h->tA); free(h->tB); free(h->tA14); free(h->tB14);
+    free(h->spx); { int k; for (k = 0; k < 3; k++) { free(h->spy[k]); free(h->sph[k]); } }
     free(h->q); free(h->ljtype); free(h);
 }
 
@@ -449,6 +605,7 @@ void orc_set_options(OrcNB *h, double damp, double inner, double outer, double l
     h->damp = damp; h->inner = inner; h->outer = outer; h->list = list;
     h->dielectric = dielectric; h->scale14 = elecScale14;
     h->checkForInverses = checkForInverses; h->expandFactor = imageExpandFactor;
+    if (!h->useAnalytic) orc_set_interaction_form(h, 0, h->density);      /* the splines depend on the cutoffs */
 }
 
 /* ---------------------------------------------------------------------------------------------------

@@ -23,6 +23,8 @@ void   orc_set_fixed(OrcNB *h, int nfixed, const int *fixed);
 void   orc_set_centering(OrcNB *h, int on);                      /* NBModelABFS.useCentering (call after orc_set_fixed) */   /* NBModelABFSState_SetUp's fixedAtoms; 0 clears */
 void   orc_set_options(OrcNB *h, double damp, double inner, double outer, double list,
                        double dielectric, double elecScale14, int checkForInverses, int imageExpandFactor);
+/* PairwiseInteractionABFS.{useAnalyticForm, splinePointDensity} + MakeSplines (pMolecule.PairwiseInteraction.pyx:204-239); after orc_set_options */
+void   orc_set_interaction_form(OrcNB *h, int useAnalyticForm, int splinePointDensity);
 /* same contract as refnb_energy (oracle/ref_driver.h); timings[2] = list update, energy */
 int    orc_energy(OrcNB *h, const double *xyz, const double *box, int forceNew,
                   double *energies, double *grad, double *dEdM, double *timings);
@@ -37,6 +39,10 @@ void   orc_get_image_pairs(OrcNB *h, int k, int *pairs);
 void   orc_get_image_coordinates(OrcNB *h, int k, double *xyz);
 
 void   orc_make_factors(double damp, double inner, double outer, double *out21);
+/* spline tables of PairwiseInteractionABFS_Make*Spline: which = 0 electrostatic kJ/mol, 1 LJ-A, 2 LJ-B, 3 electrostatic atomic units;
+ * returns the number of points (x = NULL: only that); x, y, h: abscissae r^2, ordinates, second derivatives */
+int    orc_make_spline(int which, double damp, double inner, double outer, int density, double *x, double *y, double *h);
+void   orc_spline_evaluate(int n, const double *x, const double *y, const double *h, double x0, double *f, double *g);
 void   orc_make_M(const double *box6, double *M9, double *invM9);
 /* single pair: returns energies e[2] = {elect, lj} and dF = dE/d(r^2) for qij (already scaled), Aij, Bij */
 void   orc_pair(const double *f21, double r2, double qij, double Aij, double Bij, double *e2, double *dF);

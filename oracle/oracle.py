@@ -42,6 +42,10 @@ def _lib():
     lib.orc_get_image_coordinates.argtypes = [vp, C.c_int, dp]
     lib.orc_make_factors.argtypes = [C.c_double] * 3 + [dp]
     lib.orc_make_M.argtypes = [dp, dp, dp]
+    lib.orc_set_interaction_form.argtypes = [vp, C.c_int, C.c_int]
+    lib.orc_make_spline.restype = C.c_int
+    lib.orc_make_spline.argtypes = [C.c_int] + [C.c_double] * 3 + [C.c_int, dp, dp, dp]
+    lib.orc_spline_evaluate.argtypes = [C.c_int, dp, dp, dp, C.c_double, dp, dp]
     lib.orc_pair.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
     _LIB = lib
     return lib
@@ -74,7 +78,8 @@ class OracleNB:
                                      len(ex) // 2, _i(ex) if len(ex) else None, len(p14) // 2, _i(p14) if len(p14) else None,
                                      ntrans, _d(rot) if ntrans else None, _d(trn) if ntrans else None)
         self.opts = dict(dampingCutoff=0.5, innerCutoff=8.0, outerCutoff=12.0, listCutoff=13.5, dielectric=1.0,
-                         electrostaticScale14=s.get("electrostaticScale14", 1.0), checkForInverses=True, imageExpandFactor=0)
+                         electrostaticScale14=s.get("electrostaticScale14", 1.0), checkForInverses=True, imageExpandFactor=0,
+                         useAnalyticForm=True, splinePointDensity=50)
         centering = bool(options.pop("useCentering", False))
         self.set_options(**options)
         if s.get("fixed") is not None and len(s["fixed"]) > 0:
@@ -94,6 +99,7 @@ class OracleNB:
         o = self.opts
         self.lib.orc_set_options(self.h, o["dampingCutoff"], o["innerCutoff"], o["outerCutoff"], o["listCutoff"],
                                  o["dielectric"], o["electrostaticScale14"], int(o["checkForInverses"]), int(o["imageExpandFactor"]))
+        self.lib.orc_set_interaction_form(self.h, int(bool(o["useAnalyticForm"])), int(o["splinePointDensity"]))
 
     def energy(self, xyz=None, box=None, force_new=False, gradients=True):
         xyz = np.ascontiguousarray(self.sys["xyz"] if xyz is None else xyz, np.float64)
@@ -150,6 +156,20 @@ def make_factors(damp, inner, outer):
     out = np.zeros(21)
     _lib().orc_make_factors(damp, inner, outer, _d(out))
     return out
+
+
+def make_spline(which, damp=0.5, inner=8.0, outer=12.0, density=50):
+    """(x, y, h) of the restated PairwiseInteractionABFS_Make*Spline: which = 0 elect. (kJ/mol), 1 LJ-A, 2 LJ-B, 3 elect. (a.u.)"""
+    n = _lib().orc_make_spline(which, damp, inner, outer, density, None, None, None)
+    x, y, h = np.zeros(n), np.zeros(n), np.zeros(n)
+    _lib().orc_make_spline(which, damp, inner, outer, density, _d(x), _d(y), _d(h))
+    return x, y, h
+
+
+def spline_evaluate(x, y, h, x0):
+    f, g = np.zeros(1), np.zeros(1)
+    _lib().orc_spline_evaluate(len(x), _d(x), _d(y), _d(h), float(x0), _d(f), _d(g))
+    return f[0], g[0]
 
 
 def make_M(box6):

@@ -26,6 +26,7 @@
 #include "Transformation3Container.h"
 #include "ImageList.h"
 #include "Selection.h"
+#include "CubicSpline.h"
 #include "ref_driver.h"
 
 struct RefNB {
@@ -150,6 +151,22 @@ int refnb_set_centering(RefNB *h, int on)
         free(idx);
         return ok;
     }
+}
+
+/* PairwiseInteractionABFS options useAnalyticForm / splinePointDensity (pMolecule.PairwiseInteraction.pyx:226-239) followed by
+ * MakeSplines as NBModelABFS.CheckPairwiseInteractions does for the MM/MM interaction (pMolecule.NBModelABFS.pyx:78-82): the three
+ * Delta/Delta splines in kJ/mol.  Call after refnb_set_options (the splines depend on the cutoffs). */
+void refnb_set_interaction_form(RefNB *h, int useAnalyticForm, int splinePointDensity)
+{
+    if (h == NULL) return;
+    h->pw->useAnalyticForm    = useAnalyticForm ? True : False;
+    h->pw->splinePointDensity = splinePointDensity;
+    CubicSpline_Deallocate(&(h->pw->electrostaticSpline));
+    CubicSpline_Deallocate(&(h->pw->lennardJonesASpline));
+    CubicSpline_Deallocate(&(h->pw->lennardJonesBSpline));
+    h->pw->electrostaticSpline = PairwiseInteractionABFS_MakeElectrostaticSpline(h->pw, False, NULL);
+    h->pw->lennardJonesASpline = PairwiseInteractionABFS_MakeLennardJonesASpline(h->pw, NULL);
+    h->pw->lennardJonesBSpline = PairwiseInteractionABFS_MakeLennardJonesBSpline(h->pw, NULL);
 }
 
 void refnb_destroy(RefNB *h)
@@ -299,6 +316,40 @@ void refnb_make_factors(double damp, double inner, double outer, double *out)
     out[11] = f.aF6; out[12] = f.aK12; out[13] = f.aShift12; out[14] = f.aF0; out[15] = f.aAlpha;
     out[16] = f.bF3; out[17] = f.bK6; out[18] = f.bShift6; out[19] = f.bF0; out[20] = f.bAlpha;
     PairwiseInteractionABFS_Deallocate(&pw);
+}
+
+/* the reference's spline tables: which = 0 electrostatic (kJ/mol; 3: atomic units), 1 LJ-A, 2 LJ-B; x, y, h hold npoints values
+ * (PairwiseInteractionABFS_Make*Spline, pM/csource/PairwiseInteraction.c:148-285; CubicSpline_MakeFromReal1DArrays,
+ * pC/csource/CubicSpline.c:309-420).  Returns the number of points (call with x = NULL to size the arrays). */
+int refnb_make_spline(int which, double damp, double inner, double outer, int density, double *x, double *y, double *hh)
+{
+    PairwiseInteractionABFS *pw = PairwiseInteractionABFS_Allocate();
+    CubicSpline *sp = NULL;
+    int n = 0, i;
+    pw->dampingCutoff = damp; pw->innerCutoff = inner; pw->outerCutoff = outer; pw->splinePointDensity = density;
+    if (which == 0)      sp = PairwiseInteractionABFS_MakeElectrostaticSpline(pw, False, NULL);
+    else if (which == 3) sp = PairwiseInteractionABFS_MakeElectrostaticSpline(pw, True, NULL);
+    else if (which == 1) sp = PairwiseInteractionABFS_MakeLennardJonesASpline(pw, NULL);
+    else                 sp = PairwiseInteractionABFS_MakeLennardJonesBSpline(pw, NULL);
+    if (sp != NULL) {
+        n = sp->length;
+        if (x != NULL) for (i = 0; i < n; i++) { x[i] = Real1DArray_Item(sp->x, i); y[i] = Real1DArray_Item(sp->y, i); hh[i] = Real1DArray_Item(sp->h, i); }
+        CubicSpline_Deallocate(&sp);
+    }
+    PairwiseInteractionABFS_Deallocate(&pw);
+    return n;
+}
+
+/* CubicSpline_Evaluate (pC/csource/CubicSpline.c) of a spline built from the given (x, y): f and g = df/dx at x0 */
+void refnb_spline_evaluate(int n, const double *x, const double *y, double x0, double *f, double *g)
+{
+    Real1DArray *ax = Real1DArray_Allocate(n, NULL), *ay = Real1DArray_Allocate(n, NULL);
+    CubicSpline *sp = NULL;
+    int i;
+    for (i = 0; i < n; i++) { Real1DArray_Item(ax, i) = x[i]; Real1DArray_Item(ay, i) = y[i]; }
+    CubicSpline_MakeFromReal1DArrays(&sp, &ax, &ay, 1, 0.0e+00, 1, 0.0e+00);
+    CubicSpline_Evaluate(sp, x0, f, g, NULL);
+    CubicSpline_Deallocate(&sp);
 }
 
 void refnb_lj_table(int ntypes, const double *eps, const double *sigma, int amber,

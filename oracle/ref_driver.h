@@ -37,6 +37,11 @@ void   refnb_set_options(RefNB *h, double damp, double inner, double outer, doub
                          double dielectric, double elecScale14, int checkForInverses, int imageExpandFactor,
                          double cellSizeFactor, int method, int useGridByCell, int sortIndices);
 
+/* PairwiseInteractionABFS.{useAnalyticForm, splinePointDensity} + MakeSplines (pMolecule.PairwiseInteraction.pyx:204-239) for the
+ * MM/MM interaction; call after refnb_set_options.  useAnalyticForm = 0: the cubic-spline branch of
+ * PairwiseInteractionABFS_MMMMEnergy (pM/csource/PairwiseInteraction.c:431-531). */
+void   refnb_set_interaction_form(RefNB *h, int useAnalyticForm, int splinePointDensity);
+
 /* One System.Energy-style call: Initialize -> Update -> MMMMEnergy.
  * xyz[3n]; box = {a,b,c,alpha,beta,gamma} (ignored when ntrans==0); grad[3n] is ACCUMULATED into (may be NULL);
  * dEdM[9] accumulated into (may be NULL); energies[6] = {emmel, emmlj, emmel14, emmlj14, eimmmel, eimmmlj}.
@@ -60,6 +65,8 @@ int    refnb_num_threads(void);
 
 /* helpers exposed for pinning the restatement */
 void   refnb_make_factors(double damp, double inner, double outer, double *out21);
+int    refnb_make_spline(int which, double damp, double inner, double outer, int density, double *x, double *y, double *h);
+void   refnb_spline_evaluate(int n, const double *x, const double *y, double x0, double *f, double *g);
 void   refnb_lj_table(int ntypes, const double *eps, const double *sigma, int amber,
                       int *tableindex, double *tableA, double *tableB);
 void   refnb_make_M(const double *box6, double *M9, double *invM9);

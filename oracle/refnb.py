@@ -51,6 +51,10 @@ def _lib(omp=False):
     lib.refnb_make_factors.argtypes = [C.c_double] * 3 + [dp]
     lib.refnb_lj_table.argtypes = [C.c_int, dp, dp, C.c_int, ip, dp, dp]
     lib.refnb_make_M.argtypes = [dp, dp, dp]
+    lib.refnb_set_interaction_form.argtypes = [vp, C.c_int, C.c_int]
+    lib.refnb_make_spline.restype = C.c_int
+    lib.refnb_make_spline.argtypes = [C.c_int] + [C.c_double] * 3 + [C.c_int, dp, dp, dp]
+    lib.refnb_spline_evaluate.argtypes = [C.c_int, dp, dp, C.c_double, dp, dp]
     _LIBS[key] = lib
     return lib
 
@@ -85,7 +89,8 @@ class RefNB:
             raise RuntimeError("refnb_create failed")
         self.opts = dict(dampingCutoff=0.5, innerCutoff=8.0, outerCutoff=12.0, listCutoff=13.5, dielectric=1.0,
                          electrostaticScale14=s.get("electrostaticScale14", 1.0), checkForInverses=True,
-                         imageExpandFactor=0, cutoffCellSizeFactor=0.5, method=0, useGridByCell=True, sortIndices=False)
+                         imageExpandFactor=0, cutoffCellSizeFactor=0.5, method=0, useGridByCell=True, sortIndices=False,
+                         useAnalyticForm=True, splinePointDensity=50)
         centering = bool(options.pop("useCentering", False))
         self.set_options(**options)
         if s.get("fixed") is not None and len(s["fixed"]) > 0:
@@ -109,6 +114,7 @@ class RefNB:
                                    o["dielectric"], o["electrostaticScale14"], int(o["checkForInverses"]),
                                    int(o["imageExpandFactor"]), o["cutoffCellSizeFactor"], int(o["method"]),
                                    int(o["useGridByCell"]), int(o["sortIndices"]))
+        self.lib.refnb_set_interaction_form(self.h, int(bool(o["useAnalyticForm"])), int(o["splinePointDensity"]))
 
     def energy(self, xyz=None, box=None, force_new=False, gradients=True):
         """Returns dict(energies[6], grad[n,3], dEdM[3,3], updated, t_update, t_energy)."""
@@ -179,6 +185,22 @@ def lj_table(eps, sigma, style):
     tb = np.zeros(nt * (nt + 1) // 2)
     _lib().refnb_lj_table(nt, _d(eps), _d(sigma), 1 if style == "amber" else 0, _i(ti), _d(ta), _d(tb))
     return ti, ta, tb
+
+
+def make_spline(which, damp=0.5, inner=8.0, outer=12.0, density=50):
+    """(x, y, h) of the reference's PairwiseInteractionABFS_Make*Spline: which = 0 elect. (kJ/mol), 1 LJ-A, 2 LJ-B, 3 elect. (a.u.)"""
+    n = _lib().refnb_make_spline(which, damp, inner, outer, density, None, None, None)
+    x, y, h = np.zeros(n), np.zeros(n), np.zeros(n)
+    _lib().refnb_make_spline(which, damp, inner, outer, density, _d(x), _d(y), _d(h))
+    return x, y, h
+
+
+def spline_evaluate(x, y, x0):
+    """CubicSpline_Evaluate of the spline the reference builds from (x, y) with zero end slopes: (f, df/dx)"""
+    f, g = np.zeros(1), np.zeros(1)
+    x = np.ascontiguousarray(x, np.float64); y = np.ascontiguousarray(y, np.float64)
+    _lib().refnb_spline_evaluate(len(x), _d(x), _d(y), float(x0), _d(f), _d(g))
+    return f[0], g[0]
 
 
 def make_M(box6):

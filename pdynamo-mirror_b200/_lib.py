@@ -36,6 +36,8 @@ SIGNATURES = {
     "nbb200_host_alloc": (vp, [C.c_size_t]),
     "nbb200_host_free": (None, [vp]),
     "PairwiseInteractionABFS_B200_MakeFactors": (None, [C.c_double] * 3 + [dp]),
+    "PairwiseInteractionABFS_B200_SetInteractionForm": (None, [vp, C.c_int, C.c_int, ip]),
+    "PairwiseInteractionABFS_B200_MakeSpline": (C.c_int, [C.c_int] + [C.c_double] * 3 + [C.c_int, dp, dp, dp]),
     "nbb200_set_stream": (None, [vp, vp]),
     "nbb200_enable_timing": (None, [vp, C.c_int]),
     "nbb200_get_timings": (None, [vp, dp]),

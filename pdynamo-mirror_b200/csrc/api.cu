@@ -371,11 +371,45 @@ void NBModelABFS_B200_SetOptions(NBB200State *state, double dampingCutoff, doubl
 {
     if (state == nullptr) return;
     State &s = *reinterpret_cast<State *>(state);
+    const bool cutoffsChanged = s.damp != dampingCutoff || s.inner != innerCutoff || s.outer != outerCutoff;
     s.damp = dampingCutoff; s.inner = innerCutoff; s.outer = outerCutoff; s.list = listCutoff;
     s.dielectric = dielectric; s.scale14 = electrostaticScale14;
     if ((s.checkForInverses != (checkForInverses != 0)) || s.expandFactor != imageExpandFactor) s.isNew = true;
     s.checkForInverses = checkForInverses != 0; s.expandFactor = imageExpandFactor;
     make_abfs_factors(s.damp, s.inner, s.outer, s.factors);
+    if (!s.useAnalytic && (cutoffsChanged || !s.splValid)) {  // the splines depend on the cutoffs (MakeSplines, pMolecule.NBModelABFS.pyx:82)
+        cudaSetDevice(s.device);
+        make_abfs_splines(s.damp, s.inner, s.outer, s.splineDensity, s.spl);
+        s.splValid = upload_spline_tables(s);
+    }
+}
+
+void PairwiseInteractionABFS_B200_SetInteractionForm(NBB200State *state, int useAnalyticForm, int splinePointDensity, int *status)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    if (!useAnalyticForm && splinePointDensity < 1) { set_error("splinePointDensity must be positive"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return; }
+    s.useAnalytic = useAnalyticForm != 0;
+    s.splineDensity = splinePointDensity;
+    s.splValid = false;
+    if (!s.useAnalytic) {
+        cudaSetDevice(s.device);
+        make_abfs_splines(s.damp, s.inner, s.outer, s.splineDensity, s.spl);
+        s.splValid = upload_spline_tables(s);
+        if (!s.splValid) set_status(status, NBB200_STATUS_LOGIC_ERROR);
+    }
+}
+
+int PairwiseInteractionABFS_B200_MakeSpline(int which, double dampingCutoff, double innerCutoff, double outerCutoff, int splinePointDensity,
+                                            double *x, double *y, double *h)
+{
+    if (which < 0 || which > 2 || splinePointDensity < 1) return 0;
+    const int n = abfs_spline_points(outerCutoff, splinePointDensity);
+    if (x == nullptr || y == nullptr || h == nullptr) return n;
+    SplineTables t;
+    make_abfs_splines(dampingCutoff, innerCutoff, outerCutoff, splinePointDensity, t);
+    for (int i = 0; i < n; i++) { x[i] = t.x[i]; y[i] = t.y[which][i]; h[i] = t.h[which][i]; }
+    return n;
 }
 
 int NBModelABFS_B200_Update(NBB200State *state, const double *xyz, const double *box6, int forceNew, int *status)

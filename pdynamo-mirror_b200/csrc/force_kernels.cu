@@ -30,6 +30,9 @@ struct ForceArgs {
     AbfsF32 F; float qScale;
     double *gradSorted; double *accum;
     double origin[3];
+    // spline form: per interval of the shared abscissae four float4 = {xf, e0, e1, e2 | e3, a0, a1, a2 | a3, b0, b1, b2 | b3, 0, 0, 0}
+    // (cubics in u = r^2 - xf of the electrostatic, LJ-A and LJ-B splines); row splN - 1 is all zero (pairs that are not evaluated)
+    const float4 *splTab; int splN; float splInvDR;
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -121,6 +124,39 @@ __device__ __noinline__ void damped_tile_fix(const AbfsF32 &F, unsigned int mask
     c[0] = fxi; c[1] = fyi; c[2] = fzi; c[3] = fxj; c[4] = fyj; c[5] = fzj; c[6] = eq; c[7] = el;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// spline form (PairwiseInteractionABFS_MMMMEnergy, second branch: pM/csource/PairwiseInteraction.c:431-531).  The reference finds the
+// interval of r^2 by bisection over x_i = (i dR)^2 (CubicSpline_EvaluateLUDST) and evaluates the three splines there
+// (CubicSpline_FastEvaluateFG); here the interval is l = floor(r / dR) and every interval holds its cubic in u = r^2 - x_l
+// (the same polynomial; at a knot either neighbour gives the same value and first two derivatives).  One instruction stream for
+// all r: the tables cover the damped core, the plain and the switched region.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sqrt_fast(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ PairOut spline_pair(const float4 *__restrict__ tab, int nrows, float invDR, bool live, float r2, float qij, float A, float B)
+{
+    int l = min((int) (sqrt_fast(r2) * invDR), nrows - 2);
+    l = live ? l : nrows - 1;
+    const float4 *row = tab + 4 * l;
+    const float4 t0 = row[0], t1 = row[1], t2 = row[2], t3 = row[3];
+    const float u = r2 - t0.x;
+    // Lennard-Jones: coefficients are linear in (A, B)
+    const float c0 = fmaf(A, t1.y, B * t2.y), c1 = fmaf(A, t1.z, B * t2.z), c2 = fmaf(A, t1.w, B * t2.w), c3 = fmaf(A, t2.x, B * t3.x);
+    PairOut o;
+    o.e1 = qij * fmaf(u, fmaf(u, fmaf(u, t1.x, t0.w), t0.z), t0.y);
+    o.e2 = fmaf(u, fmaf(u, fmaf(u, c3, c2), c1), c0);
+    const float u3 = 3.0f * u;
+    const float ge = fmaf(u, fmaf(u3, t1.x, t0.w + t0.w), t0.z);
+    const float gl = fmaf(u, fmaf(u3, c3, c2 + c2), c1);
+    o.g = -2.0f * fmaf(qij, ge, gl);                     // dG = 2 (qij dFe + A dFa + B dFb); g = -dG
+    return o;
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -142,7 +178,8 @@ struct __align__(16) WarpScratch {
     double acc[5][kTile];        // i-gradient x, y, z and the two energies of the item, one column per lane
 };
 
-template <bool kRot, int kThreads, int kMinBlocks>
+// kForm: 0 = analytic ABFS formulas, 1 = spline tables staged in shared memory, 2 = spline tables read from global memory (L1)
+template <bool kRot, int kThreads, int kMinBlocks, int kForm>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const __grid_constant__ ForceArgs A)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -152,6 +189,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
     for (int i = threadIdx.x; i < A.ntypes * A.ntypes; i += blockDim.x) {
         const float2 ab = A.ljAB[i];
         sLJ[i] = make_float4(ab.x, ab.y, ab.x * A.F.aShift12 - ab.y * A.F.bShift6, 0.f);
+    }
+    const float4 *splTab = A.splTab;
+    if (kForm == 1) {
+        float4 *sTab = sLJ + A.ntypes * A.ntypes;
+        for (int i = threadIdx.x; i < 4 * A.splN; i += blockDim.x) sTab[i] = A.splTab[i];
+        splTab = sTab;
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, m = lane & (kCluster - 1), g = lane >> 3;
@@ -248,17 +291,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
                 // masked pairs are evaluated AT the outer cutoff, where energy and force vanish (to ~1e-16 kJ/mol): pairs that are not
                 // on the list get r2 = NaN (all bits set by the sign-extended mask bit), and fminf(NaN, r2Off) = r2Off takes care of
                 // them together with the pairs beyond the cutoff; r2m doubles as the damped-core detector
-                const int off = ~(((int) (mask << (31 - k))) >> 31);               // 0 if bit k is set, else 0xffffffff
-                const float r2m = fminf(__int_as_float(__float_as_int(r2) | off), F.r2Off);
-                r2min = fminf(r2min, r2m);
-                const PairOut o = abfs_pair(F, r2m, qi * p.w, ab.x, ab.y, ab.z);
+                PairOut o;
+                if (kForm == 0) {
+                    const int off = ~(((int) (mask << (31 - k))) >> 31);               // 0 if bit k is set, else 0xffffffff
+                    const float r2m = fminf(__int_as_float(__float_as_int(r2) | off), F.r2Off);
+                    r2min = fminf(r2min, r2m);
+                    o = abfs_pair(F, r2m, qi * p.w, ab.x, ab.y, ab.z);
+                } else {
+                    // pairs off the list or beyond the cutoff read the all-zero table row (the skip of PairwiseInteraction.c:489)
+                    o = spline_pair(splTab, A.splN, A.splInvDR, ((mask >> k) & 1u) && !(r2 > F.r2Off), r2, qi * p.w, ab.x, ab.y);
+                }
                 eq += o.e1; el += o.e2;
                 fxi = fmaf(-o.g, dx, fxi); fyi = fmaf(-o.g, dy, fyi); fzi = fmaf(-o.g, dz, fzi);      // gradient = -(force on i) = -g d
                 fxj = fmaf(o.g, dx, fxj); fyj = fmaf(o.g, dy, fyj); fzj = fmaf(o.g, dz, fzj);
                 // hand the j-gradient accumulator to the lane that evaluates this j slot next
                 fxj = __shfl_sync(0xffffffffu, fxj, src); fyj = __shfl_sync(0xffffffffu, fyj, src); fzj = __shfl_sync(0xffffffffu, fzj, src);
             }
-            if (__any_sync(0xffffffffu, r2min < F.r2Damp)) {   // damped core: practically never; patch the tile with the reference formulas
+            if (kForm == 0 && __any_sync(0xffffffffu, r2min < F.r2Damp)) {   // damped core: practically never; patch the tile with the reference formulas
                 float c[8];
                 damped_tile_fix(F, mask, myPosq, ljRow, myLj, xi, yi, zi, qi, src, c);
                 fxi += c[0]; fyi += c[1]; fzi += c[2]; fxj += c[3]; fyj += c[4]; fzj += c[5];
@@ -339,7 +388,7 @@ struct F64Factors { double v[21]; };
 
 __global__ void k_pairs14(const int2 *__restrict__ pairs, int npairs, const double *__restrict__ x, const double *__restrict__ q, const int *__restrict__ ljtype,
                           const double2 *__restrict__ ljAB, int ntypes, F64Factors FF, double eScale, const int *__restrict__ invPerm, int ownLo, int ownHi,
-                          double *gradSorted, double *acc)
+                          double *gradSorted, double *acc, const double *__restrict__ spl, int splN)
 {
     const double *F = FF.v;
     double eq = 0.0, el = 0.0;
@@ -352,6 +401,29 @@ __global__ void k_pairs14(const int2 *__restrict__ pairs, int npairs, const doub
         if (r2 > F[2]) continue;
         const double qij = eScale * q[i] * q[j];
         const double2 ab = ljAB[ljtype[i] * ntypes + ljtype[j]];
+        if (spl != nullptr) {
+            // spline form in fp64 exactly as the reference evaluates it: bisection (CubicSpline_EvaluateLUDST, pC/csource/CubicSpline.c:138-159)
+            // and CubicSpline_FastEvaluateFG (pC/cinclude/CubicSpline.h:30-39); spl = x[n] then (y, h)[n] of the three splines
+            int l = 0, u = splN - 1;
+            while (u - l > 1) { const int m = (u + l) >> 1; if (spl[m] > r2) u = m; else l = m; }
+            const double d = spl[u] - spl[l], sv = (r2 - spl[l]) / d, tv = (spl[u] - r2) / d;
+            double f[3], g[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double *y = spl + (size_t) (1 + 2 * k) * splN, *h = y + splN;
+                const double hl = h[l] * d / 6.0, hu = h[u] * d / 6.0, yl = y[l], yu = y[u];
+                f[k] = tv * yl + sv * yu + d * (tv * (tv * tv - 1.0) * hl + sv * (sv * sv - 1.0) * hu);
+                g[k] = (yu - yl) / d + (-(3.0 * tv * tv - 1.0) * hl + (3.0 * sv * sv - 1.0) * hu);
+            }
+            eq += qij * f[0]; el += ab.x * f[1] + ab.y * f[2];
+            if (gradSorted != nullptr) {
+                const double dG = 2.0 * qij * g[0] + 2.0 * ab.x * g[1] + 2.0 * ab.y * g[2];
+                const double gx = dG * dx, gy = dG * dy, gz = dG * dz;
+                atomicAdd(&gradSorted[3 * si], gx); atomicAdd(&gradSorted[3 * si + 1], gy); atomicAdd(&gradSorted[3 * si + 2], gz);
+                atomicAdd(&gradSorted[3 * sj], -gx); atomicAdd(&gradSorted[3 * sj + 1], -gy); atomicAdd(&gradSorted[3 * sj + 2], -gz);
+            }
+            continue;
+        }
         double s = 0.0, s2 = 0.0, dF = 0.0, e1, e2;
         if (!(r2 < F[0])) { s2 = 1.0 / r2; s = sqrt(s2); }
         if (r2 > F[1]) {
@@ -388,21 +460,64 @@ typedef void (*ForceKernel)(ForceArgs);
 struct ForceVariant { const char *name; ForceKernel fn; int threads; };
 // launch shapes (threads per CTA x resident CTAs per SM -> register budget); NBB200_FORCE_SHAPE selects one for experiments
 static const ForceVariant kForceVariants[] = {
-    {"128x5", k_cluster_forces<false, 128, 5>, 128},      // default: 96 registers, 20 warps per SM (measured best on B200)
-    {"256x3", k_cluster_forces<false, 256, 3>, 256}, {"256x2", k_cluster_forces<false, 256, 2>, 256},
-    {"128x4", k_cluster_forces<false, 128, 4>, 128}, {"128x6", k_cluster_forces<false, 128, 6>, 128},
+    {"128x5", k_cluster_forces<false, 128, 5, 0>, 128},      // default: 96 registers, 20 warps per SM (measured best on B200)
+    {"256x3", k_cluster_forces<false, 256, 3, 0>, 256}, {"256x2", k_cluster_forces<false, 256, 2, 0>, 256},
+    {"128x4", k_cluster_forces<false, 128, 4, 0>, 128}, {"128x6", k_cluster_forces<false, 128, 6, 0>, 128},
 };
-static const ForceVariant kForceRot = {"rot", k_cluster_forces<true, 256, 2>, 256};
+static const ForceVariant kForceRot = {"rot", k_cluster_forces<true, 256, 2, 0>, 256};
+// spline form: [rotations][tables in shared memory (1) / global memory (0)]
+static const ForceVariant kForceSpline[2][2] = {
+    {{"spline-global", k_cluster_forces<false, 256, 2, 2>, 256}, {"spline", k_cluster_forces<false, 256, 2, 1>, 256}},
+    {{"spline-rot-global", k_cluster_forces<true, 256, 2, 2>, 256}, {"spline-rot", k_cluster_forces<true, 256, 2, 1>, 256}},
+};
+constexpr size_t kSplineSmemLimit = 96 * 1024;        // per CTA; two CTAs per SM stay resident
 
 void init_force_kernel_attributes()
 {
     for (const ForceVariant &v : kForceVariants) cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(kForceRot.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int r = 0; r < 2; r++) for (int m = 0; m < 2; m++) cudaFuncSetAttribute(kForceSpline[r][m].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaDeviceProp prop;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaGetDeviceProperties(&prop, dev);
     g_numSMs = prop.multiProcessorCount;
+}
+
+// spline tables of the state -> device: the fp64 tables as the reference holds them (1-4 kernel) and, for the tile kernel, the cubic
+// of every interval re-expanded about the fp32-rounded knot xf (so that u = r^2 - xf is exact in fp32), coefficients rounded to fp32
+bool upload_spline_tables(State &s)
+{
+    const int n = s.spl.points();
+    if (n < 2) { set_error("spline tables are empty"); return false; }
+    std::vector<double> h64((size_t) 7 * n);
+    std::copy(s.spl.x.begin(), s.spl.x.end(), h64.begin());
+    for (int k = 0; k < 3; k++) {
+        std::copy(s.spl.y[k].begin(), s.spl.y[k].end(), h64.begin() + (size_t) (1 + 2 * k) * n);
+        std::copy(s.spl.h[k].begin(), s.spl.h[k].end(), h64.begin() + (size_t) (2 + 2 * k) * n);
+    }
+    std::vector<float4> poly((size_t) 4 * n, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int l = 0; l + 1 < n; l++) {
+        const float xf = (float) s.spl.x[l];
+        const double dlt = (double) xf - s.spl.x[l];
+        float c[3][4];
+        for (int k = 0; k < 3; k++) {
+            double p[4];
+            spline_interval_polynomial(s.spl.x, s.spl.y[k], s.spl.h[k], l, p);
+            c[k][0] = (float) (p[0] + dlt * (p[1] + dlt * (p[2] + dlt * p[3])));
+            c[k][1] = (float) (p[1] + dlt * (2.0 * p[2] + 3.0 * dlt * p[3]));
+            c[k][2] = (float) (p[2] + 3.0 * dlt * p[3]);
+            c[k][3] = (float) p[3];
+        }
+        poly[4 * l + 0] = make_float4(xf, c[0][0], c[0][1], c[0][2]);
+        poly[4 * l + 1] = make_float4(c[0][3], c[1][0], c[1][1], c[1][2]);
+        poly[4 * l + 2] = make_float4(c[1][3], c[2][0], c[2][1], c[2][2]);
+        poly[4 * l + 3] = make_float4(c[2][3], 0.f, 0.f, 0.f);
+    }
+    if (!s.splF64.ensure(h64.size()) || !s.splPoly.ensure(poly.size())) return false;
+    NBB_CUDA(cudaMemcpy(s.splF64.p, h64.data(), sizeof(double) * h64.size(), cudaMemcpyHostToDevice));
+    NBB_CUDA(cudaMemcpy(s.splPoly.p, poly.data(), sizeof(float4) * poly.size(), cudaMemcpyHostToDevice));
+    return true;
 }
 
 bool unsort_gradients(State &s, long s0, long s1, double *d_grad)
@@ -459,6 +574,16 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
             F.k2 = (float) (2.0 / gam);
         }
         A.qScale = (float) eScale;
+        A.splTab = nullptr; A.splN = 0; A.splInvDR = 0.f;
+        const bool spline = !s.useAnalytic;
+        size_t splBytes = 0;
+        if (spline) {
+            if (!s.splValid) { set_error("spline form selected but the spline tables are not built"); return false; }
+            A.splTab = s.splPoly.p; A.splN = s.spl.points();
+            A.splInvDR = (float) ((double) (s.spl.points() - 1) / s.outer);
+            A.qScale = (float) (1.0 / s.dielectric);          // the electrostatic spline carries the unit (PairwiseInteraction.c:474)
+            splBytes = sizeof(float4) * 4 * (size_t) s.spl.points();
+        }
         A.gradSorted = wantGrad ? s.gs : nullptr; A.accum = s.accum.p;
         if (g_numSMs == 0) init_force_kernel_attributes();
         bool rot = false;                                   // any image with a genuine rotation?
@@ -468,9 +593,10 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
             for (const ForceVariant &v : kForceVariants) if (e != nullptr && std::strcmp(e, v.name) == 0) return &v;
             return &kForceVariants[0];
         }();
-        const ForceVariant &v = rot ? kForceRot : *chosen;
+        const bool splSmem = spline && splBytes <= kSplineSmemLimit;
+        const ForceVariant &v = spline ? kForceSpline[rot ? 1 : 0][splSmem ? 1 : 0] : (rot ? kForceRot : *chosen);
         const int warpsPerBlock = v.threads / 32;
-        const size_t smem = sizeof(WarpScratch) * warpsPerBlock + sizeof(float4) * (size_t) s.ntypes * s.ntypes;
+        const size_t smem = sizeof(WarpScratch) * warpsPerBlock + sizeof(float4) * (size_t) s.ntypes * s.ntypes + (splSmem ? splBytes : 0);
         if (smem > 200 * 1024) { set_error("too many LJ types for the shared-memory table"); return false; }
         int perSM = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, v.fn, v.threads, smem);
@@ -487,7 +613,8 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
         const int threads = 128, nblk = std::max(1, std::min(1184, (s.n14 + threads - 1) / threads));
         if (s.timing) cudaEventRecord(s.ev[4], s.stream);
         k_pairs14<<<nblk, threads, 0, s.stream>>>(s.pairs14.p, s.n14, s.xcur, s.q64.p, s.ljtype.p, s.ljAB14.p, s.ntypes14, FF,
-                                                    eScale * s.scale14, s.invPerm.p, s.ownLo, s.ownHi, wantGrad ? s.gs : nullptr, s.accum.p + 16 * s.nsets);
+                                                    (s.useAnalytic ? eScale : 1.0 / s.dielectric) * s.scale14, s.invPerm.p, s.ownLo, s.ownHi, wantGrad ? s.gs : nullptr,
+                                                    s.accum.p + 16 * s.nsets, s.useAnalytic ? nullptr : s.splF64.p, s.useAnalytic ? 0 : s.spl.points());
         if (s.timing) cudaEventRecord(s.ev[5], s.stream);
         s.launches += 1;
     }

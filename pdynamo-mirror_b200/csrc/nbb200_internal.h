@@ -95,6 +95,7 @@ bool touched_ranges(State &s, long *out);
 bool touched_ranges_async(State &s, long *d_out);      // the same table written to a device array, no host synchronisation                // per rank slab: [lo, hi) of the sorted positions this rank's lists reference
 
 // ---- force_kernels.cu
+bool upload_spline_tables(State &s);                     // s.spl -> s.splF64 / s.splPoly
 bool launch_forces(State &s, double *d_grad, bool sortedOnly);
 bool unsort_gradients(State &s, long s0, long s1, double *d_grad);
 void init_force_kernel_attributes();
@@ -132,6 +133,12 @@ struct State {
     bool checkForInverses = true;
     int expandFactor = 0;
     double factors[21];
+    // interaction form (PairwiseInteractionABFS.useAnalyticForm / splinePointDensity); tables rebuilt when the cutoffs change
+    bool useAnalytic = true, splValid = false;
+    int splineDensity = 50;
+    SplineTables spl;
+    DevBuf<double> splF64;          // x[n], then y[n], h[n] of the electrostatic, LJ-A and LJ-B splines (1-4 kernel, fp64)
+    DevBuf<float4> splPoly;         // [n][4] per-interval cubics in fp32 (tile kernel), last row zero
 
     // reference-state bookkeeping (NBModelABFSState)
     bool isNew = true;

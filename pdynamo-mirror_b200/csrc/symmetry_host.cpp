@@ -1,6 +1,7 @@
 // symmetry_host.cpp -- see symmetry_host.h.  Compile with -ffp-contract=off: the values produced here feed
 // fp64 pair-list membership tests that must agree bit for bit with the reference's (built without FMA).
 #include "symmetry_host.h"
+#include <vector>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -298,6 +299,94 @@ void make_abfs_factors(double damp, double inner, double outer, double *o)
     f = -s6 + o[18]; g = 6.0e+00 * s6 / damp;
     o[19] = f - 0.5e+00 * damp * g;
     o[20] = -0.5e+00 * g / damp;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// spline form of the interaction (PairwiseInteractionABFS.useAnalyticForm = False)
+// ------------------------------------------------------------------------------------------------------
+// One ordinate of PairwiseInteractionABFS_Make{Electrostatic,LennardJonesA,LennardJonesB}Spline (pM/csource/PairwiseInteraction.c:148-285):
+// the reference macros (pM/cinclude/PairwiseInteraction.h:72-165) for a unit charge product / unit A / unit B, in its operation order.
+static double abfs_ordinate(const double *F, int which, double r2)
+{
+    const double r2Damp = F[0], r2On = F[1];
+    double s = 0.0e+00, s2 = 0.0e+00;
+    if (!(r2 < r2Damp)) { s2 = 1.0e+00 / r2; s = std::sqrt(s2); }
+    const double s6 = s2 * s2 * s2;
+    if (which == 0) {
+        if (r2 > r2On) return 1.0e+00 * (s * (F[3] - r2 * (F[4] + r2 * (F[5] + F[6] * r2))) + F[8]);
+        if (r2 > r2Damp) return 1.0e+00 * (s + F[7]);
+        return 1.0e+00 * (F[9] - F[10] * r2);
+    }
+    if (which == 1) {
+        if (r2 > r2On) { const double l1 = s6 - F[11]; return 1.0e+00 * F[12] * std::pow(l1, 2); }
+        if (r2 > r2Damp) return 1.0e+00 * (s6 * s6 - F[13]);
+        return 1.0e+00 * (F[14] - F[15] * r2);
+    }
+    if (r2 > r2On) { const double l2 = (s / r2) - F[16]; return -1.0e+00 * F[17] * std::pow(l2, 2); }
+    if (r2 > r2Damp) return -1.0e+00 * (s6 - F[18]);
+    return -1.0e+00 * (F[19] - F[20] * r2);
+}
+
+// second derivatives of the cubic spline through (x, y) with zero first derivative at both ends
+// (CubicSpline_MakeFromReal1DArrays with lower/upper derivative = 1, value 0: pC/csource/CubicSpline.c:309-420).  The reference hands
+// the tridiagonal system to LAPACK dgtsv; the system is diagonally dominant, so dgtsv never interchanges rows and reduces to the plain
+// elimination below (same operations, same order: the tables agree with the reference's to the last bit).
+void spline_second_derivatives(const std::vector<double> &x, const std::vector<double> &y, std::vector<double> &h)
+{
+    const int n = (int) x.size();
+    std::vector<double> sub(n, 0.0), dia(n, 0.0), sup(n, 0.0);
+    h.assign(n, 0.0);
+    if (n < 2) return;
+    for (int i = 0; i < n; i++) {
+        const double dl = (i > 0) ? x[i] - x[i - 1] : 0.0, du = (i < n - 1) ? x[i + 1] - x[i] : 0.0;
+        if (i == 0)          { dia[0] = du / 3.0e+00; sup[0] = du / 6.0e+00; h[0] = (y[1] - y[0]) / du - 0.0e+00; }
+        else if (i == n - 1) { sub[n - 2] = dl / 6.0e+00; dia[n - 1] = dl / 3.0e+00; h[n - 1] = 0.0e+00 - (y[n - 1] - y[n - 2]) / dl; }
+        else                 { sub[i - 1] = dl / 6.0e+00; dia[i] = (dl + du) / 3.0e+00; sup[i] = du / 6.0e+00; h[i] = (y[i + 1] - y[i]) / du + (y[i - 1] - y[i]) / dl; }
+    }
+    for (int i = 0; i + 1 < n; i++) {
+        const double m = sub[i] / dia[i];
+        dia[i + 1] = dia[i + 1] - m * sup[i];
+        h[i + 1] = h[i + 1] - m * h[i];
+    }
+    h[n - 1] = h[n - 1] / dia[n - 1];
+    h[n - 2] = (h[n - 2] - sup[n - 2] * h[n - 1]) / dia[n - 2];
+    for (int i = n - 3; i >= 0; i--) h[i] = (h[i] - sup[i] * h[i + 1] - 0.0e+00 * h[i + 2]) / dia[i];
+}
+
+int abfs_spline_points(double outer, int density)
+{
+    const double a = (double) density * outer;                         // Round(), pC/cinclude/Macros.h:34
+    const int n = ((a >= 0) ? (int) (a + 0.5) : (int) (a - 0.5)) + 1;
+    return n > 2 ? n : 2;
+}
+
+void make_abfs_splines(double damp, double inner, double outer, int density, SplineTables &t)
+{
+    double F[21];
+    make_abfs_factors(damp, inner, outer, F);
+    const int n = abfs_spline_points(outer, density);
+    const double dR = outer / (double) (n - 1);
+    t.x.assign(n, 0.0);
+    for (int k = 0; k < 3; k++) t.y[k].assign(n, 0.0);
+    for (int i = 0; i < n - 1; i++) {
+        const double r = dR * (double) i, r2 = r * r;
+        t.x[i] = r2;
+        for (int k = 0; k < 3; k++) t.y[k][i] = abfs_ordinate(F, k, r2);
+    }
+    t.x[n - 1] = F[2];                                                 // (r2Off, 0) closes every table
+    for (int i = 0; i < n; i++) t.y[0][i] *= kE2AngstromToKJMol;       // the electrostatic spline carries the kJ/mol unit
+    for (int k = 0; k < 3; k++) spline_second_derivatives(t.x, t.y[k], t.h[k]);
+}
+
+// per interval [x_l, x_l+1] the cubic in u = x - x_l:  f = c0 + u (c1 + u (c2 + u c3)); algebraically the reference's
+// CubicSpline_FastEvaluateFG (pC/cinclude/CubicSpline.h:30-39) with s = u / d, t = 1 - s
+void spline_interval_polynomial(const std::vector<double> &x, const std::vector<double> &y, const std::vector<double> &h, int l, double *c4)
+{
+    const double d = x[l + 1] - x[l];
+    c4[0] = y[l];
+    c4[1] = (y[l + 1] - y[l]) / d - d * (2.0 * h[l] + h[l + 1]) / 6.0;
+    c4[2] = 0.5 * h[l];
+    c4[3] = (h[l + 1] - h[l]) / (6.0 * d);
 }
 
 }  // namespace nbb200

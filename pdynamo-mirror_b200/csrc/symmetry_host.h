@@ -86,6 +86,16 @@ void image_derivatives(double *dEdM, const Lattice &lat, const Mat3 &rotF, const
                        const double *W9, const double *G3);
 
 void make_abfs_factors(double damp, double inner, double outer, double *out21);
+
+// spline form (PairwiseInteractionABFS.useAnalyticForm = False): the reference's three tables on shared abscissae x = r^2
+struct SplineTables {
+    std::vector<double> x, y[3], h[3];          // [0] electrostatic (kJ/mol for unit charges), [1] LJ-A, [2] LJ-B; h = second derivatives
+    int points() const { return (int) x.size(); }
+};
+int  abfs_spline_points(double outer, int density);
+void make_abfs_splines(double damp, double inner, double outer, int density, SplineTables &t);
+void spline_second_derivatives(const std::vector<double> &x, const std::vector<double> &y, std::vector<double> &h);
+void spline_interval_polynomial(const std::vector<double> &x, const std::vector<double> &y, const std::vector<double> &h, int l, double *c4);
 constexpr double kE2AngstromToKJMol = (1.0e+7 * 6.0221415e+23 * 1.60217653e-19 * 1.60217653e-19) / (4.0e+00 * 3.14159265358979323846 * 8.854187817e-12);
 
 }  // namespace nbb200

@@ -19,11 +19,15 @@ _STATENAMES = ("nbState", "qcmmstate")          # pMolecule.NBModel.pyx:17
 
 
 class PairwiseInteractionABFS:
-    """Option holder for the analytic ABFS interaction (pMolecule.PairwiseInteraction.pyx)."""
+    """Option holder for the ABFS interaction (pMolecule.PairwiseInteraction.pyx:111-251): analytic form (default) or the cubic-spline
+    form (useAnalyticForm = False, splinePointDensity points per Angstrom); the spline tables themselves live in the device state
+    (PairwiseInteractionABFS_B200_SetInteractionForm) and can be inspected with MakeSplines()."""
 
     def __init__(self, **options):
+        # defaults of PairwiseInteractionABFS_Allocate (pMolecule-1.9.0/extensions/csource/PairwiseInteraction.c:28-42)
         self.dampingCutoff, self.innerCutoff, self.outerCutoff = 0.5, 8.0, 12.0
-        self.useAnalyticForm = True
+        self.useAnalyticForm, self.splinePointDensity = True, 50
+        self.electrostaticModel, self.width1, self.width2 = "Delta/Delta", 0.0, 0.0
         self.SetOptions(**options)
 
     @classmethod
@@ -31,13 +35,39 @@ class PairwiseInteractionABFS:
         return cls(**options)
 
     def SetOptions(self, **kw):
-        for key in ("dampingCutoff", "innerCutoff", "outerCutoff", "useAnalyticForm"):
+        for key in ("dampingCutoff", "electrostaticModel", "innerCutoff", "outerCutoff", "splinePointDensity", "width1", "width2"):
             if key in kw:
                 setattr(self, key, kw.pop(key))
+        if "useAnalyticForm" in kw:
+            self.useAnalyticForm = bool(kw.pop("useAnalyticForm"))
         if len(kw) > 0:
             raise ValueError("Invalid options: " + ", ".join(sorted(kw.keys())) + ".")
-        if not self.useAnalyticForm:
-            raise NotImplementedError("only the analytic form (the reference default) is implemented on the device")
+        self.CheckOptions()
+
+    def CheckOptions(self):
+        if self.electrostaticModel is None:
+            self.electrostaticModel = "Delta/Delta"
+        elif self.electrostaticModel not in ("Delta/Delta", "Delta/Gaussian", "Gaussian/Gaussian"):
+            raise ValueError("Invalid pairwise interaction electrostatic model: " + self.electrostaticModel + ".")
+        if self.electrostaticModel != "Delta/Delta":
+            raise NotImplementedError("Gaussian electrostatic models (QC/MM couplings) are not implemented on the device")
+
+    def MakeSplines(self, electrostatic=True, lennardJones=True, useAtomicUnits=False):
+        """The tables MakeSplines builds in the reference (pMolecule.PairwiseInteraction.pyx:204-214), as a dict of (x, y, h) arrays:
+        x = r^2, ordinates, second derivatives.  The device state builds the same tables itself when the spline form is selected."""
+        if useAtomicUnits:
+            raise NotImplementedError("atomic-unit splines belong to the QC/MM interactions")
+        out = {}
+        which = ([("electrostatic", 0)] if electrostatic else []) + ([("lennardJonesA", 1), ("lennardJonesB", 2)] if lennardJones else [])
+        L = _lib.lib()
+        for name, w in which:
+            n = L.PairwiseInteractionABFS_B200_MakeSpline(w, self.dampingCutoff, self.innerCutoff, self.outerCutoff, int(self.splinePointDensity), None, None, None)
+            if n <= 0:
+                raise ValueError("Invalid spline point density.")
+            x, y, h = np.zeros(n), np.zeros(n), np.zeros(n)
+            L.PairwiseInteractionABFS_B200_MakeSpline(w, self.dampingCutoff, self.innerCutoff, self.outerCutoff, int(self.splinePointDensity), d_(x), d_(y), d_(h))
+            out[name] = (x, y, h)
+        return out
 
     def MakeFactors(self):
         out = np.zeros(21)
@@ -45,7 +75,8 @@ class PairwiseInteractionABFS:
         return out
 
     def __getstate__(self):
-        return dict(dampingCutoff=self.dampingCutoff, innerCutoff=self.innerCutoff, outerCutoff=self.outerCutoff, useAnalyticForm=self.useAnalyticForm)
+        return dict(dampingCutoff=self.dampingCutoff, electrostaticModel=self.electrostaticModel, innerCutoff=self.innerCutoff, outerCutoff=self.outerCutoff,
+                    splinePointDensity=self.splinePointDensity, useAnalyticForm=self.useAnalyticForm, width1=self.width1, width2=self.width2)
 
     def __setstate__(self, state):
         self.__init__(**state)
@@ -342,6 +373,13 @@ class NBModelABFS(NBModel):
         pw = self.mmmmPairwiseInteraction
         _lib.lib().NBModelABFS_B200_SetOptions(nbState.cObject, pw.dampingCutoff, pw.innerCutoff, pw.outerCutoff, self._listCutoff,
                                                self._dielectric, self._electrostaticScale14, int(self.checkForInverses), int(self.imageExpandFactor))
+        form = (True, 0) if pw.useAnalyticForm else (False, int(pw.splinePointDensity))
+        if getattr(nbState, "_interactionForm", (True, 0)) != form:      # the library rebuilds the tables itself when the cutoffs change
+            status = C.c_int(_lib.STATUS_CONTINUE)
+            _lib.lib().PairwiseInteractionABFS_B200_SetInteractionForm(nbState.cObject, int(form[0]), form[1], C.byref(status))
+            if status.value != _lib.STATUS_CONTINUE:
+                raise CLibraryError("Unable to make the interaction splines. " + _lib.last_error())
+            nbState._interactionForm = form
 
     def SetUp(self, mmAtoms, qcAtoms, ljParameters, ljParameters14, fixedAtoms, interactions14, exclusions, symmetry, isolates, configuration, log=None):
         """Create / reuse configuration.nbState, hand over this call's coordinates and update the lists if needed."""

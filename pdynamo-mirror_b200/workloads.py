@@ -542,5 +542,11 @@ GOLDEN_CASES = {
     "w216_triclinic_centred": (WORKLOADS["w216_triclinic"], dict(useCentering=True), False),
     "w216_fixed_centred": (WORKLOADS["w216_fixed"], dict(useCentering=True), False),
 }
+# spline form of the interaction (PairwiseInteractionABFS useAnalyticForm = False): default density, a coarse table with
+# other cutoffs, 1-4 pairs + several LJ types, a crystal with rotations
+GOLDEN_CASES["w216_spline"] = (WORKLOADS["w216"], dict(useAnalyticForm=False), False)
+GOLDEN_CASES["w216_cut_spline"] = (WORKLOADS["w216"], dict(useAnalyticForm=False, splinePointDensity=20, dampingCutoff=1.0, innerCutoff=6.0, outerCutoff=9.0, listCutoff=10.5), False)
+GOLDEN_CASES["bala_spline"] = (WORKLOADS["bala"], dict(useAnalyticForm=False), False)
 for _c in CRYSTAL_NAMES:
     GOLDEN_CASES["crystal_" + _c] = (WORKLOADS["crystal_" + _c], {}, False)
+GOLDEN_CASES["crystal_GLYGLY_spline"] = (WORKLOADS["crystal_GLYGLY"], dict(useAnalyticForm=False), False)

@@ -273,12 +273,14 @@ def pair_hash(keys):
     return hashlib.sha256(np.ascontiguousarray(keys, dtype=np.int64).tobytes()).hexdigest()
 
 
-def make_golden():
+def make_golden(only=None):
     import pdynamo_mirror_b200 as p
     import oracle
     import refnb
     cases = p.workloads.GOLDEN_CASES
     for name, (maker, opts, store_pairs) in cases.items():
+        if only and name not in only:
+            continue
         w = maker()
         r = refnb.RefNB(w, **opts)
         out = r.energy(force_new=True)
@@ -305,4 +307,4 @@ if __name__ == "__main__":
         make_dhfr()
         make_crystals()
     if what in ("golden", "all"):
-        make_golden()
+        make_golden(only=sys.argv[2:])          # python make_fixtures.py golden [case ...]

@@ -52,6 +52,23 @@ def test_make_factors_matches_oracle(pkg, orc):
     assert np.array_equal(pw.MakeFactors(), orc.make_factors(1.0, 6.0, 9.0))
 
 
+def test_spline_tables_match_oracle(pkg, orc):
+    """host helper PairwiseInteractionABFS_B200_MakeSpline (what the device state uploads) against the restatement (itself bit-exact
+    against the compiled reference, tests/test_oracle.py): abscissae, ordinates and second derivatives identical"""
+    for cut in [(0.5, 8.0, 12.0, 50), (1.0, 6.0, 9.0, 20), (0.5, 8.0, 12.0, 333)]:
+        pw = pkg.PairwiseInteractionABFS(dampingCutoff=cut[0], innerCutoff=cut[1], outerCutoff=cut[2], splinePointDensity=cut[3], useAnalyticForm=False)
+        tables = pw.MakeSplines()
+        for which, name in enumerate(("electrostatic", "lennardJonesA", "lennardJonesB")):
+            for a, b in zip(tables[name], orc.make_spline(which, *cut)):
+                assert np.array_equal(a, b), (cut, name)
+    with pytest.raises(ValueError):
+        pkg.PairwiseInteractionABFS(splinePoints=3)
+    with pytest.raises(ValueError):
+        pkg.PairwiseInteractionABFS(electrostaticModel="Point/Point")
+    state = pkg.PairwiseInteractionABFS(useAnalyticForm=False, splinePointDensity=20).__getstate__()
+    assert state["useAnalyticForm"] is False and state["splinePointDensity"] == 20 and state["electrostaticModel"] == "Delta/Delta"
+
+
 def test_no_cpu_fallback(pkg):
     from pdynamo_mirror_b200 import _lib
     if _lib.lib().nbb200_device_count() > 0:

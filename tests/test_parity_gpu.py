@@ -22,9 +22,20 @@ def _hash(keys):
     return hashlib.sha256(np.ascontiguousarray(keys, dtype=np.int64).tobytes()).hexdigest()
 
 
+def nb_model(pkg, **opts):
+    """NBModelABFS from a GOLDEN_CASES option dict: the interaction-form keys belong to the MM/MM PairwiseInteractionABFS object the
+    reference's NBModelABFS takes as mmmmPairwiseInteraction (pMolecule.NBModelABFS.pyx:151)"""
+    opts = dict(opts)
+    if "useAnalyticForm" in opts or "splinePointDensity" in opts:
+        pw = dict(useAnalyticForm=opts.pop("useAnalyticForm", True), splinePointDensity=opts.pop("splinePointDensity", 50))
+        pw.update({k: opts[k] for k in ("dampingCutoff", "innerCutoff", "outerCutoff") if k in opts})
+        opts["mmmmPairwiseInteraction"] = pkg.PairwiseInteractionABFS(**pw)
+    return pkg.NBModelABFS(**opts)
+
+
 def gpu_energy(pkg, w, **opts):
     system = pkg.System.FromWorkload(w)
-    system.DefineNBModel(pkg.NBModelABFS(**opts))
+    system.DefineNBModel(nb_model(pkg, **opts))
     system.Energy(doGradients=True)
     cfg = system.configuration
     dm = cfg.symmetryParameterGradients.dEdM if hasattr(cfg, "symmetryParameterGradients") else np.zeros((3, 3))
@@ -43,7 +54,7 @@ def check_numbers(name, e, g, dm, re, rg, rdm):
 
 
 @pytest.mark.parametrize("name", ["w216", "w216_lattice", "w216_triclinic", "w216_cut", "bala", "jac", "bala_fixed", "w216_fixed", "w216_centred", "w216_triclinic_centred",
-                                  "w216_fixed_centred"])
+                                  "w216_fixed_centred", "w216_spline", "w216_cut_spline", "bala_spline"])
 def test_parity_vs_oracle_and_reference_golden(pkg, orc, name):
     maker, opts, _ = pkg.workloads.GOLDEN_CASES[name]
     w = maker()
@@ -100,6 +111,43 @@ def test_molecular_crystals_with_space_group_rotations(pkg, orc, name):
         assert np.all(np.abs(e - re) <= 1.0e-5 * np.abs(re).sum())
         assert np.sqrt(((g - rg) ** 2).mean()) <= G_TOL * np.sqrt((rg ** 2).mean())
         assert np.linalg.norm(dm - rdm) <= M_TOL * np.linalg.norm(rdm)
+
+
+def test_spline_form_crystal_with_rotations_and_large_tables(pkg, orc):
+    """Spline form (useAnalyticForm = False) through the rotation kernel on a P2_1/c crystal (golden output of the compiled reference),
+    and with a table too large for shared memory (density 400: the global-memory variant) on the 216-water box against the oracle."""
+    w = pkg.workloads.WORKLOADS["crystal_GLYGLY"]()
+    system, st, e, g, dm = gpu_energy(pkg, w, useAnalyticForm=False)
+    gold = load_golden("crystal_GLYGLY_spline")
+    ref = orc.OracleNB(w, useAnalyticForm=False).energy(force_new=True)
+    for re, rg, rdm in ((ref["energies"], ref["grad"], ref["dEdM"]), (gold["energies"], gold["grad"], gold["dEdM"])):
+        assert np.all(np.abs(e - re) <= 1.0e-5 * np.abs(re).sum())
+        assert np.sqrt(((g - rg) ** 2).mean()) <= G_TOL * np.sqrt((rg ** 2).mean())
+        assert np.linalg.norm(dm - rdm) <= M_TOL * np.linalg.norm(rdm)
+    w = pkg.workloads.WORKLOADS["w216"]()
+    for density in (400, 3):
+        system, st, e, g, dm = gpu_energy(pkg, w, useAnalyticForm=False, splinePointDensity=density)
+        ref = orc.OracleNB(w, useAnalyticForm=False, splinePointDensity=density).energy(force_new=True)
+        check_numbers("w216", e, g, dm, ref["energies"], ref["grad"], ref["dEdM"])
+
+
+def test_spline_form_follows_option_changes(pkg, orc):
+    """Switching one state between the forms and changing the cutoffs rebuilds the tables (NBModelABFS.SetOptions -> CheckPairwiseInteractions
+    -> MakeSplines, pMolecule.NBModelABFS.pyx:140-179)."""
+    w = pkg.workloads.WORKLOADS["bala"]()
+    system = pkg.System.FromWorkload(w)
+    nb = pkg.NBModelABFS()
+    system.DefineNBModel(nb)
+    o = orc.OracleNB(w)
+    for form in (dict(useAnalyticForm=False), dict(useAnalyticForm=True), dict(useAnalyticForm=False, splinePointDensity=25),
+                 dict(useAnalyticForm=False, splinePointDensity=25, dampingCutoff=0.75, innerCutoff=7.0, outerCutoff=10.0)):
+        cut = {k: v for k, v in form.items() if k.endswith("Cutoff")}
+        nb.SetOptions(mmmmPairwiseInteraction=pkg.PairwiseInteractionABFS(**form), **cut)
+        o.set_options(**form)
+        system.Energy(doGradients=True)
+        cfg = system.configuration
+        ref = o.energy(force_new=True)
+        check_numbers("bala", cfg.nbState.energies, cfg.gradients3, cfg.symmetryParameterGradients.dEdM, ref["energies"], ref["grad"], ref["dEdM"])
 
 
 def test_published_dhfr_known_answer(pkg, orc):
