@@ -357,6 +357,10 @@ def run_b200(args):
                 line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as exc:      # the baseline is reported, never required
                 line["cpu_baseline"] = {"value": None, "unit": "list-pairs/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (exc,)}
+        try:
+            line["spline_form"] = spline_block(torch, m, pairs)
+        except Exception as exc:
+            line["spline_form"] = {"error": repr(exc)}
         if args.workload != "jac" and not args.no_jac:
             try:
                 line["jac"] = jac_block(torch, local, fp32_peak_tflops)
@@ -399,6 +403,27 @@ def distributed_check(torch, dist, m, dn, w, local):
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return {"energy_rel_err": float(tmax[0]), "owned_gradient_rel_rms_err_max": float(tmax[1]), "atoms_with_gradient_all_ranks": int(t[2]), "atoms": int(w["n"])}
+
+
+def spline_block(torch, m, pairs):
+    """The same workload with the interaction in its spline form (PairwiseInteractionABFS useAnalyticForm = False, 50 points / A:
+    three cubic-spline tables looked up per pair instead of the analytic ABFS formulas)."""
+    st = C.c_int(16)
+    m.L.nbb200_set_stream(m.h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    m.L.PairwiseInteractionABFS_B200_SetInteractionForm(m.h, 0, 50, C.byref(st))
+    if st.value != 16:
+        raise RuntimeError(m._lib.last_error())
+    try:
+        e_analytic = m.e.copy()
+        ms = timed_steps(torch, lambda: m.step(rebuild=True), 5, 3, lambda: None)
+        fk = []
+        for _ in range(5):
+            m.step(rebuild=True); fk.append(m.state.Timings()["tileForces"])
+        ms_nr = timed_steps(torch, lambda: m.step(rebuild=False), 5, 3, lambda: None)
+        return {"ms_per_step": ms, "ms_per_call_no_rebuild": ms_nr, "tile_forces_ms": statistics.mean(fk), "value": pairs / (ms * 1e-3), "unit": "list-pairs/s",
+                "energies": [float(v) for v in m.e], "rel_diff_to_analytic_total": float(abs(m.e.sum() - e_analytic.sum()) / abs(e_analytic.sum()))}
+    finally:
+        m.L.PairwiseInteractionABFS_B200_SetInteractionForm(m.h, 1, 50, C.byref(st))
 
 
 def jac_block(torch, local, fp32_peak_tflops):

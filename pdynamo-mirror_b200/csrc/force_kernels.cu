@@ -30,8 +30,9 @@ struct ForceArgs {
     AbfsF32 F; float qScale;
     double *gradSorted; double *accum;
     double origin[3];
-    // spline form: per interval of the shared abscissae four float4 = {xf, e0, e1, e2 | e3, a0, a1, a2 | a3, b0, b1, b2 | b3, 0, 0, 0}
-    // (cubics in u = r^2 - xf of the electrostatic, LJ-A and LJ-B splines); row splN - 1 is all zero (pairs that are not evaluated)
+    // spline form: per interval l of the shared abscissae four float4, stored as four arrays of splN entries (tab[k * splN + l]: lanes
+    // with different l then spread over all shared-memory banks): {xf, e0, e1, e2}, {e3, a0, a1, a2}, {a3, b0, b1, b2}, {b3, 0, 0, 0}
+    // (cubics in u = r^2 - xf of the electrostatic, LJ-A and LJ-B splines); entry splN - 1 is all zero (pairs that are not evaluated)
     const float4 *splTab; int splN; float splInvDR;
 };
 
@@ -142,8 +143,8 @@ __device__ __forceinline__ PairOut spline_pair(const float4 *__restrict__ tab, i
 {
     int l = min((int) (sqrt_fast(r2) * invDR), nrows - 2);
     l = live ? l : nrows - 1;
-    const float4 *row = tab + 4 * l;
-    const float4 t0 = row[0], t1 = row[1], t2 = row[2], t3 = row[3];
+    const float4 *row = tab + l;
+    const float4 t0 = row[0], t1 = row[nrows], t2 = row[2 * nrows], t3 = row[3 * nrows];
     const float u = r2 - t0.x;
     // Lennard-Jones: coefficients are linear in (A, B)
     const float c0 = fmaf(A, t1.y, B * t2.y), c1 = fmaf(A, t1.z, B * t2.z), c2 = fmaf(A, t1.w, B * t2.w), c3 = fmaf(A, t2.x, B * t3.x);
@@ -509,10 +510,10 @@ bool upload_spline_tables(State &s)
             c[k][2] = (float) (p[2] + 3.0 * dlt * p[3]);
             c[k][3] = (float) p[3];
         }
-        poly[4 * l + 0] = make_float4(xf, c[0][0], c[0][1], c[0][2]);
-        poly[4 * l + 1] = make_float4(c[0][3], c[1][0], c[1][1], c[1][2]);
-        poly[4 * l + 2] = make_float4(c[1][3], c[2][0], c[2][1], c[2][2]);
-        poly[4 * l + 3] = make_float4(c[2][3], 0.f, 0.f, 0.f);
+        poly[l] = make_float4(xf, c[0][0], c[0][1], c[0][2]);
+        poly[(size_t) n + l] = make_float4(c[0][3], c[1][0], c[1][1], c[1][2]);
+        poly[(size_t) 2 * n + l] = make_float4(c[1][3], c[2][0], c[2][1], c[2][2]);
+        poly[(size_t) 3 * n + l] = make_float4(c[2][3], 0.f, 0.f, 0.f);
     }
     if (!s.splF64.ensure(h64.size()) || !s.splPoly.ensure(poly.size())) return false;
     NBB_CUDA(cudaMemcpy(s.splF64.p, h64.data(), sizeof(double) * h64.size(), cudaMemcpyHostToDevice));
