@@ -168,6 +168,45 @@ void nbb200_set_partition(NBB200State *state, int rank, int nranks);
 void nbb200_vv_first_half(NBB200State *state, double *d_x, double *d_v, const double *d_a, double dt);
 void nbb200_vv_second_half(NBB200State *state, double *d_v, double *d_a, const double *d_g, const double *d_mass, double dt, double *d_ke);
 
+/* Langevin velocity Verlet (pCore-1.9.0/pCore/LangevinVelocityVerletIntegrator.py:117-150, the integrator of the reference's own DHFR benchmark,
+ * benchmarks/SystemBenchmarks.py:95-101), first part of an Iteration in Cartesian variables:
+ *   x += facR1 v + facR2 a + sdR w1 / sqrt(m) ; v = facV1 v + facV2 a + (sdV1 w1 + sdV2 w2) / sqrt(m)
+ * factors7 = {facR1, facR2, facV1, facV2, sdR, sdV1, sdV2} as CalculateIntegrationConstants (:54-115) gives them; w1, w2: standard normal
+ * deviates from a counter-based generator keyed by (seed, step, coordinate).  The second part (a = -100 g / m; v += facV3 a; kinetic
+ * energy) is nbb200_vv_second_half with dt = 2 facV3.  Not applied: the projection of the deviates on the linear constraints
+ * (ApplyLinearConstraints), i.e. the centre of mass is free to diffuse. */
+void nbb200_langevin_first_half(NBB200State *state, double *d_x, double *d_v, const double *d_a, const double *d_mass, const double *factors7,
+                                unsigned long long seed, unsigned long long step);
+
+/* ---- bonded MM terms on the device --------------------------------------------------
+ * What System.Energy evaluates next to the NB model (pMolecule-1.9.0/pMolecule/System.py:272-318), for callers that keep coordinates and
+ * gradients on the device.  One opaque object holds the terms of all containers; they are evaluated by a single launch in fp64.
+ * Terms and parameters are given as the reference's containers hold them: per term the atom indices, a parameter type and QACTIVE
+ * (active == NULL: all active); per parameter type the values.  Defining a container again replaces it; nterms = 0 removes it. */
+typedef struct NBB200MMTerms NBB200MMTerms;
+NBB200MMTerms *MMTerms_B200_Allocate(int device, int natoms, int *status);
+void MMTerms_B200_Deallocate(NBB200MMTerms **terms);
+void MMTerms_B200_SetStream(NBB200MMTerms *terms, void *cudaStream);
+/* HarmonicBondContainer (pM/cinclude/HarmonicBondContainer.h:17-36; E = fc (r - eq)^2): atoms[2 nterms]; isUreyBradley selects the
+ * second container of this kind System holds (label "Urey-Bradley", pBabel CHARMMPSFFileReader.ToHarmonicUreyBradleyContainer) */
+void HarmonicBondContainer_B200_Define(NBB200MMTerms *terms, int isUreyBradley, int nterms, const int *atoms, const int *types, const unsigned char *active,
+                                       int nparameters, const double *eq, const double *fc, int *status);
+/* HarmonicAngleContainer (pM/cinclude/HarmonicAngleContainer.h:17-36; E = fc (theta - eq)^2, radians): atoms[3 nterms] */
+void HarmonicAngleContainer_B200_Define(NBB200MMTerms *terms, int nterms, const int *atoms, const int *types, const unsigned char *active,
+                                        int nparameters, const double *eq, const double *fc, int *status);
+/* FourierDihedralContainer (pM/cinclude/FourierDihedralContainer.h:14-47; E = fc (1 + cos(period phi - phase))): atoms[4 nterms] */
+void FourierDihedralContainer_B200_Define(NBB200MMTerms *terms, int nterms, const int *atoms, const int *types, const unsigned char *active,
+                                          int nparameters, const double *fc, const int *period, const double *phase, int *status);
+/* HarmonicImproperContainer (pM/cinclude/HarmonicImproperContainer.h:14-46; E = fc (phi - eq)^2): atoms[4 nterms] */
+void HarmonicImproperContainer_B200_Define(NBB200MMTerms *terms, int nterms, const int *atoms, const int *types, const unsigned char *active,
+                                           int nparameters, const double *eq, const double *fc, int *status);
+/* replace Harmonic{Bond,Angle,Improper}Container_Energy / FourierDihedralContainer_Energy (pM/csource/HarmonicBondContainer.c:149,
+ * HarmonicAngleContainer.c:157, FourierDihedralContainer.c:156, HarmonicImproperContainer.c:172): energies5 = {bond, angle, Urey-Bradley,
+ * dihedral, improper} are set; grad[3 natoms] (nullable) is ACCUMULATED into.  Host arrays / device arrays. */
+void MMTerms_B200_Energy(NBB200MMTerms *terms, const double *xyz, double *energies5, double *grad, int *status);
+void MMTerms_B200_EnergyDevice(NBB200MMTerms *terms, const double *d_xyz, double *energies5, double *d_grad, int *status);
+long MMTerms_B200_NumberOfTerms(NBB200MMTerms *terms, int kind /* 0 bond, 1 angle, 2 Urey-Bradley, 3 dihedral, 4 improper: active terms */);
+
 /* ---- several GPUs ------------------------------------------------------------
  * Every rank sorts all atoms the same way (cell order); rank r owns the contiguous slab of sorted positions
  * [s0, s1) = the i-blocks nbb200_set_partition gave it, i.e. a spatial slab.  Its lists reference, inside every other

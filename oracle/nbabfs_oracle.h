@@ -47,6 +47,15 @@ void   orc_make_M(const double *box6, double *M9, double *invM9);
 /* single pair: returns energies e[2] = {elect, lj} and dF = dE/d(r^2) for qij (already scaled), Aij, Bij */
 void   orc_pair(const double *f21, double r2, double qij, double Aij, double Bij, double *e2, double *dF);
 
+/* bonded MM terms (oracle/mmterms_oracle.c): same contract as refmm_energy (oracle/ref_driver.h) */
+void   orc_mm_energy(int n, const double *xyz,
+                     int nbond, const int *bonds, const double *bondEq, const double *bondFc,
+                     int nangle, const int *angles, const double *angleEq, const double *angleFc,
+                     int nub, const int *ubs, const double *ubEq, const double *ubFc,
+                     int ndih, const int *dihedrals, const double *dihFc, const int *dihPeriod, const double *dihPhase,
+                     int nimp, const int *impropers, const double *impEq, const double *impFc,
+                     double *energies5, double *grad);
+
 #ifdef __cplusplus
 }
 #endif

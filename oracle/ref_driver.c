@@ -27,6 +27,10 @@
 #include "ImageList.h"
 #include "Selection.h"
 #include "CubicSpline.h"
+#include "HarmonicBondContainer.h"
+#include "HarmonicAngleContainer.h"
+#include "FourierDihedralContainer.h"
+#include "HarmonicImproperContainer.h"
 #include "ref_driver.h"
 
 struct RefNB {
@@ -374,4 +378,71 @@ void refnb_make_M(const double *box, double *M9, double *invM9)
         invM9[3 * r + c] = Matrix33_Item(sp->inverseM, r, c);
     }
     SymmetryParameters_Deallocate(&sp);
+}
+
+/* The reference's bonded MM terms as System.Energy evaluates them (pMolecule-1.9.0/pMolecule/System.py:272-318): containers are filled
+ * with one parameter record per term (type = term index) and the unmodified *_Energy routines are called
+ * (pMolecule-1.9.0/extensions/csource/HarmonicBondContainer.c:149, HarmonicAngleContainer.c:157, FourierDihedralContainer.c:156,
+ * HarmonicImproperContainer.c:172).  energies5 = {bond, angle, Urey-Bradley, dihedral, improper}; grad (nullable) is accumulated into. */
+void refmm_energy(int n, const double *xyz,
+                  int nbond, const int *bonds, const double *bondEq, const double *bondFc,
+                  int nangle, const int *angles, const double *angleEq, const double *angleFc,
+                  int nub, const int *ubs, const double *ubEq, const double *ubFc,
+                  int ndih, const int *dihedrals, const double *dihFc, const int *dihPeriod, const double *dihPhase,
+                  int nimp, const int *impropers, const double *impEq, const double *impFc,
+                  double *energies5, double *grad)
+{
+    Coordinates3 *x = Coordinates3_Allocate(n), *g = (grad != NULL) ? Coordinates3_Allocate(n) : NULL;
+    int i, pass;
+    for (i = 0; i < n; i++) { Coordinates3_Item(x, i, 0) = xyz[3 * i]; Coordinates3_Item(x, i, 1) = xyz[3 * i + 1]; Coordinates3_Item(x, i, 2) = xyz[3 * i + 2]; }
+    if (g != NULL) Coordinates3_Set(g, 0.0);
+    for (i = 0; i < 5; i++) energies5[i] = 0.0;
+    for (pass = 0; pass < 2; pass++) {
+        int nt = pass ? nub : nbond; const int *a = pass ? ubs : bonds; const double *eq = pass ? ubEq : bondEq, *fc = pass ? ubFc : bondFc;
+        if (nt > 0) {
+            HarmonicBondContainer *c = HarmonicBondContainer_Allocate(nt, nt);
+            for (i = 0; i < nt; i++) {
+                c->terms[i].QACTIVE = True; c->terms[i].atom1 = a[2 * i]; c->terms[i].atom2 = a[2 * i + 1]; c->terms[i].type = i;
+                c->parameters[i].eq = eq[i]; c->parameters[i].fc = fc[i];
+            }
+            energies5[pass ? 2 : 0] = HarmonicBondContainer_Energy(c, x, g);
+            HarmonicBondContainer_Deallocate(&c);
+        }
+    }
+    if (nangle > 0) {
+        HarmonicAngleContainer *c = HarmonicAngleContainer_Allocate(nangle, nangle);
+        for (i = 0; i < nangle; i++) {
+            c->terms[i].QACTIVE = True; c->terms[i].atom1 = angles[3 * i]; c->terms[i].atom2 = angles[3 * i + 1]; c->terms[i].atom3 = angles[3 * i + 2]; c->terms[i].type = i;
+            c->parameters[i].eq = angleEq[i]; c->parameters[i].fc = angleFc[i];
+        }
+        energies5[1] = HarmonicAngleContainer_Energy(c, x, g);
+        HarmonicAngleContainer_Deallocate(&c);
+    }
+    if (ndih > 0) {
+        FourierDihedralContainer *c = FourierDihedralContainer_Allocate(ndih, ndih);
+        for (i = 0; i < ndih; i++) {
+            c->terms[i].QACTIVE = True; c->terms[i].atom1 = dihedrals[4 * i]; c->terms[i].atom2 = dihedrals[4 * i + 1];
+            c->terms[i].atom3 = dihedrals[4 * i + 2]; c->terms[i].atom4 = dihedrals[4 * i + 3]; c->terms[i].type = i;
+            c->parameters[i].fc = dihFc[i]; c->parameters[i].period = dihPeriod[i]; c->parameters[i].phase = dihPhase[i];
+        }
+        FourierDihedralContainer_FillCosSinPhases(c);
+        energies5[3] = FourierDihedralContainer_Energy(c, x, g);
+        FourierDihedralContainer_Deallocate(&c);
+    }
+    if (nimp > 0) {
+        HarmonicImproperContainer *c = HarmonicImproperContainer_Allocate(nimp, nimp);
+        for (i = 0; i < nimp; i++) {
+            c->terms[i].QACTIVE = True; c->terms[i].atom1 = impropers[4 * i]; c->terms[i].atom2 = impropers[4 * i + 1];
+            c->terms[i].atom3 = impropers[4 * i + 2]; c->terms[i].atom4 = impropers[4 * i + 3]; c->terms[i].type = i;
+            c->parameters[i].eq = impEq[i]; c->parameters[i].fc = impFc[i];
+        }
+        HarmonicImproperContainer_FillCosSinValues(c);
+        energies5[4] = HarmonicImproperContainer_Energy(c, x, g);
+        HarmonicImproperContainer_Deallocate(&c);
+    }
+    if (g != NULL) {
+        for (i = 0; i < n; i++) { grad[3 * i] += Coordinates3_Item(g, i, 0); grad[3 * i + 1] += Coordinates3_Item(g, i, 1); grad[3 * i + 2] += Coordinates3_Item(g, i, 2); }
+        Coordinates3_Deallocate(&g);
+    }
+    Coordinates3_Deallocate(&x);
 }

@@ -71,6 +71,16 @@ void   refnb_lj_table(int ntypes, const double *eps, const double *sigma, int am
                       int *tableindex, double *tableA, double *tableB);
 void   refnb_make_M(const double *box6, double *M9, double *invM9);
 
+/* bonded MM terms through the reference's own containers and *_Energy routines; per-term parameters; energies5 = {bond, angle,
+ * Urey-Bradley, dihedral, improper}; grad[3n] (nullable) accumulated into */
+void   refmm_energy(int n, const double *xyz,
+                    int nbond, const int *bonds, const double *bondEq, const double *bondFc,
+                    int nangle, const int *angles, const double *angleEq, const double *angleFc,
+                    int nub, const int *ubs, const double *ubEq, const double *ubFc,
+                    int ndih, const int *dihedrals, const double *dihFc, const int *dihPeriod, const double *dihPhase,
+                    int nimp, const int *impropers, const double *impEq, const double *impFc,
+                    double *energies5, double *grad);
+
 #ifdef __cplusplus
 }
 #endif

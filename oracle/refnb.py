@@ -50,6 +50,7 @@ def _lib(omp=False):
     lib.refnb_get_image_pairs.argtypes = [vp, C.c_int, ip]
     lib.refnb_make_factors.argtypes = [C.c_double] * 3 + [dp]
     lib.refnb_lj_table.argtypes = [C.c_int, dp, dp, C.c_int, ip, dp, dp]
+    lib.refmm_energy.argtypes = [C.c_int, dp, C.c_int, ip, dp, dp, C.c_int, ip, dp, dp, C.c_int, ip, dp, dp, C.c_int, ip, dp, ip, dp, C.c_int, ip, dp, dp, dp, dp]
     lib.refnb_make_M.argtypes = [dp, dp, dp]
     lib.refnb_set_interaction_form.argtypes = [vp, C.c_int, C.c_int]
     lib.refnb_make_spline.restype = C.c_int
@@ -209,3 +210,25 @@ def make_M(box6):
     im = np.zeros((3, 3))
     _lib().refnb_make_M(_d(b), _d(m), _d(im))
     return m, im
+
+
+def _mm_call(fn, b, xyz, gradients):
+    """b: bonded-term dict (tests/golden/dhfr_bonded.npz layout, per-term parameters); returns (energies5, grad or None)"""
+    xyz = np.ascontiguousarray(xyz, np.float64)
+    n = len(xyz)
+    ia = lambda k, w: np.ascontiguousarray(b.get(k, np.zeros((0, w), np.int32)), np.int32).reshape(-1, w)
+    da = lambda k: np.ascontiguousarray(b.get(k, np.zeros(0)), np.float64)
+    bonds, angles, ubs, dih, imp = ia("bonds", 2), ia("angles", 3), ia("ureybradleys", 2), ia("dihedrals", 4), ia("impropers", 4)
+    per = np.ascontiguousarray(b.get("dihedral_period", np.zeros(0, np.int32)), np.int32)
+    keep = [da(k) for k in ("bond_eq", "bond_fc", "angle_eq", "angle_fc", "ub_eq", "ub_fc", "dihedral_fc", "dihedral_phase", "improper_eq", "improper_fc")]
+    e = np.zeros(5)
+    g = np.zeros((n, 3)) if gradients else None
+    fn(n, _d(xyz), len(bonds), _i(bonds), _d(keep[0]), _d(keep[1]), len(angles), _i(angles), _d(keep[2]), _d(keep[3]),
+       len(ubs), _i(ubs), _d(keep[4]), _d(keep[5]), len(dih), _i(dih), _d(keep[6]), _i(per), _d(keep[7]),
+       len(imp), _i(imp), _d(keep[8]), _d(keep[9]), _d(e), _d(g))
+    return e, g
+
+
+def mm_energy(bonded, xyz, gradients=True):
+    """bonded MM terms {bond, angle, Urey-Bradley, dihedral, improper} and their gradient"""
+    return _mm_call(_lib().refmm_energy, bonded, xyz, gradients)

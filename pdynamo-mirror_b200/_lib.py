@@ -46,6 +46,17 @@ SIGNATURES = {
     "nbb200_set_gradient_overwrite": (None, [vp, C.c_int]),
     "nbb200_vv_first_half": (None, [vp, vp, vp, vp, C.c_double]),
     "nbb200_vv_second_half": (None, [vp, vp, vp, vp, vp, C.c_double, vp]),
+    "nbb200_langevin_first_half": (None, [vp, vp, vp, vp, vp, dp, C.c_ulonglong, C.c_ulonglong]),
+    "MMTerms_B200_Allocate": (vp, [C.c_int, C.c_int, ip]),
+    "MMTerms_B200_Deallocate": (None, [C.POINTER(vp)]),
+    "MMTerms_B200_SetStream": (None, [vp, vp]),
+    "HarmonicBondContainer_B200_Define": (None, [vp, C.c_int, C.c_int, ip, ip, C.c_char_p, C.c_int, dp, dp, ip]),
+    "HarmonicAngleContainer_B200_Define": (None, [vp, C.c_int, ip, ip, C.c_char_p, C.c_int, dp, dp, ip]),
+    "FourierDihedralContainer_B200_Define": (None, [vp, C.c_int, ip, ip, C.c_char_p, C.c_int, dp, ip, dp, ip]),
+    "HarmonicImproperContainer_B200_Define": (None, [vp, C.c_int, ip, ip, C.c_char_p, C.c_int, dp, dp, ip]),
+    "MMTerms_B200_Energy": (None, [vp, dp, dp, dp, ip]),
+    "MMTerms_B200_EnergyDevice": (None, [vp, vp, dp, vp, ip]),
+    "MMTerms_B200_NumberOfTerms": (C.c_long, [vp, C.c_int]),
     "nbb200_get_slab": (None, [vp, lp]),
     "nbb200_touched_ranges": (C.c_int, [vp, lp]),
     "nbb200_touched_ranges_device": (C.c_int, [vp, vp]),

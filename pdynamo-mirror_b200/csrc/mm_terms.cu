@@ -1,0 +1,368 @@
+// mm_terms.cu -- the bonded MM terms and the Langevin half step on the device (what an MD caller needs next to the NB
+// term so that coordinates, velocities and gradients never leave the GPU).
+//
+// Replaces, for device-resident coordinates / gradients,
+//   HarmonicBondContainer_Energy      pMolecule-1.9.0/extensions/csource/HarmonicBondContainer.c:149-183   (bonds and Urey-Bradley terms)
+//   HarmonicAngleContainer_Energy     pMolecule-1.9.0/extensions/csource/HarmonicAngleContainer.c:157-205
+//   FourierDihedralContainer_Energy   pMolecule-1.9.0/extensions/csource/FourierDihedralContainer.c:156-241
+//   HarmonicImproperContainer_Energy  pMolecule-1.9.0/extensions/csource/HarmonicImproperContainer.c:172-258
+// as System.Energy calls them one after the other (pMolecule-1.9.0/pMolecule/System.py:272-318), and one Iteration of
+// pCore-1.9.0/pCore/LangevinVelocityVerletIntegrator.py:117-150 in Cartesian variables.
+//
+// All terms of all containers are evaluated by ONE launch: a term is one thread (fp64 throughout; a few 10^4 terms), the term kinds are
+// laid out one after the other so that warps are uniform except at the four seams; energies are reduced per kind through shared
+// memory, gradients are accumulated with fp64 atomics.  Parameters are expanded per term when a container is defined.
+#include "../../include/nbabfs_b200.h"
+#include "nbb200_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace nbb200 {
+
+constexpr int kKinds = 5;                 // 0 bond, 1 angle, 2 Urey-Bradley, 3 Fourier dihedral, 4 harmonic improper
+
+struct TermRecord { int atom[4]; double p[4]; };    // p: bond / UB / angle {eq, fc}; dihedral {fc, cosphase, sinphase, period}; improper {fc, coseq, sineq}
+
+struct MMTerms {
+    int device = 0, natoms = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    std::vector<TermRecord> host[kKinds];
+    bool dirty = true;
+    int start[kKinds + 1] = {};
+    DevBuf<TermRecord> rec;
+    DevBuf<double> x, grad, energies;
+    double *hx = nullptr, *hg = nullptr, *he = nullptr;
+    long launches = 0;
+};
+
+struct KindStarts { int s[kKinds + 1]; };
+
+__device__ __forceinline__ void add3(double *g, int a, double x, double y, double z)
+{
+    atomicAdd(g + 3 * (size_t) a, x); atomicAdd(g + 3 * (size_t) a + 1, y); atomicAdd(g + 3 * (size_t) a + 2, z);
+}
+
+// cos / sin of a dihedral i-j-k-l and the vectors its derivatives need (shared by the Fourier dihedral and the harmonic improper)
+struct Torsion { double cosphi, sinphi, rkj, rkj2, m2, n2, mx, my, mz, nx, ny, nz, xij, yij, zij, xkj, ykj, zkj, xlk, ylk, zlk; };
+
+__device__ __forceinline__ Torsion torsion(const double *__restrict__ x, int i, int j, int k, int l)
+{
+    Torsion t;
+    t.xij = x[3 * i] - x[3 * j]; t.yij = x[3 * i + 1] - x[3 * j + 1]; t.zij = x[3 * i + 2] - x[3 * j + 2];
+    t.xkj = x[3 * k] - x[3 * j]; t.ykj = x[3 * k + 1] - x[3 * j + 1]; t.zkj = x[3 * k + 2] - x[3 * j + 2];
+    t.xlk = x[3 * l] - x[3 * k]; t.ylk = x[3 * l + 1] - x[3 * k + 1]; t.zlk = x[3 * l + 2] - x[3 * k + 2];
+    t.rkj2 = t.xkj * t.xkj + t.ykj * t.ykj + t.zkj * t.zkj;
+    t.rkj = sqrt(t.rkj2);
+    t.mx = t.yij * t.zkj - t.zij * t.ykj; t.my = t.zij * t.xkj - t.xij * t.zkj; t.mz = t.xij * t.ykj - t.yij * t.xkj;
+    t.nx = t.ylk * t.zkj - t.zlk * t.ykj; t.ny = t.zlk * t.xkj - t.xlk * t.zkj; t.nz = t.xlk * t.ykj - t.ylk * t.xkj;
+    t.m2 = t.mx * t.mx + t.my * t.my + t.mz * t.mz;
+    t.n2 = t.nx * t.nx + t.ny * t.ny + t.nz * t.nz;
+    const double mn = sqrt(t.m2 * t.n2);
+    t.cosphi = (t.mx * t.nx + t.my * t.ny + t.mz * t.nz) / mn;
+    t.sinphi = t.rkj * (t.xij * t.nx + t.yij * t.ny + t.zij * t.nz) / mn;
+    return t;
+}
+
+// gradient of a torsion term with dE/dphi = df (FourierDihedralContainer.c:212-235 = HarmonicImproperContainer.c:229-252)
+__device__ __forceinline__ void torsion_gradient(const Torsion &t, double df, int i, int j, int k, int l, double *g)
+{
+    const double dtxi = df * t.rkj * t.mx / t.m2, dtyi = df * t.rkj * t.my / t.m2, dtzi = df * t.rkj * t.mz / t.m2;
+    const double dtxl = -df * t.rkj * t.nx / t.n2, dtyl = -df * t.rkj * t.ny / t.n2, dtzl = -df * t.rkj * t.nz / t.n2;
+    const double dotij = t.xij * t.xkj + t.yij * t.ykj + t.zij * t.zkj, dotlk = t.xlk * t.xkj + t.ylk * t.ykj + t.zlk * t.zkj;
+    const double sx = (dotij * dtxi + dotlk * dtxl) / t.rkj2, sy = (dotij * dtyi + dotlk * dtyl) / t.rkj2, sz = (dotij * dtzi + dotlk * dtzl) / t.rkj2;
+    add3(g, i, dtxi, dtyi, dtzi);
+    add3(g, j, sx - dtxi, sy - dtyi, sz - dtzi);
+    add3(g, k, -sx - dtxl, -sy - dtyl, -sz - dtzl);
+    add3(g, l, dtxl, dtyl, dtzl);
+}
+
+__global__ void k_mm_terms(const TermRecord *__restrict__ rec, KindStarts K, const double *__restrict__ x, double *g, double *energies)
+{
+    __shared__ double sE[kKinds];
+    if (threadIdx.x < kKinds) sE[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < K.s[kKinds]) {
+        int kind = 0;
+        while (n >= K.s[kind + 1]) kind++;
+        const TermRecord r = rec[n];
+        const int i = r.atom[0], j = r.atom[1], k = r.atom[2], l = r.atom[3];
+        double e = 0.0;
+        if (kind == 0 || kind == 2) {                         // harmonic bond / Urey-Bradley: E = fc (r - eq)^2
+            double xij = x[3 * i] - x[3 * j], yij = x[3 * i + 1] - x[3 * j + 1], zij = x[3 * i + 2] - x[3 * j + 2];
+            const double rij = sqrt(xij * xij + yij * yij + zij * zij), disp = rij - r.p[0];
+            double df = r.p[1] * disp;
+            e = df * disp;
+            if (g != nullptr) {
+                df *= (2.0 / rij);
+                xij *= df; yij *= df; zij *= df;
+                add3(g, i, xij, yij, zij); add3(g, j, -xij, -yij, -zij);
+            }
+        } else if (kind == 1) {                               // harmonic angle i-j-k: E = fc (theta - eq)^2, |cos| clamped at 0.999999
+            double xij = x[3 * i] - x[3 * j], yij = x[3 * i + 1] - x[3 * j + 1], zij = x[3 * i + 2] - x[3 * j + 2];
+            double xkj = x[3 * k] - x[3 * j], ykj = x[3 * k + 1] - x[3 * j + 1], zkj = x[3 * k + 2] - x[3 * j + 2];
+            const double rij = sqrt(xij * xij + yij * yij + zij * zij), rkj = sqrt(xkj * xkj + ykj * ykj + zkj * zkj);
+            xij /= rij; yij /= rij; zij /= rij; xkj /= rkj; ykj /= rkj; zkj /= rkj;
+            double dot = xij * xkj + yij * ykj + zij * zkj;
+            dot = fmin(0.999999, fmax(-0.999999, dot));
+            const double disp = acos(dot) - r.p[0];
+            double df = r.p[1] * disp;
+            e = df * disp;
+            if (g != nullptr) {
+                df *= (2.0 * (-1.0 / sqrt(1.0 - dot * dot)));
+                const double dtxi = df * (xkj - dot * xij) / rij, dtyi = df * (ykj - dot * yij) / rij, dtzi = df * (zkj - dot * zij) / rij;
+                const double dtxk = df * (xij - dot * xkj) / rkj, dtyk = df * (yij - dot * ykj) / rkj, dtzk = df * (zij - dot * zkj) / rkj;
+                add3(g, i, dtxi, dtyi, dtzi); add3(g, k, dtxk, dtyk, dtzk); add3(g, j, -(dtxi + dtxk), -(dtyi + dtyk), -(dtzi + dtzk));
+            }
+        } else if (kind == 3) {                               // Fourier dihedral: E = fc (1 + cos(period phi - phase)), by the angle-addition recurrence
+            const Torsion t = torsion(x, i, j, k, l);
+            double cosn = 1.0, sinn = 0.0;
+            const int period = (int) r.p[3];
+            for (int p = 1; p <= period; p++) {
+                const double tmp = cosn * t.cosphi - sinn * t.sinphi;
+                sinn = cosn * t.sinphi + sinn * t.cosphi;
+                cosn = tmp;
+            }
+            e = r.p[0] * (1.0 + cosn * r.p[1] + sinn * r.p[2]);
+            if (g != nullptr) torsion_gradient(t, r.p[0] * r.p[3] * (cosn * r.p[2] - sinn * r.p[1]), i, j, k, l, g);
+        } else {                                              // harmonic improper: E = fc (phi - eq)^2, CHARMM's choice of inverse function
+            const Torsion t = torsion(x, i, j, k, l);
+            const double cosd = t.cosphi * r.p[1] + t.sinphi * r.p[2], sind = t.sinphi * r.p[1] - t.cosphi * r.p[2];
+            double dphi;
+            if (cosd > 0.1) dphi = asin(sind);
+            else { dphi = fabs(acos(fmax(cosd, -1.0))); if (sind < 0.0) dphi *= -1.0; }
+            const double df = r.p[0] * dphi;
+            e = df * dphi;
+            if (g != nullptr) torsion_gradient(t, 2.0 * df, i, j, k, l, g);
+        }
+        atomicAdd(&sE[kind], e);
+    }
+    __syncthreads();
+    if (threadIdx.x < kKinds && sE[threadIdx.x] != 0.0) atomicAdd(&energies[threadIdx.x], sE[threadIdx.x]);
+}
+
+static bool upload_terms(MMTerms &m)
+{
+    std::vector<TermRecord> all;
+    for (int k = 0; k < kKinds; k++) { m.start[k] = (int) all.size(); all.insert(all.end(), m.host[k].begin(), m.host[k].end()); }
+    m.start[kKinds] = (int) all.size();
+    if (!m.rec.ensure(all.size() + 1) || !m.energies.ensure(kKinds)) return false;
+    if (!all.empty()) NBB_CUDA(cudaMemcpy(m.rec.p, all.data(), sizeof(TermRecord) * all.size(), cudaMemcpyHostToDevice));
+    m.dirty = false;
+    return true;
+}
+
+static bool evaluate(MMTerms &m, const double *d_x, double *d_grad, double *energies5)
+{
+    if (m.dirty && !upload_terms(m)) return false;
+    NBB_CUDA(cudaMemsetAsync(m.energies.p, 0, sizeof(double) * kKinds, m.stream));
+    const int total = m.start[kKinds];
+    if (total > 0) {
+        KindStarts K;
+        std::memcpy(K.s, m.start, sizeof(K.s));
+        k_mm_terms<<<(total + 127) / 128, 128, 0, m.stream>>>(m.rec.p, K, d_x, d_grad, m.energies.p);
+        m.launches += 1;
+    }
+    NBB_CUDA(cudaMemcpyAsync(m.he, m.energies.p, sizeof(double) * kKinds, cudaMemcpyDeviceToHost, m.stream));
+    NBB_CUDA(cudaStreamSynchronize(m.stream));
+    if (!cuda_ok(cudaGetLastError(), "k_mm_terms")) return false;
+    for (int k = 0; k < kKinds; k++) energies5[k] = m.he[k];
+    return true;
+}
+
+// ---- Langevin velocity Verlet, first part of an Iteration (LangevinVelocityVerletIntegrator.py:117-131,139-149) in Cartesian variables:
+//   x += facR1 v + facR2 a + sdR w1 / sqrt(m) ; v = facV1 v + facV2 a + (sdV1 w1 + sdV2 w2) / sqrt(m)
+// with w1, w2 independent standard normal deviates per coordinate (the reference integrates mass-weighted variables, where the random
+// terms carry no mass factor).  Deviates: Philox-4x32-10 keyed by (seed), counter (coordinate index, step), Box-Muller.
+__device__ __forceinline__ void philox4x32(unsigned int c0, unsigned int c1, unsigned int c2, unsigned int c3, unsigned int k0, unsigned int k1, unsigned int *out)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void k_langevin_first(double *__restrict__ x, double *__restrict__ v, const double *__restrict__ a, const double *__restrict__ mass, long m,
+                                 double facR1, double facR2, double facV1, double facV2, double sdR, double sdV1, double sdV2,
+                                 unsigned long long seed, unsigned long long step)
+{
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    unsigned int r[4];
+    philox4x32((unsigned int) i, (unsigned int) ((unsigned long long) i >> 32), (unsigned int) step, (unsigned int) (step >> 32),
+               (unsigned int) seed, (unsigned int) (seed >> 32), r);
+    // two uniforms in (0, 1] with 52 bits from two words each -> Box-Muller pair
+    const double u1 = ((double) (((unsigned long long) r[0] << 20) | (r[1] >> 12)) + 1.0) * (1.0 / 4503599627370496.0);
+    const double u2 = ((double) (((unsigned long long) r[2] << 20) | (r[3] >> 12)) + 1.0) * (1.0 / 4503599627370496.0);
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    const double w1 = rad * c, w2 = rad * s, rsm = rsqrt(mass[i / 3]);
+    const double vi = v[i], ai = a[i];
+    x[i] += facR1 * vi + facR2 * ai + sdR * w1 * rsm;
+    v[i] = facV1 * vi + facV2 * ai + (sdV1 * w1 + sdV2 * w2) * rsm;
+}
+
+}  // namespace nbb200
+
+using namespace nbb200;
+
+static void mm_status(int *status, int value) { if (status != nullptr) *status = value; }
+
+extern "C" {
+
+NBB200MMTerms *MMTerms_B200_Allocate(int device, int natoms, int *status)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError(); set_error("no CUDA device available: libnbabfs_b200 has no CPU fallback"); mm_status(status, NBB200_STATUS_LOGIC_ERROR); return nullptr;
+    }
+    if (natoms <= 0) { set_error("invalid number of atoms"); mm_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr; }
+    MMTerms *m = new (std::nothrow) MMTerms();
+    if (m == nullptr) { mm_status(status, NBB200_STATUS_OUT_OF_MEMORY); return nullptr; }
+    m->device = device; m->natoms = natoms;
+    cudaSetDevice(device);
+    bool ok = cuda_ok(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    m->ownStream = ok;
+    ok = ok && m->x.ensure(3 * (size_t) natoms) && m->grad.ensure(3 * (size_t) natoms) && m->energies.ensure(kKinds);
+    ok = ok && cuda_ok(cudaMallocHost((void **) &m->hx, sizeof(double) * 3 * (size_t) natoms), "cudaMallocHost");
+    ok = ok && cuda_ok(cudaMallocHost((void **) &m->hg, sizeof(double) * 3 * (size_t) natoms), "cudaMallocHost");
+    ok = ok && cuda_ok(cudaMallocHost((void **) &m->he, sizeof(double) * 8), "cudaMallocHost");
+    if (!ok) { NBB200MMTerms *h = reinterpret_cast<NBB200MMTerms *>(m); MMTerms_B200_Deallocate(&h); mm_status(status, NBB200_STATUS_OUT_OF_MEMORY); return nullptr; }
+    return reinterpret_cast<NBB200MMTerms *>(m);
+}
+
+void MMTerms_B200_Deallocate(NBB200MMTerms **terms)
+{
+    if (terms == nullptr || *terms == nullptr) return;
+    MMTerms *m = reinterpret_cast<MMTerms *>(*terms);
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    m->rec.release(); m->x.release(); m->grad.release(); m->energies.release();
+    if (m->hx) cudaFreeHost(m->hx);
+    if (m->hg) cudaFreeHost(m->hg);
+    if (m->he) cudaFreeHost(m->he);
+    if (m->ownStream && m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    *terms = nullptr;
+}
+
+void MMTerms_B200_SetStream(NBB200MMTerms *terms, void *cudaStream)
+{
+    if (terms == nullptr) return;
+    MMTerms *m = reinterpret_cast<MMTerms *>(terms);
+    cudaSetDevice(m->device);
+    if (m->ownStream && m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+    m->stream = reinterpret_cast<cudaStream_t>(cudaStream);
+    m->ownStream = false;
+}
+
+// common part of the four Define entry points: terms with atoms / type / QACTIVE, parameters by type
+static void define_terms(NBB200MMTerms *terms, int kind, int natomsPerTerm, int nterms, const int *atoms, const int *types, const unsigned char *active,
+                         int nparameters, const double *p0, const double *p1, const double *p2, const double *p3, int *status)
+{
+    if (terms == nullptr) return;
+    MMTerms *m = reinterpret_cast<MMTerms *>(terms);
+    if (nterms < 0 || nparameters < 0 || (nterms > 0 && (atoms == nullptr || types == nullptr || p0 == nullptr || p1 == nullptr))) {
+        set_error("invalid argument to a B200 MM term container"); mm_status(status, NBB200_STATUS_INVALID_ARGUMENT); return;
+    }
+    std::vector<TermRecord> out;
+    out.reserve((size_t) nterms);
+    for (int n = 0; n < nterms; n++) {
+        if (active != nullptr && !active[n]) continue;                   // QACTIVE (fixed-atom / QC-atom deactivation in the reference)
+        const int t = types[n];
+        if (t < 0 || t >= nparameters) { set_error("term type out of range"); mm_status(status, NBB200_STATUS_INVALID_ARGUMENT); return; }
+        TermRecord r;
+        for (int a = 0; a < 4; a++) {
+            r.atom[a] = (a < natomsPerTerm) ? atoms[natomsPerTerm * n + a] : 0;
+            if (r.atom[a] < 0 || r.atom[a] >= m->natoms) { set_error("term atom out of range"); mm_status(status, NBB200_STATUS_INVALID_ARGUMENT); return; }
+        }
+        r.p[0] = p0[t]; r.p[1] = p1[t]; r.p[2] = (p2 != nullptr) ? p2[t] : 0.0; r.p[3] = (p3 != nullptr) ? p3[t] : 0.0;
+        out.push_back(r);
+    }
+    m->host[kind].swap(out);
+    m->dirty = true;
+}
+
+void HarmonicBondContainer_B200_Define(NBB200MMTerms *terms, int isUreyBradley, int nterms, const int *atoms, const int *types, const unsigned char *active,
+                                       int nparameters, const double *eq, const double *fc, int *status)
+{
+    define_terms(terms, isUreyBradley ? 2 : 0, 2, nterms, atoms, types, active, nparameters, eq, fc, nullptr, nullptr, status);
+}
+
+void HarmonicAngleContainer_B200_Define(NBB200MMTerms *terms, int nterms, const int *atoms, const int *types, const unsigned char *active,
+                                        int nparameters, const double *eq, const double *fc, int *status)
+{
+    define_terms(terms, 1, 3, nterms, atoms, types, active, nparameters, eq, fc, nullptr, nullptr, status);
+}
+
+void FourierDihedralContainer_B200_Define(NBB200MMTerms *terms, int nterms, const int *atoms, const int *types, const unsigned char *active,
+                                          int nparameters, const double *fc, const int *period, const double *phase, int *status)
+{
+    if (nparameters > 0 && (period == nullptr || phase == nullptr)) { set_error("invalid argument to a B200 MM term container"); mm_status(status, NBB200_STATUS_INVALID_ARGUMENT); return; }
+    std::vector<double> c((size_t) std::max(nparameters, 0)), s(c.size()), per(c.size());
+    for (int i = 0; i < nparameters; i++) { c[i] = std::cos(phase[i]); s[i] = std::sin(phase[i]); per[i] = (double) period[i]; }   // FourierDihedralContainer_FillCosSinPhases (:246-257)
+    define_terms(terms, 3, 4, nterms, atoms, types, active, nparameters, fc, c.data(), s.data(), per.data(), status);
+}
+
+void HarmonicImproperContainer_B200_Define(NBB200MMTerms *terms, int nterms, const int *atoms, const int *types, const unsigned char *active,
+                                           int nparameters, const double *eq, const double *fc, int *status)
+{
+    if (nparameters > 0 && eq == nullptr) { set_error("invalid argument to a B200 MM term container"); mm_status(status, NBB200_STATUS_INVALID_ARGUMENT); return; }
+    std::vector<double> c((size_t) std::max(nparameters, 0)), s(c.size());
+    for (int i = 0; i < nparameters; i++) { c[i] = std::cos(eq[i]); s[i] = std::sin(eq[i]); }                                      // HarmonicImproperContainer_FillCosSinValues (:154-165)
+    define_terms(terms, 4, 4, nterms, atoms, types, active, nparameters, fc, c.data(), s.data(), nullptr, status);
+}
+
+void MMTerms_B200_EnergyDevice(NBB200MMTerms *terms, const double *d_xyz, double *energies5, double *d_grad, int *status)
+{
+    if (terms == nullptr || d_xyz == nullptr || energies5 == nullptr) return;
+    MMTerms *m = reinterpret_cast<MMTerms *>(terms);
+    cudaSetDevice(m->device);
+    if (!evaluate(*m, d_xyz, d_grad, energies5)) mm_status(status, NBB200_STATUS_LOGIC_ERROR);
+}
+
+void MMTerms_B200_Energy(NBB200MMTerms *terms, const double *xyz, double *energies5, double *grad, int *status)
+{
+    if (terms == nullptr || xyz == nullptr || energies5 == nullptr) return;
+    MMTerms *m = reinterpret_cast<MMTerms *>(terms);
+    cudaSetDevice(m->device);
+    const size_t bytes = sizeof(double) * 3 * (size_t) m->natoms;
+    std::memcpy(m->hx, xyz, bytes);
+    bool ok = cuda_ok(cudaMemcpyAsync(m->x.p, m->hx, bytes, cudaMemcpyHostToDevice, m->stream), "H2D coordinates");
+    if (ok && grad != nullptr) ok = cuda_ok(cudaMemsetAsync(m->grad.p, 0, bytes, m->stream), "memset");
+    ok = ok && evaluate(*m, m->x.p, grad != nullptr ? m->grad.p : nullptr, energies5);
+    if (ok && grad != nullptr) {
+        ok = cuda_ok(cudaMemcpyAsync(m->hg, m->grad.p, bytes, cudaMemcpyDeviceToHost, m->stream), "D2H gradients") && cuda_ok(cudaStreamSynchronize(m->stream), "sync");
+        if (ok) for (size_t i = 0; i < 3 * (size_t) m->natoms; i++) grad[i] += m->hg[i];          // accumulated, as every term of System.Energy
+    }
+    if (!ok) mm_status(status, NBB200_STATUS_LOGIC_ERROR);
+}
+
+long MMTerms_B200_NumberOfTerms(NBB200MMTerms *terms, int kind)
+{
+    if (terms == nullptr || kind < 0 || kind >= kKinds) return 0;
+    return (long) reinterpret_cast<MMTerms *>(terms)->host[kind].size();
+}
+
+void nbb200_langevin_first_half(NBB200State *state, double *d_x, double *d_v, const double *d_a, const double *d_mass, const double *factors7,
+                                unsigned long long seed, unsigned long long step)
+{
+    if (state == nullptr || factors7 == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    const long m = 3 * (long) s.n;
+    k_langevin_first<<<(unsigned int) ((m + 255) / 256), 256, 0, s.stream>>>(d_x, d_v, d_a, d_mass, m, factors7[0], factors7[1], factors7[2], factors7[3],
+                                                                            factors7[4], factors7[5], factors7[6], seed, step);
+    s.launches += 1;
+}
+
+}  // extern "C"

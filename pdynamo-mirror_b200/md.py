@@ -2,10 +2,15 @@
 
 Mirrors one Iteration of pCore-1.9.0/pCore/VelocityVerletIntegrator.py:60-81 as driven by VelocityVerletDynamics_SystemGeometry
 (pMolecule-1.9.0/pMolecule/...), in Cartesian variables: x += dt v + dt^2/2 a; v += dt/2 a; E, g = NB(x); a = -100 g / m; v += dt/2 a.
-Coordinates, velocities, accelerations and gradients never leave the GPU; per step the host sees the 6 energies and the kinetic
-energy.  Only the NB term exists in this repository, so this is a complete force field only for bond-free systems
-(workloads.ionic_fluid)."""
+Coordinates, velocities, accelerations and gradients never leave the GPU; per step the host sees the 6 NB energies, the 5 bonded
+energies (when the system has bonded term containers, mmterms.py: evaluated on the device into the same gradient array) and the
+kinetic energy.
+
+LangevinDynamics is the integrator of the reference's own DHFR benchmark (benchmarks/SystemBenchmarks.py:95-101 ->
+LangevinDynamics_SystemGeometry -> pCore-1.9.0/pCore/LangevinVelocityVerletIntegrator.py): CalculateIntegrationConstants (:54-115) on the
+host, the Iteration (:117-150) as two kernels around the force evaluation."""
 import ctypes as C
+import math
 
 import numpy as np
 
@@ -40,6 +45,12 @@ class VelocityVerletDynamics:
         self.box = None if sp is None else np.ascontiguousarray(sp.box6, np.float64)
         self.energies, self.dEdM = np.zeros(6), np.zeros(9)
         self.updates = 0
+        self.mmterms, self.bonded = None, np.zeros(5)
+        em = system.energyModel
+        if len(getattr(em, "mmTerms", ())) > 0:
+            from .mmterms import MMTermsB200
+            self.mmterms = MMTermsB200(self.n, em.mmTerms, device=device)
+            self.mmterms.SetStream(torch.cuda.current_stream().cuda_stream)
         self.potential = self._forces(True)
         self.L.nbb200_vv_second_half(self.h, self._p(self.v), self._p(self.a), self._p(self.g), self._p(self.mass), 0.0, self._p(self.ke_dev))
         self.kinetic = float(self.ke_dev.item())
@@ -55,6 +66,9 @@ class VelocityVerletDynamics:
         self.L.NBModelABFS_B200_MMMMEnergyDevice(self.h, self._lib.d_(self.energies), self._p(self.g), self._lib.d_(self.dEdM), C.byref(st))
         if st.value != 16:
             raise RuntimeError("NB call failed: " + self._lib.last_error())
+        if self.mmterms is not None:
+            self.bonded = self.mmterms.EnergyDevice(self.x.data_ptr(), self.g.data_ptr())
+            return float(self.energies.sum() + self.bonded.sum())
         return float(self.energies.sum())
 
     def Run(self, steps, updateFrequency=0, log=None):
@@ -69,4 +83,57 @@ class VelocityVerletDynamics:
             out.append((self.potential, self.kinetic))
             if log is not None and (k + 1) % 100 == 0:
                 log("step %d: potential %.4f kinetic %.4f total %.4f" % (k + 1, self.potential, self.kinetic, self.potential + self.kinetic))
+        return out
+
+
+class LangevinDynamics(VelocityVerletDynamics):
+    """Langevin velocity Verlet dynamics on the device (pCore-1.9.0/pCore/LangevinVelocityVerletIntegrator.py); options as
+    LangevinDynamics_SystemGeometry: collisionFrequency (ps^-1), temperature (K), timeStep (ps)."""
+
+    def __init__(self, system, timeStep=0.001, temperature=300.0, collisionFrequency=25.0, seed=491831, device=0):
+        if collisionFrequency <= 0.0 or temperature < 0.0:
+            raise ValueError("Invalid temperature handling options.")
+        super().__init__(system, timeStep=timeStep, temperature=temperature, seed=seed, device=device)
+        self.collisionFrequency, self.temperature, self.seed, self.iteration = float(collisionFrequency), float(temperature), int(seed), 0
+        self.CalculateIntegrationConstants()
+
+    def CalculateIntegrationConstants(self):
+        """LangevinVelocityVerletIntegrator.CalculateIntegrationConstants (:54-115)"""
+        dt = self.dt
+        fact = self.collisionFrequency * dt
+        if fact > 0.009:
+            c0 = math.exp(-fact)
+            c1 = (1.0 - c0) / fact
+            c2 = (1.0 - c1) / fact
+            sdR = math.sqrt(dt ** 2 * (2.0 - (3.0 - 4.0 * c0 + c0 * c0) / fact) / fact)
+            sdV = math.sqrt(1.0 - c0 * c0)
+            cRV1 = dt * (1.0 - c0) ** 2 / (fact * sdR * sdV)
+            cRV2 = math.sqrt(1.0 - cRV1 * cRV1)
+        else:
+            c0 = 1.0 - fact + fact ** 2 / 2.0 - fact ** 3 / 6.0 + fact ** 4 / 24.0 - fact ** 5 / 120.0
+            c1 = 1.0 - fact / 2.0 + fact ** 2 / 6.0 - fact ** 3 / 24.0 + fact ** 4 / 120.0 - fact ** 5 / 720.0
+            c2 = 0.5 - fact / 6.0 + fact ** 2 / 24.0 - fact ** 3 / 120.0 + fact ** 4 / 720.0 - fact ** 5 / 5040.0
+            sdR = (2.0 - 3.0 * fact / 4.0 + 67.0 * fact ** 2 / 320.0 - 119.0 * fact ** 3 / 2560.0) * math.sqrt(fact / 6.0) * dt
+            sdV = (2.0 - fact + 5.0 * fact ** 2 / 12.0 - fact ** 3 / 8.0 + 79.0 * fact ** 4 / 2880.0) * math.sqrt(fact / 2.0)
+            cRV1 = (3.0 / 2.0 - 3.0 * fact / 16.0 - 51.0 * fact ** 2 / 1280.0 + 17.0 * fact ** 3 / 2048.0 + 40967.0 * fact ** 4 / 11468800.0 -
+                    57203.0 * fact ** 5 / 91750400.0) / math.sqrt(3.0)
+            cRV2 = (0.5 + 3.0 * fact / 16.0 - 9.0 * fact ** 2 / 1280.0 - 109.0 * fact ** 3 / 10240.0 + 10077.0 * fact ** 4 / 11468800.0 +
+                    14887.0 * fact ** 5 / 18350080.0)
+        kT = math.sqrt(100.0 * _KB_KJMOL * self.temperature)          # sqrt(K -> amu A^2 ps^-2), SystemGeometryObjectiveFunction.TemperatureConversionFactor
+        self.facV3 = c2 * dt
+        self.factors = np.array([c1 * dt, c2 * dt ** 2, c0, (c1 - c2) * dt, sdR * kT, cRV1 * sdV * kT, cRV2 * sdV * kT], dtype=np.float64)
+
+    def Run(self, steps, updateFrequency=0, log=None):
+        out = []
+        for k in range(steps):
+            self.iteration += 1
+            self.L.nbb200_langevin_first_half(self.h, self._p(self.x), self._p(self.v), self._p(self.a), self._p(self.mass), self._lib.d_(self.factors),
+                                              C.c_ulonglong(self.seed), C.c_ulonglong(self.iteration))
+            self.potential = self._forces(updateFrequency > 0 and (k + 1) % updateFrequency == 0)
+            self.L.nbb200_vv_second_half(self.h, self._p(self.v), self._p(self.a), self._p(self.g), self._p(self.mass), 2.0 * self.facV3, self._p(self.ke_dev))
+            self.kinetic = float(self.ke_dev.item())
+            out.append((self.potential, self.kinetic))
+            if log is not None and (k + 1) % 100 == 0:
+                log("step %d: potential %.4f kinetic %.4f total %.4f temperature %.2f" % (k + 1, self.potential, self.kinetic, self.potential + self.kinetic,
+                                                                                       2.0 * self.kinetic / (3 * self.n * _KB_KJMOL)))
         return out

@@ -81,6 +81,7 @@ class EnergyModel:
     def __init__(self):
         self.mmAtoms = self.ljParameters = self.ljParameters14 = self.exclusions = self.interactions14 = self.nbModel = None
         self.electrostaticScale14 = 1.0
+        self.mmTerms = []                      # bonded term containers (pMolecule.MMModel / EnergyModel.mmTerms), evaluated before the NB model
 
     def ClearNBModel(self, configuration):
         if self.nbModel is not None:
@@ -110,6 +111,9 @@ class System:
         em.interactions14 = SelfPairList(w["pairs14"]) if len(w["pairs14"]) else None
         em.electrostaticScale14 = w.get("electrostaticScale14", 1.0)
         self.masses = w.get("masses")
+        if w.get("bonded") is not None:
+            from .mmterms import containers_from_bonded
+            em.mmTerms = containers_from_bonded(w["bonded"])
         if w.get("fixed") is not None and len(w["fixed"]) > 0:
             self.fixedAtoms = np.ascontiguousarray(w["fixed"], np.int32)
         from ._lib import pinned_array
@@ -167,15 +171,24 @@ class System:
             if self.symmetry is not None:
                 cfg.SetTemporaryAttribute("symmetryParameterGradients", SymmetryParameterGradients())
         em = self.energyModel
-        terms = []
+        nbTerms, mmTerms = [], []
         if em.nbModel is not None:
             t1 = time.perf_counter()
             em.nbModel.SetUp(em.mmAtoms, None, em.ljParameters, em.ljParameters14, self.fixedAtoms, em.interactions14, em.exclusions, self.symmetry, None, cfg, log=log)
             t2 = time.perf_counter()
-            terms.extend(em.nbModel.Energy(cfg))
+            nbTerms = em.nbModel.Energy(cfg)
             t3 = time.perf_counter()
             self.timings["NB Set Up"] += t2 - t1
             self.timings["NB Evaluation"] += t3 - t2
+        if len(em.mmTerms) > 0:
+            # System.Energy: `for mmterm in em.mmTerms: ...Energy(coordinates3, gradients3)` (System.py:294-297); here ONE device call for all
+            # containers.  Evaluated after the NB model (which may SET the gradients, see above); the terms are reported in the reference's order.
+            if getattr(self, "_mmTermsDevice", None) is None or self._mmTermsDevice.containers != em.mmTerms:
+                from .mmterms import MMTermsB200
+                self._mmTermsDevice = MMTermsB200(len(em.mmAtoms), em.mmTerms, device=int(getattr(em.nbModel, "device", 0) or 0))
+            self._mmTermsDevice.Energy(self.coordinates3, cfg.gradients3 if doGradients else None)
+            mmTerms = self._mmTermsDevice.EnergyTerms()
+        terms = mmTerms + nbTerms
         if doGradients and self.fixedAtoms is not None and len(self.fixedAtoms) > 0:
             cfg.gradients3[np.asarray(self.fixedAtoms, np.int64)] = 0.0      # System.Energy: gradients3.SetRowSelection(fixedAtoms, 0.0) (System.py:292,313)
         cfg.SetTemporaryAttribute("energyTerms", terms)

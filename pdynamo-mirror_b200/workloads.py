@@ -407,7 +407,7 @@ def bala_water(name="bala_water"):
     return _finish(xyz, charges, ljtypes, eps, rmin, "amber", excl, p14, [ax, ay, az, 90.0, 90.0, 90.0], name, scale14=1.0)
 
 
-def dhfr_jac(name="dhfr"):
+def dhfr_jac(name="dhfr", bonded=False):
     """The reference's own JAC benchmark system (benchmarks/data/dhfr: 23 558 atoms, CHARMM22, cubic a = 62.23), from the
     fixture tests/golden/dhfr_jac.npz (tests/golden/make_fixtures.py).  Its per-term NB energies are published in
     benchmarks/log/systemBenchmarks_Serial_1ps.log:397-403 -- a known-answer vector for this path."""
@@ -416,6 +416,15 @@ def dhfr_jac(name="dhfr"):
                 eps14=d["eps14"], sigma14=d["sigma14"], scale14=1.0)
     w["published_energies"] = np.array(d["published_energies"])
     w["published_counts"] = np.array(d["published_counts"])
+    bonded = _os.path.join(_GOLDEN, "dhfr_bonded.npz")
+    if _os.path.exists(bonded):
+        # bonded terms of the same input: per-term parameters, masses, the energies the reference publishes for them
+        b = dict(np.load(bonded))
+        w["masses"] = b.pop("masses")
+        w["published_bonded"] = b.pop("published_bonded")
+        w["published_total"] = b.pop("published_total")
+        if bonded:
+            w["bonded"] = b
     return w
 
 
@@ -517,6 +526,7 @@ WORKLOADS = {
     "water4x4x4": lambda: replicated_water(4),           # 41 472 atoms: the bounded CPU sample of m1 (same generator, same density)
     "jac": lambda: jac_protein_water(),
     "dhfr": lambda: dhfr_jac(),
+    "dhfr_mm": lambda: dhfr_jac("dhfr_mm", bonded=True),        # the same system with its bonded terms (the reference's complete CHARMM22 energy model)
     "jac_lattice": lambda: jac_like(),
     "water24k_lattice": lambda: water_box(20, name="water24k_lattice"),
     "m1": lambda: replicated_water(12, name="m1"),

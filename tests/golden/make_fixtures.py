@@ -165,6 +165,130 @@ def make_dhfr():
 
 
 # ----------------------------------------------------------------------------------------------------
+# Bonded terms of the same DHFR input: PSF angle / dihedral / improper sections and the CHARMM parameter
+# sections, matched as the reference does (pBabel CHARMMParameterFileReader.ProcessBond/Angle/Dihedral/Improper :160-313 --
+# canonical keys, "X A B X" dihedral and "A X X B" improper wild cards, multi-term dihedrals, Urey-Bradley terms only where
+# the angle line carries them; CHARMMPSFFileReader.ToHarmonicBondContainer / ...Angle / ...UreyBradley / ToFourierDihedral /
+# ToHarmonicImproperContainer :410-651).  Units: kcal -> kJ (4.184), degrees -> radians; E = fc (q - q0)^2 (no 1/2).
+# ----------------------------------------------------------------------------------------------------
+_PRM_SECTIONS = ("ANGL", "ATOM", "BOND", "CMAP", "DIHE", "END", "EQUI", "HBON", "IMPH", "IMPR", "NBFI", "NBON", "NONB", "PHI", "PRIN", "SPAS", "THET")
+
+
+def _prm_sections(path):
+    out, current, pending = {}, None, ""
+    with open(path) as f:
+        for raw in f:
+            line = raw.strip()
+            k = line.find("!")
+            if k >= 0:
+                line = line[:k].strip()
+            if line.endswith("-"):
+                pending += line[:-1].strip() + " "
+                continue
+            line = (pending + line).strip()
+            pending = ""
+            if not line or line.startswith("*"):
+                continue
+            head = line.split(" ", 1)[0].upper()
+            sec = next((nm for nm in _PRM_SECTIONS if head.startswith(nm)), None)
+            if sec is not None:
+                if sec == "END":
+                    break
+                current = sec
+                continue
+            if current is not None:
+                out.setdefault(current, []).append(line.split())
+    return out
+
+
+def read_dhfr_bonded():
+    base = os.path.join(REF, "benchmarks/data/dhfr")
+    sec = _psf_sections(os.path.join(base, "dhfr.psfx"))
+    natom, body = sec["NATOM"]
+    types = [line.split()[5].upper() for line in body[:natom]]
+    masses = np.array([float(line.split()[7]) for line in body[:natom]])
+
+    def ints(tag, width):
+        count, lines = sec[tag]
+        flat = [int(v) for line in lines for v in line.split()]
+        return np.array(flat[:width * count], dtype=np.int64).reshape(-1, width) - 1
+    bonds, angles, dihedrals, impropers = ints("NBOND", 2), ints("NTHETA", 3), ints("NPHI", 4), ints("NIMPHI", 4)
+    prm = _prm_sections(os.path.join(base, "par_all22_prot.prm"))
+    KC, DEG = 4.184, np.pi / 180.0
+    pb, pa, pub, pd, pdw, pi_, piw = {}, {}, {}, {}, {}, {}, {}
+    for d in prm["BOND"]:
+        t1, t2 = d[0].upper(), d[1].upper()
+        pb.setdefault((max(t1, t2), min(t1, t2)), (KC * float(d[2]), float(d[3])))
+    for d in prm["ANGL"]:
+        t1, t2, t3 = d[0].upper(), d[1].upper(), d[2].upper()
+        key = (max(t1, t3), t2, min(t1, t3))
+        pa.setdefault(key, (KC * float(d[3]), DEG * float(d[4])))
+        if len(d) > 5:
+            pub.setdefault(key, (KC * float(d[5]), float(d[6])))
+    for d in prm["DIHE"]:
+        t1, t2, t3, t4 = [v.upper() for v in d[:4]]
+        key = (t1, t2, t3, t4) if t2 > t3 else ((max(t1, t4), t2, t3, min(t1, t4)) if t2 == t3 else (t4, t3, t2, t1))
+        tab = pdw if "X" in key else pd
+        terms = tab.get(key, [])
+        nper = int(d[5])
+        if all(t[0] != nper for t in terms):
+            terms.append((nper, KC * float(d[4]), DEG * float(d[6])))
+            terms.sort()
+            tab[key] = terms
+    for d in prm["IMPR"]:
+        t1, t2, t3, t4 = [v.upper() for v in d[:4]]
+        key = (t1, t2, t3, t4) if t1 > t4 else ((t1, max(t2, t3), min(t2, t3), t4) if t1 == t4 else (t4, t3, t2, t1))
+        (piw if "X" in key else pi_).setdefault(key, (KC * float(d[4]), DEG * float(d[6])))
+    out = dict(masses=masses)
+    # bonds
+    out["bonds"] = bonds.astype(np.int32)
+    bp = [pb[(max(types[i], types[j]), min(types[i], types[j]))] for i, j in bonds]
+    out["bond_fc"], out["bond_eq"] = np.array([v[0] for v in bp]), np.array([v[1] for v in bp])
+    # angles + Urey-Bradley
+    keys = [(max(types[i], types[k]), types[j], min(types[i], types[k])) for i, j, k in angles]
+    out["angles"] = angles.astype(np.int32)
+    out["angle_fc"], out["angle_eq"] = np.array([pa[k][0] for k in keys]), np.array([pa[k][1] for k in keys])
+    ub = [(a[0], a[2], pub[k]) for a, k in zip(angles, keys) if k in pub]
+    out["ureybradleys"] = np.array([[u[0], u[1]] for u in ub], dtype=np.int32).reshape(-1, 2)
+    out["ub_fc"], out["ub_eq"] = np.array([u[2][0] for u in ub]), np.array([u[2][1] for u in ub])
+    # dihedrals: one term per (dihedral, multiplicity)
+    dt, dp = [], []
+    for i, j, k, l in dihedrals:
+        ti, tj, tk, tl = types[i], types[j], types[k], types[l]
+        key = (ti, tj, tk, tl) if tj > tk else ((max(ti, tl), tj, tk, min(ti, tl)) if tj == tk else (tl, tk, tj, ti))
+        terms = pd[key] if key in pd else pdw[("X", max(tj, tk), min(tj, tk), "X")]
+        for nper, fc, phase in terms:
+            dt.append((i, j, k, l)); dp.append((fc, nper, phase))
+    out["dihedrals"] = np.array(dt, dtype=np.int32).reshape(-1, 4)
+    out["dihedral_fc"], out["dihedral_period"], out["dihedral_phase"] = np.array([v[0] for v in dp]), np.array([v[1] for v in dp], dtype=np.int32), np.array([v[2] for v in dp])
+    # impropers
+    ip = []
+    for i, j, k, l in impropers:
+        ti, tj, tk, tl = types[i], types[j], types[k], types[l]
+        key = (ti, tj, tk, tl) if ti > tl else ((ti, max(tj, tk), min(tj, tk), tl) if ti == tl else (tl, tk, tj, ti))
+        ip.append(pi_[key] if key in pi_ else piw[(max(ti, tl), "X", "X", min(ti, tl))])
+    out["impropers"] = impropers.astype(np.int32)
+    out["improper_fc"], out["improper_eq"] = np.array([v[0] for v in ip]), np.array([v[1] for v in ip])
+    # published by the reference for this input (benchmarks/log/systemBenchmarks_Serial_1ps.log:397-400): bond, angle, Urey-Bradley, dihedral, improper; total PE; RMS gradient
+    out["published_bonded"] = np.array([12444.3942, 9454.9073, 130.3783, 3015.4953, 52.1977])
+    out["published_total"] = np.array([-375469.1160, 1.4766])
+    return out
+
+
+def make_dhfr_bonded():
+    d = read_dhfr_bonded()
+    np.savez_compressed(os.path.join(HERE, "dhfr_bonded.npz"), **d)
+    print("dhfr bonded: %d bonds, %d angles, %d Urey-Bradley, %d dihedral terms, %d impropers" %
+          (len(d["bonds"]), len(d["angles"]), len(d["ureybradleys"]), len(d["dihedrals"]), len(d["impropers"])))
+    # golden output of the compiled reference's own containers (HarmonicBondContainer_Energy ... through oracle/ref_driver.c: refmm_energy)
+    import refnb
+    xyz = np.load(os.path.join(HERE, "dhfr_jac.npz"))["xyz"]
+    e, g = refnb.mm_energy(d, xyz)
+    np.savez_compressed(os.path.join(HERE, "golden_dhfr_bonded.npz"), energies=e, grad=g)
+    print("reference bonded energies", e, "published", d["published_bonded"])
+
+
+# ----------------------------------------------------------------------------------------------------
 # The 12 molecular crystals of pMolecule-1.9.0/tests/CrystalMMEnergies.py (:30-63): AMBER top/crd files from
 # pMolecule-1.9.0/data/molecularCrystals, space-group operations and cell parameters from the test file.  Non-P1 space
 # groups exercise rotations S != I, self-inverse images (scale 0.5), inverse-pair skipping and triclinic cells.
@@ -305,6 +429,9 @@ if __name__ == "__main__":
     if what in ("inputs", "all"):
         make_inputs()
         make_dhfr()
+        make_dhfr_bonded()
         make_crystals()
+    if what == "bonded":
+        make_dhfr_bonded()
     if what in ("golden", "all"):
         make_golden(only=sys.argv[2:])          # python make_fixtures.py golden [case ...]

@@ -15,7 +15,7 @@ HEADER = os.path.join(ROOT, "include", "nbabfs_b200.h")
 def declared_functions():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:NBModelABFS|PairListGenerator|PairwiseInteractionABFS|nbb200)\w*)\s*\(", text)))
+    return sorted(set(re.findall(r"\b((?:NBModelABFS|PairListGenerator|PairwiseInteractionABFS|nbb200|MMTerms_B200|HarmonicBondContainer|HarmonicAngleContainer|FourierDihedralContainer|HarmonicImproperContainer)\w*)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol(pkg):

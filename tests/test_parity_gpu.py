@@ -561,3 +561,133 @@ def test_full_size_m1_properties(pkg):
     rep = g_b.reshape(1728, 648, 3)
     rms = np.sqrt((g_u ** 2).mean())
     assert np.sqrt(((rep - g_u[None]) ** 2).mean()) <= 2e-5 * rms
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# bonded MM terms and Langevin dynamics on the device
+# ------------------------------------------------------------------------------------------------------------------------------
+def test_bonded_terms_parity_and_published_dhfr_total(pkg, orc):
+    """DHFR with its complete CHARMM22 energy model through System.Energy: the five bonded terms against the oracle and the compiled
+    reference's golden output (fp64 kernels: 1e-12), every term and the total potential energy against the values the reference
+    publishes (benchmarks/log/systemBenchmarks_Serial_1ps.log:397-403: 11 terms to 4 decimals, total -375469.1160, RMS gradient 1.4766)."""
+    w = pkg.workloads.WORKLOADS["dhfr_mm"]()
+    system = pkg.System.FromWorkload(w)
+    system.DefineNBModel(pkg.NBModelABFS())
+    total = system.Energy(doGradients=True)
+    terms = system.configuration.energyTerms
+    assert [k for k, _ in terms] == ["Harmonic Bond", "Harmonic Angle", "Urey-Bradley", "Fourier Dihedral", "Harmonic Improper", "MM/MM Elect.", "MM/MM LJ",
+                                     "MM/MM 1-4 Elect.", "MM/MM 1-4 LJ", "MM/MM Image Elect.", "MM/MM Image LJ"]
+    e5 = np.array([v for _, v in terms[:5]])
+    re, rg = orc.mm_energy(w["bonded"], w["xyz"])
+    gold = load_golden("dhfr_bonded")
+    assert np.all(np.abs(e5 - re) <= 1e-12 * np.abs(re)) and np.all(np.abs(e5 - gold["energies"]) <= 1e-12 * np.abs(gold["energies"]))
+    assert np.all(np.abs(e5 - w["published_bonded"]) < 6.0e-5)
+    assert abs(total - w["published_total"][0]) <= E_TOL * abs(w["published_total"][0])
+    g = system.configuration.gradients3
+    nb = orc.OracleNB(w).energy(force_new=True)
+    gref = nb["grad"] + rg
+    # this is a minimised structure: bonded and non-bonded gradients (RMS 23 and 23 kJ/mol/A) cancel to an RMS of 1.48; the error bar of the
+    # fp32 NB pair math is relative to the NB gradient it computes (the bonded part is fp64)
+    nb_rms = np.sqrt((nb["grad"] ** 2).mean())
+    assert nb_rms > 5.0 * np.sqrt((gref ** 2).mean())
+    assert np.sqrt(((g - gref) ** 2).mean()) <= G_TOL * nb_rms
+    assert abs(np.sqrt((g ** 2).sum() / (3 * len(g))) - w["published_total"][1]) < 6.0e-5          # "RMS Gradient" of the reference's log
+    # the bonded gradient alone, host arrays, and one container through the reference's per-container call
+    own = pkg.MMTermsB200(w["n"], system.energyModel.mmTerms)
+    gb = np.zeros_like(rg)
+    own.Energy(w["xyz"], gb)
+    assert np.abs(gb - rg).max() <= 1e-9 * np.abs(rg).max() and np.abs(gb - gold["grad"]).max() <= 1e-9 * np.abs(rg).max()
+    assert abs(system.energyModel.mmTerms[3].Energy(w["xyz"]) - re[3]) <= 1e-12 * abs(re[3])
+    # overwriteGradients (the NB call sets the array) composes with the bonded terms
+    system.energyModel.nbModel.SetOptions(overwriteGradients=True)
+    system.Energy(doGradients=True)
+    assert np.sqrt(((system.configuration.gradients3 - gref) ** 2).mean()) <= G_TOL * nb_rms
+
+
+def test_bonded_terms_distorted_geometries_and_inactive_terms(pkg, orc):
+    """random distorted geometries (angle clamp, both improper branches, periods 1-6) against the oracle; QACTIVE = False terms are skipped"""
+    from test_oracle import _random_bonded
+    rng = np.random.default_rng(5)
+    for _ in range(3):
+        b, x = _random_bonded(rng)
+        cs = pkg.mmterms.containers_from_bonded(b)
+        dev = pkg.MMTermsB200(len(x), cs)
+        g = np.zeros_like(x)
+        e = dev.Energy(x, g)
+        re, rg = orc.mm_energy(b, x)
+        assert np.all(np.abs(e - re) <= 1e-11 * np.abs(re)), (e, re)
+        assert np.abs(g - rg).max() <= 1e-9 * np.abs(rg).max()
+    keep = rng.random(len(b["bonds"])) < 0.5
+    c = pkg.HarmonicBondContainer(b["bonds"], np.arange(len(b["bonds"])), dict(eq=b["bond_eq"], fc=b["bond_fc"]), active=keep)
+    b2 = dict(bonds=b["bonds"][keep], bond_eq=b["bond_eq"][keep], bond_fc=b["bond_fc"][keep])
+    assert abs(c.Energy(x) - orc.mm_energy(b2, x)[0][0]) <= 1e-11 * orc.mm_energy(b2, x)[0][0]
+    # shared parameter table (types), as the reference's containers hold them
+    types = rng.integers(0, 4, len(b["bonds"])).astype(np.int32)
+    eq4, fc4 = rng.uniform(0.9, 1.6, 4), rng.uniform(500, 3000, 4)
+    c = pkg.HarmonicBondContainer(b["bonds"], types, dict(eq=eq4, fc=fc4))
+    b3 = dict(bonds=b["bonds"], bond_eq=eq4[types], bond_fc=fc4[types])
+    assert abs(c.Energy(x) - orc.mm_energy(b3, x)[0][0]) <= 1e-11 * orc.mm_energy(b3, x)[0][0]
+
+
+def test_langevin_random_terms_have_the_right_statistics(pkg):
+    """nbb200_langevin_first_half with v = a = 0: x gets sdR w1 / sqrt(m), v gets (sdV1 w1 + sdV2 w2) / sqrt(m) with independent standard
+    normal w1, w2 (LangevinVelocityVerletIntegrator.RandomForces :139-149); different steps give independent deviates, the same
+    (seed, step) the same ones."""
+    import ctypes as C
+    import torch
+    from pdynamo_mirror_b200 import _lib
+    w = pkg.workloads.WORKLOADS["jac"]()
+    system = pkg.System.FromWorkload(w)
+    system.DefineNBModel(pkg.NBModelABFS())
+    system.Energy(doGradients=False)
+    h, n = system.configuration.nbState.cObject, w["n"]
+    _lib.lib().nbb200_set_stream(h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    mass = torch.full((n,), 4.0, dtype=torch.float64, device="cuda")
+    fac = np.array([0.0, 0.0, 1.0, 0.0, 2.0, 3.0, 4.0])
+
+    def draw(seed, step):
+        x = torch.zeros((n, 3), dtype=torch.float64, device="cuda"); v = torch.zeros_like(x); a = torch.zeros_like(x)
+        _lib.lib().nbb200_langevin_first_half(h, C.c_void_p(x.data_ptr()), C.c_void_p(v.data_ptr()), C.c_void_p(a.data_ptr()), C.c_void_p(mass.data_ptr()),
+                                              _lib.d_(fac), C.c_ulonglong(seed), C.c_ulonglong(step))
+        torch.cuda.synchronize()
+        return x.cpu().numpy().ravel(), v.cpu().numpy().ravel()
+    x1, v1 = draw(7, 1)
+    w1 = x1 / (2.0 / 2.0)                                   # sdR / sqrt(m)
+    w2 = (v1 * 2.0 - 3.0 * w1) / 4.0
+    m = len(w1)
+    for z in (w1, w2):
+        assert abs(z.mean()) < 5.0 / np.sqrt(m) and abs(z.var() - 1.0) < 5.0 * np.sqrt(2.0 / m)
+        assert abs((z ** 4).mean() - 3.0) < 0.1 and np.abs(z).max() < 7.0
+    assert abs((w1 * w2).mean()) < 5.0 / np.sqrt(m)
+    x2, _ = draw(7, 2)
+    assert abs((x1 * x2).mean()) < 5.0 / np.sqrt(m) and not np.array_equal(x1, x2)
+    x3, v3 = draw(7, 1)
+    assert np.array_equal(x1, x3) and np.array_equal(v1, v3)
+    assert not np.array_equal(draw(8, 1)[0], x1)
+
+
+def test_langevin_dynamics_of_dhfr_with_all_terms(pkg):
+    """The reference's own benchmark protocol (benchmarks/SystemBenchmarks.py:95-101: Langevin, 25 ps^-1, 300 K, 1 fs) on DHFR with bonded and
+    non-bonded terms, everything on the device: the dynamics is stable and thermostatted, the first potential energy is the published one,
+    and with a tiny collision frequency and zero temperature noise the integrator reduces to velocity Verlet (energy conservation)."""
+    w = pkg.workloads.WORKLOADS["dhfr_mm"]()
+    system = pkg.System.FromWorkload(w)
+    system.DefineNBModel(pkg.NBModelABFS())
+    md = pkg.md.LangevinDynamics(system, timeStep=0.001, temperature=300.0, collisionFrequency=25.0)
+    assert abs(md.potential - w["published_total"][0]) <= E_TOL * abs(w["published_total"][0])
+    traj = md.Run(300)
+    temps = np.array([2.0 * k / (3 * md.n * 8.314472e-3) for _, k in traj])
+    assert np.all(np.isfinite(temps)) and 270.0 < temps[-100:].mean() < 320.0, temps[-100:].mean()
+    pot = np.array([p for p, _ in traj])
+    assert pot[-1] > pot[0] and pot[-1] < 0.7 * pot[0]           # the minimised benchmark structure heats up to ~ -2.9e5 kJ/mol (reference log: -291914 after 1 ps)
+    assert md.updates >= 2
+    # no friction, no noise: plain velocity Verlet, the total energy is conserved
+    system2 = pkg.System.FromWorkload(w)
+    system2.DefineNBModel(pkg.NBModelABFS())
+    nve = pkg.md.LangevinDynamics(system2, timeStep=0.0005, temperature=0.0, collisionFrequency=1.0e-9)
+    nve.v.copy_(md.v); nve.x.copy_(md.x)
+    nve.potential = nve._forces(True)
+    nve.L.nbb200_vv_second_half(nve.h, nve._p(nve.v), nve._p(nve.a), nve._p(nve.g), nve._p(nve.mass), 0.0, nve._p(nve.ke_dev))
+    t2 = nve.Run(200)
+    tot = np.array([p + k for p, k in t2]); kin = np.array([k for _, k in t2])
+    assert np.abs(tot - tot[0]).max() < 2.0e-3 * kin.mean(), (np.abs(tot - tot[0]).max(), kin.mean())
