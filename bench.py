@@ -366,6 +366,7 @@ def run_b200(args):
                 line["jac"] = jac_block(torch, local, fp32_peak_tflops)
                 line["md"] = md_block(torch, local)
                 line["md_device"] = md_device_block(torch, local)
+                line["md_dhfr"] = md_dhfr_block(torch, local)
             except Exception as exc:
                 line["jac"] = {"error": repr(exc)}
     else:
@@ -499,6 +500,39 @@ def md_device_block(torch, local, steps=1000):
         out[label] = {"steps_per_s": steps / wall, "ms_per_step": 1e3 * wall / steps, "steps": steps, "list_updates": md.updates - u0,
                       "total_energy_drift_over_kinetic": float(np.abs(tot - e0).max() / kin.mean()), "temperature_K": float(2.0 * kin.mean() / (3 * md.n * 8.314472e-3))}
     return out
+
+
+def md_dhfr_block(torch, local, steps=1000):
+    """The reference's own system benchmark (benchmarks/SystemBenchmarks.py: DHFR, CHARMM22, NBModelABFS defaults; one energy + gradient
+    evaluation, then 1000 steps of Langevin velocity Verlet dynamics, 1 fs, 300 K, collision frequency 25 ps^-1) with the complete energy
+    model -- five bonded terms + the NB model -- and the integrator on the device.  Published wall times of the reference for exactly
+    this protocol: benchmarks/log/systemBenchmarks_{Serial,OMP4,OMP8}_1ps.log (hardware unspecified, ca. 2013)."""
+    import pdynamo_mirror_b200 as p
+    w = make_workload("dhfr_mm")
+    sysm = p.System.FromWorkload(w)
+    sysm.DefineNBModel(p.NBModelABFS(device=local))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    md = p.md.LangevinDynamics(sysm, timeStep=0.001, temperature=300.0, collisionFrequency=25.0, device=local)     # includes the initial Energy(doGradients=True)
+    e0 = md.potential
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    traj = md.Run(steps)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    wall, loop = t2 - t0, t2 - t1
+    kin = np.array([k for _, k in traj]); pot = np.array([q for q, _ in traj])
+    temp = 2.0 * kin / (3 * md.n * 8.314472e-3)
+    return {"workload": workload_description("dhfr_mm", w) + " + 23592 bonds, 11584 angles, 2117 Urey-Bradley, 7000 dihedral, 418 improper terms",
+            "protocol": "Energy(doGradients) + %d Langevin velocity-Verlet steps (1 fs, 300 K, 25 ps^-1), displacement-triggered list updates" % steps,
+            "wall_s": wall, "wall_note": "state creation (device allocations, first list build), the initial energy call and the %d steps -- what the reference's 'Total' covers" % steps,
+            "steps_per_s": steps / loop, "ms_per_step": 1e3 * loop / steps, "list_updates": int(md.updates),
+            "potential_energy_t0": e0, "potential_energy_published_t0": float(w["published_total"][0]),
+            "potential_energy_1ps": float(pot[-1]), "potential_energy_mean": float(pot[100:].mean()), "temperature_mean_K": float(temp[100:].mean()),
+            "reference_published": {"serial_wall_s": 656.276, "omp4_wall_s": 269.0, "omp8_wall_s": 201.5, "potential_energy_1ps": -291914.13095708,
+                                    "potential_energy_mean": -293191.47148015, "temperature_mean_K": 293.73476041, "list_updates": 73,
+                                    "source": "benchmarks/log/systemBenchmarks_Serial_1ps.log:405-465 (different random numbers: compare statistics, not trajectories)"},
+            "speedup_vs_published_serial": 656.276 / wall, "speedup_vs_published_omp8": 201.5 / wall}
 
 
 def main():

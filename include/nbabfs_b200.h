@@ -205,6 +205,10 @@ void HarmonicImproperContainer_B200_Define(NBB200MMTerms *terms, int nterms, con
  * dihedral, improper} are set; grad[3 natoms] (nullable) is ACCUMULATED into.  Host arrays / device arrays. */
 void MMTerms_B200_Energy(NBB200MMTerms *terms, const double *xyz, double *energies5, double *grad, int *status);
 void MMTerms_B200_EnergyDevice(NBB200MMTerms *terms, const double *d_xyz, double *energies5, double *d_grad, int *status);
+/* the device call in two halves, for callers that overlap it with other work on the same stream (e.g. enqueue before the NB call, collect
+ * after it: one host synchronisation less per MD step): Enqueue launches the kernel, Collect waits and returns the energies */
+void MMTerms_B200_EnergyDeviceEnqueue(NBB200MMTerms *terms, const double *d_xyz, double *d_grad, int *status);
+void MMTerms_B200_EnergyDeviceCollect(NBB200MMTerms *terms, double *energies5, int *status);
 long MMTerms_B200_NumberOfTerms(NBB200MMTerms *terms, int kind /* 0 bond, 1 angle, 2 Urey-Bradley, 3 dihedral, 4 improper: active terms */);
 
 /* ---- several GPUs ------------------------------------------------------------

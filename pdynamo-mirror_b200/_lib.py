@@ -56,6 +56,8 @@ SIGNATURES = {
     "HarmonicImproperContainer_B200_Define": (None, [vp, C.c_int, ip, ip, C.c_char_p, C.c_int, dp, dp, ip]),
     "MMTerms_B200_Energy": (None, [vp, dp, dp, dp, ip]),
     "MMTerms_B200_EnergyDevice": (None, [vp, vp, dp, vp, ip]),
+    "MMTerms_B200_EnergyDeviceEnqueue": (None, [vp, vp, vp, ip]),
+    "MMTerms_B200_EnergyDeviceCollect": (None, [vp, dp, ip]),
     "MMTerms_B200_NumberOfTerms": (C.c_long, [vp, C.c_int]),
     "nbb200_get_slab": (None, [vp, lp]),
     "nbb200_touched_ranges": (C.c_int, [vp, lp]),

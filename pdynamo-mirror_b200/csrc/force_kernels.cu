@@ -30,10 +30,10 @@ struct ForceArgs {
     AbfsF32 F; float qScale;
     double *gradSorted; double *accum;
     double origin[3];
-    // spline form: per interval l of the shared abscissae four float4, stored as four arrays of splN entries (tab[k * splN + l]: lanes
-    // with different l then spread over all shared-memory banks): {xf, e0, e1, e2}, {e3, a0, a1, a2}, {a3, b0, b1, b2}, {b3, 0, 0, 0}
-    // (cubics in u = r^2 - xf of the electrostatic, LJ-A and LJ-B splines); entry splN - 1 is all zero (pairs that are not evaluated)
-    const float4 *splTab; int splN; float splInvDR;
+    // spline form: per interval l of the shared abscissae three float4 = the cubics {c0, c1, c2, c3} in u = r^2 - xf_l of the electrostatic,
+    // LJ-A and LJ-B splines, stored as three arrays of splN entries (tab[k * splN + l]: lanes with different l spread over all
+    // shared-memory banks); xf_l = fl((l dR) * (l dR)) in fp32 is recomputed per pair; entry splN - 1 is all zero (pairs not evaluated)
+    const float4 *splTab; int splN; float splInvDR, splDR;
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -139,20 +139,21 @@ __device__ __forceinline__ float sqrt_fast(float x)
     return y;
 }
 
-__device__ __forceinline__ PairOut spline_pair(const float4 *__restrict__ tab, int nrows, float invDR, bool live, float r2, float qij, float A, float B)
+__device__ __forceinline__ PairOut spline_pair(const float4 *__restrict__ tab, int nrows, float invDR, float dR, bool live, float r2, float qij, float A, float B)
 {
     int l = min((int) (sqrt_fast(r2) * invDR), nrows - 2);
     l = live ? l : nrows - 1;
     const float4 *row = tab + l;
-    const float4 t0 = row[0], t1 = row[nrows], t2 = row[2 * nrows], t3 = row[3 * nrows];
-    const float u = r2 - t0.x;
+    const float4 te = row[0], ta = row[nrows], tb = row[2 * nrows];
+    const float rl = __fmul_rn((float) l, dR);
+    const float u = r2 - __fmul_rn(rl, rl);              // the expansion point of the stored cubics (upload_spline_tables), not contracted
     // Lennard-Jones: coefficients are linear in (A, B)
-    const float c0 = fmaf(A, t1.y, B * t2.y), c1 = fmaf(A, t1.z, B * t2.z), c2 = fmaf(A, t1.w, B * t2.w), c3 = fmaf(A, t2.x, B * t3.x);
+    const float c0 = fmaf(A, ta.x, B * tb.x), c1 = fmaf(A, ta.y, B * tb.y), c2 = fmaf(A, ta.z, B * tb.z), c3 = fmaf(A, ta.w, B * tb.w);
     PairOut o;
-    o.e1 = qij * fmaf(u, fmaf(u, fmaf(u, t1.x, t0.w), t0.z), t0.y);
+    o.e1 = qij * fmaf(u, fmaf(u, fmaf(u, te.w, te.z), te.y), te.x);
     o.e2 = fmaf(u, fmaf(u, fmaf(u, c3, c2), c1), c0);
     const float u3 = 3.0f * u;
-    const float ge = fmaf(u, fmaf(u3, t1.x, t0.w + t0.w), t0.z);
+    const float ge = fmaf(u, fmaf(u3, te.w, te.z + te.z), te.y);
     const float gl = fmaf(u, fmaf(u3, c3, c2 + c2), c1);
     o.g = -2.0f * fmaf(qij, ge, gl);                     // dG = 2 (qij dFe + A dFa + B dFb); g = -dG
     return o;
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
     const float4 *splTab = A.splTab;
     if (kForm == 1) {
         float4 *sTab = sLJ + A.ntypes * A.ntypes;
-        for (int i = threadIdx.x; i < 4 * A.splN; i += blockDim.x) sTab[i] = A.splTab[i];
+        for (int i = threadIdx.x; i < 3 * A.splN; i += blockDim.x) sTab[i] = A.splTab[i];
         splTab = sTab;
     }
     __syncthreads();
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
                     o = abfs_pair(F, r2m, qi * p.w, ab.x, ab.y, ab.z);
                 } else {
                     // pairs off the list or beyond the cutoff read the all-zero table row (the skip of PairwiseInteraction.c:489)
-                    o = spline_pair(splTab, A.splN, A.splInvDR, ((mask >> k) & 1u) && !(r2 > F.r2Off), r2, qi * p.w, ab.x, ab.y);
+                    o = spline_pair(splTab, A.splN, A.splInvDR, A.splDR, ((mask >> k) & 1u) && !(r2 > F.r2Off), r2, qi * p.w, ab.x, ab.y);
                 }
                 eq += o.e1; el += o.e2;
                 fxi = fmaf(-o.g, dx, fxi); fyi = fmaf(-o.g, dy, fyi); fzi = fmaf(-o.g, dz, fzi);      // gradient = -(force on i) = -g d
@@ -486,7 +487,8 @@ void init_force_kernel_attributes()
 }
 
 // spline tables of the state -> device: the fp64 tables as the reference holds them (1-4 kernel) and, for the tile kernel, the cubic
-// of every interval re-expanded about the fp32-rounded knot xf (so that u = r^2 - xf is exact in fp32), coefficients rounded to fp32
+// of every interval re-expanded about the fp32 point xf_l = fl(fl(l dR)^2) the kernel recomputes (u = r^2 - xf is then exact in fp32),
+// coefficients rounded to fp32
 bool upload_spline_tables(State &s)
 {
     const int n = s.spl.points();
@@ -497,9 +499,12 @@ bool upload_spline_tables(State &s)
         std::copy(s.spl.y[k].begin(), s.spl.y[k].end(), h64.begin() + (size_t) (1 + 2 * k) * n);
         std::copy(s.spl.h[k].begin(), s.spl.h[k].end(), h64.begin() + (size_t) (2 + 2 * k) * n);
     }
-    std::vector<float4> poly((size_t) 4 * n, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<float4> poly((size_t) 3 * n, make_float4(0.f, 0.f, 0.f, 0.f));
+    const float dRf = (float) (s.outer / (double) (n - 1));
     for (int l = 0; l + 1 < n; l++) {
-        const float xf = (float) s.spl.x[l];
+        volatile float rl = (float) l * dRf;            // the kernel's fp32 expansion point fl(fl(l dR)^2), rounded product by product
+        volatile float xfv = rl * rl;
+        const float xf = xfv;
         const double dlt = (double) xf - s.spl.x[l];
         float c[3][4];
         for (int k = 0; k < 3; k++) {
@@ -510,10 +515,7 @@ bool upload_spline_tables(State &s)
             c[k][2] = (float) (p[2] + 3.0 * dlt * p[3]);
             c[k][3] = (float) p[3];
         }
-        poly[l] = make_float4(xf, c[0][0], c[0][1], c[0][2]);
-        poly[(size_t) n + l] = make_float4(c[0][3], c[1][0], c[1][1], c[1][2]);
-        poly[(size_t) 2 * n + l] = make_float4(c[1][3], c[2][0], c[2][1], c[2][2]);
-        poly[(size_t) 3 * n + l] = make_float4(c[2][3], 0.f, 0.f, 0.f);
+        for (int k = 0; k < 3; k++) poly[(size_t) k * n + l] = make_float4(c[k][0], c[k][1], c[k][2], c[k][3]);
     }
     if (!s.splF64.ensure(h64.size()) || !s.splPoly.ensure(poly.size())) return false;
     NBB_CUDA(cudaMemcpy(s.splF64.p, h64.data(), sizeof(double) * h64.size(), cudaMemcpyHostToDevice));
@@ -575,15 +577,16 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
             F.k2 = (float) (2.0 / gam);
         }
         A.qScale = (float) eScale;
-        A.splTab = nullptr; A.splN = 0; A.splInvDR = 0.f;
+        A.splTab = nullptr; A.splN = 0; A.splInvDR = 0.f; A.splDR = 0.f;
         const bool spline = !s.useAnalytic;
         size_t splBytes = 0;
         if (spline) {
             if (!s.splValid) { set_error("spline form selected but the spline tables are not built"); return false; }
             A.splTab = s.splPoly.p; A.splN = s.spl.points();
             A.splInvDR = (float) ((double) (s.spl.points() - 1) / s.outer);
+            A.splDR = (float) (s.outer / (double) (s.spl.points() - 1));
             A.qScale = (float) (1.0 / s.dielectric);          // the electrostatic spline carries the unit (PairwiseInteraction.c:474)
-            splBytes = sizeof(float4) * 4 * (size_t) s.spl.points();
+            splBytes = sizeof(float4) * 3 * (size_t) s.spl.points();
         }
         A.gradSorted = wantGrad ? s.gs : nullptr; A.accum = s.accum.p;
         if (g_numSMs == 0) init_force_kernel_attributes();

@@ -156,7 +156,8 @@ static bool upload_terms(MMTerms &m)
     return true;
 }
 
-static bool evaluate(MMTerms &m, const double *d_x, double *d_grad, double *energies5)
+// enqueue only: the kernel and the copy of the five energies into pinned memory; collect() waits for them
+static bool enqueue(MMTerms &m, const double *d_x, double *d_grad)
 {
     if (m.dirty && !upload_terms(m)) return false;
     NBB_CUDA(cudaMemsetAsync(m.energies.p, 0, sizeof(double) * kKinds, m.stream));
@@ -168,10 +169,19 @@ static bool evaluate(MMTerms &m, const double *d_x, double *d_grad, double *ener
         m.launches += 1;
     }
     NBB_CUDA(cudaMemcpyAsync(m.he, m.energies.p, sizeof(double) * kKinds, cudaMemcpyDeviceToHost, m.stream));
+    return cuda_ok(cudaGetLastError(), "k_mm_terms");
+}
+
+static bool collect(MMTerms &m, double *energies5)
+{
     NBB_CUDA(cudaStreamSynchronize(m.stream));
-    if (!cuda_ok(cudaGetLastError(), "k_mm_terms")) return false;
     for (int k = 0; k < kKinds; k++) energies5[k] = m.he[k];
     return true;
+}
+
+static bool evaluate(MMTerms &m, const double *d_x, double *d_grad, double *energies5)
+{
+    return enqueue(m, d_x, d_grad) && collect(m, energies5);
 }
 
 // ---- Langevin velocity Verlet, first part of an Iteration (LangevinVelocityVerletIntegrator.py:117-131,139-149) in Cartesian variables:
@@ -328,6 +338,22 @@ void MMTerms_B200_EnergyDevice(NBB200MMTerms *terms, const double *d_xyz, double
     MMTerms *m = reinterpret_cast<MMTerms *>(terms);
     cudaSetDevice(m->device);
     if (!evaluate(*m, d_xyz, d_grad, energies5)) mm_status(status, NBB200_STATUS_LOGIC_ERROR);
+}
+
+void MMTerms_B200_EnergyDeviceEnqueue(NBB200MMTerms *terms, const double *d_xyz, double *d_grad, int *status)
+{
+    if (terms == nullptr || d_xyz == nullptr) return;
+    MMTerms *m = reinterpret_cast<MMTerms *>(terms);
+    cudaSetDevice(m->device);
+    if (!enqueue(*m, d_xyz, d_grad)) mm_status(status, NBB200_STATUS_LOGIC_ERROR);
+}
+
+void MMTerms_B200_EnergyDeviceCollect(NBB200MMTerms *terms, double *energies5, int *status)
+{
+    if (terms == nullptr || energies5 == nullptr) return;
+    MMTerms *m = reinterpret_cast<MMTerms *>(terms);
+    cudaSetDevice(m->device);
+    if (!collect(*m, energies5)) mm_status(status, NBB200_STATUS_LOGIC_ERROR);
 }
 
 void MMTerms_B200_Energy(NBB200MMTerms *terms, const double *xyz, double *energies5, double *grad, int *status)

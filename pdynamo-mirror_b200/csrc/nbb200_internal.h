@@ -138,7 +138,7 @@ struct State {
     int splineDensity = 50;
     SplineTables spl;
     DevBuf<double> splF64;          // x[n], then y[n], h[n] of the electrostatic, LJ-A and LJ-B splines (1-4 kernel, fp64)
-    DevBuf<float4> splPoly;         // [4][n] per-interval cubics in fp32 (tile kernel), last row zero
+    DevBuf<float4> splPoly;         // [3][n] per-interval cubics in fp32 (tile kernel), last row zero
 
     // reference-state bookkeeping (NBModelABFSState)
     bool isNew = true;

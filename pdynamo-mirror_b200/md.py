@@ -62,12 +62,14 @@ class VelocityVerletDynamics:
     def _forces(self, force_new):
         st = C.c_int(16)
         self.g.zero_()
+        if self.mmterms is not None:
+            self.mmterms.EnqueueDevice(self.x.data_ptr(), self.g.data_ptr())       # runs ahead of the NB kernels on the same stream; collected below
         self.updates += self.L.NBModelABFS_B200_UpdateDevice(self.h, self._p(self.x), self._lib.d_(self.box), 1 if force_new else 0, C.byref(st))
         self.L.NBModelABFS_B200_MMMMEnergyDevice(self.h, self._lib.d_(self.energies), self._p(self.g), self._lib.d_(self.dEdM), C.byref(st))
         if st.value != 16:
             raise RuntimeError("NB call failed: " + self._lib.last_error())
         if self.mmterms is not None:
-            self.bonded = self.mmterms.EnergyDevice(self.x.data_ptr(), self.g.data_ptr())
+            self.bonded = self.mmterms.CollectDevice()
             return float(self.energies.sum() + self.bonded.sum())
         return float(self.energies.sum())
 

@@ -142,6 +142,20 @@ class MMTermsB200:
             raise CLibraryError("MM term evaluation failed. " + _lib.last_error())
         return self.energies
 
+    def EnqueueDevice(self, x_ptr, g_ptr):
+        """launch only (same stream as the caller's other work); CollectDevice() waits and returns the energies"""
+        status = C.c_int(_lib.STATUS_CONTINUE)
+        _lib.lib().MMTerms_B200_EnergyDeviceEnqueue(self.cObject, C.c_void_p(x_ptr), C.c_void_p(g_ptr) if g_ptr else None, C.byref(status))
+        if status.value != _lib.STATUS_CONTINUE:
+            raise CLibraryError("MM term evaluation failed. " + _lib.last_error())
+
+    def CollectDevice(self):
+        status = C.c_int(_lib.STATUS_CONTINUE)
+        _lib.lib().MMTerms_B200_EnergyDeviceCollect(self.cObject, d_(self.energies), C.byref(status))
+        if status.value != _lib.STATUS_CONTINUE:
+            raise CLibraryError("MM term evaluation failed. " + _lib.last_error())
+        return self.energies
+
     def EnergyTerms(self):
         """(label, value) pairs in System.Energy's order for the containers present"""
         return [(c.label, float(self.energies[c.kind])) for c in self.containers]

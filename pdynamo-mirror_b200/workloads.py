@@ -416,10 +416,10 @@ def dhfr_jac(name="dhfr", bonded=False):
                 eps14=d["eps14"], sigma14=d["sigma14"], scale14=1.0)
     w["published_energies"] = np.array(d["published_energies"])
     w["published_counts"] = np.array(d["published_counts"])
-    bonded = _os.path.join(_GOLDEN, "dhfr_bonded.npz")
-    if _os.path.exists(bonded):
+    bonded_path = _os.path.join(_GOLDEN, "dhfr_bonded.npz")
+    if _os.path.exists(bonded_path):
         # bonded terms of the same input: per-term parameters, masses, the energies the reference publishes for them
-        b = dict(np.load(bonded))
+        b = dict(np.load(bonded_path))
         w["masses"] = b.pop("masses")
         w["published_bonded"] = b.pop("published_bonded")
         w["published_total"] = b.pop("published_total")

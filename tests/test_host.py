@@ -75,3 +75,13 @@ def test_workloads_are_deterministic_and_sized(pkg):
         s = (s * 6364136223846793005 + 1442695040888963407) % (1 << 64)
         ref.append((s >> 11) / float(1 << 53))
     assert np.array_equal(a, np.array(ref))
+
+
+def test_dhfr_workloads_nb_only_and_complete(pkg):
+    """'dhfr' is the NB-only system of the NB parity tests; 'dhfr_mm' adds the bonded containers in the order CHARMMPSFFileReader.ToSystem does"""
+    a, b = pkg.workloads.WORKLOADS["dhfr"](), pkg.workloads.WORKLOADS["dhfr_mm"]()
+    assert "bonded" not in a and len(pkg.System.FromWorkload(a).energyModel.mmTerms) == 0
+    labels = [c.label for c in pkg.System.FromWorkload(b).energyModel.mmTerms]
+    assert labels == ["Harmonic Bond", "Harmonic Angle", "Urey-Bradley", "Fourier Dihedral", "Harmonic Improper"]
+    assert [len(c) for c in pkg.System.FromWorkload(b).energyModel.mmTerms] == [23592, 11584, 2117, 7000, 418]
+    assert abs(b["masses"].sum() - a["masses"].sum()) == 0.0 and len(a["masses"]) == a["n"]
