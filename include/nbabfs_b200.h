@@ -106,10 +106,21 @@ int NBModelABFS_B200_UpdateDevice(NBB200State *state, const double *d_xyz, const
 void NBModelABFS_B200_MMMMEnergy(NBB200State *state, double *energies, double *grad, double *dEdM, int *status);
 /* on != 0: NBModelABFS_B200_MMMMEnergy SETS grad[3n] instead of accumulating into it (dE/dM is still accumulated).  For a caller
  * that evaluates the NB term first: System.Energy's zero fill of gradients3 (pMolecule-1.9.0/pMolecule/System.py:272-318) and the
- * upload of the array are then not needed.  Default 0 = the reference's accumulation. */
+ * upload of the array are then not needed.  Default 0 = the reference's accumulation.  The device-array calls (...MMMMEnergyDevice,
+ * ...MMMMEnergyDeviceDeferred) honour it as well: d_grad is then SET by the NB term (no zero fill by the caller). */
 void nbb200_set_gradient_overwrite(NBB200State *state, int on);
 /* same, gradients accumulated into a device array d_grad[3n] (nullable) */
 void NBModelABFS_B200_MMMMEnergyDevice(NBB200State *state, double *energies, double *d_grad, double *dEdM, int *status);
+
+/* The device call WITHOUT its host synchronisation, for MD loops that keep everything on the device: the kernels are enqueued and the call
+ * returns; energies[6] and dEdM[9] (caller-owned, must stay valid) are written at the state's next synchronisation point -- the
+ * list-update decision of the next NBModelABFS_B200_Update* call, any other energy call, or nbb200_flush.  d_grad is complete in stream
+ * order as usual.  With this, one MD step needs a single host wait (the update decision) instead of three. */
+void NBModelABFS_B200_MMMMEnergyDeviceDeferred(NBB200State *state, double *energies, double *d_grad, double *dEdM, int *status);
+void nbb200_flush(NBB200State *state, int *status);
+/* enqueue a device-to-host copy of a few bytes (e.g. the kinetic energy of nbb200_vv_second_half) into page-locked host memory on the state's
+ * stream; valid after the next synchronisation point */
+void nbb200_copy_to_host_async(NBB200State *state, const void *d_src, void *h_pinned_dst, size_t bytes);
 
 /* ---- list inspection: what PairList / ImageList hold in the reference ------------------------------
  * statistics of NBModelABFSState (pM/cinclude/NBModelABFSState.h:38-71) */
@@ -209,6 +220,8 @@ void MMTerms_B200_EnergyDevice(NBB200MMTerms *terms, const double *d_xyz, double
  * after it: one host synchronisation less per MD step): Enqueue launches the kernel, Collect waits and returns the energies */
 void MMTerms_B200_EnergyDeviceEnqueue(NBB200MMTerms *terms, const double *d_xyz, double *d_grad, int *status);
 void MMTerms_B200_EnergyDeviceCollect(NBB200MMTerms *terms, double *energies5, int *status);
+/* the energies of the last completed Enqueue WITHOUT a synchronisation: for callers that know the stream has been synchronised since */
+void MMTerms_B200_LastEnergies(NBB200MMTerms *terms, double *energies5);
 long MMTerms_B200_NumberOfTerms(NBB200MMTerms *terms, int kind /* 0 bond, 1 angle, 2 Urey-Bradley, 3 dihedral, 4 improper: active terms */);
 
 /* ---- several GPUs ------------------------------------------------------------

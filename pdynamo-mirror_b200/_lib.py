@@ -24,6 +24,9 @@ SIGNATURES = {
     "NBModelABFS_B200_UpdateDevice": (C.c_int, [vp, vp, dp, C.c_int, ip]),
     "NBModelABFS_B200_MMMMEnergy": (None, [vp, dp, dp, dp, ip]),
     "NBModelABFS_B200_MMMMEnergyDevice": (None, [vp, dp, vp, dp, ip]),
+    "NBModelABFS_B200_MMMMEnergyDeviceDeferred": (None, [vp, dp, vp, dp, ip]),
+    "nbb200_flush": (None, [vp, ip]),
+    "nbb200_copy_to_host_async": (None, [vp, vp, vp, C.c_size_t]),
     "NBModelABFSState_B200_NumberOfPairs": (C.c_long, [vp, C.c_int]),
     "NBModelABFSState_B200_NumberOfImages": (C.c_int, [vp]),
     "NBModelABFSState_B200_NumberOfImagePairs": (C.c_long, [vp]),
@@ -58,6 +61,7 @@ SIGNATURES = {
     "MMTerms_B200_EnergyDevice": (None, [vp, vp, dp, vp, ip]),
     "MMTerms_B200_EnergyDeviceEnqueue": (None, [vp, vp, vp, ip]),
     "MMTerms_B200_EnergyDeviceCollect": (None, [vp, dp, ip]),
+    "MMTerms_B200_LastEnergies": (None, [vp, dp]),
     "MMTerms_B200_NumberOfTerms": (C.c_long, [vp, C.c_int]),
     "nbb200_get_slab": (None, [vp, lp]),
     "nbb200_touched_ranges": (C.c_int, [vp, lp]),

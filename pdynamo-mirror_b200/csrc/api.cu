@@ -52,6 +52,7 @@ static void destroy(State *s)
     if (s->hx) cudaFreeHost(s->hx);
     if (s->hgrad) cudaFreeHost(s->hgrad);
     if (s->hsmall) cudaFreeHost(s->hsmall);
+    if (s->hacc) cudaFreeHost(s->hacc);
     if (s->hops) cudaFreeHost(s->hops);
     if (s->haveEvents) for (auto &e : s->ev) cudaEventDestroy(e);
     if (s->ownStream && s->stream) cudaStreamDestroy(s->stream);
@@ -158,9 +159,26 @@ static std::vector<int> live_images(State &s)
     return live;
 }
 
+static void energy_finish(State &s, double *energies, bool haveGrad, double *dEdM, const double *acc = nullptr, const Lattice *lat = nullptr);
+
+// results of a deferred energy call: valid once the stream has been synchronised after it
+static void finish_pending(State &s)
+{
+    if (!s.pending) return;
+    s.pending = false;
+    energy_finish(s, s.pendEnergies, s.pendHaveGrad, s.pendDEdM, s.hacc, &s.pendLattice);
+}
+static void flush_pending(State &s)
+{
+    if (!s.pending) return;
+    cudaStreamSynchronize(s.stream);
+    finish_pending(s);
+}
+
 static int update_common(State &s, const double *box6, int forceNew, int *status, int decided = -1)
 {
     s.numberOfCalls += 1;
+    if (s.pending && (forceNew || s.isNew || decided >= 0 || s.list != s.stListCutoff || s.outer != s.stOuterCutoff)) flush_pending(s);   // no displacement check below
     if (s.trans.n > 0) {
         if (box6 == nullptr) { set_error("box6 is required when transformations are present"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return 0; }
         s.lattice.set_crystal(box6);
@@ -177,6 +195,7 @@ static int update_common(State &s, const double *box6, int forceNew, int *status
         const double buffac = 0.5 * (s.list - s.stOuterCutoff);
         double maxr2 = 0.0; int exceeded = 0;
         if (!displacement_check(s, buffac * buffac, &maxr2, &exceeded)) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
+        finish_pending(s);                                   // the check synchronised the stream: a deferred energy call before it is complete
         checked = true;
         doUpdate = exceeded != 0;
         maxDisp = std::sqrt(maxr2);
@@ -216,7 +235,7 @@ static int update_common(State &s, const double *box6, int forceNew, int *status
 
 // enqueue one energy evaluation on the state's stream: image operations (only when the lattice or the lists changed),
 // force kernels, read-back of the accumulators.  No synchronisation here.
-static bool energy_enqueue(State &s, double *d_grad, bool sortedOnly = false)
+static bool energy_enqueue(State &s, double *d_grad, bool sortedOnly = false, double *target = nullptr)
 {
     // energy-time image operations: Orthogonalize(S, t + (a,b,c)) with the CURRENT lattice (NBModelABFS.c:1246-1256)
     const bool latticeSame = s.opsValid && s.opsGeneration == s.numberOfUpdates && std::memcmp(s.opsLattice.v, s.lattice.M.v, sizeof(double) * 9) == 0;
@@ -247,14 +266,15 @@ static bool energy_enqueue(State &s, double *d_grad, bool sortedOnly = false)
     if (!launch_forces(s, d_grad, sortedOnly)) return false;
     const size_t accumCount = (size_t) 16 * (s.nsets + 1);
     if (accumCount > kSmallDoubles) { set_error("too many images for the result buffer"); return false; }
-    NBB_CUDA(cudaMemcpyAsync(s.hsmall, s.accum.p, sizeof(double) * accumCount, cudaMemcpyDeviceToHost, s.stream));
+    NBB_CUDA(cudaMemcpyAsync(target != nullptr ? target : s.hsmall, s.accum.p, sizeof(double) * accumCount, cudaMemcpyDeviceToHost, s.stream));
     return true;
 }
 
 // after the stream has been synchronised: energies, dE/dM, timings from the accumulators
-static void energy_finish(State &s, double *energies, bool haveGrad, double *dEdM)
+static void energy_finish(State &s, double *energies, bool haveGrad, double *dEdM, const double *acc, const Lattice *lat)
 {
-    const double *acc = s.hsmall;
+    if (acc == nullptr) acc = s.hsmall;
+    if (lat == nullptr) lat = &s.lattice;
     for (int k = 0; k < 6; k++) energies[k] = 0.0;
     energies[NBB200_EMMEL] = acc[0]; energies[NBB200_EMMLJ] = acc[1];
     for (int k = 1; k < s.nsets; k++) { energies[NBB200_EIMMMEL] += acc[16 * k]; energies[NBB200_EIMMMLJ] += acc[16 * k + 1]; }
@@ -263,7 +283,7 @@ static void energy_finish(State &s, double *energies, bool haveGrad, double *dEd
         for (int k = 1; k < s.nsets; k++) {
             const CandidateImage &im = s.plan.images[k - 1];
             const double xt[3] = {s.trans.trans[3 * im.t] + (double) im.a, s.trans.trans[3 * im.t + 1] + (double) im.b, s.trans.trans[3 * im.t + 2] + (double) im.c};
-            image_derivatives(dEdM, s.lattice, s.trans.rot[im.t], xt, acc + 16 * k + 5, acc + 16 * k + 2);
+            image_derivatives(dEdM, *lat, s.trans.rot[im.t], xt, acc + 16 * k + 5, acc + 16 * k + 2);
         }
     }
     if (s.timing) {
@@ -439,6 +459,7 @@ void NBModelABFS_B200_MMMMEnergy(NBB200State *state, double *energies, double *g
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
     if (s.xcur == nullptr) { set_error("MMMMEnergy called before Update"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+    flush_pending(s);
     double *dg = nullptr;
     const bool direct = grad != nullptr && is_pinned_host(grad);       // accumulate on the device, DMA straight into the caller's array
     const bool upload = direct && !s.gradOverwrite;                      // overwrite mode: the caller's values are not needed at all
@@ -469,8 +490,38 @@ void NBModelABFS_B200_MMMMEnergyDevice(NBB200State *state, double *energies, dou
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
     if (s.xcur == nullptr) { set_error("MMMMEnergy called before Update"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+    flush_pending(s);
     if (energy_enqueue(s, d_grad) && cuda_ok(cudaStreamSynchronize(s.stream), "sync")) energy_finish(s, energies, d_grad != nullptr, dEdM);
     else set_status(status, NBB200_STATUS_LOGIC_ERROR);
+}
+
+void NBModelABFS_B200_MMMMEnergyDeviceDeferred(NBB200State *state, double *energies, double *d_grad, double *dEdM, int *status)
+{
+    if (state == nullptr || energies == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (s.xcur == nullptr) { set_error("MMMMEnergy called before Update"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+    flush_pending(s);
+    if (s.hacc == nullptr && !cuda_ok(cudaMallocHost((void **) &s.hacc, sizeof(double) * kSmallDoubles), "cudaMallocHost")) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return; }
+    if (!energy_enqueue(s, d_grad, false, s.hacc)) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+    s.pending = true; s.pendEnergies = energies; s.pendDEdM = dEdM; s.pendHaveGrad = d_grad != nullptr; s.pendLattice = s.lattice;
+}
+
+void nbb200_flush(NBB200State *state, int *status)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (!cuda_ok(cudaStreamSynchronize(s.stream), "sync")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+    finish_pending(s);
+}
+
+void nbb200_copy_to_host_async(NBB200State *state, const void *d_src, void *h_pinned_dst, size_t bytes)
+{
+    if (state == nullptr || d_src == nullptr || h_pinned_dst == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    cuda_ok(cudaMemcpyAsync(h_pinned_dst, d_src, bytes, cudaMemcpyDeviceToHost, s.stream), "D2H");
 }
 
 long NBModelABFSState_B200_NumberOfPairs(NBB200State *state, int image)
@@ -688,6 +739,7 @@ void NBModelABFS_B200_MMMMEnergySorted(NBB200State *state, double *energies, dou
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
     if (s.xcur == nullptr) { set_error("MMMMEnergy called before Update"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+    flush_pending(s);
     if (energy_enqueue(s, nullptr, true) && cuda_ok(cudaStreamSynchronize(s.stream), "sync")) energy_finish(s, energies, true, dEdM);
     else set_status(status, NBB200_STATUS_LOGIC_ERROR);
 }

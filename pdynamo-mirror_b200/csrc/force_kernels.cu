@@ -374,12 +374,14 @@ __global__ void k_pack_records(const double *__restrict__ x, const int *__restri
     recB[s] = make_float4((float) KX, (float) KY, (float) KZ, __int_as_float(ljtype[a]));
 }
 
-__global__ void k_unsort_gradients(const double *__restrict__ gs, const int *__restrict__ sAtom, int s0, int n, double *__restrict__ grad)
+// assign != 0: the NB term SETS the caller's gradient (every atom has exactly one sorted position) instead of accumulating into it
+__global__ void k_unsort_gradients(const double *__restrict__ gs, const int *__restrict__ sAtom, int s0, int n, double *__restrict__ grad, int assign)
 {
     const int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int a = sAtom[s];
-    grad[3 * a] += gs[3 * s]; grad[3 * a + 1] += gs[3 * s + 1]; grad[3 * a + 2] += gs[3 * s + 2];
+    if (assign) { grad[3 * a] = gs[3 * s]; grad[3 * a + 1] = gs[3 * s + 1]; grad[3 * a + 2] = gs[3 * s + 2]; }
+    else { grad[3 * a] += gs[3 * s]; grad[3 * a + 1] += gs[3 * s + 1]; grad[3 * a + 2] += gs[3 * s + 2]; }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -523,11 +525,11 @@ bool upload_spline_tables(State &s)
     return true;
 }
 
-bool unsort_gradients(State &s, long s0, long s1, double *d_grad)
+bool unsort_gradients(State &s, long s0, long s1, double *d_grad, bool assign)
 {
     if (s1 <= s0 || d_grad == nullptr || s.gs == nullptr) return true;
     const int threads = 256;
-    k_unsort_gradients<<<(unsigned int) ((s1 - s0 + threads - 1) / threads), threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad);
+    k_unsort_gradients<<<(unsigned int) ((s1 - s0 + threads - 1) / threads), threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0);
     s.launches += 1;
     return cuda_ok(cudaGetLastError(), "k_unsort_gradients");
 }
@@ -622,7 +624,8 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
         if (s.timing) cudaEventRecord(s.ev[5], s.stream);
         s.launches += 1;
     }
-    if (d_grad != nullptr && !unsort_gradients(s, 0, s.n, d_grad)) return false;
+    // device-array calls honour nbb200_set_gradient_overwrite too (the host-array call handles it with its own staging buffer: d_grad = s.grad.p)
+    if (d_grad != nullptr && !unsort_gradients(s, 0, s.n, d_grad, s.gradOverwrite && d_grad != s.grad.p && s.nranks == 1)) return false;
     return cuda_ok(cudaGetLastError(), "force kernels");
 }
 

@@ -373,6 +373,13 @@ void MMTerms_B200_Energy(NBB200MMTerms *terms, const double *xyz, double *energi
     if (!ok) mm_status(status, NBB200_STATUS_LOGIC_ERROR);
 }
 
+void MMTerms_B200_LastEnergies(NBB200MMTerms *terms, double *energies5)
+{
+    if (terms == nullptr || energies5 == nullptr) return;
+    const MMTerms *m = reinterpret_cast<MMTerms *>(terms);
+    for (int k = 0; k < kKinds; k++) energies5[k] = m->he[k];
+}
+
 long MMTerms_B200_NumberOfTerms(NBB200MMTerms *terms, int kind)
 {
     if (terms == nullptr || kind < 0 || kind >= kKinds) return 0;

@@ -97,7 +97,7 @@ bool touched_ranges_async(State &s, long *d_out);      // the same table written
 // ---- force_kernels.cu
 bool upload_spline_tables(State &s);                     // s.spl -> s.splF64 / s.splPoly
 bool launch_forces(State &s, double *d_grad, bool sortedOnly);
-bool unsort_gradients(State &s, long s0, long s1, double *d_grad);
+bool unsort_gradients(State &s, long s0, long s1, double *d_grad, bool assign = false);
 void init_force_kernel_attributes();
 
 struct State {
@@ -152,6 +152,12 @@ struct State {
     const double *xcur = nullptr;   // coordinates of the current call (s.x.p or a caller-owned device array)
     double *hx = nullptr, *hgrad = nullptr;      // pinned staging
     double *hsmall = nullptr;                    // pinned small results
+    // deferred energy call (MMMMEnergyDeviceDeferred): the accumulators land in their own pinned buffer; energies / dE/dM are written to the
+    // caller's arrays at the state's next synchronisation point (the list-update decision of the next Update, or nbb200_flush)
+    double *hacc = nullptr;
+    bool pending = false, pendHaveGrad = false;
+    double *pendEnergies = nullptr, *pendDEdM = nullptr;
+    Lattice pendLattice;
     void *hops = nullptr;                        // pinned staging of the image operations
     Mat3 opsLattice{}; long opsGeneration = -1; bool opsValid = false;
     size_t hcap = 0;

@@ -73,18 +73,56 @@ class VelocityVerletDynamics:
             return float(self.energies.sum() + self.bonded.sum())
         return float(self.energies.sum())
 
+    def _first_half(self):
+        self.L.nbb200_vv_first_half(self.h, self._p(self.x), self._p(self.v), self._p(self.a), self.dt)
+
+    def _second_half_dt(self):
+        return self.dt
+
     def Run(self, steps, updateFrequency=0, log=None):
-        """steps velocity-Verlet steps; updateFrequency > 0 forces a list rebuild every that many steps (0: the reference's displacement
-        heuristic only).  Returns the list of (potential, kinetic) per step."""
+        """steps integration steps; updateFrequency > 0 forces a list rebuild every that many steps (0: the reference's displacement
+        heuristic only).  Returns the list of (potential, kinetic) per step.
+
+        The loop is pipelined: per step the host waits ONCE, for the list-update decision (NBModelABFS_B200_UpdateDevice); the energy call is
+        deferred (NBModelABFS_B200_MMMMEnergyDeviceDeferred), the bonded energies and the kinetic energy are copied to page-locked memory in
+        stream order, and the numbers of step k are picked up after the decision of step k + 1 (or the final flush)."""
         out = []
-        for k in range(steps):
-            self.L.nbb200_vv_first_half(self.h, self._p(self.x), self._p(self.v), self._p(self.a), self.dt)
-            self.potential = self._forces(updateFrequency > 0 and (k + 1) % updateFrequency == 0)
-            self.L.nbb200_vv_second_half(self.h, self._p(self.v), self._p(self.a), self._p(self.g), self._p(self.mass), self.dt, self._p(self.ke_dev))
-            self.kinetic = float(self.ke_dev.item())
+        st = C.c_int(16)
+        if getattr(self, "_ke_host", None) is None:
+            self._ke_host = self._lib.pinned_array((2,))
+        ke_ptr = [C.c_void_p(self._ke_host.ctypes.data), C.c_void_p(self._ke_host.ctypes.data + 8)]
+        dt2 = self._second_half_dt()
+
+        def harvest(k):
+            if self.mmterms is not None:
+                self.bonded = self.mmterms.LastEnergies()
+            self.potential = float(self.energies.sum() + (self.bonded.sum() if self.mmterms is not None else 0.0))
+            self.kinetic = float(self._ke_host[k & 1])
             out.append((self.potential, self.kinetic))
             if log is not None and (k + 1) % 100 == 0:
-                log("step %d: potential %.4f kinetic %.4f total %.4f" % (k + 1, self.potential, self.kinetic, self.potential + self.kinetic))
+                log("step %d: potential %.4f kinetic %.4f total %.4f temperature %.2f" % (k + 1, self.potential, self.kinetic, self.potential + self.kinetic,
+                                                                                       2.0 * self.kinetic / (3 * self.n * _KB_KJMOL)))
+        self.L.nbb200_set_gradient_overwrite(self.h, 1)        # the NB term sets g (no zero fill), the bonded terms then accumulate
+        try:
+            for k in range(steps):
+                self._first_half()
+                force_new = updateFrequency > 0 and (k + 1) % updateFrequency == 0
+                self.updates += self.L.NBModelABFS_B200_UpdateDevice(self.h, self._p(self.x), self._lib.d_(self.box), 1 if force_new else 0, C.byref(st))
+                # the decision synchronised the stream: step k - 1 is complete, its NB energies are in self.energies.  Enqueue first, read after.
+                self.L.NBModelABFS_B200_MMMMEnergyDeviceDeferred(self.h, self._lib.d_(self.energies), self._p(self.g), self._lib.d_(self.dEdM), C.byref(st))
+                if k > 0:
+                    harvest(k - 1)
+                if self.mmterms is not None:
+                    self.mmterms.EnqueueDevice(self.x.data_ptr(), self.g.data_ptr())
+                self.L.nbb200_vv_second_half(self.h, self._p(self.v), self._p(self.a), self._p(self.g), self._p(self.mass), dt2, self._p(self.ke_dev))
+                self.L.nbb200_copy_to_host_async(self.h, self._p(self.ke_dev), ke_ptr[k & 1], 8)
+                if st.value != 16:
+                    raise RuntimeError("NB call failed: " + self._lib.last_error())
+        finally:
+            self.L.nbb200_set_gradient_overwrite(self.h, 0)
+        if steps > 0:
+            self.L.nbb200_flush(self.h, C.byref(st))
+            harvest(steps - 1)
         return out
 
 
@@ -125,17 +163,10 @@ class LangevinDynamics(VelocityVerletDynamics):
         self.facV3 = c2 * dt
         self.factors = np.array([c1 * dt, c2 * dt ** 2, c0, (c1 - c2) * dt, sdR * kT, cRV1 * sdV * kT, cRV2 * sdV * kT], dtype=np.float64)
 
-    def Run(self, steps, updateFrequency=0, log=None):
-        out = []
-        for k in range(steps):
-            self.iteration += 1
-            self.L.nbb200_langevin_first_half(self.h, self._p(self.x), self._p(self.v), self._p(self.a), self._p(self.mass), self._lib.d_(self.factors),
-                                              C.c_ulonglong(self.seed), C.c_ulonglong(self.iteration))
-            self.potential = self._forces(updateFrequency > 0 and (k + 1) % updateFrequency == 0)
-            self.L.nbb200_vv_second_half(self.h, self._p(self.v), self._p(self.a), self._p(self.g), self._p(self.mass), 2.0 * self.facV3, self._p(self.ke_dev))
-            self.kinetic = float(self.ke_dev.item())
-            out.append((self.potential, self.kinetic))
-            if log is not None and (k + 1) % 100 == 0:
-                log("step %d: potential %.4f kinetic %.4f total %.4f temperature %.2f" % (k + 1, self.potential, self.kinetic, self.potential + self.kinetic,
-                                                                                       2.0 * self.kinetic / (3 * self.n * _KB_KJMOL)))
-        return out
+    def _first_half(self):
+        self.iteration += 1
+        self.L.nbb200_langevin_first_half(self.h, self._p(self.x), self._p(self.v), self._p(self.a), self._p(self.mass), self._lib.d_(self.factors),
+                                          C.c_ulonglong(self.seed), C.c_ulonglong(self.iteration))
+
+    def _second_half_dt(self):
+        return 2.0 * self.facV3                # v += facV3 a  (LangevinVelocityVerletIntegrator.py:133)

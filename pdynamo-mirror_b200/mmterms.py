@@ -156,6 +156,11 @@ class MMTermsB200:
             raise CLibraryError("MM term evaluation failed. " + _lib.last_error())
         return self.energies
 
+    def LastEnergies(self):
+        """the energies of the last enqueued evaluation, no synchronisation (the caller knows the stream has been synchronised since)"""
+        _lib.lib().MMTerms_B200_LastEnergies(self.cObject, d_(self.energies))
+        return self.energies
+
     def EnergyTerms(self):
         """(label, value) pairs in System.Energy's order for the containers present"""
         return [(c.label, float(self.energies[c.kind])) for c in self.containers]

@@ -1,5 +1,13 @@
-"""Short driver for ncu captures: a few rebuild + energy steps on one workload through the C-ABI (device-resident)."""
-import sys, os
+"""Short driver for ncu captures: a few rebuild + energy steps on one workload through the C-ABI (device-resident).
+
+    python scripts/profile_run.py <workload> <steps> [analytic|spline|md]
+
+spline: the same steps with the interaction in its spline form (PairwiseInteractionABFS_B200_SetInteractionForm);
+md:     <steps> Langevin velocity-Verlet steps with bonded terms on the device (workload dhfr_mm)."""
+import ctypes as C
+import os
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
@@ -7,9 +15,22 @@ import bench
 
 name = sys.argv[1] if len(sys.argv) > 1 else "jac"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+mode = sys.argv[3] if len(sys.argv) > 3 else "analytic"
 w = bench.make_workload(name)
-m = bench.DeviceModel(w, 0)
-for _ in range(steps):
-    m.step(rebuild=True)
-torch.cuda.synchronize()
-print(name, m.state.Counters(), m.state.Timings())
+if mode == "md":
+    import pdynamo_mirror_b200 as p
+    sysm = p.System.FromWorkload(w)
+    sysm.DefineNBModel(p.NBModelABFS())
+    md = p.md.LangevinDynamics(sysm)
+    md.Run(steps)
+    torch.cuda.synchronize()
+    print(name, "md", md.potential, md.kinetic, md.updates)
+else:
+    m = bench.DeviceModel(w, 0)
+    if mode == "spline":
+        st = C.c_int(16)
+        m.L.PairwiseInteractionABFS_B200_SetInteractionForm(m.h, 0, 50, C.byref(st))
+    for _ in range(steps):
+        m.step(rebuild=True)
+    torch.cuda.synchronize()
+    print(name, mode, m.state.Counters(), m.state.Timings(), m.e)
