@@ -131,6 +131,59 @@ def test_spline_form_crystal_with_rotations_and_large_tables(pkg, orc):
         check_numbers("w216", e, g, dm, ref["energies"], ref["grad"], ref["dEdM"])
 
 
+@pytest.mark.parametrize("name", ["bala_fixed", "w216_triclinic_centred", "w216_fixed_centred"])
+def test_spline_form_with_fixed_atoms_and_centring(pkg, orc, name):
+    """the spline form composes with the list options (fixed atoms: pairs of two fixed atoms leave all lists incl. 1-4; useCentering: lists
+    and energies on the centred coordinates), against the oracle in its spline form"""
+    maker, opts, _ = pkg.workloads.GOLDEN_CASES[name]
+    w = maker()
+    opts = dict(opts, useAnalyticForm=False, splinePointDensity=40)
+    system, st, e, g, dm = gpu_energy(pkg, w, **opts)
+    o = orc.OracleNB(w, **opts)
+    ref = o.energy(force_new=True)
+    assert np.array_equal(orc.canonical_primary(st.Pairs(-1)), orc.canonical_primary(o.primary_pairs()))
+    rg = ref["grad"].copy()
+    if w.get("fixed") is not None:
+        rg[w["fixed"]] = 0.0
+    check_numbers(name, e, g, dm, ref["energies"], rg, ref["dEdM"])
+
+
+def test_deferred_energy_call_matches_the_synchronous_one(pkg):
+    """NBModelABFS_B200_MMMMEnergyDeviceDeferred: results appear at the next synchronisation point (the next Update's decision or nbb200_flush)
+    and equal the synchronous call's; the device-array overwrite mode sets the gradient instead of accumulating."""
+    import ctypes as C
+    import torch
+    from pdynamo_mirror_b200 import _lib
+    w = pkg.workloads.WORKLOADS["dhfr"]()
+    system, st, e, g, dm = gpu_energy(pkg, w)
+    L, h = _lib.lib(), st.cObject
+    L.nbb200_set_stream(h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    x = torch.from_numpy(w["xyz"]).cuda()
+    box = np.ascontiguousarray(w["box"], np.float64)
+    status = C.c_int(16)
+    gd = torch.full((w["n"], 3), 7.0, dtype=torch.float64, device="cuda")
+    e1, m1 = np.full(6, np.nan), np.zeros(9)
+    L.NBModelABFS_B200_UpdateDevice(h, C.c_void_p(x.data_ptr()), _lib.d_(box), 0, C.byref(status))
+    L.nbb200_set_gradient_overwrite(h, 1)
+    L.NBModelABFS_B200_MMMMEnergyDeviceDeferred(h, _lib.d_(e1), C.c_void_p(gd.data_ptr()), _lib.d_(m1), C.byref(status))
+    L.nbb200_set_gradient_overwrite(h, 0)
+    assert np.all(np.isnan(e1))                                   # nothing has been handed over yet
+    L.nbb200_flush(h, C.byref(status))
+    assert status.value == 16 and np.allclose(e1, e, rtol=1e-12, atol=1e-9)
+    assert np.allclose(gd.cpu().numpy(), g, rtol=1e-12, atol=1e-9)          # set, not accumulated onto the 7.0
+    assert np.allclose(m1.reshape(3, 3), dm, rtol=1e-12, atol=1e-9)
+    # handed over by the next Update's decision
+    e2 = np.full(6, np.nan)
+    L.NBModelABFS_B200_MMMMEnergyDeviceDeferred(h, _lib.d_(e2), None, None, C.byref(status))
+    L.NBModelABFS_B200_UpdateDevice(h, C.c_void_p(x.data_ptr()), _lib.d_(box), 0, C.byref(status))
+    assert np.allclose(e2, e, rtol=1e-12, atol=1e-9)
+    # ... also when that Update rebuilds the lists without a displacement check
+    e3 = np.full(6, np.nan)
+    L.NBModelABFS_B200_MMMMEnergyDeviceDeferred(h, _lib.d_(e3), None, None, C.byref(status))
+    L.NBModelABFS_B200_UpdateDevice(h, C.c_void_p(x.data_ptr()), _lib.d_(box), 1, C.byref(status))
+    assert np.allclose(e3, e, rtol=1e-12, atol=1e-9) and status.value == 16
+
+
 def test_spline_form_follows_option_changes(pkg, orc):
     """Switching one state between the forms and changing the cutoffs rebuilds the tables (NBModelABFS.SetOptions -> CheckPairwiseInteractions
     -> MakeSplines, pMolecule.NBModelABFS.pyx:140-179)."""
@@ -289,18 +342,19 @@ def test_standalone_generators_vs_bruteforce(pkg, orc):
     assert len(gen.CrossPairListFromDoubleCoordinates3(x1, far)) == 0
 
 
-def test_partitioned_states_sum_to_the_whole(pkg):
+@pytest.mark.parametrize("form", [{}, dict(useAnalyticForm=False)])
+def test_partitioned_states_sum_to_the_whole(pkg, form):
     """Section 8e on one GPU: two states owning complementary i-block slabs give partial energies / gradients / pair
-    counts that add up to the unpartitioned result (the NCCL all-reduce of bench.py sums exactly these)."""
+    counts that add up to the unpartitioned result (the NCCL all-reduce of bench.py sums exactly these); analytic and spline form."""
     import ctypes as C
     from pdynamo_mirror_b200 import _lib
     w = pkg.workloads.WORKLOADS["water3x3x3"]()
-    system, st, e, g, dm = gpu_energy(pkg, w)
+    system, st, e, g, dm = gpu_energy(pkg, w, **form)
     total_pairs = st.NumberOfPairs() + st.NumberOfImagePairs()
     es, gs, dms, pairs = np.zeros(6), np.zeros_like(g), np.zeros((3, 3)), 0
     for rank in range(3):
         s2 = pkg.System.FromWorkload(w)
-        s2.DefineNBModel(pkg.NBModelABFS())
+        s2.DefineNBModel(nb_model(pkg, **form))
         s2.Energy()
         _lib.lib().nbb200_set_partition(s2.configuration.nbState.cObject, rank, 3)
         s2.Energy(doGradients=True)
