@@ -515,7 +515,10 @@ __device__ __forceinline__ void emit_tile(const TileArgs &A, int lane, int clust
     if (lane == 0) { st->chunkBase = base; st->chunkUsed = close ? 0 : used; }
 }
 
-__global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
+#ifndef NBB_BUILD_MINBLOCKS
+#define NBB_BUILD_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(kBuildThreads, NBB_BUILD_MINBLOCKS) k_build_tiles(TileArgs A)
 {
     __shared__ BuildWarp sw[kBuildWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
