@@ -45,7 +45,7 @@ static void destroy(State *s)
     s->cellStart.release(); s->cellFill.release(); s->scanTmp.release(); s->order.release(); s->order2.release();
     s->sX.release(); s->sAtom.release(); s->invPerm.release(); s->blockBox.release();
     s->tileDesc.release(); s->recA.release(); s->recB.release(); s->gradSorted.release(); s->items.release(); s->rangeTab.release(); s->rangeOut.release(); s->setPairs.release(); s->accum.release();
-    s->pairBuf.release(); s->pairCursor.release();
+    s->pairBuf.release(); s->pairCursor.release(); s->splF64.release(); s->splPoly.release();
     for (int r = 0; r < State::kMaxPeers; r++) if (s->peerOpened[r]) { cudaIpcCloseMemHandle(s->peerGs[r]); cudaIpcCloseMemHandle(s->peerXs[r]); cudaIpcCloseMemHandle(s->peerSig[r]); }
     s->symGs.release(); s->symXs.release(); s->symSig.release(); s->sigStage.release();
     if (s->counters) cudaFree(s->counters);

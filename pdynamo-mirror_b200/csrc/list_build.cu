@@ -515,10 +515,13 @@ __device__ __forceinline__ void emit_tile(const TileArgs &A, int lane, int clust
     if (lane == 0) { st->chunkBase = base; st->chunkUsed = close ? 0 : used; }
 }
 
-#ifndef NBB_BUILD_MINBLOCKS
-#define NBB_BUILD_MINBLOCKS 1
-#endif
+// 80 registers / 6 CTAs per SM with the plain bound; -DNBB_BUILD_MINBLOCKS=7 (72 registers) measured no faster, and an explicit
+// minimum of 1 lets ptxas take 132 registers (builder 1.59 -> 2.33 ms): keep the plain form as the default
+#ifdef NBB_BUILD_MINBLOCKS
 __global__ void __launch_bounds__(kBuildThreads, NBB_BUILD_MINBLOCKS) k_build_tiles(TileArgs A)
+#else
+__global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
+#endif
 {
     __shared__ BuildWarp sw[kBuildWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
