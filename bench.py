@@ -291,7 +291,10 @@ def run_b200(args):
 
     value = pairs / (ms * 1e-3)
     sm_max = float(pk.get("sm_max_mhz", 1965.0))
-    fp32_peak_tflops = SM_COUNT * FP32_LANES * 2 * sm_max * 1e6 / 1e12
+    nominal_tflops = SM_COUNT * FP32_LANES * 2 * sm_max * 1e6 / 1e12
+    st_peak = C.c_int(16)
+    measured_tflops = float(m.L.nbb200_measure_fp32_peak(local, C.byref(st_peak)))      # register-only FMA chains, live on this GPU
+    fp32_peak_tflops = measured_tflops if (st_peak.value == 16 and measured_tflops > 0.5 * nominal_tflops) else nominal_tflops
     achieved_tflops = (pairs / world) * FLOP_PER_LIST_PAIR / (force_ms * 1e-3) / 1e12 if force_ms > 0 else 0.0
     n, nimg = w["n"], counters["images"]
     nexcl = len(w["exclusions"])
@@ -310,7 +313,10 @@ def run_b200(args):
         "kernels_ms": {"list_rebuild": build_ms, "tile_forces": force_ms, "pairs14": tm["pairs14"], "displacement_check": tm["displacementCheck"]},
         "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
                      "traffic": ncu_traffic(args.workload, world), "kernel": "k_cluster_forces", "flop_per_list_pair": FLOP_PER_LIST_PAIR,
-                     "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (sm_max_mhz, %s); MEASURED_PEAKS.json holds no FP32 figure" % (sm_max, pk_kind)},
+                     "peak_source": ("measured live: register-only FMA chains on all SMs (nbb200_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x %.0f MHz = %.2f TFLOP/s; "
+                                     "MEASURED_PEAKS.json (%s) holds no FP32 figure" % (sm_max, nominal_tflops, pk_kind)) if fp32_peak_tflops == measured_tflops else
+                                    "148 SM x 128 FP32 lanes x 2 x %.0f MHz (sm_max_mhz, %s); the live FMA measurement failed" % (sm_max, pk_kind),
+                     "peak_nominal": nominal_tflops},
         "roofline_list_build": {"bound": "hbm", "achieved": list_bytes / world / (build_ms * 1e-3) / 1e9 if build_ms > 0 else 0.0, "peak": float(pk.get("hbm_gbs", 6650.0)),
                                 "unit": "GB/s", "frac": (list_bytes / world / (build_ms * 1e-3) / 1e9) / float(pk.get("hbm_gbs", 6650.0)) if build_ms > 0 else 0.0,
                                 "algorithmic_bytes": list_bytes, "note": "all rebuild kernels together; bytes = SURVEY.md 8d atom-pair-equivalent figure"},

@@ -157,6 +157,9 @@ void PairwiseInteractionABFS_B200_MakeFactors(double dampingCutoff, double inner
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------
  * Use the caller's CUDA stream (e.g. torch's current stream) so that the caller's events bracket the work. */
 void nbb200_set_stream(NBB200State *state, void *cudaStream);
+/* the FP32 (non-tensor) roofline denominator measured on this device: sustained TFLOP/s of register-only FMA chains on every lane of
+ * every SM (about 60 ms; SURVEY.md 8d asks for the measured figure instead of lanes x clock) */
+double nbb200_measure_fp32_peak(int device, int *status);
 /* Device time of the phases of the LAST Update / MMMMEnergy pair, from CUDA events on the state's stream (ms):
  * out[0] list rebuild (all kernels), out[1] tile-pair force kernel, out[2] 1-4 kernel, out[3] displacement check,
  * out[4] explicit pair expansion (last GetPairs), out[5..7] reserved.  Enabled by nbb200_enable_timing(state, 1). */

@@ -42,6 +42,7 @@ SIGNATURES = {
     "PairwiseInteractionABFS_B200_SetInteractionForm": (None, [vp, C.c_int, C.c_int, ip]),
     "PairwiseInteractionABFS_B200_MakeSpline": (C.c_int, [C.c_int] + [C.c_double] * 3 + [C.c_int, dp, dp, dp]),
     "nbb200_set_stream": (None, [vp, vp]),
+    "nbb200_measure_fp32_peak": (C.c_double, [C.c_int, ip]),
     "nbb200_enable_timing": (None, [vp, C.c_int]),
     "nbb200_get_timings": (None, [vp, dp]),
     "nbb200_get_counters": (None, [vp, lp]),

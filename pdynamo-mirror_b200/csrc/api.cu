@@ -1080,6 +1080,49 @@ void nbb200_vv_second_half(NBB200State *state, double *d_v, double *d_a, const d
     s.launches += 1;
 }
 
+/* ---- FP32 roofline denominator, measured: register-only FMA chains (no memory traffic), every lane of every SM busy ---- */
+static __global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float b, float c)
+{
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = (float) (threadIdx.x + i) * 1.0e-3f;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) a[i] = fmaf(a[i], b, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += a[i];
+    out[(size_t) blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+double nbb200_measure_fp32_peak(int device, int *status)
+{
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0.0; }
+    cudaDeviceProp prop;
+    if (!cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0.0; }
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+    float *out = nullptr;
+    if (!cuda_ok(cudaMalloc((void **) &out, sizeof(float) * (size_t) blocks * threads), "cudaMalloc")) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return 0.0; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_fma_peak<<<blocks, threads>>>(out, 2000, 0.999999f, 1.0e-7f);                    // warm-up: clocks ramp
+    double best = 0.0;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0);
+        k_fma_peak<<<blocks, threads>>>(out, iters, 0.999999f, 1.0e-7f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 16.0 * (double) iters * (double) blocks * threads;
+        if (ms > 0.f) best = std::max(best, flops / (ms * 1.0e-3) / 1.0e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    if (!cuda_ok(cudaGetLastError(), "k_fma_peak")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0.0; }
+    return best;
+}
+
 void nbb200_set_gradient_overwrite(NBB200State *state, int on)
 {
     if (state != nullptr) reinterpret_cast<State *>(state)->gradOverwrite = on != 0;
