@@ -18,7 +18,20 @@ _KB_KJMOL = 1.3806505e-23 * 6.0221415e+23 * 1.0e-3          # kJ mol^-1 K^-1 (co
 
 
 class VelocityVerletDynamics:
-    def __init__(self, system, timeStep=0.001, temperature=300.0, seed=491831, device=0):
+    """Velocity Verlet dynamics on the device; options as VelocityVerletDynamics_SystemGeometry / VelocityVerletIntegrator
+    (pCore-1.9.0/pCore/VelocityVerletIntegrator.py:17-104): timeStep (ps), temperature = the start temperature of the Maxwell velocities,
+    and the temperature handling temperatureScaleFrequency / temperatureScaleOption ("constant", "exponential", "linear") /
+    temperatureStart / temperatureStop (velocities are scaled to the target temperature every temperatureScaleFrequency steps)."""
+
+    def __init__(self, system, timeStep=0.001, temperature=300.0, seed=491831, device=0, temperatureScaleFrequency=0, temperatureScaleOption=None,
+                 temperatureStart=None, temperatureStop=None):
+        self.temperatureScaleFrequency = int(temperatureScaleFrequency)
+        self.temperatureScaleOption = temperatureScaleOption.capitalize() if isinstance(temperatureScaleOption, str) else None
+        if self.temperatureScaleOption not in ("Constant", "Exponential", "Linear") or self.temperatureScaleFrequency <= 0:
+            self.temperatureScaleOption = None
+        self.temperatureStart = float(temperature if temperatureStart is None else temperatureStart)
+        self.temperatureStop = self.temperatureStart if (temperatureStop is None or self.temperatureScaleOption == "Constant") else float(temperatureStop)
+        self.time, self.numberOfIterations = 0.0, 0
         import torch
         from . import _lib
         self.torch, self.L, self._lib = torch, _lib.lib(), _lib
@@ -76,6 +89,15 @@ class VelocityVerletDynamics:
     def _first_half(self):
         self.L.nbb200_vv_first_half(self.h, self._p(self.x), self._p(self.v), self._p(self.a), self.dt)
 
+    def TargetTemperature(self, time, total_time):
+        """VelocityVerletIntegrator.TargetTemperature / TemperatureHandlingOptions (:85-104)"""
+        t0, t1 = self.temperatureStart, self.temperatureStop
+        if self.temperatureScaleOption == "Exponential":
+            return max(0.0, t0 * math.exp(math.log(t1 / t0) / total_time * time))
+        if self.temperatureScaleOption == "Linear":
+            return max(0.0, t0 + (t1 - t0) / total_time * time)
+        return max(0.0, t0)
+
     def _second_half_dt(self):
         return self.dt
 
@@ -93,11 +115,14 @@ class VelocityVerletDynamics:
         ke_ptr = [C.c_void_p(self._ke_host.ctypes.data), C.c_void_p(self._ke_host.ctypes.data + 8)]
         dt2 = self._second_half_dt()
 
-        def harvest(k):
+        scaling = self.temperatureScaleOption is not None and self.temperatureScaleFrequency < steps
+        t_begin, total_time = self.time, steps * self.dt
+
+        def harvest(k, ke_scale=1.0):
             if self.mmterms is not None:
                 self.bonded = self.mmterms.LastEnergies()
             self.potential = float(self.energies.sum() + (self.bonded.sum() if self.mmterms is not None else 0.0))
-            self.kinetic = float(self._ke_host[k & 1])
+            self.kinetic = float(self._ke_host[k & 1]) * ke_scale
             out.append((self.potential, self.kinetic))
             if log is not None and (k + 1) % 100 == 0:
                 log("step %d: potential %.4f kinetic %.4f total %.4f temperature %.2f" % (k + 1, self.potential, self.kinetic, self.potential + self.kinetic,
@@ -110,17 +135,26 @@ class VelocityVerletDynamics:
                 self.updates += self.L.NBModelABFS_B200_UpdateDevice(self.h, self._p(self.x), self._lib.d_(self.box), 1 if force_new else 0, C.byref(st))
                 # the decision synchronised the stream: step k - 1 is complete, its NB energies are in self.energies.  Enqueue first, read after.
                 self.L.NBModelABFS_B200_MMMMEnergyDeviceDeferred(self.h, self._lib.d_(self.energies), self._p(self.g), self._lib.d_(self.dEdM), C.byref(st))
-                if k > 0:
+                if k > 0 and len(out) < k:
                     harvest(k - 1)
                 if self.mmterms is not None:
                     self.mmterms.EnqueueDevice(self.x.data_ptr(), self.g.data_ptr())
                 self.L.nbb200_vv_second_half(self.h, self._p(self.v), self._p(self.a), self._p(self.g), self._p(self.mass), dt2, self._p(self.ke_dev))
                 self.L.nbb200_copy_to_host_async(self.h, self._p(self.ke_dev), ke_ptr[k & 1], 8)
+                self.numberOfIterations += 1
+                self.time += self.dt
                 if st.value != 16:
                     raise RuntimeError("NB call failed: " + self._lib.last_error())
+                if scaling and self.numberOfIterations % self.temperatureScaleFrequency == 0:
+                    # temperature scaling needs this step's kinetic energy: one extra host wait on these (rare) steps
+                    self.L.nbb200_flush(self.h, C.byref(st))
+                    temp = 2.0 * float(self._ke_host[k & 1]) / (3 * self.n * _KB_KJMOL)
+                    scale = self.TargetTemperature(self.time - t_begin, total_time) / temp if temp > 0.0 else 1.0
+                    self.v.mul_(math.sqrt(scale))
+                    harvest(k, scale)
         finally:
             self.L.nbb200_set_gradient_overwrite(self.h, 0)
-        if steps > 0:
+        if steps > 0 and len(out) < steps:
             self.L.nbb200_flush(self.h, C.byref(st))
             harvest(steps - 1)
         return out

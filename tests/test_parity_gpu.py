@@ -745,3 +745,26 @@ def test_langevin_dynamics_of_dhfr_with_all_terms(pkg):
     t2 = nve.Run(200)
     tot = np.array([p + k for p, k in t2]); kin = np.array([k for _, k in t2])
     assert np.abs(tot - tot[0]).max() < 2.0e-3 * kin.mean(), (np.abs(tot - tot[0]).max(), kin.mean())
+
+
+def test_velocity_verlet_temperature_scaling(pkg):
+    """VelocityVerletIntegrator's temperature handling (pCore-1.9.0/pCore/VelocityVerletIntegrator.py:60-104): every temperatureScaleFrequency
+    steps the velocities are scaled to the target temperature (constant, or a linear ramp) -- the kinetic energy reported for those steps is
+    the scaled one; between them the dynamics is plain velocity Verlet."""
+    w = pkg.workloads.WORKLOADS["ionic23k"]()
+    kB = 8.314472e-3
+    for option, stop in (("constant", None), ("linear", 150.0)):
+        system = pkg.System.FromWorkload(w)
+        system.DefineNBModel(pkg.NBModelABFS())
+        md = pkg.md.VelocityVerletDynamics(system, timeStep=0.001, temperature=300.0, temperatureScaleFrequency=20, temperatureScaleOption=option,
+                                           temperatureStart=300.0, temperatureStop=stop)
+        traj = md.Run(100)
+        assert len(traj) == 100 and md.numberOfIterations == 100
+        temps = np.array([2.0 * k / (3 * md.n * kB) for _, k in traj])
+        for step in (20, 40, 60, 80, 100):
+            target = 300.0 if stop is None else 300.0 + (stop - 300.0) * step / 100.0
+            assert abs(temps[step - 1] - target) < 1e-6 * target, (option, step, temps[step - 1], target)
+        assert np.all(np.abs(np.diff(temps)[[0, 1, 2, 25, 50]]) < 30.0)
+        # the scaled velocities are the ones the dynamics continues with
+        ke = 0.5 * 0.01 * float((md.mass[:, None] * md.v * md.v).sum().item())
+        assert abs(ke - traj[-1][1]) < 1e-9 * ke
