@@ -192,12 +192,24 @@ void nbb200_vv_second_half(NBB200State *state, double *d_v, double *d_a, const d
 void nbb200_langevin_first_half(NBB200State *state, double *d_x, double *d_v, const double *d_a, const double *d_mass, const double *factors7,
                                 unsigned long long seed, unsigned long long step);
 
+/* forward declaration (bonded terms, below) */
+typedef struct NBB200MMTerms NBB200MMTerms;
+/* nsteps MD steps in one call (the loop of VelocityVerletIntegrator / LangevinVelocityVerletIntegrator around Accelerations(), everything on
+ * the device): per step first half (velocity Verlet with timeStep, or Langevin when langevinFactors7 != NULL: seed, iteration = firstIteration + k),
+ * list-update decision (the reference's heuristic; updateFrequency > 0 forces a rebuild every that many steps), NB energy + gradients, bonded
+ * terms (terms nullable), second half with secondHalfDt (= timeStep, or 2 facV3 for Langevin).  d_x, d_v, d_a, d_g, d_mass, d_ke: device arrays
+ * (3n, 3n, 3n, 3n, n, 1 doubles).  potential[nsteps], kinetic[nsteps] (nullable): per-step energies in kJ/mol; nbEnergies6 / bondedEnergies5
+ * (nullable): the terms of the last step.  One host wait per step.  Returns the number of list updates. */
+int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int updateFrequency, double *d_x, double *d_v, double *d_a, double *d_g,
+                  const double *d_mass, const double *box6, double timeStep, const double *langevinFactors7, double secondHalfDt,
+                  unsigned long long seed, unsigned long long firstIteration, double *d_ke, double *potential, double *kinetic,
+                  double *nbEnergies6, double *bondedEnergies5, int *status);
+
 /* ---- bonded MM terms on the device --------------------------------------------------
  * What System.Energy evaluates next to the NB model (pMolecule-1.9.0/pMolecule/System.py:272-318), for callers that keep coordinates and
  * gradients on the device.  One opaque object holds the terms of all containers; they are evaluated by a single launch in fp64.
  * Terms and parameters are given as the reference's containers hold them: per term the atom indices, a parameter type and QACTIVE
  * (active == NULL: all active); per parameter type the values.  Defining a container again replaces it; nterms = 0 removes it. */
-typedef struct NBB200MMTerms NBB200MMTerms;
 NBB200MMTerms *MMTerms_B200_Allocate(int device, int natoms, int *status);
 void MMTerms_B200_Deallocate(NBB200MMTerms **terms);
 void MMTerms_B200_SetStream(NBB200MMTerms *terms, void *cudaStream);

@@ -123,7 +123,8 @@ static State *create(int device, int n, const double *charges, const int *ljtype
              cuda_ok(cudaMemcpy(s->exclPtr.p, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice), "H2D") &&
              cuda_ok(cudaMemcpy(s->exclCol.p, col.data(), sizeof(int) * col.size(), cudaMemcpyHostToDevice), "H2D") &&
              cuda_ok(cudaMemcpy(s->pairs14.p, p14.data(), sizeof(int2) * p14.size(), cudaMemcpyHostToDevice), "H2D") &&
-             cuda_ok(cudaMemset(s->counters, 0, sizeof(DeviceCounters)), "memset");
+             cuda_ok(cudaMemset(s->counters, 0, sizeof(DeviceCounters)), "memset") &&
+             cuda_ok(cudaDeviceSynchronize(), "set-up copies");   // a pageable H2D copy returns once STAGED; kernels on non-blocking streams must not overtake the DMA
     }
     if (ok) {
         for (auto &e : s->ev) ok = ok && cuda_ok(cudaEventCreate(&e), "cudaEventCreate");
@@ -166,7 +167,7 @@ static void finish_pending(State &s)
 {
     if (!s.pending) return;
     s.pending = false;
-    energy_finish(s, s.pendEnergies, s.pendHaveGrad, s.pendDEdM, s.hacc, &s.pendLattice);
+    energy_finish(s, s.pendEnergies, s.pendHaveGrad, s.pendDEdM, s.pendAcc != nullptr ? s.pendAcc : s.hacc, &s.pendLattice);
 }
 static void flush_pending(State &s)
 {
@@ -265,7 +266,7 @@ static bool energy_enqueue(State &s, double *d_grad, bool sortedOnly = false, do
     }
     if (!launch_forces(s, d_grad, sortedOnly)) return false;
     const size_t accumCount = (size_t) 16 * (s.nsets + 1);
-    if (accumCount > kSmallDoubles) { set_error("too many images for the result buffer"); return false; }
+    if (accumCount > kSmallDoubles - 16) { set_error("too many images for the result buffer"); return false; }      // the tail holds nbb200_md_run's kinetic-energy slots
     NBB_CUDA(cudaMemcpyAsync(target != nullptr ? target : s.hsmall, s.accum.p, sizeof(double) * accumCount, cudaMemcpyDeviceToHost, s.stream));
     return true;
 }
@@ -343,7 +344,8 @@ void NBModelABFSState_B200_SetFixedAtoms(NBB200State *state, int nfixed, const i
     bool ok = s.fixedFlag.ensure((size_t) s.n) && s.pairs14.ensure(std::max<size_t>(1, keep.size()));
     cudaStreamSynchronize(s.stream);
     ok = ok && cuda_ok(cudaMemcpy(s.fixedFlag.p, flag.data(), (size_t) s.n, cudaMemcpyHostToDevice), "H2D fixed") &&
-         (keep.empty() || cuda_ok(cudaMemcpy(s.pairs14.p, keep.data(), sizeof(int2) * keep.size(), cudaMemcpyHostToDevice), "H2D 1-4"));
+         (keep.empty() || cuda_ok(cudaMemcpy(s.pairs14.p, keep.data(), sizeof(int2) * keep.size(), cudaMemcpyHostToDevice), "H2D 1-4")) &&
+         cuda_ok(cudaDeviceSynchronize(), "set-up copies");
     if (!ok) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return; }
     s.nfixed = nfixed; s.n14 = (int) keep.size();
     s.hostFixed = (nfixed > 0) ? flag : std::vector<unsigned char>();
@@ -381,7 +383,8 @@ void NBModelABFSState_B200_SetUpCentering(NBB200State *state, int useCentering, 
     bool ok = s.isoPtr.ensure(ptr.size()) && s.isoIdx.ensure((size_t) std::max(1, m));
     cudaStreamSynchronize(s.stream);
     ok = ok && cuda_ok(cudaMemcpy(s.isoPtr.p, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice), "H2D isolates") &&
-         cuda_ok(cudaMemcpy(s.isoIdx.p, idx.data(), sizeof(int) * (size_t) m, cudaMemcpyHostToDevice), "H2D isolates");
+         cuda_ok(cudaMemcpy(s.isoIdx.p, idx.data(), sizeof(int) * (size_t) m, cudaMemcpyHostToDevice), "H2D isolates") &&
+         cuda_ok(cudaDeviceSynchronize(), "set-up copies");
     if (!ok) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return; }
     s.nisolates = niso; s.useCentering = true;
 }
@@ -504,7 +507,7 @@ void NBModelABFS_B200_MMMMEnergyDeviceDeferred(NBB200State *state, double *energ
     flush_pending(s);
     if (s.hacc == nullptr && !cuda_ok(cudaMallocHost((void **) &s.hacc, sizeof(double) * kSmallDoubles), "cudaMallocHost")) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return; }
     if (!energy_enqueue(s, d_grad, false, s.hacc)) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
-    s.pending = true; s.pendEnergies = energies; s.pendDEdM = dEdM; s.pendHaveGrad = d_grad != nullptr; s.pendLattice = s.lattice;
+    s.pending = true; s.pendEnergies = energies; s.pendDEdM = dEdM; s.pendHaveGrad = d_grad != nullptr; s.pendLattice = s.lattice; s.pendAcc = s.hacc;
 }
 
 void nbb200_flush(NBB200State *state, int *status)
@@ -609,7 +612,7 @@ static long standalone(int device, int n1, const double *xyz1, int n2, const dou
     if (ok && xyz2 != nullptr) {
         ok = n2 > 0 && x2.ensure(3 * (size_t) n2) && cuda_ok(cudaMemcpy(x2.p, xyz2, sizeof(double) * 3 * (size_t) n2, cudaMemcpyHostToDevice), "H2D");
     }
-    ok = ok && build_lists_standalone(*s, xyz2 != nullptr ? x2.p : nullptr, n2) && expand_pairs(*s);
+    ok = ok && cuda_ok(cudaDeviceSynchronize(), "input copies") && build_lists_standalone(*s, xyz2 != nullptr ? x2.p : nullptr, n2) && expand_pairs(*s);
     if (ok) {
         const int set = (xyz2 != nullptr) ? 1 : 0;
         const unsigned long long lo = s->pairOffsets[set], hi = s->pairOffsets[set + 1];
@@ -1121,6 +1124,126 @@ double nbb200_measure_fp32_peak(int device, int *status)
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
     if (!cuda_ok(cudaGetLastError(), "k_fma_peak")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0.0; }
     return best;
+}
+
+/* ---- the MD loop itself, native: what pdynamo-mirror_b200/md.py:Run does per step, without the interpreter between the calls
+ * and without a host wait on the critical path.
+ *
+ * The list-update decision of a step needs the new coordinates, so a loop that waits for it leaves the GPU idle once per step (wake-up +
+ * launch latency, ~30 us of a 110-200 us step).  Here a step is enqueued OPTIMISTICALLY on the current lists -- displacement check, energy
+ * kernels, bonded terms, second half -- and the host reads the check's result while the GPU is busy with that step.  In 13 of 14 steps (the
+ * reference's DHFR run) no update was due and the host is already enqueueing the next step; otherwise the step is taken back (v -= f a with
+ * the accelerations it produced; x is not touched by a second half), the lists are rebuilt through the ordinary path and the step is
+ * evaluated again.  Results of step k (energies, bonded energies, kinetic energy) land in page-locked memory in stream order, in two
+ * alternating slots, and are read after the decision of step k + 1. ---- */
+static __global__ void k_axpy(double *__restrict__ y, const double *__restrict__ x, double c, long m)
+{
+    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) y[i] += c * x[i];
+}
+
+int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int updateFrequency, double *d_x, double *d_v, double *d_a, double *d_g,
+                  const double *d_mass, const double *box6, double timeStep, const double *langevinFactors7, double secondHalfDt,
+                  unsigned long long seed, unsigned long long firstIteration, double *d_ke, double *potential, double *kinetic,
+                  double *nbEnergies6, double *bondedEnergies5, int *status)
+{
+    if (state == nullptr || d_x == nullptr || d_v == nullptr || d_a == nullptr || d_g == nullptr || d_mass == nullptr || d_ke == nullptr || nsteps < 0) {
+        set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return 0;
+    }
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    flush_pending(s);
+    if (s.hacc == nullptr && !cuda_ok(cudaMallocHost((void **) &s.hacc, sizeof(double) * kSmallDoubles), "cudaMallocHost")) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return 0; }
+    if (!s.bboxDev.ensure(64)) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return 0; }
+    if (terms != nullptr) MMTerms_B200_SetStream(terms, s.stream);       // stream order is what hands the results over
+    // page-locked result slots (two of each): accumulators of the energy call, kinetic energy, displacement maximum
+    double *haccSlot[2] = {s.hacc, s.hacc + kSmallDoubles / 2};
+    double *hke = s.hacc + (kSmallDoubles - 8), *hdisp = s.hacc + (kSmallDoubles - 16);
+    double *d_disp = s.bboxDev.p + 8;
+    if ((size_t) 16 * (s.nsets + 1) > kSmallDoubles / 2 - 16) { set_error("too many images for the result slots"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
+    cudaEvent_t evDisp;
+    if (!cuda_ok(cudaEventCreateWithFlags(&evDisp, cudaEventDisableTiming), "cudaEventCreate")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
+    const long m = 3 * (long) s.n;
+    const bool savedOverwrite = s.gradOverwrite;
+    s.gradOverwrite = true;                                            // the NB term sets d_g, the bonded terms accumulate
+    static const bool noSpeculation = std::getenv("NBB200_MD_NO_SPECULATION") != nullptr;
+    int updates = 0;
+    bool ok = true;
+    double eStep[2][6], dEdM[9], e5[5] = {0, 0, 0, 0, 0};
+    for (int c = 0; c < 6; c++) eStep[0][c] = eStep[1][c] = 0.0;
+
+    // everything of step k after its first half, on the lists as they are: energy (deferred into slot k & 1), bonded terms, second half, kinetic energy
+    auto enqueue_step = [&](int k) -> bool {
+        for (int c = 0; c < 9; c++) dEdM[c] = 0.0;
+        if (!energy_enqueue(s, d_g, false, haccSlot[k & 1])) return false;
+        if (terms != nullptr && !mmterms_enqueue_slot(terms, d_x, d_g, k & 1)) return false;
+        nbb200_vv_second_half(state, d_v, d_a, d_g, d_mass, secondHalfDt, d_ke);
+        return cuda_ok(cudaMemcpyAsync(hke + (k & 1), d_ke, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H kinetic energy");
+    };
+    // the numbers of a completed step: accumulators -> energies (energy_finish; must run while the lists the step used are still current),
+    // bonded slot, kinetic slot
+    auto harvest = [&](int k, bool nbDone) {
+        double *e6 = eStep[k & 1];
+        if (!nbDone) energy_finish(s, e6, true, dEdM, haccSlot[k & 1], &s.lattice);
+        double pot = e6[0] + e6[1] + e6[2] + e6[3] + e6[4] + e6[5];
+        if (terms != nullptr) { mmterms_read_slot(terms, k & 1, e5); pot += e5[0] + e5[1] + e5[2] + e5[3] + e5[4]; }
+        if (potential != nullptr) potential[k] = pot;
+        if (kinetic != nullptr) kinetic[k] = hke[k & 1];
+    };
+
+    for (int k = 0; k < nsteps && ok; k++) {
+        if (langevinFactors7 != nullptr) nbb200_langevin_first_half(state, d_x, d_v, d_a, d_mass, langevinFactors7, seed, firstIteration + (unsigned long long) k);
+        else nbb200_vv_first_half(state, d_x, d_v, d_a, timeStep);
+        s.xcur = d_x;
+        const bool forced = updateFrequency > 0 && (k + 1) % updateFrequency == 0;
+        bool latticeSame = s.trans.n == 0;
+        if (!latticeSame && s.haveRefLattice && box6 != nullptr) {
+            Lattice now = s.lattice;
+            now.set_crystal(box6);
+            latticeSame = std::memcmp(now.M.v, s.refLattice.M.v, sizeof(double) * 9) == 0;
+        }
+        const bool speculate = !noSpeculation && !forced && !s.isNew && !s.useCentering && s.nranks == 1 && !s.timing && latticeSame &&
+                               s.list == s.stListCutoff && s.outer == s.stOuterCutoff;
+        bool needSync = !speculate;
+        if (speculate) {
+            // optimistic: the check of CheckForUpdate (NBModelABFS.c:691-746) and the whole step go out together
+            ok = displacement_enqueue(s, d_x, d_disp) &&
+                 cuda_ok(cudaMemcpyAsync(hdisp + (k & 1), d_disp, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H displacement") &&
+                 cuda_ok(cudaEventRecord(evDisp, s.stream), "event") && enqueue_step(k) && cuda_ok(cudaEventSynchronize(evDisp), "event wait");
+            if (!ok) { set_status(status, NBB200_STATUS_LOGIC_ERROR); break; }
+            // the stream has passed the check of step k: step k - 1 is complete
+            if (k > 0) harvest(k - 1, false);
+            s.numberOfCalls += 1;
+            const double buffac = 0.5 * (s.list - s.stOuterCutoff);
+            if (hdisp[k & 1] > buffac * buffac) {
+                // an update was due: take the step back (x is untouched by a second half) and go through the ordinary path
+                k_axpy<<<(unsigned int) ((m + 255) / 256), 256, 0, s.stream>>>(d_v, d_a, -0.5 * secondHalfDt, m);
+                s.launches += 1;
+                s.numberOfCalls -= 1;
+                needSync = true;
+            }
+        }
+        if (needSync) {
+            int st = NBB200_STATUS_CONTINUE;
+            const bool owed = !speculate && k > 0;                                  // step k - 1 has not been harvested yet
+            if (owed) {      // its accumulators are turned into energies inside update_common: after the first wait, BEFORE the lists may change
+                s.pending = true; s.pendEnergies = eStep[(k - 1) & 1]; s.pendDEdM = dEdM; s.pendHaveGrad = true; s.pendLattice = s.lattice; s.pendAcc = haccSlot[(k - 1) & 1];
+            }
+            updates += update_common(s, box6, forced ? 1 : 0, &st);
+            if (st != NBB200_STATUS_CONTINUE) { ok = false; set_status(status, st); break; }
+            if (owed) { flush_pending(s); harvest(k - 1, true); }
+            if (!enqueue_step(k)) { ok = false; set_status(status, NBB200_STATUS_LOGIC_ERROR); break; }
+        }
+    }
+    cudaStreamSynchronize(s.stream);
+    s.pending = false;
+    if (ok && nsteps > 0) harvest(nsteps - 1, false);
+    cudaEventDestroy(evDisp);
+    s.gradOverwrite = savedOverwrite;
+    const double *last = eStep[(nsteps > 0 ? nsteps - 1 : 0) & 1];
+    if (nbEnergies6 != nullptr) std::memcpy(nbEnergies6, last, sizeof(double) * 6);
+    if (bondedEnergies5 != nullptr) std::memcpy(bondedEnergies5, e5, sizeof(e5));
+    return updates;
 }
 
 void nbb200_set_gradient_overwrite(NBB200State *state, int on)

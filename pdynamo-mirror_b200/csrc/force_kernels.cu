@@ -522,6 +522,7 @@ bool upload_spline_tables(State &s)
     if (!s.splF64.ensure(h64.size()) || !s.splPoly.ensure(poly.size())) return false;
     NBB_CUDA(cudaMemcpy(s.splF64.p, h64.data(), sizeof(double) * h64.size(), cudaMemcpyHostToDevice));
     NBB_CUDA(cudaMemcpy(s.splPoly.p, poly.data(), sizeof(float4) * poly.size(), cudaMemcpyHostToDevice));
+    NBB_CUDA(cudaDeviceSynchronize());       // pageable copies return once staged: the kernels of s.stream must not overtake the DMA
     return true;
 }
 

@@ -152,12 +152,15 @@ static bool upload_terms(MMTerms &m)
     m.start[kKinds] = (int) all.size();
     if (!m.rec.ensure(all.size() + 1) || !m.energies.ensure(kKinds)) return false;
     if (!all.empty()) NBB_CUDA(cudaMemcpy(m.rec.p, all.data(), sizeof(TermRecord) * all.size(), cudaMemcpyHostToDevice));
+    // a pageable H2D copy returns once the data is STAGED; the DMA runs on the legacy stream, which a non-blocking stream does not wait for:
+    // without this the kernel can read a partly uploaded record array (seen as wrong dihedral / improper energies, the tail of the array)
+    NBB_CUDA(cudaDeviceSynchronize());
     m.dirty = false;
     return true;
 }
 
 // enqueue only: the kernel and the copy of the five energies into pinned memory; collect() waits for them
-static bool enqueue(MMTerms &m, const double *d_x, double *d_grad)
+static bool enqueue(MMTerms &m, const double *d_x, double *d_grad, int slot = 0)
 {
     if (m.dirty && !upload_terms(m)) return false;
     NBB_CUDA(cudaMemsetAsync(m.energies.p, 0, sizeof(double) * kKinds, m.stream));
@@ -168,7 +171,7 @@ static bool enqueue(MMTerms &m, const double *d_x, double *d_grad)
         k_mm_terms<<<(total + 127) / 128, 128, 0, m.stream>>>(m.rec.p, K, d_x, d_grad, m.energies.p);
         m.launches += 1;
     }
-    NBB_CUDA(cudaMemcpyAsync(m.he, m.energies.p, sizeof(double) * kKinds, cudaMemcpyDeviceToHost, m.stream));
+    NBB_CUDA(cudaMemcpyAsync(m.he + 8 * (slot & 1), m.energies.p, sizeof(double) * kKinds, cudaMemcpyDeviceToHost, m.stream));
     return cuda_ok(cudaGetLastError(), "k_mm_terms");
 }
 
@@ -245,7 +248,7 @@ NBB200MMTerms *MMTerms_B200_Allocate(int device, int natoms, int *status)
     ok = ok && m->x.ensure(3 * (size_t) natoms) && m->grad.ensure(3 * (size_t) natoms) && m->energies.ensure(kKinds);
     ok = ok && cuda_ok(cudaMallocHost((void **) &m->hx, sizeof(double) * 3 * (size_t) natoms), "cudaMallocHost");
     ok = ok && cuda_ok(cudaMallocHost((void **) &m->hg, sizeof(double) * 3 * (size_t) natoms), "cudaMallocHost");
-    ok = ok && cuda_ok(cudaMallocHost((void **) &m->he, sizeof(double) * 8), "cudaMallocHost");
+    ok = ok && cuda_ok(cudaMallocHost((void **) &m->he, sizeof(double) * 16), "cudaMallocHost");      // two slots of 8
     if (!ok) { NBB200MMTerms *h = reinterpret_cast<NBB200MMTerms *>(m); MMTerms_B200_Deallocate(&h); mm_status(status, NBB200_STATUS_OUT_OF_MEMORY); return nullptr; }
     return reinterpret_cast<NBB200MMTerms *>(m);
 }
@@ -379,6 +382,24 @@ void MMTerms_B200_LastEnergies(NBB200MMTerms *terms, double *energies5)
     const MMTerms *m = reinterpret_cast<MMTerms *>(terms);
     for (int k = 0; k < kKinds; k++) energies5[k] = m->he[k];
 }
+
+}  // extern "C"
+
+// internal (nbb200_md_run): two result slots, so that a step's energies stay readable while the next step is already in flight
+namespace nbb200 {
+bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot)
+{
+    MMTerms *m = reinterpret_cast<MMTerms *>(terms);
+    return enqueue(*m, d_x, d_grad, slot);
+}
+void mmterms_read_slot(NBB200MMTerms *terms, int slot, double *energies5)
+{
+    const MMTerms *m = reinterpret_cast<MMTerms *>(terms);
+    for (int k = 0; k < kKinds; k++) energies5[k] = m->he[8 * (slot & 1) + k];
+}
+}
+
+extern "C" {
 
 long MMTerms_B200_NumberOfTerms(NBB200MMTerms *terms, int kind)
 {

@@ -94,6 +94,13 @@ bool centre_coordinates(State &s, const double *d_xin, bool doUpdate);   // useC
 bool touched_ranges(State &s, long *out);
 bool touched_ranges_async(State &s, long *d_out);      // the same table written to a device array, no host synchronisation                // per rank slab: [lo, hi) of the sorted positions this rank's lists reference
 
+// ---- mm_terms.cu (used by nbb200_md_run)
+}  // namespace nbb200
+struct NBB200MMTerms;
+namespace nbb200 {
+bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot);
+void mmterms_read_slot(NBB200MMTerms *terms, int slot, double *energies5);
+
 // ---- force_kernels.cu
 bool upload_spline_tables(State &s);                     // s.spl -> s.splF64 / s.splPoly
 bool launch_forces(State &s, double *d_grad, bool sortedOnly);
@@ -156,7 +163,7 @@ struct State {
     // caller's arrays at the state's next synchronisation point (the list-update decision of the next Update, or nbb200_flush)
     double *hacc = nullptr;
     bool pending = false, pendHaveGrad = false;
-    double *pendEnergies = nullptr, *pendDEdM = nullptr;
+    double *pendEnergies = nullptr, *pendDEdM = nullptr, *pendAcc = nullptr;
     Lattice pendLattice;
     void *hops = nullptr;                        // pinned staging of the image operations
     Mat3 opsLattice{}; long opsGeneration = -1; bool opsValid = false;

@@ -101,13 +101,43 @@ class VelocityVerletDynamics:
     def _second_half_dt(self):
         return self.dt
 
-    def Run(self, steps, updateFrequency=0, log=None):
+    def _langevin_factors(self):
+        return None
+
+    def RunNative(self, steps, updateFrequency=0):
+        """The same loop inside the library (nbb200_md_run): no interpreter between the launches of a step."""
+        pot, kin = np.zeros(steps), np.zeros(steps)
+        st = C.c_int(16)
+        fac = self._langevin_factors()
+        first = getattr(self, "iteration", 0) + 1
+        self.updates += self.L.nbb200_md_run(self.h, C.c_void_p(self.mmterms.cObject) if self.mmterms is not None else None, int(steps), int(updateFrequency),
+                                             self._p(self.x), self._p(self.v), self._p(self.a), self._p(self.g), self._p(self.mass), self._lib.d_(self.box),
+                                             self.dt, self._lib.d_(fac) if fac is not None else None, self._second_half_dt(), C.c_ulonglong(getattr(self, "seed", 0)),
+                                             C.c_ulonglong(first), self._p(self.ke_dev), self._lib.d_(pot), self._lib.d_(kin), self._lib.d_(self.energies),
+                                             self._lib.d_(self.bonded), C.byref(st))
+        if st.value != 16:
+            raise RuntimeError("MD run failed: " + self._lib.last_error())
+        if hasattr(self, "iteration"):
+            self.iteration += steps
+        self.numberOfIterations += steps
+        self.time += steps * self.dt
+        if steps > 0:
+            self.potential, self.kinetic = float(pot[-1]), float(kin[-1])
+        return list(zip(pot.tolist(), kin.tolist()))
+
+    def Run(self, steps, updateFrequency=0, log=None, native=None):
         """steps integration steps; updateFrequency > 0 forces a list rebuild every that many steps (0: the reference's displacement
-        heuristic only).  Returns the list of (potential, kinetic) per step.
+        heuristic only).  Returns the list of (potential, kinetic) per step.  native (default: when there is neither logging nor
+        temperature scaling): run the loop inside the library (RunNative).
 
         The loop is pipelined: per step the host waits ONCE, for the list-update decision (NBModelABFS_B200_UpdateDevice); the energy call is
         deferred (NBModelABFS_B200_MMMMEnergyDeviceDeferred), the bonded energies and the kinetic energy are copied to page-locked memory in
         stream order, and the numbers of step k are picked up after the decision of step k + 1 (or the final flush)."""
+        scaling = self.temperatureScaleOption is not None and self.temperatureScaleFrequency < steps
+        if native is None:
+            native = log is None and not scaling
+        if native and steps > 0:
+            return self.RunNative(steps, updateFrequency)
         out = []
         st = C.c_int(16)
         if getattr(self, "_ke_host", None) is None:
@@ -115,7 +145,6 @@ class VelocityVerletDynamics:
         ke_ptr = [C.c_void_p(self._ke_host.ctypes.data), C.c_void_p(self._ke_host.ctypes.data + 8)]
         dt2 = self._second_half_dt()
 
-        scaling = self.temperatureScaleOption is not None and self.temperatureScaleFrequency < steps
         t_begin, total_time = self.time, steps * self.dt
 
         def harvest(k, ke_scale=1.0):
@@ -204,3 +233,6 @@ class LangevinDynamics(VelocityVerletDynamics):
 
     def _second_half_dt(self):
         return 2.0 * self.facV3                # v += facV3 a  (LangevinVelocityVerletIntegrator.py:133)
+
+    def _langevin_factors(self):
+        return self.factors

@@ -768,3 +768,24 @@ def test_velocity_verlet_temperature_scaling(pkg):
         # the scaled velocities are the ones the dynamics continues with
         ke = 0.5 * 0.01 * float((md.mass[:, None] * md.v * md.v).sum().item())
         assert abs(ke - traj[-1][1]) < 1e-9 * ke
+
+
+@pytest.mark.parametrize("kind", ["verlet", "langevin"])
+def test_native_md_loop_equals_the_python_loop(pkg, kind):
+    """nbb200_md_run (the loop inside the library) issues the same kernels in the same order as md.py's loop: identical trajectories,
+    energies and list-update counts -- velocity Verlet on the ionic fluid, Langevin (counter-based deviates: same seed, same steps) on DHFR
+    with its bonded terms."""
+    w = pkg.workloads.WORKLOADS["ionic23k" if kind == "verlet" else "dhfr_mm"]()
+    runs = []
+    for native in (False, True):
+        system = pkg.System.FromWorkload(w)
+        system.DefineNBModel(pkg.NBModelABFS())
+        md = pkg.md.VelocityVerletDynamics(system) if kind == "verlet" else pkg.md.LangevinDynamics(system)
+        a = md.Run(25, native=native)
+        b = md.Run(15, updateFrequency=5, native=native)           # a second call continues the trajectory (and the deviate counter)
+        runs.append((np.array(a + b), md.x.cpu().numpy(), md.updates, md.potential, md.kinetic))
+    (t0, x0, u0, p0, k0), (t1, x1, u1, p1, k1) = runs
+    assert t0.shape == t1.shape == (40, 2) and u0 == u1
+    assert np.allclose(t0, t1, rtol=1e-9, atol=1e-6), np.abs(t0 - t1).max()
+    assert np.abs(x0 - x1).max() < 1e-9
+    assert abs(p0 - p1) <= 1e-9 * abs(p0) and abs(k0 - k1) <= 1e-9 * abs(k0)
