@@ -789,3 +789,89 @@ def test_native_md_loop_equals_the_python_loop(pkg, kind):
     assert np.allclose(t0, t1, rtol=1e-9, atol=1e-6), np.abs(t0 - t1).max()
     assert np.abs(x0 - x1).max() < 1e-9
     assert abs(p0 - p1) <= 1e-9 * abs(p0) and abs(k0 - k1) <= 1e-9 * abs(k0)
+
+
+def _random_system(pkg, rng, case):
+    """A random periodic molecular liquid: chains of 1-6 atoms (bonded exclusions up to 1-4, 1-4 pairs) on a jittered lattice in a random
+    orthorhombic or triclinic P1 cell, 4 LJ types, neutral-ish random charges."""
+    from pdynamo_mirror_b200.workloads import _finish, _bond_exclusions
+    nmol = int(rng.integers(40, 700))
+    lengths = rng.integers(1, 7, nmol)
+    n = int(lengths.sum())
+    density = rng.uniform(0.03, 0.11)                           # atoms / A^3 (water: 0.1)
+    vol = n / density
+    if case % 2 == 0:
+        f = rng.uniform(0.8, 1.25, 3); f /= f.prod() ** (1.0 / 3.0)
+        box = np.concatenate([vol ** (1.0 / 3.0) * f, [90.0, 90.0, 90.0]])
+    else:
+        ang = rng.uniform(75.0, 105.0, 3)
+        ca, cb, cg = np.cos(np.radians(ang))
+        vfac = np.sqrt(1.0 - ca * ca - cb * cb - cg * cg + 2.0 * ca * cb * cg)
+        f = rng.uniform(0.85, 1.2, 3); f /= f.prod() ** (1.0 / 3.0)
+        box = np.concatenate([(vol / vfac) ** (1.0 / 3.0) * f, ang])
+    M = np.zeros((3, 3))                                         # lattice vectors as columns (SymmetryParameters_MakeM convention is irrelevant here:
+    a, b, c = box[:3]; al, be, ga = np.radians(box[3:])          # any interior points do)
+    M[:, 0] = [a, 0, 0]; M[:, 1] = [b * np.cos(ga), b * np.sin(ga), 0]
+    cx = c * np.cos(be); cy = c * (np.cos(al) - np.cos(be) * np.cos(ga)) / np.sin(ga)
+    M[:, 2] = [cx, cy, np.sqrt(max(c * c - cx * cx - cy * cy, 1e-9))]
+    mols = []
+    for L in lengths:
+        # an extended zigzag chain (bond 1.5 A, ~110 degrees) in a random orientation: 1-4 distances >= 2.5 A, 1-5 >= 3.7 A
+        u = rng.standard_normal(3); u /= np.linalg.norm(u)
+        v = np.cross(u, rng.standard_normal(3)); v /= np.linalg.norm(v)
+        p0 = M @ rng.random(3)
+        pts = [p0 + 1.23 * k * u + (0.43 if k % 2 else -0.43) * v + rng.uniform(-0.05, 0.05, 3) for k in range(L)]
+        mols.append(np.array(pts))
+    # drop molecules that clash (any intermolecular minimum-image contact below 2 A): the sweep is about cells, cutoffs and lists, not about
+    # the fp32 conditioning of r^-12 at 0.3 A
+    allx = np.concatenate(mols); owner = np.repeat(np.arange(len(mols)), [len(p_) for p_ in mols])
+    Minv = np.linalg.inv(M)
+    keep = np.ones(len(mols), bool)
+    frac = allx @ Minv.T
+    for a_ in range(len(allx)):
+        if not keep[owner[a_]]:
+            continue
+        df = frac[a_ + 1:] - frac[a_]
+        df -= np.rint(df)
+        d2 = ((df @ M.T) ** 2).sum(1)
+        bad = np.nonzero((d2 < 4.0) & (owner[a_ + 1:] != owner[a_]) & keep[owner[a_ + 1:]])[0]
+        keep[owner[a_ + 1:][bad]] = False
+    xyz, bonds, start = [], [], 0
+    for mi, pts in enumerate(mols):
+        if not keep[mi]:
+            continue
+        for k in range(1, len(pts)):
+            bonds.append((start + k - 1, start + k))
+        xyz.extend(pts); start += len(pts)
+    xyz = np.array(xyz)
+    n = len(xyz)
+    q = rng.uniform(-0.8, 0.8, n); q -= q.mean()
+    types = rng.integers(0, 4, n).astype(np.int32)
+    eps, sig = rng.uniform(0.05, 0.8, 4), rng.uniform(1.5, 3.4, 4)
+    excl, p14 = _bond_exclusions(n, np.array(bonds, dtype=np.int64).reshape(-1, 2)) if bonds else (np.zeros((0, 2), np.int32), np.zeros((0, 2), np.int32))
+    w = _finish(xyz, q, types, eps, sig, "amber" if case % 3 else "opls", excl, p14, box, "random%d" % case, eps14=0.5 * eps, sigma14=sig, scale14=float(rng.choice([1.0, 0.5])))
+    damp = rng.uniform(0.3, 1.0); inner = rng.uniform(4.0, 7.0); outer = inner + rng.uniform(1.5, 4.0); lst = outer + rng.uniform(0.8, 2.0)
+    opts = dict(dampingCutoff=float(damp), innerCutoff=float(inner), outerCutoff=float(outer), listCutoff=float(lst), dielectric=float(rng.choice([1.0, 2.5])))
+    if case % 4 == 3:
+        opts.update(useAnalyticForm=False, splinePointDensity=int(rng.integers(20, 80)))
+    return w, opts
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_random_cells_cutoffs_topologies(pkg, orc, case):
+    """Randomised sweep: orthorhombic and triclinic cells from ~25 to ~45 A (1 to ~30 images), random cutoffs, densities, chain
+    topologies, LJ combination rules, 1-4 scales, dielectric, both interaction forms.  Lists bit-exact as sets against the oracle (primary
+    and every image, same image order and scales), numbers within the bars."""
+    rng = np.random.default_rng(1000 + case)
+    w, opts = _random_system(pkg, rng, case)
+    system, st, e, g, dm = gpu_energy(pkg, w, **opts)
+    o = orc.OracleNB(w, **opts)
+    ref = o.energy(force_new=True)
+    assert np.array_equal(orc.canonical_primary(st.Pairs(-1)), orc.canonical_primary(o.primary_pairs()))
+    gi, oi = st.Images(), o.images()
+    assert [(x["t"], x["a"], x["b"], x["c"], x["scale"], x["npairs"]) for x in gi] == [(x["t"], x["a"], x["b"], x["c"], x["scale"], len(x["pairs"])) for x in oi]
+    for x, y in zip(gi, oi):
+        assert np.array_equal(orc.canonical_cross(x["pairs"]), orc.canonical_cross(y["pairs"]))
+    assert st.NumberOf14Pairs() == o.counts()["pairs14"]
+    # random liquids have steep contacts and strongly cancelling terms: the bars are those of the ill-conditioned stress cases
+    check_numbers("perturbed", e, g, dm, ref["energies"], ref["grad"], ref["dEdM"])
