@@ -45,7 +45,7 @@ static void destroy(State *s)
     s->cellStart.release(); s->cellFill.release(); s->scanTmp.release(); s->order.release(); s->order2.release();
     s->sX.release(); s->sAtom.release(); s->invPerm.release(); s->blockBox.release();
     s->tileDesc.release(); s->recA.release(); s->recB.release(); s->gradSorted.release(); s->items.release(); s->rangeTab.release(); s->rangeOut.release(); s->setPairs.release(); s->accum.release();
-    s->pairBuf.release(); s->pairCursor.release(); s->splF64.release(); s->splPoly.release();
+    s->pairBuf.release(); s->pairCursor.release(); s->splF64.release(); s->splPoly.release(); s->mdScalars.release();
     for (int r = 0; r < State::kMaxPeers; r++) if (s->peerOpened[r]) { cudaIpcCloseMemHandle(s->peerGs[r]); cudaIpcCloseMemHandle(s->peerXs[r]); cudaIpcCloseMemHandle(s->peerSig[r]); }
     s->symGs.release(); s->symXs.release(); s->symSig.release(); s->sigStage.release();
     if (s->counters) cudaFree(s->counters);
@@ -1049,8 +1049,9 @@ static __global__ void k_vv_first(double *__restrict__ x, double *__restrict__ v
 
 // second half: a = -100 g / m (kJ mol^-1 A^-1 amu^-1 -> A ps^-2) ; v += dt/2 a ; kinetic energy 0.5 * 0.01 * sum m v^2 (kJ/mol)
 static __global__ void k_vv_second(double *__restrict__ v, double *__restrict__ a, const double *__restrict__ g, const double *__restrict__ mass, double dt, long m,
-                                   double *__restrict__ ke)
+                                   double *__restrict__ ke, double *__restrict__ zeroOther = nullptr)
 {
+    if (zeroOther != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zeroOther = 0.0;      // two-slot use (nbb200_md_run): prepares the next step's slot
     double local = 0.0;
     for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long) gridDim.x * blockDim.x) {
         const double mi = mass[i / 3], ai = -100.0 * g[i] / mi;
@@ -1154,31 +1155,41 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
     cudaSetDevice(s.device);
     flush_pending(s);
     if (s.hacc == nullptr && !cuda_ok(cudaMallocHost((void **) &s.hacc, sizeof(double) * kSmallDoubles), "cudaMallocHost")) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return 0; }
-    if (!s.bboxDev.ensure(64)) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return 0; }
+    if (!s.mdScalars.ensure(32)) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return 0; }
     if (terms != nullptr) MMTerms_B200_SetStream(terms, s.stream);       // stream order is what hands the results over
     // page-locked result slots (two of each): accumulators of the energy call, kinetic energy, displacement maximum
     double *haccSlot[2] = {s.hacc, s.hacc + kSmallDoubles / 2};
     double *hke = s.hacc + (kSmallDoubles - 8), *hdisp = s.hacc + (kSmallDoubles - 16);
-    double *d_disp = s.bboxDev.p + 8;
+    // device scalars in two alternating slots each: the kernel that fills slot k & 1 clears the other one for the next step (no memsets)
+    double *d_disp2 = s.mdScalars.p, *d_ke2 = s.mdScalars.p + 8;
+    if (!cuda_ok(cudaMemsetAsync(s.mdScalars.p, 0, sizeof(double) * 32, s.stream), "memset")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
     if ((size_t) 16 * (s.nsets + 1) > kSmallDoubles / 2 - 16) { set_error("too many images for the result slots"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
     cudaEvent_t evDisp;
     if (!cuda_ok(cudaEventCreateWithFlags(&evDisp, cudaEventDisableTiming), "cudaEventCreate")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
     const long m = 3 * (long) s.n;
     const bool savedOverwrite = s.gradOverwrite;
     s.gradOverwrite = true;                                            // the NB term sets d_g, the bonded terms accumulate
+    // fused mode: the five memsets of a step are folded into neighbouring kernels (accumulators + cursor by k_pack_records, sorted gradient by
+    // k_unsort_gradients, the two-slot scalars by the kernel that fills the other slot).  NBB200_MD_FUSED=1 enables it.
+    static const bool fusedMode = []() { const char *e = std::getenv("NBB200_MD_FUSED"); return e != nullptr && std::atoi(e) != 0; }();      // default off until measured
+    s.mdFused = fusedMode;
     static const bool noSpeculation = std::getenv("NBB200_MD_NO_SPECULATION") != nullptr;
-    int updates = 0;
+    int updates = 0, nspec = 0;
     bool ok = true;
     double eStep[2][6], dEdM[9], e5[5] = {0, 0, 0, 0, 0};
     for (int c = 0; c < 6; c++) eStep[0][c] = eStep[1][c] = 0.0;
 
     // everything of step k after its first half, on the lists as they are: energy (deferred into slot k & 1), bonded terms, second half, kinetic energy
-    auto enqueue_step = [&](int k) -> bool {
+    // redo: the step is evaluated a second time after it was taken back -- its result slots hold the first attempt and are cleared explicitly
+    auto enqueue_step = [&](int k, bool redo) -> bool {
         for (int c = 0; c < 9; c++) dEdM[c] = 0.0;
         if (!energy_enqueue(s, d_g, false, haccSlot[k & 1])) return false;
-        if (terms != nullptr && !mmterms_enqueue_slot(terms, d_x, d_g, k & 1)) return false;
-        nbb200_vv_second_half(state, d_v, d_a, d_g, d_mass, secondHalfDt, d_ke);
-        return cuda_ok(cudaMemcpyAsync(hke + (k & 1), d_ke, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H kinetic energy");
+        if (terms != nullptr && !mmterms_enqueue_slot(terms, d_x, d_g, k & 1, fusedMode && !redo)) return false;
+        if ((redo || !fusedMode) && !cuda_ok(cudaMemsetAsync(d_ke2 + (k & 1), 0, sizeof(double), s.stream), "memset")) return false;
+        k_vv_second<<<(unsigned int) std::min<long>(148 * 8, (m + 255) / 256), 256, 0, s.stream>>>(d_v, d_a, d_g, d_mass, secondHalfDt, m, d_ke2 + (k & 1),
+                                                                                                  fusedMode ? d_ke2 + ((k + 1) & 1) : nullptr);
+        s.launches += 1;
+        return cuda_ok(cudaMemcpyAsync(hke + (k & 1), d_ke2 + (k & 1), sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H kinetic energy");
     };
     // the numbers of a completed step: accumulators -> energies (energy_finish; must run while the lists the step used are still current),
     // bonded slot, kinetic slot
@@ -1207,9 +1218,11 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
         bool needSync = !speculate;
         if (speculate) {
             // optimistic: the check of CheckForUpdate (NBModelABFS.c:691-746) and the whole step go out together
-            ok = displacement_enqueue(s, d_x, d_disp) &&
+            double *d_disp = d_disp2 + (nspec & 1), *d_dispOther = d_disp2 + ((nspec + 1) & 1);
+            nspec += 1;
+            ok = displacement_enqueue(s, d_x, d_disp, fusedMode ? d_dispOther : nullptr) &&
                  cuda_ok(cudaMemcpyAsync(hdisp + (k & 1), d_disp, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H displacement") &&
-                 cuda_ok(cudaEventRecord(evDisp, s.stream), "event") && enqueue_step(k) && cuda_ok(cudaEventSynchronize(evDisp), "event wait");
+                 cuda_ok(cudaEventRecord(evDisp, s.stream), "event") && enqueue_step(k, false) && cuda_ok(cudaEventSynchronize(evDisp), "event wait");
             if (!ok) { set_status(status, NBB200_STATUS_LOGIC_ERROR); break; }
             // the stream has passed the check of step k: step k - 1 is complete
             if (k > 0) harvest(k - 1, false);
@@ -1232,13 +1245,16 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
             updates += update_common(s, box6, forced ? 1 : 0, &st);
             if (st != NBB200_STATUS_CONTINUE) { ok = false; set_status(status, st); break; }
             if (owed) { flush_pending(s); harvest(k - 1, true); }
-            if (!enqueue_step(k)) { ok = false; set_status(status, NBB200_STATUS_LOGIC_ERROR); break; }
+            if (!enqueue_step(k, speculate)) { ok = false; set_status(status, NBB200_STATUS_LOGIC_ERROR); break; }      // speculate here: the step was taken back
         }
     }
     cudaStreamSynchronize(s.stream);
     s.pending = false;
     if (ok && nsteps > 0) harvest(nsteps - 1, false);
     cudaEventDestroy(evDisp);
+    if (nsteps > 0) cudaMemcpyAsync(d_ke, d_ke2 + ((nsteps - 1) & 1), sizeof(double), cudaMemcpyDeviceToDevice, s.stream);      // the caller's kinetic-energy scalar: the last step's
+    cudaStreamSynchronize(s.stream);
+    s.mdFused = false; s.gsZeroed = false;
     s.gradOverwrite = savedOverwrite;
     const double *last = eStep[(nsteps > 0 ? nsteps - 1 : 0) & 1];
     if (nbEnergies6 != nullptr) std::memcpy(nbEnergies6, last, sizeof(double) * 6);

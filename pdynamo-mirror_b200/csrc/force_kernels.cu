@@ -363,9 +363,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
 // per energy call: atom records in sorted order from the current coordinates, and the way back for the gradients
 // ------------------------------------------------------------------------------------------------------
 __global__ void k_pack_records(const double *__restrict__ x, const int *__restrict__ sAtom, int n, const float *__restrict__ q32, const int *__restrict__ ljtype,
-                               double ox, double oy, double oz, float4 *__restrict__ recA, float4 *__restrict__ recB)
+                               double ox, double oy, double oz, float4 *__restrict__ recA, float4 *__restrict__ recB, double *__restrict__ zero = nullptr, int zeroCount = 0)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    // fused mode (nbb200_md_run): the accumulators + work cursor of the force kernels are cleared here instead of by a memset of their own
+    if (zero != nullptr) for (int i = s; i < zeroCount; i += gridDim.x * blockDim.x) zero[i] = 0.0;
     if (s >= n) return;
     const int a = sAtom[s];
     const double X = x[3 * a] - ox, Y = x[3 * a + 1] - oy, Z = x[3 * a + 2] - oz;
@@ -375,13 +377,15 @@ __global__ void k_pack_records(const double *__restrict__ x, const int *__restri
 }
 
 // assign != 0: the NB term SETS the caller's gradient (every atom has exactly one sorted position) instead of accumulating into it
-__global__ void k_unsort_gradients(const double *__restrict__ gs, const int *__restrict__ sAtom, int s0, int n, double *__restrict__ grad, int assign)
+// clear != 0 (fused mode): the sorted accumulator is left zeroed for the next call (no memset of its own)
+__global__ void k_unsort_gradients(double *__restrict__ gs, const int *__restrict__ sAtom, int s0, int n, double *__restrict__ grad, int assign, int clear = 0)
 {
     const int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const int a = sAtom[s];
     if (assign) { grad[3 * a] = gs[3 * s]; grad[3 * a + 1] = gs[3 * s + 1]; grad[3 * a + 2] = gs[3 * s + 2]; }
     else { grad[3 * a] += gs[3 * s]; grad[3 * a + 1] += gs[3 * s + 1]; grad[3 * a + 2] += gs[3 * s + 2]; }
+    if (clear) { gs[3 * s] = 0.0; gs[3 * s + 1] = 0.0; gs[3 * s + 2] = 0.0; }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -526,11 +530,11 @@ bool upload_spline_tables(State &s)
     return true;
 }
 
-bool unsort_gradients(State &s, long s0, long s1, double *d_grad, bool assign)
+bool unsort_gradients(State &s, long s0, long s1, double *d_grad, bool assign, bool clear)
 {
     if (s1 <= s0 || d_grad == nullptr || s.gs == nullptr) return true;
     const int threads = 256;
-    k_unsort_gradients<<<(unsigned int) ((s1 - s0 + threads - 1) / threads), threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0);
+    k_unsort_gradients<<<(unsigned int) ((s1 - s0 + threads - 1) / threads), threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0, clear ? 1 : 0);
     s.launches += 1;
     return cuda_ok(cudaGetLastError(), "k_unsort_gradients");
 }
@@ -549,13 +553,15 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
     const int nitems = (int) s.hostCounters.itemCount;
     const size_t accumCount = (size_t) 16 * (s.nsets + 1);
     if (!s.accum.ensure(accumCount + 1)) return false;                    // + one slot that holds the work cursor: a single memset
-    NBB_CUDA(cudaMemsetAsync(s.accum.p, 0, sizeof(double) * (accumCount + 1), s.stream));
+    const bool fusedZero = s.mdFused && nitems > 0;           // k_pack_records clears the accumulators and the cursor in fused mode
+    if (!fusedZero) NBB_CUDA(cudaMemsetAsync(s.accum.p, 0, sizeof(double) * (accumCount + 1), s.stream));
     unsigned int *workCursor = reinterpret_cast<unsigned int *>(s.accum.p + accumCount);
     const double eScale = (1.0 / s.dielectric) * kE2AngstromToKJMol;
     if (nitems > 0) {
         if (!s.recA.ensure((size_t) s.n) || !s.recB.ensure((size_t) s.n)) return false;
         const int pthreads = 256, pblocks = (s.n + pthreads - 1) / pthreads;
-        k_pack_records<<<pblocks, pthreads, 0, s.stream>>>(s.xcur, s.sAtom.p, s.n, s.q32.p, s.ljtype.p, s.grid.lo[0], s.grid.lo[1], s.grid.lo[2], s.recA.p, s.recB.p);
+        k_pack_records<<<pblocks, pthreads, 0, s.stream>>>(s.xcur, s.sAtom.p, s.n, s.q32.p, s.ljtype.p, s.grid.lo[0], s.grid.lo[1], s.grid.lo[2], s.recA.p, s.recB.p,
+                                                            fusedZero ? s.accum.p : nullptr, (int) (accumCount + 1));
         ForceArgs A;
         A.items = s.items.p; A.nitems = nitems; A.workCursor = workCursor;
         A.tileDesc = s.tileDesc.p; A.recA = s.recA.p; A.recB = s.recB.p; A.n = s.n;
@@ -626,7 +632,9 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
         s.launches += 1;
     }
     // device-array calls honour nbb200_set_gradient_overwrite too (the host-array call handles it with its own staging buffer: d_grad = s.grad.p)
-    if (d_grad != nullptr && !unsort_gradients(s, 0, s.n, d_grad, s.gradOverwrite && d_grad != s.grad.p && s.nranks == 1)) return false;
+    const bool clearGs = s.mdFused && s.gsExternal == nullptr && s.nranks == 1 && d_grad != nullptr;
+    if (d_grad != nullptr && !unsort_gradients(s, 0, s.n, d_grad, s.gradOverwrite && d_grad != s.grad.p && s.nranks == 1, clearGs)) return false;
+    if (clearGs) s.gsZeroed = true;                          // the whole accumulator (3 n) has just been cleared by the unsort pass
     return cuda_ok(cudaGetLastError(), "force kernels");
 }
 

@@ -134,8 +134,9 @@ bool device_bbox(State &s, int nops, double *hostMin, double *hostExt)
 // The reference's early exit only matters when an update happens (then the maximum is not used further).
 // ------------------------------------------------------------------------------------------------------
 __global__ void k_displacement(const double *__restrict__ x, const double *__restrict__ xref, int n, const unsigned char *__restrict__ fixed, double buffacsq,
-                               unsigned long long *__restrict__ out)
+                               unsigned long long *__restrict__ out, unsigned long long *__restrict__ zeroOther = nullptr)
 {
+    if (zeroOther != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zeroOther = 0ULL;     // two-slot use (nbb200_md_run): prepares the next step's slot
     double m = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (fixed != nullptr && fixed[i]) continue;              // NBModelABFS.c:723-739: fixed atoms do not trigger updates
@@ -165,12 +166,13 @@ bool displacement_check(State &s, double buffacsq, double *maxr2, int *exceeded)
     return true;
 }
 
-bool displacement_enqueue(State &s, const double *d_x, double *d_out)
+bool displacement_enqueue(State &s, const double *d_x, double *d_out, double *d_zeroOther)
 {
-    NBB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), s.stream));
+    if (d_zeroOther == nullptr) NBB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), s.stream));       // else: d_out was zeroed by the previous two-slot call
     const int threads = 256;
     const int nblk = std::max(1, std::min(1184, (s.n + threads - 1) / threads));
-    k_displacement<<<nblk, threads, 0, s.stream>>>(d_x, s.xref.p, s.n, s.nfixed > 0 ? s.fixedFlag.p : nullptr, 0.0, reinterpret_cast<unsigned long long *>(d_out));
+    k_displacement<<<nblk, threads, 0, s.stream>>>(d_x, s.xref.p, s.n, s.nfixed > 0 ? s.fixedFlag.p : nullptr, 0.0, reinterpret_cast<unsigned long long *>(d_out),
+                                                  reinterpret_cast<unsigned long long *>(d_zeroOther));
     s.launches += 1;
     return cuda_ok(cudaGetLastError(), "k_displacement");
 }

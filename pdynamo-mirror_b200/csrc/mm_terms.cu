@@ -31,7 +31,7 @@ struct MMTerms {
     cudaStream_t stream = nullptr;
     bool ownStream = false;
     std::vector<TermRecord> host[kKinds];
-    bool dirty = true;
+    bool dirty = true, slotsZeroed = false;
     int start[kKinds + 1] = {};
     DevBuf<TermRecord> rec;
     DevBuf<double> x, grad, energies;
@@ -80,8 +80,9 @@ __device__ __forceinline__ void torsion_gradient(const Torsion &t, double df, in
     add3(g, l, dtxl, dtyl, dtzl);
 }
 
-__global__ void k_mm_terms(const TermRecord *__restrict__ rec, KindStarts K, const double *__restrict__ x, double *g, double *energies)
+__global__ void k_mm_terms(const TermRecord *__restrict__ rec, KindStarts K, const double *__restrict__ x, double *g, double *energies, double *zeroOther)
 {
+    if (zeroOther != nullptr && blockIdx.x == 0 && threadIdx.x < kKinds) zeroOther[threadIdx.x] = 0.0;   // two-slot use: prepares the next step's accumulators
     __shared__ double sE[kKinds];
     if (threadIdx.x < kKinds) sE[threadIdx.x] = 0.0;
     __syncthreads();
@@ -150,7 +151,7 @@ static bool upload_terms(MMTerms &m)
     std::vector<TermRecord> all;
     for (int k = 0; k < kKinds; k++) { m.start[k] = (int) all.size(); all.insert(all.end(), m.host[k].begin(), m.host[k].end()); }
     m.start[kKinds] = (int) all.size();
-    if (!m.rec.ensure(all.size() + 1) || !m.energies.ensure(kKinds)) return false;
+    if (!m.rec.ensure(all.size() + 1) || !m.energies.ensure(16)) return false;
     if (!all.empty()) NBB_CUDA(cudaMemcpy(m.rec.p, all.data(), sizeof(TermRecord) * all.size(), cudaMemcpyHostToDevice));
     // a pageable H2D copy returns once the data is STAGED; the DMA runs on the legacy stream, which a non-blocking stream does not wait for:
     // without this the kernel can read a partly uploaded record array (seen as wrong dihedral / improper energies, the tail of the array)
@@ -160,18 +161,23 @@ static bool upload_terms(MMTerms &m)
 }
 
 // enqueue only: the kernel and the copy of the five energies into pinned memory; collect() waits for them
-static bool enqueue(MMTerms &m, const double *d_x, double *d_grad, int slot = 0)
+// fused (nbb200_md_run, alternating slots): the device accumulators have two slots of 8 doubles; the kernel of slot s zeroes slot 1 - s for the
+// next step, so no memset is enqueued
+static bool enqueue(MMTerms &m, const double *d_x, double *d_grad, int slot = 0, bool fused = false)
 {
     if (m.dirty && !upload_terms(m)) return false;
-    NBB_CUDA(cudaMemsetAsync(m.energies.p, 0, sizeof(double) * kKinds, m.stream));
     const int total = m.start[kKinds];
+    fused = fused && total > 0;
+    double *acc = m.energies.p + 8 * (slot & 1);
+    if (fused && !m.slotsZeroed) { NBB_CUDA(cudaMemsetAsync(m.energies.p, 0, sizeof(double) * 16, m.stream)); m.slotsZeroed = true; }
+    if (!fused) { NBB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * kKinds, m.stream)); m.slotsZeroed = false; }
     if (total > 0) {
         KindStarts K;
         std::memcpy(K.s, m.start, sizeof(K.s));
-        k_mm_terms<<<(total + 127) / 128, 128, 0, m.stream>>>(m.rec.p, K, d_x, d_grad, m.energies.p);
+        k_mm_terms<<<(total + 127) / 128, 128, 0, m.stream>>>(m.rec.p, K, d_x, d_grad, acc, fused ? m.energies.p + 8 * ((slot + 1) & 1) : nullptr);
         m.launches += 1;
     }
-    NBB_CUDA(cudaMemcpyAsync(m.he + 8 * (slot & 1), m.energies.p, sizeof(double) * kKinds, cudaMemcpyDeviceToHost, m.stream));
+    NBB_CUDA(cudaMemcpyAsync(m.he + 8 * (slot & 1), acc, sizeof(double) * kKinds, cudaMemcpyDeviceToHost, m.stream));
     return cuda_ok(cudaGetLastError(), "k_mm_terms");
 }
 
@@ -245,7 +251,7 @@ NBB200MMTerms *MMTerms_B200_Allocate(int device, int natoms, int *status)
     cudaSetDevice(device);
     bool ok = cuda_ok(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking), "cudaStreamCreate");
     m->ownStream = ok;
-    ok = ok && m->x.ensure(3 * (size_t) natoms) && m->grad.ensure(3 * (size_t) natoms) && m->energies.ensure(kKinds);
+    ok = ok && m->x.ensure(3 * (size_t) natoms) && m->grad.ensure(3 * (size_t) natoms) && m->energies.ensure(16);
     ok = ok && cuda_ok(cudaMallocHost((void **) &m->hx, sizeof(double) * 3 * (size_t) natoms), "cudaMallocHost");
     ok = ok && cuda_ok(cudaMallocHost((void **) &m->hg, sizeof(double) * 3 * (size_t) natoms), "cudaMallocHost");
     ok = ok && cuda_ok(cudaMallocHost((void **) &m->he, sizeof(double) * 16), "cudaMallocHost");      // two slots of 8
@@ -387,10 +393,10 @@ void MMTerms_B200_LastEnergies(NBB200MMTerms *terms, double *energies5)
 
 // internal (nbb200_md_run): two result slots, so that a step's energies stay readable while the next step is already in flight
 namespace nbb200 {
-bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot)
+bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot, bool fused)
 {
     MMTerms *m = reinterpret_cast<MMTerms *>(terms);
-    return enqueue(*m, d_x, d_grad, slot);
+    return enqueue(*m, d_x, d_grad, slot, fused);
 }
 void mmterms_read_slot(NBB200MMTerms *terms, int slot, double *energies5)
 {

@@ -89,7 +89,7 @@ bool build_lists(State &s);                              // everything between "
 bool expand_pairs(State &s);                             // explicit (i,j) pairs per list from the tile masks
 bool device_bbox(State &s, int nops, double *hostMin, double *hostExt);
 bool displacement_check(State &s, double buffacsq, double *maxr2, int *exceeded);
-bool displacement_enqueue(State &s, const double *d_x, double *d_out);   // max |x - xref|^2 into a device double, no host synchronisation
+bool displacement_enqueue(State &s, const double *d_x, double *d_out, double *d_zeroOther = nullptr);   // max |x - xref|^2 into a device double, no host synchronisation
 bool centre_coordinates(State &s, const double *d_xin, bool doUpdate);   // useCentering: fills s.xc (and s.isoT on updates)
 bool touched_ranges(State &s, long *out);
 bool touched_ranges_async(State &s, long *d_out);      // the same table written to a device array, no host synchronisation                // per rank slab: [lo, hi) of the sorted positions this rank's lists reference
@@ -98,13 +98,13 @@ bool touched_ranges_async(State &s, long *d_out);      // the same table written
 }  // namespace nbb200
 struct NBB200MMTerms;
 namespace nbb200 {
-bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot);
+bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot, bool fused = false);
 void mmterms_read_slot(NBB200MMTerms *terms, int slot, double *energies5);
 
 // ---- force_kernels.cu
 bool upload_spline_tables(State &s);                     // s.spl -> s.splF64 / s.splPoly
 bool launch_forces(State &s, double *d_grad, bool sortedOnly);
-bool unsort_gradients(State &s, long s0, long s1, double *d_grad, bool assign = false);
+bool unsort_gradients(State &s, long s0, long s1, double *d_grad, bool assign = false, bool clear = false);
 void init_force_kernel_attributes();
 
 struct State {
@@ -180,6 +180,7 @@ struct State {
     DevBuf<double> visitDisp;                    // per visit 3 doubles
     DevBuf<int> visitInfo;                       // per visit: t, image
     DevBuf<double> bboxDev;                      // reduction output
+    DevBuf<double> mdScalars;                    // nbb200_md_run: two-slot device scalars (displacement maximum, kinetic energy)
 
     // extended atoms and the sort
     BuildGrid grid;
@@ -212,6 +213,7 @@ struct State {
     bool peerOpened[kMaxPeers] = {};
     bool peersReady = false;
     bool gradOverwrite = false;                  // MMMMEnergy (host arrays) sets the caller's gradient instead of accumulating
+    bool mdFused = false;                        // inside nbb200_md_run: memsets folded into neighbouring kernels (accumulators by k_pack_records, sorted gradient by k_unsort_gradients)
     bool gsZeroed = false;                       // the caller zeroed the sorted gradient for this call already (before the ranks' barrier)                        // touched sorted range per rank slab (min, max+1)
     DevBuf<unsigned long long> setPairs;         // per set list-pair counts
     DeviceCounters *counters = nullptr;
