@@ -398,6 +398,10 @@ bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_gra
     MMTerms *m = reinterpret_cast<MMTerms *>(terms);
     return enqueue(*m, d_x, d_grad, slot, fused);
 }
+void mmterms_reset_slots(NBB200MMTerms *terms)        // start of a run: the slot the first step uses may hold an earlier run's last energies
+{
+    reinterpret_cast<MMTerms *>(terms)->slotsZeroed = false;
+}
 void mmterms_read_slot(NBB200MMTerms *terms, int slot, double *energies5)
 {
     const MMTerms *m = reinterpret_cast<MMTerms *>(terms);

@@ -100,6 +100,7 @@ struct NBB200MMTerms;
 namespace nbb200 {
 bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot, bool fused = false);
 void mmterms_read_slot(NBB200MMTerms *terms, int slot, double *energies5);
+void mmterms_reset_slots(NBB200MMTerms *terms);
 
 // ---- force_kernels.cu
 bool upload_spline_tables(State &s);                     // s.spl -> s.splF64 / s.splPoly

@@ -875,3 +875,17 @@ def test_random_cells_cutoffs_topologies(pkg, orc, case):
     assert st.NumberOf14Pairs() == o.counts()["pairs14"]
     # random liquids have steep contacts and strongly cancelling terms: the bars are those of the ill-conditioned stress cases
     check_numbers("perturbed", e, g, dm, ref["energies"], ref["grad"], ref["dEdM"])
+
+
+def test_native_md_loop_without_fusion_and_speculation_in_a_subprocess():
+    """The switches of nbb200_md_run are read once per process: run the equivalence test again with the memsets unfused and the optimistic
+    execution off (NBB200_MD_FUSED=0, NBB200_MD_NO_SPECULATION=1) in a child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in (dict(NBB200_MD_FUSED="0"), dict(NBB200_MD_NO_SPECULATION="1")):
+        env = dict(os.environ, **extra)
+        out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_parity_gpu.py"), "-m", "gpu", "-x", "-q", "-k", "test_native_md_loop_equals"],
+                             cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "2 passed" in out.stdout, (extra, out.stdout[-2000:], out.stderr[-2000:])
