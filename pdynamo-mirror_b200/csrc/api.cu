@@ -1242,7 +1242,7 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
             if (owed) {      // its accumulators are turned into energies inside update_common: after the first wait, BEFORE the lists may change
                 s.pending = true; s.pendEnergies = eStep[(k - 1) & 1]; s.pendDEdM = dEdM; s.pendHaveGrad = true; s.pendLattice = s.lattice; s.pendAcc = haccSlot[(k - 1) & 1];
             }
-            updates += update_common(s, box6, forced ? 1 : 0, &st);
+            updates += update_common(s, box6, forced ? 1 : 0, &st, speculate ? 1 : -1);     // after a take-back the decision is known: no second displacement check
             if (st != NBB200_STATUS_CONTINUE) { ok = false; set_status(status, st); break; }
             if (owed) { flush_pending(s); harvest(k - 1, true); }
             if (!enqueue_step(k, speculate)) { ok = false; set_status(status, NBB200_STATUS_LOGIC_ERROR); break; }      // speculate here: the step was taken back
