@@ -189,6 +189,37 @@ class VelocityVerletDynamics:
         return out
 
 
+def langevin_constants(timeStep, collisionFrequency, temperature, forceSeries=None):
+    """The integration constants of LangevinVelocityVerletIntegrator.CalculateIntegrationConstants (pCore-1.9.0/pCore/LangevinVelocityVerletIntegrator.py:54-115):
+    returns (factors7, facV3) with factors7 = (facR1, facR2, facV1, facV2, sdR, sdV1, sdV2), the random-term factors already multiplied by
+    sqrt(kT) in dynamics units (amu A^2 ps^-2).  Exponential formulae for collisionFrequency * timeStep > 0.009, series expansions (valid to
+    fact^5) below; forceSeries (testing) overrides the choice."""
+    dt = float(timeStep)
+    fact = collisionFrequency * dt
+    series = (fact <= 0.009) if forceSeries is None else bool(forceSeries)
+    if not series:
+        c0 = math.exp(-fact)
+        c1 = (1.0 - c0) / fact
+        c2 = (1.0 - c1) / fact
+        sdR = math.sqrt(dt ** 2 * (2.0 - (3.0 - 4.0 * c0 + c0 * c0) / fact) / fact)
+        sdV = math.sqrt(1.0 - c0 * c0)
+        cRV1 = dt * (1.0 - c0) ** 2 / (fact * sdR * sdV)
+        cRV2 = math.sqrt(1.0 - cRV1 * cRV1)
+    else:
+        c0 = 1.0 - fact + fact ** 2 / 2.0 - fact ** 3 / 6.0 + fact ** 4 / 24.0 - fact ** 5 / 120.0
+        c1 = 1.0 - fact / 2.0 + fact ** 2 / 6.0 - fact ** 3 / 24.0 + fact ** 4 / 120.0 - fact ** 5 / 720.0
+        c2 = 0.5 - fact / 6.0 + fact ** 2 / 24.0 - fact ** 3 / 120.0 + fact ** 4 / 720.0 - fact ** 5 / 5040.0
+        sdR = (2.0 - 3.0 * fact / 4.0 + 67.0 * fact ** 2 / 320.0 - 119.0 * fact ** 3 / 2560.0) * math.sqrt(fact / 6.0) * dt
+        sdV = (2.0 - fact + 5.0 * fact ** 2 / 12.0 - fact ** 3 / 8.0 + 79.0 * fact ** 4 / 2880.0) * math.sqrt(fact / 2.0)
+        cRV1 = (3.0 / 2.0 - 3.0 * fact / 16.0 - 51.0 * fact ** 2 / 1280.0 + 17.0 * fact ** 3 / 2048.0 + 40967.0 * fact ** 4 / 11468800.0 -
+                57203.0 * fact ** 5 / 91750400.0) / math.sqrt(3.0)
+        cRV2 = (0.5 + 3.0 * fact / 16.0 - 9.0 * fact ** 2 / 1280.0 - 109.0 * fact ** 3 / 10240.0 + 10077.0 * fact ** 4 / 11468800.0 +
+                14887.0 * fact ** 5 / 18350080.0)
+    kT = math.sqrt(100.0 * _KB_KJMOL * temperature)          # sqrt(K -> amu A^2 ps^-2), SystemGeometryObjectiveFunction.TemperatureConversionFactor
+    factors = np.array([c1 * dt, c2 * dt ** 2, c0, (c1 - c2) * dt, sdR * kT, cRV1 * sdV * kT, cRV2 * sdV * kT], dtype=np.float64)
+    return factors, c2 * dt
+
+
 class LangevinDynamics(VelocityVerletDynamics):
     """Langevin velocity Verlet dynamics on the device (pCore-1.9.0/pCore/LangevinVelocityVerletIntegrator.py); options as
     LangevinDynamics_SystemGeometry: collisionFrequency (ps^-1), temperature (K), timeStep (ps)."""
@@ -202,29 +233,7 @@ class LangevinDynamics(VelocityVerletDynamics):
 
     def CalculateIntegrationConstants(self):
         """LangevinVelocityVerletIntegrator.CalculateIntegrationConstants (:54-115)"""
-        dt = self.dt
-        fact = self.collisionFrequency * dt
-        if fact > 0.009:
-            c0 = math.exp(-fact)
-            c1 = (1.0 - c0) / fact
-            c2 = (1.0 - c1) / fact
-            sdR = math.sqrt(dt ** 2 * (2.0 - (3.0 - 4.0 * c0 + c0 * c0) / fact) / fact)
-            sdV = math.sqrt(1.0 - c0 * c0)
-            cRV1 = dt * (1.0 - c0) ** 2 / (fact * sdR * sdV)
-            cRV2 = math.sqrt(1.0 - cRV1 * cRV1)
-        else:
-            c0 = 1.0 - fact + fact ** 2 / 2.0 - fact ** 3 / 6.0 + fact ** 4 / 24.0 - fact ** 5 / 120.0
-            c1 = 1.0 - fact / 2.0 + fact ** 2 / 6.0 - fact ** 3 / 24.0 + fact ** 4 / 120.0 - fact ** 5 / 720.0
-            c2 = 0.5 - fact / 6.0 + fact ** 2 / 24.0 - fact ** 3 / 120.0 + fact ** 4 / 720.0 - fact ** 5 / 5040.0
-            sdR = (2.0 - 3.0 * fact / 4.0 + 67.0 * fact ** 2 / 320.0 - 119.0 * fact ** 3 / 2560.0) * math.sqrt(fact / 6.0) * dt
-            sdV = (2.0 - fact + 5.0 * fact ** 2 / 12.0 - fact ** 3 / 8.0 + 79.0 * fact ** 4 / 2880.0) * math.sqrt(fact / 2.0)
-            cRV1 = (3.0 / 2.0 - 3.0 * fact / 16.0 - 51.0 * fact ** 2 / 1280.0 + 17.0 * fact ** 3 / 2048.0 + 40967.0 * fact ** 4 / 11468800.0 -
-                    57203.0 * fact ** 5 / 91750400.0) / math.sqrt(3.0)
-            cRV2 = (0.5 + 3.0 * fact / 16.0 - 9.0 * fact ** 2 / 1280.0 - 109.0 * fact ** 3 / 10240.0 + 10077.0 * fact ** 4 / 11468800.0 +
-                    14887.0 * fact ** 5 / 18350080.0)
-        kT = math.sqrt(100.0 * _KB_KJMOL * self.temperature)          # sqrt(K -> amu A^2 ps^-2), SystemGeometryObjectiveFunction.TemperatureConversionFactor
-        self.facV3 = c2 * dt
-        self.factors = np.array([c1 * dt, c2 * dt ** 2, c0, (c1 - c2) * dt, sdR * kT, cRV1 * sdV * kT, cRV2 * sdV * kT], dtype=np.float64)
+        self.factors, self.facV3 = langevin_constants(self.dt, self.collisionFrequency, self.temperature)
 
     def _first_half(self):
         self.iteration += 1

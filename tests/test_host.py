@@ -85,3 +85,28 @@ def test_dhfr_workloads_nb_only_and_complete(pkg):
     assert labels == ["Harmonic Bond", "Harmonic Angle", "Urey-Bradley", "Fourier Dihedral", "Harmonic Improper"]
     assert [len(c) for c in pkg.System.FromWorkload(b).energyModel.mmTerms] == [23592, 11584, 2117, 7000, 418]
     assert abs(b["masses"].sum() - a["masses"].sum()) == 0.0 and len(a["masses"]) == a["n"]
+
+
+def test_langevin_integration_constants(pkg):
+    """CalculateIntegrationConstants (pCore-1.9.0/pCore/LangevinVelocityVerletIntegrator.py:54-115): the exponential formulae and the series
+    expansions (valid to fact^5) are two transcriptions of the same functions -- they must agree where both are accurate; plus the limits
+    (no friction: velocity Verlet, no noise) and the fluctuation-dissipation balance of the velocity update."""
+    from pdynamo_mirror_b200.md import langevin_constants, _KB_KJMOL
+    dt, T = 0.001, 300.0
+    for gamma in (2.0, 5.0, 9.0, 20.0):                       # fact = 0.002 ... 0.02: both branches are accurate to better than 1e-9 relative
+        a, va = langevin_constants(dt, gamma, T, forceSeries=False)
+        b, vb = langevin_constants(dt, gamma, T, forceSeries=True)
+        # the exponential form of sdR / cRV1 cancels badly at small fact (that is why the reference switches): compare at the accuracy it has
+        tol = np.array([1e-10, 1e-9, 1e-12, 1e-9, 3e-6, 3e-6, 3e-5])
+        assert np.all(np.abs(a - b) <= tol * np.abs(b)), (gamma, (a - b) / b)
+        assert abs(va - vb) <= 1e-9 * abs(vb)
+    f, v3 = langevin_constants(dt, 1.0e-9, 0.0)                # no friction, no noise
+    assert np.allclose(f[:4], [dt, 0.5 * dt * dt, 1.0, 0.5 * dt], rtol=1e-8) and np.all(f[4:] == 0.0) and abs(v3 - 0.5 * dt) < 1e-12
+    # stationary velocity variance: v' = c0 v + noise with variance sdV1^2 + sdV2^2 must keep <v^2> = kT (per unit mass, dynamics units)
+    for gamma in (1.0, 25.0, 200.0):
+        f, _ = langevin_constants(dt, gamma, T)
+        kT = 100.0 * _KB_KJMOL * T
+        assert abs((f[5] ** 2 + f[6] ** 2) - kT * (1.0 - f[2] ** 2)) <= 1e-9 * kT
+    # the reference benchmark's values (25 ps^-1, 1 fs): exponential branch
+    f, _ = langevin_constants(0.001, 25.0, 300.0)
+    assert 0.975 < f[2] < 0.9754 and f[4] > 0 and f[5] > 0 and f[6] > 0
