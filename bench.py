@@ -373,6 +373,8 @@ def run_b200(args):
                 line["md"] = md_block(torch, local)
                 line["md_device"] = md_device_block(torch, local)
                 line["md_dhfr"] = md_dhfr_block(torch, local)
+                if rank == 0 and not args.no_cpu:
+                    line["md_dhfr"]["reference_same_box"] = md_dhfr_reference_estimate()
             except Exception as exc:
                 line["jac"] = {"error": repr(exc)}
     else:
@@ -539,6 +541,32 @@ def md_dhfr_block(torch, local, steps=1000):
                                     "potential_energy_mean": -293191.47148015, "temperature_mean_K": 293.73476041, "list_updates": 73,
                                     "source": "benchmarks/log/systemBenchmarks_Serial_1ps.log:405-465 (different random numbers: compare statistics, not trajectories)"},
             "speedup_vs_published_serial": 656.276 / wall, "speedup_vs_published_omp8": 201.5 / wall}
+
+
+def md_dhfr_reference_estimate():
+    """What one MD step of the same DHFR system costs the reference's own C code on THIS box's host cores (compiled reference, OpenMP build
+    where available): NB energy + gradients on existing lists, a list update (amortised over the 13.7 calls per update of the reference's run),
+    the five bonded terms.  An estimate of the reference's step rate to put next to the published wall times (unknown 2013 hardware)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refnb
+    w = make_workload("dhfr_mm")
+    omp = refnb.available(omp=True)
+    if not refnb.available(omp=omp):
+        return {"unavailable": "oracle/_ref not built"}
+    model = refnb.RefNB(w, omp=omp)
+    first = model.energy(force_new=True)
+    t_e, t_u = [], [first["t_update"]]
+    for _ in range(3):
+        t_e.append(model.energy(force_new=False)["t_energy"])
+    t_u.append(model.energy(force_new=True)["t_update"])
+    t0 = time.perf_counter()
+    for _ in range(3):
+        refnb.mm_energy(w["bonded"], w["xyz"])
+    t_b = (time.perf_counter() - t0) / 3.0
+    per_step = min(t_e) + min(t_u) / 13.7 + t_b
+    return {"cores": model.num_threads() if omp else 1, "nb_energy_s": float(min(t_e)), "list_update_s": float(min(t_u)), "bonded_terms_s": float(t_b),
+            "estimated_s_per_step": float(per_step), "estimated_steps_per_s": float(1.0 / per_step),
+            "note": "compiled reference C on this box; list update amortised over 13.7 calls (the reference's own DHFR statistics); Python integrator overhead of the reference not included"}
 
 
 def main():
