@@ -1047,6 +1047,31 @@ static __global__ void k_vv_first(double *__restrict__ x, double *__restrict__ v
     v[i] = vi + 0.5 * dt * ai;
 }
 
+// first half fused with the displacement check of CheckForUpdate (nbb200_md_run): one thread per atom, |x - xref|^2 into the running maximum
+static __global__ void k_vv_first_disp(double *__restrict__ x, double *__restrict__ v, const double *__restrict__ a, double dt, int n, const double *__restrict__ xref,
+                                       const unsigned char *__restrict__ fixed, unsigned long long *__restrict__ out, unsigned long long *__restrict__ zeroOther)
+{
+    if (zeroOther != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zeroOther = 0ULL;
+    const int atom = blockIdx.x * blockDim.x + threadIdx.x;
+    double r2 = 0.0;
+    if (atom < n) {
+        double d[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const long i = 3 * (long) atom + c;
+            const double ai = a[i], vi = v[i];
+            double xi = x[i];
+            xi += dt * vi + 0.5 * dt * dt * ai;
+            x[i] = xi;
+            v[i] = vi + 0.5 * dt * ai;
+            d[c] = xi - xref[i];
+        }
+        if (fixed == nullptr || !fixed[atom]) r2 = __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));
+    }
+    for (int off = 16; off > 0; off >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, off));
+    if ((threadIdx.x & 31) == 0 && r2 > 0.0) atomicMax(out, (unsigned long long) __double_as_longlong(r2));
+}
+
 // second half: a = -100 g / m (kJ mol^-1 A^-1 amu^-1 -> A ps^-2) ; v += dt/2 a ; kinetic energy 0.5 * 0.01 * sum m v^2 (kJ/mol)
 static __global__ void k_vv_second(double *__restrict__ v, double *__restrict__ a, const double *__restrict__ g, const double *__restrict__ mass, double dt, long m,
                                    double *__restrict__ ke, double *__restrict__ zeroOther = nullptr)
@@ -1203,8 +1228,6 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
     };
 
     for (int k = 0; k < nsteps && ok; k++) {
-        if (langevinFactors7 != nullptr) nbb200_langevin_first_half(state, d_x, d_v, d_a, d_mass, langevinFactors7, seed, firstIteration + (unsigned long long) k);
-        else nbb200_vv_first_half(state, d_x, d_v, d_a, timeStep);
         s.xcur = d_x;
         const bool forced = updateFrequency > 0 && (k + 1) % updateFrequency == 0;
         bool latticeSame = s.trans.n == 0;
@@ -1215,12 +1238,22 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
         }
         const bool speculate = !noSpeculation && !forced && !s.isNew && !s.useCentering && s.nranks == 1 && !s.timing && latticeSame &&
                                s.list == s.stListCutoff && s.outer == s.stOuterCutoff;
+        const bool fusedFirst = speculate && fusedMode;         // first half and displacement check in one kernel
+        double *d_disp = d_disp2 + (nspec & 1), *d_dispOther = d_disp2 + ((nspec + 1) & 1);
+        if (fusedFirst) {
+            if (langevinFactors7 != nullptr) ok = langevin_first_disp(s, d_x, d_v, d_a, d_mass, langevinFactors7, seed, firstIteration + (unsigned long long) k, d_disp, d_dispOther);
+            else {
+                k_vv_first_disp<<<(s.n + 127) / 128, 128, 0, s.stream>>>(d_x, d_v, d_a, timeStep, s.n, s.xref.p, s.nfixed > 0 ? s.fixedFlag.p : nullptr,
+                                                                        reinterpret_cast<unsigned long long *>(d_disp), reinterpret_cast<unsigned long long *>(d_dispOther));
+                s.launches += 1;
+            }
+        } else if (langevinFactors7 != nullptr) nbb200_langevin_first_half(state, d_x, d_v, d_a, d_mass, langevinFactors7, seed, firstIteration + (unsigned long long) k);
+        else nbb200_vv_first_half(state, d_x, d_v, d_a, timeStep);
         bool needSync = !speculate;
         if (speculate) {
             // optimistic: the check of CheckForUpdate (NBModelABFS.c:691-746) and the whole step go out together
-            double *d_disp = d_disp2 + (nspec & 1), *d_dispOther = d_disp2 + ((nspec + 1) & 1);
             nspec += 1;
-            ok = displacement_enqueue(s, d_x, d_disp, fusedMode ? d_dispOther : nullptr) &&
+            ok = ok && (fusedFirst || displacement_enqueue(s, d_x, d_disp, nullptr)) &&
                  cuda_ok(cudaMemcpyAsync(hdisp + (k & 1), d_disp, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H displacement") &&
                  cuda_ok(cudaEventRecord(evDisp, s.stream), "event") && enqueue_step(k, false) && cuda_ok(cudaEventSynchronize(evDisp), "event wait");
             if (!ok) { set_status(status, NBB200_STATUS_LOGIC_ERROR); break; }

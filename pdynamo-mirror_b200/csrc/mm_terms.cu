@@ -230,6 +230,53 @@ __global__ void k_langevin_first(double *__restrict__ x, double *__restrict__ v,
     v[i] = facV1 * vi + facV2 * ai + (sdV1 * w1 + sdV2 * w2) * rsm;
 }
 
+// the same first part fused with the displacement check of CheckForUpdate (pM/csource/NBModelABFS.c:691-746) for nbb200_md_run: one thread per
+// atom updates its three coordinates (same deviates: the Philox counter is the coordinate index) and contributes |x - xref|^2 to the maximum
+__global__ void k_langevin_first_disp(double *__restrict__ x, double *__restrict__ v, const double *__restrict__ a, const double *__restrict__ mass, int n,
+                                      double facR1, double facR2, double facV1, double facV2, double sdR, double sdV1, double sdV2,
+                                      unsigned long long seed, unsigned long long step, const double *__restrict__ xref, const unsigned char *__restrict__ fixed,
+                                      unsigned long long *__restrict__ out, unsigned long long *__restrict__ zeroOther)
+{
+    if (zeroOther != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zeroOther = 0ULL;
+    const int atom = blockIdx.x * blockDim.x + threadIdx.x;
+    double r2 = 0.0;
+    if (atom < n) {
+        const double rsm = rsqrt(mass[atom]);
+        double d[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const long i = 3 * (long) atom + c;
+            unsigned int r[4];
+            philox4x32((unsigned int) i, (unsigned int) ((unsigned long long) i >> 32), (unsigned int) step, (unsigned int) (step >> 32),
+                       (unsigned int) seed, (unsigned int) (seed >> 32), r);
+            const double u1 = ((double) (((unsigned long long) r[0] << 20) | (r[1] >> 12)) + 1.0) * (1.0 / 4503599627370496.0);
+            const double u2 = ((double) (((unsigned long long) r[2] << 20) | (r[3] >> 12)) + 1.0) * (1.0 / 4503599627370496.0);
+            const double rad = sqrt(-2.0 * log(u1));
+            double sn, cs;
+            sincospi(2.0 * u2, &sn, &cs);
+            const double w1 = rad * cs, w2 = rad * sn;
+            const double vi = v[i], ai = a[i];
+            const double xn = x[i] + (facR1 * vi + facR2 * ai + sdR * w1 * rsm);
+            x[i] = xn;
+            v[i] = facV1 * vi + facV2 * ai + (sdV1 * w1 + sdV2 * w2) * rsm;
+            d[c] = xn - xref[i];
+        }
+        if (fixed == nullptr || !fixed[atom]) r2 = __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));
+    }
+    for (int off = 16; off > 0; off >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, off));
+    if ((threadIdx.x & 31) == 0 && r2 > 0.0) atomicMax(out, (unsigned long long) __double_as_longlong(r2));
+}
+
+bool langevin_first_disp(State &s, double *d_x, double *d_v, const double *d_a, const double *d_mass, const double *f7, unsigned long long seed,
+                         unsigned long long step, double *d_out, double *d_zeroOther)
+{
+    k_langevin_first_disp<<<(s.n + 127) / 128, 128, 0, s.stream>>>(d_x, d_v, d_a, d_mass, s.n, f7[0], f7[1], f7[2], f7[3], f7[4], f7[5], f7[6], seed, step, s.xref.p,
+                                                                   s.nfixed > 0 ? s.fixedFlag.p : nullptr, reinterpret_cast<unsigned long long *>(d_out),
+                                                                   reinterpret_cast<unsigned long long *>(d_zeroOther));
+    s.launches += 1;
+    return cuda_ok(cudaGetLastError(), "k_langevin_first_disp");
+}
+
 }  // namespace nbb200
 
 using namespace nbb200;

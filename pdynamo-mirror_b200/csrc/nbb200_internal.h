@@ -101,6 +101,8 @@ namespace nbb200 {
 bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot, bool fused = false);
 void mmterms_read_slot(NBB200MMTerms *terms, int slot, double *energies5);
 void mmterms_reset_slots(NBB200MMTerms *terms);
+bool langevin_first_disp(State &s, double *d_x, double *d_v, const double *d_a, const double *d_mass, const double *f7, unsigned long long seed,
+                         unsigned long long step, double *d_out, double *d_zeroOther);
 
 // ---- force_kernels.cu
 bool upload_spline_tables(State &s);                     // s.spl -> s.splF64 / s.splPoly
