@@ -147,6 +147,10 @@ def run_reference(args):
     if rank != 0:
         return
     sample = args.ref_sample
+    # torchrun exports OMP_NUM_THREADS=1 to every rank when the variable is unset; the reference arm runs on rank 0 alone and is meant to
+    # use all the host threads it can, so the team size is restored here (before libgomp is loaded with the reference library)
+    if os.environ.get("NBB_REF_THREADS") or "TORCHELASTIC_RUN_ID" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(int(os.environ.get("NBB_REF_THREADS") or len(os.sched_getaffinity(0))))
     base, w = cpu_reference(sample, max(1, args.steps), max(0, min(args.warmup, 1)))
     wl = workload_description(args.workload, make_workload(args.workload))
     line = {"metric": "NBModelABFS list-pair interactions per second (pair-list rebuild + energy + gradients per call)",
