@@ -385,8 +385,32 @@ def run_b200(args):
         line["distributed_check"] = distributed_check(torch, dist, m, dn, w, local)
         line["halo"] = {"halo_atoms_per_step_no_rebuild": int(dn.halo_atoms()), "transport": dn.transport,
                         "atoms_owned": int(dn.slabs[rank][1] - dn.slabs[rank][0]), "list_updates": dn.updates}
-        line["e2e"] = {"value": value, "unit": "list-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                       "note": "multi-rank runs keep coordinates and gradients device-resident; the host end-to-end path is measured at N=1"}
+        # end to end with HOST buffers on every rank: the replicated caller holds all coordinates in page-locked memory; per step every rank
+        # uploads them, runs the distributed call (forced rebuild, as the timed steps above) and reads back its gradient array (the rows of
+        # its own slab are filled) and the summed energies.  Wall clock between barriers, max over ranks.
+        xh = m.x.cpu().pin_memory()
+        gh = torch.empty_like(xh).pin_memory()
+
+        def e2e_step():
+            m.x.copy_(xh, non_blocking=True)
+            m.g.zero_()
+            dn.call(m.x, m.box, m.g, force_rebuild=True)
+            gh.copy_(m.g, non_blocking=True)
+            dn.results()                                 # the energies and dE/dM on the host
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(args.warmup):
+            e2e_step()
+        barrier(); torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize(); barrier()
+        e2e_ms = allmax((time.perf_counter() - t1) / args.steps * 1e3)
+        line["e2e"] = {"value": pairs / (e2e_ms * 1e-3), "unit": "list-pairs/s", "ms_per_step": e2e_ms,
+                       "h2d_bytes_per_step": 24 * n * world, "d2h_bytes_per_step": (24 * n + 15 * 8) * world,
+                       "api": "DistributedNB.call(x, box, g, force_rebuild=True) on every rank with page-locked host arrays: full coordinate upload and "
+                              "gradient download per rank (bytes summed over the ranks), energies read on the host; wall clock, max over ranks"}
     if dn is not None and os.environ.get("NBB200_DIST_PROFILE"):
         for label, forced in (("rebuild", True), ("no-rebuild", False)):
             dn.profile = {}
