@@ -301,6 +301,25 @@ def test_vacuum_and_ragged_sizes(pkg, orc, n):
     assert np.sqrt(((g - ref["grad"]) ** 2).mean()) <= G_TOL * np.sqrt((ref["grad"] ** 2).mean()) + 1e-12
 
 
+@pytest.mark.parametrize("n", [1, 2])
+def test_one_and_two_atom_systems(pkg, orc, n):
+    """The smallest inputs: a lone atom (no pair at all) and two oxygens of different molecules (one pair, not excluded)."""
+    w0 = pkg.workloads.WORKLOADS["w216"]()
+    idx = np.array([0, 3][:n])
+    w = _vacuum(w0)
+    w["xyz"], w["charges"], w["ljtypes"], w["n"] = w0["xyz"][idx].copy(), w0["charges"][idx].copy(), w0["ljtypes"][idx].copy(), n
+    w["exclusions"], w["pairs14"] = w0["exclusions"][:0].copy(), w0["pairs14"][:0].copy()
+    system, st, e, g, dm = gpu_energy(pkg, w)
+    o = orc.OracleNB(w)
+    ref = o.energy(force_new=True)
+    assert st.NumberOfPairs() == n - 1 == len(o.primary_pairs()) and st.NumberOfImages() == 0
+    assert np.array_equal(orc.canonical_primary(st.Pairs(-1)), orc.canonical_primary(o.primary_pairs()))
+    assert abs(e.sum() - ref["energies"].sum()) <= E_TOL * np.abs(ref["energies"]).sum()
+    assert np.sqrt(((g - ref["grad"]) ** 2).mean()) <= G_TOL * np.sqrt((ref["grad"] ** 2).mean())
+    if n == 2:
+        assert e[0] != 0.0 and e[1] != 0.0 and np.allclose(g[0], -g[1], rtol=0, atol=1e-9 * np.abs(g).max())
+
+
 def test_all_atoms_excluded_gives_empty_list(pkg):
     w = _vacuum(pkg.workloads.WORKLOADS["w216"](), 3)          # one water: all three pairs excluded
     system, st, e, g, dm = gpu_energy(pkg, w)
