@@ -446,3 +446,162 @@ void refmm_energy(int n, const double *xyz,
     }
     Coordinates3_Deallocate(&x);
 }
+
+/* ------------------------------------------------------------------------------------------------------------------------------
+ * QC/MM entry points of NBModelABFS (second half; NOT yet built on the B200 side -- these drivers exist so that the
+ * golden vectors of that row are pinned by the compiled reference before any kernel is written).
+ *
+ * Call order of the Cython layer with QC atoms present (pMolecule.NBModelABFS.pyx:108-135,181-273): SetUp creates the state with
+ * qcAtoms and the three QC/MM work arrays of QCMMInteractionState; Energy calls NBModelABFS_MMMMEnergy then
+ * NBModelABFS_QCMMEnergyLJ (NBModelABFS.c:306-378); the QC model calls QCMMPotentials (NBModelABFS.c:449-498) before the SCF and
+ * QCMMGradients (NBModelABFS.c:383-444) after it with the QC charges.  The QC region here has no boundary (link) atoms and uses
+ * the MM link-atom coupling, so mmCharges are the MM charges with the QC atoms deactivated (EnergyModel.DeactivateQCAtomMMTerms,
+ * pMolecule/EnergyModel.py:129-140 -> MMAtomContainer QACTIVE flags) and mmCoordinates3 aliases coordinates3
+ * (NBModelABFSState.c:300).  The qcmm / qcqc pairwise interactions carry the point-charge electrostatic spline in atomic units
+ * (NBModelABFS.CheckPairwiseInteractions, pMolecule.NBModelABFS.pyx:83-97).
+ * ------------------------------------------------------------------------------------------------------------------------------ */
+#include "QCAtomContainer.h"
+#include "Real1DArray.h"
+#include "SymmetricMatrix.h"
+
+struct RefQC {
+    RefNB                   *nb;
+    int                      nqc;
+    QCAtomContainer         *qc;
+    Real1DArray             *qcCharges, *qcmmPotentials;
+    SymmetricMatrix         *qcqcPotentials;
+    PairwiseInteractionABFS *pwqcmm, *pwqcqc;
+};
+
+void refqc_destroy(RefQC *q)
+{
+    if (q == NULL) return;
+    refnb_destroy(q->nb);                                   /* the state only aliases the QC arrays */
+    PairwiseInteractionABFS_Deallocate(&(q->pwqcmm));
+    PairwiseInteractionABFS_Deallocate(&(q->pwqcqc));
+    SymmetricMatrix_Deallocate(&(q->qcqcPotentials));
+    Real1DArray_Deallocate(&(q->qcmmPotentials));
+    Real1DArray_Deallocate(&(q->qcCharges));
+    QCAtomContainer_Deallocate(&(q->qc));
+    free(q);
+}
+
+static PairwiseInteractionABFS *make_qc_interaction(const NBModelABFS *nb, int density)
+{
+    PairwiseInteractionABFS *pw = PairwiseInteractionABFS_Allocate();
+    if (pw == NULL) return NULL;
+    pw->dampingCutoff = nb->dampingCutoff; pw->innerCutoff = nb->innerCutoff; pw->outerCutoff = nb->outerCutoff;
+    pw->splinePointDensity = density;
+    pw->electrostaticSpline = PairwiseInteractionABFS_MakeElectrostaticSpline(pw, True, NULL);      /* atomic units */
+    return pw;
+}
+
+RefQC *refqc_create(int n, const double *charges, const int *ljtypes,
+                    int ntypes, const int *tableindex, const double *tableA, const double *tableB,
+                    int ntypes14, const int *tableindex14, const double *tableA14, const double *tableB14,
+                    int nexcl, const int *exclPairs, int n14, const int *pairs14,
+                    int ntrans, const double *rot, const double *trans,
+                    int nqc, const int *qcIndex, const int *qcAtomicNumber, int splinePointDensity)
+{
+    int i;
+    Status status = Status_Continue;
+    RefQC *q = (RefQC *) calloc(1, sizeof(RefQC));
+    if (q == NULL || nqc <= 0) { free(q); return NULL; }
+    q->nb = refnb_create(n, charges, ljtypes, ntypes, tableindex, tableA, tableB, ntypes14, tableindex14, tableA14, tableB14,
+                         nexcl, exclPairs, n14, pairs14, ntrans, rot, trans);
+    if (q->nb == NULL) { free(q); return NULL; }
+    q->nqc = nqc;
+    q->qc  = QCAtomContainer_Allocate(nqc);
+    for (i = 0; i < nqc; i++) {
+        q->qc->data[i].index        = qcIndex[i];
+        q->qc->data[i].atomicNumber = qcAtomicNumber[i];
+        q->qc->data[i].center       = i;
+        q->nb->mm->data[qcIndex[i]].QACTIVE = False;
+    }
+    q->qcCharges      = Real1DArray_Allocate(nqc, &status);
+    q->qcmmPotentials = Real1DArray_Allocate(nqc, &status);
+    if (ntrans > 0) q->qcqcPotentials = SymmetricMatrix_Allocate(nqc);
+    q->nb->nb->qcmmCoupling = QCMMLinkAtomCoupling_MM;
+    /* the state is created anew with the QC atoms, as SetUp does for a new configuration */
+    NBModelABFSState_Deallocate(&(q->nb->st));
+    q->nb->st = NBModelABFSState_SetUp(q->nb->mm, q->qc, NULL, q->nb->excl, q->nb->i14, q->nb->lj, q->nb->lj14,
+                                       q->qcCharges, q->qcmmPotentials, q->qcqcPotentials, q->nb->tc, q->nb->nb->qcmmCoupling);
+    q->pwqcmm = make_qc_interaction(q->nb->nb, splinePointDensity);
+    q->pwqcqc = make_qc_interaction(q->nb->nb, splinePointDensity);
+    if (q->nb->st == NULL || q->pwqcmm == NULL || q->pwqcqc == NULL || status != Status_Continue) { refqc_destroy(q); return NULL; }
+    return q;
+}
+
+/* One full pass: Update, MM/MM energy, QC/MM LJ energy, QC/MM potentials, and (given QC charges) the QC/MM electrostatic gradients.
+ * energies[10] = emmel, emmlj, emmel14, emmlj14, eimmmel, eimmmlj, eqcmmlj, eqcmmlj14, eimqcmmlj, eimqcqclj
+ * potentials[nqc] (atomic units), qcqc[nqc (nqc + 1) / 2] (packed lower triangle; image QC/QC potentials, only with symmetry),
+ * gradLJ[3n] = gradients after the MM/MM + LJ calls, gradEl[3n] = what QCMMGradients adds for the given qcCharges. */
+int refqc_energy(RefQC *q, const double *xyz, const double *box, const double *qcCharges,
+                 double *energies, double *potentials, double *qcqc, double *gradLJ, double *gradEl, double *dEdM)
+{
+    RefNB *h = q->nb;
+    NBModelABFSState *st = h->st;
+    int i, updated;
+    Status status = Status_Continue;
+    for (i = 0; i < h->n; i++) {
+        Coordinates3_Item(h->x, i, 0) = xyz[3 * i]; Coordinates3_Item(h->x, i, 1) = xyz[3 * i + 1]; Coordinates3_Item(h->x, i, 2) = xyz[3 * i + 2];
+    }
+    Coordinates3_Set(h->g, 0.0);
+    if (h->ntrans > 0) {
+        SymmetryParameters_SetCrystalParameters(h->sp, box[0], box[1], box[2], box[3], box[4], box[5]);
+        Matrix33_Set(h->spg->dEdM, 0.0);
+    }
+    st->isNew = True;
+    NBModelABFSState_Initialize(st, h->x, h->sp, h->g, h->spg);
+    updated = (int) NBModelABFS_Update(h->nb, h->gen, st, &status);
+    if (status != Status_Continue) return -1;
+    NBModelABFS_MMMMEnergy(h->nb, h->pw, st);
+    NBModelABFS_QCMMEnergyLJ(h->nb, h->pw, st);
+    energies[0] = st->emmel;   energies[1] = st->emmlj;   energies[2] = st->emmel14; energies[3] = st->emmlj14;
+    energies[4] = st->eimmmel; energies[5] = st->eimmmlj;
+    energies[6] = st->eqcmmlj; energies[7] = st->eqcmmlj14; energies[8] = st->eimqcmmlj; energies[9] = st->eimqcqclj;
+    for (i = 0; i < h->n; i++) {
+        gradLJ[3 * i] = Coordinates3_Item(h->g, i, 0); gradLJ[3 * i + 1] = Coordinates3_Item(h->g, i, 1); gradLJ[3 * i + 2] = Coordinates3_Item(h->g, i, 2);
+    }
+    Real1DArray_Set(q->qcmmPotentials, 0.0);
+    if (q->qcqcPotentials != NULL) SymmetricMatrix_Set_Zero(q->qcqcPotentials);
+    NBModelABFS_QCMMPotentials(h->nb, q->pwqcmm, q->pwqcqc, st);
+    for (i = 0; i < q->nqc; i++) potentials[i] = Real1DArray_Item(q->qcmmPotentials, i);
+    if (q->qcqcPotentials != NULL && qcqc != NULL) {
+        int j, k = 0;
+        for (i = 0; i < q->nqc; i++) for (j = 0; j <= i; j++) qcqc[k++] = SymmetricMatrix_Get_Component(q->qcqcPotentials, i, j);
+    }
+    for (i = 0; i < q->nqc; i++) Real1DArray_Item(q->qcCharges, i) = qcCharges[i];
+    NBModelABFS_QCMMGradients(h->nb, q->pwqcmm, q->pwqcqc, st);
+    for (i = 0; i < h->n; i++) {
+        gradEl[3 * i]     = Coordinates3_Item(h->g, i, 0) - gradLJ[3 * i];
+        gradEl[3 * i + 1] = Coordinates3_Item(h->g, i, 1) - gradLJ[3 * i + 1];
+        gradEl[3 * i + 2] = Coordinates3_Item(h->g, i, 2) - gradLJ[3 * i + 2];
+    }
+    if (dEdM != NULL && h->spg != NULL) {
+        int r, c;
+        for (r = 0; r < 3; r++) for (c = 0; c < 3; c++) dEdM[3 * r + c] = Matrix33_Item(h->spg->dEdM, r, c);
+    }
+    return updated;
+}
+
+/* list sizes: nbmmmm, nbqcmmlj, nbqcmmel, nbmmmm14, nbqcmmlj14, nbqcmmel14, and images / pairs of inbmmmm, inbqcmmlj, inbqcmmel, inbqcqclj, inbqcqcel */
+void refqc_counts(RefQC *q, long *out)
+{
+    NBModelABFSState *st = q->nb->st;
+    PairList  *pl[6] = { st->nbmmmm, st->nbqcmmlj, st->nbqcmmel, st->nbmmmm14, st->nbqcmmlj14, st->nbqcmmel14 };
+    ImageList *il[5] = { st->inbmmmm, st->inbqcmmlj, st->inbqcmmel, st->inbqcqclj, st->inbqcqcel };
+    int k;
+    for (k = 0; k < 6; k++) out[k] = (pl[k] == NULL) ? 0 : (long) pl[k]->npairs;
+    for (k = 0; k < 5; k++) {
+        out[6 + 2 * k]     = (il[k] == NULL) ? 0 : (long) ImageList_NumberOfImages(il[k]);
+        out[6 + 2 * k + 1] = (il[k] == NULL) ? 0 : (long) ImageList_NumberOfPairs(il[k]);
+    }
+}
+
+/* which = 0 nbmmmm, 1 nbqcmmlj, 2 nbqcmmel (first index of a QC/MM pair = position in the QC container) */
+void refqc_get_pairs(RefQC *q, int which, int *pairs)
+{
+    NBModelABFSState *st = q->nb->st;
+    dump_pairs(which == 0 ? st->nbmmmm : (which == 1 ? st->nbqcmmlj : st->nbqcmmel), pairs);
+}

@@ -81,6 +81,20 @@ void   refmm_energy(int n, const double *xyz,
                     int nimp, const int *impropers, const double *impEq, const double *impFc,
                     double *energies5, double *grad);
 
+/* QC/MM entry points of NBModelABFS with a QC region without boundary atoms, MM link-atom coupling (see ref_driver.c) */
+typedef struct RefQC RefQC;
+RefQC *refqc_create(int n, const double *charges, const int *ljtypes,
+                    int ntypes, const int *tableindex, const double *tableA, const double *tableB,
+                    int ntypes14, const int *tableindex14, const double *tableA14, const double *tableB14,
+                    int nexcl, const int *exclPairs, int n14, const int *pairs14,
+                    int ntrans, const double *rot, const double *trans,
+                    int nqc, const int *qcIndex, const int *qcAtomicNumber, int splinePointDensity);
+void   refqc_destroy(RefQC *q);
+int    refqc_energy(RefQC *q, const double *xyz, const double *box, const double *qcCharges,
+                    double *energies10, double *potentials, double *qcqc, double *gradLJ, double *gradEl, double *dEdM);
+void   refqc_counts(RefQC *q, long *out16);
+void   refqc_get_pairs(RefQC *q, int which, int *pairs);
+
 #ifdef __cplusplus
 }
 #endif

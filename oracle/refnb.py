@@ -56,6 +56,14 @@ def _lib(omp=False):
     lib.refnb_make_spline.restype = C.c_int
     lib.refnb_make_spline.argtypes = [C.c_int] + [C.c_double] * 3 + [C.c_int, dp, dp, dp]
     lib.refnb_spline_evaluate.argtypes = [C.c_int, dp, dp, C.c_double, dp, dp]
+    if hasattr(lib, "refqc_create"):
+        lib.refqc_create.restype = vp
+        lib.refqc_create.argtypes = lib.refnb_create.argtypes + [C.c_int, ip, ip, C.c_int]
+        lib.refqc_destroy.argtypes = [vp]
+        lib.refqc_energy.restype = C.c_int
+        lib.refqc_energy.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, dp, dp]
+        lib.refqc_counts.argtypes = [vp, C.POINTER(C.c_long)]
+        lib.refqc_get_pairs.argtypes = [vp, C.c_int, ip]
     _LIBS[key] = lib
     return lib
 
@@ -232,3 +240,69 @@ def _mm_call(fn, b, xyz, gradients):
 def mm_energy(bonded, xyz, gradients=True):
     """bonded MM terms {bond, angle, Urey-Bradley, dihedral, improper} and their gradient"""
     return _mm_call(_lib().refmm_energy, bonded, xyz, gradients)
+
+
+class RefQC:
+    """The reference NBModelABFS with a QC region (no boundary atoms, MM link-atom coupling): MM/MM energy, QC/MM LJ energy, QC/MM
+    potentials and electrostatic gradients through the compiled reference (oracle/ref_driver.c, refqc_*).  Default options only
+    (ABFS 0.5 / 8 / 12 / 13.5 A, dielectric 1, electrostaticScale14 1)."""
+
+    COUNT_LABELS = ("nbmmmm", "nbqcmmlj", "nbqcmmel", "nbmmmm14", "nbqcmmlj14", "nbqcmmel14", "inbmmmm_images", "inbmmmm_pairs", "inbqcmmlj_images",
+                    "inbqcmmlj_pairs", "inbqcmmel_images", "inbqcmmel_pairs", "inbqcqclj_images", "inbqcqclj_pairs", "inbqcqcel_images", "inbqcqcel_pairs")
+
+    def __init__(self, system, qc_index, qc_atomic_numbers, spline_point_density=50):
+        self.lib = _lib(False)
+        s = self.sys = system
+        self.n = s["n"]
+        q = np.ascontiguousarray(s["charges"], np.float64)
+        lt = np.ascontiguousarray(s["ljtypes"], np.int32)
+        ex = np.ascontiguousarray(s["exclusions"], np.int32).reshape(-1)
+        p14 = np.ascontiguousarray(s["pairs14"], np.int32).reshape(-1)
+        rot = np.ascontiguousarray(s["rot"], np.float64).reshape(-1)
+        trn = np.ascontiguousarray(s["trans"], np.float64).reshape(-1)
+        self.ntrans = 0 if s["box"] is None else len(s["trans"])
+        self.qc_index = np.ascontiguousarray(qc_index, np.int32)
+        zs = np.ascontiguousarray(qc_atomic_numbers, np.int32)
+        self.nqc = len(self.qc_index)
+        self.h = self.lib.refqc_create(self.n, _d(q), _i(lt), s["ntypes"], _i(s["tableindex"]), _d(s["tableA"]), _d(s["tableB"]),
+                                       s["ntypes"], _i(s["tableindex14"]), _d(s["tableA14"]), _d(s["tableB14"]),
+                                       len(ex) // 2, _i(ex) if len(ex) else None, len(p14) // 2, _i(p14) if len(p14) else None,
+                                       self.ntrans, _d(rot) if self.ntrans else None, _d(trn) if self.ntrans else None,
+                                       self.nqc, _i(self.qc_index), _i(zs), int(spline_point_density))
+        if not self.h:
+            raise RuntimeError("refqc_create failed")
+
+    def energy(self, qc_charges, xyz=None, box=None):
+        xyz = np.ascontiguousarray(self.sys["xyz"] if xyz is None else xyz, np.float64)
+        box = self.sys["box"] if box is None else box
+        boxa = None if box is None else np.ascontiguousarray(box, np.float64)
+        qcq = np.ascontiguousarray(qc_charges, np.float64)
+        e, pot, qcqc = np.zeros(10), np.zeros(self.nqc), np.zeros(self.nqc * (self.nqc + 1) // 2)
+        g_lj, g_el, dm = np.zeros((self.n, 3)), np.zeros((self.n, 3)), np.zeros((3, 3))
+        rc = self.lib.refqc_energy(self.h, _d(xyz), _d(boxa), _d(qcq), _d(e), _d(pot), _d(qcqc), _d(g_lj), _d(g_el), _d(dm))
+        if rc < 0:
+            raise RuntimeError("refqc_energy failed")
+        counts = (C.c_long * 16)()
+        self.lib.refqc_counts(self.h, counts)
+        return dict(energies=e, potentials=pot, qcqc_potentials=qcqc, grad_lj=g_lj, grad_el=g_el, dEdM=dm,
+                    counts=dict(zip(self.COUNT_LABELS, [int(v) for v in counts])))
+
+    def pairs(self, which):
+        """which: 0 nbmmmm, 1 nbqcmmlj, 2 nbqcmmel (first column of a QC/MM pair = position in the QC container)."""
+        counts = (C.c_long * 16)()
+        self.lib.refqc_counts(self.h, counts)
+        p = np.zeros((int(counts[which]), 2), np.int32)
+        if len(p):
+            self.lib.refqc_get_pairs(self.h, which, _i(p))
+        return p
+
+    def close(self):
+        if self.h:
+            self.lib.refqc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -3,6 +3,7 @@
 
   python tests/golden/make_fixtures.py inputs    # input-structure fixtures read from reference data files
   python tests/golden/make_fixtures.py golden    # golden outputs of the COMPILED reference (oracle/_ref) on committed inputs
+  python tests/golden/make_fixtures.py qcmm      # golden outputs of the QC/MM entry points (QC region without boundary atoms)
 
 Inputs:
   water216_cubicBox.npz  <- book/data/mol/water216_cubicBox.mol (equilibrated 216-water box of book Example 20,
@@ -424,6 +425,41 @@ def make_golden(only=None):
         r.close()
 
 
+# ----------------------------------------------------------------------------------------------------
+# QC/MM entry points of NBModelABFS (second half): golden vectors of the COMPILED reference for a QC region
+# without boundary atoms (oracle/ref_driver.c refqc_*, oracle/refnb.py RefQC).  The B200 side of this row is not built yet;
+# the vectors pin it in advance.  QC charges: the MM charges of the QC atoms scaled by 0.9 (any fixed vector would do).
+# ----------------------------------------------------------------------------------------------------
+QCMM_CASES = {"w216": ("w216", [0, 1, 2], [8, 1, 1], False), "w216_vacuum": ("w216", [3, 4, 5], [8, 1, 1], True),
+              "bala": ("bala", list(range(22)), [1] * 22, False),
+              "crystal_GLYGLY": ("crystal_GLYGLY", list(range(17)), [1] * 17, False)}      # the whole asymmetric unit: QC/QC image lists only
+
+
+def qcmm_case(name):
+    import pdynamo_mirror_b200 as p
+    wname, idx, zs, vacuum = QCMM_CASES[name]
+    w = p.workloads.WORKLOADS[wname]()
+    if vacuum:
+        w = dict(w)
+        w["box"], w["rot"], w["trans"] = None, np.zeros((0, 3, 3)), np.zeros((0, 3))
+    return w, np.array(idx, np.int32), np.array(zs, np.int32), 0.9 * np.asarray(w["charges"], np.float64)[idx]
+
+
+def make_qcmm():
+    import refnb
+    for name in QCMM_CASES:
+        w, idx, zs, qcq = qcmm_case(name)
+        r = refnb.RefQC(w, idx, zs)
+        out = r.energy(qcq)
+        keys = {k: np.array(sorted(map(tuple, r.pairs(which).tolist())), dtype=np.int32).reshape(-1, 2) for which, k in ((1, "nbqcmmlj"), (2, "nbqcmmel"))}
+        np.savez_compressed(os.path.join(HERE, "golden_qcmm_%s.npz" % name), qc_index=idx, qc_charges=qcq, energies=out["energies"],
+                            potentials=out["potentials"], qcqc_potentials=out["qcqc_potentials"], grad_lj=out["grad_lj"], grad_el=out["grad_el"],
+                            dEdM=out["dEdM"], count_labels=np.array(refnb.RefQC.COUNT_LABELS), counts=np.array([out["counts"][k] for k in refnb.RefQC.COUNT_LABELS]),
+                            nbqcmmlj=keys["nbqcmmlj"], nbqcmmel=keys["nbqcmmel"])
+        print(name, out["energies"][6:], out["potentials"][:3], out["counts"])
+        r.close()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("inputs", "all"):
@@ -433,5 +469,7 @@ if __name__ == "__main__":
         make_crystals()
     if what == "bonded":
         make_dhfr_bonded()
+    if what in ("qcmm", "all"):
+        make_qcmm()
     if what in ("golden", "all"):
         make_golden(only=sys.argv[2:])          # python make_fixtures.py golden [case ...]
