@@ -63,6 +63,13 @@ NBB200State *NBModelABFSState_B200_SetUp(int device, int n, const double *charge
  * GenerateLists14, pM/csource/NBModelABFS.c:1113-1128) and CheckForUpdate ignores fixed atoms (:723-739).  Call after SetUp, before the
  * first Update; nfixed = 0 clears.  Marks the state new (lists are rebuilt). */
 void NBModelABFSState_B200_SetFixedAtoms(NBB200State *state, int nfixed, const int *fixed, int *status);
+/* the qcAtoms argument of NBModelABFSState_SetUp, first part (pM/csource/NBModelABFSState.c:348-353: mmSelection = complement of the pure
+ * QC selection): the listed atoms leave every MM/MM list -- primary and image lists (and-selection of GenerateLists / GenerateImageLists,
+ * pM/csource/NBModelABFS.c:508-623) and the 1-4 list (GenerateLists14, :1113-1128) -- so that NBModelABFS_B200_MMMMEnergy returns what
+ * NBModelABFS_MMMMEnergy returns with a QC region present.  QC regions without boundary (link) atoms only; not with useCentering or
+ * partitions.  The QC/MM entry points (NBModelABFS_QCMMEnergyLJ / _QCMMPotentials / _QCMMGradients, NBModelABFS.c:306-498) have no
+ * counterpart here yet.  Call after SetUp, before the first Update; nqc = 0 clears.  Marks the state new. */
+void NBModelABFSState_B200_SetQCAtoms(NBB200State *state, int nqc, const int *qcAtoms, int *status);
 /* replaces NBModelABFSState_SetUpCentering (pM/csource/NBModelABFSState.c:425-450; NBModelABFS option useCentering): the isolates
  * (connected components of the exclusion graph; those with a fixed atom stay) are moved into the primary cell by whole lattice vectors at
  * every list update and carried along in between (NBModelABFSState_InitializeCoordinates3, :278-311); lists and energies are evaluated on

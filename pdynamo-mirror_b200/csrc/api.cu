@@ -37,7 +37,7 @@ static void destroy(State *s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     s->q32.release(); s->q64.release(); s->ljtype.release(); s->ljAB.release(); s->ljAB14.release();
-    s->exclPtr.release(); s->exclCol.release(); s->pairs14.release(); s->fixedFlag.release();
+    s->exclPtr.release(); s->exclCol.release(); s->pairs14.release(); s->fixedFlag.release(); s->qcFlag.release();
     s->isoPtr.release(); s->isoIdx.release(); s->xc.release(); s->isoT.release();
     s->x.release(); s->xref.release(); s->grad.release();
     s->imageOps.release(); s->imageBoxes.release(); s->baseOpsDev.release(); s->visitDisp.release(); s->visitInfo.release(); s->bboxDev.release();
@@ -340,7 +340,7 @@ void NBModelABFSState_B200_SetFixedAtoms(NBB200State *state, int nfixed, const i
     }
     // GenerateLists14 -> SelfPairList_FromSelfPairList(interactions14, mmSelection, freeSelection): at least one free atom
     std::vector<int2> keep;
-    for (const int2 &p : s.pairs14All) if (nfixed == 0 || !(flag[p.x] && flag[p.y])) keep.push_back(p);
+    for (const int2 &p : s.pairs14All) if ((nfixed == 0 || !(flag[p.x] && flag[p.y])) && (s.hostQC.empty() || !(s.hostQC[p.x] || s.hostQC[p.y]))) keep.push_back(p);
     bool ok = s.fixedFlag.ensure((size_t) s.n) && s.pairs14.ensure(std::max<size_t>(1, keep.size()));
     cudaStreamSynchronize(s.stream);
     ok = ok && cuda_ok(cudaMemcpy(s.fixedFlag.p, flag.data(), (size_t) s.n, cudaMemcpyHostToDevice), "H2D fixed") &&
@@ -349,6 +349,35 @@ void NBModelABFSState_B200_SetFixedAtoms(NBB200State *state, int nfixed, const i
     if (!ok) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return; }
     s.nfixed = nfixed; s.n14 = (int) keep.size();
     s.hostFixed = (nfixed > 0) ? flag : std::vector<unsigned char>();
+    s.isNew = true;
+}
+
+/* Pure QC atoms (NBModelABFSState_SetUp with qcAtoms, NBModelABFSState.c:348-353: mmSelection = complement of the pure QC
+ * selection).  They leave every MM/MM list -- primary, image (GenerateLists / GenerateImageLists and-selection, NBModelABFS.c:508-623) and
+ * 1-4 (GenerateLists14) -- so that NBModelABFS_B200_MMMMEnergy returns what the reference's NBModelABFS_MMMMEnergy returns with a QC region
+ * present.  The QC/MM entry points themselves (QCMMEnergyLJ, QCMMPotentials, QCMMGradients) are not built; boundary atoms are not handled. */
+void NBModelABFSState_B200_SetQCAtoms(NBB200State *state, int nqc, const int *qcAtoms, int *status)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (nqc < 0 || (nqc > 0 && qcAtoms == nullptr)) { set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return; }
+    if (nqc > 0 && (s.useCentering || s.nranks > 1)) { set_error("QC atoms with useCentering or several partitions are not supported"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return; }
+    std::vector<unsigned char> flag((size_t) s.n, 0);
+    for (int k = 0; k < nqc; k++) {
+        if (qcAtoms[k] < 0 || qcAtoms[k] >= s.n) { set_error("QC atom index out of range"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return; }
+        flag[qcAtoms[k]] = 1;
+    }
+    std::vector<int2> keep;
+    for (const int2 &p : s.pairs14All) if ((nqc == 0 || !(flag[p.x] || flag[p.y])) && (s.hostFixed.empty() || !(s.hostFixed[p.x] && s.hostFixed[p.y]))) keep.push_back(p);
+    bool ok = s.qcFlag.ensure((size_t) s.n) && s.pairs14.ensure(std::max<size_t>(1, keep.size()));
+    cudaStreamSynchronize(s.stream);
+    ok = ok && cuda_ok(cudaMemcpy(s.qcFlag.p, flag.data(), (size_t) s.n, cudaMemcpyHostToDevice), "H2D QC flags") &&
+         (keep.empty() || cuda_ok(cudaMemcpy(s.pairs14.p, keep.data(), sizeof(int2) * keep.size(), cudaMemcpyHostToDevice), "H2D 1-4")) &&
+         cuda_ok(cudaDeviceSynchronize(), "set-up copies");
+    if (!ok) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return; }
+    s.nqc = nqc; s.n14 = (int) keep.size();
+    s.hostQC = (nqc > 0) ? flag : std::vector<unsigned char>();
     s.isNew = true;
 }
 

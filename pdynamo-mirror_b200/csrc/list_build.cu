@@ -447,6 +447,7 @@ struct TileArgs {
     const ImageBoxDev *imageBoxes;     // [nsets], slot 0 unused
     const int *exclPtr; const int *exclCol;
     const unsigned char *fixed;        // nullable: per-atom flags of the fixed atoms
+    const unsigned char *inactive;     // nullable: per-atom flags of the atoms that are on no MM/MM list (pure QC atoms: mmSelection, NBModelABFSState.c:351)
     unsigned int *tileDesc; unsigned int tileCap;
     WorkItem *items; unsigned int itemCap;
     unsigned long long *setPairs;
@@ -472,6 +473,7 @@ struct __align__(16) BuildWarp {
     unsigned int bloom[kBloomWords];             // sorted positions (mod 2048) of the exclusion partners of the block atoms
     unsigned int sub[kSubBlocks][2 * kTile];     // per i-cluster: j reference | column byte << 24
     SubStream st[kSubBlocks];
+    unsigned int activeMask, padw[3];            // block atoms that may appear on a list (kept in shared memory: the builder is register bound)
 };
 
 // write the first `count` (<= 32) entries of a cluster queue as one tile.  The queue holds COLUMN bytes (bit i = cluster atom i
@@ -519,6 +521,8 @@ __device__ __forceinline__ void emit_tile(const TileArgs &A, int lane, int clust
 
 // 80 registers / 6 CTAs per SM with the plain bound; -DNBB_BUILD_MINBLOCKS=7 (72 registers) measured no faster, and an explicit
 // minimum of 1 lets ptxas take 132 registers (builder 1.59 -> 2.33 ms): keep the plain form as the default
+// kQC: a QC region is present (A.inactive); a separate instantiation, so that the ordinary builder compiles exactly as without it
+template <bool kQC>
 #ifdef NBB_BUILD_MINBLOCKS
 __global__ void __launch_bounds__(kBuildThreads, NBB_BUILD_MINBLOCKS) k_build_tiles(TileArgs A)
 #else
@@ -576,6 +580,12 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
     if (A.fixed != nullptr) {
         const int sb = b * kTile + lane;
         freeMask = __ballot_sync(0xffffffffu, !(sb < A.n && A.fixed[A.sAtom[sb]]));
+    }
+    if (kQC) {
+        const int sb = b * kTile + lane;
+        const unsigned int act = __ballot_sync(0xffffffffu, !(sb < A.n && A.inactive[A.sAtom[sb]]));
+        if (lane == 0) W.activeMask = act;
+        __syncwarp();
     }
     const BuildGrid g = A.grid;
     int c0[3], c1[3];
@@ -695,6 +705,7 @@ __global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
                     }
                 }
                 if (colmask != 0u && A.fixed != nullptr && A.fixed[A.sAtom[s]]) colmask &= freeMask;   // fixed j: free i atoms only
+                if (kQC && colmask != 0u) colmask = A.inactive[A.sAtom[s]] ? 0u : (colmask & W.activeMask);   // both atoms in the MM selection
                 if (colmask != 0u) {
                     if (set == 0) {
                         if ((s >> 5) == b) colmask &= (1u << (s & 31)) - 1u;          // own block: i < j only, no self pair
@@ -1011,10 +1022,12 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
             A.sX = s.sX.p; A.sAtom = s.sAtom.p; A.invPerm = s.invPerm.p; A.cellStart = s.cellStart.p; A.blockBox = s.blockBox.p;
             A.imageBoxes = s.imageBoxes.p; A.exclPtr = s.exclPtr.p; A.exclCol = s.exclCol.p;
             A.fixed = s.nfixed > 0 ? s.fixedFlag.p : nullptr;
+            A.inactive = s.nqc > 0 ? s.qcFlag.p : nullptr;
             A.tileDesc = s.tileDesc.p; A.tileCap = (unsigned int) cap;
             A.items = s.items.p; A.itemCap = (unsigned int) s.itemCap; A.setPairs = s.setPairs.p; A.counters = s.counters;
             const long warps = (long) myBlocks * s.nsets * A.split;
-            k_build_tiles<<<(unsigned int) ((warps + kBuildWarps - 1) / kBuildWarps), kBuildThreads, 0, s.stream>>>(A);
+            if (A.inactive != nullptr) k_build_tiles<true><<<(unsigned int) ((warps + kBuildWarps - 1) / kBuildWarps), kBuildThreads, 0, s.stream>>>(A);
+            else k_build_tiles<false><<<(unsigned int) ((warps + kBuildWarps - 1) / kBuildWarps), kBuildThreads, 0, s.stream>>>(A);
             s.launches += 1;
         }
         NBB_CUDA(cudaMemcpyAsync(&s.hostCounters, s.counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, s.stream));

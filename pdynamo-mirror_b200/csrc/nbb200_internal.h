@@ -129,6 +129,9 @@ struct State {
     std::vector<int2> pairs14All;                // as given to SetUp; pairs14 / n14 hold the ones with at least one free atom
     DevBuf<unsigned char> fixedFlag;             // per atom, 1 = fixed (NBModelABFSState_SetUp's fixedAtoms); unused when nfixed == 0
     int nfixed = 0;
+    DevBuf<unsigned char> qcFlag;                // per atom, 1 = pure QC atom: on no MM/MM list (NBModelABFSState_SetUp's qcAtoms); unused when nqc == 0
+    int nqc = 0;
+    std::vector<unsigned char> hostQC;
     std::vector<int> hostExclPtr, hostExclCol;   // host copy of the exclusion CSR (isolates for useCentering)
     std::vector<unsigned char> hostFixed;
     // useCentering (NBModelABFSState_SetUpCentering): isolates = connected components of the exclusion graph

@@ -162,6 +162,15 @@ class NBModelABFSState:
             _lib.lib().NBModelABFSState_B200_Deallocate(C.byref(h))
         self.cObject, self.isOwner = None, False
 
+    def SetQCAtoms(self, indices):
+        """Pure QC atoms leave every MM/MM list (NBModelABFSState_SetUp's qcAtoms -> mmSelection, NBModelABFSState.c:348-353).  Low-level: the
+        plugin's SetUp still refuses QC atoms, because the QC/MM entry points (QCMMEnergyLJ / QCMMPotentials / QCMMGradients) are not built."""
+        idx = np.ascontiguousarray(indices, np.int32).reshape(-1)
+        status = C.c_int(_lib.STATUS_CONTINUE)
+        _lib.lib().NBModelABFSState_B200_SetQCAtoms(self.cObject, len(idx), i_(idx) if len(idx) else None, C.byref(status))
+        if status.value != _lib.STATUS_CONTINUE:
+            raise CLibraryError("Unable to set the QC atoms. " + _lib.last_error())
+
     def GetEnergies(self, energies):
         """Append (label, value) tuples; same non-NULL-list gating as pMolecule.NBModelABFSState.pyx:41-59."""
         e = self.energies

@@ -320,6 +320,57 @@ def test_one_and_two_atom_systems(pkg, orc, n):
         assert e[0] != 0.0 and e[1] != 0.0 and np.allclose(g[0], -g[1], rtol=0, atol=1e-9 * np.abs(g).max())
 
 
+def _null_type_workload(w, idx):
+    """The same system with the atoms idx given zero charge and an extra LJ type whose A and B vanish with every type: each pair with
+    such an atom contributes exactly nothing, so energies and gradients equal those of the MM/MM lists without these atoms."""
+    v = dict(w)
+    nt, new = w["ntypes"], w["ntypes"] + 1
+    for tag in ("", "14"):
+        ti, ta, tb = np.asarray(w["tableindex" + tag]).reshape(nt, nt), np.asarray(w["tableA" + tag]), np.asarray(w["tableB" + tag])
+        tin = np.full((new, new), len(ta), ti.dtype)
+        tin[:nt, :nt] = ti
+        pad = new * (new + 1) // 2 - len(ta)
+        v["tableindex" + tag], v["tableA" + tag], v["tableB" + tag] = np.ascontiguousarray(tin.reshape(-1)), np.concatenate([ta, np.zeros(pad)]), np.concatenate([tb, np.zeros(pad)])
+    v["ntypes"] = new
+    v["charges"], v["ljtypes"] = np.array(w["charges"], np.float64), np.array(w["ljtypes"], np.int32)
+    v["charges"][idx] = 0.0
+    v["ljtypes"][idx] = nt
+    return v
+
+
+@pytest.mark.parametrize("name", ["w216", "w216_vacuum", "bala", "crystal_GLYGLY"])
+def test_mm_lists_and_energies_with_a_qc_region(pkg, orc, name):
+    """NBModelABFSState_B200_SetQCAtoms: with a QC region present the MM/MM lists hold MM atoms only and NBModelABFS_MMMMEnergy returns
+    the reference's values (golden_qcmm_*: compiled reference with qcAtoms, tests/golden/make_fixtures.py qcmm); gradients against the
+    oracle on the equivalent null-type system.  The QC/MM terms themselves are not built."""
+    q = load_golden("qcmm_" + name)
+    idx = q["qc_index"]
+    w = pkg.workloads.WORKLOADS["w216" if name == "w216_vacuum" else name]()
+    if name == "w216_vacuum":
+        w = _vacuum(w)
+    system, st, e_full, g_full, _ = gpu_energy(pkg, w, electrostaticScale14=1.0)
+    st.SetQCAtoms(idx)
+    system.configuration.gradients3[:] = 0.0
+    system.Energy(doGradients=True)
+    e, g = st.energies.copy(), system.configuration.gradients3.copy()
+    counts = dict(zip([str(s) for s in q["count_labels"]], q["counts"].tolist()))
+    assert st.NumberOfPairs() == counts["nbmmmm"] and st.NumberOf14Pairs() == counts["nbmmmm14"]
+    assert st.NumberOfImagePairs() == counts["inbmmmm_pairs"]
+    ref = q["energies"][:6]
+    floor = 1.0e-7 * np.abs(e_full).sum()
+    for k in range(6):
+        assert abs(e[k] - ref[k]) <= E_TOL * abs(ref[k]) + floor, (name, k, e[k], ref[k])
+    assert np.abs(g[idx]).max() <= 1.0e-8 * np.abs(g_full).max()   # masked lanes are evaluated at the outer cutoff, where the fp32 force is ~1e-10 of a typical one, not exactly 0
+    o = orc.OracleNB(_null_type_workload(w, idx), electrostaticScale14=1.0).energy(force_new=True)
+    assert np.abs(o["energies"] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).sum())
+    if np.abs(o["grad"]).max() > 0:
+        assert np.sqrt(((g - o["grad"]) ** 2).mean()) <= G_TOL * np.sqrt((o["grad"] ** 2).mean())
+    st.SetQCAtoms([])                                           # cleared: the all-MM numbers are back
+    system.configuration.gradients3[:] = 0.0
+    system.Energy(doGradients=True)
+    assert np.allclose(st.energies, e_full, rtol=1e-12, atol=1e-9) and st.NumberOfPairs() > counts["nbmmmm"] - 1
+
+
 def test_all_atoms_excluded_gives_empty_list(pkg):
     w = _vacuum(pkg.workloads.WORKLOADS["w216"](), 3)          # one water: all three pairs excluded
     system, st, e, g, dm = gpu_energy(pkg, w)
