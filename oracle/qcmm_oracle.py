@@ -78,3 +78,47 @@ def qcmm(w, qc_index, qc_charges, damp=0.5, inner=8.0, outer=12.0, density=50, d
                     g_el[j] -= c * d[j]
     e.update(potentials=pot, grad_lj=g_lj, grad_el=g_el)
     return e
+
+
+def qcqc_images(w, qc_index, damp=0.5, inner=8.0, outer=12.0, density=50, dielectric=1.0):
+    """The QC/QC image terms for a cell with space-group operations (MMMMImageEnergy on inbqcqclj, NBModelABFS.c:356-376; QCQCImagePotentials,
+    NBModelABFS.c:470-476): images x' = (M S M^-1) x + M (t + (a, b, c)) (NBModelABFS.c:1161-1313) of the QC atoms, every operation except the
+    identity with weight one half (the reference keeps one operation of each inverse pair with scale 1 and self-inverse ones with scale 0.5).
+    Returns dict(eimqcqclj, qcqc_potentials (packed lower triangle, atomic units), grad_lj[n, 3])."""
+    x = np.asarray(w["xyz"], np.float64)
+    qc = np.asarray(qc_index)
+    nq = len(qc)
+    M, invM = oracle.make_M(w["box"])
+    frac = x @ invM.T
+    spread = np.ceil(frac.max(0) - frac.min(0)).astype(int) + 1          # the operations move the molecule inside the cell
+    heights = 1.0 / np.linalg.norm(invM, axis=1)
+    k = np.ceil(outer / heights).astype(int) + spread
+    rng = [np.arange(-k[d], k[d] + 1) for d in range(3)]
+    abc = np.array(np.meshgrid(*rng, indexing="ij")).reshape(3, -1).T
+    nt = w["ntypes"]
+    ti = np.asarray(w["tableindex"]).reshape(nt, nt)
+    tA, tB = np.asarray(w["tableA"]), np.asarray(w["tableB"])
+    lt = np.asarray(w["ljtypes"])
+    f = oracle.make_factors(damp, inner, outer)
+    sx, sy, sh = oracle.make_spline(3, damp, inner, outer, density)
+    r2off = outer * outer
+    e, W, g = 0.0, np.zeros((nq, nq)), np.zeros((len(x), 3))
+    for S, t in zip(np.asarray(w["rot"]).reshape(-1, 3, 3), np.asarray(w["trans"]).reshape(-1, 3)):
+        R = M @ S @ invM
+        identity_op = np.array_equal(S, np.eye(3)) and not np.any(t)
+        base = x[qc] @ R.T
+        for s in abc:
+            if identity_op and not np.any(s):
+                continue
+            xi = base + M @ (t + s)
+            d = x[qc][:, None, :] - xi[None, :, :]                         # primary q (rows) against image q' (columns)
+            r2 = (d * d).sum(2)
+            for a, b in zip(*np.nonzero(r2 <= r2off)):
+                tt = ti[lt[qc[a]], lt[qc[b]]]
+                _, elj, dF = oracle.pair(f, float(r2[a, b]), 0.0, float(tA[tt]), float(tB[tt]))
+                e += 0.5 * elj
+                g[qc[a]] += 0.5 * 2.0 * dF * d[a, b]
+                g[qc[b]] -= 0.5 * 2.0 * dF * (R.T @ d[a, b])
+                W[a, b] += 0.5 * oracle.spline_evaluate(sx, sy, sh, float(r2[a, b]))[0] / dielectric
+    W = 0.5 * (W + W.T)
+    return dict(eimqcqclj=e, qcqc_potentials=W[np.tril_indices(nq)], grad_lj=g)
