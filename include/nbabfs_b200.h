@@ -70,6 +70,12 @@ void NBModelABFSState_B200_SetFixedAtoms(NBB200State *state, int nfixed, const i
  * partitions.  The QC/MM entry points (NBModelABFS_QCMMEnergyLJ / _QCMMPotentials / _QCMMGradients, NBModelABFS.c:306-498) have no
  * counterpart here yet.  Call after SetUp, before the first Update; nqc = 0 clears.  Marks the state new. */
 void NBModelABFSState_B200_SetQCAtoms(NBB200State *state, int nqc, const int *qcAtoms, int *status);
+/* replaces NBModelABFS_QCMMEnergyLJ (pM/csource/NBModelABFS.c:306-378) for a QC region set with NBModelABFSState_B200_SetQCAtoms, in vacuum
+ * or in a P1 cell, analytic form of the interaction: energies4 = {eqcmmlj, eqcmmlj14 (0 without boundary atoms), eimqcmmlj, eimqcqclj}
+ * (NBModelABFSState.h:51-57); grad[3n] (host, nullable) is accumulated into.  Uses the coordinates and lattice of the last Update.  One fp64
+ * launch over QC atoms x (cell + translated copies): the sums do not depend on the lists (csrc/qcmm.cu).  dE/dM of the image part, the
+ * spline form, space-group operations and the electrostatic entry points (_QCMMPotentials, _QCMMGradients) are not built. */
+void NBModelABFS_B200_QCMMEnergyLJ(NBB200State *state, double *energies4, double *grad, int *status);
 /* replaces NBModelABFSState_SetUpCentering (pM/csource/NBModelABFSState.c:425-450; NBModelABFS option useCentering): the isolates
  * (connected components of the exclusion graph; those with a fixed atom stay) are moved into the primary cell by whole lattice vectors at
  * every list update and carried along in between (NBModelABFSState_InitializeCoordinates3, :278-311); lists and energies are evaluated on

@@ -91,6 +91,8 @@ static State *create(int device, int n, const double *charges, const int *ljtype
     for (int i = 0; i < n; i++) q32[i] = (float) charges[i];
     std::vector<float2> ab((size_t) ntypes * ntypes);
     for (int i = 0; i < ntypes * ntypes; i++) { ab[i].x = (float) tableA[tableindex[i]]; ab[i].y = (float) tableB[tableindex[i]]; }
+    s->hostLJ64.resize((size_t) ntypes * ntypes);
+    for (int i = 0; i < ntypes * ntypes; i++) { s->hostLJ64[i].x = tableA[tableindex[i]]; s->hostLJ64[i].y = tableB[tableindex[i]]; }
     std::vector<double2> ab14((size_t) ntypes14 * ntypes14);
     for (int i = 0; i < ntypes14 * ntypes14; i++) { ab14[i].x = tableA14[tableindex14[i]]; ab14[i].y = tableB14[tableindex14[i]]; }
     // symmetric exclusion CSR (SelfPairList_MakeConnections, pCore-1.9.0/extensions/csource/PairList.c:458-526)

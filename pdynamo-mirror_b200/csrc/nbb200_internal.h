@@ -132,6 +132,7 @@ struct State {
     DevBuf<unsigned char> qcFlag;                // per atom, 1 = pure QC atom: on no MM/MM list (NBModelABFSState_SetUp's qcAtoms); unused when nqc == 0
     int nqc = 0;
     std::vector<unsigned char> hostQC;
+    std::vector<double2> hostLJ64;               // [nt*nt] (A, B) expanded table in fp64 (QC/MM LJ term, qcmm.cu)
     std::vector<int> hostExclPtr, hostExclCol;   // host copy of the exclusion CSR (isolates for useCentering)
     std::vector<unsigned char> hostFixed;
     // useCentering (NBModelABFSState_SetUpCentering): isolates = connected components of the exclusion graph

@@ -171,6 +171,21 @@ class NBModelABFSState:
         if status.value != _lib.STATUS_CONTINUE:
             raise CLibraryError("Unable to set the QC atoms. " + _lib.last_error())
 
+    def QCMMEnergyLJ(self, gradients3=None):
+        """NBModelABFS_QCMMEnergyLJ for the QC atoms of SetQCAtoms (vacuum / P1 cells, analytic form): returns (eqcmmlj, eqcmmlj14, eimqcmmlj,
+        eimqcqclj); gradients3[n, 3] (host, optional) is accumulated into.  Low-level, see SetQCAtoms."""
+        e = np.zeros(4)
+        status = C.c_int(_lib.STATUS_CONTINUE)
+        g = None
+        if gradients3 is not None:
+            if not (gradients3.flags["C_CONTIGUOUS"] and gradients3.dtype == np.float64):
+                raise ValueError("gradients3 must be a C-contiguous float64 array")
+            g = d_(gradients3)
+        _lib.lib().NBModelABFS_B200_QCMMEnergyLJ(self.cObject, d_(e), g, C.byref(status))
+        if status.value != _lib.STATUS_CONTINUE:
+            raise CLibraryError("QC/MM LJ energy failed. " + _lib.last_error())
+        return e
+
     def GetEnergies(self, energies):
         """Append (label, value) tuples; same non-NULL-list gating as pMolecule.NBModelABFSState.pyx:41-59."""
         e = self.energies

@@ -371,6 +371,39 @@ def test_mm_lists_and_energies_with_a_qc_region(pkg, orc, name):
     assert np.allclose(st.energies, e_full, rtol=1e-12, atol=1e-9) and st.NumberOfPairs() > counts["nbmmmm"] - 1
 
 
+@pytest.mark.parametrize("name", ["w216", "w216_vacuum", "bala"])
+def test_qcmm_lennard_jones_term(pkg, orc, name):
+    """NBModelABFS_B200_QCMMEnergyLJ (csrc/qcmm.cu, one fp64 launch over QC atoms x cell + translated copies) against the compiled
+    reference's NBModelABFS_QCMMEnergyLJ (golden_qcmm_*): the three energies, and the gradient after removing the MM/MM part."""
+    q = load_golden("qcmm_" + name)
+    idx = q["qc_index"]
+    w = pkg.workloads.WORKLOADS["w216" if name == "w216_vacuum" else name]()
+    if name == "w216_vacuum":
+        w = _vacuum(w)
+    system, st, _, _, _ = gpu_energy(pkg, w)
+    st.SetQCAtoms(idx)
+    system.Energy(doGradients=True)                             # the Update with the QC region in place
+    g = np.zeros((w["n"], 3))
+    e4 = st.QCMMEnergyLJ(g)
+    ref = q["energies"]
+    scale = max(1.0, np.abs(ref[6:]).sum())
+    assert abs(e4[0] - ref[6]) <= 1e-10 * scale and e4[1] == 0.0 and abs(e4[2] - ref[8]) <= 1e-10 * scale and abs(e4[3] - ref[9]) <= 1e-10 * scale, (e4, ref[6:])
+    mm = orc.OracleNB(_null_type_workload(w, idx), electrostaticScale14=1.0).energy(force_new=True)
+    gref = q["grad_lj"] - mm["grad"]
+    assert np.abs(g - gref).max() <= 1e-9 * max(1.0, np.abs(q["grad_lj"]).max())
+    assert np.array_equal(st.QCMMEnergyLJ(), e4) or np.allclose(st.QCMMEnergyLJ(), e4, rtol=1e-13, atol=1e-13)      # atomics: summation order may differ
+
+
+def test_qcmm_lennard_jones_term_refuses_what_it_cannot_do(pkg):
+    w = pkg.workloads.WORKLOADS["crystal_GLYGLY"]()
+    system, st, _, _, _ = gpu_energy(pkg, w)
+    assert np.all(st.QCMMEnergyLJ() == 0.0)                      # no QC atoms: the term is empty
+    st.SetQCAtoms(np.arange(17))
+    system.Energy(doGradients=True)
+    with pytest.raises(Exception, match="space-group"):
+        st.QCMMEnergyLJ()
+
+
 def test_all_atoms_excluded_gives_empty_list(pkg):
     w = _vacuum(pkg.workloads.WORKLOADS["w216"](), 3)          # one water: all three pairs excluded
     system, st, e, g, dm = gpu_energy(pkg, w)
