@@ -99,7 +99,8 @@ void NBModelABFS_B200_SetOptions(NBB200State *state, double dampingCutoff, doubl
  * LennardJonesB}Spline, :148-285, splinePointDensity points per Angstrom, reference default 50) are built from the state's cutoffs
  * and rebuilt by NBModelABFS_B200_SetOptions.  Default: analytic form (pM/csource/PairwiseInteraction.c:34). */
 void PairwiseInteractionABFS_B200_SetInteractionForm(NBB200State *state, int useAnalyticForm, int splinePointDensity, int *status);
-/* host helper: the table PairwiseInteractionABFS_Make*Spline builds (which = 0 electrostatic in kJ/mol, 1 LJ-A, 2 LJ-B): abscissae
+/* host helper: the table PairwiseInteractionABFS_Make*Spline builds (which = 0 electrostatic in kJ/mol, 1 LJ-A, 2 LJ-B, 3 electrostatic in
+ * atomic units = useAtomicUnits, the spline of the QC/MM and QC/QC interactions, pM/csource/PairwiseInteraction.c:187): abscissae
  * x = r^2, ordinates y and second derivatives h as CubicSpline_MakeFromReal1DArrays leaves them (pC/csource/CubicSpline.c:309-420).
  * Returns the number of points (pM/cinclude/PairwiseInteraction.h:166-167); with x, y or h NULL only that. */
 int PairwiseInteractionABFS_B200_MakeSpline(int which, double dampingCutoff, double innerCutoff, double outerCutoff, int splinePointDensity,

@@ -457,9 +457,15 @@ void PairwiseInteractionABFS_B200_SetInteractionForm(NBB200State *state, int use
 int PairwiseInteractionABFS_B200_MakeSpline(int which, double dampingCutoff, double innerCutoff, double outerCutoff, int splinePointDensity,
                                             double *x, double *y, double *h)
 {
-    if (which < 0 || which > 2 || splinePointDensity < 1) return 0;
+    if (which < 0 || which > 3 || splinePointDensity < 1) return 0;
     const int n = abfs_spline_points(outerCutoff, splinePointDensity);
     if (x == nullptr || y == nullptr || h == nullptr) return n;
+    if (which == 3) {                                        // electrostatic spline in atomic units (the QC/MM and QC/QC interactions)
+        std::vector<double> vx, vy, vh;
+        make_abfs_electrostatic_spline_au(dampingCutoff, innerCutoff, outerCutoff, splinePointDensity, vx, vy, vh);
+        for (int i = 0; i < n; i++) { x[i] = vx[i]; y[i] = vy[i]; h[i] = vh[i]; }
+        return n;
+    }
     SplineTables t;
     make_abfs_splines(dampingCutoff, innerCutoff, outerCutoff, splinePointDensity, t);
     for (int i = 0; i < n; i++) { x[i] = t.x[i]; y[i] = t.y[which][i]; h[i] = t.h[which][i]; }

@@ -378,6 +378,27 @@ void make_abfs_splines(double damp, double inner, double outer, int density, Spl
     for (int k = 0; k < 3; k++) spline_second_derivatives(t.x, t.y[k], t.h[k]);
 }
 
+// PairwiseInteractionABFS_MakeElectrostaticSpline with useAtomicUnits (pM/csource/PairwiseInteraction.c:149-200, scale :187): the spline the
+// QC/MM and QC/QC interactions carry (NBModelABFS.CheckPairwiseInteractions, pMolecule.NBModelABFS.pyx:83-97) -- potentials in atomic units
+// over r^2 in Angstrom^2
+void make_abfs_electrostatic_spline_au(double damp, double inner, double outer, int density, std::vector<double> &x, std::vector<double> &y, std::vector<double> &h)
+{
+    double F[21];
+    make_abfs_factors(damp, inner, outer, F);
+    const int n = abfs_spline_points(outer, density);
+    const double dR = outer / (double) (n - 1);
+    const double scale = 1.0e+00 / (1.0e-10 / 5.291772083e-11);       // 1 / UNITS_LENGTH_ANGSTROMS_TO_BOHRS (pC/cinclude/Units.h:21,55-57)
+    x.assign(n, 0.0); y.assign(n, 0.0);
+    for (int i = 0; i < n - 1; i++) {
+        const double r = dR * (double) i, r2 = r * r;
+        x[i] = r2;
+        y[i] = abfs_ordinate(F, 0, r2);
+    }
+    x[n - 1] = F[2];
+    for (int i = 0; i < n; i++) y[i] *= scale;
+    spline_second_derivatives(x, y, h);
+}
+
 // per interval [x_l, x_l+1] the cubic in u = x - x_l:  f = c0 + u (c1 + u (c2 + u c3)); algebraically the reference's
 // CubicSpline_FastEvaluateFG (pC/cinclude/CubicSpline.h:30-39) with s = u / d, t = 1 - s
 void spline_interval_polynomial(const std::vector<double> &x, const std::vector<double> &y, const std::vector<double> &h, int l, double *c4)

@@ -95,6 +95,7 @@ struct SplineTables {
 int  abfs_spline_points(double outer, int density);
 void make_abfs_splines(double damp, double inner, double outer, int density, SplineTables &t);
 void spline_second_derivatives(const std::vector<double> &x, const std::vector<double> &y, std::vector<double> &h);
+void make_abfs_electrostatic_spline_au(double damp, double inner, double outer, int density, std::vector<double> &x, std::vector<double> &y, std::vector<double> &h);
 void spline_interval_polynomial(const std::vector<double> &x, const std::vector<double> &y, const std::vector<double> &h, int l, double *c4);
 constexpr double kE2AngstromToKJMol = (1.0e+7 * 6.0221415e+23 * 1.60217653e-19 * 1.60217653e-19) / (4.0e+00 * 3.14159265358979323846 * 8.854187817e-12);
 

@@ -55,10 +55,9 @@ class PairwiseInteractionABFS:
     def MakeSplines(self, electrostatic=True, lennardJones=True, useAtomicUnits=False):
         """The tables MakeSplines builds in the reference (pMolecule.PairwiseInteraction.pyx:204-214), as a dict of (x, y, h) arrays:
         x = r^2, ordinates, second derivatives.  The device state builds the same tables itself when the spline form is selected."""
-        if useAtomicUnits:
-            raise NotImplementedError("atomic-unit splines belong to the QC/MM interactions")
         out = {}
-        which = ([("electrostatic", 0)] if electrostatic else []) + ([("lennardJonesA", 1), ("lennardJonesB", 2)] if lennardJones else [])
+        # useAtomicUnits: the electrostatic spline of the QC/MM and QC/QC interactions (PairwiseInteractionABFS_MakeElectrostaticSpline, True)
+        which = ([("electrostatic", 3 if useAtomicUnits else 0)] if electrostatic else []) + ([("lennardJonesA", 1), ("lennardJonesB", 2)] if lennardJones else [])
         L = _lib.lib()
         for name, w in which:
             n = L.PairwiseInteractionABFS_B200_MakeSpline(w, self.dampingCutoff, self.innerCutoff, self.outerCutoff, int(self.splinePointDensity), None, None, None)

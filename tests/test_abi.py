@@ -61,6 +61,10 @@ def test_spline_tables_match_oracle(pkg, orc):
         for which, name in enumerate(("electrostatic", "lennardJonesA", "lennardJonesB")):
             for a, b in zip(tables[name], orc.make_spline(which, *cut)):
                 assert np.array_equal(a, b), (cut, name)
+        au = pw.MakeSplines(lennardJones=False, useAtomicUnits=True)            # the spline of the QC/MM and QC/QC interactions
+        assert list(au) == ["electrostatic"]
+        for a, b in zip(au["electrostatic"], orc.make_spline(3, *cut)):
+            assert np.array_equal(a, b), (cut, "electrostatic, atomic units")
     with pytest.raises(ValueError):
         pkg.PairwiseInteractionABFS(splinePoints=3)
     with pytest.raises(ValueError):
