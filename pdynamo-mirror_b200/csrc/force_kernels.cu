@@ -6,13 +6,18 @@
 // SymmetryParameterGradients_ImageDerivatives (pM/csource/SymmetryParameterGradients.c:158-238).
 //
 // k_cluster_forces: one warp per work item (= one i-cluster of 8 sorted atoms x up to `chunkTiles` tiles of 32 j slots of one
-// image).  Lane (g, m) owns cluster atom m and, per tile, j slot `lane`; group g (8 lanes) walks the 8 slots 8g .. 8g+7 in 8
-// steps: at step k lane (g, m) evaluates (i = m, j = 8g + (m + k) % 8) and then hands its j data position AND its j-force
-// accumulator to the next lane of the group (warp shuffles), so both the i and the j force are plain register accumulations
-// (no shared-memory atomics, Newton's third law used once per pair).  All atom data come from per-call RECORDS in sorted
-// order (two float4 per atom: grid-relative fp32 coordinates split as K + xl with K a multiple of 8 A, charge, LJ type), so
-// the j gather of a tile is two coalesced 128-bit loads per lane; pair math is fp32 in cluster-local coordinates
-// (exact K differences plus one rounding), accumulation per 32 steps in fp32, across tiles / into global memory in fp64.
+// image).  Lane l OWNS j slot l of the current tile (its record, its gradient accumulator, the column byte of its descriptor:
+// bit i = the pair (cluster atom i, this j) is on the list) and walks the 8 cluster atoms two at a time: the i atoms are staged
+// once per item in shared memory as PAIRS {x0, x1, y0, y1}, {z0, z1, q0, q1}, read back with broadcast 128-bit loads, and the two
+// pairs (i0, j), (i1, j) are evaluated together with packed fp32 arithmetic (FFMA2 / FMUL2 / FADD2 of sm_100: one issue slot for
+// two operations, scalar operands broadcast for free).  Measured on B200 (scripts/microbench/mix_bench.cu): a packed
+// instruction occupies the FMA pipe for two cycles and the half-rate ALU instructions (FSEL, FSETP, FMNMX, LOP3) issue in its shadow,
+// whereas a scalar FFMA followed by an ALU instruction costs the sum of both -- the region selects are therefore free next to packed math.
+// The j gradient stays in the lane's registers (no shuffles in the pair loop: SHFL costs 4 cycles per scheduler); the i gradients are
+// 24 fp32 accumulators per lane, reduced across the warp by a reduce-scatter every kFlushTiles tiles and added to the sorted
+// gradient in fp64.  All atom data come from per-call RECORDS in sorted order (two float4 per atom: grid-relative fp32 coordinates
+// split as K + xl with K a multiple of 8 A, charge, LJ type), pair math is fp32 in cluster-local coordinates (exact K differences
+// plus one rounding), accumulation across tiles / into global memory in fp64.
 // Gradients are accumulated in sorted order and scattered to atom order by k_unsort_gradients.
 #include "nbb200_internal.h"
 #include <algorithm>
@@ -24,7 +29,7 @@ namespace nbb200 {
 
 struct ForceArgs {
     const WorkItem *items; int nitems; unsigned int *workCursor;
-    const unsigned int *tileDesc;
+    const unsigned int *tileDesc; int chunkTiles; int exp;
     const float4 *recA, *recB; int n;
     const float2 *ljAB; int ntypes;
     const ImageOpDev *ops;
@@ -98,32 +103,104 @@ __device__ __forceinline__ PairOut abfs_pair(const AbfsF32 &F, float r2, float q
     return o;
 }
 
-// Slow path for tiles that contain a pair inside the damped core, r^2 < r2Damp (reference: PairwiseInteraction.h:72-119,
-// third branches, with s = s2 = 0): returns the CORRECTION (damped minus what abfs_pair produced) for this lane's
-// accumulators c = {fxi, fyi, fzi, fxj, fyj, fzj, eq, el}; the j part is rotated home like in the main loop.
-__device__ __noinline__ void damped_tile_fix(const AbfsF32 &F, unsigned int mask, const float4 *myPosq, const unsigned char *ljRow, const int *myLj,
-                                            float xi, float yi, float zi, float qi, int src, float *c)
+// ------------------------------------------------------------------------------------------------------
+// packed fp32 (sm_100 FFMA2 / FMUL2 / FADD2): two pairs per instruction.  bc() broadcasts a scalar (a register, uniform-register or
+// constant operand modifier in SASS, no instruction); negation is an operand modifier as well.
+// ------------------------------------------------------------------------------------------------------
+typedef float2 f2;
+__device__ __forceinline__ f2 bc(float v) { return make_float2(v, v); }
+__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return __fadd2_rn(a, neg2(b)); }
+__device__ __forceinline__ f2 sel2(bool p0, bool p1, f2 a, f2 b) { return make_float2(p0 ? a.x : b.x, p1 ? a.y : b.y); }
+
+// the two pairs (i0, j), (i1, j) at once: the same formulas as abfs_pair.  eq, el: running energy sums; g = -2 dE/d(r^2) of both pairs.
+// lj0, lj1: shared-memory byte addresses of the pairs' LJ entries.  Every entry is TWO float4: {A, B, A aShift12 - B bShift6, 0} for
+// the plain region and {A aK12, B bK6, 0, 0} for the switched one -- the region then selects an address (one predicated add) instead of
+// three coefficients per pair; the shifts inside the brackets (aF6, bF3) and the plain-region Coulomb shift are blended with
+// pi = 1 / 0 (plain / switched), which turns a subtraction into an FFMA2 of the same cost.  What is left for the ALU pipe per pair: the
+// region test, pi, the two selects of the Coulomb switch and the list-mask select.
+__device__ __forceinline__ float4 lds128(unsigned int addr)
 {
-    float fxi = 0.f, fyi = 0.f, fzi = 0.f, fxj = 0.f, fyj = 0.f, fzj = 0.f, eq = 0.f, el = 0.f;
-    for (int k = 0; k < kCluster; k++) {
-        const float4 p = myPosq[k];
-        const float4 ab = *reinterpret_cast<const float4 *>(ljRow + myLj[k]);
-        const float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void abfs_pair2(const AbfsF32 &F, f2 r2, f2 qij, unsigned int lj0, unsigned int lj1, f2 &eq, f2 &el, f2 &g)
+{
+    const f2 s = make_float2(rsqrt_fast(r2.x), rsqrt_fast(r2.y));
+    const bool p0 = r2.x <= F.r2On, p1 = r2.y <= F.r2On;
+    const float4 ab0 = lds128(p0 ? lj0 : lj0 + 16u), ab1 = lds128(p1 ? lj1 : lj1 + 16u);
+    const f2 r = mul2(r2, s), s2 = mul2(s, s), s3 = mul2(s, s2), s6 = mul2(s3, s3);
+    const f2 one = bc(1.0f);
+    const f2 sg = make_float2(p0 ? 0.0f : 1.0f, p1 ? 0.0f : 1.0f);          // sigma = 1 - pi
+    // Coulomb
+    const f2 t = sub2(bc(F.rOff), r);
+    const f2 C = fma2(fma2(fma2(t, bc(F.n6), bc(F.n5)), t, bc(F.n4)), t, bc(F.n3));
+    const f2 t3C = mul2(mul2(t, t), mul2(t, C));
+    const f2 G = sel2(p0, p1, one, t3C);
+    const f2 u = sub2(bc(F.r2Off), r2);
+    const f2 Qs = mul2(mul2(u, u), fma2(u, bc(-F.k2), bc(F.k1)));
+    const f2 Q = sel2(p0, p1, one, Qs);
+    const f2 sh = fma2(sg, bc(-F.qShift1), bc(F.qShift1));               // plain: qShift1, switched: 0
+    eq = fma2(qij, fma2(s, G, sh), eq);
+    const f2 gq = mul2(mul2(qij, s3), Q);
+    // Lennard-Jones (the table entries of the two pairs sit in unrelated registers: their products are scalar)
+    const f2 la = fma2(sg, bc(-F.aF6), s6), lb = fma2(sg, bc(-F.bF3), s3);
+    const f2 X = make_float2(ab0.x * la.x, ab1.x * la.y), Y = make_float2(ab0.y * lb.x, ab1.y * lb.y);
+    el = fma2(X, la, el); el = fma2(neg2(Y), lb, el); el.x -= ab0.z; el.y -= ab1.z;
+    const f2 m = fma2(bc(2.0f), mul2(X, s6), neg2(mul2(Y, s3)));
+    g = fma2(mul2(bc(6.0f), s2), m, gq);
+}
+
+// per-warp staging of the work item's i-cluster, two atoms per entry; the landing zone of the asynchronous record copies (one slot per
+// lane: the two records of the lane's j atom of the NEXT tile, in flight during the current tile without holding registers); the
+// fp64 sums of the item (touched once per kFlushTiles tiles)
+struct __align__(16) IStage {
+    float4 xy[kCluster / 2];        // {x0, x1, y0, y1} cluster-local
+    float4 zq[kCluster / 2];        // {z0, z1, q0, q1} charges times the electrostatic conversion factor
+    int2   row[kCluster / 2];       // byte offsets of the atoms' LJ-table rows
+    int2   pad[kCluster / 2];
+    float4 recA[kTile], recB[kTile];
+    double sum[3][kTile];           // per lane: Coulomb energy, LJ energy, component (lane & 3) of the summed i gradients
+};
+
+// Slow path for tiles that contain a pair inside the damped core, r^2 < r2Damp (reference: PairwiseInteraction.h:72-119,
+// third branches, with s = s2 = 0).  The lane's j gradient and the energies get the CORRECTION (damped minus what abfs_pair2
+// produced) through c = {gxj, gyj, gzj, eq, el}; the i side goes straight to the sorted gradient (and, for images, into the G
+// sums of the image) in fp64 -- this path is practically never taken.
+__device__ __noinline__ void damped_tile_fix(const AbfsF32 &F, unsigned int mask, const IStage *ist, const unsigned char *ljBase, int ljoff, float xj, float yj, float zj,
+                                            float qj, double *gradI, double sc, double *accImage, float *c)
+{
+    float fxj = 0.f, fyj = 0.f, fzj = 0.f, eq = 0.f, el = 0.f;
+    const float *xy = reinterpret_cast<const float *>(ist->xy), *zq = reinterpret_cast<const float *>(ist->zq);
+    const int *row = reinterpret_cast<const int *>(ist->row);
+    for (int i = 0; i < kCluster; i++) {
+        const int p = i >> 1, h = i & 1;
+        const float dx = xy[4 * p + h] - xj, dy = xy[4 * p + 2 + h] - yj, dz = zq[4 * p + h] - zj;
         const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-        if (((mask >> k) & 1u) && (r2 < F.r2Damp)) {
-            const float qij = qi * p.w;
-            const PairOut o = abfs_pair(F, r2, qij, ab.x, ab.y, ab.z);
+        if (((mask >> i) & 1u) && (r2 < F.r2Damp)) {
+            const float4 ab = *reinterpret_cast<const float4 *>(ljBase + row[i] + ljoff);      // the plain-region half of the entry
+            const float qij = zq[4 * p + 2 + h] * qj;
+            const PairOut o = abfs_pair(F, F.r2Damp, qij, ab.x, ab.y, ab.z);      // what the main path evaluated: the pair at the boundary of the core
             const float e1 = qij * fmaf(-F.qAlpha, r2, F.qF0);
             const float e2 = ab.x * fmaf(-F.aAlpha, r2, F.aF0) - ab.y * fmaf(-F.bAlpha, r2, F.bF0);
             const float g = -2.0f * (-qij * F.qAlpha - ab.x * F.aAlpha + ab.y * F.bAlpha) - o.g;
             eq += e1 - o.e1; el += e2 - o.e2;
             const float gx = g * dx, gy = g * dy, gz = g * dz;
-            fxi -= gx; fyi -= gy; fzi -= gz;
             fxj += gx; fyj += gy; fzj += gz;
+            if (gradI != nullptr) {
+                atomicAdd(gradI + 3 * i, -sc * (double) gx); atomicAdd(gradI + 3 * i + 1, -sc * (double) gy); atomicAdd(gradI + 3 * i + 2, -sc * (double) gz);
+            }
+            if (accImage != nullptr) {          // G = sum of the image atoms' gradients = minus the i-side sum
+                atomicAdd(accImage + 2, sc * (double) gx); atomicAdd(accImage + 3, sc * (double) gy); atomicAdd(accImage + 4, sc * (double) gz);
+            }
         }
-        fxj = __shfl_sync(0xffffffffu, fxj, src); fyj = __shfl_sync(0xffffffffu, fyj, src); fzj = __shfl_sync(0xffffffffu, fzj, src);
     }
-    c[0] = fxi; c[1] = fyi; c[2] = fzi; c[3] = fxj; c[4] = fyj; c[5] = fzj; c[6] = eq; c[7] = el;
+    c[0] = fxj; c[1] = fyj; c[2] = fzj; c[3] = eq; c[4] = el;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -166,58 +243,117 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-constexpr int kGroups = kTile / kCluster;            // slot groups of a tile = lanes per cluster atom
-constexpr int kFlushTiles = 4;                       // fp32 accumulators are flushed to fp64 every 4 tiles = 32 terms
+// ------------------------------------------------------------------------------------------------------
+// bulk asynchronous copy (TMA engine, UBLKCP in SASS) of a work item's descriptor stream into shared memory: the tiles of an item
+// are contiguous in the pool (<= chunkTiles x 128 B), so ONE lane issues ONE cp.async.bulk per item, one item ahead, and the
+// completion is signalled through an mbarrier (complete_tx); the lanes then read their descriptor words with LDS.  With plain
+// LDG prefetches ptxas put the descriptor and the record loads on one scoreboard and the record gather of every tile waited for
+// the descriptor load issued just before it (26 % of all stall samples, profiles/README.md).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int smem_addr(const void *p) { return (unsigned int) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned int mbar, unsigned int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned int mbar, unsigned int bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_copy_g2s(unsigned int dst, const void *src, unsigned int bytes, unsigned int mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void cp_async16(unsigned int dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned int mbar, unsigned int parity)
+{
+    asm volatile("{\n.reg .pred p;\nNBB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra NBB_DONE;\nbra NBB_WAIT;\nNBB_DONE:\n}" :: "r"(mbar), "r"(parity) : "memory");
+}
 
-// per-warp staging of one j tile: per group of 8 slots the entries are duplicated (16) so that slot (m + k) needs no wrap-around
-struct __align__(16) JStage {
-    float4 posq[kGroups][2 * kCluster];      // x, y, z (cluster-local), charge
-    int    ljoff[kGroups][2 * kCluster];     // byte offset of the LJ-table row of the j type
-};
+constexpr int kLJEntryBytes = 2 * (int) sizeof(float4);     // plain-region and switched-region coefficients of a type pair
+constexpr int kFlushTiles = 8;                       // the fp32 i-gradient / energy accumulators are flushed to fp64 every 8 tiles
 
-// per-warp shared scratch: staged j tile + fp64 accumulators of the work item (kept out of registers)
-struct __align__(16) WarpScratch {
-    JStage j;
-    double acc[5][kTile];        // i-gradient x, y, z and the two energies of the item, one column per lane
-};
+// sum over the warp of 24 values per lane (8 cluster atoms x 3 components, v[3 a + c]), scattered: afterwards v[0..2] of every lane
+// hold the complete x, y, z sums of atom (lane >> 2) & 7 (the four lanes of a quad hold the same numbers)
+__device__ __forceinline__ void reduce_scatter_24(float (&v)[24], int lane)
+{
+    const bool up1 = (lane & 16) != 0;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        const float keep = up1 ? v[k + 12] : v[k], send = up1 ? v[k] : v[k + 12];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    const bool up2 = (lane & 8) != 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const float keep = up2 ? v[k + 6] : v[k], send = up2 ? v[k] : v[k + 6];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const bool up3 = (lane & 4) != 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float keep = up3 ? v[k + 3] : v[k], send = up3 ? v[k] : v[k + 3];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { v[k] += __shfl_xor_sync(0xffffffffu, v[k], 2); v[k] += __shfl_xor_sync(0xffffffffu, v[k], 1); }
+}
 
 // kForm: 0 = analytic ABFS formulas, 1 = spline tables staged in shared memory, 2 = spline tables read from global memory (L1)
 template <bool kRot, int kThreads, int kMinBlocks, int kForm>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const __grid_constant__ ForceArgs A)
 {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    WarpScratch *ws = reinterpret_cast<WarpScratch *>(smemRaw) + (threadIdx.x >> 5);
-    JStage *stage = &ws->j;
-    float4 *sLJ = reinterpret_cast<float4 *>(smemRaw + sizeof(WarpScratch) * (kThreads / 32));  // [ntypes*ntypes] (A, B, A aShift12 - B bShift6, 0)
-    for (int i = threadIdx.x; i < A.ntypes * A.ntypes; i += blockDim.x) {
-        const float2 ab = A.ljAB[i];
-        sLJ[i] = make_float4(ab.x, ab.y, ab.x * A.F.aShift12 - ab.y * A.F.bShift6, 0.f);
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    // per warp: two descriptor buffers of chunkTiles tiles (128 B each), the staged i-cluster, two mbarriers; then the tables of the CTA
+    const size_t warpBytes = 2 * (size_t) A.chunkTiles * kTile * sizeof(unsigned int) + sizeof(IStage) + 32;
+    unsigned char *warpBase = smemRaw + warpBytes * (threadIdx.x >> 5);
+    const unsigned int *sDesc = reinterpret_cast<const unsigned int *>(warpBase);
+    IStage *ist = reinterpret_cast<IStage *>(warpBase + 2 * (size_t) A.chunkTiles * kTile * sizeof(unsigned int));
+    const unsigned int mbar0 = smem_addr(reinterpret_cast<unsigned char *>(ist) + sizeof(IStage));
+    // LJ table with one extra, all-zero row and column (index ntypes): empty j slots and the padding rows of the last cluster carry that
+    // type and a zero charge, so that their pairs contribute exactly nothing wherever their coordinates lie.  An entry is two float4:
+    // {A, B, A aShift12 - B bShift6, 0} for the plain region, {A aK12, B bK6, 0, 0} for the switched region (see abfs_pair2)
+    const int nt1 = A.ntypes + 1;
+    float4 *sLJ = reinterpret_cast<float4 *>(smemRaw + warpBytes * (kThreads / 32));  // [nt1 * nt1][2]
+    for (int i = threadIdx.x; i < nt1 * nt1; i += blockDim.x) {
+        const int ti = i / nt1, tj = i - ti * nt1;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f), e2 = e;
+        if (ti < A.ntypes && tj < A.ntypes) {
+            const float2 ab = A.ljAB[ti * A.ntypes + tj];
+            e = make_float4(ab.x, ab.y, ab.x * A.F.aShift12 - ab.y * A.F.bShift6, 0.f);
+            e2 = make_float4(ab.x * A.F.aK12, ab.y * A.F.bK6, 0.f, 0.f);
+        }
+        sLJ[2 * i] = e; sLJ[2 * i + 1] = e2;
     }
     const float4 *splTab = A.splTab;
     if (kForm == 1) {
-        float4 *sTab = sLJ + A.ntypes * A.ntypes;
+        float4 *sTab = sLJ + 2 * nt1 * nt1;
         for (int i = threadIdx.x; i < 3 * A.splN; i += blockDim.x) sTab[i] = A.splTab[i];
         splTab = sTab;
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31, m = lane & (kCluster - 1), g = lane >> 3;
+    const int lane = threadIdx.x & 31;
     const AbfsF32 &F = A.F;
-    const int src = (lane & 24) | ((lane + 1) & 7);
     const unsigned char *ljBase = reinterpret_cast<const unsigned char *>(sLJ);
-    const float4 *myPosq = stage->posq[g] + m;
-    const int *myLj = stage->ljoff[g] + m;
+    const unsigned int ljBaseS = smem_addr(sLJ);
+    const int comp = lane & 3, atomOfLane = (lane >> 2) & (kCluster - 1);     // after a reduce-scatter: this lane adds component `comp` of that atom
 
-    // work items are claimed one ahead: the cursor atomic and the item record of the NEXT item are in flight during this one
+    if ((threadIdx.x & 31) == 0) { mbar_init(mbar0, 1); mbar_init(mbar0 + 8, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+
+    // work items are claimed one ahead: the cursor atomic, the item record and the descriptor stream of the NEXT item are in flight during this one
     unsigned int itNext = 0;
     if (lane == 0) itNext = atomicAdd(A.workCursor, 1u);
     itNext = __shfl_sync(0xffffffffu, itNext, 0);
     WorkItem wiNext = A.items[min(itNext, (unsigned int) (A.nitems - 1))];
-    for (;;) {
+    unsigned int seq = 0;                                   // items processed by this warp: buffer = seq & 1, mbarrier parity = (seq >> 1) & 1
+    if (lane == 0 && itNext < (unsigned int) A.nitems) {
+        const unsigned int bytes = (unsigned int) wiNext.tileCount * kTile * sizeof(unsigned int);
+        mbar_expect_tx(mbar0, bytes);
+        bulk_copy_g2s(smem_addr(sDesc), A.tileDesc + (size_t) wiNext.tileStart * kTile, bytes, mbar0);
+    }
+    for (;; seq++) {
         if (itNext >= (unsigned int) A.nitems) break;
         const WorkItem wi = wiNext;
         if (lane == 0) itNext = atomicAdd(A.workCursor, 1u);
         itNext = __shfl_sync(0xffffffffu, itNext, 0);
         wiNext = A.items[min(itNext, (unsigned int) (A.nitems - 1))];
+        const unsigned int *myDesc = sDesc + (size_t) (seq & 1u) * A.chunkTiles * kTile + lane;
         const ImageOpDev *op = A.ops + wi.image;
         const bool isImage = wi.image > 0;
         const bool pureT = kRot ? (op->pureTranslation != 0) : true;
@@ -226,98 +362,116 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
         // cluster-local frame: K of the first cluster atom (a multiple of 8 A, exact in fp32)
         const int s0 = wi.block * kCluster;
         const float4 kref = A.recB[s0];
-        // i atom of this lane (the four groups hold the same 8 atoms)
-        const int si = s0 + m;
-        const bool ivalid = si < A.n;
-        float xi = 0.f, yi = 0.f, zi = 0.f, qi = 0.f;
-        const unsigned char *ljRow = ljBase;
-        if (ivalid) {
+        __syncwarp();                                       // the previous item's last tile has been consumed
+        if (lane < kCluster) {
+            // padding rows of the last cluster read the null record (index n): far away, zero charge, null LJ type
+            const int si = min(s0 + lane, A.n);
             const float4 ra = A.recA[si], rb = A.recB[si];
-            xi = (rb.x - kref.x) + ra.x; yi = (rb.y - kref.y) + ra.y; zi = (rb.z - kref.z) + ra.z;
-            qi = ra.w * A.qScale;
-            ljRow = ljBase + (size_t) __float_as_int(rb.w) * A.ntypes * sizeof(float4);
+            // the small part tl of a pure translation (|tl| <= 4 A) is taken off the i atoms instead of being added to every j atom
+            float tlx = 0.f, tly = 0.f, tlz = 0.f;
+            if (isImage && pureT) { tlx = op->tl[0]; tly = op->tl[1]; tlz = op->tl[2]; }
+            const float xi = (rb.x - kref.x) + (ra.x - tlx), yi = (rb.y - kref.y) + (ra.y - tly), zi = (rb.z - kref.z) + (ra.z - tlz);
+            float *xy = reinterpret_cast<float *>(ist->xy), *zq = reinterpret_cast<float *>(ist->zq);
+            const int p = lane >> 1, h = lane & 1;
+            xy[4 * p + h] = xi; xy[4 * p + 2 + h] = yi; zq[4 * p + h] = zi; zq[4 * p + 2 + h] = ra.w * A.qScale;
+            reinterpret_cast<int *>(ist->row)[lane] = __float_as_int(rb.w) * nt1 * kLJEntryBytes;
         }
-        // j offsets: X'_local = (K_j + ok) + (xl_j + ol), ok exact
-        float okx = -kref.x, oky = -kref.y, okz = -kref.z, olx = 0.f, oly = 0.f, olz = 0.f;
-        if (isImage && pureT) { okx += op->kt[0]; oky += op->kt[1]; okz += op->kt[2]; olx = op->tl[0]; oly = op->tl[1]; olz = op->tl[2]; }
-#pragma unroll
-        for (int c = 0; c < 5; c++) ws->acc[c][lane] = 0.0;
+        __syncwarp();
+        // j offsets: X'_local = (K_j + ok) + xl_j, ok exact (kt: the part of a pure translation that is a multiple of 8 A)
+        float okx = -kref.x, oky = -kref.y, okz = -kref.z;
+        if (isImage && pureT) { okx += op->kt[0]; oky += op->kt[1]; okz += op->kt[2]; }
         double W[9];
         if (kRot) {
 #pragma unroll
             for (int k = 0; k < 9; k++) W[k] = 0.0;
         }
+        double *gradI = (A.gradSorted != nullptr) ? A.gradSorted + 3 * (size_t) s0 : nullptr;
+        const bool flushLane = comp < 3 && s0 + atomOfLane < A.n;
 
-        // software pipeline over the tiles: the descriptor of tile t+2 and the records of tile t+1 are in flight during tile t
-        size_t T = (size_t) wi.tileStart * kTile + lane;
-        unsigned int dCur = A.tileDesc[T];
-        unsigned int dNext = (wi.tileCount > 1) ? A.tileDesc[T + kTile] : kEmptySlot;
-        float4 ja = make_float4(0.f, 0.f, 0.f, 0.f), jb = ja;
-        if ((dCur & kEmptySlot) != kEmptySlot) { ja = A.recA[dCur & kEmptySlot]; jb = A.recB[dCur & kEmptySlot]; }
-        float fxi = 0.f, fyi = 0.f, fzi = 0.f, eq = 0.f, el = 0.f;
+        // the item's descriptors have landed in shared memory (bulk copy issued one item ago) ...
+        mbar_wait(mbar0 + 8 * (seq & 1u), (seq >> 1) & 1u);
+        if (lane == 0 && itNext < (unsigned int) A.nitems) {
+            // ... and the next item's stream goes to the other buffer: its last reader (the item before this one) finished before the
+            // __syncwarp at the top of this item
+            const unsigned int nb = (seq + 1u) & 1u, bytes = (unsigned int) wiNext.tileCount * kTile * sizeof(unsigned int);
+            mbar_expect_tx(mbar0 + 8 * nb, bytes);
+            bulk_copy_g2s(smem_addr(sDesc + (size_t) nb * A.chunkTiles * kTile), A.tileDesc + (size_t) wiNext.tileStart * kTile, bytes, mbar0 + 8 * nb);
+        }
+        // the j atom of the lane for the current tile, in cluster-local coordinates; empty slots point at the null record (index n): far
+        // away, zero charge, null LJ type -- their pairs contribute exactly nothing
+        float xj, yj, zj, qj;
+        unsigned int ljS, sj, mask;
+        double xj64 = 0.0, yj64 = 0.0, zj64 = 0.0;          // primary coordinates of j (rotations only)
+        unsigned int dN = 0u;
+        const unsigned int myRecA = smem_addr(&ist->recA[lane]), myRecB = smem_addr(&ist->recB[lane]);
+        auto fetch_j = [&](int t) {                          // records of tile t (beyond the item: the null record): asynchronous copies, no registers in flight
+            dN = (t < wi.tileCount) ? myDesc[t * kTile] : kEmptySlot;
+            const unsigned int s = min(dN & kEmptySlot, (unsigned int) A.n);
+            cp_async16(myRecA, A.recA + s); cp_async16(myRecB, A.recB + s);
+        };
+        auto unpack_j = [&]() {
+            cp_async_wait_all();
+            const float4 ra = lds128(myRecA), rb = lds128(myRecB);
+            sj = min(dN & kEmptySlot, (unsigned int) A.n);
+            mask = dN >> 24;                                 // empty slots carry a zero byte
+            if (kRot && isImage && !pureT) {
+                const double X = (double) rb.x + (double) ra.x, Y = (double) rb.y + (double) ra.y, Z = (double) rb.z + (double) ra.z;
+                xj64 = X + A.origin[0]; yj64 = Y + A.origin[1]; zj64 = Z + A.origin[2];
+                const double px = op->R[0] * X + op->R[1] * Y + op->R[2] * Z + op->cr[0];
+                const double py = op->R[3] * X + op->R[4] * Y + op->R[5] * Z + op->cr[1];
+                const double pz = op->R[6] * X + op->R[7] * Y + op->R[8] * Z + op->cr[2];
+                xj = (float) (px - (double) kref.x); yj = (float) (py - (double) kref.y); zj = (float) (pz - (double) kref.z);
+            } else { xj = (rb.x + okx) + ra.x; yj = (rb.y + oky) + ra.y; zj = (rb.z + okz) + ra.z; }
+            qj = ra.w;
+            ljS = ljBaseS + (unsigned int) (__float_as_int(rb.w) * kLJEntryBytes);
+        };
+        fetch_j(0);
+        unpack_j();
+        fetch_j(1);
+        f2 fi[kCluster / 2][3];                             // gradient on the cluster atoms, pair p = atoms (2p, 2p+1)
+#pragma unroll
+        for (int p = 0; p < kCluster / 2; p++) { fi[p][0] = bc(0.f); fi[p][1] = bc(0.f); fi[p][2] = bc(0.f); }
+        f2 eq = bc(0.f), el = bc(0.f);
+        ist->sum[0][lane] = 0.0; ist->sum[1][lane] = 0.0; ist->sum[2][lane] = 0.0;      // per lane: energies of the item, component `comp` of the summed i gradients
         for (int t = 0; t < wi.tileCount; t++) {
-            const unsigned int d = dCur;
-            const float4 a = ja, b = jb;
-            dCur = dNext;
-            if ((dCur & kEmptySlot) != kEmptySlot) { ja = A.recA[dCur & kEmptySlot]; jb = A.recB[dCur & kEmptySlot]; }
-            dNext = (t + 2 < wi.tileCount) ? A.tileDesc[T + 2 * kTile] : kEmptySlot;
-            T += kTile;
-            const unsigned int sj = d & kEmptySlot, mask = d >> 24;
-            const bool has = sj != kEmptySlot;
-            float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
-            int lj = 0;
-            double xj64 = 0.0, yj64 = 0.0, zj64 = 0.0;          // primary coordinates of j (rotations only)
-            if (has) {
-                if (kRot && isImage && !pureT) {
-                    const double X = (double) b.x + (double) a.x, Y = (double) b.y + (double) a.y, Z = (double) b.z + (double) a.z;
-                    xj64 = X + A.origin[0]; yj64 = Y + A.origin[1]; zj64 = Z + A.origin[2];
-                    const double px = op->R[0] * X + op->R[1] * Y + op->R[2] * Z + op->cr[0];
-                    const double py = op->R[3] * X + op->R[4] * Y + op->R[5] * Z + op->cr[1];
-                    const double pz = op->R[6] * X + op->R[7] * Y + op->R[8] * Z + op->cr[2];
-                    pj = make_float4((float) (px - (double) kref.x), (float) (py - (double) kref.y), (float) (pz - (double) kref.z), a.w);
-                } else pj = make_float4((b.x + okx) + (a.x + olx), (b.y + oky) + (a.y + oly), (b.z + okz) + (a.z + olz), a.w);
-                lj = __float_as_int(b.w) * (int) sizeof(float4);
-            }
-            __syncwarp();                                   // previous tile fully consumed
-            stage->posq[g][m] = pj; stage->posq[g][m + kCluster] = pj;
-            stage->ljoff[g][m] = lj; stage->ljoff[g][m + kCluster] = lj;
-            __syncwarp();
-
-            float fxj = 0.f, fyj = 0.f, fzj = 0.f;
+            f2 fj[3] = {bc(0.f), bc(0.f), bc(0.f)};
             float r2min = F.r2Off;
 #pragma unroll
-            for (int k = 0; k < kCluster; k++) {
-                const float4 p = myPosq[k];                 // j slot 8 g + (m + k) % 8
-                const float4 ab = *reinterpret_cast<const float4 *>(ljRow + myLj[k]);
-                const float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
-                const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                // masked pairs are evaluated AT the outer cutoff, where energy and force vanish (to ~1e-16 kJ/mol): pairs that are not
-                // on the list get r2 = NaN (all bits set by the sign-extended mask bit), and fminf(NaN, r2Off) = r2Off takes care of
-                // them together with the pairs beyond the cutoff; r2m doubles as the damped-core detector
-                PairOut o;
+            for (int p = 0; p < kCluster / 2; p++) {
+                const float4 XY = ist->xy[p], ZQ = ist->zq[p];
+                const int2 rows = ist->row[p];
+                const f2 dx = sub2(make_float2(XY.x, XY.y), bc(xj)), dy = sub2(make_float2(XY.z, XY.w), bc(yj)), dz = sub2(make_float2(ZQ.x, ZQ.y), bc(zj));
+                f2 r2 = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
+                const f2 qij = mul2(make_float2(ZQ.z, ZQ.w), bc(qj));
+                const bool on0 = (mask >> (2 * p)) & 1u, on1 = (mask >> (2 * p + 1)) & 1u;
+                f2 g;
                 if (kForm == 0) {
-                    const int off = ~(((int) (mask << (31 - k))) >> 31);               // 0 if bit k is set, else 0xffffffff
-                    const float r2m = fminf(__int_as_float(__float_as_int(r2) | off), F.r2Off);
-                    r2min = fminf(r2min, r2m);
-                    o = abfs_pair(F, r2m, qi * p.w, ab.x, ab.y, ab.z);
+                    // pairs that are not on the list or beyond the outer cutoff are evaluated AT the outer cutoff, where energy and force vanish;
+                    // pairs inside the damped core are evaluated at its boundary and corrected by the slow path below
+                    r2.x = fminf(on0 ? r2.x : F.r2Off, F.r2Off); r2.y = fminf(on1 ? r2.y : F.r2Off, F.r2Off);
+                    r2min = fminf(r2min, fminf(r2.x, r2.y));
+                    r2.x = fmaxf(r2.x, F.r2Damp); r2.y = fmaxf(r2.y, F.r2Damp);
+                    abfs_pair2(F, r2, qij, ljS + (unsigned int) rows.x, ljS + (unsigned int) rows.y, eq, el, g);
                 } else {
                     // pairs off the list or beyond the cutoff read the all-zero table row (the skip of PairwiseInteraction.c:489)
-                    o = spline_pair(splTab, A.splN, A.splInvDR, A.splDR, ((mask >> k) & 1u) && !(r2 > F.r2Off), r2, qi * p.w, ab.x, ab.y);
+                    const float4 ab0 = lds128(ljS + (unsigned int) rows.x), ab1 = lds128(ljS + (unsigned int) rows.y);
+                    const PairOut o0 = spline_pair(splTab, A.splN, A.splInvDR, A.splDR, on0 && !(r2.x > F.r2Off), r2.x, qij.x, ab0.x, ab0.y);
+                    const PairOut o1 = spline_pair(splTab, A.splN, A.splInvDR, A.splDR, on1 && !(r2.y > F.r2Off), r2.y, qij.y, ab1.x, ab1.y);
+                    eq = add2(eq, make_float2(o0.e1, o1.e1)); el = add2(el, make_float2(o0.e2, o1.e2));
+                    g = make_float2(o0.g, o1.g);
                 }
-                eq += o.e1; el += o.e2;
-                fxi = fmaf(-o.g, dx, fxi); fyi = fmaf(-o.g, dy, fyi); fzi = fmaf(-o.g, dz, fzi);      // gradient = -(force on i) = -g d
-                fxj = fmaf(o.g, dx, fxj); fyj = fmaf(o.g, dy, fyj); fzj = fmaf(o.g, dz, fzj);
-                // hand the j-gradient accumulator to the lane that evaluates this j slot next
-                fxj = __shfl_sync(0xffffffffu, fxj, src); fyj = __shfl_sync(0xffffffffu, fyj, src); fzj = __shfl_sync(0xffffffffu, fzj, src);
+                const f2 ng = neg2(g);
+                fi[p][0] = fma2(ng, dx, fi[p][0]); fi[p][1] = fma2(ng, dy, fi[p][1]); fi[p][2] = fma2(ng, dz, fi[p][2]);      // gradient = -(force on i) = -g d
+                fj[0] = fma2(g, dx, fj[0]); fj[1] = fma2(g, dy, fj[1]); fj[2] = fma2(g, dz, fj[2]);
             }
+            float fxj = fj[0].x + fj[0].y, fyj = fj[1].x + fj[1].y, fzj = fj[2].x + fj[2].y;
             if (kForm == 0 && __any_sync(0xffffffffu, r2min < F.r2Damp)) {   // damped core: practically never; patch the tile with the reference formulas
-                float c[8];
-                damped_tile_fix(F, mask, myPosq, ljRow, myLj, xi, yi, zi, qi, src, c);
-                fxi += c[0]; fyi += c[1]; fzi += c[2]; fxj += c[3]; fyj += c[4]; fzj += c[5];
-                eq += c[6]; el += c[7];
+                float c[5];
+                damped_tile_fix(F, mask, ist, ljBase, (int) (ljS - ljBaseS), xj, yj, zj, qj, gradI, sc, isImage ? A.accum + 16 * wi.image : nullptr, c);
+                fxj += c[0]; fyj += c[1]; fzj += c[2];
+                eq.x += c[3]; el.x += c[4];
             }
-            // after 8 hand-overs inside the group the accumulator of j slot `lane` is back in this lane
-            if (has) {
+            if (sj < (unsigned int) A.n) {
                 double gx = sc * (double) fxj, gy = sc * (double) fyj, gz = sc * (double) fzj;       // gradient on the (image) atom
                 if (kRot && isImage && !pureT) {
                     W[0] += gx * xj64; W[1] += gx * yj64; W[2] += gx * zj64;
@@ -328,30 +482,43 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
                     const double rz = op->R[2] * gx + op->R[5] * gy + op->R[8] * gz;
                     gx = rx; gy = ry; gz = rz;
                 }
-                if (A.gradSorted != nullptr) {
+                if (A.gradSorted != nullptr && A.exp != 1) {
+                    if (A.exp == 2) { double *gp = A.gradSorted + sj; atomicAdd(gp, gx); atomicAdd(gp + A.n, gy); atomicAdd(gp + 2 * (size_t) A.n, gz); }
+                    else if (A.exp == 3) { float *gp = reinterpret_cast<float *>(A.gradSorted) + 4 * (size_t) sj; asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(gp), "f"((float) gx), "f"((float) gy), "f"((float) gz), "f"(0.f) : "memory"); }
+                    else {
                     double *gp = A.gradSorted + 3 * (size_t) sj;
                     atomicAdd(gp, gx); atomicAdd(gp + 1, gy); atomicAdd(gp + 2, gz);
+                    }
                 }
             }
+            // the next tile's j atom from the records that have been in flight during this tile, then the records of the tile after it
+            unpack_j();
+            fetch_j(t + 2);
             if (((t + 1) % kFlushTiles) == 0 || t + 1 == wi.tileCount) {
-                ws->acc[0][lane] += (double) fxi; ws->acc[1][lane] += (double) fyi; ws->acc[2][lane] += (double) fzi;
-                ws->acc[3][lane] += (double) eq;  ws->acc[4][lane] += (double) el;
-                fxi = 0.f; fyi = 0.f; fzi = 0.f; eq = 0.f; el = 0.f;
+                ist->sum[0][lane] += (double) (eq.x + eq.y); ist->sum[1][lane] += (double) (el.x + el.y);
+                eq = bc(0.f); el = bc(0.f);
+                float v[3 * kCluster];
+#pragma unroll
+                for (int p = 0; p < kCluster / 2; p++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { v[6 * p + c] = fi[p][c].x; v[6 * p + 3 + c] = fi[p][c].y; fi[p][c] = bc(0.f); }
+                reduce_scatter_24(v, lane);
+                const double mine = sc * (double) (comp == 0 ? v[0] : (comp == 1 ? v[1] : v[2]));
+                if (flushLane) {
+                    ist->sum[2][lane] += mine;
+                    if (gradI != nullptr) atomicAdd(gradI + 3 * atomOfLane + comp, mine);
+                }
             }
         }
-        // every lane holds the partial i gradient of its group's slots
-        const double fix = ws->acc[0][lane], fiy = ws->acc[1][lane], fiz = ws->acc[2][lane];
-        if (ivalid && A.gradSorted != nullptr) {
-            double *gp = A.gradSorted + 3 * (size_t) si;
-            atomicAdd(gp, sc * fix); atomicAdd(gp + 1, sc * fiy); atomicAdd(gp + 2, sc * fiz);
-        }
         double *acc = A.accum + 16 * wi.image;
-        const double eQ = warp_sum(ws->acc[3][lane]) * sc, eL = warp_sum(ws->acc[4][lane]) * sc;
+        const double eQ = warp_sum(ist->sum[0][lane]) * sc, eL = warp_sum(ist->sum[1][lane]) * sc;
         if (lane == 0) { atomicAdd(&acc[0], eQ); atomicAdd(&acc[1], eL); }
         if (isImage) {
-            // sum over the image atoms of their gradient = minus the sum of the i-side gradients of this item (Newton's third law)
-            const double G0 = -warp_sum(fix) * sc, G1 = -warp_sum(fiy) * sc, G2 = -warp_sum(fiz) * sc;
-            if (lane == 0) { atomicAdd(&acc[2], G0); atomicAdd(&acc[3], G1); atomicAdd(&acc[4], G2); }
+            // sum over the image atoms of their gradient = minus the sum of the i-side gradients of this item (Newton's third law);
+            // lanes with the same `comp` hold the partial sums of that component
+            double gsum = ist->sum[2][lane];
+            for (int off = 4; off < 32; off <<= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, off);
+            if (lane < 3) atomicAdd(&acc[2 + lane], -gsum);
             if (kRot && !pureT) {
 #pragma unroll
                 for (int k = 0; k < 9; k++) { const double w = warp_sum(W[k]); if (lane == 0) atomicAdd(&acc[5 + k], w); }
@@ -363,12 +530,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
 // ------------------------------------------------------------------------------------------------------
 // per energy call: atom records in sorted order from the current coordinates, and the way back for the gradients
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_pack_records(const double *__restrict__ x, const int *__restrict__ sAtom, int n, const float *__restrict__ q32, const int *__restrict__ ljtype,
+__global__ void k_pack_records(const double *__restrict__ x, const int *__restrict__ sAtom, int n, int ntypes, const float *__restrict__ q32, const int *__restrict__ ljtype,
                                double ox, double oy, double oz, float4 *__restrict__ recA, float4 *__restrict__ recB, double *__restrict__ zero = nullptr, int zeroCount = 0)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     // fused mode (nbb200_md_run): the accumulators + work cursor of the force kernels are cleared here instead of by a memset of their own
     if (zero != nullptr) for (int i = s; i < zeroCount; i += gridDim.x * blockDim.x) zero[i] = 0.0;
+    if (s == n) {       // the null record: what empty tile slots and the padding rows of the last cluster read (far away, no charge, null LJ type)
+        recA[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+        recB[n] = make_float4(-1.0e15f, -1.0e15f, -1.0e15f, __int_as_float(ntypes));
+    }
     if (s >= n) return;
     const int a = sAtom[s];
     const double X = x[3 * a] - ox, Y = x[3 * a + 1] - oy, Z = x[3 * a + 2] - oz;
@@ -473,9 +644,9 @@ typedef void (*ForceKernel)(ForceArgs);
 struct ForceVariant { const char *name; ForceKernel fn; int threads; };
 // launch shapes (threads per CTA x resident CTAs per SM -> register budget); NBB200_FORCE_SHAPE selects one for experiments
 static const ForceVariant kForceVariants[] = {
-    {"128x5", k_cluster_forces<false, 128, 5, 0>, 128},      // default: 96 registers, 20 warps per SM (measured best on B200)
-    {"256x3", k_cluster_forces<false, 256, 3, 0>, 256}, {"256x2", k_cluster_forces<false, 256, 2, 0>, 256},
-    {"128x4", k_cluster_forces<false, 128, 4, 0>, 128}, {"128x6", k_cluster_forces<false, 128, 6, 0>, 128},
+    {"128x4", k_cluster_forces<false, 128, 4, 0>, 128},      // default: 128 registers (no spills), 16 warps per SM
+    {"128x5", k_cluster_forces<false, 128, 5, 0>, 128}, {"256x2", k_cluster_forces<false, 256, 2, 0>, 256},
+    {"128x3", k_cluster_forces<false, 128, 3, 0>, 128}, {"64x8", k_cluster_forces<false, 64, 8, 0>, 64},
 };
 static const ForceVariant kForceRot = {"rot", k_cluster_forces<true, 256, 2, 0>, 256};
 // spline form: [rotations][tables in shared memory (1) / global memory (0)]
@@ -483,7 +654,7 @@ static const ForceVariant kForceSpline[2][2] = {
     {{"spline-global", k_cluster_forces<false, 256, 2, 2>, 256}, {"spline", k_cluster_forces<false, 256, 2, 1>, 256}},
     {{"spline-rot-global", k_cluster_forces<true, 256, 2, 2>, 256}, {"spline-rot", k_cluster_forces<true, 256, 2, 1>, 256}},
 };
-constexpr size_t kSplineSmemLimit = 96 * 1024;        // per CTA; two CTAs per SM stay resident
+constexpr size_t kSplineSmemLimit = 40 * 1024;        // per CTA, next to 67 KB of descriptor buffers: two CTAs per SM stay resident
 
 void init_force_kernel_attributes()
 {
@@ -565,19 +736,19 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
     unsigned int *workCursor = reinterpret_cast<unsigned int *>(s.accum.p + accumCount);
     const double eScale = (1.0 / s.dielectric) * kE2AngstromToKJMol;
     if (nitems > 0) {
-        if (!s.recA.ensure((size_t) s.n) || !s.recB.ensure((size_t) s.n)) return false;
-        const int pthreads = 256, pblocks = (s.n + pthreads - 1) / pthreads;
-        k_pack_records<<<pblocks, pthreads, 0, s.stream>>>(s.xcur, s.sAtom.p, s.n, s.q32.p, s.ljtype.p, s.grid.lo[0], s.grid.lo[1], s.grid.lo[2], s.recA.p, s.recB.p,
+        if (!s.recA.ensure((size_t) s.n + 1) || !s.recB.ensure((size_t) s.n + 1)) return false;
+        const int pthreads = 256, pblocks = (s.n + 1 + pthreads - 1) / pthreads;
+        k_pack_records<<<pblocks, pthreads, 0, s.stream>>>(s.xcur, s.sAtom.p, s.n, s.ntypes, s.q32.p, s.ljtype.p, s.grid.lo[0], s.grid.lo[1], s.grid.lo[2], s.recA.p, s.recB.p,
                                                             fusedZero ? s.accum.p : nullptr, (int) (accumCount + 1));
         ForceArgs A;
         A.items = s.items.p; A.nitems = nitems; A.workCursor = workCursor;
-        A.tileDesc = s.tileDesc.p; A.recA = s.recA.p; A.recB = s.recB.p; A.n = s.n;
+        A.tileDesc = s.tileDesc.p; A.chunkTiles = s.chunkTiles; { static const int e = []() { const char *v = std::getenv("NBB200_EXP"); return v ? std::atoi(v) : 0; }(); A.exp = e; } A.recA = s.recA.p; A.recB = s.recB.p; A.n = s.n;
         A.ljAB = s.ljAB.p; A.ntypes = s.ntypes;
         A.ops = s.imageOps.p;
         for (int d = 0; d < 3; d++) A.origin[d] = s.grid.lo[d];
         const double *f = s.factors;
         AbfsF32 &F = A.F;
-        F.r2Damp = (float) f[0]; F.r2On = (float) f[1]; F.r2Off = (float) f[2];
+        F.r2Damp = (float) std::min(f[0], f[1]); F.r2On = (float) f[1]; F.r2Off = (float) f[2];      // the switched region takes precedence (PairwiseInteraction.h:72-119)
         F.a = (float) f[3]; F.b = (float) f[4]; F.c = (float) f[5]; F.d = (float) f[6]; F.c3 = (float) (3.0 * f[5]); F.d5 = (float) (5.0 * f[6]);
         F.qShift1 = (float) f[7]; F.qShift2 = (float) f[8]; F.qF0 = (float) f[9]; F.qAlpha = (float) f[10];
         F.aF6 = (float) f[11]; F.aK12 = (float) f[12]; F.aShift12 = (float) f[13]; F.aF0 = (float) f[14]; F.aAlpha = (float) f[15];
@@ -616,7 +787,8 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
         const bool splSmem = spline && splBytes <= kSplineSmemLimit;
         const ForceVariant &v = spline ? kForceSpline[rot ? 1 : 0][splSmem ? 1 : 0] : (rot ? kForceRot : *chosen);
         const int warpsPerBlock = v.threads / 32;
-        const size_t smem = sizeof(WarpScratch) * warpsPerBlock + sizeof(float4) * (size_t) s.ntypes * s.ntypes + (splSmem ? splBytes : 0);
+        const size_t warpBytes = 2 * (size_t) s.chunkTiles * kTile * sizeof(unsigned int) + sizeof(IStage) + 32;
+        const size_t smem = warpBytes * warpsPerBlock + kLJEntryBytes * (size_t) (s.ntypes + 1) * (s.ntypes + 1) + (splSmem ? splBytes : 0);
         if (smem > 200 * 1024) { set_error("too many LJ types for the shared-memory table"); return false; }
         int perSM = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, v.fn, v.threads, smem);

@@ -476,23 +476,11 @@ struct __align__(16) BuildWarp {
     unsigned int activeMask, padw[3];            // block atoms that may appear on a list (kept in shared memory: the builder is register bound)
 };
 
-// write the first `count` (<= 32) entries of a cluster queue as one tile.  The queue holds COLUMN bytes (bit i = cluster atom i
-// pairs with this j); the force kernel wants, in lane (g, m) = (slot group, cluster atom), the ROW byte whose bit k is the pair
-// (atom m, slot 8 g + (m + k) % 8): an 8 x 8 transpose plus rotation inside each group of 8 lanes.
+// write the first `count` (<= 32) entries of a cluster queue as one tile: lane l of the force kernel owns j slot l, the high byte of
+// its descriptor word is the COLUMN byte (bit i = cluster atom i pairs with this j) exactly as the queue holds it
 __device__ __forceinline__ void emit_tile(const TileArgs &A, int lane, int cluster, int set, const unsigned int *queue, int count, SubStream *st)
 {
     const unsigned int word = (lane < count) ? queue[lane] : kEmptySlot;
-    const int m = lane & 7;
-    // 8 x 8 bit transpose inside each group of 8 lanes (three block-swap stages), then rotate right by m
-    unsigned int row = word >> 24;
-#pragma unroll
-    for (int stg = 0; stg < 3; stg++) {
-        const int sh = 4 >> stg;
-        const unsigned int msk = (stg == 0) ? 0x0fu : (stg == 1) ? 0x33u : 0x55u;
-        const unsigned int o = __shfl_xor_sync(0xffffffffu, row, sh);
-        row = (lane & sh) ? ((row & ~msk & 0xffu) | ((o & ~msk & 0xffu) >> sh)) : ((row & msk) | ((o & msk) << sh));
-    }
-    row = ((row >> m) | (row << (kCluster - m))) & 0xffu;           // bit k <-> slot (m + k) % 8 of the group
     int used = st->chunkUsed;
     unsigned int base = st->chunkBase;
     if (used == 0 && count > 0) {
@@ -501,7 +489,7 @@ __device__ __forceinline__ void emit_tile(const TileArgs &A, int lane, int clust
     }
     const bool fits = (unsigned long long) base + (unsigned int) A.chunkTiles <= (unsigned long long) A.tileCap;
     if (count > 0) {                                               // count == 0: only close the open chunk of the stream
-        if (fits) A.tileDesc[((size_t) base + used) * kTile + lane] = (word & kEmptySlot) | (row << 24);
+        if (fits) A.tileDesc[((size_t) base + used) * kTile + lane] = word;
         else if (lane == 0) atomicOr(&A.counters->overflow, 2u);
         used += 1;
     }
@@ -769,9 +757,9 @@ __global__ void k_expand_pairs(const WorkItem *__restrict__ items, int nitems, c
         const int ai = (si < n) ? sAtom[si] : -1;
         for (int t = 0; t < wi.tileCount; t++) {
             const unsigned int d = tileDesc[((size_t) wi.tileStart + t) * kTile + lane];
-            const unsigned int sj = d & kEmptySlot, row = d >> 24;       // bit k <-> j slot (lane & 24) | ((m + k) & 7)
+            const unsigned int sj = d & kEmptySlot, col = (sj == kEmptySlot) ? 0u : (d >> 24);     // bit i <-> cluster atom i
             const int aj = (sj == kEmptySlot) ? -1 : ((rawJ && wi.image > 0) ? (int) sj : sAtom[sj]);
-            const int cnt = __popc(row);
+            const int cnt = __popc(col);
             int inc = cnt;
             for (int off = 1; off < 32; off <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += u; }
             const int total = __shfl_sync(0xffffffffu, inc, 31);
@@ -781,8 +769,8 @@ __global__ void k_expand_pairs(const WorkItem *__restrict__ items, int nitems, c
             unsigned long long pos = base + (unsigned long long) (inc - cnt);
 #pragma unroll
             for (int k = 0; k < kCluster; k++) {
-                const int j = __shfl_sync(0xffffffffu, aj, (lane & 24) | ((m + k) & 7));
-                if ((row >> k) & 1u) { pairs[2 * pos] = ai; pairs[2 * pos + 1] = j; pos++; }
+                const int i = __shfl_sync(0xffffffffu, ai, k);               // lanes 0..7 hold the cluster atoms
+                if ((col >> k) & 1u) { pairs[2 * pos] = i; pairs[2 * pos + 1] = aj; pos++; }
             }
         }
     }

@@ -23,6 +23,10 @@ template <int MODE> __global__ void k(float *out, int iters, float seed)
             if (MODE == 9) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
             if (MODE == 10) asm volatile("add.s32 %0, %0, %1;" : "+r"(u[i]) : "r"(3));
             if (MODE == 11) asm volatile("{.reg .pred p; setp.lt.s32 p, %0, 0; selp.u32 %0, %0, %1, p;}" : "+r"(u[i]) : "r"(7u));
+            if (MODE == 13) { asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c)); if ((i & 3) == 3) asm volatile("{.reg .pred p; setp.ne.s32 p, %2, 0; selp.f32 %0, %0, %1, p;}" : "+f"(a[i]) : "f"(b), "r"(it & 1)); }
+            if (MODE == 14) { asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c)); if ((i & 1) == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[i]) : "r"(u[(i + 1) % CHAINS]), "r"(0x5555u)); }
+            if (MODE == 15) { asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c)); if ((i & 3) == 3) a[i] = __shfl_sync(0xffffffffu, a[i], (lane + 1) & 31); }
+            if (MODE == 16) { asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c)); if ((i & 1) == 1) asm volatile("{.reg .pred p; setp.ne.s32 p, %2, 0; selp.f32 %0, %0, %1, p;}" : "+f"(a[i]) : "f"(b), "r"(it & 1)); }
             if (MODE == 12) { double d = (double) a[i]; asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d) : "d"(1e-9)); a[i] = (float) d; }
         }
     }
@@ -45,5 +49,6 @@ int main()
 {
     run<0>("FFMA", 1); run<1>("FADD", 1); run<2>("FMUL", 1); run<3>("FMNMX", 1); run<4>("FSETP+FSEL", 2); run<5>("FSEL (+setp.ne)", 1);
     run<6>("LOP3", 1); run<7>("SHL", 1); run<8>("SHFL", 1); run<9>("MUFU.RSQ", 1); run<10>("IADD", 1); run<11>("ISETP+SEL", 2); run<12>("F2F+DADD+F2F", 3);
+    run<13>("4 FFMA : 1 FSEL", 1.25); run<14>("2 FFMA : 1 LOP3", 1.5); run<15>("4 FFMA : 1 SHFL", 1.25); run<16>("2 FFMA : 1 FSEL", 1.5);
     return 0;
 }
