@@ -286,9 +286,9 @@ def run_b200(args):
     # per-kernel device times of the last rebuild step (library events on the same stream)
     tm = m.state.Timings()
     # average the force-kernel time over a few more rebuild steps, live
-    fk, lb = [], []
+    fk, lb, pr = [], [], []
     for _ in range(max(3, min(args.steps, 10))):
-        step_rebuild(); t = m.state.Timings(); fk.append(t["tileForces"]); lb.append(t["listRebuild"])
+        step_rebuild(); t = m.state.Timings(); fk.append(t["tileForces"]); lb.append(t["listRebuild"]); pr.append(t.get("prune", 0.0))
     ms_nr = allmax(timed_steps(torch, step_norebuild, args.steps, args.warmup, barrier))
     clocks = sampler.stop() if sampler is not None else None
     force_ms, build_ms = allmax(statistics.mean(fk)), allmax(statistics.mean(lb))
@@ -314,7 +314,7 @@ def run_b200(args):
                    "parallelism": ("1 GPU" if world == 1 else "%d spatial slabs of the cell-sorted order; per step NCCL send/recv of all slab positions (list rebuild) "
                                    "or halo positions (no rebuild) and of halo gradient contributions to their owners, all-reduce of 15 scalars" % world)},
         "no_rebuild": {"ms_per_call": ms_nr, "value": pairs / (ms_nr * 1e-3), "unit": "list-pairs/s"},
-        "kernels_ms": {"list_rebuild": build_ms, "tile_forces": force_ms, "pairs14": tm["pairs14"], "displacement_check": tm["displacementCheck"]},
+        "kernels_ms": {"list_rebuild": build_ms, "tile_forces": force_ms, "prune": allmax(statistics.mean(pr)), "pairs14": tm["pairs14"], "displacement_check": tm["displacementCheck"]},
         "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
                      "traffic": ncu_traffic(args.workload, world), "kernel": "k_cluster_forces", "flop_per_list_pair": FLOP_PER_LIST_PAIR,
                      "peak_source": ("measured live: register-only FMA chains on all SMs (nbb200_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x %.0f MHz = %.2f TFLOP/s; "

@@ -36,7 +36,7 @@ static void destroy(State *s)
     if (s == nullptr) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    s->q32.release(); s->q64.release(); s->ljtype.release(); s->ljAB.release(); s->ljAB14.release();
+    s->q32.release(); s->q64.release(); s->ljtype.release(); s->ljAB.release(); s->ljAB14.release(); s->typeFree.release();
     s->exclPtr.release(); s->exclCol.release(); s->pairs14.release(); s->fixedFlag.release(); s->qcFlag.release();
     s->isoPtr.release(); s->isoIdx.release(); s->xc.release(); s->isoT.release();
     s->x.release(); s->xref.release(); s->grad.release();
@@ -44,7 +44,7 @@ static void destroy(State *s)
     s->eX.release(); s->eAtom.release(); s->eSet.release(); s->eKey.release(); s->eSortBuf.release();
     s->cellStart.release(); s->cellFill.release(); s->scanTmp.release(); s->order.release(); s->order2.release();
     s->sX.release(); s->sAtom.release(); s->invPerm.release(); s->blockBox.release();
-    s->tileDesc.release(); s->recA.release(); s->recB.release(); s->gradSorted.release(); s->items.release(); s->rangeTab.release(); s->rangeOut.release(); s->setPairs.release(); s->accum.release();
+    s->tileDesc.release(); s->tileDescIn.release(); s->itemsIn.release(); s->xprune.release(); s->pruneDisp.release(); s->recA.release(); s->recB.release(); s->gradSorted.release(); s->items.release(); s->rangeTab.release(); s->rangeOut.release(); s->setPairs.release(); s->accum.release();
     s->pairBuf.release(); s->pairCursor.release(); s->splF64.release(); s->splPoly.release(); s->mdScalars.release();
     for (int r = 0; r < State::kMaxPeers; r++) if (s->peerOpened[r]) { cudaIpcCloseMemHandle(s->peerGs[r]); cudaIpcCloseMemHandle(s->peerXs[r]); cudaIpcCloseMemHandle(s->peerSig[r]); }
     s->symGs.release(); s->symXs.release(); s->symSig.release(); s->sigStage.release();
@@ -93,6 +93,8 @@ static State *create(int device, int n, const double *charges, const int *ljtype
     for (int i = 0; i < ntypes * ntypes; i++) { ab[i].x = (float) tableA[tableindex[i]]; ab[i].y = (float) tableB[tableindex[i]]; }
     s->hostLJ64.resize((size_t) ntypes * ntypes);
     for (int i = 0; i < ntypes * ntypes; i++) { s->hostLJ64[i].x = tableA[tableindex[i]]; s->hostLJ64[i].y = tableB[tableindex[i]]; }
+    std::vector<unsigned char> typeFree((size_t) ntypes + 1, 1);
+    for (int i = 0; i < ntypes; i++) for (int j = 0; j < ntypes; j++) if (ab[(size_t) i * ntypes + j].x != 0.f || ab[(size_t) i * ntypes + j].y != 0.f || ab[(size_t) j * ntypes + i].x != 0.f || ab[(size_t) j * ntypes + i].y != 0.f) typeFree[i] = 0;
     std::vector<double2> ab14((size_t) ntypes14 * ntypes14);
     for (int i = 0; i < ntypes14 * ntypes14; i++) { ab14[i].x = tableA14[tableindex14[i]]; ab14[i].y = tableB14[tableindex14[i]]; }
     // symmetric exclusion CSR (SelfPairList_MakeConnections, pCore-1.9.0/extensions/csource/PairList.c:458-526)
@@ -108,7 +110,7 @@ static State *create(int device, int n, const double *charges, const int *ljtype
     std::vector<int2> p14((size_t) std::max(1, n14));
     for (int k = 0; k < n14; k++) { p14[k].x = pairs14[2 * k]; p14[k].y = pairs14[2 * k + 1]; }
     s->pairs14All.assign(p14.begin(), p14.begin() + n14);
-    ok = ok && s->q32.ensure(n) && s->q64.ensure(n) && s->ljtype.ensure(n) && s->ljAB.ensure(ab.size()) && s->ljAB14.ensure(ab14.size()) &&
+    ok = ok && s->q32.ensure(n) && s->q64.ensure(n) && s->ljtype.ensure(n) && s->ljAB.ensure(ab.size()) && s->ljAB14.ensure(ab14.size()) && s->typeFree.ensure(typeFree.size()) &&
          s->exclPtr.ensure(ptr.size()) && s->exclCol.ensure(col.size()) && s->pairs14.ensure(p14.size()) &&
          s->x.ensure(3 * (size_t) n) && s->xref.ensure(3 * (size_t) n) && s->grad.ensure(3 * (size_t) n);
     ok = ok && cuda_ok(cudaMalloc((void **) &s->counters, sizeof(DeviceCounters)), "cudaMalloc counters");
@@ -122,6 +124,7 @@ static State *create(int device, int n, const double *charges, const int *ljtype
              cuda_ok(cudaMemcpy(s->ljtype.p, ljtypes, sizeof(int) * n, cudaMemcpyHostToDevice), "H2D") &&
              cuda_ok(cudaMemcpy(s->ljAB.p, ab.data(), sizeof(float2) * ab.size(), cudaMemcpyHostToDevice), "H2D") &&
              cuda_ok(cudaMemcpy(s->ljAB14.p, ab14.data(), sizeof(double2) * ab14.size(), cudaMemcpyHostToDevice), "H2D") &&
+             cuda_ok(cudaMemcpy(s->typeFree.p, typeFree.data(), typeFree.size(), cudaMemcpyHostToDevice), "H2D") &&
              cuda_ok(cudaMemcpy(s->exclPtr.p, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice), "H2D") &&
              cuda_ok(cudaMemcpy(s->exclCol.p, col.data(), sizeof(int) * col.size(), cudaMemcpyHostToDevice), "H2D") &&
              cuda_ok(cudaMemcpy(s->pairs14.p, p14.data(), sizeof(int2) * p14.size(), cudaMemcpyHostToDevice), "H2D") &&
@@ -294,6 +297,8 @@ static void energy_finish(State &s, double *energies, bool haveGrad, double *dEd
         s.timings[1] = s.timings[2] = 0.0;
         if (s.hostCounters.itemCount > 0) { cudaEventElapsedTime(&ms, s.ev[2], s.ev[3]); s.timings[1] = ms; }
         if (s.n14 > 0) { cudaEventElapsedTime(&ms, s.ev[4], s.ev[5]); s.timings[2] = ms; }
+        s.timings[5] = 0.0;
+        if (s.hostCounters.itemCount > 0 && s.pruneCall > 0 && cudaEventElapsedTime(&ms, s.ev[10], s.ev[11]) == cudaSuccess) s.timings[5] = ms;      // the rolling prune (an almost empty launch when nothing was due)
     }
 }
 

@@ -31,7 +31,7 @@ struct ForceArgs {
     const WorkItem *items; int nitems; unsigned int *workCursor;
     const unsigned int *tileDesc; int chunkTiles; int exp;
     const float4 *recA, *recB; int n;
-    const float2 *ljAB; int ntypes;
+    const float2 *ljAB; int ntypes; const unsigned char *typeFree;
     const ImageOpDev *ops;
     AbfsF32 F; float qScale;
     double *gradSorted; double *accum;
@@ -129,12 +129,15 @@ __device__ __forceinline__ float4 lds128(unsigned int addr)
     return v;
 }
 
+// kLJ = false: both cluster atoms of the pair are of a type without any Lennard-Jones interaction (TIP3P hydrogens ...): Coulomb only
+template <bool kLJ>
 __device__ __forceinline__ void abfs_pair2(const AbfsF32 &F, f2 r2, f2 qij, unsigned int lj0, unsigned int lj1, f2 &eq, f2 &el, f2 &g)
 {
     const f2 s = make_float2(rsqrt_fast(r2.x), rsqrt_fast(r2.y));
     const bool p0 = r2.x <= F.r2On, p1 = r2.y <= F.r2On;
-    const float4 ab0 = lds128(p0 ? lj0 : lj0 + 16u), ab1 = lds128(p1 ? lj1 : lj1 + 16u);
-    const f2 r = mul2(r2, s), s2 = mul2(s, s), s3 = mul2(s, s2), s6 = mul2(s3, s3);
+    float4 ab0, ab1;
+    if (kLJ) { ab0 = lds128(p0 ? lj0 : lj0 + 16u); ab1 = lds128(p1 ? lj1 : lj1 + 16u); }
+    const f2 r = mul2(r2, s), s2 = mul2(s, s), s3 = mul2(s, s2);
     const f2 one = bc(1.0f);
     const f2 sg = make_float2(p0 ? 0.0f : 1.0f, p1 ? 0.0f : 1.0f);          // sigma = 1 - pi
     // Coulomb
@@ -148,7 +151,9 @@ __device__ __forceinline__ void abfs_pair2(const AbfsF32 &F, f2 r2, f2 qij, unsi
     const f2 sh = fma2(sg, bc(-F.qShift1), bc(F.qShift1));               // plain: qShift1, switched: 0
     eq = fma2(qij, fma2(s, G, sh), eq);
     const f2 gq = mul2(mul2(qij, s3), Q);
+    if (!kLJ) { g = gq; return; }
     // Lennard-Jones (the table entries of the two pairs sit in unrelated registers: their products are scalar)
+    const f2 s6 = mul2(s3, s3);
     const f2 la = fma2(sg, bc(-F.aF6), s6), lb = fma2(sg, bc(-F.bF3), s3);
     const f2 X = make_float2(ab0.x * la.x, ab1.x * la.y), Y = make_float2(ab0.y * lb.x, ab1.y * lb.y);
     el = fma2(X, la, el); el = fma2(neg2(Y), lb, el); el.x -= ab0.z; el.y -= ab1.z;
@@ -363,6 +368,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
         const int s0 = wi.block * kCluster;
         const float4 kref = A.recB[s0];
         __syncwarp();                                       // the previous item's last tile has been consumed
+        bool ljFree = false;
         if (lane < kCluster) {
             // padding rows of the last cluster read the null record (index n): far away, zero charge, null LJ type
             const int si = min(s0 + lane, A.n);
@@ -375,7 +381,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
             const int p = lane >> 1, h = lane & 1;
             xy[4 * p + h] = xi; xy[4 * p + 2 + h] = yi; zq[4 * p + h] = zi; zq[4 * p + 2 + h] = ra.w * A.qScale;
             reinterpret_cast<int *>(ist->row)[lane] = __float_as_int(rb.w) * nt1 * kLJEntryBytes;
+            ljFree = A.typeFree[__float_as_int(rb.w)] != 0;
         }
+        // pairs of cluster atoms that are both of a type without Lennard-Jones interaction (the builder moves such atoms to the front of
+        // every cluster): Coulomb only
+        const unsigned int freeBits = __ballot_sync(0xffffffffu, ljFree);
         __syncwarp();
         // j offsets: X'_local = (K_j + ok) + xl_j, ok exact (kt: the part of a pure translation that is a multiple of 8 A)
         float okx = -kref.x, oky = -kref.y, okz = -kref.z;
@@ -451,7 +461,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
                     r2.x = fminf(on0 ? r2.x : F.r2Off, F.r2Off); r2.y = fminf(on1 ? r2.y : F.r2Off, F.r2Off);
                     r2min = fminf(r2min, fminf(r2.x, r2.y));
                     r2.x = fmaxf(r2.x, F.r2Damp); r2.y = fmaxf(r2.y, F.r2Damp);
-                    abfs_pair2(F, r2, qij, ljS + (unsigned int) rows.x, ljS + (unsigned int) rows.y, eq, el, g);
+                    if (((freeBits >> (2 * p)) & 3u) == 3u) abfs_pair2<false>(F, r2, qij, 0u, 0u, eq, el, g);
+                    else abfs_pair2<true>(F, r2, qij, ljS + (unsigned int) rows.x, ljS + (unsigned int) rows.y, eq, el, g);
                 } else {
                     // pairs off the list or beyond the cutoff read the all-zero table row (the skip of PairwiseInteraction.c:489)
                     const float4 ab0 = lds128(ljS + (unsigned int) rows.x), ab1 = lds128(ljS + (unsigned int) rows.y);
@@ -531,7 +542,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
 // per energy call: atom records in sorted order from the current coordinates, and the way back for the gradients
 // ------------------------------------------------------------------------------------------------------
 __global__ void k_pack_records(const double *__restrict__ x, const int *__restrict__ sAtom, int n, int ntypes, const float *__restrict__ q32, const int *__restrict__ ljtype,
-                               double ox, double oy, double oz, float4 *__restrict__ recA, float4 *__restrict__ recB, double *__restrict__ zero = nullptr, int zeroCount = 0)
+                               double ox, double oy, double oz, float4 *__restrict__ recA, float4 *__restrict__ recB, double *__restrict__ zero, int zeroCount,
+                               const double *__restrict__ xprune, unsigned long long *__restrict__ pruneDisp, int slot)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     // fused mode (nbb200_md_run): the accumulators + work cursor of the force kernels are cleared here instead of by a memset of their own
@@ -540,12 +552,137 @@ __global__ void k_pack_records(const double *__restrict__ x, const int *__restri
         recA[n] = make_float4(0.f, 0.f, 0.f, 0.f);
         recB[n] = make_float4(-1.0e15f, -1.0e15f, -1.0e15f, __int_as_float(ntypes));
     }
-    if (s >= n) return;
-    const int a = sAtom[s];
-    const double X = x[3 * a] - ox, Y = x[3 * a + 1] - oy, Z = x[3 * a + 2] - oz;
-    const double KX = 8.0 * rint(X * 0.125), KY = 8.0 * rint(Y * 0.125), KZ = 8.0 * rint(Z * 0.125);
-    recA[s] = make_float4((float) (X - KX), (float) (Y - KY), (float) (Z - KZ), q32[a]);
-    recB[s] = make_float4((float) KX, (float) KY, (float) KZ, __int_as_float(ljtype[a]));
+    double moved = 0.0;
+    if (s < n) {
+        const int a = sAtom[s];
+        const double xa = x[3 * a], ya = x[3 * a + 1], za = x[3 * a + 2];
+        const double X = xa - ox, Y = ya - oy, Z = za - oz;
+        const double KX = 8.0 * rint(X * 0.125), KY = 8.0 * rint(Y * 0.125), KZ = 8.0 * rint(Z * 0.125);
+        recA[s] = make_float4((float) (X - KX), (float) (Y - KY), (float) (Z - KZ), q32[a]);
+        recB[s] = make_float4((float) KX, (float) KY, (float) KZ, __int_as_float(ljtype[a]));
+        if (xprune != nullptr) {
+            const double dx = xa - xprune[3 * a], dy = ya - xprune[3 * a + 1], dz = za - xprune[3 * a + 2];
+            moved = dx * dx + dy * dy + dz * dz;
+        }
+    }
+    if (pruneDisp != nullptr) {
+        // rolling prune: how far has any atom moved since the inner lists were made?  Two slots by call parity: this call's maximum goes to
+        // `slot` (k_prune of this call reads it after this kernel), the other one is cleared for the next call
+        if (xprune != nullptr) {
+            for (int off = 16; off > 0; off >>= 1) moved = fmax(moved, __shfl_xor_sync(0xffffffffu, moved, off));
+            if ((threadIdx.x & 31) == 0 && moved > 0.0) atomicMax(&pruneDisp[slot], (unsigned long long) __double_as_longlong(moved));
+        }
+        if (s == 0) pruneDisp[slot ^ 1] = 0ULL;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// rolling prune.  The lists hold every pair within listCutoff (13.5 A) at the last rebuild; the interaction vanishes beyond outerCutoff
+// (12 A), so at any moment about a quarter of the j entries of a cluster hold no pair that contributes.  k_prune copies every work
+// item's descriptor stream into the inner pool without the entries whose 8 pairs are all beyond outerCutoff + buffer (at the same tile
+// offsets: the inner stream of an item is never longer than the outer one -- no allocation, no atomics) and clears the mask bits of the
+// pairs beyond that radius.  The inner pool stays valid until an atom has moved by more than buffer / 2; the decision is taken on the
+// device (`force`: the host knows that the lists or the lattice changed), so that a call costs one almost empty launch when nothing is due.
+// A pair that is dropped here is beyond outerCutoff whenever the inner pool is used, i.e. it contributes exactly nothing in the
+// reference as well (PairwiseInteraction.c:389): the sums are unchanged.
+// ------------------------------------------------------------------------------------------------------
+struct PruneArgs {
+    const WorkItem *items; int nitems; const unsigned int *tileDesc;
+    WorkItem *itemsIn; unsigned int *tileDescIn;
+    const float4 *recA, *recB; int n;
+    const ImageOpDev *ops;
+    float rc2;                                   // (outerCutoff + buffer)^2 with a rounding margin
+    double thr2;                                 // (buffer / 2)^2
+    int force, slot;
+    unsigned long long *pruneDisp;
+    const double *x; double *xprune;
+};
+
+constexpr int kPruneWarps = 8;
+
+template <bool kRot>
+__global__ void __launch_bounds__(kPruneWarps * 32) k_prune(const __grid_constant__ PruneArgs P)
+{
+    if (!P.force && !(__longlong_as_double((long long) P.pruneDisp[P.slot]) > P.thr2)) return;
+    __shared__ float4 sI[kPruneWarps][kCluster];          // per warp: the i-cluster as pairs {x0, x1, y0, y1} [4], {z0, z1, -, -} [4]
+    __shared__ unsigned int sQ[kPruneWarps][2 * kTile];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long gw = (long) blockIdx.x * kPruneWarps + warp, nw = (long) gridDim.x * kPruneWarps;
+    // the coordinates this prune refers to
+    for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < 3L * P.n; i += (long) gridDim.x * blockDim.x) P.xprune[i] = P.x[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.pruneDisp[2], 1ULL);
+    float4 *myI = sI[warp];
+    unsigned int *queue = sQ[warp];
+    const unsigned int ltMask = (1u << lane) - 1u;
+    for (long it = gw; it < P.nitems; it += nw) {
+        const WorkItem wi = P.items[it];
+        const ImageOpDev *op = P.ops + wi.image;
+        const bool isImage = wi.image > 0;
+        const bool pureT = kRot ? (op->pureTranslation != 0) : true;
+        const int s0 = wi.block * kCluster;
+        const float4 kref = P.recB[s0];
+        __syncwarp();
+        if (lane < kCluster) {
+            const int si = min(s0 + lane, P.n);
+            const float4 ra = P.recA[si], rb = P.recB[si];
+            float tlx = 0.f, tly = 0.f, tlz = 0.f;
+            if (isImage && pureT) { tlx = op->tl[0]; tly = op->tl[1]; tlz = op->tl[2]; }
+            float *xy = reinterpret_cast<float *>(myI), *zq = reinterpret_cast<float *>(myI + kCluster / 2);
+            const int p = lane >> 1, h = lane & 1;
+            xy[4 * p + h] = (rb.x - kref.x) + (ra.x - tlx); xy[4 * p + 2 + h] = (rb.y - kref.y) + (ra.y - tly); zq[4 * p + h] = (rb.z - kref.z) + (ra.z - tlz);
+        }
+        __syncwarp();
+        float okx = -kref.x, oky = -kref.y, okz = -kref.z;
+        if (isImage && pureT) { okx += op->kt[0]; oky += op->kt[1]; okz += op->kt[2]; }
+        int cnt = 0, outTiles = 0;
+        unsigned int *out = P.tileDescIn + (size_t) wi.tileStart * kTile + lane;
+        const unsigned int *in = P.tileDesc + (size_t) wi.tileStart * kTile + lane;
+        // two-deep software pipeline: descriptor of tile t+2 and records of tile t+1 in flight during tile t
+        unsigned int d0 = in[0], d1 = (wi.tileCount > 1) ? in[kTile] : kEmptySlot;
+        float4 ra0 = P.recA[min(d0 & kEmptySlot, (unsigned int) P.n)], rb0 = P.recB[min(d0 & kEmptySlot, (unsigned int) P.n)];
+        __syncwarp();
+        for (int t = 0; t < wi.tileCount; t++) {
+            const unsigned int d2 = (t + 2 < wi.tileCount) ? in[(size_t) (t + 2) * kTile] : kEmptySlot;
+            const unsigned int s1 = min(d1 & kEmptySlot, (unsigned int) P.n);
+            const float4 ra1 = P.recA[s1], rb1 = P.recB[s1];
+            const unsigned int d = d0;
+            const float4 ra = ra0, rb = rb0;
+            d0 = d1; d1 = d2; ra0 = ra1; rb0 = rb1;
+            float xj, yj, zj;
+            if (kRot && isImage && !pureT) {
+                const double X = (double) rb.x + (double) ra.x, Y = (double) rb.y + (double) ra.y, Z = (double) rb.z + (double) ra.z;
+                xj = (float) (op->R[0] * X + op->R[1] * Y + op->R[2] * Z + op->cr[0] - (double) kref.x);
+                yj = (float) (op->R[3] * X + op->R[4] * Y + op->R[5] * Z + op->cr[1] - (double) kref.y);
+                zj = (float) (op->R[6] * X + op->R[7] * Y + op->R[8] * Z + op->cr[2] - (double) kref.z);
+            } else { xj = (rb.x + okx) + ra.x; yj = (rb.y + oky) + ra.y; zj = (rb.z + okz) + ra.z; }
+            // sign bits of r^2 - rc^2, shifted in pair by pair: bit 7 - i of `sgn` <-> cluster atom i
+            unsigned int sgn = 0u;
+#pragma unroll
+            for (int p = 0; p < kCluster / 2; p++) {
+                const float4 XY = myI[p], ZQ = myI[kCluster / 2 + p];
+                const f2 dx = sub2(make_float2(XY.x, XY.y), bc(xj)), dy = sub2(make_float2(XY.z, XY.w), bc(yj)), dz = sub2(make_float2(ZQ.x, ZQ.y), bc(zj));
+                const f2 e = sub2(fma2(dx, dx, fma2(dy, dy, mul2(dz, dz))), bc(P.rc2));
+                sgn = __funnelshift_l(__float_as_uint(e.x), sgn, 1);
+                sgn = __funnelshift_l(__float_as_uint(e.y), sgn, 1);
+            }
+            const unsigned int keepMask = (d >> 24) & (__brev(sgn) >> 24);
+            const unsigned int bal = __ballot_sync(0xffffffffu, keepMask != 0u);
+            if (keepMask != 0u) queue[cnt + __popc(bal & ltMask)] = (d & kEmptySlot) | (keepMask << 24);
+            cnt += __popc(bal);
+            __syncwarp();
+            if (cnt >= kTile) {
+                out[(size_t) outTiles * kTile] = queue[lane];
+                const unsigned int rest = queue[kTile + lane];
+                __syncwarp();
+                queue[lane] = rest;
+                cnt -= kTile; outTiles += 1;
+                __syncwarp();
+            }
+        }
+        // the remainder; an item that lost every entry keeps one empty tile (the force kernel's bulk copies are never empty)
+        if (cnt > 0 || outTiles == 0) { out[(size_t) outTiles * kTile] = (lane < cnt) ? queue[lane] : kEmptySlot; outTiles += 1; }
+        if (lane == 0) { WorkItem w = wi; w.tileCount = outTiles; P.itemsIn[it] = w; }
+    }
 }
 
 // assign != 0: the NB term SETS the caller's gradient (every atom has exactly one sorted position) instead of accumulating into it
@@ -737,13 +874,52 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
     const double eScale = (1.0 / s.dielectric) * kE2AngstromToKJMol;
     if (nitems > 0) {
         if (!s.recA.ensure((size_t) s.n + 1) || !s.recB.ensure((size_t) s.n + 1)) return false;
+        if (g_numSMs == 0) init_force_kernel_attributes();
+        // rolling prune: only when it can remove something (outer + buffer < list)
+        static const double bufferOverride = []() { const char *e = std::getenv("NBB200_PRUNE_BUFFER"); return e ? std::atof(e) : -1.0; }();
+        const double pruneBuffer = bufferOverride >= 0.0 ? bufferOverride : s.pruneBuffer;
+        // the first energy call on freshly built lists walks the pool as built (a prune costs about as much as it saves in one call); the
+        // inner pool is made at the next call on the same lists and refreshed on the device's own decision afterwards.
+        // NBB200_PRUNE_EAGER=1: prune right after every rebuild
+        static const bool eager = []() { const char *e = std::getenv("NBB200_PRUNE_EAGER"); return e != nullptr && std::atoi(e) != 0; }();
+        bool prune = pruneBuffer > 0.0 && s.outer + pruneBuffer < s.list - 1.0e-9;
+        if (prune && !eager && s.outerCallGeneration != s.numberOfUpdates) { prune = false; s.outerCallGeneration = s.numberOfUpdates; }
+        const int slot = (int) (s.pruneCall & 1);
+        if (prune) {
+            if (!s.tileDescIn.ensure(s.tileCap * kTile) || !s.itemsIn.ensure(s.itemCap) || !s.xprune.ensure(3 * (size_t) s.n)) return false;
+            if (s.pruneDisp.p == nullptr) {
+                if (!s.pruneDisp.ensure(4)) return false;
+                NBB_CUDA(cudaMemsetAsync(s.pruneDisp.p, 0, sizeof(unsigned long long) * 4, s.stream));
+                s.pruneListGeneration = -1;
+            }
+        }
+        const bool pruneForce = prune && (s.pruneListGeneration != s.numberOfUpdates || !s.pruneLatticeValid || std::memcmp(s.pruneLattice.v, s.lattice.M.v, sizeof(double) * 9) != 0);
         const int pthreads = 256, pblocks = (s.n + 1 + pthreads - 1) / pthreads;
         k_pack_records<<<pblocks, pthreads, 0, s.stream>>>(s.xcur, s.sAtom.p, s.n, s.ntypes, s.q32.p, s.ljtype.p, s.grid.lo[0], s.grid.lo[1], s.grid.lo[2], s.recA.p, s.recB.p,
-                                                            fusedZero ? s.accum.p : nullptr, (int) (accumCount + 1));
+                                                            fusedZero ? s.accum.p : nullptr, (int) (accumCount + 1),
+                                                            (prune && !pruneForce) ? s.xprune.p : nullptr, s.pruneDisp.p, slot);
+        bool rot = false;                                   // any image with a genuine rotation?
+        for (const RealSpaceOp &b : s.plan.baseOps) rot = rot || !b.pureTranslation;
+        if (prune) {
+            PruneArgs P;
+            P.items = s.items.p; P.nitems = nitems; P.tileDesc = s.tileDesc.p; P.itemsIn = s.itemsIn.p; P.tileDescIn = s.tileDescIn.p;
+            P.recA = s.recA.p; P.recB = s.recB.p; P.n = s.n; P.ops = s.imageOps.p;
+            const double rc = s.outer + pruneBuffer;
+            P.rc2 = (float) (rc * rc * (1.0 + 2.0e-5) + 1.0e-3);
+            P.thr2 = 0.25 * pruneBuffer * pruneBuffer;
+            P.force = pruneForce ? 1 : 0; P.slot = slot; P.pruneDisp = s.pruneDisp.p; P.x = s.xcur; P.xprune = s.xprune.p;
+            const int blocks = std::max(1, std::min(g_numSMs * 8, (nitems + 7) / 8));
+            if (s.timing) cudaEventRecord(s.ev[10], s.stream);
+            if (rot) k_prune<true><<<blocks, 256, 0, s.stream>>>(P); else k_prune<false><<<blocks, 256, 0, s.stream>>>(P);
+            if (s.timing) cudaEventRecord(s.ev[11], s.stream);
+            s.launches += 1;
+            s.pruneListGeneration = s.numberOfUpdates; s.pruneLattice = s.lattice.M; s.pruneLatticeValid = true;
+            s.pruneCall += 1;
+        }
         ForceArgs A;
-        A.items = s.items.p; A.nitems = nitems; A.workCursor = workCursor;
-        A.tileDesc = s.tileDesc.p; A.chunkTiles = s.chunkTiles; { static const int e = []() { const char *v = std::getenv("NBB200_EXP"); return v ? std::atoi(v) : 0; }(); A.exp = e; } A.recA = s.recA.p; A.recB = s.recB.p; A.n = s.n;
-        A.ljAB = s.ljAB.p; A.ntypes = s.ntypes;
+        A.items = prune ? s.itemsIn.p : s.items.p; A.nitems = nitems; A.workCursor = workCursor;
+        A.tileDesc = prune ? s.tileDescIn.p : s.tileDesc.p; A.chunkTiles = s.chunkTiles; { static const int e = []() { const char *v = std::getenv("NBB200_EXP"); return v ? std::atoi(v) : 0; }(); A.exp = e; } A.recA = s.recA.p; A.recB = s.recB.p; A.n = s.n;
+        A.ljAB = s.ljAB.p; A.ntypes = s.ntypes; A.typeFree = s.typeFree.p;
         A.ops = s.imageOps.p;
         for (int d = 0; d < 3; d++) A.origin[d] = s.grid.lo[d];
         const double *f = s.factors;
@@ -776,9 +952,6 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
             splBytes = sizeof(float4) * 3 * (size_t) s.spl.points();
         }
         A.gradSorted = wantGrad ? s.gs : nullptr; A.accum = s.accum.p;
-        if (g_numSMs == 0) init_force_kernel_attributes();
-        bool rot = false;                                   // any image with a genuine rotation?
-        for (const RealSpaceOp &b : s.plan.baseOps) rot = rot || !b.pureTranslation;
         static const ForceVariant *chosen = []() {
             const char *e = std::getenv("NBB200_FORCE_SHAPE");
             for (const ForceVariant &v : kForceVariants) if (e != nullptr && std::strcmp(e, v.name) == 0) return &v;

@@ -413,6 +413,38 @@ __global__ void k_sort_cells(const unsigned int *__restrict__ cellStart, int nke
     }
 }
 
+// Inside every aligned run of 8 sorted primary atoms (= one i-cluster of the force kernel) the atoms whose type has no Lennard-Jones
+// interaction at all (TIP3P hydrogens ...) are moved to the front, stably: the force kernel evaluates the cluster atoms two at a time and
+// skips the Lennard-Jones part of a pair of atoms when both are of such a type.  Atoms never leave their grid cell (the cell ranges of
+// the sorted order are what the tile builder scans): a run that straddles a cell boundary is partitioned piece by piece.
+__global__ void k_group_lj_free(int n, const int *__restrict__ ljtype, const unsigned char *__restrict__ typeFree, BuildGrid g, double *__restrict__ sX, int *__restrict__ sAtom,
+                                int *__restrict__ invPerm)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;            // sorted position; 8 consecutive lanes = one cluster
+    const int lane = threadIdx.x & 31, base = lane & ~(kCluster - 1), rel = lane - base;
+    const bool valid = s < n;
+    const int a = valid ? sAtom[s] : -1;
+    double x = 0.0, y = 0.0, z = 0.0;
+    if (valid) { x = sX[3 * s]; y = sX[3 * s + 1]; z = sX[3 * s + 2]; }
+    const int key = valid ? snake_cell(g, cell_coord(x, g.lo[0], g.invh, g.dim[0]), cell_coord(y, g.lo[1], g.invh, g.dim[1]), cell_coord(z, g.lo[2], g.invh, g.dim[2])) : -1 - lane;
+    const bool isFree = valid && typeFree[ljtype[a]] != 0;
+    // lanes of the same cluster that sit in the same cell
+    unsigned int piece = 0u;
+#pragma unroll
+    for (int k = 0; k < kCluster; k++) if (__shfl_sync(0xffffffffu, key, base + k) == key) piece |= 1u << k;
+    const unsigned int balFree = (__ballot_sync(0xffffffffu, isFree) >> base) & piece;
+    const unsigned int below = (1u << rel) - 1u;
+    // stable partition of the piece: free atoms first, then the others
+    const int first = __ffs((int) piece) - 1;
+    const int dst = first + (isFree ? __popc(balFree & below) : __popc(balFree) + __popc(piece & ~balFree & below));
+    __syncwarp();
+    if (valid) {
+        const int p = (s & ~(kCluster - 1)) + dst;
+        sX[3 * p] = x; sX[3 * p + 1] = y; sX[3 * p + 2] = z;
+        sAtom[p] = a; invPerm[a] = p;
+    }
+}
+
 // per i-block (32 consecutive sorted primary atoms): min, max, centre
 __global__ void k_block_boxes(const double *__restrict__ sX, int n, int nblocks, double *__restrict__ blockBox)
 {
@@ -965,6 +997,7 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     // capacity is noticed with the counters that come back after the tile builder
     k_scatter<<<(unsigned int) ((neMax + 255) / 256), 256, 0, s.stream>>>(s.eKey.p, s.n, extUpperBound, s.counters, s.cellStart.p, s.cellFill.p, s.order.p);
     k_sort_cells<<<(nkeys + 7) / 8, 256, 0, s.stream>>>(s.cellStart.p, nkeys, s.eSortBuf.p, s.order.p, s.eX.p, s.eAtom.p, s.eSet.p, s.sX.p, s.sAtom.p, s.invPerm.p);
+    if (s.typeFree.p != nullptr) { k_group_lj_free<<<(s.n + 255) / 256, 256, 0, s.stream>>>(s.n, s.ljtype.p, s.typeFree.p, s.grid, s.sX.p, s.sAtom.p, s.invPerm.p); s.launches += 1; }
     s.nblocks = (s.n + kTile - 1) / kTile;
     if (!s.blockBox.ensure((size_t) 9 * s.nblocks)) return false;
     k_block_boxes<<<(s.nblocks * 32 + 255) / 256, 256, 0, s.stream>>>(s.sX.p, s.n, s.nblocks, s.blockBox.p);

@@ -123,6 +123,7 @@ struct State {
     DevBuf<double> q64;
     DevBuf<int> ljtype;
     DevBuf<float2> ljAB;            // [nt*nt] (A, B) expanded table, fp32
+    DevBuf<unsigned char> typeFree; // [nt + 1] 1 = the type has no Lennard-Jones interaction with any type (TIP3P hydrogens ...); [nt] = the null type
     DevBuf<double2> ljAB14;         // [nt14*nt14] fp64 for the 1-4 kernel
     DevBuf<int> exclPtr, exclCol;   // symmetric CSR
     DevBuf<int2> pairs14;
@@ -205,6 +206,15 @@ struct State {
     bool rawJ = false;                           // stand-alone cross lists: the j field of sets > 0 is an index into the second array
     DevBuf<unsigned int> tileDesc;
     DevBuf<WorkItem> items; size_t itemCap = 0;
+    // rolling prune (force_kernels.cu): the force kernel walks an INNER copy of the tile pool that holds only the j entries with a pair inside
+    // outerCutoff + pruneBuffer; it is refreshed on the device when the lists were rebuilt, the lattice changed or an atom moved by more
+    // than pruneBuffer / 2 since the last prune (decided on the device, no host round trip)
+    double pruneBuffer = 0.5;                    // A; <= 0 or outer + buffer >= list: no pruning, the force kernel walks the pool as built
+    DevBuf<unsigned int> tileDescIn; DevBuf<WorkItem> itemsIn;
+    DevBuf<double> xprune;                       // coordinates at the last prune
+    DevBuf<unsigned long long> pruneDisp;        // two slots (call parity): max |x - xprune|^2 of the current call as the bits of a double, [2]: number of prunes
+    long pruneCall = 0, pruneListGeneration = -1, outerCallGeneration = -1;   // outerCallGeneration: the lists of that update have had their first energy call (on the pool as built)
+    Mat3 pruneLattice{}; bool pruneLatticeValid = false;
     // per energy call: atom records in sorted order (A: xl, yl, zl, q; B: Kx, Ky, Kz, LJ type) and the sorted-order gradient
     DevBuf<float4> recA, recB;
     DevBuf<double> gradSorted;

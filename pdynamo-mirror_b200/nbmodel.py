@@ -240,7 +240,7 @@ class NBModelABFSState:
     def Timings(self):
         out = np.zeros(8)
         _lib.lib().nbb200_get_timings(self.cObject, d_(out))
-        return dict(listRebuild=out[0], tileForces=out[1], pairs14=out[2], displacementCheck=out[3], pairExpansion=out[4])
+        return dict(listRebuild=out[0], tileForces=out[1], pairs14=out[2], displacementCheck=out[3], pairExpansion=out[4], prune=out[5])
 
     def Summary(self, log=None):
         if log is not None:

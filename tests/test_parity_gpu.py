@@ -18,6 +18,15 @@ E_TOL, G_TOL, M_TOL = 1.0e-6, 1.0e-5, 1.0e-5
 ILL_CONDITIONED = {"w216_lattice": 2.0e-5, "perturbed": 2.0e-5}
 
 
+
+def same_call(a, b):
+    """Two evaluations of the same coordinates on the same lists.  The first call after a list update walks the tile pool as built, later
+    calls the pruned inner pool (rolling prune): the fp32 partial sums are formed in another order, so the results agree to the fp32
+    summation noise (measured ~2e-8 relative), far inside the 1e-6 / 1e-5 parity bars, not bit for bit."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.allclose(a, b, rtol=5e-7, atol=5e-7 * max(1e-300, np.abs(b).max()))
+
+
 def _hash(keys):
     return hashlib.sha256(np.ascontiguousarray(keys, dtype=np.int64).tobytes()).hexdigest()
 
@@ -169,19 +178,19 @@ def test_deferred_energy_call_matches_the_synchronous_one(pkg):
     L.nbb200_set_gradient_overwrite(h, 0)
     assert np.all(np.isnan(e1))                                   # nothing has been handed over yet
     L.nbb200_flush(h, C.byref(status))
-    assert status.value == 16 and np.allclose(e1, e, rtol=1e-12, atol=1e-9)
-    assert np.allclose(gd.cpu().numpy(), g, rtol=1e-12, atol=1e-9)          # set, not accumulated onto the 7.0
-    assert np.allclose(m1.reshape(3, 3), dm, rtol=1e-12, atol=1e-9)
+    assert status.value == 16 and same_call(e1, e)
+    assert same_call(gd.cpu().numpy(), g)          # set, not accumulated onto the 7.0
+    assert same_call(m1.reshape(3, 3), dm)
     # handed over by the next Update's decision
     e2 = np.full(6, np.nan)
     L.NBModelABFS_B200_MMMMEnergyDeviceDeferred(h, _lib.d_(e2), None, None, C.byref(status))
     L.NBModelABFS_B200_UpdateDevice(h, C.c_void_p(x.data_ptr()), _lib.d_(box), 0, C.byref(status))
-    assert np.allclose(e2, e, rtol=1e-12, atol=1e-9)
+    assert same_call(e2, e)
     # ... also when that Update rebuilds the lists without a displacement check
     e3 = np.full(6, np.nan)
     L.NBModelABFS_B200_MMMMEnergyDeviceDeferred(h, _lib.d_(e3), None, None, C.byref(status))
     L.NBModelABFS_B200_UpdateDevice(h, C.c_void_p(x.data_ptr()), _lib.d_(box), 1, C.byref(status))
-    assert np.allclose(e3, e, rtol=1e-12, atol=1e-9) and status.value == 16
+    assert same_call(e3, e) and status.value == 16
 
 
 def test_spline_form_follows_option_changes(pkg, orc):
@@ -263,7 +272,8 @@ def test_options_change_triggers_rebuild_and_dielectric_scales(pkg, orc):
     system, st, e, g, dm = gpu_energy(pkg, w)
     system.energyModel.nbModel.SetOptions(dielectric=2.0, electrostaticScale14=0.3)
     system.Energy(doGradients=True)
-    assert abs(st.energies[0] - 0.5 * e[0]) <= 1e-9 * abs(e[0]) and abs(st.energies[1] - e[1]) <= 1e-12 * abs(e[1])
+    # the second call walks the pruned inner pool: fp32 summation noise between the two calls (see same_call)
+    assert abs(st.energies[0] - 0.5 * e[0]) <= 5e-7 * abs(e[0]) and abs(st.energies[1] - e[1]) <= 5e-7 * abs(e[1])
     nup = st.numberOfUpdates
     system.energyModel.nbModel.SetOptions(listCutoff=14.5)
     system.Energy(doGradients=True)
@@ -368,7 +378,7 @@ def test_mm_lists_and_energies_with_a_qc_region(pkg, orc, name):
     st.SetQCAtoms([])                                           # cleared: the all-MM numbers are back
     system.configuration.gradients3[:] = 0.0
     system.Energy(doGradients=True)
-    assert np.allclose(st.energies, e_full, rtol=1e-12, atol=1e-9) and st.NumberOfPairs() > counts["nbmmmm"] - 1
+    assert same_call(st.energies, e_full) and st.NumberOfPairs() > counts["nbmmmm"] - 1
 
 
 @pytest.mark.parametrize("name", ["w216", "w216_vacuum", "bala"])
@@ -687,16 +697,16 @@ def test_overwrite_gradients_option(pkg):
         s2.DefineNBModel(model)
         s2.Energy(doGradients=True)
         cfg = s2.configuration
-        assert np.allclose(cfg.gradients3, g, rtol=1e-12, atol=1e-9)
+        assert same_call(cfg.gradients3, g)
         garbage = cfg.gradients3 if pinned else np.empty_like(g)
         garbage[...] = 1.0e6
         cfg.gradients3 = garbage
         model.Energy(cfg)
-        assert np.allclose(garbage, g, rtol=1e-12, atol=1e-9)
+        assert same_call(garbage, g)
         model.SetOptions(overwriteGradients=False)            # and back to accumulation
         garbage[...] = 1.0
         model.Energy(cfg)
-        assert np.allclose(garbage, g + 1.0, rtol=1e-12, atol=1e-9)
+        assert same_call(garbage, g + 1.0)
 
 
 def test_full_size_m1_properties(pkg):
