@@ -113,7 +113,8 @@ def workload_description(name, w):
 # --------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the compiled, unmodified reference C code (oracle/_ref) on the host cores
 # --------------------------------------------------------------------------------------------------------------
-def cpu_reference(sample_name, steps, warmup):
+def cpu_reference(sample_name, steps, warmup, budget_s=None):
+    """budget_s: stop after the step that exceeds this wall-clock budget (at least one timed step is always taken)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import refnb
     omp = refnb.available(omp=True)
@@ -127,18 +128,21 @@ def cpu_reference(sample_name, steps, warmup):
         model = refnb.RefNB(w, omp=omp)
         cores = model.num_threads() if omp else 1
     times, upd, ene, pairs = [], [], [], 0
+    t_start = time.perf_counter()
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         out = model.energy(force_new=True)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt); upd.append(out["t_update"]); ene.append(out["t_energy"])
+        if budget_s is not None and times and time.perf_counter() - t_start + dt > budget_s:
+            break
     c = model.counts()
     pairs = c["primary"] + c["image_pairs"]
     best = min(times)
-    return dict(value=pairs / best, unit="list-pairs/s", cores=cores, kind=kind,
+    return dict(value=pairs / best, unit="list-pairs/s", cores=cores, kind=kind, steps_run=len(times),
                 sample="%s (%d atoms, %d list pairs): forced list rebuild + E+grad per step, best of %d after %d warm-up; "
-                       "rebuild %.3f s (serial in the reference), E+grad %.3f s" % (sample_name, w["n"], pairs, steps, warmup, min(upd), min(ene)),
+                       "rebuild %.3f s (serial in the reference), E+grad %.3f s" % (sample_name, w["n"], pairs, len(times), min(warmup, it), min(upd), min(ene)),
                 ms_per_step=1e3 * best, pairs=pairs, n=w["n"], ms_rebuild=1e3 * min(upd), ms_energy=1e3 * min(ene)), w
 
 
@@ -151,13 +155,22 @@ def run_reference(args):
     # use all the host threads it can, so the team size is restored here (before libgomp is loaded with the reference library)
     if os.environ.get("NBB_REF_THREADS") or "TORCHELASTIC_RUN_ID" in os.environ:
         os.environ["OMP_NUM_THREADS"] = str(int(os.environ.get("NBB_REF_THREADS") or len(os.sched_getaffinity(0))))
-    base, w = cpu_reference(sample, max(1, args.steps), max(0, min(args.warmup, 1)))
-    wl = workload_description(args.workload, make_workload(args.workload))
+    # the reference arm runs the WORKLOAD ITSELF (same input as the B200 arm) unless a sample is asked for with --ref-sample: one step of
+    # the 1.1 M-atom box takes the reference ~30 s (its list generator is serial), so the number of steps is cut by a wall-clock budget
+    # (NBB_REF_BUDGET_S, default 100 s; at least one step) and the steps actually taken are reported
+    same = args.ref_sample_explicit is None
+    name = args.workload if same else sample
+    budget = float(os.environ.get("NBB_REF_BUDGET_S", "100"))
+    base, w = cpu_reference(name, max(1, args.steps), 0 if same else max(0, min(args.warmup, 1)), budget_s=budget)
+    wl = workload_description(args.workload, make_workload(args.workload) if not same else w)
     line = {"metric": "NBModelABFS list-pair interactions per second (pair-list rebuild + energy + gradients per call)",
-            "value": base["value"], "unit": "list-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "value": base["value"], "unit": "list-pairs/s", "n_gpus": args.gpus, "steps": base["steps_run"], "warmup": 0 if same else min(args.warmup, 1),
+            "steps_requested": args.steps, "warmup_requested": args.warmup,
             "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": wl, "sample": sample, "note": "reference CPU implementation timed on a bounded sample of the workload"},
+            "config": {"workload": wl, "sample": name, "same_config": bool(same),
+                       "note": ("the reference's CPU implementation on the workload itself; steps cut to a %g s budget (best step reported)" % budget) if same
+                               else "reference CPU implementation timed on a bounded sample of the workload"},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "list-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -474,12 +487,24 @@ def jac_block(torch, local, fp32_peak_tflops):
     fk, lb = [], []
     for _ in range(10):
         m.step(rebuild=True); t = m.state.Timings(); fk.append(t["tileForces"]); lb.append(t["listRebuild"])
+    ms_nr_sync = timed_steps(torch, lambda: m.step(rebuild=False), 50, 5, lambda: None)
+    fk_nr = []
+    for _ in range(10):
+        m.step(rebuild=False); fk_nr.append(m.state.Timings()["tileForces"])
+    # the same calls with the optimistic update decision (nbb200_set_optimistic_updates): one host synchronisation per call instead of two
+    m.L.nbb200_enable_timing(m.h, 0)
+    m.L.nbb200_set_optimistic_updates(m.h, 1)
     ms_nr = timed_steps(torch, lambda: m.step(rebuild=False), 50, 5, lambda: None)
-    f = statistics.mean(fk)
+    m.L.nbb200_set_optimistic_updates(m.h, 0)
+    m.L.nbb200_enable_timing(m.h, 1)
+    f, f_nr = statistics.mean(fk), statistics.mean(fk_nr)
     ach = pairs * FLOP_PER_LIST_PAIR / (f * 1e-3) / 1e12
-    return {"workload": workload_description("dhfr", w) + " (the reference's own JAC benchmark input, benchmarks/data/dhfr)", "list_pairs": pairs, "ms_per_call_rebuild": ms, "ms_per_call_no_rebuild": ms_nr,
+    return {"workload": workload_description("dhfr", w) + " (the reference's own JAC benchmark input, benchmarks/data/dhfr)", "list_pairs": pairs, "ms_per_call_rebuild": ms,
+            "ms_per_call_no_rebuild": ms_nr, "ms_per_call_no_rebuild_two_syncs": ms_nr_sync,
+            "no_rebuild_note": "Update + MMMMEnergy on device arrays, lists kept; optimistic update decision (one synchronisation per call); two_syncs: the plain call pair",
             "value": pairs / (ms * 1e-3), "value_no_rebuild": pairs / (ms_nr * 1e-3), "unit": "list-pairs/s",
-            "kernels_ms": {"list_rebuild": statistics.mean(lb), "tile_forces": f}, "roofline_frac_fp32": ach / fp32_peak_tflops}
+            "kernels_ms": {"list_rebuild": statistics.mean(lb), "tile_forces": f, "tile_forces_no_rebuild": f_nr}, "roofline_frac_fp32": ach / fp32_peak_tflops,
+            "roofline_frac_fp32_no_rebuild": pairs * FLOP_PER_LIST_PAIR / (f_nr * 1e-3) / 1e12 / fp32_peak_tflops}
 
 
 def md_block(torch, local, steps=300):
@@ -609,6 +634,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-jac", action="store_true")
     args = ap.parse_args()
+    args.ref_sample_explicit = args.ref_sample
     if args.ref_sample is None:
         args.ref_sample = "water4x4x4" if args.workload == "m1" else args.workload
     if args.warmup < 3 and args.impl == "b200":

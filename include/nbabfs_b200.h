@@ -123,6 +123,14 @@ void NBModelABFS_B200_MMMMEnergy(NBB200State *state, double *energies, double *g
  * upload of the array are then not needed.  Default 0 = the reference's accumulation.  The device-array calls (...MMMMEnergyDevice,
  * ...MMMMEnergyDeviceDeferred) honour it as well: d_grad is then SET by the NB term (no zero fill by the caller). */
 void nbb200_set_gradient_overwrite(NBB200State *state, int on);
+/* Optimistic update decision for the device-array calls (one host synchronisation per Update + MMMMEnergyDevice pair instead of two):
+ * NBModelABFS_B200_UpdateDevice enqueues CheckForUpdate's displacement test (pM/csource/NBModelABFS.c:691-746) and returns 0 at once;
+ * the NBModelABFS_B200_MMMMEnergyDevice that follows evaluates on the current lists and reads the decision with its own results.  When
+ * an update was due, nothing of that evaluation is handed out: the lists are rebuilt at the same coordinates and the call is evaluated
+ * again, so the results are those of the plain call sequence; NBModelABFSState numberOfUpdates is current after the energy call. */
+void nbb200_set_optimistic_updates(NBB200State *state, int on);
+/* NBModelABFSState.numberOfCalls / .numberOfUpdates (pM/cinclude/NBModelABFSState.h:38,42, printed by NBModelABFSState.StatisticsSummary) */
+void NBModelABFSState_B200_GetStatistics(NBB200State *state, long *numberOfCalls, long *numberOfUpdates);
 /* same, gradients accumulated into a device array d_grad[3n] (nullable) */
 void NBModelABFS_B200_MMMMEnergyDevice(NBB200State *state, double *energies, double *d_grad, double *dEdM, int *status);
 

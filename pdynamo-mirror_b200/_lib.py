@@ -50,6 +50,8 @@ SIGNATURES = {
     "nbb200_get_counters": (None, [vp, lp]),
     "nbb200_set_partition": (None, [vp, C.c_int, C.c_int]),
     "nbb200_set_gradient_overwrite": (None, [vp, C.c_int]),
+    "nbb200_set_optimistic_updates": (None, [vp, C.c_int]),
+    "NBModelABFSState_B200_GetStatistics": (None, [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
     "nbb200_vv_first_half": (None, [vp, vp, vp, vp, C.c_double]),
     "nbb200_vv_second_half": (None, [vp, vp, vp, vp, vp, C.c_double, vp]),
     "nbb200_md_run": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, dp, C.c_double, dp, C.c_double, C.c_ulonglong, C.c_ulonglong, vp, dp, dp, dp, dp, ip]),

@@ -185,7 +185,7 @@ static int update_common(State &s, const double *box6, int forceNew, int *status
 {
     s.numberOfCalls += 1;
     if (s.pending && (forceNew || s.isNew || decided >= 0 || s.list != s.stListCutoff || s.outer != s.stOuterCutoff)) flush_pending(s);   // no displacement check below
-    if (s.trans.n > 0) {
+    if (s.trans.n > 0 && !s.keepLattice) {
         if (box6 == nullptr) { set_error("box6 is required when transformations are present"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return 0; }
         s.lattice.set_crystal(box6);
     }
@@ -197,6 +197,17 @@ static int update_common(State &s, const double *box6, int forceNew, int *status
     if (s.timing) { s.timings[0] = 0.0; s.timings[3] = 0.0; }
     bool checked = false;
     if (decided >= 0) doUpdate = doUpdate || decided != 0;       // several ranks: the displacement decision was taken collectively by the caller
+    s.optPending = false;
+    if (!doUpdate && decided < 0 && s.optimistic && s.nranks == 1 && !s.useCentering && !s.pending && !s.timing &&
+        (s.trans.n == 0 || (s.haveRefLattice && std::memcmp(s.lattice.M.v, s.refLattice.M.v, sizeof(double) * 9) == 0))) {
+        // optimistic decision: the check is enqueued, its result comes back with the energy call's synchronisation (see State::optimistic)
+        const double buffac = 0.5 * (s.list - s.stOuterCutoff);
+        if (!s.optDisp.ensure(2) || !displacement_enqueue(s, s.xcur, s.optDisp.p) ||
+            !cuda_ok(cudaMemcpyAsync(s.hsmall + (kSmallDoubles - 8), s.optDisp.p, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
+        s.optPending = true; s.optThr2 = buffac * buffac;
+        s.isNew = false;
+        return 0;
+    }
     if (!doUpdate && decided < 0) {
         const double buffac = 0.5 * (s.list - s.stOuterCutoff);
         double maxr2 = 0.0; int exceeded = 0;
@@ -536,7 +547,25 @@ void NBModelABFS_B200_MMMMEnergyDevice(NBB200State *state, double *energies, dou
     cudaSetDevice(s.device);
     if (s.xcur == nullptr) { set_error("MMMMEnergy called before Update"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
     flush_pending(s);
-    if (energy_enqueue(s, d_grad) && cuda_ok(cudaStreamSynchronize(s.stream), "sync")) energy_finish(s, energies, d_grad != nullptr, dEdM);
+    if (s.optPending) { s.condDisp = s.optDisp.p; s.condThr2 = s.optThr2; }
+    bool ok = energy_enqueue(s, d_grad) && cuda_ok(cudaStreamSynchronize(s.stream), "sync");
+    s.condDisp = nullptr;
+    if (ok && s.optPending) {
+        s.optPending = false;
+        if (s.hsmall[kSmallDoubles - 8] > s.optThr2) {
+            // an update was due: nothing of the evaluation above has been handed out; rebuild at these coordinates and evaluate again
+            s.numberOfCalls -= 1;
+            const bool opt = s.optimistic;
+            s.optimistic = false;
+            int st = NBB200_STATUS_CONTINUE;
+            s.keepLattice = true;                       // the lattice of the Update call that is being completed
+            update_common(s, nullptr, 1, &st);
+            s.keepLattice = false;
+            s.optimistic = opt;
+            ok = st == NBB200_STATUS_CONTINUE && energy_enqueue(s, d_grad) && cuda_ok(cudaStreamSynchronize(s.stream), "sync");
+        }
+    }
+    if (ok) energy_finish(s, energies, d_grad != nullptr, dEdM);
     else set_status(status, NBB200_STATUS_LOGIC_ERROR);
 }
 
@@ -1335,6 +1364,19 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
     if (nbEnergies6 != nullptr) std::memcpy(nbEnergies6, last, sizeof(double) * 6);
     if (bondedEnergies5 != nullptr) std::memcpy(bondedEnergies5, e5, sizeof(e5));
     return updates;
+}
+
+void NBModelABFSState_B200_GetStatistics(NBB200State *state, long *numberOfCalls, long *numberOfUpdates)
+{
+    if (state == nullptr) return;
+    const State &s = *reinterpret_cast<State *>(state);
+    if (numberOfCalls != nullptr) *numberOfCalls = s.numberOfCalls;
+    if (numberOfUpdates != nullptr) *numberOfUpdates = s.numberOfUpdates;
+}
+
+void nbb200_set_optimistic_updates(NBB200State *state, int on)
+{
+    if (state != nullptr) reinterpret_cast<State *>(state)->optimistic = on != 0;
 }
 
 void nbb200_set_gradient_overwrite(NBB200State *state, int on)

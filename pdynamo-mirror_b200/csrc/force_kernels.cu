@@ -170,6 +170,7 @@ struct __align__(16) IStage {
     int2   row[kCluster / 2];       // byte offsets of the atoms' LJ-table rows
     int2   pad[kCluster / 2];
     float4 recA[kTile], recB[kTile];
+    float4 nextA[kCluster], nextB[kCluster];   // records of the NEXT item's cluster atoms (asynchronous copies issued one item ahead)
     double sum[3][kTile];           // per lane: Coulomb energy, LJ energy, component (lane & 3) of the summed i gradients
 };
 
@@ -352,6 +353,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
         mbar_expect_tx(mbar0, bytes);
         bulk_copy_g2s(smem_addr(sDesc), A.tileDesc + (size_t) wiNext.tileStart * kTile, bytes, mbar0);
     }
+    // the records of an item's cluster atoms are copied one item ahead as well (padding rows of the last cluster: the null record, index n)
+    auto fetch_i = [&](const WorkItem &w) {
+        if (lane < kCluster) {
+            const int si = min(w.block * kCluster + lane, A.n);
+            cp_async16(smem_addr(&ist->nextA[lane]), A.recA + si); cp_async16(smem_addr(&ist->nextB[lane]), A.recB + si);
+        }
+    };
+    if (itNext < (unsigned int) A.nitems) fetch_i(wiNext);
     for (;; seq++) {
         if (itNext >= (unsigned int) A.nitems) break;
         const WorkItem wi = wiNext;
@@ -366,13 +375,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
 
         // cluster-local frame: K of the first cluster atom (a multiple of 8 A, exact in fp32)
         const int s0 = wi.block * kCluster;
-        const float4 kref = A.recB[s0];
-        __syncwarp();                                       // the previous item's last tile has been consumed
+        cp_async_wait_all();
+        __syncwarp();                                       // the previous item's last tile has been consumed; this item's cluster records have landed
+        const float4 kref = ist->nextB[0];
         bool ljFree = false;
+        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+        if (lane < kCluster) { ra = ist->nextA[lane]; rb = ist->nextB[lane]; }
+        __syncwarp();                                       // ... and have been read: the slots are free for the next item's
         if (lane < kCluster) {
-            // padding rows of the last cluster read the null record (index n): far away, zero charge, null LJ type
-            const int si = min(s0 + lane, A.n);
-            const float4 ra = A.recA[si], rb = A.recB[si];
             // the small part tl of a pure translation (|tl| <= 4 A) is taken off the i atoms instead of being added to every j atom
             float tlx = 0.f, tly = 0.f, tlz = 0.f;
             if (isImage && pureT) { tlx = op->tl[0]; tly = op->tl[1]; tlz = op->tl[2]; }
@@ -400,6 +410,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
 
         // the item's descriptors have landed in shared memory (bulk copy issued one item ago) ...
         mbar_wait(mbar0 + 8 * (seq & 1u), (seq >> 1) & 1u);
+        if (itNext < (unsigned int) A.nitems) fetch_i(wiNext);
         if (lane == 0 && itNext < (unsigned int) A.nitems) {
             // ... and the next item's stream goes to the other buffer: its last reader (the item before this one) finished before the
             // __syncwarp at the top of this item
@@ -690,10 +701,12 @@ __global__ void __launch_bounds__(kPruneWarps * 32) k_prune(const __grid_constan
 // the plain one keeps gs const / read-only (the combined one measured 9 x slower on the 1.1 M-atom box: 143 vs 16 us)
 template <bool kClear>
 __global__ void k_unsort_gradients(typename std::conditional<kClear, double, const double>::type *__restrict__ gs, const int *__restrict__ sAtom, int s0, int n,
-                                   double *__restrict__ grad, int assign)
+                                   double *__restrict__ grad, int assign, const double *__restrict__ cond, double condThr2)
 {
     const int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
+    // optimistic update decision: the lists turned out to be stale (an atom moved beyond the buffer) -- this evaluation is discarded
+    if (cond != nullptr && *cond > condThr2) return;
     const int a = sAtom[s];
     const double gx = gs[3 * s], gy = gs[3 * s + 1], gz = gs[3 * s + 2];
     if (assign) { grad[3 * a] = gx; grad[3 * a + 1] = gy; grad[3 * a + 2] = gz; }
@@ -848,8 +861,8 @@ bool unsort_gradients(State &s, long s0, long s1, double *d_grad, bool assign, b
     if (s1 <= s0 || d_grad == nullptr || s.gs == nullptr) return true;
     const int threads = 256;
     const unsigned int blocks = (unsigned int) ((s1 - s0 + threads - 1) / threads);
-    if (clear) k_unsort_gradients<true><<<blocks, threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0);
-    else k_unsort_gradients<false><<<blocks, threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0);
+    if (clear) k_unsort_gradients<true><<<blocks, threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0, s.condDisp, s.condThr2);
+    else k_unsort_gradients<false><<<blocks, threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0, s.condDisp, s.condThr2);
     s.launches += 1;
     return cuda_ok(cudaGetLastError(), "k_unsort_gradients");
 }
@@ -952,20 +965,35 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
             splBytes = sizeof(float4) * 3 * (size_t) s.spl.points();
         }
         A.gradSorted = wantGrad ? s.gs : nullptr; A.accum = s.accum.p;
+        static const bool forcedShape = std::getenv("NBB200_FORCE_SHAPE") != nullptr;
         static const ForceVariant *chosen = []() {
             const char *e = std::getenv("NBB200_FORCE_SHAPE");
             for (const ForceVariant &v : kForceVariants) if (e != nullptr && std::strcmp(e, v.name) == 0) return &v;
             return &kForceVariants[0];
         }();
         const bool splSmem = spline && splBytes <= kSplineSmemLimit;
-        const ForceVariant &v = spline ? kForceSpline[rot ? 1 : 0][splSmem ? 1 : 0] : (rot ? kForceRot : *chosen);
-        const int warpsPerBlock = v.threads / 32;
         const size_t warpBytes = 2 * (size_t) s.chunkTiles * kTile * sizeof(unsigned int) + sizeof(IStage) + 32;
-        const size_t smem = warpBytes * warpsPerBlock + kLJEntryBytes * (size_t) (s.ntypes + 1) * (s.ntypes + 1) + (splSmem ? splBytes : 0);
-        if (smem > 200 * 1024) { set_error("too many LJ types for the shared-memory table"); return false; }
-        int perSM = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, v.fn, v.threads, smem);
-        if (perSM < 1) perSM = 1;
+        const size_t tableBytes = kLJEntryBytes * (size_t) (s.ntypes + 1) * (s.ntypes + 1) + (splSmem ? splBytes : 0);
+        auto resident_warps = [&](const ForceVariant &f, size_t &smemOut, int &perSMOut) {
+            smemOut = warpBytes * (f.threads / 32) + tableBytes;
+            if (smemOut > 200 * 1024) return 0;
+            perSMOut = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMOut, f.fn, f.threads, smemOut);
+            return perSMOut * (f.threads / 32);
+        };
+        // launch shape: the default unless the tables of the CTA (LJ entries of all type pairs: 41 KB for 35 types) cost it resident warps --
+        // then the wide CTA, whose eight warps share one copy (DHFR: 12 -> 16 warps per SM)
+        const ForceVariant *pick = spline ? &kForceSpline[rot ? 1 : 0][splSmem ? 1 : 0] : (rot ? &kForceRot : chosen);
+        size_t smem = 0; int perSM = 0;
+        int warps = resident_warps(*pick, smem, perSM);
+        if (!spline && !rot && !forcedShape) {
+            size_t smem2 = 0; int perSM2 = 0;
+            const int warps2 = resident_warps(kForceVariants[2], smem2, perSM2);      // 256x2
+            if (warps2 > warps) { pick = &kForceVariants[2]; smem = smem2; perSM = perSM2; warps = warps2; }
+        }
+        if (warps == 0) { set_error("too many LJ types for the shared-memory table"); return false; }
+        const ForceVariant &v = *pick;
+        const int warpsPerBlock = v.threads / 32;
         const int grid = std::max(1, std::min(g_numSMs * perSM, (nitems + warpsPerBlock - 1) / warpsPerBlock));
         if (s.timing) cudaEventRecord(s.ev[2], s.stream);
         v.fn<<<grid, v.threads, smem, s.stream>>>(A);

@@ -107,7 +107,7 @@ bool langevin_first_disp(State &s, double *d_x, double *d_v, const double *d_a, 
 // ---- force_kernels.cu
 bool upload_spline_tables(State &s);                     // s.spl -> s.splF64 / s.splPoly
 bool launch_forces(State &s, double *d_grad, bool sortedOnly);
-bool unsort_gradients(State &s, long s0, long s1, double *d_grad, bool assign = false, bool clear = false);
+bool unsort_gradients(State &s, long s0, long s1, double *d_grad, bool assign = false, bool clear = false);   // honours s.condDisp
 void init_force_kernel_attributes();
 
 struct State {
@@ -229,6 +229,15 @@ struct State {
     DevBuf<double> sigStage;                     // device staging: [0] local displacement maximum, [1..16] scalars, [17..32] results, [33] timeout flag
     bool peerOpened[kMaxPeers] = {};
     bool peersReady = false;
+    // optimistic update decision (nbb200_set_optimistic_updates): Update enqueues the displacement check without waiting for it, the
+    // energy call that follows evaluates on the current lists and its one synchronisation brings the decision back; when an update was
+    // due after all the gradient is not handed out (the unsort pass looks at the device-side maximum), the lists are rebuilt and the
+    // call is repeated
+    bool optimistic = false, optPending = false, keepLattice = false;
+    double optThr2 = 0.0;
+    DevBuf<double> optDisp;                      // device: max |x - xref|^2 of the pending decision
+    const double *condDisp = nullptr;            // unsort pass: skip when *condDisp > condThr2
+    double condThr2 = 0.0;
     bool gradOverwrite = false;                  // MMMMEnergy (host arrays) sets the caller's gradient instead of accumulating
     bool mdFused = false;                        // inside nbb200_md_run: memsets folded into neighbouring kernels (accumulators by k_pack_records, sorted gradient by k_unsort_gradients)
     bool gsZeroed = false;                       // the caller zeroed the sorted gradient for this call already (before the ranks' barrier)                        // touched sorted range per rank slab (min, max+1)

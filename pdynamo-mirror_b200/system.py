@@ -50,6 +50,10 @@ class SymmetryParameters:
     def __init__(self, a, b, c, alpha=90.0, beta=90.0, gamma=90.0):
         self.box6 = np.array([a, b, c, alpha, beta, gamma], dtype=np.float64)
 
+    def SetCrystalParameters(self, a, b, c, alpha, beta, gamma):
+        """pMolecule.SymmetryParameters.SetCrystalParameters (pM/pyrex/pMolecule.SymmetryParameters.pyx): new cell lengths and angles"""
+        self.box6 = np.array([a, b, c, alpha, beta, gamma], dtype=np.float64)
+
 
 class SymmetryParameterGradients:
     def __init__(self):

@@ -294,6 +294,24 @@ def water216_real(box=None, name="w216", wrap=False):
                    _water_topology(nw), np.zeros((0, 2), np.int32), a if box is None else box, name, scale14=0.5)
 
 
+def water216_example20(name="w216_mm"):
+    """Book Example 20 as the reference sets it up: the 216-water box with the OPLS "bookSmallExamples" MM model, i.e. the NB terms of
+    `w216` plus the flexible-water bonded terms (parameters/forceFields/opls/bookSmallExamples/harmonicBondParameters.yaml:26 HW-OW
+    0.9572 A / 529.60, harmonicAngleParameters.yaml:34 HW-OW-HW 104.52 deg / 34.05, ureyBradleyParameters.yaml:20 HW..HW 1.5139 A / 38.25,
+    kcal/mol units).  Known answer: the potential energy the reference prints for the stored coordinates,
+    book/logs/Example20.log:70 (time 0): -8285.33515551 kJ/mol."""
+    w = water216_real(name=name)
+    nw = w["n"] // 3
+    o = 3 * np.arange(nw, dtype=np.int32)
+    bonds = np.stack([np.concatenate([o, o]), np.concatenate([o + 1, o + 2])], axis=1).astype(np.int32)
+    w["bonded"] = dict(bonds=bonds, bond_eq=np.full(len(bonds), 0.9572), bond_fc=np.full(len(bonds), 529.60 * KCAL),
+                       angles=np.stack([o + 1, o, o + 2], axis=1).astype(np.int32), angle_eq=np.full(nw, np.deg2rad(104.52)), angle_fc=np.full(nw, 34.05 * KCAL),
+                       ureybradleys=np.stack([o + 1, o + 2], axis=1).astype(np.int32), ub_eq=np.full(nw, 1.5139), ub_fc=np.full(nw, 38.25 * KCAL))
+    w["masses"] = np.tile([15.9994, 1.00794, 1.00794], nw)
+    w["published_potential_energy"] = -8285.33515551
+    return w
+
+
 def replicated_water_xyz(nx, ny, nz, jitter=0.02, seed=4242):
     """The equilibrated box wrapped by molecule into [0,a)^3 and replicated nx x ny x nz times, plus a small jitter so
     that replicas are not exact copies.  Returns (xyz, nwaters, (ax, ay, az))."""
@@ -518,6 +536,7 @@ WORKLOADS = {
     "w216": lambda: water216_real(),
     "bala_fixed": _bala_fixed,
     "w216_fixed": _w216_fixed,
+    "w216_mm": water216_example20,                        # book Example 20: the same box with the OPLS flexible-water bonded terms
     "w216_lattice": lambda: water_box(6, name="w216_lattice"),
     "w216_triclinic": lambda: water216_real(box=[21.5, 22.0, 23.0, 85.0, 95.0, 100.0], name="w216_triclinic", wrap=True),
     "bala": lambda: bala_water(),

@@ -425,6 +425,34 @@ def make_golden(only=None):
         r.close()
 
 
+
+# ----------------------------------------------------------------------------------------------------
+# the headline workload itself (1 119 744-atom water box, bench.py's m1) through the compiled reference: energies, dE/dM, list sizes, a
+# 65 536-row sample of the gradient and eight seeded random projections of the whole gradient (what a GPU test can compare at the
+# size the bench runs at; the full fp64 gradient would be 27 MB).  About a minute and ~20 GB on the OpenMP build.
+# ----------------------------------------------------------------------------------------------------
+def m1_projection_vectors(n, count=8, seed=20261017):
+    rng = np.random.default_rng(seed)
+    return [rng.standard_normal((n, 3)) for _ in range(count)]
+
+
+def make_golden_m1():
+    import pdynamo_mirror_b200 as p
+    import refnb
+    w = p.workloads.WORKLOADS["m1"]()
+    r = refnb.RefNB(w, omp=True)
+    out = r.energy(force_new=True)
+    c = r.counts()
+    g = out["grad"]
+    rows = np.sort(np.random.default_rng(7).choice(w["n"], 65536, replace=False))
+    proj = np.array([float((v * g).sum()) for v in m1_projection_vectors(w["n"])])
+    data = dict(energies=out["energies"], dEdM=out["dEdM"], counts=np.array([c[k] for k in sorted(c)], dtype=np.int64), count_keys=np.array(sorted(c)),
+                grad_rows=rows, grad_sample=g[rows], grad_rms=float(np.sqrt((g * g).mean())), grad_sum=g.sum(axis=0), grad_proj=proj)
+    np.savez_compressed(os.path.join(HERE, "golden_m1.npz"), **data)
+    print("m1", out["energies"], c)
+    r.close()
+
+
 # ----------------------------------------------------------------------------------------------------
 # QC/MM entry points of NBModelABFS (second half): golden vectors of the COMPILED reference for a QC region
 # without boundary atoms (oracle/ref_driver.c refqc_*, oracle/refnb.py RefQC).  The B200 side of this row is not built yet;
@@ -473,3 +501,5 @@ if __name__ == "__main__":
         make_qcmm()
     if what in ("golden", "all"):
         make_golden(only=sys.argv[2:])          # python make_fixtures.py golden [case ...]
+    if what == "m1":
+        make_golden_m1()                        # the 1.1 M-atom bench workload (not part of "all": a minute of CPU, ~20 GB)

@@ -267,6 +267,51 @@ def test_update_heuristic_and_stale_lists(pkg, orc):
     assert np.linalg.norm((cfg.symmetryParameterGradients.dEdM - 1.0) - ref["dEdM"]) <= M_TOL * np.linalg.norm(ref["dEdM"])
 
 
+def test_optimistic_update_decision_equals_the_plain_sequence(pkg, orc):
+    """nbb200_set_optimistic_updates: Update enqueues CheckForUpdate's displacement test and the energy call reads the decision with its
+    results (one host synchronisation per call pair).  Same numbers, same update counts as the plain sequence -- also for the call in
+    which an update turns out to be due (that evaluation is discarded on the device and repeated on the new lists)."""
+    import ctypes as C
+    import torch
+    from pdynamo_mirror_b200 import _lib
+    w = pkg.workloads.WORKLOADS["bala"]()
+    u = pkg.workloads.lcg_uniform(11, 3 * w["n"]).reshape(-1, 3)
+    xs = [w["xyz"] + (2 * u - 1) * a for a in (0.0, 0.2, 0.35)]
+    x3 = xs[2].copy(); x3[40] += np.array([0.0, 1.1, 0.0]); xs.append(x3)            # beyond the buffer: update due
+    xs.append(x3 + (2 * u - 1) * 0.1)
+    results = {}
+    for mode in (0, 1):
+        system, st, e, g, dm = gpu_energy(pkg, w)
+        L, h = _lib.lib(), st.cObject
+        L.nbb200_set_stream(h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        L.nbb200_set_optimistic_updates(h, mode)
+        box = np.ascontiguousarray(w["box"], np.float64)
+        out = []
+        for x in xs:
+            xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+            gd = torch.full((w["n"], 3), 3.0, dtype=torch.float64, device="cuda")
+            status = C.c_int(16)
+            en, m9 = np.zeros(6), np.zeros(9)
+            L.NBModelABFS_B200_UpdateDevice(h, C.c_void_p(xd.data_ptr()), _lib.d_(box), 0, C.byref(status))
+            L.NBModelABFS_B200_MMMMEnergyDevice(h, _lib.d_(en), C.c_void_p(gd.data_ptr()), _lib.d_(m9), C.byref(status))
+            assert status.value == 16, _lib.last_error()
+            ncalls, nupd = C.c_long(0), C.c_long(0)
+            L.NBModelABFSState_B200_GetStatistics(h, C.byref(ncalls), C.byref(nupd))
+            out.append((en.copy(), gd.cpu().numpy() - 3.0, m9.copy(), nupd.value))
+        results[mode] = out
+        L.nbb200_set_optimistic_updates(h, 0)
+    o = orc.OracleNB(w)
+    o.energy(force_new=True)
+    for k, x in enumerate(xs):
+        ref = o.energy(xyz=x)
+        (e0, g0, m0, n0), (e1, g1, m1, n1) = results[0][k], results[1][k]
+        assert n0 == n1, (k, n0, n1)
+        assert same_call(e1, e0) and same_call(g1, g0) and same_call(m1, m0), k
+        assert abs(e1.sum() - ref["energies"].sum()) <= ILL_CONDITIONED["perturbed"] * abs(ref["energies"].sum())
+        assert np.sqrt(((g1 - ref["grad"]) ** 2).mean()) <= G_TOL * np.sqrt((ref["grad"] ** 2).mean())
+    assert results[1][3][3] == results[1][2][3] + 1          # the fourth call rebuilt the lists
+
+
 def test_options_change_triggers_rebuild_and_dielectric_scales(pkg, orc):
     w = pkg.workloads.WORKLOADS["w216"]()
     system, st, e, g, dm = gpu_energy(pkg, w)
@@ -728,6 +773,119 @@ def test_full_size_m1_properties(pkg):
     rep = g_b.reshape(1728, 648, 3)
     rms = np.sqrt((g_u ** 2).mean())
     assert np.sqrt(((rep - g_u[None]) ** 2).mean()) <= 2e-5 * rms
+
+
+def test_headline_workload_against_the_compiled_reference(pkg):
+    """The bench workload itself (m1: 1 119 744 atoms, 575 293 088 list pairs) against golden outputs of the compiled reference
+    (tests/golden/golden_m1.npz, made by `make_fixtures.py m1` from oracle/_ref): six energies and their sum at 1e-6, dE/dM at 1e-5, list
+    sizes exactly, a 65 536-row sample of the gradient at 1e-5 relative RMS, eight seeded random projections of the WHOLE gradient."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_fixtures import m1_projection_vectors
+    gold = load_golden("m1")
+    w = pkg.workloads.WORKLOADS["m1"]()
+    system, st, e, g, dm = gpu_energy(pkg, w)
+    counts = dict(zip([str(k) for k in gold["count_keys"]], [int(v) for v in gold["counts"]]))
+    assert st.NumberOfPairs() == counts["primary"] and st.NumberOfImagePairs() == counts["image_pairs"] and st.NumberOfImages() == counts["images"]
+    re = gold["energies"]
+    assert abs(e.sum() - re.sum()) <= E_TOL * abs(re.sum())
+    for k in range(6):
+        assert abs(e[k] - re[k]) <= E_TOL * abs(re[k]), (k, e[k], re[k])
+    assert np.linalg.norm(dm - gold["dEdM"]) <= M_TOL * np.linalg.norm(gold["dEdM"])
+    rows, gs = gold["grad_rows"], gold["grad_sample"]
+    assert np.sqrt(((g[rows] - gs) ** 2).mean()) <= G_TOL * np.sqrt((gs ** 2).mean())
+    assert abs(np.sqrt((g * g).mean()) - float(gold["grad_rms"])) <= G_TOL * float(gold["grad_rms"])
+    # v standard normal: v . (g - g_ref) is of the size of |g - g_ref| = (relative RMS error) x rms x sqrt(3 n)
+    scale = float(gold["grad_rms"]) * np.sqrt(3.0 * w["n"])
+    for v, ref in zip(m1_projection_vectors(w["n"]), gold["grad_proj"]):
+        assert abs(float((v * g).sum()) - float(ref)) <= 5.0 * G_TOL * scale
+    # a second call walks the pruned inner pool: the same numbers
+    system.Energy(doGradients=True)
+    e2 = system.configuration.nbState.energies
+    assert abs(e2.sum() - re.sum()) <= E_TOL * abs(re.sum())
+    g2 = system.configuration.gradients3
+    assert np.sqrt(((g2[rows] - gs) ** 2).mean()) <= G_TOL * np.sqrt((gs ** 2).mean())
+
+
+def test_published_example20_potential_energy(pkg, orc):
+    """Config 1's published number: book/logs/Example20.log:70 prints the potential energy of the stored 216-water box with the OPLS
+    model (NB terms + flexible-water bonded terms) as -8285.33515551 kJ/mol; System.Energy of the mirror, everything on the device."""
+    w = pkg.workloads.WORKLOADS["w216_mm"]()
+    system = pkg.System.FromWorkload(w)
+    system.DefineNBModel(pkg.NBModelABFS())
+    total = system.Energy(doGradients=True)
+    assert abs(total - w["published_potential_energy"]) <= E_TOL * abs(w["published_potential_energy"]), total
+    o = orc.OracleNB(w)
+    ref = o.energy(force_new=True)
+    e5, g5 = orc.mm_energy(w["bonded"], w["xyz"])
+    rg = ref["grad"] + g5
+    assert np.sqrt(((system.configuration.gradients3 - rg) ** 2).mean()) <= G_TOL * np.sqrt((rg ** 2).mean())
+
+
+@pytest.mark.parametrize("case", ["pair_03", "pair_045", "water_damp3", "water_damp3_spline", "bala_damp2"])
+def test_pairs_inside_the_damped_core(pkg, orc, case):
+    """The third branches of the ABFS macros (PairwiseInteraction.h:72-119: r < dampingCutoff, including the sign of the LJ-B term the
+    reference has there): a two-atom system at 0.3 / 0.45 A, and condensed systems with a damping cutoff so large (3 A / 2 A) that
+    thousands of listed pairs sit inside the core -- the slow path of the tile kernel (damped_tile_fix) against the oracle."""
+    opts = {}
+    if case.startswith("pair"):
+        w0 = pkg.workloads.WORKLOADS["w216"]()
+        w = _vacuum(w0)
+        r = 0.3 if case == "pair_03" else 0.45
+        w["xyz"] = np.array([[0.0, 0.0, 0.0], [r * 0.6, r * 0.0, r * 0.8]])
+        w["charges"], w["ljtypes"], w["n"] = w0["charges"][[0, 3]].copy(), w0["ljtypes"][[0, 3]].copy(), 2
+        w["exclusions"], w["pairs14"] = w0["exclusions"][:0].copy(), w0["pairs14"][:0].copy()
+    elif case.startswith("water"):
+        w = pkg.workloads.WORKLOADS["w216"]()
+        opts = dict(dampingCutoff=3.0)
+        if case.endswith("spline"):
+            opts.update(useAnalyticForm=False)
+    else:
+        w = pkg.workloads.WORKLOADS["bala"]()
+        opts = dict(dampingCutoff=2.0)
+    system, st, e, g, dm = gpu_energy(pkg, w, **opts)
+    o = orc.OracleNB(w, **opts)
+    ref = o.energy(force_new=True)
+    x = w["xyz"]
+    if not case.startswith("pair"):
+        # the case means something only if listed pairs really are inside the core
+        pr = o.primary_pairs()
+        d = np.linalg.norm(x[pr[:, 0]] - x[pr[:, 1]], axis=1)
+        assert (d < opts["dampingCutoff"]).sum() > 500
+    assert np.array_equal(orc.canonical_primary(st.Pairs(-1)), orc.canonical_primary(o.primary_pairs()))
+    re = ref["energies"]
+    assert abs(e.sum() - re.sum()) <= E_TOL * np.abs(re).sum(), (e, re)
+    for k in range(6):
+        assert abs(e[k] - re[k]) <= E_TOL * np.abs(re).sum(), (k, e[k], re[k])
+    # spline form with a 3 A core: the fp32 cubic tables across the kink at the core boundary, where the LJ term is steep (thousands of
+    # kJ/mol/A per pair against an RMS gradient of 45), leave 1.4e-5 -- a stress case of the table form, not of the slow path tested here
+    gtol = 3.0e-5 if case.endswith("spline") else G_TOL
+    assert np.sqrt(((g - ref["grad"]) ** 2).mean()) <= gtol * np.sqrt((ref["grad"] ** 2).mean())
+
+
+def test_lattice_change_update_decision(pkg, orc):
+    """CheckForImageUpdate (NBModelABFS.c:635-684) on the device path: with unchanged coordinates a small change of the lattice keeps
+    the lists (both sides evaluate the old lists with the new image translations), a larger one rebuilds them; energies, gradients and
+    dE/dM agree with the oracle after each call, and the two sides take the same decisions."""
+    w = pkg.workloads.WORKLOADS["w216"]()
+    system, st, e, g, dm = gpu_energy(pkg, w)
+    o = orc.OracleNB(w)
+    o.energy(force_new=True)
+    a0 = float(np.asarray(w["box"], dtype=np.float64).reshape(-1)[0])
+    decisions = []
+    for scale in (1.0005, 1.002, 1.02, 1.021, 0.97):
+        box = [a0 * scale] * 3 + [90.0] * 3
+        system.symmetryParameters.SetCrystalParameters(*box)
+        nup = st.numberOfUpdates
+        system.Energy(doGradients=True)
+        ref = o.energy(box=box)
+        decisions.append((st.numberOfUpdates - nup, int(ref["updated"])))
+        assert decisions[-1][0] == decisions[-1][1], (scale, decisions)
+        cfg = system.configuration
+        check_numbers("perturbed", st.energies, cfg.gradients3, cfg.symmetryParameterGradients.dEdM, ref["energies"], ref["grad"], ref["dEdM"])
+        if ref["updated"]:
+            assert np.array_equal(orc.canonical_primary(st.Pairs(-1)), orc.canonical_primary(o.primary_pairs()))
+    assert any(d[0] == 0 for d in decisions) and any(d[0] == 1 for d in decisions), decisions
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
