@@ -239,7 +239,9 @@ def run_b200(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.pop("NCCL_DEBUG", None)          # NCCL prints its version banner on stdout at any debug level: keep stdout to the one JSON line
+        # NCCL prints its banner / debug lines on stdout by default: send them to stderr so that stdout stays the one JSON line while the
+        # driver can still read NCCL_DEBUG=INFO output (rank counts, transports)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
 
     def barrier():
@@ -324,8 +326,13 @@ def run_b200(args):
         "config": {"workload": workload_description(args.workload, w), "list_pairs": pairs, "step": "forced list rebuild + E + gradients",
                    "l2": "inputs (coordinates + tile lists, %.0f MB) %s L2; timed iterations run back to back" %
                          ((counters["tiles"] * 128 + 80 * n) / 1e6, "exceed" if counters["tiles"] * 128 + 80 * n > 126e6 else "fit in"),
-                   "parallelism": ("1 GPU" if world == 1 else "%d spatial slabs of the cell-sorted order; per step NCCL send/recv of all slab positions (list rebuild) "
-                                   "or halo positions (no rebuild) and of halo gradient contributions to their owners, all-reduce of 15 scalars" % world)},
+                   "parallelism": ("1 GPU" if world == 1 else
+                                   ("%d spatial slabs of the cell-sorted order; per step every rank reads the slab positions (list rebuild) or halo positions (no rebuild) "
+                                    "it needs FROM its peers' memory and adds its halo gradient contributions INTO their accumulators with plain kernels over CUDA-IPC mapped "
+                                    "buffers (NVLink peer loads / fp64 atomics), update decision and the 15 scalars through flag areas in peer memory; NCCL only hands the "
+                                    "IPC handles round at set-up" % world) if (dn is not None and dn.transport == "peer") else
+                                   ("%d spatial slabs of the cell-sorted order; per step NCCL send/recv of all slab positions (list rebuild) or halo positions (no rebuild) "
+                                    "and of halo gradient contributions to their owners, all-reduce of 15 scalars" % world))},
         "no_rebuild": {"ms_per_call": ms_nr, "value": pairs / (ms_nr * 1e-3), "unit": "list-pairs/s"},
         "kernels_ms": {"list_rebuild": build_ms, "tile_forces": force_ms, "prune": allmax(statistics.mean(pr)), "pairs14": tm["pairs14"], "displacement_check": tm["displacementCheck"]},
         "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,

@@ -67,15 +67,25 @@ void NBModelABFSState_B200_SetFixedAtoms(NBB200State *state, int nfixed, const i
  * QC selection): the listed atoms leave every MM/MM list -- primary and image lists (and-selection of GenerateLists / GenerateImageLists,
  * pM/csource/NBModelABFS.c:508-623) and the 1-4 list (GenerateLists14, :1113-1128) -- so that NBModelABFS_B200_MMMMEnergy returns what
  * NBModelABFS_MMMMEnergy returns with a QC region present.  QC regions without boundary (link) atoms only; not with useCentering or
- * partitions.  The QC/MM entry points (NBModelABFS_QCMMEnergyLJ / _QCMMPotentials / _QCMMGradients, NBModelABFS.c:306-498) have no
- * counterpart here yet.  Call after SetUp, before the first Update; nqc = 0 clears.  Marks the state new. */
+ * partitions.  The QC/MM entry points (NBModelABFS_QCMMEnergyLJ / _QCMMPotentials / _QCMMGradients, NBModelABFS.c:306-498) follow.
+ * Call after SetUp, before the first Update; nqc = 0 clears.  Marks the state new. */
 void NBModelABFSState_B200_SetQCAtoms(NBB200State *state, int nqc, const int *qcAtoms, int *status);
-/* replaces NBModelABFS_QCMMEnergyLJ (pM/csource/NBModelABFS.c:306-378) for a QC region set with NBModelABFSState_B200_SetQCAtoms, in vacuum
- * or in a P1 cell, analytic form of the interaction: energies4 = {eqcmmlj, eqcmmlj14 (0 without boundary atoms), eimqcmmlj, eimqcqclj}
- * (NBModelABFSState.h:51-57); grad[3n] (host, nullable) is accumulated into.  Uses the coordinates and lattice of the last Update.  One fp64
- * launch over QC atoms x (cell + translated copies): the sums do not depend on the lists (csrc/qcmm.cu).  dE/dM of the image part, the
- * spline form, space-group operations and the electrostatic entry points (_QCMMPotentials, _QCMMGradients) are not built. */
-void NBModelABFS_B200_QCMMEnergyLJ(NBB200State *state, double *energies4, double *grad, int *status);
+/* The QC/MM entry points for a QC region set with NBModelABFSState_B200_SetQCAtoms (no boundary atoms), after an Update.  Supported:
+ * vacuum, P1 cells, and cells with space-group operations when every atom is a QC atom (QC/QC image terms only); analytic form of the
+ * MM/MM interaction for the LJ term.  One fp64 launch per call over (QC atom) x (image operation) x (atom): the sums do not depend on
+ * the reference's pair lists (every pair within the outer cutoff is on a valid list, pairs beyond it are skipped).
+ *
+ * NBModelABFS_QCMMEnergyLJ (pM/csource/NBModelABFS.c:306-378): energies4 = {eqcmmlj, eqcmmlj14 (0 without boundary atoms), eimqcmmlj,
+ * eimqcqclj}; grad[3 n] (host, nullable) and dEdM[9] (nullable: the image terms' SymmetryParameterGradients_ImageDerivatives) are
+ * accumulated into. */
+void NBModelABFS_B200_QCMMEnergyLJ(NBB200State *state, double *energies4, double *grad, double *dEdM, int *status);
+/* NBModelABFS_QCMMPotentials (NBModelABFS.c:454-498): electrostatic potentials of the MM charges (and their images) on the QC atoms in
+ * atomic units, potentials[nqc], and the QC/QC image potentials qcqcPotentials[nqc (nqc + 1) / 2] (packed lower triangle, SymmetricMatrix
+ * order); both are incremented, not reset, like the reference's; either may be NULL.  QC atoms are numbered in ascending atom index. */
+void NBModelABFS_B200_QCMMPotentials(NBB200State *state, double *potentials, double *qcqcPotentials, int *status);
+/* NBModelABFS_QCMMGradients (NBModelABFS.c:383-449): gradients of the QC/MM and QC/QC image electrostatic interactions for the QC charges
+ * qcCharges[nqc], regular units; grad[3 n] (host) and dEdM[9] (nullable) are accumulated into. */
+void NBModelABFS_B200_QCMMGradients(NBB200State *state, const double *qcCharges, double *grad, double *dEdM, int *status);
 /* replaces NBModelABFSState_SetUpCentering (pM/csource/NBModelABFSState.c:425-450; NBModelABFS option useCentering): the isolates
  * (connected components of the exclusion graph; those with a fixed atom stay) are moved into the primary cell by whole lattice vectors at
  * every list update and carried along in between (NBModelABFSState_InitializeCoordinates3, :278-311); lists and energies are evaluated on

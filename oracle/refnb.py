@@ -12,16 +12,23 @@ _LIBS = {}
 ENERGY_LABELS = ("MM/MM Elect.", "MM/MM LJ", "MM/MM 1-4 Elect.", "MM/MM 1-4 LJ", "MM/MM Image Elect.", "MM/MM Image LJ")
 
 
+def _path(omp=False):
+    # omp == "shim": the same driver and reference containers with the reference's NBModelABFS.c / NBModelABFSState.c replaced by
+    # pdynamo-mirror_b200/csrc/compat_shim.c on top of libnbabfs_b200.so (oracle/Makefile: libshim_nbabfs.so) -- the boundary under test
+    name = "libshim_nbabfs.so" if omp == "shim" else ("libref_nbabfs_omp.so" if omp else "libref_nbabfs.so")
+    return os.path.join(_HERE, "_ref", name)
+
+
 def available(omp=False):
-    return os.path.exists(os.path.join(_HERE, "_ref", "libref_nbabfs_omp.so" if omp else "libref_nbabfs.so"))
+    return os.path.exists(_path(omp))
 
 
 def _lib(omp=False):
-    key = bool(omp)
+    key = omp if omp == "shim" else bool(omp)
     if key in _LIBS:
         return _LIBS[key]
-    path = os.path.join(_HERE, "_ref", "libref_nbabfs_omp.so" if omp else "libref_nbabfs.so")
-    lib = C.CDLL(path)
+    path = _path(omp)
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
     lib.refnb_create.restype = vp
     lib.refnb_create.argtypes = [C.c_int, dp, ip, C.c_int, ip, dp, dp, C.c_int, ip, dp, dp,
@@ -250,8 +257,8 @@ class RefQC:
     COUNT_LABELS = ("nbmmmm", "nbqcmmlj", "nbqcmmel", "nbmmmm14", "nbqcmmlj14", "nbqcmmel14", "inbmmmm_images", "inbmmmm_pairs", "inbqcmmlj_images",
                     "inbqcmmlj_pairs", "inbqcmmel_images", "inbqcmmel_pairs", "inbqcqclj_images", "inbqcqclj_pairs", "inbqcqcel_images", "inbqcqcel_pairs")
 
-    def __init__(self, system, qc_index, qc_atomic_numbers, spline_point_density=50):
-        self.lib = _lib(False)
+    def __init__(self, system, qc_index, qc_atomic_numbers, spline_point_density=50, omp=False):
+        self.lib = _lib(omp)
         s = self.sys = system
         self.n = s["n"]
         q = np.ascontiguousarray(s["charges"], np.float64)

@@ -19,7 +19,9 @@ SIGNATURES = {
     "NBModelABFSState_B200_Deallocate": (None, [C.POINTER(vp)]),
     "NBModelABFSState_B200_SetFixedAtoms": (None, [vp, C.c_int, ip, ip]),
     "NBModelABFSState_B200_SetQCAtoms": (None, [vp, C.c_int, ip, ip]),
-    "NBModelABFS_B200_QCMMEnergyLJ": (None, [vp, dp, dp, ip]),
+    "NBModelABFS_B200_QCMMEnergyLJ": (None, [vp, dp, dp, dp, ip]),
+    "NBModelABFS_B200_QCMMPotentials": (None, [vp, dp, dp, ip]),
+    "NBModelABFS_B200_QCMMGradients": (None, [vp, dp, dp, dp, ip]),
     "NBModelABFSState_B200_SetUpCentering": (None, [vp, C.c_int, ip]),
     "NBModelABFS_B200_SetOptions": (None, [vp] + [C.c_double] * 6 + [C.c_int, C.c_int]),
     "NBModelABFS_B200_Update": (C.c_int, [vp, dp, dp, C.c_int, ip]),

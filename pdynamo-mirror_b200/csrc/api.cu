@@ -36,7 +36,7 @@ static void destroy(State *s)
     if (s == nullptr) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    s->q32.release(); s->q64.release(); s->ljtype.release(); s->ljAB.release(); s->ljAB14.release(); s->typeFree.release();
+    s->q32.release(); s->q64.release(); s->ljtype.release(); s->ljAB.release(); s->ljAB14.release(); s->typeFree.release(); s->qcIdxDev.release(); s->qcSlotDev.release(); s->qcWork.release(); s->qcImagesDev.release(); s->qcMMqDev.release(); s->qcAccDev.release(); s->qcGradDev.release(); s->qcSplDev.release(); s->qcPotDev.release(); s->qcLJDev.release();
     s->exclPtr.release(); s->exclCol.release(); s->pairs14.release(); s->fixedFlag.release(); s->qcFlag.release();
     s->isoPtr.release(); s->isoIdx.release(); s->xc.release(); s->isoT.release();
     s->x.release(); s->xref.release(); s->grad.release();

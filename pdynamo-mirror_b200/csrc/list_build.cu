@@ -539,15 +539,15 @@ __device__ __forceinline__ void emit_tile(const TileArgs &A, int lane, int clust
     if (lane == 0) { st->chunkBase = base; st->chunkUsed = close ? 0 : used; }
 }
 
-// 80 registers / 6 CTAs per SM with the plain bound; -DNBB_BUILD_MINBLOCKS=7 (72 registers) measured no faster, and an explicit
-// minimum of 1 lets ptxas take 132 registers (builder 1.59 -> 2.33 ms): keep the plain form as the default
+// The kernel is bound by latency (dependent loads of the scan, shared-memory queues): resident warps matter more than registers per
+// thread.  Measured on B200 (M1, whole rebuild): plain bound 86 registers / 5 CTAs per SM 1.84 ms, 6 CTAs 1.75 ms, 7 CTAs (72 registers)
+// 1.71 ms; an explicit minimum of 1 lets ptxas take 132 registers (2.33 ms).  -DNBB_BUILD_MINBLOCKS=n overrides.
 // kQC: a QC region is present (A.inactive); a separate instantiation, so that the ordinary builder compiles exactly as without it
-template <bool kQC>
-#ifdef NBB_BUILD_MINBLOCKS
-__global__ void __launch_bounds__(kBuildThreads, NBB_BUILD_MINBLOCKS) k_build_tiles(TileArgs A)
-#else
-__global__ void __launch_bounds__(kBuildThreads) k_build_tiles(TileArgs A)
+#ifndef NBB_BUILD_MINBLOCKS
+#define NBB_BUILD_MINBLOCKS 7
 #endif
+template <bool kQC>
+__global__ void __launch_bounds__(kBuildThreads, NBB_BUILD_MINBLOCKS) k_build_tiles(TileArgs A)
 {
     __shared__ BuildWarp sw[kBuildWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

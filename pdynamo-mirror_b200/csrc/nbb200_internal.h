@@ -133,6 +133,10 @@ struct State {
     DevBuf<unsigned char> qcFlag;                // per atom, 1 = pure QC atom: on no MM/MM list (NBModelABFSState_SetUp's qcAtoms); unused when nqc == 0
     int nqc = 0;
     std::vector<unsigned char> hostQC;
+    // QC/MM entry points (qcmm.cu): device copies of what a call needs
+    DevBuf<int> qcIdxDev, qcSlotDev;
+    DevBuf<double> qcWork, qcImagesDev, qcMMqDev, qcAccDev, qcGradDev, qcSplDev, qcPotDev;
+    DevBuf<double2> qcLJDev;
     std::vector<double2> hostLJ64;               // [nt*nt] (A, B) expanded table in fp64 (QC/MM LJ term, qcmm.cu)
     std::vector<int> hostExclPtr, hostExclCol;   // host copy of the exclusion CSR (isolates for useCentering)
     std::vector<unsigned char> hostFixed;

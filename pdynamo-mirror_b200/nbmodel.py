@@ -136,6 +136,27 @@ class PairListGenerator:
         return self._take(n, pp, status)
 
 
+class QCMMInteractionState:
+    """pMolecule.QCMMInteractionState (pM/pyrex/pMolecule.QCMMInteractionState.pyx:12-52, pM/cinclude/QCMMInteractionState.h): the arrays through
+    which a QC model and the NB model talk -- QC charges in, potentials on the QC atoms (atomic units) and, with symmetry, the packed QC/QC image
+    potentials out.  QC atoms in ascending atom index."""
+
+    def __init__(self, extent, includeQCQC=False):
+        self.qcCharges = np.zeros(extent)
+        self.qcmmPotentials = np.zeros(extent)
+        self.qcqcPotentials = np.zeros(extent * (extent + 1) // 2) if includeQCQC else None
+
+    @classmethod
+    def WithExtent(cls, extent, includeQCQC=False):
+        return cls(extent, includeQCQC=includeQCQC)
+
+    def Initialize(self):
+        """QCMMInteractionState_Initialize: potentials are incremented by the NB model, so the QC model clears them first"""
+        self.qcmmPotentials[:] = 0.0
+        if self.qcqcPotentials is not None:
+            self.qcqcPotentials[:] = 0.0
+
+
 class NBModelABFSState:
     """Owner of the device-resident NB state (lists, reference coordinates, statistics)."""
     LABELS = ("MM/MM Elect.", "MM/MM LJ", "MM/MM 1-4 Elect.", "MM/MM 1-4 LJ", "MM/MM Image Elect.", "MM/MM Image LJ")
@@ -148,6 +169,8 @@ class NBModelABFSState:
         self.hasSymmetry = False
         self.numberOfCalls = 0
         self.numberOfUpdates = 0
+        self.nqc = 0
+        self.qcEnergies = None
 
     def __del__(self):
         try:
@@ -162,28 +185,48 @@ class NBModelABFSState:
         self.cObject, self.isOwner = None, False
 
     def SetQCAtoms(self, indices):
-        """Pure QC atoms leave every MM/MM list (NBModelABFSState_SetUp's qcAtoms -> mmSelection, NBModelABFSState.c:348-353).  Low-level: the
-        plugin's SetUp still refuses QC atoms, because the QC/MM entry points (QCMMEnergyLJ / QCMMPotentials / QCMMGradients) are not built."""
+        """Pure QC atoms leave every MM/MM list (NBModelABFSState_SetUp's qcAtoms -> mmSelection, NBModelABFSState.c:348-353); the QC/MM
+        entry points (QCMMEnergyLJ / QCMMPotentials / QCMMGradients) then act on them."""
         idx = np.ascontiguousarray(indices, np.int32).reshape(-1)
+        self.nqc = len(idx)
         status = C.c_int(_lib.STATUS_CONTINUE)
         _lib.lib().NBModelABFSState_B200_SetQCAtoms(self.cObject, len(idx), i_(idx) if len(idx) else None, C.byref(status))
         if status.value != _lib.STATUS_CONTINUE:
             raise CLibraryError("Unable to set the QC atoms. " + _lib.last_error())
 
-    def QCMMEnergyLJ(self, gradients3=None):
-        """NBModelABFS_QCMMEnergyLJ for the QC atoms of SetQCAtoms (vacuum / P1 cells, analytic form): returns (eqcmmlj, eqcmmlj14, eimqcmmlj,
-        eimqcqclj); gradients3[n, 3] (host, optional) is accumulated into.  Low-level, see SetQCAtoms."""
+    @staticmethod
+    def _host_array(a, what):
+        if a is None:
+            return None
+        if not (isinstance(a, np.ndarray) and a.flags["C_CONTIGUOUS"] and a.dtype == np.float64):
+            raise ValueError(what + " must be a C-contiguous float64 array")
+        return d_(a)
+
+    def QCMMEnergyLJ(self, gradients3=None, dEdM=None):
+        """NBModelABFS_QCMMEnergyLJ for the QC atoms of SetQCAtoms: returns (eqcmmlj, eqcmmlj14, eimqcmmlj, eimqcqclj); gradients3[n, 3] and
+        dEdM[3, 3] (host, optional) are accumulated into."""
         e = np.zeros(4)
         status = C.c_int(_lib.STATUS_CONTINUE)
-        g = None
-        if gradients3 is not None:
-            if not (gradients3.flags["C_CONTIGUOUS"] and gradients3.dtype == np.float64):
-                raise ValueError("gradients3 must be a C-contiguous float64 array")
-            g = d_(gradients3)
-        _lib.lib().NBModelABFS_B200_QCMMEnergyLJ(self.cObject, d_(e), g, C.byref(status))
+        _lib.lib().NBModelABFS_B200_QCMMEnergyLJ(self.cObject, d_(e), self._host_array(gradients3, "gradients3"), self._host_array(dEdM, "dEdM"), C.byref(status))
         if status.value != _lib.STATUS_CONTINUE:
             raise CLibraryError("QC/MM LJ energy failed. " + _lib.last_error())
+        self.qcEnergies = e
         return e
+
+    def QCMMPotentials(self, qcmmPotentials, qcqcPotentials=None):
+        """NBModelABFS_QCMMPotentials: potentials on the QC atoms (atomic units) and the packed QC/QC image potentials, incremented in place."""
+        status = C.c_int(_lib.STATUS_CONTINUE)
+        _lib.lib().NBModelABFS_B200_QCMMPotentials(self.cObject, self._host_array(qcmmPotentials, "qcmmPotentials"), self._host_array(qcqcPotentials, "qcqcPotentials"), C.byref(status))
+        if status.value != _lib.STATUS_CONTINUE:
+            raise CLibraryError("QC/MM potentials failed. " + _lib.last_error())
+
+    def QCMMGradients(self, qcCharges, gradients3, dEdM=None):
+        """NBModelABFS_QCMMGradients: electrostatic QC/MM and QC/QC image gradients for the given QC charges, accumulated in place."""
+        status = C.c_int(_lib.STATUS_CONTINUE)
+        q = np.ascontiguousarray(qcCharges, np.float64)
+        _lib.lib().NBModelABFS_B200_QCMMGradients(self.cObject, d_(q), self._host_array(gradients3, "gradients3"), self._host_array(dEdM, "dEdM"), C.byref(status))
+        if status.value != _lib.STATUS_CONTINUE:
+            raise CLibraryError("QC/MM gradients failed. " + _lib.last_error())
 
     def GetEnergies(self, energies):
         """Append (label, value) tuples; same non-NULL-list gating as pMolecule.NBModelABFSState.pyx:41-59."""
@@ -194,9 +237,15 @@ class NBModelABFSState:
         if self.NumberOf14Pairs() > 0:
             energies.append((self.LABELS[2], float(e[2])))
             energies.append((self.LABELS[3], float(e[3])))
+        qe = getattr(self, "qcEnergies", None)
+        if qe is not None and self.nqc > 0:                     # order of pMolecule.NBModelABFSState.pyx:41-59
+            energies.append(("QC/MM LJ", float(qe[0])))
         if self.NumberOfImages() > 0:
             energies.append((self.LABELS[4], float(e[4])))
             energies.append((self.LABELS[5], float(e[5])))
+        if qe is not None and self.nqc > 0 and self.hasSymmetry:
+            energies.append(("QC/MM Image LJ", float(qe[2])))
+            energies.append(("QC/QC Image LJ", float(qe[3])))
 
     # list inspection -------------------------------------------------------------------------------
     def NumberOfPairs(self, image=-1):
@@ -408,8 +457,12 @@ class NBModelABFS(NBModel):
         """Create / reuse configuration.nbState, hand over this call's coordinates and update the lists if needed."""
         if configuration is None:
             return
+        qcIndices = None
         if qcAtoms is not None and len(qcAtoms) > 0:
-            raise NotImplementedError("QC atoms: the QC/MM entry points stay on the CPU reference (SURVEY.md 2.2)")
+            # QC regions without boundary (link) atoms: the indices of the pure QC atoms (QCAtomContainer_MakePureSelection)
+            if getattr(qcAtoms, "nboundary", 0):
+                raise NotImplementedError("QC regions with boundary atoms are not implemented on the device")
+            qcIndices = np.ascontiguousarray(getattr(qcAtoms, "indices", qcAtoms), np.int32).reshape(-1)
         L = _lib.lib()
         if not hasattr(configuration, "nbState"):
             transformations = getattr(symmetry, "transformations", None) if symmetry is not None else None
@@ -445,6 +498,10 @@ class NBModelABFS(NBModel):
             L.NBModelABFSState_B200_SetUpCentering(nbState.cObject, 1 if self.useCentering else 0, C.byref(status))
             if status.value != _lib.STATUS_CONTINUE:
                 raise CLibraryError("Unable to create NB state. " + _lib.last_error())
+            if qcIndices is not None:
+                # qcmmstate = QCMMInteractionState.WithExtent ( qcAtoms.size, includeQCQC = ( ctransformations != NULL ) )  (pMolecule.NBModelABFS.pyx:218-219)
+                setattr(configuration, "qcmmstate", QCMMInteractionState(len(qcIndices), includeQCQC=ntr > 0))
+                nbState.SetQCAtoms(np.sort(qcIndices))
             setattr(configuration, "nbState", nbState)
         nbState = configuration.nbState
         self._push_options(nbState)
@@ -481,8 +538,26 @@ class NBModelABFS(NBModel):
             _lib.lib().NBModelABFS_B200_MMMMEnergy(nbState.cObject, d_(nbState.energies), d_(g), d_(dEdM), C.byref(status))
             if status.value != _lib.STATUS_CONTINUE:
                 raise CLibraryError("NB energy evaluation failed. " + _lib.last_error())
+            if nbState.nqc > 0:                                  # NBModelABFS_QCMMEnergyLJ ( ... )  (pMolecule.NBModelABFS.pyx:120)
+                nbState.QCMMEnergyLJ(g, dEdM)
             nbState.GetEnergies(energies)
         return energies
+
+    def QCMMGradients(self, configuration):
+        """Calculate the QC/MM electrostatic gradients (pMolecule.NBModelABFS.pyx:124-130): configuration.qcmmstate.qcCharges in,
+        configuration.gradients3 / symmetryParameterGradients accumulated into."""
+        if hasattr(configuration, "nbState") and hasattr(configuration, "qcmmstate"):
+            g = getattr(configuration, "gradients3", None)
+            if g is None:
+                return
+            spg = getattr(configuration, "symmetryParameterGradients", None)
+            configuration.nbState.QCMMGradients(configuration.qcmmstate.qcCharges, g, None if spg is None else spg.dEdM)
+
+    def QCMMPotentials(self, configuration):
+        """Calculate the QC/MM electrostatic potentials (pMolecule.NBModelABFS.pyx:132-138) into configuration.qcmmstate."""
+        if hasattr(configuration, "nbState") and hasattr(configuration, "qcmmstate"):
+            st = configuration.qcmmstate
+            configuration.nbState.QCMMPotentials(st.qcmmPotentials, st.qcqcPotentials)
 
     def Summary(self, log=None):
         if log is not None:

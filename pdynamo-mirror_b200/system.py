@@ -134,6 +134,15 @@ class System:
     symmetryParameters = property(lambda self: self.configuration.symmetryParameters,
                                   lambda self, v: setattr(self.configuration, "symmetryParameters", v))
 
+    def DefineQCRegion(self, indices):
+        """Stand-in for System.DefineQCModel ( qcModel, qcSelection = ... ) (pMolecule/System.py): the atoms of the QC region (no boundary
+        atoms).  The NB model then keeps them off the MM/MM lists and serves the QC/MM entry points; the QC model itself is out of scope."""
+        if self.energyModel is None:
+            self.energyModel = EnergyModel()
+        self.energyModel.qcAtoms = None if indices is None or len(indices) == 0 else np.sort(np.asarray(indices, dtype=np.int32))
+        if self.energyModel.nbModel is not None:
+            self.energyModel.nbModel.Clear(self.configuration)          # the NB state is set up anew with the QC region
+
     def DefineNBModel(self, nbModel):
         if isinstance(nbModel, NBModel):
             if self.energyModel is None:
@@ -178,7 +187,7 @@ class System:
         nbTerms, mmTerms = [], []
         if em.nbModel is not None:
             t1 = time.perf_counter()
-            em.nbModel.SetUp(em.mmAtoms, None, em.ljParameters, em.ljParameters14, self.fixedAtoms, em.interactions14, em.exclusions, self.symmetry, None, cfg, log=log)
+            em.nbModel.SetUp(em.mmAtoms, getattr(em, "qcAtoms", None), em.ljParameters, em.ljParameters14, self.fixedAtoms, em.interactions14, em.exclusions, self.symmetry, None, cfg, log=log)
             t2 = time.perf_counter()
             nbTerms = em.nbModel.Energy(cfg)
             t3 = time.perf_counter()

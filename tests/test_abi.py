@@ -29,6 +29,27 @@ def test_library_exports_every_declared_symbol(pkg):
     assert set(_lib.SIGNATURES) == set(names), set(_lib.SIGNATURES) ^ set(names)
 
 
+def test_reference_interface_shim_exports_the_reference_names():
+    """csrc/compat_shim.c replaces the translation units NBModelABFS.c / NBModelABFSState.c: the shim build (oracle/_ref/libshim_nbabfs.so, made
+    where the reference headers exist) must define every function those units export (pM/cinclude/NBModelABFS.h:39-46,
+    NBModelABFSState.h:132-161) and resolve the computation in libnbabfs_b200.so, not in the reference."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libshim_nbabfs.so")
+    if not os.path.exists(path):
+        pytest.skip("shim library not built (no reference tree here)")
+    syms = subprocess.run(["nm", "-D", path], capture_output=True, text=True).stdout
+    defined = set(re.findall(r" T (\w+)", syms))
+    undefined = set(re.findall(r" U (\w+)", syms))
+    for name in ("NBModelABFS_Allocate", "NBModelABFS_Clone", "NBModelABFS_Deallocate", "NBModelABFS_Update", "NBModelABFS_MMMMEnergy", "NBModelABFS_QCMMEnergyLJ",
+                 "NBModelABFS_QCMMPotentials", "NBModelABFS_QCMMGradients", "NBModelABFSState_Allocate", "NBModelABFSState_Deallocate", "NBModelABFSState_SetUp",
+                 "NBModelABFSState_SetUpCentering", "NBModelABFSState_Initialize", "NBModelABFSState_InitializeCoordinates3", "NBModelABFSState_GridInitialize",
+                 "NBModelABFSState_GridFinalize", "NBModelABFSState_StatisticsAccumulate", "NBModelABFSState_StatisticsInitialize"):
+        assert name in defined, name
+    assert {"NBModelABFSState_B200_SetUp", "NBModelABFS_B200_Update", "NBModelABFS_B200_MMMMEnergy"} <= undefined
+    # the reference's own pair-list generator / pair kernels are not behind these entry points any more
+    text = open(os.path.join(ROOT, "pdynamo-mirror_b200", "csrc", "compat_shim.c")).read()
+    assert "PairListGenerator_SelfPairList" not in text and "PairwiseInteractionABFS_MMMMEnergy" not in text
+
+
 def test_library_is_self_contained(pkg):
     from pdynamo_mirror_b200 import _lib
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout

@@ -397,7 +397,9 @@ def _null_type_workload(w, idx):
 def test_mm_lists_and_energies_with_a_qc_region(pkg, orc, name):
     """NBModelABFSState_B200_SetQCAtoms: with a QC region present the MM/MM lists hold MM atoms only and NBModelABFS_MMMMEnergy returns
     the reference's values (golden_qcmm_*: compiled reference with qcAtoms, tests/golden/make_fixtures.py qcmm); gradients against the
-    oracle on the equivalent null-type system.  The QC/MM terms themselves are not built."""
+    oracle on the equivalent null-type system.  (The MM/MM term alone: the C-ABI call, not the plugin's Energy, which adds the QC/MM LJ term.)"""
+    import ctypes as C
+    from pdynamo_mirror_b200 import _lib
     q = load_golden("qcmm_" + name)
     idx = q["qc_index"]
     w = pkg.workloads.WORKLOADS["w216" if name == "w216_vacuum" else name]()
@@ -406,8 +408,10 @@ def test_mm_lists_and_energies_with_a_qc_region(pkg, orc, name):
     system, st, e_full, g_full, _ = gpu_energy(pkg, w, electrostaticScale14=1.0)
     st.SetQCAtoms(idx)
     system.configuration.gradients3[:] = 0.0
-    system.Energy(doGradients=True)
-    e, g = st.energies.copy(), system.configuration.gradients3.copy()
+    system.Energy(doGradients=True)                              # Update with the QC region in place (+ the QC/MM LJ term, not looked at here)
+    e, g, status = np.zeros(6), np.zeros((w["n"], 3)), C.c_int(16)
+    _lib.lib().NBModelABFS_B200_MMMMEnergy(st.cObject, _lib.d_(e), _lib.d_(g), None, C.byref(status))
+    assert status.value == 16
     counts = dict(zip([str(s) for s in q["count_labels"]], q["counts"].tolist()))
     assert st.NumberOfPairs() == counts["nbmmmm"] and st.NumberOf14Pairs() == counts["nbmmmm14"]
     assert st.NumberOfImagePairs() == counts["inbmmmm_pairs"]
@@ -453,10 +457,98 @@ def test_qcmm_lennard_jones_term_refuses_what_it_cannot_do(pkg):
     w = pkg.workloads.WORKLOADS["crystal_GLYGLY"]()
     system, st, _, _, _ = gpu_energy(pkg, w)
     assert np.all(st.QCMMEnergyLJ() == 0.0)                      # no QC atoms: the term is empty
-    st.SetQCAtoms(np.arange(17))
-    system.Energy(doGradients=True)
+    st.SetQCAtoms(np.arange(5))                                  # MM atoms AND space-group rotations: not covered
     with pytest.raises(Exception, match="space-group"):
-        st.QCMMEnergyLJ()
+        system.Energy(doGradients=True)                          # the plugin's Energy adds the QC/MM LJ term (pMolecule.NBModelABFS.pyx:120)
+
+
+@pytest.mark.parametrize("name", ["w216", "w216_vacuum", "bala", "crystal_GLYGLY"])
+def test_qcmm_entry_points_through_the_plugin(pkg, orc, name):
+    """The three QC/MM entry points of NBModelABFS (NBModelABFS.c:306-498) on the device, through the plugin surface (System.DefineQCRegion ->
+    NBModelABFS.SetUp with qcAtoms -> Energy / QCMMPotentials / QCMMGradients and configuration.qcmmstate), against the golden vectors of
+    the compiled reference: QC/MM and QC/QC image LJ energies, potentials on the QC atoms, packed QC/QC image potentials, the LJ and the
+    electrostatic gradients and the complete dE/dM -- a periodic water box, the same in vacuum, a solvated solute, and a P2_1/c crystal whose
+    asymmetric unit is the QC region (space-group rotations)."""
+    q = load_golden("qcmm_" + name)
+    idx = q["qc_index"]
+    w = pkg.workloads.WORKLOADS["w216" if name == "w216_vacuum" else name]()
+    if name == "w216_vacuum":
+        w = _vacuum(w)
+    system = pkg.System.FromWorkload(w)
+    system.DefineQCRegion(idx)
+    system.DefineNBModel(pkg.NBModelABFS())
+    system.Energy(doGradients=True)
+    cfg = system.configuration
+    st, model = cfg.nbState, system.energyModel.nbModel
+    ref = q["energies"]
+    terms = dict(cfg.energyTerms)
+    scale = max(1.0, np.abs(ref[6:]).sum())
+    assert abs(terms["QC/MM LJ"] - ref[6]) <= 1e-10 * scale
+    if w["box"] is not None:
+        assert abs(terms["QC/MM Image LJ"] - ref[8]) <= 1e-10 * scale and abs(terms["QC/QC Image LJ"] - ref[9]) <= 1e-10 * scale
+    # MM/MM terms with the QC region present
+    assert abs(st.energies.sum() - ref[:6].sum()) <= E_TOL * max(np.abs(ref[:6]).sum(), 1e-30)
+    # LJ gradient: MM/MM (fp32 tile kernel) + QC/MM (fp64) against the reference's total
+    g_lj = cfg.gradients3.copy()
+    rms = max(np.sqrt((q["grad_lj"] ** 2).mean()), 1e-30)
+    assert np.sqrt(((g_lj - q["grad_lj"]) ** 2).mean()) <= G_TOL * rms
+    # the QC/MM part alone at fp64 accuracy
+    g_qc = np.zeros((w["n"], 3))
+    dm_qc = np.zeros((3, 3))
+    e4 = st.QCMMEnergyLJ(g_qc, dm_qc)
+    if name != "crystal_GLYGLY":
+        mm = orc.OracleNB(_null_type_workload(w, idx), electrostaticScale14=1.0).energy(force_new=True)
+        assert np.abs(g_qc - (q["grad_lj"] - mm["grad"])).max() <= 1e-9 * max(1.0, np.abs(q["grad_lj"]).max())
+    else:
+        assert np.abs(g_qc - q["grad_lj"]).max() <= 1e-9 * np.abs(q["grad_lj"]).max()          # every atom is a QC atom: no MM/MM part
+    # potentials (atomic units) into configuration.qcmmstate
+    qs = cfg.qcmmstate
+    qs.Initialize()
+    model.QCMMPotentials(cfg)
+    assert np.allclose(qs.qcmmPotentials, q["potentials"], rtol=1e-10, atol=1e-13)
+    if qs.qcqcPotentials is not None:
+        assert np.abs(qs.qcqcPotentials - q["qcqc_potentials"]).max() <= 1e-10 * max(np.abs(q["qcqc_potentials"]).max(), 1e-30)
+    model.QCMMPotentials(cfg)                                     # incremented, not reset
+    assert np.allclose(qs.qcmmPotentials, 2.0 * q["potentials"], rtol=1e-10, atol=1e-13)
+    # electrostatic gradients for the QC charges of the fixture
+    qs.qcCharges[:] = q["qc_charges"]
+    g_before = cfg.gradients3.copy()
+    model.QCMMGradients(cfg)
+    g_el = cfg.gradients3 - g_before
+    assert np.abs(g_el - q["grad_el"]).max() <= 1e-9 * max(np.abs(q["grad_el"]).max(), 1e-30)
+    # dE/dM: MM/MM image terms (fp32 pair math) + QC LJ image terms + QC electrostatic image terms
+    if w["box"] is not None:
+        dm = cfg.symmetryParameterGradients.dEdM
+        assert np.linalg.norm(dm - q["dEdM"]) <= M_TOL * max(np.linalg.norm(q["dEdM"]), 1e-30), (dm, q["dEdM"])
+
+
+def test_qcmm_shift_range_follows_the_coordinates(pkg, orc):
+    """Molecules that have diffused several cells away from the primary one still find their periodic copies: the translations come from
+    the bounding boxes, not from an assumed spread (the same energies and potentials as for the wrapped coordinates)."""
+    w = pkg.workloads.WORKLOADS["w216"]()
+    a = float(np.asarray(w["box"]).reshape(-1)[0])
+    idx = np.array([0, 1, 2])
+    out = []
+    for shift in (0, 1):
+        v = dict(w)
+        x = w["xyz"].copy()
+        if shift:
+            mol = np.arange(w["n"]) // 3
+            x[(mol % 7 == 3)] += np.array([5 * a, -4 * a, 0.0])      # whole molecules, whole lattice vectors
+            x[(mol % 11 == 5)] += np.array([0.0, 3 * a, -6 * a])
+        v["xyz"] = x
+        system = pkg.System.FromWorkload(v)
+        system.DefineQCRegion(idx)
+        system.DefineNBModel(pkg.NBModelABFS())
+        system.Energy(doGradients=True)
+        cfg = system.configuration
+        cfg.qcmmstate.Initialize()
+        system.energyModel.nbModel.QCMMPotentials(cfg)
+        out.append((dict(cfg.energyTerms), cfg.qcmmstate.qcmmPotentials.copy()))
+    (t0, p0), (t1, p1) = out
+    for key in ("QC/MM LJ", "QC/MM Image LJ"):
+        assert abs((t0["QC/MM LJ"] + t0["QC/MM Image LJ"]) - (t1["QC/MM LJ"] + t1["QC/MM Image LJ"])) <= 1e-9 * abs(t0["QC/MM LJ"] + t0["QC/MM Image LJ"])
+    assert np.allclose(p0, p1, rtol=1e-9, atol=1e-12)
 
 
 def test_all_atoms_excluded_gives_empty_list(pkg):
@@ -1160,3 +1252,93 @@ def test_native_md_loop_without_fusion_and_speculation_in_a_subprocess():
         out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_parity_gpu.py"), "-m", "gpu", "-x", "-q", "-k", "test_native_md_loop_equals"],
                              cwd=root, env=env, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and "2 passed" in out.stdout, (extra, out.stdout[-2000:], out.stderr[-2000:])
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# the boundary: the reference's own C interface (struct types, names, signatures) on top of the device library
+# ------------------------------------------------------------------------------------------------------------------------------
+def _shim():
+    refnb = pytest.importorskip("refnb")
+    if not refnb.available("shim"):
+        pytest.skip("oracle/_ref/libshim_nbabfs.so is not built (needs the reference headers: oracle/Makefile, target ref)")
+    return refnb
+
+
+@pytest.mark.parametrize("name", ["w216", "bala", "bala_fixed", "w216_centred", "w216_spline", "crystal_GLYGLY", "crystal_WABZOO"])
+def test_reference_c_interface_shim(pkg, orc, name):
+    """csrc/compat_shim.c exports NBModelABFSState_SetUp / _Initialize / _SetUpCentering, NBModelABFS_Update and NBModelABFS_MMMMEnergy with the
+    reference's signatures (pM/cinclude/NBModelABFS.h:39-46, NBModelABFSState.h:132-161).  oracle/ref_driver.c -- the driver that runs the
+    UNMODIFIED reference through pMolecule.NBModelABFS.pyx's call sequence -- is linked against it instead of the reference's two translation
+    units: same reference containers in, same NBModelABFSState struct read back, results against the golden outputs of the reference."""
+    refnb = _shim()
+    maker, opts, _ = pkg.workloads.GOLDEN_CASES[name]
+    w = maker()
+    g = load_golden(name)
+    r = refnb.RefNB(w, omp="shim", **opts)
+    out = r.energy(force_new=True)
+    assert out["updated"]
+    if name.startswith("crystal_"):                               # small residual energies of a few dozen atoms: the crystal tests' bound
+        assert np.all(np.abs(out["energies"] - g["energies"]) <= 1.0e-5 * np.abs(g["energies"]).sum())
+        assert np.sqrt(((out["grad"] - g["grad"]) ** 2).mean()) <= G_TOL * np.sqrt((g["grad"] ** 2).mean())
+        assert np.linalg.norm(out["dEdM"] - g["dEdM"]) <= M_TOL * np.linalg.norm(g["dEdM"])
+    else:
+        check_numbers(name, out["energies"], out["grad"], out["dEdM"], g["energies"], g["grad"], g["dEdM"])
+    prim = orc.canonical_primary(r.primary_pairs())              # the PairList objects hung into the reference's state struct
+    assert len(prim) == int(g["nprimary"]) and _hash(prim) == str(g["primary_hash"])
+    imgs = r.images()
+    meta = np.array([[im["t"], im["a"], im["b"], im["c"], len(im["pairs"])] for im in imgs], dtype=np.int64).reshape(-1, 5)
+    assert np.array_equal(meta, g["image_meta"]) and np.array_equal(np.array([im["scale"] for im in imgs]), g["image_scale"])
+    for k, im in enumerate(imgs):
+        assert _hash(orc.canonical_cross(im["pairs"])) == str(g["image_hashes"][k])
+    c = r.counts()
+    assert c["primary"] == int(g["nprimary"]) and c["images"] == len(g["image_meta"]) and c["image_pairs"] == int(g["image_meta"][:, 4].sum()) if len(g["image_meta"]) else True
+    # a second call at displaced coordinates: the update decision and the numbers of the oracle
+    o = orc.OracleNB(w, **opts)
+    o.energy(force_new=True)
+    u = pkg.workloads.lcg_uniform(7, 3 * w["n"]).reshape(-1, 3)
+    free = np.setdiff1d(np.arange(w["n"]), np.asarray(w["fixed"]) if w.get("fixed") is not None else np.zeros(0, int))
+    for kick, expect in ((0.0, False), (1.3, True)):
+        x = w["xyz"] + (2 * u - 1) * 0.2                          # at most 0.35 A: inside the buffer
+        x[free[len(free) // 2], 0] += kick                        # one free atom beyond it: update due
+        if w.get("fixed") is not None:
+            x[w["fixed"]] = w["xyz"][w["fixed"]]
+        a, b = r.energy(xyz=x), o.energy(xyz=x)
+        assert a["updated"] == b["updated"] == expect
+        rg = b["grad"].copy()
+        if w.get("fixed") is not None:
+            rg[w["fixed"]] = 0.0
+        ag = a["grad"].copy()
+        if w.get("fixed") is not None:
+            ag[w["fixed"]] = 0.0
+        if name.startswith("crystal_"):
+            assert np.all(np.abs(a["energies"] - b["energies"]) <= 2.0e-5 * np.abs(b["energies"]).sum())
+            assert np.sqrt(((ag - rg) ** 2).mean()) <= G_TOL * np.sqrt((rg ** 2).mean())
+        else:
+            check_numbers("perturbed", a["energies"], ag, a["dEdM"], b["energies"], rg, b["dEdM"])
+    r.close()
+
+
+@pytest.mark.parametrize("name", ["w216", "bala", "crystal_GLYGLY"])
+def test_reference_c_interface_shim_qcmm(pkg, name):
+    """The QC/MM entry points through the same shim (NBModelABFS_QCMMEnergyLJ / _QCMMPotentials / _QCMMGradients with a QCAtomContainer,
+    Real1DArray QC charges / potentials and the SymmetricMatrix of QC/QC image potentials) against the golden vectors of the reference."""
+    refnb = _shim()
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("make_fixtures", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_fixtures.py"))
+    fx = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fx)
+    w, idx, zs, qcq = fx.qcmm_case(name)
+    q = load_golden("qcmm_" + name)
+    r = refnb.RefQC(w, idx, zs, omp="shim")
+    out = r.energy(qcq)
+    e, ref = out["energies"], q["energies"]
+    assert abs(e[:6].sum() - ref[:6].sum()) <= E_TOL * max(np.abs(ref[:6]).sum(), 1e-30)
+    scale = max(1.0, np.abs(ref[6:]).sum())
+    assert np.abs(e[6:] - ref[6:]).max() <= 1e-10 * scale
+    assert np.allclose(out["potentials"], q["potentials"], rtol=1e-10, atol=1e-13)
+    assert np.abs(out["qcqc_potentials"] - q["qcqc_potentials"]).max() <= 1e-10 * max(np.abs(q["qcqc_potentials"]).max(), 1e-30)
+    assert np.abs(out["grad_el"] - q["grad_el"]).max() <= 1e-9 * max(np.abs(q["grad_el"]).max(), 1e-30)
+    assert np.sqrt(((out["grad_lj"] - q["grad_lj"]) ** 2).mean()) <= G_TOL * max(np.sqrt((q["grad_lj"] ** 2).mean()), 1e-30)
+    if w["box"] is not None:
+        assert np.linalg.norm(out["dEdM"] - q["dEdM"]) <= M_TOL * max(np.linalg.norm(q["dEdM"]), 1e-30)
+    r.close()
