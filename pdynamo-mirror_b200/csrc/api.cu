@@ -971,8 +971,11 @@ static __global__ void k_signal_b(PeerPtrs sig, int rank, int nranks, double ste
     dst[kSigFlagB + rank] = step;
 }
 
-// wait for all ranks' flags (bounded spin: ~2 s, then the timeout flag is raised instead of hanging the GPU), then reduce
-static __global__ void k_wait(double *sigOwn, int flagBase, int nranks, double step, int mode /* 0: max of disp, 1: sum of scalars */, double *out, double *timeout)
+// wait for all ranks' flags, then reduce.  The spin is bounded (so that a rank that died cannot hang the GPU for ever) by `maxSpins`
+// sleeps of ~200 ns: NBB200_PEER_TIMEOUT_S, default 120 s -- long enough for a peer that is checkpointing, logging, collecting garbage
+// or sitting in a debugger between two calls; all ranks must reach the same call within that time.  The time-out flag is cleared by
+// every wait that completes, and a wait that timed out hands out NaN instead of sums of incomplete data.
+static __global__ void k_wait(double *sigOwn, int flagBase, int nranks, double step, int mode /* 0: max of disp, 1: sum of scalars */, double *out, double *timeout, long maxSpins)
 {
     __shared__ int ok;
     if (threadIdx.x == 0) ok = 1;
@@ -981,19 +984,30 @@ static __global__ void k_wait(double *sigOwn, int flagBase, int nranks, double s
     if (r < nranks) {
         volatile double *f = sigOwn + flagBase + r;
         long spins = 0;
-        while (*f < step) { __nanosleep(200); if (++spins > 10000000L) { ok = 0; break; } }
+        while (*f < step) { __nanosleep(200); if (++spins > maxSpins) { ok = 0; break; } }
     }
     __threadfence_system();
     __syncthreads();
     volatile double *v = sigOwn;
+    const double bad = __longlong_as_double(0x7ff8000000000000LL);
     if (mode == 0) {
-        if (threadIdx.x == 0) { double m = 0.0; for (int k = 0; k < nranks; k++) m = fmax(m, v[kSigDisp + k]); out[0] = m; }
+        if (threadIdx.x == 0) { double m = 0.0; for (int k = 0; k < nranks; k++) m = fmax(m, v[kSigDisp + k]); out[0] = ok ? m : bad; }
     } else if (threadIdx.x < 15) {
         double t = 0.0;
         for (int k = 0; k < nranks; k++) t += v[kSigScal + 16 * k + threadIdx.x];
-        out[threadIdx.x] = t;
+        out[threadIdx.x] = ok ? t : bad;
     }
-    if (threadIdx.x == 0 && !ok) *timeout = 1.0;
+    if (threadIdx.x == 0) *timeout = ok ? 0.0 : 1.0;
+}
+
+static long peer_max_spins()
+{
+    static const long spins = []() {
+        const char *e = std::getenv("NBB200_PEER_TIMEOUT_S");
+        const double seconds = (e != nullptr && std::atof(e) > 0.0) ? std::atof(e) : 120.0;
+        return (long) (seconds / 250.0e-9);                  // a sleep of 200 ns plus the poll itself
+    }();
+    return spins;
 }
 
 /* after nbb200_peer_begin: tell every rank that this rank's accumulator is zeroed and its positions are published, together with its
@@ -1020,7 +1034,7 @@ double nbb200_peer_wait_begin(NBB200State *state, long step, int needValue, int 
     if (state == nullptr) return 0.0;
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
-    k_wait<<<1, 32, 0, s.stream>>>(s.symSig.p, kSigFlagA, s.nranks, (double) step, 0, s.sigStage.p + 17, s.sigStage.p + 33);
+    k_wait<<<1, 32, 0, s.stream>>>(s.symSig.p, kSigFlagA, s.nranks, (double) step, 0, s.sigStage.p + 17, s.sigStage.p + 33, peer_max_spins());
     s.launches += 1;
     if (!needValue) return 1.0e300;                            // the caller knows the decision (forced rebuild): ordering only, no host wait
     double out[17] = {0};
@@ -1053,7 +1067,7 @@ void nbb200_peer_wait_end(NBB200State *state, long step)
     if (state == nullptr) return;
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
-    k_wait<<<1, 32, 0, s.stream>>>(s.symSig.p, kSigFlagB, s.nranks, (double) step, 1, s.sigStage.p + 34, s.sigStage.p + 33);
+    k_wait<<<1, 32, 0, s.stream>>>(s.symSig.p, kSigFlagB, s.nranks, (double) step, 1, s.sigStage.p + 34, s.sigStage.p + 33, peer_max_spins());
     s.launches += 1;
     cudaMemcpyAsync(s.hsmall + (kSmallDoubles - 128), s.sigStage.p + 33, sizeof(double) * 17, cudaMemcpyDeviceToHost, s.stream);   // [timeout, 15 sums]
 }

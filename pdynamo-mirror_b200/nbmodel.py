@@ -534,8 +534,14 @@ class NBModelABFS(NBModel):
                 raise TypeError("gradients3 must be a C-contiguous float64 array (it is accumulated into in place)")
             dEdM = None if spg is None else spg.dEdM
             status = C.c_int(_lib.STATUS_CONTINUE)
-            _lib.lib().nbb200_set_gradient_overwrite(nbState.cObject, 1 if self.overwriteGradients else 0)
+            # System.Energy of the mirror evaluates the NB term first on a gradient array it has declared zero: setting = accumulating
+            known_zero = bool(getattr(configuration, "gradientsAreZero", False)) and g is not None
+            if known_zero:
+                configuration.gradientsAreZero = False
+            _lib.lib().nbb200_set_gradient_overwrite(nbState.cObject, 1 if (self.overwriteGradients or known_zero) else 0)
             _lib.lib().NBModelABFS_B200_MMMMEnergy(nbState.cObject, d_(nbState.energies), d_(g), d_(dEdM), C.byref(status))
+            if known_zero and not self.overwriteGradients:       # the state keeps the model's own option between calls
+                _lib.lib().nbb200_set_gradient_overwrite(nbState.cObject, 0)
             if status.value != _lib.STATUS_CONTINUE:
                 raise CLibraryError("NB energy evaluation failed. " + _lib.last_error())
             if nbState.nqc > 0:                                  # NBModelABFS_QCMMEnergyLJ ( ... )  (pMolecule.NBModelABFS.pyx:120)

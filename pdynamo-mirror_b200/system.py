@@ -66,7 +66,7 @@ class Symmetry:
 
 
 class Configuration:
-    _TEMPORARY = ("energyTerms", "gradients3", "symmetryParameterGradients")
+    _TEMPORARY = ("energyTerms", "gradients3", "symmetryParameterGradients", "gradientsAreZero")
 
     def __init__(self):
         self.coordinates3 = None
@@ -171,14 +171,17 @@ class System:
         cfg.ClearTemporaryAttributes()
         if doGradients:
             n = len(self.energyModel.mmAtoms)
-            # System.Energy zeroes gradients3 and every term accumulates (pMolecule-1.9.0/pMolecule/System.py:272-318).  The NB model
-            # is the only (hence the first) term of this mirror: with overwriteGradients it SETS the array, which fuses the zero fill
-            # into the NB call (no host memset, no upload); the default keeps the reference's fill + accumulate.
-            overwrite = bool(getattr(self.energyModel.nbModel, "overwriteGradients", False))
+            # System.Energy zeroes gradients3 and every term accumulates (pMolecule-1.9.0/pMolecule/System.py:272-318).  In this mirror the NB
+            # model is evaluated FIRST, on an array this method has just "zeroed": 0 + g = g exactly, so the zero fill, its upload and the
+            # accumulation collapse into "the NB term sets the array" (flag gradientsAreZero, consumed by NBModelABFS.Energy) -- the same
+            # numbers as fill + accumulate, without touching 2 x 24 n bytes on the host.  A caller that hands its own gradient array to
+            # NBModelABFS.Energy gets the reference's accumulate semantics (option overwriteGradients = False).
             if self._gradients is None or self._gradients.shape[0] != n:
                 from ._lib import pinned_array
                 self._gradients = pinned_array((n, 3))          # reused, page-locked gradient storage
-            elif not overwrite:
+            if self.energyModel.nbModel is not None:
+                cfg.SetTemporaryAttribute("gradientsAreZero", True)
+            else:
                 self._gradients.fill(0.0)
             cfg.SetTemporaryAttribute("gradients3", self._gradients)
             if self.symmetry is not None:
