@@ -470,7 +470,8 @@ __global__ void k_block_boxes(const double *__restrict__ sX, int n, int nblocks,
 // force kernel.
 // ------------------------------------------------------------------------------------------------------
 struct TileArgs {
-    int n, nblocks, nsets, firstBlock, myBlocks, selfEnabled, chunkTiles, rawJ, split;
+    int n, nblocks, nsets, firstBlock, myBlocks, selfEnabled, chunkTiles, rawJ, split, splitShift, imgParts, imgShift;
+    unsigned int totalWarps, primaryWarps;
     double cutoff, cutoff2;
     BuildGrid grid;
     const double *sX; const int *sAtom; const int *invPerm;
@@ -492,9 +493,11 @@ constexpr int kBloomWords = 64;
 constexpr int kScanUnroll = 4;                  // stage A keeps this many 32-candidate chunks in flight
 constexpr int kCandRing = 256;                  // >= 32 * (kScanUnroll + 1), power of two
 
-// per-warp stream state of one i-cluster (kept in shared memory: the stream loop is not unrolled, code size matters more
-// than the few broadcast loads -- the first version of this kernel spent most of its time on instruction-cache misses)
-struct SubStream { int count; unsigned int chunkBase; int chunkUsed; int pad; };
+// per-warp stream state of the four i-clusters: the open chunk's first tile in shared memory (read once per emitted tile), everything else
+// packed into two registers (one byte per cluster): `counts` = entries waiting in the queue, `state` = tiles used in the open chunk
+// (bits 0-5) and which half of the 64-entry ring the queue starts in (bit 6).  The stream loop is not unrolled: code size matters
+// (the first version of this kernel spent most of its time on instruction-cache misses)
+constexpr unsigned int kNoChunk = 0xffffffffu;  // the pool overflowed when this chunk was claimed: tiles are counted, not written
 
 struct __align__(16) BuildWarp {
     double sxi[kTile][3];                        // exact coordinates of the block atoms
@@ -503,41 +506,10 @@ struct __align__(16) BuildWarp {
     int rowStart[kTile], rowCount[kTile];
     float4 cand[kCandRing];                      // ring of the candidates that survived the box reject: block-local fp32 x, y, z and the sorted position
     unsigned int bloom[kBloomWords];             // sorted positions (mod 2048) of the exclusion partners of the block atoms
-    unsigned int sub[kSubBlocks][2 * kTile];     // per i-cluster: j reference | column byte << 24
-    SubStream st[kSubBlocks];
+    unsigned int sub[kSubBlocks][2 * kTile];     // per i-cluster: ring of j reference | column byte << 24
+    unsigned int chunkBase[kSubBlocks];
     unsigned int activeMask, padw[3];            // block atoms that may appear on a list (kept in shared memory: the builder is register bound)
 };
-
-// write the first `count` (<= 32) entries of a cluster queue as one tile: lane l of the force kernel owns j slot l, the high byte of
-// its descriptor word is the COLUMN byte (bit i = cluster atom i pairs with this j) exactly as the queue holds it
-__device__ __forceinline__ void emit_tile(const TileArgs &A, int lane, int cluster, int set, const unsigned int *queue, int count, SubStream *st)
-{
-    const unsigned int word = (lane < count) ? queue[lane] : kEmptySlot;
-    int used = st->chunkUsed;
-    unsigned int base = st->chunkBase;
-    if (used == 0 && count > 0) {
-        if (lane == 0) base = atomicAdd(&A.counters->tileTotal, (unsigned int) A.chunkTiles);
-        base = __shfl_sync(0xffffffffu, base, 0);
-    }
-    const bool fits = (unsigned long long) base + (unsigned int) A.chunkTiles <= (unsigned long long) A.tileCap;
-    if (count > 0) {                                               // count == 0: only close the open chunk of the stream
-        if (fits) A.tileDesc[((size_t) base + used) * kTile + lane] = word;
-        else if (lane == 0) atomicOr(&A.counters->overflow, 2u);
-        used += 1;
-    }
-    const bool close = used == A.chunkTiles || count < kTile;      // chunk full, or the (padded) last tile of the stream
-    if (close && fits && lane == 0) {
-        const unsigned int pos = atomicAdd(&A.counters->itemCount, 1u);
-        if (pos < A.itemCap) {
-            WorkItem w;
-            w.block = cluster; w.image = set; w.tileStart = (int) base; w.tileCount = used;
-            A.items[pos] = w;
-        } else atomicOr(&A.counters->overflow, 4u);
-        atomicAdd(&A.counters->tilesUsed, (unsigned int) used);
-    }
-    __syncwarp();
-    if (lane == 0) { st->chunkBase = base; st->chunkUsed = close ? 0 : used; }
-}
 
 // The kernel is bound by latency (dependent loads of the scan, shared-memory queues): resident warps matter more than registers per
 // thread.  Measured on B200 (M1, whole rebuild): plain bound 86 registers / 5 CTAs per SM 1.84 ms, 6 CTAs 1.75 ms, 7 CTAs (72 registers)
@@ -551,24 +523,46 @@ __global__ void __launch_bounds__(kBuildThreads, NBB_BUILD_MINBLOCKS) k_build_ti
 {
     __shared__ BuildWarp sw[kBuildWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long wg = (long) blockIdx.x * kBuildWarps + warp;
-    if (wg >= (long) A.myBlocks * A.nsets * A.split) return;           // whole warps leave: no CTA barrier below
-    // small systems: the rows of one (block, set) are dealt to `split` warps (each with its own j streams)
-    const int part = (int) (wg % A.split);
-    const long wb = wg / A.split;
-    const int set = (int) (wb / A.myBlocks), b = A.firstBlock + (int) (wb % A.myBlocks);
-    if (set == 0 && !A.selfEnabled) return;
-    BuildWarp &W = sw[warp];
+    const unsigned int wg = blockIdx.x * kBuildWarps + warp;
+    if (wg >= A.totalWarps) return;                                    // whole warps leave: no CTA barrier below
+    // Units: one warp per (block, part) for the primary set, then one warp per (block, part, image part) that walks the image sets
+    // whose list-time box overlaps the block (most (block, image) combinations of a large system do not: a warp per combination
+    // spent 8 % of the kernel's instructions on warps that left at once).  Small systems deal the rows of a (block, set) to `split`
+    // warps and the image sets of a block to `imgParts` warps (powers of two), each with its own j streams.
+    // image units come FIRST in the grid: they are few, short on arithmetic and long on latency (one row walk per overlapping set)
+    // (placed behind the primary units they were a tail of 0.1 ms on the 1.1 M-atom box)
+    const unsigned int imageWarps = A.totalWarps - A.primaryWarps;
+    const bool imageUnit = wg < imageWarps;
+    const unsigned int wu = imageUnit ? wg : wg - imageWarps;
+    const int part = (int) (wu & (unsigned int) (A.split - 1));
+    const unsigned int wr = wu >> A.splitShift;
+    const int ip = imageUnit ? (int) (wr & (unsigned int) (A.imgParts - 1)) : 0;
+    const int b = A.firstBlock + (int) (imageUnit ? (wr >> A.imgShift) : wr);
+    if (!imageUnit && !A.selfEnabled) return;
+    const double reach = A.cutoff + 1.0e-6;
     double sbox[9];
 #pragma unroll
-    for (int d = 0; d < 9; d++) sbox[d] = A.blockBox[9 * b + d];
-    const double reach = A.cutoff + 1.0e-6;
-    if (set > 0) {                                           // whole-image prefilter
-        const ImageBoxDev ib = A.imageBoxes[set];
-        bool overlap = true;
-        for (int d = 0; d < 3; d++) overlap = overlap && (ib.lo[d] <= sbox[3 + d] + reach) && (ib.hi[d] >= sbox[d] - reach);
-        if (!overlap) return;
+    for (int d = 0; d < 6; d++) sbox[d] = A.blockBox[9 * b + d];
+    int set = 0, setBase = 1;
+    unsigned int pending = 0u;
+    if (imageUnit) {                                         // first overlapping image set, or leave
+        while (pending == 0u && setBase < A.nsets) {
+            const int sc = setBase + lane;
+            bool overlap = sc < A.nsets && ((sc - 1) & (A.imgParts - 1)) == ip;
+            if (overlap) {
+                const ImageBoxDev ib = A.imageBoxes[sc];
+                for (int d = 0; d < 3; d++) overlap = overlap && (ib.lo[d] <= sbox[3 + d] + reach) && (ib.hi[d] >= sbox[d] - reach);
+            }
+            pending = __ballot_sync(0xffffffffu, overlap);
+            setBase += kTile;
+        }
+        if (pending == 0u) return;
+        set = setBase - kTile + __ffs(pending) - 1;
+        pending &= pending - 1u;
     }
+#pragma unroll
+    for (int d = 6; d < 9; d++) sbox[d] = A.blockBox[9 * b + d];
+    BuildWarp &W = sw[warp];
     {
         const int s = b * kTile + lane;
         float f[3];
@@ -583,7 +577,7 @@ __global__ void __launch_bounds__(kBuildThreads, NBB_BUILD_MINBLOCKS) k_build_ti
         // exclusions can only remove pairs whose partner is excluded by a block atom: a small Bloom filter over the partners'
         // sorted positions spares almost every candidate the dependent global loads of its exclusion list
         W.bloom[lane] = 0u; W.bloom[lane + 32] = 0u;
-        if (lane < kSubBlocks) { W.st[lane].count = 0; W.st[lane].chunkBase = 0u; W.st[lane].chunkUsed = 0; }
+        if (lane < kSubBlocks) W.chunkBase[lane] = 0u;
         __syncwarp();
         if (set == 0 && s < A.n) {
             const int ai = A.sAtom[s];
@@ -627,8 +621,9 @@ __global__ void __launch_bounds__(kBuildThreads, NBB_BUILD_MINBLOCKS) k_build_ti
     const float c2f = (float) A.cutoff2;
     const unsigned int ltMask = (1u << lane) - 1u;
 
+    for (;;) {                                   // the sets of this unit: the primary set, or the overlapping image sets one after the other
     int candHead = 0, candTail = 0;
-    unsigned int counts = 0u;                    // entries waiting in the four cluster queues, one byte each
+    unsigned int counts = 0u, state = 0u;        // per cluster, one byte each: entries waiting in the queue; tiles used in the open chunk | ring half << 6
     unsigned long long myPairs = 0;
     // scan cursor: rows are taken in batches of 32 (row tables in shared memory), each row in units of kScanUnroll chunks
     int rowBase = -kTile, nrows = 0, r = 0, base = 0, rs = 0, rc = 0;
@@ -745,34 +740,78 @@ __global__ void __launch_bounds__(kBuildThreads, NBB_BUILD_MINBLOCKS) k_build_ti
             }
             candHead += count;
             myPairs += __popc(colmask);
-            // push the candidate into the queues of the clusters it pairs with (unrolled, no barrier in between) ...
+            // push the candidate into the queues (64-entry rings) of the clusters it pairs with (unrolled, no barrier in between) ...
 #pragma unroll
             for (int q = 0; q < kSubBlocks; q++) {
                 const unsigned int byte = (colmask >> (kCluster * q)) & 0xffu;
                 const unsigned int bal = __ballot_sync(0xffffffffu, byte != 0u);
-                if (byte != 0u) W.sub[q][((counts >> (8 * q)) & 0xffu) + __popc(bal & ltMask)] = jref | (byte << 24);
+                const unsigned int tail = ((state >> (8 * q + 1)) & 32u) + ((counts >> (8 * q)) & 0xffu);
+                if (byte != 0u) W.sub[q][(tail + __popc(bal & ltMask)) & (2 * kTile - 1)] = jref | (byte << 24);
                 counts += (unsigned int) __popc(bal) << (8 * q);
             }
             __syncwarp();
-            // ... and emit full tiles (at the very end: whatever is left, and close the open chunks)
-#pragma unroll 1
+            // ... and emit full tiles (at the very end: whatever is left, and close the open chunks).  A tile = the first 32 entries of
+            // the ring: lane l of the force kernel owns j slot l, the high byte of its word is the column byte exactly as queued
+#pragma unroll                                   // compile-time byte positions: 1.53 -> 1.48 ms (M1 rebuild) against the rolled loop
             for (int q = 0; q < kSubBlocks; q++) {
-                const int cnt = (int) ((counts >> (8 * q)) & 0xffu);
-                const bool flushNow = flushed && (cnt > 0 || W.st[q].chunkUsed > 0);
-                if (cnt < kTile && !flushNow) continue;
+                const int sh = 8 * q;
+                const int cnt = (int) ((counts >> sh) & 0xffu);
+                const unsigned int stq = (state >> sh) & 0xffu;
+                int used = (int) (stq & 63u);
+                if (cnt < kTile && !(flushed && (cnt | used) != 0)) continue;
                 const int n = min(cnt, kTile);
-                emit_tile(A, lane, kSubBlocks * b + q, set, W.sub[q], n, &W.st[q]);
-                const unsigned int rest = W.sub[q][kTile + lane];
-                __syncwarp();
-                W.sub[q][lane] = rest;
-                counts -= (unsigned int) n << (8 * q);
-                __syncwarp();
+                const unsigned int half = stq & 64u;                         // ring half the queue starts in (x 32 entries / 2)
+                unsigned int base = W.chunkBase[q];
+                if (used == 0 && n > 0) {                                    // open a chunk (= the next work item of this stream)
+                    if (lane == 0) base = atomicAdd(&A.counters->tileTotal, (unsigned int) A.chunkTiles);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base > A.tileCap - (unsigned int) A.chunkTiles) {   // host: tileCap >= chunkTiles, tileCap * 32 < 2^31
+                        if (lane == 0) atomicOr(&A.counters->overflow, 2u);
+                        base = kNoChunk;
+                    }
+                    if (lane == 0) W.chunkBase[q] = base;
+                }
+                if (n > 0) {
+                    const unsigned int word = (lane < n) ? W.sub[q][(half >> 1) + lane] : kEmptySlot;
+                    if (base != kNoChunk) A.tileDesc[(base + (unsigned int) used) * kTile + lane] = word;
+                    used += 1;
+                }
+                const bool close = used == A.chunkTiles || n < kTile;       // chunk full, or the (padded) last tile of the stream
+                if (close && base != kNoChunk && lane == 0) {
+                    const unsigned int pos = atomicAdd(&A.counters->itemCount, 1u);
+                    if (pos < A.itemCap) {
+                        WorkItem w;
+                        w.block = kSubBlocks * b + q; w.image = set; w.tileStart = (int) base; w.tileCount = used;
+                        A.items[pos] = w;
+                    } else atomicOr(&A.counters->overflow, 4u);
+                    atomicAdd(&A.counters->tilesUsed, (unsigned int) used);
+                }
+                const unsigned int nst = (close ? 0u : (unsigned int) used) | ((n == kTile) ? (half ^ 64u) : half);
+                state = (state & ~(0xffu << sh)) | (nst << sh);
+                counts -= (unsigned int) n << sh;
+                __syncwarp();                                                // ring slots and chunkBase are reused by the next pushes / tiles
             }
         }
         if (done) break;
     }
     for (int o = 16; o > 0; o >>= 1) myPairs += __shfl_xor_sync(0xffffffffu, myPairs, o);
     if (lane == 0 && myPairs) atomicAdd(&A.setPairs[set], myPairs);
+    // ---- next overlapping image set of this unit
+    if (!imageUnit) break;
+    while (pending == 0u && setBase < A.nsets) {
+        const int sc = setBase + lane;
+        bool overlap = sc < A.nsets && ((sc - 1) & (A.imgParts - 1)) == ip;
+        if (overlap) {
+            const ImageBoxDev ib = A.imageBoxes[sc];
+            for (int d = 0; d < 3; d++) overlap = overlap && (ib.lo[d] <= sbox[3 + d] + reach) && (ib.hi[d] >= sbox[d] - reach);
+        }
+        pending = __ballot_sync(0xffffffffu, overlap);
+        setBase += kTile;
+    }
+    if (pending == 0u) break;
+    set = setBase - kTile + __ffs(pending) - 1;
+    pending &= pending - 1u;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1028,6 +1067,7 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     }
     for (int attempt = 0; attempt < 4; attempt++) {
         if (cap * kTile >= ((size_t) 1 << 31)) { set_error("tile pool exceeds 2^31 descriptor words"); return false; }
+        cap = std::max(cap, (size_t) chunk);
         s.tileCap = cap;
         s.itemCap = cap / chunk + 64;
         if (!s.tileDesc.ensure(cap * kTile) || !s.items.ensure(s.itemCap) || !s.setPairs.ensure((size_t) s.nsets)) return false;
@@ -1037,7 +1077,17 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
             TileArgs A;
             A.n = s.n; A.nblocks = s.nblocks; A.nsets = s.nsets; A.firstBlock = b0; A.myBlocks = myBlocks; A.selfEnabled = selfEnabled ? 1 : 0;
             A.chunkTiles = chunk; A.rawJ = s.rawJ ? 1 : 0;
-            A.split = split;
+            A.split = split; A.splitShift = 0;
+            while ((1 << A.splitShift) < split) A.splitShift++;
+            // image sets of a block: one warp walks them all on large systems, up to 32 warps share them when the GPU would stay empty
+            static const int imgOverride = []() { const char *e = std::getenv("NBB200_IMG_PARTS"); return e ? std::atoi(e) : 0; }();
+            int imgParts = 1;
+            while (imgParts < 32 && imgParts < s.nsets - 1 && (long) myBlocks * split * imgParts < 4 * splitTarget) imgParts *= 2;
+            if (imgOverride > 0) { imgParts = 1; while (imgParts < imgOverride && imgParts < 32) imgParts *= 2; }
+            A.imgParts = imgParts; A.imgShift = 0;
+            while ((1 << A.imgShift) < imgParts) A.imgShift++;
+            A.primaryWarps = (unsigned int) ((long) myBlocks * split);
+            A.totalWarps = A.primaryWarps + (s.nsets > 1 ? A.primaryWarps * (unsigned int) imgParts : 0u);
             A.cutoff = s.list; A.cutoff2 = s.list * s.list;
             A.grid = s.grid;
             A.sX = s.sX.p; A.sAtom = s.sAtom.p; A.invPerm = s.invPerm.p; A.cellStart = s.cellStart.p; A.blockBox = s.blockBox.p;
@@ -1046,7 +1096,7 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
             A.inactive = s.nqc > 0 ? s.qcFlag.p : nullptr;
             A.tileDesc = s.tileDesc.p; A.tileCap = (unsigned int) cap;
             A.items = s.items.p; A.itemCap = (unsigned int) s.itemCap; A.setPairs = s.setPairs.p; A.counters = s.counters;
-            const long warps = (long) myBlocks * s.nsets * A.split;
+            const long warps = (long) A.totalWarps;
             if (A.inactive != nullptr) k_build_tiles<true><<<(unsigned int) ((warps + kBuildWarps - 1) / kBuildWarps), kBuildThreads, 0, s.stream>>>(A);
             else k_build_tiles<false><<<(unsigned int) ((warps + kBuildWarps - 1) / kBuildWarps), kBuildThreads, 0, s.stream>>>(A);
             s.launches += 1;

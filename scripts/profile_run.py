@@ -1,8 +1,9 @@
 """Short driver for ncu captures: a few rebuild + energy steps on one workload through the C-ABI (device-resident).
 
-    python scripts/profile_run.py <workload> <steps> [analytic|spline|md]
+    python scripts/profile_run.py <workload> <steps> [analytic|spline|md|norebuild]
 
 spline: the same steps with the interaction in its spline form (PairwiseInteractionABFS_B200_SetInteractionForm);
+norebuild: one rebuild step, then <steps> calls on slightly displaced coordinates that keep the lists (rolling prune + inner pool);
 md:     <steps> Langevin velocity-Verlet steps with bonded terms on the device (workload dhfr_mm)."""
 import ctypes as C
 import os
@@ -30,7 +31,15 @@ else:
     if mode == "spline":
         st = C.c_int(16)
         m.L.PairwiseInteractionABFS_B200_SetInteractionForm(m.h, 0, 50, C.byref(st))
-    for _ in range(steps):
+    if mode == "norebuild":
         m.step(rebuild=True)
+        g = torch.Generator(device=m.x.device).manual_seed(5)
+        x0 = m.x.clone()
+        for k in range(steps):
+            m.x.copy_(x0 + 0.03 * (k + 1) * torch.randn(x0.shape, generator=g, device=x0.device, dtype=x0.dtype).clamp_(-2, 2))
+            m.step(rebuild=False)
+    else:
+        for _ in range(steps):
+            m.step(rebuild=True)
     torch.cuda.synchronize()
     print(name, mode, m.state.Counters(), m.state.Timings(), m.e)
