@@ -11,6 +11,7 @@ from pCore.Selection                       cimport Selection, CSelection
 from pCore.Status                          cimport Status, Status_Continue
 from pCore.Transformation3Container        cimport Transformation3Container, CTransformation3Container
 from pCore.Matrix33                        cimport CMatrix33, Matrix33_GetItem
+from pCore.Real2DArray                     cimport CReal2DArray
 from pMolecule.LJParameterContainer        cimport LJParameterContainer, CLJParameterContainer
 from pMolecule.MMAtomContainer             cimport MMAtomContainer, CMMAtomContainer
 from pMolecule.NBModel                     cimport NBModel

@@ -144,10 +144,10 @@ cdef class NBModelABFSB200 ( NBModel ):
             if ( nbState.cObject == NULL ) or ( status != Status_Continue ): raise CLibraryError ( "Unable to create the NB state: " + nbb200_last_error ( ) )
             nbState.isOwner = True
             if fixedAtoms is not None:
-                fixedAtoms.cObject.QSORTED = fixedAtoms.cObject.QSORTED   # . The indices array is current after Selection_Sort / MakeFlags.
                 NBModelABFSState_B200_SetFixedAtoms ( nbState.cObject, fixedAtoms.cObject.nindices, fixedAtoms.cObject.indices, &status )
             if ( qcAtoms is not None ) and ( qcAtoms.size > 0 ):
-                pure = qcAtoms.GetPureSelection ( ) if hasattr ( qcAtoms, "GetPureSelection" ) else qcAtoms.QCAtomSelection ( )
+                boundary = set ( qcAtoms.BoundaryAtomSelection ( ) )          # . Boundary atoms stay on the MM/MM lists (NBModelABFSState.c:351).
+                pure     = [ i for i in qcAtoms.QCAtomSelection ( ) if i not in boundary ]
                 qc   = Memory_Allocate_Array_Integer ( len ( pure ) )
                 for i from 0 <= i < len ( pure ): qc[i] = pure[i]
                 NBModelABFSState_B200_SetQCAtoms ( nbState.cObject, len ( pure ), qc, &status )
@@ -178,6 +178,7 @@ cdef class NBModelABFSB200 ( NBModel ):
         cdef NBModelABFSB200State       nbState
         cdef Coordinates3               gradients3
         cdef SymmetryParameterGradients symmetryParameterGradients
+        cdef CReal2DArray *cmatrix
         cdef Real *cgradients
         cdef Real *cdEdM
         cdef int   status
@@ -192,7 +193,8 @@ cdef class NBModelABFSB200 ( NBModel ):
                 cgradients = gradients3.cObject.data
             if getattr ( configuration, "symmetryParameterGradients", None ) is not None:
                 symmetryParameterGradients = configuration.symmetryParameterGradients
-                cdEdM = < Real * > symmetryParameterGradients.cObject.dEdM      # . Matrix33 is a Real2DArray view: use Matrix33_Data in a build.
+                cmatrix = < CReal2DArray * > symmetryParameterGradients.cObject.dEdM     # . Matrix33 is a Real2DArray (Matrix33.h): compact 3 x 3.
+                cdEdM   = &cmatrix.data[cmatrix.offset]
             NBModelABFS_B200_MMMMEnergy ( nbState.cObject, nbState.energies, cgradients, cdEdM, &status )
             if status != Status_Continue: raise CLibraryError ( "NB energy evaluation failed: " + nbb200_last_error ( ) )
             nbState.GetEnergies ( energies )
