@@ -203,6 +203,13 @@ void nbb200_get_counters(NBB200State *state, long *out8);
 /* spatial decomposition over ranks (section 8e): this state evaluates only the i-blocks b with b % nranks == rank
  * in units of contiguous chunks; energies/gradients are then partial sums to be reduced by the caller (NCCL). */
 void nbb200_set_partition(NBB200State *state, int rank, int nranks);
+/* Several ranks: restrict this rank's sort (scatter, in-cell sort, grouping, block boxes, record pack) to the grid cells its slab can see
+ * -- the cells within listCutoff of an owned atom plus the home cells of the atoms whose images fall there; the cell histogram and its
+ * prefix sum (the GLOBAL sorted positions all ranks agree on) are still computed from all atoms.  Outside those cells the rank has no
+ * sorted-position -> atom map: callers exchange positions through the peer-memory transport below (owners publish their atoms' indices
+ * with their positions); the message transport (nbb200_gather_sorted / _scatter_sorted over whole slabs) needs the unrestricted sort.
+ * The reference has no counterpart (its only parallelism is an OpenMP team, NBModelABFSState.c:401). */
+void nbb200_set_restricted_sort(NBB200State *state, int on);
 
 /* ---- velocity Verlet on the device -----------------------------------------------------
  * One step of pCore-1.9.0/pCore/VelocityVerletIntegrator.py:60-81 (Iteration) in Cartesian variables, for callers that keep
@@ -294,6 +301,9 @@ int  NBModelABFS_B200_UpdateDeviceDecided(NBB200State *state, const double *d_xy
 /* NBModelABFS_B200_MMMMEnergyDevice that leaves the gradient in SORTED order in the sorted-gradient buffer (partial: own i atoms and
  * the j atoms of the own lists, 1-4 pairs whose first atom is owned) */
 void NBModelABFS_B200_MMMMEnergySorted(NBB200State *state, double *energies, double *dEdM, int *status);
+/* ... in two halves: Enqueue launches the kernels, Finish waits and hands the energies out; nbb200_peer_push_gradients may go in between */
+void NBModelABFS_B200_MMMMEnergySortedEnqueue(NBB200State *state, int *status);
+void NBModelABFS_B200_MMMMEnergySortedFinish(NBB200State *state, double *energies, double *dEdM, int *status);
 /* out[k] = x[atom(s0 + k)], x[atom(s0 + k)] = in[k], grad[atom(s)] += sortedGradient[s] for k < count; device arrays, 3 doubles per atom */
 void nbb200_gather_sorted(NBB200State *state, const double *d_x, long s0, long count, double *d_out);
 void nbb200_scatter_sorted(NBB200State *state, const double *d_in, long s0, long count, double *d_x);

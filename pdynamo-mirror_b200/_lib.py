@@ -51,6 +51,7 @@ SIGNATURES = {
     "nbb200_get_timings": (None, [vp, dp]),
     "nbb200_get_counters": (None, [vp, lp]),
     "nbb200_set_partition": (None, [vp, C.c_int, C.c_int]),
+    "nbb200_set_restricted_sort": (None, [vp, C.c_int]),
     "nbb200_set_gradient_overwrite": (None, [vp, C.c_int]),
     "nbb200_set_optimistic_updates": (None, [vp, C.c_int]),
     "NBModelABFSState_B200_GetStatistics": (None, [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
@@ -78,6 +79,8 @@ SIGNATURES = {
     "nbb200_max_displacement": (C.c_double, [vp, vp, ip]),
     "NBModelABFS_B200_UpdateDeviceDecided": (C.c_int, [vp, vp, dp, C.c_int, ip]),
     "NBModelABFS_B200_MMMMEnergySorted": (None, [vp, dp, dp, ip]),
+    "NBModelABFS_B200_MMMMEnergySortedEnqueue": (None, [vp, ip]),
+    "NBModelABFS_B200_MMMMEnergySortedFinish": (None, [vp, dp, dp, ip]),
     "nbb200_gather_sorted": (None, [vp, vp, C.c_long, C.c_long, vp]),
     "nbb200_scatter_sorted": (None, [vp, vp, C.c_long, C.c_long, vp]),
     "nbb200_unsort_add": (None, [vp, C.c_long, C.c_long, vp]),

@@ -818,12 +818,44 @@ void NBModelABFS_B200_MMMMEnergySorted(NBB200State *state, double *energies, dou
     else set_status(status, NBB200_STATUS_LOGIC_ERROR);
 }
 
+/* the same call in two halves, so that work that only depends on the kernels (the gradient push to the peers) can be enqueued before the
+ * host waits for the energies */
+void NBModelABFS_B200_MMMMEnergySortedEnqueue(NBB200State *state, int *status)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (s.xcur == nullptr) { set_error("MMMMEnergy called before Update"); set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+    flush_pending(s);
+    if (!energy_enqueue(s, nullptr, true)) set_status(status, NBB200_STATUS_LOGIC_ERROR);
+}
+
+void NBModelABFS_B200_MMMMEnergySortedFinish(NBB200State *state, double *energies, double *dEdM, int *status)
+{
+    if (state == nullptr || energies == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (cuda_ok(cudaStreamSynchronize(s.stream), "sync")) energy_finish(s, energies, true, dEdM);
+    else set_status(status, NBB200_STATUS_LOGIC_ERROR);
+}
+
 static __global__ void k_gather_sorted_x(const double *__restrict__ x, const int *__restrict__ sAtom, long s0, long count, double *__restrict__ out)
 {
     const long k = (long) blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     const int a = sAtom[s0 + k];
     out[3 * k] = x[3 * a]; out[3 * k + 1] = x[3 * a + 1]; out[3 * k + 2] = x[3 * a + 2];
+}
+
+// the own slab as the peers read it: positions by sorted position and, behind them, the atom index of every position (a peer that
+// sorts only its own neighbourhood has no valid sAtom for this slab)
+static __global__ void k_publish_slab(const double *__restrict__ x, const int *__restrict__ sAtom, long s0, long count, double *__restrict__ xs, int *__restrict__ ids)
+{
+    const long k = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int a = sAtom[s0 + k];
+    xs[3 * (s0 + k)] = x[3 * a]; xs[3 * (s0 + k) + 1] = x[3 * a + 1]; xs[3 * (s0 + k) + 2] = x[3 * a + 2];
+    ids[s0 + k] = a;
 }
 
 static __global__ void k_scatter_sorted_x(const double *__restrict__ in, const int *__restrict__ sAtom, long s0, long count, double *__restrict__ x)
@@ -861,13 +893,15 @@ void nbb200_unsort_add(NBB200State *state, long s0, long count, double *d_grad)
 }
 
 /* ---- peer memory: the halo exchanges as plain kernels over NVLink (no NCCL call on the data path) ---- */
+// the exported position buffer: 3 n doubles (by sorted position), then -- 16-byte aligned -- n ints: the atom index of every position
+__host__ __device__ static inline long xs_ids_offset(long n) { return (3 * n + 1) & ~1L; }
 struct PeerPtrs { double *p[State::kMaxPeers]; };
 struct SlabEdges { long s[State::kMaxPeers + 1]; };
 
-// positions: x[atom(s)] = xs_owner[s] for the sorted positions this rank needs from rank r = blockIdx.y >> 1:
-// the whole slab of r (list rebuild: slab edges given) or the halo range (r, h = blockIdx.y & 1) of the device table
-static __global__ void k_peer_pull(PeerPtrs xs, SlabEdges edges, const long *__restrict__ table, int rank, int nranks, int wholeSlabs,
-                                   const int *__restrict__ sAtom, double *__restrict__ x)
+// positions, step 1: copy what this rank needs from rank r = blockIdx.y >> 1 -- the whole slab of r (list rebuild: slab edges given)
+// with its atom indices, or the halo range (r, h = blockIdx.y & 1) of the device table -- into the SAME sorted positions of the own
+// buffer: flat, coalesced 8-byte reads over NVLink (reading the three coordinates of an atom per thread fetched every sector three times)
+static __global__ void k_peer_copy(PeerPtrs xs, SlabEdges edges, const long *__restrict__ table, int rank, int nranks, int wholeSlabs, long n, double *__restrict__ mine)
 {
     const int r = blockIdx.y >> 1, h = blockIdx.y & 1;
     if (r == rank) return;
@@ -875,9 +909,45 @@ static __global__ void k_peer_pull(PeerPtrs xs, SlabEdges edges, const long *__r
     if (wholeSlabs) { if (h) return; lo = edges.s[r]; hi = edges.s[r + 1]; }
     else { const long *t = table + ((long) r * 2 + h) * 2; lo = t[0]; hi = t[1]; }
     const double *src = xs.p[r];
+    const long stride = (long) gridDim.x * blockDim.x, t0 = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (!wholeSlabs) {                                       // halo ranges: a few thousand atoms, arbitrary alignment
+        for (long k = 3 * lo + t0; k < 3 * hi; k += stride) mine[k] = src[k];
+        return;
+    }
+    // whole slabs start at a multiple of 32 atoms (768 bytes): 16-byte loads, four in flight per thread (the NVLink round trip is what
+    // limits a one-load-at-a-time loop)
+    const long v0 = 3 * lo / 2, v1 = 3 * hi / 2;             // double2 units; 3 * lo is even
+    const double2 *s2 = reinterpret_cast<const double2 *>(src);
+    double2 *d2 = reinterpret_cast<double2 *>(mine);
+    long k = v0 + t0;
+    for (; k + 3 * stride < v1; k += 4 * stride) {
+        const double2 a = s2[k], b = s2[k + stride], c = s2[k + 2 * stride], d = s2[k + 3 * stride];
+        d2[k] = a; d2[k + stride] = b; d2[k + 2 * stride] = c; d2[k + 3 * stride] = d;
+    }
+    for (; k < v1; k += stride) d2[k] = s2[k];
+    if (t0 == 0 && ((3 * hi) & 1)) mine[3 * hi - 1] = src[3 * hi - 1];
+    const int *sid = reinterpret_cast<const int *>(src + xs_ids_offset(n));
+    int *did = reinterpret_cast<int *>(mine + xs_ids_offset(n));
+    const long w0 = lo / 4, w1 = hi / 4;                     // int4 units; lo is a multiple of 4
+    const int4 *s4 = reinterpret_cast<const int4 *>(sid);
+    int4 *d4 = reinterpret_cast<int4 *>(did);
+    for (long q = w0 + t0; q < w1; q += stride) d4[q] = s4[q];
+    for (long q = 4 * w1 + t0; q < hi; q += stride) did[q] = sid[q];
+}
+
+// step 2 (local): x[atom(s)] = xs[s]; atom(s) from the owner's indices (whole slabs) or the own sort (halo ranges: always inside the cells this rank sorts)
+static __global__ void k_peer_scatter(const double *__restrict__ mine, SlabEdges edges, const long *__restrict__ table, int rank, int nranks, int wholeSlabs, long n,
+                                      const int *__restrict__ sAtom, double *__restrict__ x)
+{
+    const int r = blockIdx.y >> 1, h = blockIdx.y & 1;
+    if (r == rank) return;
+    long lo, hi;
+    if (wholeSlabs) { if (h) return; lo = edges.s[r]; hi = edges.s[r + 1]; }
+    else { const long *t = table + ((long) r * 2 + h) * 2; lo = t[0]; hi = t[1]; }
+    const int *ids = wholeSlabs ? reinterpret_cast<const int *>(mine + xs_ids_offset(n)) : sAtom;
     for (long s = lo + (long) blockIdx.x * blockDim.x + threadIdx.x; s < hi; s += (long) gridDim.x * blockDim.x) {
-        const int a = sAtom[s];
-        x[3 * a] = src[3 * s]; x[3 * a + 1] = src[3 * s + 1]; x[3 * a + 2] = src[3 * s + 2];
+        const int a = ids[s];
+        x[3 * a] = mine[3 * s]; x[3 * a + 1] = mine[3 * s + 1]; x[3 * a + 2] = mine[3 * s + 2];
     }
 }
 
@@ -907,7 +977,7 @@ int nbb200_peer_export(NBB200State *state, char *handles192)
     if (state == nullptr || handles192 == nullptr) return 0;
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
-    if (!s.symGs.ensure(3 * (size_t) s.n) || !s.symXs.ensure(3 * (size_t) s.n) || !s.symSig.ensure(kSigDoubles) || !s.sigStage.ensure(64)) return 0;
+    if (!s.symGs.ensure(3 * (size_t) s.n) || !s.symXs.ensure((size_t) xs_ids_offset(s.n) + ((size_t) s.n + 1) / 2 + 1) || !s.symSig.ensure(kSigDoubles) || !s.sigStage.ensure(64)) return 0;
     cudaMemset(s.symSig.p, 0, sizeof(double) * kSigDoubles);
     cudaMemset(s.sigStage.p, 0, sizeof(double) * 64);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1091,7 +1161,7 @@ void nbb200_peer_begin(NBB200State *state, const double *d_x, long s0, long coun
     cudaMemsetAsync(s.symGs.p, 0, sizeof(double) * 3 * (size_t) s.n, s.stream);
     s.gsZeroed = true;
     if (count > 0 && d_x != nullptr) {
-        k_gather_sorted_x<<<(unsigned int) ((count + 255) / 256), 256, 0, s.stream>>>(d_x, s.sAtom.p, s0, count, s.symXs.p + 3 * s0);
+        k_publish_slab<<<(unsigned int) ((count + 255) / 256), 256, 0, s.stream>>>(d_x, s.sAtom.p, s0, count, s.symXs.p, reinterpret_cast<int *>(s.symXs.p + xs_ids_offset(s.n)));
         s.launches += 1;
     }
 }
@@ -1105,8 +1175,10 @@ void nbb200_peer_pull_positions(NBB200State *state, const long *d_table, const l
     PeerPtrs P; SlabEdges E;
     for (int r = 0; r < State::kMaxPeers; r++) P.p[r] = s.peerXs[r];
     for (int r = 0; r <= State::kMaxPeers; r++) E.s[r] = (slabEdges != nullptr && r <= s.nranks) ? slabEdges[r] : 0;
-    k_peer_pull<<<dim3(wholeSlabs ? 148 : 32, 2 * s.nranks), 256, 0, s.stream>>>(P, E, d_table, s.rank, s.nranks, wholeSlabs, s.sAtom.p, d_x);
-    s.launches += 1;
+    const dim3 grid(wholeSlabs ? 148 : 32, 2 * s.nranks);
+    k_peer_copy<<<grid, 256, 0, s.stream>>>(P, E, d_table, s.rank, s.nranks, wholeSlabs, (long) s.n, s.symXs.p);
+    k_peer_scatter<<<grid, 256, 0, s.stream>>>(s.symXs.p, E, d_table, s.rank, s.nranks, wholeSlabs, (long) s.n, s.sAtom.p, d_x);
+    s.launches += 2;
 }
 
 /* after the energy call: add this rank's halo contributions into their owners' accumulators */
@@ -1403,6 +1475,13 @@ void nbb200_set_partition(NBB200State *state, int rank, int nranks)
     if (state == nullptr || nranks < 1 || rank < 0 || rank >= nranks || nranks > State::kMaxPeers) return;
     State &s = *reinterpret_cast<State *>(state);
     s.rank = rank; s.nranks = nranks; s.isNew = true;
+}
+
+void nbb200_set_restricted_sort(NBB200State *state, int on)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    s.restrictSort = on != 0; s.isNew = true;
 }
 
 }  // extern "C"

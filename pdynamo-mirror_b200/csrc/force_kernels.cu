@@ -564,8 +564,8 @@ __global__ void k_pack_records(const double *__restrict__ x, const int *__restri
         recB[n] = make_float4(-1.0e15f, -1.0e15f, -1.0e15f, __int_as_float(ntypes));
     }
     double moved = 0.0;
-    if (s < n) {
-        const int a = sAtom[s];
+    const int a = (s < n) ? sAtom[s] : -1;                   // -1: a position of a cell this rank does not see (restricted sort, several ranks)
+    if (a >= 0) {
         const double xa = x[3 * a], ya = x[3 * a + 1], za = x[3 * a + 2];
         const double X = xa - ox, Y = ya - oy, Z = za - oz;
         const double KX = 8.0 * rint(X * 0.125), KY = 8.0 * rint(Y * 0.125), KZ = 8.0 * rint(Z * 0.125);
@@ -708,6 +708,7 @@ __global__ void k_unsort_gradients(typename std::conditional<kClear, double, con
     // optimistic update decision: the lists turned out to be stale (an atom moved beyond the buffer) -- this evaluation is discarded
     if (cond != nullptr && *cond > condThr2) return;
     const int a = sAtom[s];
+    if (a < 0) return;                                       // restricted sort (several ranks): not a position this rank sees
     const double gx = gs[3 * s], gy = gs[3 * s + 1], gz = gs[3 * s + 2];
     if (assign) { grad[3 * a] = gx; grad[3 * a + 1] = gy; grad[3 * a + 2] = gz; }
     else { grad[3 * a] += gx; grad[3 * a + 1] += gy; grad[3 * a + 2] += gz; }

@@ -370,26 +370,76 @@ __global__ void k_scan_add(unsigned int *out, const unsigned int *__restrict__ s
     if (i == n) out[n] = *grand;
 }
 
-__global__ void k_scatter(const int *__restrict__ eKey, int n, unsigned int extCap, const DeviceCounters *__restrict__ counters, const unsigned int *__restrict__ cellStart,
-                          unsigned int *cellFill, int *order)
+// ---- several ranks (spatial decomposition of the sort): the global cell histogram / prefix sum is computed by everybody (the sorted
+// positions are global), but a rank scatters, sorts, groups and packs only the cells its slab can see:
+//   need[c]         (image entries)  cell c lies within 3 cells (>= listCutoff: the cell edge is listCutoff / 2) of a cell that holds an owned atom
+//   need[ncell + c] (primary atoms)  the same, or one of the cell's atoms has an image copy in a wanted cell (the force kernel reads the
+//                                    PRIMARY record of an image atom and sends its gradient to the primary atom's owner)
+__device__ __forceinline__ void snake_decode(const BuildGrid &g, int idx, int &cx, int &cy, int &cz)
+{
+    const int col = idx / g.dim[2], zz = idx - col * g.dim[2];
+    cz = snake_reversed(col) ? g.dim[2] - 1 - zz : zz;
+    cx = col / g.dim[1];
+    const int yy = col - cx * g.dim[1];
+    cy = (cx & 1) ? g.dim[1] - 1 - yy : yy;
+}
+
+__global__ void k_mark_needed(const unsigned int *__restrict__ cellStart, BuildGrid g, unsigned int ownLo, unsigned int ownHi, unsigned char *__restrict__ need)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.ncell) return;
+    int cx, cy, cz;
+    snake_decode(g, c, cx, cy, cz);
+    bool wanted = false;
+    for (int ax = max(0, cx - 3); ax <= min(g.dim[0] - 1, cx + 3) && !wanted; ax++)
+        for (int ay = max(0, cy - 3); ay <= min(g.dim[1] - 1, cy + 3) && !wanted; ay++) {
+            // the z run of a column is contiguous in the snake order: one range test
+            const int k0 = snake_cell(g, ax, ay, max(0, cz - 3)), k1 = snake_cell(g, ax, ay, min(g.dim[2] - 1, cz + 3));
+            const unsigned int lo = cellStart[min(k0, k1)], hi = cellStart[max(k0, k1) + 1];
+            wanted = hi > lo && lo < ownHi && hi > ownLo;
+        }
+    need[c] = wanted ? 1 : 0;
+    need[g.ncell + c] = wanted ? 1 : 0;
+}
+
+__global__ void k_mark_image_sources(const int *__restrict__ eKey, const int *__restrict__ eSet, const int *__restrict__ eAtom, int n, unsigned int extCap,
+                                     const DeviceCounters *__restrict__ counters, int ncell, unsigned char *need)
+{
+    const int e = n + blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n + (int) min(counters->extCount, extCap)) return;
+    if (need[eKey[e] - eSet[e] * ncell]) need[ncell + eKey[eAtom[e]]] = 1;          // entry of a primary atom = its atom index
+}
+
+__global__ void k_scatter(const int *__restrict__ eKey, const int *__restrict__ eSet, int n, unsigned int extCap, const DeviceCounters *__restrict__ counters,
+                          const unsigned int *__restrict__ cellStart, unsigned int *cellFill, int *order, const unsigned char *__restrict__ need, int ncell)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int ne = n + (int) min(counters->extCount, extCap);      // read on the device: no host round trip between the kernels of a rebuild
     if (e >= ne) return;
     const int key = eKey[e];
+    if (need != nullptr) {
+        const int set = eSet[e];
+        if (!need[set == 0 ? ncell + key : key - set * ncell]) return;
+    }
     order[cellStart[key] + atomicAdd(&cellFill[key], 1u)] = e;
 }
 
 // deterministic order inside each cell: rank sort by (sub-cell key, atom index), one warp per cell; the sorted arrays (coordinates,
-// atom index, inverse permutation of the primary atoms) are written in the same pass
+// atom index, inverse permutation of the primary atoms) are written in the same pass.  (One warp per 32 keys of the mostly empty image
+// sets, walking the ones with work, was slower: 140 instead of 89 us on the 1.1 M-atom box; CTAs of 1024 threads: 107 us.)
 __global__ void k_sort_cells(const unsigned int *__restrict__ cellStart, int nkeys, const unsigned long long *__restrict__ eSort, const int *__restrict__ order,
                              const double *__restrict__ eX, const int *__restrict__ eAtom, const int *__restrict__ eSet,
-                             double *__restrict__ sX, int *__restrict__ sAtom, int *__restrict__ invPerm)
+                             double *__restrict__ sX, int *__restrict__ sAtom, int *__restrict__ invPerm, const unsigned char *__restrict__ need, int ncell)
 {
     const int key = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (key >= nkeys) return;
     const int lo = (int) cellStart[key], m = (int) cellStart[key + 1] - lo;
     if (m <= 0) return;
+    if (need != nullptr && !need[key < ncell ? ncell + key : key % ncell]) {
+        // a cell this rank does not see: its primary positions are marked (no record is packed for them), image positions stay unwritten
+        if (key < ncell) for (int k = lane; k < m; k += 32) sAtom[lo + k] = -1;
+        return;
+    }
     for (int base = 0; base < m; base += 32) {
         const bool mine = base + lane < m;
         const int e = mine ? order[lo + base + lane] : 0;
@@ -422,8 +472,8 @@ __global__ void k_group_lj_free(int n, const int *__restrict__ ljtype, const uns
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;            // sorted position; 8 consecutive lanes = one cluster
     const int lane = threadIdx.x & 31, base = lane & ~(kCluster - 1), rel = lane - base;
-    const bool valid = s < n;
-    const int a = valid ? sAtom[s] : -1;
+    const int a = (s < n) ? sAtom[s] : -1;
+    const bool valid = a >= 0;                                      // restricted sort: positions of cells this rank does not see hold -1
     double x = 0.0, y = 0.0, z = 0.0;
     if (valid) { x = sX[3 * s]; y = sX[3 * s + 1]; z = sX[3 * s + 2]; }
     const int key = valid ? snake_cell(g, cell_coord(x, g.lo[0], g.invh, g.dim[0]), cell_coord(y, g.lo[1], g.invh, g.dim[1]), cell_coord(z, g.lo[2], g.invh, g.dim[2])) : -1 - lane;
@@ -446,10 +496,10 @@ __global__ void k_group_lj_free(int n, const int *__restrict__ ljtype, const uns
 }
 
 // per i-block (32 consecutive sorted primary atoms): min, max, centre
-__global__ void k_block_boxes(const double *__restrict__ sX, int n, int nblocks, double *__restrict__ blockBox)
+__global__ void k_block_boxes(const double *__restrict__ sX, int n, int firstBlock, int nblocks, double *__restrict__ blockBox)
 {
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (b >= nblocks) return;
+    const int b = firstBlock + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (b >= firstBlock + nblocks) return;
     const int s = b * kTile + lane;
     double mn[3], mx[3];
     for (int d = 0; d < 3; d++) { const double v = (s < n) ? sX[3 * s + d] : 0.0; mn[d] = (s < n) ? v : 1e300; mx[d] = (s < n) ? v : -1e300; }
@@ -1034,18 +1084,31 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     NBB_CUDA(cudaMemsetAsync(s.cellFill.p, 0, sizeof(unsigned int) * nkeys, s.stream));
     // the number of extended atoms actually appended stays on the device (no host synchronisation here); an overflow of the extended
     // capacity is noticed with the counters that come back after the tile builder
-    k_scatter<<<(unsigned int) ((neMax + 255) / 256), 256, 0, s.stream>>>(s.eKey.p, s.n, extUpperBound, s.counters, s.cellStart.p, s.cellFill.p, s.order.p);
-    k_sort_cells<<<(nkeys + 7) / 8, 256, 0, s.stream>>>(s.cellStart.p, nkeys, s.eSortBuf.p, s.order.p, s.eX.p, s.eAtom.p, s.eSet.p, s.sX.p, s.sAtom.p, s.invPerm.p);
-    if (s.typeFree.p != nullptr) { k_group_lj_free<<<(s.n + 255) / 256, 256, 0, s.stream>>>(s.n, s.ljtype.p, s.typeFree.p, s.grid, s.sX.p, s.sAtom.p, s.invPerm.p); s.launches += 1; }
     s.nblocks = (s.n + kTile - 1) / kTile;
-    if (!s.blockBox.ensure((size_t) 9 * s.nblocks)) return false;
-    k_block_boxes<<<(s.nblocks * 32 + 255) / 256, 256, 0, s.stream>>>(s.sX.p, s.n, s.nblocks, s.blockBox.p);
-    s.launches += 3;
-
-    // tiles: a global pool handed out in chunks (= work items); sized from the pair density, retried once with the exact need
     const int b0 = (int) (((long) s.nblocks * s.rank) / s.nranks), b1 = (int) (((long) s.nblocks * (s.rank + 1)) / s.nranks);
     const int myBlocks = b1 - b0;
     s.ownLo = b0 * kTile; s.ownHi = std::min(s.n, b1 * kTile);
+    // several ranks: only the cells this rank's slab can see are scattered, sorted and (later) packed; the standalone generators and a
+    // single rank sort everything
+    const unsigned char *need = nullptr;
+    const int ncell = s.grid.ncell;
+    if (s.restrictSort && s.nranks > 1 && selfEnabled && !s.rawJ) {
+        if (!s.cellNeed.ensure((size_t) 2 * ncell)) return false;
+        k_mark_needed<<<(ncell + 127) / 128, 128, 0, s.stream>>>(s.cellStart.p, s.grid, (unsigned int) s.ownLo, (unsigned int) s.ownHi, s.cellNeed.p);
+        if (extUpperBound > 0)
+            k_mark_image_sources<<<(extUpperBound + 255) / 256, 256, 0, s.stream>>>(s.eKey.p, s.eSet.p, s.eAtom.p, s.n, extUpperBound, s.counters, ncell, s.cellNeed.p);
+        NBB_CUDA(cudaMemsetAsync(s.invPerm.p, 0xff, sizeof(int) * (size_t) s.n, s.stream));      // atoms of unseen cells: no sorted position (-1)
+        s.launches += 2;
+        need = s.cellNeed.p;
+    }
+    k_scatter<<<(unsigned int) ((neMax + 255) / 256), 256, 0, s.stream>>>(s.eKey.p, s.eSet.p, s.n, extUpperBound, s.counters, s.cellStart.p, s.cellFill.p, s.order.p, need, ncell);
+    k_sort_cells<<<(nkeys + 7) / 8, 256, 0, s.stream>>>(s.cellStart.p, nkeys, s.eSortBuf.p, s.order.p, s.eX.p, s.eAtom.p, s.eSet.p, s.sX.p, s.sAtom.p, s.invPerm.p, need, ncell);
+    if (s.typeFree.p != nullptr) { k_group_lj_free<<<(s.n + 255) / 256, 256, 0, s.stream>>>(s.n, s.ljtype.p, s.typeFree.p, s.grid, s.sX.p, s.sAtom.p, s.invPerm.p); s.launches += 1; }
+    if (!s.blockBox.ensure((size_t) 9 * s.nblocks)) return false;
+    if (myBlocks > 0) k_block_boxes<<<(myBlocks * 32 + 255) / 256, 256, 0, s.stream>>>(s.sX.p, s.n, b0, myBlocks, s.blockBox.p);     // the builder reads the own blocks' boxes only
+    s.launches += 3;
+
+    // tiles: a global pool handed out in chunks (= work items); sized from the pair density, retried once with the exact need
     // tiles per chunk / work item: long items amortise the per-item prologue of the force kernel, short ones keep small systems spread over all SMs
     static const int chunkOverride = []() { const char *e = std::getenv("NBB200_CHUNK"); return e ? std::atoi(e) : 0; }();
     const int chunk = chunkOverride > 0 ? chunkOverride : ((s.n >= 400000) ? 32 : (s.n >= 60000 ? 16 : 8));

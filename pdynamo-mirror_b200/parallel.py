@@ -198,6 +198,9 @@ class DistributedNB:
         if self.transport == "peer":
             self.gs = self.xs = None
             self.step, self.sums = 0, np.zeros(15)
+            # spatial decomposition of the sort: this rank scatters / sorts / packs only the cells its slab can see (the owners publish
+            # the atom indices of their slabs together with the positions, so nobody needs the whole sorted-position -> atom map)
+            self.L.nbb200_set_restricted_sort(self.h, 1)
         else:
             self.gs = torch.zeros((n, 3), dtype=torch.float64, device=device)
             self.xs = torch.zeros((n, 3), dtype=torch.float64, device=device)
@@ -296,14 +299,18 @@ class DistributedNB:
                 self.tab_host.copy_(self.tab_all, non_blocking=True)
             self.slabs = self._slabs()
         self.first, self.box = False, box.copy()
-        L.NBModelABFS_B200_MMMMEnergySorted(self.h, self._lib.d_(self.energies), self._lib.d_(self.dEdM), C.byref(st))
+        if peer:
+            # the push to the owners only depends on the kernels: it is enqueued before the host waits for the energies
+            L.NBModelABFS_B200_MMMMEnergySortedEnqueue(self.h, C.byref(st))
+            L.nbb200_peer_push_gradients(self.h, C.c_void_p(self.tab_mine.data_ptr()))
+            L.NBModelABFS_B200_MMMMEnergySortedFinish(self.h, self._lib.d_(self.energies), self._lib.d_(self.dEdM), C.byref(st))
+        else:
+            L.NBModelABFS_B200_MMMMEnergySorted(self.h, self._lib.d_(self.energies), self._lib.d_(self.dEdM), C.byref(st))
         if st.value != 16:
             raise RuntimeError("distributed energy failed: " + self._lib.last_error())
         self._tick("energy")
         s0, s1 = self.slabs[self.rank]
         if peer:
-            L.nbb200_peer_push_gradients(self.h, C.c_void_p(self.tab_mine.data_ptr()))
-            self._tick("gradients")
             scal = np.concatenate([self.energies, self.dEdM])
             L.nbb200_peer_signal_end(self.h, self.step, self._lib.d_(scal))
             L.nbb200_peer_wait_end(self.h, self.step)          # on the stream: all pushes into the own slab are complete, scalars summed

@@ -28,6 +28,10 @@ if mode == "md":
     print(name, "md", md.potential, md.kinetic, md.updates)
 else:
     m = bench.DeviceModel(w, 0)
+    if os.environ.get("PROFILE_PARTITION"):                 # "r/R": this process plays rank r of R (restricted sort), no peers: kernel times of one rank
+        r, R = (int(v) for v in os.environ["PROFILE_PARTITION"].split("/"))
+        m.L.nbb200_set_partition(m.h, r, R)
+        m.L.nbb200_set_restricted_sort(m.h, int(os.environ.get("PROFILE_RESTRICT", "1")))
     if mode == "spline":
         st = C.c_int(16)
         m.L.PairwiseInteractionABFS_B200_SetInteractionForm(m.h, 0, 50, C.byref(st))

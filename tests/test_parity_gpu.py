@@ -702,6 +702,7 @@ def test_peer_memory_transport_three_partitions_one_gpu(pkg):
         s2 = pkg.System.FromWorkload(w); s2.DefineNBModel(pkg.NBModelABFS()); s2.Energy()
         h = s2.configuration.nbState.cObject
         L.nbb200_set_partition(h, rank, R)
+        L.nbb200_set_restricted_sort(h, 1)                   # each partition sorts only the cells its slab can see, as DistributedNB does
         assert L.nbb200_peer_export(h, C.create_string_buffer(192)) == 1
         systems.append(s2); hs.append(h)
         xs.append(torch.from_numpy(x0).cuda())
@@ -759,25 +760,40 @@ def test_peer_memory_transport_three_partitions_one_gpu(pkg):
         assert status.value == 16, _lib.last_error()
         return total.cpu().numpy(), sums
 
+    def owners():
+        # which atoms does each partition own after a rebuild?  the owners' gradient rows are the non-zero rows of the unsort
+        rows_ = []
+        for r in range(R):
+            t = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+            torch.cuda.synchronize()
+            s0, s1 = slabs[r]
+            L.nbb200_unsort_add(hs[r], s0, s1 - s0, C.c_void_p(t.data_ptr()))
+            L.nbb200_peer_read_sums(hs[r], _lib.d_(np.zeros(15)), C.byref(status))          # synchronises the state's stream
+            rows_.append(np.nonzero(np.abs(t.cpu().numpy()).sum(1) > 0)[0])
+        assert sum(len(a) for a in rows_) == n
+        return rows_
+
+    def check(g, sums, e_ref, g_ref):
+        for out in sums:
+            assert np.allclose(out[:6], e_ref, rtol=2e-7, atol=1e-6)
+        assert np.sqrt(((g - g_ref) ** 2).mean()) <= 2e-6 * np.sqrt((g_ref ** 2).mean())
+
     g, sums = one_call(1, True, x0)
-    # which atoms does each partition own (for the second call)?  the owners' gradient rows are the non-zero rows of the unsort
-    owner_rows = []
-    for r in range(R):
-        t = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
-        torch.cuda.synchronize()
-        s0, s1 = slabs[r]
-        L.nbb200_unsort_add(hs[r], s0, s1 - s0, C.c_void_p(t.data_ptr()))
-        L.nbb200_peer_read_sums(hs[r], _lib.d_(np.zeros(15)), C.byref(status))          # synchronises the state's stream
-        owner_rows.append(np.nonzero(np.abs(t.cpu().numpy()).sum(1) > 0)[0])
-    sys_atoms = owner_rows
-    assert sum(len(a) for a in sys_atoms) == n
-    for out in sums:
-        assert np.allclose(out[:6], e0, rtol=2e-7, atol=1e-6)
-    assert np.sqrt(((g - g0) ** 2).mean()) <= 2e-6 * np.sqrt((g0 ** 2).mean())
+    sys_atoms = owners()
+    check(g, sums, e0, g0)
     g, sums = one_call(2, False, x1)
-    for out in sums:
-        assert np.allclose(out[:6], e1, rtol=2e-7, atol=1e-6)
-    assert np.sqrt(((g - g1) ** 2).mean()) <= 2e-6 * np.sqrt((g1 ** 2).mean())
+    check(g, sums, e1, g1)
+    # a second rebuild, now from restricted sorts (nobody holds the whole sorted-position -> atom map any more: the whole-slab pull uses
+    # the indices the owners publish), and a halo-only call on the new lists
+    x2 = x1 + 0.04 * np.cos(0.7 * np.arange(x0.size).reshape(-1, 3))
+    x3 = x2 + 0.05 * np.sin(1.3 * np.arange(x0.size).reshape(-1, 3))
+    for step, forced, xn in ((3, True, x2), (4, False, x3)):
+        ref.coordinates3[...] = xn; ref.Energy(doGradients=True)
+        er, gr = ref.configuration.nbState.energies.copy(), ref.configuration.gradients3.copy()
+        g, sums = one_call(step, forced, xn)
+        if forced:
+            sys_atoms = owners()
+        check(g, sums, er, gr)
 
 
 def test_centring_is_carried_between_updates(pkg, orc):
