@@ -416,19 +416,15 @@ def run_b200(args):
         line["distributed_check"] = distributed_check(torch, dist, m, dn, w, local)
         line["halo"] = {"halo_atoms_per_step_no_rebuild": int(dn.halo_atoms()), "transport": dn.transport,
                         "atoms_owned": int(dn.slabs[rank][1] - dn.slabs[rank][0]), "list_updates": dn.updates}
-        # end to end with HOST buffers on every rank: the replicated caller holds all coordinates in page-locked memory; per step every rank
-        # uploads them, runs the distributed call (forced rebuild, as the timed steps above) and reads back its gradient array (the rows of
-        # its own slab are filled) and the summed energies.  Wall clock between barriers, max over ranks.
-        xh = m.x.cpu().pin_memory()
-        gh = torch.empty_like(xh).pin_memory()
+        # end to end with HOST arrays on every rank (DistributedNB.call_host): per step a rank uploads the positions of the atoms it owns,
+        # runs the distributed call (forced rebuild, as the timed steps above), downloads the gradients of its atoms and their indices
+        # (the slabs change with every rebuild) and accumulates them into its host gradient array; the summed energies are read on the
+        # host.  Wall clock between barriers, max over ranks.
+        xh = w["xyz"].copy()
+        gh = np.zeros_like(xh)
 
         def e2e_step():
-            m.x.copy_(xh, non_blocking=True)
-            m.g.zero_()
-            dn.call(m.x, m.box, m.g, force_rebuild=True)
-            gh.copy_(m.g, non_blocking=True)
-            dn.results()                                 # the energies and dE/dM on the host
-            torch.cuda.current_stream().synchronize()
+            dn.call_host(xh, m.box, gh, force_rebuild=True)
 
         for _ in range(args.warmup):
             e2e_step()
@@ -438,10 +434,22 @@ def run_b200(args):
             e2e_step()
         torch.cuda.synchronize(); barrier()
         e2e_ms = allmax((time.perf_counter() - t1) / args.steps * 1e3)
+        own = allsum(float(dn._own_count))
+        # self-check of the host path: the rows it fills are the owned atoms' gradients of a device-array call on the same coordinates
+        gh[:] = 0.0
+        dn.call_host(xh, m.box, gh, force_rebuild=True)
+        ids = dn._stage_ids.numpy()[:dn._own_count].astype(np.int64)
+        m.x.copy_(torch.from_numpy(xh)); m.g.zero_()
+        dn.call(m.x, m.box, m.g, force_rebuild=True); dn.results()
+        gd = m.g.cpu().numpy()
+        host_err = allmax(float(np.abs(gh[ids] - gd[ids]).max() / max(1e-300, np.abs(gd[ids]).max())))
+        host_rows = allsum(float(np.count_nonzero(np.abs(gh).sum(1))))
         line["e2e"] = {"value": pairs / (e2e_ms * 1e-3), "unit": "list-pairs/s", "ms_per_step": e2e_ms,
-                       "h2d_bytes_per_step": 24 * n * world, "d2h_bytes_per_step": (24 * n + 15 * 8) * world,
-                       "api": "DistributedNB.call(x, box, g, force_rebuild=True) on every rank with page-locked host arrays: full coordinate upload and "
-                              "gradient download per rank (bytes summed over the ranks), energies read on the host; wall clock, max over ranks"}
+                       "h2d_bytes_per_step": int(24 * own), "d2h_bytes_per_step": int(28 * own) + 15 * 8 * world,
+                       "api": "DistributedNB.call_host(x, box, g, force_rebuild=True) on every rank with host numpy arrays: a rank uploads the positions of the "
+                              "atoms it owns and downloads their gradients and indices (bytes summed over the ranks), energies read on the host; wall "
+                              "clock, max over ranks",
+                       "check": {"owned_rows_rel_err_vs_device_call": host_err, "rows_filled_all_ranks": int(host_rows), "atoms": n}}
     if dn is not None and os.environ.get("NBB200_DIST_PROFILE"):
         for label, forced in (("rebuild", True), ("no-rebuild", False)):
             dn.profile = {}

@@ -210,6 +210,13 @@ void nbb200_set_partition(NBB200State *state, int rank, int nranks);
  * with their positions); the message transport (nbb200_gather_sorted / _scatter_sorted over whole slabs) needs the unrestricted sort.
  * The reference has no counterpart (its only parallelism is an OpenMP team, NBModelABFSState.c:401). */
 void nbb200_set_restricted_sort(NBB200State *state, int on);
+/* Host callers on several ranks: enqueue the copies of the own slab's gradient (sorted order, 3 (s1 - s0) doubles) and of the atom index of
+ * every position of the slab into page-locked host memory; stream ordered, no wait.  (s0, s1 from nbb200_get_slab.) */
+void nbb200_own_slab_to_host(NBB200State *state, double *h_grad, int *h_atoms);
+/* host-side companions (plain CPU loops over rows of three doubles, a few threads: NBB200_HOST_THREADS, default 4):
+ * out[k] = x[atoms[k]] (what to upload) and g[atoms[k]] += in[k] (where the downloaded gradients go); the atoms of a slab are distinct */
+void nbb200_host_gather_rows(const double *x, const int *atoms, long count, double *out);
+void nbb200_host_scatter_add_rows(double *g, const int *atoms, long count, const double *in);
 
 /* ---- velocity Verlet on the device -----------------------------------------------------
  * One step of pCore-1.9.0/pCore/VelocityVerletIntegrator.py:60-81 (Iteration) in Cartesian variables, for callers that keep

@@ -52,6 +52,9 @@ SIGNATURES = {
     "nbb200_get_counters": (None, [vp, lp]),
     "nbb200_set_partition": (None, [vp, C.c_int, C.c_int]),
     "nbb200_set_restricted_sort": (None, [vp, C.c_int]),
+    "nbb200_own_slab_to_host": (None, [vp, vp, vp]),
+    "nbb200_host_gather_rows": (None, [vp, vp, C.c_long, vp]),
+    "nbb200_host_scatter_add_rows": (None, [vp, vp, C.c_long, vp]),
     "nbb200_set_gradient_overwrite": (None, [vp, C.c_int]),
     "nbb200_set_optimistic_updates": (None, [vp, C.c_int]),
     "NBModelABFSState_B200_GetStatistics": (None, [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]),

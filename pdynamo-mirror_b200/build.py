@@ -15,7 +15,7 @@ OUT = os.path.join(HERE, "libnbabfs_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unused-function"] + os.environ.get("NBB200_NVCC_FLAGS", "").split()
-UNITS = [("api.cu", []), ("list_build.cu", ["-fmad=false"]), ("force_kernels.cu", []), ("mm_terms.cu", ["-fmad=false"]), ("qcmm.cu", ["-fmad=false"]), ("symmetry_host.cpp", [])]
+UNITS = [("api.cu", []), ("list_build.cu", ["-fmad=false"]), ("force_kernels.cu", []), ("mm_terms.cu", ["-fmad=false"]), ("qcmm.cu", ["-fmad=false"]), ("symmetry_host.cpp", []), ("host_rows.cpp", [])]
 
 
 def _newer(src, dst):

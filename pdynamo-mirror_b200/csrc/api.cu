@@ -1477,6 +1477,20 @@ void nbb200_set_partition(NBB200State *state, int rank, int nranks)
     s.rank = rank; s.nranks = nranks; s.isNew = true;
 }
 
+/* several ranks, host callers: the gradient of the own slab (sorted order, 3 (s1 - s0) doubles) and the atom index of every position of
+ * the slab, copied to page-locked host memory on the stream (no wait) -- what a caller that keeps coordinates and gradients on the host
+ * downloads per call instead of whole arrays; the indices say which rows of its arrays they are (and which coordinates to upload next time) */
+void nbb200_own_slab_to_host(NBB200State *state, double *h_grad, int *h_atoms)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    const size_t cnt = (size_t) std::max(0, s.ownHi - s.ownLo);
+    if (cnt == 0) return;
+    if (h_grad != nullptr && s.gs != nullptr) cudaMemcpyAsync(h_grad, s.gs + 3 * (size_t) s.ownLo, sizeof(double) * 3 * cnt, cudaMemcpyDeviceToHost, s.stream);
+    if (h_atoms != nullptr) cudaMemcpyAsync(h_atoms, s.sAtom.p + s.ownLo, sizeof(int) * cnt, cudaMemcpyDeviceToHost, s.stream);
+}
+
 void nbb200_set_restricted_sort(NBB200State *state, int on)
 {
     if (state == nullptr) return;
