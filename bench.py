@@ -451,6 +451,11 @@ def run_b200(args):
                               "clock, max over ranks",
                        "check": {"owned_rows_rel_err_vs_device_call": host_err, "rows_filled_all_ranks": int(host_rows), "atoms": n}}
     if dn is not None and os.environ.get("NBB200_DIST_PROFILE"):
+        dn.host_profile = {}
+        for _ in range(10):
+            dn.call_host(xh, m.box, gh, force_rebuild=True)
+        log("[bench] rank %d call_host phases (ms/step, synchronised): %s" % (rank, {k: round(100.0 * v, 3) for k, v in dn.host_profile.items()}))
+        dn.host_profile = None
         for label, forced in (("rebuild", True), ("no-rebuild", False)):
             dn.profile = {}
             for _ in range(10):

@@ -139,6 +139,10 @@ void nbb200_set_gradient_overwrite(NBB200State *state, int on);
  * an update was due, nothing of that evaluation is handed out: the lists are rebuilt at the same coordinates and the call is evaluated
  * again, so the results are those of the plain call sequence; NBModelABFSState numberOfUpdates is current after the energy call. */
 void nbb200_set_optimistic_updates(NBB200State *state, int on);
+/* Hint: the caller evaluates many calls per list (dynamics, minimisation).  Small systems then give the tile builder whole sort blocks per
+ * warp instead of dealing their cell rows to several warps: the rebuild takes longer, every energy call on the lists is faster (fewer
+ * padded tiles).  Results do not depend on it beyond the fp32 summation order. */
+void nbb200_set_list_reuse_hint(NBB200State *state, int on);
 /* NBModelABFSState.numberOfCalls / .numberOfUpdates (pM/cinclude/NBModelABFSState.h:38,42, printed by NBModelABFSState.StatisticsSummary) */
 void NBModelABFSState_B200_GetStatistics(NBB200State *state, long *numberOfCalls, long *numberOfUpdates);
 /* same, gradients accumulated into a device array d_grad[3n] (nullable) */

@@ -57,6 +57,7 @@ SIGNATURES = {
     "nbb200_host_scatter_add_rows": (None, [vp, vp, C.c_long, vp]),
     "nbb200_set_gradient_overwrite": (None, [vp, C.c_int]),
     "nbb200_set_optimistic_updates": (None, [vp, C.c_int]),
+    "nbb200_set_list_reuse_hint": (None, [vp, C.c_int]),
     "NBModelABFSState_B200_GetStatistics": (None, [vp, C.POINTER(C.c_long), C.POINTER(C.c_long)]),
     "nbb200_vv_first_half": (None, [vp, vp, vp, vp, C.c_double]),
     "nbb200_vv_second_half": (None, [vp, vp, vp, vp, vp, C.c_double, vp]),

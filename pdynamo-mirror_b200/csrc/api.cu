@@ -1465,6 +1465,11 @@ void nbb200_set_optimistic_updates(NBB200State *state, int on)
     if (state != nullptr) reinterpret_cast<State *>(state)->optimistic = on != 0;
 }
 
+void nbb200_set_list_reuse_hint(NBB200State *state, int on)
+{
+    if (state != nullptr) reinterpret_cast<State *>(state)->listReuseHint = on != 0;
+}
+
 void nbb200_set_gradient_overwrite(NBB200State *state, int on)
 {
     if (state != nullptr) reinterpret_cast<State *>(state)->gradOverwrite = on != 0;

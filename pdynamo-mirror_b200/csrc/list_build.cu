@@ -1115,7 +1115,10 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     if (chunk != s.chunkTiles) { s.chunkTiles = chunk; s.tileCap = 0; }
     // small systems: deal the rows of a block to several warps until the GPU is full (each part has its own, padded, j streams)
     int split = 1;
-    static const long splitTarget = []() { const char *e = std::getenv("NBB200_SPLIT_TARGET"); return (e && std::atol(e) > 0) ? std::atol(e) : 148L * 16; }();
+    static const long splitEnv = []() { const char *e = std::getenv("NBB200_SPLIT_TARGET"); return (e && std::atol(e) > 0) ? std::atol(e) : 0L; }();
+    // dynamics rebuilds every ten steps or more (nbb200_set_list_reuse_hint): whole blocks per warp -- fewer padded tiles, the force kernel
+    // of every step gains more (DHFR 73 -> 68 us) than the rarer rebuild loses (0.26 -> 0.36 ms); single calls keep the faster rebuild
+    const long splitTarget = splitEnv > 0 ? splitEnv : (s.listReuseHint ? 148L * 8 : 148L * 16);
     while (split < 8 && (long) myBlocks * split * 2 <= splitTarget) split *= 2;
     size_t cap = s.tileCap;
     if (cap == 0) {

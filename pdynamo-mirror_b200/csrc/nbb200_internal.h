@@ -224,6 +224,7 @@ struct State {
     DevBuf<double> gradSorted;
     double *gs = nullptr, *gsExternal = nullptr;   // sorted-order gradient of the last call: own buffer or one set by the caller (section 8e)
     int ownLo = 0, ownHi = 0;                    // sorted positions of the i-blocks this rank owns (whole system for one rank)
+    bool listReuseHint = false;                  // the caller evaluates many calls per list (dynamics): the builder favours the force kernel (nbb200_set_list_reuse_hint)
     bool restrictSort = false;                   // several ranks: sort / pack only the cells this rank's slab can see (nbb200_set_restricted_sort)
     DevBuf<unsigned char> cellNeed;              // [2 * ncell]: image entries wanted in this cell | primary atoms wanted in this cell
     DevBuf<int> rangeTab; DevBuf<long> rangeOut;

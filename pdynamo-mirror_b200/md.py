@@ -43,6 +43,7 @@ class VelocityVerletDynamics:
         self.n = self.state.n
         dev = "cuda:%d" % device
         self.L.nbb200_set_stream(self.h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self.L.nbb200_set_list_reuse_hint(self.h, 1)         # dynamics: ten or more calls per list
         masses = np.asarray(getattr(system, "masses", None) if getattr(system, "masses", None) is not None else np.ones(self.n), np.float64)
         self.mass = torch.from_numpy(masses).to(dev)
         self.x = torch.from_numpy(np.ascontiguousarray(system.coordinates3, np.float64)).to(dev)

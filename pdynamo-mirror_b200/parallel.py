@@ -206,6 +206,7 @@ class DistributedNB:
             self.xs = torch.zeros((n, 3), dtype=torch.float64, device=device)
             self.L.nbb200_set_sorted_gradient_buffer(self.h, C.c_void_p(self.gs.data_ptr()))
         self.profile = None                                  # set to a dict to collect wall-clock seconds per phase (synchronising: debugging only)
+        self.host_profile = None                             # the same for call_host
         self.first, self.box, self.slabs = True, None, None
         self.energies, self.dEdM = np.zeros(6), np.zeros(9)
         self.updates = 0
@@ -337,6 +338,7 @@ class DistributedNB:
         first call (which uploads everything once) a rank uploads only the positions of the atoms it owns and downloads only their
         gradients -- 24 n / R bytes each way instead of 24 n -- plus the owned atoms' indices (they change with every list rebuild).
         The owned rows of g_host are ACCUMULATED into (the reference's semantics); returns (updated, energies[6], dEdM[3, 3])."""
+        import time
         torch, L = self.torch, self.L
         if self.transport != "peer":
             raise RuntimeError("call_host needs the peer-memory transport")
@@ -345,6 +347,9 @@ class DistributedNB:
         n = self.n
         if not hasattr(self, "_xdev"):
             dev = self.flag.device
+            import os
+            # host row gather / scatter-add threads of this rank (read once by the library): the ranks of a box share its cores
+            os.environ.setdefault("NBB200_HOST_THREADS", str(max(1, min(8, (os.cpu_count() or 8) // max(1, self.world)))))
             self._xdev = torch.from_numpy(np.ascontiguousarray(x_host)).to(dev)
             self._stage_x = torch.empty((n, 3), dtype=torch.float64).pin_memory()
             self._stage_g = torch.empty((n, 3), dtype=torch.float64).pin_memory()
@@ -352,19 +357,30 @@ class DistributedNB:
             self._stage_dev = torch.empty((n, 3), dtype=torch.float64, device=dev)
             self._own_count = 0
         elif self._own_count > 0:
+            t0 = time.perf_counter() if self.host_profile is not None else 0.0
             s0, s1 = self.slabs[self.rank]
             cnt = self._own_count
             L.nbb200_host_gather_rows(C.c_void_p(x_host.ctypes.data), C.c_void_p(self._stage_ids.data_ptr()), cnt, C.c_void_p(self._stage_x.data_ptr()))
             self._stage_dev[:cnt].copy_(self._stage_x[:cnt], non_blocking=True)
             L.nbb200_scatter_sorted(self.h, C.c_void_p(self._stage_dev.data_ptr()), s0, cnt, C.c_void_p(self._xdev.data_ptr()))
+        if self.host_profile is not None:
+            torch.cuda.synchronize(); t1 = time.perf_counter()
         updated = self.call(self._xdev, box, None, force_rebuild)
+        if self.host_profile is not None:
+            torch.cuda.synchronize(); t2 = time.perf_counter()
         s0, s1 = self.slabs[self.rank]
         self._own_count = cnt = s1 - s0
         L.nbb200_own_slab_to_host(self.h, C.c_void_p(self._stage_g.data_ptr()), C.c_void_p(self._stage_ids.data_ptr()))
         e, dEdM = self.results()                             # synchronises the stream: the copies above have landed
+        if self.host_profile is not None:
+            t3 = time.perf_counter()
         if g_host is not None and cnt > 0:
             # every atom has one sorted position: no duplicate rows
             L.nbb200_host_scatter_add_rows(C.c_void_p(g_host.ctypes.data), C.c_void_p(self._stage_ids.data_ptr()), cnt, C.c_void_p(self._stage_g.data_ptr()))
+        if self.host_profile is not None and "t0" in locals():
+            t4 = time.perf_counter()
+            for k, v in (("gather+upload", t1 - t0), ("call", t2 - t1), ("download", t3 - t2), ("scatter-add", t4 - t3)):
+                self.host_profile[k] = self.host_profile.get(k, 0.0) + v
         return updated, e, dEdM
 
     def results(self):
