@@ -202,8 +202,9 @@ static int update_common(State &s, const double *box6, int forceNew, int *status
         (s.trans.n == 0 || (s.haveRefLattice && std::memcmp(s.lattice.M.v, s.refLattice.M.v, sizeof(double) * 9) == 0))) {
         // optimistic decision: the check is enqueued, its result comes back with the energy call's synchronisation (see State::optimistic)
         const double buffac = 0.5 * (s.list - s.stOuterCutoff);
-        if (!s.optDisp.ensure(2) || !displacement_enqueue(s, s.xcur, s.optDisp.p) ||
-            !cuda_ok(cudaMemcpyAsync(s.hsmall + (kSmallDoubles - 8), s.optDisp.p, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
+        // (the maximum travels to the host with the energy call: energy_enqueue)
+        if (!s.optDisp.ensure(2) || !displacement_enqueue(s, s.xcur, s.optDisp.p)) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
+        s.optDispCopied = false;
         s.optPending = true; s.optThr2 = buffac * buffac;
         s.isNew = false;
         return 0;
@@ -280,10 +281,27 @@ static bool energy_enqueue(State &s, double *d_grad, bool sortedOnly = false, do
         NBB_CUDA(cudaMemcpyAsync(s.imageOps.p, ops, sizeof(ImageOpDev) * (size_t) s.nsets, cudaMemcpyHostToDevice, s.stream));
         s.opsLattice = s.lattice.M; s.opsGeneration = s.numberOfUpdates; s.opsValid = true;
     }
-    if (!launch_forces(s, d_grad, sortedOnly)) return false;
     const size_t accumCount = (size_t) 16 * (s.nsets + 1);
     if (accumCount > kSmallDoubles - 16) { set_error("too many images for the result buffer"); return false; }      // the tail holds nbb200_md_run's kinetic-energy slots
-    NBB_CUDA(cudaMemcpyAsync(target != nullptr ? target : s.hsmall, s.accum.p, sizeof(double) * accumCount, cudaMemcpyDeviceToHost, s.stream));
+    // the accumulators (and the displacement maximum of an optimistic update decision) reach the host through the unsort pass when the call has
+    // one (PublishArgs: stores into page-locked memory), through copy operations otherwise
+    static const bool noPublish = std::getenv("NBB200_NO_PUBLISH") != nullptr;
+    double *hostAcc = target != nullptr ? target : s.hsmall;
+    const bool dispOwed = s.optPending && !s.optDispCopied;
+    s.pubDone = false;
+    if (!noPublish) {
+        if (!s.accum.ensure(accumCount + 1)) return false;                  // (launch_forces sizes it the same way)
+        s.pubSrc[0] = s.accum.p; s.pubDst[0] = hostAcc; s.pubCount[0] = (int) accumCount;
+        s.pubSrc[1] = dispOwed ? s.optDisp.p : nullptr; s.pubDst[1] = s.hsmall + (kSmallDoubles - 8); s.pubCount[1] = dispOwed ? 1 : 0;
+    }
+    const bool okForces = launch_forces(s, d_grad, sortedOnly);
+    s.pubSrc[0] = s.pubSrc[1] = nullptr; s.pubCount[0] = s.pubCount[1] = 0;
+    if (!okForces) return false;
+    if (!s.pubDone) {
+        NBB_CUDA(cudaMemcpyAsync(hostAcc, s.accum.p, sizeof(double) * accumCount, cudaMemcpyDeviceToHost, s.stream));
+        if (dispOwed) NBB_CUDA(cudaMemcpyAsync(s.hsmall + (kSmallDoubles - 8), s.optDisp.p, sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    }
+    if (dispOwed) s.optDispCopied = true;
     return true;
 }
 
@@ -1206,7 +1224,8 @@ static __global__ void k_vv_first(double *__restrict__ x, double *__restrict__ v
 
 // first half fused with the displacement check of CheckForUpdate (nbb200_md_run): one thread per atom, |x - xref|^2 into the running maximum
 static __global__ void k_vv_first_disp(double *__restrict__ x, double *__restrict__ v, const double *__restrict__ a, double dt, int n, const double *__restrict__ xref,
-                                       const unsigned char *__restrict__ fixed, unsigned long long *__restrict__ out, unsigned long long *__restrict__ zeroOther)
+                                       const unsigned char *__restrict__ fixed, unsigned long long *__restrict__ out, unsigned long long *__restrict__ zeroOther,
+                                       unsigned int *ticket, double *h_out)
 {
     if (zeroOther != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zeroOther = 0ULL;
     const int atom = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1227,13 +1246,19 @@ static __global__ void k_vv_first_disp(double *__restrict__ x, double *__restric
     }
     for (int off = 16; off > 0; off >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, off));
     if ((threadIdx.x & 31) == 0 && r2 > 0.0) atomicMax(out, (unsigned long long) __double_as_longlong(r2));
+    // the maximum goes straight into page-locked host memory (no copy operation in the stream)
+    if (ticket != nullptr && last_block_done(ticket) && threadIdx.x == 0) *h_out = __longlong_as_double((long long) *reinterpret_cast<volatile unsigned long long *>(out));
 }
 
 // second half: a = -100 g / m (kJ mol^-1 A^-1 amu^-1 -> A ps^-2) ; v += dt/2 a ; kinetic energy 0.5 * 0.01 * sum m v^2 (kJ/mol)
+// ticket / h_ke / pub (nbb200_md_run): the kinetic energy (last CTA) and the bonded energies of the step (complete before this kernel) are stored into
+// page-locked host memory -- no copy operations in the stream
 static __global__ void k_vv_second(double *__restrict__ v, double *__restrict__ a, const double *__restrict__ g, const double *__restrict__ mass, double dt, long m,
-                                   double *__restrict__ ke, double *__restrict__ zeroOther = nullptr)
+                                   double *__restrict__ ke, double *__restrict__ zeroOther = nullptr, unsigned int *ticket = nullptr, double *h_ke = nullptr,
+                                   const double *pubSrc = nullptr, double *pubDst = nullptr, int pubCount = 0)
 {
     if (zeroOther != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zeroOther = 0.0;      // two-slot use (nbb200_md_run): prepares the next step's slot
+    if (blockIdx.x == 0 && threadIdx.x < pubCount) pubDst[threadIdx.x] = pubSrc[threadIdx.x];
     double local = 0.0;
     for (long i = (long) blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long) gridDim.x * blockDim.x) {
         const double mi = mass[i / 3], ai = -100.0 * g[i] / mi;
@@ -1243,6 +1268,7 @@ static __global__ void k_vv_second(double *__restrict__ v, double *__restrict__ 
     }
     for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
     if ((threadIdx.x & 31) == 0) atomicAdd(ke, 0.5 * 0.01 * local);
+    if (ticket != nullptr && last_block_done(ticket) && threadIdx.x == 0) *h_ke = *reinterpret_cast<volatile double *>(ke);
 }
 
 void nbb200_vv_first_half(NBB200State *state, double *d_x, double *d_v, const double *d_a, double dt)
@@ -1363,14 +1389,22 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
 
     // everything of step k after its first half, on the lists as they are: energy (deferred into slot k & 1), bonded terms, second half, kinetic energy
     // redo: the step is evaluated a second time after it was taken back -- its result slots hold the first attempt and are cleared explicitly
+    // results reach the host by stores into page-locked memory from the kernels that complete them (no copy operations in the stream: each one
+    // costs a few microseconds between two small kernels); NBB200_NO_PUBLISH=1 keeps the copies
+    static const bool publish = std::getenv("NBB200_NO_PUBLISH") == nullptr;
+    unsigned int *d_ticket = reinterpret_cast<unsigned int *>(s.mdScalars.p + 16);      // [0]: first half, [1]: second half (zeroed above, left at zero by the kernels)
     auto enqueue_step = [&](int k, bool redo) -> bool {
         for (int c = 0; c < 9; c++) dEdM[c] = 0.0;
         if (!energy_enqueue(s, d_g, false, haccSlot[k & 1])) return false;
-        if (terms != nullptr && !mmterms_enqueue_slot(terms, d_x, d_g, k & 1, fusedMode && !redo)) return false;
+        if (terms != nullptr && !mmterms_enqueue_slot(terms, d_x, d_g, k & 1, fusedMode && !redo, publish)) return false;
         if ((redo || !fusedMode) && !cuda_ok(cudaMemsetAsync(d_ke2 + (k & 1), 0, sizeof(double), s.stream), "memset")) return false;
+        const double *pubSrc = nullptr; double *pubDst = nullptr;
+        if (terms != nullptr && publish) mmterms_slot_pointers(terms, k & 1, &pubSrc, &pubDst);
         k_vv_second<<<(unsigned int) std::min<long>(148 * 8, (m + 255) / 256), 256, 0, s.stream>>>(d_v, d_a, d_g, d_mass, secondHalfDt, m, d_ke2 + (k & 1),
-                                                                                                  fusedMode ? d_ke2 + ((k + 1) & 1) : nullptr);
+                                                                                                  fusedMode ? d_ke2 + ((k + 1) & 1) : nullptr,
+                                                                                                  publish ? d_ticket + 1 : nullptr, hke + (k & 1), pubSrc, pubDst, pubSrc != nullptr ? 5 : 0);
         s.launches += 1;
+        if (publish) return cuda_ok(cudaGetLastError(), "k_vv_second");
         return cuda_ok(cudaMemcpyAsync(hke + (k & 1), d_ke2 + (k & 1), sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H kinetic energy");
     };
     // the numbers of a completed step: accumulators -> energies (energy_finish; must run while the lists the step used are still current),
@@ -1398,10 +1432,12 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
         const bool fusedFirst = speculate && fusedMode;         // first half and displacement check in one kernel
         double *d_disp = d_disp2 + (nspec & 1), *d_dispOther = d_disp2 + ((nspec + 1) & 1);
         if (fusedFirst) {
-            if (langevinFactors7 != nullptr) ok = langevin_first_disp(s, d_x, d_v, d_a, d_mass, langevinFactors7, seed, firstIteration + (unsigned long long) k, d_disp, d_dispOther);
+            if (langevinFactors7 != nullptr) ok = langevin_first_disp(s, d_x, d_v, d_a, d_mass, langevinFactors7, seed, firstIteration + (unsigned long long) k, d_disp, d_dispOther,
+                                                                      d_ticket, publish ? hdisp + (k & 1) : nullptr);
             else {
                 k_vv_first_disp<<<(s.n + 127) / 128, 128, 0, s.stream>>>(d_x, d_v, d_a, timeStep, s.n, s.xref.p, s.nfixed > 0 ? s.fixedFlag.p : nullptr,
-                                                                        reinterpret_cast<unsigned long long *>(d_disp), reinterpret_cast<unsigned long long *>(d_dispOther));
+                                                                        reinterpret_cast<unsigned long long *>(d_disp), reinterpret_cast<unsigned long long *>(d_dispOther),
+                                                                        publish ? d_ticket : nullptr, hdisp + (k & 1));
                 s.launches += 1;
             }
         } else if (langevinFactors7 != nullptr) nbb200_langevin_first_half(state, d_x, d_v, d_a, d_mass, langevinFactors7, seed, firstIteration + (unsigned long long) k);
@@ -1411,7 +1447,7 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
             // optimistic: the check of CheckForUpdate (NBModelABFS.c:691-746) and the whole step go out together
             nspec += 1;
             ok = ok && (fusedFirst || displacement_enqueue(s, d_x, d_disp, nullptr)) &&
-                 cuda_ok(cudaMemcpyAsync(hdisp + (k & 1), d_disp, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H displacement") &&
+                 ((fusedFirst && publish) || cuda_ok(cudaMemcpyAsync(hdisp + (k & 1), d_disp, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H displacement")) &&
                  cuda_ok(cudaEventRecord(evDisp, s.stream), "event") && enqueue_step(k, false) && cuda_ok(cudaEventSynchronize(evDisp), "event wait");
             if (!ok) { set_status(status, NBB200_STATUS_LOGIC_ERROR); break; }
             // the stream has passed the check of step k: step k - 1 is complete

@@ -271,6 +271,7 @@ __device__ __forceinline__ void mbar_wait(unsigned int mbar, unsigned int parity
 }
 
 constexpr int kLJEntryBytes = 2 * (int) sizeof(float4);     // plain-region and switched-region coefficients of a type pair
+constexpr int kFuseMaxAtoms = 262144;
 constexpr int kFlushTiles = 8;                       // the fp32 i-gradient / energy accumulators are flushed to fp64 every 8 tiles
 
 // sum over the warp of 24 values per lane (8 cluster atoms x 3 components, v[3 a + c]), scattered: afterwards v[0..2] of every lane
@@ -396,6 +397,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
         // pairs of cluster atoms that are both of a type without Lennard-Jones interaction (the builder moves such atoms to the front of
         // every cluster): Coulomb only
         const unsigned int freeBits = __ballot_sync(0xffffffffu, ljFree);
+        // pattern of Coulomb-only atom PAIRS: 0..4 = the first nf pairs and no other, 5 = anything else (decided step by step)
+        const unsigned int pairFree = (freeBits & (freeBits >> 1)) & 0x55u;
+        const int variant = (A.exp & 8) ? 5 : pairFree == 0u ? 0 : pairFree == 0x01u ? 1 : pairFree == 0x05u ? 2 : pairFree == 0x15u ? 3 : pairFree == 0x55u ? 4 : 5;
         __syncwarp();
         // j offsets: X'_local = (K_j + ok) + xl_j, ok exact (kt: the part of a pure translation that is a multiple of 8 A)
         float okx = -kref.x, oky = -kref.y, okz = -kref.z;
@@ -457,10 +461,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
         for (int t = 0; t < wi.tileCount; t++) {
             f2 fj[3] = {bc(0.f), bc(0.f), bc(0.f)};
             float r2min = F.r2Off;
-#pragma unroll
-            for (int p = 0; p < kCluster / 2; p++) {
+            // one double step: cluster atoms 2p, 2p + 1 against the lane's j atom.  LJ: 1 = with the Lennard-Jones part, 0 = Coulomb only, -1 = decided
+            // at run time from the cluster's types (a warp-uniform branch)
+            auto step = [&](auto P, auto LJ) {
+                constexpr int p = decltype(P)::value;
+                constexpr int lj = decltype(LJ)::value;
                 const float4 XY = ist->xy[p], ZQ = ist->zq[p];
-                const int2 rows = ist->row[p];
                 const f2 dx = sub2(make_float2(XY.x, XY.y), bc(xj)), dy = sub2(make_float2(XY.z, XY.w), bc(yj)), dz = sub2(make_float2(ZQ.x, ZQ.y), bc(zj));
                 f2 r2 = fma2(dx, dx, fma2(dy, dy, mul2(dz, dz)));
                 const f2 qij = mul2(make_float2(ZQ.z, ZQ.w), bc(qj));
@@ -472,10 +478,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
                     r2.x = fminf(on0 ? r2.x : F.r2Off, F.r2Off); r2.y = fminf(on1 ? r2.y : F.r2Off, F.r2Off);
                     r2min = fminf(r2min, fminf(r2.x, r2.y));
                     r2.x = fmaxf(r2.x, F.r2Damp); r2.y = fmaxf(r2.y, F.r2Damp);
-                    if (((freeBits >> (2 * p)) & 3u) == 3u) abfs_pair2<false>(F, r2, qij, 0u, 0u, eq, el, g);
-                    else abfs_pair2<true>(F, r2, qij, ljS + (unsigned int) rows.x, ljS + (unsigned int) rows.y, eq, el, g);
+                    if (lj == 0 || (lj < 0 && ((freeBits >> (2 * p)) & 3u) == 3u)) abfs_pair2<false>(F, r2, qij, 0u, 0u, eq, el, g);
+                    else {
+                        const int2 rows = ist->row[p];
+                        abfs_pair2<true>(F, r2, qij, ljS + (unsigned int) rows.x, ljS + (unsigned int) rows.y, eq, el, g);
+                    }
                 } else {
                     // pairs off the list or beyond the cutoff read the all-zero table row (the skip of PairwiseInteraction.c:489)
+                    const int2 rows = ist->row[p];
                     const float4 ab0 = lds128(ljS + (unsigned int) rows.x), ab1 = lds128(ljS + (unsigned int) rows.y);
                     const PairOut o0 = spline_pair(splTab, A.splN, A.splInvDR, A.splDR, on0 && !(r2.x > F.r2Off), r2.x, qij.x, ab0.x, ab0.y);
                     const PairOut o1 = spline_pair(splTab, A.splN, A.splInvDR, A.splDR, on1 && !(r2.y > F.r2Off), r2.y, qij.y, ab1.x, ab1.y);
@@ -485,7 +495,28 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
                 const f2 ng = neg2(g);
                 fi[p][0] = fma2(ng, dx, fi[p][0]); fi[p][1] = fma2(ng, dy, fi[p][1]); fi[p][2] = fma2(ng, dz, fi[p][2]);      // gradient = -(force on i) = -g d
                 fj[0] = fma2(g, dx, fj[0]); fj[1] = fma2(g, dy, fj[1]); fj[2] = fma2(g, dz, fj[2]);
-            }
+            };
+            // the four double steps of the tile as ONE basic block per pattern of Coulomb-only atom pairs (the builder moves the atoms without
+            // Lennard-Jones interaction to the front of the cluster: the first nf pairs): without a branch between the steps ptxas overlaps
+            // the reciprocal square root and the dependent chains of neighbouring steps
+            auto steps = [&](auto NF) {
+                constexpr int nf = decltype(NF)::value;
+                using std::integral_constant;
+                step(integral_constant<int, 0>{}, integral_constant<int, (nf < 0 ? -1 : (0 < nf ? 0 : 1))>{});
+                step(integral_constant<int, 1>{}, integral_constant<int, (nf < 0 ? -1 : (1 < nf ? 0 : 1))>{});
+                step(integral_constant<int, 2>{}, integral_constant<int, (nf < 0 ? -1 : (2 < nf ? 0 : 1))>{});
+                step(integral_constant<int, 3>{}, integral_constant<int, (nf < 0 ? -1 : (3 < nf ? 0 : 1))>{});
+            };
+            if (kForm == 0) {
+                switch (variant) {
+                    case 0: steps(std::integral_constant<int, 0>{}); break;
+                    case 1: steps(std::integral_constant<int, 1>{}); break;
+                    case 2: steps(std::integral_constant<int, 2>{}); break;
+                    case 3: steps(std::integral_constant<int, 3>{}); break;
+                    case 4: steps(std::integral_constant<int, 4>{}); break;
+                    default: steps(std::integral_constant<int, -1>{}); break;
+                }
+            } else steps(std::integral_constant<int, -2>{});
             float fxj = fj[0].x + fj[0].y, fyj = fj[1].x + fj[1].y, fzj = fj[2].x + fj[2].y;
             if (kForm == 0 && __any_sync(0xffffffffu, r2min < F.r2Damp)) {   // damped core: practically never; patch the tile with the reference formulas
                 float c[5];
@@ -504,13 +535,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
                     const double rz = op->R[2] * gx + op->R[5] * gy + op->R[8] * gz;
                     gx = rx; gy = ry; gz = rz;
                 }
-                if (A.gradSorted != nullptr && A.exp != 1) {
-                    if (A.exp == 2) { double *gp = A.gradSorted + sj; atomicAdd(gp, gx); atomicAdd(gp + A.n, gy); atomicAdd(gp + 2 * (size_t) A.n, gz); }
-                    else if (A.exp == 3) { float *gp = reinterpret_cast<float *>(A.gradSorted) + 4 * (size_t) sj; asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(gp), "f"((float) gx), "f"((float) gy), "f"((float) gz), "f"(0.f) : "memory"); }
-                    else {
+                if (A.gradSorted != nullptr) {
                     double *gp = A.gradSorted + 3 * (size_t) sj;
                     atomicAdd(gp, gx); atomicAdd(gp + 1, gy); atomicAdd(gp + 2, gz);
-                    }
                 }
             }
             // the next tile's j atom from the records that have been in flight during this tile, then the records of the tile after it
@@ -699,19 +726,31 @@ __global__ void __launch_bounds__(kPruneWarps * 32) k_prune(const __grid_constan
 // assign != 0: the NB term SETS the caller's gradient (every atom has exactly one sorted position) instead of accumulating into it
 // kClear (fused mode of nbb200_md_run): the sorted accumulator is left zeroed for the next call (no memset of its own).  Two instantiations:
 // the plain one keeps gs const / read-only (the combined one measured 9 x slower on the 1.1 M-atom box: 143 vs 16 us)
+// pub: results of the call that are complete when this kernel starts (the accumulators of the force kernels, the displacement maximum of an
+// optimistic update decision) are written straight into page-locked host memory by the first CTA -- the call then needs no copy operation of its
+// own in the stream (a small device-to-host copy between two kernels costs several microseconds of engine switching)
+struct PublishArgs { const double *src[2]; double *dst[2]; int count[2]; };
+
 template <bool kClear>
 __global__ void k_unsort_gradients(typename std::conditional<kClear, double, const double>::type *__restrict__ gs, const int *__restrict__ sAtom, int s0, int n,
-                                   double *__restrict__ grad, int assign, const double *__restrict__ cond, double condThr2)
+                                   double *__restrict__ grad, int assign, const double *__restrict__ cond, double condThr2, const PublishArgs pub)
 {
+    if (blockIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            for (int i = threadIdx.x; i < pub.count[k]; i += blockDim.x) pub.dst[k][i] = pub.src[k][i];
+    }
     const int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     // optimistic update decision: the lists turned out to be stale (an atom moved beyond the buffer) -- this evaluation is discarded
-    if (cond != nullptr && *cond > condThr2) return;
+    const bool discard = cond != nullptr && *cond > condThr2;
     const int a = sAtom[s];
     if (a < 0) return;                                       // restricted sort (several ranks): not a position this rank sees
     const double gx = gs[3 * s], gy = gs[3 * s + 1], gz = gs[3 * s + 2];
-    if (assign) { grad[3 * a] = gx; grad[3 * a + 1] = gy; grad[3 * a + 2] = gz; }
-    else { grad[3 * a] += gx; grad[3 * a + 1] += gy; grad[3 * a + 2] += gz; }
+    if (!discard) {
+        if (assign) { grad[3 * a] = gx; grad[3 * a + 1] = gy; grad[3 * a + 2] = gz; }
+        else { grad[3 * a] += gx; grad[3 * a + 1] += gy; grad[3 * a + 2] += gz; }
+    }
     if constexpr (kClear) { gs[3 * s] = 0.0; gs[3 * s + 1] = 0.0; gs[3 * s + 2] = 0.0; }
 }
 
@@ -862,8 +901,11 @@ bool unsort_gradients(State &s, long s0, long s1, double *d_grad, bool assign, b
     if (s1 <= s0 || d_grad == nullptr || s.gs == nullptr) return true;
     const int threads = 256;
     const unsigned int blocks = (unsigned int) ((s1 - s0 + threads - 1) / threads);
-    if (clear) k_unsort_gradients<true><<<blocks, threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0, s.condDisp, s.condThr2);
-    else k_unsort_gradients<false><<<blocks, threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0, s.condDisp, s.condThr2);
+    PublishArgs pub;
+    for (int k = 0; k < 2; k++) { pub.src[k] = s.pubSrc[k]; pub.dst[k] = s.pubDst[k]; pub.count[k] = (s.pubSrc[k] != nullptr && s.pubDst[k] != nullptr) ? s.pubCount[k] : 0; }
+    if (pub.count[0] > 0 || pub.count[1] > 0) s.pubDone = true;
+    if (clear) k_unsort_gradients<true><<<blocks, threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0, s.condDisp, s.condThr2, pub);
+    else k_unsort_gradients<false><<<blocks, threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0, s.condDisp, s.condThr2, pub);
     s.launches += 1;
     return cuda_ok(cudaGetLastError(), "k_unsort_gradients");
 }
@@ -882,7 +924,12 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
     const int nitems = (int) s.hostCounters.itemCount;
     const size_t accumCount = (size_t) 16 * (s.nsets + 1);
     if (!s.accum.ensure(accumCount + 1)) return false;                    // + one slot that holds the work cursor: a single memset
-    const bool fusedZero = s.mdFused && nitems > 0;           // k_pack_records clears the accumulators and the cursor in fused mode
+    // fused mode: the memsets of a call are folded into neighbouring kernels (accumulators + work cursor by k_pack_records, the sorted gradient by
+    // the unsort pass of the previous call).  Always inside nbb200_md_run; for ordinary calls on systems up to kFuseMaxAtoms atoms, where a call is
+    // bound by the latency of its stream operations (on the 1.1 M-atom box the clearing unsort pass costs 0.13 ms more than a memset)
+    static const bool fuseSmall = std::getenv("NBB200_NO_FUSE") == nullptr;
+    const bool fused = s.mdFused || (fuseSmall && s.nranks == 1 && s.n <= kFuseMaxAtoms);
+    const bool fusedZero = fused && nitems > 0;           // k_pack_records clears the accumulators and the cursor in fused mode
     if (!fusedZero) NBB_CUDA(cudaMemsetAsync(s.accum.p, 0, sizeof(double) * (accumCount + 1), s.stream));
     unsigned int *workCursor = reinterpret_cast<unsigned int *>(s.accum.p + accumCount);
     const double eScale = (1.0 / s.dielectric) * kE2AngstromToKJMol;
@@ -1013,7 +1060,7 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
         s.launches += 1;
     }
     // device-array calls honour nbb200_set_gradient_overwrite too (the host-array call handles it with its own staging buffer: d_grad = s.grad.p)
-    const bool clearGs = s.mdFused && s.gsExternal == nullptr && s.nranks == 1 && d_grad != nullptr;
+    const bool clearGs = fused && s.gsExternal == nullptr && s.nranks == 1 && d_grad != nullptr;
     if (d_grad != nullptr && !unsort_gradients(s, 0, s.n, d_grad, s.gradOverwrite && d_grad != s.grad.p && s.nranks == 1, clearGs)) return false;
     if (clearGs) s.gsZeroed = true;                          // the whole accumulator (3 n) has just been cleared by the unsort pass
     return cuda_ok(cudaGetLastError(), "force kernels");

@@ -163,7 +163,7 @@ static bool upload_terms(MMTerms &m)
 // enqueue only: the kernel and the copy of the five energies into pinned memory; collect() waits for them
 // fused (nbb200_md_run, alternating slots): the device accumulators have two slots of 8 doubles; the kernel of slot s zeroes slot 1 - s for the
 // next step, so no memset is enqueued
-static bool enqueue(MMTerms &m, const double *d_x, double *d_grad, int slot = 0, bool fused = false)
+static bool enqueue(MMTerms &m, const double *d_x, double *d_grad, int slot = 0, bool fused = false, bool noCopy = false)
 {
     if (m.dirty && !upload_terms(m)) return false;
     const int total = m.start[kKinds];
@@ -177,7 +177,7 @@ static bool enqueue(MMTerms &m, const double *d_x, double *d_grad, int slot = 0,
         k_mm_terms<<<(total + 127) / 128, 128, 0, m.stream>>>(m.rec.p, K, d_x, d_grad, acc, fused ? m.energies.p + 8 * ((slot + 1) & 1) : nullptr);
         m.launches += 1;
     }
-    NBB_CUDA(cudaMemcpyAsync(m.he + 8 * (slot & 1), acc, sizeof(double) * kKinds, cudaMemcpyDeviceToHost, m.stream));
+    if (!noCopy) NBB_CUDA(cudaMemcpyAsync(m.he + 8 * (slot & 1), acc, sizeof(double) * kKinds, cudaMemcpyDeviceToHost, m.stream));       // noCopy: a later kernel of the caller hands the slot over
     return cuda_ok(cudaGetLastError(), "k_mm_terms");
 }
 
@@ -235,7 +235,7 @@ __global__ void k_langevin_first(double *__restrict__ x, double *__restrict__ v,
 __global__ void k_langevin_first_disp(double *__restrict__ x, double *__restrict__ v, const double *__restrict__ a, const double *__restrict__ mass, int n,
                                       double facR1, double facR2, double facV1, double facV2, double sdR, double sdV1, double sdV2,
                                       unsigned long long seed, unsigned long long step, const double *__restrict__ xref, const unsigned char *__restrict__ fixed,
-                                      unsigned long long *__restrict__ out, unsigned long long *__restrict__ zeroOther)
+                                      unsigned long long *__restrict__ out, unsigned long long *__restrict__ zeroOther, unsigned int *ticket, double *h_out)
 {
     if (zeroOther != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zeroOther = 0ULL;
     const int atom = blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,14 +265,16 @@ __global__ void k_langevin_first_disp(double *__restrict__ x, double *__restrict
     }
     for (int off = 16; off > 0; off >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, off));
     if ((threadIdx.x & 31) == 0 && r2 > 0.0) atomicMax(out, (unsigned long long) __double_as_longlong(r2));
+    // the maximum goes straight into page-locked host memory (no copy operation in the stream)
+    if (ticket != nullptr && last_block_done(ticket) && threadIdx.x == 0) *h_out = __longlong_as_double((long long) *reinterpret_cast<volatile unsigned long long *>(out));
 }
 
 bool langevin_first_disp(State &s, double *d_x, double *d_v, const double *d_a, const double *d_mass, const double *f7, unsigned long long seed,
-                         unsigned long long step, double *d_out, double *d_zeroOther)
+                         unsigned long long step, double *d_out, double *d_zeroOther, unsigned int *ticket, double *h_out)
 {
     k_langevin_first_disp<<<(s.n + 127) / 128, 128, 0, s.stream>>>(d_x, d_v, d_a, d_mass, s.n, f7[0], f7[1], f7[2], f7[3], f7[4], f7[5], f7[6], seed, step, s.xref.p,
                                                                    s.nfixed > 0 ? s.fixedFlag.p : nullptr, reinterpret_cast<unsigned long long *>(d_out),
-                                                                   reinterpret_cast<unsigned long long *>(d_zeroOther));
+                                                                   reinterpret_cast<unsigned long long *>(d_zeroOther), h_out != nullptr ? ticket : nullptr, h_out);
     s.launches += 1;
     return cuda_ok(cudaGetLastError(), "k_langevin_first_disp");
 }
@@ -440,10 +442,15 @@ void MMTerms_B200_LastEnergies(NBB200MMTerms *terms, double *energies5)
 
 // internal (nbb200_md_run): two result slots, so that a step's energies stay readable while the next step is already in flight
 namespace nbb200 {
-bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot, bool fused)
+bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot, bool fused, bool noCopy)
 {
     MMTerms *m = reinterpret_cast<MMTerms *>(terms);
-    return enqueue(*m, d_x, d_grad, slot, fused);
+    return enqueue(*m, d_x, d_grad, slot, fused, noCopy);
+}
+void mmterms_slot_pointers(NBB200MMTerms *terms, int slot, const double **d_energies, double **h_energies)
+{
+    MMTerms *m = reinterpret_cast<MMTerms *>(terms);
+    *d_energies = m->energies.p + 8 * (slot & 1); *h_energies = m->he + 8 * (slot & 1);
 }
 void mmterms_reset_slots(NBB200MMTerms *terms)        // start of a run: the slot the first step uses may hold an earlier run's last energies
 {

@@ -98,11 +98,12 @@ bool touched_ranges_async(State &s, long *d_out);      // the same table written
 }  // namespace nbb200
 struct NBB200MMTerms;
 namespace nbb200 {
-bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot, bool fused = false);
+bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot, bool fused = false, bool noCopy = false);
+void mmterms_slot_pointers(NBB200MMTerms *terms, int slot, const double **d_energies, double **h_energies);
 void mmterms_read_slot(NBB200MMTerms *terms, int slot, double *energies5);
 void mmterms_reset_slots(NBB200MMTerms *terms);
 bool langevin_first_disp(State &s, double *d_x, double *d_v, const double *d_a, const double *d_mass, const double *f7, unsigned long long seed,
-                         unsigned long long step, double *d_out, double *d_zeroOther);
+                         unsigned long long step, double *d_out, double *d_zeroOther, unsigned int *ticket = nullptr, double *h_out = nullptr);
 
 // ---- force_kernels.cu
 bool upload_spline_tables(State &s);                     // s.spl -> s.splF64 / s.splPoly
@@ -240,12 +241,14 @@ struct State {
     // energy call that follows evaluates on the current lists and its one synchronisation brings the decision back; when an update was
     // due after all the gradient is not handed out (the unsort pass looks at the device-side maximum), the lists are rebuilt and the
     // call is repeated
-    bool optimistic = false, optPending = false, keepLattice = false;
+    bool optimistic = false, optPending = false, keepLattice = false, optDispCopied = false;
     double optThr2 = 0.0;
     DevBuf<double> optDisp;                      // device: max |x - xref|^2 of the pending decision
     const double *condDisp = nullptr;            // unsort pass: skip when *condDisp > condThr2
     double condThr2 = 0.0;
     bool gradOverwrite = false;                  // MMMMEnergy (host arrays) sets the caller's gradient instead of accumulating
+    // results published by the unsort pass of an energy call instead of a copy operation (force_kernels.cu: PublishArgs); set by energy_enqueue
+    const double *pubSrc[2] = {nullptr, nullptr}; double *pubDst[2] = {nullptr, nullptr}; int pubCount[2] = {0, 0}; bool pubDone = false;
     bool mdFused = false;                        // inside nbb200_md_run: memsets folded into neighbouring kernels (accumulators by k_pack_records, sorted gradient by k_unsort_gradients)
     bool gsZeroed = false;                       // the caller zeroed the sorted gradient for this call already (before the ranks' barrier)                        // touched sorted range per rank slab (min, max+1)
     DevBuf<unsigned long long> setPairs;         // per set list-pair counts
@@ -266,5 +269,26 @@ struct State {
     double timings[8] = {};
     bool haveEvents = false;
 };
+
+
+#ifdef __CUDACC__
+// true in every thread of the LAST CTA of the grid to arrive here, after the global writes and atomics of all CTAs before this point have
+// become visible: that CTA may read what the grid reduced with atomics and hand it on (here: store it into page-locked host memory, which
+// spares the stream a small copy operation).  `ticket` counts the CTAs and is left at zero for the next launch.  Every thread of the CTA
+// must call it.
+__device__ __forceinline__ bool last_block_done(unsigned int *ticket)
+{
+    __shared__ bool lastBlock;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        lastBlock = t == gridDim.x - 1;
+        if (lastBlock) { *ticket = 0u; __threadfence(); }
+    }
+    __syncthreads();
+    return lastBlock;
+}
+#endif
 
 }  // namespace nbb200
