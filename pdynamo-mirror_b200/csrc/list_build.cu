@@ -865,6 +865,330 @@ __global__ void __launch_bounds__(kBuildThreads, NBB_BUILD_MINBLOCKS) k_build_ti
 }
 
 // ------------------------------------------------------------------------------------------------------
+// the cooperative variant for small systems: the FOUR warps of a CTA work on one (block, set) -- each walks every fourth cell row (stages A
+// and B exactly as above) -- and push into ONE ring per i-cluster in shared memory (the slots of a step are dealt per
+// cluster, in warp order: the warps publish their entry counts, a CTA barrier, every warp writes behind the warps before it); after a second
+// barrier warp q alone emits the full tiles of cluster q and owns its chunk state.  Four times the warps of the one-warp-per-block builder
+// (a 23 k-atom box fills a fifth of the GPU with it) without splitting the j streams: dealing the rows to independent warps gives every
+// part its own, padded, streams and the force kernel pays for the padding at every call.  The ring (256 entries) holds what is waiting
+// (< 32 after an emission) plus the entries of one step (<= 128).
+// ------------------------------------------------------------------------------------------------------
+constexpr int kCoopRing = 256;                   // positions are tracked bytewise
+struct CoopQueues {
+    unsigned int ring[kSubBlocks][kCoopRing];
+    unsigned int count[kBuildWarps];             // per warp: entries of the current step per cluster, one byte each
+};
+
+template <bool kQC>
+__global__ void __launch_bounds__(kBuildThreads, NBB_BUILD_MINBLOCKS) k_build_tiles_coop(TileArgs A)
+{
+    static_assert(kBuildWarps == kSubBlocks, "warp q of the CTA owns the stream of cluster q");
+    __shared__ BuildWarp sw[kBuildWarps];
+    __shared__ CoopQueues cq;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int wg = blockIdx.x * kBuildWarps + warp;
+    if (wg >= A.totalWarps) return;                                    // whole warps leave: no CTA barrier below
+    // Units: one warp per (block, part) for the primary set, then one warp per (block, part, image part) that walks the image sets
+    // whose list-time box overlaps the block (most (block, image) combinations of a large system do not: a warp per combination
+    // spent 8 % of the kernel's instructions on warps that left at once).  Small systems deal the rows of a (block, set) to `split`
+    // warps and the image sets of a block to `imgParts` warps (powers of two), each with its own j streams.
+    // image units come FIRST in the grid: they are few, short on arithmetic and long on latency (one row walk per overlapping set)
+    // (placed behind the primary units they were a tail of 0.1 ms on the 1.1 M-atom box)
+    const unsigned int imageWarps = A.totalWarps - A.primaryWarps;
+    const bool imageUnit = wg < imageWarps;
+    const unsigned int wu = imageUnit ? wg : wg - imageWarps;
+    const int part = (int) (wu & (unsigned int) (A.split - 1));
+    const unsigned int wr = wu >> A.splitShift;
+    const int ip = imageUnit ? (int) (wr & (unsigned int) (A.imgParts - 1)) : 0;
+    const int b = A.firstBlock + (int) (imageUnit ? (wr >> A.imgShift) : wr);
+    if (!imageUnit && !A.selfEnabled) return;
+    const double reach = A.cutoff + 1.0e-6;
+    double sbox[9];
+#pragma unroll
+    for (int d = 0; d < 6; d++) sbox[d] = A.blockBox[9 * b + d];
+    int set = 0, setBase = 1;
+    unsigned int pending = 0u;
+    if (imageUnit) {                                         // first overlapping image set, or leave
+        while (pending == 0u && setBase < A.nsets) {
+            const int sc = setBase + lane;
+            bool overlap = sc < A.nsets && ((sc - 1) & (A.imgParts - 1)) == ip;
+            if (overlap) {
+                const ImageBoxDev ib = A.imageBoxes[sc];
+                for (int d = 0; d < 3; d++) overlap = overlap && (ib.lo[d] <= sbox[3 + d] + reach) && (ib.hi[d] >= sbox[d] - reach);
+            }
+            pending = __ballot_sync(0xffffffffu, overlap);
+            setBase += kTile;
+        }
+        if (pending == 0u) return;
+        set = setBase - kTile + __ffs(pending) - 1;
+        pending &= pending - 1u;
+    }
+#pragma unroll
+    for (int d = 6; d < 9; d++) sbox[d] = A.blockBox[9 * b + d];
+    BuildWarp &W = sw[warp];
+    {
+        const int s = b * kTile + lane;
+        float f[3];
+        for (int d = 0; d < 3; d++) {
+            const double v = (s < A.n) ? A.sX[3 * s + d] : 1.0e30;            // padding rows never pass the test
+            W.sxi[lane][d] = v;
+            f[d] = (s < A.n) ? (float) (v - sbox[6 + d]) : 1.0e15f;
+        }
+        float *pxy = reinterpret_cast<float *>(W.sxy), *pzz = reinterpret_cast<float *>(W.szz);
+        const int m = lane & 15, h = lane >> 4;
+        pxy[4 * m + h] = f[0]; pxy[4 * m + 2 + h] = f[1]; pzz[2 * m + h] = f[2];
+        // exclusions can only remove pairs whose partner is excluded by a block atom: a small Bloom filter over the partners'
+        // sorted positions spares almost every candidate the dependent global loads of its exclusion list
+        W.bloom[lane] = 0u; W.bloom[lane + 32] = 0u;
+        if (lane < kSubBlocks) W.chunkBase[lane] = 0u;
+        __syncwarp();
+        if (set == 0 && s < A.n) {
+            const int ai = A.sAtom[s];
+            for (int k = A.exclPtr[ai]; k < A.exclPtr[ai + 1]; k++) {
+                const int sp = A.invPerm[A.exclCol[k]];
+                atomicOr(&W.bloom[(sp >> 5) & (kBloomWords - 1)], 1u << (sp & 31));
+            }
+        }
+    }
+    __syncwarp();
+
+    // fixed atoms: a pair stays on the lists only if one of its atoms is free (orSelection = freeSelection of the reference generators)
+    unsigned int freeMask = 0xffffffffu;
+    if (A.fixed != nullptr) {
+        const int sb = b * kTile + lane;
+        freeMask = __ballot_sync(0xffffffffu, !(sb < A.n && A.fixed[A.sAtom[sb]]));
+    }
+    if (kQC) {
+        const int sb = b * kTile + lane;
+        const unsigned int act = __ballot_sync(0xffffffffu, !(sb < A.n && A.inactive[A.sAtom[sb]]));
+        if (lane == 0) W.activeMask = act;
+        __syncwarp();
+    }
+    const BuildGrid g = A.grid;
+    int c0[3], c1[3];
+    double maxAbs = 0.0;
+    for (int d = 0; d < 3; d++) {
+        c0[d] = cell_coord(sbox[d] - reach, g.lo[d], g.invh, g.dim[d]);
+        c1[d] = cell_coord(sbox[3 + d] + reach, g.lo[d], g.invh, g.dim[d]);
+        maxAbs = fmax(maxAbs, 0.5 * (sbox[3 + d] - sbox[d]) + reach);
+    }
+    const int nrowsY = c1[1] - c0[1] + 1, nrowsTotal = (c1[0] - c0[0] + 1) * nrowsY;
+    // box reject in fp32: half extents of the block box around its centre; candidates are at most ~maxAbs away when they matter, so the
+    // rounding of the local coordinates (<= 6e-8 * maxAbs each) moves r2 by far less than the margin
+    const float hx = (float) (0.5 * (sbox[3] - sbox[0])), hy = (float) (0.5 * (sbox[4] - sbox[1])), hz = (float) (0.5 * (sbox[5] - sbox[2]));
+    const float reject2f = (float) (A.cutoff2 * (1.0 + 1.0e-5) + 1.0e-3);
+    // fp32 prefilter: |r2_fp32 - r2_exact| <= eps for every candidate that survives the box reject (block-local coordinates,
+    // magnitude <= maxAbs); decisions inside the band are taken by the exact fp64 predicate
+    const double delta = 6.0e-7 * maxAbs;
+    const float eps = (float) (2.0 * (3.5 * reach * delta + 3.0e-7 * A.cutoff2) + 2.0e-5);   // also covers the rounding of cutoff^2 to fp32
+    const float c2f = (float) A.cutoff2;
+    const unsigned int ltMask = (1u << lane) - 1u;
+
+    for (;;) {                                   // the sets of this unit: the primary set, or the overlapping image sets one after the other
+    int candHead = 0, candTail = 0;
+    unsigned int head = 0u;                      // warp q: ring position of the first waiting entry of cluster q
+    int avail = 0, used = 0;                     // warp q: entries waiting in the ring of cluster q; tiles used in its open chunk
+    unsigned int chunkBase = 0u, tailPos = 0u;   // tailPos: ring positions (mod 256, one byte per cluster) behind the last entry, tracked by every warp
+    unsigned long long myPairs = 0;
+    // scan cursor: rows are taken in batches of 32 (row tables in shared memory), each row in units of kScanUnroll chunks
+    int rowBase = -kTile, nrows = 0, r = 0, base = 0, rs = 0, rc = 0;
+    bool done = false;
+
+    // every step: scan (stage A) when fewer than 32 candidates are waiting, one batch of distance tests (stage B), push; barrier; warp q emits
+    for (;;) {
+        if (!done && candTail - candHead < kTile) {
+            // ---- advance the scan cursor to the next unit with work
+            while (!done && base >= rc) {
+                r += A.split;
+                if (r >= nrows) {
+                    rowBase += kTile;
+                    if (rowBase >= nrowsTotal) { done = true; break; }
+                    nrows = min(kTile, nrowsTotal - rowBase);
+                    __syncwarp();                                    // everybody is done with the previous row tables
+                    if (lane < nrows) {
+                        const int rr = rowBase + lane, cx = c0[0] + rr / nrowsY, cy = c0[1] + rr % nrowsY;
+                        // z range of this row: only the part of the column of cells that can be within reach of the block box
+                        const double xlo = g.lo[0] + cx * g.h, ylo = g.lo[1] + cy * g.h;
+                        const double ex = fmax(0.0, fmax(sbox[0] - (xlo + g.h), xlo - sbox[3])), ey = fmax(0.0, fmax(sbox[1] - (ylo + g.h), ylo - sbox[4]));
+                        const double rem = reach * reach - ex * ex - ey * ey;
+                        int start = 0, end = 0;
+                        if (rem >= 0.0) {
+                            const double dz = sqrt(rem) + 1.0e-6;
+                            const int z0 = cell_coord(sbox[2] - dz, g.lo[2], g.invh, g.dim[2]), z1 = cell_coord(sbox[5] + dz, g.lo[2], g.invh, g.dim[2]);
+                            const int keyLo = set * g.ncell + min(snake_cell(g, cx, cy, z0), snake_cell(g, cx, cy, z1));   // the z run is contiguous either way
+                            start = (int) A.cellStart[keyLo]; end = (int) A.cellStart[keyLo + (z1 - z0) + 1];
+                            if (set == 0) start = max(start, b * kTile);     // primary list: each unordered pair once (own block: triangle in stage B)
+                        }
+                        W.rowStart[lane] = start;
+                        W.rowCount[lane] = max(0, end - start);
+                    }
+                    __syncwarp();
+                    r = part;
+                    if (r >= nrows) { rc = 0; base = 0; continue; }
+                }
+                rs = W.rowStart[r]; rc = W.rowCount[r]; base = 0;
+            }
+
+            // ---- stage A: box reject of kScanUnroll chunks of 32 candidates; all loads first, the scan is latency bound
+            if (!done) {
+                double xj[kScanUnroll], yj[kScanUnroll], zj[kScanUnroll];
+    #pragma unroll
+                for (int u = 0; u < kScanUnroll; u++) {
+                    const int c = base + u * kTile + lane;
+                    xj[u] = 1.0e30; yj[u] = 1.0e30; zj[u] = 1.0e30;                 // out of range: rejected by the box test
+                    if (c < rc) { const int s = rs + c; xj[u] = A.sX[3 * s]; yj[u] = A.sX[3 * s + 1]; zj[u] = A.sX[3 * s + 2]; }
+                }
+    #pragma unroll
+                for (int u = 0; u < kScanUnroll; u++) {
+                    if (base + u * kTile < rc) {
+                        // conservative reject against the block box, in block-local fp32 (the threshold carries the rounding margin)
+                        const float fx = (float) (xj[u] - sbox[6]), fy = (float) (yj[u] - sbox[7]), fz = (float) (zj[u] - sbox[8]);
+                        const float ex = fmaxf(0.f, fabsf(fx) - hx), ey = fmaxf(0.f, fabsf(fy) - hy), ez = fmaxf(0.f, fabsf(fz) - hz);
+                        const bool keep = fmaf(ex, ex, fmaf(ey, ey, ez * ez)) <= reject2f;
+                        const unsigned int bal = __ballot_sync(0xffffffffu, keep);
+                        if (keep) W.cand[(candTail + __popc(bal & ltMask)) & (kCandRing - 1)] = make_float4(fx, fy, fz, __int_as_float(rs + base + u * kTile + lane));
+                        candTail += __popc(bal);
+                    }
+                }
+                base += kTile * kScanUnroll;
+                __syncwarp();
+            }
+        }
+        unsigned int colmask = 0u, jref = 0u, bal[kSubBlocks];
+        {
+            const int count = (candTail - candHead >= kTile || done) ? min(kTile, candTail - candHead) : 0;
+            if (lane < count) {
+                const float4 cj = W.cand[(candHead + lane) & (kCandRing - 1)];
+                const int s = __float_as_int(cj.w);
+                const float fx = cj.x, fy = cj.y, fz = cj.z;
+                float band = 1.0e30f;                        // min over the block atoms of |r2 - cutoff^2|
+                const f32x2 fx2 = pk2(fx, fx), fy2 = pk2(fy, fy), fz2 = pk2(fz, fz), c22 = pk2(c2f, c2f);
+                unsigned int ca = 0u, cb = 0u;               // sign bits of r2 - cutoff^2, shifted in from the right
+#pragma unroll
+                for (int i = 0; i < kTile / 2; i++) {        // block atoms i and i + 16 in one packed evaluation
+                    const float4 pxy = W.sxy[i];
+                    const float2 pz = W.szz[i];
+                    const f32x2 dx = sub2(pk2(pxy.x, pxy.y), fx2), dy = sub2(pk2(pxy.z, pxy.w), fy2), dz = sub2(pk2(pz.x, pz.y), fz2);
+                    float ta, tb;
+                    unpk2(sub2(fma2(dx, dx, fma2(dy, dy, mul2(dz, dz))), c22), ta, tb);
+                    ca = __funnelshift_l(__float_as_uint(ta), ca, 1);
+                    cb = __funnelshift_l(__float_as_uint(tb), cb, 1);
+                    band = fminf(band, fminf(fabsf(ta), fabsf(tb)));
+                }
+                colmask = (__brev(ca) >> 16) | (__brev(cb) & 0xffff0000u);     // r2 < cutoff^2 (equality sits inside the band)
+                if (band <= eps) {                           // some distance is within the fp32 error band: the reference predicate decides
+                    colmask = 0u;
+                    const double xj = A.sX[3 * s], yj = A.sX[3 * s + 1], zj = A.sX[3 * s + 2];
+                    for (int i = 0; i < kTile; i++) {
+                        const double r2 = ref_dist2(W.sxi[i][0] - xj, W.sxi[i][1] - yj, W.sxi[i][2] - zj);
+                        colmask |= (r2 <= A.cutoff2) ? (1u << i) : 0u;
+                    }
+                }
+                if (colmask != 0u && A.fixed != nullptr && A.fixed[A.sAtom[s]]) colmask &= freeMask;   // fixed j: free i atoms only
+                if (kQC && colmask != 0u) colmask = A.inactive[A.sAtom[s]] ? 0u : (colmask & W.activeMask);   // both atoms in the MM selection
+                if (colmask != 0u) {
+                    if (set == 0) {
+                        if ((s >> 5) == b) colmask &= (1u << (s & 31)) - 1u;          // own block: i < j only, no self pair
+                        if ((W.bloom[(s >> 5) & (kBloomWords - 1)] >> (s & 31)) & 1u) {
+                            const int atom = A.sAtom[s];
+                            for (int k = A.exclPtr[atom]; k < A.exclPtr[atom + 1]; k++) {
+                                const int sp = A.invPerm[A.exclCol[k]];
+                                if ((sp >> 5) == b) colmask &= ~(1u << (sp & 31));
+                            }
+                        }
+                        jref = (unsigned int) s;                                      // primary atoms: sorted position = extended position
+                    } else {
+                        const int atom = A.sAtom[s];
+                        jref = A.rawJ ? (unsigned int) atom : (unsigned int) A.invPerm[atom];
+                    }
+                }
+            }
+            candHead += count;
+            myPairs += __popc(colmask);
+            // how many entries this warp adds to each cluster's ring (one byte per cluster): published, then everybody knows everybody's
+            // share and the entries land in warp order -- the streams are the same from run to run (the fp32 partial sums of the force
+            // kernel follow the entry order: a first version that reserved the slots with atomics was not reproducible beyond ~1e-8)
+#pragma unroll
+            for (int q = 0; q < kSubBlocks; q++) {
+                const unsigned int byte = (colmask >> (kCluster * q)) & 0xffu;
+                bal[q] = __ballot_sync(0xffffffffu, byte != 0u);
+            }
+            if (lane == 0) cq.count[warp] = (unsigned int) __popc(bal[0]) | ((unsigned int) __popc(bal[1]) << 8) | ((unsigned int) __popc(bal[2]) << 16) | ((unsigned int) __popc(bal[3]) << 24);
+        }
+        const bool allDone = __syncthreads_and(done && candTail == candHead) != 0;
+        {
+            unsigned int before = 0u, total = 0u;                // bytewise: at most 4 x 32 per cluster, no carries
+#pragma unroll
+            for (int w2 = 0; w2 < kBuildWarps; w2++) { const unsigned int c = cq.count[w2]; total += c; before += (w2 < warp) ? c : 0u; }
+            const unsigned int mine = __vadd4(tailPos, before);  // ring positions (mod 256) of this warp's first entry per cluster
+#pragma unroll
+            for (int q = 0; q < kSubBlocks; q++) {
+                const unsigned int byte = (colmask >> (kCluster * q)) & 0xffu;
+                if (byte != 0u) cq.ring[q][(((mine >> (8 * q)) & 0xffu) + __popc(bal[q] & ltMask)) & (kCoopRing - 1)] = jref | (byte << 24);
+            }
+            tailPos = __vadd4(tailPos, total);
+            avail += (int) ((total >> (8 * warp)) & 0xffu);
+        }
+        __syncthreads();
+        // warp q: the full tiles of cluster q (at the very end: whatever is left, and close the open chunk)
+        {
+            const int q = warp;
+            bool flushed = false;
+            while (avail >= kTile || (allDone && !flushed && (avail | used) != 0)) {
+                const int n = min(avail, kTile);
+                flushed = n < kTile;
+                if (used == 0 && n > 0) {                                    // open a chunk (= the next work item of this stream)
+                    if (lane == 0) chunkBase = atomicAdd(&A.counters->tileTotal, (unsigned int) A.chunkTiles);
+                    chunkBase = __shfl_sync(0xffffffffu, chunkBase, 0);
+                    if (chunkBase > A.tileCap - (unsigned int) A.chunkTiles) {
+                        if (lane == 0) atomicOr(&A.counters->overflow, 2u);
+                        chunkBase = kNoChunk;
+                    }
+                }
+                if (n > 0) {
+                    const unsigned int word = (lane < n) ? cq.ring[q][(head + lane) & (kCoopRing - 1)] : kEmptySlot;
+                    if (chunkBase != kNoChunk) A.tileDesc[(chunkBase + (unsigned int) used) * kTile + lane] = word;
+                    used += 1;
+                    head += (unsigned int) n;
+                    avail -= n;
+                }
+                const bool close = used == A.chunkTiles || n < kTile;       // chunk full, or the (padded) last tile of the stream
+                if (close && chunkBase != kNoChunk && lane == 0 && used > 0) {
+                    const unsigned int pos = atomicAdd(&A.counters->itemCount, 1u);
+                    if (pos < A.itemCap) {
+                        WorkItem w;
+                        w.block = kSubBlocks * b + q; w.image = set; w.tileStart = (int) chunkBase; w.tileCount = used;
+                        A.items[pos] = w;
+                    } else atomicOr(&A.counters->overflow, 4u);
+                    atomicAdd(&A.counters->tilesUsed, (unsigned int) used);
+                }
+                if (close) used = 0;
+            }
+        }
+        if (allDone) break;
+    }
+    for (int o = 16; o > 0; o >>= 1) myPairs += __shfl_xor_sync(0xffffffffu, myPairs, o);
+    if (lane == 0 && myPairs) atomicAdd(&A.setPairs[set], myPairs);
+    // ---- next overlapping image set of this unit
+    if (!imageUnit) break;
+    while (pending == 0u && setBase < A.nsets) {
+        const int sc = setBase + lane;
+        bool overlap = sc < A.nsets && ((sc - 1) & (A.imgParts - 1)) == ip;
+        if (overlap) {
+            const ImageBoxDev ib = A.imageBoxes[sc];
+            for (int d = 0; d < 3; d++) overlap = overlap && (ib.lo[d] <= sbox[3 + d] + reach) && (ib.hi[d] >= sbox[d] - reach);
+        }
+        pending = __ballot_sync(0xffffffffu, overlap);
+        setBase += kTile;
+    }
+    if (pending == 0u) break;
+    set = setBase - kTile + __ffs(pending) - 1;
+    pending &= pending - 1u;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------
 // explicit pair lists from the tiles: one warp per work item; pairs of set k land in [pairOffsets[k], ...)
 // ------------------------------------------------------------------------------------------------------
 __global__ void k_expand_pairs(const WorkItem *__restrict__ items, int nitems, const unsigned int *__restrict__ tileDesc,
@@ -1120,6 +1444,12 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     // of every step gains more (DHFR 73 -> 68 us) than the rarer rebuild loses (0.26 -> 0.36 ms); single calls keep the faster rebuild
     const long splitTarget = splitEnv > 0 ? splitEnv : (s.listReuseHint ? 148L * 8 : 148L * 16);
     while (split < 8 && (long) myBlocks * split * 2 <= splitTarget) split *= 2;
+    // cooperative builder (k_build_tiles_coop): four warps per block with shared j streams, when one warp per block leaves the GPU short of
+    // warps (148 SMs x 28 builder warps).  NBB200_COOP=0 / 1 forces it off / on
+    static const int coopEnv = []() { const char *e = std::getenv("NBB200_COOP"); return e ? std::atoi(e) : -1; }();
+    static const long coopBlocks = []() { const char *e = std::getenv("NBB200_COOP_BLOCKS"); return (e && std::atol(e) > 0) ? std::atol(e) : 148L * 28; }();
+    const bool coop = coopEnv >= 0 ? coopEnv != 0 : (long) myBlocks <= coopBlocks;
+    if (coop) split = kBuildWarps;
     size_t cap = s.tileCap;
     if (cap == 0) {
         // expected list pairs from the mean density inside the search box; 8 x 32 tiles are about half full
@@ -1128,7 +1458,7 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
         const double density = std::min(0.2, (double) s.n / vol);
         const double pairsPerAtom = 0.5 * density * (4.0 / 3.0) * 3.14159265358979 * s.list * s.list * s.list + 8.0;
         const double tiles = pairsPerAtom * ((double) s.n * myBlocks / std::max(1, s.nblocks)) / (kCluster * kTile * 0.5);
-        const double streams = (double) kSubBlocks * myBlocks * std::min(s.nsets, 6) * split;
+        const double streams = (double) kSubBlocks * myBlocks * std::min(s.nsets, 6) * (coop ? 1 : split);
         cap = (size_t) (1.2 * tiles + streams * chunk) + 1024;
     }
     for (int attempt = 0; attempt < 4; attempt++) {
@@ -1163,8 +1493,12 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
             A.tileDesc = s.tileDesc.p; A.tileCap = (unsigned int) cap;
             A.items = s.items.p; A.itemCap = (unsigned int) s.itemCap; A.setPairs = s.setPairs.p; A.counters = s.counters;
             const long warps = (long) A.totalWarps;
-            if (A.inactive != nullptr) k_build_tiles<true><<<(unsigned int) ((warps + kBuildWarps - 1) / kBuildWarps), kBuildThreads, 0, s.stream>>>(A);
-            else k_build_tiles<false><<<(unsigned int) ((warps + kBuildWarps - 1) / kBuildWarps), kBuildThreads, 0, s.stream>>>(A);
+            const unsigned int ctas = (unsigned int) ((warps + kBuildWarps - 1) / kBuildWarps);
+            if (coop) {
+                if (A.inactive != nullptr) k_build_tiles_coop<true><<<ctas, kBuildThreads, 0, s.stream>>>(A);
+                else k_build_tiles_coop<false><<<ctas, kBuildThreads, 0, s.stream>>>(A);
+            } else if (A.inactive != nullptr) k_build_tiles<true><<<ctas, kBuildThreads, 0, s.stream>>>(A);
+            else k_build_tiles<false><<<ctas, kBuildThreads, 0, s.stream>>>(A);
             s.launches += 1;
         }
         NBB_CUDA(cudaMemcpyAsync(&s.hostCounters, s.counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, s.stream));
