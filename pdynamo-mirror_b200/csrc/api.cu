@@ -59,7 +59,7 @@ static void destroy(State *s)
     delete s;
 }
 
-constexpr size_t kSmallDoubles = 1 << 16;
+// (kSmallDoubles: nbb200_internal.h)
 constexpr size_t kOpsBytes = 4096 * sizeof(ImageOpDev);
 
 static State *create(int device, int n, const double *charges, const int *ljtypes,

@@ -73,7 +73,8 @@ __device__ __forceinline__ int cell_coord(double v, double lo, double invh, int 
 // bounding boxes of the primary coordinates (op 0) and of the coordinates transformed by each base operation
 // (Coordinates3_EnclosingOrthorhombicBox, pC/csource/Coordinates3.c:498-...): partial min/max per CTA, then one CTA.
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_bbox_partial(const double *__restrict__ x, int n, const double *__restrict__ ops, int nops, double *__restrict__ partial)
+__global__ void k_bbox(const double *__restrict__ x, int n, const double *__restrict__ ops, int nops, double *__restrict__ partial, unsigned int *ticket,
+                       double *__restrict__ out, double *__restrict__ hostOut)
 {
     // partial[(blockIdx.x * (nops) + o) * 6 + {min xyz, max xyz}]
     extern __shared__ double sh[];
@@ -100,16 +101,16 @@ __global__ void k_bbox_partial(const double *__restrict__ x, int n, const double
         }
         __syncthreads();
     }
-}
-
-__global__ void k_bbox_final(const double *__restrict__ partial, int nblk, int nops, double *__restrict__ out)
-{
-    const int idx = blockIdx.x;                                  // o*6 + c, one warp each
-    const int c = idx % 6, lane = threadIdx.x;
-    double v = (c < 3) ? 1e300 : -1e300;
-    for (int k = lane; k < nblk; k += 32) { const double u = partial[(size_t) k * nops * 6 + idx]; v = (c < 3) ? fmin(v, u) : fmax(v, u); }
-    for (int off = 16; off > 0; off >>= 1) { const double u = __shfl_xor_sync(0xffffffffu, v, off); v = (c < 3) ? fmin(v, u) : fmax(v, u); }
-    if (lane == 0) out[idx] = v;
+    // the last CTA to finish reduces the partial boxes and stores the result into page-locked host memory as well: one launch, no copy operation
+    if (!last_block_done(ticket)) return;
+    const int lane = threadIdx.x & 31, nblk = (int) gridDim.x;
+    for (int idx = threadIdx.x >> 5; idx < nops * 6; idx += blockDim.x >> 5) {        // idx = o * 6 + c, one warp each
+        const int c = idx % 6;
+        double v = (c < 3) ? 1e300 : -1e300;
+        for (int k = lane; k < nblk; k += 32) { const double u = __ldcg(partial + (size_t) k * nops * 6 + idx); v = (c < 3) ? fmin(v, u) : fmax(v, u); }
+        for (int off = 16; off > 0; off >>= 1) { const double u = __shfl_xor_sync(0xffffffffu, v, off); v = (c < 3) ? fmin(v, u) : fmax(v, u); }
+        if (lane == 0) { out[idx] = v; hostOut[idx] = v; }
+    }
 }
 
 bool device_bbox(State &s, int nops, double *hostMin, double *hostExt)
@@ -118,11 +119,14 @@ bool device_bbox(State &s, int nops, double *hostMin, double *hostExt)
     int nblk = std::min(512, (s.n + threads * 4 - 1) / (threads * 4));
     if (nblk < 1) nblk = 1;
     if (!s.bboxDev.ensure((size_t) (nblk + 1) * nops * 6)) return false;
+    if ((size_t) nops * 6 > kSmallDoubles - 16) { set_error("too many transformations for the result buffer"); return false; }
+    if (s.ticket.p == nullptr) {
+        if (!s.ticket.ensure(4)) return false;
+        NBB_CUDA(cudaMemsetAsync(s.ticket.p, 0, sizeof(unsigned int) * 4, s.stream));
+    }
     double *partial = s.bboxDev.p + (size_t) nops * 6;
-    k_bbox_partial<<<nblk, threads, (threads / 32) * 6 * sizeof(double), s.stream>>>(s.xcur, s.n, s.baseOpsDev.p, nops, partial);
-    k_bbox_final<<<nops * 6, 32, 0, s.stream>>>(partial, nblk, nops, s.bboxDev.p);
-    s.launches += 2;
-    NBB_CUDA(cudaMemcpyAsync(s.hsmall, s.bboxDev.p, sizeof(double) * nops * 6, cudaMemcpyDeviceToHost, s.stream));
+    k_bbox<<<nblk, threads, (threads / 32) * 6 * sizeof(double), s.stream>>>(s.xcur, s.n, s.baseOpsDev.p, nops, partial, s.ticket.p, s.bboxDev.p, s.hsmall);
+    s.launches += 1;
     NBB_CUDA(cudaStreamSynchronize(s.stream));
     for (int o = 0; o < nops; o++)
         for (int d = 0; d < 3; d++) { hostMin[3 * o + d] = s.hsmall[6 * o + d]; hostExt[3 * o + d] = s.hsmall[6 * o + 3 + d] - s.hsmall[6 * o + d]; }
@@ -468,7 +472,7 @@ __global__ void k_sort_cells(const unsigned int *__restrict__ cellStart, int nke
 // skips the Lennard-Jones part of a pair of atoms when both are of such a type.  Atoms never leave their grid cell (the cell ranges of
 // the sorted order are what the tile builder scans): a run that straddles a cell boundary is partitioned piece by piece.
 __global__ void k_group_lj_free(int n, const int *__restrict__ ljtype, const unsigned char *__restrict__ typeFree, BuildGrid g, double *__restrict__ sX, int *__restrict__ sAtom,
-                                int *__restrict__ invPerm)
+                                int *__restrict__ invPerm, int firstBlock, int nblocks, double *__restrict__ blockBox)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;            // sorted position; 8 consecutive lanes = one cluster
     const int lane = threadIdx.x & 31, base = lane & ~(kCluster - 1), rel = lane - base;
@@ -492,6 +496,15 @@ __global__ void k_group_lj_free(int n, const int *__restrict__ ljtype, const uns
         const int p = (s & ~(kCluster - 1)) + dst;
         sX[3 * p] = x; sX[3 * p + 1] = y; sX[3 * p + 2] = z;
         sAtom[p] = a; invPerm[a] = p;
+    }
+    // the box of the sort block (this warp's 32 atoms: the grouping leaves the set unchanged) -- k_block_boxes folded in
+    const int b = s >> 5;
+    if (blockBox != nullptr && b >= firstBlock && b < firstBlock + nblocks) {
+        double v[6] = {s < n ? x : 1e300, s < n ? y : 1e300, s < n ? z : 1e300, s < n ? x : -1e300, s < n ? y : -1e300, s < n ? z : -1e300};
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            for (int off = 16; off > 0; off >>= 1) { v[d] = fmin(v[d], __shfl_xor_sync(0xffffffffu, v[d], off)); v[3 + d] = fmax(v[3 + d], __shfl_xor_sync(0xffffffffu, v[3 + d], off)); }
+        if (lane < 3) { blockBox[9 * b + lane] = v[lane]; blockBox[9 * b + 3 + lane] = v[3 + lane]; blockBox[9 * b + 6 + lane] = 0.5 * (v[lane] + v[3 + lane]); }
     }
 }
 
@@ -1427,10 +1440,11 @@ static bool sort_and_tile(State &s, bool selfEnabled, unsigned int extUpperBound
     }
     k_scatter<<<(unsigned int) ((neMax + 255) / 256), 256, 0, s.stream>>>(s.eKey.p, s.eSet.p, s.n, extUpperBound, s.counters, s.cellStart.p, s.cellFill.p, s.order.p, need, ncell);
     k_sort_cells<<<(nkeys + 7) / 8, 256, 0, s.stream>>>(s.cellStart.p, nkeys, s.eSortBuf.p, s.order.p, s.eX.p, s.eAtom.p, s.eSet.p, s.sX.p, s.sAtom.p, s.invPerm.p, need, ncell);
-    if (s.typeFree.p != nullptr) { k_group_lj_free<<<(s.n + 255) / 256, 256, 0, s.stream>>>(s.n, s.ljtype.p, s.typeFree.p, s.grid, s.sX.p, s.sAtom.p, s.invPerm.p); s.launches += 1; }
     if (!s.blockBox.ensure((size_t) 9 * s.nblocks)) return false;
-    if (myBlocks > 0) k_block_boxes<<<(myBlocks * 32 + 255) / 256, 256, 0, s.stream>>>(s.sX.p, s.n, b0, myBlocks, s.blockBox.p);     // the builder reads the own blocks' boxes only
-    s.launches += 3;
+    // (the builder reads the own blocks' boxes only; the grouping pass writes them when it runs)
+    if (s.typeFree.p != nullptr) { k_group_lj_free<<<(s.n + 255) / 256, 256, 0, s.stream>>>(s.n, s.ljtype.p, s.typeFree.p, s.grid, s.sX.p, s.sAtom.p, s.invPerm.p, b0, myBlocks, s.blockBox.p); s.launches += 1; }
+    else if (myBlocks > 0) { k_block_boxes<<<(myBlocks * 32 + 255) / 256, 256, 0, s.stream>>>(s.sX.p, s.n, b0, myBlocks, s.blockBox.p); s.launches += 1; }
+    s.launches += 2;
 
     // tiles: a global pool handed out in chunks (= work items); sized from the pair density, retried once with the exact need
     // tiles per chunk / work item: long items amortise the per-item prologue of the force kernel, short ones keep small systems spread over all SMs

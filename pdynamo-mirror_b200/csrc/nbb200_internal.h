@@ -13,6 +13,7 @@ constexpr int kTile = 32;            // atoms per sort block (one builder warp) 
 constexpr int kCluster = 8;          // atoms per i-cluster of the force kernel: a tile is 8 i atoms x 32 j slots
 constexpr int kBuildThreads = 128;   // CTA size of the tile builder (four independent warps)
 constexpr unsigned int kEmptySlot = 0x00FFFFFFu;    // j field of an unused tile slot; atoms / sorted positions use 24 bits
+constexpr size_t kSmallDoubles = 1 << 16;           // doubles in the page-locked result buffers (State::hsmall, hacc)
 constexpr int kMaxAtoms = 0x00FFFFFF;               // hence at most 16.7 M atoms per state
 
 void set_error(const std::string &msg);
@@ -193,6 +194,7 @@ struct State {
     DevBuf<double> visitDisp;                    // per visit 3 doubles
     DevBuf<int> visitInfo;                       // per visit: t, image
     DevBuf<double> bboxDev;                      // reduction output
+    DevBuf<unsigned int> ticket;                 // CTA counters of the kernels that finish with last_block_done (left at zero by them)
     DevBuf<double> mdScalars;                    // nbb200_md_run: two-slot device scalars (displacement maximum, kinetic energy)
 
     // extended atoms and the sort
