@@ -590,7 +590,7 @@ def md_device_block(torch, local, steps=1000):
         wall = time.perf_counter() - t0
         tot = np.array([a + b for a, b in traj]); kin = np.array([b for _, b in traj])
         out[label] = {"steps_per_s": steps / wall, "ms_per_step": 1e3 * wall / steps, "steps": steps, "list_updates": md.updates - u0,
-                      "total_energy_drift_over_kinetic": float(np.abs(tot - e0).max() / kin.mean()), "temperature_K": float(2.0 * kin.mean() / (3 * md.n * 8.314472e-3))}
+                      "total_energy_drift_over_kinetic": float(np.abs(tot - e0).max() / kin.mean()), "temperature_K": float(2.0 * kin.mean() / (md.degreesOfFreedom * 8.314472e-3))}
     return out
 
 
@@ -614,7 +614,7 @@ def md_dhfr_block(torch, local, steps=1000):
     t2 = time.perf_counter()
     wall, loop = t2 - t0, t2 - t1
     kin = np.array([k for _, k in traj]); pot = np.array([q for q, _ in traj])
-    temp = 2.0 * kin / (3 * md.n * 8.314472e-3)
+    temp = 2.0 * kin / (md.degreesOfFreedom * 8.314472e-3)
     return {"workload": workload_description("dhfr_mm", w) + " + 23592 bonds, 11584 angles, 2117 Urey-Bradley, 7000 dihedral, 418 improper terms",
             "protocol": "Energy(doGradients) + %d Langevin velocity-Verlet steps (1 fs, 300 K, 25 ps^-1), displacement-triggered list updates" % steps,
             "wall_s": wall, "wall_note": "state creation (device allocations, first list build), the initial energy call and the %d steps -- what the reference's 'Total' covers" % steps,

@@ -237,10 +237,16 @@ void nbb200_vv_second_half(NBB200State *state, double *d_v, double *d_a, const d
  *   x += facR1 v + facR2 a + sdR w1 / sqrt(m) ; v = facV1 v + facV2 a + (sdV1 w1 + sdV2 w2) / sqrt(m)
  * factors7 = {facR1, facR2, facV1, facV2, sdR, sdV1, sdV2} as CalculateIntegrationConstants (:54-115) gives them; w1, w2: standard normal
  * deviates from a counter-based generator keyed by (seed, step, coordinate).  The second part (a = -100 g / m; v += facV3 a; kinetic
- * energy) is nbb200_vv_second_half with dt = 2 facV3.  Not applied: the projection of the deviates on the linear constraints
- * (ApplyLinearConstraints), i.e. the centre of mass is free to diffuse. */
+ * energy) is nbb200_vv_second_half with dt = 2 facV3.  The projection of the deviates on the linear constraints (ApplyLinearConstraints,
+ * :143,148) is applied when nbb200_set_langevin_constraints has switched it on. */
 void nbb200_langevin_first_half(NBB200State *state, double *d_x, double *d_v, const double *d_a, const double *d_mass, const double *factors7,
                                 unsigned long long seed, unsigned long long step);
+/* ApplyLinearConstraints of the Langevin integrator for the constraint set RemoveRotationTranslation builds for a periodic system
+ * (pMolecule-1.9.0/pMolecule/SystemGeometryObjectiveFunction.py:213-240: translation only; MolecularDynamics.py:27-32 switches it on by default):
+ * both random vectors of a step are projected on the complement of the three mass-weighted translation vectors, i.e. the random terms carry no
+ * net momentum.  totalMass = the sum of the masses passed as d_mass.  Applies to nbb200_langevin_first_half and nbb200_md_run.  (Systems with
+ * fixed atoms have no such constraints in the reference, :220; rotations are only removed for non-periodic systems: not built.) */
+void nbb200_set_langevin_constraints(NBB200State *state, int removeTranslation, double totalMass);
 
 /* forward declaration (bonded terms, below) */
 typedef struct NBB200MMTerms NBB200MMTerms;

@@ -63,6 +63,7 @@ SIGNATURES = {
     "nbb200_vv_second_half": (None, [vp, vp, vp, vp, vp, C.c_double, vp]),
     "nbb200_md_run": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, dp, C.c_double, dp, C.c_double, C.c_ulonglong, C.c_ulonglong, vp, dp, dp, dp, dp, ip]),
     "nbb200_langevin_first_half": (None, [vp, vp, vp, vp, vp, dp, C.c_ulonglong, C.c_ulonglong]),
+    "nbb200_set_langevin_constraints": (None, [vp, C.c_int, C.c_double]),
     "MMTerms_B200_Allocate": (vp, [C.c_int, C.c_int, ip]),
     "MMTerms_B200_Deallocate": (None, [C.POINTER(vp)]),
     "MMTerms_B200_SetStream": (None, [vp, vp]),

@@ -40,7 +40,7 @@ static void destroy(State *s)
     s->exclPtr.release(); s->exclCol.release(); s->pairs14.release(); s->fixedFlag.release(); s->qcFlag.release();
     s->isoPtr.release(); s->isoIdx.release(); s->xc.release(); s->isoT.release();
     s->x.release(); s->xref.release(); s->grad.release();
-    s->imageOps.release(); s->imageBoxes.release(); s->baseOpsDev.release(); s->visitDisp.release(); s->visitInfo.release(); s->bboxDev.release();
+    s->imageOps.release(); s->imageBoxes.release(); s->baseOpsDev.release(); s->visitDisp.release(); s->visitInfo.release(); s->bboxDev.release(); s->ticket.release(); s->lcSums.release(); s->lcW.release();
     s->eX.release(); s->eAtom.release(); s->eSet.release(); s->eKey.release(); s->eSortBuf.release();
     s->cellStart.release(); s->cellFill.release(); s->scanTmp.release(); s->order.release(); s->order2.release();
     s->sX.release(); s->sAtom.release(); s->invPerm.release(); s->blockBox.release();
@@ -1224,8 +1224,7 @@ static __global__ void k_vv_first(double *__restrict__ x, double *__restrict__ v
 
 // first half fused with the displacement check of CheckForUpdate (nbb200_md_run): one thread per atom, |x - xref|^2 into the running maximum
 static __global__ void k_vv_first_disp(double *__restrict__ x, double *__restrict__ v, const double *__restrict__ a, double dt, int n, const double *__restrict__ xref,
-                                       const unsigned char *__restrict__ fixed, unsigned long long *__restrict__ out, unsigned long long *__restrict__ zeroOther,
-                                       unsigned int *ticket, double *h_out)
+                                       const unsigned char *__restrict__ fixed, unsigned long long *__restrict__ out, unsigned long long *__restrict__ zeroOther)
 {
     if (zeroOther != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zeroOther = 0ULL;
     const int atom = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1246,15 +1245,13 @@ static __global__ void k_vv_first_disp(double *__restrict__ x, double *__restric
     }
     for (int off = 16; off > 0; off >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, off));
     if ((threadIdx.x & 31) == 0 && r2 > 0.0) atomicMax(out, (unsigned long long) __double_as_longlong(r2));
-    // the maximum goes straight into page-locked host memory (no copy operation in the stream)
-    if (ticket != nullptr && last_block_done(ticket) && threadIdx.x == 0) *h_out = __longlong_as_double((long long) *reinterpret_cast<volatile unsigned long long *>(out));
 }
 
 // second half: a = -100 g / m (kJ mol^-1 A^-1 amu^-1 -> A ps^-2) ; v += dt/2 a ; kinetic energy 0.5 * 0.01 * sum m v^2 (kJ/mol)
-// ticket / h_ke / pub (nbb200_md_run): the kinetic energy (last CTA) and the bonded energies of the step (complete before this kernel) are stored into
-// page-locked host memory -- no copy operations in the stream
+// pub (nbb200_md_run): the bonded energies of the step (complete before this kernel starts) are stored into page-locked host memory -- no copy
+// operation in the stream
 static __global__ void k_vv_second(double *__restrict__ v, double *__restrict__ a, const double *__restrict__ g, const double *__restrict__ mass, double dt, long m,
-                                   double *__restrict__ ke, double *__restrict__ zeroOther = nullptr, unsigned int *ticket = nullptr, double *h_ke = nullptr,
+                                   double *__restrict__ ke, double *__restrict__ zeroOther = nullptr,
                                    const double *pubSrc = nullptr, double *pubDst = nullptr, int pubCount = 0)
 {
     if (zeroOther != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zeroOther = 0.0;      // two-slot use (nbb200_md_run): prepares the next step's slot
@@ -1268,7 +1265,6 @@ static __global__ void k_vv_second(double *__restrict__ v, double *__restrict__ 
     }
     for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
     if ((threadIdx.x & 31) == 0) atomicAdd(ke, 0.5 * 0.01 * local);
-    if (ticket != nullptr && last_block_done(ticket) && threadIdx.x == 0) *h_ke = *reinterpret_cast<volatile double *>(ke);
 }
 
 void nbb200_vv_first_half(NBB200State *state, double *d_x, double *d_v, const double *d_a, double dt)
@@ -1392,7 +1388,9 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
     // results reach the host by stores into page-locked memory from the kernels that complete them (no copy operations in the stream: each one
     // costs a few microseconds between two small kernels); NBB200_NO_PUBLISH=1 keeps the copies
     static const bool publish = std::getenv("NBB200_NO_PUBLISH") == nullptr;
-    unsigned int *d_ticket = reinterpret_cast<unsigned int *>(s.mdScalars.p + 16);      // [0]: first half, [1]: second half (zeroed above, left at zero by the kernels)
+    // (who stores what: the accumulators by the unsort pass of the step; the bonded energies by the second half; the displacement maximum of
+    // step k and the kinetic energy of step k - 1 by the first kernel of step k's energy call -- always a kernel that STARTS after the value is
+    // complete: letting the producing kernel's last CTA do it costs a __threadfence behind its bulk stores, ~4 us per kernel on this GPU)
     auto enqueue_step = [&](int k, bool redo) -> bool {
         for (int c = 0; c < 9; c++) dEdM[c] = 0.0;
         if (!energy_enqueue(s, d_g, false, haccSlot[k & 1])) return false;
@@ -1402,7 +1400,7 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
         if (terms != nullptr && publish) mmterms_slot_pointers(terms, k & 1, &pubSrc, &pubDst);
         k_vv_second<<<(unsigned int) std::min<long>(148 * 8, (m + 255) / 256), 256, 0, s.stream>>>(d_v, d_a, d_g, d_mass, secondHalfDt, m, d_ke2 + (k & 1),
                                                                                                   fusedMode ? d_ke2 + ((k + 1) & 1) : nullptr,
-                                                                                                  publish ? d_ticket + 1 : nullptr, hke + (k & 1), pubSrc, pubDst, pubSrc != nullptr ? 5 : 0);
+                                                                                                  pubSrc, pubDst, pubSrc != nullptr ? 5 : 0);
         s.launches += 1;
         if (publish) return cuda_ok(cudaGetLastError(), "k_vv_second");
         return cuda_ok(cudaMemcpyAsync(hke + (k & 1), d_ke2 + (k & 1), sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H kinetic energy");
@@ -1432,12 +1430,10 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
         const bool fusedFirst = speculate && fusedMode;         // first half and displacement check in one kernel
         double *d_disp = d_disp2 + (nspec & 1), *d_dispOther = d_disp2 + ((nspec + 1) & 1);
         if (fusedFirst) {
-            if (langevinFactors7 != nullptr) ok = langevin_first_disp(s, d_x, d_v, d_a, d_mass, langevinFactors7, seed, firstIteration + (unsigned long long) k, d_disp, d_dispOther,
-                                                                      d_ticket, publish ? hdisp + (k & 1) : nullptr);
+            if (langevinFactors7 != nullptr) ok = langevin_first_disp(s, d_x, d_v, d_a, d_mass, langevinFactors7, seed, firstIteration + (unsigned long long) k, d_disp, d_dispOther);
             else {
                 k_vv_first_disp<<<(s.n + 127) / 128, 128, 0, s.stream>>>(d_x, d_v, d_a, timeStep, s.n, s.xref.p, s.nfixed > 0 ? s.fixedFlag.p : nullptr,
-                                                                        reinterpret_cast<unsigned long long *>(d_disp), reinterpret_cast<unsigned long long *>(d_dispOther),
-                                                                        publish ? d_ticket : nullptr, hdisp + (k & 1));
+                                                                        reinterpret_cast<unsigned long long *>(d_disp), reinterpret_cast<unsigned long long *>(d_dispOther));
                 s.launches += 1;
             }
         } else if (langevinFactors7 != nullptr) nbb200_langevin_first_half(state, d_x, d_v, d_a, d_mass, langevinFactors7, seed, firstIteration + (unsigned long long) k);
@@ -1446,9 +1442,21 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
         if (speculate) {
             // optimistic: the check of CheckForUpdate (NBModelABFS.c:691-746) and the whole step go out together
             nspec += 1;
-            ok = ok && (fusedFirst || displacement_enqueue(s, d_x, d_disp, nullptr)) &&
-                 ((fusedFirst && publish) || cuda_ok(cudaMemcpyAsync(hdisp + (k & 1), d_disp, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H displacement")) &&
-                 cuda_ok(cudaEventRecord(evDisp, s.stream), "event") && enqueue_step(k, false) && cuda_ok(cudaEventSynchronize(evDisp), "event wait");
+            ok = ok && (fusedFirst || displacement_enqueue(s, d_x, d_disp, nullptr));
+            if (ok && publish) {
+                s.prePubSrc[0] = d_disp; s.prePubDst[0] = hdisp + (k & 1);
+                s.prePubSrc[1] = k > 0 ? d_ke2 + ((k - 1) & 1) : nullptr; s.prePubDst[1] = hke + ((k - 1) & 1);
+                s.prePubEvent = evDisp; s.prePubDone = false;
+                ok = enqueue_step(k, false);
+                s.prePubSrc[0] = s.prePubSrc[1] = nullptr; s.prePubEvent = nullptr;
+                if (ok && !s.prePubDone)                    // no tile kernel in this call (no pairs): copy operations, event behind them
+                    ok = cuda_ok(cudaMemcpyAsync(hdisp + (k & 1), d_disp, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H displacement") &&
+                         (k == 0 || cuda_ok(cudaMemcpyAsync(hke + ((k - 1) & 1), d_ke2 + ((k - 1) & 1), sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H kinetic energy")) &&
+                         cuda_ok(cudaEventRecord(evDisp, s.stream), "event");
+                ok = ok && cuda_ok(cudaEventSynchronize(evDisp), "event wait");
+            } else
+                ok = ok && cuda_ok(cudaMemcpyAsync(hdisp + (k & 1), d_disp, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H displacement") &&
+                     cuda_ok(cudaEventRecord(evDisp, s.stream), "event") && enqueue_step(k, false) && cuda_ok(cudaEventSynchronize(evDisp), "event wait");
             if (!ok) { set_status(status, NBB200_STATUS_LOGIC_ERROR); break; }
             // the stream has passed the check of step k: step k - 1 is complete
             if (k > 0) harvest(k - 1, false);
@@ -1465,6 +1473,7 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
         if (needSync) {
             int st = NBB200_STATUS_CONTINUE;
             const bool owed = !speculate && k > 0;                                  // step k - 1 has not been harvested yet
+            if (owed && publish && !cuda_ok(cudaMemcpyAsync(hke + ((k - 1) & 1), d_ke2 + ((k - 1) & 1), sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H kinetic energy")) { ok = false; break; }
             if (owed) {      // its accumulators are turned into energies inside update_common: after the first wait, BEFORE the lists may change
                 s.pending = true; s.pendEnergies = eStep[(k - 1) & 1]; s.pendDEdM = dEdM; s.pendHaveGrad = true; s.pendLattice = s.lattice; s.pendAcc = haccSlot[(k - 1) & 1];
             }
@@ -1474,6 +1483,7 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
             if (!enqueue_step(k, speculate)) { ok = false; set_status(status, NBB200_STATUS_LOGIC_ERROR); break; }      // speculate here: the step was taken back
         }
     }
+    if (nsteps > 0 && publish) cudaMemcpyAsync(hke + ((nsteps - 1) & 1), d_ke2 + ((nsteps - 1) & 1), sizeof(double), cudaMemcpyDeviceToHost, s.stream);
     cudaStreamSynchronize(s.stream);
     s.pending = false;
     if (ok && nsteps > 0) harvest(nsteps - 1, false);

@@ -576,13 +576,23 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_cluster_forces(const _
     }
 }
 
+// pub: results of the call that are complete when this kernel starts (the accumulators of the force kernels, the displacement maximum of an
+// optimistic update decision) are written straight into page-locked host memory by the first CTA -- the call then needs no copy operation of its
+// own in the stream (a small device-to-host copy between two kernels costs several microseconds of engine switching)
+struct PublishArgs { const double *src[2]; double *dst[2]; int count[2]; };
+
 // ------------------------------------------------------------------------------------------------------
 // per energy call: atom records in sorted order from the current coordinates, and the way back for the gradients
 // ------------------------------------------------------------------------------------------------------
 __global__ void k_pack_records(const double *__restrict__ x, const int *__restrict__ sAtom, int n, int ntypes, const float *__restrict__ q32, const int *__restrict__ ljtype,
                                double ox, double oy, double oz, float4 *__restrict__ recA, float4 *__restrict__ recB, double *__restrict__ zero, int zeroCount,
-                               const double *__restrict__ xprune, unsigned long long *__restrict__ pruneDisp, int slot)
+                               const double *__restrict__ xprune, unsigned long long *__restrict__ pruneDisp, int slot, const PublishArgs pub)
 {
+    if (blockIdx.x == 0) {       // nbb200_md_run: the displacement maximum of this step's first half and the kinetic energy of the previous step
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            for (int i = threadIdx.x; i < pub.count[k]; i += blockDim.x) pub.dst[k][i] = pub.src[k][i];
+    }
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     // fused mode (nbb200_md_run): the accumulators + work cursor of the force kernels are cleared here instead of by a memset of their own
     if (zero != nullptr) for (int i = s; i < zeroCount; i += gridDim.x * blockDim.x) zero[i] = 0.0;
@@ -726,11 +736,6 @@ __global__ void __launch_bounds__(kPruneWarps * 32) k_prune(const __grid_constan
 // assign != 0: the NB term SETS the caller's gradient (every atom has exactly one sorted position) instead of accumulating into it
 // kClear (fused mode of nbb200_md_run): the sorted accumulator is left zeroed for the next call (no memset of its own).  Two instantiations:
 // the plain one keeps gs const / read-only (the combined one measured 9 x slower on the 1.1 M-atom box: 143 vs 16 us)
-// pub: results of the call that are complete when this kernel starts (the accumulators of the force kernels, the displacement maximum of an
-// optimistic update decision) are written straight into page-locked host memory by the first CTA -- the call then needs no copy operation of its
-// own in the stream (a small device-to-host copy between two kernels costs several microseconds of engine switching)
-struct PublishArgs { const double *src[2]; double *dst[2]; int count[2]; };
-
 template <bool kClear>
 __global__ void k_unsort_gradients(typename std::conditional<kClear, double, const double>::type *__restrict__ gs, const int *__restrict__ sAtom, int s0, int n,
                                    double *__restrict__ grad, int assign, const double *__restrict__ cond, double condThr2, const PublishArgs pub)
@@ -956,9 +961,13 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
         }
         const bool pruneForce = prune && (s.pruneListGeneration != s.numberOfUpdates || !s.pruneLatticeValid || std::memcmp(s.pruneLattice.v, s.lattice.M.v, sizeof(double) * 9) != 0);
         const int pthreads = 256, pblocks = (s.n + 1 + pthreads - 1) / pthreads;
+        PublishArgs prePub;
+        for (int k = 0; k < 2; k++) { prePub.src[k] = s.prePubSrc[k]; prePub.dst[k] = s.prePubDst[k]; prePub.count[k] = (s.prePubSrc[k] != nullptr && s.prePubDst[k] != nullptr) ? 1 : 0; }
         k_pack_records<<<pblocks, pthreads, 0, s.stream>>>(s.xcur, s.sAtom.p, s.n, s.ntypes, s.q32.p, s.ljtype.p, s.grid.lo[0], s.grid.lo[1], s.grid.lo[2], s.recA.p, s.recB.p,
                                                             fusedZero ? s.accum.p : nullptr, (int) (accumCount + 1),
-                                                            (prune && !pruneForce) ? s.xprune.p : nullptr, s.pruneDisp.p, slot);
+                                                            (prune && !pruneForce) ? s.xprune.p : nullptr, s.pruneDisp.p, slot, prePub);
+        if (prePub.count[0] > 0 || prePub.count[1] > 0 || s.prePubEvent != nullptr) s.prePubDone = true;
+        if (s.prePubEvent != nullptr) cudaEventRecord(s.prePubEvent, s.stream);
         bool rot = false;                                   // any image with a genuine rotation?
         for (const RealSpaceOp &b : s.plan.baseOps) rot = rot || !b.pureTranslation;
         if (prune) {

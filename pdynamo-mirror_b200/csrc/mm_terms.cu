@@ -209,74 +209,157 @@ __device__ __forceinline__ void philox4x32(unsigned int c0, unsigned int c1, uns
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-__global__ void k_langevin_first(double *__restrict__ x, double *__restrict__ v, const double *__restrict__ a, const double *__restrict__ mass, long m,
-                                 double facR1, double facR2, double facV1, double facV2, double sdR, double sdV1, double sdV2,
-                                 unsigned long long seed, unsigned long long step)
+// the two deviates of coordinate i at step `step`: two uniforms in (0, 1] with 52 bits from two Philox words each -> Box-Muller pair
+__device__ __forceinline__ void langevin_deviates(long i, unsigned long long step, unsigned long long seed, double &w1, double &w2)
 {
-    const long i = (long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
     unsigned int r[4];
     philox4x32((unsigned int) i, (unsigned int) ((unsigned long long) i >> 32), (unsigned int) step, (unsigned int) (step >> 32),
                (unsigned int) seed, (unsigned int) (seed >> 32), r);
-    // two uniforms in (0, 1] with 52 bits from two words each -> Box-Muller pair
     const double u1 = ((double) (((unsigned long long) r[0] << 20) | (r[1] >> 12)) + 1.0) * (1.0 / 4503599627370496.0);
     const double u2 = ((double) (((unsigned long long) r[2] << 20) | (r[3] >> 12)) + 1.0) * (1.0 / 4503599627370496.0);
     const double rad = sqrt(-2.0 * log(u1));
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    const double w1 = rad * c, w2 = rad * s, rsm = rsqrt(mass[i / 3]);
-    const double vi = v[i], ai = a[i];
-    x[i] += facR1 * vi + facR2 * ai + sdR * w1 * rsm;
-    v[i] = facV1 * vi + facV2 * ai + (sdV1 * w1 + sdV2 * w2) * rsm;
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    w1 = rad * cs; w2 = rad * sn;
 }
 
-// the same first part fused with the displacement check of CheckForUpdate (pM/csource/NBModelABFS.c:691-746) for nbb200_md_run: one thread per
-// atom updates its three coordinates (same deviates: the Philox counter is the coordinate index) and contributes |x - xref|^2 to the maximum
+// ApplyLinearConstraints on the random vectors (LangevinVelocityVerletIntegrator.py:139-149 -> SystemGeometryObjectiveFunction.ApplyLinearConstraints,
+// pMolecule-1.9.0/pMolecule/SystemGeometryObjectiveFunction.py:99-101) for the constraint set of a periodic system after RemoveRotationTranslation
+// (:213-240): the three mass-weighted translation vectors c_d[i] = sqrt(m_i / M).  Projecting them out of a deviate vector w (mass-weighted
+// variables) is w_id -= sqrt(m_i) S_d / M with S_d = sum_j sqrt(m_j) w_jd, i.e. in Cartesian variables the constant S_d / M is taken off every
+// atom's random displacement.  The sums need all deviates of a step before the first one is used: the kernel of step k reads sums[k % 3]
+// (made by the kernel of step k - 1, or by k_langevin_sums at the start of a run), accumulates the sums of step k + 1 into sums[(k + 1) % 3]
+// from the deviates of that step (counter based: they depend on nothing but (seed, coordinate, step)) and clears sums[(k + 2) % 3].
+// Every deviate is still generated once: the kernel that needs the sums of step k + 1 stores that step's deviates for the next launch.
+struct LangevinConstraint {
+    const double *sumsIn;            // [6]: S1_xyz, S2_xyz of this step; null: no constraints
+    double *sumsOut, *zeroNext;      // [6] each
+    const double2 *wIn;              // [3n] the deviates (w1, w2) of this step, stored by the previous launch (or k_langevin_sums)
+    double2 *wOut;                   // [3n] those of the next step
+    double invTotalMass;
+};
+
+__device__ __forceinline__ void langevin_accumulate_next(const LangevinConstraint &LC, double (&acc)[6])
+{
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        for (int off = 16; off > 0; off >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) if (acc[k] != 0.0) atomicAdd(LC.sumsOut + k, acc[k]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 6) LC.zeroNext[threadIdx.x] = 0.0;
+}
+
+// the sums of one step on their own (start of a run, or a step that does not follow the previous call's)
+__global__ void k_langevin_sums(const double *__restrict__ mass, int n, unsigned long long seed, unsigned long long step, double *__restrict__ sums, double2 *__restrict__ wOut)
+{
+    const int atom = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (atom < n) {
+        const double sm = sqrt(mass[atom]);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            double w1, w2;
+            langevin_deviates(3 * (long) atom + c, step, seed, w1, w2);
+            wOut[3 * (long) atom + c] = make_double2(w1, w2);
+            acc[c] = sm * w1; acc[3 + c] = sm * w2;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        for (int off = 16; off > 0; off >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) if (acc[k] != 0.0) atomicAdd(sums + k, acc[k]);
+    }
+}
+
+// one thread per atom (its three coordinates; the Philox counter is the coordinate index).  xref != null: fused with the displacement check of
+// CheckForUpdate (pM/csource/NBModelABFS.c:691-746) for nbb200_md_run -- |x - xref|^2 into the running maximum
 __global__ void k_langevin_first_disp(double *__restrict__ x, double *__restrict__ v, const double *__restrict__ a, const double *__restrict__ mass, int n,
                                       double facR1, double facR2, double facV1, double facV2, double sdR, double sdV1, double sdV2,
                                       unsigned long long seed, unsigned long long step, const double *__restrict__ xref, const unsigned char *__restrict__ fixed,
-                                      unsigned long long *__restrict__ out, unsigned long long *__restrict__ zeroOther, unsigned int *ticket, double *h_out)
+                                      unsigned long long *__restrict__ out, unsigned long long *__restrict__ zeroOther, const LangevinConstraint LC)
 {
     if (zeroOther != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zeroOther = 0ULL;
     const int atom = blockIdx.x * blockDim.x + threadIdx.x;
     double r2 = 0.0;
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     if (atom < n) {
-        const double rsm = rsqrt(mass[atom]);
+        const double mi = mass[atom], rsm = rsqrt(mi), sm = sqrt(mi);
         double d[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const long i = 3 * (long) atom + c;
-            unsigned int r[4];
-            philox4x32((unsigned int) i, (unsigned int) ((unsigned long long) i >> 32), (unsigned int) step, (unsigned int) (step >> 32),
-                       (unsigned int) seed, (unsigned int) (seed >> 32), r);
-            const double u1 = ((double) (((unsigned long long) r[0] << 20) | (r[1] >> 12)) + 1.0) * (1.0 / 4503599627370496.0);
-            const double u2 = ((double) (((unsigned long long) r[2] << 20) | (r[3] >> 12)) + 1.0) * (1.0 / 4503599627370496.0);
-            const double rad = sqrt(-2.0 * log(u1));
-            double sn, cs;
-            sincospi(2.0 * u2, &sn, &cs);
-            const double w1 = rad * cs, w2 = rad * sn;
+            double w1, w2, n1, n2;                           // n: the deviates in Cartesian variables
+            if (LC.sumsIn != nullptr) {
+                const double2 ws = LC.wIn[i];
+                w1 = ws.x; w2 = ws.y;
+                n1 = w1 * rsm - LC.sumsIn[c] * LC.invTotalMass; n2 = w2 * rsm - LC.sumsIn[3 + c] * LC.invTotalMass;
+                double v1, v2;
+                langevin_deviates(i, step + 1ULL, seed, v1, v2);
+                LC.wOut[i] = make_double2(v1, v2);
+                acc[c] = sm * v1; acc[3 + c] = sm * v2;
+            } else {
+                langevin_deviates(i, step, seed, w1, w2);
+                n1 = w1 * rsm; n2 = w2 * rsm;
+            }
             const double vi = v[i], ai = a[i];
-            const double xn = x[i] + (facR1 * vi + facR2 * ai + sdR * w1 * rsm);
+            const double xn = x[i] + (facR1 * vi + facR2 * ai + sdR * n1);
             x[i] = xn;
-            v[i] = facV1 * vi + facV2 * ai + (sdV1 * w1 + sdV2 * w2) * rsm;
-            d[c] = xn - xref[i];
+            v[i] = facV1 * vi + facV2 * ai + (sdV1 * n1 + sdV2 * n2);
+            if (xref != nullptr) d[c] = xn - xref[i];
         }
-        if (fixed == nullptr || !fixed[atom]) r2 = __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));
+        if (xref != nullptr && (fixed == nullptr || !fixed[atom])) r2 = __dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2]));
     }
+    if (LC.sumsIn != nullptr) langevin_accumulate_next(LC, acc);
+    if (xref == nullptr) return;
     for (int off = 16; off > 0; off >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, off));
     if ((threadIdx.x & 31) == 0 && r2 > 0.0) atomicMax(out, (unsigned long long) __double_as_longlong(r2));
-    // the maximum goes straight into page-locked host memory (no copy operation in the stream)
-    if (ticket != nullptr && last_block_done(ticket) && threadIdx.x == 0) *h_out = __longlong_as_double((long long) *reinterpret_cast<volatile unsigned long long *>(out));
+}
+
+// constraint bookkeeping of one first-half launch at `step`: which sums to read, where the next step's go (State::lc*)
+static bool langevin_constraint(State &s, const double *d_mass, unsigned long long seed, unsigned long long step, LangevinConstraint &LC)
+{
+    LC.sumsIn = nullptr; LC.sumsOut = nullptr; LC.zeroNext = nullptr; LC.wIn = nullptr; LC.wOut = nullptr; LC.invTotalMass = 0.0;
+    if (!s.lcOn) return true;
+    const size_t m = 3 * (size_t) s.n;
+    if (!s.lcSums.ensure(18) || !s.lcW.ensure(2 * m)) return false;
+    if (!(s.lcValid && s.lcStep == step && s.lcSeed == seed)) {
+        NBB_CUDA(cudaMemsetAsync(s.lcSums.p, 0, sizeof(double) * 18, s.stream));
+        k_langevin_sums<<<(s.n + 127) / 128, 128, 0, s.stream>>>(d_mass, s.n, seed, step, s.lcSums.p + 6 * (step % 3ULL), s.lcW.p + (step & 1ULL) * m);
+        s.launches += 1;
+    }
+    LC.wIn = s.lcW.p + (step & 1ULL) * m; LC.wOut = s.lcW.p + ((step + 1ULL) & 1ULL) * m;
+    LC.sumsIn = s.lcSums.p + 6 * (step % 3ULL); LC.sumsOut = s.lcSums.p + 6 * ((step + 1ULL) % 3ULL); LC.zeroNext = s.lcSums.p + 6 * ((step + 2ULL) % 3ULL);
+    LC.invTotalMass = 1.0 / s.lcTotalMass;
+    s.lcValid = true; s.lcStep = step + 1ULL; s.lcSeed = seed;
+    return true;
 }
 
 bool langevin_first_disp(State &s, double *d_x, double *d_v, const double *d_a, const double *d_mass, const double *f7, unsigned long long seed,
-                         unsigned long long step, double *d_out, double *d_zeroOther, unsigned int *ticket, double *h_out)
+                         unsigned long long step, double *d_out, double *d_zeroOther)
 {
+    LangevinConstraint LC;
+    if (!langevin_constraint(s, d_mass, seed, step, LC)) return false;
     k_langevin_first_disp<<<(s.n + 127) / 128, 128, 0, s.stream>>>(d_x, d_v, d_a, d_mass, s.n, f7[0], f7[1], f7[2], f7[3], f7[4], f7[5], f7[6], seed, step, s.xref.p,
                                                                    s.nfixed > 0 ? s.fixedFlag.p : nullptr, reinterpret_cast<unsigned long long *>(d_out),
-                                                                   reinterpret_cast<unsigned long long *>(d_zeroOther), h_out != nullptr ? ticket : nullptr, h_out);
+                                                                   reinterpret_cast<unsigned long long *>(d_zeroOther), LC);
     s.launches += 1;
     return cuda_ok(cudaGetLastError(), "k_langevin_first_disp");
+}
+
+bool langevin_first(State &s, double *d_x, double *d_v, const double *d_a, const double *d_mass, const double *f7, unsigned long long seed, unsigned long long step)
+{
+    LangevinConstraint LC;
+    if (!langevin_constraint(s, d_mass, seed, step, LC)) return false;
+    k_langevin_first_disp<<<(s.n + 127) / 128, 128, 0, s.stream>>>(d_x, d_v, d_a, d_mass, s.n, f7[0], f7[1], f7[2], f7[3], f7[4], f7[5], f7[6], seed, step, nullptr,
+                                                                   nullptr, nullptr, nullptr, LC);
+    s.launches += 1;
+    return cuda_ok(cudaGetLastError(), "k_langevin_first");
 }
 
 }  // namespace nbb200
@@ -477,10 +560,15 @@ void nbb200_langevin_first_half(NBB200State *state, double *d_x, double *d_v, co
     if (state == nullptr || factors7 == nullptr) return;
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
-    const long m = 3 * (long) s.n;
-    k_langevin_first<<<(unsigned int) ((m + 255) / 256), 256, 0, s.stream>>>(d_x, d_v, d_a, d_mass, m, factors7[0], factors7[1], factors7[2], factors7[3],
-                                                                            factors7[4], factors7[5], factors7[6], seed, step);
-    s.launches += 1;
+    langevin_first(s, d_x, d_v, d_a, d_mass, factors7, seed, step);
+}
+
+void nbb200_set_langevin_constraints(NBB200State *state, int removeTranslation, double totalMass)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    s.lcOn = removeTranslation != 0 && totalMass > 0.0;
+    s.lcTotalMass = totalMass; s.lcValid = false;
 }
 
 }  // extern "C"

@@ -103,8 +103,9 @@ bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_gra
 void mmterms_slot_pointers(NBB200MMTerms *terms, int slot, const double **d_energies, double **h_energies);
 void mmterms_read_slot(NBB200MMTerms *terms, int slot, double *energies5);
 void mmterms_reset_slots(NBB200MMTerms *terms);
+bool langevin_first(State &s, double *d_x, double *d_v, const double *d_a, const double *d_mass, const double *f7, unsigned long long seed, unsigned long long step);
 bool langevin_first_disp(State &s, double *d_x, double *d_v, const double *d_a, const double *d_mass, const double *f7, unsigned long long seed,
-                         unsigned long long step, double *d_out, double *d_zeroOther, unsigned int *ticket = nullptr, double *h_out = nullptr);
+                         unsigned long long step, double *d_out, double *d_zeroOther);
 
 // ---- force_kernels.cu
 bool upload_spline_tables(State &s);                     // s.spl -> s.splF64 / s.splPoly
@@ -251,6 +252,10 @@ struct State {
     bool gradOverwrite = false;                  // MMMMEnergy (host arrays) sets the caller's gradient instead of accumulating
     // results published by the unsort pass of an energy call instead of a copy operation (force_kernels.cu: PublishArgs); set by energy_enqueue
     const double *pubSrc[2] = {nullptr, nullptr}; double *pubDst[2] = {nullptr, nullptr}; int pubCount[2] = {0, 0}; bool pubDone = false;
+    // Langevin dynamics: the random vectors are projected on the translation constraints (mm_terms.cu: LangevinConstraint)
+    bool lcOn = false, lcValid = false; double lcTotalMass = 0.0; unsigned long long lcStep = 0, lcSeed = 0; DevBuf<double> lcSums; DevBuf<double2> lcW;
+    // nbb200_md_run: two scalars stored into page-locked memory by the first kernel of the energy call (k_pack_records), and an event behind it
+    const double *prePubSrc[2] = {nullptr, nullptr}; double *prePubDst[2] = {nullptr, nullptr}; cudaEvent_t prePubEvent = nullptr; bool prePubDone = false;
     bool mdFused = false;                        // inside nbb200_md_run: memsets folded into neighbouring kernels (accumulators by k_pack_records, sorted gradient by k_unsort_gradients)
     bool gsZeroed = false;                       // the caller zeroed the sorted gradient for this call already (before the ranks' barrier)                        // touched sorted range per rank slab (min, max+1)
     DevBuf<unsigned long long> setPairs;         // per set list-pair counts

@@ -24,7 +24,7 @@ class VelocityVerletDynamics:
     temperatureStart / temperatureStop (velocities are scaled to the target temperature every temperatureScaleFrequency steps)."""
 
     def __init__(self, system, timeStep=0.001, temperature=300.0, seed=491831, device=0, temperatureScaleFrequency=0, temperatureScaleOption=None,
-                 temperatureStart=None, temperatureStop=None):
+                 temperatureStart=None, temperatureStop=None, removeRotationTranslation=True):
         self.temperatureScaleFrequency = int(temperatureScaleFrequency)
         self.temperatureScaleOption = temperatureScaleOption.capitalize() if isinstance(temperatureScaleOption, str) else None
         if self.temperatureScaleOption not in ("Constant", "Exponential", "Linear") or self.temperatureScaleFrequency <= 0:
@@ -55,6 +55,13 @@ class VelocityVerletDynamics:
         v -= (v * masses[:, None]).sum(0) / masses.sum()                               # no net momentum
         self.v = torch.from_numpy(v).to(dev)
         self.ke_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+        # removeRotationTranslation (pMoleculeScripts/MolecularDynamics.py:27-32 -> SystemGeometryObjectiveFunction.RemoveRotationTranslation,
+        # pMolecule-1.9.0/pMolecule/SystemGeometryObjectiveFunction.py:213-240): a periodic system loses its three translations (rotations only
+        # without symmetry: not built), nothing is done when there are fixed atoms; the temperature is taken over the remaining degrees of freedom
+        fixed = getattr(system, "fixedAtoms", None)
+        self.removeTranslation = bool(removeRotationTranslation) and (fixed is None or len(fixed) == 0)
+        self.totalMass = float(masses.sum())
+        self.degreesOfFreedom = 3 * self.n - (3 if self.removeTranslation else 0)
         sp = system.symmetryParameters
         self.box = None if sp is None else np.ascontiguousarray(sp.box6, np.float64)
         self.energies, self.dEdM = np.zeros(6), np.zeros(9)
@@ -156,7 +163,7 @@ class VelocityVerletDynamics:
             out.append((self.potential, self.kinetic))
             if log is not None and (k + 1) % 100 == 0:
                 log("step %d: potential %.4f kinetic %.4f total %.4f temperature %.2f" % (k + 1, self.potential, self.kinetic, self.potential + self.kinetic,
-                                                                                       2.0 * self.kinetic / (3 * self.n * _KB_KJMOL)))
+                                                                                       2.0 * self.kinetic / (self.degreesOfFreedom * _KB_KJMOL)))
         self.L.nbb200_set_gradient_overwrite(self.h, 1)        # the NB term sets g (no zero fill), the bonded terms then accumulate
         try:
             for k in range(steps):
@@ -178,7 +185,7 @@ class VelocityVerletDynamics:
                 if scaling and self.numberOfIterations % self.temperatureScaleFrequency == 0:
                     # temperature scaling needs this step's kinetic energy: one extra host wait on these (rare) steps
                     self.L.nbb200_flush(self.h, C.byref(st))
-                    temp = 2.0 * float(self._ke_host[k & 1]) / (3 * self.n * _KB_KJMOL)
+                    temp = 2.0 * float(self._ke_host[k & 1]) / (self.degreesOfFreedom * _KB_KJMOL)
                     scale = self.TargetTemperature(self.time - t_begin, total_time) / temp if temp > 0.0 else 1.0
                     self.v.mul_(math.sqrt(scale))
                     harvest(k, scale)
@@ -225,12 +232,14 @@ class LangevinDynamics(VelocityVerletDynamics):
     """Langevin velocity Verlet dynamics on the device (pCore-1.9.0/pCore/LangevinVelocityVerletIntegrator.py); options as
     LangevinDynamics_SystemGeometry: collisionFrequency (ps^-1), temperature (K), timeStep (ps)."""
 
-    def __init__(self, system, timeStep=0.001, temperature=300.0, collisionFrequency=25.0, seed=491831, device=0):
+    def __init__(self, system, timeStep=0.001, temperature=300.0, collisionFrequency=25.0, seed=491831, device=0, removeRotationTranslation=True):
         if collisionFrequency <= 0.0 or temperature < 0.0:
             raise ValueError("Invalid temperature handling options.")
-        super().__init__(system, timeStep=timeStep, temperature=temperature, seed=seed, device=device)
+        super().__init__(system, timeStep=timeStep, temperature=temperature, seed=seed, device=device, removeRotationTranslation=removeRotationTranslation)
         self.collisionFrequency, self.temperature, self.seed, self.iteration = float(collisionFrequency), float(temperature), int(seed), 0
         self.CalculateIntegrationConstants()
+        # RandomForces: ApplyLinearConstraints on both random vectors (LangevinVelocityVerletIntegrator.py:139-149)
+        self.L.nbb200_set_langevin_constraints(self.h, 1 if self.removeTranslation else 0, self.totalMass)
 
     def CalculateIntegrationConstants(self):
         """LangevinVelocityVerletIntegrator.CalculateIntegrationConstants (:54-115)"""

@@ -1106,6 +1106,53 @@ def test_langevin_random_terms_have_the_right_statistics(pkg):
     assert not np.array_equal(draw(8, 1)[0], x1)
 
 
+def test_langevin_random_terms_projected_on_the_translation_constraints(pkg):
+    """nbb200_set_langevin_constraints: ApplyLinearConstraints on both random vectors (LangevinVelocityVerletIntegrator.py:139-149) for the
+    constraint set of a periodic system (SystemGeometryObjectiveFunction.RemoveRotationTranslation: the three mass-weighted translations).
+    With v = a = 0 the kernel's output IS the projected random term: it equals the unprojected deviates minus sqrt(m_i) S_d / M in
+    mass-weighted variables (numpy restatement of Real2DArray.ProjectOutOfArray for these vectors), carries no net momentum, and does not depend
+    on whether the sums of a step were made by the previous step's kernel or on their own."""
+    import ctypes as C
+    import torch
+    from pdynamo_mirror_b200 import _lib
+    w = pkg.workloads.WORKLOADS["jac"]()
+    system = pkg.System.FromWorkload(w)
+    system.DefineNBModel(pkg.NBModelABFS())
+    system.Energy(doGradients=False)
+    L, h, n = _lib.lib(), system.configuration.nbState.cObject, w["n"]
+    L.nbb200_set_stream(h, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    masses = 1.0 + 15.0 * pkg.workloads.lcg_uniform(5, n)
+    mass = torch.from_numpy(masses).cuda()
+    fac = np.array([0.0, 0.0, 1.0, 0.0, 2.0, 3.0, 4.0])
+
+    def draw(seed, step):
+        x = torch.zeros((n, 3), dtype=torch.float64, device="cuda"); v = torch.zeros_like(x); a = torch.zeros_like(x)
+        L.nbb200_langevin_first_half(h, C.c_void_p(x.data_ptr()), C.c_void_p(v.data_ptr()), C.c_void_p(a.data_ptr()), C.c_void_p(mass.data_ptr()),
+                                     _lib.d_(fac), C.c_ulonglong(seed), C.c_ulonglong(step))
+        torch.cuda.synchronize()
+        return x.cpu().numpy(), v.cpu().numpy()
+    L.nbb200_set_langevin_constraints(h, 0, 0.0)
+    x0, v0 = draw(11, 5)
+    L.nbb200_set_langevin_constraints(h, 1, float(masses.sum()))
+    x1, v1 = draw(11, 5)                                     # sums made on their own
+    # mass-weighted deviates of the unprojected call, projected in numpy
+    sm = np.sqrt(masses)[:, None]
+    w1 = x0 / 2.0 * sm
+    w2 = (v0 * sm - 3.0 * w1) / 4.0
+    c = sm / np.sqrt(masses.sum())                           # the three translation vectors share this column, one per Cartesian component
+    p1 = w1 - c * (c * w1).sum(0)
+    p2 = w2 - c * (c * w2).sum(0)
+    assert np.abs(x1 - 2.0 * p1 / sm).max() < 1e-12 and np.abs(v1 - (3.0 * p1 + 4.0 * p2) / sm).max() < 1e-12
+    assert np.abs((masses[:, None] * x1).sum(0)).max() < 1e-9 * np.abs(masses[:, None] * x1).sum()      # no net momentum in either random term
+    assert np.abs((masses[:, None] * v1).sum(0)).max() < 1e-9 * np.abs(masses[:, None] * v1).sum()
+    assert np.abs(x1 - x0).max() > 1e-6                      # and the projection did something
+    x2, v2 = draw(11, 6)                                     # sums of step 6 were accumulated by the kernel of step 5
+    L.nbb200_set_langevin_constraints(h, 1, float(masses.sum()))      # forget them: step 6 again with sums made on their own
+    x3, v3 = draw(11, 6)
+    assert np.abs(x2 - x3).max() < 1e-12 and np.abs(v2 - v3).max() < 1e-12
+    L.nbb200_set_langevin_constraints(h, 0, 0.0)
+
+
 def test_langevin_dynamics_of_dhfr_with_all_terms(pkg):
     """The reference's own benchmark protocol (benchmarks/SystemBenchmarks.py:95-101: Langevin, 25 ps^-1, 300 K, 1 fs) on DHFR with bonded and
     non-bonded terms, everything on the device: the dynamics is stable and thermostatted, the first potential energy is the published one,
@@ -1116,7 +1163,7 @@ def test_langevin_dynamics_of_dhfr_with_all_terms(pkg):
     md = pkg.md.LangevinDynamics(system, timeStep=0.001, temperature=300.0, collisionFrequency=25.0)
     assert abs(md.potential - w["published_total"][0]) <= E_TOL * abs(w["published_total"][0])
     traj = md.Run(300)
-    temps = np.array([2.0 * k / (3 * md.n * 8.314472e-3) for _, k in traj])
+    temps = np.array([2.0 * k / (md.degreesOfFreedom * 8.314472e-3) for _, k in traj])
     assert np.all(np.isfinite(temps)) and 270.0 < temps[-100:].mean() < 320.0, temps[-100:].mean()
     pot = np.array([p for p, _ in traj])
     assert pot[-1] > pot[0] and pot[-1] < 0.7 * pot[0]           # the minimised benchmark structure heats up to ~ -2.9e5 kJ/mol (reference log: -291914 after 1 ps)
@@ -1146,7 +1193,7 @@ def test_velocity_verlet_temperature_scaling(pkg):
                                            temperatureStart=300.0, temperatureStop=stop)
         traj = md.Run(100)
         assert len(traj) == 100 and md.numberOfIterations == 100
-        temps = np.array([2.0 * k / (3 * md.n * kB) for _, k in traj])
+        temps = np.array([2.0 * k / (md.degreesOfFreedom * kB) for _, k in traj])
         for step in (20, 40, 60, 80, 100):
             target = 300.0 if stop is None else 300.0 + (stop - 300.0) * step / 100.0
             assert abs(temps[step - 1] - target) < 1e-6 * target, (option, step, temps[step - 1], target)
