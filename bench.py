@@ -416,7 +416,7 @@ def run_b200(args):
         line["distributed_check"] = distributed_check(torch, dist, m, dn, w, local)
         line["halo"] = {"halo_atoms_per_step_no_rebuild": int(dn.halo_atoms()), "transport": dn.transport,
                         "atoms_owned": int(dn.slabs[rank][1] - dn.slabs[rank][0]), "list_updates": dn.updates}
-        # end to end with HOST arrays on every rank (DistributedNB.call_host): per step a rank uploads the positions of the atoms it owns,
+        # end to end with HOST arrays on every rank (DistributedNB.call_host): per step a rank uploads its contiguous chunk of the positions,
         # runs the distributed call (forced rebuild, as the timed steps above), downloads the gradients of its atoms and their indices
         # (the slabs change with every rebuild) and accumulates them into its host gradient array; the summed energies are read on the
         # host.  Wall clock between barriers, max over ranks.
@@ -435,21 +435,24 @@ def run_b200(args):
         torch.cuda.synchronize(); barrier()
         e2e_ms = allmax((time.perf_counter() - t1) / args.steps * 1e3)
         own = allsum(float(dn._own_count))
-        # self-check of the host path: the rows it fills are the owned atoms' gradients of a device-array call on the same coordinates
+        # self-check of the host path: the rows of this rank's chunk are the gradients a device-array call gives on the same coordinates (that
+        # call leaves every atom's gradient with the rank that owns it: summed over the ranks for the comparison, outside the timed region)
         gh[:] = 0.0
         dn.call_host(xh, m.box, gh, force_rebuild=True)
-        ids = dn._stage_ids.numpy()[:dn._own_count].astype(np.int64)
+        c0, c1 = (n * rank) // world, (n * (rank + 1)) // world
         m.x.copy_(torch.from_numpy(xh)); m.g.zero_()
         dn.call(m.x, m.box, m.g, force_rebuild=True); dn.results()
-        gd = m.g.cpu().numpy()
-        host_err = allmax(float(np.abs(gh[ids] - gd[ids]).max() / max(1e-300, np.abs(gd[ids]).max())))
+        gfull = m.g.clone()
+        dist.all_reduce(gfull)
+        gd = gfull.cpu().numpy()
+        host_err = allmax(float(np.abs(gh[c0:c1] - gd[c0:c1]).max() / max(1e-300, np.abs(gd).max())))
         host_rows = allsum(float(np.count_nonzero(np.abs(gh).sum(1))))
         line["e2e"] = {"value": pairs / (e2e_ms * 1e-3), "unit": "list-pairs/s", "ms_per_step": e2e_ms,
-                       "h2d_bytes_per_step": int(24 * own), "d2h_bytes_per_step": int(28 * own) + 15 * 8 * world,
-                       "api": "DistributedNB.call_host(x, box, g, force_rebuild=True) on every rank with host numpy arrays: a rank uploads the positions of the "
-                              "atoms it owns and downloads their gradients and indices (bytes summed over the ranks), energies read on the host; wall "
-                              "clock, max over ranks",
-                       "check": {"owned_rows_rel_err_vs_device_call": host_err, "rows_filled_all_ranks": int(host_rows), "atoms": n}}
+                       "h2d_bytes_per_step": int(24 * own), "d2h_bytes_per_step": int(24 * own) + 15 * 8 * world,
+                       "api": "DistributedNB.call_host(x, box, g, force_rebuild=True) on every rank with host numpy arrays: rank r uploads the contiguous "
+                              "rows [n r / R, n (r + 1) / R) of x and downloads the same rows of the gradient (bytes summed over the ranks), the device "
+                              "redistributes over peer memory; energies read on the host; wall clock, max over ranks",
+                       "check": {"chunk_rows_rel_err_vs_device_call": host_err, "rows_filled_all_ranks": int(host_rows), "atoms": n}}
     if dn is not None and os.environ.get("NBB200_DIST_PROFILE"):
         dn.host_profile = {}
         for _ in range(10):

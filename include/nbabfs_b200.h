@@ -222,6 +222,25 @@ void nbb200_own_slab_to_host(NBB200State *state, double *h_grad, int *h_atoms);
 void nbb200_host_gather_rows(const double *x, const int *atoms, long count, double *out);
 void nbb200_host_scatter_add_rows(double *g, const int *atoms, long count, const double *in);
 
+/* Host callers on several ranks, without row gathers on the host (DistributedNB.call_host): rank r moves the contiguous rows
+ * [n r / R, n (r + 1) / R) of the caller's host arrays, the device redistributes over peer memory.  Per call:
+ *   nbb200_chunk_upload(h_x, a0, count); nbb200_chunk_signal(step, 0); nbb200_chunk_wait(step, 0); nbb200_chunk_gather_owned(d_x);
+ *   ... the distributed call (nbb200_peer_begin ... nbb200_peer_wait_end) ...
+ *   nbb200_chunk_scatter_gradients(); nbb200_chunk_signal(step, 1); nbb200_chunk_wait(step, 1); nbb200_chunk_download_add(h_g, a0, count);
+ * The chunk buffers are exported / imported like the other peer buffers (two IPC handles, 128 bytes).  There is no counterpart in the
+ * reference (one process, host arrays). */
+int nbb200_peer_export_chunks(NBB200State *state, char *handles128);
+int nbb200_peer_import_chunks(NBB200State *state, int rank, const char *handles128);
+int nbb200_peer_attach_local_chunks(NBB200State *state, int rank, NBB200State *other);
+void nbb200_chunk_upload(NBB200State *state, const double *h_x, long a0, long count);
+void nbb200_chunk_signal(NBB200State *state, long step, int which);
+void nbb200_chunk_wait(NBB200State *state, long step, int which);
+void nbb200_chunk_gather_owned(NBB200State *state, double *d_x);
+void nbb200_chunk_scatter_gradients(NBB200State *state);
+int nbb200_chunk_download_add(NBB200State *state, double *h_g, long a0, long count);   /* 0: failed (time-out of a peer, bad range) */
+void nbb200_host_copy(double *dst, const double *src, long m);
+void nbb200_host_add(double *dst, const double *src, long m);
+
 /* ---- velocity Verlet on the device -----------------------------------------------------
  * One step of pCore-1.9.0/pCore/VelocityVerletIntegrator.py:60-81 (Iteration) in Cartesian variables, for callers that keep
  * coordinates, velocities, accelerations and gradients resident on the device between NB calls (device arrays, 3 n doubles; units

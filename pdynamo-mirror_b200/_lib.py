@@ -54,6 +54,17 @@ SIGNATURES = {
     "nbb200_set_restricted_sort": (None, [vp, C.c_int]),
     "nbb200_own_slab_to_host": (None, [vp, vp, vp]),
     "nbb200_host_gather_rows": (None, [vp, vp, C.c_long, vp]),
+    "nbb200_host_copy": (None, [vp, vp, C.c_long]),
+    "nbb200_host_add": (None, [vp, vp, C.c_long]),
+    "nbb200_peer_export_chunks": (C.c_int, [vp, C.c_char_p]),
+    "nbb200_peer_import_chunks": (C.c_int, [vp, C.c_int, C.c_char_p]),
+    "nbb200_peer_attach_local_chunks": (C.c_int, [vp, C.c_int, vp]),
+    "nbb200_chunk_upload": (None, [vp, vp, C.c_long, C.c_long]),
+    "nbb200_chunk_signal": (None, [vp, C.c_long, C.c_int]),
+    "nbb200_chunk_wait": (None, [vp, C.c_long, C.c_int]),
+    "nbb200_chunk_gather_owned": (None, [vp, vp]),
+    "nbb200_chunk_scatter_gradients": (None, [vp]),
+    "nbb200_chunk_download_add": (C.c_int, [vp, vp, C.c_long, C.c_long]),
     "nbb200_host_scatter_add_rows": (None, [vp, vp, C.c_long, vp]),
     "nbb200_set_gradient_overwrite": (None, [vp, C.c_int]),
     "nbb200_set_optimistic_updates": (None, [vp, C.c_int]),

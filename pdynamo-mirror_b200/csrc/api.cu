@@ -3,6 +3,7 @@
 // (pMolecule-1.9.0/extensions/csource/NBModelABFS.c:508-623) and NBModelABFS_MMMMEnergy (:228-301).
 #include "../../include/nbabfs_b200.h"
 #include "nbb200_internal.h"
+#include <chrono>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -31,6 +32,19 @@ static bool is_pinned_host(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
+// a caller's pageable host array -> device through a page-locked staging array, in a few pieces: the threaded streaming-store copy of piece
+// k + 1 (csrc/host_rows.cpp) overlaps the DMA of piece k.  The stream must not be reading the staging array any more.
+static bool staged_upload(State &s, double *d_dst, const double *h_src, double *h_stage, long m)
+{
+    const long pieces = std::max(1L, std::min(4L, m / (1L << 18)));
+    for (long p = 0; p < pieces; p++) {
+        const long k0 = (m * p) / pieces, k1 = (m * (p + 1)) / pieces;
+        nbb200_host_copy(h_stage + k0, h_src + k0, k1 - k0);
+        if (!cuda_ok(cudaMemcpyAsync(d_dst + k0, h_stage + k0, sizeof(double) * (size_t) (k1 - k0), cudaMemcpyHostToDevice, s.stream), "H2D")) return false;
+    }
+    return true;
+}
+
 static void destroy(State *s)
 {
     if (s == nullptr) return;
@@ -46,6 +60,8 @@ static void destroy(State *s)
     s->sX.release(); s->sAtom.release(); s->invPerm.release(); s->blockBox.release();
     s->tileDesc.release(); s->tileDescIn.release(); s->itemsIn.release(); s->xprune.release(); s->pruneDisp.release(); s->recA.release(); s->recB.release(); s->gradSorted.release(); s->items.release(); s->rangeTab.release(); s->rangeOut.release(); s->setPairs.release(); s->accum.release();
     s->pairBuf.release(); s->pairCursor.release(); s->splF64.release(); s->splPoly.release(); s->mdScalars.release();
+    for (auto &e : s->chunkEvents) if (e != nullptr) cudaEventDestroy(e);
+    for (int r = 0; r < State::kMaxPeers; r++) if (s->peerChunkOpened[r]) { cudaIpcCloseMemHandle(s->peerXc[r]); cudaIpcCloseMemHandle(s->peerGc[r]); }
     for (int r = 0; r < State::kMaxPeers; r++) if (s->peerOpened[r]) { cudaIpcCloseMemHandle(s->peerGs[r]); cudaIpcCloseMemHandle(s->peerXs[r]); cudaIpcCloseMemHandle(s->peerSig[r]); }
     s->symGs.release(); s->symXs.release(); s->symSig.release(); s->sigStage.release();
     if (s->counters) cudaFree(s->counters);
@@ -75,6 +91,13 @@ static State *create(int device, int n, const double *charges, const int *ljtype
         set_error("invalid argument to NBModelABFSState_B200_SetUp"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr;
     }
     for (int i = 0; i < n; i++) if (ljtypes[i] < 0 || ljtypes[i] >= ntypes) { set_error("ljtype out of range"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr; }
+    // the reference's LJParameterContainer holds ntypes (ntypes + 1) / 2 entries (a full square table is accepted as well): an index beyond
+    // ntypes^2 cannot be a valid one
+    for (int i = 0; i < ntypes * ntypes; i++) if (tableindex[i] < 0 || tableindex[i] >= ntypes * ntypes) { set_error("LJ table index out of range"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr; }
+    if (tableindex14 != nullptr) {
+        if (ntypes14 <= 0 || tableA14 == nullptr || tableB14 == nullptr) { set_error("invalid 1-4 LJ table"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr; }
+        for (int i = 0; i < ntypes14 * ntypes14; i++) if (tableindex14[i] < 0 || tableindex14[i] >= ntypes14 * ntypes14) { set_error("1-4 LJ table index out of range"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr; }
+    }
     for (int k = 0; k < 2 * nexcl; k++) if (exclPairs[k] < 0 || exclPairs[k] >= n) { set_error("exclusion index out of range"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr; }
     for (int k = 0; k < 2 * n14; k++) if (pairs14[k] < 0 || pairs14[k] >= n) { set_error("1-4 index out of range"); set_status(status, NBB200_STATUS_INVALID_ARGUMENT); return nullptr; }
     State *s = new (std::nothrow) State();
@@ -391,7 +414,8 @@ void NBModelABFSState_B200_SetFixedAtoms(NBB200State *state, int nfixed, const i
 /* Pure QC atoms (NBModelABFSState_SetUp with qcAtoms, NBModelABFSState.c:348-353: mmSelection = complement of the pure QC
  * selection).  They leave every MM/MM list -- primary, image (GenerateLists / GenerateImageLists and-selection, NBModelABFS.c:508-623) and
  * 1-4 (GenerateLists14) -- so that NBModelABFS_B200_MMMMEnergy returns what the reference's NBModelABFS_MMMMEnergy returns with a QC region
- * present.  The QC/MM entry points themselves (QCMMEnergyLJ, QCMMPotentials, QCMMGradients) are not built; boundary atoms are not handled. */
+ * present.  The QC/MM entry points themselves are NBModelABFS_B200_QCMMEnergyLJ / _QCMMPotentials / _QCMMGradients (qcmm.cu); boundary (link)
+ * atoms are not handled. */
 void NBModelABFSState_B200_SetQCAtoms(NBB200State *state, int nqc, const int *qcAtoms, int *status)
 {
     if (state == nullptr) return;
@@ -511,9 +535,11 @@ int NBModelABFS_B200_Update(NBB200State *state, const double *xyz, const double 
     if (state == nullptr || xyz == nullptr) return 0;
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
-    const double *src = xyz;
-    if (!is_pinned_host(xyz)) { std::memcpy(s.hx, xyz, sizeof(double) * 3 * (size_t) s.n); src = s.hx; }
-    if (!cuda_ok(cudaMemcpyAsync(s.x.p, src, sizeof(double) * 3 * (size_t) s.n, cudaMemcpyHostToDevice, s.stream), "H2D coordinates")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
+    if (s.hostXChecked != (const void *) xyz) { s.hostXChecked = xyz; s.hostXPinned = is_pinned_host(xyz); }       // (the query is slow for pageable memory)
+    bool up;
+    if (s.hostXPinned) up = cuda_ok(cudaMemcpyAsync(s.x.p, xyz, sizeof(double) * 3 * (size_t) s.n, cudaMemcpyHostToDevice, s.stream), "H2D coordinates");
+    else { cudaStreamSynchronize(s.stream); up = staged_upload(s, s.x.p, xyz, s.hx, 3 * (long) s.n); }
+    if (!up) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
     s.xcur = s.x.p;
     return update_common(s, box6, forceNew, status);
 }
@@ -552,7 +578,7 @@ void NBModelABFS_B200_MMMMEnergy(NBB200State *state, double *energies, double *g
         if (grad != nullptr && !direct) {
             const size_t m = 3 * (size_t) s.n;
             if (s.gradOverwrite) std::memcpy(grad, s.hgrad, sizeof(double) * m);
-            else for (size_t i = 0; i < m; i++) grad[i] += s.hgrad[i];
+            else nbb200_host_add(grad, s.hgrad, (long) m);
         }
     }
     if (!ok) set_status(status, NBB200_STATUS_LOGIC_ERROR);
@@ -988,7 +1014,9 @@ constexpr int kSigFlagA = 0;                                   // [kMaxPeers] st
 constexpr int kSigDisp = State::kMaxPeers;                     // [kMaxPeers] the peers' displacement maxima (1e300: rebuild requested)
 constexpr int kSigFlagB = 2 * State::kMaxPeers;                // [kMaxPeers] step of "gradients pushed, scalars written"
 constexpr int kSigScal = 3 * State::kMaxPeers;                 // [kMaxPeers][16] the peers' 15 scalars
-constexpr int kSigDoubles = 3 * State::kMaxPeers + 16 * State::kMaxPeers;
+constexpr int kSigFlagC = 19 * State::kMaxPeers;               // [kMaxPeers] step of "host rows of my chunk uploaded" (nbb200_chunk_*)
+constexpr int kSigFlagD = 20 * State::kMaxPeers;               // [kMaxPeers] step of "gradients of my slab written into the chunk buffers"
+constexpr int kSigDoubles = 21 * State::kMaxPeers;
 
 int nbb200_peer_export(NBB200State *state, char *handles192)
 {
@@ -1080,7 +1108,7 @@ static __global__ void k_wait(double *sigOwn, int flagBase, int nranks, double s
     const double bad = __longlong_as_double(0x7ff8000000000000LL);
     if (mode == 0) {
         if (threadIdx.x == 0) { double m = 0.0; for (int k = 0; k < nranks; k++) m = fmax(m, v[kSigDisp + k]); out[0] = ok ? m : bad; }
-    } else if (threadIdx.x < 15) {
+    } else if (mode == 1 && threadIdx.x < 15) {
         double t = 0.0;
         for (int k = 0; k < nranks; k++) t += v[kSigScal + 16 * k + threadIdx.x];
         out[threadIdx.x] = ok ? t : bad;
@@ -1209,6 +1237,192 @@ void nbb200_peer_push_gradients(NBB200State *state, const long *d_table)
     for (int r = 0; r < State::kMaxPeers; r++) P.p[r] = s.peerGs[r];
     k_peer_push<<<dim3(32, 2 * s.nranks), 256, 0, s.stream>>>(P, d_table, s.rank, s.nranks, s.symGs.p);
     s.launches += 1;
+}
+
+/* ---- host callers on several ranks: atom-order CHUNKS between host and device, redistribution over peer memory ----
+ * A caller that keeps coordinates and gradients in host arrays (DistributedNB.call_host) should not gather / scatter rows on the host: rank r
+ * moves the CONTIGUOUS rows [n r / R, n (r + 1) / R) of the host arrays (one DMA each way), and the device sorts out who needs what -- a rank
+ * gathers the positions of the atoms it owns from the chunk buffers of the ranks that uploaded them, and writes the gradients of its atoms into
+ * the chunk buffers of the ranks that download them, with plain loads / stores over NVLink; two more flag rounds order the phases. */
+static __device__ __forceinline__ int chunk_of(long a, const SlabEdges &E, int nranks, long n)
+{
+    int r = (int) ((a * nranks) / n);
+    while (r > 0 && a < E.s[r]) r--;
+    while (r < nranks - 1 && a >= E.s[r + 1]) r++;
+    return r;
+}
+
+static __global__ void k_chunk_gather(PeerPtrs xc, SlabEdges E, int nranks, long n, const int *__restrict__ sAtom, long s0, long count, double *__restrict__ x)
+{
+    const long k = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int a = sAtom[s0 + k];
+    if (a < 0) return;
+    const double *src = xc.p[chunk_of(a, E, nranks, n)] + 3 * (long) a;
+    x[3 * (long) a] = src[0]; x[3 * (long) a + 1] = src[1]; x[3 * (long) a + 2] = src[2];
+}
+
+static __global__ void k_chunk_scatter(PeerPtrs gc, SlabEdges E, int nranks, long n, const int *__restrict__ sAtom, long s0, long count, const double *__restrict__ gs)
+{
+    const long k = (long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int a = sAtom[s0 + k];
+    if (a < 0) return;
+    double *dst = gc.p[chunk_of(a, E, nranks, n)] + 3 * (long) a;
+    const double *g = gs + 3 * (s0 + k);
+    dst[0] = g[0]; dst[1] = g[1]; dst[2] = g[2];
+}
+
+static __global__ void k_signal_flag(PeerPtrs sig, int rank, int nranks, double step, int flagBase)
+{
+    const int r = threadIdx.x;
+    if (r >= nranks) return;
+    volatile double *dst = sig.p[r];
+    __threadfence_system();
+    dst[flagBase + rank] = step;
+}
+
+static SlabEdges chunk_edges(const State &s)
+{
+    SlabEdges E;
+    for (int r = 0; r <= State::kMaxPeers; r++) E.s[r] = (r <= s.nranks) ? ((long) s.n * r) / s.nranks : (long) s.n;
+    return E;
+}
+
+int nbb200_peer_export_chunks(NBB200State *state, char *handles128)
+{
+    if (state == nullptr || handles128 == nullptr) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (!s.symXc.ensure(3 * (size_t) s.n) || !s.symGc.ensure(3 * (size_t) s.n)) return 0;
+    cudaIpcMemHandle_t hx, hg;
+    if (!cuda_ok(cudaIpcGetMemHandle(&hx, s.symXc.p), "cudaIpcGetMemHandle") || !cuda_ok(cudaIpcGetMemHandle(&hg, s.symGc.p), "cudaIpcGetMemHandle")) return 0;
+    std::memcpy(handles128, &hx, 64); std::memcpy(handles128 + 64, &hg, 64);
+    return 1;
+}
+
+int nbb200_peer_import_chunks(NBB200State *state, int rank, const char *handles128)
+{
+    if (state == nullptr || handles128 == nullptr || rank < 0 || rank >= State::kMaxPeers) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (rank == s.rank) { s.peerXc[rank] = s.symXc.p; s.peerGc[rank] = s.symGc.p; return s.symXc.p != nullptr ? 1 : 0; }
+    cudaIpcMemHandle_t hx, hg;
+    std::memcpy(&hx, handles128, 64); std::memcpy(&hg, handles128 + 64, 64);
+    void *px = nullptr, *pg = nullptr;
+    if (!cuda_ok(cudaIpcOpenMemHandle(&px, hx, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle") ||
+        !cuda_ok(cudaIpcOpenMemHandle(&pg, hg, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return 0;
+    s.peerXc[rank] = (double *) px; s.peerGc[rank] = (double *) pg; s.peerChunkOpened[rank] = true;
+    return 1;
+}
+
+/* same-process variant (see nbb200_peer_attach_local) */
+int nbb200_peer_attach_local_chunks(NBB200State *state, int rank, NBB200State *other)
+{
+    if (state == nullptr || other == nullptr || rank < 0 || rank >= State::kMaxPeers) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    State &o = *reinterpret_cast<State *>(other);
+    if (o.symXc.p == nullptr || o.symGc.p == nullptr) return 0;
+    s.peerXc[rank] = o.symXc.p; s.peerGc[rank] = o.symGc.p;
+    return 1;
+}
+
+/* host rows [a0, a0 + count) of h_x (the base of the caller's [n][3] array) -> this rank's chunk buffer, same offsets; page-locked arrays go
+ * by one DMA, others through the state's page-locked staging array (threaded copy).  Stream ordered. */
+void nbb200_chunk_upload(NBB200State *state, const double *h_x, long a0, long count)
+{
+    if (state == nullptr || h_x == nullptr || count <= 0) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (s.symXc.p == nullptr || a0 < 0 || a0 + count > s.n) { set_error("nbb200_chunk_upload: chunk buffers are not exported or the range is invalid"); return; }
+    const double *src = h_x + 3 * a0;
+    // (the query is slow for pageable memory: asked once per array)
+    if (s.hostXChecked != (const void *) h_x) { s.hostXChecked = h_x; s.hostXPinned = is_pinned_host(src); }
+    if (s.hostXPinned) {
+        cuda_ok(cudaMemcpyAsync(s.symXc.p + 3 * a0, src, sizeof(double) * 3 * (size_t) count, cudaMemcpyHostToDevice, s.stream), "H2D chunk");
+        return;
+    }
+    cudaStreamSynchronize(s.stream);                           // the staging array may still feed an earlier copy
+    staged_upload(s, s.symXc.p + 3 * a0, src, s.hx + 3 * a0, 3 * count);
+}
+
+/* which = 0: "my chunk is uploaded"; 1: "the gradients of my slab are written".  Stream ordered, no host wait. */
+void nbb200_chunk_signal(NBB200State *state, long step, int which)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    PeerPtrs P;
+    for (int r = 0; r < State::kMaxPeers; r++) P.p[r] = s.peerSig[r];
+    k_signal_flag<<<1, 32, 0, s.stream>>>(P, s.rank, s.nranks, (double) step, which == 0 ? kSigFlagC : kSigFlagD);
+    s.launches += 1;
+}
+
+void nbb200_chunk_wait(NBB200State *state, long step, int which)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    k_wait<<<1, 32, 0, s.stream>>>(s.symSig.p, which == 0 ? kSigFlagC : kSigFlagD, s.nranks, (double) step, 2, s.sigStage.p + 50, s.sigStage.p + 51, peer_max_spins());
+    s.launches += 1;
+}
+
+/* after nbb200_chunk_wait(step, 0): the positions of the atoms this rank owns (its slab of the current lists), from the chunk buffers of the
+ * ranks that uploaded them, into d_x (atom order) */
+void nbb200_chunk_gather_owned(NBB200State *state, double *d_x)
+{
+    if (state == nullptr || d_x == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    const long count = (long) std::max(0, s.ownHi - s.ownLo);
+    if (count == 0) return;
+    PeerPtrs P;
+    for (int r = 0; r < State::kMaxPeers; r++) P.p[r] = s.peerXc[r];
+    k_chunk_gather<<<(unsigned int) ((count + 255) / 256), 256, 0, s.stream>>>(P, chunk_edges(s), s.nranks, (long) s.n, s.sAtom.p, (long) s.ownLo, count, d_x);
+    s.launches += 1;
+}
+
+/* after nbb200_peer_wait_end: the (complete) gradients of this rank's slab go to the chunk buffers of the ranks that download those atoms */
+void nbb200_chunk_scatter_gradients(NBB200State *state)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    const long count = (long) std::max(0, s.ownHi - s.ownLo);
+    if (count == 0 || s.gs == nullptr) return;
+    PeerPtrs P;
+    for (int r = 0; r < State::kMaxPeers; r++) P.p[r] = s.peerGc[r];
+    k_chunk_scatter<<<(unsigned int) ((count + 255) / 256), 256, 0, s.stream>>>(P, chunk_edges(s), s.nranks, (long) s.n, s.sAtom.p, (long) s.ownLo, count, s.gs);
+    s.launches += 1;
+}
+
+/* after nbb200_chunk_wait(step, 1): rows [a0, a0 + count) of this rank's gradient chunk buffer are ADDED to the same rows of h_g (the base of
+ * the caller's [n][3] array).  Synchronises the stream. */
+int nbb200_chunk_download_add(NBB200State *state, double *h_g, long a0, long count)
+{
+    if (state == nullptr || h_g == nullptr || count < 0) return 0;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    if (s.symGc.p == nullptr || a0 < 0 || a0 + count > s.n) { set_error("nbb200_chunk_download_add: chunk buffers are not exported or the range is invalid"); return 0; }
+    double *flag = s.hsmall + (kSmallDoubles - 200);           // the time-out flag of the last nbb200_chunk_wait
+    bool ok = cuda_ok(cudaMemcpyAsync(flag, s.sigStage.p + 51, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H");
+    // a few pieces: the host adds piece k while the DMA of piece k + 1 runs
+    const long m = 3 * count, pieces = std::max(1L, std::min(4L, m / (1L << 18)));
+    if (s.chunkEvents[0] == nullptr) for (auto &e : s.chunkEvents) ok = ok && cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    for (long p = 0; p < pieces && ok && m > 0; p++) {
+        const long k0 = (m * p) / pieces, k1 = (m * (p + 1)) / pieces;
+        ok = cuda_ok(cudaMemcpyAsync(s.hgrad + 3 * a0 + k0, s.symGc.p + 3 * a0 + k0, sizeof(double) * (size_t) (k1 - k0), cudaMemcpyDeviceToHost, s.stream), "D2H chunk") &&
+             cuda_ok(cudaEventRecord(s.chunkEvents[p], s.stream), "event");
+    }
+    for (long p = 0; p < pieces && ok && m > 0; p++) {
+        const long k0 = (m * p) / pieces, k1 = (m * (p + 1)) / pieces;
+        ok = cuda_ok(cudaEventSynchronize(s.chunkEvents[p]), "event wait");
+        if (ok && p == 0 && *flag != 0.0) { set_error("time-out waiting for the other ranks (chunk exchange)"); ok = false; }
+        if (ok) nbb200_host_add(h_g + 3 * a0 + k0, s.hgrad + 3 * a0 + k0, k1 - k0);
+    }
+    ok = cuda_ok(cudaStreamSynchronize(s.stream), "sync") && ok;
+    if (ok && m == 0 && *flag != 0.0) { set_error("time-out waiting for the other ranks (chunk exchange)"); ok = false; }
+    return ok ? 1 : 0;
 }
 
 /* ---- velocity Verlet on the device (pCore-1.9.0/pCore/VelocityVerletIntegrator.py:60-81 in Cartesian variables) ---- */

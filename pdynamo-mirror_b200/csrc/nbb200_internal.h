@@ -239,6 +239,12 @@ struct State {
     double *peerGs[kMaxPeers] = {}, *peerXs[kMaxPeers] = {}, *peerSig[kMaxPeers] = {};
     DevBuf<double> sigStage;                     // device staging: [0] local displacement maximum, [1..16] scalars, [17..32] results, [33] timeout flag
     bool peerOpened[kMaxPeers] = {};
+    // host callers, several ranks: atom-order chunk buffers (positions as uploaded by the rank that holds the host rows; gradients as downloaded by it)
+    DevBuf<double> symXc, symGc;
+    double *peerXc[kMaxPeers] = {}, *peerGc[kMaxPeers] = {};
+    bool peerChunkOpened[kMaxPeers] = {};
+    cudaEvent_t chunkEvents[4] = {nullptr, nullptr, nullptr, nullptr};
+    const void *hostXChecked = nullptr; bool hostXPinned = false;      // nbb200_chunk_upload: is the caller's array page-locked?
     bool peersReady = false;
     // optimistic update decision (nbb200_set_optimistic_updates): Update enqueues the displacement check without waiting for it, the
     // energy call that follows evaluates on the current lists and its one synchronisation brings the decision back; when an update was

@@ -188,6 +188,14 @@ class DistributedNB:
             allh = allh.cpu().numpy().tobytes()
             for r in range(world):
                 ok = ok and bool(self.L.nbb200_peer_import(self.h, r, allh[192 * r:192 * (r + 1)]))
+            buf2 = C.create_string_buffer(128)                  # atom-order chunk buffers of call_host
+            ok = ok and bool(self.L.nbb200_peer_export_chunks(self.h, buf2))
+            mine2 = torch.frombuffer(bytearray(buf2.raw), dtype=torch.uint8).to(device)
+            allh2 = torch.empty(128 * world, dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allh2, mine2, group=group)
+            allh2 = allh2.cpu().numpy().tobytes()
+            for r in range(world):
+                ok = ok and bool(self.L.nbb200_peer_import_chunks(self.h, r, allh2[128 * r:128 * (r + 1)]))
             agreed = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=device)
             dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=group)   # also: every signal area is zeroed and mapped before the first call
             if float(agreed.item()) < 1.0:
@@ -334,10 +342,12 @@ class DistributedNB:
         return updated
 
     def call_host(self, x_host, box, g_host=None, force_rebuild=False):
-        """The same call for a caller that keeps coordinates and gradients in HOST arrays (x_host[n, 3], g_host[n, 3], numpy): after the
-        first call (which uploads everything once) a rank uploads only the positions of the atoms it owns and downloads only their
-        gradients -- 24 n / R bytes each way instead of 24 n -- plus the owned atoms' indices (they change with every list rebuild).
-        The owned rows of g_host are ACCUMULATED into (the reference's semantics); returns (updated, energies[6], dEdM[3, 3])."""
+        """The same call for a caller that keeps coordinates and gradients in HOST arrays (x_host[n, 3], g_host[n, 3], numpy).  No row gathers on
+        the host: rank r moves the CONTIGUOUS rows [n r / R, n (r + 1) / R) of the two arrays (24 n / R bytes each way, one DMA each), and the
+        device redistributes over peer memory -- a rank gathers the positions of the atoms it owns from the chunk buffers of the ranks that
+        uploaded them and writes the gradients of its atoms into the chunk buffers of the ranks that download them (nbb200_chunk_*).  The first
+        call uploads everything once.  The rows of the rank's chunk of g_host are ACCUMULATED into (the reference's semantics); returns
+        (updated, energies[6], dEdM[3, 3])."""
         import time
         torch, L = self.torch, self.L
         if self.transport != "peer":
@@ -345,41 +355,45 @@ class DistributedNB:
         if x_host.dtype != np.float64 or not x_host.flags.c_contiguous or (g_host is not None and (g_host.dtype != np.float64 or not g_host.flags.c_contiguous)):
             raise TypeError("call_host takes C-contiguous float64 arrays")
         n = self.n
+        c0, c1 = (n * self.rank) // self.world, (n * (self.rank + 1)) // self.world
+        prof = self.host_profile is not None
+        t0 = time.perf_counter() if prof else 0.0
         if not hasattr(self, "_xdev"):
-            dev = self.flag.device
             import os
-            # host row gather / scatter-add threads of this rank (read once by the library): the ranks of a box share its cores
+            # threads of the host copies of this rank (read once by the library): the ranks of a box share its cores
             os.environ.setdefault("NBB200_HOST_THREADS", str(max(1, min(8, (os.cpu_count() or 8) // max(1, self.world)))))
-            self._xdev = torch.from_numpy(np.ascontiguousarray(x_host)).to(dev)
-            self._stage_x = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-            self._stage_g = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-            self._stage_ids = torch.empty(n, dtype=torch.int32).pin_memory()
-            self._stage_dev = torch.empty((n, 3), dtype=torch.float64, device=dev)
-            self._own_count = 0
-        elif self._own_count > 0:
-            t0 = time.perf_counter() if self.host_profile is not None else 0.0
-            s0, s1 = self.slabs[self.rank]
-            cnt = self._own_count
-            L.nbb200_host_gather_rows(C.c_void_p(x_host.ctypes.data), C.c_void_p(self._stage_ids.data_ptr()), cnt, C.c_void_p(self._stage_x.data_ptr()))
-            self._stage_dev[:cnt].copy_(self._stage_x[:cnt], non_blocking=True)
-            L.nbb200_scatter_sorted(self.h, C.c_void_p(self._stage_dev.data_ptr()), s0, cnt, C.c_void_p(self._xdev.data_ptr()))
-        if self.host_profile is not None:
+            self._xdev = torch.from_numpy(np.ascontiguousarray(x_host)).to(self.flag.device)
+            self._hcall = 0
+        else:
+            self._hcall += 1
+            L.nbb200_chunk_upload(self.h, C.c_void_p(x_host.ctypes.data), c0, c1 - c0)
+            if prof:
+                ta = time.perf_counter(); torch.cuda.synchronize(); tb = time.perf_counter()
+                self.host_profile["upload: host copy"] = self.host_profile.get("upload: host copy", 0.0) + ta - t0
+                self.host_profile["upload: DMA"] = self.host_profile.get("upload: DMA", 0.0) + tb - ta
+            L.nbb200_chunk_signal(self.h, self._hcall, 0)
+            L.nbb200_chunk_wait(self.h, self._hcall, 0)          # on the stream: every rank's rows are on its device
+            L.nbb200_chunk_gather_owned(self.h, C.c_void_p(self._xdev.data_ptr()))
+        if prof:
             torch.cuda.synchronize(); t1 = time.perf_counter()
         updated = self.call(self._xdev, box, None, force_rebuild)
-        if self.host_profile is not None:
+        if prof:
             torch.cuda.synchronize(); t2 = time.perf_counter()
-        s0, s1 = self.slabs[self.rank]
-        self._own_count = cnt = s1 - s0
-        L.nbb200_own_slab_to_host(self.h, C.c_void_p(self._stage_g.data_ptr()), C.c_void_p(self._stage_ids.data_ptr()))
-        e, dEdM = self.results()                             # synchronises the stream: the copies above have landed
-        if self.host_profile is not None:
+        self._own_count = c1 - c0
+        if g_host is not None:
+            self._gcall = getattr(self, "_gcall", 0) + 1
+            L.nbb200_chunk_scatter_gradients(self.h)              # behind nbb200_peer_wait_end: the slab's gradients are complete
+            L.nbb200_chunk_signal(self.h, self._gcall, 1)
+            L.nbb200_chunk_wait(self.h, self._gcall, 1)
+            if prof:
+                torch.cuda.synchronize(); tc = time.perf_counter()
+                self.host_profile["scatter + flags"] = self.host_profile.get("scatter + flags", 0.0) + tc - t2
+            if not L.nbb200_chunk_download_add(self.h, C.c_void_p(g_host.ctypes.data), c0, c1 - c0):
+                raise RuntimeError("distributed gradient download failed: " + self._lib.last_error())
+        e, dEdM = self.results()                             # synchronises the stream
+        if prof:
             t3 = time.perf_counter()
-        if g_host is not None and cnt > 0:
-            # every atom has one sorted position: no duplicate rows
-            L.nbb200_host_scatter_add_rows(C.c_void_p(g_host.ctypes.data), C.c_void_p(self._stage_ids.data_ptr()), cnt, C.c_void_p(self._stage_g.data_ptr()))
-        if self.host_profile is not None and "t0" in locals():
-            t4 = time.perf_counter()
-            for k, v in (("gather+upload", t1 - t0), ("call", t2 - t1), ("download", t3 - t2), ("scatter-add", t4 - t3)):
+            for k, v in (("upload+gather", t1 - t0), ("call", t2 - t1), ("scatter+download+add", t3 - t2)):
                 self.host_profile[k] = self.host_profile.get(k, 0.0) + v
         return updated, e, dEdM
 

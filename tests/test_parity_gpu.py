@@ -711,20 +711,34 @@ def test_peer_memory_transport_three_partitions_one_gpu(pkg):
         L.nbb200_set_partition(h, rank, R)
         L.nbb200_set_restricted_sort(h, 1)                   # each partition sorts only the cells its slab can see, as DistributedNB does
         assert L.nbb200_peer_export(h, C.create_string_buffer(192)) == 1
+        assert L.nbb200_peer_export_chunks(h, C.create_string_buffer(128)) == 1      # host callers: atom-order chunk buffers
         systems.append(s2); hs.append(h)
         xs.append(torch.from_numpy(x0).cuda())
         rows.append(torch.zeros(4 * R, dtype=torch.int64, device="cuda"))
     for a in range(R):
         for b in range(R):
             assert L.nbb200_peer_attach_local(hs[a], b, hs[b]) == 1
+            assert L.nbb200_peer_attach_local_chunks(hs[a], b, hs[b]) == 1
     status = C.c_int(16)
     slabs = None
+    chunk = [((n * r) // R, (n * (r + 1)) // R) for r in range(R)]
 
-    def one_call(step, forced, xnew):
+    def one_call(step, forced, xnew, host_chunks=False):
+        """host_chunks: the host-array path of DistributedNB.call_host -- partition r uploads the contiguous rows chunk[r] of the host array
+        and the owners gather their atoms' positions from the chunk buffers; afterwards the owners scatter their gradients into the chunk
+        buffers and partition r downloads rows chunk[r] (returned as a third value, assembled over the partitions)."""
         nonlocal slabs
         total = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
         es = []
-        if slabs is not None:
+        if slabs is not None and host_chunks:
+            xh = np.ascontiguousarray(xnew)
+            for r in range(R):
+                L.nbb200_chunk_upload(hs[r], C.c_void_p(xh.ctypes.data), chunk[r][0], chunk[r][1] - chunk[r][0])
+                L.nbb200_chunk_signal(hs[r], step, 0)
+            for r in range(R):
+                L.nbb200_chunk_wait(hs[r], step, 0)
+                L.nbb200_chunk_gather_owned(hs[r], C.c_void_p(xs[r].data_ptr()))
+        elif slabs is not None:
             for r in range(R):                               # a rank only knows its own atoms' new positions
                 own = torch.from_numpy(np.ascontiguousarray(sys_atoms[r]))
                 xs[r][own.cuda()] = torch.from_numpy(xnew[sys_atoms[r]]).cuda()
@@ -765,6 +779,15 @@ def test_peer_memory_transport_three_partitions_one_gpu(pkg):
             L.nbb200_peer_read_sums(hs[r], _lib.d_(out), C.byref(status))
             sums.append(out)
         assert status.value == 16, _lib.last_error()
+        if host_chunks:
+            gh = np.full((n, 3), 0.5)                        # accumulated into: the caller's values stay
+            for r in range(R):
+                L.nbb200_chunk_scatter_gradients(hs[r])
+                L.nbb200_chunk_signal(hs[r], step, 1)
+            for r in range(R):
+                L.nbb200_chunk_wait(hs[r], step, 1)
+                assert L.nbb200_chunk_download_add(hs[r], C.c_void_p(gh.ctypes.data), chunk[r][0], chunk[r][1] - chunk[r][0]) == 1, _lib.last_error()
+            return total.cpu().numpy(), sums, gh - 0.5
         return total.cpu().numpy(), sums
 
     def owners():
@@ -801,6 +824,17 @@ def test_peer_memory_transport_three_partitions_one_gpu(pkg):
         if forced:
             sys_atoms = owners()
         check(g, sums, er, gr)
+    # the same two kinds of call through the host-array path (contiguous chunks each way, redistribution over peer memory)
+    x4 = x3 + 0.03 * np.sin(2.1 * np.arange(x0.size).reshape(-1, 3))
+    x5 = x4 + 0.05 * np.cos(0.4 * np.arange(x0.size).reshape(-1, 3))
+    for step, forced, xn in ((5, True, x4), (6, False, x5)):
+        ref.coordinates3[...] = xn; ref.Energy(doGradients=True)
+        er, gr = ref.configuration.nbState.energies.copy(), ref.configuration.gradients3.copy()
+        g, sums, gh = one_call(step, forced, xn, host_chunks=True)
+        if forced:
+            sys_atoms = owners()
+        check(g, sums, er, gr)
+        assert np.abs(gh - g).max() <= 1e-12 * np.abs(g).max()      # every row exactly once, the owners' values
 
 
 def test_centring_is_carried_between_updates(pkg, orc):
