@@ -430,7 +430,10 @@ __global__ void k_scatter(const int *__restrict__ eKey, const int *__restrict__ 
 
 // deterministic order inside each cell: rank sort by (sub-cell key, atom index), one warp per cell; the sorted arrays (coordinates,
 // atom index, inverse permutation of the primary atoms) are written in the same pass.  (One warp per 32 keys of the mostly empty image
-// sets, walking the ones with work, was slower: 140 instead of 89 us on the 1.1 M-atom box; CTAs of 1024 threads: 107 us.)
+// sets, walking the ones with work, was slower: 140 instead of 89 us on the 1.1 M-atom box; so were, in round 2, that walk for the image
+// sets only (rebuild 1.48 -> 1.51 ms) and a persistent grid that claims groups of 32 keys from a cursor (1.52 ms; DHFR 215 -> 250 us):
+// the rank sort of an occupied cell is a serial chain, and a warp that owns several occupied cells runs them one after the other.  CTAs
+// of 1024 threads: 107 us.)
 __global__ void k_sort_cells(const unsigned int *__restrict__ cellStart, int nkeys, const unsigned long long *__restrict__ eSort, const int *__restrict__ order,
                              const double *__restrict__ eX, const int *__restrict__ eAtom, const int *__restrict__ eSet,
                              double *__restrict__ sX, int *__restrict__ sAtom, int *__restrict__ invPerm, const unsigned char *__restrict__ need, int ncell)
