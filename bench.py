@@ -419,42 +419,57 @@ def run_b200(args):
         line["halo"] = {"halo_atoms_per_step_no_rebuild": int(dn.halo_atoms()), "transport": dn.transport,
                         "atoms_owned": int(dn.slabs[rank][1] - dn.slabs[rank][0]), "list_updates": dn.updates}
         # end to end with HOST arrays on every rank (DistributedNB.call_host): per step a rank uploads its contiguous chunk of the positions,
-        # runs the distributed call (forced rebuild, as the timed steps above), downloads the gradients of its atoms and their indices
-        # (the slabs change with every rebuild) and accumulates them into its host gradient array; the summed energies are read on the
-        # host.  Wall clock between barriers, max over ranks.
-        xh = w["xyz"].copy()
-        gh = np.zeros_like(xh)
+        # runs the distributed call (forced rebuild, as the timed steps above) and downloads the same rows of the gradient; the summed energies
+        # are read on the host.  Wall clock between barriers, max over ranks.  Headline (`e2e`): the arrays and the semantics of the one-GPU
+        # leg -- page-locked arrays as the mirror's System allocates them, the gradient rows SET (System.Energy's freshly zeroed array, NB term
+        # first: the zero fill is folded into the call).  Extra (`e2e_accumulate`): plain numpy arrays, rows accumulated into (staging copies
+        # and a host add on every rank).
+        from pdynamo_mirror_b200._lib import pinned_array
 
-        def e2e_step():
-            dn.call_host(xh, m.box, gh, force_rebuild=True)
+        def host_leg(xh, gh, overwrite):
+            for _ in range(args.warmup):
+                dn.call_host(xh, m.box, gh, force_rebuild=True, overwrite=overwrite)
+            barrier(); torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            for _ in range(args.steps):
+                dn.call_host(xh, m.box, gh, force_rebuild=True, overwrite=overwrite)
+            torch.cuda.synchronize(); barrier()
+            return allmax((time.perf_counter() - t1) / args.steps * 1e3)
 
-        for _ in range(args.warmup):
-            e2e_step()
-        barrier(); torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        torch.cuda.synchronize(); barrier()
-        e2e_ms = allmax((time.perf_counter() - t1) / args.steps * 1e3)
+        xh = pinned_array((n, 3)); xh[...] = w["xyz"]
+        gh = pinned_array((n, 3)); gh[...] = 0.0
+        e2e_ms = host_leg(xh, gh, True)
         own = allsum(float(dn._own_count))
         # self-check of the host path: the rows of this rank's chunk are the gradients a device-array call gives on the same coordinates (that
         # call leaves every atom's gradient with the rank that owns it: summed over the ranks for the comparison, outside the timed region)
-        gh[:] = 0.0
-        dn.call_host(xh, m.box, gh, force_rebuild=True)
+        gh[...] = 7.0                                        # overwritten, not added to
+        dn.call_host(xh, m.box, gh, force_rebuild=True, overwrite=True)
         c0, c1 = (n * rank) // world, (n * (rank + 1)) // world
-        m.x.copy_(torch.from_numpy(xh)); m.g.zero_()
+        m.x.copy_(torch.from_numpy(np.ascontiguousarray(xh))); m.g.zero_()
         dn.call(m.x, m.box, m.g, force_rebuild=True); dn.results()
         gfull = m.g.clone()
         dist.all_reduce(gfull)
         gd = gfull.cpu().numpy()
         host_err = allmax(float(np.abs(gh[c0:c1] - gd[c0:c1]).max() / max(1e-300, np.abs(gd).max())))
-        host_rows = allsum(float(np.count_nonzero(np.abs(gh).sum(1))))
+        host_rows = allsum(float(c1 - c0))
+        xp = w["xyz"].copy()
+        gp = np.zeros_like(xp)
+        acc_ms = host_leg(xp, gp, False)
+        gp[:] = 0.0
+        dn.call_host(xp, m.box, gp, force_rebuild=True)
+        acc_err = allmax(float(np.abs(gp[c0:c1] - gd[c0:c1]).max() / max(1e-300, np.abs(gd).max())))
         line["e2e"] = {"value": pairs / (e2e_ms * 1e-3), "unit": "list-pairs/s", "ms_per_step": e2e_ms,
                        "h2d_bytes_per_step": int(24 * own), "d2h_bytes_per_step": int(24 * own) + 15 * 8 * world,
-                       "api": "DistributedNB.call_host(x, box, g, force_rebuild=True) on every rank with host numpy arrays: rank r uploads the contiguous "
-                              "rows [n r / R, n (r + 1) / R) of x and downloads the same rows of the gradient (bytes summed over the ranks), the device "
-                              "redistributes over peer memory; energies read on the host; wall clock, max over ranks",
-                       "check": {"chunk_rows_rel_err_vs_device_call": host_err, "rows_filled_all_ranks": int(host_rows), "atoms": n}}
+                       "api": "DistributedNB.call_host(x, box, g, force_rebuild=True, overwrite=True) on every rank with page-locked host arrays (as the "
+                              "one-GPU leg: the mirror's System allocates them page-locked and its gradient array is freshly zeroed, NB term first): rank r "
+                              "uploads the contiguous rows [n r / R, n (r + 1) / R) of x and downloads the same rows of the gradient (bytes summed over the "
+                              "ranks), the device redistributes over peer memory; energies read on the host; wall clock, max over ranks",
+                       "check": {"chunk_rows_rel_err_vs_device_call": host_err, "rows_checked_all_ranks": int(host_rows), "atoms": n}}
+        line["e2e_accumulate"] = {"value": pairs / (acc_ms * 1e-3), "unit": "list-pairs/s", "ms_per_step": acc_ms,
+                                  "h2d_bytes_per_step": int(24 * own), "d2h_bytes_per_step": int(24 * own) + 15 * 8 * world,
+                                  "api": "the same call with plain (pageable) numpy arrays and the rows ACCUMULATED into the caller's gradient array: staging copies "
+                                         "through page-locked memory and a host add on every rank",
+                                  "check": {"chunk_rows_rel_err_vs_device_call": acc_err}}
     if dn is not None and os.environ.get("NBB200_DIST_PROFILE"):
         dn.host_profile = {}
         for _ in range(10):

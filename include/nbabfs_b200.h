@@ -238,6 +238,9 @@ void nbb200_chunk_wait(NBB200State *state, long step, int which);
 void nbb200_chunk_gather_owned(NBB200State *state, double *d_x);
 void nbb200_chunk_scatter_gradients(NBB200State *state);
 int nbb200_chunk_download_add(NBB200State *state, double *h_g, long a0, long count);   /* 0: failed (time-out of a peer, bad range) */
+/* overwrite != 0: the rows are SET instead of added to (System.Energy's own, freshly zeroed gradient array with the NB term first: the zero fill
+ * is folded into the call, as nbb200_set_gradient_overwrite does on one GPU); a page-locked h_g then receives them by one DMA */
+int nbb200_chunk_download(NBB200State *state, double *h_g, long a0, long count, int overwrite);
 void nbb200_host_copy(double *dst, const double *src, long m);
 void nbb200_host_add(double *dst, const double *src, long m);
 

@@ -65,6 +65,7 @@ SIGNATURES = {
     "nbb200_chunk_gather_owned": (None, [vp, vp]),
     "nbb200_chunk_scatter_gradients": (None, [vp]),
     "nbb200_chunk_download_add": (C.c_int, [vp, vp, C.c_long, C.c_long]),
+    "nbb200_chunk_download": (C.c_int, [vp, vp, C.c_long, C.c_long, C.c_int]),
     "nbb200_host_scatter_add_rows": (None, [vp, vp, C.c_long, vp]),
     "nbb200_set_gradient_overwrite": (None, [vp, C.c_int]),
     "nbb200_set_optimistic_updates": (None, [vp, C.c_int]),

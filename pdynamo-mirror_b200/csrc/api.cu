@@ -1398,16 +1398,25 @@ void nbb200_chunk_scatter_gradients(NBB200State *state)
 
 /* after nbb200_chunk_wait(step, 1): rows [a0, a0 + count) of this rank's gradient chunk buffer are ADDED to the same rows of h_g (the base of
  * the caller's [n][3] array).  Synchronises the stream. */
-int nbb200_chunk_download_add(NBB200State *state, double *h_g, long a0, long count)
+int nbb200_chunk_download(NBB200State *state, double *h_g, long a0, long count, int overwrite)
 {
     if (state == nullptr || h_g == nullptr || count < 0) return 0;
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
-    if (s.symGc.p == nullptr || a0 < 0 || a0 + count > s.n) { set_error("nbb200_chunk_download_add: chunk buffers are not exported or the range is invalid"); return 0; }
+    if (s.symGc.p == nullptr || a0 < 0 || a0 + count > s.n) { set_error("nbb200_chunk_download: chunk buffers are not exported or the range is invalid"); return 0; }
     double *flag = s.hsmall + (kSmallDoubles - 200);           // the time-out flag of the last nbb200_chunk_wait
     bool ok = cuda_ok(cudaMemcpyAsync(flag, s.sigStage.p + 51, sizeof(double), cudaMemcpyDeviceToHost, s.stream), "D2H");
-    // a few pieces: the host adds piece k while the DMA of piece k + 1 runs
-    const long m = 3 * count, pieces = std::max(1L, std::min(4L, m / (1L << 18)));
+    const long m = 3 * count;
+    if (s.hostGChecked != (const void *) h_g) { s.hostGChecked = h_g; s.hostGPinned = is_pinned_host(h_g + 3 * a0); }
+    if (overwrite && s.hostGPinned) {
+        // the caller's rows are set, and its array is page-locked: one DMA straight into it
+        if (m > 0) ok = ok && cuda_ok(cudaMemcpyAsync(h_g + 3 * a0, s.symGc.p + 3 * a0, sizeof(double) * (size_t) m, cudaMemcpyDeviceToHost, s.stream), "D2H chunk");
+        ok = cuda_ok(cudaStreamSynchronize(s.stream), "sync") && ok;
+        if (ok && *flag != 0.0) { set_error("time-out waiting for the other ranks (chunk exchange)"); ok = false; }
+        return ok ? 1 : 0;
+    }
+    // a few pieces: the host adds (or copies) piece k while the DMA of piece k + 1 runs
+    const long pieces = std::max(1L, std::min(4L, m / (1L << 18)));
     if (s.chunkEvents[0] == nullptr) for (auto &e : s.chunkEvents) ok = ok && cuda_ok(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
     for (long p = 0; p < pieces && ok && m > 0; p++) {
         const long k0 = (m * p) / pieces, k1 = (m * (p + 1)) / pieces;
@@ -1418,12 +1427,15 @@ int nbb200_chunk_download_add(NBB200State *state, double *h_g, long a0, long cou
         const long k0 = (m * p) / pieces, k1 = (m * (p + 1)) / pieces;
         ok = cuda_ok(cudaEventSynchronize(s.chunkEvents[p]), "event wait");
         if (ok && p == 0 && *flag != 0.0) { set_error("time-out waiting for the other ranks (chunk exchange)"); ok = false; }
-        if (ok) nbb200_host_add(h_g + 3 * a0 + k0, s.hgrad + 3 * a0 + k0, k1 - k0);
+        if (ok && overwrite) nbb200_host_copy(h_g + 3 * a0 + k0, s.hgrad + 3 * a0 + k0, k1 - k0);
+        else if (ok) nbb200_host_add(h_g + 3 * a0 + k0, s.hgrad + 3 * a0 + k0, k1 - k0);
     }
     ok = cuda_ok(cudaStreamSynchronize(s.stream), "sync") && ok;
     if (ok && m == 0 && *flag != 0.0) { set_error("time-out waiting for the other ranks (chunk exchange)"); ok = false; }
     return ok ? 1 : 0;
 }
+
+int nbb200_chunk_download_add(NBB200State *state, double *h_g, long a0, long count) { return nbb200_chunk_download(state, h_g, a0, count, 0); }
 
 /* ---- velocity Verlet on the device (pCore-1.9.0/pCore/VelocityVerletIntegrator.py:60-81 in Cartesian variables) ---- */
 // first half: x += dt v + dt^2/2 a ; v += dt/2 a

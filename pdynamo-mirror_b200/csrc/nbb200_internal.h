@@ -244,6 +244,7 @@ struct State {
     double *peerXc[kMaxPeers] = {}, *peerGc[kMaxPeers] = {};
     bool peerChunkOpened[kMaxPeers] = {};
     cudaEvent_t chunkEvents[4] = {nullptr, nullptr, nullptr, nullptr};
+    const void *hostGChecked = nullptr; bool hostGPinned = false;
     const void *hostXChecked = nullptr; bool hostXPinned = false;      // nbb200_chunk_upload: is the caller's array page-locked?
     bool peersReady = false;
     // optimistic update decision (nbb200_set_optimistic_updates): Update enqueues the displacement check without waiting for it, the

@@ -341,13 +341,15 @@ class DistributedNB:
         self._tick("scalars")
         return updated
 
-    def call_host(self, x_host, box, g_host=None, force_rebuild=False):
+    def call_host(self, x_host, box, g_host=None, force_rebuild=False, overwrite=False):
         """The same call for a caller that keeps coordinates and gradients in HOST arrays (x_host[n, 3], g_host[n, 3], numpy).  No row gathers on
         the host: rank r moves the CONTIGUOUS rows [n r / R, n (r + 1) / R) of the two arrays (24 n / R bytes each way, one DMA each), and the
         device redistributes over peer memory -- a rank gathers the positions of the atoms it owns from the chunk buffers of the ranks that
         uploaded them and writes the gradients of its atoms into the chunk buffers of the ranks that download them (nbb200_chunk_*).  The first
-        call uploads everything once.  The rows of the rank's chunk of g_host are ACCUMULATED into (the reference's semantics); returns
-        (updated, energies[6], dEdM[3, 3])."""
+        call uploads everything once.  The rows of the rank's chunk of g_host are ACCUMULATED into (the reference's semantics) -- or, with
+        overwrite, SET (System.Energy's own freshly zeroed gradient array with the NB term first: the zero fill is folded into the call, as the
+        one-GPU plugin does); page-locked arrays (pdynamo_mirror_b200._lib.pinned_array, what the mirror's System allocates) travel by one DMA each
+        way without a staging copy.  Returns (updated, energies[6], dEdM[3, 3])."""
         import time
         torch, L = self.torch, self.L
         if self.transport != "peer":
@@ -388,7 +390,7 @@ class DistributedNB:
             if prof:
                 torch.cuda.synchronize(); tc = time.perf_counter()
                 self.host_profile["scatter + flags"] = self.host_profile.get("scatter + flags", 0.0) + tc - t2
-            if not L.nbb200_chunk_download_add(self.h, C.c_void_p(g_host.ctypes.data), c0, c1 - c0):
+            if not L.nbb200_chunk_download(self.h, C.c_void_p(g_host.ctypes.data), c0, c1 - c0, 1 if overwrite else 0):
                 raise RuntimeError("distributed gradient download failed: " + self._lib.last_error())
         e, dEdM = self.results()                             # synchronises the stream
         if prof:

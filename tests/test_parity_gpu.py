@@ -780,14 +780,16 @@ def test_peer_memory_transport_three_partitions_one_gpu(pkg):
             sums.append(out)
         assert status.value == 16, _lib.last_error()
         if host_chunks:
-            gh = np.full((n, 3), 0.5)                        # accumulated into: the caller's values stay
+            overwrite = host_chunks == 2                     # 1: accumulated into a plain array (the caller's values stay); 2: set, page-locked array
+            gh = _lib.pinned_array((n, 3)) if overwrite else np.zeros((n, 3))
+            gh[...] = 0.5
             for r in range(R):
                 L.nbb200_chunk_scatter_gradients(hs[r])
                 L.nbb200_chunk_signal(hs[r], step, 1)
             for r in range(R):
                 L.nbb200_chunk_wait(hs[r], step, 1)
-                assert L.nbb200_chunk_download_add(hs[r], C.c_void_p(gh.ctypes.data), chunk[r][0], chunk[r][1] - chunk[r][0]) == 1, _lib.last_error()
-            return total.cpu().numpy(), sums, gh - 0.5
+                assert L.nbb200_chunk_download(hs[r], C.c_void_p(gh.ctypes.data), chunk[r][0], chunk[r][1] - chunk[r][0], 1 if overwrite else 0) == 1, _lib.last_error()
+            return total.cpu().numpy(), sums, (np.array(gh) if overwrite else gh - 0.5)
         return total.cpu().numpy(), sums
 
     def owners():
@@ -830,7 +832,7 @@ def test_peer_memory_transport_three_partitions_one_gpu(pkg):
     for step, forced, xn in ((5, True, x4), (6, False, x5)):
         ref.coordinates3[...] = xn; ref.Energy(doGradients=True)
         er, gr = ref.configuration.nbState.energies.copy(), ref.configuration.gradients3.copy()
-        g, sums, gh = one_call(step, forced, xn, host_chunks=True)
+        g, sums, gh = one_call(step, forced, xn, host_chunks=1 if forced else 2)
         if forced:
             sys_atoms = owners()
         check(g, sums, er, gr)
