@@ -569,9 +569,9 @@ def md_block(torch, local, steps=300):
     w = make_workload("dhfr")
     n = w["n"]
     out = {}
-    for label, freq in (("displacement_triggered", 0), ("update_every_10", 10)):
+    for label, freq, opt in (("displacement_triggered", 0, False), ("update_every_10", 10, False), ("displacement_triggered_optimistic", 0, True)):
         sysm = p.System.FromWorkload(w)
-        sysm.DefineNBModel(p.NBModelABFS(device=local, updateFrequency=freq))
+        sysm.DefineNBModel(p.NBModelABFS(device=local, updateFrequency=freq, optimisticUpdates=opt))
         rng = np.random.Generator(np.random.PCG64(491831))
         sysm.Energy(doGradients=True)
         x = sysm.coordinates3
@@ -585,7 +585,8 @@ def md_block(torch, local, steps=300):
         st = sysm.configuration.nbState
         out[label] = {"steps_per_s": steps / wall, "ms_per_step": 1e3 * wall / steps, "steps": steps, "list_updates": int(st.numberOfUpdates) - 1,
                       "nb_setup_ms_per_step": 1e3 * sysm.timings["NB Set Up"] / (steps + 1), "nb_evaluation_ms_per_step": 1e3 * sysm.timings["NB Evaluation"] / (steps + 1)}
-    out["note"] = ("synthetic random-walk trajectory, NB term only, host arrays every step; for scale: the reference spends 0.587 s (serial) / 0.122 s "
+    out["note"] = ("synthetic random-walk trajectory, NB term only, host arrays every step; _optimistic: NBModelABFS(optimisticUpdates=True), the update decision "
+                   "read with the results of the energy call (one host wait per step instead of two); for scale: the reference spends 0.587 s (serial) / 0.122 s "
                    "(8 OpenMP threads) per NB evaluation and 0.68 s per list update on this system (benchmarks/log/systemBenchmarks_*_1ps.log)")
     return out
 

@@ -165,8 +165,31 @@ static State *create(int device, int n, const double *charges, const int *ljtype
     return s;
 }
 
+static int update_common(State &s, const double *box6, int forceNew, int *status, int decided = -1);
+
+// an optimistic update decision is still open (Update has been called, the energy call that reads the decision has not): entry points that
+// hand out the lists themselves settle it first -- wait for the displacement maximum, rebuild when it asks for it
+static void settle_optimistic(State &s)
+{
+    if (!s.optPending) return;
+    s.optPending = false;
+    double disp = 0.0;
+    if (cudaMemcpyAsync(s.hsmall + (kSmallDoubles - 8), s.optDisp.p, sizeof(double), cudaMemcpyDeviceToHost, s.stream) == cudaSuccess &&
+        cudaStreamSynchronize(s.stream) == cudaSuccess) disp = s.hsmall[kSmallDoubles - 8];
+    else disp = 1.0e300;
+    if (disp > s.optThr2) {
+        s.numberOfCalls -= 1;
+        const bool opt = s.optimistic;
+        s.optimistic = false; s.keepLattice = true;
+        int st = NBB200_STATUS_CONTINUE;
+        update_common(s, nullptr, 1, &st, -1);
+        s.keepLattice = false; s.optimistic = opt;
+    }
+}
+
 static void fetch_pair_counts(State &s)
 {
+    settle_optimistic(s);
     if (s.pairCountsValid) return;
     std::vector<unsigned long long> cnt((size_t) s.nsets, 0ULL);
     if (s.setPairs.p != nullptr && s.nsets > 0) {
@@ -204,7 +227,7 @@ static void flush_pending(State &s)
     finish_pending(s);
 }
 
-static int update_common(State &s, const double *box6, int forceNew, int *status, int decided = -1)
+static int update_common(State &s, const double *box6, int forceNew, int *status, int decided)
 {
     s.numberOfCalls += 1;
     if (s.pending && (forceNew || s.isNew || decided >= 0 || s.list != s.stListCutoff || s.outer != s.stOuterCutoff)) flush_pending(s);   // no displacement check below
@@ -221,7 +244,7 @@ static int update_common(State &s, const double *box6, int forceNew, int *status
     bool checked = false;
     if (decided >= 0) doUpdate = doUpdate || decided != 0;       // several ranks: the displacement decision was taken collectively by the caller
     s.optPending = false;
-    if (!doUpdate && decided < 0 && s.optimistic && s.nranks == 1 && !s.useCentering && !s.pending && !s.timing &&
+    if (!doUpdate && decided < 0 && s.optimistic && s.nranks == 1 && s.nqc == 0 && !s.useCentering && !s.pending && !s.timing &&
         (s.trans.n == 0 || (s.haveRefLattice && std::memcmp(s.lattice.M.v, s.refLattice.M.v, sizeof(double) * 9) == 0))) {
         // optimistic decision: the check is enqueued, its result comes back with the energy call's synchronisation (see State::optimistic)
         const double buffac = 0.5 * (s.list - s.stOuterCutoff);
@@ -570,9 +593,30 @@ void NBModelABFS_B200_MMMMEnergy(NBB200State *state, double *energies, double *g
                                 : cuda_ok(cudaMemsetAsync(dg, 0, gbytes, s.stream), "memset grad");
         if (!ok0) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
     }
+    // optimistic update decision (nbb200_set_optimistic_updates): the displacement check of the Update call comes back with this call's results
+    if (s.optPending) { s.condDisp = s.optDisp.p; s.condThr2 = s.optThr2; }
     bool ok = energy_enqueue(s, dg);
     if (ok && grad != nullptr) ok = cuda_ok(cudaMemcpyAsync(direct ? grad : s.hgrad, dg, gbytes, cudaMemcpyDeviceToHost, s.stream), "D2H grad");
     ok = ok && cuda_ok(cudaStreamSynchronize(s.stream), "sync");          // the one synchronisation of the call
+    s.condDisp = nullptr;
+    if (ok && s.optPending) {
+        s.optPending = false;
+        if (s.hsmall[kSmallDoubles - 8] > s.optThr2) {
+            // an update was due: the unsort pass left the staging gradient as it was prepared above (the caller's values, or zeros); rebuild at
+            // these coordinates and evaluate again
+            s.numberOfCalls -= 1;
+            const bool opt = s.optimistic;
+            s.optimistic = false;
+            int st = NBB200_STATUS_CONTINUE;
+            s.keepLattice = true;                       // the lattice of the Update call that is being completed
+            update_common(s, nullptr, 1, &st);
+            s.keepLattice = false;
+            s.optimistic = opt;
+            ok = st == NBB200_STATUS_CONTINUE && energy_enqueue(s, dg);
+            if (ok && grad != nullptr) ok = cuda_ok(cudaMemcpyAsync(direct ? grad : s.hgrad, dg, gbytes, cudaMemcpyDeviceToHost, s.stream), "D2H grad");
+            ok = ok && cuda_ok(cudaStreamSynchronize(s.stream), "sync");
+        }
+    }
     if (ok) {
         energy_finish(s, energies, grad != nullptr, dEdM);
         if (grad != nullptr && !direct) {
@@ -694,6 +738,7 @@ long NBModelABFSState_B200_GetPairs(NBB200State *state, int image, int *pairs, i
     if (state == nullptr) return 0;
     State &s = *reinterpret_cast<State *>(state);
     cudaSetDevice(s.device);
+    settle_optimistic(s);
     if (!expand_pairs(s)) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return -1; }
     int set = 0;
     if (image >= 0) {

@@ -363,9 +363,11 @@ class NBModelABFS(NBModel):
     """Atom-based force-switching NB model on the GPU; drop-in for pMolecule.NBModelABFS.
 
     Extra (non-reference) options, all optional: device (CUDA ordinal, default 0), updateFrequency (force a list rebuild every
-    k-th call; default 0 = the reference's displacement heuristic only) and overwriteGradients (default False = the reference's
+    k-th call; default 0 = the reference's displacement heuristic only), overwriteGradients (default False = the reference's
     accumulation into configuration.gradients3; True: the NB call SETS the gradients, for callers that evaluate the NB term first
-    and so need neither a zero fill of the host array nor its upload)."""
+    and so need neither a zero fill of the host array nor its upload) and optimisticUpdates (default False; True: SetUp enqueues
+    CheckForUpdate's displacement test without waiting for it and Energy reads the decision with its results -- one host wait per
+    SetUp + Energy pair, the same numbers and update counts; a call in which an update turns out to be due is evaluated twice)."""
 
     def _Initialize(self):
         self.generator = None
@@ -379,13 +381,14 @@ class NBModelABFS(NBModel):
         self.checkForInverses, self.dampingCutoff, self._dielectric, self._electrostaticScale14 = True, 0.5, 1.0, 1.0
         self.imageExpandFactor, self._innerCutoff, self._listCutoff, self._outerCutoff = 0, 8.0, 13.5, 12.0
         self.qcmmCoupling, self.useCentering = "RC Coupling", False
-        self.device, self.updateFrequency, self.overwriteGradients = 0, 0, False
+        self.device, self.updateFrequency, self.overwriteGradients, self.optimisticUpdates = 0, 0, False, False
 
     def __getstate__(self):
         state = dict(checkForInverses=self.checkForInverses, imageExpandFactor=self.imageExpandFactor, dampingCutoff=self.dampingCutoff,
                      dielectric=self._dielectric, electrostaticScale14=self._electrostaticScale14, innerCutoff=self._innerCutoff,
                      listCutoff=self._listCutoff, outerCutoff=self._outerCutoff, qcmmCoupling=self.qcmmCoupling, useCentering=self.useCentering,
-                     device=self.device, updateFrequency=self.updateFrequency, overwriteGradients=self.overwriteGradients)
+                     device=self.device, updateFrequency=self.updateFrequency, overwriteGradients=self.overwriteGradients,
+                     optimisticUpdates=getattr(self, "optimisticUpdates", False))
         if self.generator is not None:
             state["generator"] = self.generator
         if self.mmmmPairwiseInteraction is not None:
@@ -413,7 +416,7 @@ class NBModelABFS(NBModel):
                       imageExpandFactor="imageExpandFactor", innerCutoff="_innerCutoff", listCutoff="_listCutoff", outerCutoff="_outerCutoff",
                       mmmmPairwiseInteraction="mmmmPairwiseInteraction", qcmmPairwiseInteraction="qcmmPairwiseInteraction",
                       qcqcPairwiseInteraction="qcqcPairwiseInteraction", device="device", updateFrequency="updateFrequency",
-                      overwriteGradients="overwriteGradients")
+                      overwriteGradients="overwriteGradients", optimisticUpdates="optimisticUpdates")
         for key, attr in simple.items():
             if key in kw:
                 setattr(self, attr, kw.pop(key))
@@ -445,6 +448,7 @@ class NBModelABFS(NBModel):
         pw = self.mmmmPairwiseInteraction
         _lib.lib().NBModelABFS_B200_SetOptions(nbState.cObject, pw.dampingCutoff, pw.innerCutoff, pw.outerCutoff, self._listCutoff,
                                                self._dielectric, self._electrostaticScale14, int(self.checkForInverses), int(self.imageExpandFactor))
+        _lib.lib().nbb200_set_optimistic_updates(nbState.cObject, 1 if getattr(self, "optimisticUpdates", False) else 0)
         form = (True, 0) if pw.useAnalyticForm else (False, int(pw.splinePointDensity))
         if getattr(nbState, "_interactionForm", (True, 0)) != form:      # the library rebuilds the tables itself when the cutoffs change
             status = C.c_int(_lib.STATUS_CONTINUE)
@@ -544,6 +548,10 @@ class NBModelABFS(NBModel):
                 _lib.lib().nbb200_set_gradient_overwrite(nbState.cObject, 0)
             if status.value != _lib.STATUS_CONTINUE:
                 raise CLibraryError("NB energy evaluation failed. " + _lib.last_error())
+            if getattr(self, "optimisticUpdates", False):        # an update may have been decided (and done) inside the energy call: the library counts
+                ncalls, nupd = C.c_long(0), C.c_long(0)
+                _lib.lib().NBModelABFSState_B200_GetStatistics(nbState.cObject, C.byref(ncalls), C.byref(nupd))
+                nbState.numberOfUpdates = int(nupd.value)
             if nbState.nqc > 0:                                  # NBModelABFS_QCMMEnergyLJ ( ... )  (pMolecule.NBModelABFS.pyx:120)
                 nbState.QCMMEnergyLJ(g, dEdM)
             nbState.GetEnergies(energies)

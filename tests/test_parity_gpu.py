@@ -319,6 +319,44 @@ def test_optimistic_update_decision_equals_the_plain_sequence(pkg, orc):
     assert results[1][3][3] == results[1][2][3] + 1          # the fourth call rebuilt the lists
 
 
+def test_optimistic_update_decision_through_the_plugin_with_host_arrays(pkg):
+    """NBModelABFS(optimisticUpdates=True): the host-array calls (NBModelABFS_B200_Update / _MMMMEnergy, what System.Energy drives) with the
+    displacement decision read together with the results -- same energies, gradients and update counts as the default sequence along a
+    trajectory that crosses the update criterion twice; the pair lists handed out after an open decision are the settled ones."""
+    w = pkg.workloads.WORKLOADS["bala"]()
+    u = pkg.workloads.lcg_uniform(23, 3 * w["n"]).reshape(-1, 3)
+    xs = [w["xyz"] + (2 * u - 1) * a for a in (0.0, 0.15, 0.3)]
+    x3 = xs[2].copy(); x3[17] += np.array([1.2, 0.0, 0.0]); xs.append(x3)                # beyond the buffer: update due
+    xs.append(x3 + (2 * u - 1) * 0.1)
+    x5 = xs[4].copy(); x5[80] += np.array([0.0, 0.0, -1.3]); xs.append(x5)               # and again
+    runs = {}
+    for opt in (False, True):
+        system = pkg.System.FromWorkload(w)
+        system.DefineNBModel(pkg.NBModelABFS(optimisticUpdates=opt))
+        out = []
+        for x in xs:
+            system.coordinates3[...] = x
+            system.Energy(doGradients=True)
+            st = system.configuration.nbState
+            out.append((st.energies.copy(), system.configuration.gradients3.copy(), int(st.numberOfUpdates)))
+        runs[opt] = out
+        if opt:                                              # an open decision is settled by the getters: Update on moved coordinates, then the lists
+            x6 = xs[5].copy(); x6[3] += np.array([0.0, 1.4, 0.0])
+            system.coordinates3[...] = x6
+            em = system.energyModel
+            em.nbModel.SetUp(em.mmAtoms, None, em.ljParameters, em.ljParameters14, None, em.interactions14, em.exclusions, system.symmetry, None, system.configuration)
+            pairs_open = st.Pairs(-1)
+            ref = pkg.System.FromWorkload(w); ref.DefineNBModel(pkg.NBModelABFS()); ref.coordinates3[...] = x6; ref.Energy(doGradients=False)
+            a = np.sort(np.sort(np.asarray(pairs_open).reshape(-1, 2), axis=1).view("i4,i4"), axis=0)
+            b = np.sort(np.sort(np.asarray(ref.configuration.nbState.Pairs(-1)).reshape(-1, 2), axis=1).view("i4,i4"), axis=0)
+            assert np.array_equal(a, b)
+    for k in range(len(xs)):
+        (e0, g0, n0), (e1, g1, n1) = runs[False][k], runs[True][k]
+        assert n0 == n1, (k, n0, n1)
+        assert same_call(e1, e0) and same_call(g1, g0), k
+    assert runs[True][-1][2] == 3                            # the first build and the two crossings
+
+
 def test_options_change_triggers_rebuild_and_dielectric_scales(pkg, orc):
     w = pkg.workloads.WORKLOADS["w216"]()
     system, st, e, g, dm = gpu_energy(pkg, w)
