@@ -3,7 +3,6 @@
 // (pMolecule-1.9.0/extensions/csource/NBModelABFS.c:508-623) and NBModelABFS_MMMMEnergy (:228-301).
 #include "../../include/nbabfs_b200.h"
 #include "nbb200_internal.h"
-#include <chrono>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>

@@ -110,3 +110,33 @@ def test_langevin_integration_constants(pkg):
     # the reference benchmark's values (25 ps^-1, 1 fs): exponential branch
     f, _ = langevin_constants(0.001, 25.0, 300.0)
     assert 0.975 < f[2] < 0.9754 and f[4] > 0 and f[5] > 0 and f[6] > 0
+
+
+def test_host_row_helpers_of_the_multi_gpu_host_path(pkg):
+    """csrc/host_rows.cpp (no GPU involved): the threaded streaming-store copy into staging memory, the threaded add, and the row gather /
+    scatter-add companions -- sizes below and above the threading threshold, a destination that is not 16-byte aligned, repeated calls on
+    the persistent pool."""
+    import ctypes as C
+    from pdynamo_mirror_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.Generator(np.random.PCG64(7))
+    for m in (5, 32768 + 3, 3 * 250001):
+        a = rng.random(m)
+        b = np.zeros(m + 1)[1:]                              # 8 mod 16: the head of the streaming copy
+        for _ in range(3):
+            L.nbb200_host_copy(C.c_void_p(b.ctypes.data), C.c_void_p(a.ctypes.data), m)
+        assert np.array_equal(a, b)
+        g = np.ones(m)
+        for _ in range(4):
+            L.nbb200_host_add(C.c_void_p(g.ctypes.data), C.c_void_p(a.ctypes.data), m)
+        assert np.allclose(g, 1.0 + 4.0 * a, rtol=0, atol=1e-14)
+    n = 100000
+    x = rng.random((n, 3))
+    ids = rng.permutation(n).astype(np.int32)[:70000]
+    out = np.zeros((len(ids), 3))
+    L.nbb200_host_gather_rows(C.c_void_p(x.ctypes.data), C.c_void_p(ids.ctypes.data), len(ids), C.c_void_p(out.ctypes.data))
+    assert np.array_equal(out, x[ids])
+    acc = np.zeros((n, 3))
+    L.nbb200_host_scatter_add_rows(C.c_void_p(acc.ctypes.data), C.c_void_p(ids.ctypes.data), len(ids), C.c_void_p(out.ctypes.data))
+    ref = np.zeros((n, 3)); ref[ids] = x[ids]
+    assert np.array_equal(acc, ref)
