@@ -1648,7 +1648,8 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
     static const bool fusedMode = []() { const char *e = std::getenv("NBB200_MD_FUSED"); return e == nullptr || std::atoi(e) != 0; }();      // measured: DHFR Langevin 5.08 -> 5.36 k steps/s, ionic NVE 9.9 -> 11.1 k steps/s
     s.mdFused = fusedMode;
     static const bool noSpeculation = std::getenv("NBB200_MD_NO_SPECULATION") != nullptr;
-    int updates = 0, nspec = 0;
+    int updates = 0, nspec = 0, dispKnown = 0;
+    double dispLast = 0.0, dispBefore = 0.0;          // displacement maxima (A) of the last two optimistic steps since the last list update
     bool ok = true;
     double eStep[2][6], dEdM[9], e5[5] = {0, 0, 0, 0, 0};
     for (int c = 0; c < 6; c++) eStep[0][c] = eStep[1][c] = 0.0;
@@ -1661,13 +1662,47 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
     // (who stores what: the accumulators by the unsort pass of the step; the bonded energies by the second half; the displacement maximum of
     // step k and the kinetic energy of step k - 1 by the first kernel of step k's energy call -- always a kernel that STARTS after the value is
     // complete: letting the producing kernel's last CTA do it costs a __threadfence behind its bulk stores, ~4 us per kernel on this GPU)
+    // the bonded terms run on a side stream NEXT TO the NB kernels of the step: they add into the NB state's sorted-order accumulator (rows
+    // invPerm[atom]) and the unsort pass waits for them -- 12 us of a latency-bound kernel leave the critical path.  NBB200_MD_NO_SIDE_STREAM=1:
+    // behind the unsort pass, into d_g, as the Python loop does
+    static const bool sideOff = std::getenv("NBB200_MD_NO_SIDE_STREAM") != nullptr;
+    const bool sideBonded = !sideOff && terms != nullptr && fusedMode && publish && s.nranks == 1 && s.gsExternal == nullptr;
+    cudaStream_t sideStream = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    if (sideBonded && !(cuda_ok(cudaStreamCreateWithFlags(&sideStream, cudaStreamNonBlocking), "cudaStreamCreate") &&
+                        cuda_ok(cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming), "cudaEventCreate") &&
+                        cuda_ok(cudaEventCreateWithFlags(&evJoin, cudaEventDisableTiming), "cudaEventCreate"))) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return 0; }
     auto enqueue_step = [&](int k, bool redo) -> bool {
         for (int c = 0; c < 9; c++) dEdM[c] = 0.0;
-        if (!energy_enqueue(s, d_g, false, haccSlot[k & 1])) return false;
-        if (terms != nullptr && !mmterms_enqueue_slot(terms, d_x, d_g, k & 1, fusedMode && !redo, publish)) return false;
-        if ((redo || !fusedMode) && !cuda_ok(cudaMemsetAsync(d_ke2 + (k & 1), 0, sizeof(double), s.stream), "memset")) return false;
+        const bool side = sideBonded && s.hostCounters.itemCount > 0;
+        if (side) {
+            if (!s.gradSorted.ensure(3 * (size_t) s.n)) return false;
+            if (!s.gsZeroed) {                               // nobody has cleared the accumulator for this call yet
+                if (!cuda_ok(cudaMemsetAsync(s.gradSorted.p, 0, sizeof(double) * 3 * (size_t) s.n, s.stream), "memset")) return false;
+                s.gsZeroed = true;
+            }
+            if (!cuda_ok(cudaEventRecord(evFork, s.stream), "event") || !cuda_ok(cudaStreamWaitEvent(sideStream, evFork, 0), "wait") ||
+                !mmterms_enqueue_slot(terms, d_x, s.gradSorted.p, k & 1, fusedMode && !redo, publish, s.invPerm.p, sideStream) ||
+                !cuda_ok(cudaEventRecord(evJoin, sideStream), "event")) return false;
+            s.preUnsortEvent = evJoin;
+        }
         const double *pubSrc = nullptr; double *pubDst = nullptr;
         if (terms != nullptr && publish) mmterms_slot_pointers(terms, k & 1, &pubSrc, &pubDst);
+        // with the bonded terms already in the sorted accumulator (or none at all) nothing stands between the unsort pass and the second half:
+        // one kernel does both
+        const bool fuseSecond = fusedMode && publish && (side || terms == nullptr) && s.nranks == 1 && s.gsExternal == nullptr && s.hostCounters.itemCount > 0;
+        if (fuseSecond) {
+            if (redo && !cuda_ok(cudaMemsetAsync(d_ke2 + (k & 1), 0, sizeof(double), s.stream), "memset")) return false;
+            s.secondHalf.v = d_v; s.secondHalf.a = d_a; s.secondHalf.mass = d_mass; s.secondHalf.dt = secondHalfDt; s.secondHalf.ke = d_ke2 + (k & 1);
+            s.secondHalf.zeroOther = d_ke2 + ((k + 1) & 1); s.secondHalf.pubSrc = pubSrc; s.secondHalf.pubDst = pubDst; s.secondHalf.pubCount = pubSrc != nullptr ? 5 : 0;
+        }
+        s.secondHalfDone = false;
+        const bool okE = energy_enqueue(s, d_g, false, haccSlot[k & 1]);
+        s.preUnsortEvent = nullptr; s.secondHalf.v = nullptr;
+        if (!okE) return false;
+        if (s.secondHalfDone) return true;
+        if (terms != nullptr && !side && !mmterms_enqueue_slot(terms, d_x, d_g, k & 1, fusedMode && !redo, publish)) return false;
+        if ((redo || !fusedMode) && !fuseSecond && !cuda_ok(cudaMemsetAsync(d_ke2 + (k & 1), 0, sizeof(double), s.stream), "memset")) return false;
         k_vv_second<<<(unsigned int) std::min<long>(148 * 8, (m + 255) / 256), 256, 0, s.stream>>>(d_v, d_a, d_g, d_mass, secondHalfDt, m, d_ke2 + (k & 1),
                                                                                                   fusedMode ? d_ke2 + ((k + 1) & 1) : nullptr,
                                                                                                   pubSrc, pubDst, pubSrc != nullptr ? 5 : 0);
@@ -1695,7 +1730,13 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
             now.set_crystal(box6);
             latticeSame = std::memcmp(now.M.v, s.refLattice.M.v, sizeof(double) * 9) == 0;
         }
-        const bool speculate = !noSpeculation && !forced && !s.isNew && !s.useCentering && s.nranks == 1 && !s.timing && latticeSame &&
+        // when the displacement maximum of the last two steps extrapolates beyond the buffer, an update is probably due at this step: an
+        // optimistic step would be thrown away (~a whole step of GPU time), waiting for the decision costs a short bubble.
+        // NBB200_MD_NO_PREDICTION=1: always optimistic
+        static const bool noPrediction = std::getenv("NBB200_MD_NO_PREDICTION") != nullptr;
+        const double bufferDist = 0.5 * (s.list - s.stOuterCutoff);
+        const bool updateLikely = !noPrediction && dispKnown >= 2 && dispLast + (dispLast - dispBefore) + 0.02 * bufferDist > bufferDist;
+        const bool speculate = !noSpeculation && !forced && !updateLikely && !s.isNew && !s.useCentering && s.nranks == 1 && !s.timing && latticeSame &&
                                s.list == s.stListCutoff && s.outer == s.stOuterCutoff;
         const bool fusedFirst = speculate && fusedMode;         // first half and displacement check in one kernel
         double *d_disp = d_disp2 + (nspec & 1), *d_dispOther = d_disp2 + ((nspec + 1) & 1);
@@ -1732,6 +1773,7 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
             if (k > 0) harvest(k - 1, false);
             s.numberOfCalls += 1;
             const double buffac = 0.5 * (s.list - s.stOuterCutoff);
+            dispBefore = dispLast; dispLast = std::sqrt(hdisp[k & 1]); dispKnown += 1;
             if (hdisp[k & 1] > buffac * buffac) {
                 // an update was due: take the step back (x is untouched by a second half) and go through the ordinary path
                 k_axpy<<<(unsigned int) ((m + 255) / 256), 256, 0, s.stream>>>(d_v, d_a, -0.5 * secondHalfDt, m);
@@ -1747,7 +1789,10 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
             if (owed) {      // its accumulators are turned into energies inside update_common: after the first wait, BEFORE the lists may change
                 s.pending = true; s.pendEnergies = eStep[(k - 1) & 1]; s.pendDEdM = dEdM; s.pendHaveGrad = true; s.pendLattice = s.lattice; s.pendAcc = haccSlot[(k - 1) & 1];
             }
-            updates += update_common(s, box6, forced ? 1 : 0, &st, speculate ? 1 : -1);     // after a take-back the decision is known: no second displacement check
+            const int updated = update_common(s, box6, forced ? 1 : 0, &st, speculate ? 1 : -1);     // after a take-back the decision is known: no second displacement check
+            updates += updated;
+            if (updated) { dispKnown = 0; dispLast = dispBefore = 0.0; }             // new reference coordinates
+            else if (!speculate) { const double grow = dispLast - dispBefore; dispBefore = dispLast; dispLast += grow; }   // (not measured on the host: keep extrapolating)
             if (st != NBB200_STATUS_CONTINUE) { ok = false; set_status(status, st); break; }
             if (owed) { flush_pending(s); harvest(k - 1, true); }
             if (!enqueue_step(k, speculate)) { ok = false; set_status(status, NBB200_STATUS_LOGIC_ERROR); break; }      // speculate here: the step was taken back
@@ -1758,6 +1803,7 @@ int nbb200_md_run(NBB200State *state, NBB200MMTerms *terms, int nsteps, int upda
     s.pending = false;
     if (ok && nsteps > 0) harvest(nsteps - 1, false);
     cudaEventDestroy(evDisp);
+    if (sideStream != nullptr) { cudaStreamSynchronize(sideStream); cudaStreamDestroy(sideStream); cudaEventDestroy(evFork); cudaEventDestroy(evJoin); }
     if (nsteps > 0) cudaMemcpyAsync(d_ke, d_ke2 + ((nsteps - 1) & 1), sizeof(double), cudaMemcpyDeviceToDevice, s.stream);      // the caller's kinetic-energy scalar: the last step's
     cudaStreamSynchronize(s.stream);
     s.mdFused = false; s.gsZeroed = false;

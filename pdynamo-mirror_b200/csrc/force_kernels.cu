@@ -759,6 +759,42 @@ __global__ void k_unsort_gradients(typename std::conditional<kClear, double, con
     if constexpr (kClear) { gs[3 * s] = 0.0; gs[3 * s + 1] = 0.0; gs[3 * s + 2] = 0.0; }
 }
 
+// nbb200_md_run: unsort pass and second half of the velocity-Verlet / Langevin step in one launch -- the gradient of sorted position s goes
+// to atom sAtom[s] (set, not added: the NB term comes first, the bonded terms have been added in sorted order), a = -100 g / m, v += dt/2 a,
+// kinetic energy 0.5 * 0.01 * sum m v^2; the sorted accumulator is left zeroed; the first CTA stores the accumulators of the energy call and
+// the bonded energies of the step into page-locked host memory
+__global__ void k_unsort_second_half(double *__restrict__ gs, const int *__restrict__ sAtom, int n, double *__restrict__ grad, const PublishArgs pub,
+                                     double *__restrict__ v, double *__restrict__ a, const double *__restrict__ mass, double dt, double *__restrict__ ke,
+                                     double *__restrict__ zeroOther, const double *pubSrc, double *pubDst, int pubCount)
+{
+    if (blockIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            for (int i = threadIdx.x; i < pub.count[k]; i += blockDim.x) pub.dst[k][i] = pub.src[k][i];
+        if (threadIdx.x < pubCount) pubDst[threadIdx.x] = pubSrc[threadIdx.x];
+        if (zeroOther != nullptr && threadIdx.x == 0) *zeroOther = 0.0;
+    }
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    double local = 0.0;
+    if (s < n) {
+        const int at = sAtom[s];
+        if (at >= 0) {
+            const double mi = mass[at];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double g = gs[3 * (size_t) s + c];
+                gs[3 * (size_t) s + c] = 0.0;
+                grad[3 * (size_t) at + c] = g;
+                const double ai = -100.0 * g / mi, vi = v[3 * (size_t) at + c] + 0.5 * dt * ai;
+                a[3 * (size_t) at + c] = ai; v[3 * (size_t) at + c] = vi;
+                local += mi * vi * vi;
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+    if ((threadIdx.x & 31) == 0 && local != 0.0) atomicAdd(ke, 0.5 * 0.01 * local);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // 1-4 interactions: explicit pair list, their own LJ table and electrostatic scale, never imaged
 // (NBModelABFS_MMMMEnergy third call, pM/csource/NBModelABFS.c:275-294).  A few thousand pairs: plain fp64.
@@ -909,6 +945,13 @@ bool unsort_gradients(State &s, long s0, long s1, double *d_grad, bool assign, b
     PublishArgs pub;
     for (int k = 0; k < 2; k++) { pub.src[k] = s.pubSrc[k]; pub.dst[k] = s.pubDst[k]; pub.count[k] = (s.pubSrc[k] != nullptr && s.pubDst[k] != nullptr) ? s.pubCount[k] : 0; }
     if (pub.count[0] > 0 || pub.count[1] > 0) s.pubDone = true;
+    if (clear && assign && s.secondHalf.v != nullptr && s0 == 0 && s1 == s.n && s.condDisp == nullptr) {
+        const State::SecondHalf &h = s.secondHalf;
+        k_unsort_second_half<<<blocks, threads, 0, s.stream>>>(s.gs, s.sAtom.p, s.n, d_grad, pub, h.v, h.a, h.mass, h.dt, h.ke, h.zeroOther, h.pubSrc, h.pubDst, h.pubCount);
+        s.secondHalfDone = true;
+        s.launches += 1;
+        return cuda_ok(cudaGetLastError(), "k_unsort_second_half");
+    }
     if (clear) k_unsort_gradients<true><<<blocks, threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0, s.condDisp, s.condThr2, pub);
     else k_unsort_gradients<false><<<blocks, threads, 0, s.stream>>>(s.gs, s.sAtom.p, (int) s0, (int) s1, d_grad, assign ? 1 : 0, s.condDisp, s.condThr2, pub);
     s.launches += 1;
@@ -1069,6 +1112,7 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
         s.launches += 1;
     }
     // device-array calls honour nbb200_set_gradient_overwrite too (the host-array call handles it with its own staging buffer: d_grad = s.grad.p)
+    if (s.preUnsortEvent != nullptr && d_grad != nullptr) NBB_CUDA(cudaStreamWaitEvent(s.stream, s.preUnsortEvent, 0));
     const bool clearGs = fused && s.gsExternal == nullptr && s.nranks == 1 && d_grad != nullptr;
     if (d_grad != nullptr && !unsort_gradients(s, 0, s.n, d_grad, s.gradOverwrite && d_grad != s.grad.p && s.nranks == 1, clearGs)) return false;
     if (clearGs) s.gsZeroed = true;                          // the whole accumulator (3 n) has just been cleared by the unsort pass

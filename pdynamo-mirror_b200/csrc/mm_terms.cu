@@ -80,7 +80,10 @@ __device__ __forceinline__ void torsion_gradient(const Torsion &t, double df, in
     add3(g, l, dtxl, dtyl, dtzl);
 }
 
-__global__ void k_mm_terms(const TermRecord *__restrict__ rec, KindStarts K, const double *__restrict__ x, double *g, double *energies, double *zeroOther)
+// perm (nbb200_md_run): gradients go to row perm[atom] of g -- the NB state's sorted-order accumulator, so that the bonded terms can run next
+// to the NB kernels of the step instead of behind its unsort pass
+__global__ void k_mm_terms(const TermRecord *__restrict__ rec, KindStarts K, const double *__restrict__ x, double *g, double *energies, double *zeroOther,
+                           const int *__restrict__ perm)
 {
     if (zeroOther != nullptr && blockIdx.x == 0 && threadIdx.x < kKinds) zeroOther[threadIdx.x] = 0.0;   // two-slot use: prepares the next step's accumulators
     __shared__ double sE[kKinds];
@@ -92,6 +95,8 @@ __global__ void k_mm_terms(const TermRecord *__restrict__ rec, KindStarts K, con
         while (n >= K.s[kind + 1]) kind++;
         const TermRecord r = rec[n];
         const int i = r.atom[0], j = r.atom[1], k = r.atom[2], l = r.atom[3];
+        int gi = i, gj = j, gk = k, gl = l;                   // gradient rows
+        if (perm != nullptr) { gi = perm[i]; gj = perm[j]; gk = perm[k]; gl = perm[l]; }
         double e = 0.0;
         if (kind == 0 || kind == 2) {                         // harmonic bond / Urey-Bradley: E = fc (r - eq)^2
             double xij = x[3 * i] - x[3 * j], yij = x[3 * i + 1] - x[3 * j + 1], zij = x[3 * i + 2] - x[3 * j + 2];
@@ -101,7 +106,7 @@ __global__ void k_mm_terms(const TermRecord *__restrict__ rec, KindStarts K, con
             if (g != nullptr) {
                 df *= (2.0 / rij);
                 xij *= df; yij *= df; zij *= df;
-                add3(g, i, xij, yij, zij); add3(g, j, -xij, -yij, -zij);
+                add3(g, gi, xij, yij, zij); add3(g, gj, -xij, -yij, -zij);
             }
         } else if (kind == 1) {                               // harmonic angle i-j-k: E = fc (theta - eq)^2, |cos| clamped at 0.999999
             double xij = x[3 * i] - x[3 * j], yij = x[3 * i + 1] - x[3 * j + 1], zij = x[3 * i + 2] - x[3 * j + 2];
@@ -117,7 +122,7 @@ __global__ void k_mm_terms(const TermRecord *__restrict__ rec, KindStarts K, con
                 df *= (2.0 * (-1.0 / sqrt(1.0 - dot * dot)));
                 const double dtxi = df * (xkj - dot * xij) / rij, dtyi = df * (ykj - dot * yij) / rij, dtzi = df * (zkj - dot * zij) / rij;
                 const double dtxk = df * (xij - dot * xkj) / rkj, dtyk = df * (yij - dot * ykj) / rkj, dtzk = df * (zij - dot * zkj) / rkj;
-                add3(g, i, dtxi, dtyi, dtzi); add3(g, k, dtxk, dtyk, dtzk); add3(g, j, -(dtxi + dtxk), -(dtyi + dtyk), -(dtzi + dtzk));
+                add3(g, gi, dtxi, dtyi, dtzi); add3(g, gk, dtxk, dtyk, dtzk); add3(g, gj, -(dtxi + dtxk), -(dtyi + dtyk), -(dtzi + dtzk));
             }
         } else if (kind == 3) {                               // Fourier dihedral: E = fc (1 + cos(period phi - phase)), by the angle-addition recurrence
             const Torsion t = torsion(x, i, j, k, l);
@@ -129,7 +134,7 @@ __global__ void k_mm_terms(const TermRecord *__restrict__ rec, KindStarts K, con
                 cosn = tmp;
             }
             e = r.p[0] * (1.0 + cosn * r.p[1] + sinn * r.p[2]);
-            if (g != nullptr) torsion_gradient(t, r.p[0] * r.p[3] * (cosn * r.p[2] - sinn * r.p[1]), i, j, k, l, g);
+            if (g != nullptr) torsion_gradient(t, r.p[0] * r.p[3] * (cosn * r.p[2] - sinn * r.p[1]), gi, gj, gk, gl, g);
         } else {                                              // harmonic improper: E = fc (phi - eq)^2, CHARMM's choice of inverse function
             const Torsion t = torsion(x, i, j, k, l);
             const double cosd = t.cosphi * r.p[1] + t.sinphi * r.p[2], sind = t.sinphi * r.p[1] - t.cosphi * r.p[2];
@@ -138,7 +143,7 @@ __global__ void k_mm_terms(const TermRecord *__restrict__ rec, KindStarts K, con
             else { dphi = fabs(acos(fmax(cosd, -1.0))); if (sind < 0.0) dphi *= -1.0; }
             const double df = r.p[0] * dphi;
             e = df * dphi;
-            if (g != nullptr) torsion_gradient(t, 2.0 * df, i, j, k, l, g);
+            if (g != nullptr) torsion_gradient(t, 2.0 * df, gi, gj, gk, gl, g);
         }
         atomicAdd(&sE[kind], e);
     }
@@ -163,21 +168,22 @@ static bool upload_terms(MMTerms &m)
 // enqueue only: the kernel and the copy of the five energies into pinned memory; collect() waits for them
 // fused (nbb200_md_run, alternating slots): the device accumulators have two slots of 8 doubles; the kernel of slot s zeroes slot 1 - s for the
 // next step, so no memset is enqueued
-static bool enqueue(MMTerms &m, const double *d_x, double *d_grad, int slot = 0, bool fused = false, bool noCopy = false)
+static bool enqueue(MMTerms &m, const double *d_x, double *d_grad, int slot = 0, bool fused = false, bool noCopy = false, const int *perm = nullptr, cudaStream_t on = nullptr)
 {
+    const cudaStream_t st = on != nullptr ? on : m.stream;
     if (m.dirty && !upload_terms(m)) return false;
     const int total = m.start[kKinds];
     fused = fused && total > 0;
     double *acc = m.energies.p + 8 * (slot & 1);
-    if (fused && !m.slotsZeroed) { NBB_CUDA(cudaMemsetAsync(m.energies.p, 0, sizeof(double) * 16, m.stream)); m.slotsZeroed = true; }
-    if (!fused) { NBB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * kKinds, m.stream)); m.slotsZeroed = false; }
+    if (fused && !m.slotsZeroed) { NBB_CUDA(cudaMemsetAsync(m.energies.p, 0, sizeof(double) * 16, st)); m.slotsZeroed = true; }
+    if (!fused) { NBB_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * kKinds, st)); m.slotsZeroed = false; }
     if (total > 0) {
         KindStarts K;
         std::memcpy(K.s, m.start, sizeof(K.s));
-        k_mm_terms<<<(total + 127) / 128, 128, 0, m.stream>>>(m.rec.p, K, d_x, d_grad, acc, fused ? m.energies.p + 8 * ((slot + 1) & 1) : nullptr);
+        k_mm_terms<<<(total + 127) / 128, 128, 0, st>>>(m.rec.p, K, d_x, d_grad, acc, fused ? m.energies.p + 8 * ((slot + 1) & 1) : nullptr, perm);
         m.launches += 1;
     }
-    if (!noCopy) NBB_CUDA(cudaMemcpyAsync(m.he + 8 * (slot & 1), acc, sizeof(double) * kKinds, cudaMemcpyDeviceToHost, m.stream));       // noCopy: a later kernel of the caller hands the slot over
+    if (!noCopy) NBB_CUDA(cudaMemcpyAsync(m.he + 8 * (slot & 1), acc, sizeof(double) * kKinds, cudaMemcpyDeviceToHost, st));       // noCopy: a later kernel of the caller hands the slot over
     return cuda_ok(cudaGetLastError(), "k_mm_terms");
 }
 
@@ -525,10 +531,10 @@ void MMTerms_B200_LastEnergies(NBB200MMTerms *terms, double *energies5)
 
 // internal (nbb200_md_run): two result slots, so that a step's energies stay readable while the next step is already in flight
 namespace nbb200 {
-bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot, bool fused, bool noCopy)
+bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot, bool fused, bool noCopy, const int *perm, cudaStream_t on)
 {
     MMTerms *m = reinterpret_cast<MMTerms *>(terms);
-    return enqueue(*m, d_x, d_grad, slot, fused, noCopy);
+    return enqueue(*m, d_x, d_grad, slot, fused, noCopy, perm, on);
 }
 void mmterms_slot_pointers(NBB200MMTerms *terms, int slot, const double **d_energies, double **h_energies)
 {

@@ -99,7 +99,8 @@ bool touched_ranges_async(State &s, long *d_out);      // the same table written
 }  // namespace nbb200
 struct NBB200MMTerms;
 namespace nbb200 {
-bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot, bool fused = false, bool noCopy = false);
+bool mmterms_enqueue_slot(NBB200MMTerms *terms, const double *d_x, double *d_grad, int slot, bool fused = false, bool noCopy = false,
+                          const int *perm = nullptr, cudaStream_t on = nullptr);   // perm: gradient rows perm[atom]; on: another stream than the container's
 void mmterms_slot_pointers(NBB200MMTerms *terms, int slot, const double **d_energies, double **h_energies);
 void mmterms_read_slot(NBB200MMTerms *terms, int slot, double *energies5);
 void mmterms_reset_slots(NBB200MMTerms *terms);
@@ -263,6 +264,11 @@ struct State {
     bool lcOn = false, lcValid = false; double lcTotalMass = 0.0; unsigned long long lcStep = 0, lcSeed = 0; DevBuf<double> lcSums; DevBuf<double2> lcW;
     // nbb200_md_run: two scalars stored into page-locked memory by the first kernel of the energy call (k_pack_records), and an event behind it
     const double *prePubSrc[2] = {nullptr, nullptr}; double *prePubDst[2] = {nullptr, nullptr}; cudaEvent_t prePubEvent = nullptr; bool prePubDone = false;
+    // nbb200_md_run: the unsort pass also does the second half of the integrator step (force_kernels.cu: k_unsort_second_half)
+    struct SecondHalf { double *v = nullptr, *a = nullptr; const double *mass = nullptr; double dt = 0.0; double *ke = nullptr, *zeroOther = nullptr;
+                        const double *pubSrc = nullptr; double *pubDst = nullptr; int pubCount = 0; } secondHalf;
+    bool secondHalfDone = false;
+    cudaEvent_t preUnsortEvent = nullptr;        // nbb200_md_run: the unsort pass waits for it (bonded terms accumulated into the sorted gradient on a side stream)
     bool mdFused = false;                        // inside nbb200_md_run: memsets folded into neighbouring kernels (accumulators by k_pack_records, sorted gradient by k_unsort_gradients)
     bool gsZeroed = false;                       // the caller zeroed the sorted gradient for this call already (before the ranks' barrier)                        // touched sorted range per rank slab (min, max+1)
     DevBuf<unsigned long long> setPairs;         // per set list-pair counts
