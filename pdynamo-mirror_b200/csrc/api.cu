@@ -60,6 +60,7 @@ static void destroy(State *s)
     s->tileDesc.release(); s->tileDescIn.release(); s->itemsIn.release(); s->xprune.release(); s->pruneDisp.release(); s->recA.release(); s->recB.release(); s->gradSorted.release(); s->items.release(); s->rangeTab.release(); s->rangeOut.release(); s->setPairs.release(); s->accum.release();
     s->pairBuf.release(); s->pairCursor.release(); s->splF64.release(); s->splPoly.release(); s->mdScalars.release();
     for (auto &e : s->chunkEvents) if (e != nullptr) cudaEventDestroy(e);
+    if (s->sideStream != nullptr) { cudaStreamSynchronize(s->sideStream); cudaStreamDestroy(s->sideStream); cudaEventDestroy(s->evPack); cudaEventDestroy(s->evSide14); }
     for (int r = 0; r < State::kMaxPeers; r++) if (s->peerChunkOpened[r]) { cudaIpcCloseMemHandle(s->peerXc[r]); cudaIpcCloseMemHandle(s->peerGc[r]); }
     for (int r = 0; r < State::kMaxPeers; r++) if (s->peerOpened[r]) { cudaIpcCloseMemHandle(s->peerGs[r]); cudaIpcCloseMemHandle(s->peerXs[r]); cudaIpcCloseMemHandle(s->peerSig[r]); }
     s->symGs.release(); s->symXs.release(); s->symSig.release(); s->sigStage.release();

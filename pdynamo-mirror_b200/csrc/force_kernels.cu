@@ -981,6 +981,21 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
     if (!fusedZero) NBB_CUDA(cudaMemsetAsync(s.accum.p, 0, sizeof(double) * (accumCount + 1), s.stream));
     unsigned int *workCursor = reinterpret_cast<unsigned int *>(s.accum.p + accumCount);
     const double eScale = (1.0 / s.dielectric) * kE2AngstromToKJMol;
+    // inside nbb200_md_run the 1-4 kernel (a few thousand pairs, fp64: ~5 us, latency bound) runs on a side stream NEXT TO the tile kernel: it
+    // needs the cleared accumulators (behind k_pack_records) and nothing else of this call.  NBB200_NO_SIDE14=1: behind the tile kernel
+    bool pairs14Done = false, pairs14Side = false;
+    auto launch_pairs14 = [&](cudaStream_t st) {
+        F64Factors FF;
+        std::memcpy(FF.v, s.factors, sizeof(FF.v));
+        const int threads = 128, nblk = std::max(1, std::min(1184, (s.n14 + threads - 1) / threads));
+        if (s.timing) cudaEventRecord(s.ev[4], st);
+        k_pairs14<<<nblk, threads, 0, st>>>(s.pairs14.p, s.n14, s.xcur, s.q64.p, s.ljtype.p, s.ljAB14.p, s.ntypes14, FF,
+                                            (s.useAnalytic ? eScale : 1.0 / s.dielectric) * s.scale14, s.invPerm.p, s.ownLo, s.ownHi, wantGrad ? s.gs : nullptr,
+                                            s.accum.p + 16 * s.nsets, s.useAnalytic ? nullptr : s.splF64.p, s.useAnalytic ? 0 : s.spl.points());
+        if (s.timing) cudaEventRecord(s.ev[5], st);
+        s.launches += 1;
+        pairs14Done = true;
+    };
     if (nitems > 0) {
         if (!s.recA.ensure((size_t) s.n + 1) || !s.recB.ensure((size_t) s.n + 1)) return false;
         if (g_numSMs == 0) init_force_kernel_attributes();
@@ -1011,6 +1026,19 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
                                                             (prune && !pruneForce) ? s.xprune.p : nullptr, s.pruneDisp.p, slot, prePub);
         if (prePub.count[0] > 0 || prePub.count[1] > 0 || s.prePubEvent != nullptr) s.prePubDone = true;
         if (s.prePubEvent != nullptr) cudaEventRecord(s.prePubEvent, s.stream);
+        static const bool side14Off = std::getenv("NBB200_NO_SIDE14") != nullptr;
+        if (s.n14 > 0 && !side14Off && !s.timing && s.mdFused) {     // inside nbb200_md_run only: for a single call the two event operations cost more than the overlap saves (measured: DHFR rebuild call 0.35 -> 0.39 ms)
+            if (s.sideStream == nullptr) {
+                NBB_CUDA(cudaStreamCreateWithFlags(&s.sideStream, cudaStreamNonBlocking));
+                NBB_CUDA(cudaEventCreateWithFlags(&s.evPack, cudaEventDisableTiming));
+                NBB_CUDA(cudaEventCreateWithFlags(&s.evSide14, cudaEventDisableTiming));
+            }
+            NBB_CUDA(cudaEventRecord(s.evPack, s.stream));
+            NBB_CUDA(cudaStreamWaitEvent(s.sideStream, s.evPack, 0));
+            launch_pairs14(s.sideStream);
+            NBB_CUDA(cudaEventRecord(s.evSide14, s.sideStream));
+            pairs14Side = true;
+        }
         bool rot = false;                                   // any image with a genuine rotation?
         for (const RealSpaceOp &b : s.plan.baseOps) rot = rot || !b.pureTranslation;
         if (prune) {
@@ -1100,17 +1128,8 @@ bool launch_forces(State &s, double *d_grad, bool sortedOnly)
         if (s.timing) cudaEventRecord(s.ev[3], s.stream);
         s.launches += 2;
     }
-    if (s.n14 > 0) {
-        F64Factors FF;
-        std::memcpy(FF.v, s.factors, sizeof(FF.v));
-        const int threads = 128, nblk = std::max(1, std::min(1184, (s.n14 + threads - 1) / threads));
-        if (s.timing) cudaEventRecord(s.ev[4], s.stream);
-        k_pairs14<<<nblk, threads, 0, s.stream>>>(s.pairs14.p, s.n14, s.xcur, s.q64.p, s.ljtype.p, s.ljAB14.p, s.ntypes14, FF,
-                                                    (s.useAnalytic ? eScale : 1.0 / s.dielectric) * s.scale14, s.invPerm.p, s.ownLo, s.ownHi, wantGrad ? s.gs : nullptr,
-                                                    s.accum.p + 16 * s.nsets, s.useAnalytic ? nullptr : s.splF64.p, s.useAnalytic ? 0 : s.spl.points());
-        if (s.timing) cudaEventRecord(s.ev[5], s.stream);
-        s.launches += 1;
-    }
+    if (s.n14 > 0 && !pairs14Done) launch_pairs14(s.stream);
+    if (pairs14Side) NBB_CUDA(cudaStreamWaitEvent(s.stream, s.evSide14, 0));      // whoever reads the accumulators next is behind the 1-4 kernel
     // device-array calls honour nbb200_set_gradient_overwrite too (the host-array call handles it with its own staging buffer: d_grad = s.grad.p)
     if (s.preUnsortEvent != nullptr && d_grad != nullptr) NBB_CUDA(cudaStreamWaitEvent(s.stream, s.preUnsortEvent, 0));
     const bool clearGs = fused && s.gsExternal == nullptr && s.nranks == 1 && d_grad != nullptr;

@@ -268,6 +268,7 @@ struct State {
     struct SecondHalf { double *v = nullptr, *a = nullptr; const double *mass = nullptr; double dt = 0.0; double *ke = nullptr, *zeroOther = nullptr;
                         const double *pubSrc = nullptr; double *pubDst = nullptr; int pubCount = 0; } secondHalf;
     bool secondHalfDone = false;
+    cudaStream_t sideStream = nullptr; cudaEvent_t evPack = nullptr, evSide14 = nullptr;      // launch_forces: the 1-4 kernel next to the tile kernel
     cudaEvent_t preUnsortEvent = nullptr;        // nbb200_md_run: the unsort pass waits for it (bonded terms accumulated into the sorted gradient on a side stream)
     bool mdFused = false;                        // inside nbb200_md_run: memsets folded into neighbouring kernels (accumulators by k_pack_records, sorted gradient by k_unsort_gradients)
     bool gsZeroed = false;                       // the caller zeroed the sorted gradient for this call already (before the ranks' barrier)                        // touched sorted range per rank slab (min, max+1)
