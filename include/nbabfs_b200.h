@@ -371,6 +371,9 @@ double nbb200_peer_wait_begin(NBB200State *state, long step, int needValue, int 
 void nbb200_peer_pull_positions(NBB200State *state, const long *d_row, const long *slabEdges, int wholeSlabs, double *d_x);
 void nbb200_peer_push_gradients(NBB200State *state, const long *d_row);
 void nbb200_peer_signal_end(NBB200State *state, long step, const double *scal15);
+/* the same with the scalars computed from the accumulators of the enqueued energy call by a kernel (no host wait before the signal; the per-rank
+ * energies stay on the device, nbb200_peer_read_sums hands out the sums) */
+void nbb200_peer_signal_end_device(NBB200State *state, long step, int *status);
 void nbb200_peer_wait_end(NBB200State *state, long step);                                   /* on the stream; no host wait */
 void nbb200_peer_read_sums(NBB200State *state, double *sum15, int *status);                 /* synchronises; the sums of the last wait_end */
 

@@ -110,6 +110,7 @@ SIGNATURES = {
     "nbb200_peer_signal_begin": (None, [vp, C.c_long, vp, C.c_int]),
     "nbb200_peer_wait_begin": (C.c_double, [vp, C.c_long, C.c_int, ip]),
     "nbb200_peer_signal_end": (None, [vp, C.c_long, dp]),
+    "nbb200_peer_signal_end_device": (None, [vp, C.c_long, ip]),
     "nbb200_peer_wait_end": (None, [vp, C.c_long]),
     "nbb200_peer_read_sums": (None, [vp, dp, ip]),
 }

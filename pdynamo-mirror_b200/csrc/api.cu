@@ -1221,6 +1221,66 @@ void nbb200_peer_signal_end(NBB200State *state, long step, const double *scal15)
     s.launches += 1;
 }
 
+// the 15 scalars of a call (6 energies, dE/dM) from the accumulators ON THE DEVICE: dE/dM is linear in the per-image sums (W[9], G[3]) --
+// dEdM = sum_k M_k [W_k; G_k] with M_k (9 x 12) made on the host from image_derivatives (symmetry_host.cpp) applied to unit vectors
+static __global__ void k_scalars(const double *__restrict__ acc, int nsets, const double *__restrict__ mat, double *__restrict__ out15)
+{
+    const int t = threadIdx.x;
+    if (t < 9) {
+        double v = 0.0;
+        for (int k = 1; k < nsets; k++) {
+            const double *M = mat + (size_t) (k - 1) * 108 + 12 * t, *a = acc + 16 * k;
+            for (int j = 0; j < 9; j++) v += M[j] * a[5 + j];
+            for (int j = 0; j < 3; j++) v += M[9 + j] * a[2 + j];
+        }
+        out15[6 + t] = v;
+    } else if (t < 15) {
+        const int e = t - 9;
+        double v = 0.0;
+        if (e == NBB200_EMMEL) v = acc[0];
+        else if (e == NBB200_EMMLJ) v = acc[1];
+        else if (e == NBB200_EIMMMEL) { for (int k = 1; k < nsets; k++) v += acc[16 * k]; }
+        else if (e == NBB200_EIMMMLJ) { for (int k = 1; k < nsets; k++) v += acc[16 * k + 1]; }
+        else if (e == NBB200_EMMEL14) v = acc[16 * nsets];
+        else if (e == NBB200_EMMLJ14) v = acc[16 * nsets + 1];
+        out15[e] = v;
+    }
+}
+
+/* the same hand-over as nbb200_peer_signal_end, with the scalars taken from the accumulators of the energy call that has just been enqueued
+ * (NBModelABFS_B200_MMMMEnergySortedEnqueue) by a kernel: no host wait between the energy kernels and the signal.  The per-rank energies are
+ * not handed to the host; nbb200_peer_read_sums gives the sums over the ranks. */
+void nbb200_peer_signal_end_device(NBB200State *state, long step, int *status)
+{
+    if (state == nullptr) return;
+    State &s = *reinterpret_cast<State *>(state);
+    cudaSetDevice(s.device);
+    const int nimg = s.nsets - 1;
+    if (!(s.scalMatValid && s.scalMatGeneration == s.numberOfUpdates && std::memcmp(s.scalMatLattice.v, s.lattice.M.v, sizeof(double) * 9) == 0)) {
+        std::vector<double> mat((size_t) 108 * std::max(1, nimg), 0.0);
+        for (int k = 0; k < nimg; k++) {
+            const CandidateImage &im = s.plan.images[k];
+            const double xt[3] = {s.trans.trans[3 * im.t] + (double) im.a, s.trans.trans[3 * im.t + 1] + (double) im.b, s.trans.trans[3 * im.t + 2] + (double) im.c};
+            for (int j = 0; j < 12; j++) {
+                double W[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, G[3] = {0, 0, 0}, out[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                if (j < 9) W[j] = 1.0; else G[j - 9] = 1.0;
+                image_derivatives(out, s.lattice, s.trans.rot[im.t], xt, W, G);
+                for (int t = 0; t < 9; t++) mat[(size_t) k * 108 + 12 * t + j] = out[t];
+            }
+        }
+        if (!s.scalMat.ensure(mat.size())) { set_status(status, NBB200_STATUS_OUT_OF_MEMORY); return; }
+        // (a pageable copy: staged by the driver before the call returns, ordered on the stream)
+        if (!cuda_ok(cudaMemcpyAsync(s.scalMat.p, mat.data(), sizeof(double) * mat.size(), cudaMemcpyHostToDevice, s.stream), "H2D")) { set_status(status, NBB200_STATUS_LOGIC_ERROR); return; }
+        cudaStreamSynchronize(s.stream);                       // rare (list update or lattice change): keeps `mat` alive until the DMA is done
+        s.scalMatValid = true; s.scalMatGeneration = s.numberOfUpdates; s.scalMatLattice = s.lattice.M;
+    }
+    k_scalars<<<1, 32, 0, s.stream>>>(s.accum.p, s.nsets, s.scalMat.p, s.sigStage.p + 1);
+    PeerPtrs P;
+    for (int r = 0; r < State::kMaxPeers; r++) P.p[r] = s.peerSig[r];
+    k_signal_b<<<1, 32, 0, s.stream>>>(P, s.rank, s.nranks, (double) step, s.sigStage.p + 1);
+    s.launches += 2;
+}
+
 /* wait (on the stream) until every rank has signalled the end of `step`: all pushes into this rank's accumulator are complete and the
  * scalars are summed; no host wait -- nbb200_peer_read_sums fetches them */
 void nbb200_peer_wait_end(NBB200State *state, long step)

@@ -240,6 +240,7 @@ struct State {
     double *peerGs[kMaxPeers] = {}, *peerXs[kMaxPeers] = {}, *peerSig[kMaxPeers] = {};
     DevBuf<double> sigStage;                     // device staging: [0] local displacement maximum, [1..16] scalars, [17..32] results, [33] timeout flag
     bool peerOpened[kMaxPeers] = {};
+    DevBuf<double> scalMat; bool scalMatValid = false; long scalMatGeneration = -1; Mat3 scalMatLattice;      // nbb200_peer_signal_end_device: dE/dM as a linear map of the image sums
     // host callers, several ranks: atom-order chunk buffers (positions as uploaded by the rank that holds the host rows; gradients as downloaded by it)
     DevBuf<double> symXc, symGc;
     double *peerXc[kMaxPeers] = {}, *peerGc[kMaxPeers] = {};

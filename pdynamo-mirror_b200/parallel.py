@@ -213,6 +213,8 @@ class DistributedNB:
             self.gs = torch.zeros((n, 3), dtype=torch.float64, device=device)
             self.xs = torch.zeros((n, 3), dtype=torch.float64, device=device)
             self.L.nbb200_set_sorted_gradient_buffer(self.h, C.c_void_p(self.gs.data_ptr()))
+        import os
+        self.host_scalars = os.environ.get("NBB200_HOST_SCALARS") is not None      # the round-1 hand-over of the scalars through the host
         self.profile = None                                  # set to a dict to collect wall-clock seconds per phase (synchronising: debugging only)
         self.host_profile = None                             # the same for call_host
         self.first, self.box, self.slabs = True, None, None
@@ -312,7 +314,12 @@ class DistributedNB:
             # the push to the owners only depends on the kernels: it is enqueued before the host waits for the energies
             L.NBModelABFS_B200_MMMMEnergySortedEnqueue(self.h, C.byref(st))
             L.nbb200_peer_push_gradients(self.h, C.c_void_p(self.tab_mine.data_ptr()))
-            L.NBModelABFS_B200_MMMMEnergySortedFinish(self.h, self._lib.d_(self.energies), self._lib.d_(self.dEdM), C.byref(st))
+            if not self.host_scalars:
+                # the 15 scalars go from the accumulators to the peers' signal areas by kernels: no host wait inside the call at all
+                # (self.energies / self.dEdM, this rank's own terms, are not updated: results() has the sums over the ranks)
+                L.nbb200_peer_signal_end_device(self.h, self.step, C.byref(st))
+            else:
+                L.NBModelABFS_B200_MMMMEnergySortedFinish(self.h, self._lib.d_(self.energies), self._lib.d_(self.dEdM), C.byref(st))
         else:
             L.NBModelABFS_B200_MMMMEnergySorted(self.h, self._lib.d_(self.energies), self._lib.d_(self.dEdM), C.byref(st))
         if st.value != 16:
@@ -320,8 +327,9 @@ class DistributedNB:
         self._tick("energy")
         s0, s1 = self.slabs[self.rank]
         if peer:
-            scal = np.concatenate([self.energies, self.dEdM])
-            L.nbb200_peer_signal_end(self.h, self.step, self._lib.d_(scal))
+            if self.host_scalars:
+                scal = np.concatenate([self.energies, self.dEdM])
+                L.nbb200_peer_signal_end(self.h, self.step, self._lib.d_(scal))
             L.nbb200_peer_wait_end(self.h, self.step)          # on the stream: all pushes into the own slab are complete, scalars summed
             if g is not None:
                 L.nbb200_unsort_add(self.h, s0, s1 - s0, C.c_void_p(g.data_ptr()))

@@ -801,7 +801,10 @@ def test_peer_memory_transport_three_partitions_one_gpu(pkg):
             ee, dd = np.zeros(6), np.zeros(9)
             L.NBModelABFS_B200_MMMMEnergySorted(hs[r], _lib.d_(ee), _lib.d_(dd), C.byref(status))
             L.nbb200_peer_push_gradients(hs[r], C.c_void_p(rows[r].data_ptr()))
-            L.nbb200_peer_signal_end(hs[r], step, _lib.d_(np.concatenate([ee, dd])))
+            if host_chunks:                                  # the scalars from the accumulators to the peers by kernels (what DistributedNB.call does)
+                L.nbb200_peer_signal_end_device(hs[r], step, C.byref(status))
+            else:
+                L.nbb200_peer_signal_end(hs[r], step, _lib.d_(np.concatenate([ee, dd])))
             es.append(ee)
         assert status.value == 16, _lib.last_error()
         if forced:
@@ -874,6 +877,9 @@ def test_peer_memory_transport_three_partitions_one_gpu(pkg):
         if forced:
             sys_atoms = owners()
         check(g, sums, er, gr)
+        dmr = ref.configuration.symmetryParameterGradients.dEdM.reshape(-1)       # the device-made scalars carry dE/dM as well
+        for out in sums:
+            assert np.linalg.norm(out[6:] - dmr) <= 1e-5 * np.linalg.norm(dmr)
         assert np.abs(gh - g).max() <= 1e-12 * np.abs(g).max()      # every row exactly once, the owners' values
 
 
